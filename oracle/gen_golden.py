@@ -1,0 +1,119 @@
+"""Generate tests/golden/*.npz from the LIVE reference (run in the build container only).
+
+TEST INFRASTRUCTURE ONLY.  Usage:  python -m oracle.gen_golden
+Imports /root/reference through oracle/ref_shim.py (nothing is copied) and dumps small seeded
+input/output vectors so the GPU box -- which has no /root/reference -- can pin the oracle and the
+CUDA path against the reference's actual outputs.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from oracle import ref_shim, vtn_oracle
+
+GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+TINY_HP = dict(idim=80, odim=80, dprenet_layers=2, dprenet_units=16, adim=32, aheads=2, elayers=1, eunits=48,
+               dlayers=2, dunits=48, postnet_layers=3, postnet_filts=5, postnet_chans=16,
+               decoder_reduction_factor=2)
+
+
+def gen_vtn_tiny():
+    from seq2seq_vc.losses import Seq2SeqLoss
+    from seq2seq_vc.models import VTN
+
+    torch.manual_seed(7)
+    model = VTN(dprenet_dropout_rate=0.0, **TINY_HP)
+    ref_shim.disable_dropout(model)
+    # de-trivialise LayerNorm / BatchNorm affine params and PE alphas so they are exercised
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith("alpha"):
+                p.fill_(0.7 if "encoder" in n else 1.3)
+            elif p.dim() == 1 and ("norm" in n or ".1." in n):
+                p.add_(0.1 * torch.randn_like(p))
+    model.train()
+    sd0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    xs, ilens, ys, labels, olens = vtn_oracle.synthetic_batch(3, 48, 37, ilens=[48, 41, 30], olens=[37, 30, 21], seed=11)
+    out = model(xs, torch.tensor(ilens), ys, labels, torch.tensor(olens))
+    l1, bce = Seq2SeqLoss()(*out[:6])
+    (l1 + bce).backward()
+    dump = {"sd." + k: v.numpy() for k, v in sd0.items()}
+    dump.update({"grad." + k: p.grad.numpy() for k, p in model.named_parameters()})
+    dump.update({"bn_after." + k: v.numpy() for k, v in model.state_dict().items() if "running_" in k})
+    dump.update(xs=xs.numpy(), ilens=np.array(ilens), ys=ys.numpy(), labels=labels.numpy(), olens=np.array(olens),
+                after_outs=out[0].detach().numpy(), before_outs=out[1].detach().numpy(),
+                logits=out[2].detach().numpy(), ys_out=out[3].numpy(), labels_out=out[4].numpy(),
+                olens_out=out[5].numpy(), ilens_ds_st=out[6][1].numpy(), olens_in=out[6][2].numpy(),
+                l1_loss=l1.detach().numpy(), bce_loss=bce.detach().numpy())
+    for i, a in enumerate(out[6][0]):
+        dump[f"att_ws.{i}"] = a.detach().numpy()
+    # eval-mode (running-stat BatchNorm) forward on the *updated* running stats
+    model.eval()
+    with torch.no_grad():
+        oute = model(xs, torch.tensor(ilens), ys, labels, torch.tensor(olens))
+    dump["eval_after_outs"] = oute[0].numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "vtn_tiny.npz"), **dump)
+    print("vtn_tiny:", len(dump), "arrays")
+
+
+def gen_mas():
+    from seq2seq_vc.modules.alignments import _monotonic_alignment_search, viterbi_decode
+
+    rng = np.random.default_rng(3)
+    dump = {}
+    shapes = [(1, 1), (5, 3), (7, 7), (17, 1), (33, 32), (64, 13), (96, 24), (50, 50)]
+    for n, (tm, ti) in enumerate(shapes):
+        for kind in ("rand", "ties", "inf"):
+            lp = torch.log_softmax(torch.from_numpy(rng.standard_normal((tm, ti)).astype(np.float32)), -1).numpy()
+            if kind == "ties":
+                lp = (np.round(lp * 2) / 2).astype(np.float32)
+            if kind == "inf" and ti > 1:
+                lp[:, ti // 2:] = -np.inf
+            dump[f"lp.{n}.{kind}"] = lp
+            dump[f"path.{n}.{kind}"] = _monotonic_alignment_search(lp).astype(np.int64)
+    B, TF, TT = 6, 72, 20
+    lp = torch.log_softmax(torch.from_numpy(rng.standard_normal((B, TF, TT)).astype(np.float32)), -1)
+    tl = torch.tensor([20, 17, 9, 20, 1, 12])
+    fl = torch.tensor([72, 60, 40, 20, 33, 71])
+    for b in range(B):  # the reference masks padded text columns with -inf before log_softmax
+        lp[b, :, tl[b]:] = -np.inf
+    ds, bin_loss = viterbi_decode(lp, tl, fl)
+    dump.update(vd_lp=lp.numpy(), vd_tl=tl.numpy(), vd_fl=fl.numpy(), vd_ds=ds.numpy(), vd_bin_loss=np.float32(bin_loss))
+    np.savez_compressed(os.path.join(GOLDEN, "mas.npz"), **dump)
+    print("mas:", len(dump), "arrays")
+
+
+def gen_kats():
+    """Docstring known-answer examples of the reference."""
+    from seq2seq_vc.layers.utils import make_non_pad_mask, make_pad_mask
+    from seq2seq_vc.losses.guided_attention_loss import GuidedAttentionLoss
+    from seq2seq_vc.modules.transformer.mask import subsequent_mask
+
+    dump = dict(pad_mask_532=make_pad_mask([5, 3, 2]).numpy(), non_pad_mask_532=make_non_pad_mask([5, 3, 2]).numpy(),
+                subsequent_mask_3=subsequent_mask(3).numpy())
+    ga = GuidedAttentionLoss(sigma=0.4)
+    dump["ga_5x5"] = ga._make_guided_attention_mask(torch.tensor(5), torch.tensor(5), 0.4).numpy()
+    dump["ga_6x3"] = ga._make_guided_attention_mask(torch.tensor(3), torch.tensor(6), 0.4).numpy()
+    dump["ga_masks_52_85"] = ga._make_masks(torch.tensor([5, 2]), torch.tensor([8, 5])).numpy()
+    # a seeded multi-head guided-attention loss value
+    from seq2seq_vc.losses.guided_attention_loss import GuidedMultiHeadAttentionLoss
+
+    g = torch.Generator().manual_seed(5)
+    att = torch.softmax(torch.randn(3, 4, 12, 9, generator=g), -1)
+    il, ol = torch.tensor([9, 7, 4]), torch.tensor([12, 10, 5])
+    dump.update(gmh_att=att.numpy(), gmh_ilens=il.numpy(), gmh_olens=ol.numpy(),
+                gmh_loss=GuidedMultiHeadAttentionLoss(sigma=0.4, alpha=1.0)(att, il, ol).numpy())
+    np.savez_compressed(os.path.join(GOLDEN, "kats.npz"), **dump)
+    print("kats:", len(dump), "arrays")
+
+
+if __name__ == "__main__":
+    ref_shim.install()
+    os.makedirs(GOLDEN, exist_ok=True)
+    gen_vtn_tiny()
+    gen_mas()
+    gen_kats()
