@@ -1,0 +1,269 @@
+/*
+ * s2svc_b200.h -- C ABI of libs2svc_b200.so: the B200 (sm_100a) kernels behind the seq2seq-vc
+ * training hot path.
+ *
+ * The reference (unilight/seq2seq-vc) is pure Python; it has no FFI of its own.  Each entry point
+ * below therefore names the reference *function* whose arithmetic it replaces (file:line relative
+ * to the reference root).  INTEGRATION.md shows the ctypes binding a reference maintainer adds.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless its name ends in _host;
+ *  - no entry point allocates, synchronises the device, or keeps global mutable state other than a
+ *    once-initialised driver-entry-point / function-attribute cache; all are re-entrant across
+ *    streams; workspaces are passed by the caller;
+ *  - return value: S2S_OK (0) or a negative S2S_ERR_* code; s2s_last_error() returns the message
+ *    of the last failure on the calling thread;
+ *  - `stream` is a cudaStream_t passed as void* so that the header needs no CUDA include;
+ *  - `dtype` arguments are S2S_F32 / S2S_BF16 and describe activations in HBM; statistics,
+ *    parameters (gamma/beta/bias), parameter gradients and losses are always float32;
+ *  - per-utterance lengths are int32 device arrays.
+ */
+#ifndef S2SVC_B200_H_
+#define S2SVC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S2S_OK 0
+#define S2S_ERR_INVALID (-1)
+#define S2S_ERR_UNSUPPORTED (-2)
+#define S2S_ERR_CUDA (-3)
+
+#define S2S_F32 0
+#define S2S_BF16 1
+
+#define S2S_ABI_VERSION 4
+
+const char* s2s_last_error(void);
+int s2s_abi_version(void);
+/* 0 when the current device is compute capability 10.x (B200), else S2S_ERR_UNSUPPORTED */
+int s2s_device_check(void);
+/* number of kernel launches issued through this library by the calling process (for bench.py) */
+int64_t s2s_launch_count(void);
+
+/* Counter-based dropout: element idx is dropped iff hash(seed', stream, idx) < p * 2^32 where
+ * seed' = seed + (seed_dev ? *seed_dev : 0); kept values are scaled by 1/(1-p).  Backward kernels
+ * regenerate the mask from the same triple.  seed_dev lets a CUDA graph replay see a new seed. */
+typedef struct {
+    float p;
+    uint64_t seed;
+    uint64_t stream;
+    const uint64_t* seed_dev;
+} s2s_dropout_t;
+
+/* -------------------------------------------------------------------------------------------
+ * GEMM  (replaces every torch.nn.Linear / torch.matmul / Conv1d / Conv2d-as-im2col on the path:
+ *        modules/transformer/attention.py:40-111, positionwise_feed_forward.py:30-32,
+ *        subsampling.py:58-94, pre_postnets.py:60-66,105-185, models/vtn.py:181-182,249-251)
+ *
+ *   C[b1,b2][m,n] = epilogue( alpha * sum_{t<taps} sum_{k<K} A[b1,b2][m + t, k] * B[b1,b2][n, t, k] )
+ *   A(m,k) = A + b1*a_bs1 + b2*a_bs2 + m*a_rs + k*a_cs      (element strides; a_rs==1 or a_cs==1)
+ *   B(n,t,k) = B + b1*b_bs1 + b2*b_bs2 + n*b_rs + t*b_ts + k*b_cs
+ *   C(m,n) = C + b1*c_bs1 + b2*c_bs2 + m*c_rs + n           (residual R uses the same strides)
+ *   epilogue: (+ bias[n]) -> relu? -> dropout? -> (+ R[m,n]) -> (+ C[m,n] if accumulate)
+ *             -> row mask -> store
+ *   row mask (mask_period > 0): rows with ((m + mask_offset) % mask_period) outside
+ *   [mask_lo, mask_hi) are stored as 0 (halo rows of the zero-padded conv1d layout).
+ * mode 0: fp32 CUDA-core path (operands f32 or bf16, fp32 FMA accumulate) -- the parity path.
+ * mode 1: bf16 tcgen05 tensor-core path (operands must be bf16, TMEM fp32 accumulate).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int M, N, K, taps;
+    const void* A; int a_dtype; int64_t a_rs, a_cs, a_bs1, a_bs2;
+    const void* B; int b_dtype; int64_t b_rs, b_cs, b_ts, b_bs1, b_bs2;
+    void* C; int c_dtype; int64_t c_rs, c_bs1, c_bs2;
+    int batch1, batch2;
+    const float* bias;
+    const void* R;          /* optional residual, dtype c_dtype, strides of C */
+    float alpha;
+    int relu;
+    int accumulate;
+    s2s_dropout_t drop;
+    int mask_period, mask_offset, mask_lo, mask_hi;
+} s2s_gemm_t;
+
+int s2s_gemm(const s2s_gemm_t* g, int mode, void* stream);
+
+/* -------------------------------------------------------------------------------------------
+ * LayerNorm over the last dim, eps = 1e-12 in the reference (modules/transformer/layer_norm.py:12-42)
+ * fwd: y = (x - mean) * rstd * gamma + beta ; saves mean / rstd (float32, one per row)
+ * bwd: dx (+ dres when given: the gradient arriving over the residual branch) ; dgamma += ,
+ *      dbeta += (float32 accumulate into the caller's gradient buffers)
+ * ------------------------------------------------------------------------------------------- */
+int s2s_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,
+                      float* rstd, int64_t rows, int d, float eps, int dtype, void* stream);
+int s2s_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean,
+                      const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta,
+                      int64_t rows, int d, int dtype, void* stream);
+
+/* out[c] += sum_r x[r, c]  (bias gradients); x row stride ld */
+int s2s_colsum(const void* x, int64_t rows, int cols, int64_t ld, float* out, int dtype, void* stream);
+/* dx = dy * (y > 0 ? scale : 0): backward of relu followed by dropout (scale = 1/(1-p)) */
+int s2s_relu_bwd(const void* dy, const void* y, void* dx, int64_t n, float scale, int dtype, void* stream);
+/* out = a + b (elementwise; out may alias a or b): residual joins that no GEMM epilogue absorbs
+ * (models/vtn.py:257-259 postnet residual, gradient joins of the residual branches) */
+int s2s_add(const void* a, const void* b, void* out, int64_t n, int dtype, void* stream);
+/* dx[r,c] = dy[r,c] * dropout_factor(idx = r*cols + c): backward of an epilogue dropout */
+int s2s_dropout_bwd(const void* dy, void* dx, int64_t rows, int cols, const s2s_dropout_t* drop, int dtype,
+                    void* stream);
+
+/* -------------------------------------------------------------------------------------------
+ * Masked softmax over the key axis (modules/transformer/attention.py:76-85):
+ * S is (B, H, T1, ld) with T2 <= ld valid columns, already scaled by 1/sqrt(d_k).  Key j of batch b
+ * is visible to query i iff j < klens[b] and (!causal or j <= i).  P = softmax over visible keys,
+ * exact zeros elsewhere (also for rows with no visible key).  In place (P may equal S).
+ * If Pd != NULL it also receives dropout(P) (attention dropout, attention.py:85).
+ * bwd: dS = scale * P * (dP - sum_j P_j dP_j), in place over dP; when drop->p > 0, dP is first
+ * multiplied by the regenerated dropout factor.
+ * ------------------------------------------------------------------------------------------- */
+int s2s_softmax_fwd(const void* S, void* P, void* Pd, const int32_t* klens, int B, int H, int T1, int T2,
+                    int64_t ld, int causal, const s2s_dropout_t* drop, int dtype, void* stream);
+int s2s_softmax_bwd(const void* P, void* dP, int B, int H, int T1, int T2, int64_t ld, float scale,
+                    const s2s_dropout_t* drop, int dtype, void* stream);
+
+/* -------------------------------------------------------------------------------------------
+ * ScaledPositionalEncoding (layers/positional_encoding.py:73-106): y = dropout(x + alpha * pe[t])
+ * pe is the float32 sinusoid table (>= T rows of d); alpha is a device scalar.
+ * bwd: dx = dy * mask ; dalpha += sum(dy * mask * pe)
+ * ------------------------------------------------------------------------------------------- */
+int s2s_scaled_pe_fwd(const void* x, const float* pe, const float* alpha, void* y, int B, int T, int d,
+                      const s2s_dropout_t* drop, int dtype, void* stream);
+int s2s_scaled_pe_bwd(const void* dy, const float* pe, void* dx, float* dalpha, int B, int T, int d,
+                      const s2s_dropout_t* drop, int dtype, void* stream);
+
+/* -------------------------------------------------------------------------------------------
+ * Conv2dSubsampling front end (modules/transformer/subsampling.py:58-94).
+ * conv1: x (B, T, F) float32 -> relu(conv2d(1->C, 3x3, stride 2)) stored channels-last
+ *        y1 (B, T1, F1, C), T1 = (T-1)/2, F1 = (F-1)/2;  w (C, 1, 3, 3) float32, bias (C).
+ * conv1_bwd: dw += , dbias += from dy1 (already relu-masked by the caller via s2s_relu_bwd).
+ * im2col_s2: y1 (B, T1, F1, C) -> col (B*T2*F2, 9*C), column order (kt, kf, c), stride 2.
+ * col2im_s2: the adjoint scatter (gather form), dcol -> dy1.
+ * ------------------------------------------------------------------------------------------- */
+int s2s_conv1_fwd(const float* x, const float* w, const float* bias, void* y1, int B, int T, int F, int C,
+                  int dtype, void* stream);
+int s2s_conv1_bwd(const float* x, const void* dy1, float* dw, float* dbias, int B, int T, int F, int C,
+                  int dtype, void* stream);
+int s2s_im2col_s2(const void* y1, void* col, int B, int T1, int F1, int C, int dtype, void* stream);
+int s2s_col2im_s2(const void* dcol, void* dy1, int B, int T1, int F1, int C, int dtype, void* stream);
+
+/* Decoder input glue (models/vtn.py:227-243,523-527): out[b, 0] = 0, out[b, l] = ys[b, l*r - 1]
+ * for l >= 1;  ys (B, L, odim) float32 -> out (B, Lr, odim) dtype. */
+int s2s_shift_thin(const float* ys, void* out, int B, int L, int Lr, int odim, int r, int dtype, void* stream);
+/* Target glue (models/vtn.py:262-274): olens_out = olens - olens % r ; labels_out = labels with
+ * labels_out[b, olens_out[b]-1] = 1 ; (B, Lin) -> (B, Lout), Lout <= Lin. */
+int s2s_fix_targets(const float* labels, const int32_t* olens, float* labels_out, int32_t* olens_out, int B,
+                    int Lin, int Lout, int r, void* stream);
+
+/* -------------------------------------------------------------------------------------------
+ * Postnet BatchNorm1d(+tanh) in training/eval mode over a zero-haloed channels-last buffer
+ * (modules/pre_postnets.py:105-185).  x is (B, Lp, C) with frames at rows [halo, halo+L) of each
+ * utterance; statistics run over all B*L frames INCLUDING padded frames (the reference applies no mask).
+ * bn_stats: sums[0:C] += sum x, sums[C:2C] += sum x^2 (float32; caller zeroes)
+ * bn_finalize: mean/invstd from sums (biased var, eps) and running-stat update
+ *              (momentum, unbiased var; modules see torch.nn.BatchNorm1d); running_* may be NULL.
+ * bn_apply: y = act((x - mean) * invstd * gamma + beta), act = tanh or identity, then dropout;
+ *           halo rows of y are written as zeros.
+ * bn_bwd_reduce: sums[0:C] += sum dz, sums[C:2C] += sum dz * xhat with dz = dy * mask * act'(y)
+ * bn_bwd_apply: dx = gamma * invstd * (dz - sums0/n - xhat * sums1/n); dgamma += sums1, dbeta += sums0;
+ *               halo rows of dx are zeros.  (eval mode: pass sums == NULL -> dx = gamma*invstd*dz)
+ * ------------------------------------------------------------------------------------------- */
+int s2s_bn_stats(const void* x, float* sums, int B, int L, int halo, int C, int dtype, void* stream);
+int s2s_bn_finalize(const float* sums, float* mean, float* invstd, float* running_mean, float* running_var,
+                    int64_t count, int C, float eps, float momentum, void* stream);
+int s2s_bn_apply(const void* x, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                 void* y, int B, int L, int halo, int C, int use_tanh, const s2s_dropout_t* drop, int dtype,
+                 void* stream);
+int s2s_bn_bwd_reduce(const void* dy, const void* y, const void* x, const float* mean, const float* invstd,
+                      const float* gamma, const float* beta, float* sums, int B, int L, int halo, int C,
+                      int use_tanh, const s2s_dropout_t* drop, int dtype, void* stream);
+int s2s_bn_bwd_apply(const void* dy, const void* y, const void* x, const float* mean, const float* invstd,
+                     const float* gamma, const float* beta, const float* sums, void* dx, float* dgamma,
+                     float* dbeta, int B, int L, int halo, int C, int use_tanh, const s2s_dropout_t* drop,
+                     int dtype, void* stream);
+/* eval-mode statistics: mean = running_mean, invstd = rsqrt(running_var + eps) */
+int s2s_bn_eval_stats(const float* running_mean, const float* running_var, float* mean, float* invstd, int C,
+                      float eps, void* stream);
+/* copy (B, L, C) <-> haloed (B, L + 2*halo, C) ; halo rows zeroed on pad */
+int s2s_pad_rows(const void* x, void* y, int B, int L, int halo, int C, int dtype, void* stream);
+int s2s_unpad_rows(const void* x, void* y, int B, int L, int halo, int C, int dtype, void* stream);
+
+/* -------------------------------------------------------------------------------------------
+ * Seq2SeqLoss (losses/seq2seq_loss.py:13-59): masked mean L1(after) + L1(before) and
+ * BCE-with-logits(pos_weight) over frames l < olens[b].  losses[0] = l1, losses[1] = bce.
+ * Also writes the gradients of (l1 + bce) w.r.t. after / before / logits (zero on padded frames).
+ * after/before/logits are `dtype` with L frames per utterance; ys (B, L_ys, odim) and labels
+ * (B, L_labels) are float32 and may be longer than L (only the first L frames are read).
+ * workspace: >= 4 floats, zeroed by the call.
+ * ------------------------------------------------------------------------------------------- */
+int s2s_seq2seq_loss(const void* after, const void* before, const void* logits, const float* ys,
+                     const float* labels, const int32_t* olens, int B, int L, int L_ys, int L_labels, int odim,
+                     float pos_weight, float* losses, void* d_after, void* d_before, void* d_logits,
+                     float* workspace, int dtype, void* stream);
+
+/* -------------------------------------------------------------------------------------------
+ * GuidedMultiHeadAttentionLoss (losses/guided_attention_loss.py:6-165):
+ * loss = alpha * mean over (b, h, t < olens[b], s < ilens[b]) of att * (1 - exp(-(s/ilen - t/olen)^2 / (2 sigma^2)))
+ * att (B, H, T_out, ld) with T_in valid columns.  d_att (optional) receives d loss / d att.
+ * workspace: >= 2 floats.
+ * ------------------------------------------------------------------------------------------- */
+int s2s_guided_attn_loss(const void* att, const int32_t* ilens, const int32_t* olens, int B, int H, int T_out,
+                         int T_in, int64_t ld, float sigma, float alpha, float* loss, void* d_att,
+                         float* workspace, int dtype, void* stream);
+
+/* -------------------------------------------------------------------------------------------
+ * Optimizer tail (trainers/ar_vc.py:99-107): clip_grad_norm_(max_norm) + Adam on flat float32
+ * buffers.  sqnorm: out[0] += sum g^2 (caller zeroes).  adam_step: g' = g * grad_scale *
+ * min(1, max_norm / (sqrt(sqnorm * grad_scale^2) + 1e-6)); Adam(lr, beta1, beta2, eps) with
+ * bias correction for step *step_dev (float32 device scalar, already incremented);
+ * lr is read from *lr_dev.  If p_bf16 != NULL the updated parameter is also written as bf16.
+ * ------------------------------------------------------------------------------------------- */
+int s2s_sqnorm(const float* g, int64_t n, float* out, void* stream);
+int s2s_adam_step(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, const float* lr_dev,
+                  float beta1, float beta2, float eps, float weight_decay, const float* step_dev,
+                  const float* sqnorm, float max_norm, float grad_scale, void* stream);
+/* step bookkeeping on device: step[0] += 1 ; seed[0] += 1 */
+int s2s_step_advance(float* step, uint64_t* seed, void* stream);
+
+/* dtype conversion / weight packing */
+int s2s_cast(const void* in, void* out, int64_t n, int in_dtype, int out_dtype, void* stream);
+/* out[n][b][a] (+)= in[n][a][b] : transpose of the two trailing dims (conv weight packing and the
+ * adjoint un-packing of the packed gradient) */
+int s2s_transpose_last2(const void* in, void* out, int N, int A, int Bd, int in_dtype, int out_dtype,
+                        int accumulate, void* stream);
+
+/* Conv1d weight packing (modules/pre_postnets.py:105-185): w (OC, IC, K) float32 ->
+ * wp (OC, K, IC) for the forward taps-GEMM and wpt (IC, K, OC) with wpt[ic][u][oc] = w[oc][ic][K-1-u]
+ * for the input-gradient taps-GEMM; out_dtype applies to both (either may be NULL). */
+int s2s_pack_conv1d_w(const float* w, void* wp, void* wpt, int OC, int IC, int K, int out_dtype, void* stream);
+
+/* -------------------------------------------------------------------------------------------
+ * Monotonic alignment search + duration count (modules/alignments.py:63-93, 281-310).
+ * log_p (B, T_feats, T_text) float32; per utterance the slice [:feats_lens[b], :text_lens[b]] is
+ * searched with the reference's exact arithmetic (float32 sequential prefix on row 0, float64 DP,
+ * ">=" tie rule).  paths (B, T_feats) int32 (-1 beyond feats_len), ds (B, T_text) float32 counts.
+ * bin_loss[0] = -(1/B) sum_b mean_t log_p[b, t, path_t]; d_log_p (optional, may be NULL) gets its
+ * gradient.  workspace: B * T_text * T_feats doubles (query s2s_mas_workspace_bytes).
+ * ------------------------------------------------------------------------------------------- */
+size_t s2s_mas_workspace_bytes(int B, int T_feats, int T_text);
+int s2s_mas(const float* log_p, const int32_t* text_lens, const int32_t* feats_lens, int B, int T_feats,
+            int T_text, int32_t* paths, float* ds, float* bin_loss, float* d_log_p, void* workspace,
+            size_t workspace_bytes, void* stream);
+
+/* -------------------------------------------------------------------------------------------
+ * STFT -> log-mel (bin/preprocess.py:30-92 + librosa semantics): wav (B, n_samples) float32 ->
+ * mel (B, 1 + n_samples/hop, n_mels) float32.  center=True reflect padding, window (n_fft) float32
+ * (periodic Hann zero-padded to n_fft by the caller), mel_basis (n_mels, 1 + n_fft/2) float32,
+ * out = log10(max(eps, |STFT| @ basis^T)) (log_base: 10, 2 or 0 for natural).
+ * n_fft must be a power of two <= 4096.
+ * ------------------------------------------------------------------------------------------- */
+int s2s_logmel(const float* wav, const float* window, const float* mel_basis, float* mel, int B, int n_samples,
+               int n_fft, int hop, int n_mels, float eps, float log_base, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* S2SVC_B200_H_ */

@@ -1,0 +1,10 @@
+"""seq2seq-vc hot path on B200: hand-written sm_100a kernels behind the reference's model surface.
+
+Public surface (mirrors seq2seq_vc.models / seq2seq_vc.losses / bin.preprocess names):
+    VTN, Seq2SeqLoss, GuidedMultiHeadAttentionLoss, viterbi_decode, logmelfilterbank
+The native library (libs2svc_b200.so) is loaded lazily on first use; there is no CPU fallback.
+"""
+from .vtn_engine import VTNEngine, default_hparams  # noqa: F401
+from .api import VTN, Seq2SeqLoss, GuidedMultiHeadAttentionLoss, VTNTrainStep, viterbi_decode, logmelfilterbank  # noqa: F401
+
+AR_VC_MODELS = [VTN]

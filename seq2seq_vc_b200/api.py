@@ -1,0 +1,443 @@
+"""Host-side mirror of the reference's plugin surface for the hot path.
+
+Same names, constructor kwargs, call signatures, return structures and state-dict keys as
+ * seq2seq_vc.models.VTN                                  (models/vtn.py:14-300)
+ * seq2seq_vc.losses.Seq2SeqLoss                          (losses/seq2seq_loss.py:13-59)
+ * seq2seq_vc.losses.GuidedMultiHeadAttentionLoss         (losses/guided_attention_loss.py:133-165)
+ * seq2seq_vc.modules.alignments.viterbi_decode           (modules/alignments.py:281-310)
+ * seq2seq_vc.bin.preprocess.logmelfilterbank             (bin/preprocess.py:30-92)
+so that `getattr(module, config["model_type"])(**config["model_params"]).to(device)` and the
+reference trainers work unchanged.  Every arithmetic step runs in libs2svc_b200.so; a missing
+library or a CPU tensor raises (there is no fallback).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import S2SError
+from .vtn_engine import VTNEngine, default_hparams
+
+_f32 = torch.float32
+_i32 = torch.int32
+
+
+def _host_lens(v) -> List[int]:
+    if isinstance(v, torch.Tensor):
+        return [int(x) for x in v.detach().cpu().tolist()]
+    return [int(x) for x in v]
+
+
+# =================================================================================================
+# module tree that reproduces the reference's parameter names and attribute seams
+# =================================================================================================
+class _Node(torch.nn.Module):
+    """Parameter container; integer indexing walks digit-named children (Sequential/ModuleList-like)."""
+
+    def __getitem__(self, idx):
+        keys = sorted((k for k in self._modules if k.isdigit()), key=int)
+        if not keys and "out" in self._modules:      # Conv2dSubsampling.__getitem__ (subsampling.py:96-105)
+            if idx != -1:
+                raise NotImplementedError("Support only `-1` (for `reset_parameters`).")
+            return self._modules["out"][idx]
+        return self._modules[keys[idx]]
+
+    def __len__(self):
+        return len([k for k in self._modules if k.isdigit()])
+
+    def forward(self, *a, **k):
+        raise S2SError("sub-modules of the B200 VTN are parameter containers; call the model itself")
+
+
+class MultiHeadedAttention(_Node):
+    """Holds linear_{q,k,v,out}; `.attn` is refreshed by every model forward (attention.py:81-85)."""
+    attn = None
+
+
+class _VTNFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, xs, ys, ilens, olens, *params):
+        eng = model.engine
+        after, before, logits = eng.forward(xs, ys, ilens, olens)
+        ctx.model = model
+        ctx.token = model._fwd_token
+        # outputs are engine-owned buffers: hand out copies so later forwards cannot clobber them
+        return after.clone(), before.clone(), logits.clone()
+
+    @staticmethod
+    def backward(ctx, d_after, d_before, d_logits):
+        model = ctx.model
+        if ctx.token != model._fwd_token:
+            raise S2SError("backward() after a newer forward(): the engine keeps one set of activations")
+        eng = model.engine
+        fresh = all(p.grad is None for p in model.parameters())
+        dt = eng.adt
+        eng.backward(d_after.to(dt).contiguous(), d_before.to(dt).contiguous(), d_logits.to(dt).contiguous(), zero_grad=fresh)
+        model._bind_grads()
+        return (None,) * (5 + len(model._param_names))
+
+
+class VTN(torch.nn.Module):
+    """Drop-in for seq2seq_vc.models.VTN (transformer encoder/decoder variant)."""
+
+    def __init__(self, idim, odim, dprenet_layers=2, dprenet_units=256, adim=384, aheads=4, encoder_type="transformer",
+                 decoder_type="transformer", elayers=6, eunits=1536, dlayers=6, dunits=1536, postnet_layers=5, postnet_filts=5,
+                 postnet_chans=256, positionwise_layer_type: str = "linear", positionwise_conv_kernel_size: int = 1,
+                 dprenet_dropout_rate=0.5, transformer_enc_dropout_rate: float = 0.1,
+                 transformer_enc_positional_dropout_rate: float = 0.1, transformer_enc_attn_dropout_rate: float = 0.1,
+                 use_batch_norm=True, encoder_normalize_before=True, decoder_normalize_before=False,
+                 encoder_concat_after=False, decoder_concat_after=False, decoder_reduction_factor=2, spk_embed_dim=None,
+                 spk_embed_integration_type="add", initial_encoder_alpha=1.0, initial_decoder_alpha=1.0,
+                 use_guided_attn_loss=False, num_heads_applied_guided_attn=2, num_layers_applied_guided_attn=2,
+                 conformer_rel_pos_type: str = "legacy", conformer_pos_enc_layer_type: str = "rel_pos",
+                 conformer_self_attn_layer_type: str = "rel_selfattn", use_macaron_style_in_conformer: bool = True,
+                 use_cnn_in_conformer: bool = True, zero_triu: bool = False, conformer_enc_kernel_size: int = 7,
+                 conformer_dec_kernel_size: int = 31, compute_dtype: str = "float32", device=None, seed: int = 0):
+        super().__init__()
+        unsupported = []
+        if encoder_type != "transformer" or decoder_type != "transformer":
+            unsupported.append("encoder_type/decoder_type != 'transformer'")
+        if positionwise_layer_type != "linear":
+            unsupported.append("positionwise_layer_type != 'linear'")
+        if not use_batch_norm or not encoder_normalize_before or decoder_normalize_before:
+            unsupported.append("non-default normalisation wiring")
+        if encoder_concat_after or decoder_concat_after or spk_embed_dim is not None:
+            unsupported.append("concat_after / speaker embeddings")
+        if unsupported:
+            raise NotImplementedError("B200 VTN hot path does not cover: " + ", ".join(unsupported))
+        self.idim, self.odim = idim, odim
+        self.spk_embed_dim = None
+        self.decoder_reduction_factor = decoder_reduction_factor
+        self.use_guided_attn_loss = use_guided_attn_loss
+        self.num_heads_applied_guided_attn = num_heads_applied_guided_attn
+        self.num_layers_applied_guided_attn = num_layers_applied_guided_attn
+        self.encoder_type, self.decoder_type = encoder_type, decoder_type
+        self.hp = default_hparams(idim=idim, odim=odim, dprenet_layers=dprenet_layers, dprenet_units=dprenet_units, adim=adim,
+                                  aheads=aheads, elayers=elayers, eunits=eunits, dlayers=dlayers, dunits=dunits,
+                                  postnet_layers=postnet_layers, postnet_filts=postnet_filts, postnet_chans=postnet_chans,
+                                  dprenet_dropout_rate=dprenet_dropout_rate,
+                                  transformer_enc_dropout_rate=transformer_enc_dropout_rate,
+                                  decoder_reduction_factor=decoder_reduction_factor,
+                                  initial_encoder_alpha=initial_encoder_alpha, initial_decoder_alpha=initial_decoder_alpha)
+        self._bf16 = compute_dtype in ("bf16", "bfloat16", torch.bfloat16)
+        self._seed = seed
+        self._fwd_token = 0
+        self.engine: Optional[VTNEngine] = None
+        dev = torch.device(device) if device is not None else torch.device("cpu")
+        self._build(dev)
+
+    # ---- construction / device movement -------------------------------------------------------
+    def _build(self, device, state: Optional[Dict[str, torch.Tensor]] = None) -> None:
+        self.engine = VTNEngine(self.hp, device=device, bf16=self._bf16, seed=self._seed)
+        if state is not None:
+            self.engine.load_state_dict(state)
+        self._modules.clear()
+        self._param_names: List[str] = []
+        st = self.engine.store
+        for name in st.names():
+            node, leaf = self._node_for(name)
+            node.register_parameter(leaf, torch.nn.Parameter(st.p(name), requires_grad=True))
+            self._param_names.append(name)
+        for name, buf in self.engine.buffers.items():
+            node, leaf = self._node_for(name)
+            node.register_buffer(leaf, buf)
+
+    def _node_for(self, dotted: str):
+        parts = dotted.split(".")
+        node = self
+        for i, part in enumerate(parts[:-1]):
+            nxt = node._modules.get(part)
+            if nxt is None:
+                nxt = MultiHeadedAttention() if part in ("self_attn", "src_attn") else _Node()
+                node.add_module(part, nxt)
+            node = nxt
+        return node, parts[-1]
+
+    def _apply(self, fn, recurse=True):
+        """.to(device) / .cuda(): move the flat stores as a whole and re-bind the parameter views."""
+        probe = fn(torch.zeros(1, dtype=_f32, device=self.engine.device))
+        if probe.dtype != _f32:
+            raise NotImplementedError("parameters stay float32; select bf16 compute with compute_dtype='bf16'")
+        if probe.device != self.engine.device:
+            state = {k: v.detach().cpu() for k, v in self.engine.state_dict().items()}
+            self._build(probe.device, state)
+        return self
+
+    def _bind_grads(self) -> None:
+        st = self.engine.store
+        for name, p in self.named_parameters():
+            g = st.g(name)
+            if p.grad is None or p.grad.data_ptr() != g.data_ptr():
+                p.grad = g
+
+    def train(self, mode: bool = True):
+        super().train(mode)
+        if self.engine is not None:
+            self.engine.training = bool(mode)
+        return self
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        out = super().load_state_dict(state_dict, strict=strict)
+        self.engine.p16_dirty = True
+        return out
+
+    # ---- forward (vtn.py:207-300) ----------------------------------------------------------------
+    def forward(self, xs, ilens, ys, labels, olens, spembs=None, *args, **kwargs):
+        if not xs.is_cuda:
+            raise S2SError("seq2seq_vc_b200.VTN runs on a B200 only (no CPU fallback): move the model and batch to cuda")
+        eng = self.engine
+        eng.p16_dirty = True       # parameters may have been updated by an external optimizer
+        il, ol = _host_lens(ilens), _host_lens(olens)
+        r = self.decoder_reduction_factor
+        max_ilen, max_olen = max(il), max(ol)
+        xs = xs[:, :max_ilen].to(_f32).contiguous()
+        ys = ys[:, :max_olen].to(_f32).contiguous()
+        labels = labels[:, :max_olen].to(_f32).contiguous()
+        if r > 1:
+            assert all(o >= r for o in ol), "Output length must be greater than or equal to reduction factor."
+        self._fwd_token += 1
+        after, before, logits = _VTNFunction.apply(self, xs, ys, il, ol, *self.parameters())
+        Lo = after.shape[1]
+        # target fix-ups (vtn.py:262-274)
+        olens_out = torch.tensor(eng.olens_fix_host, dtype=torch.int64, device=xs.device)
+        if r > 1:
+            labels_out = torch.empty(labels.shape[0], Lo, dtype=_f32, device=xs.device)
+            ops.fix_targets(labels, eng.olens_fix, labels_out, None, r)
+        else:
+            labels_out = labels
+        ys_out = ys[:, :Lo]
+        ilens_ds_st = torch.tensor(eng.ilens_ds_st, dtype=torch.int64, device=xs.device)
+        olens_in = torch.tensor(eng.olens_in_host, dtype=torch.int64, device=xs.device)
+        att_ws = []
+        for name, P in eng.attn.items():
+            node = self.get_submodule(name)
+            node.attn = P.float() if P.dtype != _f32 else P
+        for l in reversed(range(self.hp["dlayers"])):           # vtn.py:280-287 (list, last layer first)
+            att_ws.append(self.decoder.decoders[l].src_attn.attn)
+        return after.float(), before.float(), logits.float(), ys_out, labels_out, olens_out, (att_ws, ilens_ds_st, olens_in)
+
+
+# =================================================================================================
+# losses
+# =================================================================================================
+class _Seq2SeqLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, after, before, logits, ys, labels, olens_dev, pos_weight):
+        B, L, odim = after.shape
+        dev = after.device
+        losses = torch.empty(2, dtype=_f32, device=dev)
+        ws = torch.empty(4, dtype=_f32, device=dev)
+        d_after, d_before, d_logits = torch.empty_like(after), torch.empty_like(before), torch.empty_like(logits)
+        ops.seq2seq_loss(after, before, logits, ys, labels, olens_dev, pos_weight, losses, d_after, d_before, d_logits, ws)
+        ctx.save_for_backward(d_after, d_before, d_logits)
+        return losses[0], losses[1]
+
+    @staticmethod
+    def backward(ctx, g_l1, g_bce):
+        d_after, d_before, d_logits = ctx.saved_tensors
+        return d_after * g_l1, d_before * g_l1, d_logits * g_bce, None, None, None, None
+
+
+class Seq2SeqLoss(torch.nn.Module):
+    """Drop-in for seq2seq_vc.losses.Seq2SeqLoss: one fused pass gives both losses and their gradients."""
+
+    def __init__(self, use_masking=True, use_weighted_masking=False, bce_pos_weight=10.0):
+        super().__init__()
+        assert (use_masking != use_weighted_masking) or not use_masking
+        if not use_masking or use_weighted_masking:
+            raise NotImplementedError("only use_masking=True (the reference default and every shipped recipe)")
+        self.bce_pos_weight = float(bce_pos_weight)
+
+    def forward(self, after_outs, before_outs, logits, ys, labels, olens):
+        olens_dev = torch.as_tensor(_host_lens(olens), dtype=_i32).to(after_outs.device) if not (
+            isinstance(olens, torch.Tensor) and olens.is_cuda) else olens.to(_i32)
+        c = lambda t: t.to(_f32).contiguous()
+        return _Seq2SeqLossFn.apply(c(after_outs), c(before_outs), c(logits), c(ys), c(labels), olens_dev, self.bce_pos_weight)
+
+
+class _GuidedAttnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, att, ilens_dev, olens_dev, sigma, alpha):
+        B, H, T_out, T_in = att.shape
+        loss = torch.empty(1, dtype=_f32, device=att.device)
+        ws = torch.empty(2, dtype=_f32, device=att.device)
+        d_att = torch.empty_like(att)
+        ops.guided_attn_loss(att, ilens_dev, olens_dev, T_in, sigma, alpha, loss, d_att, ws)
+        ctx.save_for_backward(d_att)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (d_att,) = ctx.saved_tensors
+        return d_att * g, None, None, None, None
+
+
+class GuidedMultiHeadAttentionLoss(torch.nn.Module):
+    """Drop-in for losses.GuidedMultiHeadAttentionLoss: att_ws (B, H, T_out, T_in) -> scalar."""
+
+    def __init__(self, sigma=0.4, alpha=1.0, reset_always=True):
+        super().__init__()
+        self.sigma, self.alpha = float(sigma), float(alpha)
+
+    def forward(self, att_ws, ilens, olens):
+        dev = att_ws.device
+        il = torch.as_tensor(_host_lens(ilens), dtype=_i32).to(dev)
+        ol = torch.as_tensor(_host_lens(olens), dtype=_i32).to(dev)
+        if att_ws.dim() == 3:
+            att_ws = att_ws.unsqueeze(1)
+        return _GuidedAttnFn.apply(att_ws.to(_f32).contiguous(), il, ol, self.sigma, self.alpha)
+
+
+GuidedAttentionLoss = GuidedMultiHeadAttentionLoss
+
+
+# =================================================================================================
+# monotonic alignment search (operator seam `self.viterbi_func`, aas_vc.py:132,402-404)
+# =================================================================================================
+class _ViterbiFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, log_p_attn, text_lens_dev, feats_lens_dev):
+        paths, ds, bin_loss, d_log_p = ops.mas(log_p_attn, text_lens_dev, feats_lens_dev, want_grad=True)
+        ctx.save_for_backward(d_log_p)
+        ctx.mark_non_differentiable(ds)
+        return ds, bin_loss[0], paths
+
+    @staticmethod
+    def backward(ctx, g_ds, g_bin, g_paths):
+        (d_log_p,) = ctx.saved_tensors
+        return d_log_p * g_bin, None, None
+
+
+def viterbi_decode(log_p_attn, text_lengths, feats_lengths, return_paths: bool = False):
+    """(B, T_feats, T_text) float32 -> (ds float32 (B, T_text), bin_loss 0-d); bit-exact paths/durations."""
+    dev = log_p_attn.device
+    tl = torch.as_tensor(_host_lens(text_lengths), dtype=_i32).to(dev)
+    fl = torch.as_tensor(_host_lens(feats_lengths), dtype=_i32).to(dev)
+    ds, bin_loss, paths = _ViterbiFn.apply(log_p_attn.to(_f32).contiguous(), tl, fl)
+    return (ds, bin_loss, paths) if return_paths else (ds, bin_loss)
+
+
+# =================================================================================================
+# STFT -> log-mel (bin/preprocess.py:30-92)
+# =================================================================================================
+def _slaney_mel_points(n: int, fmin: float, fmax: float) -> np.ndarray:
+    """n mel-spaced frequencies (Hz) between fmin and fmax on the Slaney scale (linear < 1 kHz, log above)."""
+    f_sp, brk = 200.0 / 3.0, 1000.0
+    brk_mel, step = brk / f_sp, math.log(6.4) / 27.0
+
+    def to_mel(f):
+        return brk_mel + math.log(f / brk) / step if f >= brk else f / f_sp
+
+    m = np.linspace(to_mel(fmin), to_mel(fmax), n)
+    return np.where(m >= brk_mel, brk * np.exp(step * (m - brk_mel)), f_sp * m)
+
+
+_BASIS_CACHE: Dict[tuple, np.ndarray] = {}
+
+
+def mel_filterbank(sr: int, n_fft: int, n_mels: int, fmin: float, fmax: float) -> np.ndarray:
+    """Slaney-normalised triangular filters on the rFFT bin frequencies, float32 (n_mels, 1 + n_fft/2)."""
+    key = (sr, n_fft, n_mels, float(fmin), float(fmax))
+    if key not in _BASIS_CACHE:
+        edges = _slaney_mel_points(n_mels + 2, fmin, fmax)
+        bins = np.arange(1 + n_fft // 2, dtype=np.float64) * (sr / n_fft)
+        lo, ce, hi = edges[:-2, None], edges[1:-1, None], edges[2:, None]
+        tri = np.minimum((bins[None] - lo) / (ce - lo), (hi - bins[None]) / (hi - ce))
+        tri = np.maximum(tri, 0.0) * (2.0 / (hi - lo))
+        _BASIS_CACHE[key] = tri.astype(np.float32)
+    return _BASIS_CACHE[key]
+
+
+def hann_window(n_fft: int, win_length: Optional[int]) -> np.ndarray:
+    wl = n_fft if win_length is None else int(win_length)
+    w = 0.5 - 0.5 * np.cos(2.0 * np.pi * np.arange(wl) / wl)
+    out = np.zeros(n_fft, dtype=np.float32)
+    off = (n_fft - wl) // 2
+    out[off:off + wl] = w
+    return out
+
+
+def logmel_batch(wav: torch.Tensor, sampling_rate: int, fft_size=1024, hop_size=256, win_length=None, num_mels=80,
+                 fmin=None, fmax=None, eps=1e-10, log_base=10.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Batched device entry: wav (B, n_samples) float32 CUDA -> (B, 1 + n_samples // hop, num_mels) float32."""
+    fmin = 0.0 if fmin is None else fmin
+    fmax = sampling_rate / 2.0 if fmax is None else fmax
+    dev = wav.device
+    key = (dev, sampling_rate, fft_size, win_length, num_mels, fmin, fmax)
+    c = _DEV_CACHE.get(key)
+    if c is None:
+        c = (torch.from_numpy(hann_window(fft_size, win_length)).to(dev),
+             torch.from_numpy(mel_filterbank(sampling_rate, fft_size, num_mels, fmin, fmax)).to(dev))
+        _DEV_CACHE[key] = c
+    B, ns = wav.shape
+    if out is None:
+        out = torch.empty(B, 1 + ns // hop_size, num_mels, dtype=_f32, device=dev)
+    return ops.logmel(wav, c[0], c[1], out, fft_size, hop_size, eps, log_base)
+
+
+_DEV_CACHE: Dict[tuple, tuple] = {}
+
+
+def logmelfilterbank(audio, sampling_rate, fft_size=1024, hop_size=256, win_length=None, window="hann", num_mels=80,
+                     fmin=None, fmax=None, eps=1e-10, log_base=10.0):
+    """Reference signature (preprocess.py:30-42): 1-D numpy audio -> ndarray (frames, num_mels)."""
+    if window != "hann":
+        raise NotImplementedError("only the hann window (every shipped recipe) is implemented")
+    if log_base not in (None, 2.0, 10.0):
+        raise ValueError(f"{log_base} is not supported.")
+    wav = torch.from_numpy(np.ascontiguousarray(audio, dtype=np.float32)).cuda().unsqueeze(0)
+    mel = logmel_batch(wav, sampling_rate, fft_size, hop_size, win_length, num_mels, fmin, fmax, eps, log_base)
+    return mel[0].cpu().numpy()
+
+
+# =================================================================================================
+# fused training step (trainers/ar_vc.py:59-112 without the host round trips)
+# =================================================================================================
+class VTNTrainStep:
+    """forward + Seq2SeqLoss + backward (+ gradient all-reduce) + clip + Adam + WarmupLR, device-resident.
+
+    Mirrors ARVCTrainer._train_step for a VTN model; lengths arrive as host ints (the collater's
+    CPU tensors) so the step never synchronises.  With ``use_graph`` the launch sequence of one
+    (B, T, L) signature is captured once in a CUDA graph and replayed.
+    """
+
+    def __init__(self, model, lr: float = 8e-5, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
+                 grad_norm: float = 1.0, warmup_steps: int = 4000, bce_pos_weight: float = 10.0, use_graph: bool = False,
+                 process_group=None):
+        self.engine: VTNEngine = model.engine if hasattr(model, "engine") else model
+        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self.grad_norm, self.warmup = grad_norm, warmup_steps
+        self.pos_weight = bce_pos_weight
+        self.steps = 0
+        self.use_graph = use_graph
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        self._graphs: Dict[tuple, tuple] = {}
+
+    def lr_at(self, step: int) -> float:
+        """WarmupLR (schedulers/warmup_lr.py:54-61): lr * warmup^0.5 * min(step^-0.5, step * warmup^-1.5)."""
+        s = max(step, 1)
+        return self.lr * self.warmup ** 0.5 * min(s ** -0.5, s * self.warmup ** -1.5)
+
+    def _body(self, xs, ys, labels, ilens, olens):
+        eng = self.engine
+        eng.forward(xs, ys, ilens, olens)
+        eng.loss(ys, labels, self.pos_weight)
+        eng.backward(eng.d_after, eng.d_before, eng.d_logits)
+        if self.world > 1:
+            torch.distributed.all_reduce(eng.store.G, group=self.pg)
+        eng.optimizer_step(self.grad_norm, self.betas, self.eps, self.wd, grad_scale=1.0 / self.world)
+
+    def __call__(self, xs, ilens, ys, labels, olens):
+        """xs (B,T,idim), ys (B,L,odim), labels (B,L): float32 CUDA tensors trimmed to the batch maxima."""
+        eng = self.engine
+        self.steps += 1
+        eng.lr_dev.fill_(self.lr_at(self.steps))
+        self._body(xs, ys, labels, ilens, olens)
+        return eng.losses

@@ -1,0 +1,185 @@
+// Shared device/host helpers for the seq2seq-vc B200 hot-path kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/s2svc_b200.h"
+
+namespace s2s {
+
+// ---------------------------------------------------------------------------------------------
+// error reporting (thread-local last-error string, returned through s2s_last_error())
+// ---------------------------------------------------------------------------------------------
+char* last_error_buf();
+int set_error(int code, const char* fmt, ...);
+void count_launch();
+
+#define S2S_REQUIRE(cond, ...)                                         \
+    do {                                                               \
+        if (!(cond)) return s2s::set_error(S2S_ERR_INVALID, __VA_ARGS__); \
+    } while (0)
+
+#define S2S_CUDA_OK(expr)                                                                      \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            return s2s::set_error(S2S_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,               \
+                                  cudaGetErrorString(_e), __FILE__, __LINE__);                 \
+    } while (0)
+
+#define S2S_LAUNCH_OK()                                                                        \
+    do {                                                                                       \
+        s2s::count_launch();                                                                   \
+        cudaError_t _e = cudaGetLastError();                                                   \
+        if (_e != cudaSuccess)                                                                 \
+            return s2s::set_error(S2S_ERR_CUDA, "kernel launch failed: %s (%s:%d)",           \
+                                  cudaGetErrorString(_e), __FILE__, __LINE__);                 \
+    } while (0)
+
+inline int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+static inline long ceil_div_l(long a, long b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------------------------
+// dtype helpers: activations are f32 or bf16 in HBM, math is always f32 in registers
+// ---------------------------------------------------------------------------------------------
+typedef __nv_bfloat16 bf16;
+
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// 4-wide vector access (16 B for f32, 8 B for bf16); pointers must be aligned accordingly
+template <typename T> struct Vec4;
+template <> struct Vec4<float> {
+    static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+        float4 t = *reinterpret_cast<const float4*>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+template <> struct Vec4<bf16> {
+    static __device__ __forceinline__ void load(const bf16* p, float (&v)[4]) {
+        uint2 t = *reinterpret_cast<const uint2*>(p);
+        __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&t.x);
+        __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&t.y);
+        v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+    }
+    static __device__ __forceinline__ void store(bf16* p, const float (&v)[4]) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+        __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+        uint2 t;
+        t.x = *reinterpret_cast<uint32_t*>(&a);
+        t.y = *reinterpret_cast<uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(p) = t;
+    }
+};
+
+// runtime dtype -> template dispatch
+#define S2S_DISPATCH_DTYPE(dt, T, ...)                         \
+    do {                                                       \
+        if ((dt) == S2S_F32) { typedef float T; __VA_ARGS__; } \
+        else if ((dt) == S2S_BF16) { typedef s2s::bf16 T; __VA_ARGS__; } \
+        else return s2s::set_error(S2S_ERR_INVALID, "bad dtype %d", (int)(dt)); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// warp / block reductions
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// block-wide sum; `red` must hold >= 32 floats of shared memory. All threads get the result.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    float r = (lane < nw) ? red[lane] : 0.f;
+    r = warp_sum(r);
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// counter-based dropout RNG: keep(idx) is a pure function of (seed, stream, idx) so the backward
+// pass regenerates the forward mask instead of storing it.  p is the DROP probability.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mix32(uint64_t x) {
+    // splitmix64 finaliser
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+    x ^= x >> 27; x *= 0x94d049bb133111ebull;
+    x ^= x >> 31;
+    return (uint32_t)(x >> 32);
+}
+struct Dropout {
+    float p;          // drop probability; 0 disables
+    float scale;      // 1/(1-p)
+    uint32_t thresh;  // drop if rnd < thresh
+    uint64_t key;     // mixes seed and stream
+    const uint64_t* seed_dev;  // optional device-resident seed increment (CUDA-graph replays)
+};
+inline Dropout make_dropout(const s2s_dropout_t* d) {
+    Dropout r;
+    float p = d ? d->p : 0.f;
+    r.p = p;
+    r.scale = (p > 0.f && p < 1.f) ? 1.f / (1.f - p) : 1.f;
+    double t = (double)p * 4294967296.0;
+    r.thresh = (p <= 0.f) ? 0u : (t >= 4294967295.0 ? 4294967295u : (uint32_t)t);
+    uint64_t seed = d ? d->seed : 0, stream_id = d ? d->stream : 0;
+    r.key = seed * 0x9e3779b97f4a7c15ull + stream_id * 0xd1b54a32d192ed03ull + 0x2545f4914f6cdd1dull;
+    r.seed_dev = d ? d->seed_dev : nullptr;
+    return r;
+}
+// call once per thread at kernel start: folds the device-resident seed into the key
+__device__ __forceinline__ void dropout_resolve(Dropout& d) {
+    if (d.thresh != 0u && d.seed_dev) d.key += (*d.seed_dev) * 0x9e3779b97f4a7c15ull;
+}
+// returns the multiplicative factor (0 or scale) for element idx
+__device__ __forceinline__ float dropout_factor(const Dropout& d, uint64_t idx) {
+    if (d.thresh == 0u) return 1.f;
+    uint32_t r = mix32(d.key + idx * 0x9e3779b97f4a7c15ull);
+    return (r < d.thresh) ? 0.f : d.scale;
+}
+
+// grid size for grid-stride elementwise kernels: enough CTAs to fill the chip a few times over
+inline unsigned ew_grid(long n_items, int per_block) {
+    long b = ceil_div_l(n_items, per_block);
+    long cap = (long)num_sms() * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (unsigned)b;
+}
+
+}  // namespace s2s

@@ -1,0 +1,561 @@
+// HBM-bound normalisation kernels: LayerNorm fwd/bwd, column reductions (bias / affine grads),
+// relu / dropout backward, and the postnet BatchNorm(+tanh) pipeline over zero-haloed
+// channels-last buffers.  All kernels read each input once per pass with 4-wide vector access
+// when the channel count allows it; statistics and parameter gradients are float32.
+#include "common.cuh"
+
+namespace s2s {
+
+template <typename T, int VEC> struct VLoad;
+template <typename T> struct VLoad<T, 4> {
+    static __device__ __forceinline__ void ld(const T* p, float (&v)[4]) { Vec4<T>::load(p, v); }
+    static __device__ __forceinline__ void st(T* p, const float (&v)[4]) { Vec4<T>::store(p, v); }
+};
+template <typename T> struct VLoad<T, 1> {
+    static __device__ __forceinline__ void ld(const T* p, float (&v)[1]) { v[0] = to_f<T>(*p); }
+    static __device__ __forceinline__ void st(T* p, const float (&v)[1]) { *p = from_f<T>(v[0]); }
+};
+
+static inline bool vec4_ok(int cols, int64_t ld, const void* a, const void* b = nullptr, const void* c = nullptr,
+                           const void* d = nullptr) {
+    auto al = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    return (cols % 4 == 0) && (ld % 4 == 0) && al(a) && al(b) && al(c) && al(d);
+}
+
+// =============================================================================================
+// LayerNorm
+// =============================================================================================
+template <typename T, int VEC>
+__global__ void __launch_bounds__(128) ln_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, T* __restrict__ y,
+                                                     float* __restrict__ mean, float* __restrict__ rstd, long rows,
+                                                     int d, float eps) {
+    const int lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const T* xr = x + row * d;
+    float s = 0.f;
+    for (int c = lane * VEC; c < d; c += 32 * VEC) {
+        float v[VEC];
+        VLoad<T, VEC>::ld(xr + c, v);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) s += v[i];
+    }
+    const float mu = warp_sum(s) / (float)d;
+    float q = 0.f;
+    for (int c = lane * VEC; c < d; c += 32 * VEC) {
+        float v[VEC];
+        VLoad<T, VEC>::ld(xr + c, v);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) { float t = v[i] - mu; q += t * t; }
+    }
+    const float rs = rsqrtf(warp_sum(q) / (float)d + eps);
+    T* yr = y + row * d;
+    for (int c = lane * VEC; c < d; c += 32 * VEC) {
+        float v[VEC], o[VEC];
+        VLoad<T, VEC>::ld(xr + c, v);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o[i] = (v[i] - mu) * rs * gamma[c + i] + beta[c + i];
+        VLoad<T, VEC>::st(yr + c, o);
+    }
+    if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(128) ln_bwd_dx_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                        const float* __restrict__ gamma,
+                                                        const float* __restrict__ mean,
+                                                        const float* __restrict__ rstd, const T* __restrict__ dres,
+                                                        T* __restrict__ dx, long rows, int d) {
+    const int lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const T* xr = x + row * d;
+    const T* gr = dy + row * d;
+    const float mu = mean[row], rs = rstd[row];
+    float a = 0.f, b = 0.f;
+    for (int c = lane * VEC; c < d; c += 32 * VEC) {
+        float v[VEC], g[VEC];
+        VLoad<T, VEC>::ld(xr + c, v);
+        VLoad<T, VEC>::ld(gr + c, g);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            float gg = g[i] * gamma[c + i];
+            a += gg;
+            b += gg * (v[i] - mu) * rs;
+        }
+    }
+    a = warp_sum(a) / (float)d;
+    b = warp_sum(b) / (float)d;
+    T* dr = dx + row * d;
+    const T* rr = dres ? dres + row * d : nullptr;
+    for (int c = lane * VEC; c < d; c += 32 * VEC) {
+        float v[VEC], g[VEC], o[VEC];
+        VLoad<T, VEC>::ld(xr + c, v);
+        VLoad<T, VEC>::ld(gr + c, g);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o[i] = rs * (g[i] * gamma[c + i] - a - (v[i] - mu) * rs * b);
+        if (rr) {
+            float e[VEC];
+            VLoad<T, VEC>::ld(rr + c, e);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) o[i] += e[i];
+        }
+        VLoad<T, VEC>::st(dr + c, o);
+    }
+}
+
+// =============================================================================================
+// Generic column reduction: out_k[c] += sum_r f_k(r, c).  blockDim = (32, 8); each thread owns
+// VEC consecutive columns; grid = (col tiles, row chunks); cross-warp reduce in shared memory and
+// one float atomicAdd per (k, column, row chunk).
+// =============================================================================================
+template <int NOUT, int VEC, typename F>
+__global__ void __launch_bounds__(256) colreduce_kernel(F f, long rows, int cols) {
+    __shared__ float red[8][NOUT][32 * VEC];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int c0 = (blockIdx.x * 32 + tx) * VEC;
+    float acc[NOUT][VEC];
+#pragma unroll
+    for (int k = 0; k < NOUT; ++k)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[k][v] = 0.f;
+    const long per = (rows + gridDim.y - 1) / gridDim.y;
+    const long r0 = (long)blockIdx.y * per;
+    const long r1 = (r0 + per < rows) ? r0 + per : rows;
+    if (c0 < cols)
+        for (long r = r0 + ty; r < r1; r += 8) f(r, c0, acc);
+#pragma unroll
+    for (int k = 0; k < NOUT; ++k)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) red[ty][k][tx * VEC + v] = acc[k][v];
+    __syncthreads();
+    // 256 threads sum NOUT * 32 * VEC entries over the 8 row-warps
+    for (int e = ty * 32 + tx; e < NOUT * 32 * VEC; e += 256) {
+        int k = e / (32 * VEC), cc = e % (32 * VEC);
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[w][k][cc];
+        int c = blockIdx.x * 32 * VEC + cc;
+        if (c < cols) atomicAdd(f.out(k, c), s);
+    }
+}
+
+template <int NOUT, int VEC, typename F>
+static int launch_colreduce(F f, long rows, int cols, cudaStream_t st) {
+    if (rows <= 0 || cols <= 0) return S2S_OK;
+    unsigned gx = (unsigned)ceil_div_l(cols, 32 * VEC);
+    long want = (long)num_sms() * 4 / gx;
+    if (want < 1) want = 1;
+    long maxy = ceil_div_l(rows, 64);
+    if (want > maxy) want = maxy;
+    if (want < 1) want = 1;
+    colreduce_kernel<NOUT, VEC, F><<<dim3(gx, (unsigned)want), dim3(32, 8), 0, st>>>(f, rows, cols);
+    S2S_LAUNCH_OK();
+    return S2S_OK;
+}
+
+template <typename T, int VEC> struct ColsumF {
+    const T* x; long ld; float* o;
+    __device__ __forceinline__ void operator()(long r, int c0, float (&acc)[1][VEC]) const {
+        float v[VEC];
+        VLoad<T, VEC>::ld(x + r * ld + c0, v);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[0][i] += v[i];
+    }
+    __device__ __forceinline__ float* out(int, int c) const { return o + c; }
+};
+
+template <typename T, int VEC> struct LNGradF {
+    const T* dy; const T* x; const float* mean; const float* rstd; int d; float* dgamma; float* dbeta;
+    __device__ __forceinline__ void operator()(long r, int c0, float (&acc)[2][VEC]) const {
+        float v[VEC], g[VEC];
+        VLoad<T, VEC>::ld(x + r * d + c0, v);
+        VLoad<T, VEC>::ld(dy + r * d + c0, g);
+        const float mu = mean[r], rs = rstd[r];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) { acc[0][i] += g[i] * (v[i] - mu) * rs; acc[1][i] += g[i]; }
+    }
+    __device__ __forceinline__ float* out(int k, int c) const { return (k == 0 ? dgamma : dbeta) + c; }
+};
+
+// =============================================================================================
+// elementwise: relu backward, dropout backward
+// =============================================================================================
+template <typename T>
+__global__ void relu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx, long n,
+                                float scale) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+        dx[i] = from_f<T>(to_f<T>(y[i]) > 0.f ? to_f<T>(dy[i]) * scale : 0.f);
+}
+template <typename T>
+__global__ void dropout_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, long n, Dropout drop) {
+    dropout_resolve(drop);
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+        dx[i] = from_f<T>(to_f<T>(dy[i]) * dropout_factor(drop, (uint64_t)i));
+}
+
+// =============================================================================================
+// BatchNorm over (B, L) frames of a haloed (B, Lp = L + 2*halo, C) buffer
+// =============================================================================================
+struct BNGeom {
+    int L, Lp, halo, C;
+    __device__ __forceinline__ long phys(long r) const {  // frame index -> physical row
+        long b = r / L;
+        int l = (int)(r - b * L);
+        return b * Lp + halo + l;
+    }
+};
+
+template <typename T, int VEC> struct BNStatsF {
+    const T* x; BNGeom g; float* sums;
+    __device__ __forceinline__ void operator()(long r, int c0, float (&acc)[2][VEC]) const {
+        float v[VEC];
+        VLoad<T, VEC>::ld(x + g.phys(r) * g.C + c0, v);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) { acc[0][i] += v[i]; acc[1][i] += v[i] * v[i]; }
+    }
+    __device__ __forceinline__ float* out(int k, int c) const { return sums + k * g.C + c; }
+};
+
+__global__ void bn_finalize_kernel(const float* __restrict__ sums, float* __restrict__ mean,
+                                   float* __restrict__ invstd, float* running_mean, float* running_var, long count,
+                                   int C, float eps, float momentum) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float n = (float)count;
+    float mu = sums[c] / n;
+    float var = sums[C + c] / n - mu * mu;
+    var = fmaxf(var, 0.f);
+    mean[c] = mu;
+    invstd[c] = rsqrtf(var + eps);
+    if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mu;
+    if (running_var) {
+        float unb = count > 1 ? var * n / (n - 1.f) : var;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * unb;
+    }
+}
+
+__global__ void bn_eval_stats_kernel(const float* __restrict__ rm, const float* __restrict__ rv,
+                                     float* __restrict__ mean, float* __restrict__ invstd, int C, float eps) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    mean[c] = rm[c];
+    invstd[c] = rsqrtf(rv[c] + eps);
+}
+
+template <typename T, int VEC>
+__global__ void bn_apply_kernel(const T* __restrict__ x, const float* __restrict__ mean,
+                                const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, T* __restrict__ y, int B, BNGeom g, int use_tanh,
+                                Dropout drop) {
+    dropout_resolve(drop);
+    const int cv = g.C / VEC;
+    const long total = (long)B * g.Lp * cv;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        int c = (int)(i % cv) * VEC;
+        long prow = i / cv;
+        int lp = (int)(prow % g.Lp);
+        long b = prow / g.Lp;
+        float o[VEC];
+        int l = lp - g.halo;
+        if (l < 0 || l >= g.L) {
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) o[k] = 0.f;
+        } else {
+            float v[VEC];
+            VLoad<T, VEC>::ld(x + prow * g.C + c, v);
+            uint64_t idx = (uint64_t)((b * g.L + l) * (long)g.C + c);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                float t = (v[k] - mean[c + k]) * invstd[c + k] * gamma[c + k] + beta[c + k];
+                if (use_tanh) t = tanhf(t);
+                o[k] = t * dropout_factor(drop, idx + k);
+            }
+        }
+        VLoad<T, VEC>::st(y + prow * g.C + c, o);
+    }
+}
+
+// dz = dy * dropmask * act'(y_pre_dropout); y holds the post-activation, post-dropout output.
+// With dropout the pre-dropout activation is recomputed from x so tanh' stays exact.
+template <typename T, int VEC>
+__device__ __forceinline__ void bn_dz(const T* dy, const T* y, const T* x, const float* mean, const float* invstd,
+                                      const float* gamma, const float* beta, const BNGeom& g, long r, int c0,
+                                      int use_tanh, const Dropout& drop, float (&dz)[VEC], float (&xhat)[VEC]) {
+    long prow = g.phys(r);
+    float gy[VEC], xv[VEC];
+    VLoad<T, VEC>::ld(dy + prow * g.C + c0, gy);
+    VLoad<T, VEC>::ld(x + prow * g.C + c0, xv);
+    uint64_t idx = (uint64_t)(r * (long)g.C + c0);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+        xhat[k] = (xv[k] - mean[c0 + k]) * invstd[c0 + k];
+        float t = gy[k] * dropout_factor(drop, idx + k);
+        if (use_tanh) {
+            float a = tanhf(xhat[k] * gamma[c0 + k] + beta[c0 + k]);
+            t *= (1.f - a * a);
+        }
+        dz[k] = t;
+    }
+}
+
+template <typename T, int VEC> struct BNBwdF {
+    const T* dy; const T* y; const T* x; const float* mean; const float* invstd; const float* gamma;
+    const float* beta; BNGeom g; int use_tanh; Dropout drop; float* sums;
+    __device__ __forceinline__ void operator()(long r, int c0, float (&acc)[2][VEC]) const {
+        float dz[VEC], xh[VEC];
+        Dropout d = drop;
+        dropout_resolve(d);
+        bn_dz<T, VEC>(dy, y, x, mean, invstd, gamma, beta, g, r, c0, use_tanh, d, dz, xh);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) { acc[0][k] += dz[k]; acc[1][k] += dz[k] * xh[k]; }
+    }
+    __device__ __forceinline__ float* out(int k, int c) const { return sums + k * g.C + c; }
+};
+
+template <typename T, int VEC>
+__global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T* __restrict__ x,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    const float* __restrict__ sums, T* __restrict__ dx, int B, BNGeom g,
+                                    int use_tanh, Dropout drop) {
+    dropout_resolve(drop);
+    const int cv = g.C / VEC;
+    const long total = (long)B * g.Lp * cv;
+    const float inv_n = 1.f / (float)((long)B * g.L);
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        int c = (int)(i % cv) * VEC;
+        long prow = i / cv;
+        int lp = (int)(prow % g.Lp);
+        long b = prow / g.Lp;
+        int l = lp - g.halo;
+        float o[VEC];
+        if (l < 0 || l >= g.L) {
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) o[k] = 0.f;
+        } else {
+            float dz[VEC], xh[VEC];
+            bn_dz<T, VEC>(dy, y, x, mean, invstd, gamma, beta, g, b * g.L + l, c, use_tanh, drop, dz, xh);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                float t = dz[k];
+                if (sums) t -= sums[c + k] * inv_n + xh[k] * sums[g.C + c + k] * inv_n;
+                o[k] = t * gamma[c + k] * invstd[c + k];
+            }
+        }
+        VLoad<T, VEC>::st(dx + prow * g.C + c, o);
+    }
+}
+
+__global__ void bn_param_grad_kernel(const float* __restrict__ sums, float* dgamma, float* dbeta, int C) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    if (dbeta) dbeta[c] += sums[c];
+    if (dgamma) dgamma[c] += sums[C + c];
+}
+
+template <typename T, int VEC>
+__global__ void pad_rows_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int L, int halo, int C, int to_padded) {
+    const int cv = C / VEC, Lp = L + 2 * halo;
+    const long total = (long)B * (to_padded ? Lp : L) * cv;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        int c = (int)(i % cv) * VEC;
+        long row = i / cv;
+        float v[VEC];
+        if (to_padded) {
+            int lp = (int)(row % Lp);
+            long b = row / Lp;
+            int l = lp - halo;
+            if (l < 0 || l >= L) {
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) v[k] = 0.f;
+            } else {
+                VLoad<T, VEC>::ld(x + (b * L + l) * C + c, v);
+            }
+            VLoad<T, VEC>::st(y + row * C + c, v);
+        } else {
+            int l = (int)(row % L);
+            long b = row / L;
+            VLoad<T, VEC>::ld(x + (b * Lp + halo + l) * C + c, v);
+            VLoad<T, VEC>::st(y + row * C + c, v);
+        }
+    }
+}
+
+}  // namespace s2s
+
+using namespace s2s;
+
+#define S2S_VEC_DISPATCH(ok, VEC, ...)                \
+    do {                                              \
+        if (ok) { constexpr int VEC = 4; __VA_ARGS__; } \
+        else { constexpr int VEC = 1; __VA_ARGS__; }  \
+    } while (0)
+
+extern "C" int s2s_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,
+                                 float* rstd, int64_t rows, int d, float eps, int dtype, void* stream) {
+    S2S_REQUIRE(x && gamma && beta && y && mean && rstd && d > 0, "layernorm_fwd: null pointer or bad d");
+    if (rows <= 0) return S2S_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    bool ok = vec4_ok(d, d, x, y);
+    S2S_DISPATCH_DTYPE(dtype, T, S2S_VEC_DISPATCH(ok, VEC, (ln_fwd_kernel<T, VEC><<<(unsigned)ceil_div_l(rows, 4), 128, 0, st>>>(
+        (const T*)x, gamma, beta, (T*)y, mean, rstd, rows, d, eps))));
+    S2S_LAUNCH_OK();
+    return S2S_OK;
+}
+
+extern "C" int s2s_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean,
+                                 const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta,
+                                 int64_t rows, int d, int dtype, void* stream) {
+    S2S_REQUIRE(dy && x && gamma && mean && rstd && d > 0, "layernorm_bwd: null pointer or bad d");
+    if (rows <= 0) return S2S_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    bool ok = vec4_ok(d, d, x, dy, dx, dres);
+    if (dx) {
+        S2S_DISPATCH_DTYPE(dtype, T, S2S_VEC_DISPATCH(ok, VEC, (ln_bwd_dx_kernel<T, VEC><<<(unsigned)ceil_div_l(rows, 4), 128, 0, st>>>(
+            (const T*)dy, (const T*)x, gamma, mean, rstd, (const T*)dres, (T*)dx, rows, d))));
+        S2S_LAUNCH_OK();
+    }
+    if (dgamma && dbeta) {
+        int rc = S2S_OK;
+        S2S_DISPATCH_DTYPE(dtype, T, S2S_VEC_DISPATCH(ok, VEC, {
+            LNGradF<T, VEC> f{(const T*)dy, (const T*)x, mean, rstd, d, dgamma, dbeta};
+            rc = launch_colreduce<2, VEC>(f, rows, d, st);
+        }));
+        return rc;
+    }
+    return S2S_OK;
+}
+
+extern "C" int s2s_colsum(const void* x, int64_t rows, int cols, int64_t ld, float* out, int dtype, void* stream) {
+    S2S_REQUIRE(x && out && cols > 0 && ld >= cols, "colsum: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    bool ok = vec4_ok(cols, ld, x);
+    int rc = S2S_OK;
+    S2S_DISPATCH_DTYPE(dtype, T, S2S_VEC_DISPATCH(ok, VEC, {
+        ColsumF<T, VEC> f{(const T*)x, (long)ld, out};
+        rc = launch_colreduce<1, VEC>(f, rows, cols, st);
+    }));
+    return rc;
+}
+
+extern "C" int s2s_relu_bwd(const void* dy, const void* y, void* dx, int64_t n, float scale, int dtype, void* stream) {
+    S2S_REQUIRE(dy && y && dx, "relu_bwd: null pointer");
+    if (n <= 0) return S2S_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    S2S_DISPATCH_DTYPE(dtype, T, (relu_bwd_kernel<T><<<ew_grid(n, 256 * 4), 256, 0, st>>>((const T*)dy, (const T*)y, (T*)dx, n, scale)));
+    S2S_LAUNCH_OK();
+    return S2S_OK;
+}
+
+extern "C" int s2s_dropout_bwd(const void* dy, void* dx, int64_t rows, int cols, const s2s_dropout_t* drop, int dtype,
+                               void* stream) {
+    S2S_REQUIRE(dy && dx, "dropout_bwd: null pointer");
+    long n = (long)rows * cols;
+    if (n <= 0) return S2S_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    Dropout d = make_dropout(drop);
+    S2S_DISPATCH_DTYPE(dtype, T, (dropout_bwd_kernel<T><<<ew_grid(n, 256 * 4), 256, 0, st>>>((const T*)dy, (T*)dx, n, d)));
+    S2S_LAUNCH_OK();
+    return S2S_OK;
+}
+
+extern "C" int s2s_bn_stats(const void* x, float* sums, int B, int L, int halo, int C, int dtype, void* stream) {
+    S2S_REQUIRE(x && sums && B > 0 && L > 0 && C > 0 && halo >= 0, "bn_stats: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    BNGeom g{L, L + 2 * halo, halo, C};
+    bool ok = vec4_ok(C, C, x);
+    int rc = S2S_OK;
+    S2S_DISPATCH_DTYPE(dtype, T, S2S_VEC_DISPATCH(ok, VEC, {
+        BNStatsF<T, VEC> f{(const T*)x, g, sums};
+        rc = launch_colreduce<2, VEC>(f, (long)B * L, C, st);
+    }));
+    return rc;
+}
+
+extern "C" int s2s_bn_finalize(const float* sums, float* mean, float* invstd, float* running_mean,
+                               float* running_var, int64_t count, int C, float eps, float momentum, void* stream) {
+    S2S_REQUIRE(sums && mean && invstd && count > 0 && C > 0, "bn_finalize: bad arguments");
+    bn_finalize_kernel<<<(unsigned)ceil_div_l(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, mean, invstd, running_mean,
+                                                                                      running_var, count, C, eps, momentum);
+    S2S_LAUNCH_OK();
+    return S2S_OK;
+}
+
+extern "C" int s2s_bn_eval_stats(const float* running_mean, const float* running_var, float* mean, float* invstd, int C,
+                                 float eps, void* stream) {
+    S2S_REQUIRE(running_mean && running_var && mean && invstd && C > 0, "bn_eval_stats: bad arguments");
+    bn_eval_stats_kernel<<<(unsigned)ceil_div_l(C, 128), 128, 0, (cudaStream_t)stream>>>(running_mean, running_var, mean, invstd, C, eps);
+    S2S_LAUNCH_OK();
+    return S2S_OK;
+}
+
+extern "C" int s2s_bn_apply(const void* x, const float* mean, const float* invstd, const float* gamma,
+                            const float* beta, void* y, int B, int L, int halo, int C, int use_tanh,
+                            const s2s_dropout_t* drop, int dtype, void* stream) {
+    S2S_REQUIRE(x && mean && invstd && gamma && beta && y && B > 0 && L > 0 && C > 0, "bn_apply: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    BNGeom g{L, L + 2 * halo, halo, C};
+    Dropout d = make_dropout(drop);
+    bool ok = vec4_ok(C, C, x, y);
+    long total = (long)B * g.Lp * C;
+    S2S_DISPATCH_DTYPE(dtype, T, S2S_VEC_DISPATCH(ok, VEC, (bn_apply_kernel<T, VEC><<<ew_grid(total / VEC, 256), 256, 0, st>>>(
+        (const T*)x, mean, invstd, gamma, beta, (T*)y, B, g, use_tanh, d))));
+    S2S_LAUNCH_OK();
+    return S2S_OK;
+}
+
+extern "C" int s2s_bn_bwd_reduce(const void* dy, const void* y, const void* x, const float* mean,
+                                 const float* invstd, const float* gamma, const float* beta, float* sums, int B,
+                                 int L, int halo, int C, int use_tanh, const s2s_dropout_t* drop, int dtype,
+                                 void* stream) {
+    S2S_REQUIRE(dy && x && mean && invstd && gamma && beta && sums, "bn_bwd_reduce: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    BNGeom g{L, L + 2 * halo, halo, C};
+    Dropout d = make_dropout(drop);
+    bool ok = vec4_ok(C, C, x, dy);
+    int rc = S2S_OK;
+    S2S_DISPATCH_DTYPE(dtype, T, S2S_VEC_DISPATCH(ok, VEC, {
+        BNBwdF<T, VEC> f{(const T*)dy, (const T*)y, (const T*)x, mean, invstd, gamma, beta, g, use_tanh, d, sums};
+        rc = launch_colreduce<2, VEC>(f, (long)B * L, C, st);
+    }));
+    return rc;
+}
+
+extern "C" int s2s_bn_bwd_apply(const void* dy, const void* y, const void* x, const float* mean,
+                                const float* invstd, const float* gamma, const float* beta, const float* sums,
+                                void* dx, float* dgamma, float* dbeta, int B, int L, int halo, int C, int use_tanh,
+                                const s2s_dropout_t* drop, int dtype, void* stream) {
+    S2S_REQUIRE(dy && x && mean && invstd && gamma && beta && dx, "bn_bwd_apply: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    BNGeom g{L, L + 2 * halo, halo, C};
+    Dropout d = make_dropout(drop);
+    bool ok = vec4_ok(C, C, x, dy, dx);
+    long total = (long)B * g.Lp * C;
+    S2S_DISPATCH_DTYPE(dtype, T, S2S_VEC_DISPATCH(ok, VEC, (bn_bwd_apply_kernel<T, VEC><<<ew_grid(total / VEC, 256), 256, 0, st>>>(
+        (const T*)dy, (const T*)y, (const T*)x, mean, invstd, gamma, beta, sums, (T*)dx, B, g, use_tanh, d))));
+    S2S_LAUNCH_OK();
+    if (sums && (dgamma || dbeta)) {
+        bn_param_grad_kernel<<<(unsigned)ceil_div_l(C, 128), 128, 0, st>>>(sums, dgamma, dbeta, C);
+        S2S_LAUNCH_OK();
+    }
+    return S2S_OK;
+}
+
+static int pad_rows_impl(const void* x, void* y, int B, int L, int halo, int C, int dtype, void* stream, int to_padded) {
+    S2S_REQUIRE(x && y && B > 0 && L > 0 && C > 0 && halo >= 0, "pad_rows: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    bool ok = vec4_ok(C, C, x, y);
+    long total = (long)B * (L + 2 * halo) * C;
+    S2S_DISPATCH_DTYPE(dtype, T, S2S_VEC_DISPATCH(ok, VEC, (pad_rows_kernel<T, VEC><<<ew_grid(total / VEC, 256), 256, 0, st>>>(
+        (const T*)x, (T*)y, B, L, halo, C, to_padded))));
+    S2S_LAUNCH_OK();
+    return S2S_OK;
+}
+extern "C" int s2s_pad_rows(const void* x, void* y, int B, int L, int halo, int C, int dtype, void* stream) {
+    return pad_rows_impl(x, y, B, L, halo, C, dtype, stream, 1);
+}
+extern "C" int s2s_unpad_rows(const void* x, void* y, int B, int L, int halo, int C, int dtype, void* stream) {
+    return pad_rows_impl(x, y, B, L, halo, C, dtype, stream, 0);
+}

@@ -1,0 +1,328 @@
+"""Tensor-level wrappers over the C ABI (include/s2svc_b200.h).
+
+Each function takes torch CUDA tensors as *memory handles* (pointer + shape + strides), checks
+layouts, and issues exactly the C call; no arithmetic happens in PyTorch.  GEMM_MODE selects the
+s2s_gemm path: 0 = fp32 CUDA-core (parity), 1 = bf16 tcgen05.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import NO_DROP, Drop, GemmDesc, check, dt, ptr, stream
+
+_i32 = torch.int32
+
+
+def _L():
+    return _lib.load()
+
+
+def _batch_strides(t: torch.Tensor, nb: int) -> Tuple[int, int, int, int]:
+    """(size1, size2, stride1, stride2) of the (up to two) leading batch dims of t."""
+    if nb == 0:
+        return 1, 1, 0, 0
+    if nb == 1:
+        return 1, t.shape[0], 0, t.stride(0)
+    return t.shape[0], t.shape[1], t.stride(0), t.stride(1)
+
+
+def _lead_strides(t: torch.Tensor, core: int) -> Tuple[int, int]:
+    """Strides of the leading batch dims of an operand (missing dims broadcast with stride 0)."""
+    n = t.dim() - core
+    if n == 0:
+        return 0, 0
+    if n == 1:
+        return 0, t.stride(0)
+    assert n == 2
+    return t.stride(0), t.stride(1)
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, *, bias: Optional[torch.Tensor] = None,
+         residual: Optional[torch.Tensor] = None, alpha: float = 1.0, relu: bool = False,
+         accumulate: bool = False, drop: Drop = NO_DROP, taps: int = 1,
+         row_mask: Optional[Tuple[int, int, int, int]] = None, mode: int = 0, M: Optional[int] = None) -> torch.Tensor:
+    """c[..., m, n] = epilogue(alpha * sum_t sum_k a[..., m + t, k] * b[..., n, (t,) k]).
+
+    a: (..., rows, K); b: (..., N, K) or (..., N, taps, K) when taps > 1; c: (..., M, N).
+    Leading batch dims (0-2) come from c; a / b with fewer dims broadcast (stride 0).
+    """
+    nb = c.dim() - 2
+    assert 0 <= nb <= 2
+    Mc, N = c.shape[-2], c.shape[-1]
+    M = Mc if M is None else M
+    K = a.shape[-1]
+    assert c.stride(-1) == 1 or N == 1, "C must be contiguous along n"
+    g = GemmDesc()
+    g.M, g.N, g.K, g.taps = M, N, K, taps
+    g.A, g.a_dtype = ptr(a), dt(a)
+    g.a_rs, g.a_cs = a.stride(-2), a.stride(-1)
+    if a.shape[-1] == 1:
+        g.a_cs = 1
+    g.a_bs1, g.a_bs2 = _lead_strides(a, 2)
+    g.B, g.b_dtype = ptr(b), dt(b)
+    if taps > 1:
+        assert b.shape[-2] == taps and b.shape[-3] == N and b.shape[-1] == K
+        g.b_rs, g.b_ts, g.b_cs = b.stride(-3), b.stride(-2), b.stride(-1)
+        nbb_core = 3
+    else:
+        assert b.shape[-2] == N and b.shape[-1] == K, (b.shape, N, K)
+        g.b_rs, g.b_ts, g.b_cs = b.stride(-2), 0, b.stride(-1)
+        nbb_core = 2
+    if K == 1:
+        g.b_cs = 1
+    g.b_bs1, g.b_bs2 = _lead_strides(b, nbb_core)
+    g.C, g.c_dtype = ptr(c), dt(c)
+    g.c_rs = c.stride(-2)
+    g.batch1, g.batch2, g.c_bs1, g.c_bs2 = _batch_strides(c, nb)
+    g.bias = ptr(bias)
+    if residual is not None:
+        assert residual.dtype == c.dtype and residual.stride() == c.stride(), "residual must share C's layout"
+    g.R = ptr(residual)
+    g.alpha, g.relu, g.accumulate = float(alpha), int(relu), int(accumulate)
+    g.drop = drop.c()
+    if row_mask is not None:
+        g.mask_period, g.mask_offset, g.mask_lo, g.mask_hi = row_mask
+    check(_L().s2s_gemm(ctypes.byref(g), mode, stream()), "s2s_gemm")
+    return c
+
+
+def layernorm_fwd(x, gamma, beta, y, mean, rstd, eps=1e-12):
+    d = x.shape[-1]
+    rows = x.numel() // d
+    assert x.is_contiguous() and y.is_contiguous()
+    check(_L().s2s_layernorm_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(mean), ptr(rstd), rows, d, eps, dt(x), stream()),
+          "layernorm_fwd")
+    return y
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, dres=None):
+    d = x.shape[-1]
+    rows = x.numel() // d
+    assert dy.is_contiguous() and x.is_contiguous() and (dres is None or dres.is_contiguous())
+    check(_L().s2s_layernorm_bwd(ptr(dy), ptr(x), ptr(gamma), ptr(mean), ptr(rstd), ptr(dres), ptr(dx), ptr(dgamma), ptr(dbeta), rows, d,
+                                 dt(x), stream()), "layernorm_bwd")
+    return dx
+
+
+def colsum(x2d, out):
+    """out[c] += sum_r x2d[r, c]"""
+    assert x2d.dim() == 2 and x2d.stride(1) == 1
+    check(_L().s2s_colsum(ptr(x2d), x2d.shape[0], x2d.shape[1], x2d.stride(0), ptr(out), dt(x2d), stream()), "colsum")
+
+
+def relu_bwd(dy, y, dx, scale=1.0):
+    assert dy.is_contiguous() and y.is_contiguous() and dx.is_contiguous()
+    check(_L().s2s_relu_bwd(ptr(dy), ptr(y), ptr(dx), dy.numel(), scale, dt(dy), stream()), "relu_bwd")
+    return dx
+
+
+def dropout_bwd(dy, dx, drop: Drop):
+    assert dy.is_contiguous() and dx.is_contiguous()
+    cols = dy.shape[-1]
+    check(_L().s2s_dropout_bwd(ptr(dy), ptr(dx), dy.numel() // cols, cols, ctypes.byref(drop.c()), dt(dy), stream()), "dropout_bwd")
+    return dx
+
+
+def add(a, b, out):
+    assert a.is_contiguous() and b.is_contiguous() and out.is_contiguous() and a.dtype == b.dtype == out.dtype
+    check(_L().s2s_add(ptr(a), ptr(b), ptr(out), a.numel(), dt(a), stream()), "add")
+    return out
+
+
+def softmax_fwd(S, klens, causal: bool, T2: int, Pd=None, drop: Drop = NO_DROP):
+    """In place over S (B, H, T1, ld); columns >= T2 are written as zeros."""
+    B, H, T1, ld = S.shape
+    assert S.is_contiguous()
+    check(_L().s2s_softmax_fwd(ptr(S), ptr(S), ptr(Pd), ptr(klens), B, H, T1, T2, ld, int(causal), ctypes.byref(drop.c()),
+                               dt(S), stream()), "softmax_fwd")
+    return S
+
+
+def softmax_bwd(P, dP, T2: int, scale: float, drop: Drop = NO_DROP):
+    B, H, T1, ld = P.shape
+    assert P.is_contiguous() and dP.is_contiguous()
+    check(_L().s2s_softmax_bwd(ptr(P), ptr(dP), B, H, T1, T2, ld, scale, ctypes.byref(drop.c()), dt(P), stream()), "softmax_bwd")
+    return dP
+
+
+def scaled_pe_fwd(x, pe, alpha, y, drop: Drop = NO_DROP):
+    B, T, d = x.shape
+    assert x.is_contiguous() and y.is_contiguous() and pe.shape[0] >= T and pe.shape[1] == d and pe.is_contiguous()
+    check(_L().s2s_scaled_pe_fwd(ptr(x), ptr(pe), ptr(alpha), ptr(y), B, T, d, ctypes.byref(drop.c()), dt(x), stream()), "scaled_pe_fwd")
+    return y
+
+
+def scaled_pe_bwd(dy, pe, dx, dalpha, drop: Drop = NO_DROP):
+    B, T, d = dy.shape
+    assert dy.is_contiguous()
+    check(_L().s2s_scaled_pe_bwd(ptr(dy), ptr(pe), ptr(dx), ptr(dalpha), B, T, d, ctypes.byref(drop.c()), dt(dy), stream()), "scaled_pe_bwd")
+    return dx
+
+
+def conv1_fwd(x, w, bias, y1):
+    B, T, F = x.shape
+    C = w.shape[0]
+    assert x.dtype == torch.float32 and x.is_contiguous() and w.is_contiguous() and y1.is_contiguous()
+    check(_L().s2s_conv1_fwd(ptr(x), ptr(w), ptr(bias), ptr(y1), B, T, F, C, dt(y1), stream()), "conv1_fwd")
+    return y1
+
+
+def conv1_bwd(x, dy1, dw, dbias):
+    B, T, F = x.shape
+    C = dy1.shape[-1]
+    check(_L().s2s_conv1_bwd(ptr(x), ptr(dy1), ptr(dw), ptr(dbias), B, T, F, C, dt(dy1), stream()), "conv1_bwd")
+
+
+def im2col_s2(y1, col):
+    B, T1, F1, C = y1.shape
+    check(_L().s2s_im2col_s2(ptr(y1), ptr(col), B, T1, F1, C, dt(y1), stream()), "im2col_s2")
+    return col
+
+
+def col2im_s2(dcol, dy1):
+    B, T1, F1, C = dy1.shape
+    check(_L().s2s_col2im_s2(ptr(dcol), ptr(dy1), B, T1, F1, C, dt(dy1), stream()), "col2im_s2")
+    return dy1
+
+
+def shift_thin(ys, out, r):
+    B, L, odim = ys.shape
+    Lr = out.shape[1]
+    assert ys.dtype == torch.float32 and ys.is_contiguous() and out.is_contiguous()
+    check(_L().s2s_shift_thin(ptr(ys), ptr(out), B, L, Lr, odim, r, dt(out), stream()), "shift_thin")
+    return out
+
+
+def fix_targets(labels, olens, labels_out, olens_out, r):
+    B, Lin = labels.shape
+    Lout = labels_out.shape[1]
+    assert labels.is_contiguous() and labels_out.is_contiguous() and olens.dtype == _i32
+    check(_L().s2s_fix_targets(ptr(labels), ptr(olens), ptr(labels_out), ptr(olens_out), B, Lin, Lout, r, stream()), "fix_targets")
+
+
+def bn_stats(x, sums, L, halo):
+    B, Lp, C = x.shape
+    check(_L().s2s_bn_stats(ptr(x), ptr(sums), B, L, halo, C, dt(x), stream()), "bn_stats")
+
+
+def bn_finalize(sums, mean, invstd, running_mean, running_var, count, eps=1e-5, momentum=0.1):
+    C = mean.numel()
+    check(_L().s2s_bn_finalize(ptr(sums), ptr(mean), ptr(invstd), ptr(running_mean), ptr(running_var), count, C, eps, momentum,
+                               stream()), "bn_finalize")
+
+
+def bn_apply(x, mean, invstd, gamma, beta, y, L, halo, use_tanh, drop: Drop = NO_DROP):
+    B, Lp, C = x.shape
+    check(_L().s2s_bn_apply(ptr(x), ptr(mean), ptr(invstd), ptr(gamma), ptr(beta), ptr(y), B, L, halo, C, int(use_tanh),
+                            ctypes.byref(drop.c()), dt(x), stream()), "bn_apply")
+    return y
+
+
+def bn_bwd_reduce(dy, y, x, mean, invstd, gamma, beta, sums, L, halo, use_tanh, drop: Drop = NO_DROP):
+    B, Lp, C = x.shape
+    check(_L().s2s_bn_bwd_reduce(ptr(dy), ptr(y), ptr(x), ptr(mean), ptr(invstd), ptr(gamma), ptr(beta), ptr(sums), B, L, halo, C,
+                                 int(use_tanh), ctypes.byref(drop.c()), dt(x), stream()), "bn_bwd_reduce")
+
+
+def bn_bwd_apply(dy, y, x, mean, invstd, gamma, beta, sums, dx, dgamma, dbeta, L, halo, use_tanh, drop: Drop = NO_DROP):
+    B, Lp, C = x.shape
+    check(_L().s2s_bn_bwd_apply(ptr(dy), ptr(y), ptr(x), ptr(mean), ptr(invstd), ptr(gamma), ptr(beta), ptr(sums), ptr(dx),
+                                ptr(dgamma), ptr(dbeta), B, L, halo, C, int(use_tanh), ctypes.byref(drop.c()), dt(x), stream()),
+          "bn_bwd_apply")
+    return dx
+
+
+def bn_eval_stats(running_mean, running_var, mean, invstd, eps=1e-5):
+    check(_L().s2s_bn_eval_stats(ptr(running_mean), ptr(running_var), ptr(mean), ptr(invstd), mean.numel(), eps, stream()),
+          "bn_eval_stats")
+
+
+def pack_conv1d_w(w, wp, wpt):
+    OC, IC, K = w.shape
+    assert w.dtype == torch.float32 and w.is_contiguous()
+    od = dt(wp if wp is not None else wpt)
+    check(_L().s2s_pack_conv1d_w(ptr(w), ptr(wp), ptr(wpt), OC, IC, K, od, stream()), "pack_conv1d_w")
+
+
+def pad_rows(x, y, halo):
+    B, L, C = x.shape
+    check(_L().s2s_pad_rows(ptr(x), ptr(y), B, L, halo, C, dt(x), stream()), "pad_rows")
+    return y
+
+
+def unpad_rows(x, y, halo):
+    B, L, C = y.shape
+    check(_L().s2s_unpad_rows(ptr(x), ptr(y), B, L, halo, C, dt(x), stream()), "unpad_rows")
+    return y
+
+
+def seq2seq_loss(after, before, logits, ys, labels, olens, pos_weight, losses, d_after, d_before, d_logits, ws):
+    B, L, odim = after.shape
+    assert after.dtype == before.dtype == logits.dtype and ys.dtype == torch.float32 and labels.dtype == torch.float32
+    assert all(t.is_contiguous() for t in (after, before, logits, ys, labels))
+    check(_L().s2s_seq2seq_loss(ptr(after), ptr(before), ptr(logits), ptr(ys), ptr(labels), ptr(olens), B, L, ys.shape[1],
+                                labels.shape[1], odim, pos_weight,
+                                ptr(losses), ptr(d_after), ptr(d_before), ptr(d_logits), ptr(ws), dt(after), stream()),
+          "seq2seq_loss")
+
+
+def guided_attn_loss(att, ilens, olens, T_in, sigma, alpha, loss, d_att, ws):
+    B, H, T_out, ld = att.shape
+    assert att.is_contiguous()
+    check(_L().s2s_guided_attn_loss(ptr(att), ptr(ilens), ptr(olens), B, H, T_out, T_in, ld, sigma, alpha, ptr(loss), ptr(d_att),
+                                    ptr(ws), dt(att), stream()), "guided_attn_loss")
+
+
+def sqnorm(g, out):
+    check(_L().s2s_sqnorm(ptr(g), g.numel(), ptr(out), stream()), "sqnorm")
+
+
+def adam_step(p, g, m, v, p16, lr_dev, beta1, beta2, eps, wd, step_dev, sqn, max_norm, grad_scale=1.0):
+    check(_L().s2s_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), ptr(p16), p.numel(), ptr(lr_dev), beta1, beta2, eps, wd,
+                             ptr(step_dev), ptr(sqn), max_norm, grad_scale, stream()), "adam_step")
+
+
+def step_advance(step_dev, seed_dev):
+    check(_L().s2s_step_advance(ptr(step_dev), ptr(seed_dev), stream()), "step_advance")
+
+
+def cast(src, dst):
+    assert src.is_contiguous() and dst.is_contiguous() and src.numel() == dst.numel()
+    check(_L().s2s_cast(ptr(src), ptr(dst), src.numel(), dt(src), dt(dst), stream()), "cast")
+    return dst
+
+
+def transpose_last2(src, dst, N, A, Bd, accumulate=False):
+    """dst[n][b][a] (+)= src[n][a][b]"""
+    assert src.is_contiguous() and dst.is_contiguous() and src.numel() == N * A * Bd == dst.numel()
+    check(_L().s2s_transpose_last2(ptr(src), ptr(dst), N, A, Bd, dt(src), dt(dst), int(accumulate), stream()), "transpose_last2")
+    return dst
+
+
+def mas(log_p, text_lens, feats_lens, want_grad: bool = False):
+    """Monotonic alignment search.  Returns (paths int32 (B,T_feats), ds f32 (B,T_text), bin_loss f32 (1,), d_log_p|None)."""
+    B, TF, TT = log_p.shape
+    assert log_p.dtype == torch.float32 and log_p.is_contiguous()
+    dev = log_p.device
+    paths = torch.empty(B, TF, dtype=_i32, device=dev)
+    ds = torch.empty(B, TT, dtype=torch.float32, device=dev)
+    bin_loss = torch.empty(1, dtype=torch.float32, device=dev)
+    d_log_p = torch.zeros_like(log_p) if want_grad else None
+    nbytes = int(_L().s2s_mas_workspace_bytes(B, TF, TT))
+    ws = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=dev)
+    check(_L().s2s_mas(ptr(log_p), ptr(text_lens), ptr(feats_lens), B, TF, TT, ptr(paths), ptr(ds), ptr(bin_loss), ptr(d_log_p),
+                       ptr(ws), nbytes, stream()), "mas")
+    return paths, ds, bin_loss, d_log_p
+
+
+def logmel(wav, window, basis, mel, n_fft, hop, eps, log_base):
+    B, ns = wav.shape
+    n_mels = basis.shape[0]
+    assert wav.dtype == torch.float32 and wav.is_contiguous() and mel.is_contiguous()
+    check(_L().s2s_logmel(ptr(wav), ptr(window), ptr(basis), ptr(mel), B, ns, n_fft, hop, n_mels, eps,
+                          0.0 if log_base is None else float(log_base), stream()), "logmel")
+    return mel

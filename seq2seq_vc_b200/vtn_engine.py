@@ -1,0 +1,781 @@
+"""VTN training step on B200: explicit forward / backward over the C-ABI kernels.
+
+This is the hot path behind ``seq2seq_vc_b200.VTN`` (reference: seq2seq_vc/models/vtn.py:207-300,
+modules/transformer/{encoder,decoder,encoder_layer,decoder_layer,attention,subsampling}.py,
+modules/pre_postnets.py, losses/seq2seq_loss.py:30-59, trainers/ar_vc.py:99-107).  There is no
+autograd tape: every activation the backward pass needs lives in a named, shape-cached HBM buffer,
+the backward is written out op by op, and dropout masks are regenerated from a counter-based RNG,
+so one step is a fixed sequence of kernel launches that can be captured in a CUDA graph.
+
+PyTorch is used only to own device memory; all arithmetic happens in libs2svc_b200.so.
+
+Data layout in HBM
+  activations   (B, T, d) row-major ("tokens x channels"), dtype f32 (parity mode) or bf16
+  attention     scores / probabilities (B, H, T1, ld) with ld = T2 rounded up to 8
+  conv buffers  channels-last; postnet buffers carry a zero halo of (k-1)/2 frames per utterance
+                so that Conv1d is a `taps`-GEMM over overlapping row windows (no im2col)
+  parameters    one flat float32 buffer (ParamStore.P) + flat grads / Adam moments (+ bf16 shadow)
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+from ._lib import NO_DROP, Drop
+from .params import ParamStore
+
+_f32 = torch.float32
+_i32 = torch.int32
+
+
+def _r8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def default_hparams(**over) -> dict:
+    """Constructor defaults of the reference VTN (seq2seq_vc/models/vtn.py:15-62)."""
+    hp = dict(idim=80, odim=80, dprenet_layers=2, dprenet_units=256, adim=384, aheads=4, elayers=6, eunits=1536,
+              dlayers=6, dunits=1536, postnet_layers=5, postnet_filts=5, postnet_chans=256,
+              dprenet_dropout_rate=0.5, transformer_enc_dropout_rate=0.1,
+              # fixed by the reference's Encoder / Decoder / Postnet defaults
+              enc_positional_dropout_rate=0.1, dec_dropout_rate=0.1, dec_positional_dropout_rate=0.1,
+              postnet_dropout_rate=0.5, decoder_reduction_factor=2,
+              initial_encoder_alpha=1.0, initial_decoder_alpha=1.0)
+    hp.update(over)
+    return hp
+
+
+def sinusoid_table(length: int, d_model: int, device) -> torch.Tensor:
+    """PE table of seq2seq_vc/layers/positional_encoding.py:36-57 (host-built once, float32)."""
+    pos = torch.arange(0, length, dtype=_f32).unsqueeze(1)
+    div = torch.exp(torch.arange(0, d_model, 2, dtype=_f32) * -(math.log(10000.0) / d_model))
+    pe = torch.zeros(length, d_model)
+    pe[:, 0::2] = torch.sin(pos * div)
+    pe[:, 1::2] = torch.cos(pos * div)
+    return pe.to(device)
+
+
+def param_groups(hp: dict) -> List[List[Tuple[str, Tuple[int, ...]]]]:
+    """Reference state-dict names / shapes, grouped so that fused operands are contiguous."""
+    d, idim, odim = hp["adim"], hp["idim"], hp["odim"]
+    f2 = ((idim - 1) // 2 - 1) // 2
+    g: List[List[Tuple[str, Tuple[int, ...]]]] = []
+
+    def lin(name, o, i):
+        g.append([(name + ".weight", (o, i))])
+        g.append([(name + ".bias", (o,))])
+
+    def ln(name, n):
+        g.append([(name + ".weight", (n,))])
+        g.append([(name + ".bias", (n,))])
+
+    def mha(name, fuse):
+        g.append([(f"{name}.{s}.weight", (d, d)) for s in fuse])
+        g.append([(f"{name}.{s}.bias", (d,)) for s in fuse])
+        for s in ("linear_q", "linear_k", "linear_v", "linear_out"):
+            if s not in fuse:
+                lin(f"{name}.{s}", d, d)
+
+    g.append([("encoder.embed.conv.0.weight", (d, 1, 3, 3))])
+    g.append([("encoder.embed.conv.0.bias", (d,))])
+    g.append([("encoder.embed.conv.2.weight", (d, d, 3, 3))])
+    g.append([("encoder.embed.conv.2.bias", (d,))])
+    lin("encoder.embed.out.0", d, d * f2)
+    g.append([("encoder.embed.out.1.alpha", ())])
+    for l in range(hp["elayers"]):
+        p = f"encoder.encoders.{l}"
+        mha(p + ".self_attn", ("linear_q", "linear_k", "linear_v"))
+        lin(p + ".feed_forward.w_1", hp["eunits"], d)
+        lin(p + ".feed_forward.w_2", d, hp["eunits"])
+        ln(p + ".norm1", d)
+        ln(p + ".norm2", d)
+    ln("encoder.after_norm", d)
+    u = hp["dprenet_units"]
+    for i in range(hp["dprenet_layers"]):
+        lin(f"decoder.embed.0.0.prenet.{i}.0", u, odim if i == 0 else u)
+    lin("decoder.embed.0.1", d, u)
+    g.append([("decoder.embed.1.alpha", ())])
+    for l in range(hp["dlayers"]):
+        p = f"decoder.decoders.{l}"
+        mha(p + ".self_attn", ("linear_q", "linear_k", "linear_v"))
+        mha(p + ".src_attn", ("linear_k", "linear_v"))
+        lin(p + ".feed_forward.w_1", hp["dunits"], d)
+        lin(p + ".feed_forward.w_2", d, hp["dunits"])
+        for n in ("norm1", "norm2", "norm3"):
+            ln(f"{p}.{n}", d)
+    r = hp["decoder_reduction_factor"]
+    lin("feat_out", odim * r, d)
+    lin("prob_out", r, d)
+    ch, k = hp["postnet_chans"], hp["postnet_filts"]
+    for i in range(hp["postnet_layers"]):
+        ic = odim if i == 0 else ch
+        oc = odim if i == hp["postnet_layers"] - 1 else ch
+        g.append([(f"postnet.postnet.{i}.0.weight", (oc, ic, k))])
+        ln(f"postnet.postnet.{i}.1", oc)
+    return g
+
+
+def buffer_specs(hp: dict) -> List[Tuple[str, Tuple[int, ...], torch.dtype]]:
+    """Non-trainable state-dict entries (BatchNorm running statistics)."""
+    out = []
+    ch, odim = hp["postnet_chans"], hp["odim"]
+    for i in range(hp["postnet_layers"]):
+        oc = odim if i == hp["postnet_layers"] - 1 else ch
+        p = f"postnet.postnet.{i}.1"
+        out += [(p + ".running_mean", (oc,), _f32), (p + ".running_var", (oc,), _f32),
+                (p + ".num_batches_tracked", (), torch.int64)]
+    return out
+
+
+class VTNEngine:
+    """Owns parameters, activation buffers and the explicit forward/backward of one VTN step."""
+
+    def __init__(self, hp: dict, device="cuda:0", bf16: bool = False, seed: int = 0):
+        self.hp = default_hparams(**hp)
+        hp = self.hp
+        assert hp["adim"] % hp["aheads"] == 0
+        self.device = torch.device(device)
+        self.bf16 = bool(bf16)
+        self.adt = torch.bfloat16 if bf16 else _f32
+        self.mode = 1 if bf16 else 0
+        self.store = ParamStore(param_groups(hp), self.device, bf16_shadow=bf16)
+        self.buffers: Dict[str, torch.Tensor] = {}
+        for name, shape, dt in buffer_specs(hp):
+            self.buffers[name] = (torch.ones if name.endswith("running_var") else torch.zeros)(shape, dtype=dt, device=self.device)
+        self.training = True
+        self.base_seed = int(seed)
+        self.seed_dev = torch.zeros(1, dtype=torch.int64, device=self.device)   # advanced once per step
+        self.step_dev = torch.zeros(1, dtype=_f32, device=self.device)
+        self.lr_dev = torch.zeros(1, dtype=_f32, device=self.device)
+        self._pe: Dict[int, torch.Tensor] = {}
+        self._bufs: Dict[Tuple, torch.Tensor] = {}
+        self._sig: Optional[Tuple] = None
+        self._site = 0
+        self.attn: Dict[str, torch.Tensor] = {}      # every attention map of the last forward
+        self.losses = torch.zeros(2, dtype=_f32, device=self.device)
+        self._loss_ws = torch.zeros(4, dtype=_f32, device=self.device)
+        self._sqn = torch.zeros(1, dtype=_f32, device=self.device)
+        self.p16_dirty = True
+        self.init_parameters(seed)
+
+    # ------------------------------------------------------------------ parameters
+    def init_parameters(self, seed: int = 0) -> None:
+        """torch-default Linear / Conv init distributions (uniform +-1/sqrt(fan_in)); LN/BN affine = 1/0."""
+        g = torch.Generator().manual_seed(seed)
+        hp = self.hp
+        for name, (off, shape) in self.store.offsets.items():
+            n = 1
+            for s in shape:
+                n *= s
+            if name.endswith("alpha"):
+                v = torch.full((1,), hp["initial_encoder_alpha"] if name.startswith("encoder") else hp["initial_decoder_alpha"])
+            elif "norm" in name or (name.startswith("postnet") and ".1." in name):
+                v = torch.ones(n) if name.endswith("weight") else torch.zeros(n)
+            else:
+                wname = name[:-5] + ".weight" if name.endswith(".bias") else name
+                wshape = self.store.offsets[wname][1]
+                fan_in = 1
+                for s in wshape[1:]:
+                    fan_in *= s
+                v = (torch.rand(n, generator=g) * 2 - 1) / math.sqrt(fan_in)
+            self.store.P[off:off + n].copy_(v.to(self.device))
+        self.p16_dirty = True
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        for name in self.store.names():
+            self.store.p(name).copy_(sd[name].to(self.device, _f32).reshape(self.store.offsets[name][1]))
+        for name, buf in self.buffers.items():
+            if name in sd:
+                buf.copy_(sd[name].to(self.device, buf.dtype))
+        self.p16_dirty = True
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        sd = {name: self.store.p(name).detach().clone() for name in self.store.names()}
+        sd.update({k: v.detach().clone() for k, v in self.buffers.items()})
+        return sd
+
+    def W(self, name: str) -> torch.Tensor:
+        """GEMM operand view of a weight: float32 master in parity mode, bf16 shadow otherwise."""
+        return self.store.p16(name) if self.bf16 else self.store.p(name)
+
+    def Wspan(self, names: Sequence[str], shape) -> torch.Tensor:
+        return self.store.span(self.store.P16 if self.bf16 else self.store.P, list(names), shape)
+
+    def sync_shadow(self) -> None:
+        if self.bf16 and self.p16_dirty:
+            ops.cast(self.store.P, self.store.P16)
+        self.p16_dirty = False
+
+    # ------------------------------------------------------------------ buffers
+    def buf(self, name: str, shape, dtype=None, zero: bool = False) -> torch.Tensor:
+        dtype = dtype or self.adt
+        key = (self._sig, name)
+        t = self._bufs.get(key)
+        if t is None:
+            t = (torch.zeros if zero else torch.empty)(tuple(shape), dtype=dtype, device=self.device)
+            self._bufs[key] = t
+        else:
+            assert tuple(t.shape) == tuple(shape) and t.dtype == dtype, (name, t.shape, shape)
+        return t
+
+    def pe(self, d: int, length: int) -> torch.Tensor:
+        t = self._pe.get(d)
+        if t is None or t.shape[0] < length:
+            t = sinusoid_table(max(length, 2048), d, self.device)
+            self._pe[d] = t
+        return t
+
+    def drop(self, p: float) -> Drop:
+        """Next dropout site of the step (forward and backward enumerate sites in the same order)."""
+        self._site += 1
+        if not self.training or p <= 0.0:
+            return NO_DROP
+        return Drop(p, self.base_seed, self._site, self.seed_dev)
+
+    # ------------------------------------------------------------------ building blocks
+    def _lin_fwd(self, x2d, w, bias, out, relu=False, drop=NO_DROP, residual=None):
+        mode = self.mode if (w.shape[0] >= 8) else 0
+        return ops.gemm(x2d, w, out, bias=bias, relu=relu, drop=drop, residual=residual, mode=mode)
+
+    def _lin_bwd(self, dy2d, x2d, w, gw, gb, dx=None, dx_residual=None, dx_accumulate=False):
+        """dW += dy^T x ; db += colsum(dy) ; dx = dy W (+ residual | += )."""
+        mode = self.mode if (w.shape[0] >= 8) else 0
+        if gw is not None:
+            ops.gemm(dy2d.t(), x2d.t(), gw, accumulate=True, mode=mode)
+        if gb is not None:
+            ops.colsum(dy2d, gb)
+        if dx is not None:
+            ops.gemm(dy2d, w.t(), dx, residual=dx_residual, accumulate=dx_accumulate, mode=mode)
+        return dx
+
+    def _ln_fwd(self, x, name, tag):
+        B_, T_, d = x.shape
+        y = self.buf(tag + ".y", x.shape)
+        mean = self.buf(tag + ".mean", (B_ * T_,), _f32)
+        rstd = self.buf(tag + ".rstd", (B_ * T_,), _f32)
+        ops.layernorm_fwd(x, self.store.p(name + ".weight"), self.store.p(name + ".bias"), y, mean, rstd, 1e-12)
+        return y
+
+    def _ln_bwd(self, dy, x, name, tag, dx, dres=None):
+        ops.layernorm_bwd(dy, x, self.store.p(name + ".weight"), self.buf(tag + ".mean", (x.shape[0] * x.shape[1],), _f32),
+                          self.buf(tag + ".rstd", (x.shape[0] * x.shape[1],), _f32), dx, self.store.g(name + ".weight"),
+                          self.store.g(name + ".bias"), dres=dres)
+        return dx
+
+    def _attn_core_fwd(self, q, k, v, klens, causal, tag, store_name):
+        """q (B,T1,H,dk) / k, v (B,T2,H,dk) strided views -> ctx (B,T1,d); keeps P for backward."""
+        B_, T1, H, dk = q.shape
+        T2 = k.shape[1]
+        ld = _r8(T2)
+        P = self.buf(tag + ".P", (B_, H, T1, ld))
+        # S[b,h] = q_bh k_bh^T / sqrt(dk)   (reference: attention.py:95-104)
+        ops.gemm(q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3), P[..., :T2], alpha=1.0 / math.sqrt(dk), mode=self.mode)
+        ops.softmax_fwd(P, klens, causal, T2)
+        self.attn[store_name] = P[..., :T2]
+        ctx = self.buf(tag + ".ctx", (B_, T1, H * dk))
+        # ctx[b,t,h,:] = sum_s P[b,h,t,s] v[b,s,h,:]
+        ops.gemm(P[..., :T2], v.permute(0, 2, 3, 1), ctx.view(B_, T1, H, dk).permute(0, 2, 1, 3), mode=self.mode)
+        return ctx
+
+    def _attn_core_bwd(self, dctx, q, k, v, dq, dk_, dv, tag, d_att=None):
+        """Gradients of the attention core; dq/dk_/dv are (B,T,H,dk) strided views to be filled."""
+        B_, T1, H, dk = q.shape
+        T2 = k.shape[1]
+        ld = _r8(T2)
+        P = self.buf(tag + ".P", (B_, H, T1, ld))
+        dP = self._scratch("dP", (B_, H, T1, ld))
+        dctx4 = dctx.view(B_, T1, H, dk).permute(0, 2, 1, 3)
+        # dP[b,h,t,s] = sum_j dctx[b,t,h,j] v[b,s,h,j]
+        ops.gemm(dctx4, v.permute(0, 2, 1, 3), dP[..., :T2], mode=self.mode)
+        # dv[b,s,h,j] = sum_t P[b,h,t,s] dctx[b,t,h,j]
+        ops.gemm(P[..., :T2].transpose(-1, -2), dctx4.transpose(-1, -2), dv.permute(0, 2, 1, 3), mode=self.mode)
+        if d_att is not None:
+            ops.add(dP, d_att, dP)
+        ops.softmax_bwd(P, dP, T2, 1.0 / math.sqrt(dk))
+        dS = dP
+        # dq[b,t,h,j] = sum_s dS[t,s] k[s,j] ; dk[b,s,h,j] = sum_t dS[t,s] q[t,j]
+        ops.gemm(dS[..., :T2], k.permute(0, 2, 3, 1), dq.permute(0, 2, 1, 3), mode=self.mode)
+        ops.gemm(dS[..., :T2].transpose(-1, -2), q.permute(0, 2, 3, 1), dk_.permute(0, 2, 1, 3), mode=self.mode)
+
+    def _scratch(self, name, shape, dtype=None):
+        """Step-local scratch, shared between layers (sized to the largest request)."""
+        dtype = dtype or self.adt
+        n = 1
+        for s in shape:
+            n *= s
+        key = ("scratch", name, dtype)
+        t = self._bufs.get(key)
+        if t is None or t.numel() < n:
+            t = torch.empty(max(n, 1), dtype=dtype, device=self.device)
+            self._bufs[key] = t
+        return t[:n].view(shape)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, xs: torch.Tensor, ys: torch.Tensor, ilens: Sequence[int], olens: Sequence[int]):
+        """xs (B,T,idim) / ys (B,L,odim) float32 device tensors already trimmed to max length.
+
+        Returns (after (B,L',odim), before, logits (B,L')) in activation dtype; attention maps in
+        self.attn; L' = (L // r) * r.
+        """
+        hp, st = self.hp, self.store
+        B, T, idim = xs.shape
+        L, odim = ys.shape[1], ys.shape[2]
+        r, d, H = hp["decoder_reduction_factor"], hp["adim"], hp["aheads"]
+        dk = d // H
+        assert xs.dtype == _f32 and ys.dtype == _f32 and xs.is_contiguous() and ys.is_contiguous()
+        T1, F1 = (T - 1) // 2, (idim - 1) // 2
+        T2, F2 = (T1 - 1) // 2, (F1 - 1) // 2
+        Lr = L // r
+        self._sig = (B, T, L, self.training)
+        self._site = 0
+        self.attn = {}
+        self.sync_shadow()
+        self.shapes = dict(B=B, T=T, L=L, T1=T1, F1=F1, T2=T2, F2=F2, Lr=Lr)
+
+        # per-utterance lengths -> one small H2D copy (lens come from the CPU collater)
+        ilens = [int(v) for v in ilens]
+        olens = [int(v) for v in olens]
+        klens_enc = [min(T2, (i + 3) // 4) for i in ilens]           # mask[:, :, :-2:2][:, :, :-2:2] (subsampling.py:92-94)
+        olens_in = [o // r for o in olens]
+        olens_fix = [o - o % r for o in olens]
+        lens_host = torch.tensor([klens_enc, olens_in, olens_fix], dtype=_i32)
+        lens = self.buf("lens", (3, B), _i32)
+        lens.copy_(lens_host, non_blocking=True)
+        self.klens_enc, self.olens_in, self.olens_fix = lens[0], lens[1], lens[2]
+        self.ilens_ds_st = [((i - 2 + 1) // 2 - 2 + 1) // 2 for i in ilens]   # vtn.py:279
+        self.olens_in_host, self.olens_fix_host = olens_in, olens_fix
+
+        # ---- packed conv weights (activation dtype)
+        w2p = self.buf("w.conv2p", (d, 9, d))          # [oc][tap][ic]
+        ops.transpose_last2(st.p("encoder.embed.conv.2.weight"), w2p, d, d, 9)
+        woutp = self.buf("w.outp", (d, F2, d))         # [n][f][c]
+        ops.transpose_last2(st.p("encoder.embed.out.0.weight"), woutp, d, d, F2)
+
+        # ---- encoder front end (subsampling.py:74-94)
+        self.xs = xs
+        y1 = self.buf("enc.y1", (B, T1, F1, d))
+        ops.conv1_fwd(xs, st.p("encoder.embed.conv.0.weight"), st.p("encoder.embed.conv.0.bias"), y1)
+        col = self._scratch("col", (B * T2 * F2, 9 * d))
+        ops.im2col_s2(y1, col)
+        y2 = self.buf("enc.y2", (B * T2 * F2, d))
+        ops.gemm(col, w2p.view(d, 9 * d), y2, bias=st.p("encoder.embed.conv.2.bias"), relu=True, mode=self.mode)
+        elin = self.buf("enc.elin", (B * T2, d))
+        ops.gemm(y2.view(B * T2, F2 * d), woutp.view(d, F2 * d), elin, bias=st.p("encoder.embed.out.0.bias"), mode=self.mode)
+        x = self.buf("enc.x0", (B, T2, d))
+        ops.scaled_pe_fwd(elin.view(B, T2, d), self.pe(d, T2), st.p("encoder.embed.out.1.alpha"), x,
+                          self.drop(hp["enc_positional_dropout_rate"]))
+
+        # ---- encoder layers (pre-LN; encoder_layer.py:61-119)
+        pe_ = hp["transformer_enc_dropout_rate"]
+        for l in range(hp["elayers"]):
+            p = f"encoder.encoders.{l}"
+            n1 = self._ln_fwd(x, p + ".norm1", p + ".ln1")
+            qkv = self.buf(p + ".qkv", (B, T2, 3, H, dk))
+            self._lin_fwd(n1.view(B * T2, d), self.Wspan([p + ".self_attn.linear_q.weight"], (3 * d, d)),
+                          st.span(st.P, [p + ".self_attn.linear_q.bias"], (3 * d,)), qkv.view(B * T2, 3 * d))
+            ctx = self._attn_core_fwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], self.klens_enc, False, p + ".sa", p + ".self_attn")
+            xm = self.buf(p + ".xmid", (B, T2, d))
+            self._lin_fwd(ctx.view(B * T2, d), self.W(p + ".self_attn.linear_out.weight"), st.p(p + ".self_attn.linear_out.bias"),
+                          xm.view(B * T2, d), drop=self.drop(pe_), residual=x.view(B * T2, d))
+            n2 = self._ln_fwd(xm, p + ".norm2", p + ".ln2")
+            h = self.buf(p + ".ffh", (B * T2, hp["eunits"]))
+            self._lin_fwd(n2.view(B * T2, d), self.W(p + ".feed_forward.w_1.weight"), st.p(p + ".feed_forward.w_1.bias"), h,
+                          relu=True, drop=self.drop(pe_))
+            xn = self.buf(p + ".xout", (B, T2, d))
+            self._lin_fwd(h, self.W(p + ".feed_forward.w_2.weight"), st.p(p + ".feed_forward.w_2.bias"), xn.view(B * T2, d),
+                          drop=self.drop(pe_), residual=xm.view(B * T2, d))
+            x = xn
+        self.enc_last = x
+        mem = self._ln_fwd(x, "encoder.after_norm", "enc.after")
+
+        # ---- decoder input (vtn.py:227-243,523-527; pre_postnets.py:60-66)
+        ys_in = self.buf("dec.ys_in", (B, Lr, odim))
+        ops.shift_thin(ys, ys_in, r)
+        u = hp["dprenet_units"]
+        hcur = ys_in.view(B * Lr, odim)
+        for i in range(hp["dprenet_layers"]):
+            nm = f"decoder.embed.0.0.prenet.{i}.0"
+            out = self.buf(f"dec.prenet{i}", (B * Lr, u))
+            # Prenet dropout is always on in the reference (pre_postnets.py:65), also in eval()
+            self._site += 1
+            pd = hp["dprenet_dropout_rate"]
+            dr = Drop(pd, self.base_seed, self._site, self.seed_dev) if pd > 0 else NO_DROP
+            self._lin_fwd(hcur, self.W(nm + ".weight"), st.p(nm + ".bias"), out, relu=True, drop=dr)
+            hcur = out
+        dlin = self.buf("dec.elin", (B * Lr, d))
+        self._lin_fwd(hcur, self.W("decoder.embed.0.1.weight"), st.p("decoder.embed.0.1.bias"), dlin)
+        x = self.buf("dec.x0", (B, Lr, d))
+        ops.scaled_pe_fwd(dlin.view(B, Lr, d), self.pe(d, Lr), st.p("decoder.embed.1.alpha"), x,
+                          self.drop(hp["dec_positional_dropout_rate"]))
+
+        # ---- decoder layers (post-LN; decoder_layer.py:63-134)
+        pdrop = hp["dec_dropout_rate"]
+        for l in range(hp["dlayers"]):
+            p = f"decoder.decoders.{l}"
+            qkv = self.buf(p + ".qkv", (B, Lr, 3, H, dk))
+            self._lin_fwd(x.view(B * Lr, d), self.Wspan([p + ".self_attn.linear_q.weight"], (3 * d, d)),
+                          st.span(st.P, [p + ".self_attn.linear_q.bias"], (3 * d,)), qkv.view(B * Lr, 3 * d))
+            ctx = self._attn_core_fwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], self.olens_in, True, p + ".sa", p + ".self_attn")
+            t1 = self.buf(p + ".t1", (B, Lr, d))
+            self._lin_fwd(ctx.view(B * Lr, d), self.W(p + ".self_attn.linear_out.weight"), st.p(p + ".self_attn.linear_out.bias"),
+                          t1.view(B * Lr, d), drop=self.drop(pdrop), residual=x.view(B * Lr, d))
+            x1 = self._ln_fwd(t1, p + ".norm1", p + ".ln1")
+            q = self.buf(p + ".q", (B, Lr, H, dk))
+            self._lin_fwd(x1.view(B * Lr, d), self.W(p + ".src_attn.linear_q.weight"), st.p(p + ".src_attn.linear_q.bias"),
+                          q.view(B * Lr, d))
+            kv = self.buf(p + ".kv", (B, T2, 2, H, dk))
+            self._lin_fwd(mem.view(B * T2, d), self.Wspan([p + ".src_attn.linear_k.weight"], (2 * d, d)),
+                          st.span(st.P, [p + ".src_attn.linear_k.bias"], (2 * d,)), kv.view(B * T2, 2 * d))
+            ctx2 = self._attn_core_fwd(q, kv[:, :, 0], kv[:, :, 1], self.klens_enc, False, p + ".ca", p + ".src_attn")
+            t2 = self.buf(p + ".t2", (B, Lr, d))
+            self._lin_fwd(ctx2.view(B * Lr, d), self.W(p + ".src_attn.linear_out.weight"), st.p(p + ".src_attn.linear_out.bias"),
+                          t2.view(B * Lr, d), drop=self.drop(pdrop), residual=x1.view(B * Lr, d))
+            x2 = self._ln_fwd(t2, p + ".norm2", p + ".ln2")
+            h = self.buf(p + ".ffh", (B * Lr, hp["dunits"]))
+            self._lin_fwd(x2.view(B * Lr, d), self.W(p + ".feed_forward.w_1.weight"), st.p(p + ".feed_forward.w_1.bias"), h,
+                          relu=True, drop=self.drop(pdrop))
+            t3 = self.buf(p + ".t3", (B, Lr, d))
+            self._lin_fwd(h, self.W(p + ".feed_forward.w_2.weight"), st.p(p + ".feed_forward.w_2.bias"), t3.view(B * Lr, d),
+                          drop=self.drop(pdrop), residual=x2.view(B * Lr, d))
+            x = self._ln_fwd(t3, p + ".norm3", p + ".ln3")
+        zs = x
+
+        # ---- output heads (vtn.py:249-251)
+        Lo = Lr * r
+        before = self.buf("out.before", (B, Lo, odim))
+        self._lin_fwd(zs.view(B * Lr, d), self.W("feat_out.weight"), st.p("feat_out.bias"), before.view(B * Lr, odim * r))
+        logits = self.buf("out.logits", (B, Lo))
+        self._lin_fwd(zs.view(B * Lr, d), self.W("prob_out.weight"), st.p("prob_out.bias"), logits.view(B * Lr, r))
+        self.zs = zs
+
+        # ---- postnet (pre_postnets.py:105-185): Conv1d(k) as taps-GEMM over haloed channels-last rows
+        n_post, k = hp["postnet_layers"], hp["postnet_filts"]
+        after = self.buf("out.after", (B, Lo, odim))
+        if n_post > 0:
+            halo = (k - 1) // 2
+            Lp = Lo + 2 * halo
+            ypad = self.buf("post.in", (B, Lp, odim))
+            ops.pad_rows(before, ypad, halo)
+            for i in range(n_post):
+                pn = f"postnet.postnet.{i}"
+                w = st.p(pn + ".0.weight")
+                oc, ic = w.shape[0], w.shape[1]
+                wp = self.buf(f"w.post{i}p", (oc, k, ic))
+                wpt = self.buf(f"w.post{i}pt", (ic, k, oc))
+                ops.pack_conv1d_w(w, wp, wpt)
+                z = self.buf(f"post.z{i}", (B, Lp, oc))
+                M = B * Lp - 2 * halo
+                ops.gemm(ypad.view(B * Lp, ic), wp, z.view(B * Lp, oc)[halo:], taps=k, row_mask=(Lp, halo, halo, halo + Lo),
+                         mode=self.mode, M=M)
+                mean = self.buf(f"post.mean{i}", (oc,), _f32)
+                invstd = self.buf(f"post.invstd{i}", (oc,), _f32)
+                if self.training:
+                    sums = self.buf(f"post.sums{i}", (2 * oc,), _f32)
+                    sums.zero_()
+                    ops.bn_stats(z, sums, Lo, halo)
+                    ops.bn_finalize(sums, mean, invstd, self.buffers[pn + ".1.running_mean"], self.buffers[pn + ".1.running_var"],
+                                    B * Lo)
+                    self.buffers[pn + ".1.num_batches_tracked"] += 1
+                else:
+                    ops.bn_eval_stats(self.buffers[pn + ".1.running_mean"], self.buffers[pn + ".1.running_var"], mean, invstd)
+                y = self.buf(f"post.y{i}", (B, Lp, oc))
+                ops.bn_apply(z, mean, invstd, st.p(pn + ".1.weight"), st.p(pn + ".1.bias"), y, Lo, halo, i != n_post - 1,
+                             self.drop(hp["postnet_dropout_rate"]))
+                ypad = y
+            post = self._scratch("post.out", (B, Lo, odim))
+            ops.unpad_rows(ypad, post, halo)
+            ops.add(before, post, after)
+        else:
+            after.copy_(before)
+        self.before, self.after, self.logits = before, after, logits
+        return after, before, logits
+
+    # ------------------------------------------------------------------ loss
+    def loss(self, ys: torch.Tensor, labels: torch.Tensor, pos_weight: float = 10.0):
+        """Seq2SeqLoss value + gradient w.r.t. the three outputs (losses/seq2seq_loss.py:30-59)."""
+        B, Lo, odim = self.after.shape
+        r = self.hp["decoder_reduction_factor"]
+        labels_fix = self.buf("loss.labels", (B, Lo), _f32)
+        olens_out = self.buf("loss.olens", (B,), _i32)
+        if r > 1:
+            ops.fix_targets(labels, self.olens_fix, labels_fix, olens_out, r)      # vtn.py:262-274
+        else:
+            labels_fix.copy_(labels[:, :Lo])
+        self.labels_fix = labels_fix
+        self.d_after = self.buf("loss.d_after", self.after.shape)
+        self.d_before = self.buf("loss.d_before", self.after.shape)
+        self.d_logits = self.buf("loss.d_logits", self.logits.shape)
+        ops.seq2seq_loss(self.after, self.before, self.logits, ys, labels_fix, self.olens_fix, pos_weight, self.losses,
+                         self.d_after, self.d_before, self.d_logits, self._loss_ws)
+        return self.losses
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, d_after: torch.Tensor, d_before: torch.Tensor, d_logits: torch.Tensor,
+                 d_att: Optional[Dict[str, torch.Tensor]] = None, zero_grad: bool = True) -> None:
+        """Accumulates parameter gradients into ParamStore.G (d_* are overwritten as scratch)."""
+        hp, st = self.hp, self.store
+        s = self.shapes
+        B, T, L, T1, F1, T2, F2, Lr = s["B"], s["T"], s["L"], s["T1"], s["F1"], s["T2"], s["F2"], s["Lr"]
+        r, d, H, odim = hp["decoder_reduction_factor"], hp["adim"], hp["aheads"], hp["odim"]
+        dk = d // H
+        Lo = Lr * r
+        d_att = d_att or {}
+        if zero_grad:
+            st.G.zero_()
+        # dropout sites are re-enumerated in forward order; collect them first
+        sites = self._site_table()
+
+        # ---- postnet
+        n_post, k = hp["postnet_layers"], hp["postnet_filts"]
+        dbefore_tot = self._scratch("dbefore", (B, Lo, odim))
+        if n_post > 0:
+            halo = (k - 1) // 2
+            Lp = Lo + 2 * halo
+            dy = self._scratch("post.dy_a", (B, Lp, odim))
+            ops.pad_rows(d_after, dy, halo)
+            for i in reversed(range(n_post)):
+                pn = f"postnet.postnet.{i}"
+                w = st.p(pn + ".0.weight")
+                oc, ic = w.shape[0], w.shape[1]
+                z = self.buf(f"post.z{i}", (B, Lp, oc))
+                y = self.buf(f"post.y{i}", (B, Lp, oc))
+                xin = self.buf(f"post.y{i - 1}", (B, Lp, ic)) if i > 0 else self.buf("post.in", (B, Lp, odim))
+                mean = self.buf(f"post.mean{i}", (oc,), _f32)
+                invstd = self.buf(f"post.invstd{i}", (oc,), _f32)
+                drop = sites[f"post{i}"]
+                dz = self._scratch(f"post.dz{i % 2}", (B, Lp, oc))
+                gam, bet = st.p(pn + ".1.weight"), st.p(pn + ".1.bias")
+                if self.training:
+                    sums = self._scratch("post.bsums", (2 * oc,), _f32)
+                    sums.zero_()
+                    ops.bn_bwd_reduce(dy, y, z, mean, invstd, gam, bet, sums, Lo, halo, i != n_post - 1, drop)
+                    ops.bn_bwd_apply(dy, y, z, mean, invstd, gam, bet, sums, dz, st.g(pn + ".1.weight"), st.g(pn + ".1.bias"),
+                                     Lo, halo, i != n_post - 1, drop)
+                else:
+                    sums = self._scratch("post.bsums", (2 * oc,), _f32)
+                    sums.zero_()
+                    ops.bn_bwd_reduce(dy, y, z, mean, invstd, gam, bet, sums, Lo, halo, i != n_post - 1, drop)
+                    ops.bn_bwd_apply(dy, y, z, mean, invstd, gam, bet, None, dz, None, None, Lo, halo, i != n_post - 1, drop)
+                    ops.add(st.g(pn + ".1.bias"), sums[:oc], st.g(pn + ".1.bias"))
+                    ops.add(st.g(pn + ".1.weight"), sums[oc:], st.g(pn + ".1.weight"))
+                M = B * Lp - 2 * halo
+                # dWp[oc][(t, ic)] = sum_m dz[m + halo][oc] * xin[m + t][ic]  (overlapping-window view of xin)
+                gwp = self._scratch("post.gwp", (oc, k * ic), _f32)
+                xin_flat = xin.view(B * Lp * ic)
+                win = torch.as_strided(xin_flat, (k * ic, M), (1, ic))
+                ops.gemm(dz.view(B * Lp, oc)[halo:halo + M].t(), win, gwp, mode=self.mode)
+                ops.transpose_last2(gwp, st.g(pn + ".0.weight"), oc, k, ic, accumulate=True)
+                # dxin = conv_transpose(dz): taps-GEMM with the flipped, transposed kernel
+                dxin = self._scratch(f"post.dx{i % 2}", (B, Lp, ic))
+                wpt = self.buf(f"w.post{i}pt", (ic, k, oc))
+                if halo > 0:
+                    dxin.view(B * Lp, ic)[:halo].zero_()
+                    dxin.view(B * Lp, ic)[B * Lp - halo:].zero_()
+                ops.gemm(dz.view(B * Lp, oc), wpt, dxin.view(B * Lp, ic)[halo:], taps=k, row_mask=(Lp, halo, halo, halo + Lo),
+                         mode=self.mode, M=M)
+                dy = dxin
+            dpost_in = self._scratch("post.dunpad", (B, Lo, odim))
+            ops.unpad_rows(dy, dpost_in, halo)
+            ops.add(d_after, d_before, dbefore_tot)
+            ops.add(dbefore_tot, dpost_in, dbefore_tot)
+        else:
+            ops.add(d_after, d_before, dbefore_tot)
+
+        # ---- output heads
+        zs = self.zs
+        g = self._scratch("g.dec_a", (B, Lr, d))
+        self._lin_bwd(dbefore_tot.view(B * Lr, odim * r), zs.view(B * Lr, d), self.W("feat_out.weight"), st.g("feat_out.weight"),
+                      st.g("feat_out.bias"), dx=g.view(B * Lr, d))
+        self._lin_bwd(d_logits.view(B * Lr, r), zs.view(B * Lr, d), self.W("prob_out.weight"), st.g("prob_out.weight"),
+                      st.g("prob_out.bias"), dx=g.view(B * Lr, d), dx_accumulate=True)
+
+        # ---- decoder layers (reverse)
+        mem = self.buf("enc.after.y", (B, T2, d))
+        dmem = self._scratch("g.mem", (B, T2, d))
+        dmem.zero_()
+        gt = self._scratch("g.dec_b", (B, Lr, d))
+        gd = self._scratch("g.dec_c", (B * Lr, d))
+        for l in reversed(range(hp["dlayers"])):
+            p = f"decoder.decoders.{l}"
+            xin = self.buf(f"decoder.decoders.{l - 1}.ln3.y", (B, Lr, d)) if l > 0 else self.buf("dec.x0", (B, Lr, d))
+            t1, t2, t3 = (self.buf(p + f".t{i}", (B, Lr, d)) for i in (1, 2, 3))
+            x1 = self.buf(p + ".ln1.y", (B, Lr, d))
+            x2 = self.buf(p + ".ln2.y", (B, Lr, d))
+            h = self.buf(p + ".ffh", (B * Lr, hp["dunits"]))
+            # x3 = LN3(t3), t3 = drop(h W2) + x2
+            dt3 = self._ln_bwd(g, t3, p + ".norm3", p + ".ln3", gt)
+            df = self._drop_bwd(dt3.view(B * Lr, d), sites[p + ".ff2"], gd)
+            dh = self._scratch("g.ffh", (B * Lr, hp["dunits"]))
+            self._lin_bwd(df, h, self.W(p + ".feed_forward.w_2.weight"), st.g(p + ".feed_forward.w_2.weight"),
+                          st.g(p + ".feed_forward.w_2.bias"), dx=dh)
+            ops.relu_bwd(dh, h, dh, sites[p + ".ff1"].scale)
+            dx2 = g
+            self._lin_bwd(dh, x2.view(B * Lr, d), self.W(p + ".feed_forward.w_1.weight"), st.g(p + ".feed_forward.w_1.weight"),
+                          st.g(p + ".feed_forward.w_1.bias"), dx=dx2.view(B * Lr, d), dx_residual=dt3.view(B * Lr, d))
+            # x2 = LN2(t2), t2 = drop(ctx2 Wo) + x1
+            dt2 = self._ln_bwd(dx2, t2, p + ".norm2", p + ".ln2", gt)
+            do = self._drop_bwd(dt2.view(B * Lr, d), sites[p + ".ca_out"], gd)
+            ctx2 = self.buf(p + ".ca.ctx", (B, Lr, d))
+            dctx = self._scratch("g.ctx", (B, Lr, d))
+            self._lin_bwd(do, ctx2.view(B * Lr, d), self.W(p + ".src_attn.linear_out.weight"), st.g(p + ".src_attn.linear_out.weight"),
+                          st.g(p + ".src_attn.linear_out.bias"), dx=dctx.view(B * Lr, d))
+            q = self.buf(p + ".q", (B, Lr, H, dk))
+            kv = self.buf(p + ".kv", (B, T2, 2, H, dk))
+            dq = self._scratch("g.q", (B, Lr, H, dk))
+            dkv = self._scratch("g.kv", (B, T2, 2, H, dk))
+            self._attn_core_bwd(dctx, q, kv[:, :, 0], kv[:, :, 1], dq, dkv[:, :, 0], dkv[:, :, 1], p + ".ca", d_att.get(p + ".src_attn"))
+            self._lin_bwd(dkv.view(B * T2, 2 * d), mem.view(B * T2, d), self.Wspan([p + ".src_attn.linear_k.weight"], (2 * d, d)),
+                          st.span(st.G, [p + ".src_attn.linear_k.weight"], (2 * d, d)), st.span(st.G, [p + ".src_attn.linear_k.bias"], (2 * d,)),
+                          dx=dmem.view(B * T2, d), dx_accumulate=True)
+            dx1 = g
+            self._lin_bwd(dq.view(B * Lr, d), x1.view(B * Lr, d), self.W(p + ".src_attn.linear_q.weight"), st.g(p + ".src_attn.linear_q.weight"),
+                          st.g(p + ".src_attn.linear_q.bias"), dx=dx1.view(B * Lr, d), dx_residual=dt2.view(B * Lr, d))
+            # x1 = LN1(t1), t1 = drop(ctx Wo) + xin
+            dt1 = self._ln_bwd(dx1, t1, p + ".norm1", p + ".ln1", gt)
+            do = self._drop_bwd(dt1.view(B * Lr, d), sites[p + ".sa_out"], gd)
+            ctx = self.buf(p + ".sa.ctx", (B, Lr, d))
+            self._lin_bwd(do, ctx.view(B * Lr, d), self.W(p + ".self_attn.linear_out.weight"), st.g(p + ".self_attn.linear_out.weight"),
+                          st.g(p + ".self_attn.linear_out.bias"), dx=dctx.view(B * Lr, d))
+            qkv = self.buf(p + ".qkv", (B, Lr, 3, H, dk))
+            dqkv = self._scratch("g.qkv", (B, Lr, 3, H, dk))
+            self._attn_core_bwd(dctx, qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2], p + ".sa",
+                                d_att.get(p + ".self_attn"))
+            self._lin_bwd(dqkv.view(B * Lr, 3 * d), xin.view(B * Lr, d), self.Wspan([p + ".self_attn.linear_q.weight"], (3 * d, d)),
+                          st.span(st.G, [p + ".self_attn.linear_q.weight"], (3 * d, d)), st.span(st.G, [p + ".self_attn.linear_q.bias"], (3 * d,)),
+                          dx=g.view(B * Lr, d), dx_residual=dt1.view(B * Lr, d))
+
+        # ---- decoder input layer
+        de = gt
+        ops.scaled_pe_bwd(g, self.pe(d, Lr), de, st.g("decoder.embed.1.alpha"), sites["dec.pe"])
+        u = hp["dprenet_units"]
+        npre = hp["dprenet_layers"]
+        hin = self.buf(f"dec.prenet{npre - 1}", (B * Lr, u)) if npre > 0 else self.buf("dec.ys_in", (B, Lr, odim)).view(B * Lr, odim)
+        pbufs = ("g.prenet_a", "g.prenet_b")
+        dhp = self._scratch(pbufs[0], (B * Lr, u)) if npre > 0 else None
+        self._lin_bwd(de.view(B * Lr, d), hin, self.W("decoder.embed.0.1.weight"), st.g("decoder.embed.0.1.weight"),
+                      st.g("decoder.embed.0.1.bias"), dx=dhp)
+        for i in reversed(range(npre)):
+            nm = f"decoder.embed.0.0.prenet.{i}.0"
+            hout = self.buf(f"dec.prenet{i}", (B * Lr, u))
+            ops.relu_bwd(dhp, hout, dhp, sites[f"prenet{i}"].scale)
+            hin = self.buf(f"dec.prenet{i - 1}", (B * Lr, u)) if i > 0 else self.buf("dec.ys_in", (B, Lr, odim)).view(B * Lr, odim)
+            dnext = self._scratch(pbufs[(npre - i) % 2], (B * Lr, u)) if i > 0 else None
+            self._lin_bwd(dhp, hin, self.W(nm + ".weight"), st.g(nm + ".weight"), st.g(nm + ".bias"), dx=dnext)
+            dhp = dnext
+
+        # ---- encoder (reverse)
+        ge = self._scratch("g.enc_a", (B, T2, d))
+        gte = self._scratch("g.enc_b", (B, T2, d))
+        gde = self._scratch("g.enc_c", (B * T2, d))
+        self._ln_bwd(dmem, self.enc_last, "encoder.after_norm", "enc.after", ge)
+        g = ge
+        for l in reversed(range(hp["elayers"])):
+            p = f"encoder.encoders.{l}"
+            xin = self.buf(f"encoder.encoders.{l - 1}.xout", (B, T2, d)) if l > 0 else self.buf("enc.x0", (B, T2, d))
+            xm = self.buf(p + ".xmid", (B, T2, d))
+            n1 = self.buf(p + ".ln1.y", (B, T2, d))
+            n2 = self.buf(p + ".ln2.y", (B, T2, d))
+            h = self.buf(p + ".ffh", (B * T2, hp["eunits"]))
+            df = self._drop_bwd(g.view(B * T2, d), sites[p + ".ff2"], gde)
+            dh = self._scratch("g.effh", (B * T2, hp["eunits"]))
+            self._lin_bwd(df, h, self.W(p + ".feed_forward.w_2.weight"), st.g(p + ".feed_forward.w_2.weight"),
+                          st.g(p + ".feed_forward.w_2.bias"), dx=dh)
+            ops.relu_bwd(dh, h, dh, sites[p + ".ff1"].scale)
+            dn2 = gte
+            self._lin_bwd(dh, n2.view(B * T2, d), self.W(p + ".feed_forward.w_1.weight"), st.g(p + ".feed_forward.w_1.weight"),
+                          st.g(p + ".feed_forward.w_1.bias"), dx=dn2.view(B * T2, d))
+            gm = self._scratch("g.enc_d", (B, T2, d))
+            self._ln_bwd(dn2, xm, p + ".norm2", p + ".ln2", gm, dres=g)          # g_mid = g + LN2'(dn2)
+            do = self._drop_bwd(gm.view(B * T2, d), sites[p + ".sa_out"], gde)
+            ctx = self.buf(p + ".sa.ctx", (B, T2, d))
+            dctx = self._scratch("g.ectx", (B, T2, d))
+            self._lin_bwd(do, ctx.view(B * T2, d), self.W(p + ".self_attn.linear_out.weight"), st.g(p + ".self_attn.linear_out.weight"),
+                          st.g(p + ".self_attn.linear_out.bias"), dx=dctx.view(B * T2, d))
+            qkv = self.buf(p + ".qkv", (B, T2, 3, H, dk))
+            dqkv = self._scratch("g.eqkv", (B, T2, 3, H, dk))
+            self._attn_core_bwd(dctx, qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2], p + ".sa",
+                                d_att.get(p + ".self_attn"))
+            dn1 = gte
+            self._lin_bwd(dqkv.view(B * T2, 3 * d), n1.view(B * T2, d), self.Wspan([p + ".self_attn.linear_q.weight"], (3 * d, d)),
+                          st.span(st.G, [p + ".self_attn.linear_q.weight"], (3 * d, d)), st.span(st.G, [p + ".self_attn.linear_q.bias"], (3 * d,)),
+                          dx=dn1.view(B * T2, d))
+            self._ln_bwd(dn1, xin, p + ".norm1", p + ".ln1", g, dres=gm)          # g_prev = g_mid + LN1'(dn1)
+
+        # ---- encoder front end
+        delin = gte
+        ops.scaled_pe_bwd(g, self.pe(d, T2), delin, st.g("encoder.embed.out.1.alpha"), sites["enc.pe"])
+        y2 = self.buf("enc.y2", (B * T2 * F2, d))
+        woutp = self.buf("w.outp", (d, F2, d))
+        gwoutp = self._scratch("g.woutp", (d, F2 * d), _f32)
+        dy2 = self._scratch("g.y2", (B * T2 * F2, d))
+        mode = self.mode
+        ops.gemm(delin.view(B * T2, d).t(), y2.view(B * T2, F2 * d).t(), gwoutp, mode=mode)
+        ops.transpose_last2(gwoutp, st.g("encoder.embed.out.0.weight"), d, F2, d, accumulate=True)
+        ops.colsum(delin.view(B * T2, d), st.g("encoder.embed.out.0.bias"))
+        ops.gemm(delin.view(B * T2, d), woutp.view(d, F2 * d).t(), dy2.view(B * T2, F2 * d), mode=mode)
+        ops.relu_bwd(dy2, y2, dy2, 1.0)
+        w2p = self.buf("w.conv2p", (d, 9, d))
+        col = self._scratch("col", (B * T2 * F2, 9 * d))
+        y1 = self.buf("enc.y1", (B, T1, F1, d))
+        ops.im2col_s2(y1, col)                      # recompute the patch matrix instead of keeping ~1 GB alive
+        gw2p = self._scratch("g.w2p", (d, 9 * d), _f32)
+        ops.gemm(dy2.t(), col.t(), gw2p, mode=mode)
+        ops.transpose_last2(gw2p, st.g("encoder.embed.conv.2.weight"), d, 9, d, accumulate=True)
+        ops.colsum(dy2, st.g("encoder.embed.conv.2.bias"))
+        dcol = col
+        ops.gemm(dy2, w2p.view(d, 9 * d).t(), dcol, mode=mode)
+        dy1 = self._scratch("g.y1", (B, T1, F1, d))
+        ops.col2im_s2(dcol, dy1)
+        ops.relu_bwd(dy1, y1, dy1, 1.0)
+        ops.conv1_bwd(self.xs, dy1, st.g("encoder.embed.conv.0.weight"), st.g("encoder.embed.conv.0.bias"))
+
+    def _drop_bwd(self, dy2d, drop: Drop, out):
+        if drop.p <= 0.0:
+            return dy2d
+        o = out[: dy2d.shape[0]].view(dy2d.shape) if out.shape != dy2d.shape else out
+        return ops.dropout_bwd(dy2d, o, drop)
+
+    def _site_table(self) -> Dict[str, Drop]:
+        """Re-enumerate the forward's dropout sites (same order as forward())."""
+        hp = self.hp
+        saved = self._site
+        self._site = 0
+        t: Dict[str, Drop] = {}
+        t["enc.pe"] = self.drop(hp["enc_positional_dropout_rate"])
+        for l in range(hp["elayers"]):
+            p = f"encoder.encoders.{l}"
+            t[p + ".sa_out"] = self.drop(hp["transformer_enc_dropout_rate"])
+            t[p + ".ff1"] = self.drop(hp["transformer_enc_dropout_rate"])
+            t[p + ".ff2"] = self.drop(hp["transformer_enc_dropout_rate"])
+        for i in range(hp["dprenet_layers"]):
+            self._site += 1
+            pd = hp["dprenet_dropout_rate"]
+            t[f"prenet{i}"] = Drop(pd, self.base_seed, self._site, self.seed_dev) if pd > 0 else NO_DROP
+        t["dec.pe"] = self.drop(hp["dec_positional_dropout_rate"])
+        for l in range(hp["dlayers"]):
+            p = f"decoder.decoders.{l}"
+            t[p + ".sa_out"] = self.drop(hp["dec_dropout_rate"])
+            t[p + ".ca_out"] = self.drop(hp["dec_dropout_rate"])
+            t[p + ".ff1"] = self.drop(hp["dec_dropout_rate"])
+            t[p + ".ff2"] = self.drop(hp["dec_dropout_rate"])
+        for i in range(hp["postnet_layers"]):
+            t[f"post{i}"] = self.drop(hp["postnet_dropout_rate"])
+        assert saved == 0 or saved == self._site, (saved, self._site)
+        return t
+
+    # ------------------------------------------------------------------ optimizer tail
+    def optimizer_step(self, max_norm: float = 1.0, betas=(0.9, 0.999), eps: float = 1e-8,
+                       weight_decay: float = 0.0, grad_scale: float = 1.0) -> None:
+        """clip_grad_norm_(max_norm) + Adam over the flat buffers (trainers/ar_vc.py:99-107).
+
+        The learning rate is read from the device scalar ``self.lr_dev`` (set by the caller)."""
+        st = self.store
+        ops.step_advance(self.step_dev, self.seed_dev)
+        self._sqn.zero_()
+        ops.sqnorm(st.G, self._sqn)
+        ops.adam_step(st.P, st.G, st.M, st.V, st.P16, self.lr_dev, betas[0], betas[1], eps, weight_decay, self.step_dev,
+                      self._sqn, max_norm, grad_scale)
+        self.p16_dirty = False  # adam_step refreshed the bf16 shadow

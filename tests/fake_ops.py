@@ -1,0 +1,378 @@
+"""CPU stand-ins for seq2seq_vc_b200.ops -- TEST INFRASTRUCTURE ONLY.
+
+Implements the *contract* of each C-ABI entry point (include/s2svc_b200.h) with plain torch CPU
+ops so that the host-side orchestration of the engine (buffer wiring, strides, the hand-written
+backward pass, parameter packing) can be checked against the oracle / golden vectors without a
+GPU.  Installed only by tests via monkeypatch; the product never imports this module and has no
+CPU path of its own.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from seq2seq_vc_b200._lib import NO_DROP
+
+
+def _nodrop(drop):
+    assert drop is None or drop.p == 0.0, "fake ops model the deterministic path only"
+
+
+def gemm(a, b, c, *, bias=None, residual=None, alpha=1.0, relu=False, accumulate=False, drop=NO_DROP, taps=1,
+         row_mask=None, mode=0, M=None):
+    _nodrop(drop)
+    Mc, N = c.shape[-2], c.shape[-1]
+    M = Mc if M is None else M
+    acc = None
+    for t in range(taps):
+        at = a[..., t:t + M, :].double()
+        bt = (b[..., t, :] if taps > 1 else b).double()
+        term = at @ bt.transpose(-1, -2)
+        acc = term if acc is None else acc + term
+    v = acc * alpha
+    if bias is not None:
+        v = v + bias.double()
+    if relu:
+        v = torch.relu(v)
+    if residual is not None:
+        v = v + residual[..., :M, :].double()
+    if accumulate:
+        v = v + c[..., :M, :].double()
+    if row_mask is not None:
+        period, off, lo, hi = row_mask
+        ph = (torch.arange(M) + off) % period
+        ok = (ph >= lo) & (ph < hi)
+        v = v * ok[:, None].double()
+    c[..., :M, :] = v.to(c.dtype)
+    return c
+
+
+def layernorm_fwd(x, gamma, beta, y, mean, rstd, eps=1e-12):
+    d = x.shape[-1]
+    x2 = x.reshape(-1, d).double()
+    mu = x2.mean(-1)
+    var = x2.var(-1, unbiased=False)
+    rs = torch.rsqrt(var + eps)
+    y.copy_((((x2 - mu[:, None]) * rs[:, None]) * gamma.double() + beta.double()).reshape(x.shape).to(y.dtype))
+    mean.copy_(mu.float())
+    rstd.copy_(rs.float())
+    return y
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, dres=None):
+    d = x.shape[-1]
+    x2, g2 = x.reshape(-1, d).double(), dy.reshape(-1, d).double()
+    xh = (x2 - mean.double()[:, None]) * rstd.double()[:, None]
+    gg = g2 * gamma.double()
+    a = gg.mean(-1, keepdim=True)
+    b = (gg * xh).mean(-1, keepdim=True)
+    out = rstd.double()[:, None] * (gg - a - xh * b)
+    if dres is not None:
+        out = out + dres.reshape(-1, d).double()
+    if dx is not None:
+        dx.copy_(out.reshape(dx.shape).to(dx.dtype))
+    if dgamma is not None:
+        dgamma += (g2 * xh).sum(0).float()
+        dbeta += g2.sum(0).float()
+    return dx
+
+
+def colsum(x2d, out):
+    out += x2d.double().sum(0).float()
+
+
+def relu_bwd(dy, y, dx, scale=1.0):
+    dx.copy_(torch.where(y > 0, dy * scale, torch.zeros_like(dy)))
+    return dx
+
+
+def dropout_bwd(dy, dx, drop):
+    _nodrop(drop)
+    dx.copy_(dy)
+    return dx
+
+
+def add(a, b, out):
+    out.copy_(a + b)
+    return out
+
+
+def softmax_fwd(S, klens, causal, T2, Pd=None, drop=NO_DROP):
+    _nodrop(drop)
+    B, H, T1, ld = S.shape
+    j = torch.arange(ld)[None, None, None, :]
+    i = torch.arange(T1)[None, None, :, None]
+    vis = (j < klens.long()[:, None, None, None]) & (j < T2)
+    if causal:
+        vis = vis & (j <= i)
+    s = S.double().masked_fill(~vis, -1e300)
+    p = torch.softmax(s, -1).masked_fill(~vis, 0.0)
+    S.copy_(p.to(S.dtype))
+    return S
+
+
+def softmax_bwd(P, dP, T2, scale, drop=NO_DROP):
+    _nodrop(drop)
+    p, g = P.double(), dP.double()
+    p = p.clone()
+    p[..., T2:] = 0
+    g = torch.where(p != 0, g, torch.zeros_like(g))
+    dot = (p * g).sum(-1, keepdim=True)
+    dP.copy_((scale * p * (g - dot)).to(dP.dtype))
+    return dP
+
+
+def scaled_pe_fwd(x, pe, alpha, y, drop=NO_DROP):
+    _nodrop(drop)
+    T, d = x.shape[1], x.shape[2]
+    y.copy_((x.double() + alpha.double() * pe[:T].double()[None]).to(y.dtype))
+    return y
+
+
+def scaled_pe_bwd(dy, pe, dx, dalpha, drop=NO_DROP):
+    _nodrop(drop)
+    T = dy.shape[1]
+    if dx is not None:
+        dx.copy_(dy)
+    dalpha += (dy.double() * pe[:T].double()[None]).sum().float()
+    return dx
+
+
+def conv1_fwd(x, w, bias, y1):
+    out = torch.relu(torch.nn.functional.conv2d(x.unsqueeze(1).double(), w.double(), bias.double(), stride=2))  # (B,C,T1,F1)
+    y1.copy_(out.permute(0, 2, 3, 1).to(y1.dtype))
+    return y1
+
+
+def conv1_bwd(x, dy1, dw, dbias):
+    B, T, F = x.shape
+    g = dy1.double().permute(0, 3, 1, 2)  # (B,C,T1,F1)
+    xs = x.double().unsqueeze(1)
+    w = torch.zeros(dw.shape, dtype=torch.float64, requires_grad=True)
+    out = torch.nn.functional.conv2d(xs, w, None, stride=2)
+    (gw,) = torch.autograd.grad(out, w, g)
+    dw += gw.float()
+    dbias += g.sum((0, 2, 3)).float()
+
+
+def im2col_s2(y1, col):
+    B, T1, F1, C = y1.shape
+    T2, F2 = (T1 - 1) // 2, (F1 - 1) // 2
+    out = col.view(B, T2, F2, 9, C)
+    for kt in range(3):
+        for kf in range(3):
+            out[:, :, :, kt * 3 + kf, :] = y1[:, kt:kt + 2 * T2:2, kf:kf + 2 * F2:2, :]
+    return col
+
+
+def col2im_s2(dcol, dy1):
+    B, T1, F1, C = dy1.shape
+    T2, F2 = (T1 - 1) // 2, (F1 - 1) // 2
+    src = dcol.view(B, T2, F2, 9, C)
+    acc = torch.zeros(dy1.shape, dtype=torch.float64)
+    for kt in range(3):
+        for kf in range(3):
+            acc[:, kt:kt + 2 * T2:2, kf:kf + 2 * F2:2, :] += src[:, :, :, kt * 3 + kf, :].double()
+    dy1.copy_(acc.to(dy1.dtype))
+    return dy1
+
+
+def shift_thin(ys, out, r):
+    B, L, odim = ys.shape
+    Lr = out.shape[1]
+    out.zero_()
+    for l in range(1, Lr):
+        if l * r - 1 < L:
+            out[:, l] = ys[:, l * r - 1].to(out.dtype)
+    return out
+
+
+def fix_targets(labels, olens, labels_out, olens_out, r):
+    Lout = labels_out.shape[1]
+    labels_out.copy_(labels[:, :Lout])
+    for b in range(labels.shape[0]):
+        o = int(olens[b])
+        o -= o % r
+        if 0 <= o - 1 < Lout:
+            labels_out[b, o - 1] = 1.0
+        if olens_out is not None:
+            olens_out[b] = o
+
+
+def _valid(x, L, halo):
+    return x[:, halo:halo + L]
+
+
+def bn_stats(x, sums, L, halo):
+    C = x.shape[-1]
+    v = _valid(x, L, halo).double().reshape(-1, C)
+    sums[:C] += v.sum(0).float()
+    sums[C:] += (v * v).sum(0).float()
+
+
+def bn_finalize(sums, mean, invstd, running_mean, running_var, count, eps=1e-5, momentum=0.1):
+    C = mean.numel()
+    mu = sums[:C].double() / count
+    var = (sums[C:].double() / count - mu * mu).clamp_min(0)
+    mean.copy_(mu.float())
+    invstd.copy_(torch.rsqrt(var + eps).float())
+    if running_mean is not None:
+        running_mean.copy_(((1 - momentum) * running_mean.double() + momentum * mu).float())
+    if running_var is not None:
+        unb = var * count / (count - 1) if count > 1 else var
+        running_var.copy_(((1 - momentum) * running_var.double() + momentum * unb).float())
+
+
+def bn_eval_stats(running_mean, running_var, mean, invstd, eps=1e-5):
+    mean.copy_(running_mean)
+    invstd.copy_(torch.rsqrt(running_var.double() + eps).float())
+
+
+def bn_apply(x, mean, invstd, gamma, beta, y, L, halo, use_tanh, drop=NO_DROP):
+    _nodrop(drop)
+    y.zero_()
+    t = (_valid(x, L, halo).double() - mean.double()) * invstd.double() * gamma.double() + beta.double()
+    if use_tanh:
+        t = torch.tanh(t)
+    y[:, halo:halo + L] = t.to(y.dtype)
+    return y
+
+
+def _bn_dz(dy, x, mean, invstd, gamma, beta, L, halo, use_tanh):
+    xh = (_valid(x, L, halo).double() - mean.double()) * invstd.double()
+    dz = _valid(dy, L, halo).double()
+    if use_tanh:
+        a = torch.tanh(xh * gamma.double() + beta.double())
+        dz = dz * (1 - a * a)
+    return dz, xh
+
+
+def bn_bwd_reduce(dy, y, x, mean, invstd, gamma, beta, sums, L, halo, use_tanh, drop=NO_DROP):
+    _nodrop(drop)
+    C = x.shape[-1]
+    dz, xh = _bn_dz(dy, x, mean, invstd, gamma, beta, L, halo, use_tanh)
+    sums[:C] += dz.reshape(-1, C).sum(0).float()
+    sums[C:] += (dz * xh).reshape(-1, C).sum(0).float()
+
+
+def bn_bwd_apply(dy, y, x, mean, invstd, gamma, beta, sums, dx, dgamma, dbeta, L, halo, use_tanh, drop=NO_DROP):
+    _nodrop(drop)
+    B, Lp, C = x.shape
+    dz, xh = _bn_dz(dy, x, mean, invstd, gamma, beta, L, halo, use_tanh)
+    t = dz
+    if sums is not None:
+        n = B * L
+        t = dz - sums[:C].double() / n - xh * sums[C:].double() / n
+    dx.zero_()
+    dx[:, halo:halo + L] = (t * gamma.double() * invstd.double()).to(dx.dtype)
+    if sums is not None:
+        if dbeta is not None:
+            dbeta += sums[:C]
+        if dgamma is not None:
+            dgamma += sums[C:]
+    return dx
+
+
+def pack_conv1d_w(w, wp, wpt):
+    if wp is not None:
+        wp.copy_(w.permute(0, 2, 1).to(wp.dtype))
+    if wpt is not None:
+        wpt.copy_(w.flip(-1).permute(1, 2, 0).to(wpt.dtype))
+
+
+def pad_rows(x, y, halo):
+    L = x.shape[1]
+    y.zero_()
+    y[:, halo:halo + L] = x
+    return y
+
+
+def unpad_rows(x, y, halo):
+    L = y.shape[1]
+    y.copy_(x[:, halo:halo + L])
+    return y
+
+
+def seq2seq_loss(after, before, logits, ys, labels, olens, pos_weight, losses, d_after, d_before, d_logits, ws):
+    B, L, odim = after.shape
+    m = (torch.arange(L)[None, :] < olens.long()[:, None])
+    nf = m.sum().double()
+    y = ys[:, :L].double()
+    da, db = after.double() - y, before.double() - y
+    m3 = m[..., None].double()
+    l1 = ((da.abs() * m3).sum() + (db.abs() * m3).sum()) / (nf * odim)
+    x, t = logits.double(), labels[:, :L].double()
+    lw = 1 + (pos_weight - 1) * t
+    sp = torch.nn.functional.softplus(-x)
+    bce = ((((1 - t) * x + lw * sp)) * m.double()).sum() / nf
+    losses[0], losses[1] = l1.float(), bce.float()
+    if d_after is not None:
+        d_after.copy_((torch.sign(da) * m3 / (nf * odim)).to(d_after.dtype))
+        d_before.copy_((torch.sign(db) * m3 / (nf * odim)).to(d_before.dtype))
+        d_logits.copy_((((1 - t) - lw * torch.sigmoid(-x)) * m.double() / nf).to(d_logits.dtype))
+
+
+def guided_attn_loss(att, ilens, olens, T_in, sigma, alpha, loss, d_att, ws):
+    B, H, T_out, ld = att.shape
+    s = torch.arange(ld, dtype=torch.float64)[None, None, None, :]
+    t = torch.arange(T_out, dtype=torch.float64)[None, None, :, None]
+    il = ilens.double()[:, None, None, None]
+    ol = olens.double()[:, None, None, None]
+    w = 1 - torch.exp(-((s / il - t / ol) ** 2) / (2 * sigma * sigma))
+    m = (s < il) & (s < T_in) & (t < ol)
+    cnt = m.expand(B, H, T_out, ld).sum().double()
+    loss[0] = (alpha * (w * att.double() * m).sum() / cnt).float()
+    if d_att is not None:
+        d_att.copy_((alpha * w * m / cnt).expand(B, H, T_out, ld).to(d_att.dtype))
+
+
+def sqnorm(g, out):
+    out += (g.double() ** 2).sum().float()
+
+
+def adam_step(p, g, m, v, p16, lr_dev, beta1, beta2, eps, wd, step_dev, sqn, max_norm, grad_scale=1.0):
+    coef = grad_scale
+    if sqn is not None and max_norm > 0:
+        total = math.sqrt(float(sqn)) * grad_scale
+        coef *= min(1.0, max_norm / (total + 1e-6))
+    step = float(step_dev)
+    lr = float(lr_dev)
+    gi = g * coef + wd * p
+    m.mul_(beta1).add_(gi, alpha=1 - beta1)
+    v.mul_(beta2).addcmul_(gi, gi, value=1 - beta2)
+    bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
+    p.sub_((lr / bc1) * m / (v.sqrt() / math.sqrt(bc2) + eps))
+    if p16 is not None:
+        p16.copy_(p.to(p16.dtype))
+
+
+def step_advance(step_dev, seed_dev):
+    step_dev += 1
+    seed_dev += 1
+
+
+def cast(src, dst):
+    dst.copy_(src.to(dst.dtype))
+    return dst
+
+
+def transpose_last2(src, dst, N, A, Bd, accumulate=False):
+    s = src.reshape(N, A, Bd).transpose(1, 2).to(dst.dtype)
+    d = dst.view(N, Bd, A)
+    if accumulate:
+        d += s
+    else:
+        d.copy_(s)
+    return dst
+
+
+ALL = [n for n, f in list(globals().items()) if callable(f) and not n.startswith("_") and n not in ("NO_DROP",)]
+
+
+def install(monkeypatch):
+    import seq2seq_vc_b200.ops as ops
+
+    for n in ALL:
+        if hasattr(ops, n) and n not in ("mas", "logmel"):
+            monkeypatch.setattr(ops, n, globals()[n])
