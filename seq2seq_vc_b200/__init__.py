@@ -4,6 +4,7 @@ Public surface (mirrors seq2seq_vc.models / seq2seq_vc.losses / bin.preprocess n
     VTN, Seq2SeqLoss, GuidedMultiHeadAttentionLoss, viterbi_decode, logmelfilterbank
 The native library (libs2svc_b200.so) is loaded lazily on first use; there is no CPU fallback.
 """
+from ._lib import S2SError  # noqa: F401
 from .vtn_engine import VTNEngine, default_hparams  # noqa: F401
 from .api import VTN, Seq2SeqLoss, GuidedMultiHeadAttentionLoss, VTNTrainStep, viterbi_decode, logmelfilterbank  # noqa: F401
 

@@ -14,5 +14,5 @@ for s in $SRCS; do
   fi
 done
 for p in "${pids[@]}"; do wait $p; done
-nvcc -shared -o $OUT _obj/*.o -lcuda
+nvcc -Wno-deprecated-gpu-targets -shared -o $OUT _obj/*.o -lcuda
 echo "built $OUT"

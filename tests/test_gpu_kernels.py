@@ -1,0 +1,316 @@
+"""Per-kernel parity: every C-ABI entry point vs its float64 torch-CPU contract (tests/fake_ops.py)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import fake_ops as F
+
+pytestmark = pytest.mark.gpu
+
+DT = [torch.float32, torch.bfloat16]
+
+
+def tol(dt, scale=1.0):
+    return (2e-5 if dt == torch.float32 else 2e-2) * scale
+
+
+def dev(*ts):
+    return [None if t is None else t.cuda() for t in ts]
+
+
+def close(a, b, atol, what=""):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    err = (a - b).abs().max().item()
+    assert err <= atol, f"{what}: max abs err {err} > {atol}"
+
+
+def rnd(*shape, dt=torch.float32, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed + sum(shape))
+    return (torch.randn(*shape, generator=g) * scale).to(dt)
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from seq2seq_vc_b200 import _lib, ops
+
+    _lib.device_check()
+    return ops
+
+
+@pytest.mark.parametrize("mode,dt", [(0, torch.float32), (0, torch.bfloat16), (1, torch.bfloat16)])
+@pytest.mark.parametrize("M,N,K", [(64, 48, 32), (257, 130, 72), (1000, 384, 384), (127, 8, 19 * 16)])
+def test_gemm_plain_and_epilogue(ops, mode, dt, M, N, K):
+    a, b = rnd(M, K, dt=dt, seed=1), rnd(N, K, dt=dt, seed=2, scale=1 / math.sqrt(K))
+    bias, res = rnd(N, seed=3), rnd(M, N, dt=dt, seed=4)
+    for kw in (dict(), dict(bias=bias, relu=True), dict(bias=bias, residual=res, alpha=0.5), dict(accumulate=True)):
+        c0 = rnd(M, N, dt=dt, seed=5)
+        ref = F.gemm(a, b, c0.clone(), **kw)
+        da, db, dc = dev(a, b, c0.clone())
+        dkw = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in kw.items()}
+        ops.gemm(da, db, dc, mode=mode, **dkw)
+        close(dc, ref, tol(dt, 2), f"gemm {kw.keys()}")
+
+
+@pytest.mark.parametrize("mode,dt", [(0, torch.float32), (1, torch.bfloat16)])
+def test_gemm_transposed_operands_and_f32_accumulate(ops, mode, dt):
+    M, N, K = 96, 200, 333          # dW = dy^T x : both operands contiguous along the non-reduced dim
+    dy, x = rnd(K, M, dt=dt, seed=1), rnd(K, N, dt=dt, seed=2)
+    g0 = rnd(M, N, seed=3)
+    ref = F.gemm(dy.t(), x.t(), g0.clone(), accumulate=True)
+    ddy, dx, dg = dev(dy, x, g0.clone())
+    ops.gemm(ddy.t(), dx.t(), dg, accumulate=True, mode=mode)
+    close(dg, ref, tol(dt, 20), "dW gemm")
+    w = rnd(N, M, dt=dt, seed=4)    # dx = dy W : B operand n-major
+    c = torch.zeros(K, M, dtype=dt)
+    ref = F.gemm(x, w.t(), c.clone())
+    dxx, dw, dc = dev(x, w, c)
+    ops.gemm(dxx, dw.t(), dc, mode=mode)
+    close(dc, ref, tol(dt, 20), "dx gemm")
+
+
+@pytest.mark.parametrize("mode,dt", [(0, torch.float32), (1, torch.bfloat16)])
+@pytest.mark.parametrize("T1,T2,dk", [(37, 29, 16), (128, 127, 48), (64, 200, 64)])
+def test_gemm_attention_views(ops, mode, dt, T1, T2, dk):
+    B, H = 3, 4
+    d = H * dk
+    qkv = rnd(B, T1, 3, H, dk, dt=dt, seed=1)
+    kv = rnd(B, T2, 2, H, dk, dt=dt, seed=2)
+    ld = (T2 + 7) // 8 * 8
+    q, k, v = qkv[:, :, 0], kv[:, :, 0], kv[:, :, 1]
+    P = torch.zeros(B, H, T1, ld, dtype=dt)
+    ref = F.gemm(q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3), P.clone()[..., :T2], alpha=1 / math.sqrt(dk))
+    dq, dkv, dP = dev(qkv, kv, P)
+    ops.gemm(dq[:, :, 0].permute(0, 2, 1, 3), dkv[:, :, 0].permute(0, 2, 1, 3), dP[..., :T2], alpha=1 / math.sqrt(dk), mode=mode)
+    close(dP[..., :T2], ref, tol(dt, 4), "QK^T")
+    Pm = torch.softmax(rnd(B, H, T1, ld, seed=3), -1).to(dt)
+    ctx = torch.zeros(B, T1, d, dtype=dt)
+    ref = F.gemm(Pm[..., :T2], v.permute(0, 2, 3, 1), ctx.clone().view(B, T1, H, dk).permute(0, 2, 1, 3))
+    dPm, dctx = dev(Pm, ctx)
+    ops.gemm(dPm[..., :T2], dkv[:, :, 1].permute(0, 2, 3, 1), dctx.view(B, T1, H, dk).permute(0, 2, 1, 3), mode=mode)
+    close(dctx.view(B, T1, H, dk).permute(0, 2, 1, 3), ref, tol(dt, 2), "PV")
+    # dv[b,s,h,:] = sum_t P[t,s] dctx[t,:]  (both operands contiguous along the output dims)
+    g = rnd(B, T1, d, dt=dt, seed=4)
+    dv = torch.zeros(B, T2, 2, H, dk, dtype=dt)
+    g4 = g.view(B, T1, H, dk).permute(0, 2, 1, 3)
+    ref = F.gemm(Pm[..., :T2].transpose(-1, -2), g4.transpose(-1, -2), dv.clone()[:, :, 1].permute(0, 2, 1, 3))
+    dg, ddv = dev(g, dv)
+    ops.gemm(dPm[..., :T2].transpose(-1, -2), dg.view(B, T1, H, dk).permute(0, 2, 1, 3).transpose(-1, -2),
+             ddv[:, :, 1].permute(0, 2, 1, 3), mode=mode)
+    close(ddv[:, :, 1].permute(0, 2, 1, 3), ref, tol(dt, 4), "dV")
+
+
+@pytest.mark.parametrize("mode,dt", [(0, torch.float32), (1, torch.bfloat16)])
+def test_gemm_conv1d_taps(ops, mode, dt):
+    B, L, ic, oc, k = 3, 50, 80, 64, 5
+    halo, Lp = 2, 54
+    x = rnd(B, Lp, ic, dt=dt, seed=1)
+    x[:, :halo] = 0
+    x[:, halo + L:] = 0
+    w = rnd(oc, k, ic, dt=dt, seed=2, scale=0.1)
+    z = torch.zeros(B, Lp, oc, dtype=dt)
+    M = B * Lp - 2 * halo
+    kw = dict(taps=k, row_mask=(Lp, halo, halo, halo + L), M=M)
+    ref = z.clone()
+    F.gemm(x.view(B * Lp, ic), w, ref.view(B * Lp, oc)[halo:], **kw)
+    dx, dw, dz = dev(x, w, z)
+    ops.gemm(dx.view(B * Lp, ic), dw, dz.view(B * Lp, oc)[halo:], mode=mode, **kw)
+    close(dz, ref, tol(dt, 4), "taps gemm")
+    # against torch conv1d directly
+    y = torch.nn.functional.conv1d(x[:, halo:halo + L].float().transpose(1, 2), w.float().permute(0, 2, 1), padding=halo)
+    close(dz[:, halo:halo + L], y.transpose(1, 2), tol(dt, 8), "conv1d")
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("rows,d", [(7, 32), (1000, 384), (33, 50)])
+def test_layernorm(ops, dt, rows, d):
+    x, dy, res = rnd(rows, 1, d, dt=dt, seed=1), rnd(rows, 1, d, dt=dt, seed=2), rnd(rows, 1, d, dt=dt, seed=3)
+    gam, bet = 1 + 0.1 * rnd(d, seed=4), 0.1 * rnd(d, seed=5)
+    y, mean, rstd = torch.empty_like(x), torch.empty(rows), torch.empty(rows)
+    F.layernorm_fwd(x, gam, bet, y, mean, rstd)
+    dx, dg, db = torch.empty_like(x), torch.zeros(d), torch.zeros(d)
+    F.layernorm_bwd(dy, x, gam, mean, rstd, dx, dg, db, dres=res)
+    cx, cdy, cres, cg, cb = dev(x, dy, res, gam, bet)
+    cy, cm, cr = torch.empty_like(cx), torch.empty(rows, device="cuda"), torch.empty(rows, device="cuda")
+    ops.layernorm_fwd(cx, cg, cb, cy, cm, cr)
+    close(cy, y, tol(dt, 4), "ln fwd")
+    close(cm, mean, 1e-5, "mean")
+    cdx, cdg, cdb = torch.empty_like(cx), torch.zeros(d, device="cuda"), torch.zeros(d, device="cuda")
+    ops.layernorm_bwd(cdy, cx, cg, cm, cr, cdx, cdg, cdb, dres=cres)
+    close(cdx, dx, tol(dt, 8), "ln dx")
+    close(cdg, dg, tol(dt, 4) * math.sqrt(rows) + 1e-3, "ln dgamma")
+    close(cdb, db, tol(dt, 4) * math.sqrt(rows) + 1e-3, "ln dbeta")
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("causal", [False, True])
+def test_softmax_fwd_bwd(ops, dt, causal):
+    B, H, T1, T2 = 3, 2, 19, 21
+    ld = 24
+    S = rnd(B, H, T1, ld, dt=dt, seed=1, scale=2.0)
+    klens = torch.tensor([21, 13, 0], dtype=torch.int32)
+    P = F.softmax_fwd(S.clone(), klens, causal, T2)
+    cS, ck = dev(S, klens)
+    ops.softmax_fwd(cS, ck, causal, T2)
+    close(cS, P, tol(dt), "softmax")
+    assert (cS[2] == 0).all(), "rows without a visible key must be exactly zero"
+    dP = rnd(B, H, T1, ld, dt=dt, seed=2)
+    ref = F.softmax_bwd(P, dP.clone(), T2, 0.25)
+    cdP = dP.cuda()
+    ops.softmax_bwd(cS, cdP, T2, 0.25)
+    close(cdP, ref, tol(dt, 2), "softmax bwd")
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_scaled_pe_and_elementwise(ops, dt):
+    B, T, d = 3, 17, 32
+    x, pe, alpha = rnd(B, T, d, dt=dt, seed=1), rnd(40, d, seed=2), torch.tensor(0.7)
+    y = F.scaled_pe_fwd(x, pe, alpha, torch.empty_like(x))
+    cx, cpe, ca = dev(x, pe, alpha)
+    cy = ops.scaled_pe_fwd(cx, cpe, ca, torch.empty_like(cx))
+    close(cy, y, tol(dt), "pe fwd")
+    dal, cdal = torch.zeros(()), torch.zeros((), device="cuda")
+    F.scaled_pe_bwd(x, pe, torch.empty_like(x), dal)
+    ops.scaled_pe_bwd(cx, cpe, torch.empty_like(cx), cdal)
+    close(cdal, dal, tol(dt, 50), "dalpha")
+    a, b = rnd(1001, dt=dt, seed=3), rnd(1001, dt=dt, seed=4)
+    close(ops.add(a.cuda(), b.cuda(), torch.empty(1001, dtype=dt, device="cuda")), a + b, tol(dt), "add")
+    close(ops.relu_bwd(a.cuda(), b.cuda(), torch.empty(1001, dtype=dt, device="cuda"), 2.0), F.relu_bwd(a, b, torch.empty_like(a), 2.0), tol(dt), "relu_bwd")
+    out, cout = torch.zeros(48), torch.zeros(48, device="cuda")
+    m = rnd(300, 48, dt=dt, seed=5)
+    F.colsum(m, out)
+    ops.colsum(m.cuda(), cout)
+    close(cout, out, tol(dt, 20), "colsum")
+    src = rnd(5, 7, 9, seed=6)
+    dst = ops.transpose_last2(src.cuda(), torch.empty(5, 9, 7, dtype=dt, device="cuda"), 5, 7, 9)
+    close(dst, src.transpose(1, 2), tol(dt), "transpose")
+    w = rnd(6, 4, 5, seed=7)
+    wp, wpt = torch.empty(6, 5, 4, dtype=dt, device="cuda"), torch.empty(4, 5, 6, dtype=dt, device="cuda")
+    ops.pack_conv1d_w(w.cuda(), wp, wpt)
+    rp, rpt = torch.empty(6, 5, 4), torch.empty(4, 5, 6)
+    F.pack_conv1d_w(w, rp, rpt)
+    close(wp, rp, tol(dt), "wp")
+    close(wpt, rpt, tol(dt), "wpt")
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_conv2d_subsampling_pieces(ops, dt):
+    B, T, Fq, C = 2, 23, 80, 16
+    x, w, bias = rnd(B, T, Fq, seed=1), rnd(C, 1, 3, 3, seed=2, scale=0.3), rnd(C, seed=3, scale=0.1)
+    T1, F1 = (T - 1) // 2, (Fq - 1) // 2
+    T2, F2 = (T1 - 1) // 2, (F1 - 1) // 2
+    y1 = F.conv1_fwd(x, w, bias, torch.empty(B, T1, F1, C, dtype=dt))
+    cy1 = ops.conv1_fwd(x.cuda(), w.cuda(), bias.cuda(), torch.empty(B, T1, F1, C, dtype=dt, device="cuda"))
+    close(cy1, y1, tol(dt), "conv1")
+    col = F.im2col_s2(y1, torch.empty(B * T2 * F2, 9 * C, dtype=dt))
+    ccol = ops.im2col_s2(cy1, torch.empty(B * T2 * F2, 9 * C, dtype=dt, device="cuda"))
+    close(ccol, col, tol(dt), "im2col")
+    dcol = rnd(B * T2 * F2, 9 * C, dt=dt, seed=4)
+    dy1 = F.col2im_s2(dcol, torch.empty(B, T1, F1, C, dtype=dt))
+    cdy1 = ops.col2im_s2(dcol.cuda(), torch.empty(B, T1, F1, C, dtype=dt, device="cuda"))
+    close(cdy1, dy1, tol(dt, 4), "col2im")
+    dw, db = torch.zeros(C, 1, 3, 3), torch.zeros(C)
+    F.conv1_bwd(x, dy1, dw, db)
+    cdw, cdb = torch.zeros(C, 1, 3, 3, device="cuda"), torch.zeros(C, device="cuda")
+    ops.conv1_bwd(x.cuda(), cdy1, cdw, cdb)
+    close(cdw, dw, tol(dt, 100), "conv1 dw")
+    close(cdb, db, tol(dt, 100), "conv1 db")
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("use_tanh", [True, False])
+def test_batchnorm_pipeline(ops, dt, use_tanh):
+    B, L, halo, C = 3, 21, 2, 16
+    Lp = L + 2 * halo
+    x, dy = rnd(B, Lp, C, dt=dt, seed=1), rnd(B, Lp, C, dt=dt, seed=2)
+    gam, bet = 1 + 0.1 * rnd(C, seed=3), 0.1 * rnd(C, seed=4)
+    rm, rv = torch.zeros(C), torch.ones(C)
+
+    def run(o, to):
+        sums = to(torch.zeros(2 * C))
+        X, DY, G, Bt, RM, RV = to(x), to(dy), to(gam), to(bet), to(rm.clone()), to(rv.clone())
+        mean, invstd = to(torch.empty(C)), to(torch.empty(C))
+        o.bn_stats(X, sums, L, halo)
+        o.bn_finalize(sums, mean, invstd, RM, RV, B * L)
+        y = o.bn_apply(X, mean, invstd, G, Bt, torch.empty_like(X), L, halo, use_tanh)
+        bs = to(torch.zeros(2 * C))
+        o.bn_bwd_reduce(DY, y, X, mean, invstd, G, Bt, bs, L, halo, use_tanh)
+        dg, db = to(torch.zeros(C)), to(torch.zeros(C))
+        dx = o.bn_bwd_apply(DY, y, X, mean, invstd, G, Bt, bs, torch.empty_like(X), dg, db, L, halo, use_tanh)
+        return y, dx, dg, db, RM, RV
+
+    ref = run(F, lambda t: t)
+    got = run(ops, lambda t: t.cuda())
+    for a, b, name, s in zip(got, ref, ("y", "dx", "dgamma", "dbeta", "running_mean", "running_var"), (2, 8, 40, 40, 2, 2)):
+        close(a, b, tol(dt, s), name)
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_losses(ops, dt):
+    B, L, odim = 3, 22, 80
+    after, before, logits = rnd(B, L, odim, dt=dt, seed=1), rnd(B, L, odim, dt=dt, seed=2), rnd(B, L, dt=dt, seed=3)
+    ys, labels = rnd(B, L + 3, odim, seed=4), (rnd(B, L + 1, seed=5) > 0.5).float()
+    olens = torch.tensor([22, 10, 1], dtype=torch.int32)
+    lo, da, db, dl = torch.zeros(2), torch.empty_like(after), torch.empty_like(after), torch.empty_like(logits)
+    F.seq2seq_loss(after, before, logits, ys, labels, olens, 10.0, lo, da, db, dl, None)
+    clo = torch.zeros(2, device="cuda")
+    cda, cdb, cdl = torch.empty_like(after.cuda()), torch.empty_like(after.cuda()), torch.empty_like(logits.cuda())
+    ops.seq2seq_loss(after.cuda(), before.cuda(), logits.cuda(), ys.cuda(), labels.cuda(), olens.cuda(), 10.0, clo, cda, cdb, cdl,
+                     torch.zeros(4, device="cuda"))
+    close(clo, lo, 1e-4 if dt == torch.float32 else 1e-3, "losses")
+    close(cda, da, 1e-6, "d_after")
+    close(cdl, dl, 1e-4, "d_logits")
+    z = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "kats.npz"))
+    att = torch.from_numpy(z["gmh_att"]).to(dt)
+    loss = torch.zeros(1, device="cuda")
+    ops.guided_attn_loss(att.cuda(), torch.from_numpy(z["gmh_ilens"]).int().cuda(), torch.from_numpy(z["gmh_olens"]).int().cuda(),
+                         att.shape[-1], 0.4, 1.0, loss, torch.empty_like(att.cuda()), torch.zeros(2, device="cuda"))
+    assert abs(loss.item() - float(z["gmh_loss"])) <= (1e-5 if dt == torch.float32 else 2e-3)
+
+
+def test_glue_and_optimizer(ops):
+    ys = rnd(2, 9, 5, seed=1)
+    out = ops.shift_thin(ys.cuda(), torch.empty(2, 4, 5, device="cuda"), 2)
+    close(out, F.shift_thin(ys, torch.empty(2, 4, 5), 2), 0, "shift_thin")
+    labels, olens = torch.zeros(2, 9), torch.tensor([9, 5], dtype=torch.int32)
+    lo, oo = torch.empty(2, 8), torch.empty(2, dtype=torch.int32)
+    F.fix_targets(labels, olens, lo, oo, 2)
+    clo, coo = torch.empty(2, 8, device="cuda"), torch.empty(2, dtype=torch.int32, device="cuda")
+    ops.fix_targets(labels.cuda(), olens.cuda(), clo, coo, 2)
+    close(clo, lo, 0, "labels")
+    assert coo.tolist() == oo.tolist()
+    n = 100003
+    p, g = rnd(n, seed=2), rnd(n, seed=3, scale=0.01)
+    m, v = torch.zeros(n), torch.zeros(n)
+    cp, cg, cm, cv = dev(p.clone(), g, m.clone(), v.clone())
+    step, lr, sq = torch.tensor([1.0]), torch.tensor([1e-3]), torch.zeros(1)
+    F.sqnorm(g, sq)
+    F.adam_step(p, g, m, v, None, lr, 0.9, 0.999, 1e-8, 0.0, step, sq, 1.0)
+    csq = torch.zeros(1, device="cuda")
+    ops.sqnorm(cg, csq)
+    close(csq, sq, 1e-4 * float(sq), "sqnorm")
+    p16 = torch.empty(n, dtype=torch.bfloat16, device="cuda")
+    ops.adam_step(cp, cg, cm, cv, p16, lr.cuda(), 0.9, 0.999, 1e-8, 0.0, step.cuda(), csq, 1.0)
+    close(cp, p, 1e-6, "adam p")
+    close(p16, p, 2e-2, "bf16 shadow")
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_dropout_is_consistent_between_forward_and_backward(ops, dt):
+    from seq2seq_vc_b200._lib import Drop
+
+    M, N, K = 300, 64, 32
+    a, b = rnd(M, K, dt=dt, seed=1), rnd(N, K, dt=dt, seed=2)
+    seed_dev = torch.tensor([5], dtype=torch.int64, device="cuda")
+    drop = Drop(0.3, seed=11, site=4, seed_dev=seed_dev)
+    for mode in ((0, 1) if dt == torch.bfloat16 else (0,)):
+        plain = ops.gemm(a.cuda(), b.cuda(), torch.empty(M, N, dtype=dt, device="cuda"), mode=mode).float()
+        dropped = ops.gemm(a.cuda(), b.cuda(), torch.empty(M, N, dtype=dt, device="cuda"), drop=drop, mode=mode).float()
+        mask = ops.dropout_bwd(torch.ones(M, N, dtype=dt, device="cuda"), torch.empty(M, N, dtype=dt, device="cuda"), drop).float()
+        frac = (mask == 0).float().mean().item()
+        assert abs(frac - 0.3) < 0.02, frac
+        close(dropped, plain * mask, tol(dt, 4), "dropout mask mismatch")
+    seed_dev += 1
+    mask2 = ops.dropout_bwd(torch.ones(M, N, dtype=dt, device="cuda"), torch.empty(M, N, dtype=dt, device="cuda"), drop).float()
+    assert (mask2 != mask).float().mean().item() > 0.2, "device-side seed must change the mask"

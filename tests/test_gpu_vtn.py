@@ -1,0 +1,167 @@
+"""VTN hot path on the GPU vs the reference golden vectors and the CPU oracle (through the C ABI)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vtn_oracle
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "vtn_tiny.npz")
+TINY_HP = dict(idim=80, odim=80, dprenet_layers=2, dprenet_units=16, adim=32, aheads=2, elayers=1, eunits=48,
+               dlayers=2, dunits=48, postnet_layers=3, postnet_filts=5, postnet_chans=16, decoder_reduction_factor=2)
+NO_DROPOUT = dict(dprenet_dropout_rate=0.0, transformer_enc_dropout_rate=0.0, enc_positional_dropout_rate=0.0,
+                  dec_dropout_rate=0.0, dec_positional_dropout_rate=0.0, postnet_dropout_rate=0.0)
+# BASELINE.json configs[0]: VTN-small, batch 4, src 200 / tgt 400
+C1_HP = dict(idim=80, odim=80, adim=256, aheads=4, elayers=2, dlayers=2, eunits=1024, dunits=1024, decoder_reduction_factor=2)
+C1_ILENS, C1_OLENS = [200, 180, 160, 120], [400, 380, 300, 250]
+
+
+def step(eng, xs, ilens, ys, labels, olens):
+    d = eng.device
+    after, before, logits = eng.forward(xs.to(d), ys.to(d), ilens, olens)
+    losses = eng.loss(ys.to(d), labels.to(d))
+    eng.backward(eng.d_after, eng.d_before, eng.d_logits)
+    torch.cuda.synchronize()
+    return after, before, logits, losses
+
+
+def test_golden_tiny_fp32_forward_and_grads():
+    from seq2seq_vc_b200 import VTNEngine
+
+    z = np.load(GOLDEN)
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    eng = VTNEngine(dict(TINY_HP, **NO_DROPOUT), device="cuda:0", bf16=False)
+    eng.load_state_dict(sd)
+    ilens, olens = z["ilens"].tolist(), z["olens"].tolist()
+    xs, ys, labels = (torch.from_numpy(z[k]) for k in ("xs", "ys", "labels"))
+    after, before, logits, losses = step(eng, xs[:, :max(ilens)].contiguous(), ilens, ys[:, :max(olens)].contiguous(),
+                                         labels[:, :max(olens)].contiguous(), olens)
+    # tolerances from BASELINE.json north_star: mel L1 <= 1e-4, attention-weight L1 <= 1e-3
+    assert np.abs(after.cpu().numpy() - z["after_outs"]).mean() <= 1e-4
+    assert np.abs(before.cpu().numpy() - z["before_outs"]).mean() <= 1e-4
+    assert np.abs(logits.cpu().numpy() - z["logits"]).mean() <= 1e-4
+    assert abs(losses[0].item() - float(z["l1_loss"])) <= 1e-4 and abs(losses[1].item() - float(z["bce_loss"])) <= 1e-4
+    np.testing.assert_array_equal(eng.labels_fix.cpu().numpy(), z["labels_out"])
+    nl = eng.hp["dlayers"]
+    for i in range(nl):
+        got = eng.attn[f"decoder.decoders.{nl - 1 - i}.src_attn"].cpu().numpy()
+        assert np.abs(got - z[f"att_ws.{i}"]).mean() <= 1e-3
+    for name in eng.store.names():
+        ref = z["grad." + name]
+        got = eng.store.g(name).cpu().numpy()
+        assert np.abs(got - ref).max() <= 1e-3 * (np.abs(ref).max() + 1e-5), name
+    for k in z.files:
+        if k.startswith("bn_after."):
+            np.testing.assert_allclose(eng.buffers[k[9:]].cpu().numpy(), z[k], rtol=1e-4, atol=1e-6)
+    eng.training = False
+    after_e, _, _ = eng.forward(xs[:, :max(ilens)].contiguous().cuda(), ys[:, :max(olens)].contiguous().cuda(), ilens, olens)
+    assert np.abs(after_e.cpu().numpy() - z["eval_after_outs"]).mean() <= 1e-4
+
+
+@pytest.fixture(scope="module")
+def c1():
+    hp = vtn_oracle.default_hparams(**C1_HP)
+    sd = vtn_oracle.init_state_dict(hp, seed=2)
+    batch = vtn_oracle.synthetic_batch(4, 200, 400, ilens=C1_ILENS, olens=C1_OLENS, seed=1234)
+    out, (l1, bce), grads = vtn_oracle.vtn_loss_and_grads(sd, hp, *batch)
+    return hp, sd, batch, out, float(l1), float(bce), grads
+
+
+def test_c1_vtn_small_fp32_parity(c1):
+    """BASELINE configs[0]: fp32 CUDA path vs the CPU oracle; mel L1 <= 1e-4, attention L1 <= 1e-3."""
+    from seq2seq_vc_b200 import VTNEngine
+
+    hp, sd, batch, out, l1, bce, grads = c1
+    eng = VTNEngine(dict(C1_HP, **NO_DROPOUT), device="cuda:0", bf16=False)
+    eng.load_state_dict(sd)
+    after, before, logits, losses = step(eng, *batch)
+    assert (after.cpu() - out["after_outs"].detach()).abs().mean().item() <= 1e-4
+    assert (before.cpu() - out["before_outs"].detach()).abs().mean().item() <= 1e-4
+    assert (logits.cpu() - out["logits"].detach()).abs().mean().item() <= 1e-4
+    for name, ref in out["attn"].items():
+        assert (eng.attn[name].cpu() - ref.detach()).abs().mean().item() <= 1e-3, name
+    assert abs(losses[0].item() - l1) <= 1e-4 and abs(losses[1].item() - bce) <= 1e-4
+    for name, ref in grads.items():
+        got = eng.store.g(name).cpu()
+        assert (got - ref).abs().max().item() <= 2e-3 * (ref.abs().max().item() + 1e-5), name
+
+
+def test_c1_vtn_small_bf16_tensor_core_path(c1):
+    """Same step through the bf16 tcgen05 GEMMs: drift against the fp32 oracle is bounded and reported."""
+    from seq2seq_vc_b200 import VTNEngine
+
+    hp, sd, batch, out, l1, bce, grads = c1
+    eng = VTNEngine(dict(C1_HP, **NO_DROPOUT), device="cuda:0", bf16=True)
+    eng.load_state_dict(sd)
+    after, before, logits, losses = step(eng, *batch)
+    drift = (after.float().cpu() - out["after_outs"].detach()).abs().mean().item()
+    print("bf16 after_outs mean abs drift:", drift)
+    assert drift <= 3e-2
+    assert abs(losses[0].item() - l1) <= 3e-2 * max(1.0, l1)
+    cos = []
+    for name, ref in grads.items():
+        if ref.numel() < 1000:
+            continue
+        got = eng.store.g(name).cpu().flatten()
+        cos.append(torch.nn.functional.cosine_similarity(got, ref.flatten(), dim=0).item())
+    print("bf16 gradient cosine: min", min(cos))
+    assert min(cos) >= 0.98
+
+
+def test_drop_in_module_matches_engine_and_trains():
+    from seq2seq_vc_b200 import Seq2SeqLoss, VTN
+
+    hp = dict(idim=80, odim=80, adim=64, aheads=4, elayers=1, dlayers=1, eunits=96, dunits=96, dprenet_units=32,
+              postnet_layers=2, postnet_chans=32, dprenet_dropout_rate=0.0, transformer_enc_dropout_rate=0.0)
+    model = VTN(**hp).to("cuda:0")
+    eng = model.engine
+    for k in ("enc_positional_dropout_rate", "dec_dropout_rate", "dec_positional_dropout_rate", "postnet_dropout_rate"):
+        eng.hp[k] = 0.0
+    keys = set(model.state_dict().keys())
+    assert "encoder.embed.conv.0.weight" in keys and "decoder.decoders.0.src_attn.linear_q.weight" in keys
+    assert "postnet.postnet.0.1.num_batches_tracked" in keys and "encoder.embed.out.1.alpha" in keys
+    assert model.encoder.embed[-1].alpha.shape == ()
+    xs, ilens, ys, labels, olens = vtn_oracle.synthetic_batch(2, 64, 40, ilens=[64, 50], olens=[40, 31], seed=3)
+    crit = Seq2SeqLoss()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    first = None
+    for it in range(8):
+        out = model(xs.cuda(), torch.tensor(ilens), ys.cuda(), labels.cuda(), torch.tensor(olens))
+        assert len(out) == 7 and len(out[6][0]) == 1 and out[6][0][0].shape == (2, 4, 20, 15)
+        assert model.decoder.decoders[0].src_attn.attn is out[6][0][0]
+        l1, bce = crit(*out[:6])
+        loss = l1 + bce
+        opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        first = first if first is not None else loss.item()
+    assert loss.item() < first, (first, loss.item())
+    # oracle check of the module's forward with its own current parameters
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    ohp = vtn_oracle.default_hparams(**{k: v for k, v in hp.items() if "dropout" not in k})
+    model.train()
+    out = model(xs.cuda(), torch.tensor(ilens), ys.cuda(), labels.cuda(), torch.tensor(olens))
+    ref = vtn_oracle.vtn_forward(sd, ohp, xs, ilens, ys, labels, olens, training=True)
+    assert (out[0].cpu() - ref["after_outs"]).abs().mean().item() <= 1e-4
+    assert out[5].tolist() == ref["olens"] and torch.equal(out[4].cpu(), ref["labels"])
+
+
+def test_fused_train_step_decreases_loss_with_dropout_bf16():
+    from seq2seq_vc_b200 import VTN, VTNTrainStep
+
+    torch.manual_seed(0)
+    model = VTN(idim=80, odim=80, adim=64, aheads=4, elayers=2, dlayers=2, eunits=128, dunits=128, dprenet_units=32,
+                postnet_chans=32, compute_dtype="bf16", device="cuda:0")
+    stepper = VTNTrainStep(model, lr=1e-3, warmup_steps=1)
+    xs, ilens, ys, labels, olens = vtn_oracle.synthetic_batch(4, 80, 60, ilens=[80, 70, 66, 50], olens=[60, 55, 41, 30], seed=9)
+    xs, ys, labels = xs.cuda(), ys.cuda(), labels.cuda()
+    hist = []
+    for it in range(30):
+        losses = stepper(xs, ilens, ys, labels, olens)
+        hist.append(losses.sum().item())
+    assert np.isfinite(hist).all()
+    assert np.mean(hist[-5:]) < np.mean(hist[:5]), hist

@@ -1,0 +1,76 @@
+"""The CPU oracle reproduces the committed golden vectors dumped from the live reference."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import logmel_oracle, mas_oracle, vtn_oracle
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TINY_HP = dict(idim=80, odim=80, dprenet_layers=2, dprenet_units=16, adim=32, aheads=2, elayers=1, eunits=48,
+               dlayers=2, dunits=48, postnet_layers=3, postnet_filts=5, postnet_chans=16, decoder_reduction_factor=2)
+
+
+def test_vtn_oracle_forward_loss_grads():
+    z = np.load(os.path.join(GOLD, "vtn_tiny.npz"))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    out, (l1, bce), grads = vtn_oracle.vtn_loss_and_grads(sd, TINY_HP, torch.from_numpy(z["xs"]), z["ilens"].tolist(),
+                                                          torch.from_numpy(z["ys"]), torch.from_numpy(z["labels"]),
+                                                          z["olens"].tolist())
+    assert np.abs(out["after_outs"].detach().numpy() - z["after_outs"]).max() <= 2e-5
+    assert np.abs(out["before_outs"].detach().numpy() - z["before_outs"]).max() <= 2e-5
+    assert np.abs(out["logits"].detach().numpy() - z["logits"]).max() <= 2e-5
+    assert abs(float(l1) - float(z["l1_loss"])) <= 1e-6 and abs(float(bce) - float(z["bce_loss"])) <= 1e-6
+    np.testing.assert_array_equal(out["labels"].numpy(), z["labels_out"])
+    assert out["olens"] == z["olens_out"].tolist() and out["ilens_ds_st"] == z["ilens_ds_st"].tolist()
+    for i, a in enumerate(out["att_ws"]):
+        assert np.abs(a.detach().numpy() - z[f"att_ws.{i}"]).max() <= 1e-6
+    for k, g in grads.items():
+        ref = z["grad." + k]
+        assert np.abs(g.numpy() - ref).max() <= 2e-4 * (np.abs(ref).max() + 1e-5), k
+
+
+def test_mas_oracle_matches_reference_numba():
+    z = np.load(os.path.join(GOLD, "mas.npz"))
+    keys = [k for k in z.files if k.startswith("lp.")]
+    assert len(keys) >= 20
+    for k in keys:
+        lp = z[k]
+        ref = z["path." + k[3:]]
+        np.testing.assert_array_equal(mas_oracle.mas_path_py(lp), ref)
+        paths, ds = mas_oracle.mas_batch_c(lp[None], [lp.shape[1]], [lp.shape[0]])
+        np.testing.assert_array_equal(paths[0], ref)
+    ds, bin_loss, _ = mas_oracle.viterbi_decode_oracle(z["vd_lp"], z["vd_tl"], z["vd_fl"])
+    np.testing.assert_array_equal(ds, z["vd_ds"])
+    assert abs(bin_loss - float(z["vd_bin_loss"])) <= 1e-6
+
+
+def test_reference_docstring_kats():
+    z = np.load(os.path.join(GOLD, "kats.npz"))
+    np.testing.assert_array_equal(~vtn_oracle.non_pad_mask([5, 3, 2], 5).numpy(), z["pad_mask_532"].astype(bool))
+    np.testing.assert_array_equal(vtn_oracle.causal_mask(3).numpy(), z["subsequent_mask_3"].astype(bool))
+    # guided attention matrix examples of losses/guided_attention_loss.py:72-90
+    def ga(olen, ilen, sigma=0.4):
+        t = np.arange(olen)[:, None] / olen
+        s = np.arange(ilen)[None, :] / ilen
+        return 1 - np.exp(-((s - t) ** 2) / (2 * sigma * sigma))
+    np.testing.assert_allclose(ga(5, 5), z["ga_5x5"], atol=1e-6)
+    np.testing.assert_allclose(ga(6, 3), z["ga_6x3"], atol=1e-6)
+
+
+def test_mel_filterbank_against_torchaudio():
+    ta = pytest.importorskip("torchaudio")
+    for sr, n_fft in ((48000, 2048), (16000, 1024), (24000, 2048)):
+        ours = logmel_oracle.mel_basis(sr, n_fft, 80, 0.0, sr / 2)
+        theirs = ta.functional.melscale_fbanks(n_fft // 2 + 1, 0.0, sr / 2, 80, sr, norm="slaney", mel_scale="slaney").T.numpy()
+        np.testing.assert_allclose(ours, theirs, atol=2e-6)
+
+
+def test_product_filterbank_and_window_match_oracle():
+    from seq2seq_vc_b200.api import hann_window, mel_filterbank
+
+    for sr, n_fft, fmin, fmax in ((48000, 2048, 0.0, 24000.0), (16000, 1024, 80.0, 7600.0)):
+        np.testing.assert_allclose(mel_filterbank(sr, n_fft, 80, fmin, fmax), logmel_oracle.mel_basis(sr, n_fft, 80, fmin, fmax), atol=1e-7)
+    np.testing.assert_allclose(hann_window(2048, None), logmel_oracle.hann_padded(2048, None).astype(np.float32), atol=1e-7)
+    np.testing.assert_allclose(hann_window(2048, 1200), logmel_oracle.hann_padded(2048, 1200).astype(np.float32), atol=1e-7)
