@@ -36,7 +36,7 @@ extern "C" {
 #define S2S_F32 0
 #define S2S_BF16 1
 
-#define S2S_ABI_VERSION 4
+#define S2S_ABI_VERSION 5
 
 const char* s2s_last_error(void);
 int s2s_abi_version(void);
@@ -44,6 +44,9 @@ int s2s_abi_version(void);
 int s2s_device_check(void);
 /* number of kernel launches issued through this library by the calling process (for bench.py) */
 int64_t s2s_launch_count(void);
+/* number of s2s_gemm(mode = 1) calls that could not be described to TMA (unaligned strides, N < 8)
+ * and were served by the CUDA-core kernel instead */
+int64_t s2s_tc_fallback_count(void);
 
 /* Counter-based dropout: element idx is dropped iff hash(seed', stream, idx) < p * 2^32 where
  * seed' = seed + (seed_dev ? *seed_dev : 0); kept values are scaled by 1/(1-p).  Backward kernels

@@ -1,5 +1,503 @@
-// placeholder: replaced by the tcgen05 kernel
+// bf16 tensor-core GEMM for sm_100a: TMA -> shared memory -> tcgen05.mma (TMEM accumulators) ->
+// tcgen05.ld epilogue.  Backs s2s_gemm(mode = 1).
+//
+// One persistent CTA per SM, 6 warps:
+//   warp 0      TMA producer   (cp.async.bulk.tensor, 128B-swizzled boxes, mbarrier complete_tx)
+//   warp 1      MMA issuer     (one lane issues tcgen05.mma 128 x BN x 16, commits to mbarriers);
+//               also owns the TMEM allocation (2 accumulator stages x 128 fp32 columns)
+//   warps 2-5   epilogue       (tcgen05.ld 32 lanes x 16 columns, fused alpha / bias / relu / dropout /
+//               residual / accumulate / row-mask, vectorised global stores or fp32 red.add for split-K)
+// Pipelines: STAGES-deep smem ring (full/empty mbarriers) between TMA and MMA, 2-deep TMEM ring
+// (tmem_full/tmem_empty) between MMA and epilogue, static round-robin tile scheduler.
+//
+// Operands are described by 4-D TMA tensor maps built per call from the s2s_gemm_t strides, so the
+// same kernel serves plain Linear layers, the head-strided attention views (B, H batches),
+// transposed ("MN-major") operands of the weight-gradient GEMMs, and the `taps` convolution form
+// (the tap index is a TMA coordinate: A rows shift by t, B selects weight slice t).
+// K / M / N tails are handled by TMA zero fill; nothing is padded in HBM.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
 #include "common.cuh"
+
 namespace s2s {
-int gemm_tc(const s2s_gemm_t& g, cudaStream_t st) { return set_error(S2S_ERR_UNSUPPORTED, "gemm_tc: not built"); }
+
+int gemm_simt(const s2s_gemm_t& g, cudaStream_t st);
+
+namespace tc {
+
+constexpr int BM = 128, BK = 64, MAX_BN = 128, STAGES = 6, UMMA_K = 16;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = MAX_BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int TMEM_COLS = 256;
+constexpr int NUM_THREADS = 192;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct Params {
+    CUtensorMap tmA, tmB;
+    int M, N, K, taps, batch1, batch2;
+    int a_mn, b_mn;          // 1 = operand contiguous along M / N ("MN-major"), 0 = along K
+    int BN;                  // N tile (multiple of 16, <= 128)
+    int mt, nt, kb_per_tap, kb_total, splits;
+    void* C; int c_f32; long c_rs, c_bs1, c_bs2;
+    const void* R;
+    const float* bias;
+    float alpha;
+    int relu, accumulate, atomic_out;
+    Dropout drop;
+    int mask_period, mask_offset, mask_lo, mask_hi;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor (SWIZZLE_128B, sm_100 version field = 1)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+    return d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------
+struct Item {
+    int b1, b2, m0, n0, kb0, kb1;
+};
+__device__ __forceinline__ Item decode_item(const Params& p, long item) {
+    Item it;
+    int split = (int)(item % p.splits);
+    long tile = item / p.splits;
+    int ntile = (int)(tile % p.nt);
+    tile /= p.nt;
+    int mtile = (int)(tile % p.mt);
+    int bz = (int)(tile / p.mt);
+    it.b1 = bz / p.batch2;
+    it.b2 = bz % p.batch2;
+    it.m0 = mtile * BM;
+    it.n0 = ntile * p.BN;
+    int per = (p.kb_total + p.splits - 1) / p.splits;
+    it.kb0 = split * per;
+    it.kb1 = min(p.kb_total, it.kb0 + per);
+    return it;
+}
+
+template <typename TC>
+__device__ __forceinline__ void epilogue_chunk(const Params& p, const Dropout& drop, const uint32_t (&acc)[16], TC* __restrict__ Cb,
+                                               const TC* __restrict__ Rb, int m, int n_base, long batch_lin, bool row_ok) {
+    // 16 consecutive columns of one output row
+    TC* dst = Cb + (long)m * p.c_rs + n_base;
+    const TC* rsrc = Rb ? Rb + (long)m * p.c_rs + n_base : nullptr;
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]) * p.alpha;
+    const int nvalid = min(16, p.N - n_base);
+    if (p.atomic_out) {
+        if (!row_ok) return;
+        for (int j = 0; j < nvalid; ++j) atomicAdd(reinterpret_cast<float*>(dst) + j, v[j]);
+        return;
+    }
+    if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (j < nvalid) v[j] += p.bias[n_base + j];
+    }
+    if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (drop.thresh != 0u) {
+        const uint64_t base = (uint64_t)((batch_lin + m) * (long)p.N + n_base);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] *= dropout_factor(drop, base + j);
+    }
+    const bool vec = (nvalid == 16) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
+                     (!rsrc || (reinterpret_cast<uintptr_t>(rsrc) & 15) == 0);
+    if (vec) {
+        if (rsrc) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float t[4];
+                Vec4<TC>::load(rsrc + 4 * q, t);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[4 * q + j] += t[j];
+            }
+        }
+        if (p.accumulate) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float t[4];
+                Vec4<TC>::load(dst + 4 * q, t);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[4 * q + j] += t[j];
+            }
+        }
+        if (!row_ok) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = 0.f;
+        }
+        if (sizeof(TC) == 2) {
+            uint32_t w[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                w[j] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            uint4* d4 = reinterpret_cast<uint4*>(dst);
+            d4[0] = make_uint4(w[0], w[1], w[2], w[3]);
+            d4[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        } else {
+            float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) d4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+    } else {
+        for (int j = 0; j < nvalid; ++j) {
+            float x = v[j];
+            if (rsrc) x += to_f<TC>(rsrc[j]);
+            if (p.accumulate) x += to_f<TC>(dst[j]);
+            if (!row_ok) x = 0.f;
+            dst[j] = from_f<TC>(x);
+        }
+    }
+}
+
+template <typename TC>
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ Params p) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;                    // SWIZZLE_128B tiles need 1024 B alignment
+    const uint32_t bars = base + STAGES * STAGE_BYTES;               // full[STAGES], empty[STAGES], tfull[2], tempty[2]
+    __shared__ uint32_t tmem_base_slot;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
+    auto tempty_bar = [&](int s) { return bars + 8u * (2 * STAGES + 2 + s); };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    const long total = (long)p.batch1 * p.batch2 * p.mt * p.nt * p.splits;
+    const int BN = p.BN;
+    const int b_boxes = p.b_mn ? (BN + 63) / 64 : 1;
+    const uint32_t tx_bytes = (uint32_t)A_BYTES + (uint32_t)(p.b_mn ? b_boxes * 8192 : BN * 128);
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long item = blockIdx.x; item < total; item += gridDim.x) {
+                const Item it = decode_item(p, item);
+                for (int kb = it.kb0; kb < it.kb1; ++kb) {
+                    const int t = kb / p.kb_per_tap;
+                    const int kk = (kb - t * p.kb_per_tap) * BK;
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+                    mbar_expect_tx(full_bar(stage), tx_bytes);
+                    if (p.a_mn) {
+                        tma_load_4d(sa, &p.tmA, full_bar(stage), it.m0, kk, it.b2, it.b1);
+                        tma_load_4d(sa + 8192, &p.tmA, full_bar(stage), it.m0 + 64, kk, it.b2, it.b1);
+                    } else {
+                        tma_load_4d(sa, &p.tmA, full_bar(stage), kk, it.m0 + t, it.b2, it.b1);
+                    }
+                    if (p.b_mn) {
+                        for (int j = 0; j < b_boxes; ++j)
+                            tma_load_4d(sb + 8192 * j, &p.tmB, full_bar(stage), it.n0 + 64 * j, kk, it.b2, it.b1);
+                    } else {
+                        tma_load_4d(sb, &p.tmB, full_bar(stage), kk, it.n0, p.taps > 1 ? t : it.b2, it.b1);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        int stage = 0;
+        uint32_t phase = 0;
+        long n_items = 0;
+        for (long item = blockIdx.x; item < total; item += gridDim.x, ++n_items) {
+            const Item it = decode_item(p, item);
+            const int as = (int)(n_items & 1);
+            const uint32_t aphase = (uint32_t)((n_items >> 1) & 1);
+            mbar_wait(tempty_bar(as), aphase ^ 1u);
+            tcgen05_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(as * MAX_BN);
+            for (int kb = it.kb0; kb < it.kb1; ++kb) {
+                const int t = kb / p.kb_per_tap;
+                const int kk = (kb - t * p.kb_per_tap) * BK;
+                const int ksteps = (min(BK, p.K - kk) + UMMA_K - 1) / UMMA_K;
+                mbar_wait(full_bar(stage), phase);
+                tcgen05_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+                    for (int k = 0; k < ksteps; ++k) {
+                        // K-major: 16 bf16 = 32 B inside the 128 B swizzle row; MN-major: 16 k-rows of 128 B
+                        const uint64_t adesc = p.a_mn ? smem_desc(sa + k * 2048, 8192, 1024) : smem_desc(sa + k * 32, 16, 1024);
+                        const uint64_t bdesc = p.b_mn ? smem_desc(sb + k * 2048, 8192, 1024) : smem_desc(sb + k * 32, 16, 1024);
+                        umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > it.kb0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(stage));
+                    if (kb == it.kb1 - 1) umma_commit(tfull_bar(as));
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else {
+        // ================= epilogue =================
+        Dropout drop = p.drop;
+        dropout_resolve(drop);
+        const int quarter = warp & 3;             // TMEM lane quarter this warp may access
+        long n_items = 0;
+        for (long item = blockIdx.x; item < total; item += gridDim.x, ++n_items) {
+            const Item it = decode_item(p, item);
+            const int as = (int)(n_items & 1);
+            const uint32_t aphase = (uint32_t)((n_items >> 1) & 1);
+            mbar_wait(tfull_bar(as), aphase);
+            tcgen05_fence_after();
+            const int m = it.m0 + quarter * 32 + lane;
+            const int bz = it.b1 * p.batch2 + it.b2;
+            TC* Cb = reinterpret_cast<TC*>(p.C) + it.b1 * p.c_bs1 + it.b2 * p.c_bs2;
+            const TC* Rb = p.R ? reinterpret_cast<const TC*>(p.R) + it.b1 * p.c_bs1 + it.b2 * p.c_bs2 : nullptr;
+            bool row_ok = true;
+            if (p.mask_period > 0) {
+                int ph = (m + p.mask_offset) % p.mask_period;
+                row_ok = (ph >= p.mask_lo) && (ph < p.mask_hi);
+            }
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * MAX_BN);
+            for (int c = 0; c < BN; c += 16) {
+                uint32_t acc[16];
+                tmem_ld16(taddr + c, acc);
+                tmem_ld_wait();
+                const int n_base = it.n0 + c;
+                if (m < p.M && n_base < p.N) epilogue_chunk<TC>(p, drop, acc, Cb, Rb, m, n_base, (long)bz * p.M, row_ok);
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(as));
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: tensor maps + launch
+// ---------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    });
+    return fn;
+}
+
+// dims/strides in elements, innermost first; stride[0] must be 1
+static bool make_map(CUtensorMap* map, const void* base, const long (&dim)[4], const long (&stride)[4], int box0, int box1) {
+    auto enc = get_encode();
+    if (!enc) return false;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return false;
+    cuuint64_t gdim[4], gstr[3];
+    for (int i = 0; i < 4; ++i) {
+        if (dim[i] <= 0 || dim[i] > 0xFFFFFFFFL) return false;
+        gdim[i] = (cuuint64_t)dim[i];
+    }
+    long natural = dim[0];
+    for (int i = 1; i < 4; ++i) {
+        long s = stride[i];
+        if (dim[i] == 1 || s <= 0) s = natural;       // size-1 (or broadcast over size 1) dims: any legal stride
+        if (dim[i] > 1 && stride[i] <= 0) return false;
+        if ((s * 2) % 16 != 0) {
+            if (dim[i] == 1) s = (s + 7) / 8 * 8; else return false;
+        }
+        gstr[i - 1] = (cuuint64_t)s * 2;
+        natural = s * dim[i];
+    }
+    cuuint32_t box[4] = {(cuuint32_t)box0, (cuuint32_t)box1, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+static int pick_bn(int N) {
+    int best = 128;
+    long best_cost = -1;
+    for (int bn = 128; bn >= 16; bn -= 16) {
+        long tiles = (N + bn - 1) / bn;
+        long cost = tiles * bn * 8 + tiles * 24;       // padded columns + a per-tile overhead term
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
+    }
+    return best;
+}
+
+static std::once_flag g_attr_once;
+static cudaError_t g_attr_err = cudaSuccess;
+
+}  // namespace tc
+
+static long g_tc_fallbacks = 0;
+
+int gemm_tc(const s2s_gemm_t& g, cudaStream_t st) {
+    using namespace tc;
+    const bool dt_ok = g.a_dtype == S2S_BF16 && g.b_dtype == S2S_BF16;
+    const bool taps_ok = g.taps == 1 || (g.a_cs == 1 && g.b_cs == 1 && g.batch1 * g.batch2 == 1);
+    if (!dt_ok) return set_error(S2S_ERR_UNSUPPORTED, "gemm_tc: operands must be bf16 (a=%d b=%d)", g.a_dtype, g.b_dtype);
+    Params p;
+    memset(&p, 0, sizeof(p));
+    bool ok = taps_ok && g.K > 0 && g.N >= 8;
+    p.a_mn = (g.a_cs != 1) ? 1 : 0;      // contiguous along M
+    p.b_mn = (g.b_cs != 1) ? 1 : 0;      // contiguous along N
+    if (g.K == 1) { p.a_mn = (g.a_rs == 1); p.b_mn = (g.b_rs == 1); }
+    p.BN = pick_bn(g.N);
+    if (ok) {
+        const long rowsA = (long)g.M + g.taps - 1;
+        if (!p.a_mn) {
+            long dim[4] = {g.K, rowsA, g.batch2, g.batch1}, str[4] = {1, g.a_rs, g.a_bs2, g.a_bs1};
+            ok = make_map(&p.tmA, g.A, dim, str, BK, BM);
+        } else {
+            long dim[4] = {g.M, g.K, g.batch2, g.batch1}, str[4] = {1, g.a_cs, g.a_bs2, g.a_bs1};
+            ok = make_map(&p.tmA, g.A, dim, str, 64, BK);
+        }
+    }
+    if (ok) {
+        if (!p.b_mn) {
+            if (g.taps > 1) {
+                long dim[4] = {g.K, g.N, g.taps, 1}, str[4] = {1, g.b_rs, g.b_ts, 0};
+                ok = make_map(&p.tmB, g.B, dim, str, BK, p.BN);
+            } else {
+                long dim[4] = {g.K, g.N, g.batch2, g.batch1}, str[4] = {1, g.b_rs, g.b_bs2, g.b_bs1};
+                ok = make_map(&p.tmB, g.B, dim, str, BK, p.BN);
+            }
+        } else {
+            long dim[4] = {g.N, g.K, g.batch2, g.batch1}, str[4] = {1, g.b_cs, g.b_bs2, g.b_bs1};
+            ok = make_map(&p.tmB, g.B, dim, str, 64, BK);
+        }
+    }
+    if (!ok) {   // shapes TMA cannot describe (unaligned strides, N < 8, K == 0): CUDA-core kernel, counted
+        ++g_tc_fallbacks;
+        return gemm_simt(g, st);
+    }
+    p.M = g.M; p.N = g.N; p.K = g.K; p.taps = g.taps; p.batch1 = g.batch1; p.batch2 = g.batch2;
+    p.mt = (int)ceil_div_l(g.M, BM);
+    p.nt = (int)ceil_div_l(g.N, p.BN);
+    p.kb_per_tap = (int)ceil_div_l(g.K, BK);
+    p.kb_total = p.kb_per_tap * g.taps;
+    p.C = g.C; p.c_f32 = (g.c_dtype == S2S_F32); p.c_rs = g.c_rs; p.c_bs1 = g.c_bs1; p.c_bs2 = g.c_bs2;
+    p.R = g.R; p.bias = g.bias; p.alpha = g.alpha; p.relu = g.relu; p.accumulate = g.accumulate;
+    p.drop = make_dropout(&g.drop);
+    p.mask_period = g.mask_period; p.mask_offset = g.mask_offset; p.mask_lo = g.mask_lo; p.mask_hi = g.mask_hi;
+    // split-K for skinny weight-gradient GEMMs: fp32 accumulate-in-place output, no other epilogue work
+    const long tiles = (long)g.batch1 * g.batch2 * p.mt * p.nt;
+    p.splits = 1;
+    const bool plain = p.c_f32 && g.accumulate && !g.bias && !g.R && !g.relu && p.drop.thresh == 0u && g.mask_period == 0;
+    if (plain && tiles * 2 <= num_sms() && p.kb_total >= 8) {
+        long s = num_sms() / tiles;
+        long max_s = p.kb_total / 4;
+        if (s > max_s) s = max_s;
+        if (s > 1) { p.splits = (int)s; p.atomic_out = 1; }
+    }
+    // every split must own at least one k-block
+    if (p.splits > 1) {
+        int per = (p.kb_total + p.splits - 1) / p.splits;
+        p.splits = (p.kb_total + per - 1) / per;
+    }
+    std::call_once(g_attr_once, [] {
+        g_attr_err = cudaFuncSetAttribute(gemm_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (g_attr_err == cudaSuccess)
+            g_attr_err = cudaFuncSetAttribute(gemm_tc_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    });
+    if (g_attr_err != cudaSuccess) return set_error(S2S_ERR_CUDA, "gemm_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(g_attr_err));
+    long items = tiles * p.splits;
+    unsigned grid = (unsigned)(items < num_sms() ? items : num_sms());
+    if (p.c_f32) gemm_tc_kernel<float><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
+    else gemm_tc_kernel<bf16><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
+    S2S_LAUNCH_OK();
+    return S2S_OK;
+}
+
+long tc_fallback_count() { return g_tc_fallbacks; }
+
+}  // namespace s2s
+
+extern "C" int64_t s2s_tc_fallback_count(void) { return (int64_t)s2s::tc_fallback_count(); }

@@ -562,11 +562,12 @@ class VTNEngine:
                     ops.add(st.g(pn + ".1.bias"), sums[:oc], st.g(pn + ".1.bias"))
                     ops.add(st.g(pn + ".1.weight"), sums[oc:], st.g(pn + ".1.weight"))
                 M = B * Lp - 2 * halo
-                # dWp[oc][(t, ic)] = sum_m dz[m + halo][oc] * xin[m + t][ic]  (overlapping-window view of xin)
-                gwp = self._scratch("post.gwp", (oc, k * ic), _f32)
-                xin_flat = xin.view(B * Lp * ic)
-                win = torch.as_strided(xin_flat, (k * ic, M), (1, ic))
-                ops.gemm(dz.view(B * Lp, oc)[halo:halo + M].t(), win, gwp, mode=self.mode)
+                # dWp[oc][t][ic] = sum_m dz[m + halo][oc] * xin[m + t][ic]
+                gwp = self._scratch("post.gwp", (oc, k, ic), _f32)
+                gwp.zero_()
+                dzt = dz.view(B * Lp, oc)[halo:halo + M].t()
+                for t in range(k):      # one skinny (oc x ic x M) GEMM per tap; split-K inside the kernel
+                    ops.gemm(dzt, xin.view(B * Lp, ic)[t:t + M].t(), gwp[:, t, :], accumulate=True, mode=self.mode)
                 ops.transpose_last2(gwp, st.g(pn + ".0.weight"), oc, k, ic, accumulate=True)
                 # dxin = conv_transpose(dz): taps-GEMM with the flipped, transposed kernel
                 dxin = self._scratch(f"post.dx{i % 2}", (B, Lp, ic))

@@ -310,7 +310,8 @@ def test_dropout_is_consistent_between_forward_and_backward(ops, dt):
         mask = ops.dropout_bwd(torch.ones(M, N, dtype=dt, device="cuda"), torch.empty(M, N, dtype=dt, device="cuda"), drop).float()
         frac = (mask == 0).float().mean().item()
         assert abs(frac - 0.3) < 0.02, frac
-        close(dropped, plain * mask, tol(dt, 4), "dropout mask mismatch")
+        err = ((dropped - plain * mask).abs() / (1 + plain.abs())).max().item()
+        assert err <= tol(dt, 2), f"dropout mask mismatch {err}"
     seed_dev += 1
     mask2 = ops.dropout_bwd(torch.ones(M, N, dtype=dt, device="cuda"), torch.empty(M, N, dtype=dt, device="cuda"), drop).float()
     assert (mask2 != mask).float().mean().item() > 0.2, "device-side seed must change the mask"
