@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""Benchmark of the seq2seq-vc training hot path on B200 (contract: see the task statement / DESIGN.md).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c2b64]
+
+One "step" = one full VTN training step (forward + Seq2SeqLoss + backward + gradient all-reduce +
+clip_grad_norm + Adam) over one synthetic padded mel batch.  Default workload = BASELINE.json
+configs[1]: VTN-base (6+6 layers, d=384, 8 heads, r=2), bf16 compute, batch 32 x (512 -> 1024
+frames, 80 mel) per GPU.  Metric: target mel-frames / second, whole job (sum over GPUs).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (model hparams, per-GPU batch, T, L, bf16)
+    "c2": (dict(idim=80, odim=80, adim=384, aheads=8, elayers=6, dlayers=6, eunits=1536, dunits=1536, decoder_reduction_factor=2),
+           32, 512, 1024, True, "VTN-base 6+6 d384 h8 r2, B32 x (512->1024, 80-mel), bf16"),
+    "c2b64": (dict(idim=80, odim=80, adim=384, aheads=8, elayers=6, dlayers=6, eunits=1536, dunits=1536, decoder_reduction_factor=2),
+              64, 512, 1024, True, "VTN-base 6+6 d384 h8 r2, B64 x (512->1024, 80-mel), bf16"),
+    "c1": (dict(idim=80, odim=80, adim=256, aheads=4, elayers=2, dlayers=2, eunits=1024, dunits=1024, decoder_reduction_factor=2),
+           4, 200, 400, False, "VTN-small 2+2 d256 h4 r2, B4 x (200->400, 80-mel), fp32"),
+}
+METRIC = "target mel-frames/sec, VTN-base enc-dec training step (80-mel, src512/tgt1024)"
+UNIT = "frames/s"
+
+
+def vtn_fwd_flops(hp, T, L):
+    """Forward FLOPs per utterance (SURVEY.md section 8d formulas)."""
+    d, r = hp["adim"], hp["decoder_reduction_factor"]
+    Ue, Ud = hp["eunits"], hp["dunits"]
+    T1, F1 = (T - 1) // 2, 39
+    T2, F2 = (T1 - 1) // 2, 19
+    Lr = L // r
+    conv = 2 * 9 * d * T1 * F1 + 2 * 9 * d * d * T2 * F2 + 2 * T2 * (d * F2) * d
+    enc = hp["elayers"] * (8 * T2 * d * d + 4 * T2 * T2 * d + 4 * T2 * d * Ue)
+    pre = 2 * Lr * (80 * 256 + 256 * 256 + 256 * d)
+    dec = hp["dlayers"] * (8 * Lr * d * d + 4 * Lr * Lr * d + 4 * Lr * d * d + 4 * T2 * d * d + 4 * Lr * T2 * d + 4 * Lr * d * Ud)
+    heads = 2 * Lr * d * (80 * r + r)
+    post = 2 * 5 * (Lr * r) * (80 * 256 + 3 * 256 * 256 + 256 * 80)
+    return conv + enc + pre + dec + heads + post
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons for this rank's GPU during the timed region."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.15)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        reasons = []
+        for i, name in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")):
+            if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def synthetic_batch(B, T, L, seed):
+    g = torch.Generator().manual_seed(seed)
+    xs = torch.randn(B, T, 80, generator=g)
+    ys = torch.randn(B, L, 80, generator=g)
+    labels = torch.zeros(B, L)
+    labels[:, L - 1:] = 1.0
+    return xs, [T] * B, ys, labels, [L] * B
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_port_steps(hp, B, T, L, steps, warmup):
+    """fwd + Seq2SeqLoss + bwd + clip + Adam of the oracle (plain torch fp32 CPU) on B utterances."""
+    from oracle import vtn_oracle
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    ohp = vtn_oracle.default_hparams(**hp)
+    sd = vtn_oracle.init_state_dict(ohp, seed=0)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.dtype.is_floating_point and "running_" not in k}
+    full = dict(sd)
+    full.update(params)
+    opt = torch.optim.Adam(list(params.values()), lr=8e-5)
+    xs, ilens, ys, labels, olens = synthetic_batch(B, T, L, 1234)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = vtn_oracle.vtn_forward(full, ohp, xs, ilens, ys, labels, olens, training=True)
+        l1, bce = vtn_oracle.seq2seq_loss(out["after_outs"], out["before_outs"], out["logits"], out["ys"], out["labels"], out["olens"])
+        opt.zero_grad()
+        (l1 + bce).backward()
+        torch.nn.utils.clip_grad_norm_(list(params.values()), 1.0)
+        opt.step()
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    return sum(times) / len(times)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    hp, B, T, L, bf16, desc = WORKLOADS[args.workload]
+    Bs = min(B, 4)
+    timed = max(1, min(args.steps, 6))      # bounded sample: the CPU arm must end within minutes whatever K is
+    sec = cpu_port_steps(hp, Bs, T, L, timed, max(1, min(args.warmup, 1)))
+    val = Bs * L / sec
+    cores = os.cpu_count() or 1
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "sample": f"{Bs} utterances per step (of {B}); frames/s scales linearly in B",
+                       "timed_steps": timed},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"oracle port of the reference PyTorch-CPU path, {Bs} x ({T}->{L}) per step, {torch.get_num_threads()} threads"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+def gemm_roofline(stepper, batch, dev, table_path=None):
+    """Per-launch CUDA-event timing of every tcgen05 GEMM launch of one (eager) training step."""
+    from seq2seq_vc_b200 import ops
+
+    rec = []
+    orig = ops.gemm
+
+    def timed(a, b, c, **kw):
+        if kw.get("mode", 0) != 1:
+            return orig(a, b, c, **kw)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = orig(a, b, c, **kw)
+        e1.record()
+        M = kw.get("M") or c.shape[-2]
+        nb = 1
+        for s in c.shape[:-2]:
+            nb *= s
+        key = (nb, M, c.shape[-1], a.shape[-1], kw.get("taps", 1), "Amn" if a.stride(-1) != 1 else "Ak",
+               "Bmn" if b.stride(-1) != 1 else "Bk", str(c.dtype).replace("torch.", ""), bool(kw.get("accumulate")))
+        rec.append((2.0 * nb * M * c.shape[-1] * a.shape[-1] * kw.get("taps", 1), e0, e1, key))
+        return out
+
+    ops.gemm = timed
+    try:
+        eng = stepper.engine
+        xs, ilens, ys, labels, olens = batch
+        eng.prepare(xs.shape[0], xs.shape[1], ys.shape[1], ilens, olens)
+        for _ in range(2):
+            rec.clear()
+            stepper._fwd_bwd(xs, ys, labels)
+            torch.cuda.synchronize()
+    finally:
+        ops.gemm = orig
+    flops = sum(r[0] for r in rec)
+    ms = sum(r[1].elapsed_time(r[2]) for r in rec)
+    if table_path:
+        agg = {}
+        for f, a, b, key in rec:
+            e = agg.setdefault(key, [0, 0.0, 0.0])
+            e[0] += 1
+            e[1] += a.elapsed_time(b)
+            e[2] += f
+        with open(table_path, "w") as fh:
+            fh.write("# (batch, M, N, K, taps, A-major, B-major, C dtype, accumulate): launches, total ms, TFLOP/s\n")
+            for key, (n, t, f) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                fh.write(f"{key}: n={n} ms={t:.3f} tflops={f / (t * 1e-3) / 1e12:.1f}\n")
+    return flops, ms, len(rec)
+
+
+def run_ours(args, rank, world):
+    from seq2seq_vc_b200 import VTN, VTNTrainStep, _lib
+
+    hp, B, T, L, bf16, desc = WORKLOADS[args.workload]
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _lib.device_check()
+    model = VTN(**hp, compute_dtype="bf16" if bf16 else "float32", device=dev, seed=0)
+    stepper = VTNTrainStep(model, lr=8e-5, warmup_steps=4000, use_graph=not args.no_graph)
+    xs, ilens, ys, labels, olens = synthetic_batch(B, T, L, 1234 + rank)
+    dxs, dys, dlabels = xs.to(dev), ys.to(dev), labels.to(dev)
+    pxs, pys, plabels = xs.pin_memory(), ys.pin_memory(), labels.pin_memory()
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident inputs: `value`
+    for _ in range(max(args.warmup, 3)):
+        stepper(dxs, ilens, dys, dlabels, olens)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = _lib.launch_count() + stepper.replayed_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        losses = stepper(dxs, ilens, dys, dlabels, olens)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() + stepper.replayed_launches - l0
+    # ---- end to end through the public step API with pinned HOST buffers + loss read-back: `e2e`
+    for _ in range(2):
+        stepper(pxs, ilens, pys, plabels, olens).cpu()
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        host_losses = stepper(pxs, ilens, pys, plabels, olens).cpu()      # D2H read of the step's losses
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+    clocks = sampler.stop()
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    if rank != 0:
+        return
+    assert all(map(lambda v: v == v, host_losses.tolist())), "NaN loss"
+    frames = B * L * world * args.steps
+    value = frames / (ms * 1e-3)
+    e2e = frames / (ms_e2e * 1e-3)
+    pk, pk_src = peaks()
+    flops_step = 3.0 * vtn_fwd_flops(hp, T, L) * B
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if bf16 else "f32", "data": "synthetic",
+            "config": {"workload": desc, "global_batch": B * world, "per_gpu_batch": B, "parallelism": f"dp{world}",
+                       "frames_per_sec_per_gpu": value / world, "cuda_graph": not args.no_graph,
+                       "l2": "per-step working set (activations + 0.5 GB of parameter/optimizer state) exceeds the 126 MB L2; no flush needed",
+                       "losses_last_step": host_losses.tolist(), "model_tflops_per_step": flops_step / 1e12,
+                       "model_tflops_per_sec": flops_step / (ms / args.steps * 1e-3) / 1e12,
+                       "tc_fallbacks": int(_lib.load().s2s_tc_fallback_count())},
+            "clocks": clocks,
+            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": (xs.numel() + ys.numel() + labels.numel()) * 4 + 3 * B * 4, "d2h_bytes_per_step": 8},
+            "gpu_launches": int(launches)}
+    if world == 1:
+        if bf16:
+            gf, gms, n = gemm_roofline(stepper, (dxs, ilens, dys, dlabels, olens), dev, args.gemm_table)
+            peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
+            ach = gf / (gms * 1e-3) / 1e12
+            line["roofline"] = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05.mma bf16, all shapes of one step)", "achieved": ach,
+                                "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": pk_src + " (sustained)",
+                                "launches_per_step": n, "algorithmic_gflop_per_launch_avg": gf / n / 1e9,
+                                "avg_launch_us": gms * 1e3 / n, "gemm_share_of_step": gms / (ms / args.steps),
+                                "how": "CUDA events around every mode-1 s2s_gemm launch of one eager fwd+bwd after the timed region"}
+        if not args.no_cpu_baseline:
+            Bs = min(B, 4)
+            sec = cpu_port_steps(hp, Bs, T, L, 2, 1)
+            line["cpu_baseline"] = {"value": Bs * L / sec, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                                    "sample": f"oracle port of the reference PyTorch-CPU path (fp32), {Bs} x ({T}->{L}) per step, 2 steps after 1 warm-up"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gemm-table", default=None, help="write a per-shape timing table of the tensor-core GEMM launches")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+        torch.distributed.init_process_group("nccl")
+    try:
+        run_ours(args, rank, world)
+    finally:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -36,7 +36,7 @@ extern "C" {
 #define S2S_F32 0
 #define S2S_BF16 1
 
-#define S2S_ABI_VERSION 5
+#define S2S_ABI_VERSION 6
 
 const char* s2s_last_error(void);
 int s2s_abi_version(void);
@@ -102,6 +102,15 @@ int s2s_layernorm_fwd(const void* x, const float* gamma, const float* beta, void
 int s2s_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean,
                       const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta,
                       int64_t rows, int d, int dtype, void* stream);
+
+/* Skinny linear layer with 1 <= N <= 4 output features (the stop-token head prob_out,
+ * models/vtn.py:182,251): y[r, j] = sum_k x[r, k] w[j, k] + bias[j]; x (rows, K) and w (N, K) in
+ * `dtype`.  bwd: dw[j, k] += sum_r dy[r, j] x[r, k] ; dbias[j] += sum_r dy[r, j] ;
+ * dx[r, k] (+)= sum_j dy[r, j] w[j, k].  dw / dbias / dx may each be NULL. */
+int s2s_skinny_linear_fwd(const void* x, const void* w, const float* bias, void* y, int64_t rows, int K, int N,
+                          int dtype, void* stream);
+int s2s_skinny_linear_bwd(const void* dy, const void* x, const void* w, float* dw, float* dbias, void* dx,
+                          int dx_accumulate, int64_t rows, int K, int N, int dtype, void* stream);
 
 /* out[c] += sum_r x[r, c]  (bias gradients); x row stride ld */
 int s2s_colsum(const void* x, int64_t rows, int cols, int64_t ld, float* out, int dtype, void* stream);

@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libs2svc_b200.so")
 
 S2S_F32, S2S_BF16 = 0, 1
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class S2SError(RuntimeError):
@@ -58,6 +58,8 @@ SIGNATURES = {
     "s2s_gemm": (c_int, [POINTER(GemmDesc), c_int, _P]),
     "s2s_layernorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_float, c_int, _P]),
     "s2s_layernorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P]),
+    "s2s_skinny_linear_fwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
+    "s2s_skinny_linear_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int64, c_int, c_int, c_int, _P]),
     "s2s_colsum": (c_int, [_P, c_int64, c_int, c_int64, _P, c_int, _P]),
     "s2s_relu_bwd": (c_int, [_P, _P, _P, c_int64, c_float, c_int, _P]),
     "s2s_dropout_bwd": (c_int, [_P, _P, c_int64, c_int, _DP, c_int, _P]),

@@ -18,7 +18,7 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 import torch
 
-from . import ops
+from . import _lib, ops
 from ._lib import S2SError
 from .vtn_engine import VTNEngine, default_hparams
 
@@ -400,9 +400,11 @@ def logmelfilterbank(audio, sampling_rate, fft_size=1024, hop_size=256, win_leng
 class VTNTrainStep:
     """forward + Seq2SeqLoss + backward (+ gradient all-reduce) + clip + Adam + WarmupLR, device-resident.
 
-    Mirrors ARVCTrainer._train_step for a VTN model; lengths arrive as host ints (the collater's
-    CPU tensors) so the step never synchronises.  With ``use_graph`` the launch sequence of one
-    (B, T, L) signature is captured once in a CUDA graph and replayed.
+    Mirrors ARVCTrainer._train_step (trainers/ar_vc.py:59-112) for a VTN model.  Lengths arrive as
+    host ints (the collater's CPU tensors) so the step never synchronises.  With ``use_graph`` the
+    launch sequence of one (B, T, L) batch shape is captured once into two CUDA graphs
+    (forward+loss+backward | clip+Adam) and replayed; the NCCL gradient all-reduce of the flat
+    gradient buffer runs between them (the path shards by utterance batch, bin/vc_train.py:423-431).
     """
 
     def __init__(self, model, lr: float = 8e-5, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
@@ -416,28 +418,76 @@ class VTNTrainStep:
         self.use_graph = use_graph
         self.pg = process_group
         self.world = 1
-        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(process_group)
         self._graphs: Dict[tuple, tuple] = {}
+        self.replayed_launches = 0      # kernels of this library launched through graph replays
 
     def lr_at(self, step: int) -> float:
         """WarmupLR (schedulers/warmup_lr.py:54-61): lr * warmup^0.5 * min(step^-0.5, step * warmup^-1.5)."""
         s = max(step, 1)
         return self.lr * self.warmup ** 0.5 * min(s ** -0.5, s * self.warmup ** -1.5)
 
-    def _body(self, xs, ys, labels, ilens, olens):
+    # -- the two halves of a step (each is a fixed launch sequence for a given batch shape)
+    def _fwd_bwd(self, xs, ys, labels):
         eng = self.engine
-        eng.forward(xs, ys, ilens, olens)
+        eng.forward(xs, ys)
         eng.loss(ys, labels, self.pos_weight)
         eng.backward(eng.d_after, eng.d_before, eng.d_logits)
+
+    def _allreduce(self):
         if self.world > 1:
-            torch.distributed.all_reduce(eng.store.G, group=self.pg)
-        eng.optimizer_step(self.grad_norm, self.betas, self.eps, self.wd, grad_scale=1.0 / self.world)
+            torch.distributed.all_reduce(self.engine.store.G, group=self.pg)
+
+    def _update(self):
+        self.engine.optimizer_step(self.grad_norm, self.betas, self.eps, self.wd, grad_scale=1.0 / self.world)
 
     def __call__(self, xs, ilens, ys, labels, olens):
-        """xs (B,T,idim), ys (B,L,odim), labels (B,L): float32 CUDA tensors trimmed to the batch maxima."""
+        """xs (B,T,idim), ys (B,L,odim), labels (B,L): float32 tensors trimmed to the batch maxima, either
+        CUDA-resident or pinned host memory (copied with non-blocking H2D).  Returns the device
+        tensor (l1_loss, bce_loss) of this step without synchronising."""
         eng = self.engine
         self.steps += 1
         eng.lr_dev.fill_(self.lr_at(self.steps))
-        self._body(xs, ys, labels, ilens, olens)
+        B, T, L = xs.shape[0], xs.shape[1], ys.shape[1]
+        eng.training = True
+        eng.prepare(B, T, L, ilens, olens)
+        if not self.use_graph:
+            if not xs.is_cuda:
+                xs, ys, labels = (t.to(eng.device, non_blocking=True) for t in (xs, ys, labels))
+            self._fwd_bwd(xs, ys, labels)
+            self._allreduce()
+            self._update()
+            return eng.losses
+        key = (B, T, L)
+        entry = self._graphs.get(key)
+        if entry is None:
+            sx = torch.empty(xs.shape, dtype=_f32, device=eng.device)
+            sy = torch.empty(ys.shape, dtype=_f32, device=eng.device)
+            sl = torch.empty(labels.shape, dtype=_f32, device=eng.device)
+            for dst, src in ((sx, xs), (sy, ys), (sl, labels)):
+                dst.copy_(src, non_blocking=True)
+            # one eager step first: allocates every activation buffer outside the graph's private pool
+            self._fwd_bwd(sx, sy, sl)
+            self._allreduce()
+            self._update()
+            torch.cuda.synchronize()
+            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
+            with torch.cuda.graph(g1):
+                self._fwd_bwd(sx, sy, sl)
+            with torch.cuda.graph(g2):
+                self._update()
+            self._graphs[key] = (g1, g2, sx, sy, sl, _lib.launch_count() - n0)
+            return eng.losses
+        g1, g2, sx, sy, sl, n_kernels = entry
+        if eng.p16_dirty:
+            eng.sync_shadow()
+        self.replayed_launches += n_kernels
+        for dst, src in ((sx, xs), (sy, ys), (sl, labels)):
+            if src.data_ptr() != dst.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        g1.replay()
+        self._allreduce()
+        g2.replay()
         return eng.losses

@@ -136,12 +136,12 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 // counter-based dropout RNG: keep(idx) is a pure function of (seed, stream, idx) so the backward
 // pass regenerates the forward mask instead of storing it.  p is the DROP probability.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t mix32(uint64_t x) {
-    // splitmix64 finaliser
-    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
-    x ^= x >> 27; x *= 0x94d049bb133111ebull;
-    x ^= x >> 31;
-    return (uint32_t)(x >> 32);
+__device__ __forceinline__ uint32_t mix32(uint32_t h) {
+    // murmur3 32-bit finaliser (bijective, full avalanche): 5 integer instructions
+    h ^= h >> 16; h *= 0x85ebca6bu;
+    h ^= h >> 13; h *= 0xc2b2ae35u;
+    h ^= h >> 16;
+    return h;
 }
 struct Dropout {
     float p;          // drop probability; 0 disables
@@ -169,8 +169,11 @@ __device__ __forceinline__ void dropout_resolve(Dropout& d) {
 // returns the multiplicative factor (0 or scale) for element idx
 __device__ __forceinline__ float dropout_factor(const Dropout& d, uint64_t idx) {
     if (d.thresh == 0u) return 1.f;
-    uint32_t r = mix32(d.key + idx * 0x9e3779b97f4a7c15ull);
-    return (r < d.thresh) ? 0.f : d.scale;
+    // two keyed rounds over the folded 64-bit element index
+    uint32_t h = (uint32_t)idx * 0x9e3779b1u + (uint32_t)(idx >> 32) * 0x85ebca77u + (uint32_t)d.key;
+    h = mix32(h) + (uint32_t)(d.key >> 32);
+    h = mix32(h);
+    return (h < d.thresh) ? 0.f : d.scale;
 }
 
 // grid size for grid-stride elementwise kernels: enough CTAs to fill the chip a few times over

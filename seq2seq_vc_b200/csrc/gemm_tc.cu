@@ -18,6 +18,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -28,11 +29,14 @@ int gemm_simt(const s2s_gemm_t& g, cudaStream_t st);
 
 namespace tc {
 
-constexpr int BM = 128, BK = 64, MAX_BN = 128, STAGES = 6, UMMA_K = 16;
+constexpr int BM = 128, BK = 64, MAX_BN = 128, STAGES = 5, UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = MAX_BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int TMEM_COLS = 256;
 constexpr int NUM_THREADS = 192;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+// epilogue staging: per epilogue warp 32 rows x 64 fp32 columns, row stride 68 floats (272 B) so that
+// both the row-owner writes (16 B per lane, 32 rows) and the coalesced read-back are (nearly) conflict free
+constexpr int STG_LD = 68, STG_BYTES = 32 * STG_LD * 4;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * STG_BYTES + 4 * MAX_BN * 4 + 1024 /*align slack*/ + 256 /*barriers*/;
 
 struct Params {
     CUtensorMap tmA, tmB;
@@ -45,9 +49,17 @@ struct Params {
     const float* bias;
     float alpha;
     int relu, accumulate, atomic_out;
+    int staged;              // bf16 C with 16 B-aligned rows: coalesced epilogue through shared memory
     Dropout drop;
     int mask_period, mask_offset, mask_lo, mask_hi;
+    long long* trace;        // optional: CTA 0 records globaltimer stamps of pipeline milestones (debug)
 };
+
+__device__ __forceinline__ void stamp(const Params& p, int slot) {
+    if (p.trace && blockIdx.x == 0) {
+        p.trace[slot] = clock64();
+    }
+}
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -118,101 +130,61 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
 struct Item {
     int b1, b2, m0, n0, kb0, kb1;
 };
-__device__ __forceinline__ Item decode_item(const Params& p, long item) {
+__device__ __forceinline__ Item decode_item(const Params& p, long item_l) {
     Item it;
-    int split = (int)(item % p.splits);
-    long tile = item / p.splits;
-    int ntile = (int)(tile % p.nt);
-    tile /= p.nt;
-    int mtile = (int)(tile % p.mt);
-    int bz = (int)(tile / p.mt);
-    it.b1 = bz / p.batch2;
-    it.b2 = bz % p.batch2;
-    it.m0 = mtile * BM;
-    it.n0 = ntile * p.BN;
-    int per = (p.kb_total + p.splits - 1) / p.splits;
-    it.kb0 = split * per;
+    const uint32_t item = (uint32_t)item_l;                 // host guarantees < 2^31 work items
+    const uint32_t split = item % (uint32_t)p.splits;
+    uint32_t tile = item / (uint32_t)p.splits;
+    const uint32_t ntile = tile % (uint32_t)p.nt;
+    tile /= (uint32_t)p.nt;
+    const uint32_t mtile = tile % (uint32_t)p.mt;
+    const uint32_t bz = tile / (uint32_t)p.mt;
+    it.b1 = (int)(bz / (uint32_t)p.batch2);
+    it.b2 = (int)(bz % (uint32_t)p.batch2);
+    it.m0 = (int)mtile * BM;
+    it.n0 = (int)ntile * p.BN;
+    const int per = (p.kb_total + p.splits - 1) / p.splits;
+    it.kb0 = (int)split * per;
     it.kb1 = min(p.kb_total, it.kb0 + per);
     return it;
 }
 
+// Code size matters here: the epilogue warps run this once per tile and a bloated body turns into
+// instruction-cache misses (ncu: stall_no_inst dominated the first version).  Rare paths are kept in
+// rolled loops / non-inlined helpers; only the 16-wide hot path is unrolled.
+
+// direct (row-owner) store of 16 consecutive columns of one output row; used for fp32 C (weight
+// gradients: red.add or plain stores) and for bf16 C whose rows are not 16 B aligned
 template <typename TC>
-__device__ __forceinline__ void epilogue_chunk(const Params& p, const Dropout& drop, const uint32_t (&acc)[16], TC* __restrict__ Cb,
-                                               const TC* __restrict__ Rb, int m, int n_base, long batch_lin, bool row_ok) {
-    // 16 consecutive columns of one output row
-    TC* dst = Cb + (long)m * p.c_rs + n_base;
-    const TC* rsrc = Rb ? Rb + (long)m * p.c_rs + n_base : nullptr;
-    float v[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]) * p.alpha;
-    const int nvalid = min(16, p.N - n_base);
+__device__ __noinline__ void epilogue_direct(const Params& p, const Dropout& drop, float (&v)[16], TC* __restrict__ dst,
+                                             const TC* __restrict__ rsrc, uint64_t didx, int nvalid, bool row_ok) {
     if (p.atomic_out) {
         if (!row_ok) return;
+#pragma unroll 1
         for (int j = 0; j < nvalid; ++j) atomicAdd(reinterpret_cast<float*>(dst) + j, v[j]);
         return;
     }
-    if (p.bias) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-            if (j < nvalid) v[j] += p.bias[n_base + j];
+#pragma unroll 1
+    for (int j = 0; j < nvalid; ++j) {
+        float x = v[j];
+        if (p.relu) x = fmaxf(x, 0.f);
+        x *= dropout_factor(drop, didx + j);
+        if (rsrc) x += to_f<TC>(rsrc[j]);
+        if (p.accumulate) x += to_f<TC>(dst[j]);
+        dst[j] = from_f<TC>(row_ok ? x : 0.f);
     }
-    if (p.relu) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-    }
-    if (drop.thresh != 0u) {
-        const uint64_t base = (uint64_t)((batch_lin + m) * (long)p.N + n_base);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] *= dropout_factor(drop, base + j);
-    }
-    const bool vec = (nvalid == 16) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
-                     (!rsrc || (reinterpret_cast<uintptr_t>(rsrc) & 15) == 0);
-    if (vec) {
-        if (rsrc) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float t[4];
-                Vec4<TC>::load(rsrc + 4 * q, t);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) v[4 * q + j] += t[j];
-            }
-        }
-        if (p.accumulate) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float t[4];
-                Vec4<TC>::load(dst + 4 * q, t);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) v[4 * q + j] += t[j];
-            }
-        }
-        if (!row_ok) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = 0.f;
-        }
-        if (sizeof(TC) == 2) {
-            uint32_t w[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                w[j] = *reinterpret_cast<uint32_t*>(&h);
-            }
-            uint4* d4 = reinterpret_cast<uint4*>(dst);
-            d4[0] = make_uint4(w[0], w[1], w[2], w[3]);
-            d4[1] = make_uint4(w[4], w[5], w[6], w[7]);
-        } else {
-            float4* d4 = reinterpret_cast<float4*>(dst);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) d4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        }
-    } else {
-        for (int j = 0; j < nvalid; ++j) {
-            float x = v[j];
-            if (rsrc) x += to_f<TC>(rsrc[j]);
-            if (p.accumulate) x += to_f<TC>(dst[j]);
-            if (!row_ok) x = 0.f;
-            dst[j] = from_f<TC>(x);
-        }
+}
+
+// N-tail of the coalesced path: fewer than 8 valid columns in this lane's group
+template <typename TC>
+__device__ __noinline__ void epilogue_tail(const Params& p, const float (&o)[8], TC* __restrict__ dst, const TC* __restrict__ rsrc,
+                                           int nvalid, bool row_ok) {
+#pragma unroll 1
+    for (int q = 0; q < nvalid; ++q) {
+        float x = o[q];
+        if (rsrc) x += to_f<TC>(rsrc[q]);
+        if (p.accumulate) x += to_f<TC>(dst[q]);
+        dst[q] = from_f<TC>(row_ok ? x : 0.f);
     }
 }
 
@@ -221,7 +193,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                    // SWIZZLE_128B tiles need 1024 B alignment
-    const uint32_t bars = base + STAGES * STAGE_BYTES;               // full[STAGES], empty[STAGES], tfull[2], tempty[2]
+    const uint32_t stg_base = base + STAGES * STAGE_BYTES;           // 4 x epilogue staging tiles
+    const uint32_t bias_base = stg_base + 4 * STG_BYTES;             // 4 x MAX_BN floats (one copy per epilogue warp)
+    const uint32_t bars = bias_base + 4 * MAX_BN * 4;                // full[STAGES], empty[STAGES], tfull[2], tempty[2]
     __shared__ uint32_t tmem_base_slot;
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
@@ -229,6 +203,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     auto tempty_bar = [&](int s) { return bars + 8u * (2 * STAGES + 2 + s); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) stamp(p, 0);
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
@@ -243,6 +218,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
+    if (threadIdx.x == 0) stamp(p, 1);
 
     const long total = (long)p.batch1 * p.batch2 * p.mt * p.nt * p.splits;
     const int BN = p.BN;
@@ -261,6 +237,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                     const int kk = (kb - t * p.kb_per_tap) * BK;
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+                    if (kb == it.kb0 && item == blockIdx.x) stamp(p, 2);
                     mbar_expect_tx(full_bar(stage), tx_bytes);
                     if (p.a_mn) {
                         tma_load_4d(sa, &p.tmA, full_bar(stage), it.m0, kk, it.b2, it.b1);
@@ -298,6 +275,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                 const int ksteps = (min(BK, p.K - kk) + UMMA_K - 1) / UMMA_K;
                 mbar_wait(full_bar(stage), phase);
                 tcgen05_fence_after();
+                if (lane == 0 && n_items == 0 && kb == it.kb0) stamp(p, 3);
+                if (lane == 0 && n_items == 0 && kb == it.kb1 - 1) stamp(p, 4);
                 if (lane == 0) {
                     const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
                     for (int k = 0; k < ksteps; ++k) {
@@ -318,37 +297,140 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         Dropout drop = p.drop;
         dropout_resolve(drop);
         const int quarter = warp & 3;             // TMEM lane quarter this warp may access
+        unsigned char* smem_gen = smem_raw + (base - raw);
+        float* stg = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES + quarter * STG_BYTES);
+        float* bias_s = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES + 4 * STG_BYTES) + quarter * MAX_BN;
+        const int r4 = lane >> 3, cl = (lane & 7) * 8;   // coalesced mapping: 4 rows x 8 column groups of 8
+        const bool staged = (sizeof(TC) == 2) && p.staged;
         long n_items = 0;
         for (long item = blockIdx.x; item < total; item += gridDim.x, ++n_items) {
             const Item it = decode_item(p, item);
             const int as = (int)(n_items & 1);
             const uint32_t aphase = (uint32_t)((n_items >> 1) & 1);
-            mbar_wait(tfull_bar(as), aphase);
-            tcgen05_fence_after();
-            const int m = it.m0 + quarter * 32 + lane;
-            const int bz = it.b1 * p.batch2 + it.b2;
+            const int row0 = it.m0 + quarter * 32;
+            const int m = row0 + lane;                       // row owned while reading TMEM
+            const long batch_lin = (long)(it.b1 * p.batch2 + it.b2) * p.M;
             TC* Cb = reinterpret_cast<TC*>(p.C) + it.b1 * p.c_bs1 + it.b2 * p.c_bs2;
             const TC* Rb = p.R ? reinterpret_cast<const TC*>(p.R) + it.b1 * p.c_bs1 + it.b2 * p.c_bs2 : nullptr;
-            bool row_ok = true;
-            if (p.mask_period > 0) {
-                int ph = (m + p.mask_offset) % p.mask_period;
-                row_ok = (ph >= p.mask_lo) && (ph < p.mask_hi);
-            }
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * MAX_BN);
-            for (int c = 0; c < BN; c += 16) {
-                uint32_t acc[16];
-                tmem_ld16(taddr + c, acc);
-                tmem_ld_wait();
-                const int n_base = it.n0 + c;
-                if (m < p.M && n_base < p.N) epilogue_chunk<TC>(p, drop, acc, Cb, Rb, m, n_base, (long)bz * p.M, row_ok);
-            }
-            tcgen05_fence_before();
+            // bias slice of this tile -> shared memory (hidden behind the MMA main loop)
+#pragma unroll 1
+            for (int c = lane; c < BN; c += 32) bias_s[c] = (p.bias && it.n0 + c < p.N) ? p.bias[it.n0 + c] : 0.f;
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(as));
+            // residual rows of the first 64-column half, prefetched in the coalesced mapping
+            uint4 rr[8];
+            const bool lane_cols0 = staged && Rb && cl < BN && it.n0 + cl + 8 <= p.N;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                rr[i] = make_uint4(0u, 0u, 0u, 0u);
+                if (lane_cols0 && row0 + i * 4 + r4 < p.M)
+                    rr[i] = *reinterpret_cast<const uint4*>(Rb + (long)(row0 + i * 4 + r4) * p.c_rs + it.n0 + cl);
+            }
+            mbar_wait(tfull_bar(as), aphase);
+            tcgen05_fence_after();
+            if (threadIdx.x == 64 && n_items == 0) stamp(p, 5);
+            const int halves = (BN + 63) >> 6;
+#pragma unroll 1
+            for (int h = 0; h < halves; ++h) {
+                const int ncols = min(64, BN - h * 64);
+                // ---- TMEM -> registers -> (alpha, bias, relu, dropout) -> staging tile / direct store
+#pragma unroll 1
+                for (int c = 0; c < ncols; c += 16) {
+                    uint32_t acc[16];
+                    tmem_ld16(taddr + h * 64 + c, acc);
+                    tmem_ld_wait();
+                    float v[16];
+                    const float4* b4 = reinterpret_cast<const float4*>(bias_s + h * 64 + c);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 bb = b4[q];
+                        v[4 * q + 0] = fmaf(__uint_as_float(acc[4 * q + 0]), p.alpha, bb.x);
+                        v[4 * q + 1] = fmaf(__uint_as_float(acc[4 * q + 1]), p.alpha, bb.y);
+                        v[4 * q + 2] = fmaf(__uint_as_float(acc[4 * q + 2]), p.alpha, bb.z);
+                        v[4 * q + 3] = fmaf(__uint_as_float(acc[4 * q + 3]), p.alpha, bb.w);
+                    }
+                    const int n_base = it.n0 + h * 64 + c;
+                    const uint64_t didx = (uint64_t)((batch_lin + m) * (long)p.N + n_base);
+                    if (staged) {
+                        if (p.relu) {
+#pragma unroll
+                            for (int jj = 0; jj < 16; ++jj) v[jj] = fmaxf(v[jj], 0.f);
+                        }
+                        if (drop.thresh != 0u) {
+#pragma unroll 4
+                            for (int jj = 0; jj < 16; ++jj) v[jj] *= dropout_factor(drop, didx + jj);
+                        }
+                        float4* d4 = reinterpret_cast<float4*>(stg + lane * STG_LD + c);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) d4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    } else if (m < p.M && n_base < p.N) {
+                        bool row_ok = true;
+                        if (p.mask_period > 0) {
+                            const int ph = (m + p.mask_offset) % p.mask_period;
+                            row_ok = (ph >= p.mask_lo) && (ph < p.mask_hi);
+                        }
+                        epilogue_direct<TC>(p, drop, v, Cb + (long)m * p.c_rs + n_base, Rb ? Rb + (long)m * p.c_rs + n_base : nullptr,
+                                            didx, min(16, p.N - n_base), row_ok);
+                    }
+                }
+                if (h == halves - 1) {              // all TMEM reads of this tile are done: hand the accumulator back
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (threadIdx.x == 64 && n_items == 0) stamp(p, 6);
+                    if (lane == 0) mbar_arrive(tempty_bar(as));
+                } else {
+                    __syncwarp();
+                }
+                if (!staged) continue;
+                // ---- coalesced read-back: each step covers 4 rows x (8 lanes x 8 columns), 16 B per lane
+                const int n = it.n0 + h * 64 + cl;
+                const int nvalid = (cl < ncols) ? min(8, p.N - n) : 0;
+#pragma unroll 2
+                for (int i = 0; i < 8; ++i) {
+                    const int rl = i * 4 + r4;
+                    const int row = row0 + rl;
+                    if (nvalid <= 0 || row >= p.M) continue;
+                    const float4 a0 = *reinterpret_cast<const float4*>(stg + rl * STG_LD + cl);
+                    const float4 a1 = *reinterpret_cast<const float4*>(stg + rl * STG_LD + cl + 4);
+                    float o[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                    TC* dst = Cb + (long)row * p.c_rs + n;
+                    bool row_ok = true;
+                    if (p.mask_period > 0) {
+                        const int ph = (row + p.mask_offset) % p.mask_period;
+                        row_ok = (ph >= p.mask_lo) && (ph < p.mask_hi);
+                    }
+                    if (nvalid == 8) {
+                        if (Rb) {
+                            const uint4 rv = (h == 0) ? rr[i] : *reinterpret_cast<const uint4*>(Rb + (long)row * p.c_rs + n);
+                            const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) { o[2 * q] += __low2float(r2[q]); o[2 * q + 1] += __high2float(r2[q]); }
+                        }
+                        if (p.accumulate) {
+                            const uint4 cv = *reinterpret_cast<const uint4*>(dst);
+                            const __nv_bfloat162* c2 = reinterpret_cast<const __nv_bfloat162*>(&cv);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) { o[2 * q] += __low2float(c2[q]); o[2 * q + 1] += __high2float(c2[q]); }
+                        }
+                        uint4 w;
+                        uint32_t* wp = reinterpret_cast<uint32_t*>(&w);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            __nv_bfloat162 hh = __floats2bfloat162_rn(row_ok ? o[2 * q] : 0.f, row_ok ? o[2 * q + 1] : 0.f);
+                            wp[q] = *reinterpret_cast<uint32_t*>(&hh);
+                        }
+                        *reinterpret_cast<uint4*>(dst) = w;
+                    } else {
+                        epilogue_tail<TC>(p, o, dst, Rb ? Rb + (long)row * p.c_rs + n : nullptr, nvalid, row_ok);
+                    }
+                }
+                __syncwarp();     // staging tile is reused by the next half / tile
+            }
         }
     }
     tcgen05_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) stamp(p, 7);
     if (warp == 1) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -417,6 +499,7 @@ static cudaError_t g_attr_err = cudaSuccess;
 }  // namespace tc
 
 static long g_tc_fallbacks = 0;
+static long long* g_trace = nullptr;
 
 int gemm_tc(const s2s_gemm_t& g, cudaStream_t st) {
     using namespace tc;
@@ -466,17 +549,21 @@ int gemm_tc(const s2s_gemm_t& g, cudaStream_t st) {
     p.C = g.C; p.c_f32 = (g.c_dtype == S2S_F32); p.c_rs = g.c_rs; p.c_bs1 = g.c_bs1; p.c_bs2 = g.c_bs2;
     p.R = g.R; p.bias = g.bias; p.alpha = g.alpha; p.relu = g.relu; p.accumulate = g.accumulate;
     p.drop = make_dropout(&g.drop);
+    p.trace = g_trace;
     p.mask_period = g.mask_period; p.mask_offset = g.mask_offset; p.mask_lo = g.mask_lo; p.mask_hi = g.mask_hi;
     // split-K for skinny weight-gradient GEMMs: fp32 accumulate-in-place output, no other epilogue work
     const long tiles = (long)g.batch1 * g.batch2 * p.mt * p.nt;
     p.splits = 1;
     const bool plain = p.c_f32 && g.accumulate && !g.bias && !g.R && !g.relu && p.drop.thresh == 0u && g.mask_period == 0;
+    if (plain) p.atomic_out = 1;          // fp32 accumulate-in-place: red.global.add, C is never read
     if (plain && tiles * 2 <= num_sms() && p.kb_total >= 8) {
         long s = num_sms() / tiles;
         long max_s = p.kb_total / 4;
         if (s > max_s) s = max_s;
-        if (s > 1) { p.splits = (int)s; p.atomic_out = 1; }
+        if (s > 1) p.splits = (int)s;
     }
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    p.staged = (!p.c_f32 && al16(g.C) && (g.R == nullptr || al16(g.R)) && g.c_rs % 8 == 0 && g.c_bs1 % 8 == 0 && g.c_bs2 % 8 == 0) ? 1 : 0;
     // every split must own at least one k-block
     if (p.splits > 1) {
         int per = (p.kb_total + p.splits - 1) / p.splits;
@@ -489,6 +576,7 @@ int gemm_tc(const s2s_gemm_t& g, cudaStream_t st) {
     });
     if (g_attr_err != cudaSuccess) return set_error(S2S_ERR_CUDA, "gemm_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(g_attr_err));
     long items = tiles * p.splits;
+    if (items >= (1L << 31)) return set_error(S2S_ERR_UNSUPPORTED, "gemm_tc: too many tiles");
     unsigned grid = (unsigned)(items < num_sms() ? items : num_sms());
     if (p.c_f32) gemm_tc_kernel<float><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
     else gemm_tc_kernel<bf16><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
@@ -500,4 +588,5 @@ long tc_fallback_count() { return g_tc_fallbacks; }
 
 }  // namespace s2s
 
+extern "C" void s2s_debug_gemm_trace(void* dev_buf8) { s2s::g_trace = (long long*)dev_buf8; }
 extern "C" int64_t s2s_tc_fallback_count(void) { return (int64_t)s2s::tc_fallback_count(); }

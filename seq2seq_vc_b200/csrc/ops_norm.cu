@@ -383,6 +383,84 @@ __global__ void pad_rows_kernel(const T* __restrict__ x, T* __restrict__ y, int 
     }
 }
 
+
+// =============================================================================================
+// Skinny linear layer (N <= 4 output features; the stop-token head prob_out, models/vtn.py:182,251).
+// A tensor-core tile would be > 95 % padding here and the weight-gradient GEMM has a single output
+// tile, so these are bandwidth-shaped kernels: every row of x is read once per pass.
+// =============================================================================================
+template <typename T, int VEC>
+__global__ void __launch_bounds__(128) skinny_fwd_kernel(const T* __restrict__ x, const T* __restrict__ w,
+                                                         const float* __restrict__ bias, T* __restrict__ y, long rows,
+                                                         int K, int N) {
+    const int lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const T* xr = x + row * K;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = lane * VEC; c < K; c += 32 * VEC) {
+        float v[VEC];
+        VLoad<T, VEC>::ld(xr + c, v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j < N) {
+                float wv[VEC];
+                VLoad<T, VEC>::ld(w + (long)j * K + c, wv);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) acc[j] = fmaf(v[i], wv[i], acc[j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = warp_sum(acc[j]);
+    if (lane < N) {
+        float o = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
+        y[row * N + lane] = from_f<T>(o + (bias ? bias[lane] : 0.f));
+    }
+}
+
+template <typename T, int VEC> struct SkinnyDwF {
+    const T* dy; const T* x; int K; int N; float* dw;
+    __device__ __forceinline__ void operator()(long r, int c0, float (&acc)[4][VEC]) const {
+        float v[VEC];
+        VLoad<T, VEC>::ld(x + r * K + c0, v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j < N) {
+                const float g = to_f<T>(dy[r * N + j]);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) acc[j][i] = fmaf(g, v[i], acc[j][i]);
+            }
+        }
+    }
+    __device__ __forceinline__ float* out(int k, int c) const { return dw + (long)(k < N ? k : 0) * K + c; }
+};
+
+template <typename T, int VEC>
+__global__ void skinny_dx_kernel(const T* __restrict__ dy, const T* __restrict__ w, T* __restrict__ dx, long rows, int K,
+                                 int N, int accumulate) {
+    const int kv = K / VEC;
+    const long total = rows * kv;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long r = i / kv;
+        const int c = (int)(i - r * kv) * VEC;
+        float o[VEC];
+        if (accumulate) VLoad<T, VEC>::ld(dx + r * K + c, o);
+        else {
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) o[q] = 0.f;
+        }
+        for (int j = 0; j < N; ++j) {
+            const float g = to_f<T>(dy[r * N + j]);
+            float wv[VEC];
+            VLoad<T, VEC>::ld(w + (long)j * K + c, wv);
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) o[q] = fmaf(g, wv[q], o[q]);
+        }
+        VLoad<T, VEC>::st(dx + r * K + c, o);
+    }
+}
+
 }  // namespace s2s
 
 using namespace s2s;
@@ -558,4 +636,43 @@ extern "C" int s2s_pad_rows(const void* x, void* y, int B, int L, int halo, int 
 }
 extern "C" int s2s_unpad_rows(const void* x, void* y, int B, int L, int halo, int C, int dtype, void* stream) {
     return pad_rows_impl(x, y, B, L, halo, C, dtype, stream, 0);
+}
+
+extern "C" int s2s_skinny_linear_fwd(const void* x, const void* w, const float* bias, void* y, int64_t rows, int K, int N,
+                                     int dtype, void* stream) {
+    S2S_REQUIRE(x && w && y && K > 0 && N >= 1 && N <= 4, "skinny_linear_fwd: bad arguments (N must be 1..4)");
+    if (rows <= 0) return S2S_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    bool ok = vec4_ok(K, K, x, w);
+    S2S_DISPATCH_DTYPE(dtype, T, S2S_VEC_DISPATCH(ok, VEC, (skinny_fwd_kernel<T, VEC><<<(unsigned)ceil_div_l(rows, 4), 128, 0, st>>>(
+        (const T*)x, (const T*)w, bias, (T*)y, rows, K, N))));
+    S2S_LAUNCH_OK();
+    return S2S_OK;
+}
+
+extern "C" int s2s_skinny_linear_bwd(const void* dy, const void* x, const void* w, float* dw, float* dbias, void* dx,
+                                     int dx_accumulate, int64_t rows, int K, int N, int dtype, void* stream) {
+    S2S_REQUIRE(dy && x && w && K > 0 && N >= 1 && N <= 4, "skinny_linear_bwd: bad arguments (N must be 1..4)");
+    if (rows <= 0) return S2S_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    bool ok = vec4_ok(K, K, x, w, dx);
+    int rc = S2S_OK;
+    if (dw) {
+        S2S_DISPATCH_DTYPE(dtype, T, S2S_VEC_DISPATCH(ok, VEC, {
+            SkinnyDwF<T, VEC> f{(const T*)dy, (const T*)x, K, N, dw};
+            rc = launch_colreduce<4, VEC>(f, rows, K, st);
+        }));
+        if (rc != S2S_OK) return rc;
+    }
+    if (dbias) {
+        rc = s2s_colsum(dy, rows, N, N, dbias, dtype, stream);
+        if (rc != S2S_OK) return rc;
+    }
+    if (dx) {
+        long total = (long)rows * K;
+        S2S_DISPATCH_DTYPE(dtype, T, S2S_VEC_DISPATCH(ok, VEC, (skinny_dx_kernel<T, VEC><<<ew_grid(total / VEC, 256), 256, 0, st>>>(
+            (const T*)dy, (const T*)w, (T*)dx, rows, K, N, dx_accumulate))));
+        S2S_LAUNCH_OK();
+    }
+    return S2S_OK;
 }

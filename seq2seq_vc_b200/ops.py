@@ -108,6 +108,23 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, dres=None):
     return dx
 
 
+def skinny_linear_fwd(x2d, w, bias, y2d):
+    """y2d[r, j] = x2d[r] . w[j] + bias[j] for N = w.shape[0] <= 4."""
+    rows, K = x2d.shape
+    N = w.shape[0]
+    assert x2d.is_contiguous() and w.is_contiguous() and y2d.is_contiguous() and x2d.dtype == w.dtype == y2d.dtype
+    check(_L().s2s_skinny_linear_fwd(ptr(x2d), ptr(w), ptr(bias), ptr(y2d), rows, K, N, dt(x2d), stream()), "skinny_linear_fwd")
+    return y2d
+
+
+def skinny_linear_bwd(dy2d, x2d, w, dw, dbias, dx, dx_accumulate=False):
+    rows, K = x2d.shape
+    N = w.shape[0]
+    assert dy2d.is_contiguous() and x2d.is_contiguous() and w.is_contiguous() and (dx is None or dx.is_contiguous())
+    check(_L().s2s_skinny_linear_bwd(ptr(dy2d), ptr(x2d), ptr(w), ptr(dw), ptr(dbias), ptr(dx), int(dx_accumulate), rows, K, N,
+                                     dt(x2d), stream()), "skinny_linear_bwd")
+
+
 def colsum(x2d, out):
     """out[c] += sum_r x2d[r, c]"""
     assert x2d.dim() == 2 and x2d.stride(1) == 1

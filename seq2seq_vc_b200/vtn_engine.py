@@ -159,6 +159,8 @@ class VTNEngine:
         self._loss_ws = torch.zeros(4, dtype=_f32, device=self.device)
         self._sqn = torch.zeros(1, dtype=_f32, device=self.device)
         self.p16_dirty = True
+        self._lens_host: Dict[int, torch.Tensor] = {}
+        self._prepared = None
         self.init_parameters(seed)
 
     # ------------------------------------------------------------------ parameters
@@ -237,12 +239,15 @@ class VTNEngine:
 
     # ------------------------------------------------------------------ building blocks
     def _lin_fwd(self, x2d, w, bias, out, relu=False, drop=NO_DROP, residual=None):
-        mode = self.mode if (w.shape[0] >= 8) else 0
-        return ops.gemm(x2d, w, out, bias=bias, relu=relu, drop=drop, residual=residual, mode=mode)
+        if w.shape[0] <= 4 and not relu and residual is None and drop.p == 0.0:
+            return ops.skinny_linear_fwd(x2d, w, bias, out)
+        return ops.gemm(x2d, w, out, bias=bias, relu=relu, drop=drop, residual=residual, mode=self.mode)
 
     def _lin_bwd(self, dy2d, x2d, w, gw, gb, dx=None, dx_residual=None, dx_accumulate=False):
         """dW += dy^T x ; db += colsum(dy) ; dx = dy W (+ residual | += )."""
-        mode = self.mode if (w.shape[0] >= 8) else 0
+        mode = self.mode
+        if w.shape[0] <= 4 and dx_residual is None:
+            return ops.skinny_linear_bwd(dy2d, x2d, w, gw, gb, dx, dx_accumulate)
         if gw is not None:
             ops.gemm(dy2d.t(), x2d.t(), gw, accumulate=True, mode=mode)
         if gb is not None:
@@ -314,8 +319,36 @@ class VTNEngine:
         return t[:n].view(shape)
 
     # ------------------------------------------------------------------ forward
-    def forward(self, xs: torch.Tensor, ys: torch.Tensor, ilens: Sequence[int], olens: Sequence[int]):
+    def prepare(self, B: int, T: int, L: int, ilens: Sequence[int], olens: Sequence[int]) -> None:
+        """Derive the per-utterance length vectors on the host (they arrive as CPU ints from the
+        collater) and ship them in ONE small H2D copy; never synchronises.  Kept out of forward()
+        so that a captured CUDA graph of the step only ever sees the device-resident copy."""
+        hp = self.hp
+        r = hp["decoder_reduction_factor"]
+        T2 = (((T - 1) // 2) - 1) // 2
+        self._sig = (B, T, L, self.training)
+        ilens = [int(v) for v in ilens]
+        olens = [int(v) for v in olens]
+        assert len(ilens) == B and len(olens) == B
+        klens_enc = [min(T2, (i + 3) // 4) for i in ilens]           # mask[:, :, :-2:2][:, :, :-2:2] (subsampling.py:92-94)
+        olens_in = [o // r for o in olens]
+        olens_fix = [o - o % r for o in olens]
+        host = self._lens_host.get(B)
+        if host is None:
+            host = torch.empty(3, B, dtype=_i32)
+            if self.device.type == "cuda":
+                host = host.pin_memory()
+            self._lens_host[B] = host
+        host.copy_(torch.tensor([klens_enc, olens_in, olens_fix], dtype=_i32))
+        self.buf("lens", (3, B), _i32).copy_(host, non_blocking=True)
+        self.ilens_ds_st = [((i - 2 + 1) // 2 - 2 + 1) // 2 for i in ilens]   # vtn.py:279
+        self.olens_in_host, self.olens_fix_host = olens_in, olens_fix
+        self._prepared = (B, T, L)
+
+    def forward(self, xs: torch.Tensor, ys: torch.Tensor, ilens: Optional[Sequence[int]] = None,
+                olens: Optional[Sequence[int]] = None):
         """xs (B,T,idim) / ys (B,L,odim) float32 device tensors already trimmed to max length.
+        ilens / olens: host ints; omit them when prepare() was already called for this batch.
 
         Returns (after (B,L',odim), before, logits (B,L')) in activation dtype; attention maps in
         self.attn; L' = (L // r) * r.
@@ -335,18 +368,11 @@ class VTNEngine:
         self.sync_shadow()
         self.shapes = dict(B=B, T=T, L=L, T1=T1, F1=F1, T2=T2, F2=F2, Lr=Lr)
 
-        # per-utterance lengths -> one small H2D copy (lens come from the CPU collater)
-        ilens = [int(v) for v in ilens]
-        olens = [int(v) for v in olens]
-        klens_enc = [min(T2, (i + 3) // 4) for i in ilens]           # mask[:, :, :-2:2][:, :, :-2:2] (subsampling.py:92-94)
-        olens_in = [o // r for o in olens]
-        olens_fix = [o - o % r for o in olens]
-        lens_host = torch.tensor([klens_enc, olens_in, olens_fix], dtype=_i32)
+        if ilens is not None:
+            self.prepare(B, T, L, ilens, olens)
+        assert self._prepared == (B, T, L), "prepare(B, T, L, ilens, olens) must precede forward() for this batch shape"
         lens = self.buf("lens", (3, B), _i32)
-        lens.copy_(lens_host, non_blocking=True)
         self.klens_enc, self.olens_in, self.olens_fix = lens[0], lens[1], lens[2]
-        self.ilens_ds_st = [((i - 2 + 1) // 2 - 2 + 1) // 2 for i in ilens]   # vtn.py:279
-        self.olens_in_host, self.olens_fix_host = olens_in, olens_fix
 
         # ---- packed conv weights (activation dtype)
         w2p = self.buf("w.conv2p", (d, 9, d))          # [oc][tap][ic]

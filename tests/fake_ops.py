@@ -78,6 +78,21 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, dres=None):
     return dx
 
 
+def skinny_linear_fwd(x2d, w, bias, y2d):
+    y2d.copy_((x2d.double() @ w.double().t() + (bias.double() if bias is not None else 0)).to(y2d.dtype))
+    return y2d
+
+
+def skinny_linear_bwd(dy2d, x2d, w, dw, dbias, dx, dx_accumulate=False):
+    if dw is not None:
+        dw += (dy2d.double().t() @ x2d.double()).float()
+    if dbias is not None:
+        dbias += dy2d.double().sum(0).float()
+    if dx is not None:
+        v = dy2d.double() @ w.double()
+        dx.copy_(((dx.double() + v) if dx_accumulate else v).to(dx.dtype))
+
+
 def colsum(x2d, out):
     out += x2d.double().sum(0).float()
 

@@ -315,3 +315,20 @@ def test_dropout_is_consistent_between_forward_and_backward(ops, dt):
     seed_dev += 1
     mask2 = ops.dropout_bwd(torch.ones(M, N, dtype=dt, device="cuda"), torch.empty(M, N, dtype=dt, device="cuda"), drop).float()
     assert (mask2 != mask).float().mean().item() > 0.2, "device-side seed must change the mask"
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("N", [1, 2, 4])
+def test_skinny_linear(ops, dt, N):
+    rows, K = 777, 96
+    x, w, bias, dy = rnd(rows, K, dt=dt, seed=1), rnd(N, K, dt=dt, seed=2, scale=0.1), rnd(N, seed=3), rnd(rows, N, dt=dt, seed=4)
+    y = F.skinny_linear_fwd(x, w, bias, torch.empty(rows, N, dtype=dt))
+    cy = ops.skinny_linear_fwd(x.cuda(), w.cuda(), bias.cuda(), torch.empty(rows, N, dtype=dt, device="cuda"))
+    close(cy, y, tol(dt, 4), "skinny fwd")
+    dw, db, dx = torch.zeros(N, K), torch.zeros(N), rnd(rows, K, dt=dt, seed=5)
+    cdw, cdb, cdx = dw.cuda(), db.cuda(), dx.clone().cuda()
+    F.skinny_linear_bwd(dy, x, w, dw, db, dx, True)
+    ops.skinny_linear_bwd(dy.cuda(), x.cuda(), w.cuda(), cdw, cdb, cdx, True)
+    close(cdw, dw, tol(dt, 60), "skinny dw")
+    close(cdb, db, tol(dt, 60), "skinny dbias")
+    close(cdx, dx, tol(dt, 4), "skinny dx")

@@ -1,0 +1,66 @@
+"""Micro-benchmark of s2s_gemm(mode=1) shapes (CUDA events, L2 flushed between launches)."""
+import sys, os, math, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from seq2seq_vc_b200 import ops
+
+SHAPES = {
+    "lin_dec": dict(M=16384, N=384, K=384), "ffn1": dict(M=16384, N=1536, K=384), "ffn2": dict(M=16384, N=384, K=1536),
+    "lin_enc": dict(M=4064, N=384, K=384), "conv2": dict(M=77216, N=384, K=3456), "big": dict(M=8192, N=8192, K=8192),
+    "qk": dict(M=512, N=512, K=48, batch=256), "one_tile": dict(M=128, N=128, K=384), "one_tile_longk": dict(M=128, N=128, K=8192),
+}
+
+def run(name, reps=10, flush=True):
+    s = SHAPES[name]
+    nb = s.get("batch", 1)
+    M, N, K = s["M"], s["N"], s["K"]
+    a = torch.randn(nb, M, K, device="cuda").bfloat16()
+    b = torch.randn(nb, N, K, device="cuda").bfloat16()
+    c = torch.empty(nb, M, N, device="cuda", dtype=torch.bfloat16)
+    bias = torch.randn(N, device="cuda")
+    scratch = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    if nb == 1:
+        a, b, c = a[0], b[0], c[0]
+    else:
+        a, b, c = a.view(nb // 8, 8, M, K), b.view(nb // 8, 8, N, K), c.view(nb // 8, 8, M, N)
+    ts = []
+    for i in range(reps + 3):
+        if flush:
+            scratch.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.gemm(a, b, c, bias=bias if nb == 1 else None, mode=1)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            ts.append(e0.elapsed_time(e1) * 1e3)
+    ts.sort()
+    us = ts[len(ts) // 2]
+    fl = 2.0 * nb * M * N * K
+    print(f"{name:16s} {nb}x{M}x{N}x{K}: median {us:8.1f} us  min {ts[0]:8.1f} us  {fl / us / 1e6:8.1f} TFLOP/s", flush=True)
+
+
+
+def trace(name):
+    import ctypes
+    from seq2seq_vc_b200 import _lib
+    lib = _lib.load()
+    buf = torch.zeros(16, dtype=torch.int64, device="cuda")
+    lib.s2s_debug_gemm_trace.argtypes = [ctypes.c_void_p]
+    lib.s2s_debug_gemm_trace(buf.data_ptr())
+    run(name, reps=2)
+    t = buf.cpu().tolist()
+    lib.s2s_debug_gemm_trace(None)
+    print(name, "cycles since kernel start: after-setup %d, first-TMA-issue %d, first-full %d, last-full %d, epi-start %d, epi-end %d, end %d" %
+          tuple(x - t[0] for x in t[1:8]))
+    print("   epilogue halves (cycles): h0 tmem->smem done %d, h0 stored %d, h1 tmem->smem done %d, h1 stored %d" % tuple(x - t[0] for x in t[8:12]))
+
+
+if __name__ == "__main__":
+    args = sys.argv[1:]
+    if args and args[0] == "trace":
+        for n in args[1:]:
+            trace(n)
+    else:
+        for n in (args or list(SHAPES)):
+            run(n)
