@@ -29,14 +29,15 @@ int gemm_simt(const s2s_gemm_t& g, cudaStream_t st);
 
 namespace tc {
 
-constexpr int BM = 128, BK = 64, MAX_BN = 128, STAGES = 5, UMMA_K = 16;
+constexpr int BM = 128, BK = 64, MAX_BN = 128, STAGES = 4, UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = MAX_BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int TMEM_COLS = 256;
-constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 // epilogue staging: per epilogue warp 32 rows x 64 fp32 columns, row stride 68 floats (272 B) so that
 // both the row-owner writes (16 B per lane, 32 rows) and the coalesced read-back are (nearly) conflict free
 constexpr int STG_LD = 68, STG_BYTES = 32 * STG_LD * 4;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * STG_BYTES + 4 * MAX_BN * 4 + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES + EPI_WARPS * 64 * 4 + 1024 /*align slack*/ + 256 /*barriers*/;
 
 struct Params {
     CUtensorMap tmA, tmB;
@@ -193,9 +194,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                    // SWIZZLE_128B tiles need 1024 B alignment
-    const uint32_t stg_base = base + STAGES * STAGE_BYTES;           // 4 x epilogue staging tiles
-    const uint32_t bias_base = stg_base + 4 * STG_BYTES;             // 4 x MAX_BN floats (one copy per epilogue warp)
-    const uint32_t bars = bias_base + 4 * MAX_BN * 4;                // full[STAGES], empty[STAGES], tfull[2], tempty[2]
+    const uint32_t stg_base = base + STAGES * STAGE_BYTES;           // one staging tile per epilogue warp
+    const uint32_t bias_base = stg_base + EPI_WARPS * STG_BYTES;     // 64 bias floats per epilogue warp
+    const uint32_t bars = bias_base + EPI_WARPS * 64 * 4;            // full[STAGES], empty[STAGES], tfull[2], tempty[2]
     __shared__ uint32_t tmem_base_slot;
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
@@ -206,7 +207,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     if (threadIdx.x == 0) stamp(p, 0);
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -238,6 +239,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
                     if (kb == it.kb0 && item == blockIdx.x) stamp(p, 2);
+                    if (kb == it.kb0 && (item - blockIdx.x) / gridDim.x < 4) stamp(p, 16 + 8 * (int)((item - blockIdx.x) / gridDim.x) + 5);
                     mbar_expect_tx(full_bar(stage), tx_bytes);
                     if (p.a_mn) {
                         tma_load_4d(sa, &p.tmA, full_bar(stage), it.m0, kk, it.b2, it.b1);
@@ -275,8 +277,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                 const int ksteps = (min(BK, p.K - kk) + UMMA_K - 1) / UMMA_K;
                 mbar_wait(full_bar(stage), phase);
                 tcgen05_fence_after();
-                if (lane == 0 && n_items == 0 && kb == it.kb0) stamp(p, 3);
-                if (lane == 0 && n_items == 0 && kb == it.kb1 - 1) stamp(p, 4);
+                if (lane == 0 && n_items < 4 && kb == it.kb0) stamp(p, 16 + 8 * (int)n_items + 0);
+                if (lane == 0 && n_items < 4 && kb == it.kb1 - 1) stamp(p, 16 + 8 * (int)n_items + 1);
                 if (lane == 0) {
                     const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
                     for (int k = 0; k < ksteps; ++k) {
@@ -293,15 +295,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             }
         }
     } else {
-        // ================= epilogue =================
+        // ================= epilogue: 8 warps, warp -> (TMEM lane quarter, 64-column half) =================
         Dropout drop = p.drop;
         dropout_resolve(drop);
-        const int quarter = warp & 3;             // TMEM lane quarter this warp may access
+        const int ew = warp - 2;
+        const int quarter = warp & 3;             // TMEM lanes this warp may access: 32 * (warp_id % 4) ...
+        const int ch = ew >> 2;                   // which 64-column half of the tile
         unsigned char* smem_gen = smem_raw + (base - raw);
-        float* stg = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES + quarter * STG_BYTES);
-        float* bias_s = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES + 4 * STG_BYTES) + quarter * MAX_BN;
+        float* stg = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES + ew * STG_BYTES);
+        float* bias_s = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES) + ew * 64;
         const int r4 = lane >> 3, cl = (lane & 7) * 8;   // coalesced mapping: 4 rows x 8 column groups of 8
         const bool staged = (sizeof(TC) == 2) && p.staged;
+        const int ncols = min(64, BN - ch * 64);         // columns of this warp (<= 0: idle for this tile shape)
         long n_items = 0;
         for (long item = blockIdx.x; item < total; item += gridDim.x, ++n_items) {
             const Item it = decode_item(p, item);
@@ -309,47 +314,55 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             const uint32_t aphase = (uint32_t)((n_items >> 1) & 1);
             const int row0 = it.m0 + quarter * 32;
             const int m = row0 + lane;                       // row owned while reading TMEM
+            const int nw0 = it.n0 + ch * 64;                 // first column of this warp
             const long batch_lin = (long)(it.b1 * p.batch2 + it.b2) * p.M;
             TC* Cb = reinterpret_cast<TC*>(p.C) + it.b1 * p.c_bs1 + it.b2 * p.c_bs2;
             const TC* Rb = p.R ? reinterpret_cast<const TC*>(p.R) + it.b1 * p.c_bs1 + it.b2 * p.c_bs2 : nullptr;
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * MAX_BN);
-            // bias slice of this tile -> shared memory (hidden behind the MMA main loop)
-#pragma unroll 1
-            for (int c = lane; c < BN; c += 32) bias_s[c] = (p.bias && it.n0 + c < p.N) ? p.bias[it.n0 + c] : 0.f;
-            __syncwarp();
-            // residual rows of the first 64-column half, prefetched in the coalesced mapping
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * MAX_BN + ch * 64);
+            // bias slice -> shared memory, residual rows -> registers (both hidden behind the MMA main loop)
             uint4 rr[8];
-            const bool lane_cols0 = staged && Rb && cl < BN && it.n0 + cl + 8 <= p.N;
+            if (ncols > 0) {
+                bias_s[lane] = (p.bias && nw0 + lane < p.N) ? p.bias[nw0 + lane] : 0.f;
+                bias_s[lane + 32] = (p.bias && nw0 + lane + 32 < p.N) ? p.bias[nw0 + lane + 32] : 0.f;
+            }
+            const bool pre = staged && Rb && cl < ncols && nw0 + cl + 8 <= p.N;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 rr[i] = make_uint4(0u, 0u, 0u, 0u);
-                if (lane_cols0 && row0 + i * 4 + r4 < p.M)
-                    rr[i] = *reinterpret_cast<const uint4*>(Rb + (long)(row0 + i * 4 + r4) * p.c_rs + it.n0 + cl);
+                if (pre && row0 + i * 4 + r4 < p.M)
+                    rr[i] = *reinterpret_cast<const uint4*>(Rb + (long)(row0 + i * 4 + r4) * p.c_rs + nw0 + cl);
             }
+            __syncwarp();
             mbar_wait(tfull_bar(as), aphase);
             tcgen05_fence_after();
-            if (threadIdx.x == 64 && n_items == 0) stamp(p, 5);
-            const int halves = (BN + 63) >> 6;
-#pragma unroll 1
-            for (int h = 0; h < halves; ++h) {
-                const int ncols = min(64, BN - h * 64);
-                // ---- TMEM -> registers -> (alpha, bias, relu, dropout) -> staging tile / direct store
-#pragma unroll 1
-                for (int c = 0; c < ncols; c += 16) {
-                    uint32_t acc[16];
-                    tmem_ld16(taddr + h * 64 + c, acc);
-                    tmem_ld_wait();
-                    float v[16];
-                    const float4* b4 = reinterpret_cast<const float4*>(bias_s + h * 64 + c);
+            if (threadIdx.x == 64 && n_items < 4) stamp(p, 16 + 8 * (int)n_items + 2);
+            // ---- all TMEM loads of this warp's 32 x 64 block are issued before the single wait
+            uint32_t acc[4][16];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 bb = b4[q];
-                        v[4 * q + 0] = fmaf(__uint_as_float(acc[4 * q + 0]), p.alpha, bb.x);
-                        v[4 * q + 1] = fmaf(__uint_as_float(acc[4 * q + 1]), p.alpha, bb.y);
-                        v[4 * q + 2] = fmaf(__uint_as_float(acc[4 * q + 2]), p.alpha, bb.z);
-                        v[4 * q + 3] = fmaf(__uint_as_float(acc[4 * q + 3]), p.alpha, bb.w);
+            for (int q = 0; q < 4; ++q)
+                if (q * 16 < ncols) tmem_ld16(taddr + q * 16, acc[q]);
+            tmem_ld_wait();
+            // every value is in registers: hand the accumulator stage back to the MMA warp right away
+            tcgen05_fence_before();
+            __syncwarp();
+            if (threadIdx.x == 64 && n_items < 4) stamp(p, 16 + 8 * (int)n_items + 3);
+            if (lane == 0) mbar_arrive(tempty_bar(as));
+            if (ncols <= 0) continue;
+            // ---- alpha, bias, relu, dropout in the row-owner layout
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (q * 16 < ncols) {
+                    float v[16];
+                    const float4* b4 = reinterpret_cast<const float4*>(bias_s + q * 16);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float4 bb = b4[e];
+                        v[4 * e + 0] = fmaf(__uint_as_float(acc[q][4 * e + 0]), p.alpha, bb.x);
+                        v[4 * e + 1] = fmaf(__uint_as_float(acc[q][4 * e + 1]), p.alpha, bb.y);
+                        v[4 * e + 2] = fmaf(__uint_as_float(acc[q][4 * e + 2]), p.alpha, bb.z);
+                        v[4 * e + 3] = fmaf(__uint_as_float(acc[q][4 * e + 3]), p.alpha, bb.w);
                     }
-                    const int n_base = it.n0 + h * 64 + c;
+                    const int n_base = nw0 + q * 16;
                     const uint64_t didx = (uint64_t)((batch_lin + m) * (long)p.N + n_base);
                     if (staged) {
                         if (p.relu) {
@@ -360,9 +373,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 #pragma unroll 4
                             for (int jj = 0; jj < 16; ++jj) v[jj] *= dropout_factor(drop, didx + jj);
                         }
-                        float4* d4 = reinterpret_cast<float4*>(stg + lane * STG_LD + c);
+                        float4* d4 = reinterpret_cast<float4*>(stg + lane * STG_LD + q * 16);
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) d4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        for (int e = 0; e < 4; ++e) d4[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
                     } else if (m < p.M && n_base < p.N) {
                         bool row_ok = true;
                         if (p.mask_period > 0) {
@@ -373,59 +386,52 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                                             didx, min(16, p.N - n_base), row_ok);
                     }
                 }
-                if (h == halves - 1) {              // all TMEM reads of this tile are done: hand the accumulator back
-                    tcgen05_fence_before();
-                    __syncwarp();
-                    if (threadIdx.x == 64 && n_items == 0) stamp(p, 6);
-                    if (lane == 0) mbar_arrive(tempty_bar(as));
-                } else {
-                    __syncwarp();
-                }
-                if (!staged) continue;
-                // ---- coalesced read-back: each step covers 4 rows x (8 lanes x 8 columns), 16 B per lane
-                const int n = it.n0 + h * 64 + cl;
-                const int nvalid = (cl < ncols) ? min(8, p.N - n) : 0;
-#pragma unroll 2
-                for (int i = 0; i < 8; ++i) {
-                    const int rl = i * 4 + r4;
-                    const int row = row0 + rl;
-                    if (nvalid <= 0 || row >= p.M) continue;
-                    const float4 a0 = *reinterpret_cast<const float4*>(stg + rl * STG_LD + cl);
-                    const float4 a1 = *reinterpret_cast<const float4*>(stg + rl * STG_LD + cl + 4);
-                    float o[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-                    TC* dst = Cb + (long)row * p.c_rs + n;
-                    bool row_ok = true;
-                    if (p.mask_period > 0) {
-                        const int ph = (row + p.mask_offset) % p.mask_period;
-                        row_ok = (ph >= p.mask_lo) && (ph < p.mask_hi);
-                    }
-                    if (nvalid == 8) {
-                        if (Rb) {
-                            const uint4 rv = (h == 0) ? rr[i] : *reinterpret_cast<const uint4*>(Rb + (long)row * p.c_rs + n);
-                            const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) { o[2 * q] += __low2float(r2[q]); o[2 * q + 1] += __high2float(r2[q]); }
-                        }
-                        if (p.accumulate) {
-                            const uint4 cv = *reinterpret_cast<const uint4*>(dst);
-                            const __nv_bfloat162* c2 = reinterpret_cast<const __nv_bfloat162*>(&cv);
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) { o[2 * q] += __low2float(c2[q]); o[2 * q + 1] += __high2float(c2[q]); }
-                        }
-                        uint4 w;
-                        uint32_t* wp = reinterpret_cast<uint32_t*>(&w);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            __nv_bfloat162 hh = __floats2bfloat162_rn(row_ok ? o[2 * q] : 0.f, row_ok ? o[2 * q + 1] : 0.f);
-                            wp[q] = *reinterpret_cast<uint32_t*>(&hh);
-                        }
-                        *reinterpret_cast<uint4*>(dst) = w;
-                    } else {
-                        epilogue_tail<TC>(p, o, dst, Rb ? Rb + (long)row * p.c_rs + n : nullptr, nvalid, row_ok);
-                    }
-                }
-                __syncwarp();     // staging tile is reused by the next half / tile
             }
+            if (!staged) continue;
+            __syncwarp();
+            // ---- coalesced read-back: each step covers 4 rows x (8 lanes x 8 columns), one 16 B store per lane
+            const int n = nw0 + cl;
+            const int nvalid = (cl < ncols) ? min(8, p.N - n) : 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int rl = i * 4 + r4;
+                const int row = row0 + rl;
+                if (nvalid <= 0 || row >= p.M) continue;
+                const float4 a0 = *reinterpret_cast<const float4*>(stg + rl * STG_LD + cl);
+                const float4 a1 = *reinterpret_cast<const float4*>(stg + rl * STG_LD + cl + 4);
+                float o[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                TC* dst = Cb + (long)row * p.c_rs + n;
+                bool row_ok = true;
+                if (p.mask_period > 0) {
+                    const int ph = (row + p.mask_offset) % p.mask_period;
+                    row_ok = (ph >= p.mask_lo) && (ph < p.mask_hi);
+                }
+                if (nvalid == 8) {
+                    if (Rb) {
+                        const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr[i]);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) { o[2 * q] += __low2float(r2[q]); o[2 * q + 1] += __high2float(r2[q]); }
+                    }
+                    if (p.accumulate) {
+                        const uint4 cv = *reinterpret_cast<const uint4*>(dst);
+                        const __nv_bfloat162* c2 = reinterpret_cast<const __nv_bfloat162*>(&cv);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) { o[2 * q] += __low2float(c2[q]); o[2 * q + 1] += __high2float(c2[q]); }
+                    }
+                    uint4 w;
+                    uint32_t* wp = reinterpret_cast<uint32_t*>(&w);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        __nv_bfloat162 hh = __floats2bfloat162_rn(row_ok ? o[2 * q] : 0.f, row_ok ? o[2 * q + 1] : 0.f);
+                        wp[q] = *reinterpret_cast<uint32_t*>(&hh);
+                    }
+                    *reinterpret_cast<uint4*>(dst) = w;
+                } else {
+                    epilogue_tail<TC>(p, o, dst, Rb ? Rb + (long)row * p.c_rs + n : nullptr, nvalid, row_ok);
+                }
+            }
+            if (threadIdx.x == 64 && n_items < 4) stamp(p, 16 + 8 * (int)n_items + 4);
+            __syncwarp();     // the staging tile and bias slice are rewritten for the next tile
         }
     }
     tcgen05_fence_before();

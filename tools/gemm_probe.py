@@ -41,26 +41,32 @@ def run(name, reps=10, flush=True):
 
 
 
-def trace(name):
+def trace(name, flush=True):
     import ctypes
     from seq2seq_vc_b200 import _lib
     lib = _lib.load()
-    buf = torch.zeros(16, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(64, dtype=torch.int64, device="cuda")
     lib.s2s_debug_gemm_trace.argtypes = [ctypes.c_void_p]
     lib.s2s_debug_gemm_trace(buf.data_ptr())
-    run(name, reps=2)
+    run(name, reps=2, flush=flush)
     t = buf.cpu().tolist()
     lib.s2s_debug_gemm_trace(None)
-    print(name, "cycles since kernel start: after-setup %d, first-TMA-issue %d, first-full %d, last-full %d, epi-start %d, epi-end %d, end %d" %
-          tuple(x - t[0] for x in t[1:8]))
-    print("   epilogue halves (cycles): h0 tmem->smem done %d, h0 stored %d, h1 tmem->smem done %d, h1 stored %d" % tuple(x - t[0] for x in t[8:12]))
+    t0 = t[0]
+    print(name, "flush" if flush else "warm", "cycles: setup %d, first TMA issue %d, kernel end %d" % (t[1] - t0, t[2] - t0, t[7] - t0))
+    for i in range(4):
+        r = t[16 + 8 * i: 16 + 8 * i + 6]
+        if r[0] == 0:
+            break
+        print("   tile %d: TMA first issue %d | MMA first-full %d last-full %d | epi tfull %d, tmem released %d, stored %d" %
+              (i, r[5] - t0, r[0] - t0, r[1] - t0, r[2] - t0, r[3] - t0, r[4] - t0))
 
 
 if __name__ == "__main__":
     args = sys.argv[1:]
     if args and args[0] == "trace":
         for n in args[1:]:
-            trace(n)
+            trace(n, True)
+            trace(n, False)
     else:
         for n in (args or list(SHAPES)):
             run(n)
