@@ -282,8 +282,15 @@ def run_ours(args, rank, world):
             gf, gms, n = gemm_roofline(stepper, (dxs, ilens, dys, dlabels, olens), dev, args.gemm_table)
             peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
             ach = gf / (gms * 1e-3) / 1e12
+            traffic = None
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_tc_traffic.json")))
+                if tj.get("workload") == args.workload:
+                    traffic = tj["dram_bytes_per_launch"]
+            except Exception:
+                pass
             line["roofline"] = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05.mma bf16, all shapes of one step)", "achieved": ach,
-                                "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": pk_src + " (sustained)",
+                                "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "peak_source": pk_src + " (sustained)",
                                 "launches_per_step": n, "algorithmic_gflop_per_launch_avg": gf / n / 1e9,
                                 "avg_launch_us": gms * 1e3 / n, "gemm_share_of_step": gms / (ms / args.steps),
                                 "how": "CUDA events around every mode-1 s2s_gemm launch of one eager fwd+bwd after the timed region"}

@@ -64,6 +64,103 @@ __global__ void conv1_fwd_kernel(const float* __restrict__ x, const float* __res
     }
 }
 
+// 8 output channels per thread: one index decomposition and 9 input loads feed 72 FMAs and a 16 B store
+template <typename T>
+__global__ void __launch_bounds__(256) conv1_fwd8_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, T* __restrict__ y, int B, int Tn, int F,
+                                                         int C, int T1, int F1) {
+    extern __shared__ float sw[];  // [9][C] weights then [C] bias
+    for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) sw[(i % 9) * C + i / 9] = w[i];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) sw[9 * C + i] = bias[i];
+    __syncthreads();
+    const int cg = C / 8;
+    const long total = (long)B * T1 * F1 * cg;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % cg) * 8;
+        long pos = i / cg;
+        const int f1 = (int)(pos % F1);
+        long r = pos / F1;
+        const int t1 = (int)(r % T1);
+        const long b = r / T1;
+        const float* xp = x + (b * Tn + 2 * t1) * F + 2 * f1;
+        float xv[9];
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt)
+#pragma unroll
+            for (int kf = 0; kf < 3; ++kf) xv[kt * 3 + kf] = xp[kt * F + kf];
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = sw[9 * C + c + k];
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const float4 w0 = *reinterpret_cast<const float4*>(sw + tap * C + c);
+            const float4 w1 = *reinterpret_cast<const float4*>(sw + tap * C + c + 4);
+            acc[0] = fmaf(xv[tap], w0.x, acc[0]); acc[1] = fmaf(xv[tap], w0.y, acc[1]);
+            acc[2] = fmaf(xv[tap], w0.z, acc[2]); acc[3] = fmaf(xv[tap], w0.w, acc[3]);
+            acc[4] = fmaf(xv[tap], w1.x, acc[4]); acc[5] = fmaf(xv[tap], w1.y, acc[5]);
+            acc[6] = fmaf(xv[tap], w1.z, acc[6]); acc[7] = fmaf(xv[tap], w1.w, acc[7]);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaxf(acc[k], 0.f);
+        Vec8<T>::store(y + pos * C + c, acc);
+    }
+}
+
+// weight gradient with 8 channels per thread: blockDim = (32, 8); x = channel group, y = position stripe
+template <typename T>
+__global__ void __launch_bounds__(256) conv1_bwd8_kernel(const float* __restrict__ x, const T* __restrict__ dy, float* dw,
+                                                         float* dbias, int B, int Tn, int F, int C, int T1, int F1) {
+    __shared__ float red[10][256];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int i = ty * 32 + tx; i < 10 * 256; i += 256) (&red[0][0])[i] = 0.f;
+    __syncthreads();
+    const int c0 = (blockIdx.x * 32 + tx) * 8;
+    const long rows = (long)B * T1 * F1;
+    const long per = (rows + gridDim.y - 1) / gridDim.y;
+    const long r0 = (long)blockIdx.y * per;
+    const long r1 = (r0 + per < rows) ? r0 + per : rows;
+    float acc[10][8];
+#pragma unroll
+    for (int k = 0; k < 10; ++k)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
+    if (c0 < C) {
+        for (long r = r0 + ty; r < r1; r += 8) {
+            const int f1 = (int)(r % F1);
+            const long q = r / F1;
+            const int t1 = (int)(q % T1);
+            const long b = q / T1;
+            const float* xp = x + (b * Tn + 2 * t1) * F + 2 * f1;
+            float g[8];
+            Vec8<T>::load(dy + r * C + c0, g);
+#pragma unroll
+            for (int kt = 0; kt < 3; ++kt)
+#pragma unroll
+                for (int kf = 0; kf < 3; ++kf) {
+                    const float xv = xp[kt * F + kf];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[kt * 3 + kf][j] = fmaf(g[j], xv, acc[kt * 3 + kf][j]);
+                }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[9][j] += g[j];
+        }
+#pragma unroll
+        for (int k = 0; k < 10; ++k)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) atomicAdd(&red[k][tx * 8 + j], acc[k][j]);
+    }
+    __syncthreads();
+    for (int e = ty * 32 + tx; e < 10 * 256; e += 256) {
+        const int k = e / 256, cc = e % 256;
+        const int ch = blockIdx.x * 256 + cc;
+        if (ch < C) {
+            const float v = red[k][cc];
+            if (k < 9) { if (dw) atomicAdd(dw + ch * 9 + k, v); }
+            else if (dbias) atomicAdd(dbias + ch, v);
+        }
+    }
+}
+
 // dw[c][tap] += sum_pos dy[pos][c] * x[pos @ tap]; dbias[c] += sum_pos dy[pos][c]
 // blockDim = (32, 8): x = channel, y = position stripe.
 template <typename T>
@@ -128,7 +225,11 @@ __global__ void im2col_s2_kernel(const T* __restrict__ y1, T* __restrict__ col, 
         int kt = tap / 3, kf = tap % 3;
         const T* src = y1 + (((b * T1 + 2 * t2 + kt) * F1) + 2 * f2 + kf) * C + c;
         T* dst = col + (m * 9 + tap) * C + c;
-        if (VEC == 4) {
+        if (VEC == 8) {
+            float v[8];
+            Vec8<T>::load(src, v);
+            Vec8<T>::store(dst, v);
+        } else if (VEC == 4) {
             float v[4];
             Vec4<T>::load(src, v);
             Vec4<T>::store(dst, v);
@@ -167,18 +268,28 @@ __global__ void col2im_s2_kernel(const T* __restrict__ dcol, T* __restrict__ dy1
                 if (f2 >= F2) continue;
                 long m = (b * T2 + t2) * F2 + f2;
                 const T* src = dcol + (m * 9 + kt * 3 + kf) * C + c;
-                if (VEC == 4) {
+                if (VEC == 8) {
+                    float v[8];
+                    Vec8<T>::load(src, v);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) acc[k < VEC ? k : 0] += v[k];
+                } else if (VEC == 4) {
                     float v[4];
                     Vec4<T>::load(src, v);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) acc[k] += v[k];
+                    for (int k = 0; k < 4; ++k) acc[k < VEC ? k : 0] += v[k];
                 } else {
                     acc[0] += to_f<T>(*src);
                 }
             }
         }
         T* dst = dy1 + q * C + c;
-        if (VEC == 4) {
+        if (VEC == 8) {
+            float o[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = acc[k < VEC ? k : 0];
+            Vec8<T>::store(dst, o);
+        } else if (VEC == 4) {
             float o[4] = {acc[0], acc[VEC > 1 ? 1 : 0], acc[VEC > 2 ? 2 : 0], acc[VEC > 3 ? 3 : 0]};
             Vec4<T>::store(dst, o);
         } else {
@@ -485,8 +596,13 @@ extern "C" int s2s_conv1_fwd(const float* x, const float* w, const float* bias, 
     long total = (long)B * T1 * F1 * C;
     size_t smem = (size_t)10 * C * sizeof(float);
     S2S_REQUIRE(smem <= 48 * 1024, "conv1_fwd: C too large (%d)", C);
-    S2S_DISPATCH_DTYPE(dtype, TT, (conv1_fwd_kernel<TT><<<ew_grid(total, 1024), 256, smem, (cudaStream_t)stream>>>(
-        x, w, bias, (TT*)y1, B, T, F, C, T1, F1)));
+    if (C % 8 == 0 && aligned16(y1)) {
+        S2S_DISPATCH_DTYPE(dtype, TT, (conv1_fwd8_kernel<TT><<<ew_grid(total / 8, 256), 256, smem, (cudaStream_t)stream>>>(
+            x, w, bias, (TT*)y1, B, T, F, C, T1, F1)));
+    } else {
+        S2S_DISPATCH_DTYPE(dtype, TT, (conv1_fwd_kernel<TT><<<ew_grid(total, 1024), 256, smem, (cudaStream_t)stream>>>(
+            x, w, bias, (TT*)y1, B, T, F, C, T1, F1)));
+    }
     S2S_LAUNCH_OK();
     return S2S_OK;
 }
@@ -495,13 +611,19 @@ extern "C" int s2s_conv1_bwd(const float* x, const void* dy1, float* dw, float* 
     S2S_REQUIRE(x && dy1 && B > 0 && T >= 3 && F >= 3 && C > 0, "conv1_bwd: bad arguments");
     int T1 = (T - 1) / 2, F1 = (F - 1) / 2;
     long rows = (long)B * T1 * F1;
-    unsigned gx = (unsigned)ceil_div_l(C, 32);
-    long gy = (long)num_sms() * 4 / gx;
+    const bool v8 = (C % 8 == 0) && aligned16(dy1);
+    unsigned gx = (unsigned)ceil_div_l(C, v8 ? 256 : 32);
+    long gy = (long)num_sms() * (v8 ? 2 : 4) / gx;
     if (gy < 1) gy = 1;
     if (gy > ceil_div_l(rows, 64)) gy = ceil_div_l(rows, 64);
     if (gy < 1) gy = 1;
-    S2S_DISPATCH_DTYPE(dtype, TT, (conv1_bwd_kernel<TT><<<dim3(gx, (unsigned)gy), dim3(32, 8), 0, (cudaStream_t)stream>>>(
-        x, (const TT*)dy1, dw, dbias, B, T, F, C, T1, F1)));
+    if (v8) {
+        S2S_DISPATCH_DTYPE(dtype, TT, (conv1_bwd8_kernel<TT><<<dim3(gx, (unsigned)gy), dim3(32, 8), 0, (cudaStream_t)stream>>>(
+            x, (const TT*)dy1, dw, dbias, B, T, F, C, T1, F1)));
+    } else {
+        S2S_DISPATCH_DTYPE(dtype, TT, (conv1_bwd_kernel<TT><<<dim3(gx, (unsigned)gy), dim3(32, 8), 0, (cudaStream_t)stream>>>(
+            x, (const TT*)dy1, dw, dbias, B, T, F, C, T1, F1)));
+    }
     S2S_LAUNCH_OK();
     return S2S_OK;
 }
@@ -512,7 +634,8 @@ extern "C" int s2s_im2col_s2(const void* y1, void* col, int B, int T1, int F1, i
     long total = (long)B * T2 * F2 * 9 * C;
     bool ok = (C % 4 == 0) && ((uintptr_t)y1 % 16 == 0) && ((uintptr_t)col % 16 == 0);
     S2S_DISPATCH_DTYPE(dtype, TT, {
-        if (ok) im2col_s2_kernel<TT, 4><<<ew_grid(total / 4, 256), 256, 0, (cudaStream_t)stream>>>((const TT*)y1, (TT*)col, B, T1, F1, C, T2, F2);
+        if (ok && C % 8 == 0) im2col_s2_kernel<TT, 8><<<ew_grid(total / 8, 256), 256, 0, (cudaStream_t)stream>>>((const TT*)y1, (TT*)col, B, T1, F1, C, T2, F2);
+        else if (ok) im2col_s2_kernel<TT, 4><<<ew_grid(total / 4, 256), 256, 0, (cudaStream_t)stream>>>((const TT*)y1, (TT*)col, B, T1, F1, C, T2, F2);
         else im2col_s2_kernel<TT, 1><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const TT*)y1, (TT*)col, B, T1, F1, C, T2, F2);
     });
     S2S_LAUNCH_OK();
@@ -524,7 +647,8 @@ extern "C" int s2s_col2im_s2(const void* dcol, void* dy1, int B, int T1, int F1,
     long total = (long)B * T1 * F1 * C;
     bool ok = (C % 4 == 0) && ((uintptr_t)dy1 % 16 == 0) && ((uintptr_t)dcol % 16 == 0);
     S2S_DISPATCH_DTYPE(dtype, TT, {
-        if (ok) col2im_s2_kernel<TT, 4><<<ew_grid(total / 4, 256), 256, 0, (cudaStream_t)stream>>>((const TT*)dcol, (TT*)dy1, B, T1, F1, C, T2, F2);
+        if (ok && C % 8 == 0) col2im_s2_kernel<TT, 8><<<ew_grid(total / 8, 256), 256, 0, (cudaStream_t)stream>>>((const TT*)dcol, (TT*)dy1, B, T1, F1, C, T2, F2);
+        else if (ok) col2im_s2_kernel<TT, 4><<<ew_grid(total / 4, 256), 256, 0, (cudaStream_t)stream>>>((const TT*)dcol, (TT*)dy1, B, T1, F1, C, T2, F2);
         else col2im_s2_kernel<TT, 1><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const TT*)dcol, (TT*)dy1, B, T1, F1, C, T2, F2);
     });
     S2S_LAUNCH_OK();

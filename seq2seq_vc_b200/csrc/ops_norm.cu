@@ -189,10 +189,33 @@ __global__ void relu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ 
         dx[i] = from_f<T>(to_f<T>(y[i]) > 0.f ? to_f<T>(dy[i]) * scale : 0.f);
 }
 template <typename T>
+__global__ void __launch_bounds__(256) relu_bwd8_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx,
+                                                        long n8, float scale) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
+        float g[8], a[8];
+        Vec8<T>::load(dy + 8 * i, g);
+        Vec8<T>::load(y + 8 * i, a);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g[k] = a[k] > 0.f ? g[k] * scale : 0.f;
+        Vec8<T>::store(dx + 8 * i, g);
+    }
+}
+template <typename T>
 __global__ void dropout_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, long n, Dropout drop) {
     dropout_resolve(drop);
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
         dx[i] = from_f<T>(to_f<T>(dy[i]) * dropout_factor(drop, (uint64_t)i));
+}
+template <typename T>
+__global__ void __launch_bounds__(256) dropout_bwd8_kernel(const T* __restrict__ dy, T* __restrict__ dx, long n8, Dropout drop) {
+    dropout_resolve(drop);
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
+        float g[8];
+        Vec8<T>::load(dy + 8 * i, g);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g[k] *= dropout_factor(drop, (uint64_t)(8 * i + k));
+        Vec8<T>::store(dx + 8 * i, g);
+    }
 }
 
 // =============================================================================================
@@ -522,7 +545,11 @@ extern "C" int s2s_relu_bwd(const void* dy, const void* y, void* dx, int64_t n, 
     S2S_REQUIRE(dy && y && dx, "relu_bwd: null pointer");
     if (n <= 0) return S2S_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    S2S_DISPATCH_DTYPE(dtype, T, (relu_bwd_kernel<T><<<ew_grid(n, 256 * 4), 256, 0, st>>>((const T*)dy, (const T*)y, (T*)dx, n, scale)));
+    if (n % 8 == 0 && aligned16(dy, y, dx)) {
+        S2S_DISPATCH_DTYPE(dtype, T, (relu_bwd8_kernel<T><<<ew_grid(n / 8, 256), 256, 0, st>>>((const T*)dy, (const T*)y, (T*)dx, n / 8, scale)));
+    } else {
+        S2S_DISPATCH_DTYPE(dtype, T, (relu_bwd_kernel<T><<<ew_grid(n, 256 * 4), 256, 0, st>>>((const T*)dy, (const T*)y, (T*)dx, n, scale)));
+    }
     S2S_LAUNCH_OK();
     return S2S_OK;
 }
@@ -534,7 +561,11 @@ extern "C" int s2s_dropout_bwd(const void* dy, void* dx, int64_t rows, int cols,
     if (n <= 0) return S2S_OK;
     cudaStream_t st = (cudaStream_t)stream;
     Dropout d = make_dropout(drop);
-    S2S_DISPATCH_DTYPE(dtype, T, (dropout_bwd_kernel<T><<<ew_grid(n, 256 * 4), 256, 0, st>>>((const T*)dy, (T*)dx, n, d)));
+    if (n % 8 == 0 && aligned16(dy, dx)) {
+        S2S_DISPATCH_DTYPE(dtype, T, (dropout_bwd8_kernel<T><<<ew_grid(n / 8, 256), 256, 0, st>>>((const T*)dy, (T*)dx, n / 8, d)));
+    } else {
+        S2S_DISPATCH_DTYPE(dtype, T, (dropout_bwd_kernel<T><<<ew_grid(n, 256 * 4), 256, 0, st>>>((const T*)dy, (T*)dx, n, d)));
+    }
     S2S_LAUNCH_OK();
     return S2S_OK;
 }

@@ -1,0 +1,83 @@
+"""Data-parallel step (world size 2, gloo, CPU): the flat-gradient all-reduce + 1/world scaling inside the
+Adam kernel equals one process stepping on the mean of the two ranks' gradients.  Kernels are replaced
+by their CPU contracts (tests/fake_ops.py): this covers the N>1 host logic, NCCL runs on the GPU box."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+HP = dict(idim=80, odim=80, dprenet_layers=2, dprenet_units=16, adim=32, aheads=2, elayers=1, eunits=48, dlayers=1,
+          dunits=48, postnet_layers=2, postnet_filts=5, postnet_chans=16, decoder_reduction_factor=2,
+          dprenet_dropout_rate=0.0, transformer_enc_dropout_rate=0.0, enc_positional_dropout_rate=0.0,
+          dec_dropout_rate=0.0, dec_positional_dropout_rate=0.0, postnet_dropout_rate=0.0)
+
+
+def _install_fakes():
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    import fake_ops
+    import seq2seq_vc_b200.ops as ops
+
+    for n in fake_ops.ALL:
+        if hasattr(ops, n) and n not in ("mas", "logmel"):
+            setattr(ops, n, getattr(fake_ops, n))
+
+
+def _batch(rank):
+    from oracle import vtn_oracle
+
+    return vtn_oracle.synthetic_batch(2, 40, 24, ilens=[40, 33], olens=[24, 17], seed=100 + rank)
+
+
+def _worker(rank, world, port, out_dir):
+    _install_fakes()
+    import torch.distributed as dist
+
+    from seq2seq_vc_b200 import VTNEngine, VTNTrainStep
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    eng = VTNEngine(HP, device="cpu", bf16=False, seed=5)
+    step = VTNTrainStep(eng, lr=1e-3, warmup_steps=1, use_graph=False)
+    xs, ilens, ys, labels, olens = _batch(rank)
+    for _ in range(2):
+        step(xs, ilens, ys, labels, olens)
+    torch.save(eng.store.P.clone(), os.path.join(out_dir, f"p{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_two_rank_step_matches_mean_gradient_step(tmp_path, monkeypatch):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    p0, p1 = torch.load(tmp_path / "p0.pt"), torch.load(tmp_path / "p1.pt")
+    assert torch.equal(p0, p1), "replicas diverged"
+
+    # single process: average the two ranks' gradients by hand, then the same optimizer tail
+    import fake_ops
+    from seq2seq_vc_b200 import VTNEngine, VTNTrainStep
+
+    fake_ops.install(monkeypatch)
+    engs = [VTNEngine(HP, device="cpu", bf16=False, seed=5) for _ in range(2)]
+    ref = VTNEngine(HP, device="cpu", bf16=False, seed=5)
+    stepper = VTNTrainStep(ref, lr=1e-3, warmup_steps=1)
+    for it in range(2):
+        g = torch.zeros_like(ref.store.G)
+        for r, e in enumerate(engs):
+            e.store.P.copy_(ref.store.P)
+            for k in ref.buffers:
+                pass
+            xs, ilens, ys, labels, olens = _batch(r)
+            e.forward(xs, ys, ilens, olens)
+            e.loss(ys, labels)
+            e.backward(e.d_after, e.d_before, e.d_logits)
+            g += e.store.G
+        ref.store.G.copy_(g / 2)
+        stepper.steps += 1
+        ref.lr_dev.fill_(stepper.lr_at(stepper.steps))
+        ref.optimizer_step(1.0)
+    assert (ref.store.P - p0).abs().max().item() <= 1e-6
