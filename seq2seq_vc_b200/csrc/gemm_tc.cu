@@ -1,12 +1,13 @@
 // bf16 tensor-core GEMM for sm_100a: TMA -> shared memory -> tcgen05.mma (TMEM accumulators) ->
 // tcgen05.ld epilogue.  Backs s2s_gemm(mode = 1).
 //
-// One persistent CTA per SM, 6 warps:
-//   warp 0      TMA producer   (cp.async.bulk.tensor, 128B-swizzled boxes, mbarrier complete_tx)
-//   warp 1      MMA issuer     (one lane issues tcgen05.mma 128 x BN x 16, commits to mbarriers);
-//               also owns the TMEM allocation (2 accumulator stages x 128 fp32 columns)
-//   warps 2-5   epilogue       (tcgen05.ld 32 lanes x 16 columns, fused alpha / bias / relu / dropout /
-//               residual / accumulate / row-mask, vectorised global stores or fp32 red.add for split-K)
+// One persistent CTA per SM, 10 warps:
+//   warp 0      TMA producer   (cp.async.bulk.tensor 4-D, 128B-swizzled boxes, mbarrier complete_tx)
+//   warp 1      MMA issuer     (one lane issues tcgen05.mma 128 x BN x 16 with BN <= 256, commits to
+//               mbarriers); also owns the TMEM allocation (2 accumulator stages x 256 fp32 columns)
+//   warps 2-9   epilogue       (warp -> TMEM lane quarter x two 64-column chunks; each thread owns one
+//               output row: tcgen05.ld 32x32b.x16 x4 in flight before one wait, bias broadcast by warp
+//               shuffles, 16-byte row stores or vector red.add for fp32 accumulate-in-place outputs)
 // Pipelines: STAGES-deep smem ring (full/empty mbarriers) between TMA and MMA, 2-deep TMEM ring
 // (tmem_full/tmem_empty) between MMA and epilogue, static round-robin tile scheduler.
 //
@@ -15,6 +16,18 @@
 // transposed ("MN-major") operands of the weight-gradient GEMMs, and the `taps` convolution form
 // (the tap index is a TMA coordinate: A rows shift by t, B selects weight slice t).
 // K / M / N tails are handled by TMA zero fill; nothing is padded in HBM.
+//
+// Lessons baked into the structure (ncu + in-kernel clock traces, see profiles/ and DESIGN.md):
+//  * CODE SIZE: the epilogue runs once per tile; when its straight-line body outgrew the
+//    instruction cache (a fully unrolled, feature-complete version was 47 KB; the fp32 one 1.5 MB)
+//    it ran at instruction-fetch speed (stall_no_inst) and was 2.5x slower than the MMA main loop.
+//    The kernel is therefore specialised at compile time by epilogue kind (EPI_*), rare paths live
+//    in one rolled non-inlined helper, and the tile decode is a non-inlined function.
+//  * TMEM reads contend with the accumulator traffic of the next tile's MMAs: all loads of a
+//    32 x 64 block are issued back to back before a single wait, and the accumulator stage is
+//    released as soon as a warp's values are in registers.
+//  * tcgen05.mma in cta_group::1 reads both operands from shared memory; 128 x 256 x 16 instructions
+//    (BN = 256) halve the A re-reads per FLOP compared with 128 x 128.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -29,38 +42,42 @@ int gemm_simt(const s2s_gemm_t& g, cudaStream_t st);
 
 namespace tc {
 
-constexpr int BM = 128, BK = 64, MAX_BN = 128, STAGES = 4, UMMA_K = 16;
+constexpr int BM = 128, BK = 64, MAX_BN = 256, STAGES = 4, UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = MAX_BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int TMEM_COLS = 256;
+constexpr int TMEM_COLS = 512;      // two accumulator stages x 256 fp32 columns: the whole tensor memory of the SM
 constexpr int EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
-// epilogue staging: per epilogue warp 32 rows x 64 fp32 columns, row stride 68 floats (272 B) so that
-// both the row-owner writes (16 B per lane, 32 rows) and the coalesced read-back are (nearly) conflict free
-constexpr int STG_LD = 68, STG_BYTES = 32 * STG_LD * 4;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES + EPI_WARPS * 64 * 4 + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+// epilogue specialisations (compile time, to keep every instantiation's code small)
+constexpr int EPI_BF16_PLAIN = 0;   // bf16 C = alpha * acc + bias, optional relu
+constexpr int EPI_BF16_FULL = 1;    // + dropout, residual, accumulate, row mask
+constexpr int EPI_F32 = 2;          // fp32 C: red.add (accumulate in place / split-K) or plain store of alpha * acc
 
 struct Params {
     CUtensorMap tmA, tmB;
     int M, N, K, taps, batch1, batch2;
     int a_mn, b_mn;          // 1 = operand contiguous along M / N ("MN-major"), 0 = along K
-    int BN;                  // N tile (multiple of 16, <= 128)
+    int BN;                  // N tile (multiple of 16, <= 256)
     int mt, nt, kb_per_tap, kb_total, splits;
     void* C; int c_f32; long c_rs, c_bs1, c_bs2;
     const void* R;
     const float* bias;
     float alpha;
     int relu, accumulate, atomic_out;
-    int staged;              // bf16 C with 16 B-aligned rows: coalesced epilogue through shared memory
+    int vec_ok;              // C (and R) rows are 16-byte aligned: vector loads / stores / red.add in the epilogue
     Dropout drop;
     int mask_period, mask_offset, mask_lo, mask_hi;
-    long long* trace;        // optional: CTA 0 records globaltimer stamps of pipeline milestones (debug)
+    long long* trace;        // optional (S2S_GEMM_TRACE builds): CTA 0 records clock64 stamps of pipeline milestones
 };
 
+#ifdef S2S_GEMM_TRACE
 __device__ __forceinline__ void stamp(const Params& p, int slot) {
-    if (p.trace && blockIdx.x == 0) {
-        p.trace[slot] = clock64();
-    }
+    if (p.trace && blockIdx.x == 0) p.trace[slot] = clock64();
 }
+#else
+__device__ __forceinline__ void stamp(const Params&, int) {}
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -113,6 +130,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 // shared-memory matrix descriptor (SWIZZLE_128B, sm_100 version field = 1)
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -126,14 +146,12 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
 }
 
 // ---------------------------------------------------------------------------------------------
-// kernel
+// tile scheduler
 // ---------------------------------------------------------------------------------------------
 struct Item {
     int b1, b2, m0, n0, kb0, kb1;
 };
-__device__ __forceinline__ Item decode_item(const Params& p, long item_l) {
-    Item it;
-    const uint32_t item = (uint32_t)item_l;                 // host guarantees < 2^31 work items
+__device__ __noinline__ void decode_item(const Params& p, uint32_t item, Item& it) {
     const uint32_t split = item % (uint32_t)p.splits;
     uint32_t tile = item / (uint32_t)p.splits;
     const uint32_t ntile = tile % (uint32_t)p.nt;
@@ -147,56 +165,51 @@ __device__ __forceinline__ Item decode_item(const Params& p, long item_l) {
     const int per = (p.kb_total + p.splits - 1) / p.splits;
     it.kb0 = (int)split * per;
     it.kb1 = min(p.kb_total, it.kb0 + per);
-    return it;
 }
 
-// Code size matters here: the epilogue warps run this once per tile and a bloated body turns into
-// instruction-cache misses (ncu: stall_no_inst dominated the first version).  Rare paths are kept in
-// rolled loops / non-inlined helpers; only the 16-wide hot path is unrolled.
-
-// direct (row-owner) store of 16 consecutive columns of one output row; used for fp32 C (weight
-// gradients: red.add or plain stores) and for bf16 C whose rows are not 16 B aligned
+// rare epilogue paths (column tails, unaligned rows, fp32 C with residual): rolled and out of line
 template <typename TC>
-__device__ __noinline__ void epilogue_direct(const Params& p, const Dropout& drop, float (&v)[16], TC* __restrict__ dst,
-                                             const TC* __restrict__ rsrc, uint64_t didx, int nvalid, bool row_ok) {
-    if (p.atomic_out) {
-        if (!row_ok) return;
-#pragma unroll 1
-        for (int j = 0; j < nvalid; ++j) atomicAdd(reinterpret_cast<float*>(dst) + j, v[j]);
-        return;
-    }
+__device__ __noinline__ void epilogue_scalar(const Params& p, const float* v, TC* __restrict__ dst, const TC* __restrict__ rsrc,
+                                             int nvalid, bool row_ok) {
 #pragma unroll 1
     for (int j = 0; j < nvalid; ++j) {
         float x = v[j];
-        if (p.relu) x = fmaxf(x, 0.f);
-        x *= dropout_factor(drop, didx + j);
+        if (p.atomic_out) {
+            if (row_ok) atomicAdd(reinterpret_cast<float*>(dst) + j, x);
+            continue;
+        }
         if (rsrc) x += to_f<TC>(rsrc[j]);
         if (p.accumulate) x += to_f<TC>(dst[j]);
         dst[j] = from_f<TC>(row_ok ? x : 0.f);
     }
 }
 
-// N-tail of the coalesced path: fewer than 8 valid columns in this lane's group
-template <typename TC>
-__device__ __noinline__ void epilogue_tail(const Params& p, const float (&o)[8], TC* __restrict__ dst, const TC* __restrict__ rsrc,
-                                           int nvalid, bool row_ok) {
-#pragma unroll 1
-    for (int q = 0; q < nvalid; ++q) {
-        float x = o[q];
-        if (rsrc) x += to_f<TC>(rsrc[q]);
-        if (p.accumulate) x += to_f<TC>(dst[q]);
-        dst[q] = from_f<TC>(row_ok ? x : 0.f);
+__device__ __forceinline__ void add_bf16x8(float* v, const uint4& r) {
+    const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { v[2 * e] += __low2float(r2[e]); v[2 * e + 1] += __high2float(r2[e]); }
+}
+__device__ __forceinline__ uint4 pack_bf16x8(const float* v) {
+    uint4 w;
+    uint32_t* wp = reinterpret_cast<uint32_t*>(&w);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+        wp[e] = *reinterpret_cast<uint32_t*>(&h);
     }
+    return w;
 }
 
-template <typename TC>
+// ---------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------
+template <int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ Params p) {
+    using TC = typename std::conditional<EPI == EPI_F32, float, bf16>::type;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                    // SWIZZLE_128B tiles need 1024 B alignment
-    const uint32_t stg_base = base + STAGES * STAGE_BYTES;           // one staging tile per epilogue warp
-    const uint32_t bias_base = stg_base + EPI_WARPS * STG_BYTES;     // 64 bias floats per epilogue warp
-    const uint32_t bars = bias_base + EPI_WARPS * 64 * 4;            // full[STAGES], empty[STAGES], tfull[2], tempty[2]
+    const uint32_t bars = base + STAGES * STAGE_BYTES;               // full[STAGES], empty[STAGES], tfull[2], tempty[2]
     __shared__ uint32_t tmem_base_slot;
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
@@ -221,25 +234,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     const uint32_t tmem_base = tmem_base_slot;
     if (threadIdx.x == 0) stamp(p, 1);
 
-    const long total = (long)p.batch1 * p.batch2 * p.mt * p.nt * p.splits;
+    const uint32_t total = (uint32_t)((long)p.batch1 * p.batch2 * p.mt * p.nt * p.splits);
     const int BN = p.BN;
-    const int b_boxes = p.b_mn ? (BN + 63) / 64 : 1;
-    const uint32_t tx_bytes = (uint32_t)A_BYTES + (uint32_t)(p.b_mn ? b_boxes * 8192 : BN * 128);
 
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
+            const int b_boxes = p.b_mn ? (BN + 63) / 64 : 1;
+            const uint32_t tx_bytes = (uint32_t)A_BYTES + (uint32_t)(p.b_mn ? b_boxes * 8192 : BN * 128);
             int stage = 0;
             uint32_t phase = 0;
-            for (long item = blockIdx.x; item < total; item += gridDim.x) {
-                const Item it = decode_item(p, item);
+            Item it;
+#pragma unroll 1
+            for (uint32_t item = blockIdx.x; item < total; item += gridDim.x) {
+                decode_item(p, item, it);
+#pragma unroll 1
                 for (int kb = it.kb0; kb < it.kb1; ++kb) {
                     const int t = kb / p.kb_per_tap;
                     const int kk = (kb - t * p.kb_per_tap) * BK;
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
                     if (kb == it.kb0 && item == blockIdx.x) stamp(p, 2);
-                    if (kb == it.kb0 && (item - blockIdx.x) / gridDim.x < 4) stamp(p, 16 + 8 * (int)((item - blockIdx.x) / gridDim.x) + 5);
                     mbar_expect_tx(full_bar(stage), tx_bytes);
                     if (p.a_mn) {
                         tma_load_4d(sa, &p.tmA, full_bar(stage), it.m0, kk, it.b2, it.b1);
@@ -248,6 +263,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                         tma_load_4d(sa, &p.tmA, full_bar(stage), kk, it.m0 + t, it.b2, it.b1);
                     }
                     if (p.b_mn) {
+#pragma unroll 1
                         for (int j = 0; j < b_boxes; ++j)
                             tma_load_4d(sb + 8192 * j, &p.tmB, full_bar(stage), it.n0 + 64 * j, kk, it.b2, it.b1);
                     } else {
@@ -261,16 +277,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         // ================= MMA issuer =================
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
                                ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        // K-major: 16 bf16 = 32 B inside the 128 B swizzle row; MN-major: 16 k-rows of 128 B, 64-wide groups 8 KB apart
+        const uint32_t a_step = p.a_mn ? 2048u : 32u, b_step = p.b_mn ? 2048u : 32u;
+        const uint32_t a_lbo = p.a_mn ? 8192u : 16u, b_lbo = p.b_mn ? 8192u : 16u;
         int stage = 0;
         uint32_t phase = 0;
-        long n_items = 0;
-        for (long item = blockIdx.x; item < total; item += gridDim.x, ++n_items) {
-            const Item it = decode_item(p, item);
+        uint32_t n_items = 0;
+        Item it;
+#pragma unroll 1
+        for (uint32_t item = blockIdx.x; item < total; item += gridDim.x, ++n_items) {
+            decode_item(p, item, it);
             const int as = (int)(n_items & 1);
-            const uint32_t aphase = (uint32_t)((n_items >> 1) & 1);
+            const uint32_t aphase = (n_items >> 1) & 1u;
             mbar_wait(tempty_bar(as), aphase ^ 1u);
             tcgen05_fence_after();
             const uint32_t tmem_d = tmem_base + (uint32_t)(as * MAX_BN);
+#pragma unroll 1
             for (int kb = it.kb0; kb < it.kb1; ++kb) {
                 const int t = kb / p.kb_per_tap;
                 const int kk = (kb - t * p.kb_per_tap) * BK;
@@ -281,12 +303,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                 if (lane == 0 && n_items < 4 && kb == it.kb1 - 1) stamp(p, 16 + 8 * (int)n_items + 1);
                 if (lane == 0) {
                     const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
-                    for (int k = 0; k < ksteps; ++k) {
-                        // K-major: 16 bf16 = 32 B inside the 128 B swizzle row; MN-major: 16 k-rows of 128 B
-                        const uint64_t adesc = p.a_mn ? smem_desc(sa + k * 2048, 8192, 1024) : smem_desc(sa + k * 32, 16, 1024);
-                        const uint64_t bdesc = p.b_mn ? smem_desc(sb + k * 2048, 8192, 1024) : smem_desc(sb + k * 32, 16, 1024);
-                        umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > it.kb0 || k > 0) ? 1u : 0u);
-                    }
+#pragma unroll 1
+                    for (int k = 0; k < ksteps; ++k)
+                        umma_bf16(tmem_d, smem_desc(sa + k * a_step, a_lbo, 1024), smem_desc(sb + k * b_step, b_lbo, 1024), idesc,
+                                  (kb > it.kb0 || k > 0) ? 1u : 0u);
                     umma_commit(empty_bar(stage));
                     if (kb == it.kb1 - 1) umma_commit(tfull_bar(as));
                 }
@@ -295,143 +315,138 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             }
         }
     } else {
-        // ================= epilogue: 8 warps, warp -> (TMEM lane quarter, 64-column half) =================
+        // ================= epilogue: 8 warps; warp -> TMEM lane quarter x 64-column chunks {ch, ch + 2} =================
         Dropout drop = p.drop;
-        dropout_resolve(drop);
-        const int ew = warp - 2;
+        if (EPI == EPI_BF16_FULL) dropout_resolve(drop);
         const int quarter = warp & 3;             // TMEM lanes this warp may access: 32 * (warp_id % 4) ...
-        const int ch = ew >> 2;                   // which 64-column half of the tile
-        unsigned char* smem_gen = smem_raw + (base - raw);
-        float* stg = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES + ew * STG_BYTES);
-        float* bias_s = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES) + ew * 64;
-        const int r4 = lane >> 3, cl = (lane & 7) * 8;   // coalesced mapping: 4 rows x 8 column groups of 8
-        const bool staged = (sizeof(TC) == 2) && p.staged;
-        const int ncols = min(64, BN - ch * 64);         // columns of this warp (<= 0: idle for this tile shape)
-        long n_items = 0;
-        for (long item = blockIdx.x; item < total; item += gridDim.x, ++n_items) {
-            const Item it = decode_item(p, item);
+        const int ch = (warp - 2) >> 2;           // owns 64-column chunks ch and ch + 2 of the tile
+        uint32_t n_items = 0;
+        Item it;
+#pragma unroll 1
+        for (uint32_t item = blockIdx.x; item < total; item += gridDim.x, ++n_items) {
+            decode_item(p, item, it);
             const int as = (int)(n_items & 1);
-            const uint32_t aphase = (uint32_t)((n_items >> 1) & 1);
-            const int row0 = it.m0 + quarter * 32;
-            const int m = row0 + lane;                       // row owned while reading TMEM
-            const int nw0 = it.n0 + ch * 64;                 // first column of this warp
-            const long batch_lin = (long)(it.b1 * p.batch2 + it.b2) * p.M;
-            TC* Cb = reinterpret_cast<TC*>(p.C) + it.b1 * p.c_bs1 + it.b2 * p.c_bs2;
-            const TC* Rb = p.R ? reinterpret_cast<const TC*>(p.R) + it.b1 * p.c_bs1 + it.b2 * p.c_bs2 : nullptr;
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * MAX_BN + ch * 64);
-            // bias slice -> shared memory, residual rows -> registers (both hidden behind the MMA main loop)
+            const uint32_t aphase = (n_items >> 1) & 1u;
+            const int m = it.m0 + quarter * 32 + lane;       // the output row this thread owns
+            const bool row_in = m < p.M;
+            TC* Crow = reinterpret_cast<TC*>(p.C) + it.b1 * p.c_bs1 + it.b2 * p.c_bs2 + (long)m * p.c_rs;
+            const TC* Rrow = (EPI == EPI_BF16_PLAIN || !p.R) ? nullptr
+                                 : reinterpret_cast<const TC*>(p.R) + it.b1 * p.c_bs1 + it.b2 * p.c_bs2 + (long)m * p.c_rs;
+            const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * MAX_BN);
+            bool row_ok = true;
+            if (EPI != EPI_BF16_PLAIN && p.mask_period > 0) {
+                const int ph = (m + p.mask_offset) % p.mask_period;
+                row_ok = (ph >= p.mask_lo) && (ph < p.mask_hi);
+            }
+            // bias values (lane j holds columns j and j + 32 of each 64-column chunk) and, for the full epilogue,
+            // the residual row segments of the first chunk are fetched before the accumulator is ready
+            float b00 = 0.f, b01 = 0.f, b10 = 0.f, b11 = 0.f;
+            if (EPI != EPI_F32 && p.bias) {
+                const int n0a = it.n0 + ch * 64, n0b = it.n0 + (ch + 2) * 64;
+                if (n0a + lane < p.N) b00 = p.bias[n0a + lane];
+                if (n0a + lane + 32 < p.N) b01 = p.bias[n0a + lane + 32];
+                if (n0b + lane < p.N) b10 = p.bias[n0b + lane];
+                if (n0b + lane + 32 < p.N) b11 = p.bias[n0b + lane + 32];
+            }
             uint4 rr[8];
-            if (ncols > 0) {
-                bias_s[lane] = (p.bias && nw0 + lane < p.N) ? p.bias[nw0 + lane] : 0.f;
-                bias_s[lane + 32] = (p.bias && nw0 + lane + 32 < p.N) ? p.bias[nw0 + lane + 32] : 0.f;
-            }
-            const bool pre = staged && Rb && cl < ncols && nw0 + cl + 8 <= p.N;
+            const bool res_vec = (EPI == EPI_BF16_FULL) && Rrow && p.vec_ok && row_in;
+            auto load_res = [&](int u) {
+                const int c0 = (ch + 2 * u) * 64;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                rr[i] = make_uint4(0u, 0u, 0u, 0u);
-                if (pre && row0 + i * 4 + r4 < p.M)
-                    rr[i] = *reinterpret_cast<const uint4*>(Rb + (long)(row0 + i * 4 + r4) * p.c_rs + nw0 + cl);
-            }
-            __syncwarp();
+                for (int g8 = 0; g8 < 8; ++g8) {
+                    rr[g8] = make_uint4(0u, 0u, 0u, 0u);
+                    if (res_vec && c0 + g8 * 8 < BN && it.n0 + c0 + g8 * 8 + 8 <= p.N)
+                        rr[g8] = *reinterpret_cast<const uint4*>(Rrow + it.n0 + c0 + g8 * 8);
+                }
+            };
+            if (EPI == EPI_BF16_FULL) load_res(0);
             mbar_wait(tfull_bar(as), aphase);
             tcgen05_fence_after();
             if (threadIdx.x == 64 && n_items < 4) stamp(p, 16 + 8 * (int)n_items + 2);
-            // ---- all TMEM loads of this warp's 32 x 64 block are issued before the single wait
-            uint32_t acc[4][16];
+#pragma unroll 1
+            for (int u = 0; u < 2; ++u) {
+                const int c0 = (ch + 2 * u) * 64;
+                const int ncols = min(64, BN - c0);
+                uint32_t acc[4][16];
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (q * 16 < ncols) tmem_ld16(taddr + q * 16, acc[q]);
-            tmem_ld_wait();
-            // every value is in registers: hand the accumulator stage back to the MMA warp right away
-            tcgen05_fence_before();
-            __syncwarp();
-            if (threadIdx.x == 64 && n_items < 4) stamp(p, 16 + 8 * (int)n_items + 3);
-            if (lane == 0) mbar_arrive(tempty_bar(as));
-            if (ncols <= 0) continue;
-            // ---- alpha, bias, relu, dropout in the row-owner layout
+                for (int q = 0; q < 4; ++q)
+                    if (q * 16 < ncols) tmem_ld16(tbase + c0 + q * 16, acc[q]);
+                tmem_ld_wait();
+                if (u == 1) {
+                    // every value of this warp is in registers: hand the accumulator stage back to the MMA warp
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (threadIdx.x == 64 && n_items < 4) stamp(p, 16 + 8 * (int)n_items + 3);
+                    if (lane == 0) mbar_arrive(tempty_bar(as));
+                }
+                if (ncols <= 0) continue;          // warp-uniform
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if (q * 16 < ncols) {
+                for (int q = 0; q < 4; ++q) {
+                    if (q * 16 >= ncols) continue; // warp-uniform
                     float v[16];
-                    const float4* b4 = reinterpret_cast<const float4*>(bias_s + q * 16);
+                    if (EPI == EPI_F32) {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float4 bb = b4[e];
-                        v[4 * e + 0] = fmaf(__uint_as_float(acc[q][4 * e + 0]), p.alpha, bb.x);
-                        v[4 * e + 1] = fmaf(__uint_as_float(acc[q][4 * e + 1]), p.alpha, bb.y);
-                        v[4 * e + 2] = fmaf(__uint_as_float(acc[q][4 * e + 2]), p.alpha, bb.z);
-                        v[4 * e + 3] = fmaf(__uint_as_float(acc[q][4 * e + 3]), p.alpha, bb.w);
-                    }
-                    const int n_base = nw0 + q * 16;
-                    const uint64_t didx = (uint64_t)((batch_lin + m) * (long)p.N + n_base);
-                    if (staged) {
+                        for (int jj = 0; jj < 16; ++jj) v[jj] = __uint_as_float(acc[q][jj]) * p.alpha;
+                    } else {
+                        if (p.bias) {                  // warp-uniform
+                            const float bsel = u ? ((q & 2) ? b11 : b10) : ((q & 2) ? b01 : b00);
+#pragma unroll
+                            for (int jj = 0; jj < 16; ++jj)
+                                v[jj] = fmaf(__uint_as_float(acc[q][jj]), p.alpha, __shfl_sync(0xffffffffu, bsel, (q & 1) * 16 + jj));
+                        } else {
+#pragma unroll
+                            for (int jj = 0; jj < 16; ++jj) v[jj] = __uint_as_float(acc[q][jj]) * p.alpha;
+                        }
                         if (p.relu) {
 #pragma unroll
                             for (int jj = 0; jj < 16; ++jj) v[jj] = fmaxf(v[jj], 0.f);
                         }
-                        if (drop.thresh != 0u) {
-#pragma unroll 4
-                            for (int jj = 0; jj < 16; ++jj) v[jj] *= dropout_factor(drop, didx + jj);
+                    }
+                    const int n_base = it.n0 + c0 + q * 16;
+                    if (EPI == EPI_BF16_FULL && drop.thresh != 0u) {
+                        const uint64_t didx = (uint64_t)(((long)(it.b1 * p.batch2 + it.b2) * p.M + m) * (long)p.N + n_base);
+#pragma unroll 2
+                        for (int jj = 0; jj < 16; ++jj) v[jj] *= dropout_factor(drop, didx + jj);
+                    }
+                    if (!row_in || n_base >= p.N) continue;
+                    TC* dst = Crow + n_base;
+                    const bool fast = p.vec_ok && n_base + 16 <= p.N;
+                    if (EPI == EPI_F32) {
+                        float* d32 = reinterpret_cast<float*>(dst);
+                        if (fast && p.atomic_out) {
+                            if (row_ok) {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) red_add_v4(d32 + 4 * e, v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+                            }
+                        } else if (fast && !p.R && !p.accumulate) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                *reinterpret_cast<float4*>(d32 + 4 * e) = row_ok ? make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3])
+                                                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+                        } else {
+                            epilogue_scalar<TC>(p, v, dst, Rrow ? Rrow + n_base : nullptr, min(16, p.N - n_base), row_ok);
                         }
-                        float4* d4 = reinterpret_cast<float4*>(stg + lane * STG_LD + q * 16);
+                    } else if (fast) {
+                        if (EPI == EPI_BF16_FULL) {
+                            if (Rrow) { add_bf16x8(v, rr[2 * q]); add_bf16x8(v + 8, rr[2 * q + 1]); }
+                            if (p.accumulate) {
+                                add_bf16x8(v, *reinterpret_cast<const uint4*>(dst));
+                                add_bf16x8(v + 8, *reinterpret_cast<const uint4*>(dst + 8));
+                            }
+                            if (!row_ok) {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) d4[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
-                    } else if (m < p.M && n_base < p.N) {
-                        bool row_ok = true;
-                        if (p.mask_period > 0) {
-                            const int ph = (m + p.mask_offset) % p.mask_period;
-                            row_ok = (ph >= p.mask_lo) && (ph < p.mask_hi);
+                                for (int jj = 0; jj < 16; ++jj) v[jj] = 0.f;
+                            }
                         }
-                        epilogue_direct<TC>(p, drop, v, Cb + (long)m * p.c_rs + n_base, Rb ? Rb + (long)m * p.c_rs + n_base : nullptr,
-                                            didx, min(16, p.N - n_base), row_ok);
+                        *reinterpret_cast<uint4*>(dst) = pack_bf16x8(v);
+                        *reinterpret_cast<uint4*>(dst + 8) = pack_bf16x8(v + 8);
+                    } else {
+                        epilogue_scalar<TC>(p, v, dst, Rrow ? Rrow + n_base : nullptr, min(16, p.N - n_base), row_ok);
                     }
                 }
-            }
-            if (!staged) continue;
-            __syncwarp();
-            // ---- coalesced read-back: each step covers 4 rows x (8 lanes x 8 columns), one 16 B store per lane
-            const int n = nw0 + cl;
-            const int nvalid = (cl < ncols) ? min(8, p.N - n) : 0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int rl = i * 4 + r4;
-                const int row = row0 + rl;
-                if (nvalid <= 0 || row >= p.M) continue;
-                const float4 a0 = *reinterpret_cast<const float4*>(stg + rl * STG_LD + cl);
-                const float4 a1 = *reinterpret_cast<const float4*>(stg + rl * STG_LD + cl + 4);
-                float o[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-                TC* dst = Cb + (long)row * p.c_rs + n;
-                bool row_ok = true;
-                if (p.mask_period > 0) {
-                    const int ph = (row + p.mask_offset) % p.mask_period;
-                    row_ok = (ph >= p.mask_lo) && (ph < p.mask_hi);
-                }
-                if (nvalid == 8) {
-                    if (Rb) {
-                        const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr[i]);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) { o[2 * q] += __low2float(r2[q]); o[2 * q + 1] += __high2float(r2[q]); }
-                    }
-                    if (p.accumulate) {
-                        const uint4 cv = *reinterpret_cast<const uint4*>(dst);
-                        const __nv_bfloat162* c2 = reinterpret_cast<const __nv_bfloat162*>(&cv);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) { o[2 * q] += __low2float(c2[q]); o[2 * q + 1] += __high2float(c2[q]); }
-                    }
-                    uint4 w;
-                    uint32_t* wp = reinterpret_cast<uint32_t*>(&w);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        __nv_bfloat162 hh = __floats2bfloat162_rn(row_ok ? o[2 * q] : 0.f, row_ok ? o[2 * q + 1] : 0.f);
-                        wp[q] = *reinterpret_cast<uint32_t*>(&hh);
-                    }
-                    *reinterpret_cast<uint4*>(dst) = w;
-                } else {
-                    epilogue_tail<TC>(p, o, dst, Rb ? Rb + (long)row * p.c_rs + n : nullptr, nvalid, row_ok);
-                }
+                if (EPI == EPI_BF16_FULL && u == 0) load_res(1);
             }
             if (threadIdx.x == 64 && n_items < 4) stamp(p, 16 + 8 * (int)n_items + 4);
-            __syncwarp();     // the staging tile and bias slice are rewritten for the next tile
         }
     }
     tcgen05_fence_before();
@@ -489,9 +504,9 @@ static bool make_map(CUtensorMap* map, const void* base, const long (&dim)[4], c
 }
 
 static int pick_bn(int N) {
-    int best = 128;
+    int best = 256;
     long best_cost = -1;
-    for (int bn = 128; bn >= 16; bn -= 16) {
+    for (int bn = 256; bn >= 16; bn -= 16) {
         long tiles = (N + bn - 1) / bn;
         long cost = tiles * bn * 8 + tiles * 24;       // padded columns + a per-tile overhead term
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
@@ -569,23 +584,28 @@ int gemm_tc(const s2s_gemm_t& g, cudaStream_t st) {
         if (s > 1) p.splits = (int)s;
     }
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-    p.staged = (!p.c_f32 && al16(g.C) && (g.R == nullptr || al16(g.R)) && g.c_rs % 8 == 0 && g.c_bs1 % 8 == 0 && g.c_bs2 % 8 == 0) ? 1 : 0;
+    const int epb = p.c_f32 ? 4 : 8;
+    p.vec_ok = (al16(g.C) && (g.R == nullptr || al16(g.R)) && g.c_rs % epb == 0 && g.c_bs1 % epb == 0 && g.c_bs2 % epb == 0) ? 1 : 0;
     // every split must own at least one k-block
     if (p.splits > 1) {
         int per = (p.kb_total + p.splits - 1) / p.splits;
         p.splits = (p.kb_total + per - 1) / per;
     }
     std::call_once(g_attr_once, [] {
-        g_attr_err = cudaFuncSetAttribute(gemm_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        g_attr_err = cudaFuncSetAttribute(gemm_tc_kernel<EPI_BF16_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (g_attr_err == cudaSuccess)
-            g_attr_err = cudaFuncSetAttribute(gemm_tc_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+            g_attr_err = cudaFuncSetAttribute(gemm_tc_kernel<EPI_BF16_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (g_attr_err == cudaSuccess)
+            g_attr_err = cudaFuncSetAttribute(gemm_tc_kernel<EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     });
     if (g_attr_err != cudaSuccess) return set_error(S2S_ERR_CUDA, "gemm_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(g_attr_err));
     long items = tiles * p.splits;
     if (items >= (1L << 31)) return set_error(S2S_ERR_UNSUPPORTED, "gemm_tc: too many tiles");
     unsigned grid = (unsigned)(items < num_sms() ? items : num_sms());
-    if (p.c_f32) gemm_tc_kernel<float><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
-    else gemm_tc_kernel<bf16><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
+    const bool plain_bf16 = !g.R && !g.accumulate && p.drop.thresh == 0u && g.mask_period == 0;
+    if (p.c_f32) gemm_tc_kernel<EPI_F32><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
+    else if (plain_bf16) gemm_tc_kernel<EPI_BF16_PLAIN><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
+    else gemm_tc_kernel<EPI_BF16_FULL><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
     S2S_LAUNCH_OK();
     return S2S_OK;
 }
