@@ -30,6 +30,8 @@ WORKLOADS = {
            32, 512, 1024, True, "VTN-base 6+6 d384 h8 r2, B32 x (512->1024, 80-mel), bf16"),
     "c2b64": (dict(idim=80, odim=80, adim=384, aheads=8, elayers=6, dlayers=6, eunits=1536, dunits=1536, decoder_reduction_factor=2),
               64, 512, 1024, True, "VTN-base 6+6 d384 h8 r2, B64 x (512->1024, 80-mel), bf16"),
+    "c4": (dict(idim=80, odim=80, adim=384, aheads=4, elayers=6, dlayers=6, eunits=1536, dunits=1536, decoder_reduction_factor=2),
+           64, 160, 1000, True, "TransformerTTS 6+6 d384 h4 r2, B64 x (160 tokens -> 1000 frames, 80-mel), bf16"),
     "c1": (dict(idim=80, odim=80, adim=256, aheads=4, elayers=2, dlayers=2, eunits=1024, dunits=1024, decoder_reduction_factor=2),
            4, 200, 400, False, "VTN-small 2+2 d256 h4 r2, B4 x (200->400, 80-mel), fp32"),
 }
@@ -37,7 +39,7 @@ METRIC = "target mel-frames/sec, VTN-base enc-dec training step (80-mel, src512/
 UNIT = "frames/s"
 
 
-def vtn_fwd_flops(hp, T, L):
+def vtn_fwd_flops(hp, T, L, tts=False):
     """Forward FLOPs per utterance (SURVEY.md section 8d formulas)."""
     d, r = hp["adim"], hp["decoder_reduction_factor"]
     Ue, Ud = hp["eunits"], hp["dunits"]
@@ -45,6 +47,8 @@ def vtn_fwd_flops(hp, T, L):
     T2, F2 = (T1 - 1) // 2, 19
     Lr = L // r
     conv = 2 * 9 * d * T1 * F1 + 2 * 9 * d * d * T2 * F2 + 2 * T2 * (d * F2) * d
+    if tts:
+        T2, conv = T + 1, 0
     enc = hp["elayers"] * (8 * T2 * d * d + 4 * T2 * T2 * d + 4 * T2 * d * Ue)
     pre = 2 * Lr * (80 * 256 + 256 * 256 + 256 * d)
     dec = hp["dlayers"] * (8 * Lr * d * d + 4 * Lr * Lr * d + 4 * Lr * d * d + 4 * T2 * d * d + 4 * Lr * T2 * d + 4 * Lr * d * Ud)
@@ -88,9 +92,9 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
-def synthetic_batch(B, T, L, seed):
+def synthetic_batch(B, T, L, seed, tts=False):
     g = torch.Generator().manual_seed(seed)
-    xs = torch.randn(B, T, 80, generator=g)
+    xs = torch.randint(1, 79, (B, T), generator=g) if tts else torch.randn(B, T, 80, generator=g)
     ys = torch.randn(B, L, 80, generator=g)
     labels = torch.zeros(B, L)
     labels[:, L - 1:] = 1.0
@@ -107,22 +111,29 @@ def peaks():
 # --------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference path on the host cores
 # --------------------------------------------------------------------------------------------------
-def cpu_port_steps(hp, B, T, L, steps, warmup):
+def cpu_port_steps(hp, B, T, L, steps, warmup, tts=False):
     """fwd + Seq2SeqLoss + bwd + clip + Adam of the oracle (plain torch fp32 CPU) on B utterances."""
     from oracle import vtn_oracle
 
     torch.set_num_threads(os.cpu_count() or 1)
     ohp = vtn_oracle.default_hparams(**hp)
     sd = vtn_oracle.init_state_dict(ohp, seed=0)
+    if tts:
+        sd = {k: v for k, v in sd.items() if not k.startswith("encoder.embed.")}
+        emb = torch.randn(hp["idim"], hp["adim"])
+        emb[0] = 0
+        sd["encoder.embed.0.weight"] = emb
+        sd["encoder.embed.1.alpha"] = torch.tensor(1.0)
     params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.dtype.is_floating_point and "running_" not in k}
     full = dict(sd)
     full.update(params)
     opt = torch.optim.Adam(list(params.values()), lr=8e-5)
-    xs, ilens, ys, labels, olens = synthetic_batch(B, T, L, 1234)
+    xs, ilens, ys, labels, olens = synthetic_batch(B, T, L, 1234, tts)
     times = []
+    fwd = vtn_oracle.tts_forward if tts else vtn_oracle.vtn_forward
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        out = vtn_oracle.vtn_forward(full, ohp, xs, ilens, ys, labels, olens, training=True)
+        out = fwd(full, ohp, xs, ilens, ys, labels, olens, training=True)
         l1, bce = vtn_oracle.seq2seq_loss(out["after_outs"], out["before_outs"], out["logits"], out["ys"], out["labels"], out["olens"])
         opt.zero_grad()
         (l1 + bce).backward()
@@ -139,7 +150,7 @@ def run_reference(args, rank):
     hp, B, T, L, bf16, desc = WORKLOADS[args.workload]
     Bs = min(B, 4)
     timed = max(1, min(args.steps, 6))      # bounded sample: the CPU arm must end within minutes whatever K is
-    sec = cpu_port_steps(hp, Bs, T, L, timed, max(1, min(args.warmup, 1)))
+    sec = cpu_port_steps(hp, Bs, T, L, timed, max(1, min(args.warmup, 1)), args.workload == "c4")
     val = Bs * L / sec
     cores = os.cpu_count() or 1
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -207,16 +218,17 @@ def gemm_roofline(stepper, batch, dev, table_path=None):
 
 
 def run_ours(args, rank, world):
-    from seq2seq_vc_b200 import VTN, VTNTrainStep, _lib
+    from seq2seq_vc_b200 import VTN, TransformerTTS, VTNTrainStep, _lib
 
     hp, B, T, L, bf16, desc = WORKLOADS[args.workload]
+    tts = args.workload == "c4"
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     _lib.device_check()
-    model = VTN(**hp, compute_dtype="bf16" if bf16 else "float32", device=dev, seed=0)
+    model = (TransformerTTS if tts else VTN)(**hp, compute_dtype="bf16" if bf16 else "float32", device=dev, seed=0)
     stepper = VTNTrainStep(model, lr=8e-5, warmup_steps=4000, use_graph=not args.no_graph)
-    xs, ilens, ys, labels, olens = synthetic_batch(B, T, L, 1234 + rank)
+    xs, ilens, ys, labels, olens = synthetic_batch(B, T, L, 1234 + rank, tts)
     dxs, dys, dlabels = xs.to(dev), ys.to(dev), labels.to(dev)
     pxs, pys, plabels = xs.pin_memory(), ys.pin_memory(), labels.pin_memory()
 
@@ -263,7 +275,7 @@ def run_ours(args, rank, world):
     value = frames / (ms * 1e-3)
     e2e = frames / (ms_e2e * 1e-3)
     pk, pk_src = peaks()
-    flops_step = 3.0 * vtn_fwd_flops(hp, T, L) * B
+    flops_step = 3.0 * vtn_fwd_flops(hp, T, L, tts) * B
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if bf16 else "f32", "data": "synthetic",
@@ -275,7 +287,7 @@ def run_ours(args, rank, world):
                        "tc_fallbacks": int(_lib.load().s2s_tc_fallback_count())},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": (xs.numel() + ys.numel() + labels.numel()) * 4 + 3 * B * 4, "d2h_bytes_per_step": 8},
+                    "h2d_bytes_per_step": xs.numel() * xs.element_size() + (ys.numel() + labels.numel()) * 4 + 5 * B * 4, "d2h_bytes_per_step": 8},
             "gpu_launches": int(launches)}
     if world == 1:
         if bf16:
@@ -296,7 +308,7 @@ def run_ours(args, rank, world):
                                 "how": "CUDA events around every mode-1 s2s_gemm launch of one eager fwd+bwd after the timed region"}
         if not args.no_cpu_baseline:
             Bs = min(B, 4)
-            sec = cpu_port_steps(hp, Bs, T, L, 2, 1)
+            sec = cpu_port_steps(hp, Bs, T, L, 2, 1, tts)
             line["cpu_baseline"] = {"value": Bs * L / sec, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                                     "sample": f"oracle port of the reference PyTorch-CPU path (fp32), {Bs} x ({T}->{L}) per step, 2 steps after 1 warm-up"}
     print(json.dumps(line), flush=True)
@@ -318,6 +330,8 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank)
         return
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the single JSON line
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))

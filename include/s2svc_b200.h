@@ -36,7 +36,7 @@ extern "C" {
 #define S2S_F32 0
 #define S2S_BF16 1
 
-#define S2S_ABI_VERSION 6
+#define S2S_ABI_VERSION 7
 
 const char* s2s_last_error(void);
 int s2s_abi_version(void);
@@ -146,6 +146,21 @@ int s2s_scaled_pe_fwd(const void* x, const float* pe, const float* alpha, void* 
                       const s2s_dropout_t* drop, int dtype, void* stream);
 int s2s_scaled_pe_bwd(const void* dy, const float* pe, void* dx, float* dalpha, int B, int T, int d,
                       const s2s_dropout_t* drop, int dtype, void* stream);
+
+/* -------------------------------------------------------------------------------------------
+ * TransformerTTS encoder input layer (models/transformer_tts.py:63-77,139-142): token embedding with
+ * the <eos> append and ScaledPositionalEncoding fused:
+ *   tok(b, t) = tokens[b, t] for t < ilens[b] ; eos for t == ilens[b] ; padding_idx beyond
+ *   y[b, t, :] = dropout(weight[tok(b, t)] + alpha * pe[t]),  t < T_out (= T_in + 1)
+ * bwd: dweight[tok] += dy * mask (never for padding_idx) ; dalpha += sum(dy * mask * pe).
+ * tokens (B, T_in) int64, weight (V, d) float32.
+ * ------------------------------------------------------------------------------------------- */
+int s2s_embed_pe_fwd(const int64_t* tokens, const int32_t* ilens, const float* weight, const float* pe,
+                     const float* alpha, void* y, int B, int T_in, int T_out, int d, int eos, int padding_idx,
+                     const s2s_dropout_t* drop, int dtype, void* stream);
+int s2s_embed_pe_bwd(const void* dy, const int64_t* tokens, const int32_t* ilens, const float* pe, float* dweight,
+                     float* dalpha, int B, int T_in, int T_out, int d, int eos, int padding_idx,
+                     const s2s_dropout_t* drop, int dtype, void* stream);
 
 /* -------------------------------------------------------------------------------------------
  * Conv2dSubsampling front end (modules/transformer/subsampling.py:58-94).

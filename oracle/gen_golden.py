@@ -60,6 +60,49 @@ def gen_vtn_tiny():
     print("vtn_tiny:", len(dump), "arrays")
 
 
+TTS_HP = dict(idim=40, odim=80, dprenet_layers=2, dprenet_units=16, adim=32, aheads=4, elayers=1, eunits=48,
+              dlayers=2, dunits=48, postnet_layers=2, postnet_filts=5, postnet_chans=16, decoder_reduction_factor=2)
+
+
+def gen_tts_tiny():
+    """TransformerTTS (models/transformer_tts.py) + Seq2SeqLoss + GuidedMultiHeadAttentionLoss on token inputs."""
+    from seq2seq_vc.losses import GuidedMultiHeadAttentionLoss, Seq2SeqLoss
+    from seq2seq_vc.models.transformer_tts import TransformerTTS
+
+    torch.manual_seed(11)
+    model = TransformerTTS(dprenet_dropout_rate=0.0, use_guided_attn_loss=True, num_heads_applied_guided_attn=2,
+                           num_layers_applied_guided_attn=2, **TTS_HP)
+    ref_shim.disable_dropout(model)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith("alpha"):
+                p.fill_(0.8 if "encoder" in n else 1.2)
+    model.train()
+    sd0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(21)
+    ilens, olens = [13, 9, 5], [30, 23, 12]
+    tokens = torch.randint(1, TTS_HP["idim"] - 1, (3, 13), generator=g)
+    ys = torch.randn(3, 30, 80, generator=g)
+    labels = torch.zeros(3, 30)
+    for b in range(3):
+        tokens[b, ilens[b]:] = 0
+        ys[b, olens[b]:] = 0
+        labels[b, olens[b] - 1:] = 1.0
+    out = model(tokens, torch.tensor(ilens), ys, labels, torch.tensor(olens))
+    l1, bce = Seq2SeqLoss()(*out[:6])
+    ga = GuidedMultiHeadAttentionLoss(sigma=0.4, alpha=1.0)(out[6][0], out[6][1], out[6][2])
+    (l1 + bce + ga).backward()
+    dump = {"sd." + k: v.numpy() for k, v in sd0.items()}
+    dump.update({"grad." + k: p.grad.numpy() for k, p in model.named_parameters()})
+    dump.update(tokens=tokens.numpy(), ilens=np.array(ilens), ys=ys.numpy(), labels=labels.numpy(), olens=np.array(olens),
+                after_outs=out[0].detach().numpy(), before_outs=out[1].detach().numpy(), logits=out[2].detach().numpy(),
+                labels_out=out[4].numpy(), olens_out=out[5].numpy(), att_ws=out[6][0].detach().numpy(),
+                ilens_out=out[6][1].numpy(), olens_in=out[6][2].numpy(), l1_loss=l1.detach().numpy(),
+                bce_loss=bce.detach().numpy(), ga_loss=ga.detach().numpy())
+    np.savez_compressed(os.path.join(GOLDEN, "tts_tiny.npz"), **dump)
+    print("tts_tiny:", len(dump), "arrays")
+
+
 def gen_mas():
     from seq2seq_vc.modules.alignments import _monotonic_alignment_search, viterbi_decode
 
@@ -115,5 +158,6 @@ if __name__ == "__main__":
     ref_shim.install()
     os.makedirs(GOLDEN, exist_ok=True)
     gen_vtn_tiny()
+    gen_tts_tiny()
     gen_mas()
     gen_kats()

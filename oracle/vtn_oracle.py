@@ -112,6 +112,75 @@ def encoder(sd, hp, xs, x_mask, attn_store=None):
     return layer_norm(x, sd, "encoder.after_norm"), mask
 
 
+def encoder_tts(sd, hp, tokens, x_mask, attn_store=None):
+    """TransformerTTS encoder: Embedding(padding_idx=0) + ScaledPE input layer, then the same pre-LN
+    layers (models/transformer_tts.py:63-77, modules/transformer/encoder.py:131-135,283-329)."""
+    x = F.embedding(tokens, sd["encoder.embed.0.weight"], padding_idx=0)
+    x = x + sd["encoder.embed.1.alpha"] * sinusoid_table(x.shape[1], x.shape[-1])[None]
+    for l in range(hp["elayers"]):
+        p = f"encoder.encoders.{l}"
+        n = layer_norm(x, sd, p + ".norm1")
+        x = x + attention(sd, p + ".self_attn", n, n, x_mask, hp["aheads"], attn_store)
+        n = layer_norm(x, sd, p + ".norm2")
+        x = x + feed_forward(sd, p + ".feed_forward", n)
+    return layer_norm(x, sd, "encoder.after_norm"), x_mask
+
+
+def guided_attention_loss(att_ws, ilens, olens, sigma=0.4, alpha=1.0):
+    """GuidedMultiHeadAttentionLoss.forward, losses/guided_attention_loss.py:57-96,142-165."""
+    B, H, T_out, T_in = att_ws.shape
+    w = torch.zeros(B, T_out, T_in)
+    m = torch.zeros(B, T_out, T_in, dtype=torch.bool)
+    for b, (il, ol) in enumerate(zip(ilens, olens)):
+        gy, gx = torch.meshgrid(torch.arange(ol).float(), torch.arange(il).float(), indexing="ij")
+        w[b, :ol, :il] = 1.0 - torch.exp(-((gx / il - gy / ol) ** 2) / (2 * sigma ** 2))
+        m[b, :ol, :il] = True
+    losses = w.unsqueeze(1) * att_ws
+    return alpha * losses.masked_select(m.unsqueeze(1).expand_as(losses)).mean()
+
+
+def tts_forward(sd, hp, tokens, ilens, ys, labels, olens, training: bool = True, use_guided_attn_loss: bool = False,
+                num_heads_applied_guided_attn: int = 2, num_layers_applied_guided_attn: int = 2):
+    """TransformerTTS.forward, seq2seq_vc/models/transformer_tts.py:129-229."""
+    ilens = [int(v) for v in ilens]
+    olens = [int(v) for v in olens]
+    r, odim = hp["decoder_reduction_factor"], hp["odim"]
+    tokens = tokens[:, : max(ilens)]
+    ys = ys[:, : max(olens)]
+    labels = labels[:, : max(olens)]
+    tokens = F.pad(tokens, [0, 1], "constant", 0).clone()                         # :139-142
+    for b, l in enumerate(ilens):
+        tokens[b, l] = hp["idim"] - 1
+    ilens = [i + 1 for i in ilens]
+    attn: Dict[str, torch.Tensor] = {}
+    x_mask = non_pad_mask(ilens, tokens.shape[1]).unsqueeze(-2)
+    hs, h_mask = encoder_tts(sd, hp, tokens, x_mask, attn)
+    ys_in = ys[:, r - 1 :: r] if r > 1 else ys
+    olens_in = [o // r for o in olens]
+    ys_in = torch.cat([ys_in.new_zeros(ys_in.shape[0], 1, odim), ys_in[:, :-1]], dim=1)
+    y_mask = non_pad_mask(olens_in, ys_in.shape[1]).unsqueeze(-2) & causal_mask(ys_in.shape[1])[None]
+    zs = decoder(sd, hp, ys_in, y_mask, hs, h_mask, attn)
+    B = zs.shape[0]
+    before = linear(zs, sd, "feat_out").view(B, -1, odim)
+    logits = linear(zs, sd, "prob_out").view(B, -1)
+    after = before + postnet(sd, hp, before.transpose(1, 2), training).transpose(1, 2)
+    if r > 1:
+        olens = [o - o % r for o in olens]
+        ys = ys[:, : max(olens)]
+        labels = labels[:, : max(olens)].clone()
+        for b, o in enumerate(olens):
+            labels[b, o - 1] = 1.0
+    att_ws = []
+    if use_guided_attn_loss:                                                       # :205-219
+        for idx, l in enumerate(reversed(range(hp["dlayers"]))):
+            att_ws.append(attn[f"decoder.decoders.{l}.src_attn"][:, :num_heads_applied_guided_attn])
+            if idx + 1 == num_layers_applied_guided_attn:
+                break
+        att_ws = torch.cat(att_ws, dim=1)
+    return dict(after_outs=after, before_outs=before, logits=logits, ys=ys, labels=labels, olens=olens, att_ws=att_ws,
+                ilens=ilens, olens_in=olens_in, attn=attn)
+
+
 def decoder(sd, hp, ys_in, y_mask, memory, mem_mask, attn_store=None):
     """Transformer Decoder (post-LN), modules/transformer/decoder.py:207-237 + decoder_layer.py:63-134.
 

@@ -6,6 +6,7 @@ The native library (libs2svc_b200.so) is loaded lazily on first use; there is no
 """
 from ._lib import S2SError  # noqa: F401
 from .vtn_engine import VTNEngine, default_hparams  # noqa: F401
-from .api import VTN, Seq2SeqLoss, GuidedMultiHeadAttentionLoss, VTNTrainStep, viterbi_decode, logmelfilterbank  # noqa: F401
+from .api import VTN, TransformerTTS, Seq2SeqLoss, GuidedMultiHeadAttentionLoss, VTNTrainStep, viterbi_decode, logmelfilterbank  # noqa: F401
 
 AR_VC_MODELS = [VTN]
+AR_TTS_MODELS = [TransformerTTS]

@@ -59,26 +59,49 @@ class MultiHeadedAttention(_Node):
 
 
 class _VTNFunction(torch.autograd.Function):
+    """Whole-model autograd node: forward = engine.forward, backward = the engine's hand-written backward.
+    When `n_att` > 0 the concatenated source-attention maps (last layers x first heads) are a differentiable
+    output too, so a guided-attention loss on them back-propagates into the attention kernels."""
+
     @staticmethod
-    def forward(ctx, model, xs, ys, ilens, olens, *params):
+    def forward(ctx, model, xs, ys, ilens, olens, n_att_layers, n_att_heads, *params):
         eng = model.engine
         after, before, logits = eng.forward(xs, ys, ilens, olens)
         ctx.model = model
         ctx.token = model._fwd_token
+        ctx.att = (n_att_layers, n_att_heads)
         # outputs are engine-owned buffers: hand out copies so later forwards cannot clobber them
-        return after.clone(), before.clone(), logits.clone()
+        outs = [after.clone(), before.clone(), logits.clone()]
+        if n_att_layers > 0:
+            names = [f"decoder.decoders.{l}.src_attn" for l in reversed(range(eng.hp["dlayers"]))][:n_att_layers]
+            ctx.att_names = names
+            outs.append(torch.cat([eng.attn[n][:, :n_att_heads] for n in names], dim=1).float())
+        return tuple(outs)
 
     @staticmethod
-    def backward(ctx, d_after, d_before, d_logits):
+    def backward(ctx, d_after, d_before, d_logits, d_att_ws=None):
         model = ctx.model
         if ctx.token != model._fwd_token:
             raise S2SError("backward() after a newer forward(): the engine keeps one set of activations")
         eng = model.engine
         fresh = all(p.grad is None for p in model.parameters())
         dt = eng.adt
-        eng.backward(d_after.to(dt).contiguous(), d_before.to(dt).contiguous(), d_logits.to(dt).contiguous(), zero_grad=fresh)
+        d_att = None
+        if d_att_ws is not None and ctx.att[0] > 0:
+            nh = ctx.att[1]
+            d_att = {}
+            for i, name in enumerate(ctx.att_names):
+                P = eng.attn[name]                                            # (B, H, T1, T2) view of the (.., ld) buffer
+                full = torch.zeros(P.shape[0], P.shape[1], P.shape[2], (P.shape[3] + 7) // 8 * 8, dtype=dt, device=P.device)
+                full[:, :nh, :, :P.shape[3]] = d_att_ws[:, i * nh:(i + 1) * nh].to(dt)
+                d_att[name] = full
+
+        def z(g, like):
+            return torch.zeros_like(like, dtype=dt) if g is None else g.to(dt).contiguous()
+
+        eng.backward(z(d_after, eng.after), z(d_before, eng.before), z(d_logits, eng.logits), d_att=d_att, zero_grad=fresh)
         model._bind_grads()
-        return (None,) * (5 + len(model._param_names))
+        return (None,) * (7 + len(model._param_names))
 
 
 class VTN(torch.nn.Module):
@@ -122,7 +145,8 @@ class VTN(torch.nn.Module):
                                   dprenet_dropout_rate=dprenet_dropout_rate,
                                   transformer_enc_dropout_rate=transformer_enc_dropout_rate,
                                   decoder_reduction_factor=decoder_reduction_factor,
-                                  initial_encoder_alpha=initial_encoder_alpha, initial_decoder_alpha=initial_decoder_alpha)
+                                  initial_encoder_alpha=initial_encoder_alpha, initial_decoder_alpha=initial_decoder_alpha,
+                                  encoder_input=getattr(self, "_encoder_input", "conv2d"))
         self._bf16 = compute_dtype in ("bf16", "bfloat16", torch.bfloat16)
         self._seed = seed
         self._fwd_token = 0
@@ -200,7 +224,7 @@ class VTN(torch.nn.Module):
         if r > 1:
             assert all(o >= r for o in ol), "Output length must be greater than or equal to reduction factor."
         self._fwd_token += 1
-        after, before, logits = _VTNFunction.apply(self, xs, ys, il, ol, *self.parameters())
+        after, before, logits = _VTNFunction.apply(self, xs, ys, il, ol, 0, 0, *self.parameters())
         Lo = after.shape[1]
         # target fix-ups (vtn.py:262-274)
         olens_out = torch.tensor(eng.olens_fix_host, dtype=torch.int64, device=xs.device)
@@ -219,6 +243,64 @@ class VTN(torch.nn.Module):
         for l in reversed(range(self.hp["dlayers"])):           # vtn.py:280-287 (list, last layer first)
             att_ws.append(self.decoder.decoders[l].src_attn.attn)
         return after.float(), before.float(), logits.float(), ys_out, labels_out, olens_out, (att_ws, ilens_ds_st, olens_in)
+
+
+class TransformerTTS(VTN):
+    """Drop-in for seq2seq_vc.models.TransformerTTS (models/transformer_tts.py:13-229): token-embedding encoder,
+    same decoder / heads / postnet as VTN, guided-attention maps returned as one differentiable tensor."""
+
+    def __init__(self, idim, odim, dprenet_layers=2, dprenet_units=256, adim=384, aheads=4, elayers=6, eunits=1536, dlayers=6,
+                 dunits=1536, postnet_layers=5, postnet_filts=5, postnet_chans=256, dprenet_dropout_rate=0.5, use_batch_norm=True,
+                 encoder_normalize_before=True, decoder_normalize_before=False, encoder_concat_after=False,
+                 decoder_concat_after=False, decoder_reduction_factor=2, spk_embed_dim=None, spk_embed_integration_type="add",
+                 initial_encoder_alpha=1.0, initial_decoder_alpha=1.0, use_guided_attn_loss=False,
+                 num_heads_applied_guided_attn=2, num_layers_applied_guided_attn=2, compute_dtype: str = "float32", device=None,
+                 seed: int = 0):
+        self._encoder_input = "embed"
+        super().__init__(idim, odim, dprenet_layers=dprenet_layers, dprenet_units=dprenet_units, adim=adim, aheads=aheads,
+                         elayers=elayers, eunits=eunits, dlayers=dlayers, dunits=dunits, postnet_layers=postnet_layers,
+                         postnet_filts=postnet_filts, postnet_chans=postnet_chans, dprenet_dropout_rate=dprenet_dropout_rate,
+                         use_batch_norm=use_batch_norm, encoder_normalize_before=encoder_normalize_before,
+                         decoder_normalize_before=decoder_normalize_before, encoder_concat_after=encoder_concat_after,
+                         decoder_concat_after=decoder_concat_after, decoder_reduction_factor=decoder_reduction_factor,
+                         spk_embed_dim=spk_embed_dim, spk_embed_integration_type=spk_embed_integration_type,
+                         initial_encoder_alpha=initial_encoder_alpha, initial_decoder_alpha=initial_decoder_alpha,
+                         use_guided_attn_loss=use_guided_attn_loss, num_heads_applied_guided_attn=num_heads_applied_guided_attn,
+                         num_layers_applied_guided_attn=num_layers_applied_guided_attn, compute_dtype=compute_dtype,
+                         device=device, seed=seed)
+        self.eos = idim - 1
+        self.padding_idx = 0
+
+    def forward(self, xs, ilens, ys, labels, olens, spembs=None, *args, **kwargs):
+        if not xs.is_cuda:
+            raise S2SError("seq2seq_vc_b200.TransformerTTS runs on a B200 only (no CPU fallback)")
+        eng = self.engine
+        eng.p16_dirty = True
+        il, ol = _host_lens(ilens), _host_lens(olens)
+        r = self.decoder_reduction_factor
+        xs = xs[:, :max(il)].to(torch.int64).contiguous()
+        ys = ys[:, :max(ol)].to(_f32).contiguous()
+        labels = labels[:, :max(ol)].to(_f32).contiguous()
+        if r > 1:
+            assert all(o >= r for o in ol), "Output length must be greater than or equal to reduction factor."
+        self._fwd_token += 1
+        nl = self.num_layers_applied_guided_attn if self.use_guided_attn_loss else 0
+        nh = self.num_heads_applied_guided_attn if self.use_guided_attn_loss else 0
+        outs = _VTNFunction.apply(self, xs, ys, il, ol, nl, nh, *self.parameters())
+        after, before, logits = outs[:3]
+        att_ws = outs[3] if nl > 0 else []
+        Lo = after.shape[1]
+        olens_out = torch.tensor(eng.olens_fix_host, dtype=torch.int64, device=xs.device)
+        if r > 1:
+            labels_out = torch.empty(labels.shape[0], Lo, dtype=_f32, device=xs.device)
+            ops.fix_targets(labels, eng.olens_fix, labels_out, None, r)
+        else:
+            labels_out = labels
+        for name, P in eng.attn.items():
+            self.get_submodule(name).attn = P.float() if P.dtype != _f32 else P
+        ilens_out = torch.tensor(eng.ilens_ds_st, dtype=torch.int64, device=xs.device)      # ilens + 1 (transformer_tts.py:142)
+        olens_in = torch.tensor(eng.olens_in_host, dtype=torch.int64, device=xs.device)
+        return after.float(), before.float(), logits.float(), ys[:, :Lo], labels_out, olens_out, (att_ws, ilens_out, olens_in)
 
 
 # =================================================================================================
@@ -409,11 +491,14 @@ class VTNTrainStep:
 
     def __init__(self, model, lr: float = 8e-5, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
                  grad_norm: float = 1.0, warmup_steps: int = 4000, bce_pos_weight: float = 10.0, use_graph: bool = False,
-                 process_group=None):
+                 process_group=None, guided_attn: Optional[dict] = None):
         self.engine: VTNEngine = model.engine if hasattr(model, "engine") else model
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
         self.grad_norm, self.warmup = grad_norm, warmup_steps
         self.pos_weight = bce_pos_weight
+        # guided_attn: dict(sigma=0.4, alpha=1.0, n_layers=2, n_heads=2) adds GuidedMultiHeadAttentionLoss (trainers/ar_tts.py:49-53)
+        self.guided_attn = guided_attn
+        self.ga_loss = None
         self.steps = 0
         self.use_graph = use_graph
         self.pg = process_group
@@ -433,7 +518,10 @@ class VTNTrainStep:
         eng = self.engine
         eng.forward(xs, ys)
         eng.loss(ys, labels, self.pos_weight)
-        eng.backward(eng.d_after, eng.d_before, eng.d_logits)
+        d_att = None
+        if self.guided_attn is not None:
+            self.ga_loss, d_att = eng.guided_attention(**self.guided_attn)
+        eng.backward(eng.d_after, eng.d_before, eng.d_logits, d_att=d_att)
 
     def _allreduce(self):
         if self.world > 1:
@@ -462,7 +550,7 @@ class VTNTrainStep:
         key = (B, T, L)
         entry = self._graphs.get(key)
         if entry is None:
-            sx = torch.empty(xs.shape, dtype=_f32, device=eng.device)
+            sx = torch.empty(xs.shape, dtype=xs.dtype, device=eng.device)
             sy = torch.empty(ys.shape, dtype=_f32, device=eng.device)
             sl = torch.empty(labels.shape, dtype=_f32, device=eng.device)
             for dst, src in ((sx, xs), (sy, ys), (sl, labels)):

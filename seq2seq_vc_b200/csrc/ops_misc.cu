@@ -38,6 +38,55 @@ __global__ void scaled_pe_bwd_kernel(const T* __restrict__ dy, const float* __re
 // ---------------------------------------------------------------------------------------------
 // conv1: (B, T, F) -> relu(conv2d 1->C, 3x3, stride 2) channels-last (B, T1, F1, C)
 // ---------------------------------------------------------------------------------------------
+// Token embedding + <eos> append + ScaledPositionalEncoding (TransformerTTS encoder input layer)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ long tts_token(const int64_t* __restrict__ tokens, const int32_t* __restrict__ ilens, int b, int t,
+                                          int T_in, int eos, int pad) {
+    const int il = ilens[b];
+    if (t < il && t < T_in) return tokens[(long)b * T_in + t];
+    return (t == il) ? eos : pad;
+}
+template <typename T>
+__global__ void embed_pe_fwd_kernel(const int64_t* __restrict__ tokens, const int32_t* __restrict__ ilens,
+                                    const float* __restrict__ w, const float* __restrict__ pe, const float* __restrict__ alpha,
+                                    T* __restrict__ y, int B, int T_in, int T_out, int d, int eos, int pad, Dropout drop) {
+    dropout_resolve(drop);
+    const float a = *alpha;
+    const long n = (long)B * T_out * d;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % d);
+        const long q = i / d;
+        const int t = (int)(q % T_out);
+        const int b = (int)(q / T_out);
+        const long tok = tts_token(tokens, ilens, b, t, T_in, eos, pad);
+        const float v = w[tok * d + c] + a * pe[(long)t * d + c];
+        y[i] = from_f<T>(v * dropout_factor(drop, (uint64_t)i));
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) embed_pe_bwd_kernel(const T* __restrict__ dy, const int64_t* __restrict__ tokens,
+                                                           const int32_t* __restrict__ ilens, const float* __restrict__ pe,
+                                                           float* __restrict__ dw, float* dalpha, int B, int T_in, int T_out, int d,
+                                                           int eos, int pad, Dropout drop) {
+    __shared__ float red[32];
+    dropout_resolve(drop);
+    float acc = 0.f;
+    const long n = (long)B * T_out * d;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % d);
+        const long q = i / d;
+        const int t = (int)(q % T_out);
+        const int b = (int)(q / T_out);
+        const float g = to_f<T>(dy[i]) * dropout_factor(drop, (uint64_t)i);
+        acc += g * pe[(long)t * d + c];
+        const long tok = tts_token(tokens, ilens, b, t, T_in, eos, pad);
+        if (dw && tok != pad) atomicAdd(dw + tok * d + c, g);       // padding_idx row never receives a gradient
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0 && dalpha) atomicAdd(dalpha, acc);
+}
+
+// ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                  const float* __restrict__ bias, T* __restrict__ y, int B, int Tn, int F, int C,
@@ -776,6 +825,29 @@ extern "C" int s2s_transpose_last2(const void* in, void* out, int N, int A, int 
     else if (in_dtype == S2S_F32 && out_dtype == S2S_F32) transpose_last2_kernel<float, float><<<grid, block, 0, st>>>((const float*)in, (float*)out, A, Bd, accumulate);
     else if (in_dtype == S2S_BF16 && out_dtype == S2S_F32) transpose_last2_kernel<bf16, float><<<grid, block, 0, st>>>((const bf16*)in, (float*)out, A, Bd, accumulate);
     else return set_error(S2S_ERR_INVALID, "transpose_last2: bad dtypes %d -> %d", in_dtype, out_dtype);
+    S2S_LAUNCH_OK();
+    return S2S_OK;
+}
+
+extern "C" int s2s_embed_pe_fwd(const int64_t* tokens, const int32_t* ilens, const float* weight, const float* pe,
+                                const float* alpha, void* y, int B, int T_in, int T_out, int d, int eos, int padding_idx,
+                                const s2s_dropout_t* drop, int dtype, void* stream) {
+    S2S_REQUIRE(tokens && ilens && weight && pe && alpha && y && B > 0 && T_in > 0 && T_out > 0 && d > 0, "embed_pe_fwd: bad arguments");
+    long n = (long)B * T_out * d;
+    Dropout dr = make_dropout(drop);
+    S2S_DISPATCH_DTYPE(dtype, TT, (embed_pe_fwd_kernel<TT><<<ew_grid(n, 1024), 256, 0, (cudaStream_t)stream>>>(
+        tokens, ilens, weight, pe, alpha, (TT*)y, B, T_in, T_out, d, eos, padding_idx, dr)));
+    S2S_LAUNCH_OK();
+    return S2S_OK;
+}
+extern "C" int s2s_embed_pe_bwd(const void* dy, const int64_t* tokens, const int32_t* ilens, const float* pe, float* dweight,
+                                float* dalpha, int B, int T_in, int T_out, int d, int eos, int padding_idx,
+                                const s2s_dropout_t* drop, int dtype, void* stream) {
+    S2S_REQUIRE(dy && tokens && ilens && pe && B > 0 && T_in > 0 && T_out > 0 && d > 0, "embed_pe_bwd: bad arguments");
+    long n = (long)B * T_out * d;
+    Dropout dr = make_dropout(drop);
+    S2S_DISPATCH_DTYPE(dtype, TT, (embed_pe_bwd_kernel<TT><<<ew_grid(n, 2048), 256, 0, (cudaStream_t)stream>>>(
+        (const TT*)dy, tokens, ilens, pe, dweight, dalpha, B, T_in, T_out, d, eos, padding_idx, dr)));
     S2S_LAUNCH_OK();
     return S2S_OK;
 }

@@ -180,6 +180,24 @@ def scaled_pe_bwd(dy, pe, dx, dalpha, drop: Drop = NO_DROP):
     return dx
 
 
+def embed_pe_fwd(tokens, ilens, weight, pe, alpha, y, eos, padding_idx=0, drop: Drop = NO_DROP):
+    """y (B, T_in + 1, d) = dropout(weight[tok] + alpha * pe) with the <eos> append folded in."""
+    B, T_in = tokens.shape
+    T_out, d = y.shape[1], y.shape[2]
+    assert tokens.dtype == torch.int64 and tokens.is_contiguous() and ilens.dtype == _i32 and y.is_contiguous()
+    check(_L().s2s_embed_pe_fwd(ptr(tokens), ptr(ilens), ptr(weight), ptr(pe), ptr(alpha), ptr(y), B, T_in, T_out, d, eos, padding_idx,
+                                ctypes.byref(drop.c()), dt(y), stream()), "embed_pe_fwd")
+    return y
+
+
+def embed_pe_bwd(dy, tokens, ilens, pe, dweight, dalpha, eos, padding_idx=0, drop: Drop = NO_DROP):
+    B, T_in = tokens.shape
+    T_out, d = dy.shape[1], dy.shape[2]
+    assert dy.is_contiguous()
+    check(_L().s2s_embed_pe_bwd(ptr(dy), ptr(tokens), ptr(ilens), ptr(pe), ptr(dweight), ptr(dalpha), B, T_in, T_out, d, eos,
+                                padding_idx, ctypes.byref(drop.c()), dt(dy), stream()), "embed_pe_bwd")
+
+
 def conv1_fwd(x, w, bias, y1):
     B, T, F = x.shape
     C = w.shape[0]

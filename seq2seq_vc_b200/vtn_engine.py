@@ -43,7 +43,9 @@ def default_hparams(**over) -> dict:
               # fixed by the reference's Encoder / Decoder / Postnet defaults
               enc_positional_dropout_rate=0.1, dec_dropout_rate=0.1, dec_positional_dropout_rate=0.1,
               postnet_dropout_rate=0.5, decoder_reduction_factor=2,
-              initial_encoder_alpha=1.0, initial_decoder_alpha=1.0)
+              initial_encoder_alpha=1.0, initial_decoder_alpha=1.0,
+              # "conv2d": VTN (Conv2dSubsampling + ScaledPE); "embed": TransformerTTS (token embedding + <eos> + ScaledPE)
+              encoder_input="conv2d")
     hp.update(over)
     return hp
 
@@ -79,12 +81,16 @@ def param_groups(hp: dict) -> List[List[Tuple[str, Tuple[int, ...]]]]:
             if s not in fuse:
                 lin(f"{name}.{s}", d, d)
 
-    g.append([("encoder.embed.conv.0.weight", (d, 1, 3, 3))])
-    g.append([("encoder.embed.conv.0.bias", (d,))])
-    g.append([("encoder.embed.conv.2.weight", (d, d, 3, 3))])
-    g.append([("encoder.embed.conv.2.bias", (d,))])
-    lin("encoder.embed.out.0", d, d * f2)
-    g.append([("encoder.embed.out.1.alpha", ())])
+    if hp.get("encoder_input", "conv2d") == "embed":      # models/transformer_tts.py:63-77
+        g.append([("encoder.embed.0.weight", (idim, d))])
+        g.append([("encoder.embed.1.alpha", ())])
+    else:
+        g.append([("encoder.embed.conv.0.weight", (d, 1, 3, 3))])
+        g.append([("encoder.embed.conv.0.bias", (d,))])
+        g.append([("encoder.embed.conv.2.weight", (d, d, 3, 3))])
+        g.append([("encoder.embed.conv.2.bias", (d,))])
+        lin("encoder.embed.out.0", d, d * f2)
+        g.append([("encoder.embed.out.1.alpha", ())])
     for l in range(hp["elayers"]):
         p = f"encoder.encoders.{l}"
         mha(p + ".self_attn", ("linear_q", "linear_k", "linear_v"))
@@ -174,6 +180,10 @@ class VTNEngine:
                 n *= s
             if name.endswith("alpha"):
                 v = torch.full((1,), hp["initial_encoder_alpha"] if name.startswith("encoder") else hp["initial_decoder_alpha"])
+            elif name == "encoder.embed.0.weight" and hp["encoder_input"] == "embed":
+                v = torch.randn(shape, generator=g)
+                v[0] = 0.0                                  # nn.Embedding(padding_idx=0)
+                v = v.reshape(-1)
             elif "norm" in name or (name.startswith("postnet") and ".1." in name):
                 v = torch.ones(n) if name.endswith("weight") else torch.zeros(n)
             else:
@@ -325,23 +335,30 @@ class VTNEngine:
         so that a captured CUDA graph of the step only ever sees the device-resident copy."""
         hp = self.hp
         r = hp["decoder_reduction_factor"]
-        T2 = (((T - 1) // 2) - 1) // 2
+        embed = hp["encoder_input"] == "embed"
+        T2 = T + 1 if embed else (((T - 1) // 2) - 1) // 2
         self._sig = (B, T, L, self.training)
         ilens = [int(v) for v in ilens]
         olens = [int(v) for v in olens]
         assert len(ilens) == B and len(olens) == B
-        klens_enc = [min(T2, (i + 3) // 4) for i in ilens]           # mask[:, :, :-2:2][:, :, :-2:2] (subsampling.py:92-94)
+        if embed:
+            klens_enc = [i + 1 for i in ilens]                       # <eos> appended (transformer_tts.py:139-142)
+        else:
+            klens_enc = [min(T2, (i + 3) // 4) for i in ilens]       # mask[:, :, :-2:2][:, :, :-2:2] (subsampling.py:92-94)
         olens_in = [o // r for o in olens]
         olens_fix = [o - o % r for o in olens]
         host = self._lens_host.get(B)
         if host is None:
-            host = torch.empty(3, B, dtype=_i32)
+            host = torch.empty(5, B, dtype=_i32)
             if self.device.type == "cuda":
                 host = host.pin_memory()
             self._lens_host[B] = host
-        host.copy_(torch.tensor([klens_enc, olens_in, olens_fix], dtype=_i32))
-        self.buf("lens", (3, B), _i32).copy_(host, non_blocking=True)
-        self.ilens_ds_st = [((i - 2 + 1) // 2 - 2 + 1) // 2 for i in ilens]   # vtn.py:279
+        if embed:
+            self.ilens_ds_st = klens_enc                                        # transformer_tts.py:222 returns ilens + 1
+        else:
+            self.ilens_ds_st = [((i - 2 + 1) // 2 - 2 + 1) // 2 for i in ilens]   # vtn.py:279
+        host.copy_(torch.tensor([klens_enc, olens_in, olens_fix, ilens, self.ilens_ds_st], dtype=_i32))
+        self.buf("lens", (5, B), _i32).copy_(host, non_blocking=True)
         self.olens_in_host, self.olens_fix_host = olens_in, olens_fix
         self._prepared = (B, T, L)
 
@@ -354,13 +371,19 @@ class VTNEngine:
         self.attn; L' = (L // r) * r.
         """
         hp, st = self.hp, self.store
-        B, T, idim = xs.shape
+        embed = hp["encoder_input"] == "embed"
+        B, T = xs.shape[0], xs.shape[1]
+        idim = hp["idim"]
         L, odim = ys.shape[1], ys.shape[2]
         r, d, H = hp["decoder_reduction_factor"], hp["adim"], hp["aheads"]
         dk = d // H
-        assert xs.dtype == _f32 and ys.dtype == _f32 and xs.is_contiguous() and ys.is_contiguous()
+        assert ys.dtype == _f32 and xs.is_contiguous() and ys.is_contiguous()
+        assert xs.dtype == (torch.int64 if embed else _f32), "xs: int64 token ids (TransformerTTS) or float32 features (VTN)"
         T1, F1 = (T - 1) // 2, (idim - 1) // 2
         T2, F2 = (T1 - 1) // 2, (F1 - 1) // 2
+        if embed:
+            T1 = F1 = F2 = 0
+            T2 = T + 1
         Lr = L // r
         self._sig = (B, T, L, self.training)
         self._site = 0
@@ -371,28 +394,32 @@ class VTNEngine:
         if ilens is not None:
             self.prepare(B, T, L, ilens, olens)
         assert self._prepared == (B, T, L), "prepare(B, T, L, ilens, olens) must precede forward() for this batch shape"
-        lens = self.buf("lens", (3, B), _i32)
-        self.klens_enc, self.olens_in, self.olens_fix = lens[0], lens[1], lens[2]
+        lens = self.buf("lens", (5, B), _i32)
+        self.klens_enc, self.olens_in, self.olens_fix, self.ilens_dev, self.ilens_ds_dev = lens[0], lens[1], lens[2], lens[3], lens[4]
 
-        # ---- packed conv weights (activation dtype)
-        w2p = self.buf("w.conv2p", (d, 9, d))          # [oc][tap][ic]
-        ops.transpose_last2(st.p("encoder.embed.conv.2.weight"), w2p, d, d, 9)
-        woutp = self.buf("w.outp", (d, F2, d))         # [n][f][c]
-        ops.transpose_last2(st.p("encoder.embed.out.0.weight"), woutp, d, d, F2)
-
-        # ---- encoder front end (subsampling.py:74-94)
         self.xs = xs
-        y1 = self.buf("enc.y1", (B, T1, F1, d))
-        ops.conv1_fwd(xs, st.p("encoder.embed.conv.0.weight"), st.p("encoder.embed.conv.0.bias"), y1)
-        col = self._scratch("col", (B * T2 * F2, 9 * d))
-        ops.im2col_s2(y1, col)
-        y2 = self.buf("enc.y2", (B * T2 * F2, d))
-        ops.gemm(col, w2p.view(d, 9 * d), y2, bias=st.p("encoder.embed.conv.2.bias"), relu=True, mode=self.mode)
-        elin = self.buf("enc.elin", (B * T2, d))
-        ops.gemm(y2.view(B * T2, F2 * d), woutp.view(d, F2 * d), elin, bias=st.p("encoder.embed.out.0.bias"), mode=self.mode)
         x = self.buf("enc.x0", (B, T2, d))
-        ops.scaled_pe_fwd(elin.view(B, T2, d), self.pe(d, T2), st.p("encoder.embed.out.1.alpha"), x,
-                          self.drop(hp["enc_positional_dropout_rate"]))
+        if embed:
+            # ---- token embedding + <eos> + ScaledPE in one kernel (transformer_tts.py:63-77,139-142)
+            ops.embed_pe_fwd(xs, self.ilens_dev, st.p("encoder.embed.0.weight"), self.pe(d, T2), st.p("encoder.embed.1.alpha"), x,
+                             idim - 1, 0, self.drop(hp["enc_positional_dropout_rate"]))
+        else:
+            # ---- packed conv weights (activation dtype)
+            w2p = self.buf("w.conv2p", (d, 9, d))          # [oc][tap][ic]
+            ops.transpose_last2(st.p("encoder.embed.conv.2.weight"), w2p, d, d, 9)
+            woutp = self.buf("w.outp", (d, F2, d))         # [n][f][c]
+            ops.transpose_last2(st.p("encoder.embed.out.0.weight"), woutp, d, d, F2)
+            # ---- encoder front end (subsampling.py:74-94)
+            y1 = self.buf("enc.y1", (B, T1, F1, d))
+            ops.conv1_fwd(xs, st.p("encoder.embed.conv.0.weight"), st.p("encoder.embed.conv.0.bias"), y1)
+            col = self._scratch("col", (B * T2 * F2, 9 * d))
+            ops.im2col_s2(y1, col)
+            y2 = self.buf("enc.y2", (B * T2 * F2, d))
+            ops.gemm(col, w2p.view(d, 9 * d), y2, bias=st.p("encoder.embed.conv.2.bias"), relu=True, mode=self.mode)
+            elin = self.buf("enc.elin", (B * T2, d))
+            ops.gemm(y2.view(B * T2, F2 * d), woutp.view(d, F2 * d), elin, bias=st.p("encoder.embed.out.0.bias"), mode=self.mode)
+            ops.scaled_pe_fwd(elin.view(B, T2, d), self.pe(d, T2), st.p("encoder.embed.out.1.alpha"), x,
+                              self.drop(hp["enc_positional_dropout_rate"]))
 
         # ---- encoder layers (pre-LN; encoder_layer.py:61-119)
         pe_ = hp["transformer_enc_dropout_rate"]
@@ -537,6 +564,32 @@ class VTNEngine:
         ops.seq2seq_loss(self.after, self.before, self.logits, ys, labels_fix, self.olens_fix, pos_weight, self.losses,
                          self.d_after, self.d_before, self.d_logits, self._loss_ws)
         return self.losses
+
+    def guided_attention(self, sigma: float = 0.4, alpha: float = 1.0, n_layers: int = 2, n_heads: int = 2):
+        """GuidedMultiHeadAttentionLoss over the source-attention maps of the last `n_layers` decoder layers x first
+        `n_heads` heads (models/transformer_tts.py:205-219, losses/guided_attention_loss.py:142-165).
+        Returns (loss (1,) device tensor, {attention name: d loss / d P in the (B, H, T_out, ld) layout})."""
+        s, hp = self.shapes, self.hp
+        B, Lr, T2, H = s["B"], s["Lr"], s["T2"], hp["aheads"]
+        ld = _r8(T2)
+        nh = min(n_heads, H)
+        names = [f"decoder.decoders.{l}" for l in reversed(range(hp["dlayers"]))][:n_layers]
+        total = self.buf("ga.loss", (1,), _f32)
+        total.zero_()
+        part = self.buf("ga.part", (1,), _f32)
+        ws = self.buf("ga.ws", (2,), _f32)
+        d_att = {}
+        for p in names:
+            P = self.buf(p + ".ca.P", (B, H, Lr, ld))
+            sel = self._scratch("ga.sel", (B, nh, Lr, ld))
+            sel.copy_(P[:, :nh])
+            dsel = self._scratch("ga.dsel", (B, nh, Lr, ld))
+            ops.guided_attn_loss(sel, self.ilens_ds_dev, self.olens_in, T2, sigma, alpha / len(names), part, dsel, ws)
+            ops.add(total, part, total)
+            dfull = self.buf(p + ".ca.d_att", (B, H, Lr, ld), zero=True)      # heads >= nh stay zero
+            dfull[:, :nh].copy_(dsel)
+            d_att[p + ".src_attn"] = dfull
+        return total, d_att
 
     # ------------------------------------------------------------------ backward
     def backward(self, d_after: torch.Tensor, d_before: torch.Tensor, d_logits: torch.Tensor,
@@ -732,6 +785,10 @@ class VTNEngine:
             self._ln_bwd(dn1, xin, p + ".norm1", p + ".ln1", g, dres=gm)          # g_prev = g_mid + LN1'(dn1)
 
         # ---- encoder front end
+        if hp["encoder_input"] == "embed":
+            ops.embed_pe_bwd(g, self.xs, self.ilens_dev, self.pe(d, T2), st.g("encoder.embed.0.weight"), st.g("encoder.embed.1.alpha"),
+                             hp["idim"] - 1, 0, sites["enc.pe"])
+            return
         delin = gte
         ops.scaled_pe_bwd(g, self.pe(d, T2), delin, st.g("encoder.embed.out.1.alpha"), sites["enc.pe"])
         y2 = self.buf("enc.y2", (B * T2 * F2, d))

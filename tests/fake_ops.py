@@ -154,6 +154,38 @@ def scaled_pe_bwd(dy, pe, dx, dalpha, drop=NO_DROP):
     return dx
 
 
+def _tts_tokens(tokens, ilens, T_out, eos, pad):
+    B, T_in = tokens.shape
+    tok = torch.full((B, T_out), pad, dtype=torch.int64)
+    for b in range(B):
+        il = int(ilens[b])
+        tok[b, :min(il, T_in)] = tokens[b, :min(il, T_in)]
+        if il < T_out:
+            tok[b, il] = eos
+    return tok
+
+
+def embed_pe_fwd(tokens, ilens, weight, pe, alpha, y, eos, padding_idx=0, drop=NO_DROP):
+    _nodrop(drop)
+    T_out = y.shape[1]
+    tok = _tts_tokens(tokens, ilens, T_out, eos, padding_idx)
+    y.copy_((weight.double()[tok] + alpha.double() * pe[:T_out].double()[None]).to(y.dtype))
+    return y
+
+
+def embed_pe_bwd(dy, tokens, ilens, pe, dweight, dalpha, eos, padding_idx=0, drop=NO_DROP):
+    _nodrop(drop)
+    T_out, d = dy.shape[1], dy.shape[2]
+    tok = _tts_tokens(tokens, ilens, T_out, eos, padding_idx)
+    if dalpha is not None:
+        dalpha += (dy.double() * pe[:T_out].double()[None]).sum().float()
+    if dweight is not None:
+        g = torch.zeros(dweight.shape, dtype=torch.float64)
+        g.index_add_(0, tok.reshape(-1), dy.double().reshape(-1, d))
+        g[padding_idx] = 0
+        dweight += g.float()
+
+
 def conv1_fwd(x, w, bias, y1):
     out = torch.relu(torch.nn.functional.conv2d(x.unsqueeze(1).double(), w.double(), bias.double(), stride=2))  # (B,C,T1,F1)
     y1.copy_(out.permute(0, 2, 3, 1).to(y1.dtype))

@@ -112,3 +112,49 @@ def test_adam_step_matches_torch(engine):
     eng.lr_dev.fill_(8e-5)
     eng.optimizer_step(1.0)
     assert (eng.store.P - ref.detach()).abs().max() <= 1e-7
+
+
+# --------------------------------------------------------------------------------------------------
+# TransformerTTS (token-embedding encoder) + guided attention loss
+# --------------------------------------------------------------------------------------------------
+TTS_HP = dict(idim=40, odim=80, dprenet_layers=2, dprenet_units=16, adim=32, aheads=4, elayers=1, eunits=48,
+              dlayers=2, dunits=48, postnet_layers=2, postnet_filts=5, postnet_chans=16, decoder_reduction_factor=2,
+              encoder_input="embed")
+
+
+def run_tts_step(eng, z):
+    ilens, olens = z["ilens"].tolist(), z["olens"].tolist()
+    dev = eng.device
+    tokens = torch.from_numpy(z["tokens"])[:, :max(ilens)].contiguous().to(dev)
+    ys = torch.from_numpy(z["ys"])[:, :max(olens)].contiguous().to(dev)
+    labels = torch.from_numpy(z["labels"])[:, :max(olens)].contiguous().to(dev)
+    after, before, logits = eng.forward(tokens, ys, ilens, olens)
+    losses = eng.loss(ys, labels)
+    ga, d_att = eng.guided_attention(sigma=0.4, alpha=1.0, n_layers=2, n_heads=2)
+    eng.backward(eng.d_after, eng.d_before, eng.d_logits, d_att=d_att)
+    return after, before, logits, losses, ga
+
+
+def check_tts(eng, z, tol_out=1e-5, tol_grad=2e-4):
+    after, before, logits, losses, ga = run_tts_step(eng, z)
+    assert np.abs(after.cpu().numpy() - z["after_outs"]).mean() <= tol_out
+    assert np.abs(logits.cpu().numpy() - z["logits"]).mean() <= tol_out
+    assert abs(float(losses[0]) - float(z["l1_loss"])) <= 10 * tol_out and abs(float(losses[1]) - float(z["bce_loss"])) <= 10 * tol_out
+    assert abs(float(ga) - float(z["ga_loss"])) <= 10 * tol_out
+    assert eng.ilens_ds_st == z["ilens_out"].tolist() and eng.olens_in_host == z["olens_in"].tolist()
+    nl = eng.hp["dlayers"]
+    att = torch.cat([eng.attn[f"decoder.decoders.{l}.src_attn"][:, :2] for l in reversed(range(nl))][:2], dim=1)
+    assert np.abs(att.float().cpu().numpy() - z["att_ws"]).mean() <= 1e-5
+    for name in eng.store.names():
+        ref = z["grad." + name]
+        got = eng.store.g(name).cpu().numpy()
+        assert np.abs(got - ref).max() <= tol_grad * (np.abs(ref).max() + 1e-5), name
+
+
+def test_tts_forward_guided_attention_and_gradients(monkeypatch):
+    fake_ops.install(monkeypatch)
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "tts_tiny.npz"))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    eng = VTNEngine(dict(TTS_HP, **NO_DROPOUT), device="cpu", bf16=False)
+    eng.load_state_dict(sd)
+    check_tts(eng, z)

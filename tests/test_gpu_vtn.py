@@ -165,3 +165,58 @@ def test_fused_train_step_decreases_loss_with_dropout_bf16():
         hist.append(losses.sum().item())
     assert np.isfinite(hist).all()
     assert np.mean(hist[-5:]) < np.mean(hist[:5]), hist
+
+
+def test_transformer_tts_golden_fp32_and_dropin():
+    """TransformerTTS (BASELINE configs[3] family): engine vs the reference's golden vectors incl. the guided
+    attention loss gradient, then the drop-in module through autograd."""
+    import test_engine_host_logic as H
+    from seq2seq_vc_b200 import GuidedMultiHeadAttentionLoss, Seq2SeqLoss, TransformerTTS, VTNEngine
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "tts_tiny.npz"))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    eng = VTNEngine(dict(H.TTS_HP, **NO_DROPOUT), device="cuda:0", bf16=False)
+    eng.load_state_dict(sd)
+    H.check_tts(eng, z, tol_out=1e-4, tol_grad=1e-3)
+    torch.cuda.synchronize()
+    hp = {k: v for k, v in H.TTS_HP.items() if k != "encoder_input"}
+    model = TransformerTTS(dprenet_dropout_rate=0.0, use_guided_attn_loss=True, **hp).to("cuda:0")
+    for k in ("transformer_enc_dropout_rate", "enc_positional_dropout_rate", "dec_dropout_rate", "dec_positional_dropout_rate",
+              "postnet_dropout_rate"):
+        model.engine.hp[k] = 0.0
+    model.load_state_dict({k: v.cuda() for k, v in sd.items()})
+    ilens, olens = torch.from_numpy(z["ilens"]), torch.from_numpy(z["olens"])
+    out = model(torch.from_numpy(z["tokens"]).cuda(), ilens, torch.from_numpy(z["ys"]).cuda(), torch.from_numpy(z["labels"]).cuda(), olens)
+    assert out[6][0].shape == z["att_ws"].shape and out[6][1].tolist() == z["ilens_out"].tolist()
+    l1, bce = Seq2SeqLoss()(*out[:6])
+    ga = GuidedMultiHeadAttentionLoss(sigma=0.4, alpha=1.0)(out[6][0], out[6][1], out[6][2])
+    assert abs(ga.item() - float(z["ga_loss"])) <= 1e-4
+    (l1 + bce + ga).backward()
+    for name, p in model.named_parameters():
+        ref = z["grad." + name]
+        assert np.abs(p.grad.cpu().numpy() - ref).max() <= 1e-3 * (np.abs(ref).max() + 1e-5), name
+
+
+def test_tts_fused_step_with_guided_attention_trains():
+    from seq2seq_vc_b200 import TransformerTTS, VTNTrainStep
+
+    model = TransformerTTS(idim=40, odim=80, adim=64, aheads=4, elayers=2, dlayers=2, eunits=128, dunits=128, dprenet_units=32,
+                           postnet_chans=32, compute_dtype="bf16", device="cuda:0", use_guided_attn_loss=True)
+    step = VTNTrainStep(model, lr=1e-3, warmup_steps=1, use_graph=True, guided_attn=dict(sigma=0.4, alpha=1.0, n_layers=2, n_heads=2))
+    g = torch.Generator().manual_seed(3)
+    ilens, olens = [21, 17, 12, 9], [60, 51, 40, 33]
+    tokens = torch.randint(1, 39, (4, 21), generator=g)
+    ys = torch.randn(4, 60, 80, generator=g)
+    labels = torch.zeros(4, 60)
+    for b in range(4):
+        tokens[b, ilens[b]:] = 0
+        ys[b, olens[b]:] = 0
+        labels[b, olens[b] - 1:] = 1
+    tokens, ys, labels = tokens.cuda(), ys.cuda(), labels.cuda()
+    hist, ga = [], []
+    for it in range(30):
+        losses = step(tokens, ilens, ys, labels, olens)
+        hist.append(losses.sum().item())
+        ga.append(step.ga_loss.item())
+    assert np.isfinite(hist).all() and np.isfinite(ga).all()
+    assert np.mean(hist[-5:]) < np.mean(hist[:5])

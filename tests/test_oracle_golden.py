@@ -74,3 +74,17 @@ def test_product_filterbank_and_window_match_oracle():
         np.testing.assert_allclose(mel_filterbank(sr, n_fft, 80, fmin, fmax), logmel_oracle.mel_basis(sr, n_fft, 80, fmin, fmax), atol=1e-7)
     np.testing.assert_allclose(hann_window(2048, None), logmel_oracle.hann_padded(2048, None).astype(np.float32), atol=1e-7)
     np.testing.assert_allclose(hann_window(2048, 1200), logmel_oracle.hann_padded(2048, 1200).astype(np.float32), atol=1e-7)
+
+
+def test_tts_oracle_forward_and_guided_attention():
+    z = np.load(os.path.join(GOLD, "tts_tiny.npz"))
+    hp = dict(idim=40, odim=80, dprenet_layers=2, dprenet_units=16, adim=32, aheads=4, elayers=1, eunits=48,
+              dlayers=2, dunits=48, postnet_layers=2, postnet_filts=5, postnet_chans=16, decoder_reduction_factor=2)
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    out = vtn_oracle.tts_forward(sd, hp, torch.from_numpy(z["tokens"]), z["ilens"].tolist(), torch.from_numpy(z["ys"]),
+                                 torch.from_numpy(z["labels"]), z["olens"].tolist(), use_guided_attn_loss=True)
+    assert np.abs(out["after_outs"].numpy() - z["after_outs"]).max() <= 2e-5
+    assert np.abs(out["att_ws"].numpy() - z["att_ws"]).max() <= 1e-6
+    assert out["ilens"] == z["ilens_out"].tolist()
+    ga = vtn_oracle.guided_attention_loss(out["att_ws"], out["ilens"], out["olens_in"])
+    assert abs(float(ga) - float(z["ga_loss"])) <= 1e-6
