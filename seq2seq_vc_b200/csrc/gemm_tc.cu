@@ -503,13 +503,21 @@ static bool make_map(CUtensorMap* map, const void* base, const long (&dim)[4], c
     return r == CUDA_SUCCESS;
 }
 
-static int pick_bn(int N) {
+// N-tile choice from a small cycle model of one CTA's work (numbers from the in-kernel clock traces):
+//   tile = fixed (~1500) + epilogue (~16 / column) + k-blocks x 4 MMAs x (70 + 0.68 BN) cycles
+// total = waves(tiles) x tile.  Wide tiles amortise the A re-reads of cta_group::1 MMAs; a problem
+// with few tiles is cut finer so that all SMs work.  Split-K candidates keep wide tiles (K is split instead).
+static int pick_bn(int N, long mtiles_x_batch, long kblocks, bool splitk_candidate) {
     int best = 256;
-    long best_cost = -1;
+    double best_cost = -1.0;
+    const long sms = num_sms();
     for (int bn = 256; bn >= 16; bn -= 16) {
-        long tiles = (N + bn - 1) / bn;
-        long cost = tiles * bn * 8 + tiles * 24;       // padded columns + a per-tile overhead term
-        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
+        const long nt = (N + bn - 1) / bn;
+        const long tiles = nt * mtiles_x_batch;
+        const long waves = splitk_candidate ? tiles : (tiles + sms - 1) / sms;
+        const double mma = 4.0 * (70.0 + 0.68 * bn);      // measured: 158 cycles @ N = 128, 245 @ N = 256
+        const double cost = (double)waves * (1500.0 + 16.0 * bn + (double)kblocks * mma);
+        if (best_cost < 0 || cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
     }
     return best;
 }
@@ -533,7 +541,8 @@ int gemm_tc(const s2s_gemm_t& g, cudaStream_t st) {
     p.a_mn = (g.a_cs != 1) ? 1 : 0;      // contiguous along M
     p.b_mn = (g.b_cs != 1) ? 1 : 0;      // contiguous along N
     if (g.K == 1) { p.a_mn = (g.a_rs == 1); p.b_mn = (g.b_rs == 1); }
-    p.BN = pick_bn(g.N);
+    const bool splitk_candidate = g.c_dtype == S2S_F32 && g.accumulate && !g.bias && !g.R && !g.relu && g.drop.p <= 0.f && g.mask_period == 0;
+    p.BN = pick_bn(g.N, (long)ceil_div_l(g.M, BM) * g.batch1 * g.batch2, (long)ceil_div_l(g.K, BK) * g.taps, splitk_candidate);
     if (ok) {
         const long rowsA = (long)g.M + g.taps - 1;
         if (!p.a_mn) {
