@@ -12,7 +12,7 @@ import os
 import numpy as np
 import torch
 
-from oracle import ref_shim, vtn_oracle
+from oracle import aasvc_oracle, ref_shim, vtn_oracle
 
 GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
@@ -103,6 +103,63 @@ def gen_tts_tiny():
     print("tts_tiny:", len(dump), "arrays")
 
 
+AAS_HP = dict(idim=80, odim=80, adim=32, aheads=2, elayers=1, eunits=48, dlayers=1, dunits=48,
+              duration_predictor_input_dim=80, duration_predictor_layers=2, duration_predictor_chans=16,
+              duration_predictor_kernel_size=3, postnet_layers=2, postnet_filts=5, postnet_chans=16,
+              post_encoder_reduction_factor=4, conformer_enc_kernel_size=7, conformer_dec_kernel_size=7)
+AAS_FIXED = dict(positionwise_layer_type="linear", positionwise_conv_kernel_size=1, duration_predictor_use_encoder_outputs=False,
+                 encoder_normalize_before=True, decoder_normalize_before=True, duration_predictor_type="deterministic",
+                 encoder_input_layer="linear")
+
+
+def gen_aasvc_tiny():
+    """AASVC (models/aas_vc.py) + L1Loss + ForwardSumLoss + bin loss + DurationPredictorLoss, assembled as
+    AASVCTrainer._train_step does (trainers/aas_vc.py:73-134, lambda_align = 2.0)."""
+    from seq2seq_vc.losses import DurationPredictorLoss, ForwardSumLoss, L1Loss
+    from seq2seq_vc.models import AASVC
+
+    torch.manual_seed(13)
+    model = AASVC(**AAS_HP, **AAS_FIXED)
+    ref_shim.disable_dropout(model)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if p.dim() == 1 and ("norm" in n or "embed.1" in n or ".2." in n or ".1." in n):
+                p.add_(0.1 * torch.randn_like(p))
+    model.train()
+    sd0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    xs, ilens, ys, olens, dpi = aasvc_oracle.synthetic_batch(3, 50, 44, ilens=[50, 44, 37], olens=[44, 40, 30], seed=17)
+    ret = model(xs, torch.tensor(ilens), ys, torch.tensor(olens), dpi, dp_lengths=torch.tensor(ilens))
+    l1 = L1Loss()(ret["after_outs"], ret["before_outs"], ret["ys"], ret["olens"])
+    fs = ForwardSumLoss()(ret["log_p_attn"], ret["ilens"], ret["olens_reduced"])
+    dur = DurationPredictorLoss()(ret["d_outs"], ret["ds"], ret["ilens"])
+    (l1 + 2.0 * (fs + ret["bin_loss"]) + dur).backward()
+    dump = {"sd." + k: v.numpy() for k, v in sd0.items()}
+    dump.update({"grad." + k: p.grad.numpy() for k, p in model.named_parameters() if p.grad is not None})
+    dump.update({"bn_after." + k: v.numpy() for k, v in model.state_dict().items() if "running_" in k})
+    dump.update(xs=xs.numpy(), ilens=np.array(ilens), ys=ys.numpy(), olens=np.array(olens), dp_inputs=dpi.numpy(),
+                after_outs=ret["after_outs"].detach().numpy(), before_outs=ret["before_outs"].detach().numpy(),
+                log_p_attn=ret["log_p_attn"].detach().numpy(), ds=ret["ds"].numpy(), d_outs=ret["d_outs"].detach().numpy(),
+                ilens_out=ret["ilens"].numpy(), olens_out=ret["olens"].numpy(), l1_loss=l1.detach().numpy(),
+                forward_sum_loss=fs.detach().numpy(), bin_loss=ret["bin_loss"].detach().numpy(), duration_loss=dur.detach().numpy())
+    for n, m in model.named_modules():
+        if hasattr(m, "attn") and isinstance(getattr(m, "attn"), torch.Tensor):
+            dump["attn." + n] = m.attn.detach().numpy()
+    model.eval()
+    with torch.no_grad():
+        rete = model(xs, torch.tensor(ilens), ys, torch.tensor(olens), dpi, dp_lengths=torch.tensor(ilens))
+    dump["eval_after_outs"] = rete["after_outs"].numpy()
+    # ForwardSumLoss on its own (ragged lengths, incl. an infeasible utterance T < N that zero_infinity drops)
+    g = torch.Generator().manual_seed(23)
+    lp = torch.log_softmax(torch.randn(4, 40, 12, generator=g), -1)
+    tl, fl = torch.tensor([12, 9, 5, 12]), torch.tensor([40, 31, 17, 8])
+    lp.requires_grad_(True)
+    fsl = ForwardSumLoss()(lp, tl, fl)
+    fsl.backward()
+    dump.update(fs_lp=lp.detach().numpy(), fs_tl=tl.numpy(), fs_fl=fl.numpy(), fs_loss=fsl.detach().numpy(), fs_grad=lp.grad.numpy())
+    np.savez_compressed(os.path.join(GOLDEN, "aasvc_tiny.npz"), **dump)
+    print("aasvc_tiny:", len(dump), "arrays")
+
+
 def gen_mas():
     from seq2seq_vc.modules.alignments import _monotonic_alignment_search, viterbi_decode
 
@@ -159,5 +216,6 @@ if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     gen_vtn_tiny()
     gen_tts_tiny()
+    gen_aasvc_tiny()
     gen_mas()
     gen_kats()

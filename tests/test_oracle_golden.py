@@ -88,3 +88,60 @@ def test_tts_oracle_forward_and_guided_attention():
     assert out["ilens"] == z["ilens_out"].tolist()
     ga = vtn_oracle.guided_attention_loss(out["att_ws"], out["ilens"], out["olens_in"])
     assert abs(float(ga) - float(z["ga_loss"])) <= 1e-6
+
+
+AAS_HP = dict(idim=80, odim=80, adim=32, aheads=2, elayers=1, eunits=48, dlayers=1, dunits=48,
+              duration_predictor_input_dim=80, duration_predictor_layers=2, duration_predictor_chans=16,
+              duration_predictor_kernel_size=3, postnet_layers=2, postnet_filts=5, postnet_chans=16,
+              post_encoder_reduction_factor=4, conformer_enc_kernel_size=7, conformer_dec_kernel_size=7)
+
+
+def test_aasvc_oracle_forward_loss_grads():
+    """AASVC forward, the four losses of AASVCTrainer._train_step and every gradient vs the live-reference dump."""
+    from oracle import aasvc_oracle
+
+    z = np.load(os.path.join(GOLD, "aasvc_tiny.npz"))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    bn = {}
+    out = aasvc_oracle.aasvc_forward(sd, AAS_HP, torch.from_numpy(z["xs"]), z["ilens"].tolist(), torch.from_numpy(z["ys"]),
+                                     z["olens"].tolist(), torch.from_numpy(z["dp_inputs"]), training=True, bn_stats=bn)
+    for k in ("after_outs", "before_outs", "d_outs"):
+        assert np.abs(out[k].detach().numpy() - z[k]).max() <= 2e-5, k
+    lp, ref = out["log_p_attn"].detach().numpy(), z["log_p_attn"]
+    assert np.array_equal(np.isfinite(lp), np.isfinite(ref)) and np.abs(lp[np.isfinite(ref)] - ref[np.isfinite(ref)]).max() <= 2e-5
+    np.testing.assert_array_equal(out["ds"].numpy(), z["ds"])                      # integer alignment path: bit-exact
+    assert out["ilens"] == z["ilens_out"].tolist() and out["olens"] == z["olens_out"].tolist()
+    for k, v in bn.items():
+        assert np.abs(v.numpy() - z["bn_after." + k]).max() <= 1e-5, k
+    for k in [k for k in z.files if k.startswith("attn.")]:
+        assert np.abs(out["attn"][k[5:]].detach().numpy() - z[k]).max() <= 1e-6, k
+    _, parts, grads = aasvc_oracle.aasvc_loss_and_grads(sd, AAS_HP, torch.from_numpy(z["xs"]), z["ilens"].tolist(),
+                                                        torch.from_numpy(z["ys"]), z["olens"].tolist(), torch.from_numpy(z["dp_inputs"]))
+    for k in ("l1_loss", "forward_sum_loss", "bin_loss", "duration_loss"):
+        assert abs(float(parts[k]) - float(z[k])) <= 2e-6 * max(1.0, abs(float(z[k]))), k
+    gmax = max(np.abs(z[k]).max() for k in z.files if k.startswith("grad."))
+    for k, g in grads.items():
+        ref = z["grad." + k]
+        # gradients that are zero in exact arithmetic (key bias under softmax, biases ahead of BatchNorm) are round-off noise
+        assert np.abs(g.numpy() - ref).max() <= 2e-4 * np.abs(ref).max() + 2e-6 * gmax, k
+
+
+def test_forward_sum_oracle_matches_reference_ctc():
+    """Hand-rolled alpha recursion vs the reference's F.ctc_loss path incl. an infeasible utterance (zero_infinity)."""
+    from oracle import aasvc_oracle
+
+    z = np.load(os.path.join(GOLD, "aasvc_tiny.npz"))
+    lp = torch.from_numpy(z["fs_lp"]).requires_grad_(True)
+    loss = aasvc_oracle.forward_sum_loss(lp, z["fs_tl"].tolist(), z["fs_fl"].tolist())
+    assert abs(float(loss) - float(z["fs_loss"])) <= 1e-5
+    (g,) = torch.autograd.grad(loss, lp)
+    assert np.abs(g.numpy() - z["fs_grad"]).max() <= 1e-5
+
+
+def test_rel_shift_restatement():
+    """bd'[i, j] = bd[i, T-1-i+j] is exactly the reference's pad/view/slice rel_shift (attention.py:237-260)."""
+    T = 7
+    x = torch.arange(2 * 3 * T * (2 * T - 1), dtype=torch.float32).view(2, 3, T, 2 * T - 1)
+    xp = torch.cat([torch.zeros(2, 3, T, 1), x], dim=-1).view(2, 3, 2 * T, T)[:, :, 1:].reshape(2, 3, T, 2 * T - 1)[..., :T]
+    idx = T - 1 - torch.arange(T)[:, None] + torch.arange(T)[None, :]
+    assert torch.equal(xp, torch.gather(x, 3, idx[None, None].expand(2, 3, T, T)))

@@ -49,3 +49,34 @@ def test_mas_fuzz_against_numba(ref):
         ref_path = _monotonic_alignment_search(lp)
         paths, _ = mas_oracle.mas_batch_c(lp[None], [ti], [tm])
         np.testing.assert_array_equal(paths[0], ref_path)
+
+
+def test_aasvc_against_live_reference(ref):
+    from oracle import aasvc_oracle as ao
+    from seq2seq_vc.losses import DurationPredictorLoss, ForwardSumLoss, L1Loss
+    from seq2seq_vc.models import AASVC
+
+    hp = dict(idim=80, odim=80, adim=32, aheads=2, elayers=2, eunits=48, dlayers=1, dunits=64, duration_predictor_input_dim=80,
+              duration_predictor_layers=2, duration_predictor_chans=16, duration_predictor_kernel_size=3, postnet_layers=2,
+              postnet_filts=5, postnet_chans=16, post_encoder_reduction_factor=4, conformer_enc_kernel_size=7,
+              conformer_dec_kernel_size=15)
+    torch.manual_seed(5)
+    model = AASVC(positionwise_layer_type="linear", positionwise_conv_kernel_size=1, duration_predictor_use_encoder_outputs=False,
+                  encoder_normalize_before=True, decoder_normalize_before=True, duration_predictor_type="deterministic",
+                  encoder_input_layer="linear", **hp)
+    ref_shim.disable_dropout(model)
+    model.train()
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    spec = dict(ao.state_dict_spec(hp))
+    assert set(spec) == set(sd) and all(tuple(sd[k].shape) == tuple(spec[k]) for k in sd)
+    xs, ilens, ys, olens, dpi = ao.synthetic_batch(2, 61, 52, ilens=[61, 47], olens=[52, 33], seed=9)
+    ret = model(xs, torch.tensor(ilens), ys, torch.tensor(olens), dpi, dp_lengths=torch.tensor(ilens))
+    out = ao.aasvc_forward(sd, hp, xs, ilens, ys, olens, dpi, training=True)
+    assert (out["after_outs"] - ret["after_outs"]).abs().max() <= 2e-5
+    assert torch.equal(out["ds"], ret["ds"])
+    _, parts = ao.aasvc_losses(out)
+    fs = ForwardSumLoss()(ret["log_p_attn"], ret["ilens"], ret["olens_reduced"])
+    l1 = L1Loss()(ret["after_outs"], ret["before_outs"], ret["ys"], ret["olens"])
+    dur = DurationPredictorLoss()(ret["d_outs"], ret["ds"], ret["ilens"])
+    assert abs(float(parts["forward_sum_loss"]) - float(fs)) <= 1e-5 and abs(float(parts["l1_loss"]) - float(l1)) <= 1e-6
+    assert abs(float(parts["duration_loss"]) - float(dur)) <= 1e-6 and abs(float(parts["bin_loss"]) - float(ret["bin_loss"])) <= 1e-6
