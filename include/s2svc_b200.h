@@ -36,7 +36,7 @@ extern "C" {
 #define S2S_F32 0
 #define S2S_BF16 1
 
-#define S2S_ABI_VERSION 7
+#define S2S_ABI_VERSION 8
 
 const char* s2s_last_error(void);
 int s2s_abi_version(void);
@@ -192,7 +192,8 @@ int s2s_fix_targets(const float* labels, const int32_t* olens, float* labels_out
  * bn_stats: sums[0:C] += sum x, sums[C:2C] += sum x^2 (float32; caller zeroes)
  * bn_finalize: mean/invstd from sums (biased var, eps) and running-stat update
  *              (momentum, unbiased var; modules see torch.nn.BatchNorm1d); running_* may be NULL.
- * bn_apply: y = act((x - mean) * invstd * gamma + beta), act = tanh or identity, then dropout;
+ * bn_apply: y = act((x - mean) * invstd * gamma + beta), then dropout; `use_tanh` selects act: 0 identity,
+ *           1 tanh (postnet), 2 Swish (Conformer ConvolutionModule, modules/conformer/convolution.py:75, halo = 0);
  *           halo rows of y are written as zeros.
  * bn_bwd_reduce: sums[0:C] += sum dz, sums[C:2C] += sum dz * xhat with dz = dy * mask * act'(y)
  * bn_bwd_apply: dx = gamma * invstd * (dz - sums0/n - xhat * sums1/n); dgamma += sums1, dbeta += sums0;
@@ -289,6 +290,85 @@ int s2s_mas(const float* log_p, const int32_t* text_lens, const int32_t* feats_l
  * ------------------------------------------------------------------------------------------- */
 int s2s_logmel(const float* wav, const float* window, const float* mel_basis, float* mel, int B, int n_samples,
                int n_fft, int hop, int n_mels, float eps, float log_base, void* stream);
+
+/* ===========================================================================================
+ * Conformer block (AAS-VC encoder / decoder): modules/conformer/encoder_layer.py:79-179,
+ * modules/conformer/convolution.py:56-79, modules/transformer/attention.py:209-305.
+ * =========================================================================================== */
+
+/* RelPositionMultiHeadedAttention query biases (attention.py:284-287): qu = q + pos_bias_u, qv = q + pos_bias_v.
+ * q is (rows, d) with row stride ldq (a slice of the fused QKV buffer); u, v are (d) = (H, d_k) float32. */
+int s2s_bias_add2(const void* q, int64_t ldq, const float* u, const float* v, void* qu, void* qv, int64_t rows, int d,
+                  int dtype, void* stream);
+/* out (row stride ldo) = a + b: joins d(qu) + d(qv) into the dQ slice of the fused dQKV buffer */
+int s2s_add_strided(const void* a, const void* b, void* out, int64_t ldo, int64_t rows, int d, int dtype, void* stream);
+/* rel_shift (attention.py:237-260) folded into a gather: S[b,h,i,j] += BD[h,b,i,T-1-i+j].  S (B,H,T,ldS) holds
+ * matrix_ac (pre-scaled by the GEMM), BD (H,B,T,ldB >= 2T-1) holds matrix_bd before the shift. */
+int s2s_relshift_add(void* S, const void* BD, int B, int H, int T, int64_t ldS, int64_t ldB, int dtype, void* stream);
+/* adjoint of the gather: dBD[h,b,i,k] = dS[b,h,i,k-(T-1-i)] inside the band, 0 elsewhere (every column written) */
+int s2s_relshift_bwd(const void* dS, void* dBD, int B, int H, int T, int64_t ldS, int64_t ldB, int dtype, void* stream);
+/* GLU over channels (convolution.py:69): x (rows, 2C) -> y (rows, C) = x[:, :C] * sigmoid(x[:, C:]); dx (rows, 2C) */
+int s2s_glu_fwd(const void* x, void* y, int64_t rows, int C, int dtype, void* stream);
+int s2s_glu_bwd(const void* dy, const void* x, void* dx, int64_t rows, int C, int dtype, void* stream);
+/* depthwise Conv1d over time (convolution.py:37-45,72): x, y (B, T, C) channels-last, w (C, K) float32 (the
+ * reference's (C,1,K) weight), bias (C) or NULL, zero padding (K-1)/2 per utterance; K odd.  The reference applies
+ * no padding mask, neither do these.  bwd: dx (may be NULL) and dw (C, K) += (may be NULL); dbias = s2s_colsum(dy). */
+int s2s_dwconv_fwd(const void* x, const float* w, const float* bias, void* y, int B, int T, int C, int K, int dtype,
+                   void* stream);
+int s2s_dwconv_bwd(const void* dy, const void* x, const float* w, void* dx, float* dw, int B, int T, int C, int K,
+                   int dtype, void* stream);
+/* Swish FFN activation (conformer/swish.py:13-18) + dropout: y = dropout(x * sigmoid(x)); x is kept for backward */
+int s2s_swish_fwd(const void* x, void* y, int64_t n, const s2s_dropout_t* drop, int dtype, void* stream);
+int s2s_swish_bwd(const void* dy, const void* x, void* dx, int64_t n, const s2s_dropout_t* drop, int dtype,
+                  void* stream);
+/* y = x * scale * mask1 * mask2: RelPositionalEncoding's x * sqrt(d) between the input-layer dropout and the
+ * positional dropout (layers/positional_encoding.py:303-309, conformer/encoder.py:117-123).  Its own adjoint. */
+int s2s_scale_dropout(const void* x, void* y, int64_t n, float scale, const s2s_dropout_t* drop1,
+                      const s2s_dropout_t* drop2, int dtype, void* stream);
+/* y += alpha * x */
+int s2s_axpy(const void* x, void* y, int64_t n, float alpha, int dtype, void* stream);
+/* out[r, :] = s[r] * x[r, :] with s float32 per row */
+int s2s_rowscale(const void* x, const float* s, void* out, int64_t rows, int C, int dtype, void* stream);
+/* y[b,i,:] = sum_{j in [start[i], start[i]+count[i])} x[b,j,:]: nearest-neighbour F.interpolate over time
+ * (models/aas_vc.py:339-351; count = 1) and its adjoint (runs of destination rows per source row). */
+int s2s_gather_rows(const void* x, const int32_t* start, const int32_t* count, void* y, int B, int Tin, int Tout, int C,
+                    int dtype, void* stream);
+
+/* ===========================================================================================
+ * AAS-VC alignment block
+ * =========================================================================================== */
+
+/* AlignmentModule distance + log-softmax (modules/alignments.py:50-60): logp[b,t,s] =
+ * log_softmax_s(-||feats[b,t,:] - text[b,s,:]||_2) with text padding (s >= text_lens[b]) = -inf.
+ * feats (B,T_feats,C), text (B,T_text,C) in `dtype`; logp (B,T_feats,T_text) and lse (B,T_feats) float32
+ * (lse = log sum_s exp(-dist), kept so that backward recovers dist = -(logp + lse)). */
+int s2s_align_logp_fwd(const void* feats, const void* text, const int32_t* text_lens, float* logp, float* lse, int B,
+                       int T_feats, int T_text, int C, int dtype, void* stream);
+/* backward: W[b,t,s] = (d loss / d dist) / dist (B,T_feats,ldW) in `dtype`, rowsum (B,T_feats), colsum (B,T_text) so
+ * that d_feats = rowsum * feats - W text and d_text = colsum * text - W^T feats (two s2s_gemm + s2s_rowscale). */
+int s2s_align_logp_bwd(const float* dlogp, const float* logp, const float* lse, const int32_t* text_lens, void* W,
+                       float* rowsum, float* colsum, int B, int T_feats, int T_text, int64_t ldW, int dtype,
+                       void* stream);
+/* ForwardSumLoss (losses/forward_sum_loss.py:26-76): loss = mean_b [ CTC-NLL_b / N_b ] over the lattice
+ * [blank,1,blank,...,N,blank] with emission logp + prior for labels and the constant blank_logp for blanks;
+ * infeasible utterances contribute 0 (zero_infinity).  prior (B,T_feats,T_text) float32 is the beta-binomial
+ * log-prior built on the host (forward_sum_loss.py:78-116).  alpha_ws: (B,T_feats,T_text) float32 workspace.
+ * dlogp (may be NULL) receives grad_scale * d loss / d logp exactly as torch's ctc_loss backward defines it for
+ * the reference: (exp(lp) - exp(alpha + beta - lp + nll)) / (N_b * B); entries outside (feats_len, text_len) = 0. */
+int s2s_forward_sum(const float* logp, const float* prior, const int32_t* text_lens, const int32_t* feats_lens, int B,
+                    int T_feats, int T_text, float blank_logp, float* alpha_ws, float* loss, float* dlogp,
+                    float grad_scale, void* stream);
+/* GaussianUpsampling weights (modules/length_regulator.py:111-154): P[b,t,:] = softmax_s(-delta (t' - c_s)^2),
+ * c = cumsum(ds) - ds/2, t' = t for t < feats_lens[b] else 0, s >= text_lens[b] masked.  P (B,T_feats,ldP) `dtype`;
+ * the expansion itself is s2s_gemm(P, hs). */
+int s2s_gauss_weights(const float* ds, const int32_t* feats_lens, const int32_t* text_lens, void* P, int B, int T_feats,
+                      int T_text, int64_t ldP, float delta, int dtype, void* stream);
+/* DurationPredictor output masking/clamp + DurationPredictorLoss (modules/duration_predictor.py:98-101,
+ * models/aas_vc.py:408-410, losses/duration_predictor_loss.py:29-50): d_outs = min(pre * mask, clamp_max),
+ * loss = mean over s < text_lens[b] of (d_outs - log(ds + offset))^2, d_pre = grad_scale * d loss / d pre. */
+int s2s_duration_loss(const void* pre, const float* ds, const int32_t* text_lens, int B, int T_text, float offset,
+                      float clamp_max, float grad_scale, float* d_outs, float* loss, void* d_pre, int dtype,
+                      void* stream);
 
 #ifdef __cplusplus
 }

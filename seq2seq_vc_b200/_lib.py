@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libs2svc_b200.so")
 
 S2S_F32, S2S_BF16 = 0, 1
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 
 class S2SError(RuntimeError):
@@ -95,6 +95,25 @@ SIGNATURES = {
     "s2s_mas_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "s2s_mas": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
     "s2s_logmel": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_float, _P]),
+    "s2s_bias_add2": (c_int, [_P, c_int64, _P, _P, _P, _P, c_int64, c_int, c_int, _P]),
+    "s2s_add_strided": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, c_int, _P]),
+    "s2s_relshift_add": (c_int, [_P, _P, c_int, c_int, c_int, c_int64, c_int64, c_int, _P]),
+    "s2s_relshift_bwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int64, c_int64, c_int, _P]),
+    "s2s_glu_fwd": (c_int, [_P, _P, c_int64, c_int, c_int, _P]),
+    "s2s_glu_bwd": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P]),
+    "s2s_dwconv_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "s2s_dwconv_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "s2s_swish_fwd": (c_int, [_P, _P, c_int64, _DP, c_int, _P]),
+    "s2s_swish_bwd": (c_int, [_P, _P, _P, c_int64, _DP, c_int, _P]),
+    "s2s_scale_dropout": (c_int, [_P, _P, c_int64, c_float, _DP, _DP, c_int, _P]),
+    "s2s_axpy": (c_int, [_P, _P, c_int64, c_float, c_int, _P]),
+    "s2s_rowscale": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P]),
+    "s2s_gather_rows": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "s2s_align_logp_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "s2s_align_logp_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int64, c_int, _P]),
+    "s2s_forward_sum": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_float, _P, _P, _P, c_float, _P]),
+    "s2s_gauss_weights": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int64, c_float, c_int, _P]),
+    "s2s_duration_loss": (c_int, [_P, _P, _P, c_int, c_int, c_float, c_float, c_float, _P, _P, _P, c_int, _P]),
 }
 
 _lib = None

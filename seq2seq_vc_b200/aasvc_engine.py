@@ -1,0 +1,782 @@
+"""AAS-VC (Conformer, non-autoregressive) training step on B200: explicit forward / backward over the C-ABI kernels.
+
+Hot path behind ``seq2seq_vc_b200.AASVC`` (reference: seq2seq_vc/models/aas_vc.py:279-471 teacher-forced branch,
+modules/conformer/{encoder,encoder_layer,convolution}.py, modules/transformer/attention.py:209-305,
+layers/positional_encoding.py:238-309, modules/alignments.py:12-60,281-310, modules/length_regulator.py:100-154,
+modules/duration_predictor.py:27-128, losses/{l1_loss,forward_sum_loss,duration_predictor_loss}.py and the loss
+assembly of trainers/aas_vc.py:56-134).  Configuration family: egs/arctic/vc2/conf/aas_vc.melmelmel.v1.yaml with the
+deterministic duration predictor (encoder / decoder reduction factor 1, `linear` input layer, macaron + CNN conformer
+blocks, rel_pos / rel_selfattn, pre-LN, Conv2dSubsampling projection of the duration-predictor input).
+
+As in VTNEngine there is no autograd tape: activations live in named HBM buffers, the backward is written out op by
+op, dropout masks are regenerated from a counter-based RNG, and nothing synchronises with the host -- the monotonic
+alignment search, the forward-sum recursion and the beta-binomial prior lookup all stay on the device / in a cached
+device tensor, so one step is a fixed launch sequence that can be captured in a CUDA graph.
+
+Data layout in HBM
+  activations    (B, T, d) row-major, f32 (parity mode) or bf16; conv-module tensors are channels-last too
+  attention      ac / probabilities (B, H, T, ld) with ld = T rounded up to 8; the un-shifted rel-pos term bd is
+                 (H, B, T, ldb >= 2T-1) so that both of its GEMMs see one (B*T)-row operand per head
+  alignment      log_p_attn (B, T_feats, T_text) float32 (the reference's 4-D (B,T_feats,T_text,C) difference tensor is
+                 never formed); prior / alpha workspace share that shape
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+from ._lib import NO_DROP, Drop
+from .engine_base import EngineBase, _r8
+
+_f32 = torch.float32
+_i32 = torch.int32
+
+EMBED_LN_EPS = 1e-5     # torch.nn.LayerNorm default in the `linear` input layer (conformer/encoder.py:119)
+
+
+def default_hparams(**over) -> dict:
+    """model_params of egs/arctic/vc2/conf/aas_vc.melmelmel.v1.yaml (+ the constructor defaults of AASVC)."""
+    hp = dict(idim=80, odim=80, adim=384, aheads=2, elayers=4, eunits=1536, dlayers=4, dunits=1536,
+              duration_predictor_input_dim=80, duration_predictor_layers=2, duration_predictor_chans=256,
+              duration_predictor_kernel_size=3, postnet_layers=5, postnet_filts=5, postnet_chans=256,
+              post_encoder_reduction_factor=4, conformer_enc_kernel_size=15, conformer_dec_kernel_size=15,
+              transformer_enc_dropout_rate=0.2, transformer_enc_positional_dropout_rate=0.2,
+              transformer_enc_attn_dropout_rate=0.2, transformer_dec_dropout_rate=0.2,
+              transformer_dec_positional_dropout_rate=0.2, transformer_dec_attn_dropout_rate=0.2,
+              duration_predictor_dropout_rate=0.1, postnet_dropout_rate=0.5, lambda_align=2.0)
+    hp.update(over)
+    return hp
+
+
+def rel_pos_table(T: int, d: int) -> torch.Tensor:
+    """pos_emb (2T-1, d) of RelPositionalEncoding (layers/positional_encoding.py:263-309): row k = PE(T-1-k)."""
+    pos = torch.arange(T - 1, -T, -1, dtype=_f32).unsqueeze(1)
+    div = torch.exp(torch.arange(0, d, 2, dtype=_f32) * -(math.log(10000.0) / d))
+    pe = torch.zeros(2 * T - 1, d)
+    pe[:, 0::2] = torch.sin(pos * div)
+    pe[:, 1::2] = torch.cos(pos * div)
+    return pe
+
+
+def beta_binomial_log_prior(N: int, T: int) -> torch.Tensor:
+    """(T, N) float32 log-pmf of BetaBinomial(k; n=N, a=t, b=T-t+1), t = 1..T, k = 0..N-1, exactly the table
+    ForwardSumLoss._generate_prior builds with scipy on the host (losses/forward_sum_loss.py:100-114); float64 lgamma
+    on the host, cast to float32 before the add as the reference does (:48-49)."""
+    k = torch.arange(N, dtype=torch.float64)[None, :]
+    a = torch.arange(1, T + 1, dtype=torch.float64)[:, None]
+    b = T - a + 1
+    n = float(N)
+    lg = torch.lgamma
+    log_binom = lg(torch.tensor(n + 1, dtype=torch.float64)) - lg(k + 1) - lg(n - k + 1)
+    betaln = lambda x, y: lg(x) + lg(y) - lg(x + y)
+    return (log_binom + betaln(k + a, n - k + b) - betaln(a, b)).to(_f32)
+
+
+def nearest_index(T_in: int, T_out: int) -> List[int]:
+    """Source row of every output row for F.interpolate(mode="nearest") (aas_vc.py:345-348): floor(dst * scale) with
+    scale = T_in / T_out in float32, clamped to T_in - 1."""
+    scale = torch.tensor(T_in, dtype=_f32) / torch.tensor(T_out, dtype=_f32)
+    idx = torch.floor(torch.arange(T_out, dtype=_f32) * scale).to(torch.int64).clamp_(max=T_in - 1)
+    return idx.tolist()
+
+
+def param_groups(hp: dict) -> List[List[Tuple[str, Tuple[int, ...]]]]:
+    """Reference state-dict names / shapes; Q/K/V projections of every attention are adjacent (one fused GEMM)."""
+    d, H, pr = hp["adim"], hp["aheads"], hp["post_encoder_reduction_factor"]
+    idim, odim = hp["idim"], hp["odim"]
+    g: List[List[Tuple[str, Tuple[int, ...]]]] = []
+
+    def lin(name, o, i, bias=True):
+        g.append([(name + ".weight", (o, i))])
+        if bias:
+            g.append([(name + ".bias", (o,))])
+
+    def ln(name, n):
+        g.append([(name + ".weight", (n,))])
+        g.append([(name + ".bias", (n,))])
+
+    def conformer(prefix, n_layers, dm, units, k):
+        for l in range(n_layers):
+            p = f"{prefix}.encoders.{l}"
+            g.append([(p + ".self_attn.pos_bias_u", (H, dm // H))])
+            g.append([(p + ".self_attn.pos_bias_v", (H, dm // H))])
+            g.append([(f"{p}.self_attn.{s}.weight", (dm, dm)) for s in ("linear_q", "linear_k", "linear_v")])
+            g.append([(f"{p}.self_attn.{s}.bias", (dm,)) for s in ("linear_q", "linear_k", "linear_v")])
+            lin(p + ".self_attn.linear_out", dm, dm)
+            lin(p + ".self_attn.linear_pos", dm, dm, bias=False)
+            for ff in ("feed_forward", "feed_forward_macaron"):
+                lin(f"{p}.{ff}.w_1", units, dm)
+                lin(f"{p}.{ff}.w_2", dm, units)
+            g.append([(p + ".conv_module.pointwise_conv1.weight", (2 * dm, dm, 1))])
+            g.append([(p + ".conv_module.pointwise_conv1.bias", (2 * dm,))])
+            g.append([(p + ".conv_module.depthwise_conv.weight", (dm, 1, k))])
+            g.append([(p + ".conv_module.depthwise_conv.bias", (dm,))])
+            ln(p + ".conv_module.norm", dm)
+            g.append([(p + ".conv_module.pointwise_conv2.weight", (dm, dm, 1))])
+            g.append([(p + ".conv_module.pointwise_conv2.bias", (dm,))])
+            for n in ("norm_ff", "norm_mha", "norm_ff_macaron", "norm_conv", "norm_final"):
+                ln(f"{p}.{n}", dm)
+        ln(prefix + ".after_norm", dm)
+
+    lin("encoder.embed.0", d, idim)
+    ln("encoder.embed.1", d)
+    conformer("encoder", hp["elayers"], d, hp["eunits"], hp["conformer_enc_kernel_size"])
+    ch, k = hp["duration_predictor_chans"], hp["duration_predictor_kernel_size"]
+    for i in range(hp["duration_predictor_layers"]):
+        g.append([(f"duration_predictor.conv.{i}.0.weight", (ch, d if i == 0 else ch, k))])
+        g.append([(f"duration_predictor.conv.{i}.0.bias", (ch,))])
+        ln(f"duration_predictor.conv.{i}.2", ch)
+    lin("duration_predictor.linear", 1, ch)
+    f2 = ((hp["duration_predictor_input_dim"] - 1) // 2 - 1) // 2
+    g.append([("duration_predictor_projection.conv.0.weight", (d, 1, 3, 3))])
+    g.append([("duration_predictor_projection.conv.0.bias", (d,))])
+    g.append([("duration_predictor_projection.conv.2.weight", (d, d, 3, 3))])
+    g.append([("duration_predictor_projection.conv.2.bias", (d,))])
+    lin("duration_predictor_projection.out", d, d * f2)
+    C = d * pr
+    for n, ic, kk in (("t_conv1", C, 3), ("t_conv2", C, 1), ("f_conv1", odim, 3), ("f_conv2", C, 3), ("f_conv3", C, 1)):
+        g.append([(f"alignment_module.{n}.weight", (C, ic, kk))])
+        g.append([(f"alignment_module.{n}.bias", (C,))])
+    conformer("decoder", hp["dlayers"], C, hp["dunits"], hp["conformer_dec_kernel_size"])
+    lin("feat_out", odim, C)
+    pc, pk = hp["postnet_chans"], hp["postnet_filts"]
+    for i in range(hp["postnet_layers"]):
+        ic = odim if i == 0 else pc
+        oc = odim if i == hp["postnet_layers"] - 1 else pc
+        g.append([(f"postnet.postnet.{i}.0.weight", (oc, ic, pk))])
+        ln(f"postnet.postnet.{i}.1", oc)
+    return g
+
+
+def buffer_specs(hp: dict) -> List[Tuple[str, Tuple[int, ...], torch.dtype]]:
+    """BatchNorm running statistics (conformer conv modules and postnet)."""
+    out = []
+
+    def bn(p, c):
+        out.extend([(p + ".running_mean", (c,), _f32), (p + ".running_var", (c,), _f32), (p + ".num_batches_tracked", (), torch.int64)])
+
+    d, C = hp["adim"], hp["adim"] * hp["post_encoder_reduction_factor"]
+    for l in range(hp["elayers"]):
+        bn(f"encoder.encoders.{l}.conv_module.norm", d)
+    for l in range(hp["dlayers"]):
+        bn(f"decoder.encoders.{l}.conv_module.norm", C)
+    for i in range(hp["postnet_layers"]):
+        bn(f"postnet.postnet.{i}.1", hp["odim"] if i == hp["postnet_layers"] - 1 else hp["postnet_chans"])
+    return out
+
+
+class AASVCEngine(EngineBase):
+    """Owns parameters, activation buffers and the explicit forward / loss / backward of one AAS-VC step."""
+
+    LOSS_NAMES = ("l1_loss", "forward_sum_loss", "bin_loss", "duration_loss")
+
+    def __init__(self, hp: dict, device="cuda:0", bf16: bool = False, seed: int = 0):
+        self.hp = default_hparams(**hp)
+        hp = self.hp
+        assert hp["adim"] % hp["aheads"] == 0
+        self._setup(param_groups(hp), buffer_specs(hp), device, bf16, seed)
+        self.losses = torch.zeros(4, dtype=_f32, device=self.device)       # l1, forward-sum, bin, duration
+        self._l1_pair = torch.zeros(2, dtype=_f32, device=self.device)
+        self._loss_ws = torch.zeros(4, dtype=_f32, device=self.device)
+        self._one = torch.ones(1, dtype=_f32, device=self.device)
+        self._prior_cache: Dict[Tuple, torch.Tensor] = {}
+        self._prior_tables: Dict[Tuple[int, int], torch.Tensor] = {}
+        self._relpe: Dict[Tuple[int, int], torch.Tensor] = {}
+        self._interp: Dict[Tuple[int, int], Tuple[torch.Tensor, ...]] = {}
+        self.init_parameters(seed)
+
+    # ------------------------------------------------------------------ parameters
+    def init_parameters(self, seed: int = 0) -> None:
+        """torch-default Linear / Conv init distributions (uniform +-1/sqrt(fan_in)); LN/BN affine = 1/0; xavier-uniform
+        pos_bias_u/v (attention.py:233-234)."""
+        g = torch.Generator().manual_seed(seed)
+        for name, (off, shape) in self.store.offsets.items():
+            n = 1
+            for s in shape:
+                n *= s
+            is_affine = (("norm" in name) or name.startswith("encoder.embed.1") or (name.startswith("postnet") and ".1." in name)
+                         or (name.startswith("duration_predictor.conv") and name.split(".")[-2] == "2"))
+            if is_affine:
+                v = torch.ones(n) if name.endswith("weight") else torch.zeros(n)
+            elif "pos_bias" in name:
+                bound = math.sqrt(6.0 / (shape[0] + shape[1]))
+                v = (torch.rand(n, generator=g) * 2 - 1) * bound
+            else:
+                wname = name[:-5] + ".weight" if name.endswith(".bias") else name
+                wshape = self.store.offsets[wname][1]
+                fan_in = 1
+                for s in wshape[1:]:
+                    fan_in *= s
+                v = (torch.rand(n, generator=g) * 2 - 1) / math.sqrt(fan_in)
+            self.store.P[off:off + n].copy_(v.to(self.device))
+        self.p16_dirty = True
+
+    # ------------------------------------------------------------------ host-side preparation (no device sync)
+    def prepare(self, B: int, T: int, L: int, ilens: Sequence[int], olens: Sequence[int]) -> None:
+        """Length vectors, the beta-binomial prior and the interpolation index for this batch: built on the host from
+        the CPU ints the collater provides, cached by value, shipped with non-blocking copies."""
+        hp = self.hp
+        pr = hp["post_encoder_reduction_factor"]
+        ilens = [int(v) for v in ilens]
+        olens = [int(v) for v in olens]
+        assert len(ilens) == B and len(olens) == B and max(ilens) <= T and max(olens) <= L
+        Tt = T // pr
+        assert Tt >= 1, "source too short for the post-encoder reduction factor"
+        tlens = [i // pr for i in ilens]
+        assert all(t >= 1 for t in tlens) and all(o >= 1 for o in olens)
+        self._sig = (B, T, L, self.training)
+        host = self._lens_host.get(B)
+        if host is None:
+            host = torch.empty(3, B, dtype=_i32)
+            if self.device.type == "cuda":
+                host = host.pin_memory()
+            self._lens_host[B] = host
+        host.copy_(torch.tensor([ilens, tlens, olens], dtype=_i32))
+        self.buf("lens", (3, B), _i32).copy_(host, non_blocking=True)
+        self.ilens_host, self.tlens_host, self.olens_host = ilens, tlens, olens
+        # beta-binomial prior (B, L, Tt): -inf never enters the kernel (it only reads t < olen, k < tlen)
+        key = (L, Tt, tuple(tlens), tuple(olens))
+        prior = self._prior_cache.get(key)
+        if prior is None:
+            ph = torch.zeros(B, L, Tt, dtype=_f32)
+            for b in range(B):
+                tab = self._prior_tables.get((tlens[b], olens[b]))
+                if tab is None:
+                    tab = beta_binomial_log_prior(tlens[b], olens[b])
+                    self._prior_tables[(tlens[b], olens[b])] = tab
+                ph[b, :olens[b], :tlens[b]] = tab
+            prior = ph.to(self.device, non_blocking=True)
+            if len(self._prior_cache) > 8:
+                self._prior_cache.clear()
+            self._prior_cache[key] = prior
+        self.prior = prior
+        self._prepared = (B, T, L)
+
+    def _rel_table(self, T: int, d: int) -> torch.Tensor:
+        t = self._relpe.get((T, d))
+        if t is None:
+            t = rel_pos_table(T, d).to(self.device)
+            self._relpe[(T, d)] = t
+        return t
+
+    def _interp_tables(self, T_in: int, T_out: int):
+        """(start, ones) for the forward gather and (run start, run length) per source row for its adjoint."""
+        t = self._interp.get((T_in, T_out))
+        if t is None:
+            idx = nearest_index(T_in, T_out)
+            first = [0] * T_in
+            cnt = [0] * T_in
+            for j, i in enumerate(idx):
+                if cnt[i] == 0:
+                    first[i] = j
+                cnt[i] += 1
+            mk = lambda v: torch.tensor(v, dtype=_i32).to(self.device)
+            t = (mk(idx), mk([1] * T_out), mk(first), mk(cnt))
+            self._interp[(T_in, T_out)] = t
+        return t
+
+    # ------------------------------------------------------------------ conformer block
+    def _ffn_fwd(self, x, p, ff, tag, U, rate, out):
+        """out = x + 0.5 * dropout(w_2(dropout(swish(w_1 LN(x)))))   (encoder_layer.py:115-123,157-163)."""
+        st = self.store
+        B, T, dm = x.shape
+        norm = "norm_ff_macaron" if ff == "feed_forward_macaron" else "norm_ff"
+        n = self._ln_fwd(x, f"{p}.{norm}", f"{tag}.ln")
+        hpre = self.buf(tag + ".hpre", (B * T, U))
+        self._lin_fwd(n.view(B * T, dm), self.W(f"{p}.{ff}.w_1.weight"), st.p(f"{p}.{ff}.w_1.bias"), hpre)
+        h = self.buf(tag + ".h", (B * T, U))
+        ops.swish_fwd(hpre, h, self.named_drop(tag + ".d1", rate))
+        bh = self.buf(tag + ".bhalf", (dm,), _f32)
+        ops.scale_dropout(st.p(f"{p}.{ff}.w_2.bias"), bh, 0.5)
+        ops.gemm(h, self.W(f"{p}.{ff}.w_2.weight"), out.view(B * T, dm), bias=bh, alpha=0.5, drop=self.named_drop(tag + ".d2", rate),
+                 residual=x.view(B * T, dm), mode=self.mode)
+        return out
+
+    def _ffn_bwd(self, g, x, p, ff, tag, U, rate, gout):
+        """g = d(out) (B,T,dm) -> gout = d(x) = g + LN'(...) ; accumulates the FFN parameter gradients."""
+        st = self.store
+        B, T, dm = x.shape
+        norm = "norm_ff_macaron" if ff == "feed_forward_macaron" else "norm_ff"
+        n = self.buf(f"{tag}.ln.y", (B, T, dm))
+        hpre = self.buf(tag + ".hpre", (B * T, U))
+        h = self.buf(tag + ".h", (B * T, U))
+        dy = self._scratch("cf.dy", (B * T, dm))
+        ops.scale_dropout(g.view(B * T, dm), dy, 0.5, self.named_drop(tag + ".d2", rate))
+        dh = self._scratch("cf.dh", (B * T, U))
+        self._lin_bwd(dy, h, self.W(f"{p}.{ff}.w_2.weight"), st.g(f"{p}.{ff}.w_2.weight"), st.g(f"{p}.{ff}.w_2.bias"), dx=dh)
+        ops.swish_bwd(dh, hpre, dh, self.named_drop(tag + ".d1", rate))
+        dn = self._scratch("cf.dn", (B, T, dm))
+        self._lin_bwd(dh, n.view(B * T, dm), self.W(f"{p}.{ff}.w_1.weight"), st.g(f"{p}.{ff}.w_1.weight"), st.g(f"{p}.{ff}.w_1.bias"),
+                      dx=dn.view(B * T, dm))
+        self._ln_bwd(dn, x, f"{p}.{norm}", f"{tag}.ln", gout, dres=g)
+        return gout
+
+    def _relattn_fwd(self, x, p, tag, H, klens, pos_emb, rate, attn_rate, out):
+        """out = x + dropout(RelPositionMultiHeadedAttention(LN(x)))   (encoder_layer.py:125-150, attention.py:262-305)."""
+        st = self.store
+        B, T, dm = x.shape
+        dk = dm // H
+        ld, ldb = _r8(T), _r8(2 * T - 1)
+        sc = 1.0 / math.sqrt(dk)
+        n = self._ln_fwd(x, p + ".norm_mha", tag + ".ln")
+        qkv = self.buf(tag + ".qkv", (B, T, 3, H, dk))
+        self._lin_fwd(n.view(B * T, dm), self.Wspan([p + ".self_attn.linear_q.weight"], (3 * dm, dm)),
+                      st.span(st.P, [p + ".self_attn.linear_q.bias"], (3 * dm,)), qkv.view(B * T, 3 * dm))
+        qu = self.buf(tag + ".qu", (B, T, H, dk))
+        qv = self.buf(tag + ".qv", (B, T, H, dk))
+        ops.bias_add2(qkv.view(B * T, 3 * dm)[:, :dm], st.p(p + ".self_attn.pos_bias_u"), st.p(p + ".self_attn.pos_bias_v"), qu, qv)
+        pp = self.buf(tag + ".pp", (2 * T - 1, H, dk))
+        self._lin_fwd(pos_emb, self.W(p + ".self_attn.linear_pos.weight"), None, pp.view(2 * T - 1, dm))
+        k, v = qkv[:, :, 1], qkv[:, :, 2]
+        P = self.buf(tag + ".P", (B, H, T, ld))
+        ops.gemm(qu.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3), P[..., :T], alpha=sc, mode=self.mode)        # matrix_ac
+        BD = self._scratch("cf.bd", (H, B * T, ldb))
+        ops.gemm(qv.view(B * T, H, dk).permute(1, 0, 2), pp.permute(1, 0, 2), BD[..., :2 * T - 1], alpha=sc, mode=self.mode)   # matrix_bd
+        ops.relshift_add(P, BD.view(H, B, T, ldb), T)
+        drop = self.named_drop(tag + ".attn", attn_rate)
+        Pd = self.buf(tag + ".Pd", (B, H, T, ld)) if drop.p > 0 else None
+        ops.softmax_fwd(P, klens, False, T, Pd, drop)
+        self.attn[p + ".self_attn"] = P[..., :T]
+        Pv = Pd if Pd is not None else P
+        ctx = self.buf(tag + ".ctx", (B, T, dm))
+        ops.gemm(Pv[..., :T], v.permute(0, 2, 3, 1), ctx.view(B, T, H, dk).permute(0, 2, 1, 3), mode=self.mode)
+        self._lin_fwd(ctx.view(B * T, dm), self.W(p + ".self_attn.linear_out.weight"), st.p(p + ".self_attn.linear_out.bias"),
+                      out.view(B * T, dm), drop=self.named_drop(tag + ".out", rate), residual=x.view(B * T, dm))
+        return out
+
+    def _relattn_bwd(self, g, x, p, tag, H, pos_emb, rate, attn_rate, gout):
+        st = self.store
+        B, T, dm = x.shape
+        dk = dm // H
+        ld, ldb = _r8(T), _r8(2 * T - 1)
+        sc = 1.0 / math.sqrt(dk)
+        mode = self.mode
+        n = self.buf(tag + ".ln.y", (B, T, dm))
+        qkv = self.buf(tag + ".qkv", (B, T, 3, H, dk))
+        qu = self.buf(tag + ".qu", (B, T, H, dk))
+        qv = self.buf(tag + ".qv", (B, T, H, dk))
+        pp = self.buf(tag + ".pp", (2 * T - 1, H, dk))
+        P = self.buf(tag + ".P", (B, H, T, ld))
+        drop = self.named_drop(tag + ".attn", attn_rate)
+        Pv = self.buf(tag + ".Pd", (B, H, T, ld)) if drop.p > 0 else P
+        ctx = self.buf(tag + ".ctx", (B, T, dm))
+        k, v = qkv[:, :, 1], qkv[:, :, 2]
+        do = self._drop_bwd(g.view(B * T, dm), self.named_drop(tag + ".out", rate), self._scratch("cf.dy", (B * T, dm)))
+        dctx = self._scratch("cf.dctx", (B, T, dm))
+        self._lin_bwd(do, ctx.view(B * T, dm), self.W(p + ".self_attn.linear_out.weight"), st.g(p + ".self_attn.linear_out.weight"),
+                      st.g(p + ".self_attn.linear_out.bias"), dx=dctx.view(B * T, dm))
+        dqkv = self._scratch("cf.dqkv", (B, T, 3, H, dk))
+        dk_, dv = dqkv[:, :, 1], dqkv[:, :, 2]
+        dP = self._scratch("cf.dP", (B, H, T, ld))
+        dctx4 = dctx.view(B, T, H, dk).permute(0, 2, 1, 3)
+        ops.gemm(dctx4, v.permute(0, 2, 1, 3), dP[..., :T], mode=mode)
+        ops.gemm(Pv[..., :T].transpose(-1, -2), dctx4.transpose(-1, -2), dv.permute(0, 2, 1, 3), mode=mode)
+        ops.softmax_bwd(P, dP, T, sc, drop)
+        dS = dP                                                                  # gradient w.r.t. the un-scaled ac and bd'
+        dBD = self._scratch("cf.bd", (H, B * T, ldb))
+        ops.relshift_bwd(dS, dBD.view(H, B, T, ldb), T)
+        dqu = self._scratch("cf.dqu", (B, T, H, dk))
+        dqv = self._scratch("cf.dqv", (B, T, H, dk))
+        ops.gemm(dS[..., :T], k.permute(0, 2, 3, 1), dqu.permute(0, 2, 1, 3), mode=mode)
+        ops.gemm(dS[..., :T].transpose(-1, -2), qu.permute(0, 2, 3, 1), dk_.permute(0, 2, 1, 3), mode=mode)
+        ops.gemm(dBD[..., :2 * T - 1], pp.permute(1, 2, 0), dqv.view(B * T, H, dk).permute(1, 0, 2), mode=mode)
+        dpp = self._scratch("cf.dpp", (2 * T - 1, H, dk))
+        ops.gemm(dBD[..., :2 * T - 1].transpose(-1, -2), qv.view(B * T, H, dk).permute(1, 2, 0), dpp.permute(1, 0, 2), mode=mode)
+        self._lin_bwd(dpp.view(2 * T - 1, dm), pos_emb, self.W(p + ".self_attn.linear_pos.weight"), st.g(p + ".self_attn.linear_pos.weight"),
+                      None, dx=None)
+        ops.colsum(dqu.view(B * T, dm), st.g(p + ".self_attn.pos_bias_u").view(dm))
+        ops.colsum(dqv.view(B * T, dm), st.g(p + ".self_attn.pos_bias_v").view(dm))
+        ops.add_strided(dqu.view(B * T, dm), dqv.view(B * T, dm), dqkv.view(B * T, 3 * dm)[:, :dm])
+        dn = self._scratch("cf.dn", (B, T, dm))
+        self._lin_bwd(dqkv.view(B * T, 3 * dm), n.view(B * T, dm), self.Wspan([p + ".self_attn.linear_q.weight"], (3 * dm, dm)),
+                      st.span(st.G, [p + ".self_attn.linear_q.weight"], (3 * dm, dm)), st.span(st.G, [p + ".self_attn.linear_q.bias"], (3 * dm,)),
+                      dx=dn.view(B * T, dm))
+        self._ln_bwd(dn, x, p + ".norm_mha", tag + ".ln", gout, dres=g)
+        return gout
+
+    def _convmod_fwd(self, x, p, tag, K, rate, out):
+        """out = x + dropout(ConvolutionModule(LN(x)))   (encoder_layer.py:152-158, convolution.py:56-79)."""
+        st = self.store
+        B, T, dm = x.shape
+        cm = p + ".conv_module"
+        n = self._ln_fwd(x, p + ".norm_conv", tag + ".ln")
+        pw1 = self.buf(tag + ".pw1", (B * T, 2 * dm))
+        self._lin_fwd(n.view(B * T, dm), self.W(cm + ".pointwise_conv1.weight").view(2 * dm, dm), st.p(cm + ".pointwise_conv1.bias"), pw1)
+        glu = self.buf(tag + ".glu", (B, T, dm))
+        ops.glu_fwd(pw1, glu)
+        z = self.buf(tag + ".z", (B, T, dm))
+        ops.dwconv_fwd(glu, st.p(cm + ".depthwise_conv.weight").view(dm, K), st.p(cm + ".depthwise_conv.bias"), z)
+        mean = self.buf(tag + ".mean", (dm,), _f32)
+        invstd = self.buf(tag + ".invstd", (dm,), _f32)
+        if self.training:
+            sums = self.buf(tag + ".sums", (2 * dm,), _f32)
+            sums.zero_()
+            ops.bn_stats(z, sums, T, 0)
+            ops.bn_finalize(sums, mean, invstd, self.buffers[cm + ".norm.running_mean"], self.buffers[cm + ".norm.running_var"], B * T)
+            self.buffers[cm + ".norm.num_batches_tracked"] += 1
+        else:
+            ops.bn_eval_stats(self.buffers[cm + ".norm.running_mean"], self.buffers[cm + ".norm.running_var"], mean, invstd)
+        y = self.buf(tag + ".y", (B, T, dm))
+        ops.bn_apply(z, mean, invstd, st.p(cm + ".norm.weight"), st.p(cm + ".norm.bias"), y, T, 0, 2)
+        self._lin_fwd(y.view(B * T, dm), self.W(cm + ".pointwise_conv2.weight").view(dm, dm), st.p(cm + ".pointwise_conv2.bias"),
+                      out.view(B * T, dm), drop=self.named_drop(tag + ".out", rate), residual=x.view(B * T, dm))
+        return out
+
+    def _convmod_bwd(self, g, x, p, tag, K, rate, gout):
+        st = self.store
+        B, T, dm = x.shape
+        cm = p + ".conv_module"
+        n = self.buf(tag + ".ln.y", (B, T, dm))
+        pw1 = self.buf(tag + ".pw1", (B * T, 2 * dm))
+        glu = self.buf(tag + ".glu", (B, T, dm))
+        z = self.buf(tag + ".z", (B, T, dm))
+        y = self.buf(tag + ".y", (B, T, dm))
+        mean = self.buf(tag + ".mean", (dm,), _f32)
+        invstd = self.buf(tag + ".invstd", (dm,), _f32)
+        do = self._drop_bwd(g.view(B * T, dm), self.named_drop(tag + ".out", rate), self._scratch("cf.dy", (B * T, dm)))
+        dy = self._scratch("cf.dctx", (B, T, dm))
+        self._lin_bwd(do, y.view(B * T, dm), self.W(cm + ".pointwise_conv2.weight").view(dm, dm),
+                      st.g(cm + ".pointwise_conv2.weight").view(dm, dm), st.g(cm + ".pointwise_conv2.bias"), dx=dy.view(B * T, dm))
+        gam, bet = st.p(cm + ".norm.weight"), st.p(cm + ".norm.bias")
+        sums = self._scratch("cf.bsums", (2 * dm,), _f32)
+        sums.zero_()
+        dz = self._scratch("cf.dz", (B, T, dm))
+        ops.bn_bwd_reduce(dy, y, z, mean, invstd, gam, bet, sums, T, 0, 2)
+        if self.training:
+            ops.bn_bwd_apply(dy, y, z, mean, invstd, gam, bet, sums, dz, st.g(cm + ".norm.weight"), st.g(cm + ".norm.bias"), T, 0, 2)
+        else:
+            ops.bn_bwd_apply(dy, y, z, mean, invstd, gam, bet, None, dz, None, None, T, 0, 2)
+            ops.add(st.g(cm + ".norm.bias"), sums[:dm], st.g(cm + ".norm.bias"))
+            ops.add(st.g(cm + ".norm.weight"), sums[dm:], st.g(cm + ".norm.weight"))
+        dglu = self._scratch("cf.dglu", (B, T, dm))
+        ops.dwconv_bwd(dz, glu, st.p(cm + ".depthwise_conv.weight").view(dm, K), dglu, st.g(cm + ".depthwise_conv.weight").view(dm, K))
+        ops.colsum(dz.view(B * T, dm), st.g(cm + ".depthwise_conv.bias"))
+        dpw1 = self._scratch("cf.dpw1", (B * T, 2 * dm))
+        ops.glu_bwd(dglu.view(B * T, dm), pw1, dpw1)
+        dn = self._scratch("cf.dn", (B, T, dm))
+        self._lin_bwd(dpw1, n.view(B * T, dm), self.W(cm + ".pointwise_conv1.weight").view(2 * dm, dm),
+                      st.g(cm + ".pointwise_conv1.weight").view(2 * dm, dm), st.g(cm + ".pointwise_conv1.bias"), dx=dn.view(B * T, dm))
+        self._ln_bwd(dn, x, p + ".norm_conv", tag + ".ln", gout, dres=g)
+        return gout
+
+    def _conformer_fwd(self, x, prefix, n_layers, H, U, K, klens, rate, pos_rate, attn_rate):
+        """RelPositionalEncoding dropout of pos_emb + n conformer blocks + after_norm (conformer/encoder.py:249-293)."""
+        B, T, dm = x.shape
+        zero = self._scratch("cf.zero_pe", (1, 2 * T - 1, dm))
+        zero.zero_()
+        pos_emb = self.buf(prefix + ".pos_emb", (2 * T - 1, dm))
+        ops.scaled_pe_fwd(zero, self._rel_table(T, dm), self._one, pos_emb.view(1, 2 * T - 1, dm), self.named_drop(prefix + ".posemb", pos_rate))
+        for l in range(n_layers):
+            p = f"{prefix}.encoders.{l}"
+            x1 = self._ffn_fwd(x, p, "feed_forward_macaron", p + ".mac", U, rate, self.buf(p + ".x1", (B, T, dm)))
+            x2 = self._relattn_fwd(x1, p, p + ".sa", H, klens, pos_emb, rate, attn_rate, self.buf(p + ".x2", (B, T, dm)))
+            x3 = self._convmod_fwd(x2, p, p + ".cv", K, rate, self.buf(p + ".x3", (B, T, dm)))
+            x4 = self._ffn_fwd(x3, p, "feed_forward", p + ".ff", U, rate, self.buf(p + ".x4", (B, T, dm)))
+            x = self._ln_fwd(x4, p + ".norm_final", p + ".lnz")
+        self._last[prefix] = x
+        return self._ln_fwd(x, prefix + ".after_norm", prefix + ".after")
+
+    def _conformer_bwd(self, g, x0, prefix, n_layers, H, U, K, rate, pos_rate, attn_rate):
+        """g = d(after_norm output) -> returns d(x0) (input of the first block, after the positional scaling)."""
+        B, T, dm = x0.shape
+        pos_emb = self.buf(prefix + ".pos_emb", (2 * T - 1, dm))
+        ga = self._scratch(prefix + ".ga", (B, T, dm))
+        gb = self._scratch(prefix + ".gb", (B, T, dm))
+        self._ln_bwd(g, self._last[prefix], prefix + ".after_norm", prefix + ".after", ga)
+        cur, other = ga, gb
+        for l in reversed(range(n_layers)):
+            p = f"{prefix}.encoders.{l}"
+            xin = self.buf(f"{prefix}.encoders.{l - 1}.lnz.y", (B, T, dm)) if l > 0 else x0
+            x1, x2, x3, x4 = (self.buf(p + f".x{i}", (B, T, dm)) for i in (1, 2, 3, 4))
+            self._ln_bwd(cur, x4, p + ".norm_final", p + ".lnz", other)
+            cur, other = other, cur
+            self._ffn_bwd(cur, x3, p, "feed_forward", p + ".ff", U, rate, other)
+            cur, other = other, cur
+            self._convmod_bwd(cur, x2, p, p + ".cv", K, rate, other)
+            cur, other = other, cur
+            self._relattn_bwd(cur, x1, p, p + ".sa", H, pos_emb, rate, attn_rate, other)
+            cur, other = other, cur
+            self._ffn_bwd(cur, xin, p, "feed_forward_macaron", p + ".mac", U, rate, other)
+            cur, other = other, cur
+        return cur
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, xs: torch.Tensor, ys: torch.Tensor, dp_inputs: torch.Tensor, ilens: Optional[Sequence[int]] = None,
+                olens: Optional[Sequence[int]] = None):
+        """xs (B,T,idim), ys (B,L,odim), dp_inputs (B,T_dp,dp_idim) float32 device tensors already trimmed to the max
+        lengths.  Returns (after (B,L,odim), before) in activation dtype; also sets self.log_p_attn (B,L,T_text) f32,
+        self.ds (B,T_text) f32, self.d_outs (B,T_text) f32, self.paths, self.attn."""
+        hp, st = self.hp, self.store
+        B, T, idim = xs.shape
+        L, odim = ys.shape[1], ys.shape[2]
+        d, H, pr = hp["adim"], hp["aheads"], hp["post_encoder_reduction_factor"]
+        C, Tt = d * pr, T // pr
+        assert xs.dtype == _f32 and ys.dtype == _f32 and dp_inputs.dtype == _f32
+        assert xs.is_contiguous() and ys.is_contiguous() and dp_inputs.is_contiguous()
+        self._sig = (B, T, L, self.training)
+        self.attn = {}
+        self._last: Dict[str, torch.Tensor] = {}
+        self.sync_shadow()
+        if ilens is not None:
+            self.prepare(B, T, L, ilens, olens)
+        assert self._prepared == (B, T, L), "prepare(B, T, L, ilens, olens) must precede forward() for this batch shape"
+        lens = self.buf("lens", (3, B), _i32)
+        self.ilens_dev, self.tlens_dev, self.olens_dev = lens[0], lens[1], lens[2]
+        self.shapes = dict(B=B, T=T, L=L, Tt=Tt, Tdp=dp_inputs.shape[1])
+        self.xs, self.dp_inputs = xs, dp_inputs
+        er, epr, ear = hp["transformer_enc_dropout_rate"], hp["transformer_enc_positional_dropout_rate"], hp["transformer_enc_attn_dropout_rate"]
+        dr_, dpr, dar = hp["transformer_dec_dropout_rate"], hp["transformer_dec_positional_dropout_rate"], hp["transformer_dec_attn_dropout_rate"]
+
+        # ---- encoder input layer: Linear -> LayerNorm(1e-5) -> dropout -> x * sqrt(d) -> dropout (conformer/encoder.py:117-123)
+        xa = xs
+        if self.bf16:
+            xa = ops.cast(xs, self.buf("enc.xs16", (B, T, idim)))
+        e0 = self.buf("enc.e0", (B, T, d))
+        self._lin_fwd(xa.view(B * T, idim), self.W("encoder.embed.0.weight"), st.p("encoder.embed.0.bias"), e0.view(B * T, d))
+        ln0 = self._ln_fwd(e0, "encoder.embed.1", "enc.ln0", EMBED_LN_EPS)
+        x0 = self.buf("enc.x0", (B, T, d))
+        ops.scale_dropout(ln0, x0, math.sqrt(d), self.named_drop("enc.embed.drop", er), self.named_drop("enc.pos", epr))
+        henc = self._conformer_fwd(x0, "encoder", hp["elayers"], H, hp["eunits"], hp["conformer_enc_kernel_size"], self.ilens_dev,
+                                   er, epr, ear)
+
+        # ---- post-encoder reduction (aas_vc.py:319-332): (B,T,d) -> (B,Tt,C)
+        if T % pr == 0:
+            hs = henc.view(B, Tt, C)
+        else:
+            hs = self.buf("hs.red", (B, Tt, C))
+            hs.view(B, Tt * pr, d).copy_(henc[:, :Tt * pr])
+        self.hs = hs
+
+        # ---- duration-predictor input: Conv2dSubsampling projection + nearest interpolation (aas_vc.py:335-351)
+        Tdp = dp_inputs.shape[1]
+        Tp = (((Tdp - 1) // 2) - 1) // 2
+        proj = self._conv2d_sub_fwd(dp_inputs, "duration_predictor_projection", "duration_predictor_projection.out", "dpp")
+        idx, ones, _, _ = self._interp_tables(Tp, Tt)
+        dpi = self.buf("dp.in", (B, Tt, d))
+        ops.gather_rows(proj.view(B, Tp, d), idx, ones, dpi)
+
+        # ---- alignment module (alignments.py:28-60)
+        ya = ys
+        if self.bf16:
+            ya = ops.cast(ys, self.buf("al.ys16", (B, L, odim)))
+        tpad = ops.pad_rows(hs, self.buf("al.tpad", (B, Tt + 2, C)), 1)
+        t1 = self._conv1d_fwd(tpad, "alignment_module.t_conv1", Tt, True, "al.t1")
+        t1u = ops.unpad_rows(t1, self.buf("al.t1u", (B, Tt, C)), 1)
+        text = self.buf("al.text", (B, Tt, C))
+        self._lin_fwd(t1u.view(B * Tt, C), self.W("alignment_module.t_conv2.weight").view(C, C), st.p("alignment_module.t_conv2.bias"),
+                      text.view(B * Tt, C))
+        fpad = ops.pad_rows(ya, self.buf("al.fpad", (B, L + 2, odim)), 1)
+        f1 = self._conv1d_fwd(fpad, "alignment_module.f_conv1", L, True, "al.f1")
+        f2 = self._conv1d_fwd(f1, "alignment_module.f_conv2", L, True, "al.f2")
+        f2u = ops.unpad_rows(f2, self.buf("al.f2u", (B, L, C)), 1)
+        feats = self.buf("al.feats", (B, L, C))
+        self._lin_fwd(f2u.view(B * L, C), self.W("alignment_module.f_conv3.weight").view(C, C), st.p("alignment_module.f_conv3.bias"),
+                      feats.view(B * L, C))
+        logp = self.buf("al.logp", (B, L, Tt), _f32)
+        lse = self.buf("al.lse", (B, L), _f32)
+        ops.align_logp_fwd(feats, text, self.tlens_dev, logp, lse)
+        self.log_p_attn = logp
+
+        # ---- monotonic alignment search (alignments.py:281-310): durations + bin loss (+ its gradient), on the device
+        self.paths = self.buf("mas.paths", (B, L), _i32)
+        self.ds = self.buf("mas.ds", (B, Tt), _f32)
+        self.d_logp_mas = self.buf("mas.dlogp", (B, L, Tt), _f32)
+        self.d_logp_mas.zero_()
+        ops.mas_into(logp, self.tlens_dev, self.olens_dev, self.paths, self.ds, self.losses[2:3], self.d_logp_mas,
+                     self._mas_ws(B, L, Tt))
+
+        # ---- duration predictor (duration_predictor.py:83-101)
+        k = hp["duration_predictor_kernel_size"]
+        halo = (k - 1) // 2
+        ch = hp["duration_predictor_chans"]
+        cur = dpi
+        for i in range(hp["duration_predictor_layers"]):
+            ic = cur.shape[2]
+            xp = ops.pad_rows(cur, self.buf(f"dp.pad{i}", (B, Tt + 2 * halo, ic)), halo)
+            z = self._conv1d_fwd(xp, f"duration_predictor.conv.{i}.0", Tt, True, f"dp.c{i}")
+            zu = ops.unpad_rows(z, self.buf(f"dp.zu{i}", (B, Tt, ch)), halo)
+            nl = self._ln_fwd(zu, f"duration_predictor.conv.{i}.2", f"dp.ln{i}")
+            drop = self.named_drop(f"dp.drop{i}", hp["duration_predictor_dropout_rate"])
+            if drop.p > 0:
+                nl = ops.scale_dropout(nl, self.buf(f"dp.do{i}", (B, Tt, ch)), 1.0, drop)
+            cur = nl
+        self.dp_last = cur
+        self.dp_pre = self.buf("dp.pre", (B * Tt, 1))
+        self._lin_fwd(cur.view(B * Tt, ch), self.W("duration_predictor.linear.weight"), st.p("duration_predictor.linear.bias"), self.dp_pre)
+
+        # ---- Gaussian upsampling (length_regulator.py:111-154)
+        ldp = _r8(Tt)
+        Pg = self.buf("up.P", (B, L, ldp))
+        ops.gauss_weights(self.ds, self.olens_dev, self.tlens_dev, Pg)
+        up = self.buf("up.out", (B, L, C))
+        ops.gemm(Pg[..., :Tt], hs.transpose(1, 2), up, mode=self.mode)
+
+        # ---- decoder: RelPositionalEncoding (x * sqrt(C), dropout) + conformer blocks (aas_vc.py:449-452)
+        xd0 = self.buf("dec.x0", (B, L, C))
+        ops.scale_dropout(up, xd0, math.sqrt(C), self.named_drop("dec.pos", dpr))
+        zs = self._conformer_fwd(xd0, "decoder", hp["dlayers"], H, hp["dunits"], hp["conformer_dec_kernel_size"], self.olens_dev,
+                                 dr_, dpr, dar)
+        self.zs = zs
+        before = self.buf("out.before", (B, L, odim))
+        self._lin_fwd(zs.view(B * L, C), self.W("feat_out.weight"), st.p("feat_out.bias"), before.view(B * L, odim))
+        after = self._postnet_fwd(before, lambda i: self.named_drop(f"post{i}", hp["postnet_dropout_rate"]))
+        self.before, self.after = before, after
+        return after, before
+
+    def _mas_ws(self, B, L, Tt):
+        n = ops.mas_workspace_bytes(B, L, Tt)
+        return self.buf("mas.ws", (max(n, 8),), torch.uint8)
+
+    # ------------------------------------------------------------------ losses
+    def loss(self, ys: torch.Tensor, duration_loss: bool = True):
+        """L1Loss + ForwardSumLoss + bin loss + DurationPredictorLoss as AASVCTrainer._train_step assembles them
+        (trainers/aas_vc.py:73-134): total = l1 + lambda_align * (forward_sum + bin) + duration.  Fills self.losses
+        (l1, forward_sum, bin, duration) and the gradients w.r.t. after / before / log_p_attn / duration pre-activation."""
+        hp = self.hp
+        B, L, odim = self.after.shape
+        Tt = self.shapes["Tt"]
+        lam = float(hp["lambda_align"])
+        self.d_after = self.buf("loss.d_after", self.after.shape)
+        self.d_before = self.buf("loss.d_before", self.after.shape)
+        zl = self.buf("loss.zero_logits", (B, L), zero=True)
+        zlab = self.buf("loss.zero_labels", (B, L), _f32, zero=True)
+        dzl = self.buf("loss.d_logits", (B, L))
+        ops.seq2seq_loss(self.after, self.before, zl, ys, zlab, self.olens_dev, 1.0, self._l1_pair, self.d_after, self.d_before, dzl,
+                         self._loss_ws)
+        self.losses[0:1].copy_(self._l1_pair[0:1])
+        # forward-sum: writes lambda * d(fs)/d(logp) into d_logp, then += lambda * d(bin)/d(logp) from the MAS kernel
+        self.d_logp = self.buf("loss.d_logp", (B, L, Tt), _f32)
+        alpha_ws = self.buf("loss.alpha", (B, L, Tt), _f32)
+        ops.forward_sum(self.log_p_attn, self.prior, self.tlens_dev, self.olens_dev, alpha_ws, self.losses[1:2], self.d_logp, lam)
+        ops.axpy(self.d_logp_mas, self.d_logp, lam)
+        self.d_outs = self.buf("dp.d_outs", (B, Tt), _f32)
+        self.d_dp_pre = self.buf("dp.d_pre", (B * Tt, 1))
+        ops.duration_loss(self.dp_pre, self.ds, self.tlens_dev, self.d_outs, self.losses[3:4], self.d_dp_pre,
+                          1.0 if duration_loss else 0.0)
+        return self.losses
+
+    def total_loss(self) -> torch.Tensor:
+        lam = float(self.hp["lambda_align"])
+        return self.losses[0] + lam * (self.losses[1] + self.losses[2]) + self.losses[3]
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, zero_grad: bool = True) -> None:
+        """Accumulates every parameter gradient of the loss assembled by loss() into ParamStore.G."""
+        hp, st = self.hp, self.store
+        s = self.shapes
+        B, T, L, Tt = s["B"], s["T"], s["L"], s["Tt"]
+        d, H, pr, odim = hp["adim"], hp["aheads"], hp["post_encoder_reduction_factor"], hp["odim"]
+        C = d * pr
+        mode = self.mode
+        if zero_grad:
+            st.G.zero_()
+        er, epr, ear = hp["transformer_enc_dropout_rate"], hp["transformer_enc_positional_dropout_rate"], hp["transformer_enc_attn_dropout_rate"]
+        dr_, dpr, dar = hp["transformer_dec_dropout_rate"], hp["transformer_dec_positional_dropout_rate"], hp["transformer_dec_attn_dropout_rate"]
+
+        # ---- postnet + feat_out
+        dbefore = self._postnet_bwd(self.d_after, self.d_before, lambda i: self.named_drop(f"post{i}", hp["postnet_dropout_rate"]))
+        gz = self._scratch("g.zs", (B, L, C))
+        self._lin_bwd(dbefore.view(B * L, odim), self.zs.view(B * L, C), self.W("feat_out.weight"), st.g("feat_out.weight"),
+                      st.g("feat_out.bias"), dx=gz.view(B * L, C))
+        # ---- decoder
+        xd0 = self.buf("dec.x0", (B, L, C))
+        gx = self._conformer_bwd(gz, xd0, "decoder", hp["dlayers"], H, hp["dunits"], hp["conformer_dec_kernel_size"], dr_, dpr, dar)
+        gup = self._scratch("g.up", (B, L, C))
+        ops.scale_dropout(gx, gup, math.sqrt(C), self.named_drop("dec.pos", dpr))
+        # ---- Gaussian upsampling: d_hs = P^T d_up   (ds carries no gradient: it is the integer MAS output)
+        ldp = _r8(Tt)
+        Pg = self.buf("up.P", (B, L, ldp))
+        dhs = self._scratch("g.hs", (B, Tt, C))
+        ops.gemm(Pg[..., :Tt].transpose(1, 2), gup.transpose(1, 2), dhs, mode=mode)
+
+        # ---- duration predictor
+        ch = hp["duration_predictor_chans"]
+        k = hp["duration_predictor_kernel_size"]
+        halo = (k - 1) // 2
+        gcur = self._scratch("g.dp_a", (B, Tt, ch))
+        self._lin_bwd(self.d_dp_pre, self.dp_last.view(B * Tt, ch), self.W("duration_predictor.linear.weight"),
+                      st.g("duration_predictor.linear.weight"), st.g("duration_predictor.linear.bias"), dx=gcur.view(B * Tt, ch))
+        gdpi = None
+        for i in reversed(range(hp["duration_predictor_layers"])):
+            ic = d if i == 0 else ch
+            drop = self.named_drop(f"dp.drop{i}", hp["duration_predictor_dropout_rate"])
+            if drop.p > 0:
+                gcur = ops.scale_dropout(gcur, self._scratch("g.dp_b", (B, Tt, ch)), 1.0, drop)
+            zu = self.buf(f"dp.zu{i}", (B, Tt, ch))
+            gzu = self._scratch("g.dp_c", (B, Tt, ch))
+            self._ln_bwd(gcur, zu, f"duration_predictor.conv.{i}.2", f"dp.ln{i}", gzu)
+            ops.relu_bwd(gzu, zu, gzu, 1.0)
+            gzp = ops.pad_rows(gzu, self._scratch("g.dp_zp", (B, Tt + 2 * halo, ch)), halo)
+            xp = self.buf(f"dp.pad{i}", (B, Tt + 2 * halo, ic))
+            gxp = self._scratch(f"g.dp_xp{i % 2}", (B, Tt + 2 * halo, ic))
+            self._conv1d_bwd(gzp, xp, f"duration_predictor.conv.{i}.0", Tt, f"dp.c{i}", gxp)
+            gnext = self._scratch(f"g.dp_n{i % 2}", (B, Tt, ic))
+            ops.unpad_rows(gxp, gnext, halo)
+            gcur = gnext
+        gdpi = gcur                                                                                   # (B, Tt, d)
+        Tdp = s["Tdp"]
+        Tp = (((Tdp - 1) // 2) - 1) // 2
+        _, _, first, cnt = self._interp_tables(Tp, Tt)
+        gproj = self._scratch("g.dpproj", (B, Tp, d))
+        ops.gather_rows(gdpi, first, cnt, gproj)
+        self._conv2d_sub_bwd(gproj.view(B * Tp, d), self.dp_inputs, "duration_predictor_projection", "duration_predictor_projection.out", "dpp")
+
+        # ---- alignment module: d(log_p_attn) -> d(feats), d(text)
+        ldw = _r8(Tt)
+        Wm = self._scratch("g.alW", (B, L, ldw))
+        rowsum = self._scratch("g.alrow", (B, L), _f32)
+        colsum = self._scratch("g.alcol", (B, Tt), _f32)
+        ops.align_logp_bwd(self.d_logp, self.log_p_attn, self.buf("al.lse", (B, L), _f32), self.tlens_dev, Wm, rowsum, colsum)
+        feats = self.buf("al.feats", (B, L, C))
+        text = self.buf("al.text", (B, Tt, C))
+        dfeats = self._scratch("g.alfeats", (B, L, C))
+        dtext = self._scratch("g.altext", (B, Tt, C))
+        ops.rowscale(feats, rowsum, dfeats)
+        ops.gemm(Wm[..., :Tt], text.transpose(1, 2), dfeats, alpha=-1.0, residual=dfeats, mode=mode)
+        ops.rowscale(text, colsum, dtext)
+        ops.gemm(Wm[..., :Tt].transpose(1, 2), feats.transpose(1, 2), dtext, alpha=-1.0, residual=dtext, mode=mode)
+        # feats path: f_conv3 (k1) <- relu f_conv2 (k3) <- relu f_conv1 (k3) <- ys
+        f2u = self.buf("al.f2u", (B, L, C))
+        gf2u = self._scratch("g.al_a", (B, L, C))
+        self._lin_bwd(dfeats.view(B * L, C), f2u.view(B * L, C), self.W("alignment_module.f_conv3.weight").view(C, C),
+                      st.g("alignment_module.f_conv3.weight").view(C, C), st.g("alignment_module.f_conv3.bias"), dx=gf2u.view(B * L, C))
+        ops.relu_bwd(gf2u, f2u, gf2u, 1.0)
+        gf2p = ops.pad_rows(gf2u, self._scratch("g.al_p", (B, L + 2, C)), 1)
+        f1 = self.buf("al.f1.z", (B, L + 2, C))
+        gf1 = self._scratch("g.al_p2", (B, L + 2, C))
+        self._conv1d_bwd(gf2p, f1, "alignment_module.f_conv2", L, "al.f2", gf1)
+        ops.relu_bwd(gf1, f1, gf1, 1.0)
+        self._conv1d_bwd(gf1, self.buf("al.fpad", (B, L + 2, odim)), "alignment_module.f_conv1", L, "al.f1", None)
+        # text path: t_conv2 (k1) <- relu t_conv1 (k3) <- hs
+        t1u = self.buf("al.t1u", (B, Tt, C))
+        gt1u = self._scratch("g.al_a", (B, Tt, C))
+        self._lin_bwd(dtext.view(B * Tt, C), t1u.view(B * Tt, C), self.W("alignment_module.t_conv2.weight").view(C, C),
+                      st.g("alignment_module.t_conv2.weight").view(C, C), st.g("alignment_module.t_conv2.bias"), dx=gt1u.view(B * Tt, C))
+        ops.relu_bwd(gt1u, t1u, gt1u, 1.0)
+        gt1p = ops.pad_rows(gt1u, self._scratch("g.al_p", (B, Tt + 2, C)), 1)
+        ghp = self._scratch("g.al_p2", (B, Tt + 2, C))
+        self._conv1d_bwd(gt1p, self.buf("al.tpad", (B, Tt + 2, C)), "alignment_module.t_conv1", Tt, "al.t1", ghp)
+        ghs_al = self._scratch("g.al_hs", (B, Tt, C))
+        ops.unpad_rows(ghp, ghs_al, 1)
+        ops.add(dhs, ghs_al, dhs)
+
+        # ---- back through the post-encoder reduction into the encoder
+        if T % pr == 0:
+            genc = dhs.view(B, T, d)
+        else:
+            genc = self._scratch("g.enc_full", (B, T, d))
+            genc.zero_()
+            genc[:, :Tt * pr].copy_(dhs.view(B, Tt * pr, d))
+        x0 = self.buf("enc.x0", (B, T, d))
+        gx0 = self._conformer_bwd(genc, x0, "encoder", hp["elayers"], H, hp["eunits"], hp["conformer_enc_kernel_size"], er, epr, ear)
+        gln0 = self._scratch("g.ln0", (B, T, d))
+        ops.scale_dropout(gx0, gln0, math.sqrt(d), self.named_drop("enc.embed.drop", er), self.named_drop("enc.pos", epr))
+        e0 = self.buf("enc.e0", (B, T, d))
+        ge0 = self._scratch("g.e0", (B, T, d))
+        self._ln_bwd(gln0, e0, "encoder.embed.1", "enc.ln0", ge0)
+        xa = self.buf("enc.xs16", (B, T, hp["idim"])) if self.bf16 else self.xs
+        self._lin_bwd(ge0.view(B * T, d), xa.view(B * T, hp["idim"]), self.W("encoder.embed.0.weight"), st.g("encoder.embed.0.weight"),
+                      st.g("encoder.embed.0.bias"), dx=None)

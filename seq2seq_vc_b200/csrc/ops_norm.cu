@@ -292,7 +292,8 @@ __global__ void bn_apply_kernel(const T* __restrict__ x, const float* __restrict
 #pragma unroll
             for (int k = 0; k < VEC; ++k) {
                 float t = (v[k] - mean[c + k]) * invstd[c + k] * gamma[c + k] + beta[c + k];
-                if (use_tanh) t = tanhf(t);
+                if (use_tanh == 1) t = tanhf(t);
+                else if (use_tanh == 2) t = t / (1.f + __expf(-t));      // Swish (conformer/convolution.py:75)
                 o[k] = t * dropout_factor(drop, idx + k);
             }
         }
@@ -315,9 +316,13 @@ __device__ __forceinline__ void bn_dz(const T* dy, const T* y, const T* x, const
     for (int k = 0; k < VEC; ++k) {
         xhat[k] = (xv[k] - mean[c0 + k]) * invstd[c0 + k];
         float t = gy[k] * dropout_factor(drop, idx + k);
-        if (use_tanh) {
+        if (use_tanh == 1) {
             float a = tanhf(xhat[k] * gamma[c0 + k] + beta[c0 + k]);
             t *= (1.f - a * a);
+        } else if (use_tanh == 2) {
+            float z = xhat[k] * gamma[c0 + k] + beta[c0 + k];
+            float sg = 1.f / (1.f + __expf(-z));
+            t *= sg * (1.f + z * (1.f - sg));
         }
         dz[k] = t;
     }

@@ -251,6 +251,7 @@ def bn_finalize(sums, mean, invstd, running_mean, running_var, count, eps=1e-5, 
 
 
 def bn_apply(x, mean, invstd, gamma, beta, y, L, halo, use_tanh, drop: Drop = NO_DROP):
+    """use_tanh: activation code -- 0/False identity, 1/True tanh, 2 Swish."""
     B, Lp, C = x.shape
     check(_L().s2s_bn_apply(ptr(x), ptr(mean), ptr(invstd), ptr(gamma), ptr(beta), ptr(y), B, L, halo, C, int(use_tanh),
                             ctypes.byref(drop.c()), dt(x), stream()), "bn_apply")
@@ -354,6 +355,18 @@ def mas(log_p, text_lens, feats_lens, want_grad: bool = False):
     return paths, ds, bin_loss, d_log_p
 
 
+def mas_workspace_bytes(B: int, TF: int, TT: int) -> int:
+    return int(_L().s2s_mas_workspace_bytes(B, TF, TT))
+
+
+def mas_into(log_p, text_lens, feats_lens, paths, ds, bin_loss, d_log_p, ws):
+    """s2s_mas into caller-owned buffers (no allocation: CUDA-graph friendly).  d_log_p must be pre-zeroed."""
+    B, TF, TT = log_p.shape
+    assert log_p.dtype == torch.float32 and log_p.is_contiguous() and paths.dtype == _i32 and ds.dtype == torch.float32
+    check(_L().s2s_mas(ptr(log_p), ptr(text_lens), ptr(feats_lens), B, TF, TT, ptr(paths), ptr(ds), ptr(bin_loss), ptr(d_log_p),
+                       ptr(ws), ws.numel(), stream()), "mas")
+
+
 def logmel(wav, window, basis, mel, n_fft, hop, eps, log_base):
     B, ns = wav.shape
     n_mels = basis.shape[0]
@@ -361,3 +374,155 @@ def logmel(wav, window, basis, mel, n_fft, hop, eps, log_base):
     check(_L().s2s_logmel(ptr(wav), ptr(window), ptr(basis), ptr(mel), B, ns, n_fft, hop, n_mels, eps,
                           0.0 if log_base is None else float(log_base), stream()), "logmel")
     return mel
+
+
+# ----------------------------------------------------------------------------------------------
+# Conformer block
+# ----------------------------------------------------------------------------------------------
+def bias_add2(q, u, v, qu, qv):
+    """qu = q + u, qv = q + v for a (rows, d) view q with arbitrary row stride (slice of the fused QKV buffer)."""
+    d = q.shape[-1]
+    rows = q.numel() // d
+    assert q.stride(-1) == 1 and qu.is_contiguous() and qv.is_contiguous()
+    q2 = q.reshape(rows, d) if q.is_contiguous() else q
+    ldq = q.stride(-2) if q.dim() >= 2 else d
+    if q.dim() > 2:     # (B, T, d) slice of (B, T, 3, d): uniform row stride required
+        assert all(q.stride(i) == q.stride(i + 1) * q.shape[i + 1] for i in range(q.dim() - 2)), "non-uniform row stride"
+    check(_L().s2s_bias_add2(ptr(q2), ldq, ptr(u), ptr(v), ptr(qu), ptr(qv), rows, d, dt(q), stream()), "bias_add2")
+
+
+def add_strided(a, b, out):
+    """out (rows, d; uniform row stride) = a + b with a, b contiguous."""
+    d = out.shape[-1]
+    rows = out.numel() // d
+    assert a.is_contiguous() and b.is_contiguous() and out.stride(-1) == 1
+    if out.dim() > 2:
+        assert all(out.stride(i) == out.stride(i + 1) * out.shape[i + 1] for i in range(out.dim() - 2)), "non-uniform row stride"
+    check(_L().s2s_add_strided(ptr(a), ptr(b), ptr(out), out.stride(-2), rows, d, dt(out), stream()), "add_strided")
+    return out
+
+
+def relshift_add(S, BD, T):
+    """S (B,H,T,ldS) += rel_shift(BD) with BD stored (H,B,T,ldB)."""
+    B, H, T1, ldS = S.shape
+    assert S.is_contiguous() and BD.is_contiguous() and BD.shape[:3] == (H, B, T1) and T1 == T
+    check(_L().s2s_relshift_add(ptr(S), ptr(BD), B, H, T, ldS, BD.shape[3], dt(S), stream()), "relshift_add")
+    return S
+
+
+def relshift_bwd(dS, dBD, T):
+    B, H, T1, ldS = dS.shape
+    assert dS.is_contiguous() and dBD.is_contiguous() and dBD.shape[:3] == (H, B, T1) and T1 == T
+    check(_L().s2s_relshift_bwd(ptr(dS), ptr(dBD), B, H, T, ldS, dBD.shape[3], dt(dS), stream()), "relshift_bwd")
+    return dBD
+
+
+def glu_fwd(x, y):
+    C = y.shape[-1]
+    assert x.is_contiguous() and y.is_contiguous() and x.shape[-1] == 2 * C
+    check(_L().s2s_glu_fwd(ptr(x), ptr(y), y.numel() // C, C, dt(x), stream()), "glu_fwd")
+    return y
+
+
+def glu_bwd(dy, x, dx):
+    C = dy.shape[-1]
+    assert dy.is_contiguous() and x.is_contiguous() and dx.is_contiguous()
+    check(_L().s2s_glu_bwd(ptr(dy), ptr(x), ptr(dx), dy.numel() // C, C, dt(x), stream()), "glu_bwd")
+    return dx
+
+
+def dwconv_fwd(x, w, bias, y):
+    B, T, C = x.shape
+    K = w.shape[-1]
+    assert x.is_contiguous() and y.is_contiguous() and w.is_contiguous() and w.dtype == torch.float32 and w.numel() == C * K
+    check(_L().s2s_dwconv_fwd(ptr(x), ptr(w), ptr(bias), ptr(y), B, T, C, K, dt(x), stream()), "dwconv_fwd")
+    return y
+
+
+def dwconv_bwd(dy, x, w, dx, dw):
+    B, T, C = x.shape
+    K = w.shape[-1]
+    assert dy.is_contiguous() and x.is_contiguous() and (dx is None or dx.is_contiguous())
+    check(_L().s2s_dwconv_bwd(ptr(dy), ptr(x), ptr(w), ptr(dx), ptr(dw), B, T, C, K, dt(x), stream()), "dwconv_bwd")
+
+
+def swish_fwd(x, y, drop: Drop = NO_DROP):
+    assert x.is_contiguous() and y.is_contiguous()
+    check(_L().s2s_swish_fwd(ptr(x), ptr(y), x.numel(), ctypes.byref(drop.c()), dt(x), stream()), "swish_fwd")
+    return y
+
+
+def swish_bwd(dy, x, dx, drop: Drop = NO_DROP):
+    assert dy.is_contiguous() and x.is_contiguous() and dx.is_contiguous()
+    check(_L().s2s_swish_bwd(ptr(dy), ptr(x), ptr(dx), x.numel(), ctypes.byref(drop.c()), dt(x), stream()), "swish_bwd")
+    return dx
+
+
+def scale_dropout(x, y, scale, drop1: Drop = NO_DROP, drop2: Drop = NO_DROP):
+    assert x.is_contiguous() and y.is_contiguous()
+    check(_L().s2s_scale_dropout(ptr(x), ptr(y), x.numel(), float(scale), ctypes.byref(drop1.c()), ctypes.byref(drop2.c()),
+                                 dt(x), stream()), "scale_dropout")
+    return y
+
+
+def axpy(x, y, alpha):
+    assert x.is_contiguous() and y.is_contiguous() and x.dtype == y.dtype and x.numel() == y.numel()
+    check(_L().s2s_axpy(ptr(x), ptr(y), x.numel(), float(alpha), dt(x), stream()), "axpy")
+    return y
+
+
+def rowscale(x, s, out):
+    C = x.shape[-1]
+    assert x.is_contiguous() and out.is_contiguous() and s.dtype == torch.float32 and s.numel() == x.numel() // C
+    check(_L().s2s_rowscale(ptr(x), ptr(s), ptr(out), x.numel() // C, C, dt(x), stream()), "rowscale")
+    return out
+
+
+def gather_rows(x, start, count, y):
+    B, Tin, C = x.shape
+    Tout = y.shape[1]
+    assert x.is_contiguous() and y.is_contiguous() and start.dtype == _i32 and count.dtype == _i32 and start.numel() == Tout
+    check(_L().s2s_gather_rows(ptr(x), ptr(start), ptr(count), ptr(y), B, Tin, Tout, C, dt(x), stream()), "gather_rows")
+    return y
+
+
+# ----------------------------------------------------------------------------------------------
+# AAS-VC alignment block
+# ----------------------------------------------------------------------------------------------
+def align_logp_fwd(feats, text, text_lens, logp, lse):
+    B, TF, C = feats.shape
+    TT = text.shape[1]
+    assert feats.is_contiguous() and text.is_contiguous() and logp.dtype == torch.float32 and logp.is_contiguous()
+    check(_L().s2s_align_logp_fwd(ptr(feats), ptr(text), ptr(text_lens), ptr(logp), ptr(lse), B, TF, TT, C, dt(feats), stream()),
+          "align_logp_fwd")
+    return logp
+
+
+def align_logp_bwd(dlogp, logp, lse, text_lens, W, rowsum, colsum):
+    B, TF, TT = logp.shape
+    assert dlogp.is_contiguous() and logp.is_contiguous() and W.is_contiguous() and dlogp.dtype == torch.float32
+    check(_L().s2s_align_logp_bwd(ptr(dlogp), ptr(logp), ptr(lse), ptr(text_lens), ptr(W), ptr(rowsum), ptr(colsum), B, TF, TT,
+                                  W.shape[-1], dt(W), stream()), "align_logp_bwd")
+
+
+def forward_sum(logp, prior, text_lens, feats_lens, alpha_ws, loss, dlogp, grad_scale=1.0, blank_logp=-1.0):
+    B, TF, TT = logp.shape
+    assert logp.is_contiguous() and prior.is_contiguous() and prior.shape == logp.shape and alpha_ws.numel() >= logp.numel()
+    check(_L().s2s_forward_sum(ptr(logp), ptr(prior), ptr(text_lens), ptr(feats_lens), B, TF, TT, float(blank_logp), ptr(alpha_ws),
+                               ptr(loss), ptr(dlogp), float(grad_scale), stream()), "forward_sum")
+
+
+def gauss_weights(ds, feats_lens, text_lens, P, delta=0.1):
+    B, TF, ld = P.shape
+    TT = ds.shape[1]
+    assert ds.dtype == torch.float32 and ds.is_contiguous() and P.is_contiguous()
+    check(_L().s2s_gauss_weights(ptr(ds), ptr(feats_lens), ptr(text_lens), ptr(P), B, TF, TT, ld, float(delta), dt(P), stream()),
+          "gauss_weights")
+    return P
+
+
+def duration_loss(pre, ds, text_lens, d_outs, loss, d_pre, grad_scale=1.0, offset=1.0, clamp_max=10.0):
+    B, TT = ds.shape
+    assert pre.is_contiguous() and ds.is_contiguous() and pre.numel() == B * TT
+    check(_L().s2s_duration_loss(ptr(pre), ptr(ds), ptr(text_lens), B, TT, float(offset), float(clamp_max), float(grad_scale),
+                                 ptr(d_outs), ptr(loss), ptr(d_pre), dt(pre), stream()), "duration_loss")

@@ -25,14 +25,11 @@ import torch
 
 from . import ops
 from ._lib import NO_DROP, Drop
+from .engine_base import EngineBase, _r8, sinusoid_table
 from .params import ParamStore
 
 _f32 = torch.float32
 _i32 = torch.int32
-
-
-def _r8(n: int) -> int:
-    return (n + 7) // 8 * 8
 
 
 def default_hparams(**over) -> dict:
@@ -48,16 +45,6 @@ def default_hparams(**over) -> dict:
               encoder_input="conv2d")
     hp.update(over)
     return hp
-
-
-def sinusoid_table(length: int, d_model: int, device) -> torch.Tensor:
-    """PE table of seq2seq_vc/layers/positional_encoding.py:36-57 (host-built once, float32)."""
-    pos = torch.arange(0, length, dtype=_f32).unsqueeze(1)
-    div = torch.exp(torch.arange(0, d_model, 2, dtype=_f32) * -(math.log(10000.0) / d_model))
-    pe = torch.zeros(length, d_model)
-    pe[:, 0::2] = torch.sin(pos * div)
-    pe[:, 1::2] = torch.cos(pos * div)
-    return pe.to(device)
 
 
 def param_groups(hp: dict) -> List[List[Tuple[str, Tuple[int, ...]]]]:
@@ -136,37 +123,16 @@ def buffer_specs(hp: dict) -> List[Tuple[str, Tuple[int, ...], torch.dtype]]:
     return out
 
 
-class VTNEngine:
+class VTNEngine(EngineBase):
     """Owns parameters, activation buffers and the explicit forward/backward of one VTN step."""
 
     def __init__(self, hp: dict, device="cuda:0", bf16: bool = False, seed: int = 0):
         self.hp = default_hparams(**hp)
         hp = self.hp
         assert hp["adim"] % hp["aheads"] == 0
-        self.device = torch.device(device)
-        self.bf16 = bool(bf16)
-        self.adt = torch.bfloat16 if bf16 else _f32
-        self.mode = 1 if bf16 else 0
-        self.store = ParamStore(param_groups(hp), self.device, bf16_shadow=bf16)
-        self.buffers: Dict[str, torch.Tensor] = {}
-        for name, shape, dt in buffer_specs(hp):
-            self.buffers[name] = (torch.ones if name.endswith("running_var") else torch.zeros)(shape, dtype=dt, device=self.device)
-        self.training = True
-        self.base_seed = int(seed)
-        self.seed_dev = torch.zeros(1, dtype=torch.int64, device=self.device)   # advanced once per step
-        self.step_dev = torch.zeros(1, dtype=_f32, device=self.device)
-        self.lr_dev = torch.zeros(1, dtype=_f32, device=self.device)
-        self._pe: Dict[int, torch.Tensor] = {}
-        self._bufs: Dict[Tuple, torch.Tensor] = {}
-        self._sig: Optional[Tuple] = None
-        self._site = 0
-        self.attn: Dict[str, torch.Tensor] = {}      # every attention map of the last forward
+        self._setup(param_groups(hp), buffer_specs(hp), device, bf16, seed)
         self.losses = torch.zeros(2, dtype=_f32, device=self.device)
         self._loss_ws = torch.zeros(4, dtype=_f32, device=self.device)
-        self._sqn = torch.zeros(1, dtype=_f32, device=self.device)
-        self.p16_dirty = True
-        self._lens_host: Dict[int, torch.Tensor] = {}
-        self._prepared = None
         self.init_parameters(seed)
 
     # ------------------------------------------------------------------ parameters
@@ -196,137 +162,12 @@ class VTNEngine:
             self.store.P[off:off + n].copy_(v.to(self.device))
         self.p16_dirty = True
 
-    def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
-        for name in self.store.names():
-            self.store.p(name).copy_(sd[name].to(self.device, _f32).reshape(self.store.offsets[name][1]))
-        for name, buf in self.buffers.items():
-            if name in sd:
-                buf.copy_(sd[name].to(self.device, buf.dtype))
-        self.p16_dirty = True
-
-    def state_dict(self) -> Dict[str, torch.Tensor]:
-        sd = {name: self.store.p(name).detach().clone() for name in self.store.names()}
-        sd.update({k: v.detach().clone() for k, v in self.buffers.items()})
-        return sd
-
-    def W(self, name: str) -> torch.Tensor:
-        """GEMM operand view of a weight: float32 master in parity mode, bf16 shadow otherwise."""
-        return self.store.p16(name) if self.bf16 else self.store.p(name)
-
-    def Wspan(self, names: Sequence[str], shape) -> torch.Tensor:
-        return self.store.span(self.store.P16 if self.bf16 else self.store.P, list(names), shape)
-
-    def sync_shadow(self) -> None:
-        if self.bf16 and self.p16_dirty:
-            ops.cast(self.store.P, self.store.P16)
-        self.p16_dirty = False
 
     # ------------------------------------------------------------------ buffers
-    def buf(self, name: str, shape, dtype=None, zero: bool = False) -> torch.Tensor:
-        dtype = dtype or self.adt
-        key = (self._sig, name)
-        t = self._bufs.get(key)
-        if t is None:
-            t = (torch.zeros if zero else torch.empty)(tuple(shape), dtype=dtype, device=self.device)
-            self._bufs[key] = t
-        else:
-            assert tuple(t.shape) == tuple(shape) and t.dtype == dtype, (name, t.shape, shape)
-        return t
 
-    def pe(self, d: int, length: int) -> torch.Tensor:
-        t = self._pe.get(d)
-        if t is None or t.shape[0] < length:
-            t = sinusoid_table(max(length, 2048), d, self.device)
-            self._pe[d] = t
-        return t
-
-    def drop(self, p: float) -> Drop:
-        """Next dropout site of the step (forward and backward enumerate sites in the same order)."""
-        self._site += 1
-        if not self.training or p <= 0.0:
-            return NO_DROP
-        return Drop(p, self.base_seed, self._site, self.seed_dev)
 
     # ------------------------------------------------------------------ building blocks
-    def _lin_fwd(self, x2d, w, bias, out, relu=False, drop=NO_DROP, residual=None):
-        if w.shape[0] <= 4 and not relu and residual is None and drop.p == 0.0:
-            return ops.skinny_linear_fwd(x2d, w, bias, out)
-        return ops.gemm(x2d, w, out, bias=bias, relu=relu, drop=drop, residual=residual, mode=self.mode)
 
-    def _lin_bwd(self, dy2d, x2d, w, gw, gb, dx=None, dx_residual=None, dx_accumulate=False):
-        """dW += dy^T x ; db += colsum(dy) ; dx = dy W (+ residual | += )."""
-        mode = self.mode
-        if w.shape[0] <= 4 and dx_residual is None:
-            return ops.skinny_linear_bwd(dy2d, x2d, w, gw, gb, dx, dx_accumulate)
-        if gw is not None:
-            ops.gemm(dy2d.t(), x2d.t(), gw, accumulate=True, mode=mode)
-        if gb is not None:
-            ops.colsum(dy2d, gb)
-        if dx is not None:
-            ops.gemm(dy2d, w.t(), dx, residual=dx_residual, accumulate=dx_accumulate, mode=mode)
-        return dx
-
-    def _ln_fwd(self, x, name, tag):
-        B_, T_, d = x.shape
-        y = self.buf(tag + ".y", x.shape)
-        mean = self.buf(tag + ".mean", (B_ * T_,), _f32)
-        rstd = self.buf(tag + ".rstd", (B_ * T_,), _f32)
-        ops.layernorm_fwd(x, self.store.p(name + ".weight"), self.store.p(name + ".bias"), y, mean, rstd, 1e-12)
-        return y
-
-    def _ln_bwd(self, dy, x, name, tag, dx, dres=None):
-        ops.layernorm_bwd(dy, x, self.store.p(name + ".weight"), self.buf(tag + ".mean", (x.shape[0] * x.shape[1],), _f32),
-                          self.buf(tag + ".rstd", (x.shape[0] * x.shape[1],), _f32), dx, self.store.g(name + ".weight"),
-                          self.store.g(name + ".bias"), dres=dres)
-        return dx
-
-    def _attn_core_fwd(self, q, k, v, klens, causal, tag, store_name):
-        """q (B,T1,H,dk) / k, v (B,T2,H,dk) strided views -> ctx (B,T1,d); keeps P for backward."""
-        B_, T1, H, dk = q.shape
-        T2 = k.shape[1]
-        ld = _r8(T2)
-        P = self.buf(tag + ".P", (B_, H, T1, ld))
-        # S[b,h] = q_bh k_bh^T / sqrt(dk)   (reference: attention.py:95-104)
-        ops.gemm(q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3), P[..., :T2], alpha=1.0 / math.sqrt(dk), mode=self.mode)
-        ops.softmax_fwd(P, klens, causal, T2)
-        self.attn[store_name] = P[..., :T2]
-        ctx = self.buf(tag + ".ctx", (B_, T1, H * dk))
-        # ctx[b,t,h,:] = sum_s P[b,h,t,s] v[b,s,h,:]
-        ops.gemm(P[..., :T2], v.permute(0, 2, 3, 1), ctx.view(B_, T1, H, dk).permute(0, 2, 1, 3), mode=self.mode)
-        return ctx
-
-    def _attn_core_bwd(self, dctx, q, k, v, dq, dk_, dv, tag, d_att=None):
-        """Gradients of the attention core; dq/dk_/dv are (B,T,H,dk) strided views to be filled."""
-        B_, T1, H, dk = q.shape
-        T2 = k.shape[1]
-        ld = _r8(T2)
-        P = self.buf(tag + ".P", (B_, H, T1, ld))
-        dP = self._scratch("dP", (B_, H, T1, ld))
-        dctx4 = dctx.view(B_, T1, H, dk).permute(0, 2, 1, 3)
-        # dP[b,h,t,s] = sum_j dctx[b,t,h,j] v[b,s,h,j]
-        ops.gemm(dctx4, v.permute(0, 2, 1, 3), dP[..., :T2], mode=self.mode)
-        # dv[b,s,h,j] = sum_t P[b,h,t,s] dctx[b,t,h,j]
-        ops.gemm(P[..., :T2].transpose(-1, -2), dctx4.transpose(-1, -2), dv.permute(0, 2, 1, 3), mode=self.mode)
-        if d_att is not None:
-            ops.add(dP, d_att, dP)
-        ops.softmax_bwd(P, dP, T2, 1.0 / math.sqrt(dk))
-        dS = dP
-        # dq[b,t,h,j] = sum_s dS[t,s] k[s,j] ; dk[b,s,h,j] = sum_t dS[t,s] q[t,j]
-        ops.gemm(dS[..., :T2], k.permute(0, 2, 3, 1), dq.permute(0, 2, 1, 3), mode=self.mode)
-        ops.gemm(dS[..., :T2].transpose(-1, -2), q.permute(0, 2, 3, 1), dk_.permute(0, 2, 1, 3), mode=self.mode)
-
-    def _scratch(self, name, shape, dtype=None):
-        """Step-local scratch, shared between layers (sized to the largest request)."""
-        dtype = dtype or self.adt
-        n = 1
-        for s in shape:
-            n *= s
-        key = ("scratch", name, dtype)
-        t = self._bufs.get(key)
-        if t is None or t.numel() < n:
-            t = torch.empty(max(n, 1), dtype=dtype, device=self.device)
-            self._bufs[key] = t
-        return t[:n].view(shape)
 
     # ------------------------------------------------------------------ forward
     def prepare(self, B: int, T: int, L: int, ilens: Sequence[int], olens: Sequence[int]) -> None:
@@ -505,44 +346,7 @@ class VTNEngine:
         self.zs = zs
 
         # ---- postnet (pre_postnets.py:105-185): Conv1d(k) as taps-GEMM over haloed channels-last rows
-        n_post, k = hp["postnet_layers"], hp["postnet_filts"]
-        after = self.buf("out.after", (B, Lo, odim))
-        if n_post > 0:
-            halo = (k - 1) // 2
-            Lp = Lo + 2 * halo
-            ypad = self.buf("post.in", (B, Lp, odim))
-            ops.pad_rows(before, ypad, halo)
-            for i in range(n_post):
-                pn = f"postnet.postnet.{i}"
-                w = st.p(pn + ".0.weight")
-                oc, ic = w.shape[0], w.shape[1]
-                wp = self.buf(f"w.post{i}p", (oc, k, ic))
-                wpt = self.buf(f"w.post{i}pt", (ic, k, oc))
-                ops.pack_conv1d_w(w, wp, wpt)
-                z = self.buf(f"post.z{i}", (B, Lp, oc))
-                M = B * Lp - 2 * halo
-                ops.gemm(ypad.view(B * Lp, ic), wp, z.view(B * Lp, oc)[halo:], taps=k, row_mask=(Lp, halo, halo, halo + Lo),
-                         mode=self.mode, M=M)
-                mean = self.buf(f"post.mean{i}", (oc,), _f32)
-                invstd = self.buf(f"post.invstd{i}", (oc,), _f32)
-                if self.training:
-                    sums = self.buf(f"post.sums{i}", (2 * oc,), _f32)
-                    sums.zero_()
-                    ops.bn_stats(z, sums, Lo, halo)
-                    ops.bn_finalize(sums, mean, invstd, self.buffers[pn + ".1.running_mean"], self.buffers[pn + ".1.running_var"],
-                                    B * Lo)
-                    self.buffers[pn + ".1.num_batches_tracked"] += 1
-                else:
-                    ops.bn_eval_stats(self.buffers[pn + ".1.running_mean"], self.buffers[pn + ".1.running_var"], mean, invstd)
-                y = self.buf(f"post.y{i}", (B, Lp, oc))
-                ops.bn_apply(z, mean, invstd, st.p(pn + ".1.weight"), st.p(pn + ".1.bias"), y, Lo, halo, i != n_post - 1,
-                             self.drop(hp["postnet_dropout_rate"]))
-                ypad = y
-            post = self._scratch("post.out", (B, Lo, odim))
-            ops.unpad_rows(ypad, post, halo)
-            ops.add(before, post, after)
-        else:
-            after.copy_(before)
+        after = self._postnet_fwd(before, lambda i: self.drop(hp["postnet_dropout_rate"]))
         self.before, self.after, self.logits = before, after, logits
         return after, before, logits
 
@@ -608,61 +412,7 @@ class VTNEngine:
         sites = self._site_table()
 
         # ---- postnet
-        n_post, k = hp["postnet_layers"], hp["postnet_filts"]
-        dbefore_tot = self._scratch("dbefore", (B, Lo, odim))
-        if n_post > 0:
-            halo = (k - 1) // 2
-            Lp = Lo + 2 * halo
-            dy = self._scratch("post.dy_a", (B, Lp, odim))
-            ops.pad_rows(d_after, dy, halo)
-            for i in reversed(range(n_post)):
-                pn = f"postnet.postnet.{i}"
-                w = st.p(pn + ".0.weight")
-                oc, ic = w.shape[0], w.shape[1]
-                z = self.buf(f"post.z{i}", (B, Lp, oc))
-                y = self.buf(f"post.y{i}", (B, Lp, oc))
-                xin = self.buf(f"post.y{i - 1}", (B, Lp, ic)) if i > 0 else self.buf("post.in", (B, Lp, odim))
-                mean = self.buf(f"post.mean{i}", (oc,), _f32)
-                invstd = self.buf(f"post.invstd{i}", (oc,), _f32)
-                drop = sites[f"post{i}"]
-                dz = self._scratch(f"post.dz{i % 2}", (B, Lp, oc))
-                gam, bet = st.p(pn + ".1.weight"), st.p(pn + ".1.bias")
-                if self.training:
-                    sums = self._scratch("post.bsums", (2 * oc,), _f32)
-                    sums.zero_()
-                    ops.bn_bwd_reduce(dy, y, z, mean, invstd, gam, bet, sums, Lo, halo, i != n_post - 1, drop)
-                    ops.bn_bwd_apply(dy, y, z, mean, invstd, gam, bet, sums, dz, st.g(pn + ".1.weight"), st.g(pn + ".1.bias"),
-                                     Lo, halo, i != n_post - 1, drop)
-                else:
-                    sums = self._scratch("post.bsums", (2 * oc,), _f32)
-                    sums.zero_()
-                    ops.bn_bwd_reduce(dy, y, z, mean, invstd, gam, bet, sums, Lo, halo, i != n_post - 1, drop)
-                    ops.bn_bwd_apply(dy, y, z, mean, invstd, gam, bet, None, dz, None, None, Lo, halo, i != n_post - 1, drop)
-                    ops.add(st.g(pn + ".1.bias"), sums[:oc], st.g(pn + ".1.bias"))
-                    ops.add(st.g(pn + ".1.weight"), sums[oc:], st.g(pn + ".1.weight"))
-                M = B * Lp - 2 * halo
-                # dWp[oc][t][ic] = sum_m dz[m + halo][oc] * xin[m + t][ic]
-                gwp = self._scratch("post.gwp", (oc, k, ic), _f32)
-                gwp.zero_()
-                dzt = dz.view(B * Lp, oc)[halo:halo + M].t()
-                for t in range(k):      # one skinny (oc x ic x M) GEMM per tap; split-K inside the kernel
-                    ops.gemm(dzt, xin.view(B * Lp, ic)[t:t + M].t(), gwp[:, t, :], accumulate=True, mode=self.mode)
-                ops.transpose_last2(gwp, st.g(pn + ".0.weight"), oc, k, ic, accumulate=True)
-                # dxin = conv_transpose(dz): taps-GEMM with the flipped, transposed kernel
-                dxin = self._scratch(f"post.dx{i % 2}", (B, Lp, ic))
-                wpt = self.buf(f"w.post{i}pt", (ic, k, oc))
-                if halo > 0:
-                    dxin.view(B * Lp, ic)[:halo].zero_()
-                    dxin.view(B * Lp, ic)[B * Lp - halo:].zero_()
-                ops.gemm(dz.view(B * Lp, oc), wpt, dxin.view(B * Lp, ic)[halo:], taps=k, row_mask=(Lp, halo, halo, halo + Lo),
-                         mode=self.mode, M=M)
-                dy = dxin
-            dpost_in = self._scratch("post.dunpad", (B, Lo, odim))
-            ops.unpad_rows(dy, dpost_in, halo)
-            ops.add(d_after, d_before, dbefore_tot)
-            ops.add(dbefore_tot, dpost_in, dbefore_tot)
-        else:
-            ops.add(d_after, d_before, dbefore_tot)
+        dbefore_tot = self._postnet_bwd(d_after, d_before, lambda i: sites[f"post{i}"])
 
         # ---- output heads
         zs = self.zs
@@ -816,11 +566,6 @@ class VTNEngine:
         ops.relu_bwd(dy1, y1, dy1, 1.0)
         ops.conv1_bwd(self.xs, dy1, st.g("encoder.embed.conv.0.weight"), st.g("encoder.embed.conv.0.bias"))
 
-    def _drop_bwd(self, dy2d, drop: Drop, out):
-        if drop.p <= 0.0:
-            return dy2d
-        o = out[: dy2d.shape[0]].view(dy2d.shape) if out.shape != dy2d.shape else out
-        return ops.dropout_bwd(dy2d, o, drop)
 
     def _site_table(self) -> Dict[str, Drop]:
         """Re-enumerate the forward's dropout sites (same order as forward())."""
@@ -851,15 +596,3 @@ class VTNEngine:
         return t
 
     # ------------------------------------------------------------------ optimizer tail
-    def optimizer_step(self, max_norm: float = 1.0, betas=(0.9, 0.999), eps: float = 1e-8,
-                       weight_decay: float = 0.0, grad_scale: float = 1.0) -> None:
-        """clip_grad_norm_(max_norm) + Adam over the flat buffers (trainers/ar_vc.py:99-107).
-
-        The learning rate is read from the device scalar ``self.lr_dev`` (set by the caller)."""
-        st = self.store
-        ops.step_advance(self.step_dev, self.seed_dev)
-        self._sqn.zero_()
-        ops.sqnorm(st.G, self._sqn)
-        ops.adam_step(st.P, st.G, st.M, st.V, st.P16, self.lr_dev, betas[0], betas[1], eps, weight_decay, self.step_dev,
-                      self._sqn, max_norm, grad_scale)
-        self.p16_dirty = False  # adam_step refreshed the bf16 shadow

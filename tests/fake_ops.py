@@ -280,7 +280,9 @@ def bn_apply(x, mean, invstd, gamma, beta, y, L, halo, use_tanh, drop=NO_DROP):
     _nodrop(drop)
     y.zero_()
     t = (_valid(x, L, halo).double() - mean.double()) * invstd.double() * gamma.double() + beta.double()
-    if use_tanh:
+    if use_tanh == 2:
+        t = t * torch.sigmoid(t)
+    elif use_tanh:
         t = torch.tanh(t)
     y[:, halo:halo + L] = t.to(y.dtype)
     return y
@@ -289,7 +291,11 @@ def bn_apply(x, mean, invstd, gamma, beta, y, L, halo, use_tanh, drop=NO_DROP):
 def _bn_dz(dy, x, mean, invstd, gamma, beta, L, halo, use_tanh):
     xh = (_valid(x, L, halo).double() - mean.double()) * invstd.double()
     dz = _valid(dy, L, halo).double()
-    if use_tanh:
+    if use_tanh == 2:
+        z = xh * gamma.double() + beta.double()
+        sg = torch.sigmoid(z)
+        dz = dz * sg * (1 + z * (1 - sg))
+    elif use_tanh:
         a = torch.tanh(xh * gamma.double() + beta.double())
         dz = dz * (1 - a * a)
     return dz, xh
@@ -414,6 +420,213 @@ def transpose_last2(src, dst, N, A, Bd, accumulate=False):
     return dst
 
 
+# ---------------------------------------------------------------------------------------------- conformer / AAS-VC
+def bias_add2(q, u, v, qu, qv):
+    d = q.shape[-1]
+    qu.copy_((q.double().reshape(-1, d) + u.double().reshape(-1)).reshape(qu.shape).to(qu.dtype))
+    qv.copy_((q.double().reshape(-1, d) + v.double().reshape(-1)).reshape(qv.shape).to(qv.dtype))
+
+
+def add_strided(a, b, out):
+    out.copy_((a.double() + b.double()).reshape(out.shape).to(out.dtype))
+    return out
+
+
+def relshift_add(S, BD, T):
+    B, H = S.shape[0], S.shape[1]
+    idx = (T - 1 - torch.arange(T)[:, None] + torch.arange(T)[None, :])
+    bd = BD.permute(1, 0, 2, 3)[..., : 2 * T - 1]
+    S[..., :T] += torch.gather(bd, 3, idx[None, None].expand(B, H, T, T)).to(S.dtype)
+    return S
+
+
+def relshift_bwd(dS, dBD, T):
+    B, H = dS.shape[0], dS.shape[1]
+    idx = (T - 1 - torch.arange(T)[:, None] + torch.arange(T)[None, :])
+    out = torch.zeros(B, H, T, dBD.shape[-1], dtype=dBD.dtype)
+    out.scatter_(3, idx[None, None].expand(B, H, T, T), dS[..., :T])
+    dBD.copy_(out.permute(1, 0, 2, 3))
+    return dBD
+
+
+def glu_fwd(x, y):
+    C = y.shape[-1]
+    xd = x.double().reshape(-1, 2 * C)
+    y.copy_((xd[:, :C] * torch.sigmoid(xd[:, C:])).reshape(y.shape).to(y.dtype))
+    return y
+
+
+def glu_bwd(dy, x, dx):
+    C = dy.shape[-1]
+    xd, g = x.double().reshape(-1, 2 * C), dy.double().reshape(-1, C)
+    sg = torch.sigmoid(xd[:, C:])
+    dxv = dx.view(-1, 2 * C)
+    dxv[:, :C] = (g * sg).to(dx.dtype)
+    dxv[:, C:] = (g * xd[:, :C] * sg * (1 - sg)).to(dx.dtype)
+    return dx
+
+
+def dwconv_fwd(x, w, bias, y):
+    C, K = x.shape[-1], w.shape[-1]
+    out = torch.nn.functional.conv1d(x.double().transpose(1, 2), w.double().reshape(C, 1, K),
+                                     None if bias is None else bias.double(), padding=(K - 1) // 2, groups=C)
+    y.copy_(out.transpose(1, 2).to(y.dtype))
+    return y
+
+
+def dwconv_bwd(dy, x, w, dx, dw):
+    C, K = x.shape[-1], w.shape[-1]
+    xd = x.double().transpose(1, 2).requires_grad_(True)
+    wd = w.double().reshape(C, 1, K).requires_grad_(True)
+    out = torch.nn.functional.conv1d(xd, wd, None, padding=(K - 1) // 2, groups=C)
+    gx, gw = torch.autograd.grad(out, [xd, wd], dy.double().transpose(1, 2))
+    if dx is not None:
+        dx.copy_(gx.transpose(1, 2).to(dx.dtype))
+    if dw is not None:
+        dw += gw.reshape(dw.shape).float()
+
+
+def swish_fwd(x, y, drop=NO_DROP):
+    _nodrop(drop)
+    y.copy_((x.double() * torch.sigmoid(x.double())).to(y.dtype))
+    return y
+
+
+def swish_bwd(dy, x, dx, drop=NO_DROP):
+    _nodrop(drop)
+    xd = x.double()
+    sg = torch.sigmoid(xd)
+    dx.copy_((dy.double() * (sg + xd * sg * (1 - sg))).to(dx.dtype))
+    return dx
+
+
+def scale_dropout(x, y, scale, drop1=NO_DROP, drop2=NO_DROP):
+    _nodrop(drop1)
+    _nodrop(drop2)
+    y.copy_((x.double() * scale).to(y.dtype))
+    return y
+
+
+def axpy(x, y, alpha):
+    y += (alpha * x.double()).to(y.dtype)
+    return y
+
+
+def rowscale(x, s, out):
+    C = x.shape[-1]
+    out.copy_((x.double().reshape(-1, C) * s.double().reshape(-1, 1)).reshape(out.shape).to(out.dtype))
+    return out
+
+
+def gather_rows(x, start, count, y):
+    y.zero_()
+    for i in range(y.shape[1]):
+        for j in range(int(start[i]), int(start[i]) + int(count[i])):
+            if 0 <= j < x.shape[1]:
+                y[:, i] += x[:, j]
+    return y
+
+
+def align_logp_fwd(feats, text, text_lens, logp, lse):
+    dist = torch.norm(feats.double().unsqueeze(2) - text.double().unsqueeze(1), p=2, dim=3)
+    TT = text.shape[1]
+    pad = torch.arange(TT)[None, :] >= text_lens.long()[:, None]
+    score = (-dist).masked_fill(pad[:, None, :], -float("inf"))
+    l = torch.logsumexp(score, dim=-1)
+    logp.copy_((score - l[..., None]).float())
+    lse.copy_(l.float().reshape(lse.shape))
+    return logp
+
+
+def align_logp_bwd(dlogp, logp, lse, text_lens, W, rowsum, colsum):
+    B, TF, TT = logp.shape
+    valid = torch.arange(TT)[None, :] < text_lens.long()[:, None]
+    g = dlogp.double() * valid[:, None, :]
+    G = g.sum(-1, keepdim=True)
+    lp = logp.double()
+    dscore = g - torch.exp(lp) * G
+    dist = -(lp + lse.double().reshape(B, TF, 1))
+    w = torch.where((dist > 0) & valid[:, None, :], -dscore / dist, torch.zeros_like(dist))
+    W.zero_()
+    W[..., :TT] = w.to(W.dtype)
+    rowsum.copy_(W[..., :TT].double().sum(-1).float().reshape(rowsum.shape))
+    colsum.copy_(W[..., :TT].double().sum(1).float().reshape(colsum.shape))
+
+
+def forward_sum(logp, prior, text_lens, feats_lens, alpha_ws, loss, dlogp, grad_scale=1.0, blank_logp=-1.0):
+    from oracle import aasvc_oracle
+
+    B = logp.shape[0]
+    total = 0.0
+    if dlogp is not None:
+        dlogp.zero_()
+    lpn, prn = logp.double().numpy(), prior.double().numpy()
+    for b in range(B):
+        N, T = int(text_lens[b]), int(feats_lens[b])
+        nll, g = aasvc_oracle.ctc_forward_sum_utt(lpn[b, :T, :N] + prn[b, :T, :N])
+        total += nll / N
+        if dlogp is not None:
+            dlogp[b, :T, :N] = torch.from_numpy(g * grad_scale / (N * B)).float()
+    loss.fill_(total / B)
+
+
+def gauss_weights(ds, feats_lens, text_lens, P, delta=0.1):
+    B, TF, ld = P.shape
+    TT = ds.shape[1]
+    t = torch.arange(TF, dtype=torch.float32)[None].repeat(B, 1)
+    t = t * (torch.arange(TF)[None, :] < feats_lens.long()[:, None]).float()
+    c = ds.cumsum(-1) - ds / 2
+    e = -delta * (t.unsqueeze(-1) - c.unsqueeze(1)) ** 2
+    e = e.masked_fill((torch.arange(TT)[None, :] >= text_lens.long()[:, None])[:, None, :], -float("inf"))
+    P.zero_()
+    P[..., :TT] = torch.softmax(e.double(), dim=2).to(P.dtype)
+    return P
+
+
+def duration_loss(pre, ds, text_lens, d_outs, loss, d_pre, grad_scale=1.0, offset=1.0, clamp_max=10.0):
+    B, TT = ds.shape
+    valid = torch.arange(TT)[None, :] < text_lens.long()[:, None]
+    x = pre.double().reshape(B, TT) * valid
+    d = torch.clamp(x, max=clamp_max)
+    if d_outs is not None:
+        d_outs.copy_(d.float())
+    diff = (d - torch.log(ds.double() + offset)) * valid
+    n = valid.sum().item()
+    if loss is not None:
+        loss.fill_(float((diff ** 2).sum() / n))
+    if d_pre is not None:
+        d_pre.copy_((grad_scale * 2 * diff / n * (x <= clamp_max)).reshape(d_pre.shape).to(d_pre.dtype))
+
+
+def mas(log_p, text_lens, feats_lens, want_grad=False):
+    """Contract of s2s_mas via the numpy/C oracle (bit-exact integer path)."""
+    import numpy as np
+
+    from oracle import mas_oracle
+
+    B, TF, TT = log_p.shape
+    tl, fl = [int(v) for v in text_lens], [int(v) for v in feats_lens]
+    ds, bl, paths = mas_oracle.viterbi_decode_oracle(log_p.numpy(), tl, fl)
+    d = None
+    if want_grad:
+        d = torch.zeros_like(log_p)
+        for b in range(B):
+            d[b, torch.arange(fl[b]), torch.from_numpy(paths[b, :fl[b]].astype(np.int64))] = -1.0 / (fl[b] * B)
+    return torch.from_numpy(paths.astype(np.int32)), torch.from_numpy(ds), torch.tensor([bl], dtype=torch.float32), d
+
+
+def mas_workspace_bytes(B, TF, TT):
+    return 8
+
+
+def mas_into(log_p, text_lens, feats_lens, paths, ds, bin_loss, d_log_p, ws):
+    p_, ds_, bl_, d_ = mas(log_p, text_lens, feats_lens, want_grad=d_log_p is not None)
+    paths.copy_(p_)
+    ds.copy_(ds_)
+    bin_loss.copy_(bl_)
+    if d_log_p is not None:
+        d_log_p.copy_(d_)
+
 ALL = [n for n, f in list(globals().items()) if callable(f) and not n.startswith("_") and n not in ("NO_DROP",)]
 
 
@@ -421,5 +634,5 @@ def install(monkeypatch):
     import seq2seq_vc_b200.ops as ops
 
     for n in ALL:
-        if hasattr(ops, n) and n not in ("mas", "logmel"):
+        if hasattr(ops, n) and n not in ("logmel",):
             monkeypatch.setattr(ops, n, globals()[n])
