@@ -1,0 +1,395 @@
+"""AAS-VC hot path on the GPU through the C ABI: every new kernel vs its float64 contract (tests/fake_ops.py), the
+forward-sum kernel vs the reference's F.ctc_loss golden vectors, and the whole engine vs golden vectors dumped from
+the live reference and vs the CPU oracle.  Tolerances: mel L1 <= 1e-4, attention-weight L1 <= 1e-3 (fp32 path),
+durations (integer alignment path) bit-exact."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import fake_ops as F
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "aasvc_tiny.npz")
+AAS_HP = dict(idim=80, odim=80, adim=32, aheads=2, elayers=1, eunits=48, dlayers=1, dunits=48,
+              duration_predictor_input_dim=80, duration_predictor_layers=2, duration_predictor_chans=16,
+              duration_predictor_kernel_size=3, postnet_layers=2, postnet_filts=5, postnet_chans=16,
+              post_encoder_reduction_factor=4, conformer_enc_kernel_size=7, conformer_dec_kernel_size=7)
+NO_DROPOUT = dict(transformer_enc_dropout_rate=0.0, transformer_enc_positional_dropout_rate=0.0, transformer_enc_attn_dropout_rate=0.0,
+                  transformer_dec_dropout_rate=0.0, transformer_dec_positional_dropout_rate=0.0, transformer_dec_attn_dropout_rate=0.0,
+                  duration_predictor_dropout_rate=0.0, postnet_dropout_rate=0.0)
+DT = [torch.float32, torch.bfloat16]
+
+
+def tol(dt, scale=1.0):
+    return (2e-5 if dt == torch.float32 else 2e-2) * scale
+
+
+def close(a, b, atol, what=""):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    err = (a - b).abs().max().item()
+    assert err <= atol, f"{what}: max abs err {err} > {atol}"
+
+
+def rnd(*shape, dt=torch.float32, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed + sum(shape))
+    return (torch.randn(*shape, generator=g) * scale).to(dt)
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from seq2seq_vc_b200 import _lib, ops
+
+    _lib.device_check()
+    return ops
+
+
+# ---------------------------------------------------------------------------------------------- conformer kernels
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("rows,d", [(37, 24), (300, 384)])
+def test_bias_add2_and_add_strided(ops, dt, rows, d):
+    qkv = rnd(rows, 3 * d, dt=dt, seed=1)
+    u, v = rnd(d, seed=2), rnd(d, seed=3)
+    qu, qv = torch.empty(rows, d, dtype=dt), torch.empty(rows, d, dtype=dt)
+    F.bias_add2(qkv[:, :d], u, v, qu, qv)
+    dq = qkv.cuda()
+    gqu, gqv = torch.empty(rows, d, dtype=dt, device="cuda"), torch.empty(rows, d, dtype=dt, device="cuda")
+    ops.bias_add2(dq[:, :d], u.cuda(), v.cuda(), gqu, gqv)
+    close(gqu, qu, tol(dt), "qu")
+    close(gqv, qv, tol(dt), "qv")
+    out = torch.zeros(rows, 3 * d, dtype=dt, device="cuda")
+    ops.add_strided(gqu, gqv, out[:, :d])
+    close(out[:, :d], (qu.double() + qv.double()).to(dt), tol(dt, 2), "add_strided")
+    assert out[:, d:].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("B,H,T", [(2, 2, 7), (3, 2, 50), (2, 1, 129)])
+def test_relshift_add_and_bwd(ops, dt, B, H, T):
+    ld, ldb = (T + 7) // 8 * 8, (2 * T - 1 + 7) // 8 * 8
+    S, BD = rnd(B, H, T, ld, dt=dt, seed=1), rnd(H, B, T, ldb, dt=dt, seed=2)
+    ref = F.relshift_add(S.clone(), BD, T)
+    g = ops.relshift_add(S.cuda(), BD.cuda(), T)
+    close(g[..., :T], ref[..., :T], tol(dt, 2), "relshift_add")
+    dS = rnd(B, H, T, ld, dt=dt, seed=3)
+    dref = F.relshift_bwd(dS, torch.empty(H, B, T, ldb, dtype=dt), T)
+    dg = ops.relshift_bwd(dS.cuda(), torch.full((H, B, T, ldb), 7.0, dtype=dt, device="cuda"), T)
+    close(dg, dref, 0.0, "relshift_bwd")
+    # adjointness: <shift(BD), dS> == <BD, shift^T(dS)>
+    sh = F.relshift_add(torch.zeros(B, H, T, ld, dtype=torch.float64), BD.double(), T)
+    lhs = (sh[..., :T] * dS.double()[..., :T]).sum()
+    rhs = (BD.double() * dref.double()).sum()
+    assert abs(float(lhs - rhs)) <= 1e-6 * max(1.0, abs(float(lhs)))
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("rows,C", [(50, 12), (333, 384)])
+def test_glu_swish_scale(ops, dt, rows, C):
+    x = rnd(rows, 2 * C, dt=dt, seed=1)
+    y = F.glu_fwd(x, torch.empty(rows, C, dtype=dt))
+    gy = ops.glu_fwd(x.cuda(), torch.empty(rows, C, dtype=dt, device="cuda"))
+    close(gy, y, tol(dt), "glu_fwd")
+    dy = rnd(rows, C, dt=dt, seed=2)
+    dx = F.glu_bwd(dy, x, torch.empty(rows, 2 * C, dtype=dt))
+    gdx = ops.glu_bwd(dy.cuda(), x.cuda(), torch.empty(rows, 2 * C, dtype=dt, device="cuda"))
+    close(gdx, dx, tol(dt, 2), "glu_bwd")
+    h = rnd(rows, C, dt=dt, seed=3, scale=2.0)
+    close(ops.swish_fwd(h.cuda(), torch.empty_like(h, device="cuda")), F.swish_fwd(h, torch.empty_like(h)), tol(dt, 2), "swish_fwd")
+    close(ops.swish_bwd(dy.cuda(), h.cuda(), torch.empty_like(h, device="cuda")), F.swish_bwd(dy, h, torch.empty_like(h)), tol(dt, 2),
+          "swish_bwd")
+    close(ops.scale_dropout(h.cuda(), torch.empty_like(h, device="cuda"), 3.5), F.scale_dropout(h, torch.empty_like(h), 3.5), tol(dt, 8),
+          "scale")
+    acc = rnd(rows, C, dt=dt, seed=4)
+    close(ops.axpy(h.cuda(), acc.clone().cuda(), -0.5), F.axpy(h, acc.clone(), -0.5), tol(dt, 4), "axpy")
+    s = rnd(rows, seed=5)
+    close(ops.rowscale(h.cuda(), s.cuda(), torch.empty_like(h, device="cuda")), F.rowscale(h, s, torch.empty_like(h)), tol(dt, 8), "rowscale")
+
+
+def test_swish_dropout_fwd_bwd_consistency(ops):
+    """The backward regenerates the forward mask: d/dx sum(y * w) through the dropped swish."""
+    from seq2seq_vc_b200._lib import Drop
+
+    n = 4096
+    x = rnd(n, seed=1, scale=1.5).cuda()
+    drop = Drop(0.3, seed=5, site=9)
+    y = ops.swish_fwd(x, torch.empty_like(x), drop)
+    kept = (y != 0) | (x == 0)
+    frac = 1.0 - kept.float().mean().item()
+    assert 0.25 <= frac <= 0.35
+    ref = x * torch.sigmoid(x) / 0.7
+    close(y[kept], ref[kept], 1e-5, "kept values scaled by 1/(1-p)")
+    dy = torch.ones_like(x)
+    dx = ops.swish_bwd(dy, x, torch.empty_like(x), drop)
+    assert (dx[~kept] == 0).all()
+    sg = torch.sigmoid(x)
+    close(dx[kept], ((sg + x * sg * (1 - sg)) / 0.7)[kept], 1e-5, "swish' under the same mask")
+    y2 = ops.scale_dropout(x, torch.empty_like(x), 2.0, drop, Drop(0.2, seed=5, site=10))
+    z = (y2 == 0).float().mean().item()
+    assert 0.38 <= z <= 0.50                       # 1 - 0.7 * 0.8 = 0.44
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("B,T,C,K", [(2, 19, 12, 7), (3, 50, 32, 15), (2, 40, 384, 31), (2, 9, 16, 15)])
+def test_dwconv_fwd_bwd(ops, dt, B, T, C, K):
+    x, w, bias = rnd(B, T, C, dt=dt, seed=1), rnd(C, K, seed=2, scale=0.3), rnd(C, seed=3)
+    y = F.dwconv_fwd(x, w, bias, torch.empty(B, T, C, dtype=dt))
+    gy = ops.dwconv_fwd(x.cuda(), w.cuda(), bias.cuda(), torch.empty(B, T, C, dtype=dt, device="cuda"))
+    close(gy, y, tol(dt, 4), "dwconv_fwd")
+    dy = rnd(B, T, C, dt=dt, seed=4)
+    dx, dw = torch.empty(B, T, C, dtype=dt), torch.zeros(C, K)
+    F.dwconv_bwd(dy, x, w, dx, dw)
+    gdx, gdw = torch.empty(B, T, C, dtype=dt, device="cuda"), torch.zeros(C, K, device="cuda")
+    ops.dwconv_bwd(dy.cuda(), x.cuda(), w.cuda(), gdx, gdw)
+    close(gdx, dx, tol(dt, 4), "dwconv dx")
+    close(gdw, dw, tol(torch.float32, 20) * math.sqrt(B * T), "dwconv dw")
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_bn_swish(ops, dt):
+    B, L, C = 3, 21, 32
+    x = rnd(B, L, C, dt=dt, seed=1)
+    mean, invstd = rnd(C, seed=2, scale=0.1), rnd(C, seed=3).abs() + 0.5
+    gam, bet = rnd(C, seed=4), rnd(C, seed=5)
+    y = F.bn_apply(x, mean, invstd, gam, bet, torch.empty_like(x), L, 0, 2)
+    gy = ops.bn_apply(x.cuda(), mean.cuda(), invstd.cuda(), gam.cuda(), bet.cuda(), torch.empty_like(x, device="cuda"), L, 0, 2)
+    close(gy, y, tol(dt, 4), "bn swish fwd")
+    dy = rnd(B, L, C, dt=dt, seed=6)
+    sums = torch.zeros(2 * C)
+    F.bn_bwd_reduce(dy, y, x, mean, invstd, gam, bet, sums, L, 0, 2)
+    gs = torch.zeros(2 * C, device="cuda")
+    ops.bn_bwd_reduce(dy.cuda(), gy, x.cuda(), mean.cuda(), invstd.cuda(), gam.cuda(), bet.cuda(), gs, L, 0, 2)
+    close(gs, sums, tol(dt, 40), "bn swish sums")
+    dx, dg, db = torch.empty_like(x), torch.zeros(C), torch.zeros(C)
+    F.bn_bwd_apply(dy, y, x, mean, invstd, gam, bet, sums, dx, dg, db, L, 0, 2)
+    gdx, gdg, gdb = torch.empty_like(x, device="cuda"), torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    ops.bn_bwd_apply(dy.cuda(), gy, x.cuda(), mean.cuda(), invstd.cuda(), gam.cuda(), bet.cuda(), sums.cuda(), gdx, gdg, gdb, L, 0, 2)
+    close(gdx, dx, tol(dt, 8), "bn swish dx")
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_gather_rows(ops, dt):
+    from seq2seq_vc_b200.aasvc_engine import nearest_index
+
+    B, Tin, Tout, C = 3, 11, 12, 24
+    x = rnd(B, Tin, C, dt=dt, seed=1)
+    idx = nearest_index(Tin, Tout)
+    ref = x[:, idx]
+    st, ct = torch.tensor(idx, dtype=torch.int32), torch.ones(Tout, dtype=torch.int32)
+    got = ops.gather_rows(x.cuda(), st.cuda(), ct.cuda(), torch.empty(B, Tout, C, dtype=dt, device="cuda"))
+    close(got, ref, 0.0, "nearest gather")
+    dy = rnd(B, Tout, C, dt=dt, seed=2)
+    first, cnt = [0] * Tin, [0] * Tin
+    for j, i in enumerate(idx):
+        if cnt[i] == 0:
+            first[i] = j
+        cnt[i] += 1
+    dref = torch.zeros(B, Tin, C, dtype=torch.float64)
+    dref.index_add_(1, torch.tensor(idx), dy.double())
+    got = ops.gather_rows(dy.cuda(), torch.tensor(first, dtype=torch.int32).cuda(), torch.tensor(cnt, dtype=torch.int32).cuda(),
+                          torch.empty(B, Tin, C, dtype=dt, device="cuda"))
+    close(got, dref.to(dt), tol(dt, 4), "gather adjoint")
+
+
+# ---------------------------------------------------------------------------------------------- alignment block
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("B,TF,TT,C", [(2, 13, 5, 24), (3, 70, 33, 128), (2, 130, 65, 40)])
+def test_align_logp_fwd_bwd(ops, dt, B, TF, TT, C):
+    feats, text = rnd(B, TF, C, dt=dt, seed=1), rnd(B, TT, C, dt=dt, seed=2)
+    tl = torch.tensor([TT, max(1, TT // 2), max(1, TT - 3)][:B], dtype=torch.int32)
+    logp, lse = torch.empty(B, TF, TT), torch.empty(B, TF)
+    F.align_logp_fwd(feats, text, tl, logp, lse)
+    glogp, glse = torch.empty(B, TF, TT, device="cuda"), torch.empty(B, TF, device="cuda")
+    ops.align_logp_fwd(feats.cuda(), text.cuda(), tl.cuda(), glogp, glse)
+    fin = torch.isfinite(logp)
+    assert torch.equal(torch.isfinite(glogp).cpu(), fin)
+    close(glogp.cpu()[fin], logp[fin], 5e-5 * math.sqrt(C), "log_p_attn")     # inputs are identical (already rounded): fp32 math
+    close(glse, lse, 5e-5 * math.sqrt(C), "lse")
+    dlogp = rnd(B, TF, TT, seed=3)
+    ld = (TT + 7) // 8 * 8
+    W, rs, cs = torch.empty(B, TF, ld, dtype=dt), torch.empty(B, TF), torch.empty(B, TT)
+    F.align_logp_bwd(dlogp, logp, lse, tl, W, rs, cs)
+    gW = torch.full((B, TF, ld), 3.0, dtype=dt, device="cuda")
+    grs, gcs = torch.empty(B, TF, device="cuda"), torch.empty(B, TT, device="cuda")
+    ops.align_logp_bwd(dlogp.cuda(), logp.cuda(), lse.cuda(), tl.cuda(), gW, grs, gcs)
+    scale = W.float().abs().max().item()
+    close(gW, W, tol(dt, 2) * scale, "W")
+    close(grs, rs, tol(dt, 4) * scale * math.sqrt(TT), "rowsum")
+    close(gcs, cs, tol(dt, 4) * scale * math.sqrt(TF), "colsum")
+
+
+def test_forward_sum_matches_reference_ctc_golden(ops):
+    """Loss and gradient of the reference's ForwardSumLoss (F.ctc_loss path, incl. an infeasible utterance)."""
+    from seq2seq_vc_b200.aasvc_engine import beta_binomial_log_prior
+
+    z = np.load(GOLDEN)
+    lp = torch.from_numpy(z["fs_lp"])
+    tl, fl = z["fs_tl"].tolist(), z["fs_fl"].tolist()
+    B, TF, TT = lp.shape
+    prior = torch.zeros(B, TF, TT)
+    for b in range(B):
+        prior[b, :fl[b], :tl[b]] = beta_binomial_log_prior(tl[b], fl[b])
+    loss, g = torch.zeros(1, device="cuda"), torch.full((B, TF, TT), 5.0, device="cuda")
+    ops.forward_sum(lp.cuda(), prior.cuda(), torch.tensor(tl, dtype=torch.int32).cuda(), torch.tensor(fl, dtype=torch.int32).cuda(),
+                    torch.empty(B, TF, TT, device="cuda"), loss, g)
+    assert abs(loss.item() - float(z["fs_loss"])) <= 2e-5 * max(1.0, abs(float(z["fs_loss"])))
+    close(g, torch.from_numpy(z["fs_grad"]), 2e-5, "forward-sum gradient (torch ctc_loss backward semantics)")
+
+
+@pytest.mark.parametrize("B,TF,TT", [(3, 50, 12), (4, 200, 48), (2, 768, 192)])
+def test_forward_sum_vs_oracle(ops, B, TF, TT):
+    lp = torch.log_softmax(rnd(B, TF, TT, seed=1), -1)
+    tl = torch.tensor([TT, max(1, TT - 5), max(1, TT // 2), 1][:B], dtype=torch.int32)
+    fl = torch.tensor([TF, max(1, TF - 9), max(1, TF // 2), TF][:B], dtype=torch.int32)
+    prior = rnd(B, TF, TT, seed=2, scale=0.5) - 2.0
+    loss, g = torch.zeros(1), torch.zeros(B, TF, TT)
+    F.forward_sum(lp, prior, tl, fl, None, loss, g, grad_scale=2.0)
+    gl, gg = torch.zeros(1, device="cuda"), torch.empty(B, TF, TT, device="cuda")
+    ops.forward_sum(lp.cuda(), prior.cuda(), tl.cuda(), fl.cuda(), torch.empty(B, TF, TT, device="cuda"), gl, gg, 2.0)
+    assert abs(gl.item() - loss.item()) <= 1e-4 * max(1.0, abs(loss.item()))
+    close(gg, g, 1e-4, "forward-sum gradient")
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_gauss_weights_and_duration_loss(ops, dt):
+    B, TF, TT = 3, 44, 12
+    ds = torch.tensor([[1.] * 11 + [33.], [30.] + [1.] * 10 + [0.], [22.] + [1.] * 8 + [0.] * 3])
+    fl, tl = torch.tensor([44, 40, 30], dtype=torch.int32), torch.tensor([12, 11, 9], dtype=torch.int32)
+    ld = 16
+    P = F.gauss_weights(ds, fl, tl, torch.empty(B, TF, ld, dtype=dt))
+    gP = ops.gauss_weights(ds.cuda(), fl.cuda(), tl.cuda(), torch.full((B, TF, ld), 2.0, dtype=dt, device="cuda"))
+    close(gP, P, tol(dt), "gaussian upsampling weights")
+    assert torch.equal(gP[1, 41].cpu(), gP[1, 0].cpu())          # padded output frames replicate frame 0 (reference quirk)
+    pre = rnd(B * TT, 1, dt=dt, seed=1, scale=4.0)
+    pre[5] = 11.0
+    d_outs, loss, d_pre = torch.empty(B, TT), torch.zeros(1), torch.empty(B * TT, 1, dtype=dt)
+    F.duration_loss(pre, ds, tl, d_outs, loss, d_pre)
+    gd, gl, gp = torch.empty(B, TT, device="cuda"), torch.zeros(1, device="cuda"), torch.empty(B * TT, 1, dtype=dt, device="cuda")
+    ops.duration_loss(pre.cuda(), ds.cuda(), tl.cuda(), gd, gl, gp)
+    close(gd, d_outs, 1e-6, "d_outs")
+    assert abs(gl.item() - loss.item()) <= 1e-5 * max(1.0, loss.item())
+    close(gp, d_pre, tol(dt), "d_pre")
+    assert gd[0, 5].item() == 10.0 and gp[5].item() == 0.0       # clamp(max=10) blocks the gradient
+
+
+# ---------------------------------------------------------------------------------------------- whole engine
+def _golden():
+    z = np.load(GOLDEN)
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    return z, sd
+
+
+def _step(eng, z):
+    ilens, olens = z["ilens"].tolist(), z["olens"].tolist()
+    xs = torch.from_numpy(z["xs"])[:, :max(ilens)].contiguous().cuda()
+    ys = torch.from_numpy(z["ys"])[:, :max(olens)].contiguous().cuda()
+    dpi = torch.from_numpy(z["dp_inputs"])[:, :max(ilens)].contiguous().cuda()
+    after, before = eng.forward(xs, ys, dpi, ilens, olens)
+    losses = eng.loss(ys)
+    eng.backward()
+    torch.cuda.synchronize()
+    return after, before, losses
+
+
+def test_golden_tiny_fp32_forward_losses_grads():
+    from seq2seq_vc_b200.aasvc_engine import AASVCEngine
+
+    z, sd = _golden()
+    eng = AASVCEngine(dict(AAS_HP, **NO_DROPOUT), device="cuda:0", bf16=False)
+    eng.load_state_dict(sd)
+    after, before, losses = _step(eng, z)
+    assert np.abs(after.cpu().numpy() - z["after_outs"]).mean() <= 1e-4
+    assert np.abs(before.cpu().numpy() - z["before_outs"]).mean() <= 1e-4
+    lp, ref = eng.log_p_attn.cpu().numpy(), z["log_p_attn"]
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(lp), fin) and np.abs(lp[fin] - ref[fin]).max() <= 1e-4
+    np.testing.assert_array_equal(eng.ds.cpu().numpy(), z["ds"])                  # integer alignment path: bit-exact
+    assert np.abs(eng.d_outs.cpu().numpy() - z["d_outs"]).max() <= 1e-4
+    for i, k in enumerate(("l1_loss", "forward_sum_loss", "bin_loss", "duration_loss")):
+        assert abs(losses[i].item() - float(z[k])) <= 1e-4 * max(1.0, abs(float(z[k]))), k
+    for k in [k for k in z.files if k.startswith("attn.")]:
+        assert np.abs(eng.attn[k[5:]].cpu().numpy() - z[k]).mean() <= 1e-3, k
+    gmax = max(np.abs(z[k]).max() for k in z.files if k.startswith("grad."))
+    for name in eng.store.names():
+        ref = z["grad." + name]
+        got = eng.store.g(name).cpu().numpy()
+        assert np.abs(got - ref).max() <= 1e-3 * np.abs(ref).max() + 1e-5 * gmax, name
+    for k in z.files:
+        if k.startswith("bn_after."):
+            np.testing.assert_allclose(eng.buffers[k[9:]].cpu().numpy(), z[k], rtol=1e-4, atol=1e-6)
+    eng.training = False
+    ilens, olens = z["ilens"].tolist(), z["olens"].tolist()
+    after_e, _ = eng.forward(torch.from_numpy(z["xs"]).cuda(), torch.from_numpy(z["ys"]).cuda(), torch.from_numpy(z["dp_inputs"]).cuda(),
+                             ilens, olens)
+    assert np.abs(after_e.cpu().numpy() - z["eval_after_outs"]).mean() <= 1e-4
+
+
+def test_mid_size_fp32_vs_oracle_and_bf16_drift():
+    """A mid-size ragged batch (d=64, 2+2 layers, k=15, T=120 -> L=96): fp32 CUDA path vs the CPU oracle on the same
+    weights; then the bf16 tensor-core path with its drift printed and bounded."""
+    from oracle import aasvc_oracle as ao
+    from seq2seq_vc_b200.aasvc_engine import AASVCEngine
+
+    hp = dict(idim=80, odim=80, adim=64, aheads=2, elayers=2, eunits=128, dlayers=2, dunits=128, duration_predictor_input_dim=80,
+              duration_predictor_layers=2, duration_predictor_chans=32, duration_predictor_kernel_size=3, postnet_layers=3,
+              postnet_filts=5, postnet_chans=32, post_encoder_reduction_factor=4, conformer_enc_kernel_size=15,
+              conformer_dec_kernel_size=15)
+    sd = ao.init_state_dict(hp, seed=4)
+    ilens, olens = [120, 101, 77], [96, 90, 55]
+    xs, ilens, ys, olens, dpi = ao.synthetic_batch(3, 120, 96, ilens=ilens, olens=olens, seed=8)
+    out, parts, grads = ao.aasvc_loss_and_grads(sd, hp, xs, ilens, ys, olens, dpi)
+    eng = AASVCEngine(dict(hp, **NO_DROPOUT), device="cuda:0", bf16=False)
+    eng.load_state_dict(sd)
+    after, before = eng.forward(xs.cuda(), ys.cuda(), dpi.cuda(), ilens, olens)
+    losses = eng.loss(ys.cuda())
+    eng.backward()
+    torch.cuda.synchronize()
+    assert (after.cpu() - out["after_outs"].detach()).abs().mean().item() <= 1e-4
+    assert torch.equal(eng.ds.cpu(), out["ds"])
+    for i, k in enumerate(eng.LOSS_NAMES):
+        assert abs(losses[i].item() - float(parts[k])) <= 1e-4 * max(1.0, abs(float(parts[k]))), k
+    gmax = max(float(g.abs().max()) for g in grads.values() if g is not None)
+    for name in eng.store.names():
+        ref = grads[name]
+        got = eng.store.g(name).cpu()
+        assert (got - ref).abs().max().item() <= 2e-3 * float(ref.abs().max()) + 2e-5 * gmax, name
+    # bf16 tensor-core path: same step, drift reported (durations may legitimately differ when bf16 flips a MAS decision)
+    eng16 = AASVCEngine(dict(hp, **NO_DROPOUT), device="cuda:0", bf16=True)
+    eng16.load_state_dict(sd)
+    a16, _ = eng16.forward(xs.cuda(), ys.cuda(), dpi.cuda(), ilens, olens)
+    l16 = eng16.loss(ys.cuda())
+    eng16.backward()
+    torch.cuda.synchronize()
+    drift = (a16.float().cpu() - out["after_outs"].detach()).abs().mean().item()
+    same_ds = (eng16.ds.cpu() == out["ds"]).float().mean().item()
+    print(f"bf16 drift: after L1 {drift:.3e}, durations equal {same_ds:.3f}, losses {l16.tolist()} vs {[float(parts[k]) for k in eng.LOSS_NAMES]}")
+    assert drift <= 0.15 and torch.isfinite(l16).all()
+    assert eng16.ds.sum(1).cpu().tolist() == [float(o) for o in olens]            # durations always sum to the target length
+    g16 = eng16.store.G
+    assert torch.isfinite(g16).all()
+    cos = torch.nn.functional.cosine_similarity(g16.cpu(), eng.store.G.cpu(), dim=0).item()
+    print(f"bf16 gradient cosine vs fp32 path: {cos:.4f}")
+    assert cos >= 0.9
+
+
+def test_dropout_training_step_runs_and_is_reproducible():
+    """Default dropout rates: two forwards with the same seed state are identical, and backward is finite."""
+    from seq2seq_vc_b200.aasvc_engine import AASVCEngine
+
+    z, sd = _golden()
+    eng = AASVCEngine(dict(AAS_HP), device="cuda:0", bf16=False, seed=3)
+    eng.load_state_dict(sd)
+    a1, _, l1 = _step(eng, z)
+    a1 = a1.clone()
+    g1 = eng.store.G.clone()
+    a2, _, l2 = _step(eng, z)
+    assert torch.equal(a1, a2)                               # same masks: the forward is bit-reproducible
+    # gradients are accumulated with float atomics (split-K, column reductions): equal up to summation order
+    assert (g1 - eng.store.G).abs().max().item() <= 1e-4 * g1.abs().max().item()
+    assert torch.isfinite(g1).all() and torch.isfinite(l1).all()
+    eng.seed_dev += 1
+    a3, _, _ = _step(eng, z)
+    assert not torch.equal(a1, a3)
