@@ -32,10 +32,47 @@ WORKLOADS = {
               64, 512, 1024, True, "VTN-base 6+6 d384 h8 r2, B64 x (512->1024, 80-mel), bf16"),
     "c4": (dict(idim=80, odim=80, adim=384, aheads=4, elayers=6, dlayers=6, eunits=1536, dunits=1536, decoder_reduction_factor=2),
            64, 160, 1000, True, "TransformerTTS 6+6 d384 h4 r2, B64 x (160 tokens -> 1000 frames, 80-mel), bf16"),
+    # AAS-VC (egs/arctic/vc2/conf/aas_vc.melmelmel.v1.yaml, deterministic duration predictor): BASELINE.json configs[2]
+    "c3": (dict(idim=80, odim=80, adim=384, aheads=2, elayers=4, eunits=1536, dlayers=4, dunits=1536, duration_predictor_input_dim=80,
+                duration_predictor_layers=2, duration_predictor_chans=256, duration_predictor_kernel_size=3, postnet_layers=5,
+                postnet_filts=5, postnet_chans=256, post_encoder_reduction_factor=4, conformer_enc_kernel_size=15,
+                conformer_dec_kernel_size=15),
+           64, 768, 768, True, "AAS-VC Conformer 4+4 (enc d384, dec d1536, h2, k15), B64 x (768->768, 80-mel), bf16, MAS + forward-sum on device"),
+    "c3b16": (dict(idim=80, odim=80, adim=384, aheads=2, elayers=4, eunits=1536, dlayers=4, dunits=1536, duration_predictor_input_dim=80,
+                   duration_predictor_layers=2, duration_predictor_chans=256, duration_predictor_kernel_size=3, postnet_layers=5,
+                   postnet_filts=5, postnet_chans=256, post_encoder_reduction_factor=4, conformer_enc_kernel_size=15,
+                   conformer_dec_kernel_size=15),
+              16, 768, 768, True, "AAS-VC Conformer 4+4 (enc d384, dec d1536, h2, k15), B16 x (768->768, 80-mel), bf16 (the recipe's batch size)"),
     "c1": (dict(idim=80, odim=80, adim=256, aheads=4, elayers=2, dlayers=2, eunits=1024, dunits=1024, decoder_reduction_factor=2),
            4, 200, 400, False, "VTN-small 2+2 d256 h4 r2, B4 x (200->400, 80-mel), fp32"),
 }
 METRIC = "target mel-frames/sec, VTN-base enc-dec training step (80-mel, src512/tgt1024)"
+METRIC_AAS = "target mel-frames/sec, AAS-VC Conformer non-AR training step (80-mel, 768 frames)"
+
+
+def is_aas(workload):
+    return workload.startswith("c3")
+
+
+def aasvc_fwd_flops(hp, T, L):
+    """Forward FLOPs per utterance of AASVC (linear_pos is batch-independent and left out)."""
+    d, pr = hp["adim"], hp["post_encoder_reduction_factor"]
+    C, Tt = d * pr, T // pr
+
+    def conformer(n, dm, U, K, Tn):
+        per = 8 * Tn * dm * U + 8 * Tn * dm * dm + 4 * Tn * Tn * dm + 2 * Tn * (2 * Tn - 1) * dm + 6 * Tn * dm * dm + 2 * Tn * dm * K
+        return n * per
+
+    T1, F1 = (T - 1) // 2, 39
+    T2, F2 = (T1 - 1) // 2, 19
+    dp_proj = 2 * 9 * d * T1 * F1 + 2 * 9 * d * d * T2 * F2 + 2 * T2 * (d * F2) * d
+    enc = 2 * T * 80 * d + conformer(hp["elayers"], d, hp["eunits"], hp["conformer_enc_kernel_size"], T)
+    align = 2 * Tt * 4 * C * C + 2 * L * (3 * 80 * C + 4 * C * C) + 3 * L * Tt * C
+    up = 2 * L * Tt * C
+    dec = conformer(hp["dlayers"], C, hp["dunits"], hp["conformer_dec_kernel_size"], L) + 2 * L * C * 80
+    post = 2 * 5 * L * (80 * 256 + 3 * 256 * 256 + 256 * 80)
+    return dp_proj + enc + align + up + dec + post
+
 UNIT = "frames/s"
 
 
@@ -144,16 +181,45 @@ def cpu_port_steps(hp, B, T, L, steps, warmup, tts=False):
     return sum(times) / len(times)
 
 
+def cpu_port_steps_aas(hp, B, T, L, steps, warmup):
+    """fwd + the four AAS-VC losses + bwd + clip + Adam of the oracle (plain torch fp32 CPU) on B utterances."""
+    from oracle import aasvc_oracle as ao
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = ao.init_state_dict(hp, seed=0)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.dtype.is_floating_point and "running_" not in k}
+    full = dict(sd)
+    full.update(params)
+    opt = torch.optim.Adam(list(params.values()), lr=8e-5)
+    xs, ilens, ys, olens, dpi = ao.synthetic_batch(B, T, L, seed=1234)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = ao.aasvc_forward(full, hp, xs, ilens, ys, olens, dpi, training=True)
+        total, _ = ao.aasvc_losses(out)
+        opt.zero_grad()
+        total.backward()
+        torch.nn.utils.clip_grad_norm_(list(params.values()), 1.0)
+        opt.step()
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    return sum(times) / len(times)
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
     hp, B, T, L, bf16, desc = WORKLOADS[args.workload]
-    Bs = min(B, 4)
-    timed = max(1, min(args.steps, 6))      # bounded sample: the CPU arm must end within minutes whatever K is
-    sec = cpu_port_steps(hp, Bs, T, L, timed, max(1, min(args.warmup, 1)), args.workload == "c4")
+    aas = is_aas(args.workload)
+    Bs = 1 if aas else min(B, 4)
+    timed = max(1, min(args.steps, 2 if aas else 6))      # bounded sample: the CPU arm must end within minutes whatever K is
+    if aas:
+        sec = cpu_port_steps_aas(hp, Bs, T, L, timed, 1)
+    else:
+        sec = cpu_port_steps(hp, Bs, T, L, timed, max(1, min(args.warmup, 1)), args.workload == "c4")
     val = Bs * L / sec
     cores = os.cpu_count() or 1
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+    line = {"impl": "reference", "metric": METRIC_AAS if aas else METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "sample": f"{Bs} utterances per step (of {B}); frames/s scales linearly in B",
@@ -167,7 +233,7 @@ def run_reference(args, rank):
 # --------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------
-def gemm_roofline(stepper, batch, dev, table_path=None):
+def gemm_roofline(stepper, batch, dev, table_path=None, run=None):
     """Per-launch CUDA-event timing of every tcgen05 GEMM launch of one (eager) training step."""
     from seq2seq_vc_b200 import ops
 
@@ -193,14 +259,16 @@ def gemm_roofline(stepper, batch, dev, table_path=None):
     ops.gemm = timed
     try:
         eng = stepper.engine
-        xs, ilens, ys, labels, olens = batch
-        eng.prepare(xs.shape[0], xs.shape[1], ys.shape[1], ilens, olens)
+        if run is None:
+            xs, ilens, ys, labels, olens = batch
+            eng.prepare(xs.shape[0], xs.shape[1], ys.shape[1], ilens, olens)
+            run = lambda: stepper._fwd_bwd(xs, ys, labels)
         for _ in range(2):
             rec.clear()
             # park the GPU behind a ~40 ms spin so that the eager launches below queue up back to back: the
             # event pairs then bracket pure kernel execution instead of host launch latency
             torch.cuda._sleep(80_000_000)
-            stepper._fwd_bwd(xs, ys, labels)
+            run()
             torch.cuda.synchronize()
     finally:
         ops.gemm = orig
@@ -221,19 +289,42 @@ def gemm_roofline(stepper, batch, dev, table_path=None):
 
 
 def run_ours(args, rank, world):
-    from seq2seq_vc_b200 import VTN, TransformerTTS, VTNTrainStep, _lib
+    from seq2seq_vc_b200 import AASVC, AASVCTrainStep, VTN, TransformerTTS, VTNTrainStep, _lib
 
     hp, B, T, L, bf16, desc = WORKLOADS[args.workload]
     tts = args.workload == "c4"
+    aas = is_aas(args.workload)
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     _lib.device_check()
-    model = (TransformerTTS if tts else VTN)(**hp, compute_dtype="bf16" if bf16 else "float32", device=dev, seed=0)
-    stepper = VTNTrainStep(model, lr=8e-5, warmup_steps=4000, use_graph=not args.no_graph)
     xs, ilens, ys, labels, olens = synthetic_batch(B, T, L, 1234 + rank, tts)
     dxs, dys, dlabels = xs.to(dev), ys.to(dev), labels.to(dev)
     pxs, pys, plabels = xs.pin_memory(), ys.pin_memory(), labels.pin_memory()
+    if aas:
+        yaml_fixed = dict(positionwise_layer_type="linear", duration_predictor_use_encoder_outputs=False, encoder_normalize_before=True,
+                          decoder_normalize_before=True, duration_predictor_type="deterministic", encoder_input_layer="linear",
+                          transformer_enc_dropout_rate=0.2, transformer_enc_positional_dropout_rate=0.2,
+                          transformer_enc_attn_dropout_rate=0.2, transformer_dec_dropout_rate=0.2,
+                          transformer_dec_positional_dropout_rate=0.2, transformer_dec_attn_dropout_rate=0.2)
+        model = AASVC(**hp, **yaml_fixed, compute_dtype="bf16" if bf16 else "float32", device=dev, seed=0)
+        inner = AASVCTrainStep(model, lr=8e-5, warmup_steps=4000, use_graph=not args.no_graph)
+        inner.steps = 1                                   # past dp_train_start_steps: the duration loss is part of every timed step
+
+        class _Adapter:                                   # same call shape as VTNTrainStep; dp_inputs = the source mels (duration_predictor_feat: mel)
+            engine = inner.engine
+
+            def __call__(self, x, il, y, lab, ol):
+                return inner(x, il, y, ol, x)
+
+            @property
+            def replayed_launches(self):
+                return inner.replayed_launches
+
+        stepper = _Adapter()
+    else:
+        model = (TransformerTTS if tts else VTN)(**hp, compute_dtype="bf16" if bf16 else "float32", device=dev, seed=0)
+        stepper = VTNTrainStep(model, lr=8e-5, warmup_steps=4000, use_graph=not args.no_graph)
 
     def barrier():
         if world > 1:
@@ -278,8 +369,8 @@ def run_ours(args, rank, world):
     value = frames / (ms * 1e-3)
     e2e = frames / (ms_e2e * 1e-3)
     pk, pk_src = peaks()
-    flops_step = 3.0 * vtn_fwd_flops(hp, T, L, tts) * B
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+    flops_step = 3.0 * (aasvc_fwd_flops(hp, T, L) if aas else vtn_fwd_flops(hp, T, L, tts)) * B
+    line = {"metric": METRIC_AAS if aas else METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if bf16 else "f32", "data": "synthetic",
             "config": {"workload": desc, "global_batch": B * world, "per_gpu_batch": B, "parallelism": f"dp{world}",
@@ -290,11 +381,17 @@ def run_ours(args, rank, world):
                        "tc_fallbacks": int(_lib.load().s2s_tc_fallback_count())},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": xs.numel() * xs.element_size() + (ys.numel() + labels.numel()) * 4 + 5 * B * 4, "d2h_bytes_per_step": 8},
+                    "h2d_bytes_per_step": (2 * xs.numel() * 4 + ys.numel() * 4 + 3 * B * 4) if aas else
+                    (xs.numel() * xs.element_size() + (ys.numel() + labels.numel()) * 4 + 5 * B * 4),
+                    "d2h_bytes_per_step": 16 if aas else 8},
             "gpu_launches": int(launches)}
     if world == 1:
         if bf16:
-            gf, gms, n = gemm_roofline(stepper, (dxs, ilens, dys, dlabels, olens), dev, args.gemm_table)
+            run = None
+            if aas:
+                inner.engine.prepare(B, T, L, ilens, olens)
+                run = lambda: inner._fwd_bwd(dxs, dys, dxs, True)
+            gf, gms, n = gemm_roofline(stepper, (dxs, ilens, dys, dlabels, olens), dev, args.gemm_table, run)
             peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
             ach = gf / (gms * 1e-3) / 1e12
             traffic = None
@@ -310,8 +407,8 @@ def run_ours(args, rank, world):
                                 "avg_launch_us": gms * 1e3 / n, "gemm_share_of_step": gms / (ms / args.steps),
                                 "how": "CUDA events around every mode-1 s2s_gemm launch of one fwd+bwd queued behind a GPU spin (no host gaps), right after the timed region"}
         if not args.no_cpu_baseline:
-            Bs = min(B, 4)
-            sec = cpu_port_steps(hp, Bs, T, L, 2, 1, tts)
+            Bs = 1 if aas else min(B, 4)
+            sec = cpu_port_steps_aas(hp, Bs, T, L, 1, 1) if aas else cpu_port_steps(hp, Bs, T, L, 2, 1, tts)
             line["cpu_baseline"] = {"value": Bs * L / sec, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                                     "sample": f"oracle port of the reference PyTorch-CPU path (fp32), {Bs} x ({T}->{L}) per step, 2 steps after 1 warm-up"}
     print(json.dumps(line), flush=True)

@@ -312,11 +312,12 @@ int s2s_glu_fwd(const void* x, void* y, int64_t rows, int C, int dtype, void* st
 int s2s_glu_bwd(const void* dy, const void* x, void* dx, int64_t rows, int C, int dtype, void* stream);
 /* depthwise Conv1d over time (convolution.py:37-45,72): x, y (B, T, C) channels-last, w (C, K) float32 (the
  * reference's (C,1,K) weight), bias (C) or NULL, zero padding (K-1)/2 per utterance; K odd.  The reference applies
- * no padding mask, neither do these.  bwd: dx (may be NULL) and dw (C, K) += (may be NULL); dbias = s2s_colsum(dy). */
+ * no padding mask, neither do these.  bwd: dx (may be NULL), dw (C, K) += and dbias (C) += (may be NULL; dbias needs dw).
+ * K = 7 / 15 / 31 take the shared-memory tiled kernels (one channel per thread, register sliding window). */
 int s2s_dwconv_fwd(const void* x, const float* w, const float* bias, void* y, int B, int T, int C, int K, int dtype,
                    void* stream);
-int s2s_dwconv_bwd(const void* dy, const void* x, const float* w, void* dx, float* dw, int B, int T, int C, int K,
-                   int dtype, void* stream);
+int s2s_dwconv_bwd(const void* dy, const void* x, const float* w, void* dx, float* dw, float* dbias, int B, int T, int C,
+                   int K, int dtype, void* stream);
 /* Swish FFN activation (conformer/swish.py:13-18) + dropout: y = dropout(x * sigmoid(x)); x is kept for backward */
 int s2s_swish_fwd(const void* x, void* y, int64_t n, const s2s_dropout_t* drop, int dtype, void* stream);
 int s2s_swish_bwd(const void* dy, const void* x, void* dx, int64_t n, const s2s_dropout_t* drop, int dtype,
@@ -365,10 +366,12 @@ int s2s_gauss_weights(const float* ds, const int32_t* feats_lens, const int32_t*
                       int T_text, int64_t ldP, float delta, int dtype, void* stream);
 /* DurationPredictor output masking/clamp + DurationPredictorLoss (modules/duration_predictor.py:98-101,
  * models/aas_vc.py:408-410, losses/duration_predictor_loss.py:29-50): d_outs = min(pre * mask, clamp_max),
- * loss = mean over s < text_lens[b] of (d_outs - log(ds + offset))^2, d_pre = grad_scale * d loss / d pre. */
+ * loss = mean over s < text_lens[b] of (d_outs - log(ds + offset))^2, d_pre = grad_scale * d loss / d pre; when
+ * g_douts (B,T_text) is given, d_pre = g_douts * mask * [pre <= clamp_max] instead (chain rule for an external loss
+ * on d_outs).  d_outs, loss, d_pre may each be NULL. */
 int s2s_duration_loss(const void* pre, const float* ds, const int32_t* text_lens, int B, int T_text, float offset,
-                      float clamp_max, float grad_scale, float* d_outs, float* loss, void* d_pre, int dtype,
-                      void* stream);
+                      float clamp_max, float grad_scale, const float* g_douts, float* d_outs, float* loss, void* d_pre,
+                      int dtype, void* stream);
 
 #ifdef __cplusplus
 }

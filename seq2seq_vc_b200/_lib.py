@@ -102,7 +102,7 @@ SIGNATURES = {
     "s2s_glu_fwd": (c_int, [_P, _P, c_int64, c_int, c_int, _P]),
     "s2s_glu_bwd": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P]),
     "s2s_dwconv_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
-    "s2s_dwconv_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "s2s_dwconv_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "s2s_swish_fwd": (c_int, [_P, _P, c_int64, _DP, c_int, _P]),
     "s2s_swish_bwd": (c_int, [_P, _P, _P, c_int64, _DP, c_int, _P]),
     "s2s_scale_dropout": (c_int, [_P, _P, c_int64, c_float, _DP, _DP, c_int, _P]),
@@ -113,7 +113,7 @@ SIGNATURES = {
     "s2s_align_logp_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int64, c_int, _P]),
     "s2s_forward_sum": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_float, _P, _P, _P, c_float, _P]),
     "s2s_gauss_weights": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int64, c_float, c_int, _P]),
-    "s2s_duration_loss": (c_int, [_P, _P, _P, c_int, c_int, c_float, c_float, c_float, _P, _P, _P, c_int, _P]),
+    "s2s_duration_loss": (c_int, [_P, _P, _P, c_int, c_int, c_float, c_float, c_float, _P, _P, _P, _P, c_int, _P]),
 }
 
 _lib = None

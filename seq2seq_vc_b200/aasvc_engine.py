@@ -183,6 +183,7 @@ class AASVCEngine(EngineBase):
         self._loss_ws = torch.zeros(4, dtype=_f32, device=self.device)
         self._one = torch.ones(1, dtype=_f32, device=self.device)
         self._prior_cache: Dict[Tuple, torch.Tensor] = {}
+        self._prior_key: Dict[Tuple, Tuple] = {}
         self._prior_tables: Dict[Tuple[int, int], torch.Tensor] = {}
         self._relpe: Dict[Tuple[int, int], torch.Tensor] = {}
         self._interp: Dict[Tuple[int, int], Tuple[torch.Tensor, ...]] = {}
@@ -237,22 +238,27 @@ class AASVCEngine(EngineBase):
         host.copy_(torch.tensor([ilens, tlens, olens], dtype=_i32))
         self.buf("lens", (3, B), _i32).copy_(host, non_blocking=True)
         self.ilens_host, self.tlens_host, self.olens_host = ilens, tlens, olens
-        # beta-binomial prior (B, L, Tt): -inf never enters the kernel (it only reads t < olen, k < tlen)
+        # beta-binomial prior (B, L, Tt) in a shape-stable device buffer (a captured CUDA graph keeps reading it);
+        # re-filled only when the length pattern changes.  -inf never enters: the kernel reads t < olen, k < tlen only
         key = (L, Tt, tuple(tlens), tuple(olens))
-        prior = self._prior_cache.get(key)
-        if prior is None:
-            ph = torch.zeros(B, L, Tt, dtype=_f32)
-            for b in range(B):
-                tab = self._prior_tables.get((tlens[b], olens[b]))
-                if tab is None:
-                    tab = beta_binomial_log_prior(tlens[b], olens[b])
-                    self._prior_tables[(tlens[b], olens[b])] = tab
-                ph[b, :olens[b], :tlens[b]] = tab
-            prior = ph.to(self.device, non_blocking=True)
-            if len(self._prior_cache) > 8:
-                self._prior_cache.clear()
-            self._prior_cache[key] = prior
-        self.prior = prior
+        pbuf = self.buf("prior", (B, L, Tt), _f32)
+        if self._prior_key.get(self._sig) != key:
+            prior = self._prior_cache.get(key)
+            if prior is None:
+                ph = torch.zeros(B, L, Tt, dtype=_f32)
+                for b in range(B):
+                    tab = self._prior_tables.get((tlens[b], olens[b]))
+                    if tab is None:
+                        tab = beta_binomial_log_prior(tlens[b], olens[b])
+                        self._prior_tables[(tlens[b], olens[b])] = tab
+                    ph[b, :olens[b], :tlens[b]] = tab
+                prior = ph.pin_memory() if self.device.type == "cuda" else ph
+                if len(self._prior_cache) > 8:
+                    self._prior_cache.clear()
+                self._prior_cache[key] = prior
+            pbuf.copy_(prior, non_blocking=True)
+            self._prior_key[self._sig] = key
+        self.prior = pbuf
         self._prepared = (B, T, L)
 
     def _rel_table(self, T: int, d: int) -> torch.Tensor:
@@ -452,8 +458,8 @@ class AASVCEngine(EngineBase):
             ops.add(st.g(cm + ".norm.bias"), sums[:dm], st.g(cm + ".norm.bias"))
             ops.add(st.g(cm + ".norm.weight"), sums[dm:], st.g(cm + ".norm.weight"))
         dglu = self._scratch("cf.dglu", (B, T, dm))
-        ops.dwconv_bwd(dz, glu, st.p(cm + ".depthwise_conv.weight").view(dm, K), dglu, st.g(cm + ".depthwise_conv.weight").view(dm, K))
-        ops.colsum(dz.view(B * T, dm), st.g(cm + ".depthwise_conv.bias"))
+        ops.dwconv_bwd(dz, glu, st.p(cm + ".depthwise_conv.weight").view(dm, K), dglu, st.g(cm + ".depthwise_conv.weight").view(dm, K),
+                       st.g(cm + ".depthwise_conv.bias"))
         dpw1 = self._scratch("cf.dpw1", (B * T, 2 * dm))
         ops.glu_bwd(dglu.view(B * T, dm), pw1, dpw1)
         dn = self._scratch("cf.dn", (B, T, dm))
@@ -663,9 +669,21 @@ class AASVCEngine(EngineBase):
         return self.losses[0] + lam * (self.losses[1] + self.losses[2]) + self.losses[3]
 
     # ------------------------------------------------------------------ backward
-    def backward(self, zero_grad: bool = True) -> None:
-        """Accumulates every parameter gradient of the loss assembled by loss() into ParamStore.G."""
+    def forward_d_outs(self) -> torch.Tensor:
+        """d_outs = min(pre * mask, 10) without any loss (the drop-in module's forward; aas_vc.py:408-411)."""
+        B, Tt = self.shapes["B"], self.shapes["Tt"]
+        self.d_outs = self.buf("dp.d_outs", (B, Tt), _f32)
+        ops.duration_loss(self.dp_pre, self.ds, self.tlens_dev, self.d_outs, None, None)
+        return self.d_outs
+
+    def backward(self, d_after=None, d_before=None, d_logp=None, d_dp_pre=None, zero_grad: bool = True) -> None:
+        """Accumulates parameter gradients into ParamStore.G.  Defaults: the gradients loss() left behind; the drop-in
+        module passes the ones autograd hands it (d_logp already includes the bin-loss share)."""
         hp, st = self.hp, self.store
+        d_after = self.d_after if d_after is None else d_after
+        d_before = self.d_before if d_before is None else d_before
+        d_logp = self.d_logp if d_logp is None else d_logp
+        d_dp_pre = self.d_dp_pre if d_dp_pre is None else d_dp_pre
         s = self.shapes
         B, T, L, Tt = s["B"], s["T"], s["L"], s["Tt"]
         d, H, pr, odim = hp["adim"], hp["aheads"], hp["post_encoder_reduction_factor"], hp["odim"]
@@ -677,7 +695,7 @@ class AASVCEngine(EngineBase):
         dr_, dpr, dar = hp["transformer_dec_dropout_rate"], hp["transformer_dec_positional_dropout_rate"], hp["transformer_dec_attn_dropout_rate"]
 
         # ---- postnet + feat_out
-        dbefore = self._postnet_bwd(self.d_after, self.d_before, lambda i: self.named_drop(f"post{i}", hp["postnet_dropout_rate"]))
+        dbefore = self._postnet_bwd(d_after, d_before, lambda i: self.named_drop(f"post{i}", hp["postnet_dropout_rate"]))
         gz = self._scratch("g.zs", (B, L, C))
         self._lin_bwd(dbefore.view(B * L, odim), self.zs.view(B * L, C), self.W("feat_out.weight"), st.g("feat_out.weight"),
                       st.g("feat_out.bias"), dx=gz.view(B * L, C))
@@ -697,7 +715,7 @@ class AASVCEngine(EngineBase):
         k = hp["duration_predictor_kernel_size"]
         halo = (k - 1) // 2
         gcur = self._scratch("g.dp_a", (B, Tt, ch))
-        self._lin_bwd(self.d_dp_pre, self.dp_last.view(B * Tt, ch), self.W("duration_predictor.linear.weight"),
+        self._lin_bwd(d_dp_pre, self.dp_last.view(B * Tt, ch), self.W("duration_predictor.linear.weight"),
                       st.g("duration_predictor.linear.weight"), st.g("duration_predictor.linear.bias"), dx=gcur.view(B * Tt, ch))
         gdpi = None
         for i in reversed(range(hp["duration_predictor_layers"])):
@@ -729,7 +747,7 @@ class AASVCEngine(EngineBase):
         Wm = self._scratch("g.alW", (B, L, ldw))
         rowsum = self._scratch("g.alrow", (B, L), _f32)
         colsum = self._scratch("g.alcol", (B, Tt), _f32)
-        ops.align_logp_bwd(self.d_logp, self.log_p_attn, self.buf("al.lse", (B, L), _f32), self.tlens_dev, Wm, rowsum, colsum)
+        ops.align_logp_bwd(d_logp, self.log_p_attn, self.buf("al.lse", (B, L), _f32), self.tlens_dev, Wm, rowsum, colsum)
         feats = self.buf("al.feats", (B, L, C))
         text = self.buf("al.text", (B, Tt, C))
         dfeats = self._scratch("g.alfeats", (B, L, C))

@@ -297,8 +297,9 @@ __global__ void __launch_bounds__(256) gauss_weights_kernel(const float* __restr
 template <typename T>
 __global__ void __launch_bounds__(256) duration_loss_kernel(const T* __restrict__ pre, const float* __restrict__ ds,
                                                             const int32_t* __restrict__ text_lens, int B, int Tt, float offset,
-                                                            float clamp_max, float gscale, float* __restrict__ d_outs,
-                                                            float* __restrict__ loss, T* __restrict__ d_pre) {
+                                                            float clamp_max, float gscale, const float* __restrict__ g_douts,
+                                                            float* __restrict__ d_outs, float* __restrict__ loss,
+                                                            T* __restrict__ d_pre) {
     __shared__ float red[32];
     __shared__ float s_n;
     float cnt = 0.f;
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(256) duration_loss_kernel(const T* __restrict_
         if (valid) {
             const float diff = d - logf(ds[i] + offset);
             acc += diff * diff;
-            if (x <= clamp_max && nv > 0.f) g = gscale * 2.f * diff / nv;
+            if (x <= clamp_max && nv > 0.f) g = g_douts ? g_douts[i] : gscale * 2.f * diff / nv;
         }
         if (d_pre) d_pre[i] = from_f<T>(g);
     }
@@ -390,12 +391,12 @@ extern "C" int s2s_gauss_weights(const float* ds, const int32_t* feats_lens, con
 }
 
 extern "C" int s2s_duration_loss(const void* pre, const float* ds, const int32_t* text_lens, int B, int T_text, float offset,
-                                 float clamp_max, float grad_scale, float* d_outs, float* loss, void* d_pre, int dtype,
-                                 void* stream) {
+                                 float clamp_max, float grad_scale, const float* g_douts, float* d_outs, float* loss, void* d_pre,
+                                 int dtype, void* stream) {
     S2S_REQUIRE(pre && ds && text_lens && B > 0 && T_text > 0, "duration_loss: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     S2S_DISPATCH_DTYPE(dtype, T, (duration_loss_kernel<T><<<1, 256, 0, st>>>((const T*)pre, ds, text_lens, B, T_text, offset, clamp_max,
-                                                                            grad_scale, d_outs, loss, (T*)d_pre)));
+                                                                            grad_scale, g_douts, d_outs, loss, (T*)d_pre)));
     S2S_LAUNCH_OK();
     return S2S_OK;
 }

@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(128) dwconv_kernel(const T* __restrict__ x, co
 // dw[c,j] += sum_{b,t} dy[b,t,c] * x[b, t+j-pad, c].  blockDim (32 channels, 8 row lanes); grid (C/32, row chunks).
 template <typename T, int KMAX>
 __global__ void __launch_bounds__(256) dwconv_dw_kernel(const T* __restrict__ dy, const T* __restrict__ x, float* __restrict__ dw,
-                                                        int B, int Tn, int C, int K) {
+                                                        float* __restrict__ dbias, int B, int Tn, int C, int K) {
     __shared__ float red[8][32];
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int c = blockIdx.x * 32 + tx;
@@ -207,13 +207,14 @@ __global__ void __launch_bounds__(256) dwconv_dw_kernel(const T* __restrict__ dy
     const long per = (rows + gridDim.y - 1) / gridDim.y;
     const long r0 = (long)blockIdx.y * per;
     const long r1 = (r0 + per < rows) ? r0 + per : rows;
-    float acc[KMAX];
+    float acc[KMAX], accb = 0.f;
 #pragma unroll
     for (int j = 0; j < KMAX; ++j) acc[j] = 0.f;
     if (c < C) {
         for (long r = r0 + ty; r < r1; r += 8) {
             const int t = (int)(r % Tn);
             const float g = to_f<T>(dy[r * C + c]);
+            accb += g;
 #pragma unroll
             for (int j = 0; j < KMAX; ++j) {
                 const int ts = t + j - pad;
@@ -232,6 +233,150 @@ __global__ void __launch_bounds__(256) dwconv_dw_kernel(const T* __restrict__ dy
 #pragma unroll
             for (int q = 0; q < 8; ++q) s += red[q][tx];
             atomicAdd(dw + (long)c * K + j, s);
+        }
+    }
+    if (dbias) {
+        __syncthreads();
+        red[ty][tx] = accb;
+        __syncthreads();
+        if (ty == 0 && c < C) {
+            float s = 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) s += red[q][tx];
+            atomicAdd(dbias + c, s);
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Tiled depthwise conv for the common kernel sizes (K = 7 / 15 / 31): one CTA stages a (TT + K - 1) x 64-channel tile
+// of the input in shared memory with 16-byte coalesced loads (raw dtype), then every thread owns ONE channel and walks
+// its frames with the K weights and a K-deep sliding window in registers: 1 LDS + K FMA per output, HBM sees each
+// input element once (+ (K-1)/TT halo).  FLIP selects the adjoint (dx) form.
+// ---------------------------------------------------------------------------------------------
+template <typename T> struct DwTile { static constexpr int TT = (sizeof(T) == 2) ? 128 : 64; };
+
+template <typename T>
+__device__ __forceinline__ void dw_load_tile(T* __restrict__ dst, const T* __restrict__ src_b, int t_first, int rows, int Tn, int C,
+                                             int c0, bool vec) {
+    constexpr int CH = 64, E = 16 / sizeof(T);          // elements per 16-byte chunk
+    for (int i = threadIdx.x; i < rows * (CH / E); i += blockDim.x) {
+        const int r = i / (CH / E), cg = (i % (CH / E)) * E;
+        const int t = t_first + r;
+        T* d = dst + r * CH + cg;
+        if (t >= 0 && t < Tn && vec && c0 + cg + E <= C) {
+            *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(src_b + (long)t * C + c0 + cg);
+        } else {
+#pragma unroll
+            for (int k = 0; k < E; ++k)
+                d[k] = (t >= 0 && t < Tn && c0 + cg + k < C) ? src_b[(long)t * C + c0 + cg + k] : from_f<T>(0.f);
+        }
+    }
+}
+
+template <typename T, int K, bool FLIP>
+__global__ void __launch_bounds__(256) dwconv_tile_kernel(const T* __restrict__ x, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, T* __restrict__ y, int Tn, int C, int vec) {
+    constexpr int CH = 64, TT = DwTile<T>::TT, G = 4, FR = TT / G, PAD = (K - 1) / 2, ROWS = TT + K - 1;
+    __shared__ __align__(16) T xs[ROWS * CH];
+    const int b = blockIdx.z, t0 = blockIdx.x * TT, c0 = blockIdx.y * CH;
+    const T* xb = x + (long)b * Tn * C;
+    T* yb = y + (long)b * Tn * C;
+    dw_load_tile<T>(xs, xb, t0 - PAD, ROWS, Tn, C, c0, vec != 0);
+    __syncthreads();
+    const int c = threadIdx.x & 63, g = threadIdx.x >> 6;
+    if (c0 + c >= C) return;
+    float wr[K], win[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) wr[j] = w[(long)(c0 + c) * K + (FLIP ? K - 1 - j : j)];
+    const float bv = bias ? bias[c0 + c] : 0.f;
+    const T* xc = xs + (g * FR) * CH + c;
+#pragma unroll
+    for (int j = 0; j < K - 1; ++j) win[j] = to_f<T>(xc[j * CH]);
+    win[K - 1] = 0.f;
+    for (int f0 = 0; f0 < FR; f0 += K) {
+#pragma unroll
+        for (int f = 0; f < K; ++f) {
+            const int fr = f0 + f;
+            if (fr < FR) {
+                win[(f + K - 1) % K] = to_f<T>(xc[(fr + K - 1) * CH]);
+                float acc = bv;
+#pragma unroll
+                for (int j = 0; j < K; ++j) acc = fmaf(wr[j], win[(f + j) % K], acc);
+                const int t = t0 + g * FR + fr;
+                if (t < Tn) yb[(long)t * C + c0 + c] = from_f<T>(acc);
+            }
+        }
+    }
+}
+
+// dw[c,j] += sum_{b,t} dy[b,t,c] x[b,t+j-pad,c], dbias[c] += sum dy: one CTA per (64-channel tile, utterance[, time split]),
+// looping over time tiles with both operands staged in shared memory; K + 1 register accumulators per thread.
+template <typename T, int K>
+__global__ void __launch_bounds__(256) dwconv_dw_tile_kernel(const T* __restrict__ dy, const T* __restrict__ x, float* __restrict__ dw,
+                                                             float* __restrict__ dbias, int Tn, int C, int vec, int tiles_per_cta) {
+    constexpr int CH = 64, TT = DwTile<T>::TT, G = 4, FR = TT / G, PAD = (K - 1) / 2, ROWS = TT + K - 1;
+    __shared__ __align__(16) T tile[(ROWS + TT) * CH];
+    static_assert(sizeof(T) * (ROWS + TT) * CH >= sizeof(float) * (G - 1) * (K + 1) * CH, "reduction scratch must fit in the tiles");
+    T* xs = tile;
+    T* gs = tile + ROWS * CH;
+    const int b = blockIdx.z, c0 = blockIdx.x * CH;
+    const T* xb = x + (long)b * Tn * C;
+    const T* gb = dy + (long)b * Tn * C;
+    const int c = threadIdx.x & 63, g = threadIdx.x >> 6;
+    float acc[K], accb = 0.f, win[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) acc[j] = 0.f;
+    const int tile0 = blockIdx.y * tiles_per_cta;
+    for (int tile = tile0; tile < tile0 + tiles_per_cta; ++tile) {
+        const int t0 = tile * TT;
+        if (t0 >= Tn) break;
+        __syncthreads();
+        dw_load_tile<T>(xs, xb, t0 - PAD, ROWS, Tn, C, c0, vec != 0);
+        dw_load_tile<T>(gs, gb, t0, TT, Tn, C, c0, vec != 0);
+        __syncthreads();
+        const T* xc = xs + (g * FR) * CH + c;
+        const T* gc = gs + (g * FR) * CH + c;
+#pragma unroll
+        for (int j = 0; j < K - 1; ++j) win[j] = to_f<T>(xc[j * CH]);
+        win[K - 1] = 0.f;
+        for (int f0 = 0; f0 < FR; f0 += K) {
+#pragma unroll
+            for (int f = 0; f < K; ++f) {
+                const int fr = f0 + f;
+                if (fr < FR) {
+                    win[(f + K - 1) % K] = to_f<T>(xc[(fr + K - 1) * CH]);
+                    const float gv = to_f<T>(gc[fr * CH]);          // rows past T_n are zero in the tile
+                    accb += gv;
+#pragma unroll
+                    for (int j = 0; j < K; ++j) acc[j] = fmaf(gv, win[(f + j) % K], acc[j]);
+                }
+            }
+        }
+    }
+    // cross-group reduction through shared memory (re-using the x tile), then one atomic per (channel, tap)
+    __syncthreads();
+    float* red = reinterpret_cast<float*>(tile);                     // [(G-1)][K+1][CH] floats
+    if (g > 0) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) red[((g - 1) * (K + 1) + j) * CH + c] = acc[j];
+        red[((g - 1) * (K + 1) + K) * CH + c] = accb;
+    }
+    __syncthreads();
+    if (g == 0 && c0 + c < C) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            float v = acc[j];
+#pragma unroll
+            for (int q = 0; q < G - 1; ++q) v += red[(q * (K + 1) + j) * CH + c];
+            atomicAdd(dw + (long)(c0 + c) * K + j, v);
+        }
+        if (dbias) {
+            float v = accb;
+#pragma unroll
+            for (int q = 0; q < G - 1; ++q) v += red[(q * (K + 1) + K) * CH + c];
+            atomicAdd(dbias + c0 + c, v);
         }
     }
 }
@@ -423,45 +568,89 @@ extern "C" int s2s_glu_bwd(const void* dy, const void* x, void* dx, int64_t rows
     return S2S_OK;
 }
 
+template <typename TY, bool FLIP>
+static bool launch_dwconv_tile(const TY* x, const float* w, const float* bias, TY* y, int B, int T, int C, int K, cudaStream_t st) {
+    constexpr int TT = DwTile<TY>::TT;
+    if (B > 65535) return false;
+    dim3 grid((unsigned)ceil_div_l(T, TT), (unsigned)ceil_div_l(C, 64), (unsigned)B);
+    const int vec = (C % (16 / (int)sizeof(TY)) == 0) && aligned16(x, y);
+    if (K == 7) dwconv_tile_kernel<TY, 7, FLIP><<<grid, 256, 0, st>>>(x, w, bias, y, T, C, vec);
+    else if (K == 15) dwconv_tile_kernel<TY, 15, FLIP><<<grid, 256, 0, st>>>(x, w, bias, y, T, C, vec);
+    else if (K == 31) dwconv_tile_kernel<TY, 31, FLIP><<<grid, 256, 0, st>>>(x, w, bias, y, T, C, vec);
+    else return false;
+    return true;
+}
+
+template <typename TY>
+static bool launch_dwconv_dw_tile(const TY* dy, const TY* x, float* dw, float* dbias, int B, int T, int C, int K, cudaStream_t st) {
+    constexpr int TT = DwTile<TY>::TT;
+    if (B > 65535) return false;
+    const int tiles = (int)ceil_div_l(T, TT);
+    const long ctas_full = ceil_div_l(C, 64) * B;
+    int split = 1;                                         // split time only when (channel tiles x utterances) cannot fill the chip
+    while (ctas_full * split < 2L * num_sms() && split < tiles) split *= 2;
+    const int per = (int)ceil_div_l(tiles, split);
+    dim3 grid((unsigned)ceil_div_l(C, 64), (unsigned)ceil_div_l(tiles, per), (unsigned)B);
+    const int vec = (C % (16 / (int)sizeof(TY)) == 0) && aligned16(x, dy);
+    if (K == 7) dwconv_dw_tile_kernel<TY, 7><<<grid, 256, 0, st>>>(dy, x, dw, dbias, T, C, vec, per);
+    else if (K == 15) dwconv_dw_tile_kernel<TY, 15><<<grid, 256, 0, st>>>(dy, x, dw, dbias, T, C, vec, per);
+    else if (K == 31) dwconv_dw_tile_kernel<TY, 31><<<grid, 256, 0, st>>>(dy, x, dw, dbias, T, C, vec, per);
+    else return false;
+    return true;
+}
+
 extern "C" int s2s_dwconv_fwd(const void* x, const float* w, const float* bias, void* y, int B, int T, int C, int K,
                               int dtype, void* stream) {
     S2S_REQUIRE(x && w && y && B > 0 && T > 0 && C > 0 && K > 0 && (K & 1), "dwconv_fwd: bad arguments (odd K required)");
     cudaStream_t st = (cudaStream_t)stream;
-    bool ok = vec8_ok(C, C, x, y);
-    const int TT = 16;
-    long items = (long)B * ceil_div_l(T, TT) * (C / (ok ? 8 : 1));
-    S2S_DISPATCH_DTYPE(dtype, TY, S2S_VEC8_DISPATCH(ok, VEC, (dwconv_kernel<TY, VEC, false><<<ew_grid(items, 128), 128, 0, st>>>(
-        (const TY*)x, w, bias, (TY*)y, B, T, C, K, TT))));
+    bool done = false;
+    S2S_DISPATCH_DTYPE(dtype, TY, done = launch_dwconv_tile<TY, false>((const TY*)x, w, bias, (TY*)y, B, T, C, K, st));
+    if (!done) {
+        bool ok = vec8_ok(C, C, x, y);
+        const int TT = 16;
+        long items = (long)B * ceil_div_l(T, TT) * (C / (ok ? 8 : 1));
+        S2S_DISPATCH_DTYPE(dtype, TY, S2S_VEC8_DISPATCH(ok, VEC, (dwconv_kernel<TY, VEC, false><<<ew_grid(items, 128), 128, 0, st>>>(
+            (const TY*)x, w, bias, (TY*)y, B, T, C, K, TT))));
+    }
     S2S_LAUNCH_OK();
     return S2S_OK;
 }
 
-extern "C" int s2s_dwconv_bwd(const void* dy, const void* x, const float* w, void* dx, float* dw, int B, int T, int C, int K,
-                              int dtype, void* stream) {
+extern "C" int s2s_dwconv_bwd(const void* dy, const void* x, const float* w, void* dx, float* dw, float* dbias, int B, int T,
+                              int C, int K, int dtype, void* stream) {
     S2S_REQUIRE(dy && x && w && B > 0 && T > 0 && C > 0 && K > 0 && (K & 1) && K <= 63, "dwconv_bwd: bad arguments (odd K <= 63)");
+    S2S_REQUIRE(dbias == nullptr || dw != nullptr, "dwconv_bwd: dbias is produced together with dw");
     cudaStream_t st = (cudaStream_t)stream;
     if (dx) {
-        bool ok = vec8_ok(C, C, dy, dx);
-        const int TT = 16;
-        long items = (long)B * ceil_div_l(T, TT) * (C / (ok ? 8 : 1));
-        S2S_DISPATCH_DTYPE(dtype, TY, S2S_VEC8_DISPATCH(ok, VEC, (dwconv_kernel<TY, VEC, true><<<ew_grid(items, 128), 128, 0, st>>>(
-            (const TY*)dy, w, nullptr, (TY*)dx, B, T, C, K, TT))));
+        bool done = false;
+        S2S_DISPATCH_DTYPE(dtype, TY, done = launch_dwconv_tile<TY, true>((const TY*)dy, w, nullptr, (TY*)dx, B, T, C, K, st));
+        if (!done) {
+            bool ok = vec8_ok(C, C, dy, dx);
+            const int TT = 16;
+            long items = (long)B * ceil_div_l(T, TT) * (C / (ok ? 8 : 1));
+            S2S_DISPATCH_DTYPE(dtype, TY, S2S_VEC8_DISPATCH(ok, VEC, (dwconv_kernel<TY, VEC, true><<<ew_grid(items, 128), 128, 0, st>>>(
+                (const TY*)dy, w, nullptr, (TY*)dx, B, T, C, K, TT))));
+        }
         S2S_LAUNCH_OK();
     }
     if (dw) {
-        unsigned gx = (unsigned)ceil_div_l(C, 32);
-        long rows = (long)B * T;
-        long want = (long)num_sms() * 4 / gx;
-        if (want < 1) want = 1;
-        long maxy = ceil_div_l(rows, 64);
-        if (want > maxy) want = maxy;
-        dim3 grid(gx, (unsigned)want), block(32, 8);
-        S2S_DISPATCH_DTYPE(dtype, TY, {
-            if (K <= 7) dwconv_dw_kernel<TY, 7><<<grid, block, 0, st>>>((const TY*)dy, (const TY*)x, dw, B, T, C, K);
-            else if (K <= 15) dwconv_dw_kernel<TY, 15><<<grid, block, 0, st>>>((const TY*)dy, (const TY*)x, dw, B, T, C, K);
-            else if (K <= 31) dwconv_dw_kernel<TY, 31><<<grid, block, 0, st>>>((const TY*)dy, (const TY*)x, dw, B, T, C, K);
-            else dwconv_dw_kernel<TY, 63><<<grid, block, 0, st>>>((const TY*)dy, (const TY*)x, dw, B, T, C, K);
-        });
+        bool done = false;
+        S2S_DISPATCH_DTYPE(dtype, TY, done = launch_dwconv_dw_tile<TY>((const TY*)dy, (const TY*)x, dw, dbias, B, T, C, K, st));
+        if (!done) {
+            unsigned gx = (unsigned)ceil_div_l(C, 32);
+            long rows = (long)B * T;
+            long want = (long)num_sms() * 4 / gx;
+            if (want < 1) want = 1;
+            long maxy = ceil_div_l(rows, 64);
+            if (want > maxy) want = maxy;
+            dim3 grid(gx, (unsigned)want), block(32, 8);
+            S2S_DISPATCH_DTYPE(dtype, TY, {
+                if (K <= 7) dwconv_dw_kernel<TY, 7><<<grid, block, 0, st>>>((const TY*)dy, (const TY*)x, dw, dbias, B, T, C, K);
+                else if (K <= 15) dwconv_dw_kernel<TY, 15><<<grid, block, 0, st>>>((const TY*)dy, (const TY*)x, dw, dbias, B, T, C, K);
+                else if (K <= 31) dwconv_dw_kernel<TY, 31><<<grid, block, 0, st>>>((const TY*)dy, (const TY*)x, dw, dbias, B, T, C, K);
+                else dwconv_dw_kernel<TY, 63><<<grid, block, 0, st>>>((const TY*)dy, (const TY*)x, dw, dbias, B, T, C, K);
+            });
+        }
         S2S_LAUNCH_OK();
     }
     return S2S_OK;

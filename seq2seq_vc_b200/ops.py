@@ -439,11 +439,11 @@ def dwconv_fwd(x, w, bias, y):
     return y
 
 
-def dwconv_bwd(dy, x, w, dx, dw):
+def dwconv_bwd(dy, x, w, dx, dw, dbias=None):
     B, T, C = x.shape
     K = w.shape[-1]
     assert dy.is_contiguous() and x.is_contiguous() and (dx is None or dx.is_contiguous())
-    check(_L().s2s_dwconv_bwd(ptr(dy), ptr(x), ptr(w), ptr(dx), ptr(dw), B, T, C, K, dt(x), stream()), "dwconv_bwd")
+    check(_L().s2s_dwconv_bwd(ptr(dy), ptr(x), ptr(w), ptr(dx), ptr(dw), ptr(dbias), B, T, C, K, dt(x), stream()), "dwconv_bwd")
 
 
 def swish_fwd(x, y, drop: Drop = NO_DROP):
@@ -521,8 +521,9 @@ def gauss_weights(ds, feats_lens, text_lens, P, delta=0.1):
     return P
 
 
-def duration_loss(pre, ds, text_lens, d_outs, loss, d_pre, grad_scale=1.0, offset=1.0, clamp_max=10.0):
+def duration_loss(pre, ds, text_lens, d_outs, loss, d_pre, grad_scale=1.0, offset=1.0, clamp_max=10.0, g_douts=None):
     B, TT = ds.shape
     assert pre.is_contiguous() and ds.is_contiguous() and pre.numel() == B * TT
+    assert g_douts is None or (g_douts.dtype == torch.float32 and g_douts.is_contiguous() and g_douts.numel() == B * TT)
     check(_L().s2s_duration_loss(ptr(pre), ptr(ds), ptr(text_lens), B, TT, float(offset), float(clamp_max), float(grad_scale),
-                                 ptr(d_outs), ptr(loss), ptr(d_pre), dt(pre), stream()), "duration_loss")
+                                 ptr(g_douts), ptr(d_outs), ptr(loss), ptr(d_pre), dt(pre), stream()), "duration_loss")

@@ -474,7 +474,7 @@ def dwconv_fwd(x, w, bias, y):
     return y
 
 
-def dwconv_bwd(dy, x, w, dx, dw):
+def dwconv_bwd(dy, x, w, dx, dw, dbias=None):
     C, K = x.shape[-1], w.shape[-1]
     xd = x.double().transpose(1, 2).requires_grad_(True)
     wd = w.double().reshape(C, 1, K).requires_grad_(True)
@@ -484,6 +484,8 @@ def dwconv_bwd(dy, x, w, dx, dw):
         dx.copy_(gx.transpose(1, 2).to(dx.dtype))
     if dw is not None:
         dw += gw.reshape(dw.shape).float()
+    if dbias is not None:
+        dbias += dy.double().reshape(-1, C).sum(0).float()
 
 
 def swish_fwd(x, y, drop=NO_DROP):
@@ -583,7 +585,7 @@ def gauss_weights(ds, feats_lens, text_lens, P, delta=0.1):
     return P
 
 
-def duration_loss(pre, ds, text_lens, d_outs, loss, d_pre, grad_scale=1.0, offset=1.0, clamp_max=10.0):
+def duration_loss(pre, ds, text_lens, d_outs, loss, d_pre, grad_scale=1.0, offset=1.0, clamp_max=10.0, g_douts=None):
     B, TT = ds.shape
     valid = torch.arange(TT)[None, :] < text_lens.long()[:, None]
     x = pre.double().reshape(B, TT) * valid
@@ -595,7 +597,8 @@ def duration_loss(pre, ds, text_lens, d_outs, loss, d_pre, grad_scale=1.0, offse
     if loss is not None:
         loss.fill_(float((diff ** 2).sum() / n))
     if d_pre is not None:
-        d_pre.copy_((grad_scale * 2 * diff / n * (x <= clamp_max)).reshape(d_pre.shape).to(d_pre.dtype))
+        g = grad_scale * 2 * diff / n if g_douts is None else g_douts.double().reshape(B, TT) * valid
+        d_pre.copy_((g * (x <= clamp_max)).reshape(d_pre.shape).to(d_pre.dtype))
 
 
 def mas(log_p, text_lens, feats_lens, want_grad=False):

@@ -81,3 +81,76 @@ def test_two_rank_step_matches_mean_gradient_step(tmp_path, monkeypatch):
         ref.lr_dev.fill_(stepper.lr_at(stepper.steps))
         ref.optimizer_step(1.0)
     assert (ref.store.P - p0).abs().max().item() <= 1e-6
+
+
+# ---------------------------------------------------------------------------------------------- AAS-VC (same sharding rule)
+AAS_HP = dict(idim=80, odim=80, adim=32, aheads=2, elayers=1, eunits=48, dlayers=1, dunits=48, duration_predictor_input_dim=80,
+              duration_predictor_layers=2, duration_predictor_chans=16, duration_predictor_kernel_size=3, postnet_layers=2,
+              postnet_filts=5, postnet_chans=16, post_encoder_reduction_factor=4, conformer_enc_kernel_size=7,
+              conformer_dec_kernel_size=7, transformer_enc_dropout_rate=0.0, transformer_enc_positional_dropout_rate=0.0,
+              transformer_enc_attn_dropout_rate=0.0, transformer_dec_dropout_rate=0.0, transformer_dec_positional_dropout_rate=0.0,
+              transformer_dec_attn_dropout_rate=0.0, duration_predictor_dropout_rate=0.0, postnet_dropout_rate=0.0)
+
+
+def _install_fakes_all():
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    import fake_ops
+    import seq2seq_vc_b200.ops as ops
+
+    for n in fake_ops.ALL:
+        if hasattr(ops, n) and n != "logmel":
+            setattr(ops, n, getattr(fake_ops, n))
+
+
+def _aas_batch(rank):
+    from oracle import aasvc_oracle
+
+    return aasvc_oracle.synthetic_batch(2, 44, 36, ilens=[44, 37], olens=[36, 29], seed=200 + rank)
+
+
+def _aas_worker(rank, world, port, out_dir):
+    _install_fakes_all()
+    import torch.distributed as dist
+
+    from seq2seq_vc_b200 import AASVCEngine, AASVCTrainStep
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    eng = AASVCEngine(AAS_HP, device="cpu", bf16=False, seed=5)
+    step = AASVCTrainStep(eng, lr=1e-3, warmup_steps=1, use_graph=False)
+    xs, ilens, ys, olens, dpi = _aas_batch(rank)
+    for _ in range(2):
+        step(xs, ilens, ys, olens, dpi)
+    torch.save(eng.store.P.clone(), os.path.join(out_dir, f"a{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_aasvc_two_rank_step_matches_mean_gradient_step(tmp_path, monkeypatch):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_aas_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    p0, p1 = torch.load(tmp_path / "a0.pt"), torch.load(tmp_path / "a1.pt")
+    assert torch.equal(p0, p1), "replicas diverged"
+
+    import fake_ops
+    from seq2seq_vc_b200 import AASVCEngine, AASVCTrainStep
+
+    fake_ops.install(monkeypatch)
+    engs = [AASVCEngine(AAS_HP, device="cpu", bf16=False, seed=5) for _ in range(2)]
+    ref = AASVCEngine(AAS_HP, device="cpu", bf16=False, seed=5)
+    stepper = AASVCTrainStep(ref, lr=1e-3, warmup_steps=1)
+    for it in range(2):
+        g = torch.zeros_like(ref.store.G)
+        for r, e in enumerate(engs):
+            e.store.P.copy_(ref.store.P)
+            xs, ilens, ys, olens, dpi = _aas_batch(r)
+            e.forward(xs, ys, dpi, ilens, olens)
+            e.loss(ys, duration_loss=it > 0)          # trainers/aas_vc.py:113: no duration loss at step 0
+            e.backward()
+            g += e.store.G
+        ref.store.G.copy_(g / 2)
+        stepper.steps += 1
+        ref.lr_dev.fill_(stepper.lr_at(stepper.steps))
+        ref.optimizer_step(1.0)
+    assert (ref.store.P - p0).abs().max().item() <= 1e-6

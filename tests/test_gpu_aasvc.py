@@ -133,19 +133,21 @@ def test_swish_dropout_fwd_bwd_consistency(ops):
 
 
 @pytest.mark.parametrize("dt", DT)
-@pytest.mark.parametrize("B,T,C,K", [(2, 19, 12, 7), (3, 50, 32, 15), (2, 40, 384, 31), (2, 9, 16, 15)])
+@pytest.mark.parametrize("B,T,C,K", [(2, 19, 12, 7), (3, 50, 32, 15), (2, 40, 384, 31), (2, 9, 16, 15), (2, 300, 72, 15), (1, 131, 64, 5),
+                                      (3, 257, 136, 7)])
 def test_dwconv_fwd_bwd(ops, dt, B, T, C, K):
     x, w, bias = rnd(B, T, C, dt=dt, seed=1), rnd(C, K, seed=2, scale=0.3), rnd(C, seed=3)
     y = F.dwconv_fwd(x, w, bias, torch.empty(B, T, C, dtype=dt))
     gy = ops.dwconv_fwd(x.cuda(), w.cuda(), bias.cuda(), torch.empty(B, T, C, dtype=dt, device="cuda"))
     close(gy, y, tol(dt, 4), "dwconv_fwd")
     dy = rnd(B, T, C, dt=dt, seed=4)
-    dx, dw = torch.empty(B, T, C, dtype=dt), torch.zeros(C, K)
-    F.dwconv_bwd(dy, x, w, dx, dw)
-    gdx, gdw = torch.empty(B, T, C, dtype=dt, device="cuda"), torch.zeros(C, K, device="cuda")
-    ops.dwconv_bwd(dy.cuda(), x.cuda(), w.cuda(), gdx, gdw)
+    dx, dw, db = torch.empty(B, T, C, dtype=dt), torch.zeros(C, K), torch.zeros(C)
+    F.dwconv_bwd(dy, x, w, dx, dw, db)
+    gdx, gdw, gdb = torch.empty(B, T, C, dtype=dt, device="cuda"), torch.zeros(C, K, device="cuda"), torch.zeros(C, device="cuda")
+    ops.dwconv_bwd(dy.cuda(), x.cuda(), w.cuda(), gdx, gdw, gdb)
     close(gdx, dx, tol(dt, 4), "dwconv dx")
     close(gdw, dw, tol(torch.float32, 20) * math.sqrt(B * T), "dwconv dw")
+    close(gdb, db, tol(torch.float32, 20) * math.sqrt(B * T), "dwconv dbias")
 
 
 @pytest.mark.parametrize("dt", DT)
@@ -393,3 +395,78 @@ def test_dropout_training_step_runs_and_is_reproducible():
     eng.seed_dev += 1
     a3, _, _ = _step(eng, z)
     assert not torch.equal(a1, a3)
+
+
+def test_dropin_module_losses_and_autograd():
+    """seq2seq_vc_b200.AASVC + L1Loss + ForwardSumLoss + DurationPredictorLoss used exactly as AASVCTrainer._train_step
+    uses the reference classes (trainers/aas_vc.py:56-134): same kwargs, dict keys, state-dict names; gradients through
+    torch autograd match the live-reference dump."""
+    from seq2seq_vc_b200 import AASVC, DurationPredictorLoss, ForwardSumLoss, L1Loss
+
+    z, sd = _golden()
+    model = AASVC(**AAS_HP, **NO_DROPOUT, positionwise_layer_type="linear", positionwise_conv_kernel_size=1,
+                  duration_predictor_use_encoder_outputs=False, encoder_normalize_before=True, decoder_normalize_before=True,
+                  duration_predictor_type="deterministic", encoder_input_layer="linear", init_type="xavier_uniform", use_masking=True,
+                  encoder_input_conv_kernel_size=3, prodiff_denoiser_layers=20).to("cuda:0")
+    assert set(model.state_dict().keys()) == set(sd.keys())
+    model.load_state_dict(sd)
+    model.train()
+    ilens, olens = torch.from_numpy(z["ilens"]), torch.from_numpy(z["olens"])
+    xs, ys, dpi = (torch.from_numpy(z[k]).cuda() for k in ("xs", "ys", "dp_inputs"))
+    ret = model(xs, ilens, ys, olens, dpi, dp_lengths=ilens)
+    assert set(ret) >= {"before_outs", "after_outs", "ds", "ilens", "olens", "olens_reduced", "ys", "bin_loss", "log_p_attn", "d_outs"}
+    assert np.abs(ret["after_outs"].detach().cpu().numpy() - z["after_outs"]).mean() <= 1e-4
+    np.testing.assert_array_equal(ret["ds"].cpu().numpy(), z["ds"])
+    assert ret["ilens"].tolist() == z["ilens_out"].tolist() and ret["olens"].tolist() == z["olens_out"].tolist()
+    l1 = L1Loss()(ret["after_outs"], ret["before_outs"], ret["ys"], ret["olens"])
+    fs = ForwardSumLoss()(ret["log_p_attn"], ret["ilens"], ret["olens_reduced"])
+    dur = DurationPredictorLoss()(ret["d_outs"], ret["ds"], ret["ilens"])
+    for got, k in ((l1, "l1_loss"), (fs, "forward_sum_loss"), (ret["bin_loss"], "bin_loss"), (dur, "duration_loss")):
+        assert abs(got.item() - float(z[k])) <= 1e-4 * max(1.0, abs(float(z[k]))), k
+    (l1 + 2.0 * (fs + ret["bin_loss"]) + dur).backward()
+    gmax = max(np.abs(z[k]).max() for k in z.files if k.startswith("grad."))
+    for name, p in model.named_parameters():
+        ref = z["grad." + name]
+        assert p.grad is not None, name
+        assert np.abs(p.grad.cpu().numpy() - ref).max() <= 1e-3 * np.abs(ref).max() + 1e-5 * gmax, name
+    att = model.encoder.encoders[0].self_attn.attn
+    assert att is not None and tuple(att.shape) == tuple(z["attn.encoder.encoders.0.self_attn"].shape)
+    # an optimizer step through the stock torch optimizer moves the engine's flat parameters (shared storage)
+    before = model.engine.store.P.clone()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+    opt.step()
+    assert not torch.equal(before, model.engine.store.P)
+
+
+def test_fused_train_step_graph_matches_eager():
+    """AASVCTrainStep: CUDA-graph replay == eager launches (same seeds, dropout on), losses finite, parameters move."""
+    from seq2seq_vc_b200 import AASVCEngine, AASVCTrainStep
+
+    z, sd = _golden()
+    ilens, olens = z["ilens"].tolist(), z["olens"].tolist()
+    xs, ys, dpi = (torch.from_numpy(z[k]).cuda() for k in ("xs", "ys", "dp_inputs"))
+    outs = []
+    for use_graph in (False, True):
+        eng = AASVCEngine(dict(AAS_HP), device="cuda:0", bf16=False, seed=11)
+        eng.load_state_dict(sd)
+        st = AASVCTrainStep(eng, lr=1e-3, warmup_steps=10, use_graph=use_graph)
+        ls = []
+        for _ in range(4):
+            ls.append(st(xs, ilens, ys, olens, dpi).clone())
+        torch.cuda.synchronize()
+        outs.append((torch.stack(ls).cpu(), eng.store.P.clone().cpu()))
+    assert torch.isfinite(outs[0][0]).all() and torch.isfinite(outs[1][0]).all()
+    # step 0 runs without the duration loss in both modes; replays see fresh dropout seeds exactly like eager steps
+    assert (outs[0][0] - outs[1][0]).abs().max().item() <= 5e-3 * outs[0][0].abs().max().item()
+    assert (outs[0][1] - outs[1][1]).abs().max().item() <= 1e-4
+    assert (outs[0][1] - sd_flat_like(outs[0][1], sd)).abs().max().item() > 0
+
+
+def sd_flat_like(flat, sd):
+    """Flat parameter vector of the initial state (for 'did anything move' checks)."""
+    from seq2seq_vc_b200 import AASVCEngine
+
+    eng = AASVCEngine(dict(AAS_HP), device="cpu", bf16=False, seed=11)
+    eng.load_state_dict(sd)
+    return eng.store.P.clone()
