@@ -178,7 +178,7 @@ __device__ __forceinline__ uint32_t mix32(uint32_t h) {
 struct Dropout {
     float p;          // drop probability; 0 disables
     float scale;      // 1/(1-p)
-    uint32_t thresh;  // drop if rnd < thresh
+    uint32_t thresh;  // non-zero when dropout is active; a 16-bit lane is dropped iff lane < thresh (= round(p * 2^16))
     uint64_t key;     // mixes seed and stream
     const uint64_t* seed_dev;  // optional device-resident seed increment (CUDA-graph replays)
 };
@@ -187,8 +187,8 @@ inline Dropout make_dropout(const s2s_dropout_t* d) {
     float p = d ? d->p : 0.f;
     r.p = p;
     r.scale = (p > 0.f && p < 1.f) ? 1.f / (1.f - p) : 1.f;
-    double t = (double)p * 4294967296.0;
-    r.thresh = (p <= 0.f) ? 0u : (t >= 4294967295.0 ? 4294967295u : (uint32_t)t);
+    double t = (double)p * 65536.0 + 0.5;
+    r.thresh = (p <= 0.f) ? 0u : (t >= 65535.0 ? 65535u : (t < 1.0 ? 1u : (uint32_t)t));
     uint64_t seed = d ? d->seed : 0, stream_id = d ? d->stream : 0;
     r.key = seed * 0x9e3779b97f4a7c15ull + stream_id * 0xd1b54a32d192ed03ull + 0x2545f4914f6cdd1dull;
     r.seed_dev = d ? d->seed_dev : nullptr;
@@ -198,14 +198,35 @@ inline Dropout make_dropout(const s2s_dropout_t* d) {
 __device__ __forceinline__ void dropout_resolve(Dropout& d) {
     if (d.thresh != 0u && d.seed_dev) d.key += (*d.seed_dev) * 0x9e3779b97f4a7c15ull;
 }
+// One 32-bit hash serves the element PAIR (idx >> 1): the integer pipe, not HBM, bounds a per-element hash at
+// these tensor sizes (75 M elements x 14 integer ops).  Two keyed murmur rounds over the folded pair index.
+__device__ __forceinline__ uint32_t dropout_hash(const Dropout& d, uint64_t pair) {
+    uint32_t h = (uint32_t)pair * 0x9e3779b1u + (uint32_t)(pair >> 32) * 0x85ebca77u + (uint32_t)d.key;
+    h = mix32(h) + (uint32_t)(d.key >> 32);
+    return mix32(h);
+}
 // returns the multiplicative factor (0 or scale) for element idx
 __device__ __forceinline__ float dropout_factor(const Dropout& d, uint64_t idx) {
     if (d.thresh == 0u) return 1.f;
-    // two keyed rounds over the folded 64-bit element index
-    uint32_t h = (uint32_t)idx * 0x9e3779b1u + (uint32_t)(idx >> 32) * 0x85ebca77u + (uint32_t)d.key;
-    h = mix32(h) + (uint32_t)(d.key >> 32);
-    h = mix32(h);
-    return (h < d.thresh) ? 0.f : d.scale;
+    const uint32_t h = dropout_hash(d, idx >> 1);
+    const uint32_t lane = (idx & 1) ? (h >> 16) : (h & 0xffffu);
+    return (lane < d.thresh) ? 0.f : d.scale;
+}
+// factors of N consecutive elements starting at an EVEN index (N even): one hash per pair
+template <int N>
+__device__ __forceinline__ void dropout_factors(const Dropout& d, uint64_t idx, float (&m)[N]) {
+    static_assert(N % 2 == 0, "pairs");
+    if (d.thresh == 0u) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) m[k] = 1.f;
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < N; k += 2) {
+        const uint32_t h = dropout_hash(d, (idx + k) >> 1);
+        m[k] = ((h & 0xffffu) < d.thresh) ? 0.f : d.scale;
+        m[k + 1] = ((h >> 16) < d.thresh) ? 0.f : d.scale;
+    }
 }
 
 // grid size for grid-stride elementwise kernels: enough CTAs to fill the chip a few times over

@@ -396,10 +396,13 @@ __global__ void __launch_bounds__(256) swish_kernel(const T* __restrict__ g, con
             if constexpr (VEC == 8) ld8<T>(g + i * 8, reinterpret_cast<float(&)[8]>(d));
             else d[0] = to_f<T>(g[i]);
         }
+        float mk[8];
+        if constexpr (VEC == 8) dropout_factors<8>(drop, (uint64_t)i * 8, mk);
+        else mk[0] = dropout_factor(drop, (uint64_t)i);
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
             const float s = sigmoidf_(a[k]);
-            const float m = dropout_factor(drop, (uint64_t)(i * VEC + k));
+            const float m = mk[k];
             a[k] = BWD ? d[k] * m * (s + a[k] * s * (1.f - s)) : a[k] * s * m;
         }
         if constexpr (VEC == 8) st8<T>(out + i * 8, reinterpret_cast<float(&)[8]>(a));
@@ -417,11 +420,16 @@ __global__ void __launch_bounds__(256) scale_dropout_kernel(const T* __restrict_
         float a[VEC];
         if constexpr (VEC == 8) ld8<T>(x + i * 8, reinterpret_cast<float(&)[8]>(a));
         else a[0] = to_f<T>(x[i]);
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) {
-            const uint64_t idx = (uint64_t)(i * VEC + k);
-            a[k] *= scale * dropout_factor(d1, idx) * dropout_factor(d2, idx);
+        float m1[8], m2[8];
+        if constexpr (VEC == 8) {
+            dropout_factors<8>(d1, (uint64_t)i * 8, m1);
+            dropout_factors<8>(d2, (uint64_t)i * 8, m2);
+        } else {
+            m1[0] = dropout_factor(d1, (uint64_t)i);
+            m2[0] = dropout_factor(d2, (uint64_t)i);
         }
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) a[k] *= scale * m1[k] * m2[k];
         if constexpr (VEC == 8) st8<T>(y + i * 8, reinterpret_cast<float(&)[8]>(a));
         else y[i] = from_f<T>(a[0]);
     }

@@ -11,6 +11,10 @@ template <typename T> struct VLoad<T, 4> {
     static __device__ __forceinline__ void ld(const T* p, float (&v)[4]) { Vec4<T>::load(p, v); }
     static __device__ __forceinline__ void st(T* p, const float (&v)[4]) { Vec4<T>::store(p, v); }
 };
+template <typename T> struct VLoad<T, 8> {
+    static __device__ __forceinline__ void ld(const T* p, float (&v)[8]) { Vec8<T>::load(p, v); }
+    static __device__ __forceinline__ void st(T* p, const float (&v)[8]) { Vec8<T>::store(p, v); }
+};
 template <typename T> struct VLoad<T, 1> {
     static __device__ __forceinline__ void ld(const T* p, float (&v)[1]) { v[0] = to_f<T>(*p); }
     static __device__ __forceinline__ void st(T* p, const float (&v)[1]) { *p = from_f<T>(v[0]); }
@@ -105,6 +109,142 @@ __global__ void __launch_bounds__(128) ln_bwd_dx_kernel(const T* __restrict__ dy
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Row-in-registers LayerNorm (d % 8 == 0, d <= 2048): x (and dy) are read from HBM once with 16-byte loads.
+// Rows stay PACKED in registers (4 registers per 8 bf16) and are decoded on each use: the register footprint, not the
+// arithmetic, decides how many rows an SM keeps in flight.  dgamma / dbeta come from the 8-wide column reduction below
+// (a register-accumulating fused variant was measured slower: 255 registers -> 8 warps per SM).
+// ---------------------------------------------------------------------------------------------
+// raw 16-byte row chunks: 8 bf16 in 4 registers (decoded on every use) or 8 floats in 8 registers
+template <typename T> struct Raw8;
+template <> struct Raw8<bf16> {
+    uint4 r;
+    __device__ __forceinline__ void load(const bf16* p) { r = *reinterpret_cast<const uint4*>(p); }
+    __device__ __forceinline__ void get(float (&v)[8]) const {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
+    }
+};
+template <> struct Raw8<float> {
+    float4 a, b;
+    __device__ __forceinline__ void load(const float* p) { a = reinterpret_cast<const float4*>(p)[0]; b = reinterpret_cast<const float4*>(p)[1]; }
+    __device__ __forceinline__ void get(float (&v)[8]) const {
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+};
+
+template <typename T, int NV>
+__global__ void __launch_bounds__(256) ln_fwd_reg_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, T* __restrict__ y, float* __restrict__ mean,
+                                                         float* __restrict__ rstd, long rows, int d, float eps) {
+    const int lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const T* xr = x + row * d;
+    Raw8<T> raw[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int c = (j * 32 + lane) * 8;
+        if (c < d) {
+            float v[8];
+            raw[j].load(xr + c);
+            raw[j].get(v);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s += v[k];
+        }
+    }
+    const float mu = warp_sum(s) / (float)d;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int c = (j * 32 + lane) * 8;
+        if (c < d) {
+            float v[8];
+            raw[j].get(v);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { const float t = v[k] - mu; q += t * t; }
+        }
+    }
+    const float rs = rsqrtf(warp_sum(q) / (float)d + eps);
+    T* yr = y + row * d;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int c = (j * 32 + lane) * 8;
+        if (c < d) {
+            float v[8], gm[8], bt[8], o[8];
+            raw[j].get(v);
+            Vec8<float>::load(gamma + c, gm);
+            Vec8<float>::load(beta + c, bt);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = (v[k] - mu) * rs * gm[k] + bt[k];
+            Vec8<T>::store(yr + c, o);
+        }
+    }
+    if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+}
+
+template <typename T, int NV>
+__global__ void __launch_bounds__(256) ln_bwd_reg_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                         const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                         const float* __restrict__ rstd, const T* __restrict__ dres,
+                                                         T* __restrict__ dx, long rows, int d) {
+    const int lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const T* xr = x + row * d;
+    const T* gr = dy + row * d;
+    const float mu = mean[row], rs = rstd[row];
+    Raw8<T> rx[NV], rg[NV];
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int c = (j * 32 + lane) * 8;
+        if (c < d) { rx[j].load(xr + c); rg[j].load(gr + c); }
+    }
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int c = (j * 32 + lane) * 8;
+        if (c < d) {
+            float xv[8], gv[8], gm[8];
+            rx[j].get(xv);
+            rg[j].get(gv);
+            Vec8<float>::load(gamma + c, gm);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float gg = gv[k] * gm[k];
+                a += gg;
+                b += gg * (xv[k] - mu) * rs;
+            }
+        }
+    }
+    a = warp_sum(a) / (float)d;
+    b = warp_sum(b) / (float)d;
+    T* dr = dx + row * d;
+    const T* rr = dres ? dres + row * d : nullptr;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int c = (j * 32 + lane) * 8;
+        if (c < d) {
+            float xv[8], gv[8], gm[8], o[8];
+            rx[j].get(xv);
+            rg[j].get(gv);
+            Vec8<float>::load(gamma + c, gm);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = rs * (gv[k] * gm[k] - a - (xv[k] - mu) * rs * b);
+            if (rr) {
+                float e[8];
+                Vec8<T>::load(rr + c, e);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[k] += e[k];
+            }
+            Vec8<T>::store(dr + c, o);
+        }
+    }
+}
+
 // =============================================================================================
 // Generic column reduction: out_k[c] += sum_r f_k(r, c).  blockDim = (32, 8); each thread owns
 // VEC consecutive columns; grid = (col tiles, row chunks); cross-warp reduce in shared memory and
@@ -123,8 +263,10 @@ __global__ void __launch_bounds__(256) colreduce_kernel(F f, long rows, int cols
     const long per = (rows + gridDim.y - 1) / gridDim.y;
     const long r0 = (long)blockIdx.y * per;
     const long r1 = (r0 + per < rows) ? r0 + per : rows;
-    if (c0 < cols)
+    if (c0 < cols) {
+#pragma unroll(F::kUnroll)
         for (long r = r0 + ty; r < r1; r += 8) f(r, c0, acc);
+    }
 #pragma unroll
     for (int k = 0; k < NOUT; ++k)
 #pragma unroll
@@ -156,6 +298,7 @@ static int launch_colreduce(F f, long rows, int cols, cudaStream_t st) {
 }
 
 template <typename T, int VEC> struct ColsumF {
+    static constexpr int kUnroll = 4;   // rows in flight per thread in colreduce_kernel
     const T* x; long ld; float* o;
     __device__ __forceinline__ void operator()(long r, int c0, float (&acc)[1][VEC]) const {
         float v[VEC];
@@ -167,6 +310,7 @@ template <typename T, int VEC> struct ColsumF {
 };
 
 template <typename T, int VEC> struct LNGradF {
+    static constexpr int kUnroll = 4;   // rows in flight per thread in colreduce_kernel
     const T* dy; const T* x; const float* mean; const float* rstd; int d; float* dgamma; float* dbeta;
     __device__ __forceinline__ void operator()(long r, int c0, float (&acc)[2][VEC]) const {
         float v[VEC], g[VEC];
@@ -212,8 +356,10 @@ __global__ void __launch_bounds__(256) dropout_bwd8_kernel(const T* __restrict__
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
         float g[8];
         Vec8<T>::load(dy + 8 * i, g);
+        float mk[8];
+        dropout_factors<8>(drop, (uint64_t)i * 8, mk);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) g[k] *= dropout_factor(drop, (uint64_t)(8 * i + k));
+        for (int k = 0; k < 8; ++k) g[k] *= mk[k];
         Vec8<T>::store(dx + 8 * i, g);
     }
 }
@@ -224,6 +370,11 @@ __global__ void __launch_bounds__(256) dropout_bwd8_kernel(const T* __restrict__
 struct BNGeom {
     int L, Lp, halo, C;
     __device__ __forceinline__ long phys(long r) const {  // frame index -> physical row
+        if (halo == 0) return r;
+        if (r < 0x7fffffffL) {
+            const unsigned ru = (unsigned)r, b = ru / (unsigned)L;
+            return (long)b * Lp + halo + (int)(ru - b * (unsigned)L);
+        }
         long b = r / L;
         int l = (int)(r - b * L);
         return b * Lp + halo + l;
@@ -231,6 +382,7 @@ struct BNGeom {
 };
 
 template <typename T, int VEC> struct BNStatsF {
+    static constexpr int kUnroll = 4;   // rows in flight per thread in colreduce_kernel
     const T* x; BNGeom g; float* sums;
     __device__ __forceinline__ void operator()(long r, int c0, float (&acc)[2][VEC]) const {
         float v[VEC];
@@ -275,11 +427,22 @@ __global__ void bn_apply_kernel(const T* __restrict__ x, const float* __restrict
     dropout_resolve(drop);
     const int cv = g.C / VEC;
     const long total = (long)B * g.Lp * cv;
+    const bool small = total < 0x7fffffffL;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        int c = (int)(i % cv) * VEC;
-        long prow = i / cv;
-        int lp = (int)(prow % g.Lp);
-        long b = prow / g.Lp;
+        int c, lp;
+        long prow, b;
+        if (small) {                                    // 32-bit divisions: the 64-bit ones cost more than the memory traffic
+            const unsigned iu = (unsigned)i, pr = iu / (unsigned)cv;
+            c = (int)(iu - pr * (unsigned)cv) * VEC;
+            const unsigned bb = pr / (unsigned)g.Lp;
+            lp = (int)(pr - bb * (unsigned)g.Lp);
+            prow = pr; b = bb;
+        } else {
+            c = (int)(i % cv) * VEC;
+            prow = i / cv;
+            lp = (int)(prow % g.Lp);
+            b = prow / g.Lp;
+        }
         float o[VEC];
         int l = lp - g.halo;
         if (l < 0 || l >= g.L) {
@@ -329,6 +492,7 @@ __device__ __forceinline__ void bn_dz(const T* dy, const T* y, const T* x, const
 }
 
 template <typename T, int VEC> struct BNBwdF {
+    static constexpr int kUnroll = 1;   // rows in flight per thread in colreduce_kernel
     const T* dy; const T* y; const T* x; const float* mean; const float* invstd; const float* gamma;
     const float* beta; BNGeom g; int use_tanh; Dropout drop; float* sums;
     __device__ __forceinline__ void operator()(long r, int c0, float (&acc)[2][VEC]) const {
@@ -352,11 +516,22 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restric
     const int cv = g.C / VEC;
     const long total = (long)B * g.Lp * cv;
     const float inv_n = 1.f / (float)((long)B * g.L);
+    const bool small = total < 0x7fffffffL;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        int c = (int)(i % cv) * VEC;
-        long prow = i / cv;
-        int lp = (int)(prow % g.Lp);
-        long b = prow / g.Lp;
+        int c, lp;
+        long prow, b;
+        if (small) {                                    // 32-bit divisions: the 64-bit ones cost more than the memory traffic
+            const unsigned iu = (unsigned)i, pr = iu / (unsigned)cv;
+            c = (int)(iu - pr * (unsigned)cv) * VEC;
+            const unsigned bb = pr / (unsigned)g.Lp;
+            lp = (int)(pr - bb * (unsigned)g.Lp);
+            prow = pr; b = bb;
+        } else {
+            c = (int)(i % cv) * VEC;
+            prow = i / cv;
+            lp = (int)(prow % g.Lp);
+            b = prow / g.Lp;
+        }
         int l = lp - g.halo;
         float o[VEC];
         if (l < 0 || l >= g.L) {
@@ -382,6 +557,7 @@ __global__ void bn_param_grad_kernel(const float* __restrict__ sums, float* dgam
     if (dbeta) dbeta[c] += sums[c];
     if (dgamma) dgamma[c] += sums[C + c];
 }
+
 
 template <typename T, int VEC>
 __global__ void pad_rows_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int L, int halo, int C, int to_padded) {
@@ -448,6 +624,7 @@ __global__ void __launch_bounds__(128) skinny_fwd_kernel(const T* __restrict__ x
 }
 
 template <typename T, int VEC> struct SkinnyDwF {
+    static constexpr int kUnroll = 1;   // rows in flight per thread in colreduce_kernel
     const T* dy; const T* x; int K; int N; float* dw;
     __device__ __forceinline__ void operator()(long r, int c0, float (&acc)[4][VEC]) const {
         float v[VEC];
@@ -493,6 +670,13 @@ __global__ void skinny_dx_kernel(const T* __restrict__ dy, const T* __restrict__
 
 using namespace s2s;
 
+#define S2S_VEC3_DISPATCH(ok8, ok4, VEC, ...)              \
+    do {                                                   \
+        if (ok8) { constexpr int VEC = 8; __VA_ARGS__; }   \
+        else if (ok4) { constexpr int VEC = 4; __VA_ARGS__; } \
+        else { constexpr int VEC = 1; __VA_ARGS__; }       \
+    } while (0)
+
 #define S2S_VEC_DISPATCH(ok, VEC, ...)                \
     do {                                              \
         if (ok) { constexpr int VEC = 4; __VA_ARGS__; } \
@@ -504,6 +688,18 @@ extern "C" int s2s_layernorm_fwd(const void* x, const float* gamma, const float*
     S2S_REQUIRE(x && gamma && beta && y && mean && rstd && d > 0, "layernorm_fwd: null pointer or bad d");
     if (rows <= 0) return S2S_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    if (d % 8 == 0 && d <= 2048 && aligned16(x, y, gamma, beta)) {
+        const int nv = (d + 255) / 256;
+        unsigned g8 = (unsigned)ceil_div_l(rows, 8);
+#define S2S_LN_FWD(NVV) ln_fwd_reg_kernel<T, NVV><<<g8, 256, 0, st>>>((const T*)x, gamma, beta, (T*)y, mean, rstd, rows, d, eps)
+        S2S_DISPATCH_DTYPE(dtype, T, {
+            if (nv <= 1) S2S_LN_FWD(1); else if (nv <= 2) S2S_LN_FWD(2); else if (nv <= 4) S2S_LN_FWD(4);
+            else if (nv <= 6) S2S_LN_FWD(6); else S2S_LN_FWD(8);
+        });
+#undef S2S_LN_FWD
+        S2S_LAUNCH_OK();
+        return S2S_OK;
+    }
     bool ok = vec4_ok(d, d, x, y);
     S2S_DISPATCH_DTYPE(dtype, T, S2S_VEC_DISPATCH(ok, VEC, (ln_fwd_kernel<T, VEC><<<(unsigned)ceil_div_l(rows, 4), 128, 0, st>>>(
         (const T*)x, gamma, beta, (T*)y, mean, rstd, rows, d, eps))));
@@ -517,6 +713,29 @@ extern "C" int s2s_layernorm_bwd(const void* dy, const void* x, const float* gam
     S2S_REQUIRE(dy && x && gamma && mean && rstd && d > 0, "layernorm_bwd: null pointer or bad d");
     if (rows <= 0) return S2S_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    if (d % 8 == 0 && d <= 2048 && aligned16(x, dy, dx, dres) && aligned16(gamma)) {
+        const int nv = (d + 255) / 256;
+        const unsigned gp = (unsigned)ceil_div_l(rows, 8);
+#define S2S_LN_BWD(NVV) ln_bwd_reg_kernel<T, NVV><<<gp, 256, 0, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (const T*)dres, \
+                                                                     (T*)dx, rows, d)
+        if (dx) {
+            S2S_DISPATCH_DTYPE(dtype, T, {
+                if (nv <= 1) S2S_LN_BWD(1); else if (nv <= 2) S2S_LN_BWD(2); else if (nv <= 4) S2S_LN_BWD(4);
+                else if (nv <= 6) S2S_LN_BWD(6); else S2S_LN_BWD(8);
+            });
+            S2S_LAUNCH_OK();
+        }
+#undef S2S_LN_BWD
+        if (dgamma && dbeta) {
+            int rc = S2S_OK;
+            S2S_DISPATCH_DTYPE(dtype, T, {
+                LNGradF<T, 8> f{(const T*)dy, (const T*)x, mean, rstd, d, dgamma, dbeta};
+                rc = launch_colreduce<2, 8>(f, rows, d, st);
+            });
+            return rc;
+        }
+        return S2S_OK;
+    }
     bool ok = vec4_ok(d, d, x, dy, dx, dres);
     if (dx) {
         S2S_DISPATCH_DTYPE(dtype, T, S2S_VEC_DISPATCH(ok, VEC, (ln_bwd_dx_kernel<T, VEC><<<(unsigned)ceil_div_l(rows, 4), 128, 0, st>>>(
@@ -537,8 +756,15 @@ extern "C" int s2s_layernorm_bwd(const void* dy, const void* x, const float* gam
 extern "C" int s2s_colsum(const void* x, int64_t rows, int cols, int64_t ld, float* out, int dtype, void* stream) {
     S2S_REQUIRE(x && out && cols > 0 && ld >= cols, "colsum: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    bool ok = vec4_ok(cols, ld, x);
     int rc = S2S_OK;
+    if (cols % 8 == 0 && ld % 8 == 0 && aligned16(x)) {
+        S2S_DISPATCH_DTYPE(dtype, T, {
+            ColsumF<T, 8> f{(const T*)x, (long)ld, out};
+            rc = launch_colreduce<1, 8>(f, rows, cols, st);
+        });
+        return rc;
+    }
+    bool ok = vec4_ok(cols, ld, x);
     S2S_DISPATCH_DTYPE(dtype, T, S2S_VEC_DISPATCH(ok, VEC, {
         ColsumF<T, VEC> f{(const T*)x, (long)ld, out};
         rc = launch_colreduce<1, VEC>(f, rows, cols, st);
@@ -579,9 +805,9 @@ extern "C" int s2s_bn_stats(const void* x, float* sums, int B, int L, int halo, 
     S2S_REQUIRE(x && sums && B > 0 && L > 0 && C > 0 && halo >= 0, "bn_stats: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     BNGeom g{L, L + 2 * halo, halo, C};
-    bool ok = vec4_ok(C, C, x);
+    bool ok = vec4_ok(C, C, x), ok8 = (C % 8 == 0) && aligned16(x);
     int rc = S2S_OK;
-    S2S_DISPATCH_DTYPE(dtype, T, S2S_VEC_DISPATCH(ok, VEC, {
+    S2S_DISPATCH_DTYPE(dtype, T, S2S_VEC3_DISPATCH(ok8, ok, VEC, {
         BNStatsF<T, VEC> f{(const T*)x, g, sums};
         rc = launch_colreduce<2, VEC>(f, (long)B * L, C, st);
     }));

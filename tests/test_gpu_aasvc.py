@@ -388,13 +388,14 @@ def test_dropout_training_step_runs_and_is_reproducible():
     a1 = a1.clone()
     g1 = eng.store.G.clone()
     a2, _, l2 = _step(eng, z)
-    assert torch.equal(a1, a2)                               # same masks: the forward is bit-reproducible
-    # gradients are accumulated with float atomics (split-K, column reductions): equal up to summation order
-    assert (g1 - eng.store.G).abs().max().item() <= 1e-4 * g1.abs().max().item()
+    # same masks; BatchNorm statistics and gradients are accumulated with float atomics, so two runs agree up to
+    # summation order, while a different seed changes the output by orders of magnitude more
+    assert (a1 - a2).abs().max().item() <= 1e-4
+    assert (g1 - eng.store.G).abs().max().item() <= 1e-3 * g1.abs().max().item()
     assert torch.isfinite(g1).all() and torch.isfinite(l1).all()
     eng.seed_dev += 1
     a3, _, _ = _step(eng, z)
-    assert not torch.equal(a1, a3)
+    assert (a1 - a3).abs().mean().item() >= 1e-2
 
 
 def test_dropin_module_losses_and_autograd():

@@ -123,7 +123,7 @@ def test_gemm_conv1d_taps(ops, mode, dt):
 
 
 @pytest.mark.parametrize("dt", DT)
-@pytest.mark.parametrize("rows,d", [(7, 32), (1000, 384), (33, 50)])
+@pytest.mark.parametrize("rows,d", [(7, 32), (1000, 384), (33, 50), (3001, 1536), (130, 256), (65, 1032), (40, 2048), (9, 2056)])
 def test_layernorm(ops, dt, rows, d):
     x, dy, res = rnd(rows, 1, d, dt=dt, seed=1), rnd(rows, 1, d, dt=dt, seed=2), rnd(rows, 1, d, dt=dt, seed=3)
     gam, bet = 1 + 0.1 * rnd(d, seed=4), 0.1 * rnd(d, seed=5)
@@ -145,11 +145,11 @@ def test_layernorm(ops, dt, rows, d):
 
 @pytest.mark.parametrize("dt", DT)
 @pytest.mark.parametrize("causal", [False, True])
-def test_softmax_fwd_bwd(ops, dt, causal):
-    B, H, T1, T2 = 3, 2, 19, 21
-    ld = 24
+@pytest.mark.parametrize("T1,T2,ld", [(19, 21, 24), (19, 21, 21), (70, 127, 128), (33, 768, 768), (12, 1000, 1000), (5, 1030, 1032)])
+def test_softmax_fwd_bwd(ops, dt, causal, T1, T2, ld):
+    B, H = 3, 2
     S = rnd(B, H, T1, ld, dt=dt, seed=1, scale=2.0)
-    klens = torch.tensor([21, 13, 0], dtype=torch.int32)
+    klens = torch.tensor([T2, max(1, T2 // 2 + 3), 0], dtype=torch.int32)
     P = F.softmax_fwd(S.clone(), klens, causal, T2)
     cS, ck = dev(S, klens)
     ops.softmax_fwd(cS, ck, causal, T2)

@@ -9,6 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
 from seq2seq_vc_b200 import ops
+from seq2seq_vc_b200._lib import Drop
 
 
 def timeit(fn, flush, reps=8):
@@ -75,6 +76,12 @@ def main():
         "swish_bwd": (lambda: ops.swish_bwd(g, x, y), 3 * N * e),
         "layernorm_fwd": (lambda: ops.layernorm_fwd(x, gam, bet, y, mean, rstd), 2 * N * e),
         "layernorm_bwd(dx+dgamma/dbeta)": (lambda: ops.layernorm_bwd(g, x, gam, mean, rstd, y, sums[:C], sums[C:]), 3 * N * e),
+        "layernorm_bwd(dx only)": (lambda: ops.layernorm_bwd(g, x, gam, mean, rstd, y, None, None), 3 * N * e),
+        "layernorm_bwd(dgamma/dbeta only)": (lambda: ops.layernorm_bwd(g, x, gam, mean, rstd, None, sums[:C], sums[C:]), 2 * N * e),
+        "swish_fwd(p=0.2)": (lambda: ops.swish_fwd(x, y, Drop(0.2, 1, 3)), 2 * N * e),
+        "scale_dropout(p=0.2)": (lambda: ops.scale_dropout(x, y, 2.0, Drop(0.2, 1, 4)), 2 * N * e),
+        "dropout_bwd(p=0.2)": (lambda: ops.dropout_bwd(g, y, Drop(0.2, 1, 5)), 2 * N * e),
+        "softmax_fwd(P and dropped copy, p=0.2)": (lambda: ops.softmax_fwd(S, klens, False, T, dS, Drop(0.2, 1, 6)), 3 * S.numel() * e),
         "colsum": (lambda: ops.colsum(x.view(B * T, C), db), N * e),
         "bn_stats": (lambda: ops.bn_stats(x, sums, T, 0), N * e),
         "bn_apply_swish": (lambda: ops.bn_apply(x, bmean, binv, gam, bet, y, T, 0, 2), 2 * N * e),
