@@ -395,12 +395,13 @@ def run_ours(args, rank, world):
             peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
             ach = gf / (gms * 1e-3) / 1e12
             traffic = None
-            try:
-                tj = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_tc_traffic.json")))
-                if tj.get("workload") == args.workload:
-                    traffic = tj["dram_bytes_per_launch"]
-            except Exception:
-                pass
+            for fn in ("r01_gemm_tc_traffic.json", "r01_gemm_tc_traffic_c3.json"):     # ncu dram bytes per launch, per workload
+                try:
+                    tj = json.load(open(os.path.join(ROOT, "profiles", fn)))
+                    if tj.get("workload") == args.workload:
+                        traffic = tj["dram_bytes_per_launch"]
+                except Exception:
+                    pass
             line["roofline"] = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05.mma bf16, all shapes of one step)", "achieved": ach,
                                 "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "peak_source": pk_src + " (sustained)",
                                 "launches_per_step": n, "algorithmic_gflop_per_launch_avg": gf / n / 1e9,

@@ -26,8 +26,10 @@ __global__ void __launch_bounds__(256) bias_add2_kernel(const T* __restrict__ q,
     const int dv = d / VEC;
     const long total = rows * dv;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const long r = i / dv;
-        const int c = (int)(i - r * dv) * VEC;
+        long r;
+        int c;
+        if (total < 0x7fffffffL) { const unsigned iu = (unsigned)i, ru = iu / (unsigned)dv; r = ru; c = (int)(iu - ru * (unsigned)dv) * VEC; }
+        else { r = i / dv; c = (int)(i - r * dv) * VEC; }
         float a[VEC], ou[VEC], ov[VEC];
         if constexpr (VEC == 8) ld8<T>(q + r * ldq + c, reinterpret_cast<float(&)[8]>(a));
         else a[0] = to_f<T>(q[r * ldq + c]);
@@ -50,8 +52,10 @@ __global__ void __launch_bounds__(256) add_strided_kernel(const T* __restrict__ 
     const int dv = d / VEC;
     const long total = rows * dv;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const long r = i / dv;
-        const int c = (int)(i - r * dv) * VEC;
+        long r;
+        int c;
+        if (total < 0x7fffffffL) { const unsigned iu = (unsigned)i, ru = iu / (unsigned)dv; r = ru; c = (int)(iu - ru * (unsigned)dv) * VEC; }
+        else { r = i / dv; c = (int)(i - r * dv) * VEC; }
         float x[VEC], y[VEC];
         if constexpr (VEC == 8) {
             ld8<T>(a + r * d + c, reinterpret_cast<float(&)[8]>(x));
@@ -111,8 +115,10 @@ __global__ void __launch_bounds__(256) glu_fwd_kernel(const T* __restrict__ x, T
     const int cv = C / VEC;
     const long total = rows * cv;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const long r = i / cv;
-        const int c = (int)(i - r * cv) * VEC;
+        long r;
+        int c;
+        if (total < 0x7fffffffL) { const unsigned iu = (unsigned)i, ru = iu / (unsigned)cv; r = ru; c = (int)(iu - ru * (unsigned)cv) * VEC; }
+        else { r = i / cv; c = (int)(i - r * cv) * VEC; }
         float a[VEC], g[VEC];
         if constexpr (VEC == 8) {
             ld8<T>(x + r * 2 * C + c, reinterpret_cast<float(&)[8]>(a));
@@ -131,8 +137,10 @@ __global__ void __launch_bounds__(256) glu_bwd_kernel(const T* __restrict__ dy, 
     const int cv = C / VEC;
     const long total = rows * cv;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const long r = i / cv;
-        const int c = (int)(i - r * cv) * VEC;
+        long r;
+        int c;
+        if (total < 0x7fffffffL) { const unsigned iu = (unsigned)i, ru = iu / (unsigned)cv; r = ru; c = (int)(iu - ru * (unsigned)cv) * VEC; }
+        else { r = i / cv; c = (int)(i - r * cv) * VEC; }
         float a[VEC], g[VEC], d[VEC], da[VEC], dg[VEC];
         if constexpr (VEC == 8) {
             ld8<T>(x + r * 2 * C + c, reinterpret_cast<float(&)[8]>(a));
@@ -255,7 +263,13 @@ __global__ void __launch_bounds__(256) dwconv_dw_kernel(const T* __restrict__ dy
 // its frames with the K weights and a K-deep sliding window in registers: 1 LDS + K FMA per output, HBM sees each
 // input element once (+ (K-1)/TT halo).  FLIP selects the adjoint (dx) form.
 // ---------------------------------------------------------------------------------------------
-template <typename T> struct DwTile { static constexpr int TT = (sizeof(T) == 2) ? 128 : 64; };
+// frames per thread = K * REP (a whole number of window rotations: no partial unrolled pass), 4 thread groups per tile
+template <typename T, int K> struct DwTile {
+    static constexpr int TARGET = (sizeof(T) == 2) ? 32 : 16;
+    static constexpr int REP = (TARGET / K) > 0 ? (TARGET / K) : 1;
+    static constexpr int G = 4, FR = K * REP, TT = G * FR, ROWS = TT + K - 1;
+    static constexpr size_t fwd_smem = sizeof(T) * ROWS * 64, dw_smem = sizeof(T) * (ROWS + TT) * 64;
+};
 
 template <typename T>
 __device__ __forceinline__ void dw_load_tile(T* __restrict__ dst, const T* __restrict__ src_b, int t_first, int rows, int Tn, int C,
@@ -278,11 +292,11 @@ __device__ __forceinline__ void dw_load_tile(T* __restrict__ dst, const T* __res
 template <typename T, int K, bool FLIP>
 __global__ void __launch_bounds__(256) dwconv_tile_kernel(const T* __restrict__ x, const float* __restrict__ w,
                                                           const float* __restrict__ bias, T* __restrict__ y, int Tn, int C, int vec) {
-    constexpr int CH = 64, TT = DwTile<T>::TT, G = 4, FR = TT / G, PAD = (K - 1) / 2, ROWS = TT + K - 1;
+    constexpr int CH = 64, TT = DwTile<T, K>::TT, FR = DwTile<T, K>::FR, REP = DwTile<T, K>::REP, PAD = (K - 1) / 2,
+                  ROWS = DwTile<T, K>::ROWS;
     __shared__ __align__(16) T xs[ROWS * CH];
     const int b = blockIdx.z, t0 = blockIdx.x * TT, c0 = blockIdx.y * CH;
     const T* xb = x + (long)b * Tn * C;
-    T* yb = y + (long)b * Tn * C;
     dw_load_tile<T>(xs, xb, t0 - PAD, ROWS, Tn, C, c0, vec != 0);
     __syncthreads();
     const int c = threadIdx.x & 63, g = threadIdx.x >> 6;
@@ -291,22 +305,23 @@ __global__ void __launch_bounds__(256) dwconv_tile_kernel(const T* __restrict__ 
 #pragma unroll
     for (int j = 0; j < K; ++j) wr[j] = w[(long)(c0 + c) * K + (FLIP ? K - 1 - j : j)];
     const float bv = bias ? bias[c0 + c] : 0.f;
-    const T* xc = xs + (g * FR) * CH + c;
+    const T* xp = xs + (g * FR) * CH + c;                  // next window row to fetch
 #pragma unroll
-    for (int j = 0; j < K - 1; ++j) win[j] = to_f<T>(xc[j * CH]);
+    for (int j = 0; j < K - 1; ++j) { win[j] = to_f<T>(*xp); xp += CH; }
     win[K - 1] = 0.f;
-    for (int f0 = 0; f0 < FR; f0 += K) {
+    int t = t0 + g * FR;
+    T* yp = y + ((long)b * Tn + t) * C + c0 + c;
+    for (int rep = 0; rep < REP; ++rep) {
 #pragma unroll
         for (int f = 0; f < K; ++f) {
-            const int fr = f0 + f;
-            if (fr < FR) {
-                win[(f + K - 1) % K] = to_f<T>(xc[(fr + K - 1) * CH]);
-                float acc = bv;
+            win[(f + K - 1) % K] = to_f<T>(*xp);
+            xp += CH;
+            float acc = bv;
 #pragma unroll
-                for (int j = 0; j < K; ++j) acc = fmaf(wr[j], win[(f + j) % K], acc);
-                const int t = t0 + g * FR + fr;
-                if (t < Tn) yb[(long)t * C + c0 + c] = from_f<T>(acc);
-            }
+            for (int j = 0; j < K; ++j) acc = fmaf(wr[j], win[(f + j) % K], acc);
+            if (t < Tn) *yp = from_f<T>(acc);
+            yp += C;
+            ++t;
         }
     }
 }
@@ -316,7 +331,8 @@ __global__ void __launch_bounds__(256) dwconv_tile_kernel(const T* __restrict__ 
 template <typename T, int K>
 __global__ void __launch_bounds__(256) dwconv_dw_tile_kernel(const T* __restrict__ dy, const T* __restrict__ x, float* __restrict__ dw,
                                                              float* __restrict__ dbias, int Tn, int C, int vec, int tiles_per_cta) {
-    constexpr int CH = 64, TT = DwTile<T>::TT, G = 4, FR = TT / G, PAD = (K - 1) / 2, ROWS = TT + K - 1;
+    constexpr int CH = 64, TT = DwTile<T, K>::TT, G = DwTile<T, K>::G, FR = DwTile<T, K>::FR, REP = DwTile<T, K>::REP, PAD = (K - 1) / 2,
+                  ROWS = DwTile<T, K>::ROWS;
     __shared__ __align__(16) T tile[(ROWS + TT) * CH];
     static_assert(sizeof(T) * (ROWS + TT) * CH >= sizeof(float) * (G - 1) * (K + 1) * CH, "reduction scratch must fit in the tiles");
     T* xs = tile;
@@ -329,29 +345,28 @@ __global__ void __launch_bounds__(256) dwconv_dw_tile_kernel(const T* __restrict
 #pragma unroll
     for (int j = 0; j < K; ++j) acc[j] = 0.f;
     const int tile0 = blockIdx.y * tiles_per_cta;
-    for (int tile = tile0; tile < tile0 + tiles_per_cta; ++tile) {
-        const int t0 = tile * TT;
+    for (int tl = tile0; tl < tile0 + tiles_per_cta; ++tl) {
+        const int t0 = tl * TT;
         if (t0 >= Tn) break;
         __syncthreads();
         dw_load_tile<T>(xs, xb, t0 - PAD, ROWS, Tn, C, c0, vec != 0);
         dw_load_tile<T>(gs, gb, t0, TT, Tn, C, c0, vec != 0);
         __syncthreads();
-        const T* xc = xs + (g * FR) * CH + c;
-        const T* gc = gs + (g * FR) * CH + c;
+        const T* xp = xs + (g * FR) * CH + c;
+        const T* gp = gs + (g * FR) * CH + c;
 #pragma unroll
-        for (int j = 0; j < K - 1; ++j) win[j] = to_f<T>(xc[j * CH]);
+        for (int j = 0; j < K - 1; ++j) { win[j] = to_f<T>(*xp); xp += CH; }
         win[K - 1] = 0.f;
-        for (int f0 = 0; f0 < FR; f0 += K) {
+        for (int rep = 0; rep < REP; ++rep) {
 #pragma unroll
             for (int f = 0; f < K; ++f) {
-                const int fr = f0 + f;
-                if (fr < FR) {
-                    win[(f + K - 1) % K] = to_f<T>(xc[(fr + K - 1) * CH]);
-                    const float gv = to_f<T>(gc[fr * CH]);          // rows past T_n are zero in the tile
-                    accb += gv;
+                win[(f + K - 1) % K] = to_f<T>(*xp);
+                xp += CH;
+                const float gv = to_f<T>(*gp);              // rows past T_n are zero in the tile
+                gp += CH;
+                accb += gv;
 #pragma unroll
-                    for (int j = 0; j < K; ++j) acc[j] = fmaf(gv, win[(f + j) % K], acc[j]);
-                }
+                for (int j = 0; j < K; ++j) acc[j] = fmaf(gv, win[(f + j) % K], acc[j]);
             }
         }
     }
@@ -578,33 +593,45 @@ extern "C" int s2s_glu_bwd(const void* dy, const void* x, void* dx, int64_t rows
 
 template <typename TY, bool FLIP>
 static bool launch_dwconv_tile(const TY* x, const float* w, const float* bias, TY* y, int B, int T, int C, int K, cudaStream_t st) {
-    constexpr int TT = DwTile<TY>::TT;
     if (B > 65535) return false;
-    dim3 grid((unsigned)ceil_div_l(T, TT), (unsigned)ceil_div_l(C, 64), (unsigned)B);
     const int vec = (C % (16 / (int)sizeof(TY)) == 0) && aligned16(x, y);
-    if (K == 7) dwconv_tile_kernel<TY, 7, FLIP><<<grid, 256, 0, st>>>(x, w, bias, y, T, C, vec);
-    else if (K == 15) dwconv_tile_kernel<TY, 15, FLIP><<<grid, 256, 0, st>>>(x, w, bias, y, T, C, vec);
-    else if (K == 31) dwconv_tile_kernel<TY, 31, FLIP><<<grid, 256, 0, st>>>(x, w, bias, y, T, C, vec);
+    const unsigned gy = (unsigned)ceil_div_l(C, 64);
+#define S2S_DW_FWD(KK)                                                                                                 \
+    do {                                                                                                               \
+        dim3 grid((unsigned)ceil_div_l(T, DwTile<TY, KK>::TT), gy, (unsigned)B);                                       \
+        dwconv_tile_kernel<TY, KK, FLIP><<<grid, 256, 0, st>>>(x, w, bias, y, T, C, vec);                               \
+    } while (0)
+    if (K == 7) S2S_DW_FWD(7);
+    else if (K == 15) S2S_DW_FWD(15);
+    else if (K == 31) S2S_DW_FWD(31);
     else return false;
+#undef S2S_DW_FWD
     return true;
 }
 
 template <typename TY>
 static bool launch_dwconv_dw_tile(const TY* dy, const TY* x, float* dw, float* dbias, int B, int T, int C, int K, cudaStream_t st) {
-    constexpr int TT = DwTile<TY>::TT;
     if (B > 65535) return false;
-    const int tiles = (int)ceil_div_l(T, TT);
-    const long ctas_full = ceil_div_l(C, 64) * B;
-    int split = 1;                                         // split time only when (channel tiles x utterances) cannot fill the chip
-    while (ctas_full * split < 2L * num_sms() && split < tiles) split *= 2;
-    const int per = (int)ceil_div_l(tiles, split);
-    dim3 grid((unsigned)ceil_div_l(C, 64), (unsigned)ceil_div_l(tiles, per), (unsigned)B);
     const int vec = (C % (16 / (int)sizeof(TY)) == 0) && aligned16(x, dy);
-    if (K == 7) dwconv_dw_tile_kernel<TY, 7><<<grid, 256, 0, st>>>(dy, x, dw, dbias, T, C, vec, per);
-    else if (K == 15) dwconv_dw_tile_kernel<TY, 15><<<grid, 256, 0, st>>>(dy, x, dw, dbias, T, C, vec, per);
-    else if (K == 31) dwconv_dw_tile_kernel<TY, 31><<<grid, 256, 0, st>>>(dy, x, dw, dbias, T, C, vec, per);
-    else return false;
-    return true;
+    const long ctas_full = ceil_div_l(C, 64) * B;
+#define S2S_DW_DW(KK)                                                                                                  \
+    do {                                                                                                               \
+        if constexpr (DwTile<TY, KK>::dw_smem <= 48 * 1024) {                                                          \
+            const int tiles = (int)ceil_div_l(T, DwTile<TY, KK>::TT);                                                  \
+            int split = 1; /* split time only when (channel tiles x utterances) cannot fill the chip */                \
+            while (ctas_full * split < 2L * num_sms() && split < tiles) split *= 2;                                    \
+            const int per = (int)ceil_div_l(tiles, split);                                                             \
+            dim3 grid((unsigned)ceil_div_l(C, 64), (unsigned)ceil_div_l(tiles, per), (unsigned)B);                     \
+            dwconv_dw_tile_kernel<TY, KK><<<grid, 256, 0, st>>>(dy, x, dw, dbias, T, C, vec, per);                      \
+            return true;                                                                                               \
+        }                                                                                                              \
+        return false;                                                                                                  \
+    } while (0)
+    if (K == 7) S2S_DW_DW(7);
+    else if (K == 15) S2S_DW_DW(15);
+    else if (K == 31) S2S_DW_DW(31);
+#undef S2S_DW_DW
+    return false;
 }
 
 extern "C" int s2s_dwconv_fwd(const void* x, const float* w, const float* bias, void* y, int B, int T, int C, int K,

@@ -7,7 +7,8 @@ from seq2seq_vc_b200 import ops
 SHAPES = {
     "lin_dec": dict(M=16384, N=384, K=384), "ffn1": dict(M=16384, N=1536, K=384), "ffn2": dict(M=16384, N=384, K=1536),
     "lin_enc": dict(M=4064, N=384, K=384), "conv2": dict(M=77216, N=384, K=3456), "big": dict(M=8192, N=8192, K=8192),
-    "qk": dict(M=512, N=512, K=48, batch=256), "one_tile": dict(M=128, N=128, K=384), "one_tile_longk": dict(M=128, N=128, K=8192),
+    "qk": dict(M=512, N=512, K=48, batch=256), "c3_ffn": dict(M=49152, N=1536, K=1536), "c3_qkv": dict(M=49152, N=4608, K=1536),
+    "c3_qk": dict(M=768, N=768, K=768, batch=128), "one_tile": dict(M=128, N=128, K=384), "one_tile_longk": dict(M=128, N=128, K=8192),
 }
 
 def run(name, reps=10, flush=True):
