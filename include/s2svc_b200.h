@@ -36,7 +36,7 @@ extern "C" {
 #define S2S_F32 0
 #define S2S_BF16 1
 
-#define S2S_ABI_VERSION 8
+#define S2S_ABI_VERSION 9
 
 const char* s2s_last_error(void);
 int s2s_abi_version(void);
@@ -136,6 +136,19 @@ int s2s_softmax_fwd(const void* S, void* P, void* Pd, const int32_t* klens, int 
                     int64_t ld, int causal, const s2s_dropout_t* drop, int dtype, void* stream);
 int s2s_softmax_bwd(const void* P, void* dP, int B, int H, int T1, int T2, int64_t ld, float scale,
                     const s2s_dropout_t* drop, int dtype, void* stream);
+
+/* Fused attention probabilities for small head dimensions (bf16 only; d_k in {16,32,48,64,96,128}):
+ *   fwd: P = softmax_s(scale * q k^T) with the same masking contract as s2s_softmax_fwd (attention.py:95-104,76-85)
+ *   bwd: dS = scale * P * (dP - sum_s P dP), dP = dctx v^T (+ dAtt when non-NULL), i.e. s2s_gemm + s2s_softmax_bwd
+ * q / k / v / dctx are (B, T, H, d_k) views given by element strides (batch, time, head; d_k contiguous); P, dAtt, dS are
+ * (B, H, T1, ld) with ld % 8 == 0.  The product is recomputed with warp-level mma.sync in two passes so the (B,H,T1,T2)
+ * matrix crosses HBM once per direction: at d_k = 48 the QK^T GEMM is pure epilogue for the tcgen05 tile. */
+int s2s_attn_probs_fwd(const void* q, int64_t q_bs, int64_t q_ts, int64_t q_hs, const void* k, int64_t k_bs, int64_t k_ts,
+                       int64_t k_hs, void* P, const int32_t* klens, int B, int H, int T1, int T2, int dk, int64_t ld, float scale,
+                       int causal, void* stream);
+int s2s_attn_probs_bwd(const void* dctx, int64_t d_bs, int64_t d_ts, int64_t d_hs, const void* v, int64_t v_bs, int64_t v_ts,
+                       int64_t v_hs, const void* P, const void* dAtt, void* dS, int B, int H, int T1, int T2, int dk, int64_t ld,
+                       float scale, void* stream);
 
 /* -------------------------------------------------------------------------------------------
  * ScaledPositionalEncoding (layers/positional_encoding.py:73-106): y = dropout(x + alpha * pe[t])

@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libs2svc_b200.so")
 
 S2S_F32, S2S_BF16 = 0, 1
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 
 class S2SError(RuntimeError):
@@ -66,6 +66,10 @@ SIGNATURES = {
     "s2s_add": (c_int, [_P, _P, _P, c_int64, c_int, _P]),
     "s2s_softmax_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int64, c_int, _DP, c_int, _P]),
     "s2s_softmax_bwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int64, c_float, _DP, c_int, _P]),
+    "s2s_attn_probs_fwd": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int64, c_int64, c_int64, _P, _P, c_int, c_int, c_int, c_int, c_int,
+                                   c_int64, c_float, c_int, _P]),
+    "s2s_attn_probs_bwd": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int64, c_int64, c_int64, _P, _P, _P, c_int, c_int, c_int, c_int,
+                                   c_int, c_int64, c_float, _P]),
     "s2s_scaled_pe_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _DP, c_int, _P]),
     "s2s_scaled_pe_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _DP, c_int, _P]),
     "s2s_embed_pe_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _DP, c_int, _P]),

@@ -405,8 +405,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                     const int n_base = it.n0 + c0 + q * 16;
                     if (EPI == EPI_BF16_FULL && drop.thresh != 0u) {
                         const uint64_t didx = (uint64_t)(((long)(it.b1 * p.batch2 + it.b2) * p.M + m) * (long)p.N + n_base);
+                        if ((didx & 1ull) == 0ull) {                 // one hash per element pair (common.cuh: dropout_factors)
 #pragma unroll 2
-                        for (int jj = 0; jj < 16; ++jj) v[jj] *= dropout_factor(drop, didx + jj);
+                            for (int jj = 0; jj < 16; jj += 2) {
+                                const uint32_t hsh = dropout_hash(drop, (didx + jj) >> 1);
+                                v[jj] *= ((hsh & 0xffffu) < drop.thresh) ? 0.f : drop.scale;
+                                v[jj + 1] *= ((hsh >> 16) < drop.thresh) ? 0.f : drop.scale;
+                            }
+                        } else {
+#pragma unroll 2
+                            for (int jj = 0; jj < 16; ++jj) v[jj] *= dropout_factor(drop, didx + jj);
+                        }
                     }
                     if (!row_in || n_base >= p.N) continue;
                     TC* dst = Crow + n_base;

@@ -166,6 +166,29 @@ def softmax_bwd(P, dP, T2: int, scale: float, drop: Drop = NO_DROP):
     return dP
 
 
+FUSED_ATTN_DK = (16, 32, 48, 64, 96, 128)
+
+
+def attn_probs_fwd(q, k, P, klens, causal: bool, T2: int, scale: float):
+    """P (B,H,T1,ld) = masked softmax(scale * q k^T); q (B,T1,H,dk) / k (B,T2,H,dk) are strided bf16 views."""
+    B, T1, H, dk = q.shape
+    assert q.dtype == torch.bfloat16 and k.dtype == torch.bfloat16 and P.dtype == torch.bfloat16 and P.is_contiguous()
+    assert q.stride(3) == 1 and k.stride(3) == 1 and k.shape[1] == T2 and P.shape[:3] == (B, H, T1)
+    check(_L().s2s_attn_probs_fwd(ptr(q), q.stride(0), q.stride(1), q.stride(2), ptr(k), k.stride(0), k.stride(1), k.stride(2), ptr(P),
+                                  ptr(klens), B, H, T1, T2, dk, P.shape[3], float(scale), int(causal), stream()), "attn_probs_fwd")
+    return P
+
+
+def attn_probs_bwd(dctx, v, P, d_att, dS, T2: int, scale: float):
+    """dS (B,H,T1,ld) = scale * P * (dP - sum P dP), dP = dctx v^T (+ d_att); dctx (B,T1,H,dk), v (B,T2,H,dk) strided bf16 views."""
+    B, T1, H, dk = dctx.shape
+    assert dctx.dtype == torch.bfloat16 and v.dtype == torch.bfloat16 and P.is_contiguous() and dS.is_contiguous() and P.shape == dS.shape
+    assert dctx.stride(3) == 1 and v.stride(3) == 1 and v.shape[1] == T2 and (d_att is None or (d_att.is_contiguous() and d_att.shape == P.shape))
+    check(_L().s2s_attn_probs_bwd(ptr(dctx), dctx.stride(0), dctx.stride(1), dctx.stride(2), ptr(v), v.stride(0), v.stride(1), v.stride(2),
+                                  ptr(P), ptr(d_att), ptr(dS), B, H, T1, T2, dk, P.shape[3], float(scale), stream()), "attn_probs_bwd")
+    return dS
+
+
 def scaled_pe_fwd(x, pe, alpha, y, drop: Drop = NO_DROP):
     B, T, d = x.shape
     assert x.is_contiguous() and y.is_contiguous() and pe.shape[0] >= T and pe.shape[1] == d and pe.is_contiguous()

@@ -138,6 +138,25 @@ def softmax_bwd(P, dP, T2, scale, drop=NO_DROP):
     return dP
 
 
+FUSED_ATTN_DK = (16, 32, 48, 64, 96, 128)
+
+
+def attn_probs_fwd(q, k, P, klens, causal, T2, scale):
+    S = torch.einsum("bthj,bshj->bhts", q.double(), k.double()) * scale
+    P.zero_()
+    P[..., :T2] = S.to(P.dtype)
+    return softmax_fwd(P, klens, causal, T2)
+
+
+def attn_probs_bwd(dctx, v, P, d_att, dS, T2, scale):
+    dP = torch.einsum("bthj,bshj->bhts", dctx.double(), v.double())
+    dS.zero_()
+    dS[..., :T2] = dP.to(dS.dtype)
+    if d_att is not None:
+        dS += d_att
+    return softmax_bwd(P, dS, T2, scale)
+
+
 def scaled_pe_fwd(x, pe, alpha, y, drop=NO_DROP):
     _nodrop(drop)
     T, d = x.shape[1], x.shape[2]

@@ -332,3 +332,34 @@ def test_skinny_linear(ops, dt, N):
     close(cdw, dw, tol(dt, 60), "skinny dw")
     close(cdb, db, tol(dt, 60), "skinny dbias")
     close(cdx, dx, tol(dt, 4), "skinny dx")
+
+
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("B,H,T1,T2,dk", [(2, 3, 70, 70, 48), (3, 2, 130, 50, 64), (2, 4, 64, 127, 48), (2, 2, 200, 600, 96), (1, 8, 512, 512, 48),
+                                           (3, 1, 17, 9, 16)])
+def test_fused_attention_probs_fwd_bwd(ops, causal, B, H, T1, T2, dk):
+    """scores + softmax (and dP + softmax') fused kernels vs GEMM + softmax contracts; q/k/v are strided slices of a fused buffer."""
+    if causal and T1 != T2:
+        pytest.skip("causal masks are only used for self-attention")
+    dt = torch.bfloat16
+    ld = (T2 + 7) // 8 * 8
+    qkv = rnd(B, max(T1, T2), 3, H, dk, dt=dt, seed=1)
+    q, k, v = qkv[:, :T1, 0], qkv[:, :T2, 1], qkv[:, :T2, 2]
+    klens = torch.tensor([T2, max(1, T2 // 2 + 1), 0][:B], dtype=torch.int32)
+    scale = 1.0 / math.sqrt(dk)
+    P = F.attn_probs_fwd(q, k, torch.empty(B, H, T1, ld, dtype=dt), klens, causal, T2, scale)
+    dqkv = qkv.cuda()
+    gP = torch.full((B, H, T1, ld), 3.0, dtype=dt, device="cuda")
+    ops.attn_probs_fwd(dqkv[:, :T1, 0], dqkv[:, :T2, 1], gP, klens.cuda(), causal, T2, scale)
+    close(gP, P, 1.5e-2, "fused probs")
+    assert (gP.float().sum(-1).cpu() - P.float().sum(-1)).abs().max().item() <= 3e-2
+    if B == 3:
+        assert (gP[2] == 0).all(), "rows without a visible key must be exactly zero"
+    dctx = rnd(B, T1, H * dk, dt=dt, seed=2)
+    for with_att in (False, True):
+        d_att = rnd(B, H, T1, ld, dt=dt, seed=3, scale=0.5) if with_att else None
+        ref = F.attn_probs_bwd(dctx.view(B, T1, H, dk), v, P, d_att, torch.empty(B, H, T1, ld, dtype=dt), T2, scale)
+        gdS = torch.full((B, H, T1, ld), 5.0, dtype=dt, device="cuda")
+        ops.attn_probs_bwd(dctx.cuda().view(B, T1, H, dk), dqkv[:, :T2, 2], P.cuda(), None if d_att is None else d_att.cuda(), gdS, T2, scale)
+        tol_abs = 2e-2 * max(1.0, ref.float().abs().max().item())
+        close(gdS, ref, tol_abs, f"fused dS (d_att={with_att})")
