@@ -385,6 +385,9 @@ int s2s_gauss_weights(const float* ds, const int32_t* feats_lens, const int32_t*
 int s2s_duration_loss(const void* pre, const float* ds, const int32_t* text_lens, int B, int T_text, float offset,
                       float clamp_max, float grad_scale, const float* g_douts, float* d_outs, float* loss, void* d_pre,
                       int dtype, void* stream);
+/* DurationPredictor.inference + clamp (modules/duration_predictor.py:92-96, models/aas_vc.py:389):
+ * d[i] = min(max(rint(exp(pre[i]) - offset), 0), clamp_max) as float32 (integral values). */
+int s2s_duration_infer(const void* pre, float* d, int n, float offset, float clamp_max, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -466,3 +466,41 @@ def synthetic_batch(B, T, L, idim=80, odim=80, ilens=None, olens=None, seed=1234
         xs[b, ilens[b]:] = 0
         ys[b, olens[b]:] = 0
     return xs, ilens, ys, olens, xs.clone()
+
+
+def aasvc_inference(sd, hp, x, dp_input):
+    """AASVC.inference without ground truth (aas_vc.py:531-603 -> _forward(is_inference=True) :371-398): eval-mode encoder,
+    durations = clamp(round(exp(d) - 1), 0, 10) (duration_predictor.py:92-96, aas_vc.py:389), Gaussian upsampling over
+    T_feats = sum(ds) frames without masks, decoder without attention mask, postnet with running BatchNorm statistics.
+    x (T, idim), dp_input (T_dp, dp_idim) -> (outs (L, odim), d_outs (T_text,) int64)."""
+    hp = default_hparams(**hp)
+    pr, H = hp["post_encoder_reduction_factor"], hp["aheads"]
+    xs, dpi = x.unsqueeze(0), dp_input.unsqueeze(0)
+    T = xs.shape[1]
+    x_mask = non_pad_mask([T], T).unsqueeze(-2)
+    e = layer_norm(linear(xs, sd, "encoder.embed.0"), sd, "encoder.embed.1", EMBED_LN_EPS)
+    hs = conformer_layers(sd, "encoder", hp["elayers"], H, e, x_mask, False)
+    Tt = T // pr
+    hs = hs[:, : Tt * pr].reshape(1, Tt, hs.shape[2] * pr)
+    dp_in = dp_projection(sd, "duration_predictor_projection", dpi, Tt)
+    k = hp["duration_predictor_kernel_size"]
+    z = dp_in.transpose(1, 2)
+    for i in range(hp["duration_predictor_layers"]):
+        p = f"duration_predictor.conv.{i}"
+        z = torch.relu(F.conv1d(z, sd[p + ".0.weight"], sd[p + ".0.bias"], padding=(k - 1) // 2))
+        z = layer_norm(z.transpose(1, 2), sd, p + ".2").transpose(1, 2)
+    pre = linear(z.transpose(1, 2), sd, "duration_predictor.linear").squeeze(-1)
+    d_outs = torch.clamp(torch.clamp(torch.round(pre.exp() - 1.0), min=0).long(), max=MAX_DP_OUTPUT)
+    ds = d_outs.clone()
+    if ds.sum() == 0:
+        ds[ds.sum(dim=1).eq(0)] = 1                                              # length_regulator.py:127-135
+    L = int(ds.sum())
+    t = torch.arange(L, dtype=torch.float32)[None]
+    c = ds.cumsum(dim=-1) - ds / 2
+    energy = -GAUSS_DELTA * (t.unsqueeze(-1) - c.unsqueeze(1)) ** 2
+    up = torch.matmul(torch.softmax(energy, dim=2), hs)
+    full = torch.ones(1, 1, L, dtype=torch.bool)
+    zs = conformer_layers(sd, "decoder", hp["dlayers"], H, up, full, False)
+    before = linear(zs, sd, "feat_out").view(1, -1, hp["odim"])
+    after = before + postnet(sd, hp, before.transpose(1, 2), False).transpose(1, 2)
+    return after[0], d_outs[0]

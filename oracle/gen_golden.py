@@ -56,6 +56,10 @@ def gen_vtn_tiny():
     with torch.no_grad():
         oute = model(xs, torch.tensor(ilens), ys, labels, torch.tensor(olens))
     dump["eval_after_outs"] = oute[0].numpy()
+    # autoregressive inference (models/vtn.py:302-394) on the first utterance; runs to maxlen (threshold never reached first)
+    with torch.no_grad():
+        io, ip, ia = model.inference(xs[0, :ilens[0]], dict(threshold=0.9999, minlenratio=0.0, maxlenratio=1.6))
+    dump.update(inf_outs=io.numpy(), inf_probs=ip.numpy(), inf_att_ws=ia.numpy())
     np.savez_compressed(os.path.join(GOLDEN, "vtn_tiny.npz"), **dump)
     print("vtn_tiny:", len(dump), "arrays")
 
@@ -148,6 +152,16 @@ def gen_aasvc_tiny():
     with torch.no_grad():
         rete = model(xs, torch.tensor(ilens), ys, torch.tensor(olens), dpi, dp_lengths=torch.tensor(ilens))
     dump["eval_after_outs"] = rete["after_outs"].numpy()
+    # inference without ground truth (eval mode, running BatchNorm statistics as updated by the training step above);
+    # the duration-predictor bias is raised so that the predicted durations are not all zero
+    with torch.no_grad():
+        model.duration_predictor.linear.bias.add_(1.0)
+        outs, d_outs = model.inference(xs[0, :ilens[0]], dp_input=dpi[0, :ilens[0]])
+        dump.update(inf_dp_bias=model.duration_predictor.linear.bias.detach().numpy().copy(), inf_outs=outs.numpy(), inf_d_outs=d_outs.numpy())
+        model.duration_predictor.linear.bias.sub_(1.0)
+        for k, v in model.state_dict().items():
+            if "running_" in k:
+                dump["inf_bn." + k] = v.numpy().copy()
     # ForwardSumLoss on its own (ragged lengths, incl. an infeasible utterance T < N that zero_infinity drops)
     g = torch.Generator().manual_seed(23)
     lp = torch.log_softmax(torch.randn(4, 40, 12, generator=g), -1)

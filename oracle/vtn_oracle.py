@@ -376,3 +376,35 @@ def synthetic_batch(B, T, L, idim=80, odim=80, ilens=None, olens=None, seed=1234
         ys[b, olens[b]:] = 0
         labels[b, olens[b] - 1:] = 1.0
     return xs, ilens, ys, labels, olens
+
+
+def vtn_inference(sd, hp, x, threshold=0.5, minlenratio=0.0, maxlenratio=10.0):
+    """VTN.inference (models/vtn.py:302-394) restated by full-prefix recomputation (equal to forward_one_step by
+    causality); eval-mode BatchNorm; Prenet dropout must be 0 for a deterministic comparison.
+    x (T, idim) -> (outs (L, odim), probs (L,), att_ws (#dlayers, H, L/r, T'))."""
+    hp = default_hparams(**hp)
+    r, odim = hp["decoder_reduction_factor"], hp["odim"]
+    xs = x.unsqueeze(0)
+    T = xs.shape[1]
+    hs, _ = encoder(sd, hp, xs, torch.ones(1, 1, T, dtype=torch.bool))
+    T2 = hs.shape[1]
+    mem_mask = torch.ones(1, 1, T2, dtype=torch.bool)
+    maxlen, minlen = int(T2 * maxlenratio / r), int(T2 * minlenratio / r)
+    ys = hs.new_zeros(1, 1, odim)
+    outs, probs = [], []
+    idx = 0
+    while True:
+        idx += 1
+        attn: Dict[str, torch.Tensor] = {}
+        zs = decoder(sd, hp, ys, causal_mask(idx)[None], hs, mem_mask, attn)
+        z = zs[:, -1]
+        outs.append(linear(z, sd, "feat_out").view(r, odim))
+        probs.append(torch.sigmoid(linear(z, sd, "prob_out"))[0])
+        ys = torch.cat([ys, outs[-1][-1].view(1, 1, odim)], dim=1)
+        if int(sum(probs[-1] >= threshold)) > 0 or idx >= maxlen:
+            if idx < minlen:
+                continue
+            o = torch.cat(outs, dim=0).unsqueeze(0).transpose(1, 2)
+            o = o + postnet(sd, hp, o, False)
+            att = torch.stack([attn[f"decoder.decoders.{l}.src_attn"][0] for l in range(hp["dlayers"])], dim=0)
+            return o.transpose(2, 1).squeeze(0), torch.cat(probs, dim=0), att

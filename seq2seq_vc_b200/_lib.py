@@ -117,6 +117,7 @@ SIGNATURES = {
     "s2s_align_logp_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int64, c_int, _P]),
     "s2s_forward_sum": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_float, _P, _P, _P, c_float, _P]),
     "s2s_gauss_weights": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int64, c_float, c_int, _P]),
+    "s2s_duration_infer": (c_int, [_P, _P, c_int, c_float, c_float, c_int, _P]),
     "s2s_duration_loss": (c_int, [_P, _P, _P, c_int, c_int, c_float, c_float, c_float, _P, _P, _P, _P, c_int, _P]),
 }
 

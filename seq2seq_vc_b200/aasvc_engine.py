@@ -510,6 +510,88 @@ class AASVCEngine(EngineBase):
         return cur
 
     # ------------------------------------------------------------------ forward
+    def _rates(self):
+        hp = self.hp
+        return ((hp["transformer_enc_dropout_rate"], hp["transformer_enc_positional_dropout_rate"], hp["transformer_enc_attn_dropout_rate"]),
+                (hp["transformer_dec_dropout_rate"], hp["transformer_dec_positional_dropout_rate"], hp["transformer_dec_attn_dropout_rate"]))
+
+    def _encoder_side(self, xs: torch.Tensor, dp_inputs: torch.Tensor) -> None:
+        """Encoder input layer + conformer encoder + post-encoder reduction -> self.hs (B,Tt,C); duration-predictor input
+        projection + duration predictor -> self.dp_pre (B*Tt, 1) (log-domain pre-activation) and self.dp_last."""
+        hp, st = self.hp, self.store
+        B, T, idim = xs.shape
+        d, H, pr = hp["adim"], hp["aheads"], hp["post_encoder_reduction_factor"]
+        C, Tt = d * pr, T // pr
+        (er, epr, ear), _ = self._rates()
+        # ---- encoder input layer: Linear -> LayerNorm(1e-5) -> dropout -> x * sqrt(d) -> dropout (conformer/encoder.py:117-123)
+        xa = xs
+        if self.bf16:
+            xa = ops.cast(xs, self.buf("enc.xs16", (B, T, idim)))
+        e0 = self.buf("enc.e0", (B, T, d))
+        self._lin_fwd(xa.view(B * T, idim), self.W("encoder.embed.0.weight"), st.p("encoder.embed.0.bias"), e0.view(B * T, d))
+        ln0 = self._ln_fwd(e0, "encoder.embed.1", "enc.ln0", EMBED_LN_EPS)
+        x0 = self.buf("enc.x0", (B, T, d))
+        ops.scale_dropout(ln0, x0, math.sqrt(d), self.named_drop("enc.embed.drop", er), self.named_drop("enc.pos", epr))
+        henc = self._conformer_fwd(x0, "encoder", hp["elayers"], H, hp["eunits"], hp["conformer_enc_kernel_size"], self.ilens_dev,
+                                   er, epr, ear)
+        # ---- post-encoder reduction (aas_vc.py:319-332): (B,T,d) -> (B,Tt,C)
+        if T % pr == 0:
+            hs = henc.view(B, Tt, C)
+        else:
+            hs = self.buf("hs.red", (B, Tt, C))
+            hs.view(B, Tt * pr, d).copy_(henc[:, :Tt * pr])
+        self.hs = hs
+        # ---- duration-predictor input: Conv2dSubsampling projection + nearest interpolation (aas_vc.py:335-351)
+        Tdp = dp_inputs.shape[1]
+        Tp = (((Tdp - 1) // 2) - 1) // 2
+        proj = self._conv2d_sub_fwd(dp_inputs, "duration_predictor_projection", "duration_predictor_projection.out", "dpp")
+        idx, ones, _, _ = self._interp_tables(Tp, Tt)
+        dpi = self.buf("dp.in", (B, Tt, d))
+        ops.gather_rows(proj.view(B, Tp, d), idx, ones, dpi)
+        # ---- duration predictor (duration_predictor.py:83-101)
+        k = hp["duration_predictor_kernel_size"]
+        halo = (k - 1) // 2
+        ch = hp["duration_predictor_chans"]
+        cur = dpi
+        for i in range(hp["duration_predictor_layers"]):
+            ic = cur.shape[2]
+            xp = ops.pad_rows(cur, self.buf(f"dp.pad{i}", (B, Tt + 2 * halo, ic)), halo)
+            z = self._conv1d_fwd(xp, f"duration_predictor.conv.{i}.0", Tt, True, f"dp.c{i}")
+            zu = ops.unpad_rows(z, self.buf(f"dp.zu{i}", (B, Tt, ch)), halo)
+            nl = self._ln_fwd(zu, f"duration_predictor.conv.{i}.2", f"dp.ln{i}")
+            drop = self.named_drop(f"dp.drop{i}", hp["duration_predictor_dropout_rate"])
+            if drop.p > 0:
+                nl = ops.scale_dropout(nl, self.buf(f"dp.do{i}", (B, Tt, ch)), 1.0, drop)
+            cur = nl
+        self.dp_last = cur
+        self.dp_pre = self.buf("dp.pre", (B * Tt, 1))
+        self._lin_fwd(cur.view(B * Tt, ch), self.W("duration_predictor.linear.weight"), st.p("duration_predictor.linear.bias"), self.dp_pre)
+
+    def _decoder_side(self, ds: torch.Tensor, L: int):
+        """Gaussian upsampling of self.hs with durations ds (B,Tt) to L frames, conformer decoder, feat_out, postnet."""
+        hp, st = self.hp, self.store
+        hs = self.hs
+        B, Tt, C = hs.shape
+        H, odim = hp["aheads"], hp["odim"]
+        _, (dr_, dpr, dar) = self._rates()
+        # ---- Gaussian upsampling (length_regulator.py:111-154)
+        ldp = _r8(Tt)
+        Pg = self.buf("up.P", (B, L, ldp))
+        ops.gauss_weights(ds, self.olens_dev, self.tlens_dev, Pg)
+        up = self.buf("up.out", (B, L, C))
+        ops.gemm(Pg[..., :Tt], hs.transpose(1, 2), up, mode=self.mode)
+        # ---- decoder: RelPositionalEncoding (x * sqrt(C), dropout) + conformer blocks (aas_vc.py:449-452)
+        xd0 = self.buf("dec.x0", (B, L, C))
+        ops.scale_dropout(up, xd0, math.sqrt(C), self.named_drop("dec.pos", dpr))
+        zs = self._conformer_fwd(xd0, "decoder", hp["dlayers"], H, hp["dunits"], hp["conformer_dec_kernel_size"], self.olens_dev,
+                                 dr_, dpr, dar)
+        self.zs = zs
+        before = self.buf("out.before", (B, L, odim))
+        self._lin_fwd(zs.view(B * L, C), self.W("feat_out.weight"), st.p("feat_out.bias"), before.view(B * L, odim))
+        after = self._postnet_fwd(before, lambda i: self.named_drop(f"post{i}", hp["postnet_dropout_rate"]))
+        self.before, self.after = before, after
+        return after, before
+
     def forward(self, xs: torch.Tensor, ys: torch.Tensor, dp_inputs: torch.Tensor, ilens: Optional[Sequence[int]] = None,
                 olens: Optional[Sequence[int]] = None):
         """xs (B,T,idim), ys (B,L,odim), dp_inputs (B,T_dp,dp_idim) float32 device tensors already trimmed to the max
@@ -518,7 +600,7 @@ class AASVCEngine(EngineBase):
         hp, st = self.hp, self.store
         B, T, idim = xs.shape
         L, odim = ys.shape[1], ys.shape[2]
-        d, H, pr = hp["adim"], hp["aheads"], hp["post_encoder_reduction_factor"]
+        d, pr = hp["adim"], hp["post_encoder_reduction_factor"]
         C, Tt = d * pr, T // pr
         assert xs.dtype == _f32 and ys.dtype == _f32 and dp_inputs.dtype == _f32
         assert xs.is_contiguous() and ys.is_contiguous() and dp_inputs.is_contiguous()
@@ -533,36 +615,9 @@ class AASVCEngine(EngineBase):
         self.ilens_dev, self.tlens_dev, self.olens_dev = lens[0], lens[1], lens[2]
         self.shapes = dict(B=B, T=T, L=L, Tt=Tt, Tdp=dp_inputs.shape[1])
         self.xs, self.dp_inputs = xs, dp_inputs
-        er, epr, ear = hp["transformer_enc_dropout_rate"], hp["transformer_enc_positional_dropout_rate"], hp["transformer_enc_attn_dropout_rate"]
-        dr_, dpr, dar = hp["transformer_dec_dropout_rate"], hp["transformer_dec_positional_dropout_rate"], hp["transformer_dec_attn_dropout_rate"]
 
-        # ---- encoder input layer: Linear -> LayerNorm(1e-5) -> dropout -> x * sqrt(d) -> dropout (conformer/encoder.py:117-123)
-        xa = xs
-        if self.bf16:
-            xa = ops.cast(xs, self.buf("enc.xs16", (B, T, idim)))
-        e0 = self.buf("enc.e0", (B, T, d))
-        self._lin_fwd(xa.view(B * T, idim), self.W("encoder.embed.0.weight"), st.p("encoder.embed.0.bias"), e0.view(B * T, d))
-        ln0 = self._ln_fwd(e0, "encoder.embed.1", "enc.ln0", EMBED_LN_EPS)
-        x0 = self.buf("enc.x0", (B, T, d))
-        ops.scale_dropout(ln0, x0, math.sqrt(d), self.named_drop("enc.embed.drop", er), self.named_drop("enc.pos", epr))
-        henc = self._conformer_fwd(x0, "encoder", hp["elayers"], H, hp["eunits"], hp["conformer_enc_kernel_size"], self.ilens_dev,
-                                   er, epr, ear)
-
-        # ---- post-encoder reduction (aas_vc.py:319-332): (B,T,d) -> (B,Tt,C)
-        if T % pr == 0:
-            hs = henc.view(B, Tt, C)
-        else:
-            hs = self.buf("hs.red", (B, Tt, C))
-            hs.view(B, Tt * pr, d).copy_(henc[:, :Tt * pr])
-        self.hs = hs
-
-        # ---- duration-predictor input: Conv2dSubsampling projection + nearest interpolation (aas_vc.py:335-351)
-        Tdp = dp_inputs.shape[1]
-        Tp = (((Tdp - 1) // 2) - 1) // 2
-        proj = self._conv2d_sub_fwd(dp_inputs, "duration_predictor_projection", "duration_predictor_projection.out", "dpp")
-        idx, ones, _, _ = self._interp_tables(Tp, Tt)
-        dpi = self.buf("dp.in", (B, Tt, d))
-        ops.gather_rows(proj.view(B, Tp, d), idx, ones, dpi)
+        self._encoder_side(xs, dp_inputs)
+        hs = self.hs
 
         # ---- alignment module (alignments.py:28-60)
         ya = ys
@@ -594,43 +649,47 @@ class AASVCEngine(EngineBase):
         ops.mas_into(logp, self.tlens_dev, self.olens_dev, self.paths, self.ds, self.losses[2:3], self.d_logp_mas,
                      self._mas_ws(B, L, Tt))
 
-        # ---- duration predictor (duration_predictor.py:83-101)
-        k = hp["duration_predictor_kernel_size"]
-        halo = (k - 1) // 2
-        ch = hp["duration_predictor_chans"]
-        cur = dpi
-        for i in range(hp["duration_predictor_layers"]):
-            ic = cur.shape[2]
-            xp = ops.pad_rows(cur, self.buf(f"dp.pad{i}", (B, Tt + 2 * halo, ic)), halo)
-            z = self._conv1d_fwd(xp, f"duration_predictor.conv.{i}.0", Tt, True, f"dp.c{i}")
-            zu = ops.unpad_rows(z, self.buf(f"dp.zu{i}", (B, Tt, ch)), halo)
-            nl = self._ln_fwd(zu, f"duration_predictor.conv.{i}.2", f"dp.ln{i}")
-            drop = self.named_drop(f"dp.drop{i}", hp["duration_predictor_dropout_rate"])
-            if drop.p > 0:
-                nl = ops.scale_dropout(nl, self.buf(f"dp.do{i}", (B, Tt, ch)), 1.0, drop)
-            cur = nl
-        self.dp_last = cur
-        self.dp_pre = self.buf("dp.pre", (B * Tt, 1))
-        self._lin_fwd(cur.view(B * Tt, ch), self.W("duration_predictor.linear.weight"), st.p("duration_predictor.linear.bias"), self.dp_pre)
+        return self._decoder_side(self.ds, L)
 
-        # ---- Gaussian upsampling (length_regulator.py:111-154)
-        ldp = _r8(Tt)
-        Pg = self.buf("up.P", (B, L, ldp))
-        ops.gauss_weights(self.ds, self.olens_dev, self.tlens_dev, Pg)
-        up = self.buf("up.out", (B, L, C))
-        ops.gemm(Pg[..., :Tt], hs.transpose(1, 2), up, mode=self.mode)
-
-        # ---- decoder: RelPositionalEncoding (x * sqrt(C), dropout) + conformer blocks (aas_vc.py:449-452)
-        xd0 = self.buf("dec.x0", (B, L, C))
-        ops.scale_dropout(up, xd0, math.sqrt(C), self.named_drop("dec.pos", dpr))
-        zs = self._conformer_fwd(xd0, "decoder", hp["dlayers"], H, hp["dunits"], hp["conformer_dec_kernel_size"], self.olens_dev,
-                                 dr_, dpr, dar)
-        self.zs = zs
-        before = self.buf("out.before", (B, L, odim))
-        self._lin_fwd(zs.view(B * L, C), self.W("feat_out.weight"), st.p("feat_out.bias"), before.view(B * L, odim))
-        after = self._postnet_fwd(before, lambda i: self.named_drop(f"post{i}", hp["postnet_dropout_rate"]))
-        self.before, self.after = before, after
-        return after, before
+    @torch.no_grad()
+    def inference(self, x: torch.Tensor, dp_input: torch.Tensor):
+        """AASVC.inference without ground truth (aas_vc.py:531-603, _forward(is_inference=True) :371-398) for one utterance:
+        x (T, idim), dp_input (T_dp, dp_idim) float32 device tensors -> (outs (L, odim) float32, d_outs (T_text,) int64).
+        Eval-mode BatchNorm, no dropout; durations = clamp(round(exp(d) - 1), 0, 10); T_feats = sum(durations) is read back
+        to the host once (the reference does the same in GaussianUpsampling: `ds.sum().int()`)."""
+        hp = self.hp
+        T = x.shape[0]
+        pr = hp["post_encoder_reduction_factor"]
+        Tt = T // pr
+        assert Tt >= 1, "source too short for the post-encoder reduction factor"
+        was_training = self.training
+        self.training = False
+        try:
+            # eval buffers are keyed by utterance length: drop the ones of earlier utterances
+            for key in [k for k in self._bufs if isinstance(k[0], tuple) and len(k[0]) == 4 and k[0][3] is False]:
+                del self._bufs[key]
+            self._sig = (1, T, -1, False)
+            self.attn = {}
+            self._last = {}
+            self.sync_shadow()
+            mk = lambda v: torch.tensor([v], dtype=_i32).to(self.device)
+            self.ilens_dev, self.tlens_dev = mk(T), mk(Tt)
+            xs = x.to(_f32).contiguous().unsqueeze(0)
+            dpi = dp_input.to(_f32).contiguous().unsqueeze(0)
+            self._encoder_side(xs, dpi)
+            ds = self.buf("inf.ds", (1, Tt), _f32)
+            ops.duration_infer(self.dp_pre, ds)
+            L = int(ds.sum().item())                          # the one host read-back of this path
+            if L == 0:                                        # length_regulator.py:127-135 (all-zero prediction): every token gets one frame
+                ds.fill_(1.0)
+                L = Tt
+            self._sig = (1, T, L, False)
+            self.olens_dev = mk(L)
+            self.shapes = dict(B=1, T=T, L=L, Tt=Tt, Tdp=dpi.shape[1])
+            after, _ = self._decoder_side(ds, L)
+            return after[0].float().clone(), ds[0].to(torch.int64)
+        finally:
+            self.training = was_training
 
     def _mas_ws(self, B, L, Tt):
         n = ops.mas_workspace_bytes(B, L, Tt)

@@ -245,6 +245,22 @@ class VTN(torch.nn.Module):
         return after.float(), before.float(), logits.float(), ys_out, labels_out, olens_out, (att_ws, ilens_ds_st, olens_in)
 
 
+def _vtn_inference(self, x, inference_args, spemb=None, *args, **kwargs):
+    """Drop-in for VTN.inference (models/vtn.py:302-394): x (T, idim) -> (outs (L, odim), probs (L,), att_ws (#layers, #heads, L/r, T'))."""
+    if spemb is not None:
+        raise NotImplementedError("speaker embeddings are outside the hot path")
+    if not x.is_cuda:
+        raise S2SError("seq2seq_vc_b200.VTN runs on a B200 only (no CPU fallback)")
+    self.engine.p16_dirty = True
+    outs, probs, att_ws = self.engine.inference(x, inference_args["threshold"], inference_args["minlenratio"], inference_args["maxlenratio"])
+    for l in range(self.hp["dlayers"]):                    # `.attn` of the source-attention modules, as the reference leaves it
+        self.decoder.decoders[l].src_attn.attn = att_ws[l].unsqueeze(0)
+    return outs, probs, att_ws
+
+
+VTN.inference = _vtn_inference
+
+
 class TransformerTTS(VTN):
     """Drop-in for seq2seq_vc.models.TransformerTTS (models/transformer_tts.py:13-229): token-embedding encoder,
     same decoder / heads / postnet as VTN, guided-attention maps returned as one differentiable tensor."""
@@ -826,6 +842,21 @@ class AASVC(VTN):
         olens_out = torch.tensor(ol, dtype=torch.int64, device=dev)
         return dict(d_outs=d_outs, before_outs=before.float(), after_outs=after.float(), ds=ds, ilens=ilens_out, bin_loss=bin_loss,
                     log_p_attn=logp, olens_reduced=olens_out, olens=olens_out, ys=ys)
+
+
+def _aasvc_inference(self, src_speech, tgt_speech=None, spembs=None, dp_input=None, use_teacher_forcing=False):
+    """Drop-in for AASVC.inference (models/aas_vc.py:531-603) without ground truth: (T, idim) -> (outs (L, odim), d_outs (T_text,))."""
+    if tgt_speech is not None or use_teacher_forcing or spembs is not None:
+        raise NotImplementedError("inference with ground-truth targets / durations / speaker embeddings is outside the hot path")
+    if not src_speech.is_cuda:
+        raise S2SError("seq2seq_vc_b200.AASVC runs on a B200 only (no CPU fallback)")
+    if dp_input is None:
+        raise S2SError("dp_input is required (duration_predictor_use_encoder_outputs=False)")
+    self.engine.p16_dirty = True
+    return self.engine.inference(src_speech, dp_input)
+
+
+AASVC.inference = _aasvc_inference
 
 
 class AASVCTrainStep:

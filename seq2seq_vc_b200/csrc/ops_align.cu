@@ -327,6 +327,16 @@ __global__ void __launch_bounds__(256) duration_loss_kernel(const T* __restrict_
     if (threadIdx.x == 0 && loss) *loss = nv > 0.f ? acc / nv : 0.f;
 }
 
+// inference durations: d = min(max(rint(exp(pre) - offset), 0), clamp_max)   (duration_predictor.py:92-96, aas_vc.py:389)
+template <typename T>
+__global__ void duration_infer_kernel(const T* __restrict__ pre, float* __restrict__ d, int n, float offset, float clamp_max) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v = rintf(expf(to_f<T>(pre[i])) - offset);
+    v = fmaxf(v, 0.f);
+    d[i] = fminf(v, clamp_max);
+}
+
 }  // namespace s2s
 
 using namespace s2s;
@@ -397,6 +407,14 @@ extern "C" int s2s_duration_loss(const void* pre, const float* ds, const int32_t
     cudaStream_t st = (cudaStream_t)stream;
     S2S_DISPATCH_DTYPE(dtype, T, (duration_loss_kernel<T><<<1, 256, 0, st>>>((const T*)pre, ds, text_lens, B, T_text, offset, clamp_max,
                                                                             grad_scale, g_douts, d_outs, loss, (T*)d_pre)));
+    S2S_LAUNCH_OK();
+    return S2S_OK;
+}
+
+extern "C" int s2s_duration_infer(const void* pre, float* d, int n, float offset, float clamp_max, int dtype, void* stream) {
+    S2S_REQUIRE(pre && d && n > 0, "duration_infer: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    S2S_DISPATCH_DTYPE(dtype, T, (duration_infer_kernel<T><<<(unsigned)ceil_div_l(n, 256), 256, 0, st>>>((const T*)pre, d, n, offset, clamp_max)));
     S2S_LAUNCH_OK();
     return S2S_OK;
 }

@@ -550,3 +550,9 @@ def duration_loss(pre, ds, text_lens, d_outs, loss, d_pre, grad_scale=1.0, offse
     assert g_douts is None or (g_douts.dtype == torch.float32 and g_douts.is_contiguous() and g_douts.numel() == B * TT)
     check(_L().s2s_duration_loss(ptr(pre), ptr(ds), ptr(text_lens), B, TT, float(offset), float(clamp_max), float(grad_scale),
                                  ptr(g_douts), ptr(d_outs), ptr(loss), ptr(d_pre), dt(pre), stream()), "duration_loss")
+
+
+def duration_infer(pre, d, offset=1.0, clamp_max=10.0):
+    assert pre.is_contiguous() and d.is_contiguous() and d.dtype == torch.float32 and pre.numel() == d.numel()
+    check(_L().s2s_duration_infer(ptr(pre), ptr(d), d.numel(), float(offset), float(clamp_max), dt(pre), stream()), "duration_infer")
+    return d

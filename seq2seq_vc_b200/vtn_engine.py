@@ -169,6 +169,122 @@ class VTNEngine(EngineBase):
     # ------------------------------------------------------------------ building blocks
 
 
+    # ------------------------------------------------------------------ encoder / decoder stacks
+    def _encode(self, xs: torch.Tensor) -> torch.Tensor:
+        """Encoder front end + encoder layers + after_norm -> memory (B, T2, d).  Uses self.shapes / self.klens_enc."""
+        hp, st = self.hp, self.store
+        embed = hp["encoder_input"] == "embed"
+        sh = self.shapes
+        B, T, T1, F1, T2, F2 = sh["B"], sh["T"], sh["T1"], sh["F1"], sh["T2"], sh["F2"]
+        idim, d, H = hp["idim"], hp["adim"], hp["aheads"]
+        dk = d // H
+        self.xs = xs
+        x = self.buf("enc.x0", (B, T2, d))
+        if embed:
+            # ---- token embedding + <eos> + ScaledPE in one kernel (transformer_tts.py:63-77,139-142)
+            ops.embed_pe_fwd(xs, self.ilens_dev, st.p("encoder.embed.0.weight"), self.pe(d, T2), st.p("encoder.embed.1.alpha"), x,
+                             idim - 1, 0, self.drop(hp["enc_positional_dropout_rate"]))
+        else:
+            # ---- packed conv weights (activation dtype)
+            w2p = self.buf("w.conv2p", (d, 9, d))          # [oc][tap][ic]
+            ops.transpose_last2(st.p("encoder.embed.conv.2.weight"), w2p, d, d, 9)
+            woutp = self.buf("w.outp", (d, F2, d))         # [n][f][c]
+            ops.transpose_last2(st.p("encoder.embed.out.0.weight"), woutp, d, d, F2)
+            # ---- encoder front end (subsampling.py:74-94)
+            y1 = self.buf("enc.y1", (B, T1, F1, d))
+            ops.conv1_fwd(xs, st.p("encoder.embed.conv.0.weight"), st.p("encoder.embed.conv.0.bias"), y1)
+            col = self._scratch("col", (B * T2 * F2, 9 * d))
+            ops.im2col_s2(y1, col)
+            y2 = self.buf("enc.y2", (B * T2 * F2, d))
+            ops.gemm(col, w2p.view(d, 9 * d), y2, bias=st.p("encoder.embed.conv.2.bias"), relu=True, mode=self.mode)
+            elin = self.buf("enc.elin", (B * T2, d))
+            ops.gemm(y2.view(B * T2, F2 * d), woutp.view(d, F2 * d), elin, bias=st.p("encoder.embed.out.0.bias"), mode=self.mode)
+            ops.scaled_pe_fwd(elin.view(B, T2, d), self.pe(d, T2), st.p("encoder.embed.out.1.alpha"), x,
+                              self.drop(hp["enc_positional_dropout_rate"]))
+
+        # ---- encoder layers (pre-LN; encoder_layer.py:61-119)
+        pe_ = hp["transformer_enc_dropout_rate"]
+        for l in range(hp["elayers"]):
+            p = f"encoder.encoders.{l}"
+            n1 = self._ln_fwd(x, p + ".norm1", p + ".ln1")
+            qkv = self.buf(p + ".qkv", (B, T2, 3, H, dk))
+            self._lin_fwd(n1.view(B * T2, d), self.Wspan([p + ".self_attn.linear_q.weight"], (3 * d, d)),
+                          st.span(st.P, [p + ".self_attn.linear_q.bias"], (3 * d,)), qkv.view(B * T2, 3 * d))
+            ctx = self._attn_core_fwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], self.klens_enc, False, p + ".sa", p + ".self_attn")
+            xm = self.buf(p + ".xmid", (B, T2, d))
+            self._lin_fwd(ctx.view(B * T2, d), self.W(p + ".self_attn.linear_out.weight"), st.p(p + ".self_attn.linear_out.bias"),
+                          xm.view(B * T2, d), drop=self.drop(pe_), residual=x.view(B * T2, d))
+            n2 = self._ln_fwd(xm, p + ".norm2", p + ".ln2")
+            h = self.buf(p + ".ffh", (B * T2, hp["eunits"]))
+            self._lin_fwd(n2.view(B * T2, d), self.W(p + ".feed_forward.w_1.weight"), st.p(p + ".feed_forward.w_1.bias"), h,
+                          relu=True, drop=self.drop(pe_))
+            xn = self.buf(p + ".xout", (B, T2, d))
+            self._lin_fwd(h, self.W(p + ".feed_forward.w_2.weight"), st.p(p + ".feed_forward.w_2.bias"), xn.view(B * T2, d),
+                          drop=self.drop(pe_), residual=xm.view(B * T2, d))
+            x = xn
+        self.enc_last = x
+        mem = self._ln_fwd(x, "encoder.after_norm", "enc.after")
+
+        return mem
+
+    def _decode(self, ys_in: torch.Tensor, mem: torch.Tensor) -> torch.Tensor:
+        """Prenet + ScaledPE + decoder layers over the (already shifted / thinned) decoder inputs ys_in (B, Lr, odim)."""
+        hp, st = self.hp, self.store
+        B, Lr, odim = ys_in.shape
+        T2 = mem.shape[1]
+        d, H = hp["adim"], hp["aheads"]
+        dk = d // H
+        u = hp["dprenet_units"]
+        hcur = ys_in.view(B * Lr, odim)
+        for i in range(hp["dprenet_layers"]):
+            nm = f"decoder.embed.0.0.prenet.{i}.0"
+            out = self.buf(f"dec.prenet{i}", (B * Lr, u))
+            # Prenet dropout is always on in the reference (pre_postnets.py:65), also in eval()
+            self._site += 1
+            pd = hp["dprenet_dropout_rate"]
+            dr = Drop(pd, self.base_seed, self._site, self.seed_dev) if pd > 0 else NO_DROP
+            self._lin_fwd(hcur, self.W(nm + ".weight"), st.p(nm + ".bias"), out, relu=True, drop=dr)
+            hcur = out
+        dlin = self.buf("dec.elin", (B * Lr, d))
+        self._lin_fwd(hcur, self.W("decoder.embed.0.1.weight"), st.p("decoder.embed.0.1.bias"), dlin)
+        x = self.buf("dec.x0", (B, Lr, d))
+        ops.scaled_pe_fwd(dlin.view(B, Lr, d), self.pe(d, Lr), st.p("decoder.embed.1.alpha"), x,
+                          self.drop(hp["dec_positional_dropout_rate"]))
+
+        # ---- decoder layers (post-LN; decoder_layer.py:63-134)
+        pdrop = hp["dec_dropout_rate"]
+        for l in range(hp["dlayers"]):
+            p = f"decoder.decoders.{l}"
+            qkv = self.buf(p + ".qkv", (B, Lr, 3, H, dk))
+            self._lin_fwd(x.view(B * Lr, d), self.Wspan([p + ".self_attn.linear_q.weight"], (3 * d, d)),
+                          st.span(st.P, [p + ".self_attn.linear_q.bias"], (3 * d,)), qkv.view(B * Lr, 3 * d))
+            ctx = self._attn_core_fwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], self.olens_in, True, p + ".sa", p + ".self_attn")
+            t1 = self.buf(p + ".t1", (B, Lr, d))
+            self._lin_fwd(ctx.view(B * Lr, d), self.W(p + ".self_attn.linear_out.weight"), st.p(p + ".self_attn.linear_out.bias"),
+                          t1.view(B * Lr, d), drop=self.drop(pdrop), residual=x.view(B * Lr, d))
+            x1 = self._ln_fwd(t1, p + ".norm1", p + ".ln1")
+            q = self.buf(p + ".q", (B, Lr, H, dk))
+            self._lin_fwd(x1.view(B * Lr, d), self.W(p + ".src_attn.linear_q.weight"), st.p(p + ".src_attn.linear_q.bias"),
+                          q.view(B * Lr, d))
+            kv = self.buf(p + ".kv", (B, T2, 2, H, dk))
+            self._lin_fwd(mem.view(B * T2, d), self.Wspan([p + ".src_attn.linear_k.weight"], (2 * d, d)),
+                          st.span(st.P, [p + ".src_attn.linear_k.bias"], (2 * d,)), kv.view(B * T2, 2 * d))
+            ctx2 = self._attn_core_fwd(q, kv[:, :, 0], kv[:, :, 1], self.klens_enc, False, p + ".ca", p + ".src_attn")
+            t2 = self.buf(p + ".t2", (B, Lr, d))
+            self._lin_fwd(ctx2.view(B * Lr, d), self.W(p + ".src_attn.linear_out.weight"), st.p(p + ".src_attn.linear_out.bias"),
+                          t2.view(B * Lr, d), drop=self.drop(pdrop), residual=x1.view(B * Lr, d))
+            x2 = self._ln_fwd(t2, p + ".norm2", p + ".ln2")
+            h = self.buf(p + ".ffh", (B * Lr, hp["dunits"]))
+            self._lin_fwd(x2.view(B * Lr, d), self.W(p + ".feed_forward.w_1.weight"), st.p(p + ".feed_forward.w_1.bias"), h,
+                          relu=True, drop=self.drop(pdrop))
+            t3 = self.buf(p + ".t3", (B, Lr, d))
+            self._lin_fwd(h, self.W(p + ".feed_forward.w_2.weight"), st.p(p + ".feed_forward.w_2.bias"), t3.view(B * Lr, d),
+                          drop=self.drop(pdrop), residual=x2.view(B * Lr, d))
+            x = self._ln_fwd(t3, p + ".norm3", p + ".ln3")
+        zs = x
+
+        return zs
+
     # ------------------------------------------------------------------ forward
     def prepare(self, B: int, T: int, L: int, ilens: Sequence[int], olens: Sequence[int]) -> None:
         """Derive the per-utterance length vectors on the host (they arrive as CPU ints from the
@@ -238,104 +354,12 @@ class VTNEngine(EngineBase):
         lens = self.buf("lens", (5, B), _i32)
         self.klens_enc, self.olens_in, self.olens_fix, self.ilens_dev, self.ilens_ds_dev = lens[0], lens[1], lens[2], lens[3], lens[4]
 
-        self.xs = xs
-        x = self.buf("enc.x0", (B, T2, d))
-        if embed:
-            # ---- token embedding + <eos> + ScaledPE in one kernel (transformer_tts.py:63-77,139-142)
-            ops.embed_pe_fwd(xs, self.ilens_dev, st.p("encoder.embed.0.weight"), self.pe(d, T2), st.p("encoder.embed.1.alpha"), x,
-                             idim - 1, 0, self.drop(hp["enc_positional_dropout_rate"]))
-        else:
-            # ---- packed conv weights (activation dtype)
-            w2p = self.buf("w.conv2p", (d, 9, d))          # [oc][tap][ic]
-            ops.transpose_last2(st.p("encoder.embed.conv.2.weight"), w2p, d, d, 9)
-            woutp = self.buf("w.outp", (d, F2, d))         # [n][f][c]
-            ops.transpose_last2(st.p("encoder.embed.out.0.weight"), woutp, d, d, F2)
-            # ---- encoder front end (subsampling.py:74-94)
-            y1 = self.buf("enc.y1", (B, T1, F1, d))
-            ops.conv1_fwd(xs, st.p("encoder.embed.conv.0.weight"), st.p("encoder.embed.conv.0.bias"), y1)
-            col = self._scratch("col", (B * T2 * F2, 9 * d))
-            ops.im2col_s2(y1, col)
-            y2 = self.buf("enc.y2", (B * T2 * F2, d))
-            ops.gemm(col, w2p.view(d, 9 * d), y2, bias=st.p("encoder.embed.conv.2.bias"), relu=True, mode=self.mode)
-            elin = self.buf("enc.elin", (B * T2, d))
-            ops.gemm(y2.view(B * T2, F2 * d), woutp.view(d, F2 * d), elin, bias=st.p("encoder.embed.out.0.bias"), mode=self.mode)
-            ops.scaled_pe_fwd(elin.view(B, T2, d), self.pe(d, T2), st.p("encoder.embed.out.1.alpha"), x,
-                              self.drop(hp["enc_positional_dropout_rate"]))
-
-        # ---- encoder layers (pre-LN; encoder_layer.py:61-119)
-        pe_ = hp["transformer_enc_dropout_rate"]
-        for l in range(hp["elayers"]):
-            p = f"encoder.encoders.{l}"
-            n1 = self._ln_fwd(x, p + ".norm1", p + ".ln1")
-            qkv = self.buf(p + ".qkv", (B, T2, 3, H, dk))
-            self._lin_fwd(n1.view(B * T2, d), self.Wspan([p + ".self_attn.linear_q.weight"], (3 * d, d)),
-                          st.span(st.P, [p + ".self_attn.linear_q.bias"], (3 * d,)), qkv.view(B * T2, 3 * d))
-            ctx = self._attn_core_fwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], self.klens_enc, False, p + ".sa", p + ".self_attn")
-            xm = self.buf(p + ".xmid", (B, T2, d))
-            self._lin_fwd(ctx.view(B * T2, d), self.W(p + ".self_attn.linear_out.weight"), st.p(p + ".self_attn.linear_out.bias"),
-                          xm.view(B * T2, d), drop=self.drop(pe_), residual=x.view(B * T2, d))
-            n2 = self._ln_fwd(xm, p + ".norm2", p + ".ln2")
-            h = self.buf(p + ".ffh", (B * T2, hp["eunits"]))
-            self._lin_fwd(n2.view(B * T2, d), self.W(p + ".feed_forward.w_1.weight"), st.p(p + ".feed_forward.w_1.bias"), h,
-                          relu=True, drop=self.drop(pe_))
-            xn = self.buf(p + ".xout", (B, T2, d))
-            self._lin_fwd(h, self.W(p + ".feed_forward.w_2.weight"), st.p(p + ".feed_forward.w_2.bias"), xn.view(B * T2, d),
-                          drop=self.drop(pe_), residual=xm.view(B * T2, d))
-            x = xn
-        self.enc_last = x
-        mem = self._ln_fwd(x, "encoder.after_norm", "enc.after")
+        mem = self._encode(xs)
 
         # ---- decoder input (vtn.py:227-243,523-527; pre_postnets.py:60-66)
         ys_in = self.buf("dec.ys_in", (B, Lr, odim))
         ops.shift_thin(ys, ys_in, r)
-        u = hp["dprenet_units"]
-        hcur = ys_in.view(B * Lr, odim)
-        for i in range(hp["dprenet_layers"]):
-            nm = f"decoder.embed.0.0.prenet.{i}.0"
-            out = self.buf(f"dec.prenet{i}", (B * Lr, u))
-            # Prenet dropout is always on in the reference (pre_postnets.py:65), also in eval()
-            self._site += 1
-            pd = hp["dprenet_dropout_rate"]
-            dr = Drop(pd, self.base_seed, self._site, self.seed_dev) if pd > 0 else NO_DROP
-            self._lin_fwd(hcur, self.W(nm + ".weight"), st.p(nm + ".bias"), out, relu=True, drop=dr)
-            hcur = out
-        dlin = self.buf("dec.elin", (B * Lr, d))
-        self._lin_fwd(hcur, self.W("decoder.embed.0.1.weight"), st.p("decoder.embed.0.1.bias"), dlin)
-        x = self.buf("dec.x0", (B, Lr, d))
-        ops.scaled_pe_fwd(dlin.view(B, Lr, d), self.pe(d, Lr), st.p("decoder.embed.1.alpha"), x,
-                          self.drop(hp["dec_positional_dropout_rate"]))
-
-        # ---- decoder layers (post-LN; decoder_layer.py:63-134)
-        pdrop = hp["dec_dropout_rate"]
-        for l in range(hp["dlayers"]):
-            p = f"decoder.decoders.{l}"
-            qkv = self.buf(p + ".qkv", (B, Lr, 3, H, dk))
-            self._lin_fwd(x.view(B * Lr, d), self.Wspan([p + ".self_attn.linear_q.weight"], (3 * d, d)),
-                          st.span(st.P, [p + ".self_attn.linear_q.bias"], (3 * d,)), qkv.view(B * Lr, 3 * d))
-            ctx = self._attn_core_fwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], self.olens_in, True, p + ".sa", p + ".self_attn")
-            t1 = self.buf(p + ".t1", (B, Lr, d))
-            self._lin_fwd(ctx.view(B * Lr, d), self.W(p + ".self_attn.linear_out.weight"), st.p(p + ".self_attn.linear_out.bias"),
-                          t1.view(B * Lr, d), drop=self.drop(pdrop), residual=x.view(B * Lr, d))
-            x1 = self._ln_fwd(t1, p + ".norm1", p + ".ln1")
-            q = self.buf(p + ".q", (B, Lr, H, dk))
-            self._lin_fwd(x1.view(B * Lr, d), self.W(p + ".src_attn.linear_q.weight"), st.p(p + ".src_attn.linear_q.bias"),
-                          q.view(B * Lr, d))
-            kv = self.buf(p + ".kv", (B, T2, 2, H, dk))
-            self._lin_fwd(mem.view(B * T2, d), self.Wspan([p + ".src_attn.linear_k.weight"], (2 * d, d)),
-                          st.span(st.P, [p + ".src_attn.linear_k.bias"], (2 * d,)), kv.view(B * T2, 2 * d))
-            ctx2 = self._attn_core_fwd(q, kv[:, :, 0], kv[:, :, 1], self.klens_enc, False, p + ".ca", p + ".src_attn")
-            t2 = self.buf(p + ".t2", (B, Lr, d))
-            self._lin_fwd(ctx2.view(B * Lr, d), self.W(p + ".src_attn.linear_out.weight"), st.p(p + ".src_attn.linear_out.bias"),
-                          t2.view(B * Lr, d), drop=self.drop(pdrop), residual=x1.view(B * Lr, d))
-            x2 = self._ln_fwd(t2, p + ".norm2", p + ".ln2")
-            h = self.buf(p + ".ffh", (B * Lr, hp["dunits"]))
-            self._lin_fwd(x2.view(B * Lr, d), self.W(p + ".feed_forward.w_1.weight"), st.p(p + ".feed_forward.w_1.bias"), h,
-                          relu=True, drop=self.drop(pdrop))
-            t3 = self.buf(p + ".t3", (B, Lr, d))
-            self._lin_fwd(h, self.W(p + ".feed_forward.w_2.weight"), st.p(p + ".feed_forward.w_2.bias"), t3.view(B * Lr, d),
-                          drop=self.drop(pdrop), residual=x2.view(B * Lr, d))
-            x = self._ln_fwd(t3, p + ".norm3", p + ".ln3")
-        zs = x
+        zs = self._decode(ys_in, mem)
 
         # ---- output heads (vtn.py:249-251)
         Lo = Lr * r
@@ -349,6 +373,77 @@ class VTNEngine(EngineBase):
         after = self._postnet_fwd(before, lambda i: self.drop(hp["postnet_dropout_rate"]))
         self.before, self.after, self.logits = before, after, logits
         return after, before, logits
+
+    # ------------------------------------------------------------------ autoregressive inference
+    @torch.no_grad()
+    def inference(self, x: torch.Tensor, threshold: float = 0.5, minlenratio: float = 0.0, maxlenratio: float = 10.0):
+        """VTN.inference (models/vtn.py:302-394): x (T, idim) float32 -> (outs (L, odim), probs (L,), att_ws (#dlayers, H, L/r, T')).
+
+        The reference decodes with Decoder.forward_one_step, whose "cache" holds previous layer *outputs* and re-projects K/V
+        of the whole prefix every step; by causality that equals running the decoder over the prefix and reading its last
+        row, which is what this does (prefix lengths bucketed to multiples of 64 so that buffers / shapes are reused).
+        One host read-back of the stop probabilities per step, as in the reference (`int(sum(probs[-1] >= threshold))`).
+        A KV-cache single-row decode kernel is the next step for this row."""
+        hp, st = self.hp, self.store
+        assert hp["encoder_input"] != "embed", "token-input (TransformerTTS) inference is not covered"
+        r, d, H, odim, idim = hp["decoder_reduction_factor"], hp["adim"], hp["aheads"], hp["odim"], hp["idim"]
+        T = x.shape[0]
+        T1, F1 = (T - 1) // 2, (idim - 1) // 2
+        T2, F2 = (T1 - 1) // 2, (F1 - 1) // 2
+        assert T2 >= 1, "input too short for Conv2dSubsampling"
+        was_training = self.training
+        self.training = False
+        try:
+            for key in [k for k in self._bufs if isinstance(k[0], tuple) and len(k[0]) == 4 and k[0][3] is False]:
+                del self._bufs[key]
+            mk = lambda v: torch.tensor([v], dtype=_i32).to(self.device)
+            self._sig = (1, T, 0, False)
+            self._site = 0
+            self.attn = {}
+            self.sync_shadow()
+            self.shapes = dict(B=1, T=T, L=0, T1=T1, F1=F1, T2=T2, F2=F2, Lr=0)
+            self.klens_enc, self.ilens_dev = mk(T2), mk(T)            # encoder(x, None): no padding mask
+            xs = x.to(_f32).contiguous().unsqueeze(0)
+            mem = self._encode(xs)
+            site_after_encoder = self._site
+            maxlen = int(T2 * maxlenratio / r)
+            minlen = int(T2 * minlenratio / r)
+            cap = max(maxlen, 1) + 1
+            hist = torch.zeros(1, (cap + 63) // 64 * 64, odim, dtype=self.adt, device=self.device)   # decoder inputs: row 0 = zero frame
+            outs, probs = [], []
+            feat = torch.empty(1, odim * r, dtype=self.adt, device=self.device)
+            logit = torch.empty(1, r, dtype=self.adt, device=self.device)
+            idx = 0
+            while True:
+                idx += 1
+                Lq = (idx + 63) // 64 * 64
+                self._sig = (1, T, Lq, False)
+                self._site = site_after_encoder
+                self.olens_in = mk(Lq) if getattr(self, "_inf_lq", None) != Lq else self.olens_in
+                self._inf_lq = Lq
+                ys_in = self.buf("dec.ys_in", (1, Lq, odim))
+                ys_in.copy_(hist[:, :Lq])
+                zs = self._decode(ys_in, mem)                          # (1, Lq, d); rows >= idx are don't-care (causal)
+                z = zs.view(Lq, d)[idx - 1:idx]
+                self._lin_fwd(z, self.W("feat_out.weight"), st.p("feat_out.bias"), feat)
+                self._lin_fwd(z, self.W("prob_out.weight"), st.p("prob_out.bias"), logit)
+                outs.append(feat.view(r, odim).clone())
+                p_step = torch.sigmoid(logit.float()).view(r)
+                probs.append(p_step)
+                if idx < hist.shape[1]:
+                    hist[0, idx].copy_(feat.view(r, odim)[-1])
+                stop = bool((p_step >= threshold).any().item()) or idx >= maxlen     # host read-back (vtn.py:369)
+                if stop and idx >= minlen:
+                    break
+            self._inf_lq = None
+            L = idx * r
+            before = torch.cat(outs, dim=0).view(1, L, odim).contiguous()
+            self._sig = (1, T, -L, False)
+            after = self._postnet_fwd(before, lambda i: NO_DROP)
+            att = torch.stack([self.attn[f"decoder.decoders.{l}.src_attn"][0, :, :idx].float() for l in range(hp["dlayers"])], dim=0)
+            return after[0].float().clone(), torch.cat(probs, dim=0), att.clone()
+        finally:
+            self.training = was_training
 
     # ------------------------------------------------------------------ loss
     def loss(self, ys: torch.Tensor, labels: torch.Tensor, pos_weight: float = 10.0):

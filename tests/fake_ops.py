@@ -620,6 +620,11 @@ def duration_loss(pre, ds, text_lens, d_outs, loss, d_pre, grad_scale=1.0, offse
         d_pre.copy_((g * (x <= clamp_max)).reshape(d_pre.shape).to(d_pre.dtype))
 
 
+def duration_infer(pre, d, offset=1.0, clamp_max=10.0):
+    d.copy_(torch.clamp(torch.clamp(torch.round(pre.double().exp() - offset), min=0), max=clamp_max).reshape(d.shape).float())
+    return d
+
+
 def mas(log_p, text_lens, feats_lens, want_grad=False):
     """Contract of s2s_mas via the numpy/C oracle (bit-exact integer path)."""
     import numpy as np

@@ -103,3 +103,19 @@ def test_nearest_index_matches_torch_interpolate():
         x = torch.arange(tin, dtype=torch.float32)[None, None]
         ref = torch.nn.functional.interpolate(x, size=tout).long().view(-1).tolist()
         assert nearest_index(tin, tout) == ref
+
+
+def test_inference_matches_reference(engine):
+    """AASVC.inference (no ground truth): predicted durations (integers) exact, output mel vs the live-reference dump."""
+    eng, z = engine
+    sd = eng.state_dict()
+    for k in z.files:
+        if k.startswith("inf_bn."):
+            sd[k[7:]] = torch.from_numpy(z[k])
+    sd["duration_predictor.linear.bias"] = torch.from_numpy(z["inf_dp_bias"])
+    eng.load_state_dict(sd)
+    il = int(z["ilens"][0])
+    outs, d_outs = eng.inference(torch.from_numpy(z["xs"])[0, :il], torch.from_numpy(z["dp_inputs"])[0, :il])
+    np.testing.assert_array_equal(d_outs.numpy(), z["inf_d_outs"])
+    assert outs.shape == z["inf_outs"].shape and np.abs(outs.numpy() - z["inf_outs"]).mean() <= 1e-5
+    assert eng.training is True                          # restored

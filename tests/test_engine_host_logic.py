@@ -158,3 +158,20 @@ def test_tts_forward_guided_attention_and_gradients(monkeypatch):
     eng = VTNEngine(dict(TTS_HP, **NO_DROPOUT), device="cpu", bf16=False)
     eng.load_state_dict(sd)
     check_tts(eng, z)
+
+
+def test_autoregressive_inference_matches_reference(engine):
+    """VTN.inference (models/vtn.py:302-394): outputs, stop probabilities and source-attention maps vs the live-reference dump."""
+    eng, z = engine
+    sd = eng.state_dict()
+    for k in z.files:
+        if k.startswith("bn_after."):
+            sd[k[9:]] = torch.from_numpy(z[k])
+    eng.load_state_dict(sd)
+    il = int(z["ilens"][0])
+    outs, probs, att = eng.inference(torch.from_numpy(z["xs"])[0, :il], threshold=0.9999, minlenratio=0.0, maxlenratio=1.6)
+    assert outs.shape == z["inf_outs"].shape and probs.shape == z["inf_probs"].shape and att.shape == z["inf_att_ws"].shape
+    assert np.abs(outs.numpy() - z["inf_outs"]).mean() <= 1e-5
+    assert np.abs(probs.numpy() - z["inf_probs"]).max() <= 1e-5
+    assert np.abs(att.numpy() - z["inf_att_ws"]).max() <= 1e-5
+    assert eng.training is True

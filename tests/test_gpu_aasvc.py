@@ -471,3 +471,30 @@ def sd_flat_like(flat, sd):
     eng = AASVCEngine(dict(AAS_HP), device="cpu", bf16=False, seed=11)
     eng.load_state_dict(sd)
     return eng.store.P.clone()
+
+
+def test_inference_golden_and_dropin():
+    """AASVC.inference (no ground truth) on the GPU: integer durations exact, mel L1 <= 1e-4 vs the live-reference dump."""
+    from seq2seq_vc_b200 import AASVC
+    from seq2seq_vc_b200.aasvc_engine import AASVCEngine
+
+    z, sd = _golden()
+    sd = dict(sd)
+    sd.update({k[7:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("inf_bn.")})
+    sd["duration_predictor.linear.bias"] = torch.from_numpy(z["inf_dp_bias"])
+    il = int(z["ilens"][0])
+    x, dpi = torch.from_numpy(z["xs"])[0, :il].cuda(), torch.from_numpy(z["dp_inputs"])[0, :il].cuda()
+    eng = AASVCEngine(dict(AAS_HP, **NO_DROPOUT), device="cuda:0", bf16=False)
+    eng.load_state_dict(sd)
+    outs, d_outs = eng.inference(x, dpi)
+    np.testing.assert_array_equal(d_outs.cpu().numpy(), z["inf_d_outs"])
+    assert tuple(outs.shape) == z["inf_outs"].shape and np.abs(outs.cpu().numpy() - z["inf_outs"]).mean() <= 1e-4
+    model = AASVC(**AAS_HP, positionwise_layer_type="linear", duration_predictor_use_encoder_outputs=False, encoder_normalize_before=True,
+                  decoder_normalize_before=True, duration_predictor_type="deterministic", encoder_input_layer="linear").to("cuda:0")
+    model.load_state_dict(sd)
+    model.eval()
+    o2, d2 = model.inference(x, dp_input=dpi)
+    assert torch.equal(d2.cpu(), d_outs.cpu()) and np.abs(o2.cpu().numpy() - z["inf_outs"]).mean() <= 1e-4
+    # a second, longer utterance re-uses the engine (eval buffers of the previous length are dropped)
+    o3, d3 = eng.inference(torch.randn(93, 80, device="cuda"), torch.randn(93, 80, device="cuda"))
+    assert o3.shape == (int(d3.sum().item()) or 23, 80) and torch.isfinite(o3).all()

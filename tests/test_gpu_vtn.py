@@ -220,3 +220,38 @@ def test_tts_fused_step_with_guided_attention_trains():
         ga.append(step.ga_loss.item())
     assert np.isfinite(hist).all() and np.isfinite(ga).all()
     assert np.mean(hist[-5:]) < np.mean(hist[:5])
+
+
+def test_autoregressive_inference_golden_and_dropin():
+    """VTN.inference on the GPU (engine and drop-in module) vs the live-reference dump: mel L1 <= 1e-4, attention L1 <= 1e-3."""
+    from seq2seq_vc_b200 import VTN, VTNEngine
+
+    z = np.load(GOLDEN)
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    sd.update({k[9:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("bn_after.")})
+    il = int(z["ilens"][0])
+    x = torch.from_numpy(z["xs"])[0, :il].cuda()
+    eng = VTNEngine(dict(TINY_HP, **NO_DROPOUT), device="cuda:0", bf16=False)
+    eng.load_state_dict(sd)
+    outs, probs, att = eng.inference(x, threshold=0.9999, minlenratio=0.0, maxlenratio=1.6)
+    assert tuple(outs.shape) == z["inf_outs"].shape and tuple(att.shape) == z["inf_att_ws"].shape
+    assert np.abs(outs.cpu().numpy() - z["inf_outs"]).mean() <= 1e-4
+    assert np.abs(probs.cpu().numpy() - z["inf_probs"]).max() <= 1e-4
+    assert np.abs(att.cpu().numpy() - z["inf_att_ws"]).mean() <= 1e-3
+    # an early stop: a threshold every step exceeds ends after minlen steps
+    o2, p2, _ = eng.inference(x, threshold=0.0, minlenratio=0.4, maxlenratio=1.6)
+    T2 = z["inf_att_ws"].shape[-1]
+    assert o2.shape[0] == max(int(T2 * 0.4 / 2), 1) * 2 and p2.shape[0] == o2.shape[0]
+    model = VTN(**TINY_HP, dprenet_dropout_rate=0.0).to("cuda:0")
+    model.load_state_dict({k: v for k, v in sd.items()})
+    model.eval()
+    o3, p3, a3 = model.inference(x, dict(threshold=0.9999, minlenratio=0.0, maxlenratio=1.6))
+    assert np.abs(o3.cpu().numpy() - z["inf_outs"]).mean() <= 1e-4
+    assert tuple(model.decoder.decoders[0].src_attn.attn.shape) == (1,) + z["inf_att_ws"].shape[1:]
+    # longer than one 64-row bucket, bf16 path: finite and the right length
+    eng16 = VTNEngine(dict(TINY_HP, **NO_DROPOUT), device="cuda:0", bf16=True)
+    eng16.load_state_dict(sd)
+    xl = torch.randn(700, 80, device="cuda")
+    o4, p4, a4 = eng16.inference(xl, threshold=2.0, minlenratio=0.0, maxlenratio=1.0)
+    T2l = (((700 - 1) // 2) - 1) // 2
+    assert o4.shape == (int(T2l / 2) * 2, 80) and torch.isfinite(o4).all() and a4.shape[2] == int(T2l / 2)

@@ -145,3 +145,24 @@ def test_rel_shift_restatement():
     xp = torch.cat([torch.zeros(2, 3, T, 1), x], dim=-1).view(2, 3, 2 * T, T)[:, :, 1:].reshape(2, 3, T, 2 * T - 1)[..., :T]
     idx = T - 1 - torch.arange(T)[:, None] + torch.arange(T)[None, :]
     assert torch.equal(xp, torch.gather(x, 3, idx[None, None].expand(2, 3, T, T)))
+
+
+def test_inference_oracles_match_reference():
+    """Autoregressive VTN.inference and AASVC.inference restatements vs the live-reference dumps."""
+    from oracle import aasvc_oracle
+
+    z = np.load(os.path.join(GOLD, "vtn_tiny.npz"))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    sd.update({k[9:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("bn_after.")})
+    il = int(z["ilens"][0])
+    o, p, a = vtn_oracle.vtn_inference(sd, TINY_HP, torch.from_numpy(z["xs"])[0, :il], 0.9999, 0.0, 1.6)
+    assert np.abs(o.numpy() - z["inf_outs"]).max() <= 2e-5 and np.abs(p.numpy() - z["inf_probs"]).max() <= 1e-6
+    assert np.abs(a.numpy() - z["inf_att_ws"]).max() <= 1e-6
+    z = np.load(os.path.join(GOLD, "aasvc_tiny.npz"))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    sd.update({k[7:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("inf_bn.")})
+    sd["duration_predictor.linear.bias"] = torch.from_numpy(z["inf_dp_bias"])
+    il = int(z["ilens"][0])
+    outs, d = aasvc_oracle.aasvc_inference(sd, AAS_HP, torch.from_numpy(z["xs"])[0, :il], torch.from_numpy(z["dp_inputs"])[0, :il])
+    np.testing.assert_array_equal(d.numpy(), z["inf_d_outs"])
+    assert np.abs(outs.numpy() - z["inf_outs"]).max() <= 2e-5
