@@ -411,31 +411,50 @@ class VTNEngine(EngineBase):
             cap = max(maxlen, 1) + 1
             hist = torch.zeros(1, (cap + 63) // 64 * 64, odim, dtype=self.adt, device=self.device)   # decoder inputs: row 0 = zero frame
             outs, probs = [], []
-            feat = torch.empty(1, odim * r, dtype=self.adt, device=self.device)
-            logit = torch.empty(1, r, dtype=self.adt, device=self.device)
+            graphs: Dict[int, object] = {}
+            use_graph = self.device.type == "cuda"
             idx = 0
-            while True:
-                idx += 1
-                Lq = (idx + 63) // 64 * 64
+
+            def step_body(Lq):
+                """Decoder over the first Lq rows of `hist` + both output heads on every row (row idx-1 is read afterwards):
+                a fixed launch sequence per bucket, captured once into a CUDA graph and replayed for the bucket's steps."""
                 self._sig = (1, T, Lq, False)
                 self._site = site_after_encoder
-                self.olens_in = mk(Lq) if getattr(self, "_inf_lq", None) != Lq else self.olens_in
-                self._inf_lq = Lq
                 ys_in = self.buf("dec.ys_in", (1, Lq, odim))
                 ys_in.copy_(hist[:, :Lq])
                 zs = self._decode(ys_in, mem)                          # (1, Lq, d); rows >= idx are don't-care (causal)
-                z = zs.view(Lq, d)[idx - 1:idx]
-                self._lin_fwd(z, self.W("feat_out.weight"), st.p("feat_out.bias"), feat)
-                self._lin_fwd(z, self.W("prob_out.weight"), st.p("prob_out.bias"), logit)
-                outs.append(feat.view(r, odim).clone())
-                p_step = torch.sigmoid(logit.float()).view(r)
+                feat_all = self.buf("inf.feat", (Lq, odim * r))
+                logit_all = self.buf("inf.logit", (Lq, r))
+                self._lin_fwd(zs.view(Lq, d), self.W("feat_out.weight"), st.p("feat_out.bias"), feat_all)
+                self._lin_fwd(zs.view(Lq, d), self.W("prob_out.weight"), st.p("prob_out.bias"), logit_all)
+                return feat_all, logit_all
+
+            while True:
+                idx += 1
+                Lq = (idx + 63) // 64 * 64
+                if Lq not in graphs:
+                    self.olens_in = mk(Lq)
+                    feat_all, logit_all = step_body(Lq)                # eager: allocates this bucket's buffers
+                    graphs[Lq] = None
+                    if use_graph:
+                        torch.cuda.synchronize()
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g):
+                            step_body(Lq)
+                        graphs[Lq] = g
+                elif graphs[Lq] is not None:
+                    graphs[Lq].replay()
+                else:
+                    feat_all, logit_all = step_body(Lq)
+                frame = feat_all[idx - 1].view(r, odim)
+                outs.append(frame.clone())
+                p_step = torch.sigmoid(logit_all[idx - 1].float()).view(r)
                 probs.append(p_step)
                 if idx < hist.shape[1]:
-                    hist[0, idx].copy_(feat.view(r, odim)[-1])
+                    hist[0, idx].copy_(frame[-1])
                 stop = bool((p_step >= threshold).any().item()) or idx >= maxlen     # host read-back (vtn.py:369)
                 if stop and idx >= minlen:
                     break
-            self._inf_lq = None
             L = idx * r
             before = torch.cat(outs, dim=0).view(1, L, odim).contiguous()
             self._sig = (1, T, -L, False)
