@@ -40,6 +40,21 @@ __device__ __forceinline__ void stage_keys(bf16* __restrict__ ks, const AttnView
     }
 }
 
+// same, with cp.async (16-byte, zero fill past T2): the copy of block n+1 overlaps the MMAs / exps of block n
+template <int DK>
+__device__ __forceinline__ void stage_keys_async(bf16* __restrict__ ks, const AttnView& kv, int b, int h, int key0, int T2) {
+    constexpr int PITCH = DK + 8, CPR = DK / 8;
+    for (int i = threadIdx.x; i < AT_KEYS * CPR; i += blockDim.x) {
+        const int r = i / CPR, c = (i - r * CPR) * 8;
+        const int key = key0 + r;
+        const bf16* src = kv.p + (long)b * kv.bs + (long)(key < T2 ? key : 0) * kv.ts + (long)h * kv.hs + c;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ks + r * PITCH + c);
+        const int nbytes = key < T2 ? 16 : 0;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(nbytes));
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+}
+
 // 16 x 64 block of (A K^T) for this warp: acc[n][4], n = 8-key tile
 template <int DK>
 __device__ __forceinline__ void block_scores(float (&acc)[8][4], const uint32_t (&afrag)[DK / 16][4], const bf16* __restrict__ ks) {
@@ -110,7 +125,7 @@ template <int DK>
 __global__ void __launch_bounds__(128) attn_probs_fwd_kernel(AttnView q, AttnView k, bf16* __restrict__ P, const int32_t* __restrict__ klens,
                                                              int H, int T1, int T2, long ld, float scale, int causal) {
     constexpr int PITCH = DK + 8, SP = AT_KEYS + 8;
-    __shared__ __align__(16) bf16 ks[AT_KEYS * PITCH];
+    __shared__ __align__(16) bf16 ks2[2][AT_KEYS * PITCH];
     __shared__ __align__(16) bf16 stg_all[4][16 * SP];
     const int b = blockIdx.z, h = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
@@ -128,52 +143,55 @@ __global__ void __launch_bounds__(128) attn_probs_fwd_kernel(AttnView q, AttnVie
     bf16* Pb = P + ((long)b * H + h) * (long)T1 * ld;
     bf16* stg = stg_all[warp];
 
-    // ---- pass 1: row max / sum (online)
-    float m_lo = -INFINITY, m_hi = -INFINITY, s_lo = 0.f, s_hi = 0.f;
-    for (int key0 = 0; key0 < cta_lim; key0 += AT_KEYS) {
-        __syncthreads();
-        stage_keys<DK>(ks, k, b, h, key0, T2);
+    // Both passes walk the same nb key blocks; block seq+1 is copied (cp.async, double buffer) while block seq is consumed.
+    //   pass 1 (seq < nb): online row max / sum          pass 2 (seq >= nb): probabilities, written once
+    const int nb = (cta_lim + AT_KEYS - 1) / AT_KEYS;
+    const int total = 2 * nb;
+    float m_lo = -INFINITY, m_hi = -INFINITY, s_lo = 0.f, s_hi = 0.f, inv_lo = 0.f, inv_hi = 0.f;
+    if (total > 0) stage_keys_async<DK>(ks2[0], k, b, h, 0, T2);
+    for (int seq = 0; seq < total; ++seq) {
+        const int blk = seq < nb ? seq : seq - nb;
+        const int key0 = blk * AT_KEYS;
+        if (seq + 1 < total) {
+            const int nblk = (seq + 1 < nb) ? seq + 1 : seq + 1 - nb;
+            stage_keys_async<DK>(ks2[(seq + 1) & 1], k, b, h, nblk * AT_KEYS, T2);
+            asm volatile("cp.async.wait_group 1;\n" ::);
+        } else {
+            asm volatile("cp.async.wait_group 0;\n" ::);
+        }
         __syncthreads();
         float acc[8][4];
-        block_scores<DK>(acc, afrag, ks);
-        float bm_lo = -INFINITY, bm_hi = -INFINITY;
+        block_scores<DK>(acc, afrag, ks2[seq & 1]);
+        if (seq < nb) {
+            float bm_lo = -INFINITY, bm_hi = -INFINITY;
 #pragma unroll
-        for (int n = 0; n < 8; ++n) {
-            const int c = key0 + n * 8 + tig * 2;
-            acc[n][0] = (c < lim_lo) ? acc[n][0] * scale : -INFINITY;
-            acc[n][1] = (c + 1 < lim_lo) ? acc[n][1] * scale : -INFINITY;
-            acc[n][2] = (c < lim_hi) ? acc[n][2] * scale : -INFINITY;
-            acc[n][3] = (c + 1 < lim_hi) ? acc[n][3] * scale : -INFINITY;
-            bm_lo = fmaxf(bm_lo, fmaxf(acc[n][0], acc[n][1]));
-            bm_hi = fmaxf(bm_hi, fmaxf(acc[n][2], acc[n][3]));
-        }
-        bm_lo = quad_max(bm_lo);
-        bm_hi = quad_max(bm_hi);
-        const float nm_lo = fmaxf(m_lo, bm_lo), nm_hi = fmaxf(m_hi, bm_hi);
-        float bs_lo = 0.f, bs_hi = 0.f;
+            for (int n = 0; n < 8; ++n) {
+                const int c = key0 + n * 8 + tig * 2;
+                acc[n][0] = (c < lim_lo) ? acc[n][0] * scale : -INFINITY;
+                acc[n][1] = (c + 1 < lim_lo) ? acc[n][1] * scale : -INFINITY;
+                acc[n][2] = (c < lim_hi) ? acc[n][2] * scale : -INFINITY;
+                acc[n][3] = (c + 1 < lim_hi) ? acc[n][3] * scale : -INFINITY;
+                bm_lo = fmaxf(bm_lo, fmaxf(acc[n][0], acc[n][1]));
+                bm_hi = fmaxf(bm_hi, fmaxf(acc[n][2], acc[n][3]));
+            }
+            bm_lo = quad_max(bm_lo);
+            bm_hi = quad_max(bm_hi);
+            const float nm_lo = fmaxf(m_lo, bm_lo), nm_hi = fmaxf(m_hi, bm_hi);
+            float bs_lo = 0.f, bs_hi = 0.f;
 #pragma unroll
-        for (int n = 0; n < 8; ++n) {
-            if (nm_lo > -INFINITY) bs_lo += __expf(acc[n][0] - nm_lo) + __expf(acc[n][1] - nm_lo);
-            if (nm_hi > -INFINITY) bs_hi += __expf(acc[n][2] - nm_hi) + __expf(acc[n][3] - nm_hi);
-        }
-        bs_lo = quad_sum(bs_lo);
-        bs_hi = quad_sum(bs_hi);
-        s_lo = (nm_lo > -INFINITY ? s_lo * __expf(m_lo - nm_lo) : 0.f) + bs_lo;
-        s_hi = (nm_hi > -INFINITY ? s_hi * __expf(m_hi - nm_hi) : 0.f) + bs_hi;
-        m_lo = nm_lo;
-        m_hi = nm_hi;
-    }
-    const float inv_lo = s_lo > 0.f ? 1.f / s_lo : 0.f, inv_hi = s_hi > 0.f ? 1.f / s_hi : 0.f;
-
-    // ---- pass 2: probabilities, written once (columns up to ld; blocks nobody can see are zero-filled without compute)
-    for (int key0 = 0; key0 < (int)ld; key0 += AT_KEYS) {
-        uint32_t lo[8], hi[8];
-        if (key0 < cta_lim) {
-            __syncthreads();
-            stage_keys<DK>(ks, k, b, h, key0, T2);
-            __syncthreads();
-            float acc[8][4];
-            block_scores<DK>(acc, afrag, ks);
+            for (int n = 0; n < 8; ++n) {
+                if (nm_lo > -INFINITY) bs_lo += __expf(acc[n][0] - nm_lo) + __expf(acc[n][1] - nm_lo);
+                if (nm_hi > -INFINITY) bs_hi += __expf(acc[n][2] - nm_hi) + __expf(acc[n][3] - nm_hi);
+            }
+            bs_lo = quad_sum(bs_lo);
+            bs_hi = quad_sum(bs_hi);
+            s_lo = (nm_lo > -INFINITY ? s_lo * __expf(m_lo - nm_lo) : 0.f) + bs_lo;
+            s_hi = (nm_hi > -INFINITY ? s_hi * __expf(m_hi - nm_hi) : 0.f) + bs_hi;
+            m_lo = nm_lo;
+            m_hi = nm_hi;
+            if (seq == nb - 1) { inv_lo = s_lo > 0.f ? 1.f / s_lo : 0.f; inv_hi = s_hi > 0.f ? 1.f / s_hi : 0.f; }
+        } else {
+            uint32_t lo[8], hi[8];
 #pragma unroll
             for (int n = 0; n < 8; ++n) {
                 const int c = key0 + n * 8 + tig * 2;
@@ -184,11 +202,16 @@ __global__ void __launch_bounds__(128) attn_probs_fwd_kernel(AttnView q, AttnVie
                 lo[n] = pack_bf16(p0, p1);
                 hi[n] = pack_bf16(p2, p3);
             }
-        } else {
-#pragma unroll
-            for (int n = 0; n < 8; ++n) { lo[n] = 0u; hi[n] = 0u; }
+            store_tile(stg, lo, hi, Pb, ld, row0, T1, key0);
         }
-        store_tile(stg, lo, hi, Pb, ld, row0, T1, key0);
+        __syncthreads();                                   // the buffer consumed here is refilled two iterations later
+    }
+    // key blocks no row of this CTA can see (causal / padded keys) and the columns up to ld: zeros, no compute
+    {
+        uint32_t lo[8], hi[8];
+#pragma unroll
+        for (int n = 0; n < 8; ++n) { lo[n] = 0u; hi[n] = 0u; }
+        for (int key0 = nb * AT_KEYS; key0 < (int)ld; key0 += AT_KEYS) store_tile(stg, lo, hi, Pb, ld, row0, T1, key0);
     }
 }
 

@@ -125,12 +125,22 @@ __global__ void __launch_bounds__(256) conv1_fwd8_kernel(const float* __restrict
     const int cg = C / 8;
     const long total = (long)B * T1 * F1 * cg;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % cg) * 8;
-        long pos = i / cg;
-        const int f1 = (int)(pos % F1);
-        long r = pos / F1;
-        const int t1 = (int)(r % T1);
-        const long b = r / T1;
+        int c, f1, t1;
+        long pos, b;
+        if (total < 0x7fffffffL) {                      // 32-bit index split (three 64-bit divisions cost more than the 72 FMAs)
+            const unsigned iu = (unsigned)i, pu = iu / (unsigned)cg, ru = pu / (unsigned)F1, bu = ru / (unsigned)T1;
+            c = (int)(iu - pu * (unsigned)cg) * 8;
+            f1 = (int)(pu - ru * (unsigned)F1);
+            t1 = (int)(ru - bu * (unsigned)T1);
+            pos = pu; b = bu;
+        } else {
+            c = (int)(i % cg) * 8;
+            pos = i / cg;
+            f1 = (int)(pos % F1);
+            const long r = pos / F1;
+            t1 = (int)(r % T1);
+            b = r / T1;
+        }
         const float* xp = x + (b * Tn + 2 * t1) * F + 2 * f1;
         float xv[9];
 #pragma unroll
@@ -155,6 +165,44 @@ __global__ void __launch_bounds__(256) conv1_fwd8_kernel(const float* __restrict
     }
 }
 
+
+// Channel-owned variant: thread (tx, ty) keeps the 9 x 8 weights (+ bias) of ITS 8 output channels in registers and strides
+// over output positions: per position 9 broadcast input loads, 72 FMAs, one 16-byte store.  (The grid-stride kernel above
+// re-fetches 18 x 16 B of weights from shared memory per output vector with a 2-way bank conflict and is bound by that.)
+template <typename T>
+__global__ void __launch_bounds__(256) conv1_fwd_reg_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, T* __restrict__ y, int B, int Tn, int F,
+                                                            int C, int T1, int F1) {
+    const int c = threadIdx.x * 8;
+    float wr[9][8], bs[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        bs[k] = bias[c + k];
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) wr[tap][k] = w[(c + k) * 9 + tap];
+    }
+    const unsigned P = (unsigned)B * (unsigned)T1 * (unsigned)F1;
+    for (unsigned pos = blockIdx.x * blockDim.y + threadIdx.y; pos < P; pos += gridDim.x * blockDim.y) {
+        const unsigned r = pos / (unsigned)F1, b = r / (unsigned)T1;
+        const int f1 = (int)(pos - r * (unsigned)F1), t1 = (int)(r - b * (unsigned)T1);
+        const float* xp = x + ((long)b * Tn + 2 * t1) * F + 2 * f1;
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = bs[k];
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt)
+#pragma unroll
+            for (int kf = 0; kf < 3; ++kf) {
+                const float xv = xp[kt * F + kf];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] = fmaf(xv, wr[kt * 3 + kf][k], acc[k]);
+            }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaxf(acc[k], 0.f);
+        Vec8<T>::store(y + (long)pos * C + c, acc);
+    }
+}
+
 // weight gradient with 8 channels per thread: blockDim = (32, 8); x = channel group, y = position stripe
 template <typename T>
 __global__ void __launch_bounds__(256) conv1_bwd8_kernel(const float* __restrict__ x, const T* __restrict__ dy, float* dw,
@@ -175,10 +223,19 @@ __global__ void __launch_bounds__(256) conv1_bwd8_kernel(const float* __restrict
         for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
     if (c0 < C) {
         for (long r = r0 + ty; r < r1; r += 8) {
-            const int f1 = (int)(r % F1);
-            const long q = r / F1;
-            const int t1 = (int)(q % T1);
-            const long b = q / T1;
+            int f1, t1;
+            long b;
+            if (rows < 0x7fffffffL) {
+                const unsigned ru = (unsigned)r, qu = ru / (unsigned)F1, bu = qu / (unsigned)T1;
+                f1 = (int)(ru - qu * (unsigned)F1);
+                t1 = (int)(qu - bu * (unsigned)T1);
+                b = bu;
+            } else {
+                f1 = (int)(r % F1);
+                const long q = r / F1;
+                t1 = (int)(q % T1);
+                b = q / T1;
+            }
             const float* xp = x + (b * Tn + 2 * t1) * F + 2 * f1;
             float g[8];
             Vec8<T>::load(dy + r * C + c0, g);
@@ -263,14 +320,25 @@ __global__ void im2col_s2_kernel(const T* __restrict__ y1, T* __restrict__ col, 
     const int cv = C / VEC;
     const long total = (long)B * T2 * F2 * 9 * cv;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        int c = (int)(i % cv) * VEC;
-        long q = i / cv;
-        int tap = (int)(q % 9);
-        long m = q / 9;
-        int f2 = (int)(m % F2);
-        long r = m / F2;
-        int t2 = (int)(r % T2);
-        long b = r / T2;
+        int c, tap, f2, t2;
+        long m, b;
+        if (total < 0x7fffffffL) {                      // 32-bit index split: the copy is otherwise bound by 64-bit divisions
+            const unsigned iu = (unsigned)i, qu = iu / (unsigned)cv, mu = qu / 9u, ru = mu / (unsigned)F2, bu = ru / (unsigned)T2;
+            c = (int)(iu - qu * (unsigned)cv) * VEC;
+            tap = (int)(qu - mu * 9u);
+            f2 = (int)(mu - ru * (unsigned)F2);
+            t2 = (int)(ru - bu * (unsigned)T2);
+            m = mu; b = bu;
+        } else {
+            c = (int)(i % cv) * VEC;
+            const long q = i / cv;
+            tap = (int)(q % 9);
+            m = q / 9;
+            f2 = (int)(m % F2);
+            const long r = m / F2;
+            t2 = (int)(r % T2);
+            b = r / T2;
+        }
         int kt = tap / 3, kf = tap % 3;
         const T* src = y1 + (((b * T1 + 2 * t2 + kt) * F1) + 2 * f2 + kf) * C + c;
         T* dst = col + (m * 9 + tap) * C + c;
@@ -294,12 +362,22 @@ __global__ void col2im_s2_kernel(const T* __restrict__ dcol, T* __restrict__ dy1
     const int cv = C / VEC;
     const long total = (long)B * T1 * F1 * cv;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        int c = (int)(i % cv) * VEC;
-        long q = i / cv;
-        int f1 = (int)(q % F1);
-        long r = q / F1;
-        int t1 = (int)(r % T1);
-        long b = r / T1;
+        int c, f1, t1;
+        long q, b;
+        if (total < 0x7fffffffL) {
+            const unsigned iu = (unsigned)i, qu = iu / (unsigned)cv, ru = qu / (unsigned)F1, bu = ru / (unsigned)T1;
+            c = (int)(iu - qu * (unsigned)cv) * VEC;
+            f1 = (int)(qu - ru * (unsigned)F1);
+            t1 = (int)(ru - bu * (unsigned)T1);
+            q = qu; b = bu;
+        } else {
+            c = (int)(i % cv) * VEC;
+            q = i / cv;
+            f1 = (int)(q % F1);
+            const long r = q / F1;
+            t1 = (int)(r % T1);
+            b = r / T1;
+        }
         float acc[VEC];
 #pragma unroll
         for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
@@ -645,7 +723,16 @@ extern "C" int s2s_conv1_fwd(const float* x, const float* w, const float* bias, 
     long total = (long)B * T1 * F1 * C;
     size_t smem = (size_t)10 * C * sizeof(float);
     S2S_REQUIRE(smem <= 48 * 1024, "conv1_fwd: C too large (%d)", C);
-    if (C % 8 == 0 && aligned16(y1)) {
+    if (C % 8 == 0 && C / 8 <= 256 && aligned16(y1) && (long)B * T1 * F1 < 0x7fffffffL) {
+        const int cg = C / 8;
+        int ty = 256 / cg;
+        if (ty < 1) ty = 1;
+        long gx = ceil_div_l((long)B * T1 * F1, (long)ty * 16);
+        const long cap = (long)num_sms() * 8;
+        if (gx > cap) gx = cap;
+        S2S_DISPATCH_DTYPE(dtype, TT, (conv1_fwd_reg_kernel<TT><<<(unsigned)gx, dim3(cg, ty), 0, (cudaStream_t)stream>>>(
+            x, w, bias, (TT*)y1, B, T, F, C, T1, F1)));
+    } else if (C % 8 == 0 && aligned16(y1)) {
         S2S_DISPATCH_DTYPE(dtype, TT, (conv1_fwd8_kernel<TT><<<ew_grid(total / 8, 256), 256, smem, (cudaStream_t)stream>>>(
             x, w, bias, (TT*)y1, B, T, F, C, T1, F1)));
     } else {

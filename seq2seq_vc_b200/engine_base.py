@@ -131,7 +131,7 @@ class EngineBase:
         if gw is not None:
             ops.gemm(dy2d.t(), x2d.t(), gw, accumulate=True, mode=mode)
         if gb is not None:
-            ops.colsum(dy2d, gb)
+            ops.colsum(dy2d, gb)      # (a side-stream overlap with the two GEMMs was measured: no gain, the persistent GEMM owns the SMs)
         if dx is not None:
             ops.gemm(dy2d, w.t(), dx, residual=dx_residual, accumulate=dx_accumulate, mode=mode)
         return dx
