@@ -58,3 +58,27 @@ def test_product_does_not_import_oracle():
     for fn in os.listdir(pkg):
         if fn.endswith(".py"):
             assert "oracle" not in open(os.path.join(pkg, fn)).read().replace("no oracle", ""), fn
+
+
+def test_argument_validation_returns_error_codes_without_a_gpu():
+    """Entry points validate before launching: bad arguments give S2S_ERR_INVALID / S2S_ERR_UNSUPPORTED and a message
+    through s2s_last_error(), on any machine (no kernel is launched)."""
+    from seq2seq_vc_b200 import _lib
+
+    lib = _lib.load()
+    lib.s2s_last_error.restype = ctypes.c_char_p
+    assert lib.s2s_forward_sum(None, None, None, None, 1, 8, 4, -1.0, None, None, None, 1.0, None) == -1
+    assert b"forward_sum" in lib.s2s_last_error()
+    one = ctypes.c_void_p(16)          # never dereferenced: validation fails first
+    assert lib.s2s_forward_sum(one, one, one, one, 2, 100, 600, -1.0, one, one, None, 1.0, None) == -1
+    assert b"510" in lib.s2s_last_error()
+    assert lib.s2s_dwconv_fwd(one, one, None, one, 1, 10, 8, 4, 0, None) == -1            # even kernel size
+    assert b"odd K" in lib.s2s_last_error()
+    assert lib.s2s_attn_probs_fwd(one, 8, 8, 8, one, 8, 8, 8, one, None, 1, 1, 8, 8, 40, 8, 1.0, 0, None) == -2   # unsupported d_k
+    assert b"d_k" in lib.s2s_last_error()
+    assert lib.s2s_attn_probs_fwd(one, 8, 8, 8, one, 8, 8, 8, one, None, 1, 1, 8, 9, 48, 12, 1.0, 0, None) == -1  # ld % 8 != 0
+    assert lib.s2s_relshift_add(one, one, 1, 1, 8, 8, 14, 0, None) == -1                  # ldB < 2T-1
+    assert lib.s2s_glu_fwd(None, one, 4, 8, 0, None) == -1
+    assert lib.s2s_gather_rows(one, None, one, one, 1, 4, 4, 8, 0, None) == -1
+    assert lib.s2s_align_logp_fwd(one, one, one, one, one, 0, 4, 4, 8, 0, None) == -1     # B = 0
+    assert lib.s2s_glu_fwd(one, one, 4, 8, 7, None) == -1 and b"dtype" in lib.s2s_last_error()

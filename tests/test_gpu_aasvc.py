@@ -498,3 +498,37 @@ def test_inference_golden_and_dropin():
     # a second, longer utterance re-uses the engine (eval buffers of the previous length are dropped)
     o3, d3 = eng.inference(torch.randn(93, 80, device="cuda"), torch.randn(93, 80, device="cuda"))
     assert o3.shape == (int(d3.sum().item()) or 23, 80) and torch.isfinite(o3).all()
+
+
+def test_edge_cases_alignment_block(ops):
+    """Single-token text, T_feats == T_text (the only feasible path is the diagonal), zero-length rows, T < K depthwise conv."""
+    from seq2seq_vc_b200.aasvc_engine import beta_binomial_log_prior
+
+    # one text token: log-softmax over a single column is 0, MAS assigns every frame to it, forward-sum = -sum(lp)/1
+    feats, text = rnd(2, 9, 16, seed=1).cuda(), rnd(2, 3, 16, seed=2).cuda()
+    tl, fl = torch.tensor([1, 3], dtype=torch.int32).cuda(), torch.tensor([9, 3], dtype=torch.int32).cuda()
+    logp, lse = torch.empty(2, 9, 3, device="cuda"), torch.empty(2, 9, device="cuda")
+    ops.align_logp_fwd(feats, text, tl, logp, lse)
+    assert (logp[0, :, 0] == 0).all() and torch.isinf(logp[0, :, 1:]).all()
+    paths, ds, bl, _ = ops.mas(logp, tl, fl)
+    assert ds[0].tolist() == [9.0, 0.0, 0.0] and ds[1].tolist() == [1.0, 1.0, 1.0]      # diagonal when T_feats == T_text
+    prior = torch.zeros(2, 9, 3)
+    prior[0, :9, :1] = beta_binomial_log_prior(1, 9)
+    prior[1, :3, :3] = beta_binomial_log_prior(3, 3)
+    loss, g = torch.zeros(1, device="cuda"), torch.empty(2, 9, 3, device="cuda")
+    ops.forward_sum(logp, prior.cuda(), tl, fl, torch.empty(2, 9, 3, device="cuda"), loss, g)
+    lp_ref, g_ref = torch.zeros(1), torch.zeros(2, 9, 3)
+    F.forward_sum(logp.cpu(), prior, tl.cpu(), fl.cpu(), None, lp_ref, g_ref)
+    assert abs(loss.item() - lp_ref.item()) <= 1e-4 * max(1.0, abs(lp_ref.item()))
+    close(g, g_ref, 1e-5, "forward-sum gradient on degenerate lattices")
+    # depthwise conv shorter than its kernel, and a zero-row LayerNorm / colsum call
+    x, w = rnd(2, 5, 64, seed=3), rnd(64, 15, seed=4, scale=0.3)
+    y = F.dwconv_fwd(x, w, None, torch.empty(2, 5, 64))
+    close(ops.dwconv_fwd(x.cuda(), w.cuda(), None, torch.empty(2, 5, 64, device="cuda")), y, 2e-5, "dwconv T < K")
+    # Gaussian upsampling with all-zero durations in one utterance: uniform weights over the valid tokens
+    ds0 = torch.tensor([[0.0, 0.0, 0.0, 0.0], [2.0, 1.0, 0.0, 0.0]])
+    P = ops.gauss_weights(ds0.cuda(), torch.tensor([3, 3], dtype=torch.int32).cuda(), torch.tensor([4, 2], dtype=torch.int32).cuda(),
+                          torch.empty(2, 3, 8, device="cuda"))
+    ref = F.gauss_weights(ds0, torch.tensor([3, 3]), torch.tensor([4, 2]), torch.empty(2, 3, 8))
+    close(P, ref, 1e-6, "gaussian weights with zero durations")
+    assert torch.isfinite(P).all()
