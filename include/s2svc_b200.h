@@ -36,7 +36,7 @@ extern "C" {
 #define S2S_F32 0
 #define S2S_BF16 1
 
-#define S2S_ABI_VERSION 9
+#define S2S_ABI_VERSION 10
 
 const char* s2s_last_error(void);
 int s2s_abi_version(void);
@@ -388,6 +388,27 @@ int s2s_duration_loss(const void* pre, const float* ds, const int32_t* text_lens
 /* DurationPredictor.inference + clamp (modules/duration_predictor.py:92-96, models/aas_vc.py:389):
  * d[i] = min(max(rint(exp(pre[i]) - offset), 0), clamp_max) as float32 (integral values). */
 int s2s_duration_infer(const void* pre, float* d, int n, float offset, float clamp_max, int dtype, void* stream);
+
+/* ===========================================================================================
+ * Single-position decode with a KV cache (VTN.inference, models/vtn.py:302-394; Decoder.forward_one_step,
+ * modules/transformer/decoder.py:239-273).  Batch 1; the position is a DEVICE int32 so one CUDA graph serves all steps.
+ * =========================================================================================== */
+/* y[n] = act(W[n,:] . x + bias[n]) * dropout(pos * N + n) + residual[n];  W (N, K) row-major in `dtype`, x / y / residual
+ * vectors in `dtype`, bias float32 (may be NULL), pos_dev may be NULL (position 0 for the dropout counter). */
+int s2s_gemv(const void* W, const float* bias, const void* x, const void* residual, void* y, int N, int K, int relu,
+             const s2s_dropout_t* drop, const int32_t* pos_dev, int dtype, void* stream);
+/* ctx[h,:] = softmax_s(scale * q[h,:] . K[s,h,:]) V[s,h,:] over s < S with S = fixed_S (>= 0: source attention over the
+ * encoder memory) or *pos_dev + 1 (self attention); when knew / vnew (H, d_k) are given they are first stored as cache row
+ * *pos_dev.  Cache element (s, h, j) at cache + s * row_stride + h * d_k + j.  probs (float32, may be NULL) receives the
+ * weights of this step at probs + *pos_dev * probs_step_stride + h * ldp (zero-padded to ldp).  S_cap bounds S. */
+int s2s_decode_attn(const void* q, const void* knew, const void* vnew, void* kcache, void* vcache, int64_t row_stride, int H, int dk,
+                    int fixed_S, int S_cap, const int32_t* pos_dev, float scale, void* ctx, float* probs, int ldp,
+                    int64_t probs_step_stride, int dtype, void* stream);
+/* y = x + alpha * pe[*pos_dev, :]  (ScaledPositionalEncoding of the new position, eval mode) */
+int s2s_decode_pe(const void* x, const float* pe, const float* alpha, const int32_t* pos_dev, void* y, int d, int dtype, void* stream);
+/* end of a step: frames[pos] = feat (r * odim), logits[pos] = logit (r), next decoder input = last generated frame, ++*pos_dev */
+int s2s_decode_advance(const void* feat, const void* logit, void* next_in, float* frames, float* logits, int32_t* pos_dev, int odim,
+                       int r, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libs2svc_b200.so")
 
 S2S_F32, S2S_BF16 = 0, 1
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 
 class S2SError(RuntimeError):
@@ -117,6 +117,10 @@ SIGNATURES = {
     "s2s_align_logp_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int64, c_int, _P]),
     "s2s_forward_sum": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_float, _P, _P, _P, c_float, _P]),
     "s2s_gauss_weights": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int64, c_float, c_int, _P]),
+    "s2s_gemv": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _DP, _P, c_int, _P]),
+    "s2s_decode_attn": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P, c_float, _P, _P, c_int, c_int64, c_int, _P]),
+    "s2s_decode_pe": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, _P]),
+    "s2s_decode_advance": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "s2s_duration_infer": (c_int, [_P, _P, c_int, c_float, c_float, c_int, _P]),
     "s2s_duration_loss": (c_int, [_P, _P, _P, c_int, c_int, c_float, c_float, c_float, _P, _P, _P, _P, c_int, _P]),
 }

@@ -556,3 +556,36 @@ def duration_infer(pre, d, offset=1.0, clamp_max=10.0):
     assert pre.is_contiguous() and d.is_contiguous() and d.dtype == torch.float32 and pre.numel() == d.numel()
     check(_L().s2s_duration_infer(ptr(pre), ptr(d), d.numel(), float(offset), float(clamp_max), dt(pre), stream()), "duration_infer")
     return d
+
+
+# ----------------------------------------------------------------------------------------------
+# single-position decode (KV cache)
+# ----------------------------------------------------------------------------------------------
+def gemv(W, bias, x, y, residual=None, relu=False, drop: Drop = NO_DROP, pos_dev=None):
+    """y (N,) = act(W (N,K) @ x (K,) + bias) * dropout + residual."""
+    N, K = W.shape
+    assert W.is_contiguous() and x.numel() == K and y.numel() == N and W.dtype == x.dtype == y.dtype
+    check(_L().s2s_gemv(ptr(W), ptr(bias), ptr(x), ptr(residual), ptr(y), N, K, int(relu), ctypes.byref(drop.c()), ptr(pos_dev), dt(W),
+                        stream()), "gemv")
+    return y
+
+
+def decode_attn(q, knew, vnew, kcache, vcache, H, dk, fixed_S, S_cap, pos_dev, scale, ctx, probs=None, ldp=0, probs_step_stride=0):
+    """One decode step of multi-head attention over cached keys / values (see include/s2svc_b200.h: s2s_decode_attn).
+    kcache / vcache: views whose element (s, h, j) sits at base + s * row_stride + h * dk + j with row_stride = kcache.stride(0)."""
+    assert kcache.stride(-1) == 1 and vcache.stride() == kcache.stride() and kcache.dtype == q.dtype
+    check(_L().s2s_decode_attn(ptr(q), ptr(knew), ptr(vnew), ptr(kcache), ptr(vcache), kcache.stride(0), H, dk, int(fixed_S), int(S_cap),
+                               ptr(pos_dev), float(scale), ptr(ctx), ptr(probs), int(ldp), int(probs_step_stride), dt(q), stream()),
+          "decode_attn")
+    return ctx
+
+
+def decode_pe(x, pe, alpha, pos_dev, y):
+    check(_L().s2s_decode_pe(ptr(x), ptr(pe), ptr(alpha), ptr(pos_dev), ptr(y), x.numel(), dt(x), stream()), "decode_pe")
+    return y
+
+
+def decode_advance(feat, logit, next_in, frames, logits, pos_dev, odim, r):
+    assert frames.dtype == torch.float32 and logits.dtype == torch.float32 and pos_dev.dtype == _i32
+    check(_L().s2s_decode_advance(ptr(feat), ptr(logit), ptr(next_in), ptr(frames), ptr(logits), ptr(pos_dev), odim, r, dt(feat), stream()),
+          "decode_advance")

@@ -379,11 +379,124 @@ class VTNEngine(EngineBase):
     def inference(self, x: torch.Tensor, threshold: float = 0.5, minlenratio: float = 0.0, maxlenratio: float = 10.0):
         """VTN.inference (models/vtn.py:302-394): x (T, idim) float32 -> (outs (L, odim), probs (L,), att_ws (#dlayers, H, L/r, T')).
 
+        KV-cache decode: the encoder and the source-attention K/V projections run once; every step is ~70 single-row
+        kernels (s2s_gemv, s2s_decode_attn, LayerNorm, s2s_decode_pe, s2s_decode_advance) whose only step-dependent input
+        is a DEVICE position counter, so ONE captured CUDA graph is replayed for all steps.  The stop test reads the
+        step's logits back to the host each step, exactly as the reference does (`int(sum(probs[-1] >= threshold))`)."""
+        hp, st = self.hp, self.store
+        assert hp["encoder_input"] != "embed", "token-input (TransformerTTS) inference is not covered"
+        r, d, H, odim, idim = hp["decoder_reduction_factor"], hp["adim"], hp["aheads"], hp["odim"], hp["idim"]
+        dk = d // H
+        T = x.shape[0]
+        T1, F1 = (T - 1) // 2, (idim - 1) // 2
+        T2, F2 = (T1 - 1) // 2, (F1 - 1) // 2
+        assert T2 >= 1, "input too short for Conv2dSubsampling"
+        nl, u, npre = hp["dlayers"], hp["dprenet_units"], hp["dprenet_layers"]
+        was_training = self.training
+        self.training = False
+        try:
+            for key in [k for k in self._bufs if isinstance(k[0], tuple) and len(k[0]) == 4 and k[0][3] is False]:
+                del self._bufs[key]
+            mk = lambda v: torch.tensor([v], dtype=_i32).to(self.device)
+            self._sig = (1, T, 0, False)
+            self._site = 0
+            self.attn = {}
+            self.sync_shadow()
+            self.shapes = dict(B=1, T=T, L=0, T1=T1, F1=F1, T2=T2, F2=F2, Lr=0)
+            self.klens_enc, self.ilens_dev = mk(T2), mk(T)            # encoder(x, None): no padding mask
+            mem = self._encode(x.to(_f32).contiguous().unsqueeze(0))
+            site0 = self._site
+            maxlen = max(int(T2 * maxlenratio / r), 1)
+            minlen = int(T2 * minlenratio / r)
+            cap = maxlen + 1
+            ldp = _r8(T2)
+            f32b = lambda name, shape: self.buf(name, shape, _f32)
+            # source-attention K / V of every layer, projected once; self-attention caches
+            srckv, cache = [], []
+            for l in range(nl):
+                p = f"decoder.decoders.{l}"
+                kv = self.buf(f"inf.srckv{l}", (T2, 2, H, dk))
+                self._lin_fwd(mem.view(T2, d), self.Wspan([p + ".src_attn.linear_k.weight"], (2 * d, d)),
+                              st.span(st.P, [p + ".src_attn.linear_k.bias"], (2 * d,)), kv.view(T2, 2 * d))
+                srckv.append(kv)
+                cache.append(self.buf(f"inf.cache{l}", (cap, 2, H, dk)))
+            pos = self.buf("inf.pos", (1,), _i32)
+            pos.zero_()
+            nxt = self.buf("inf.next", (odim,))
+            nxt.zero_()
+            frames, logits = f32b("inf.frames", (cap, r * odim)), f32b("inf.logits", (cap, r))
+            att = f32b("inf.att", (cap, nl, H, ldp))
+            vec = lambda name, n: self.buf("inf.v." + name, (n,))
+            mean1, rstd1 = f32b("inf.mean", (1,)), f32b("inf.rstd", (1,))
+            pd = hp["dprenet_dropout_rate"]
+            sc = 1.0 / math.sqrt(dk)
+
+            def ln(xv, name, out):
+                ops.layernorm_fwd(xv.view(1, 1, d), st.p(name + ".weight"), st.p(name + ".bias"), out.view(1, 1, d), mean1, rstd1, 1e-12)
+                return out
+
+            def step():
+                h = nxt
+                for i in range(npre):                                   # Prenet dropout is always on (pre_postnets.py:65)
+                    nm = f"decoder.embed.0.0.prenet.{i}.0"
+                    dr = Drop(pd, self.base_seed, site0 + 1 + i, self.seed_dev) if pd > 0 else NO_DROP
+                    h = ops.gemv(self.W(nm + ".weight"), st.p(nm + ".bias"), h, vec(f"pre{i}", u), relu=True, drop=dr, pos_dev=pos)
+                e = ops.gemv(self.W("decoder.embed.0.1.weight"), st.p("decoder.embed.0.1.bias"), h, vec("emb", d))
+                xv = ops.decode_pe(e, self.pe(d, cap), st.p("decoder.embed.1.alpha"), pos, vec("x0", d))
+                for l in range(nl):
+                    p = f"decoder.decoders.{l}"
+                    qkv = ops.gemv(self.Wspan([p + ".self_attn.linear_q.weight"], (3 * d, d)), st.span(st.P, [p + ".self_attn.linear_q.bias"], (3 * d,)),
+                                   xv, vec(f"qkv{l}", 3 * d))
+                    ctx = ops.decode_attn(qkv[:d], qkv[d:2 * d], qkv[2 * d:], cache[l][:, 0], cache[l][:, 1], H, dk, -1, cap, pos, sc,
+                                          vec(f"ctx{l}", d))
+                    t1 = ops.gemv(self.W(p + ".self_attn.linear_out.weight"), st.p(p + ".self_attn.linear_out.bias"), ctx, vec(f"t1{l}", d), residual=xv)
+                    x1 = ln(t1, p + ".norm1", vec(f"x1{l}", d))
+                    q2 = ops.gemv(self.W(p + ".src_attn.linear_q.weight"), st.p(p + ".src_attn.linear_q.bias"), x1, vec(f"q2{l}", d))
+                    ctx2 = ops.decode_attn(q2, None, None, srckv[l][:, 0], srckv[l][:, 1], H, dk, T2, T2, pos, sc, vec(f"ctx2{l}", d),
+                                           probs=att[:, l], ldp=ldp, probs_step_stride=nl * H * ldp)
+                    t2 = ops.gemv(self.W(p + ".src_attn.linear_out.weight"), st.p(p + ".src_attn.linear_out.bias"), ctx2, vec(f"t2{l}", d), residual=x1)
+                    x2 = ln(t2, p + ".norm2", vec(f"x2{l}", d))
+                    hh = ops.gemv(self.W(p + ".feed_forward.w_1.weight"), st.p(p + ".feed_forward.w_1.bias"), x2, vec(f"ffh{l}", hp["dunits"]), relu=True)
+                    t3 = ops.gemv(self.W(p + ".feed_forward.w_2.weight"), st.p(p + ".feed_forward.w_2.bias"), hh, vec(f"t3{l}", d), residual=x2)
+                    xv = ln(t3, p + ".norm3", vec(f"x3{l}", d))
+                feat = ops.gemv(self.W("feat_out.weight"), st.p("feat_out.bias"), xv, vec("feat", odim * r))
+                logit = ops.gemv(self.W("prob_out.weight"), st.p("prob_out.bias"), xv, vec("logit", r))
+                ops.decode_advance(feat, logit, nxt, frames, logits, pos, odim, r)
+
+            graph = None
+            idx = 0
+            while True:
+                idx += 1
+                if idx == 1 or self.device.type != "cuda":
+                    step()                                              # eager (allocates the step's buffers on the first call)
+                    if idx == 1 and self.device.type == "cuda":
+                        torch.cuda.synchronize()
+                        graph = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(graph):
+                            step()
+                else:
+                    graph.replay()
+                p_step = torch.sigmoid(logits[idx - 1])
+                stop = bool((p_step >= threshold).any().item()) or idx >= maxlen        # host read-back (vtn.py:369)
+                if stop and idx >= minlen:
+                    break
+            L = idx * r
+            before = frames[:idx].reshape(1, L, odim).to(self.adt).contiguous()
+            self._sig = (1, T, -L, False)
+            after = self._postnet_fwd(before, lambda i: NO_DROP)
+            att_ws = att[:idx, :, :, :T2].permute(1, 2, 0, 3).contiguous()
+            return after[0].float().clone(), torch.sigmoid(logits[:idx]).reshape(-1).clone(), att_ws
+        finally:
+            self.training = was_training
+
+    @torch.no_grad()
+    def inference_recompute(self, x: torch.Tensor, threshold: float = 0.5, minlenratio: float = 0.0, maxlenratio: float = 10.0):
+        """Same contract as inference(), computed without a KV cache (kept as the cross-check of the decode kernels).
+
         The reference decodes with Decoder.forward_one_step, whose "cache" holds previous layer *outputs* and re-projects K/V
         of the whole prefix every step; by causality that equals running the decoder over the prefix and reading its last
         row, which is what this does (prefix lengths bucketed to multiples of 64 so that buffers / shapes are reused).
-        One host read-back of the stop probabilities per step, as in the reference (`int(sum(probs[-1] >= threshold))`).
-        A KV-cache single-row decode kernel is the next step for this row."""
+        One host read-back of the stop probabilities per step, as in the reference (`int(sum(probs[-1] >= threshold))`)."""
         hp, st = self.hp, self.store
         assert hp["encoder_input"] != "embed", "token-input (TransformerTTS) inference is not covered"
         r, d, H, odim, idim = hp["decoder_reduction_factor"], hp["adim"], hp["aheads"], hp["odim"], hp["idim"]

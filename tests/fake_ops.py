@@ -625,6 +625,51 @@ def duration_infer(pre, d, offset=1.0, clamp_max=10.0):
     return d
 
 
+def gemv(W, bias, x, y, residual=None, relu=False, drop=NO_DROP, pos_dev=None):
+    _nodrop(drop)
+    v = W.double() @ x.double().reshape(-1)
+    if bias is not None:
+        v = v + bias.double()
+    if relu:
+        v = torch.relu(v)
+    if residual is not None:
+        v = v + residual.double().reshape(-1)
+    y.copy_(v.reshape(y.shape).to(y.dtype))
+    return y
+
+
+def decode_attn(q, knew, vnew, kcache, vcache, H, dk, fixed_S, S_cap, pos_dev, scale, ctx, probs=None, ldp=0, probs_step_stride=0):
+    pos = int(pos_dev[0]) if pos_dev is not None else 0
+    if knew is not None:
+        kcache[pos].copy_(knew.reshape(kcache[pos].shape))
+        vcache[pos].copy_(vnew.reshape(vcache[pos].shape))
+    S = fixed_S if fixed_S >= 0 else pos + 1
+    qh = q.double().reshape(H, dk)
+    K = kcache[:S].double().reshape(S, H, dk)
+    V = vcache[:S].double().reshape(S, H, dk)
+    p = torch.softmax(torch.einsum("hj,shj->hs", qh, K) * scale, dim=-1)
+    ctx.copy_(torch.einsum("hs,shj->hj", p, V).reshape(ctx.shape).to(ctx.dtype))
+    if probs is not None:
+        row = probs[pos] if probs.dim() == 3 else probs          # (steps, H, ldp) view with step stride probs_step_stride, or (H, ldp)
+        assert probs.dim() != 3 or probs.stride(0) == probs_step_stride
+        row.zero_()
+        row[:, :S] = p.float()
+    return ctx
+
+
+def decode_pe(x, pe, alpha, pos_dev, y):
+    y.copy_((x.double() + float(alpha) * pe[int(pos_dev[0])].double().reshape(x.shape)).to(y.dtype))
+    return y
+
+
+def decode_advance(feat, logit, next_in, frames, logits, pos_dev, odim, r):
+    pos = int(pos_dev[0])
+    frames[pos].copy_(feat.float().reshape(-1))
+    logits[pos].copy_(logit.float().reshape(-1))
+    next_in.copy_(feat.reshape(r, odim)[-1].reshape(next_in.shape))
+    pos_dev += 1
+
+
 def mas(log_p, text_lens, feats_lens, want_grad=False):
     """Contract of s2s_mas via the numpy/C oracle (bit-exact integer path)."""
     import numpy as np

@@ -175,3 +175,6 @@ def test_autoregressive_inference_matches_reference(engine):
     assert np.abs(probs.numpy() - z["inf_probs"]).max() <= 1e-5
     assert np.abs(att.numpy() - z["inf_att_ws"]).max() <= 1e-5
     assert eng.training is True
+    # the cache-free recomputation path gives the same answer
+    o2, p2, a2 = eng.inference_recompute(torch.from_numpy(z["xs"])[0, :il], threshold=0.9999, minlenratio=0.0, maxlenratio=1.6)
+    assert np.abs(o2.numpy() - z["inf_outs"]).mean() <= 1e-5 and np.abs(a2.numpy() - z["inf_att_ws"]).max() <= 1e-5

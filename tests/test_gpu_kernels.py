@@ -363,3 +363,52 @@ def test_fused_attention_probs_fwd_bwd(ops, causal, B, H, T1, T2, dk):
         ops.attn_probs_bwd(dctx.cuda().view(B, T1, H, dk), dqkv[:, :T2, 2], P.cuda(), None if d_att is None else d_att.cuda(), gdS, T2, scale)
         tol_abs = 2e-2 * max(1.0, ref.float().abs().max().item())
         close(gdS, ref, tol_abs, f"fused dS (d_att={with_att})")
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_decode_kernels(ops, dt):
+    """Single-position decode kernels (KV cache) vs their contracts."""
+    N, K, H, dk, cap, T2 = 136, 384, 8, 48, 40, 27
+    d = H * dk
+    W, b, x, res = rnd(N, K, dt=dt, seed=1, scale=0.05), rnd(N, seed=2), rnd(K, dt=dt, seed=3), rnd(N, dt=dt, seed=4)
+    for kw in (dict(), dict(relu=True), dict(residual=res)):
+        ref = F.gemv(W, b, x, torch.empty(N, dtype=dt), **kw)
+        dkw = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in kw.items()}
+        got = ops.gemv(W.cuda(), b.cuda(), x.cuda(), torch.empty(N, dtype=dt, device="cuda"), **dkw)
+        close(got, ref, tol(dt, 4), f"gemv {list(kw)}")
+    Wo = rnd(5, 19, dt=dt, seed=5)                                     # odd K: scalar path
+    close(ops.gemv(Wo.cuda(), None, x[:19].cuda().contiguous(), torch.empty(5, dtype=dt, device="cuda")),
+          F.gemv(Wo, None, x[:19], torch.empty(5, dtype=dt)), tol(dt, 4), "gemv odd K")
+    # self attention with cache append at pos = 11, then source attention over T2 keys with probability read-out
+    cache = rnd(cap, 2, H, dk, dt=dt, seed=6)
+    qkv = rnd(3 * d, dt=dt, seed=7)
+    pos = torch.tensor([11], dtype=torch.int32)
+    c_ref = cache.clone()
+    ctx_ref = F.decode_attn(qkv[:d], qkv[d:2 * d], qkv[2 * d:], c_ref[:, 0], c_ref[:, 1], H, dk, -1, cap, pos, 0.2, torch.empty(d, dtype=dt))
+    c_gpu, dq = cache.cuda(), qkv.cuda()
+    ctx = ops.decode_attn(dq[:d], dq[d:2 * d], dq[2 * d:], c_gpu[:, 0], c_gpu[:, 1], H, dk, -1, cap, pos.cuda(), 0.2,
+                          torch.empty(d, dtype=dt, device="cuda"))
+    close(ctx, ctx_ref, tol(dt, 4), "decode self-attention")
+    assert torch.equal(c_gpu.cpu(), c_ref), "cache row `pos` must hold the new key / value, other rows untouched"
+    kv = rnd(T2, 2, H, dk, dt=dt, seed=8)
+    nl, ldp = 3, 32
+    att_ref, att = torch.zeros(cap, nl, H, ldp), torch.full((cap, nl, H, ldp), 9.0, device="cuda")
+    F.decode_attn(qkv[:d], None, None, kv[:, 0], kv[:, 1], H, dk, T2, T2, pos, 0.2, torch.empty(d, dtype=dt), probs=att_ref[:, 1], ldp=ldp,
+                  probs_step_stride=nl * H * ldp)
+    dkv = kv.cuda()
+    ops.decode_attn(dq[:d], None, None, dkv[:, 0], dkv[:, 1], H, dk, T2, T2, pos.cuda(), 0.2, torch.empty(d, dtype=dt, device="cuda"),
+                    probs=att[:, 1], ldp=ldp, probs_step_stride=nl * H * ldp)
+    close(att[11, 1], att_ref[11, 1], 1e-3 if dt == torch.bfloat16 else 1e-6, "source-attention probabilities of the step")
+    assert (att[10] == 9.0).all() and (att[11, 0] == 9.0).all()
+    # positional encoding + advance
+    pe, alpha = rnd(cap, d, seed=9), torch.tensor([0.7])
+    e = rnd(d, dt=dt, seed=10)
+    close(ops.decode_pe(e.cuda(), pe.cuda(), alpha.cuda(), pos.cuda(), torch.empty(d, dtype=dt, device="cuda")),
+          F.decode_pe(e, pe, alpha, pos, torch.empty(d, dtype=dt)), tol(dt), "decode pe")
+    r, odim = 2, 80
+    feat, logit = rnd(r * odim, dt=dt, seed=11), rnd(r, dt=dt, seed=12)
+    nxt, frames, logits, p2 = (torch.zeros(odim, dtype=dt, device="cuda"), torch.zeros(cap, r * odim, device="cuda"),
+                               torch.zeros(cap, r, device="cuda"), pos.cuda())
+    ops.decode_advance(feat.cuda(), logit.cuda(), nxt, frames, logits, p2, odim, r)
+    assert p2.item() == 12 and torch.equal(nxt.cpu(), feat[odim:]) and torch.equal(frames[11].cpu(), feat.float())
+    assert torch.equal(logits[11].cpu(), logit.float()) and frames[12].abs().sum().item() == 0
