@@ -103,6 +103,11 @@ def gen_tts_tiny():
                 labels_out=out[4].numpy(), olens_out=out[5].numpy(), att_ws=out[6][0].detach().numpy(),
                 ilens_out=out[6][1].numpy(), olens_in=out[6][2].numpy(), l1_loss=l1.detach().numpy(),
                 bce_loss=bce.detach().numpy(), ga_loss=ga.detach().numpy())
+    model.eval()
+    with torch.no_grad():
+        io, ip, ia = model.inference(tokens[0, :ilens[0]], dict(threshold=0.9999, minlenratio=0.0, maxlenratio=1.5))
+    dump.update(inf_outs=io.numpy(), inf_probs=ip.numpy(), inf_att_ws=ia.numpy())
+    dump.update({"bn_after." + k: v.numpy() for k, v in model.state_dict().items() if "running_" in k})
     np.savez_compressed(os.path.join(GOLDEN, "tts_tiny.npz"), **dump)
     print("tts_tiny:", len(dump), "arrays")
 

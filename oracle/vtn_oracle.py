@@ -378,15 +378,19 @@ def synthetic_batch(B, T, L, idim=80, odim=80, ilens=None, olens=None, seed=1234
     return xs, ilens, ys, labels, olens
 
 
-def vtn_inference(sd, hp, x, threshold=0.5, minlenratio=0.0, maxlenratio=10.0):
+def vtn_inference(sd, hp, x, threshold=0.5, minlenratio=0.0, maxlenratio=10.0, tts: bool = False):
     """VTN.inference (models/vtn.py:302-394) restated by full-prefix recomputation (equal to forward_one_step by
     causality); eval-mode BatchNorm; Prenet dropout must be 0 for a deterministic comparison.
     x (T, idim) -> (outs (L, odim), probs (L,), att_ws (#dlayers, H, L/r, T'))."""
     hp = default_hparams(**hp)
     r, odim = hp["decoder_reduction_factor"], hp["odim"]
-    xs = x.unsqueeze(0)
-    T = xs.shape[1]
-    hs, _ = encoder(sd, hp, xs, torch.ones(1, 1, T, dtype=torch.bool))
+    if tts:     # TransformerTTS.inference (models/transformer_tts.py:231-330): <eos> = idim - 1 appended, token-embedding encoder
+        xs = F.pad(x, [0, 1], "constant", hp["idim"] - 1).unsqueeze(0)
+        hs, _ = encoder_tts(sd, hp, xs, torch.ones(1, 1, xs.shape[1], dtype=torch.bool))
+    else:
+        xs = x.unsqueeze(0)
+        T = xs.shape[1]
+        hs, _ = encoder(sd, hp, xs, torch.ones(1, 1, T, dtype=torch.bool))
     T2 = hs.shape[1]
     mem_mask = torch.ones(1, 1, T2, dtype=torch.bool)
     maxlen, minlen = int(T2 * maxlenratio / r), int(T2 * minlenratio / r)

@@ -258,7 +258,7 @@ def _vtn_inference(self, x, inference_args, spemb=None, *args, **kwargs):
     return outs, probs, att_ws
 
 
-VTN.inference = _vtn_inference
+VTN.inference = _vtn_inference          # TransformerTTS inherits it: the engine appends <eos> and embeds the tokens
 
 
 class TransformerTTS(VTN):

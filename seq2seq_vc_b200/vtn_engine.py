@@ -384,12 +384,15 @@ class VTNEngine(EngineBase):
         is a DEVICE position counter, so ONE captured CUDA graph is replayed for all steps.  The stop test reads the
         step's logits back to the host each step, exactly as the reference does (`int(sum(probs[-1] >= threshold))`)."""
         hp, st = self.hp, self.store
-        assert hp["encoder_input"] != "embed", "token-input (TransformerTTS) inference is not covered"
+        embed = hp["encoder_input"] == "embed"          # TransformerTTS: token ids, <eos> appended by the embedding kernel (transformer_tts.py:254)
         r, d, H, odim, idim = hp["decoder_reduction_factor"], hp["adim"], hp["aheads"], hp["odim"], hp["idim"]
         dk = d // H
         T = x.shape[0]
         T1, F1 = (T - 1) // 2, (idim - 1) // 2
         T2, F2 = (T1 - 1) // 2, (F1 - 1) // 2
+        if embed:
+            T1 = F1 = F2 = 0
+            T2 = T + 1
         assert T2 >= 1, "input too short for Conv2dSubsampling"
         nl, u, npre = hp["dlayers"], hp["dprenet_units"], hp["dprenet_layers"]
         was_training = self.training
@@ -404,7 +407,7 @@ class VTNEngine(EngineBase):
             self.sync_shadow()
             self.shapes = dict(B=1, T=T, L=0, T1=T1, F1=F1, T2=T2, F2=F2, Lr=0)
             self.klens_enc, self.ilens_dev = mk(T2), mk(T)            # encoder(x, None): no padding mask
-            mem = self._encode(x.to(_f32).contiguous().unsqueeze(0))
+            mem = self._encode((x.to(torch.int64) if embed else x.to(_f32)).contiguous().unsqueeze(0))
             site0 = self._site
             maxlen = max(int(T2 * maxlenratio / r), 1)
             minlen = int(T2 * minlenratio / r)
@@ -498,11 +501,14 @@ class VTNEngine(EngineBase):
         row, which is what this does (prefix lengths bucketed to multiples of 64 so that buffers / shapes are reused).
         One host read-back of the stop probabilities per step, as in the reference (`int(sum(probs[-1] >= threshold))`)."""
         hp, st = self.hp, self.store
-        assert hp["encoder_input"] != "embed", "token-input (TransformerTTS) inference is not covered"
+        embed = hp["encoder_input"] == "embed"
         r, d, H, odim, idim = hp["decoder_reduction_factor"], hp["adim"], hp["aheads"], hp["odim"], hp["idim"]
         T = x.shape[0]
         T1, F1 = (T - 1) // 2, (idim - 1) // 2
         T2, F2 = (T1 - 1) // 2, (F1 - 1) // 2
+        if embed:
+            T1 = F1 = F2 = 0
+            T2 = T + 1
         assert T2 >= 1, "input too short for Conv2dSubsampling"
         was_training = self.training
         self.training = False
@@ -516,7 +522,7 @@ class VTNEngine(EngineBase):
             self.sync_shadow()
             self.shapes = dict(B=1, T=T, L=0, T1=T1, F1=F1, T2=T2, F2=F2, Lr=0)
             self.klens_enc, self.ilens_dev = mk(T2), mk(T)            # encoder(x, None): no padding mask
-            xs = x.to(_f32).contiguous().unsqueeze(0)
+            xs = (x.to(torch.int64) if embed else x.to(_f32)).contiguous().unsqueeze(0)
             mem = self._encode(xs)
             site_after_encoder = self._site
             maxlen = int(T2 * maxlenratio / r)

@@ -178,3 +178,19 @@ def test_autoregressive_inference_matches_reference(engine):
     # the cache-free recomputation path gives the same answer
     o2, p2, a2 = eng.inference_recompute(torch.from_numpy(z["xs"])[0, :il], threshold=0.9999, minlenratio=0.0, maxlenratio=1.6)
     assert np.abs(o2.numpy() - z["inf_outs"]).mean() <= 1e-5 and np.abs(a2.numpy() - z["inf_att_ws"]).max() <= 1e-5
+
+
+def test_tts_inference_matches_reference(monkeypatch):
+    """TransformerTTS.inference (<eos> append + token embedding + KV-cache decode) vs the live-reference dump."""
+    fake_ops.install(monkeypatch)
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "tts_tiny.npz"))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    sd.update({k[9:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("bn_after.")})
+    eng = VTNEngine(dict(TTS_HP, **NO_DROPOUT), device="cpu", bf16=False)
+    eng.load_state_dict(sd)
+    il = int(z["ilens"][0])
+    for fn in (eng.inference, eng.inference_recompute):
+        outs, probs, att = fn(torch.from_numpy(z["tokens"])[0, :il], threshold=0.9999, minlenratio=0.0, maxlenratio=1.5)
+        assert outs.shape == z["inf_outs"].shape and att.shape == z["inf_att_ws"].shape
+        assert np.abs(outs.numpy() - z["inf_outs"]).mean() <= 1e-5 and np.abs(probs.numpy() - z["inf_probs"]).max() <= 1e-5
+        assert np.abs(att.numpy() - z["inf_att_ws"]).max() <= 1e-5

@@ -255,3 +255,22 @@ def test_autoregressive_inference_golden_and_dropin():
     o4, p4, a4 = eng16.inference(xl, threshold=2.0, minlenratio=0.0, maxlenratio=1.0)
     T2l = (((700 - 1) // 2) - 1) // 2
     assert o4.shape == (int(T2l / 2) * 2, 80) and torch.isfinite(o4).all() and a4.shape[2] == int(T2l / 2)
+
+
+def test_tts_inference_golden():
+    """TransformerTTS.inference on the GPU through the drop-in module (KV-cache decode) vs the live-reference dump."""
+    import test_engine_host_logic as H
+    from seq2seq_vc_b200 import TransformerTTS
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "tts_tiny.npz"))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    sd.update({k[9:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("bn_after.")})
+    hp = {k: v for k, v in H.TTS_HP.items() if k != "encoder_input"}
+    model = TransformerTTS(dprenet_dropout_rate=0.0, **hp).to("cuda:0")
+    model.load_state_dict({k: v.cuda() for k, v in sd.items()})
+    model.eval()
+    il = int(z["ilens"][0])
+    outs, probs, att = model.inference(torch.from_numpy(z["tokens"])[0, :il].cuda(), dict(threshold=0.9999, minlenratio=0.0, maxlenratio=1.5))
+    assert tuple(outs.shape) == z["inf_outs"].shape and tuple(att.shape) == z["inf_att_ws"].shape
+    assert np.abs(outs.cpu().numpy() - z["inf_outs"]).mean() <= 1e-4 and np.abs(probs.cpu().numpy() - z["inf_probs"]).max() <= 1e-4
+    assert np.abs(att.cpu().numpy() - z["inf_att_ws"]).mean() <= 1e-3
