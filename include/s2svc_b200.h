@@ -303,6 +303,10 @@ int s2s_mas(const float* log_p, const int32_t* text_lens, const int32_t* feats_l
  * ------------------------------------------------------------------------------------------- */
 int s2s_logmel(const float* wav, const float* window, const float* mel_basis, float* mel, int B, int n_samples,
                int n_fft, int hop, int n_mels, float eps, float log_base, void* stream);
+/* same, with the global mean-variance normalisation of bin/normalize.py:173-193 (sklearn StandardScaler.transform) fused into
+ * the store: mel[b,t,m] = (logmel - mean[m]) / scale[m]; mean / scale are (n_mels) float32 (bin/compute_statistics.py). */
+int s2s_logmel_norm(const float* wav, const float* window, const float* mel_basis, const float* mean, const float* scale, float* mel,
+                    int B, int n_samples, int n_fft, int hop, int n_mels, float eps, float log_base, void* stream);
 
 /* ===========================================================================================
  * Conformer block (AAS-VC encoder / decoder): modules/conformer/encoder_layer.py:79-179,

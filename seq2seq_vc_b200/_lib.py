@@ -99,6 +99,7 @@ SIGNATURES = {
     "s2s_mas_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "s2s_mas": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
     "s2s_logmel": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_float, _P]),
+    "s2s_logmel_norm": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_float, _P]),
     "s2s_bias_add2": (c_int, [_P, c_int64, _P, _P, _P, _P, c_int64, c_int, c_int, _P]),
     "s2s_add_strided": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, c_int, _P]),
     "s2s_relshift_add": (c_int, [_P, _P, c_int, c_int, c_int, c_int64, c_int64, c_int, _P]),

@@ -460,8 +460,10 @@ def hann_window(n_fft: int, win_length: Optional[int]) -> np.ndarray:
 
 
 def logmel_batch(wav: torch.Tensor, sampling_rate: int, fft_size=1024, hop_size=256, win_length=None, num_mels=80,
-                 fmin=None, fmax=None, eps=1e-10, log_base=10.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Batched device entry: wav (B, n_samples) float32 CUDA -> (B, 1 + n_samples // hop, num_mels) float32."""
+                 fmin=None, fmax=None, eps=1e-10, log_base=10.0, out: Optional[torch.Tensor] = None, mean=None, scale=None) -> torch.Tensor:
+    """Batched device entry: wav (B, n_samples) float32 CUDA -> (B, 1 + n_samples // hop, num_mels) float32.
+    mean / scale (num_mels,): the global mean-variance normalisation of bin/normalize.py:173-193 (StandardScaler.transform with
+    the statistics of bin/compute_statistics.py) fused into the kernel's store -- the model then sees the kernel's output directly."""
     fmin = 0.0 if fmin is None else fmin
     fmax = sampling_rate / 2.0 if fmax is None else fmax
     dev = wav.device
@@ -474,7 +476,10 @@ def logmel_batch(wav: torch.Tensor, sampling_rate: int, fft_size=1024, hop_size=
     B, ns = wav.shape
     if out is None:
         out = torch.empty(B, 1 + ns // hop_size, num_mels, dtype=_f32, device=dev)
-    return ops.logmel(wav, c[0], c[1], out, fft_size, hop_size, eps, log_base)
+    if mean is not None:
+        mean = torch.as_tensor(mean, dtype=_f32).to(dev).contiguous()
+        scale = torch.as_tensor(scale, dtype=_f32).to(dev).contiguous()
+    return ops.logmel(wav, c[0], c[1], out, fft_size, hop_size, eps, log_base, mean, scale)
 
 
 _DEV_CACHE: Dict[tuple, tuple] = {}

@@ -59,7 +59,8 @@ struct LogmelShared {
 __global__ void __launch_bounds__(LM_WARPS * 32) logmel2048_kernel(const float* __restrict__ wav, const float* __restrict__ window,
                                                                   const float* __restrict__ basis, float* __restrict__ mel, int B,
                                                                   int ns, int hop, int n_frames, int n_mels, float eps,
-                                                                  float log_scale, int wpk_cap) {
+                                                                  float log_scale, int wpk_cap, const float* __restrict__ nmean,
+                                                                  const float* __restrict__ nscale) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NFFT = 2048, H = 1024, NB = 1025;
     float2* tw1024 = reinterpret_cast<float2*>(smem_raw);           // e^{-2 pi i j / 1024}, j < 32 only needed as base; keep 32
@@ -185,7 +186,11 @@ __global__ void __launch_bounds__(LM_WARPS * 32) logmel2048_kernel(const float* 
             acc += __shfl_xor_sync(0xffffffffu, acc, 4);
             acc += __shfl_xor_sync(0xffffffffu, acc, 2);
             acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-            if (gl == 0 && m < n_mels) out[m] = log2f(fmaxf(eps, acc)) * log_scale;
+            if (gl == 0 && m < n_mels) {
+                float v = log2f(fmaxf(eps, acc)) * log_scale;
+                if (nmean) v = (v - nmean[m]) / nscale[m];          // StandardScaler.transform (bin/normalize.py:193) fused
+                out[m] = v;
+            }
         }
         __syncwarp();
     }
@@ -197,7 +202,8 @@ __global__ void __launch_bounds__(LM_WARPS * 32) logmel2048_kernel(const float* 
 __global__ void __launch_bounds__(256) logmel_kernel(const float* __restrict__ wav, const float* __restrict__ window,
                                                      const float* __restrict__ basis, float* __restrict__ mel, int B,
                                                      int ns, int n_fft, int log2h, int hop, int n_frames, int n_mels,
-                                                     float eps, float log_scale) {
+                                                     float eps, float log_scale, const float* __restrict__ nmean,
+                                                     const float* __restrict__ nscale) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int half = n_fft >> 1, nbins = half + 1;
     float2* data = reinterpret_cast<float2*>(smem_raw);       // [half]
@@ -294,7 +300,11 @@ __global__ void __launch_bounds__(256) logmel_kernel(const float* __restrict__ w
             float acc = 0.f;
             for (int k = lo + lane; k < hi; k += 32) acc = fmaf(mag[k], wpk[off + k - lo], acc);
             acc = warp_sum(acc);
-            if (lane == 0) out[m] = log2f(fmaxf(eps, acc)) * log_scale;
+            if (lane == 0) {
+                float v = log2f(fmaxf(eps, acc)) * log_scale;
+                if (nmean) v = (v - nmean[m]) / nscale[m];
+                out[m] = v;
+            }
         }
         __syncthreads();
     }
@@ -304,8 +314,23 @@ __global__ void __launch_bounds__(256) logmel_kernel(const float* __restrict__ w
 
 using namespace s2s;
 
+static int logmel_impl(const float* wav, const float* window, const float* mel_basis, float* mel, int B, int n_samples, int n_fft,
+                       int hop, int n_mels, float eps, float log_base, const float* nmean, const float* nscale, void* stream);
+
 extern "C" int s2s_logmel(const float* wav, const float* window, const float* mel_basis, float* mel, int B,
                           int n_samples, int n_fft, int hop, int n_mels, float eps, float log_base, void* stream) {
+    return logmel_impl(wav, window, mel_basis, mel, B, n_samples, n_fft, hop, n_mels, eps, log_base, nullptr, nullptr, stream);
+}
+
+extern "C" int s2s_logmel_norm(const float* wav, const float* window, const float* mel_basis, const float* mean, const float* scale,
+                               float* mel, int B, int n_samples, int n_fft, int hop, int n_mels, float eps, float log_base,
+                               void* stream) {
+    S2S_REQUIRE(mean && scale, "logmel_norm: mean / scale are required");
+    return logmel_impl(wav, window, mel_basis, mel, B, n_samples, n_fft, hop, n_mels, eps, log_base, mean, scale, stream);
+}
+
+static int logmel_impl(const float* wav, const float* window, const float* mel_basis, float* mel, int B, int n_samples, int n_fft,
+                       int hop, int n_mels, float eps, float log_base, const float* nmean, const float* nscale, void* stream) {
     S2S_REQUIRE(wav && window && mel_basis && mel, "logmel: null pointer");
     S2S_REQUIRE(B > 0 && n_samples > 0 && hop > 0 && n_mels > 0, "logmel: bad shape");
     S2S_REQUIRE(n_fft >= 64 && n_fft <= 4096 && (n_fft & (n_fft - 1)) == 0, "logmel: n_fft %d must be a power of two in [64, 4096]", n_fft);
@@ -334,7 +359,7 @@ extern "C" int s2s_logmel(const float* wav, const float* window, const float* me
         long need = ceil_div_l(total, LM_WARPS);
         if (grid > need) grid = need;
         logmel2048_kernel<<<(unsigned)grid, LM_WARPS * 32, smem, (cudaStream_t)stream>>>(wav, window, mel_basis, mel, B, n_samples, hop,
-                                                                                         n_frames, n_mels, eps, log_scale, wpk_cap);
+                                                                                         n_frames, n_mels, eps, log_scale, wpk_cap, nmean, nscale);
         S2S_LAUNCH_OK();
         return S2S_OK;
     }
@@ -348,7 +373,7 @@ extern "C" int s2s_logmel(const float* wav, const float* window, const float* me
     long grid = (long)num_sms() * 4;
     if (grid > total) grid = total;
     logmel_kernel<<<(unsigned)grid, 256, smem, (cudaStream_t)stream>>>(wav, window, mel_basis, mel, B, n_samples, n_fft, log2n - 1,
-                                                                       hop, n_frames, n_mels, eps, log_scale);
+                                                                       hop, n_frames, n_mels, eps, log_scale, nmean, nscale);
     S2S_LAUNCH_OK();
     return S2S_OK;
 }

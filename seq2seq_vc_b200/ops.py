@@ -390,12 +390,18 @@ def mas_into(log_p, text_lens, feats_lens, paths, ds, bin_loss, d_log_p, ws):
                        ptr(ws), ws.numel(), stream()), "mas")
 
 
-def logmel(wav, window, basis, mel, n_fft, hop, eps, log_base):
+def logmel(wav, window, basis, mel, n_fft, hop, eps, log_base, mean=None, scale=None):
+    """STFT -> log-mel; with mean / scale (n_mels) the StandardScaler normalisation is fused into the store."""
     B, ns = wav.shape
     n_mels = basis.shape[0]
     assert wav.dtype == torch.float32 and wav.is_contiguous() and mel.is_contiguous()
-    check(_L().s2s_logmel(ptr(wav), ptr(window), ptr(basis), ptr(mel), B, ns, n_fft, hop, n_mels, eps,
-                          0.0 if log_base is None else float(log_base), stream()), "logmel")
+    lb = 0.0 if log_base is None else float(log_base)
+    if mean is not None:
+        assert scale is not None and mean.dtype == torch.float32 and scale.dtype == torch.float32 and mean.numel() == n_mels == scale.numel()
+        check(_L().s2s_logmel_norm(ptr(wav), ptr(window), ptr(basis), ptr(mean), ptr(scale), ptr(mel), B, ns, n_fft, hop, n_mels, eps, lb,
+                                   stream()), "logmel_norm")
+    else:
+        check(_L().s2s_logmel(ptr(wav), ptr(window), ptr(basis), ptr(mel), B, ns, n_fft, hop, n_mels, eps, lb, stream()), "logmel")
     return mel
 
 

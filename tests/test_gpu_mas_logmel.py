@@ -96,3 +96,24 @@ def test_logmel_batched_and_silence():
         ref = logmel_oracle.logmelfilterbank(wav[b], 24000, fft_size=1024, hop_size=256, num_mels=80)
         assert np.abs(mel[b] - ref).max() <= 1e-4
     assert np.allclose(mel[3], -10.0)
+
+
+@pytest.mark.parametrize("n_fft,hop", [(1024, 256), (2048, 300)])
+def test_logmel_with_fused_normalisation(n_fft, hop):
+    """STFT -> log-mel -> StandardScaler.transform (bin/normalize.py:173-193) in one kernel vs oracle log-mel + sklearn."""
+    from sklearn.preprocessing import StandardScaler
+
+    from seq2seq_vc_b200 import api
+
+    rng = np.random.default_rng(3)
+    wav = (0.1 * rng.standard_normal((3, 20000))).astype(np.float32)
+    refs = [logmel_oracle.logmelfilterbank(w, 24000, fft_size=n_fft, hop_size=hop, num_mels=80) for w in wav]
+    scaler = StandardScaler()
+    for r in refs:
+        scaler.partial_fit(r)                                   # bin/compute_statistics.py:130-132
+    got = api.logmel_batch(torch.from_numpy(wav).cuda(), 24000, fft_size=n_fft, hop_size=hop, num_mels=80,
+                           mean=scaler.mean_.astype(np.float32), scale=scaler.scale_.astype(np.float32)).cpu().numpy()
+    for b in range(3):
+        ref = scaler.transform(refs[b])
+        assert np.abs(got[b] - ref).max() <= 1e-4 / scaler.scale_.min() + 1e-5
+    assert abs(got.mean()) <= 1e-2 and abs(got.std() - 1.0) <= 5e-2
