@@ -36,7 +36,7 @@ extern "C" {
 #define S2S_F32 0
 #define S2S_BF16 1
 
-#define S2S_ABI_VERSION 10
+#define S2S_ABI_VERSION 11
 
 const char* s2s_last_error(void);
 int s2s_abi_version(void);
@@ -47,6 +47,9 @@ int64_t s2s_launch_count(void);
 /* number of s2s_gemm(mode = 1) calls that could not be described to TMA (unaligned strides, N < 8)
  * and were served by the CUDA-core kernel instead */
 int64_t s2s_tc_fallback_count(void);
+/* test hook: force the tile shape of s2s_gemm(mode = 1): 1 = one CTA per 128-row tile, 2 = CTA pairs on 256-row tiles
+ * (cta_group::2), 0 = cost model */
+void s2s_debug_gemm_tile(int cg);
 
 /* Counter-based dropout: element idx is dropped iff hash(seed', stream, idx) < p * 2^32 where
  * seed' = seed + (seed_dev ? *seed_dev : 0); kept values are scaled by 1/(1-p).  Backward kernels

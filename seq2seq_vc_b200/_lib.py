@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libs2svc_b200.so")
 
 S2S_F32, S2S_BF16 = 0, 1
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 
 class S2SError(RuntimeError):
@@ -55,6 +55,7 @@ SIGNATURES = {
     "s2s_device_check": (c_int, []),
     "s2s_launch_count": (c_int64, []),
     "s2s_tc_fallback_count": (c_int64, []),
+    "s2s_debug_gemm_tile": (None, [c_int]),
     "s2s_gemm": (c_int, [POINTER(GemmDesc), c_int, _P]),
     "s2s_layernorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_float, c_int, _P]),
     "s2s_layernorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P]),

@@ -28,6 +28,13 @@
 //    released as soon as a warp's values are in registers.
 //  * tcgen05.mma in cta_group::1 reads both operands from shared memory; 128 x 256 x 16 instructions
 //    (BN = 256) halve the A re-reads per FLOP compared with 128 x 128.
+//  * The main loop is paced by shared-memory traffic, not by the tensor pipe: one 128 x BN x 16 MMA took
+//    70 + 0.68 BN cycles (245 @ BN = 256; the pipe's floor is 128), tracking the TMA writes + operand reads per
+//    MMA.  A "tall" single-CTA tile (two M = 128 MMAs per B stage: fewer L2 bytes, same smem reads, no accumulator
+//    double buffering) was measured and lost on every shape of the step except 8192^3 (+9 %).  CG = 2 is the fix
+//    the hardware offers: a CTA pair (cluster of 2 on one TPC) issues ONE 256 x BN x 16 cta_group::2 MMA, each
+//    CTA staging its own 128 rows of A and only HALF of the B tile, so smem writes and reads per FLOP drop by a
+//    third while both CTAs keep their double-buffered 128 x BN accumulators.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -47,7 +54,9 @@ constexpr int A_BYTES = BM * BK * 2, B_BYTES = MAX_BN * BK * 2, STAGE_BYTES = A_
 constexpr int TMEM_COLS = 512;      // two accumulator stages x 256 fp32 columns: the whole tensor memory of the SM
 constexpr int EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int STG_WARP_BYTES = 32 * 128;   // epilogue staging: 32 rows x 64 bf16 columns per warp, 16-byte chunks XOR-swizzled by row
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_WARPS * STG_WARP_BYTES;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared-memory budget of one CTA");
 
 // epilogue specialisations (compile time, to keep every instantiation's code small)
 constexpr int EPI_BF16_PLAIN = 0;   // bf16 C = alpha * acc + bias, optional relu
@@ -58,7 +67,8 @@ struct Params {
     CUtensorMap tmA, tmB;
     int M, N, K, taps, batch1, batch2;
     int a_mn, b_mn;          // 1 = operand contiguous along M / N ("MN-major"), 0 = along K
-    int BN;                  // N tile (multiple of 16, <= 256)
+    int BN;                  // N tile (multiple of 16, <= 256; multiple of 32 for CTA pairs)
+    int cg;                  // 1 = one CTA per 128 x BN tile; 2 = CTA pair per 256 x BN tile (cta_group::2)
     int mt, nt, kb_per_tap, kb_total, splits;
     void* C; int c_f32; long c_rs, c_bs1, c_bs2;
     const void* R;
@@ -75,8 +85,19 @@ struct Params {
 __device__ __forceinline__ void stamp(const Params& p, int slot) {
     if (p.trace && blockIdx.x == 0) p.trace[slot] = clock64();
 }
+// cycles a role spent blocked on a barrier (CTA 0 only): slots 8 = MMA warp on full, 9 = MMA warp on tmem_empty,
+// 10 = TMA producer on empty, 11 = k-blocks issued by CTA 0
+#define TRACE_WAIT(slot, stmt)                                  \
+    do {                                                        \
+        const long long _t0 = clock64();                        \
+        stmt;                                                   \
+        if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) p.trace[slot] += clock64() - _t0; \
+    } while (0)
+#define TRACE_COUNT(slot) do { if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) p.trace[slot] += 1; } while (0)
 #else
 __device__ __forceinline__ void stamp(const Params&, int) {}
+#define TRACE_WAIT(slot, stmt) stmt
+#define TRACE_COUNT(slot) do {} while (0)
 #endif
 
 // ---------------------------------------------------------------------------------------------
@@ -109,6 +130,54 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+// ---- CTA-pair (cta_group::2) forms ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {   // same smem offset in CTA `rank` of the cluster
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// destination: the issuing CTA's own shared memory; completion bytes go to the LEADER CTA's barrier (cluster address)
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {   // arrives on the barrier at this offset in BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// one lane of a converged warp; ptxas knows a region guarded by an elect.sync predicate runs single-threaded, so the uniform
+// operands of UTCHMMA / UTMALDG / UTCBAR are moved with plain R2URs -- an `if (lane == 0)` guard instead costs an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop around EVERY such instruction (~70 cycles per MMA, measured)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -130,6 +199,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -160,7 +237,7 @@ __device__ __noinline__ void decode_item(const Params& p, uint32_t item, Item& i
     const uint32_t bz = tile / (uint32_t)p.mt;
     it.b1 = (int)(bz / (uint32_t)p.batch2);
     it.b2 = (int)(bz % (uint32_t)p.batch2);
-    it.m0 = (int)mtile * BM;
+    it.m0 = (int)mtile * BM * p.cg;
     it.n0 = (int)ntile * p.BN;
     const int per = (p.kb_total + p.splits - 1) / p.splits;
     it.kb0 = (int)split * per;
@@ -203,7 +280,7 @@ __device__ __forceinline__ uint4 pack_bf16x8(const float* v) {
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
-template <int EPI>
+template <int EPI, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ Params p) {
     using TC = typename std::conditional<EPI == EPI_F32, float, bf16>::type;
     extern __shared__ unsigned char smem_raw[];
@@ -217,66 +294,81 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     auto tempty_bar = [&](int s) { return bars + 8u * (2 * STAGES + 2 + s); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // CTA pair: rank 0 (the leader) owns the full / tmem_empty barriers and issues the MMAs for both CTAs
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
     if (threadIdx.x == 0) stamp(p, 0);
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI_WARPS); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI_WARPS * CG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CG == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tcgen05_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();   // the peer's barriers are initialised before anyone signals them
     tcgen05_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
     if (threadIdx.x == 0) stamp(p, 1);
 
     const uint32_t total = (uint32_t)((long)p.batch1 * p.batch2 * p.mt * p.nt * p.splits);
     const int BN = p.BN;
+    const int BNH = BN / CG;                                  // B columns staged by this CTA
+    const uint32_t worker = blockIdx.x / CG, n_workers = gridDim.x / CG;
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
-            const int b_boxes = p.b_mn ? (BN + 63) / 64 : 1;
-            const uint32_t tx_bytes = (uint32_t)A_BYTES + (uint32_t)(p.b_mn ? b_boxes * 8192 : BN * 128);
+        if (elect_one()) {
+            const int b_boxes = p.b_mn ? (BNH + 63) / 64 : 1;
+            // bytes landing on the (leader's) full barrier per stage: both CTAs' A and B boxes
+            const uint32_t tx_bytes = (uint32_t)CG * ((uint32_t)A_BYTES + (uint32_t)(p.b_mn ? b_boxes * 8192 : BNH * 128));
             int stage = 0;
             uint32_t phase = 0;
             Item it;
 #pragma unroll 1
-            for (uint32_t item = blockIdx.x; item < total; item += gridDim.x) {
+            for (uint32_t item = worker; item < total; item += n_workers) {
                 decode_item(p, item, it);
+                const int am0 = it.m0 + (int)rank * BM, bn0 = it.n0 + (int)rank * BNH;
 #pragma unroll 1
                 for (int kb = it.kb0; kb < it.kb1; ++kb) {
                     const int t = kb / p.kb_per_tap;
                     const int kk = (kb - t * p.kb_per_tap) * BK;
-                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    TRACE_WAIT(10, mbar_wait(empty_bar(stage), phase ^ 1u));
                     const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
-                    if (kb == it.kb0 && item == blockIdx.x) stamp(p, 2);
-                    mbar_expect_tx(full_bar(stage), tx_bytes);
+                    if (kb == it.kb0 && item == worker) stamp(p, 2);
+                    const uint32_t fb = CG == 2 ? mapa_shared(full_bar(stage), 0) : full_bar(stage);
+                    if (rank == 0) mbar_expect_tx(full_bar(stage), tx_bytes);
+                    auto load = [&](uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+                        if (CG == 2) tma_load_4d_pair(dst, map, fb, c0, c1, c2, c3);
+                        else tma_load_4d(dst, map, fb, c0, c1, c2, c3);
+                    };
                     if (p.a_mn) {
-                        tma_load_4d(sa, &p.tmA, full_bar(stage), it.m0, kk, it.b2, it.b1);
-                        tma_load_4d(sa + 8192, &p.tmA, full_bar(stage), it.m0 + 64, kk, it.b2, it.b1);
+                        load(sa, &p.tmA, am0, kk, it.b2, it.b1);
+                        load(sa + 8192, &p.tmA, am0 + 64, kk, it.b2, it.b1);
                     } else {
-                        tma_load_4d(sa, &p.tmA, full_bar(stage), kk, it.m0 + t, it.b2, it.b1);
+                        load(sa, &p.tmA, kk, am0 + t, it.b2, it.b1);
                     }
                     if (p.b_mn) {
 #pragma unroll 1
-                        for (int j = 0; j < b_boxes; ++j)
-                            tma_load_4d(sb + 8192 * j, &p.tmB, full_bar(stage), it.n0 + 64 * j, kk, it.b2, it.b1);
+                        for (int j = 0; j < b_boxes; ++j) load(sb + 8192 * j, &p.tmB, bn0 + 64 * j, kk, it.b2, it.b1);
                     } else {
-                        tma_load_4d(sb, &p.tmB, full_bar(stage), kk, it.n0, p.taps > 1 ? t : it.b2, it.b1);
+                        load(sb, &p.tmB, kk, bn0, p.taps > 1 ? t : it.b2, it.b1);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
         }
-    } else if (warp == 1) {
-        // ================= MMA issuer =================
+    } else if (warp == 1 && rank == 0) {
+        // ================= MMA issuer (leader CTA only for pairs: M = 256 spans both CTAs' A halves and accumulators) =================
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
-                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
         // K-major: 16 bf16 = 32 B inside the 128 B swizzle row; MN-major: 16 k-rows of 128 B, 64-wide groups 8 KB apart
         const uint32_t a_step = p.a_mn ? 2048u : 32u, b_step = p.b_mn ? 2048u : 32u;
         const uint32_t a_lbo = p.a_mn ? 8192u : 16u, b_lbo = p.b_mn ? 8192u : 16u;
@@ -285,11 +377,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         uint32_t n_items = 0;
         Item it;
 #pragma unroll 1
-        for (uint32_t item = blockIdx.x; item < total; item += gridDim.x, ++n_items) {
+        for (uint32_t item = worker; item < total; item += n_workers, ++n_items) {
             decode_item(p, item, it);
             const int as = (int)(n_items & 1);
             const uint32_t aphase = (n_items >> 1) & 1u;
-            mbar_wait(tempty_bar(as), aphase ^ 1u);
+            TRACE_WAIT(9, mbar_wait(tempty_bar(as), aphase ^ 1u));
             tcgen05_fence_after();
             const uint32_t tmem_d = tmem_base + (uint32_t)(as * MAX_BN);
 #pragma unroll 1
@@ -297,37 +389,57 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                 const int t = kb / p.kb_per_tap;
                 const int kk = (kb - t * p.kb_per_tap) * BK;
                 const int ksteps = (min(BK, p.K - kk) + UMMA_K - 1) / UMMA_K;
-                mbar_wait(full_bar(stage), phase);
+                TRACE_WAIT(8, mbar_wait(full_bar(stage), phase));
+                TRACE_COUNT(11);
                 tcgen05_fence_after();
                 if (lane == 0 && n_items < 4 && kb == it.kb0) stamp(p, 16 + 8 * (int)n_items + 0);
                 if (lane == 0 && n_items < 4 && kb == it.kb1 - 1) stamp(p, 16 + 8 * (int)n_items + 1);
-                if (lane == 0) {
+                if (elect_one()) {
                     const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
+                    const uint64_t ad0 = smem_desc(sa, a_lbo, 1024), bd0 = smem_desc(sb, b_lbo, 1024);
+                    // the start-address field (bits 0-13, units of 16 B) advances; no carry out of it inside a stage
+                    auto issue = [&](int k) {
+                        const uint64_t ad = ad0 + (uint64_t)((k * a_step) >> 4), bd = bd0 + (uint64_t)((k * b_step) >> 4);
+                        const uint32_t acc_flag = (kb > it.kb0 || k > 0) ? 1u : 0u;
+                        if (CG == 2) umma_bf16_pair(tmem_d, ad, bd, idesc, acc_flag); else umma_bf16(tmem_d, ad, bd, idesc, acc_flag);
+                    };
+                    if (ksteps == BK / UMMA_K) {
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k) issue(k);
+                    } else {
 #pragma unroll 1
-                    for (int k = 0; k < ksteps; ++k)
-                        umma_bf16(tmem_d, smem_desc(sa + k * a_step, a_lbo, 1024), smem_desc(sb + k * b_step, b_lbo, 1024), idesc,
-                                  (kb > it.kb0 || k > 0) ? 1u : 0u);
-                    umma_commit(empty_bar(stage));
-                    if (kb == it.kb1 - 1) umma_commit(tfull_bar(as));
+                        for (int k = 0; k < ksteps; ++k) issue(k);
+                    }
+                    if (CG == 2) {
+                        umma_commit_pair(empty_bar(stage));
+                        if (kb == it.kb1 - 1) umma_commit_pair(tfull_bar(as));
+                    } else {
+                        umma_commit(empty_bar(stage));
+                        if (kb == it.kb1 - 1) umma_commit(tfull_bar(as));
+                    }
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             }
         }
-    } else {
+    } else if (warp >= 2) {
         // ================= epilogue: 8 warps; warp -> TMEM lane quarter x 64-column chunks {ch, ch + 2} =================
         Dropout drop = p.drop;
         if (EPI == EPI_BF16_FULL) dropout_resolve(drop);
         const int quarter = warp & 3;             // TMEM lanes this warp may access: 32 * (warp_id % 4) ...
         const int ch = (warp - 2) >> 2;           // owns 64-column chunks ch and ch + 2 of the tile
+        // bf16 outputs leave through a per-warp staging buffer: each thread owns an output ROW (TMEM lane), so direct
+        // 16-byte stores touch 32 different lines per instruction (the L1 store path paced the whole epilogue: ~5.7k
+        // cycles per 128 x 256 tile); staged, every store instruction writes 4 rows x 128 contiguous bytes
+        const uint32_t stg = bars + 256u + (uint32_t)(warp - 2) * STG_WARP_BYTES;
         uint32_t n_items = 0;
         Item it;
 #pragma unroll 1
-        for (uint32_t item = blockIdx.x; item < total; item += gridDim.x, ++n_items) {
+        for (uint32_t item = worker; item < total; item += n_workers, ++n_items) {
             decode_item(p, item, it);
             const int as = (int)(n_items & 1);
             const uint32_t aphase = (n_items >> 1) & 1u;
-            const int m = it.m0 + quarter * 32 + lane;       // the output row this thread owns
+            const int m = it.m0 + (int)rank * BM + quarter * 32 + lane;       // the output row this thread owns
             const bool row_in = m < p.M;
             TC* Crow = reinterpret_cast<TC*>(p.C) + it.b1 * p.c_bs1 + it.b2 * p.c_bs2 + (long)m * p.c_rs;
             const TC* Rrow = (EPI == EPI_BF16_PLAIN || !p.R) ? nullptr
@@ -377,9 +489,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                     tcgen05_fence_before();
                     __syncwarp();
                     if (threadIdx.x == 64 && n_items < 4) stamp(p, 16 + 8 * (int)n_items + 3);
-                    if (lane == 0) mbar_arrive(tempty_bar(as));
+                    if (lane == 0) {
+                        if (CG == 2) mbar_arrive_cluster(mapa_shared(tempty_bar(as), 0)); else mbar_arrive(tempty_bar(as));
+                    }
                 }
                 if (ncols <= 0) continue;          // warp-uniform
+                // warp-uniform: the whole 64-column chunk is inside N and C rows are 16-byte aligned
+                const bool stage_chunk = (EPI != EPI_F32) && p.vec_ok && !p.accumulate && ncols == 64 && it.n0 + c0 + 64 <= p.N;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     if (q * 16 >= ncols) continue; // warp-uniform
@@ -417,7 +533,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                             for (int jj = 0; jj < 16; ++jj) v[jj] *= dropout_factor(drop, didx + jj);
                         }
                     }
-                    if (!row_in || n_base >= p.N) continue;
+                    if (!stage_chunk && (!row_in || n_base >= p.N)) continue;
                     TC* dst = Crow + n_base;
                     const bool fast = p.vec_ok && n_base + 16 <= p.N;
                     if (EPI == EPI_F32) {
@@ -438,7 +554,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                     } else if (fast) {
                         if (EPI == EPI_BF16_FULL) {
                             if (Rrow) { add_bf16x8(v, rr[2 * q]); add_bf16x8(v + 8, rr[2 * q + 1]); }
-                            if (p.accumulate) {
+                            if (p.accumulate) {          // never staged (stage_chunk excludes it)
                                 add_bf16x8(v, *reinterpret_cast<const uint4*>(dst));
                                 add_bf16x8(v + 8, *reinterpret_cast<const uint4*>(dst + 8));
                             }
@@ -447,23 +563,43 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                                 for (int jj = 0; jj < 16; ++jj) v[jj] = 0.f;
                             }
                         }
-                        *reinterpret_cast<uint4*>(dst) = pack_bf16x8(v);
-                        *reinterpret_cast<uint4*>(dst + 8) = pack_bf16x8(v + 8);
+                        if (stage_chunk) {
+                            const uint32_t rowaddr = stg + (uint32_t)lane * 128u;
+                            st_shared_v4(rowaddr + (uint32_t)(((2 * q) ^ (lane & 7)) << 4), pack_bf16x8(v));
+                            st_shared_v4(rowaddr + (uint32_t)(((2 * q + 1) ^ (lane & 7)) << 4), pack_bf16x8(v + 8));
+                        } else {
+                            *reinterpret_cast<uint4*>(dst) = pack_bf16x8(v);
+                            *reinterpret_cast<uint4*>(dst + 8) = pack_bf16x8(v + 8);
+                        }
                     } else {
                         epilogue_scalar<TC>(p, v, dst, Rrow ? Rrow + n_base : nullptr, min(16, p.N - n_base), row_ok);
                     }
                 }
                 if (EPI == EPI_BF16_FULL && u == 0) load_res(1);
+                if (stage_chunk) {
+                    __syncwarp();
+                    const int r_sub = lane >> 3, c16 = lane & 7;
+                    const int row0 = it.m0 + (int)rank * BM + quarter * 32;
+                    TC* Cblk = reinterpret_cast<TC*>(p.C) + it.b1 * p.c_bs1 + it.b2 * p.c_bs2 + it.n0 + c0 + c16 * 8;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = i * 4 + r_sub;
+                        const uint4 w = ld_shared_v4(stg + (uint32_t)r * 128u + (uint32_t)((c16 ^ (r & 7)) << 4));
+                        if (row0 + r < p.M) *reinterpret_cast<uint4*>(Cblk + (long)(row0 + r) * p.c_rs) = w;
+                    }
+                    __syncwarp();
+                }
             }
             if (threadIdx.x == 64 && n_items < 4) stamp(p, 16 + 8 * (int)n_items + 4);
         }
     }
     tcgen05_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();   // pairs: neither CTA leaves while the peer can still signal its barriers
     if (threadIdx.x == 0) stamp(p, 7);
     if (warp == 1) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -512,21 +648,33 @@ static bool make_map(CUtensorMap* map, const void* base, const long (&dim)[4], c
     return r == CUDA_SUCCESS;
 }
 
-// N-tile choice from a small cycle model of one CTA's work (numbers from the in-kernel clock traces):
-//   tile = fixed (~1500) + epilogue (~16 / column) + k-blocks x 4 MMAs x (70 + 0.68 BN) cycles
-// total = waves(tiles) x tile.  Wide tiles amortise the A re-reads of cta_group::1 MMAs; a problem
-// with few tiles is cut finer so that all SMs work.  Split-K candidates keep wide tiles (K is split instead).
-static int pick_bn(int N, long mtiles_x_batch, long kblocks, bool splitk_candidate) {
-    int best = 256;
-    double best_cost = -1.0;
+// Tile choice.  N tile from a small cycle model of one CTA's work (numbers from in-kernel clock traces):
+//   tile = fixed (~1500) + epilogue (~16 / column) + k-blocks x 4 MMAs x (70 + 0.68 BN) cycles,  total = waves(tiles) x tile.
+// Wide tiles amortise the A re-reads of cta_group::1 MMAs; a problem with few tiles is cut finer so that all SMs work.
+// Split-K candidates keep wide tiles (K is split instead).
+// CTA pairs (cg = 2, 256 x BN tiles, half of B staged per CTA): measured launch-interleaved against single-CTA tiles
+// (tools/gemm_probe.py ab, profiles/r01_gemm_pair_vs_single.txt): +5..9 % when the main loop dominates (K >= 768 and
+// N >= 768: 49152 x 4608 x 1536 runs at 1186 vs 1091 TFLOP/s), -5..12 % on short-K / narrow-N shapes whose time is
+// the epilogue and the per-tile fixed cost (16384 x 384 x 384: 20.5 vs 22.5 us) -- hence the gate below.
+struct TileChoice { int bn, cg; };
+static int g_force_cg = [] { const char* e = getenv("S2S_GEMM_CG"); return e ? atoi(e) : 0; }();   // 0 = gate below
+static TileChoice pick_tile(int M, int N, long batches, long kblocks, bool splitk_candidate) {
     const long sms = num_sms();
-    for (int bn = 256; bn >= 16; bn -= 16) {
+    int cg = 1;
+    const bool pair_ok = M > BM && N >= 32;
+    if (g_force_cg == 2) cg = pair_ok ? 2 : 1;
+    else if (g_force_cg == 0 && pair_ok && kblocks >= 12 && N >= 768 && ceil_div_l(M, 2 * BM) * batches * ceil_div_l(N, 256) >= sms / 4) cg = 2;
+    const long mtiles = ceil_div_l(M, (long)BM * cg) * batches;
+    const long workers = sms / cg;
+    TileChoice best{256, cg};
+    double best_cost = -1.0;
+    for (int bn = 256; bn >= 16 * cg; bn -= 16 * cg) {
         const long nt = (N + bn - 1) / bn;
-        const long tiles = nt * mtiles_x_batch;
-        const long waves = splitk_candidate ? tiles : (tiles + sms - 1) / sms;
-        const double mma = 4.0 * (70.0 + 0.68 * bn);      // measured: 158 cycles @ N = 128, 245 @ N = 256
+        const long tiles = nt * mtiles;
+        const long waves = splitk_candidate ? tiles : (tiles + workers - 1) / workers;
+        const double mma = 4.0 * (70.0 + 0.68 * bn / cg);
         const double cost = (double)waves * (1500.0 + 16.0 * bn + (double)kblocks * mma);
-        if (best_cost < 0 || cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+        if (best_cost < 0 || cost < best_cost - 1e-9) { best_cost = cost; best.bn = bn; }
     }
     return best;
 }
@@ -551,7 +699,9 @@ int gemm_tc(const s2s_gemm_t& g, cudaStream_t st) {
     p.b_mn = (g.b_cs != 1) ? 1 : 0;      // contiguous along N
     if (g.K == 1) { p.a_mn = (g.a_rs == 1); p.b_mn = (g.b_rs == 1); }
     const bool splitk_candidate = g.c_dtype == S2S_F32 && g.accumulate && !g.bias && !g.R && !g.relu && g.drop.p <= 0.f && g.mask_period == 0;
-    p.BN = pick_bn(g.N, (long)ceil_div_l(g.M, BM) * g.batch1 * g.batch2, (long)ceil_div_l(g.K, BK) * g.taps, splitk_candidate);
+    const TileChoice tile = pick_tile(g.M, g.N, (long)g.batch1 * g.batch2, (long)ceil_div_l(g.K, BK) * g.taps, splitk_candidate);
+    p.BN = tile.bn;
+    p.cg = tile.cg;
     if (ok) {
         const long rowsA = (long)g.M + g.taps - 1;
         if (!p.a_mn) {
@@ -566,10 +716,10 @@ int gemm_tc(const s2s_gemm_t& g, cudaStream_t st) {
         if (!p.b_mn) {
             if (g.taps > 1) {
                 long dim[4] = {g.K, g.N, g.taps, 1}, str[4] = {1, g.b_rs, g.b_ts, 0};
-                ok = make_map(&p.tmB, g.B, dim, str, BK, p.BN);
+                ok = make_map(&p.tmB, g.B, dim, str, BK, p.BN / p.cg);
             } else {
                 long dim[4] = {g.K, g.N, g.batch2, g.batch1}, str[4] = {1, g.b_rs, g.b_bs2, g.b_bs1};
-                ok = make_map(&p.tmB, g.B, dim, str, BK, p.BN);
+                ok = make_map(&p.tmB, g.B, dim, str, BK, p.BN / p.cg);
             }
         } else {
             long dim[4] = {g.N, g.K, g.batch2, g.batch1}, str[4] = {1, g.b_cs, g.b_bs2, g.b_bs1};
@@ -581,7 +731,7 @@ int gemm_tc(const s2s_gemm_t& g, cudaStream_t st) {
         return gemm_simt(g, st);
     }
     p.M = g.M; p.N = g.N; p.K = g.K; p.taps = g.taps; p.batch1 = g.batch1; p.batch2 = g.batch2;
-    p.mt = (int)ceil_div_l(g.M, BM);
+    p.mt = (int)ceil_div_l(g.M, (long)BM * p.cg);
     p.nt = (int)ceil_div_l(g.N, p.BN);
     p.kb_per_tap = (int)ceil_div_l(g.K, BK);
     p.kb_total = p.kb_per_tap * g.taps;
@@ -595,8 +745,8 @@ int gemm_tc(const s2s_gemm_t& g, cudaStream_t st) {
     p.splits = 1;
     const bool plain = p.c_f32 && g.accumulate && !g.bias && !g.R && !g.relu && p.drop.thresh == 0u && g.mask_period == 0;
     if (plain) p.atomic_out = 1;          // fp32 accumulate-in-place: red.global.add, C is never read
-    if (plain && tiles * 2 <= num_sms() && p.kb_total >= 8) {
-        long s = num_sms() / tiles;
+    if (plain && tiles * 2 <= num_sms() / p.cg && p.kb_total >= 8) {
+        long s = num_sms() / p.cg / tiles;
         long max_s = p.kb_total / 4;
         if (s > max_s) s = max_s;
         if (s > 1) p.splits = (int)s;
@@ -609,21 +759,39 @@ int gemm_tc(const s2s_gemm_t& g, cudaStream_t st) {
         int per = (p.kb_total + p.splits - 1) / p.splits;
         p.splits = (p.kb_total + per - 1) / per;
     }
+    static const void* const kernels[2][3] = {
+        {(const void*)gemm_tc_kernel<EPI_BF16_PLAIN, 1>, (const void*)gemm_tc_kernel<EPI_BF16_FULL, 1>, (const void*)gemm_tc_kernel<EPI_F32, 1>},
+        {(const void*)gemm_tc_kernel<EPI_BF16_PLAIN, 2>, (const void*)gemm_tc_kernel<EPI_BF16_FULL, 2>, (const void*)gemm_tc_kernel<EPI_F32, 2>}};
     std::call_once(g_attr_once, [] {
-        g_attr_err = cudaFuncSetAttribute(gemm_tc_kernel<EPI_BF16_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (g_attr_err == cudaSuccess)
-            g_attr_err = cudaFuncSetAttribute(gemm_tc_kernel<EPI_BF16_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (g_attr_err == cudaSuccess)
-            g_attr_err = cudaFuncSetAttribute(gemm_tc_kernel<EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        for (int c = 0; c < 2; ++c)
+            for (int e = 0; e < 3; ++e)
+                if (g_attr_err == cudaSuccess)
+                    g_attr_err = cudaFuncSetAttribute(kernels[c][e], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     });
     if (g_attr_err != cudaSuccess) return set_error(S2S_ERR_CUDA, "gemm_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(g_attr_err));
     long items = tiles * p.splits;
     if (items >= (1L << 31)) return set_error(S2S_ERR_UNSUPPORTED, "gemm_tc: too many tiles");
-    unsigned grid = (unsigned)(items < num_sms() ? items : num_sms());
+    const long workers = num_sms() / p.cg;
+    const unsigned grid = (unsigned)(items < workers ? items : workers) * (unsigned)p.cg;
     const bool plain_bf16 = !g.R && !g.accumulate && p.drop.thresh == 0u && g.mask_period == 0;
-    if (p.c_f32) gemm_tc_kernel<EPI_F32><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
-    else if (plain_bf16) gemm_tc_kernel<EPI_BF16_PLAIN><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
-    else gemm_tc_kernel<EPI_BF16_FULL><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
+    const int epi = p.c_f32 ? EPI_F32 : (plain_bf16 ? EPI_BF16_PLAIN : EPI_BF16_FULL);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    if (p.cg == 2) {       // CTA pair = thread-block cluster of 2 (placed on one TPC)
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    void* args[1] = {(void*)&p};
+    const cudaError_t lerr = cudaLaunchKernelExC(&cfg, kernels[p.cg - 1][epi], args);
+    if (lerr != cudaSuccess) return set_error(S2S_ERR_CUDA, "gemm_tc: launch failed: %s", cudaGetErrorString(lerr));
+    count_launch();
     S2S_LAUNCH_OK();
     return S2S_OK;
 }
@@ -633,4 +801,5 @@ long tc_fallback_count() { return g_tc_fallbacks; }
 }  // namespace s2s
 
 extern "C" void s2s_debug_gemm_trace(void* dev_buf8) { s2s::g_trace = (long long*)dev_buf8; }
+extern "C" void s2s_debug_gemm_tile(int cg) { s2s::tc::g_force_cg = (cg == 1 || cg == 2) ? cg : 0; }
 extern "C" int64_t s2s_tc_fallback_count(void) { return (int64_t)s2s::tc_fallback_count(); }

@@ -122,6 +122,51 @@ def test_gemm_conv1d_taps(ops, mode, dt):
     close(dz[:, halo:halo + L], y.transpose(1, 2), tol(dt, 8), "conv1d")
 
 
+def test_gemm_cta_pairs(ops):
+    """The CTA-pair variant of the tcgen05 GEMM (cluster of 2, one 256 x BN cta_group::2 MMA per k-step, each CTA staging half
+    of B), forced through the test hook, on every operand layout / epilogue the engines use; then the cost model's own
+    choice on a shape where it picks pairs."""
+    from seq2seq_vc_b200 import _lib
+    from seq2seq_vc_b200._lib import Drop
+
+    lib = _lib.load()
+    bf = torch.bfloat16
+    try:
+        lib.s2s_debug_gemm_tile(2)
+        for M, N, K in [(257, 130, 72), (1000, 384, 384), (640, 256, 200)]:
+            test_gemm_plain_and_epilogue(ops, 1, bf, M, N, K)
+        test_gemm_attention_views(ops, 1, bf, 300, 200, 64)
+        test_gemm_conv1d_taps(ops, 1, bf)
+        # weight gradient (both operands MN-major, fp32 accumulate in place, split-K) and data gradient (B MN-major)
+        M, N, K = 300, 520, 1333
+        dy, x = rnd(K, M, dt=bf, seed=1), rnd(K, N, dt=bf, seed=2)
+        g0 = rnd(M, N, seed=3)
+        ref = F.gemm(dy.t(), x.t(), g0.clone(), accumulate=True)
+        ddy, dx, dg = dev(dy, x, g0.clone())
+        ops.gemm(ddy.t(), dx.t(), dg, accumulate=True, mode=1)
+        close(dg, ref, tol(bf, 40), "pair dW gemm")
+        w = rnd(N, M, dt=bf, seed=4, scale=1 / math.sqrt(N))
+        c = torch.zeros(K, M, dtype=bf)
+        ref = F.gemm(x, w.t(), c.clone())
+        dxx, dw, dc = dev(x, w, c)
+        ops.gemm(dxx, dw.t(), dc, mode=1)
+        close(dc, ref, tol(bf, 4), "pair dx gemm")
+        # dropout + residual epilogue: same mask as the 128-row kernel (the mask is a function of the element index only)
+        a, b = rnd(900, 256, dt=bf, seed=5), rnd(384, 256, dt=bf, seed=6, scale=1 / 16)
+        res = rnd(900, 384, dt=bf, seed=7)
+        da, db, dres = dev(a, b, res)
+        outs = []
+        for cg in (2, 1):
+            lib.s2s_debug_gemm_tile(cg)
+            o = torch.empty(900, 384, dtype=bf, device="cuda")
+            ops.gemm(da, db, o, residual=dres, drop=Drop(0.3, seed=11, site=5), mode=1)
+            outs.append(o)
+        assert torch.equal(outs[0], outs[1])
+    finally:
+        lib.s2s_debug_gemm_tile(0)
+    test_gemm_plain_and_epilogue(ops, 1, bf, 40000, 512, 256)
+
+
 @pytest.mark.parametrize("dt", DT)
 @pytest.mark.parametrize("rows,d", [(7, 32), (1000, 384), (33, 50), (3001, 1536), (130, 256), (65, 1032), (40, 2048), (9, 2056)])
 def test_layernorm(ops, dt, rows, d):

@@ -8,10 +8,13 @@ SHAPES = {
     "lin_dec": dict(M=16384, N=384, K=384), "ffn1": dict(M=16384, N=1536, K=384), "ffn2": dict(M=16384, N=384, K=1536),
     "lin_enc": dict(M=4064, N=384, K=384), "conv2": dict(M=77216, N=384, K=3456), "big": dict(M=8192, N=8192, K=8192),
     "qk": dict(M=512, N=512, K=48, batch=256), "c3_ffn": dict(M=49152, N=1536, K=1536), "c3_qkv": dict(M=49152, N=4608, K=1536),
-    "c3_qk": dict(M=768, N=768, K=768, batch=128), "one_tile": dict(M=128, N=128, K=384), "one_tile_longk": dict(M=128, N=128, K=8192),
+    "c3_qk": dict(M=768, N=768, K=768, batch=128), "c3_ffn_in": dict(M=49152, N=1536, K=384), "c3_ffn_out": dict(M=49152, N=384, K=1536),
+    "c3_lin": dict(M=49152, N=384, K=384), "pv": dict(M=512, N=48, K=512, batch=256),
+    "c3_ffn3": dict(M=49152, N=3072, K=1536), "c3_ffn3o": dict(M=49152, N=1536, K=3072), "c3_qkvo": dict(M=49152, N=1536, K=4608),
+    "c2b64_lin": dict(M=32768, N=384, K=384), "c2b64_ffn1": dict(M=32768, N=1536, K=384), "c4_lin": dict(M=32000, N=512, K=512), "one_tile": dict(M=128, N=128, K=384), "one_tile_longk": dict(M=128, N=128, K=8192),
 }
 
-def run(name, reps=10, flush=True):
+def _setup(name):
     s = SHAPES[name]
     nb = s.get("batch", 1)
     M, N, K = s["M"], s["N"], s["K"]
@@ -19,27 +22,56 @@ def run(name, reps=10, flush=True):
     b = torch.randn(nb, N, K, device="cuda").bfloat16()
     c = torch.empty(nb, M, N, device="cuda", dtype=torch.bfloat16)
     bias = torch.randn(N, device="cuda")
-    scratch = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     if nb == 1:
         a, b, c = a[0], b[0], c[0]
     else:
         a, b, c = a.view(nb // 8, 8, M, K), b.view(nb // 8, 8, N, K), c.view(nb // 8, 8, M, N)
-    ts = []
-    for i in range(reps + 3):
-        if flush:
-            scratch.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        ops.gemm(a, b, c, bias=bias if nb == 1 else None, mode=1)
-        e1.record()
-        torch.cuda.synchronize()
-        if i >= 3:
-            ts.append(e0.elapsed_time(e1) * 1e3)
+    return a, b, c, (bias if nb == 1 else None), 2.0 * nb * M * N * K, f"{nb}x{M}x{N}x{K}"
+
+
+_scratch = None
+
+
+def _time_once(a, b, c, bias, flush=True):
+    global _scratch
+    if _scratch is None:
+        _scratch = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    if flush:
+        _scratch.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ops.gemm(a, b, c, bias=bias, mode=1)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3
+
+
+def run(name, reps=10, flush=True):
+    a, b, c, bias, fl, desc = _setup(name)
+    ts = [_time_once(a, b, c, bias, flush) for _ in range(reps + 3)][3:]
     ts.sort()
     us = ts[len(ts) // 2]
-    fl = 2.0 * nb * M * N * K
-    print(f"{name:16s} {nb}x{M}x{N}x{K}: median {us:8.1f} us  min {ts[0]:8.1f} us  {fl / us / 1e6:8.1f} TFLOP/s", flush=True)
+    print(f"{name:16s} {desc}: median {us:8.1f} us  min {ts[0]:8.1f} us  {fl / us / 1e6:8.1f} TFLOP/s", flush=True)
 
+
+def ab(names, rounds=9):
+    """Single-CTA tiles vs CTA pairs (s2s_debug_gemm_tile) vs the cost model's own choice, INTERLEAVED launch by launch:
+    the box's power / clock state drifts by more than the difference being measured."""
+    from seq2seq_vc_b200 import _lib
+    lib = _lib.load()
+    for n in names:
+        a, b, c, bias, fl, desc = _setup(n)
+        ts = {1: [], 2: [], 0: []}
+        for r in range(rounds + 2):
+            for cg in (1, 2, 0):
+                lib.s2s_debug_gemm_tile(cg)
+                t = _time_once(a, b, c, bias)
+                if r >= 2:
+                    ts[cg].append(t)
+        med = {cg: sorted(v)[len(v) // 2] for cg, v in ts.items()}
+        print(f"{n:12s} {desc:22s} single {med[1]:8.1f} us {fl / med[1] / 1e6:7.1f} TF | pair {med[2]:8.1f} us {fl / med[2] / 1e6:7.1f} TF"
+              f" | model {med[0]:8.1f} us {fl / med[0] / 1e6:7.1f} TF   pair/single {med[1] / med[2]:.3f}", flush=True)
+    lib.s2s_debug_gemm_tile(0)
 
 
 def trace(name, flush=True):
@@ -54,6 +86,9 @@ def trace(name, flush=True):
     lib.s2s_debug_gemm_trace(None)
     t0 = t[0]
     print(name, "flush" if flush else "warm", "cycles: setup %d, first TMA issue %d, kernel end %d" % (t[1] - t0, t[2] - t0, t[7] - t0))
+    launches = 5   # run(reps=2) = 2 + 3 warm-up launches accumulate into the wait counters
+    print("   CTA 0 per launch: %d k-blocks; MMA warp blocked on full %d cyc, on tmem_empty %d cyc; TMA producer blocked on empty %d cyc"
+          % (t[11] // launches, t[8] // launches, t[9] // launches, t[10] // launches))
     for i in range(4):
         r = t[16 + 8 * i: 16 + 8 * i + 6]
         if r[0] == 0:
@@ -64,10 +99,17 @@ def trace(name, flush=True):
 
 if __name__ == "__main__":
     args = sys.argv[1:]
-    if args and args[0] == "trace":
+    if args and args[0] == "ab":
+        ab(args[1:] or list(SHAPES))
+        sys.exit(0)
+    if args and args[0] == "trace":      # needs a library built with -DS2S_GEMM_TRACE
+        from seq2seq_vc_b200 import _lib
         for n in args[1:]:
-            trace(n, True)
-            trace(n, False)
+            for cg in (1, 2):
+                _lib.load().s2s_debug_gemm_tile(cg)
+                print("cg=%d" % cg)
+                trace(n, True)
+                trace(n, False)
     else:
         for n in (args or list(SHAPES)):
             run(n)
