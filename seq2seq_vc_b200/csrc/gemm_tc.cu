@@ -63,6 +63,24 @@ constexpr int EPI_BF16_PLAIN = 0;   // bf16 C = alpha * acc + bias, optional rel
 constexpr int EPI_BF16_FULL = 1;    // + dropout, residual, accumulate, row mask
 constexpr int EPI_F32 = 2;          // fp32 C: red.add (accumulate in place / split-K) or plain store of alpha * acc
 
+// n / d for n < 2^31 without the ~100-cycle integer-division sequence (the tile decode and the per-k-block tap split sit on
+// the single-thread critical paths of the TMA and MMA warps): q = umulhi(n, mul) >> shr, magic numbers from the host
+struct FastDiv {
+    uint32_t d, mul, shr;
+    __host__ void set(uint32_t div) {
+        d = div; mul = 0; shr = 0;
+        if (div > 1) {
+            uint32_t lg = 0;
+            while ((1ull << lg) < div) ++lg;                    // ceil(log2(d))
+            const uint32_t pw = 31 + lg;
+            mul = (uint32_t)(((1ull << pw) + div - 1) / div);
+            shr = pw - 32;
+        }
+    }
+    __device__ __forceinline__ uint32_t div(uint32_t n) const { return d == 1 ? n : (__umulhi(n, mul) >> shr); }
+    __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const { q = div(n); r = n - q * d; }
+};
+
 struct Params {
     CUtensorMap tmA, tmB;
     int M, N, K, taps, batch1, batch2;
@@ -70,6 +88,8 @@ struct Params {
     int BN;                  // N tile (multiple of 16, <= 256; multiple of 32 for CTA pairs)
     int cg;                  // 1 = one CTA per 128 x BN tile; 2 = CTA pair per 256 x BN tile (cta_group::2)
     int mt, nt, kb_per_tap, kb_total, splits;
+    int kb_per_split;
+    FastDiv d_splits, d_nt, d_mt, d_batch2, d_kbtap;
     void* C; int c_f32; long c_rs, c_bs1, c_bs2;
     const void* R;
     const float* bias;
@@ -229,19 +249,17 @@ struct Item {
     int b1, b2, m0, n0, kb0, kb1;
 };
 __device__ __noinline__ void decode_item(const Params& p, uint32_t item, Item& it) {
-    const uint32_t split = item % (uint32_t)p.splits;
-    uint32_t tile = item / (uint32_t)p.splits;
-    const uint32_t ntile = tile % (uint32_t)p.nt;
-    tile /= (uint32_t)p.nt;
-    const uint32_t mtile = tile % (uint32_t)p.mt;
-    const uint32_t bz = tile / (uint32_t)p.mt;
-    it.b1 = (int)(bz / (uint32_t)p.batch2);
-    it.b2 = (int)(bz % (uint32_t)p.batch2);
+    uint32_t tile, split, ntile, mtile, bz, b1, b2;
+    p.d_splits.divmod(item, tile, split);
+    p.d_nt.divmod(tile, tile, ntile);
+    p.d_mt.divmod(tile, bz, mtile);
+    p.d_batch2.divmod(bz, b1, b2);
+    it.b1 = (int)b1;
+    it.b2 = (int)b2;
     it.m0 = (int)mtile * BM * p.cg;
     it.n0 = (int)ntile * p.BN;
-    const int per = (p.kb_total + p.splits - 1) / p.splits;
-    it.kb0 = (int)split * per;
-    it.kb1 = min(p.kb_total, it.kb0 + per);
+    it.kb0 = (int)split * p.kb_per_split;
+    it.kb1 = min(p.kb_total, it.kb0 + p.kb_per_split);
 }
 
 // rare epilogue paths (column tails, unaligned rows, fp32 C with residual): rolled and out of line
@@ -336,10 +354,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             for (uint32_t item = worker; item < total; item += n_workers) {
                 decode_item(p, item, it);
                 const int am0 = it.m0 + (int)rank * BM, bn0 = it.n0 + (int)rank * BNH;
+                int t = (int)p.d_kbtap.div((uint32_t)it.kb0);
+                int kk = (it.kb0 - t * p.kb_per_tap) * BK;
 #pragma unroll 1
-                for (int kb = it.kb0; kb < it.kb1; ++kb) {
-                    const int t = kb / p.kb_per_tap;
-                    const int kk = (kb - t * p.kb_per_tap) * BK;
+                for (int kb = it.kb0; kb < it.kb1; ++kb, kk += BK) {
+                    if (kk >= p.kb_per_tap * BK) { kk = 0; ++t; }
                     TRACE_WAIT(10, mbar_wait(empty_bar(stage), phase ^ 1u));
                     const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
                     if (kb == it.kb0 && item == worker) stamp(p, 2);
@@ -384,10 +403,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             TRACE_WAIT(9, mbar_wait(tempty_bar(as), aphase ^ 1u));
             tcgen05_fence_after();
             const uint32_t tmem_d = tmem_base + (uint32_t)(as * MAX_BN);
+            int kk = (it.kb0 - (int)p.d_kbtap.div((uint32_t)it.kb0) * p.kb_per_tap) * BK;
 #pragma unroll 1
-            for (int kb = it.kb0; kb < it.kb1; ++kb) {
-                const int t = kb / p.kb_per_tap;
-                const int kk = (kb - t * p.kb_per_tap) * BK;
+            for (int kb = it.kb0; kb < it.kb1; ++kb, kk += BK) {
+                if (kk >= p.kb_per_tap * BK) kk = 0;
                 const int ksteps = (min(BK, p.K - kk) + UMMA_K - 1) / UMMA_K;
                 TRACE_WAIT(8, mbar_wait(full_bar(stage), phase));
                 TRACE_COUNT(11);
@@ -484,6 +503,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                 for (int q = 0; q < 4; ++q)
                     if (q * 16 < ncols) tmem_ld16(tbase + c0 + q * 16, acc[q]);
                 tmem_ld_wait();
+                if (u == 0 && threadIdx.x == 64 && n_items < 4) stamp(p, 16 + 8 * (int)n_items + 6);
                 if (u == 1) {
                     // every value of this warp is in registers: hand the accumulator stage back to the MMA warp
                     tcgen05_fence_before();
@@ -576,6 +596,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                     }
                 }
                 if (EPI == EPI_BF16_FULL && u == 0) load_res(1);
+                if (u == 0 && threadIdx.x == 64 && n_items < 4) stamp(p, 16 + 8 * (int)n_items + 7);
                 if (stage_chunk) {
                     __syncwarp();
                     const int r_sub = lane >> 3, c16 = lane & 7;
@@ -759,6 +780,9 @@ int gemm_tc(const s2s_gemm_t& g, cudaStream_t st) {
         int per = (p.kb_total + p.splits - 1) / p.splits;
         p.splits = (p.kb_total + per - 1) / per;
     }
+    p.kb_per_split = (p.kb_total + p.splits - 1) / p.splits;
+    p.d_splits.set((uint32_t)p.splits); p.d_nt.set((uint32_t)p.nt); p.d_mt.set((uint32_t)p.mt);
+    p.d_batch2.set((uint32_t)p.batch2); p.d_kbtap.set((uint32_t)p.kb_per_tap);
     static const void* const kernels[2][3] = {
         {(const void*)gemm_tc_kernel<EPI_BF16_PLAIN, 1>, (const void*)gemm_tc_kernel<EPI_BF16_FULL, 1>, (const void*)gemm_tc_kernel<EPI_F32, 1>},
         {(const void*)gemm_tc_kernel<EPI_BF16_PLAIN, 2>, (const void*)gemm_tc_kernel<EPI_BF16_FULL, 2>, (const void*)gemm_tc_kernel<EPI_F32, 2>}};

@@ -32,15 +32,26 @@ def _setup(name):
 _scratch = None
 
 
+FULL = False      # residual + dropout epilogue (EPI_BF16_FULL) instead of bias only
+_res = {}
+
+
 def _time_once(a, b, c, bias, flush=True):
     global _scratch
+    kw = {}
+    if FULL:
+        from seq2seq_vc_b200._lib import Drop
+        if c.data_ptr() not in _res:
+            _res.clear()
+            _res[c.data_ptr()] = torch.randn_like(c)
+        kw = dict(residual=_res[c.data_ptr()], drop=Drop(0.1, seed=3, site=2))
     if _scratch is None:
         _scratch = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     if flush:
         _scratch.zero_()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    ops.gemm(a, b, c, bias=bias, mode=1)
+    ops.gemm(a, b, c, bias=bias, mode=1, **kw)
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) * 1e3
@@ -90,26 +101,28 @@ def trace(name, flush=True):
     print("   CTA 0 per launch: %d k-blocks; MMA warp blocked on full %d cyc, on tmem_empty %d cyc; TMA producer blocked on empty %d cyc"
           % (t[11] // launches, t[8] // launches, t[9] // launches, t[10] // launches))
     for i in range(4):
-        r = t[16 + 8 * i: 16 + 8 * i + 6]
+        r = t[16 + 8 * i: 16 + 8 * i + 8]
         if r[0] == 0:
             break
-        print("   tile %d: TMA first issue %d | MMA first-full %d last-full %d | epi tfull %d, tmem released %d, stored %d" %
-              (i, r[5] - t0, r[0] - t0, r[1] - t0, r[2] - t0, r[3] - t0, r[4] - t0))
+        print("   tile %d: MMA first-full %d last-full %d | epilogue warp 2: tfull %d, chunk 0 in registers %d, computed %d, tmem released %d, done %d" %
+              (i, r[0] - t0, r[1] - t0, r[2] - t0, r[6] - t0, r[7] - t0, r[3] - t0, r[4] - t0))
 
 
 if __name__ == "__main__":
     args = sys.argv[1:]
+    if args and args[0] == "full":
+        FULL = True
+        args = args[1:]
     if args and args[0] == "ab":
         ab(args[1:] or list(SHAPES))
         sys.exit(0)
     if args and args[0] == "trace":      # needs a library built with -DS2S_GEMM_TRACE
         from seq2seq_vc_b200 import _lib
         for n in args[1:]:
-            for cg in (1, 2):
+            for cg in (1,):
                 _lib.load().s2s_debug_gemm_tile(cg)
                 print("cg=%d" % cg)
                 trace(n, True)
-                trace(n, False)
     else:
         for n in (args or list(SHAPES)):
             run(n)
