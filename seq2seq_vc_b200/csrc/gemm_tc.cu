@@ -312,6 +312,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     auto tempty_bar = [&](int s) { return bars + 8u * (2 * STAGES + 2 + s); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {      // descriptor fetch overlaps barrier init / TMEM allocation instead of delaying the first TMA load
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&p.tmB)) : "memory");
+    }
     // CTA pair: rank 0 (the leader) owns the full / tmem_empty barriers and issues the MMAs for both CTAs
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
     if (threadIdx.x == 0) stamp(p, 0);
@@ -515,7 +519,68 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                 }
                 if (ncols <= 0) continue;          // warp-uniform
                 // warp-uniform: the whole 64-column chunk is inside N and C rows are 16-byte aligned
-                const bool stage_chunk = (EPI != EPI_F32) && p.vec_ok && !p.accumulate && ncols == 64 && it.n0 + c0 + 64 <= p.N;
+                const bool stage_chunk = (EPI != EPI_F32) && p.vec_ok && !p.accumulate && ncols == 64 && it.n0 + c0 + 64 <= p.N &&
+                                         !(EPI == EPI_BF16_FULL && drop.thresh != 0u && (p.N & 1));   // pair-wise dropout hash: even row starts
+                if (EPI != EPI_F32 && stage_chunk) {
+                    // ---- hot path: straight-line code, no per-group bounds / alignment decisions ----
+                    const uint32_t rowaddr = stg + (uint32_t)lane * 128u;
+                    const bool has_bias = p.bias != nullptr, relu = p.relu != 0;
+                    const bool has_res = (EPI == EPI_BF16_FULL) && Rrow != nullptr;
+                    const bool has_drop = (EPI == EPI_BF16_FULL) && drop.thresh != 0u;
+                    const uint64_t didx0 = (uint64_t)(((long)(it.b1 * p.batch2 + it.b2) * p.M + m) * (long)p.N + it.n0 + c0);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float v[16];
+                        if (has_bias) {
+                            const float bsel = u ? ((q & 2) ? b11 : b10) : ((q & 2) ? b01 : b00);
+#pragma unroll
+                            for (int jj = 0; jj < 16; ++jj)
+                                v[jj] = fmaf(__uint_as_float(acc[q][jj]), p.alpha, __shfl_sync(0xffffffffu, bsel, (q & 1) * 16 + jj));
+                        } else {
+#pragma unroll
+                            for (int jj = 0; jj < 16; ++jj) v[jj] = __uint_as_float(acc[q][jj]) * p.alpha;
+                        }
+                        if (relu) {
+#pragma unroll
+                            for (int jj = 0; jj < 16; ++jj) v[jj] = fmaxf(v[jj], 0.f);
+                        }
+                        if (EPI == EPI_BF16_FULL) {
+                            if (has_drop) {
+                                const uint64_t didx = didx0 + (uint64_t)(q * 16);
+                                // one hash per element pair (common.cuh: dropout_factors); didx is even here (N even: see
+                                // stage_chunk).  Fully unrolled: a rolled loop indexes v[] dynamically, which puts it in local memory
+#pragma unroll
+                                for (int jj = 0; jj < 16; jj += 2) {
+                                    const uint32_t hsh = dropout_hash(drop, (didx + jj) >> 1);
+                                    v[jj] *= ((hsh & 0xffffu) < drop.thresh) ? 0.f : drop.scale;
+                                    v[jj + 1] *= ((hsh >> 16) < drop.thresh) ? 0.f : drop.scale;
+                                }
+                            }
+                            if (has_res) { add_bf16x8(v, rr[2 * q]); add_bf16x8(v + 8, rr[2 * q + 1]); }
+                            if (!row_ok) {
+#pragma unroll
+                                for (int jj = 0; jj < 16; ++jj) v[jj] = 0.f;
+                            }
+                        }
+                        st_shared_v4(rowaddr + (uint32_t)(((2 * q) ^ (lane & 7)) << 4), pack_bf16x8(v));
+                        st_shared_v4(rowaddr + (uint32_t)(((2 * q + 1) ^ (lane & 7)) << 4), pack_bf16x8(v + 8));
+                    }
+                    if (EPI == EPI_BF16_FULL && u == 0) load_res(1);
+                    if (u == 0 && threadIdx.x == 64 && n_items < 4) stamp(p, 16 + 8 * (int)n_items + 7);
+                    __syncwarp();
+                    const int r_sub = lane >> 3, c16 = lane & 7;
+                    const int row0 = it.m0 + (int)rank * BM + quarter * 32;
+                    TC* Cblk = reinterpret_cast<TC*>(p.C) + it.b1 * p.c_bs1 + it.b2 * p.c_bs2 + it.n0 + c0 + c16 * 8;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = i * 4 + r_sub;
+                        const uint4 w = ld_shared_v4(stg + (uint32_t)r * 128u + (uint32_t)((c16 ^ (r & 7)) << 4));
+                        if (row0 + r < p.M) *reinterpret_cast<uint4*>(Cblk + (long)(row0 + r) * p.c_rs) = w;
+                    }
+                    __syncwarp();
+                    continue;
+                }
+                // ---- generic path: column / row tails, unaligned C, accumulate-in-place, fp32 outputs ----
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     if (q * 16 >= ncols) continue; // warp-uniform
@@ -553,7 +618,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                             for (int jj = 0; jj < 16; ++jj) v[jj] *= dropout_factor(drop, didx + jj);
                         }
                     }
-                    if (!stage_chunk && (!row_in || n_base >= p.N)) continue;
+                    if (!row_in || n_base >= p.N) continue;
                     TC* dst = Crow + n_base;
                     const bool fast = p.vec_ok && n_base + 16 <= p.N;
                     if (EPI == EPI_F32) {
@@ -569,7 +634,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                                 *reinterpret_cast<float4*>(d32 + 4 * e) = row_ok ? make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3])
                                                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
                         } else {
-                            epilogue_scalar<TC>(p, v, dst, Rrow ? Rrow + n_base : nullptr, min(16, p.N - n_base), row_ok);
+                            {   // the helper takes an address: hand it a COPY, or v[] itself is forced into local memory and every
+                            // tile of the fast path pays 16 local stores per 16 columns (seen as STL in the ncu source view)
+                            float vt[16];
+#pragma unroll
+                            for (int jj = 0; jj < 16; ++jj) vt[jj] = v[jj];
+                            epilogue_scalar<TC>(p, vt, dst, Rrow ? Rrow + n_base : nullptr, min(16, p.N - n_base), row_ok);
+                        }
                         }
                     } else if (fast) {
                         if (EPI == EPI_BF16_FULL) {
@@ -583,33 +654,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                                 for (int jj = 0; jj < 16; ++jj) v[jj] = 0.f;
                             }
                         }
-                        if (stage_chunk) {
-                            const uint32_t rowaddr = stg + (uint32_t)lane * 128u;
-                            st_shared_v4(rowaddr + (uint32_t)(((2 * q) ^ (lane & 7)) << 4), pack_bf16x8(v));
-                            st_shared_v4(rowaddr + (uint32_t)(((2 * q + 1) ^ (lane & 7)) << 4), pack_bf16x8(v + 8));
-                        } else {
-                            *reinterpret_cast<uint4*>(dst) = pack_bf16x8(v);
-                            *reinterpret_cast<uint4*>(dst + 8) = pack_bf16x8(v + 8);
-                        }
+                        *reinterpret_cast<uint4*>(dst) = pack_bf16x8(v);
+                        *reinterpret_cast<uint4*>(dst + 8) = pack_bf16x8(v + 8);
                     } else {
-                        epilogue_scalar<TC>(p, v, dst, Rrow ? Rrow + n_base : nullptr, min(16, p.N - n_base), row_ok);
+                        {   // the helper takes an address: hand it a COPY, or v[] itself is forced into local memory and every
+                            // tile of the fast path pays 16 local stores per 16 columns (seen as STL in the ncu source view)
+                            float vt[16];
+#pragma unroll
+                            for (int jj = 0; jj < 16; ++jj) vt[jj] = v[jj];
+                            epilogue_scalar<TC>(p, vt, dst, Rrow ? Rrow + n_base : nullptr, min(16, p.N - n_base), row_ok);
+                        }
                     }
                 }
                 if (EPI == EPI_BF16_FULL && u == 0) load_res(1);
-                if (u == 0 && threadIdx.x == 64 && n_items < 4) stamp(p, 16 + 8 * (int)n_items + 7);
-                if (stage_chunk) {
-                    __syncwarp();
-                    const int r_sub = lane >> 3, c16 = lane & 7;
-                    const int row0 = it.m0 + (int)rank * BM + quarter * 32;
-                    TC* Cblk = reinterpret_cast<TC*>(p.C) + it.b1 * p.c_bs1 + it.b2 * p.c_bs2 + it.n0 + c0 + c16 * 8;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = i * 4 + r_sub;
-                        const uint4 w = ld_shared_v4(stg + (uint32_t)r * 128u + (uint32_t)((c16 ^ (r & 7)) << 4));
-                        if (row0 + r < p.M) *reinterpret_cast<uint4*>(Cblk + (long)(row0 + r) * p.c_rs) = w;
-                    }
-                    __syncwarp();
-                }
             }
             if (threadIdx.x == 64 && n_items < 4) stamp(p, 16 + 8 * (int)n_items + 4);
         }

@@ -33,6 +33,7 @@ _scratch = None
 
 
 FULL = False      # residual + dropout epilogue (EPI_BF16_FULL) instead of bias only
+NOBIAS = False
 _res = {}
 
 
@@ -51,7 +52,7 @@ def _time_once(a, b, c, bias, flush=True):
         _scratch.zero_()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    ops.gemm(a, b, c, bias=bias, mode=1, **kw)
+    ops.gemm(a, b, c, bias=None if NOBIAS else bias, mode=1, **kw)
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) * 1e3
@@ -112,6 +113,9 @@ if __name__ == "__main__":
     args = sys.argv[1:]
     if args and args[0] == "full":
         FULL = True
+        args = args[1:]
+    if args and args[0] == "nobias":
+        NOBIAS = True
         args = args[1:]
     if args and args[0] == "ab":
         ab(args[1:] or list(SHAPES))
