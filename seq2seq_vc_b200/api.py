@@ -866,13 +866,22 @@ AASVC.inference = _aasvc_inference
 
 class AASVCTrainStep:
     """forward + L1 / forward-sum / bin / duration losses + backward (+ gradient all-reduce) + clip + Adam + WarmupLR,
-    device-resident: mirrors AASVCTrainer._train_step (trainers/aas_vc.py:56-159) with gradient_accumulate_steps = 1.
+    device-resident: mirrors AASVCTrainer._train_step (trainers/aas_vc.py:56-159).
     With ``use_graph`` one (B, T, L) batch shape is captured into two CUDA graphs (forward+losses+backward | clip+Adam);
-    the NCCL all-reduce of the flat gradient buffer runs between them."""
+    the NCCL all-reduce of the flat gradient buffer runs between them.
+
+    ``gradient_accumulate_steps`` = k (trainers/base.py:65, aas_vc.py:141-149): every call is one micro-step whose
+    gradients are summed into the flat buffer; only the k-th one all-reduces, clips, runs Adam and advances ``steps`` /
+    the LR schedule.  The reference's ``loss / k`` is applied as one factor 1/(k * world) inside the Adam kernel (before
+    the clip), so non-boundary micro-steps do no collective and no optimizer work at all."""
 
     def __init__(self, model, lr: float = 8e-5, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
                  grad_norm: float = 1.0, warmup_steps: int = 4000, dp_train_start_steps: int = 0, use_graph: bool = False,
-                 process_group=None):
+                 process_group=None, gradient_accumulate_steps: int = 1):
+        if int(gradient_accumulate_steps) < 1:
+            raise ValueError("gradient_accumulate_steps must be >= 1")
+        self.accum = int(gradient_accumulate_steps)
+        self.backward_steps = 0                            # micro-steps so far (trainers/base.py:69)
         self.engine: AASVCEngine = model.engine if hasattr(model, "engine") else model
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
         self.grad_norm, self.warmup = grad_norm, warmup_steps
@@ -888,52 +897,61 @@ class AASVCTrainStep:
 
     lr_at = VTNTrainStep.lr_at
 
-    def _fwd_bwd(self, xs, ys, dpi, with_duration):
+    def _fwd_bwd(self, xs, ys, dpi, with_duration, fresh=True, boundary=True):
         eng = self.engine
         eng.forward(xs, ys, dpi)
         eng.loss(ys, duration_loss=with_duration)
-        eng.backward()
+        eng.backward(zero_grad=fresh)
+        if not boundary:
+            ops.step_advance(None, eng.seed_dev)           # no optimizer tail follows: still draw fresh dropout masks next time
 
     def _allreduce(self):
         if self.world > 1:
             torch.distributed.all_reduce(self.engine.store.G, group=self.pg)
 
     def _update(self):
-        self.engine.optimizer_step(self.grad_norm, self.betas, self.eps, self.wd, grad_scale=1.0 / self.world)
+        self.engine.optimizer_step(self.grad_norm, self.betas, self.eps, self.wd, grad_scale=1.0 / (self.world * self.accum))
 
     def __call__(self, xs, ilens, ys, olens, dp_inputs):
         """xs (B,T,idim), ys (B,L,odim), dp_inputs (B,T_dp,dp_idim): float32, CUDA-resident or pinned host memory.
         Returns the device tensor (l1, forward_sum, bin, duration) of this step without synchronising."""
         eng = self.engine
         with_dur = self.steps > self.dp_start          # trainers/aas_vc.py:113 (the reference skips the duration loss at step 0)
-        self.steps += 1
-        eng.lr_dev.fill_(self.lr_at(self.steps))
+        fresh = self.backward_steps % self.accum == 0  # first micro-step of an accumulation window: zero the gradient buffer
+        self.backward_steps += 1
+        boundary = self.backward_steps % self.accum == 0
+        if boundary:
+            self.steps += 1
+            eng.lr_dev.fill_(self.lr_at(self.steps))
         B, T, L = xs.shape[0], xs.shape[1], ys.shape[1]
         eng.training = True
         eng.prepare(B, T, L, ilens, olens)
         if not self.use_graph:
             if not xs.is_cuda:
                 xs, ys, dp_inputs = (t.to(eng.device, non_blocking=True) for t in (xs, ys, dp_inputs))
-            self._fwd_bwd(xs, ys, dp_inputs, with_dur)
-            self._allreduce()
-            self._update()
+            self._fwd_bwd(xs, ys, dp_inputs, with_dur, fresh, boundary)
+            if boundary:
+                self._allreduce()
+                self._update()
             return eng.losses
-        key = (B, T, L, dp_inputs.shape[1], with_dur)
+        key = (B, T, L, dp_inputs.shape[1], with_dur, fresh, boundary)
         entry = self._graphs.get(key)
         if entry is None:
             statics = [torch.empty(t.shape, dtype=_f32, device=eng.device) for t in (xs, ys, dp_inputs)]
             for dst, src in zip(statics, (xs, ys, dp_inputs)):
                 dst.copy_(src, non_blocking=True)
-            self._fwd_bwd(*statics, with_dur)             # eager step: allocates every buffer outside the graph pool
-            self._allreduce()
-            self._update()
+            self._fwd_bwd(*statics, with_dur, fresh, boundary)   # eager step: allocates every buffer outside the graph pool
+            if boundary:
+                self._allreduce()
+                self._update()
             torch.cuda.synchronize()
-            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            g1, g2 = torch.cuda.CUDAGraph(), (torch.cuda.CUDAGraph() if boundary else None)
             n0 = _lib.launch_count()
             with torch.cuda.graph(g1):
-                self._fwd_bwd(*statics, with_dur)
-            with torch.cuda.graph(g2):
-                self._update()
+                self._fwd_bwd(*statics, with_dur, fresh, boundary)
+            if boundary:
+                with torch.cuda.graph(g2):
+                    self._update()
             self._graphs[key] = (g1, g2, statics, _lib.launch_count() - n0)
             return eng.losses
         g1, g2, statics, n_kernels = entry
@@ -944,6 +962,7 @@ class AASVCTrainStep:
             if src.data_ptr() != dst.data_ptr():
                 dst.copy_(src, non_blocking=True)
         g1.replay()
-        self._allreduce()
-        g2.replay()
+        if boundary:
+            self._allreduce()
+            g2.replay()
         return eng.losses

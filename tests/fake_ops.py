@@ -420,8 +420,10 @@ def adam_step(p, g, m, v, p16, lr_dev, beta1, beta2, eps, wd, step_dev, sqn, max
 
 
 def step_advance(step_dev, seed_dev):
-    step_dev += 1
-    seed_dev += 1
+    if step_dev is not None:
+        step_dev += 1
+    if seed_dev is not None:
+        seed_dev += 1
 
 
 def cast(src, dst):

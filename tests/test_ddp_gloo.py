@@ -154,3 +154,74 @@ def test_aasvc_two_rank_step_matches_mean_gradient_step(tmp_path, monkeypatch):
         ref.lr_dev.fill_(stepper.lr_at(stepper.steps))
         ref.optimizer_step(1.0)
     assert (ref.store.P - p0).abs().max().item() <= 1e-6
+
+
+# ------------------------------------------------------------- gradient accumulation (trainers/aas_vc.py:141-149)
+def _aas_micro_batch(rank, micro):
+    from oracle import aasvc_oracle
+
+    return aasvc_oracle.synthetic_batch(2, 44, 36, ilens=[44, 37], olens=[36, 29], seed=300 + 10 * micro + rank)
+
+
+def _aas_accum_worker(rank, world, port, out_dir):
+    _install_fakes_all()
+    import torch.distributed as dist
+
+    from seq2seq_vc_b200 import AASVCEngine, AASVCTrainStep
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    calls = []
+    real = dist.all_reduce
+    dist.all_reduce = lambda *a, **k: (calls.append(1), real(*a, **k))[1]
+    eng = AASVCEngine(AAS_HP, device="cpu", bf16=False, seed=5)
+    step = AASVCTrainStep(eng, lr=1e-3, warmup_steps=1, use_graph=False, gradient_accumulate_steps=2)
+    for it in range(2):
+        for micro in range(2):
+            before = eng.store.P.clone()
+            step(*_aas_micro_batch(rank, micro))
+            if micro == 0:      # non-boundary micro-step: no collective, no optimizer work
+                assert torch.equal(before, eng.store.P) and len(calls) == it and step.steps == it
+    assert len(calls) == 2 and step.steps == 2 and step.backward_steps == 4
+    torch.save(eng.store.P.clone(), os.path.join(out_dir, f"acc{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_aasvc_gradient_accumulation_two_ranks(tmp_path, monkeypatch):
+    """2 ranks x 2 micro-steps == one process stepping on the mean of the four gradients; the all-reduce runs once per
+    optimizer step only."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_aas_accum_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    p0, p1 = torch.load(tmp_path / "acc0.pt"), torch.load(tmp_path / "acc1.pt")
+    assert torch.equal(p0, p1), "replicas diverged"
+
+    import fake_ops
+    from seq2seq_vc_b200 import AASVCEngine, AASVCTrainStep
+
+    fake_ops.install(monkeypatch)
+    e = AASVCEngine(AAS_HP, device="cpu", bf16=False, seed=5)
+    ref = AASVCEngine(AAS_HP, device="cpu", bf16=False, seed=5)
+    stepper = AASVCTrainStep(ref, lr=1e-3, warmup_steps=1)
+    for it in range(2):
+        g = torch.zeros_like(ref.store.G)
+        e.store.P.copy_(ref.store.P)
+        for r in range(2):
+            for micro in range(2):
+                xs, ilens, ys, olens, dpi = _aas_micro_batch(r, micro)
+                e.forward(xs, ys, dpi, ilens, olens)
+                e.loss(ys, duration_loss=it > 0)
+                e.backward()
+                g += e.store.G
+        ref.store.G.copy_(g / 4)
+        stepper.steps += 1
+        ref.lr_dev.fill_(stepper.lr_at(stepper.steps))
+        ref.optimizer_step(1.0)
+    assert (ref.store.P - p0).abs().max().item() <= 1e-6
+
+
+def test_aasvc_gradient_accumulation_rejects_zero():
+    from seq2seq_vc_b200 import AASVCTrainStep
+
+    with pytest.raises(ValueError):
+        AASVCTrainStep(object(), gradient_accumulate_steps=0)

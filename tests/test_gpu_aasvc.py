@@ -464,6 +464,52 @@ def test_fused_train_step_graph_matches_eager():
     assert (outs[0][1] - sd_flat_like(outs[0][1], sd)).abs().max().item() > 0
 
 
+def test_fused_train_step_gradient_accumulation():
+    """gradient_accumulate_steps = 2 (trainers/aas_vc.py:141-149): non-boundary micro-steps leave the parameters alone,
+    CUDA-graph replay == eager launches, and (dropout off) one accumulated step == one step on the hand-averaged gradient."""
+    from seq2seq_vc_b200 import AASVCEngine, AASVCTrainStep
+
+    z, sd = _golden()
+    ilens, olens = z["ilens"].tolist(), z["olens"].tolist()
+    xs, ys, dpi = (torch.from_numpy(z[k]).cuda() for k in ("xs", "ys", "dp_inputs"))
+    xs2, ys2 = xs * 0.9, ys * 1.1
+    outs = []
+    for use_graph in (False, True):
+        eng = AASVCEngine(dict(AAS_HP), device="cuda:0", bf16=False, seed=11)
+        eng.load_state_dict(sd)
+        st = AASVCTrainStep(eng, lr=1e-3, warmup_steps=10, use_graph=use_graph, gradient_accumulate_steps=2)
+        for it in range(4):
+            before = eng.store.P.clone()
+            st(xs, ilens, ys, olens, dpi)
+            assert torch.equal(before, eng.store.P) and st.steps == it
+            st(xs2, ilens, ys2, olens, dpi)
+            assert st.steps == it + 1 and not torch.equal(before, eng.store.P)
+        torch.cuda.synchronize()
+        outs.append(eng.store.P.clone().cpu())
+    assert torch.isfinite(outs[0]).all()
+    assert (outs[0] - outs[1]).abs().max().item() <= 1e-4
+
+    acc, ref = (AASVCEngine(dict(AAS_HP, **NO_DROPOUT), device="cuda:0", bf16=False, seed=11) for _ in range(2))
+    acc.load_state_dict(sd)
+    ref.load_state_dict(sd)
+    st = AASVCTrainStep(acc, lr=1e-3, warmup_steps=10, gradient_accumulate_steps=2)
+    st(xs, ilens, ys, olens, dpi)
+    st(xs2, ilens, ys2, olens, dpi)
+    g = torch.zeros_like(ref.store.G)
+    for a, b in ((xs, ys), (xs2, ys2)):
+        ref.training = True
+        ref.prepare(a.shape[0], a.shape[1], b.shape[1], ilens, olens)
+        ref.forward(a, b, dpi)
+        ref.loss(b, duration_loss=False)
+        ref.backward()
+        g += ref.store.G
+    ref.store.G.copy_(g / 2)
+    ref.lr_dev.fill_(st.lr_at(1))
+    ref.optimizer_step(1.0)
+    torch.cuda.synchronize()
+    assert (ref.store.P - acc.store.P).abs().max().item() <= 1e-5
+
+
 def sd_flat_like(flat, sd):
     """Flat parameter vector of the initial state (for 'did anything move' checks)."""
     from seq2seq_vc_b200 import AASVCEngine
