@@ -378,7 +378,8 @@ def run_ours(args, rank, world):
                        "l2": "per-step working set (activations + 0.5 GB of parameter/optimizer state) exceeds the 126 MB L2; no flush needed",
                        "losses_last_step": host_losses.tolist(), "model_tflops_per_step": flops_step / 1e12,
                        "model_tflops_per_sec": flops_step / (ms / args.steps * 1e-3) / 1e12,
-                       "tc_fallbacks": int(_lib.load().s2s_tc_fallback_count())},
+                       "tc_fallbacks": int(_lib.load().s2s_tc_fallback_count()),
+                       "gemm_pdl": int(os.environ.get("S2S_GEMM_PDL", "0") or 0)},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": (2 * xs.numel() * 4 + ys.numel() * 4 + 3 * B * 4) if aas else

@@ -338,6 +338,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     if (CG == 2) cluster_sync_all(); else __syncthreads();   // the peer's barriers are initialised before anyone signals them
     tcgen05_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
+    // Programmatic dependent launch (host: S2S_GEMM_PDL): everything above touches only this CTA's shared / tensor memory and
+    // the kernel parameters, so it may run while the previous kernel of the stream drains; nothing below (TMA reads of A / B,
+    // bias / residual reads, C writes) may.  A no-op when the launch carries no programmatic dependency.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (threadIdx.x == 0) stamp(p, 1);
 
     const uint32_t total = (uint32_t)((long)p.batch1 * p.batch2 * p.mt * p.nt * p.splits);
@@ -757,6 +761,10 @@ static TileChoice pick_tile(int M, int N, long batches, long kblocks, bool split
     return best;
 }
 
+// Programmatic dependent launch of single-CTA GEMMs (experimental, off by default): the launch may begin while the previous
+// kernel of the stream is still draining; the kernel's prologue (barrier init, TMEM allocation, descriptor prefetch) overlaps
+// that tail and griddepcontrol.wait orders every global-memory access after it.
+static int g_pdl = [] { const char* e = getenv("S2S_GEMM_PDL"); return e ? atoi(e) : 0; }();
 static std::once_flag g_attr_once;
 static cudaError_t g_attr_err = cudaSuccess;
 
@@ -866,6 +874,11 @@ int gemm_tc(const s2s_gemm_t& g, cudaStream_t st) {
     if (p.cg == 2) {       // CTA pair = thread-block cluster of 2 (placed on one TPC)
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    } else if (g_pdl) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
     }
