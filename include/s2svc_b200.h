@@ -48,7 +48,7 @@ int64_t s2s_launch_count(void);
  * and were served by the CUDA-core kernel instead */
 int64_t s2s_tc_fallback_count(void);
 /* test hook: force the tile shape of s2s_gemm(mode = 1): 1 = one CTA per 128-row tile, 2 = CTA pairs on 256-row tiles
- * (cta_group::2), 0 = cost model */
+ * (cta_group::2), 0 = cost model (also clears a pinned N tile); a value >= 16 pins the N tile to that width instead */
 void s2s_debug_gemm_tile(int cg);
 
 /* Counter-based dropout: element idx is dropped iff hash(seed', stream, idx) < p * 2^32 where

@@ -740,6 +740,7 @@ static bool make_map(CUtensorMap* map, const void* base, const long (&dim)[4], c
 // the epilogue and the per-tile fixed cost (16384 x 384 x 384: 20.5 vs 22.5 us) -- hence the gate below.
 struct TileChoice { int bn, cg; };
 static int g_force_cg = [] { const char* e = getenv("S2S_GEMM_CG"); return e ? atoi(e) : 0; }();   // 0 = gate below
+static int g_force_bn = 0;                                                                            // 0 = cost model
 static TileChoice pick_tile(int M, int N, long batches, long kblocks, bool splitk_candidate) {
     const long sms = num_sms();
     int cg = 1;
@@ -748,6 +749,7 @@ static TileChoice pick_tile(int M, int N, long batches, long kblocks, bool split
     else if (g_force_cg == 0 && pair_ok && kblocks >= 12 && N >= 768 && ceil_div_l(M, 2 * BM) * batches * ceil_div_l(N, 256) >= sms / 4) cg = 2;
     const long mtiles = ceil_div_l(M, (long)BM * cg) * batches;
     const long workers = sms / cg;
+    if (g_force_bn >= 16 * cg && g_force_bn <= MAX_BN && g_force_bn % (16 * cg) == 0) return TileChoice{g_force_bn, cg};
     TileChoice best{256, cg};
     double best_cost = -1.0;
     for (int bn = 256; bn >= 16 * cg; bn -= 16 * cg) {
@@ -895,5 +897,9 @@ long tc_fallback_count() { return g_tc_fallbacks; }
 }  // namespace s2s
 
 extern "C" void s2s_debug_gemm_trace(void* dev_buf8) { s2s::g_trace = (long long*)dev_buf8; }
-extern "C" void s2s_debug_gemm_tile(int cg) { s2s::tc::g_force_cg = (cg == 1 || cg == 2) ? cg : 0; }
+extern "C" void s2s_debug_gemm_tile(int cg) {
+    if (cg >= 16) { s2s::tc::g_force_bn = cg; return; }       // values >= 16 pin the N tile instead (cg choice untouched)
+    s2s::tc::g_force_cg = (cg == 1 || cg == 2) ? cg : 0;
+    if (cg == 0) s2s::tc::g_force_bn = 0;
+}
 extern "C" int64_t s2s_tc_fallback_count(void) { return (int64_t)s2s::tc_fallback_count(); }

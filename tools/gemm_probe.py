@@ -86,6 +86,42 @@ def ab(names, rounds=9):
     lib.s2s_debug_gemm_tile(0)
 
 
+def bn_sweep(names, bns=(64, 96, 128, 192, 256), rounds=7):
+    """Pinned N-tile widths vs the cost model's choice (0), interleaved launch by launch, cold (L2 flushed) and warm operands."""
+    from seq2seq_vc_b200 import _lib
+    lib = _lib.load()
+    for n in names:
+        a, b, c, bias, fl, desc = _setup(n)
+        for flush in (True, False):
+            ts = {bn: [] for bn in (0,) + tuple(bns)}
+            for r in range(rounds + 2):
+                for bn in ts:
+                    lib.s2s_debug_gemm_tile(0)
+                    lib.s2s_debug_gemm_tile(1)
+                    if bn:
+                        lib.s2s_debug_gemm_tile(bn)
+                    else:
+                        lib.s2s_debug_gemm_tile(0)
+                    t = _time_once(a, b, c, bias, flush)
+                    if r >= 2:
+                        ts[bn].append(t)
+            med = {bn: sorted(v)[len(v) // 2] for bn, v in ts.items()}
+            if flush:      # pinned tiles must give the model-chosen tile's result (same k order per output: bit-equal)
+                lib.s2s_debug_gemm_tile(0)
+                ops.gemm(a, b, c, bias=bias, mode=1)
+                ref = c.clone()
+                for bn in bns:
+                    lib.s2s_debug_gemm_tile(1)
+                    lib.s2s_debug_gemm_tile(bn)
+                    c.zero_()
+                    ops.gemm(a, b, c, bias=bias, mode=1)
+                    assert torch.equal(ref, c), f"{n}: BN {bn} differs from the model tile by {(ref.float() - c.float()).abs().max().item()}"
+                lib.s2s_debug_gemm_tile(0)
+            print(f"{n:12s} {desc:20s} {'cold' if flush else 'warm'} " + " | ".join(f"{'model' if bn == 0 else 'BN' + str(bn)} {med[bn]:6.1f} us" for bn in ts),
+                  flush=True)
+    lib.s2s_debug_gemm_tile(0)
+
+
 def trace(name, flush=True):
     import ctypes
     from seq2seq_vc_b200 import _lib
@@ -119,6 +155,9 @@ if __name__ == "__main__":
         args = args[1:]
     if args and args[0] == "ab":
         ab(args[1:] or list(SHAPES))
+        sys.exit(0)
+    if args and args[0] == "bn":
+        bn_sweep(args[1:] or ["lin_dec", "ffn1", "lin_enc", "c2b64_lin"])
         sys.exit(0)
     if args and args[0] == "trace":      # needs a library built with -DS2S_GEMM_TRACE
         from seq2seq_vc_b200 import _lib
