@@ -6,9 +6,11 @@ installable here: **librosa** (setup.cfg:5, ``librosa >= 0.8.0``, unpinned).  Th
 test or golden vector at that boundary, so this oracle is **PARITY UNPINNED** against librosa
 itself; it follows librosa's published algorithm for the call sites preprocess.py:63-70
 (``librosa.stft(..., window="hann", pad_mode="reflect")``, center=True default) and :76-82
-(``librosa.filters.mel``: Slaney mel scale, Slaney area normalisation, float32), and the mel
-filterbank is cross-checked against torchaudio's independent implementation
-(tests/test_logmel_oracle.py).
+(``librosa.filters.mel``: Slaney mel scale, Slaney area normalisation, float32).  The risk is bounded by
+cross-checks against independent implementations of the same algorithm (tests/test_logmel_oracle.py,
+tests/test_oracle_golden.py): scipy.signal.stft for the STFT magnitudes, transformers.audio_utils
+(mel_filter_bank / spectrogram, written to reproduce librosa) for the filterbank and the whole log-mel
+pipeline (<= 1e-5 in the log10 domain), torchaudio for the filterbank.
 
 librosa semantics restated:
  * reflect-pad n_fft//2 samples on both sides; frames = 1 + len(audio)//hop;
