@@ -93,7 +93,15 @@ def rel_attention(sd, prefix, x, pos_emb, mask, n_head, store=None):
 
 
 def ffn_swish(sd, prefix, x):
-    """PositionwiseFeedForward with Swish (conformer/encoder.py:102,181-188)."""
+    """Position-wise layer of a conformer block (conformer/encoder.py:181-198), told apart by the weight rank:
+    "linear"  -> PositionwiseFeedForward with Swish (positionwise_feed_forward.py:12-32), weights (U, d);
+    "conv1d"  -> MultiLayeredConv1d (multi_layer_conv.py:13-62): Conv1d(k) -> ReLU -> dropout -> Conv1d(k) over time with
+                 padding (k-1)//2, weights (U, d, k); the activation is ReLU whatever the encoder's activation_type."""
+    w1 = sd[prefix + ".w_1.weight"]
+    if w1.dim() == 3:
+        k = w1.shape[2]
+        h = F.relu(F.conv1d(x.transpose(1, 2), w1, sd[prefix + ".w_1.bias"], padding=(k - 1) // 2))
+        return F.conv1d(h, sd[prefix + ".w_2.weight"], sd[prefix + ".w_2.bias"], padding=(k - 1) // 2).transpose(1, 2)
     return linear(swish(linear(x, sd, prefix + ".w_1")), sd, prefix + ".w_2")
 
 
@@ -396,8 +404,13 @@ def state_dict_spec(hp) -> List:
                 lin(f"{p}.self_attn.{s}", dm, dm)
             lin(p + ".self_attn.linear_pos", dm, dm, bias=False)
             for ff in ("feed_forward", "feed_forward_macaron"):
-                lin(f"{p}.{ff}.w_1", units, dm)
-                lin(f"{p}.{ff}.w_2", dm, units)
+                if hp.get("positionwise_layer_type", "linear") == "conv1d":
+                    pk_ = hp.get("positionwise_conv_kernel_size", 1)
+                    spec.extend([(f"{p}.{ff}.w_1.weight", (units, dm, pk_)), (f"{p}.{ff}.w_1.bias", (units,)),
+                                 (f"{p}.{ff}.w_2.weight", (dm, units, pk_)), (f"{p}.{ff}.w_2.bias", (dm,))])
+                else:
+                    lin(f"{p}.{ff}.w_1", units, dm)
+                    lin(f"{p}.{ff}.w_2", dm, units)
             spec.extend([(p + ".conv_module.pointwise_conv1.weight", (2 * dm, dm, 1)), (p + ".conv_module.pointwise_conv1.bias", (2 * dm,)),
                          (p + ".conv_module.depthwise_conv.weight", (dm, 1, k)), (p + ".conv_module.depthwise_conv.bias", (dm,))])
             bn(p + ".conv_module.norm", dm)

@@ -179,6 +179,54 @@ def gen_aasvc_tiny():
     print("aasvc_tiny:", len(dump), "arrays")
 
 
+def gen_aasvc_conv1d_tiny():
+    """Same step as gen_aasvc_tiny with the position-wise layer the AASVC class defaults to (models/aas_vc.py:52-53):
+    MultiLayeredConv1d, kernel size 1, ReLU (modules/transformer/multi_layer_conv.py) instead of Linear + Swish."""
+    from seq2seq_vc.losses import DurationPredictorLoss, ForwardSumLoss, L1Loss
+    from seq2seq_vc.models import AASVC
+
+    torch.manual_seed(29)
+    model = AASVC(**AAS_HP, **dict(AAS_FIXED, positionwise_layer_type="conv1d", positionwise_conv_kernel_size=1))
+    ref_shim.disable_dropout(model)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if p.dim() == 1 and ("norm" in n or "embed.1" in n or ".2." in n or ".1." in n):
+                p.add_(0.1 * torch.randn_like(p))
+    model.train()
+    sd0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    xs, ilens, ys, olens, dpi = aasvc_oracle.synthetic_batch(3, 50, 44, ilens=[50, 41, 37], olens=[44, 38, 30], seed=31)
+    ret = model(xs, torch.tensor(ilens), ys, torch.tensor(olens), dpi, dp_lengths=torch.tensor(ilens))
+    l1 = L1Loss()(ret["after_outs"], ret["before_outs"], ret["ys"], ret["olens"])
+    fs = ForwardSumLoss()(ret["log_p_attn"], ret["ilens"], ret["olens_reduced"])
+    dur = DurationPredictorLoss()(ret["d_outs"], ret["ds"], ret["ilens"])
+    (l1 + 2.0 * (fs + ret["bin_loss"]) + dur).backward()
+    dump = {"sd." + k: v.numpy() for k, v in sd0.items()}
+    dump.update({"grad." + k: p.grad.numpy() for k, p in model.named_parameters() if p.grad is not None})
+    dump.update({"bn_after." + k: v.numpy() for k, v in model.state_dict().items() if "running_" in k})
+    dump.update(xs=xs.numpy(), ilens=np.array(ilens), ys=ys.numpy(), olens=np.array(olens), dp_inputs=dpi.numpy(),
+                after_outs=ret["after_outs"].detach().numpy(), before_outs=ret["before_outs"].detach().numpy(),
+                log_p_attn=ret["log_p_attn"].detach().numpy(), ds=ret["ds"].numpy(), d_outs=ret["d_outs"].detach().numpy(),
+                ilens_out=ret["ilens"].numpy(), olens_out=ret["olens"].numpy(), l1_loss=l1.detach().numpy(),
+                forward_sum_loss=fs.detach().numpy(), bin_loss=ret["bin_loss"].detach().numpy(), duration_loss=dur.detach().numpy())
+    for n, m in model.named_modules():
+        if hasattr(m, "attn") and isinstance(getattr(m, "attn"), torch.Tensor):
+            dump["attn." + n] = m.attn.detach().numpy()
+    model.eval()
+    with torch.no_grad():
+        rete = model(xs, torch.tensor(ilens), ys, torch.tensor(olens), dpi, dp_lengths=torch.tensor(ilens))
+    dump["eval_after_outs"] = rete["after_outs"].numpy()
+    with torch.no_grad():                                # inference as in gen_aasvc_tiny (raised duration-predictor bias)
+        model.duration_predictor.linear.bias.add_(1.0)
+        outs, d_outs = model.inference(xs[0, :ilens[0]], dp_input=dpi[0, :ilens[0]])
+        dump.update(inf_dp_bias=model.duration_predictor.linear.bias.detach().numpy().copy(), inf_outs=outs.numpy(), inf_d_outs=d_outs.numpy())
+        model.duration_predictor.linear.bias.sub_(1.0)
+        for k, v in model.state_dict().items():
+            if "running_" in k:
+                dump["inf_bn." + k] = v.numpy().copy()
+    np.savez_compressed(os.path.join(GOLDEN, "aasvc_conv1d_tiny.npz"), **dump)
+    print("aasvc_conv1d_tiny:", len(dump), "arrays")
+
+
 def gen_mas():
     from seq2seq_vc.modules.alignments import _monotonic_alignment_search, viterbi_decode
 
@@ -233,8 +281,9 @@ def gen_kats():
 if __name__ == "__main__":
     ref_shim.install()
     os.makedirs(GOLDEN, exist_ok=True)
-    gen_vtn_tiny()
-    gen_tts_tiny()
-    gen_aasvc_tiny()
-    gen_mas()
-    gen_kats()
+    import sys
+
+    gens = dict(vtn_tiny=gen_vtn_tiny, tts_tiny=gen_tts_tiny, aasvc_tiny=gen_aasvc_tiny, aasvc_conv1d_tiny=gen_aasvc_conv1d_tiny,
+                mas=gen_mas, kats=gen_kats)
+    for name in (sys.argv[1:] or list(gens)):      # e.g. `python oracle/gen_golden.py aasvc_conv1d_tiny` adds one fixture
+        gens[name]()

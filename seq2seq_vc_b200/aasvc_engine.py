@@ -46,8 +46,13 @@ def default_hparams(**over) -> dict:
               transformer_enc_dropout_rate=0.2, transformer_enc_positional_dropout_rate=0.2,
               transformer_enc_attn_dropout_rate=0.2, transformer_dec_dropout_rate=0.2,
               transformer_dec_positional_dropout_rate=0.2, transformer_dec_attn_dropout_rate=0.2,
-              duration_predictor_dropout_rate=0.1, postnet_dropout_rate=0.5, lambda_align=2.0)
+              duration_predictor_dropout_rate=0.1, postnet_dropout_rate=0.5, lambda_align=2.0,
+              # "linear": PositionwiseFeedForward + Swish (the shipped yaml); "conv1d": MultiLayeredConv1d, kernel size 1, ReLU
+              # (the AASVC class default, models/aas_vc.py:52-53)
+              positionwise_layer_type="linear")
     hp.update(over)
+    if hp["positionwise_layer_type"] not in ("linear", "conv1d"):
+        raise NotImplementedError(f"positionwise_layer_type {hp['positionwise_layer_type']!r}")
     return hp
 
 
@@ -108,8 +113,14 @@ def param_groups(hp: dict) -> List[List[Tuple[str, Tuple[int, ...]]]]:
             lin(p + ".self_attn.linear_out", dm, dm)
             lin(p + ".self_attn.linear_pos", dm, dm, bias=False)
             for ff in ("feed_forward", "feed_forward_macaron"):
-                lin(f"{p}.{ff}.w_1", units, dm)
-                lin(f"{p}.{ff}.w_2", dm, units)
+                if hp.get("positionwise_layer_type", "linear") == "conv1d":     # Conv1d(k = 1) weights keep their (out, in, 1) shape
+                    g.append([(f"{p}.{ff}.w_1.weight", (units, dm, 1))])
+                    g.append([(f"{p}.{ff}.w_1.bias", (units,))])
+                    g.append([(f"{p}.{ff}.w_2.weight", (dm, units, 1))])
+                    g.append([(f"{p}.{ff}.w_2.bias", (dm,))])
+                else:
+                    lin(f"{p}.{ff}.w_1", units, dm)
+                    lin(f"{p}.{ff}.w_2", dm, units)
             g.append([(p + ".conv_module.pointwise_conv1.weight", (2 * dm, dm, 1))])
             g.append([(p + ".conv_module.pointwise_conv1.bias", (2 * dm,))])
             g.append([(p + ".conv_module.depthwise_conv.weight", (dm, 1, k))])
@@ -286,18 +297,23 @@ class AASVCEngine(EngineBase):
 
     # ------------------------------------------------------------------ conformer block
     def _ffn_fwd(self, x, p, ff, tag, U, rate, out):
-        """out = x + 0.5 * dropout(w_2(dropout(swish(w_1 LN(x)))))   (encoder_layer.py:115-123,157-163)."""
+        """out = x + 0.5 * dropout(w_2(dropout(act(w_1 LN(x)))))   (encoder_layer.py:115-123,157-163); act = Swish for the
+        "linear" position-wise layer, ReLU (in the GEMM epilogue, with its dropout) for "conv1d" k = 1 (multi_layer_conv.py:13-62)."""
         st = self.store
         B, T, dm = x.shape
         norm = "norm_ff_macaron" if ff == "feed_forward_macaron" else "norm_ff"
         n = self._ln_fwd(x, f"{p}.{norm}", f"{tag}.ln")
-        hpre = self.buf(tag + ".hpre", (B * T, U))
-        self._lin_fwd(n.view(B * T, dm), self.W(f"{p}.{ff}.w_1.weight"), st.p(f"{p}.{ff}.w_1.bias"), hpre)
         h = self.buf(tag + ".h", (B * T, U))
-        ops.swish_fwd(hpre, h, self.named_drop(tag + ".d1", rate))
+        w1, w2 = self.W(f"{p}.{ff}.w_1.weight").view(U, dm), self.W(f"{p}.{ff}.w_2.weight").view(dm, U)
+        if self.hp["positionwise_layer_type"] == "conv1d":
+            self._lin_fwd(n.view(B * T, dm), w1, st.p(f"{p}.{ff}.w_1.bias"), h, relu=True, drop=self.named_drop(tag + ".d1", rate))
+        else:
+            hpre = self.buf(tag + ".hpre", (B * T, U))
+            self._lin_fwd(n.view(B * T, dm), w1, st.p(f"{p}.{ff}.w_1.bias"), hpre)
+            ops.swish_fwd(hpre, h, self.named_drop(tag + ".d1", rate))
         bh = self.buf(tag + ".bhalf", (dm,), _f32)
         ops.scale_dropout(st.p(f"{p}.{ff}.w_2.bias"), bh, 0.5)
-        ops.gemm(h, self.W(f"{p}.{ff}.w_2.weight"), out.view(B * T, dm), bias=bh, alpha=0.5, drop=self.named_drop(tag + ".d2", rate),
+        ops.gemm(h, w2, out.view(B * T, dm), bias=bh, alpha=0.5, drop=self.named_drop(tag + ".d2", rate),
                  residual=x.view(B * T, dm), mode=self.mode)
         return out
 
@@ -307,15 +323,18 @@ class AASVCEngine(EngineBase):
         B, T, dm = x.shape
         norm = "norm_ff_macaron" if ff == "feed_forward_macaron" else "norm_ff"
         n = self.buf(f"{tag}.ln.y", (B, T, dm))
-        hpre = self.buf(tag + ".hpre", (B * T, U))
         h = self.buf(tag + ".h", (B * T, U))
         dy = self._scratch("cf.dy", (B * T, dm))
         ops.scale_dropout(g.view(B * T, dm), dy, 0.5, self.named_drop(tag + ".d2", rate))
         dh = self._scratch("cf.dh", (B * T, U))
-        self._lin_bwd(dy, h, self.W(f"{p}.{ff}.w_2.weight"), st.g(f"{p}.{ff}.w_2.weight"), st.g(f"{p}.{ff}.w_2.bias"), dx=dh)
-        ops.swish_bwd(dh, hpre, dh, self.named_drop(tag + ".d1", rate))
+        w1, w2 = self.W(f"{p}.{ff}.w_1.weight").view(U, dm), self.W(f"{p}.{ff}.w_2.weight").view(dm, U)
+        self._lin_bwd(dy, h, w2, st.g(f"{p}.{ff}.w_2.weight").view(dm, U), st.g(f"{p}.{ff}.w_2.bias"), dx=dh)
+        if self.hp["positionwise_layer_type"] == "conv1d":
+            ops.relu_bwd(dh, h, dh, self.named_drop(tag + ".d1", rate).scale)    # h = dropout(relu(.)): zero where cut or dropped
+        else:
+            ops.swish_bwd(dh, self.buf(tag + ".hpre", (B * T, U)), dh, self.named_drop(tag + ".d1", rate))
         dn = self._scratch("cf.dn", (B, T, dm))
-        self._lin_bwd(dh, n.view(B * T, dm), self.W(f"{p}.{ff}.w_1.weight"), st.g(f"{p}.{ff}.w_1.weight"), st.g(f"{p}.{ff}.w_1.bias"),
+        self._lin_bwd(dh, n.view(B * T, dm), w1, st.g(f"{p}.{ff}.w_1.weight").view(U, dm), st.g(f"{p}.{ff}.w_1.bias"),
                       dx=dn.view(B * T, dm))
         self._ln_bwd(dn, x, f"{p}.{norm}", f"{tag}.ln", gout, dres=g)
         return gout

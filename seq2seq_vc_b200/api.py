@@ -767,8 +767,10 @@ class AASVC(VTN):
         unsupported = []
         if encoder_type != "conformer" or decoder_type != "conformer":
             unsupported.append("encoder_type/decoder_type != 'conformer'")
-        if positionwise_layer_type != "linear":
-            unsupported.append("positionwise_layer_type != 'linear'")
+        if positionwise_layer_type not in ("linear", "conv1d"):
+            unsupported.append("positionwise_layer_type not in ('linear', 'conv1d')")
+        if positionwise_layer_type == "conv1d" and positionwise_conv_kernel_size != 1:
+            unsupported.append("positionwise_conv_kernel_size != 1")
         if encoder_input_layer != "linear":
             unsupported.append("encoder_input_layer != 'linear'")
         if not (encoder_normalize_before and decoder_normalize_before):
@@ -805,7 +807,8 @@ class AASVC(VTN):
             transformer_enc_attn_dropout_rate=transformer_enc_attn_dropout_rate, transformer_dec_dropout_rate=transformer_dec_dropout_rate,
             transformer_dec_positional_dropout_rate=transformer_dec_positional_dropout_rate,
             transformer_dec_attn_dropout_rate=transformer_dec_attn_dropout_rate,
-            duration_predictor_dropout_rate=duration_predictor_dropout_rate, postnet_dropout_rate=postnet_dropout_rate)
+            duration_predictor_dropout_rate=duration_predictor_dropout_rate, postnet_dropout_rate=postnet_dropout_rate,
+            positionwise_layer_type=positionwise_layer_type)
         self._bf16 = compute_dtype in ("bf16", "bfloat16", torch.bfloat16)
         self._seed = seed
         self._fwd_token = 0

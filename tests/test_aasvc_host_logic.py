@@ -24,12 +24,16 @@ NO_DROPOUT = dict(transformer_enc_dropout_rate=0.0, transformer_enc_positional_d
                   duration_predictor_dropout_rate=0.0, postnet_dropout_rate=0.0)
 
 
-@pytest.fixture()
-def engine(monkeypatch):
+# the shipped yaml's Linear + Swish position-wise layers, and the AASVC class default (MultiLayeredConv1d k = 1 + ReLU)
+FIXTURES = {"linear": "aasvc_tiny.npz", "conv1d": "aasvc_conv1d_tiny.npz"}
+
+
+@pytest.fixture(params=sorted(FIXTURES))
+def engine(monkeypatch, request):
     fake_ops.install(monkeypatch)
-    z = np.load(GOLDEN)
+    z = np.load(os.path.join(os.path.dirname(GOLDEN), FIXTURES[request.param]))
     sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
-    eng = AASVCEngine(dict(AAS_HP, **NO_DROPOUT), device="cpu", bf16=False)
+    eng = AASVCEngine(dict(AAS_HP, positionwise_layer_type=request.param, **NO_DROPOUT), device="cpu", bf16=False)
     assert set(eng.state_dict()) == set(sd)
     eng.load_state_dict(sd)
     return eng, z
@@ -119,3 +123,22 @@ def test_inference_matches_reference(engine):
     np.testing.assert_array_equal(d_outs.numpy(), z["inf_d_outs"])
     assert outs.shape == z["inf_outs"].shape and np.abs(outs.numpy() - z["inf_outs"]).mean() <= 1e-5
     assert eng.training is True                          # restored
+
+
+def test_dropin_class_default_positionwise_layer():
+    """AASVC() defaults to positionwise_layer_type="conv1d", kernel size 1 (models/aas_vc.py:52-53): the drop-in builds the
+    reference's state dict for it ((U, d, 1) Conv1d weights), loads a reference checkpoint, and refuses wider kernels."""
+    from seq2seq_vc_b200 import AASVC
+
+    fixed = dict(duration_predictor_type="deterministic", encoder_input_layer="linear", duration_predictor_use_encoder_outputs=False,
+                 encoder_normalize_before=True, decoder_normalize_before=True)
+    z = np.load(os.path.join(os.path.dirname(GOLDEN), FIXTURES["conv1d"]))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    m = AASVC(**AAS_HP, **fixed)
+    msd = m.state_dict()
+    assert set(msd) == set(sd) and all(tuple(msd[k].shape) == tuple(sd[k].shape) for k in sd)
+    assert tuple(msd["decoder.encoders.0.feed_forward_macaron.w_2.weight"].shape) == (128, 48, 1)
+    m.load_state_dict(sd)
+    assert torch.equal(m.state_dict()["encoder.encoders.0.feed_forward.w_1.weight"], sd["encoder.encoders.0.feed_forward.w_1.weight"])
+    with pytest.raises(NotImplementedError):
+        AASVC(**AAS_HP, **fixed, positionwise_conv_kernel_size=3)

@@ -278,8 +278,8 @@ def test_gauss_weights_and_duration_loss(ops, dt):
 
 
 # ---------------------------------------------------------------------------------------------- whole engine
-def _golden():
-    z = np.load(GOLDEN)
+def _golden(fixture=None):
+    z = np.load(GOLDEN if fixture is None else os.path.join(os.path.dirname(GOLDEN), fixture))
     sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
     return z, sd
 
@@ -296,11 +296,14 @@ def _step(eng, z):
     return after, before, losses
 
 
-def test_golden_tiny_fp32_forward_losses_grads():
+@pytest.mark.parametrize("pw,fixture", [("linear", "aasvc_tiny.npz"), ("conv1d", "aasvc_conv1d_tiny.npz")])
+def test_golden_tiny_fp32_forward_losses_grads(pw, fixture):
+    """Live-reference dumps of one training step: the shipped yaml's Linear + Swish position-wise layers and the AASVC class
+    default (MultiLayeredConv1d k = 1 + ReLU, models/aas_vc.py:52-53)."""
     from seq2seq_vc_b200.aasvc_engine import AASVCEngine
 
-    z, sd = _golden()
-    eng = AASVCEngine(dict(AAS_HP, **NO_DROPOUT), device="cuda:0", bf16=False)
+    z, sd = _golden(fixture)
+    eng = AASVCEngine(dict(AAS_HP, positionwise_layer_type=pw, **NO_DROPOUT), device="cuda:0", bf16=False)
     eng.load_state_dict(sd)
     after, before, losses = _step(eng, z)
     assert np.abs(after.cpu().numpy() - z["after_outs"]).mean() <= 1e-4
@@ -396,6 +399,33 @@ def test_dropout_training_step_runs_and_is_reproducible():
     eng.seed_dev += 1
     a3, _, _ = _step(eng, z)
     assert (a1 - a3).abs().mean().item() >= 1e-2
+
+
+def test_conv1d_positionwise_dropout_and_bf16():
+    """MultiLayeredConv1d (k = 1) + ReLU position-wise layers with dropout on: same-seed steps agree, the bf16 tensor-core path
+    stays close to the fp32 one (no dropout), everything finite."""
+    from seq2seq_vc_b200.aasvc_engine import AASVCEngine
+
+    z, sd = _golden("aasvc_conv1d_tiny.npz")
+    eng = AASVCEngine(dict(AAS_HP, positionwise_layer_type="conv1d"), device="cuda:0", bf16=False, seed=3)
+    eng.load_state_dict(sd)
+    a1, _, l1 = _step(eng, z)
+    a1, g1 = a1.clone(), eng.store.G.clone()
+    a2, _, _ = _step(eng, z)
+    assert (a1 - a2).abs().max().item() <= 1e-4
+    assert (g1 - eng.store.G).abs().max().item() <= 1e-3 * g1.abs().max().item()
+    assert torch.isfinite(g1).all() and torch.isfinite(l1).all()
+    assert eng.store.g("encoder.encoders.0.feed_forward.w_1.weight").abs().max().item() > 0
+    engs = [AASVCEngine(dict(AAS_HP, positionwise_layer_type="conv1d", **NO_DROPOUT), device="cuda:0", bf16=b) for b in (False, True)]
+    outs = []
+    for e in engs:
+        e.load_state_dict(sd)
+        a, _, l = _step(e, z)
+        torch.cuda.synchronize()
+        outs.append((a.float().cpu(), e.store.G.clone().cpu()))
+        assert torch.isfinite(l).all()
+    assert (outs[0][0] - outs[1][0]).abs().mean().item() <= 0.15
+    assert torch.nn.functional.cosine_similarity(outs[0][1], outs[1][1], dim=0).item() >= 0.9
 
 
 def test_dropin_module_losses_and_autograd():

@@ -96,11 +96,13 @@ AAS_HP = dict(idim=80, odim=80, adim=32, aheads=2, elayers=1, eunits=48, dlayers
               post_encoder_reduction_factor=4, conformer_enc_kernel_size=7, conformer_dec_kernel_size=7)
 
 
-def test_aasvc_oracle_forward_loss_grads():
-    """AASVC forward, the four losses of AASVCTrainer._train_step and every gradient vs the live-reference dump."""
+@pytest.mark.parametrize("fixture", ["aasvc_tiny.npz", "aasvc_conv1d_tiny.npz"])
+def test_aasvc_oracle_forward_loss_grads(fixture):
+    """AASVC forward, the four losses of AASVCTrainer._train_step and every gradient vs the live-reference dump
+    (Linear + Swish position-wise layers of the shipped yaml; MultiLayeredConv1d k = 1 + ReLU of the class default)."""
     from oracle import aasvc_oracle
 
-    z = np.load(os.path.join(GOLD, "aasvc_tiny.npz"))
+    z = np.load(os.path.join(GOLD, fixture))
     sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
     bn = {}
     out = aasvc_oracle.aasvc_forward(sd, AAS_HP, torch.from_numpy(z["xs"]), z["ilens"].tolist(), torch.from_numpy(z["ys"]),
