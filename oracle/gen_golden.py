@@ -227,6 +227,69 @@ def gen_aasvc_conv1d_tiny():
     print("aasvc_conv1d_tiny:", len(dump), "arrays")
 
 
+SDP_HP = dict(channels=16, kernel_size=3, dds_conv_layers=3, flows=4)
+
+
+def gen_sdp_tiny():
+    """StochasticDurationPredictor (modules/duration_predictor.py:131-304) called as AASVC._forward calls it
+    (models/aas_vc.py:385-393,412-419).  The module draws its noise with torch.randn inside forward: the draw is recorded
+    here and becomes an explicit input of the oracle / kernels.  ConvFlow.proj is zero-initialised by the reference (the
+    splines start as the identity), so the weights are perturbed to exercise every spline branch incl. the linear tails."""
+    from seq2seq_vc.modules.duration_predictor import StochasticDurationPredictor
+
+    torch.manual_seed(41)
+    m = StochasticDurationPredictor(channels=SDP_HP["channels"], kernel_size=SDP_HP["kernel_size"], dropout_rate=0.5,
+                                    flows=SDP_HP["flows"], dds_conv_layers=SDP_HP["dds_conv_layers"], global_channels=-1)
+    ref_shim.disable_dropout(m)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if n.endswith(".proj.weight") and "flows" in n:
+                p.add_(0.5 * torch.randn_like(p))
+            elif n.endswith(".proj.bias") and "flows" in n:
+                p.add_(0.3 * torch.randn_like(p))
+            elif n.endswith(".m") or n.endswith(".logs"):
+                p.add_(0.2 * torch.randn_like(p))
+    m.train()
+    B, T, C = 3, 13, SDP_HP["channels"]
+    tl = [13, 9, 4]
+    g = torch.Generator().manual_seed(43)
+    dp = torch.randn(B, T, C, generator=g)
+    ds = torch.randint(0, 9, (B, T), generator=g)
+    mask = (torch.arange(T)[None, :] < torch.tensor(tl)[:, None])
+    ds = ds * mask
+    drawn = []
+    real_randn = torch.randn
+
+    def recording_randn(*a, **k):
+        t = real_randn(*a, **k)
+        drawn.append(t.clone())
+        return t
+
+    torch.randn = recording_randn
+    try:
+        torch.manual_seed(47)
+        nll = m(dp.transpose(1, 2), mask.unsqueeze(1), w=ds.unsqueeze(1).float())
+        dur_nll = nll / torch.sum(mask)
+        dur_nll.sum().backward()
+        e_q = drawn.pop()
+        m.eval()
+        with torch.no_grad():
+            d = m(dp.transpose(1, 2), mask.unsqueeze(1), inverse=True, noise_scale=0.8).squeeze(1)
+        z = drawn.pop()
+        # a second inverse pass with large noise: drives elements into the linear tails of the splines
+        with torch.no_grad():
+            d_wide = m(dp.transpose(1, 2), mask.unsqueeze(1), inverse=True, noise_scale=4.0).squeeze(1)
+        z_wide = drawn.pop()
+    finally:
+        torch.randn = real_randn
+    dump = {"sd." + k: v.detach().numpy() for k, v in m.state_dict().items()}
+    dump.update({"grad." + k: p.grad.numpy() for k, p in m.named_parameters() if p.grad is not None})
+    dump.update(dp_inputs=dp.numpy(), text_lens=np.array(tl), ds=ds.numpy(), e_q=e_q.numpy(), dur_nll=dur_nll.detach().numpy(),
+                z=z.numpy(), d_outs=torch.clamp(d, max=10).numpy(), z_wide=z_wide.numpy(), d_outs_wide=torch.clamp(d_wide, max=10).numpy())
+    np.savez_compressed(os.path.join(GOLDEN, "sdp_tiny.npz"), **dump)
+    print("sdp_tiny:", len(dump), "arrays; dur_nll", dur_nll.detach().numpy(), "d_outs", d[0].numpy())
+
+
 def gen_mas():
     from seq2seq_vc.modules.alignments import _monotonic_alignment_search, viterbi_decode
 
@@ -284,6 +347,6 @@ if __name__ == "__main__":
     import sys
 
     gens = dict(vtn_tiny=gen_vtn_tiny, tts_tiny=gen_tts_tiny, aasvc_tiny=gen_aasvc_tiny, aasvc_conv1d_tiny=gen_aasvc_conv1d_tiny,
-                mas=gen_mas, kats=gen_kats)
+                mas=gen_mas, kats=gen_kats, sdp_tiny=gen_sdp_tiny)
     for name in (sys.argv[1:] or list(gens)):      # e.g. `python oracle/gen_golden.py aasvc_conv1d_tiny` adds one fixture
         gens[name]()

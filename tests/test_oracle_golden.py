@@ -168,3 +168,74 @@ def test_inference_oracles_match_reference():
     outs, d = aasvc_oracle.aasvc_inference(sd, AAS_HP, torch.from_numpy(z["xs"])[0, :il], torch.from_numpy(z["dp_inputs"])[0, :il])
     np.testing.assert_array_equal(d.numpy(), z["inf_d_outs"])
     assert np.abs(outs.numpy() - z["inf_outs"]).max() <= 2e-5
+
+
+# ------------------------------------------------------------------ stochastic duration predictor: oracle groundwork
+SDP_HP = dict(channels=16, kernel_size=3, dds_conv_layers=3, flows=4)
+
+
+def _sdp():
+    z = np.load(os.path.join(GOLD, "sdp_tiny.npz"))
+    sd = {"duration_predictor." + k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    return z, sd
+
+
+def test_sdp_oracle_state_dict_spec():
+    from oracle import sdp_oracle
+
+    z, sd = _sdp()
+    spec = dict(sdp_oracle.state_dict_spec(SDP_HP))
+    assert set(spec) == set(sd) and all(tuple(sd[k].shape) == spec[k] for k in sd)
+
+
+def test_sdp_oracle_nll_and_gradients_match_reference():
+    """Variational duration NLL as AASVC._forward computes it (models/aas_vc.py:412-419) with the reference's recorded noise:
+    value and every parameter gradient of sum(dur_nll) vs the live-reference dump."""
+    from oracle import sdp_oracle
+
+    z, sd = _sdp()
+    sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    nll = sdp_oracle.aasvc_dur_nll(sd, "duration_predictor", SDP_HP, torch.from_numpy(z["dp_inputs"]), z["text_lens"].tolist(),
+                                   torch.from_numpy(z["ds"]), torch.from_numpy(z["e_q"]))
+    assert np.abs(nll.detach().numpy() - z["dur_nll"]).max() <= 1e-5 * np.abs(z["dur_nll"]).max()
+    nll.sum().backward()
+    gmax = max(np.abs(z[k]).max() for k in z.files if k.startswith("grad."))
+    n = 0
+    for k in z.files:
+        if k.startswith("grad."):
+            g = sd["duration_predictor." + k[5:]].grad
+            assert g is not None, k
+            assert np.abs(g.numpy() - z[k]).max() <= 2e-4 * np.abs(z[k]).max() + 2e-6 * gmax, k
+            n += 1
+    assert n == sum(1 for k in z.files if k.startswith("sd."))          # every parameter trains (x is detached, not the weights)
+
+
+def test_sdp_oracle_inverse_durations_match_reference():
+    """Inference direction (models/aas_vc.py:385-393): integer durations exact, incl. a wide-noise draw that lands in the
+    linear tails of the splines."""
+    from oracle import sdp_oracle
+
+    z, sd = _sdp()
+    for zk, dk, scale in (("z", "d_outs", 0.8), ("z_wide", "d_outs_wide", 4.0)):
+        d = sdp_oracle.aasvc_dur_inference(sd, "duration_predictor", SDP_HP, torch.from_numpy(z["dp_inputs"]), z["text_lens"].tolist(),
+                                           torch.from_numpy(z[zk]), noise_scale=scale)
+        np.testing.assert_array_equal(d.numpy(), z[dk])
+    assert (np.abs(z["z_wide"] * 4.0) > 5.0).any()                       # the tails are exercised
+
+
+def test_sdp_spline_round_trip_and_tails():
+    """Size-independent properties of the spline: inverse(forward(x)) == x, log-determinants cancel, identity outside +-5."""
+    from oracle import sdp_oracle
+
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(4, 1, 50, generator=g) * 3.0
+    uw, uh, ud = (torch.randn(4, 1, 50, n, generator=g) for n in (10, 10, 9))
+    y, lad = sdp_oracle.rq_spline_linear_tails(x, uw, uh, ud, inverse=False)
+    xr, ladr = sdp_oracle.rq_spline_linear_tails(y, uw, uh, ud, inverse=True)
+    assert (xr - x).abs().max().item() <= 2e-4 and (lad + ladr).abs().max().item() <= 2e-3
+    out = x.abs() > 5.0
+    assert out.any() and torch.equal(y[out], x[out]) and (lad[out] == 0).all()
+    xs = torch.linspace(-6, 6, 400).view(1, 1, 400)                       # one spline, many abscissae: strictly increasing
+    ys, _ = sdp_oracle.rq_spline_linear_tails(xs, uw[:1, :, :1].expand(1, 1, 400, 10), uh[:1, :, :1].expand(1, 1, 400, 10),
+                                              ud[:1, :, :1].expand(1, 1, 400, 9), inverse=False)
+    assert (torch.diff(ys.flatten()) > 0).all()
