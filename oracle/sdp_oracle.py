@@ -11,6 +11,8 @@ Differences in FORM (not in arithmetic) from the reference, chosen so that a CUD
     draws it with torch.randn inside forward; the fixtures record the reference's draw (oracle/gen_golden.py);
   * the spline is evaluated densely with clamped inputs and a select, instead of boolean-mask gather / scatter of the
     in-range elements (transform.py:61-93); out-of-range elements are the identity with log|det| = 0 in both.
+    One reference quirk is NOT reproduced: when no element at all lies inside [-5, 5] the reference's masked gather is empty
+    and torch.min() raises (transform.py:116); the dense form returns the identity for every element instead.
 Dropout is not restated (the oracle is the dropout-free function, as for the other oracles).
 
 Pinned against the live reference: tests/golden/sdp_tiny.npz (nll, every parameter gradient, inverse durations),
