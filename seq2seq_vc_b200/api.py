@@ -26,6 +26,12 @@ _f32 = torch.float32
 _i32 = torch.int32
 
 
+def _require_cuda(t: torch.Tensor, who: str) -> None:
+    """There is no CPU path: the modules refuse host tensors instead of falling back to anything."""
+    if not t.is_cuda:
+        raise S2SError(f"seq2seq_vc_b200.{who} runs on a B200 only (no CPU fallback): move the model and batch to cuda")
+
+
 def _host_lens(v) -> List[int]:
     if isinstance(v, torch.Tensor):
         return [int(x) for x in v.detach().cpu().tolist()]
@@ -191,9 +197,14 @@ class VTN(torch.nn.Module):
             self._build(probe.device, state)
         return self
 
-    def _bind_grads(self) -> None:
+    def _bind_grads(self, unused: tuple = ()) -> None:
+        """Point every parameter's .grad at its slice of the flat gradient buffer.  Parameters under the `unused` name
+        prefixes took no part in this backward: like torch autograd, leave their .grad as None if it is None (optimizers
+        skip such parameters, which keeps e.g. Adam's per-parameter step count identical to the reference's)."""
         st = self.engine.store
         for name, p in self.named_parameters():
+            if unused and p.grad is None and name.startswith(unused):
+                continue
             g = st.g(name)
             if p.grad is None or p.grad.data_ptr() != g.data_ptr():
                 p.grad = g
@@ -211,8 +222,7 @@ class VTN(torch.nn.Module):
 
     # ---- forward (vtn.py:207-300) ----------------------------------------------------------------
     def forward(self, xs, ilens, ys, labels, olens, spembs=None, *args, **kwargs):
-        if not xs.is_cuda:
-            raise S2SError("seq2seq_vc_b200.VTN runs on a B200 only (no CPU fallback): move the model and batch to cuda")
+        _require_cuda(xs, "VTN")
         eng = self.engine
         eng.p16_dirty = True       # parameters may have been updated by an external optimizer
         il, ol = _host_lens(ilens), _host_lens(olens)
@@ -249,8 +259,7 @@ def _vtn_inference(self, x, inference_args, spemb=None, *args, **kwargs):
     """Drop-in for VTN.inference (models/vtn.py:302-394): x (T, idim) -> (outs (L, odim), probs (L,), att_ws (#layers, #heads, L/r, T'))."""
     if spemb is not None:
         raise NotImplementedError("speaker embeddings are outside the hot path")
-    if not x.is_cuda:
-        raise S2SError("seq2seq_vc_b200.VTN runs on a B200 only (no CPU fallback)")
+    _require_cuda(x, "VTN")
     self.engine.p16_dirty = True
     outs, probs, att_ws = self.engine.inference(x, inference_args["threshold"], inference_args["minlenratio"], inference_args["maxlenratio"])
     for l in range(self.hp["dlayers"]):                    # `.attn` of the source-attention modules, as the reference leaves it
@@ -288,8 +297,7 @@ class TransformerTTS(VTN):
         self.padding_idx = 0
 
     def forward(self, xs, ilens, ys, labels, olens, spembs=None, *args, **kwargs):
-        if not xs.is_cuda:
-            raise S2SError("seq2seq_vc_b200.TransformerTTS runs on a B200 only (no CPU fallback)")
+        _require_cuda(xs, "TransformerTTS")
         eng = self.engine
         eng.p16_dirty = True
         il, ol = _host_lens(ilens), _host_lens(olens)
@@ -711,6 +719,7 @@ class _AASVCFunction(torch.autograd.Function):
         after, before = eng.forward(xs, ys, dp_inputs, ilens, olens)
         d_outs = eng.forward_d_outs()
         ctx.model, ctx.token = model, model._fwd_token
+        ctx.set_materialize_grads(False)      # an output the loss does not use arrives as None (d_outs before dp_train_start_steps)
         ds = eng.ds.clone()
         ctx.mark_non_differentiable(ds)
         return after.clone(), before.clone(), eng.log_p_attn.clone(), d_outs.clone(), eng.losses[2].clone(), ds
@@ -735,7 +744,8 @@ class _AASVCFunction(torch.autograd.Function):
         d_pre = torch.empty(B * Tt, 1, dtype=dt, device=eng.device)
         ops.duration_loss(eng.dp_pre, eng.ds, eng.tlens_dev, None, None, d_pre, g_douts=z(g_douts, eng.d_outs, _f32))
         eng.backward(d_after, d_before, d_logp, d_pre, zero_grad=fresh)
-        model._bind_grads()
+        # trainers/aas_vc.py:119-133: without the duration loss the predictor's parameters are not in the graph
+        model._bind_grads(unused=("duration_predictor.", "duration_predictor_projection.") if g_douts is None else ())
         return (None,) * (6 + len(model._param_names))
 
 
@@ -831,8 +841,7 @@ class AASVC(VTN):
             node.register_buffer(leaf, buf)
 
     def forward(self, src_speech, src_speech_lengths, tgt_speech, tgt_speech_lengths, dp_inputs=None, dp_lengths=None, spembs=None):
-        if not src_speech.is_cuda:
-            raise S2SError("seq2seq_vc_b200.AASVC runs on a B200 only (no CPU fallback): move the model and batch to cuda")
+        _require_cuda(src_speech, "AASVC")
         if dp_inputs is None:
             raise S2SError("dp_inputs is required (duration_predictor_use_encoder_outputs=False)")
         eng = self.engine
@@ -856,8 +865,7 @@ def _aasvc_inference(self, src_speech, tgt_speech=None, spembs=None, dp_input=No
     """Drop-in for AASVC.inference (models/aas_vc.py:531-603) without ground truth: (T, idim) -> (outs (L, odim), d_outs (T_text,))."""
     if tgt_speech is not None or use_teacher_forcing or spembs is not None:
         raise NotImplementedError("inference with ground-truth targets / durations / speaker embeddings is outside the hot path")
-    if not src_speech.is_cuda:
-        raise S2SError("seq2seq_vc_b200.AASVC runs on a B200 only (no CPU fallback)")
+    _require_cuda(src_speech, "AASVC")
     if dp_input is None:
         raise S2SError("dp_input is required (duration_predictor_use_encoder_outputs=False)")
     self.engine.p16_dirty = True

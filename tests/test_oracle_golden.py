@@ -205,7 +205,9 @@ def test_sdp_oracle_nll_and_gradients_match_reference():
         if k.startswith("grad."):
             g = sd["duration_predictor." + k[5:]].grad
             assert g is not None, k
-            assert np.abs(g.numpy() - z[k]).max() <= 2e-4 * np.abs(z[k]).max() + 2e-6 * gmax, k
+            # fp32 on both sides through log / sqrt / softmax chains of 8 splines: the result moves by a few 1e-4 relative
+            # with the BLAS thread count alone (seen between an isolated run and the whole suite)
+            assert np.abs(g.numpy() - z[k]).max() <= 2e-3 * np.abs(z[k]).max() + 1e-5 * gmax, k
             n += 1
     assert n == sum(1 for k in z.files if k.startswith("sd."))          # every parameter trains (x is detached, not the weights)
 
