@@ -183,3 +183,54 @@ def _fresh_aasvc_state():
         torch.manual_seed(5)
         _AAS0.update(RefAASVC(**AAS_HP, **AAS_FIXED, **AAS_NO_DROPOUT).state_dict())
     return _AAS0
+
+
+TTS_HP = dict(idim=40, odim=80, dprenet_layers=2, dprenet_units=16, adim=32, aheads=2, elayers=2, eunits=48, dlayers=2, dunits=48,
+              postnet_layers=2, postnet_filts=5, postnet_chans=16, decoder_reduction_factor=2, dprenet_dropout_rate=0.0,
+              use_guided_attn_loss=True, num_heads_applied_guided_attn=2, num_layers_applied_guided_attn=2)
+
+
+def test_reference_artts_trainer_drives_dropin_transformer_tts(trainers, monkeypatch):
+    """ARTTSTrainer._train_step (trainers/ar_tts.py:25-72): token inputs in the collater's 6-tuple, the reference's
+    GuidedMultiHeadAttentionLoss applied to the att_ws the drop-in returns (its gradient flows back into our backward)."""
+    _, _, outdir = trainers
+    import seq2seq_vc.trainers.ar_tts as t_tts
+    import seq2seq_vc_b200
+    from seq2seq_vc.losses import GuidedMultiHeadAttentionLoss, Seq2SeqLoss
+    from seq2seq_vc.models.transformer_tts import TransformerTTS as RefTTS
+
+    torch.manual_seed(9)
+    ref = RefTTS(**TTS_HP)
+    ref_shim.disable_dropout(ref)
+    ref.train()
+    ours = seq2seq_vc_b200.TransformerTTS(**TTS_HP)
+    for k in ("transformer_enc_dropout_rate", "enc_positional_dropout_rate", "dec_dropout_rate", "dec_positional_dropout_rate",
+              "postnet_dropout_rate"):
+        ours.engine.hp[k] = 0.0
+    ours.load_state_dict(ref.state_dict())
+    ours.train()
+    g = torch.Generator().manual_seed(33)
+    ilens, olens = [11, 7], [26, 18]
+    tokens = torch.randint(1, TTS_HP["idim"] - 1, (2, 11), generator=g)
+    ys = torch.randn(2, 26, 80, generator=g)
+    labels = torch.zeros(2, 26)
+    for b in range(2):
+        tokens[b, ilens[b]:] = 0
+        ys[b, olens[b]:] = 0
+        labels[b, olens[b] - 1:] = 1.0
+    batch = (tokens, torch.tensor(ilens), ys, labels, torch.tensor(olens), None)
+    config = dict(outdir=outdir, grad_norm=1.0, train_max_steps=10 ** 9, distributed=False, save_interval_steps=10 ** 9,
+                  eval_interval_steps=10 ** 9, log_interval_steps=10 ** 9, use_guided_attn_loss=True)
+    crit = lambda: {"Seq2SeqLoss": Seq2SeqLoss(), "guided_attn": GuidedMultiHeadAttentionLoss(sigma=0.4, alpha=1.0)}
+    t_ref = _run(t_tts.ARTTSTrainer, ref, crit(), config, batch, 3)
+    t_our = _run(t_tts.ARTTSTrainer, ours, crit(), config, batch, 3)
+    assert t_ref.steps == t_our.steps == 3
+    for k, v in t_ref.total_train_loss.items():
+        assert abs(v - t_our.total_train_loss[k]) <= 1e-4 * max(1.0, abs(v)), k
+    assert t_ref.total_train_loss["train/guided_attn_loss"] > 0
+    _compare_grads(t_ref, t_our)
+    sd_ref, sd_our = ref.state_dict(), ours.state_dict()
+    assert set(sd_ref) == set(sd_our)
+    for k, v in sd_ref.items():
+        if v.dtype.is_floating_point:
+            assert (v - sd_our[k]).abs().max().item() <= (3.5e-3 if k.endswith("linear_k.bias") else 5e-5), k
