@@ -184,6 +184,12 @@ class VTN(torch.nn.Module):
             if nxt is None:
                 nxt = MultiHeadedAttention() if part in ("self_attn", "src_attn") else _Node()
                 node.add_module(part, nxt)
+                if isinstance(nxt, MultiHeadedAttention):
+                    # registration order of the reference (attention.py:27-31), not the storage order (K / V of a source
+                    # attention are adjacent in the flat buffer): optimizer state dicts are keyed by parameter ORDER, so a
+                    # reference checkpoint's Adam moments must land on the same parameters (trainers/base.py:108-121)
+                    for child in ("linear_q", "linear_k", "linear_v", "linear_out"):
+                        nxt.add_module(child, _Node())
             node = nxt
         return node, parts[-1]
 
@@ -203,6 +209,8 @@ class VTN(torch.nn.Module):
         skip such parameters, which keeps e.g. Adam's per-parameter step count identical to the reference's)."""
         st = self.engine.store
         for name, p in self.named_parameters():
+            if not p.requires_grad:          # utils/model_io.py:95-111 freeze_modules: frozen parameters never get a gradient
+                continue
             if unused and p.grad is None and name.startswith(unused):
                 continue
             g = st.g(name)

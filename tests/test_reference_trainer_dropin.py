@@ -58,6 +58,14 @@ def _run(trainer_cls, model, criterion, config, batch, steps):
     return tr
 
 
+def _same_parameter_order(ref, ours):
+    """optimizer.state_dict() is keyed by parameter ORDER (trainers/base.py:93,120): resuming a reference checkpoint in the
+    drop-in only works if named_parameters() enumerates the same names and shapes in the same order."""
+    r = [(n, tuple(p.shape)) for n, p in ref.named_parameters()]
+    o = [(n, tuple(p.shape)) for n, p in ours.named_parameters()]
+    assert r == o, [(a, b) for a, b in zip(r, o) if a != b][:4]
+
+
 def _compare_grads(t_ref, t_our):
     """Adam divides by sqrt(v) ~ |g| in its first steps, so parameters whose gradient is (near) zero move by lr-sized steps
     decided by round-off: the tight comparison is on the gradients each optimizer step consumed; the parameters themselves
@@ -93,6 +101,7 @@ def test_reference_arvc_trainer_drives_dropin_vtn(trainers):
         ours.engine.hp[k] = 0.0       # rates the reference hard-codes too: the harness zeroes them on both sides
     ours.load_state_dict(ref.state_dict())
     ours.train()
+    _same_parameter_order(ref, ours)
     xs, ilens, ys, labels, olens = vtn_oracle.synthetic_batch(2, 40, 24, ilens=[40, 33], olens=[24, 17], seed=11)
     batch = dict(xs=xs, ys=ys, labels=labels, ilens=torch.tensor(ilens), olens=torch.tensor(olens))
     config = dict(outdir=outdir, grad_norm=1.0, train_max_steps=10 ** 9, distributed=False, save_interval_steps=10 ** 9,
@@ -149,6 +158,7 @@ def test_reference_aasvc_trainer_drives_dropin_aasvc(trainers, accum):
     ours = seq2seq_vc_b200.AASVC(**AAS_HP, **AAS_FIXED, **AAS_NO_DROPOUT)
     ours.load_state_dict(ref.state_dict())
     ours.train()
+    _same_parameter_order(ref, ours)
     xs, ilens, ys, olens, dpi = aasvc_oracle.synthetic_batch(2, 44, 36, ilens=[44, 37], olens=[36, 29], seed=21)
     batch = dict(xs=xs, ys=ys, ilens=torch.tensor(ilens), olens=torch.tensor(olens), dp_inputs=dpi, dplens=torch.tensor(ilens))
     config = dict(outdir=outdir, grad_norm=1.0, train_max_steps=10 ** 9, distributed=False, save_interval_steps=10 ** 9,
@@ -209,6 +219,7 @@ def test_reference_artts_trainer_drives_dropin_transformer_tts(trainers, monkeyp
         ours.engine.hp[k] = 0.0
     ours.load_state_dict(ref.state_dict())
     ours.train()
+    _same_parameter_order(ref, ours)
     g = torch.Generator().manual_seed(33)
     ilens, olens = [11, 7], [26, 18]
     tokens = torch.randint(1, TTS_HP["idim"] - 1, (2, 11), generator=g)
@@ -234,3 +245,55 @@ def test_reference_artts_trainer_drives_dropin_transformer_tts(trainers, monkeyp
     for k, v in sd_ref.items():
         if v.dtype.is_floating_point:
             assert (v - sd_our[k]).abs().max().item() <= (3.5e-3 if k.endswith("linear_k.bias") else 5e-5), k
+
+
+def test_reference_trainer_checkpoint_and_freeze_with_dropin(trainers, tmp_path):
+    """trainers/base.py:85-121 save_checkpoint / load_checkpoint and :226 freeze_modules (yaml `freeze-mods`, matched on
+    state-dict key prefixes, utils/model_io.py:95-111) on the drop-in VTN: a reference checkpoint loads into it and vice
+    versa, frozen prefixes stay put (no .grad, untouched by Adam and by the clip norm) while the rest trains as in the reference."""
+    ARVCTrainer, _, outdir = trainers
+    import seq2seq_vc_b200
+    from seq2seq_vc.losses import Seq2SeqLoss
+    from seq2seq_vc.models import VTN as RefVTN
+
+    torch.manual_seed(13)
+    ref = RefVTN(**VTN_HP)
+    ref_shim.disable_dropout(ref)
+    ref.train()
+    ours = seq2seq_vc_b200.VTN(**VTN_HP, transformer_enc_dropout_rate=0.0)
+    for k in ("enc_positional_dropout_rate", "dec_dropout_rate", "dec_positional_dropout_rate", "postnet_dropout_rate"):
+        ours.engine.hp[k] = 0.0
+    ours.train()
+    xs, ilens, ys, labels, olens = vtn_oracle.synthetic_batch(2, 40, 24, ilens=[40, 33], olens=[24, 17], seed=12)
+    batch = dict(xs=xs, ys=ys, labels=labels, ilens=torch.tensor(ilens), olens=torch.tensor(olens))
+    config = dict(outdir=outdir, grad_norm=1.0, train_max_steps=10 ** 9, distributed=False, save_interval_steps=10 ** 9,
+                  eval_interval_steps=10 ** 9, log_interval_steps=10 ** 9)
+    # a checkpoint written by the reference trainer around the reference model loads into the drop-in through the trainer
+    t_ref = _run(ARVCTrainer, ref, {"Seq2SeqLoss": Seq2SeqLoss()}, config, batch, 1)
+    ck = str(tmp_path / "ck" / "checkpoint-1steps.pkl")
+    t_ref.save_checkpoint(ck)
+    t_our = _run(ARVCTrainer, ours, {"Seq2SeqLoss": Seq2SeqLoss()}, config, batch, 0)
+    t_our.load_checkpoint(ck)             # parameters, Adam moments (keyed by parameter order), scheduler, step counter
+    assert t_our.steps == 1
+    for k, v in ref.state_dict().items():
+        assert torch.equal(v, ours.state_dict()[k]), k
+    # ... and back: the drop-in's checkpoint is a plain reference checkpoint
+    ck2 = str(tmp_path / "ck" / "ours.pkl")
+    t_our.save_checkpoint(ck2)
+    blob = torch.load(ck2, map_location="cpu")
+    assert set(blob) == {"optimizer", "scheduler", "steps", "epochs", "model"}
+    RefVTN(**VTN_HP).load_state_dict(blob["model"])
+    # freeze-mods: encoder prefix frozen on both sides, two more steps
+    frozen0 = {k: v.clone() for k, v in ours.state_dict().items() if k.startswith("encoder.")}
+    for t in (t_ref, t_our):
+        t.freeze_modules(["encoder"])
+        for _ in range(2):
+            t._train_step(batch)
+    assert all(p.grad is None for n, p in ours.named_parameters() if n.startswith("encoder."))
+    for k, v in frozen0.items():
+        if v.dtype.is_floating_point:
+            assert torch.equal(v, ours.state_dict()[k]), k
+    for k, v in ref.state_dict().items():
+        if v.dtype.is_floating_point:
+            assert (v - ours.state_dict()[k]).abs().max().item() <= (3.5e-3 if k.endswith("linear_k.bias") else 5e-5), k
+    assert any((v - ours.state_dict()[k]).abs().max().item() > 0 for k, v in blob["model"].items() if k.startswith("decoder.") and v.dim() > 1)
