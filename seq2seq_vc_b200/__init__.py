@@ -10,6 +10,7 @@ from .vtn_engine import VTNEngine, default_hparams  # noqa: F401
 from .aasvc_engine import AASVCEngine  # noqa: F401
 from .api import VTN, TransformerTTS, Seq2SeqLoss, GuidedMultiHeadAttentionLoss, VTNTrainStep, viterbi_decode, logmelfilterbank  # noqa: F401
 from .api import AASVC, AASVCTrainStep, L1Loss, ForwardSumLoss, DurationPredictorLoss  # noqa: F401
+from .api import DistributedDataParallel  # noqa: F401
 
 AR_VC_MODELS = [VTN]
 NAR_VC_MODELS = [AASVC]

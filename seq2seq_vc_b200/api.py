@@ -106,6 +106,7 @@ class _VTNFunction(torch.autograd.Function):
             return torch.zeros_like(like, dtype=dt) if g is None else g.to(dt).contiguous()
 
         eng.backward(z(d_after, eng.after), z(d_before, eng.before), z(d_logits, eng.logits), d_att=d_att, zero_grad=fresh)
+        model._sync_gradients()
         model._bind_grads()
         return (None,) * (7 + len(model._param_names))
 
@@ -203,6 +204,21 @@ class VTN(torch.nn.Module):
             self._build(probe.device, state)
         return self
 
+    _ddp_group = False      # set by DistributedDataParallel (None = the default process group)
+
+    def _sync_gradients(self) -> None:
+        """Data-parallel mean of the flat gradient buffer at the end of backward, when wrapped by this package's
+        DistributedDataParallel (the path shards by utterance batch: bin/vc_train.py:423-431).  Under gradient accumulation
+        the buffer already holds the rank-invariant mean of earlier micro-steps, which the mean leaves unchanged."""
+        pg = self._ddp_group
+        if pg is False or not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            return
+        world = torch.distributed.get_world_size(pg)
+        if world > 1:
+            G = self.engine.store.G
+            torch.distributed.all_reduce(G, group=pg)
+            G.mul_(1.0 / world)
+
     def _bind_grads(self, unused: tuple = ()) -> None:
         """Point every parameter's .grad at its slice of the flat gradient buffer.  Parameters under the `unused` name
         prefixes took no part in this backward: like torch autograd, leave their .grad as None if it is None (optimizers
@@ -261,6 +277,37 @@ class VTN(torch.nn.Module):
         for l in reversed(range(self.hp["dlayers"])):           # vtn.py:280-287 (list, last layer first)
             att_ws.append(self.decoder.decoders[l].src_attn.attn)
         return after.float(), before.float(), logits.float(), ys_out, labels_out, olens_out, (att_ws, ilens_ds_st, olens_in)
+
+
+class DistributedDataParallel(torch.nn.Module):
+    """Stand-in for the wrapper the reference puts around the model under --distributed (apex DistributedDataParallel,
+    bin/vc_train.py:423-431) for the drop-in modules of this package.  Their backward is one hand-written pass that fills a
+    flat gradient buffer, so autograd-hook based wrappers (torch / apex DDP) never see a gradient; this one broadcasts rank 0's
+    parameters and buffers at construction (as DDP constructors do) and makes the module average that buffer over the process
+    group at the end of every backward.  Exposes `.module` (trainers/base.py:98-101,115-118 use it for checkpoints).
+    The fused VTNTrainStep / AASVCTrainStep do their own all-reduce and do not need it."""
+
+    def __init__(self, module, process_group=None, **ignored):
+        super().__init__()
+        if not isinstance(module, VTN):
+            raise TypeError("seq2seq_vc_b200.DistributedDataParallel wraps the drop-in modules of this package")
+        self.module = module
+        module._ddp_group = process_group
+        dist = torch.distributed
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1:
+            src = dist.get_global_rank(process_group, 0) if process_group is not None else 0
+            eng = module.engine
+            dist.broadcast(eng.store.P, src=src, group=process_group)
+            for buf in eng.buffers.values():
+                if buf.dtype.is_floating_point:
+                    dist.broadcast(buf, src=src, group=process_group)
+            eng.p16_dirty = True
+
+    def forward(self, *args, **kwargs):
+        return self.module(*args, **kwargs)
+
+    def inference(self, *args, **kwargs):
+        return self.module.inference(*args, **kwargs)
 
 
 def _vtn_inference(self, x, inference_args, spemb=None, *args, **kwargs):
@@ -752,6 +799,7 @@ class _AASVCFunction(torch.autograd.Function):
         d_pre = torch.empty(B * Tt, 1, dtype=dt, device=eng.device)
         ops.duration_loss(eng.dp_pre, eng.ds, eng.tlens_dev, None, None, d_pre, g_douts=z(g_douts, eng.d_outs, _f32))
         eng.backward(d_after, d_before, d_logp, d_pre, zero_grad=fresh)
+        model._sync_gradients()
         # trainers/aas_vc.py:119-133: without the duration loss the predictor's parameters are not in the graph
         model._bind_grads(unused=("duration_predictor.", "duration_predictor_projection.") if g_douts is None else ())
         return (None,) * (6 + len(model._param_names))

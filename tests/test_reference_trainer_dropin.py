@@ -297,3 +297,78 @@ def test_reference_trainer_checkpoint_and_freeze_with_dropin(trainers, tmp_path)
         if v.dtype.is_floating_point:
             assert (v - ours.state_dict()[k]).abs().max().item() <= (3.5e-3 if k.endswith("linear_k.bias") else 5e-5), k
     assert any((v - ours.state_dict()[k]).abs().max().item() > 0 for k, v in blob["model"].items() if k.startswith("decoder.") and v.dim() > 1)
+
+
+# ------------------------------------------------------------------ --distributed (bin/vc_train.py:423-431), world size 2, gloo
+def _ddp_worker(rank, world, port, out_dir):
+    import os
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    for p in (here, os.path.dirname(here)):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+
+    import fake_ops as fo
+    import seq2seq_vc_b200
+    import seq2seq_vc_b200.api as api
+    import seq2seq_vc_b200.ops as ops
+    from oracle import ref_shim as rs, vtn_oracle as vo
+
+    rs.install()
+    for name in ("tensorboardX", "soundfile", "matplotlib", "matplotlib.pyplot", "h5py"):
+        if name not in sys.modules:
+            mod = types.ModuleType(name)
+            mod.SummaryWriter = lambda *a, **k: types.SimpleNamespace(add_scalar=lambda *a, **k: None)
+            mod.use = lambda *a, **k: None
+            sys.modules[name] = mod
+    for n in fo.ALL:
+        if hasattr(ops, n) and n != "logmel":
+            setattr(ops, n, getattr(fo, n))
+    api._require_cuda = lambda t, who: None
+    from seq2seq_vc.losses import Seq2SeqLoss
+    from seq2seq_vc.models import VTN as RefVTN
+    from seq2seq_vc.trainers.ar_vc import ARVCTrainer
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    torch.manual_seed(3)
+    ref = RefVTN(**VTN_HP)
+    rs.disable_dropout(ref)
+    ref.train()
+    torch.manual_seed(100 + rank)                   # rank-dependent init: the wrapper must broadcast rank 0's parameters
+    ours = seq2seq_vc_b200.VTN(**VTN_HP, transformer_enc_dropout_rate=0.0)
+    for k in ("enc_positional_dropout_rate", "dec_dropout_rate", "dec_positional_dropout_rate", "postnet_dropout_rate"):
+        ours.engine.hp[k] = 0.0
+    if rank == 0:
+        ours.load_state_dict(ref.state_dict())
+    ours.train()
+    xs, ilens, ys, labels, olens = vo.synthetic_batch(2, 40, 24, ilens=[40, 33 - rank], olens=[24, 17 + rank], seed=50 + rank)
+    batch = dict(xs=xs, ys=ys, labels=labels, ilens=torch.tensor(ilens), olens=torch.tensor(olens))
+    config = dict(outdir=out_dir, grad_norm=1.0, train_max_steps=10 ** 9, distributed=True, save_interval_steps=10 ** 9,
+                  eval_interval_steps=10 ** 9, log_interval_steps=10 ** 9)
+    t_ref = _run(ARVCTrainer, torch.nn.parallel.DistributedDataParallel(ref), {"Seq2SeqLoss": Seq2SeqLoss()}, config, batch, 2)
+    t_our = _run(ARVCTrainer, seq2seq_vc_b200.DistributedDataParallel(ours), {"Seq2SeqLoss": Seq2SeqLoss()}, config, batch, 2)
+    t_our.save_checkpoint(os.path.join(out_dir, f"ours{rank}.pkl"))          # goes through self.model.module
+    torch.save({k: v.clone() for k, v in ref.state_dict().items()}, os.path.join(out_dir, f"ref{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_reference_trainer_distributed_with_dropin_wrapper(trainers, tmp_path):
+    """Two ranks, rank-specific batches, ARVCTrainer with config["distributed"]: the reference model under torch DDP (apex is
+    not installed here) vs the drop-in under seq2seq_vc_b200.DistributedDataParallel land on the same parameters; the replicas
+    stay identical; the wrapper broadcast rank 0's initial parameters."""
+    import socket
+
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_ddp_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    ours0 = torch.load(tmp_path / "ours0.pkl", map_location="cpu")["model"]
+    ours1 = torch.load(tmp_path / "ours1.pkl", map_location="cpu")["model"]
+    ref0 = torch.load(tmp_path / "ref0.pt")
+    for k, v in ref0.items():
+        if v.dtype.is_floating_point and "running_" not in k:
+            assert torch.equal(ours0[k], ours1[k]), k                      # replicas in lock-step
+            assert (v - ours0[k]).abs().max().item() <= (3.5e-3 if k.endswith("linear_k.bias") else 5e-5), k
