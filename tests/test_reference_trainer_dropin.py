@@ -102,8 +102,15 @@ def test_reference_arvc_trainer_drives_dropin_vtn(trainers):
     ours.load_state_dict(ref.state_dict())
     ours.train()
     _same_parameter_order(ref, ours)
-    xs, ilens, ys, labels, olens = vtn_oracle.synthetic_batch(2, 40, 24, ilens=[40, 33], olens=[24, 17], seed=11)
-    batch = dict(xs=xs, ys=ys, labels=labels, ilens=torch.tensor(ilens), olens=torch.tensor(olens))
+    # the batch comes out of the reference's own collater (collaters/ar_vc.py:64-73): float32 zero-padded features, int64
+    # CPU lengths, stop labels, spembs None
+    from seq2seq_vc.collaters.ar_vc import ARVCCollater
+
+    rng = np.random.default_rng(11)
+    items = [dict(src_feat=rng.standard_normal((t, 80)).astype(np.float32), trg_feat=rng.standard_normal((l, 80)).astype(np.float32))
+             for t, l in ((40, 24), (33, 17))]
+    batch = ARVCCollater()(items)
+    assert batch["ilens"].dtype == torch.int64 and batch["labels"][1, 16:].eq(1).all()
     config = dict(outdir=outdir, grad_norm=1.0, train_max_steps=10 ** 9, distributed=False, save_interval_steps=10 ** 9,
                   eval_interval_steps=10 ** 9, log_interval_steps=10 ** 9)
     t_ref = _run(ARVCTrainer, ref, {"Seq2SeqLoss": Seq2SeqLoss()}, config, batch, 3)
@@ -159,8 +166,14 @@ def test_reference_aasvc_trainer_drives_dropin_aasvc(trainers, accum):
     ours.load_state_dict(ref.state_dict())
     ours.train()
     _same_parameter_order(ref, ours)
-    xs, ilens, ys, olens, dpi = aasvc_oracle.synthetic_batch(2, 44, 36, ilens=[44, 37], olens=[36, 29], seed=21)
-    batch = dict(xs=xs, ys=ys, ilens=torch.tensor(ilens), olens=torch.tensor(olens), dp_inputs=dpi, dplens=torch.tensor(ilens))
+    from seq2seq_vc.collaters.nar_vc import NARVCCollater            # collaters/nar_vc.py:71-91
+
+    rng = np.random.default_rng(21)
+    items = []
+    for t, l in ((44, 36), (37, 29)):
+        src = rng.standard_normal((t, 80)).astype(np.float32)
+        items.append(dict(src_feat=src, trg_feat=rng.standard_normal((l, 80)).astype(np.float32), dp_input=src.copy()))
+    batch = NARVCCollater()(items)
     config = dict(outdir=outdir, grad_norm=1.0, train_max_steps=10 ** 9, distributed=False, save_interval_steps=10 ** 9,
                   eval_interval_steps=10 ** 9, log_interval_steps=10 ** 9, lambda_align=2.0, dp_train_start_steps=0,
                   criterions=["L1Loss", "ForwardSumLoss", "DurationPredictorLoss"], gradient_accumulate_steps=accum)
