@@ -193,6 +193,13 @@ class AASVCEngine(EngineBase):
         self._l1_pair = torch.zeros(2, dtype=_f32, device=self.device)
         self._loss_ws = torch.zeros(4, dtype=_f32, device=self.device)
         self._one = torch.ones(1, dtype=_f32, device=self.device)
+        # flat-buffer span [a, b) of the duration predictor (+ its input projection) and its own Adam clock: see optimizer_step
+        names = self.store.names()
+        dp = [i for i, n in enumerate(names) if n.startswith(("duration_predictor.", "duration_predictor_projection."))]
+        assert dp and dp == list(range(dp[0], dp[-1] + 1)), "duration-predictor parameters must be contiguous in the flat buffer"
+        self._dp_span = (self.store.offsets[names[dp[0]]][0],
+                         self.store.offsets[names[dp[-1] + 1]][0] if dp[-1] + 1 < len(names) else self.store.numel)
+        self.dp_step_dev = torch.zeros(1, dtype=_f32, device=self.device)
         self._prior_cache: Dict[Tuple, torch.Tensor] = {}
         self._prior_key: Dict[Tuple, Tuple] = {}
         self._prior_tables: Dict[Tuple[int, int], torch.Tensor] = {}
@@ -740,7 +747,29 @@ class AASVCEngine(EngineBase):
         self.d_dp_pre = self.buf("dp.d_pre", (B * Tt, 1))
         ops.duration_loss(self.dp_pre, self.ds, self.tlens_dev, self.d_outs, self.losses[3:4], self.d_dp_pre,
                           1.0 if duration_loss else 0.0)
+        if not duration_loss:
+            self.losses[3:4].zero_()       # trainers/aas_vc.py:131-133: before dp_train_start_steps the loss is 0.0, also in the logs
         return self.losses
+
+    def optimizer_step(self, max_norm: float = 1.0, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
+                       grad_scale: float = 1.0, duration_predictor_active: bool = True) -> None:
+        """clip_grad_norm_ + Adam over the flat buffers (trainers/aas_vc.py:151-158) with torch.optim.Adam's PER-PARAMETER
+        clock: while the duration loss is off (steps <= dp_train_start_steps, aas_vc.py:119) the reference's duration
+        predictor has no .grad, Adam skips it and its bias-correction step count starts later than everybody else's.  The
+        predictor's span of the flat buffers therefore has its own device step counter and is left untouched while inactive."""
+        st = self.store
+        ops.step_advance(self.step_dev, self.seed_dev)
+        if duration_predictor_active:
+            ops.step_advance(self.dp_step_dev, None)
+        self._sqn.zero_()
+        ops.sqnorm(st.G, self._sqn)
+        a, b = self._dp_span
+        for lo, hi, step in ((0, a, self.step_dev), (a, b, self.dp_step_dev), (b, st.numel, self.step_dev)):
+            if hi <= lo or (step is self.dp_step_dev and not duration_predictor_active):
+                continue
+            ops.adam_step(st.P[lo:hi], st.G[lo:hi], st.M[lo:hi], st.V[lo:hi], st.P16[lo:hi] if st.P16 is not None else None,
+                          self.lr_dev, betas[0], betas[1], eps, weight_decay, step, self._sqn, max_norm, grad_scale)
+        self.p16_dirty = False  # adam_step refreshed the bf16 shadow
 
     def total_loss(self) -> torch.Tensor:
         lam = float(self.hp["lambda_align"])

@@ -976,8 +976,9 @@ class AASVCTrainStep:
         if self.world > 1:
             torch.distributed.all_reduce(self.engine.store.G, group=self.pg)
 
-    def _update(self):
-        self.engine.optimizer_step(self.grad_norm, self.betas, self.eps, self.wd, grad_scale=1.0 / (self.world * self.accum))
+    def _update(self, with_duration=True):
+        self.engine.optimizer_step(self.grad_norm, self.betas, self.eps, self.wd, grad_scale=1.0 / (self.world * self.accum),
+                                   duration_predictor_active=with_duration)
 
     def __call__(self, xs, ilens, ys, olens, dp_inputs):
         """xs (B,T,idim), ys (B,L,odim), dp_inputs (B,T_dp,dp_idim): float32, CUDA-resident or pinned host memory.
@@ -999,7 +1000,7 @@ class AASVCTrainStep:
             self._fwd_bwd(xs, ys, dp_inputs, with_dur, fresh, boundary)
             if boundary:
                 self._allreduce()
-                self._update()
+                self._update(with_dur)
             return eng.losses
         key = (B, T, L, dp_inputs.shape[1], with_dur, fresh, boundary)
         entry = self._graphs.get(key)
@@ -1010,7 +1011,7 @@ class AASVCTrainStep:
             self._fwd_bwd(*statics, with_dur, fresh, boundary)   # eager step: allocates every buffer outside the graph pool
             if boundary:
                 self._allreduce()
-                self._update()
+                self._update(with_dur)
             torch.cuda.synchronize()
             g1, g2 = torch.cuda.CUDAGraph(), (torch.cuda.CUDAGraph() if boundary else None)
             n0 = _lib.launch_count()
@@ -1018,7 +1019,7 @@ class AASVCTrainStep:
                 self._fwd_bwd(*statics, with_dur, fresh, boundary)
             if boundary:
                 with torch.cuda.graph(g2):
-                    self._update()
+                    self._update(with_dur)
             self._graphs[key] = (g1, g2, statics, _lib.launch_count() - n0)
             return eng.losses
         g1, g2, statics, n_kernels = entry

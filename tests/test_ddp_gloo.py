@@ -152,7 +152,7 @@ def test_aasvc_two_rank_step_matches_mean_gradient_step(tmp_path, monkeypatch):
         ref.store.G.copy_(g / 2)
         stepper.steps += 1
         ref.lr_dev.fill_(stepper.lr_at(stepper.steps))
-        ref.optimizer_step(1.0)
+        ref.optimizer_step(1.0, duration_predictor_active=it > 0)      # the predictor's Adam clock starts with its loss
     assert (ref.store.P - p0).abs().max().item() <= 1e-6
 
 
@@ -216,7 +216,7 @@ def test_aasvc_gradient_accumulation_two_ranks(tmp_path, monkeypatch):
         ref.store.G.copy_(g / 4)
         stepper.steps += 1
         ref.lr_dev.fill_(stepper.lr_at(stepper.steps))
-        ref.optimizer_step(1.0)
+        ref.optimizer_step(1.0, duration_predictor_active=it > 0)
     assert (ref.store.P - p0).abs().max().item() <= 1e-6
 
 

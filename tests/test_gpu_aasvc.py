@@ -535,7 +535,7 @@ def test_fused_train_step_gradient_accumulation():
         g += ref.store.G
     ref.store.G.copy_(g / 2)
     ref.lr_dev.fill_(st.lr_at(1))
-    ref.optimizer_step(1.0)
+    ref.optimizer_step(1.0, duration_predictor_active=False)       # first window: no duration loss yet (trainers/aas_vc.py:119)
     torch.cuda.synchronize()
     assert (ref.store.P - acc.store.P).abs().max().item() <= 1e-5
 

@@ -385,3 +385,74 @@ def test_reference_trainer_distributed_with_dropin_wrapper(trainers, tmp_path):
         if v.dtype.is_floating_point and "running_" not in k:
             assert torch.equal(ours0[k], ours1[k]), k                      # replicas in lock-step
             assert (v - ours0[k]).abs().max().item() <= (3.5e-3 if k.endswith("linear_k.bias") else 5e-5), k
+
+
+# ------------------------------------------------------------------ fused steps vs the reference trainers
+def test_fused_vtn_train_step_matches_reference_trainer(trainers):
+    """seq2seq_vc_b200.VTNTrainStep (own clip + Adam + WarmupLR on flat buffers) == ARVCTrainer._train_step around the reference
+    model with torch.optim.Adam / clip_grad_norm_ / WarmupLR: same losses, same parameters after 3 steps."""
+    ARVCTrainer, _, outdir = trainers
+    import seq2seq_vc_b200
+    from seq2seq_vc.losses import Seq2SeqLoss
+    from seq2seq_vc.models import VTN as RefVTN
+
+    torch.manual_seed(17)
+    ref = RefVTN(**VTN_HP)
+    ref_shim.disable_dropout(ref)
+    ref.train()
+    ours = seq2seq_vc_b200.VTN(**VTN_HP, transformer_enc_dropout_rate=0.0)
+    for k in ("enc_positional_dropout_rate", "dec_dropout_rate", "dec_positional_dropout_rate", "postnet_dropout_rate"):
+        ours.engine.hp[k] = 0.0
+    ours.load_state_dict(ref.state_dict())
+    xs, ilens, ys, labels, olens = vtn_oracle.synthetic_batch(2, 40, 24, ilens=[40, 33], olens=[24, 17], seed=19)
+    batch = dict(xs=xs, ys=ys, labels=labels, ilens=torch.tensor(ilens), olens=torch.tensor(olens))
+    config = dict(outdir=outdir, grad_norm=1.0, train_max_steps=10 ** 9, distributed=False, save_interval_steps=10 ** 9,
+                  eval_interval_steps=10 ** 9, log_interval_steps=10 ** 9)
+    t_ref = _run(ARVCTrainer, ref, {"Seq2SeqLoss": Seq2SeqLoss()}, config, batch, 3)       # Adam lr 1e-3, WarmupLR(3), clip 1.0
+    step = seq2seq_vc_b200.VTNTrainStep(ours, lr=1e-3, warmup_steps=3, grad_norm=1.0, bce_pos_weight=10.0)
+    tot = torch.zeros(2)
+    for _ in range(3):
+        tot += step(xs, ilens, ys, labels, olens).float().cpu()
+    assert abs(float(tot[0]) - t_ref.total_train_loss["train/l1_loss"]) <= 1e-4 * max(1.0, t_ref.total_train_loss["train/l1_loss"])
+    assert abs(float(tot[1]) - t_ref.total_train_loss["train/bce_loss"]) <= 1e-4 * max(1.0, t_ref.total_train_loss["train/bce_loss"])
+    sd_our = ours.engine.state_dict()
+    for k, v in ref.state_dict().items():
+        if v.dtype.is_floating_point:
+            assert (v - sd_our[k]).abs().max().item() <= (3.5e-3 if k.endswith("linear_k.bias") else 5e-5), k
+
+
+@pytest.mark.parametrize("accum", [1, 2])
+def test_fused_aasvc_train_step_matches_reference_trainer(trainers, accum):
+    """seq2seq_vc_b200.AASVCTrainStep == AASVCTrainer._train_step around the reference model: lambda_align = 2, no duration loss
+    before dp_train_start_steps, gradient accumulation, clip, Adam, WarmupLR."""
+    _, AASVCTrainer, outdir = trainers
+    import seq2seq_vc_b200
+    from seq2seq_vc.losses import DurationPredictorLoss, ForwardSumLoss, L1Loss
+    from seq2seq_vc.models import AASVC as RefAASVC
+
+    torch.manual_seed(23)
+    ref = RefAASVC(**AAS_HP, **AAS_FIXED, **AAS_NO_DROPOUT)
+    ref_shim.disable_dropout(ref)
+    ref.train()
+    ours = seq2seq_vc_b200.AASVC(**AAS_HP, **AAS_FIXED, **AAS_NO_DROPOUT)
+    ours.load_state_dict(ref.state_dict())
+    xs, ilens, ys, olens, dpi = aasvc_oracle.synthetic_batch(2, 44, 36, ilens=[44, 37], olens=[36, 29], seed=29)
+    batch = dict(xs=xs, ys=ys, ilens=torch.tensor(ilens), olens=torch.tensor(olens), dp_inputs=dpi, dplens=torch.tensor(ilens))
+    config = dict(outdir=outdir, grad_norm=1.0, train_max_steps=10 ** 9, distributed=False, save_interval_steps=10 ** 9,
+                  eval_interval_steps=10 ** 9, log_interval_steps=10 ** 9, lambda_align=2.0, dp_train_start_steps=0,
+                  criterions=["L1Loss", "ForwardSumLoss", "DurationPredictorLoss"], gradient_accumulate_steps=accum)
+    crit = {"L1Loss": L1Loss(), "ForwardSumLoss": ForwardSumLoss(), "DurationPredictorLoss": DurationPredictorLoss()}
+    t_ref = _run(AASVCTrainer, ref, crit, config, batch, 3 * accum)
+    step = seq2seq_vc_b200.AASVCTrainStep(ours, lr=1e-3, warmup_steps=3, grad_norm=1.0, dp_train_start_steps=0,
+                                          gradient_accumulate_steps=accum)
+    tot = torch.zeros(4)
+    for _ in range(3 * accum):
+        tot += step(xs, ilens, ys, olens, dpi).float().cpu() / accum
+    assert step.steps == t_ref.steps == 3
+    for i, k in enumerate(("train/l1_loss", "train/forward_sum_loss", "train/binary_loss", "train/duration_loss")):
+        assert abs(float(tot[i]) - t_ref.total_train_loss[k]) <= 2e-4 * max(1.0, abs(t_ref.total_train_loss[k])), k
+    sd_our = ours.engine.state_dict()
+    for k, v in ref.state_dict().items():
+        if v.dtype.is_floating_point:
+            assert (v - sd_our[k]).abs().max().item() <= 2e-3, k               # single elements: Adam-normalised round-off (see _compare_grads)
+            assert (v - sd_our[k]).abs().mean().item() <= 3e-5, k
