@@ -456,3 +456,49 @@ def test_fused_aasvc_train_step_matches_reference_trainer(trainers, accum):
         if v.dtype.is_floating_point:
             assert (v - sd_our[k]).abs().max().item() <= 2e-3, k               # single elements: Adam-normalised round-off (see _compare_grads)
             assert (v - sd_our[k]).abs().mean().item() <= 3e-5, k
+
+
+def test_fused_tts_train_step_with_guided_attention_matches_reference_trainer(trainers):
+    """VTNTrainStep(guided_attn=...) around TransformerTTS == ARTTSTrainer._train_step with use_guided_attn_loss
+    (trainers/ar_tts.py:49-53, losses/guided_attention_loss.py:109-165)."""
+    _, _, outdir = trainers
+    import seq2seq_vc.trainers.ar_tts as t_tts
+    import seq2seq_vc_b200
+    from seq2seq_vc.losses import GuidedMultiHeadAttentionLoss, Seq2SeqLoss
+    from seq2seq_vc.models.transformer_tts import TransformerTTS as RefTTS
+
+    torch.manual_seed(31)
+    ref = RefTTS(**TTS_HP)
+    ref_shim.disable_dropout(ref)
+    ref.train()
+    ours = seq2seq_vc_b200.TransformerTTS(**TTS_HP)
+    for k in ("transformer_enc_dropout_rate", "enc_positional_dropout_rate", "dec_dropout_rate", "dec_positional_dropout_rate",
+              "postnet_dropout_rate"):
+        ours.engine.hp[k] = 0.0
+    ours.load_state_dict(ref.state_dict())
+    g = torch.Generator().manual_seed(37)
+    ilens, olens = [11, 7], [26, 18]
+    tokens = torch.randint(1, TTS_HP["idim"] - 1, (2, 11), generator=g)
+    ys = torch.randn(2, 26, 80, generator=g)
+    labels = torch.zeros(2, 26)
+    for b in range(2):
+        tokens[b, ilens[b]:] = 0
+        ys[b, olens[b]:] = 0
+        labels[b, olens[b] - 1:] = 1.0
+    config = dict(outdir=outdir, grad_norm=1.0, train_max_steps=10 ** 9, distributed=False, save_interval_steps=10 ** 9,
+                  eval_interval_steps=10 ** 9, log_interval_steps=10 ** 9, use_guided_attn_loss=True)
+    crit = {"Seq2SeqLoss": Seq2SeqLoss(), "guided_attn": GuidedMultiHeadAttentionLoss(sigma=0.4, alpha=1.0)}
+    t_ref = _run(t_tts.ARTTSTrainer, ref, crit, config, (tokens, torch.tensor(ilens), ys, labels, torch.tensor(olens), None), 3)
+    step = seq2seq_vc_b200.VTNTrainStep(ours, lr=1e-3, warmup_steps=3, grad_norm=1.0,
+                                        guided_attn=dict(sigma=0.4, alpha=1.0, n_layers=2, n_heads=2))
+    tot, ga = torch.zeros(2), 0.0
+    for _ in range(3):
+        tot += step(tokens, ilens, ys, labels, olens).float().cpu()
+        ga += float(step.ga_loss)
+    assert abs(float(tot[0]) - t_ref.total_train_loss["train/l1_loss"]) <= 1e-4 * max(1.0, t_ref.total_train_loss["train/l1_loss"])
+    assert abs(float(tot[1]) - t_ref.total_train_loss["train/bce_loss"]) <= 1e-4 * max(1.0, t_ref.total_train_loss["train/bce_loss"])
+    assert abs(ga - t_ref.total_train_loss["train/guided_attn_loss"]) <= 1e-4 * max(1.0, t_ref.total_train_loss["train/guided_attn_loss"])
+    sd_our = ours.engine.state_dict()
+    for k, v in ref.state_dict().items():
+        if v.dtype.is_floating_point:
+            assert (v - sd_our[k]).abs().max().item() <= (3.5e-3 if k.endswith("linear_k.bias") else 5e-5), k
