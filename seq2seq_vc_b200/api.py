@@ -563,7 +563,72 @@ def logmelfilterbank(audio, sampling_rate, fft_size=1024, hop_size=256, win_leng
 # =================================================================================================
 # fused training step (trainers/ar_vc.py:59-112 without the host round trips)
 # =================================================================================================
-class VTNTrainStep:
+class _ReferenceCheckpoint:
+    """Checkpoints of the fused steps in the reference's layout (trainers/base.py:85-121):
+    ``{"model": state_dict, "optimizer": torch.optim.Adam state dict, "scheduler": WarmupLR state dict, "steps", "epochs"}``
+    so a run can move between the reference trainer and the fused step in either direction (`--resume`).  The Adam moments
+    live in the engine's flat M / V buffers; the optimizer state is keyed by parameter ORDER, which the drop-in modules
+    register exactly as the reference does.  Needs the drop-in module (not a bare engine) for that order."""
+
+    def _named_params(self):
+        if self._model is None:
+            raise S2SError("state_dict() / load_state_dict() need the drop-in module (VTN / TransformerTTS / AASVC), not a bare engine")
+        return [n for n, _ in self._model.named_parameters()]
+
+    def _clock_of(self, name: str) -> torch.Tensor:
+        return self.engine.step_dev
+
+    def state_dict(self, epochs: int = 0) -> dict:
+        eng, st = self.engine, self.engine.store
+        names = self._named_params()
+        skeleton = torch.optim.Adam([torch.nn.Parameter(torch.zeros(1)) for _ in names], lr=self.lr, betas=tuple(self.betas),
+                                    eps=self.eps, weight_decay=self.wd).state_dict()["param_groups"]
+        next_lr = self.lr_at(self.steps + 1)              # what scheduler.step() leaves in the group for the next step
+        skeleton[0].update(lr=next_lr, initial_lr=self.lr)
+        state = {}
+        for i, n in enumerate(names):
+            t = float(self._clock_of(n))
+            if t > 0:                                      # torch keeps no state for parameters that never had a gradient
+                state[i] = {"step": torch.tensor(t), "exp_avg": st.m(n).detach().clone(),
+                            "exp_avg_sq": st.v(n).detach().clone()}
+        sched = {"warmup_steps": self.warmup, "base_lrs": [self.lr], "last_epoch": self.steps, "_step_count": self.steps + 1,
+                 "_is_initial": False, "_get_lr_called_within_step": False, "_last_lr": [next_lr]}
+        return {"model": eng.state_dict(), "optimizer": {"state": state, "param_groups": skeleton}, "scheduler": sched,
+                "steps": self.steps, "epochs": epochs}
+
+    def load_state_dict(self, ckpt: dict, load_only_params: bool = False) -> None:
+        eng, st = self.engine, self.engine.store
+        eng.load_state_dict(ckpt["model"])
+        if load_only_params:
+            return
+        names = self._named_params()
+        grp = ckpt["optimizer"]["param_groups"]
+        if len(grp) != 1 or len(grp[0]["params"]) != len(names):
+            raise S2SError("optimizer state does not match this model (one param group over every parameter, in order)")
+        self.lr = float(grp[0].get("initial_lr", ckpt["scheduler"].get("base_lrs", [self.lr])[0]))
+        self.betas, self.eps, self.wd = tuple(grp[0]["betas"]), float(grp[0]["eps"]), float(grp[0]["weight_decay"])
+        self.warmup = int(ckpt["scheduler"].get("warmup_steps", self.warmup))
+        st.M.zero_()
+        st.V.zero_()
+        clocks = {}
+        for i, n in enumerate(names):
+            ent = ckpt["optimizer"]["state"].get(grp[0]["params"][i])
+            if ent is None:
+                continue
+            st.m(n).copy_(ent["exp_avg"].to(eng.device, _f32))
+            st.v(n).copy_(ent["exp_avg_sq"].to(eng.device, _f32))
+            clk = self._clock_of(n)
+            t = float(ent["step"])
+            if clocks.setdefault(id(clk), t) != t:
+                raise S2SError(f"parameters sharing one Adam clock carry different step counts ({n}: {t})")
+            clk.fill_(t)
+        self.steps = int(ckpt["steps"])
+        if hasattr(self, "backward_steps"):
+            self.backward_steps = self.steps * self.accum
+        self._graphs.clear()
+
+
+class VTNTrainStep(_ReferenceCheckpoint):
     """forward + Seq2SeqLoss + backward (+ gradient all-reduce) + clip + Adam + WarmupLR, device-resident.
 
     Mirrors ARVCTrainer._train_step (trainers/ar_vc.py:59-112) for a VTN model.  Lengths arrive as
@@ -577,6 +642,7 @@ class VTNTrainStep:
                  grad_norm: float = 1.0, warmup_steps: int = 4000, bce_pos_weight: float = 10.0, use_graph: bool = False,
                  process_group=None, guided_attn: Optional[dict] = None):
         self.engine: VTNEngine = model.engine if hasattr(model, "engine") else model
+        self._model = model if hasattr(model, "engine") else None
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
         self.grad_norm, self.warmup = grad_norm, warmup_steps
         self.pos_weight = bce_pos_weight
@@ -931,7 +997,7 @@ def _aasvc_inference(self, src_speech, tgt_speech=None, spembs=None, dp_input=No
 AASVC.inference = _aasvc_inference
 
 
-class AASVCTrainStep:
+class AASVCTrainStep(_ReferenceCheckpoint):
     """forward + L1 / forward-sum / bin / duration losses + backward (+ gradient all-reduce) + clip + Adam + WarmupLR,
     device-resident: mirrors AASVCTrainer._train_step (trainers/aas_vc.py:56-159).
     With ``use_graph`` one (B, T, L) batch shape is captured into two CUDA graphs (forward+losses+backward | clip+Adam);
@@ -950,6 +1016,7 @@ class AASVCTrainStep:
         self.accum = int(gradient_accumulate_steps)
         self.backward_steps = 0                            # micro-steps so far (trainers/base.py:69)
         self.engine: AASVCEngine = model.engine if hasattr(model, "engine") else model
+        self._model = model if hasattr(model, "engine") else None
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
         self.grad_norm, self.warmup = grad_norm, warmup_steps
         self.dp_start = dp_train_start_steps
@@ -963,6 +1030,10 @@ class AASVCTrainStep:
         self.replayed_launches = 0
 
     lr_at = VTNTrainStep.lr_at
+
+    def _clock_of(self, name: str) -> torch.Tensor:        # the duration predictor keeps torch Adam's per-parameter clock
+        dp = name.startswith(("duration_predictor.", "duration_predictor_projection."))
+        return self.engine.dp_step_dev if dp else self.engine.step_dev
 
     def _fwd_bwd(self, xs, ys, dpi, with_duration, fresh=True, boundary=True):
         eng = self.engine

@@ -50,6 +50,14 @@ class ParamStore:
     def g(self, name):
         return self._view(self.G, name)
 
+    def m(self, name):
+        """Adam first-moment view of one parameter."""
+        return self._view(self.M, name)
+
+    def v(self, name):
+        """Adam second-moment view of one parameter."""
+        return self._view(self.V, name)
+
     def p16(self, name):
         return self._view(self.P16, name)
 

@@ -502,3 +502,93 @@ def test_fused_tts_train_step_with_guided_attention_matches_reference_trainer(tr
     for k, v in ref.state_dict().items():
         if v.dtype.is_floating_point:
             assert (v - sd_our[k]).abs().max().item() <= (3.5e-3 if k.endswith("linear_k.bias") else 5e-5), k
+
+
+# ------------------------------------------------------------------ checkpoints move between the reference trainer and the fused steps
+def _close(sd_ref, sd_our, tol=5e-5):
+    for k, v in sd_ref.items():
+        if v.dtype.is_floating_point:
+            assert (v - sd_our[k]).abs().max().item() <= (3.5e-3 if k.endswith("linear_k.bias") else tol), k
+
+
+@pytest.mark.parametrize("family", ["vtn", "aasvc"])
+def test_checkpoints_move_between_reference_trainer_and_fused_step(trainers, tmp_path, family):
+    """trainers/base.py:85-121: a checkpoint the reference trainer wrote resumes in the fused step (parameters, Adam moments and
+    per-parameter step counts, scheduler position) and continues exactly like the reference would; and the fused step's
+    state_dict() is a checkpoint the reference trainer resumes from.  For AAS-VC the duration predictor's Adam clock is one
+    step behind everybody else's at that point (no duration loss at step 0)."""
+    ARVCTrainer, AASVCTrainer, outdir = trainers
+    import seq2seq_vc_b200
+    from seq2seq_vc.losses import DurationPredictorLoss, ForwardSumLoss, L1Loss, Seq2SeqLoss
+    from seq2seq_vc.models import AASVC as RefAASVC, VTN as RefVTN
+
+    base = dict(outdir=outdir, grad_norm=1.0, train_max_steps=10 ** 9, distributed=False, save_interval_steps=10 ** 9,
+                eval_interval_steps=10 ** 9, log_interval_steps=10 ** 9)
+    if family == "vtn":
+        def make_ref():
+            torch.manual_seed(41)
+            m = RefVTN(**VTN_HP)
+            ref_shim.disable_dropout(m)
+            return m.train()
+
+        def make_ours():
+            m = seq2seq_vc_b200.VTN(**VTN_HP, transformer_enc_dropout_rate=0.0)
+            for k in ("enc_positional_dropout_rate", "dec_dropout_rate", "dec_positional_dropout_rate", "postnet_dropout_rate"):
+                m.engine.hp[k] = 0.0
+            return m
+
+        xs, ilens, ys, labels, olens = vtn_oracle.synthetic_batch(2, 40, 24, ilens=[40, 33], olens=[24, 17], seed=43)
+        batch = dict(xs=xs, ys=ys, labels=labels, ilens=torch.tensor(ilens), olens=torch.tensor(olens))
+        trainer_cls, config = ARVCTrainer, base
+        crit = lambda: {"Seq2SeqLoss": Seq2SeqLoss()}
+        fused = lambda m: seq2seq_vc_b200.VTNTrainStep(m, lr=1e-3, warmup_steps=3, grad_norm=1.0)
+        call = lambda st: st(xs, ilens, ys, labels, olens)
+    else:
+        def make_ref():
+            torch.manual_seed(41)
+            m = RefAASVC(**AAS_HP, **AAS_FIXED, **AAS_NO_DROPOUT)
+            ref_shim.disable_dropout(m)
+            return m.train()
+
+        make_ours = lambda: seq2seq_vc_b200.AASVC(**AAS_HP, **AAS_FIXED, **AAS_NO_DROPOUT)
+        xs, ilens, ys, olens, dpi = aasvc_oracle.synthetic_batch(2, 44, 36, ilens=[44, 37], olens=[36, 29], seed=43)
+        batch = dict(xs=xs, ys=ys, ilens=torch.tensor(ilens), olens=torch.tensor(olens), dp_inputs=dpi, dplens=torch.tensor(ilens))
+        trainer_cls = AASVCTrainer
+        config = dict(base, lambda_align=2.0, dp_train_start_steps=0, criterions=["L1Loss", "ForwardSumLoss", "DurationPredictorLoss"])
+        crit = lambda: {"L1Loss": L1Loss(), "ForwardSumLoss": ForwardSumLoss(), "DurationPredictorLoss": DurationPredictorLoss()}
+        fused = lambda m: seq2seq_vc_b200.AASVCTrainStep(m, lr=1e-3, warmup_steps=3, grad_norm=1.0)
+        call = lambda st: st(xs, ilens, ys, olens, dpi)
+
+    # reference trainer: 2 steps -> checkpoint -> (a) the reference continues, (b) the fused step resumes from the file
+    ref = make_ref()
+    t_ref = _run(trainer_cls, ref, crit(), config, batch, 2)
+    ck = str(tmp_path / "ck" / "checkpoint-2steps.pkl")
+    t_ref.save_checkpoint(ck)
+    t_ref._train_step(batch)
+    ours = make_ours()
+    st = fused(ours)
+    st.load_state_dict(torch.load(ck, map_location="cpu"))
+    assert st.steps == 2
+    call(st)
+    _close(ref.state_dict(), ours.engine.state_dict())
+
+    # fused step: 2 steps -> state_dict() -> (a) the fused step continues, (b) the reference trainer resumes from the file
+    ours2 = make_ours()
+    ours2.load_state_dict(make_ref().state_dict())
+    st2 = fused(ours2)
+    call(st2)
+    call(st2)
+    ck2 = str(tmp_path / "ck" / "fused-2steps.pkl")
+    torch.save(st2.state_dict(), ck2)
+    call(st2)
+    ref2 = make_ref()
+    with torch.no_grad():
+        for p_ in ref2.parameters():
+            p_.add_(1.0)                                  # whatever it holds is replaced by the checkpoint
+    t_ref2 = _run(trainer_cls, ref2, crit(), config, batch, 0)
+    t_ref2.load_checkpoint(ck2)
+    assert t_ref2.steps == 2
+    t_ref2._train_step(batch)
+    _close(ref2.state_dict(), ours2.engine.state_dict())
+    # and both continuations agree with each other (same initial state, same batch)
+    _close(ref.state_dict(), ours2.engine.state_dict())
