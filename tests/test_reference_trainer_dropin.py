@@ -506,9 +506,12 @@ def test_fused_tts_train_step_with_guided_attention_matches_reference_trainer(tr
 
 # ------------------------------------------------------------------ checkpoints move between the reference trainer and the fused steps
 def _close(sd_ref, sd_our, tol=5e-5):
+    """Parameters whose gradient is zero in exact arithmetic (key biases: softmax shift invariance; the depthwise-conv bias in
+    front of BatchNorm) only ever see round-off, which Adam normalises into lr-sized steps: bounded by steps x lr instead."""
     for k, v in sd_ref.items():
         if v.dtype.is_floating_point:
-            assert (v - sd_our[k]).abs().max().item() <= (3.5e-3 if k.endswith("linear_k.bias") else tol), k
+            loose = k.endswith("linear_k.bias") or k.endswith("depthwise_conv.bias")
+            assert (v - sd_our[k]).abs().max().item() <= (3.5e-3 if loose else tol), k
 
 
 @pytest.mark.parametrize("family", ["vtn", "aasvc"])
