@@ -239,16 +239,12 @@ def test_reference_artts_trainer_drives_dropin_transformer_tts(trainers, monkeyp
     ours.load_state_dict(ref.state_dict())
     ours.train()
     _same_parameter_order(ref, ours)
-    g = torch.Generator().manual_seed(33)
-    ilens, olens = [11, 7], [26, 18]
-    tokens = torch.randint(1, TTS_HP["idim"] - 1, (2, 11), generator=g)
-    ys = torch.randn(2, 26, 80, generator=g)
-    labels = torch.zeros(2, 26)
-    for b in range(2):
-        tokens[b, ilens[b]:] = 0
-        ys[b, olens[b]:] = 0
-        labels[b, olens[b] - 1:] = 1.0
-    batch = (tokens, torch.tensor(ilens), ys, labels, torch.tensor(olens), None)
+    from seq2seq_vc.collaters.ar_tts import ARTTSCollater             # collaters/ar_tts.py:64: the 6-tuple batch
+
+    rng = np.random.default_rng(33)
+    batch = ARTTSCollater()([(rng.integers(1, TTS_HP["idim"] - 1, size=t), rng.standard_normal((l, 80)).astype(np.float32))
+                             for t, l in ((11, 26), (7, 18))])
+    assert batch[0].dtype == torch.int64 and batch[5] is None
     config = dict(outdir=outdir, grad_norm=1.0, train_max_steps=10 ** 9, distributed=False, save_interval_steps=10 ** 9,
                   eval_interval_steps=10 ** 9, log_interval_steps=10 ** 9, use_guided_attn_loss=True)
     crit = lambda: {"Seq2SeqLoss": Seq2SeqLoss(), "guided_attn": GuidedMultiHeadAttentionLoss(sigma=0.4, alpha=1.0)}
