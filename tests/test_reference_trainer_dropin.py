@@ -102,7 +102,9 @@ VTN_HP = dict(idim=80, odim=80, dprenet_layers=2, dprenet_units=16, adim=32, ahe
               postnet_layers=2, postnet_filts=5, postnet_chans=16, decoder_reduction_factor=2, dprenet_dropout_rate=0.0)
 
 
-def test_reference_arvc_trainer_drives_dropin_vtn(trainers):
+@pytest.mark.parametrize("criterions", ["reference", "dropin"])
+def test_reference_arvc_trainer_drives_dropin_vtn(trainers, criterions):
+    """criterions = "dropin": the criterion factory (bin/vc_train.py:397-403) resolves the loss in this package too."""
     ARVCTrainer, _, outdir = trainers
     import seq2seq_vc_b200
     from seq2seq_vc.losses import Seq2SeqLoss
@@ -129,8 +131,9 @@ def test_reference_arvc_trainer_drives_dropin_vtn(trainers):
     assert batch["ilens"].dtype == torch.int64 and batch["labels"][1, 16:].eq(1).all()
     config = dict(outdir=outdir, grad_norm=1.0, train_max_steps=10 ** 9, distributed=False, save_interval_steps=10 ** 9,
                   eval_interval_steps=10 ** 9, log_interval_steps=10 ** 9)
-    t_ref = _run(ARVCTrainer, ref, {"Seq2SeqLoss": Seq2SeqLoss()}, config, batch, 3)
-    t_our = _run(ARVCTrainer, ours, {"Seq2SeqLoss": Seq2SeqLoss()}, config, batch, 3)
+    t_ref = _run(ARVCTrainer, ref, {"Seq2SeqLoss": Seq2SeqLoss(bce_pos_weight=10.0)}, config, batch, 3)
+    our_crit = Seq2SeqLoss(bce_pos_weight=10.0) if criterions == "reference" else seq2seq_vc_b200.Seq2SeqLoss(bce_pos_weight=10.0)
+    t_our = _run(ARVCTrainer, ours, {"Seq2SeqLoss": our_crit}, config, batch, 3)
     assert t_ref.steps == t_our.steps == 3
     for k in ("train/l1_loss", "train/bce_loss", "train/loss"):
         assert abs(t_ref.total_train_loss[k] - t_our.total_train_loss[k]) <= 1e-4 * max(1.0, abs(t_ref.total_train_loss[k])), k
@@ -160,8 +163,8 @@ AAS_NO_DROPOUT = dict(transformer_enc_dropout_rate=0.0, transformer_enc_position
                       duration_predictor_dropout_rate=0.0, postnet_dropout_rate=0.0)
 
 
-@pytest.mark.parametrize("accum", [1, 2])
-def test_reference_aasvc_trainer_drives_dropin_aasvc(trainers, accum):
+@pytest.mark.parametrize("accum,criterions", [(1, "reference"), (2, "reference"), (1, "dropin")])
+def test_reference_aasvc_trainer_drives_dropin_aasvc(trainers, accum, criterions):
     """AASVCTrainer._train_step with the reference's L1Loss / ForwardSumLoss / DurationPredictorLoss and lambda_align, incl. its
     gradient_accumulate_steps path (trainers/aas_vc.py:141-149)."""
     _, AASVCTrainer, outdir = trainers
@@ -190,7 +193,9 @@ def test_reference_aasvc_trainer_drives_dropin_aasvc(trainers, accum):
                   criterions=["L1Loss", "ForwardSumLoss", "DurationPredictorLoss"], gradient_accumulate_steps=accum)
     crit = lambda: {"L1Loss": L1Loss(), "ForwardSumLoss": ForwardSumLoss(), "DurationPredictorLoss": DurationPredictorLoss()}
     t_ref = _run(AASVCTrainer, ref, crit(), config, batch, 2 * accum)
-    t_our = _run(AASVCTrainer, ours, crit(), config, batch, 2 * accum)
+    our_crit = crit() if criterions == "reference" else {"L1Loss": seq2seq_vc_b200.L1Loss(), "ForwardSumLoss": seq2seq_vc_b200.ForwardSumLoss(),
+                                                         "DurationPredictorLoss": seq2seq_vc_b200.DurationPredictorLoss()}
+    t_our = _run(AASVCTrainer, ours, our_crit, config, batch, 2 * accum)
     assert t_ref.steps == t_our.steps == 2
     for k, v in t_ref.total_train_loss.items():
         assert abs(v - t_our.total_train_loss[k]) <= 2e-4 * max(1.0, abs(v)), k
