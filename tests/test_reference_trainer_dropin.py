@@ -301,6 +301,23 @@ def test_reference_trainer_checkpoint_and_freeze_with_dropin(trainers, tmp_path)
     blob = torch.load(ck2, map_location="cpu")
     assert set(blob) == {"optimizer", "scheduler", "steps", "epochs", "model"}
     RefVTN(**VTN_HP).load_state_dict(blob["model"])
+    # init-mods (yaml `init-mods`, trainers/ar_vc.py:30-57 load_trained_modules -> utils/model_io.py:12-57): partial transfer
+    # by state-dict key prefix into a differently initialised drop-in
+    torch.manual_seed(99)
+    other = seq2seq_vc_b200.VTN(**VTN_HP, transformer_enc_dropout_rate=0.0)
+    other.load_state_dict(RefVTN(**VTN_HP).state_dict())
+    before = {k: v.clone() for k, v in other.state_dict().items()}
+    t_other = _run(ARVCTrainer, other, {"Seq2SeqLoss": Seq2SeqLoss()}, config, batch, 0)
+    t_other.load_trained_modules(ck, ["encoder", "postnet"])
+    after = other.state_dict()
+    for k, v in ref.state_dict().items():
+        if not v.dtype.is_floating_point:
+            continue
+        if k.startswith(("encoder.", "postnet.")):
+            assert torch.equal(after[k], blob["model"][k]), k
+        else:
+            assert torch.equal(after[k], before[k]), k
+    assert not torch.equal(after["encoder.embed.conv.0.weight"], before["encoder.embed.conv.0.weight"])
     # freeze-mods: encoder prefix frozen on both sides, two more steps
     frozen0 = {k: v.clone() for k, v in ours.state_dict().items() if k.startswith("encoder.")}
     for t in (t_ref, t_our):
