@@ -80,6 +80,8 @@ def _close(sd_ref, sd_our, tol=1.5e-4):
                 assert d.max().item() <= 3.5e-3, k
             else:
                 assert d.max().item() <= tol and d.mean().item() <= 1e-5, (k, d.max().item(), d.mean().item())
+        else:
+            assert torch.equal(v, sd_our[k].to(v.device)), k          # BatchNorm num_batches_tracked counters
 
 
 def _compare_grads(t_ref, t_our):
