@@ -645,6 +645,18 @@ class AASVCEngine(EngineBase):
         self._encoder_side(xs, dp_inputs)
         hs = self.hs
 
+        self._alignment_and_mas(ys)
+        return self._decoder_side(self.ds, L)
+
+    def _alignment_and_mas(self, ys: torch.Tensor) -> None:
+        """Alignment module + monotonic alignment search on self.hs (B, T_text, C) and ys (B, L, odim); needs self.shapes,
+        self.tlens_dev, self.olens_dev.  Fills self.log_p_attn, self.paths, self.ds, self.d_logp_mas, self.losses[2]."""
+        hp, st = self.hp, self.store
+        s = self.shapes
+        B, L, Tt = s["B"], s["L"], s["Tt"]
+        odim = hp["odim"]
+        C = hp["adim"] * hp["post_encoder_reduction_factor"]
+        hs = self.hs
         # ---- alignment module (alignments.py:28-60)
         ya = ys
         if self.bf16:
@@ -675,14 +687,15 @@ class AASVCEngine(EngineBase):
         ops.mas_into(logp, self.tlens_dev, self.olens_dev, self.paths, self.ds, self.losses[2:3], self.d_logp_mas,
                      self._mas_ws(B, L, Tt))
 
-        return self._decoder_side(self.ds, L)
-
     @torch.no_grad()
-    def inference(self, x: torch.Tensor, dp_input: torch.Tensor):
-        """AASVC.inference without ground truth (aas_vc.py:531-603, _forward(is_inference=True) :371-398) for one utterance:
+    def inference(self, x: torch.Tensor, dp_input: torch.Tensor, y: Optional[torch.Tensor] = None):
+        """AASVC.inference (aas_vc.py:531-603, _forward(is_inference=True) :371-398) for one utterance:
         x (T, idim), dp_input (T_dp, dp_idim) float32 device tensors -> (outs (L, odim) float32, d_outs (T_text,) int64).
         Eval-mode BatchNorm, no dropout; durations = clamp(round(exp(d) - 1), 0, 10); T_feats = sum(durations) is read back
-        to the host once (the reference does the same in GaussianUpsampling: `ds.sum().int()`)."""
+        to the host once (the reference does the same in GaussianUpsampling: `ds.sum().int()`).
+        With a ground-truth target y (L_y, odim) -- the "debug usage" the reference trainer's evaluation hook relies on
+        (trainers/aas_vc.py:243-245) -- the alignment module and the alignment search also run on (encoder output, y) and the
+        call returns (outs, d_outs, ds (T_text,) float32, log_p_attn (L_y, T_text) float32); outs still follow d_outs."""
         hp = self.hp
         T = x.shape[0]
         pr = hp["post_encoder_reduction_factor"]
@@ -703,6 +716,16 @@ class AASVCEngine(EngineBase):
             xs = x.to(_f32).contiguous().unsqueeze(0)
             dpi = dp_input.to(_f32).contiguous().unsqueeze(0)
             self._encoder_side(xs, dpi)
+            gt = None
+            if y is not None:
+                Ly = y.shape[0]
+                assert Ly >= Tt, "MAS needs at least one target frame per encoder position"
+                self._sig = (1, T, -(Ly + 2), False)          # buffers of this side computation, dropped with the other eval buffers
+                self.olens_dev = mk(Ly)
+                self.shapes = dict(B=1, T=T, L=Ly, Tt=Tt, Tdp=dpi.shape[1])
+                self._alignment_and_mas(y.to(_f32).contiguous().unsqueeze(0))
+                gt = (self.ds[0].clone(), self.log_p_attn[0].clone())
+                self._sig = (1, T, -1, False)
             ds = self.buf("inf.ds", (1, Tt), _f32)
             ops.duration_infer(self.dp_pre, ds)
             L = int(ds.sum().item())                          # the one host read-back of this path
@@ -713,6 +736,8 @@ class AASVCEngine(EngineBase):
             self.olens_dev = mk(L)
             self.shapes = dict(B=1, T=T, L=L, Tt=Tt, Tdp=dpi.shape[1])
             after, _ = self._decoder_side(ds, L)
+            if gt is not None:
+                return after[0].float().clone(), ds[0].to(torch.int64), gt[0], gt[1]
             return after[0].float().clone(), ds[0].to(torch.int64)
         finally:
             self.training = was_training

@@ -984,14 +984,20 @@ class AASVC(VTN):
 
 
 def _aasvc_inference(self, src_speech, tgt_speech=None, spembs=None, dp_input=None, use_teacher_forcing=False):
-    """Drop-in for AASVC.inference (models/aas_vc.py:531-603) without ground truth: (T, idim) -> (outs (L, odim), d_outs (T_text,))."""
-    if tgt_speech is not None or use_teacher_forcing or spembs is not None:
-        raise NotImplementedError("inference with ground-truth targets / durations / speaker embeddings is outside the hot path")
+    """Drop-in for AASVC.inference (models/aas_vc.py:531-603): (T, idim) -> (outs (L, odim), d_outs (T_text,)); with a
+    ground-truth target (the form AASVCTrainer's evaluation hook uses, trainers/aas_vc.py:243-245) the reference's 5-tuple
+    (outs, d_outs, ds, log_p_attn, ilens_) where ds / log_p_attn come from the alignment module + MAS on the target."""
+    if use_teacher_forcing or spembs is not None:
+        raise NotImplementedError("inference with ground-truth durations / speaker embeddings is outside the hot path")
     _require_cuda(src_speech, "AASVC")
     if dp_input is None:
         raise S2SError("dp_input is required (duration_predictor_use_encoder_outputs=False)")
     self.engine.p16_dirty = True
-    return self.engine.inference(src_speech, dp_input)
+    if tgt_speech is None:
+        return self.engine.inference(src_speech, dp_input)
+    outs, d_outs, ds, log_p_attn = self.engine.inference(src_speech, dp_input, tgt_speech)
+    ilens_ = torch.tensor(src_speech.shape[0] // self.post_encoder_reduction_factor, dtype=torch.int64, device=src_speech.device)
+    return outs, d_outs, ds, log_p_attn, ilens_
 
 
 AASVC.inference = _aasvc_inference

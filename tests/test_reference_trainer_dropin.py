@@ -601,3 +601,99 @@ def test_checkpoints_move_between_reference_trainer_and_fused_step(trainers, tmp
     _close(ref2.state_dict(), ours2.engine.state_dict())
     # and both continuations agree with each other (same initial state, same batch)
     _close(ref.state_dict(), ours2.engine.state_dict())
+
+
+# ------------------------------------------------------------------ the trainer's evaluation hook (trainers/base.py:165-184)
+class _RecordingPlt:
+    """matplotlib.pyplot stand-in that records every array handed to plot / imshow."""
+
+    def __init__(self):
+        self.arrays = []
+
+    def plot(self, a, *args, **kw):
+        self.arrays.append(np.array(a))
+
+    def imshow(self, a, *args, **kw):
+        self.arrays.append(np.array(a))
+
+    def __getattr__(self, name):
+        return lambda *a, **k: None
+
+
+def test_reference_trainer_eval_hook_with_dropin_inference(trainers, monkeypatch, tmp_path):
+    """ARVCTrainer._genearete_and_save_intermediate_result (trainers/ar_vc.py:114-225, called from _eval_epoch every
+    eval_interval_steps): feeds padded rows of the dev batch to model.inference(x, config["inference"], spemb=None) and plots
+    outs / probs / att_ws.  Everything it draws with the drop-in equals what it draws with the reference model."""
+    ARVCTrainer, _, outdir = trainers
+    import seq2seq_vc.trainers.ar_vc as t_ar
+    import seq2seq_vc_b200
+    from seq2seq_vc.losses import Seq2SeqLoss
+    from seq2seq_vc.models import VTN as RefVTN
+
+    torch.manual_seed(51)
+    ref = RefVTN(**VTN_HP)
+    ours = seq2seq_vc_b200.VTN(**VTN_HP)
+    ours.load_state_dict(ref.state_dict())
+    ref.eval()
+    ours.eval()
+    xs, ilens, ys, labels, olens = vtn_oracle.synthetic_batch(2, 40, 24, ilens=[40, 33], olens=[24, 17], seed=53)
+    batch = dict(xs=xs, ys=ys, labels=labels, ilens=torch.tensor(ilens), olens=torch.tensor(olens))
+    drawn = []
+    for i, model in enumerate((ref, ours)):
+        config = dict(outdir=str(tmp_path / f"run{i}"), grad_norm=1.0, train_max_steps=10 ** 9, distributed=False,
+                      inference=dict(threshold=0.5, minlenratio=0.0, maxlenratio=0.6), num_save_intermediate_results=4)
+        plt = _RecordingPlt()
+        monkeypatch.setattr(t_ar, "plt", plt)
+        tr = _run(ARVCTrainer, model, {"Seq2SeqLoss": Seq2SeqLoss()}, config, batch, 0)
+        tr._genearete_and_save_intermediate_result(batch)
+        drawn.append(plt.arrays)
+    assert len(drawn[0]) == len(drawn[1]) > 0
+    for a, b in zip(*drawn):
+        assert a.shape == b.shape
+        assert np.abs(a - b).max() <= 2e-4, np.abs(a - b).max()
+    assert any(a.ndim == 2 and a.shape[0] > 1 for a in drawn[1])
+
+
+def test_reference_aasvc_trainer_eval_hook_with_dropin_inference(trainers, monkeypatch, tmp_path):
+    """AASVCTrainer._genearete_and_save_intermediate_result (trainers/aas_vc.py:205-290) calls
+    model.inference(x[:ilen], y[:olen], spembs=None, dp_input=dp_input) -- WITH the ground-truth target -- and unpacks five
+    values (outs, d_outs, ds, log_p_attn, ilens_): the drop-in serves that form; durations from the alignment search are
+    exact, everything drawn (outs, target, log_p_attn) matches the reference model's."""
+    _, AASVCTrainer, outdir = trainers
+    import seq2seq_vc.trainers.aas_vc as t_aas
+    import seq2seq_vc_b200
+    from seq2seq_vc.losses import L1Loss
+    from seq2seq_vc.models import AASVC as RefAASVC
+
+    torch.manual_seed(61)
+    ref = RefAASVC(**AAS_HP, **AAS_FIXED, **AAS_NO_DROPOUT)
+    with torch.no_grad():
+        ref.duration_predictor.linear.bias.add_(1.0)          # so that the predicted durations are not all zero
+    ours = seq2seq_vc_b200.AASVC(**AAS_HP, **AAS_FIXED, **AAS_NO_DROPOUT)
+    ours.load_state_dict(ref.state_dict())
+    ref.eval()
+    ours.eval()
+    xs, ilens, ys, olens, dpi = aasvc_oracle.synthetic_batch(2, 44, 36, ilens=[44, 37], olens=[36, 29], seed=63)
+    batch = dict(xs=xs, ys=ys, ilens=torch.tensor(ilens), olens=torch.tensor(olens), dp_inputs=dpi, dplens=torch.tensor(ilens))
+    # the 5-tuple itself
+    r = ref.inference(xs[0, :44], ys[0, :36], spembs=None, dp_input=dpi[0])
+    o = ours.inference(xs[0, :44], ys[0, :36], spembs=None, dp_input=dpi[0])
+    assert len(r) == len(o) == 5
+    assert (r[0] - o[0]).abs().max().item() <= 2e-4 and torch.equal(r[1].long(), o[1].long())
+    assert torch.equal(r[2], o[2]) and int(r[4]) == int(o[4])                     # MAS durations: exact
+    fin = torch.isfinite(r[3])
+    assert torch.equal(fin, torch.isfinite(o[3])) and (r[3][fin] - o[3][fin]).abs().max().item() <= 2e-4
+    drawn = []
+    for i, model in enumerate((ref, ours)):
+        config = dict(outdir=str(tmp_path / f"run{i}"), grad_norm=1.0, train_max_steps=10 ** 9, distributed=False,
+                      num_save_intermediate_results=4, criterions=["L1Loss"])
+        plt = _RecordingPlt()
+        monkeypatch.setattr(t_aas, "plt", plt)
+        tr = _run(AASVCTrainer, model, {"L1Loss": L1Loss()}, config, batch, 0)
+        tr._genearete_and_save_intermediate_result(batch)
+        drawn.append(plt.arrays)
+    assert len(drawn[0]) == len(drawn[1]) > 0
+    for a, b in zip(*drawn):
+        assert a.shape == b.shape
+        m = np.isfinite(a)
+        assert np.array_equal(m, np.isfinite(b)) and np.abs(a[m] - b[m]).max() <= 2e-4
