@@ -335,7 +335,7 @@ def test_reference_trainer_checkpoint_and_freeze_with_dropin(trainers, tmp_path)
 
 
 # ------------------------------------------------------------------ --distributed (bin/vc_train.py:423-431), world size 2, gloo
-def _ddp_worker(rank, world, port, out_dir):
+def _ddp_worker(rank, world, port, out_dir, family="vtn"):
     import os
 
     here = os.path.dirname(os.path.abspath(__file__))
@@ -366,6 +366,36 @@ def _ddp_worker(rank, world, port, out_dir):
     from seq2seq_vc.trainers.ar_vc import ARVCTrainer
 
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    if family == "aasvc":
+        # AASVCTrainer with gradient_accumulate_steps = 2: every micro-step's backward averages over the ranks
+        from oracle import aasvc_oracle as ao
+        from seq2seq_vc.losses import DurationPredictorLoss, ForwardSumLoss, L1Loss
+        from seq2seq_vc.models import AASVC as RefAASVC
+        from seq2seq_vc.trainers.aas_vc import AASVCTrainer
+
+        torch.manual_seed(3)
+        ref = RefAASVC(**AAS_HP, **AAS_FIXED, **AAS_NO_DROPOUT)
+        rs.disable_dropout(ref)
+        ref.train()
+        torch.manual_seed(100 + rank)
+        ours = seq2seq_vc_b200.AASVC(**AAS_HP, **AAS_FIXED, **AAS_NO_DROPOUT)
+        if rank == 0:
+            ours.load_state_dict(ref.state_dict())
+        ours.train()
+        xs, ilens, ys, olens, dpi = ao.synthetic_batch(2, 44, 36, ilens=[44, 37 - rank], olens=[36, 29 + rank], seed=70 + rank)
+        batch = dict(xs=xs, ys=ys, ilens=torch.tensor(ilens), olens=torch.tensor(olens), dp_inputs=dpi, dplens=torch.tensor(ilens))
+        config = dict(outdir=out_dir, grad_norm=1.0, train_max_steps=10 ** 9, distributed=True, save_interval_steps=10 ** 9,
+                      eval_interval_steps=10 ** 9, log_interval_steps=10 ** 9, lambda_align=2.0, dp_train_start_steps=0,
+                      criterions=["L1Loss", "ForwardSumLoss", "DurationPredictorLoss"], gradient_accumulate_steps=2)
+        crit = lambda: {"L1Loss": L1Loss(), "ForwardSumLoss": ForwardSumLoss(), "DurationPredictorLoss": DurationPredictorLoss()}
+        # find_unused_parameters: the duration predictor takes no part in the first window (no duration loss at step 0)
+        t_ref = _run(AASVCTrainer, torch.nn.parallel.DistributedDataParallel(ref, find_unused_parameters=True), crit(), config, batch, 4)
+        t_our = _run(AASVCTrainer, seq2seq_vc_b200.DistributedDataParallel(ours), crit(), config, batch, 4)
+        assert t_ref.steps == t_our.steps == 2
+        t_our.save_checkpoint(os.path.join(out_dir, f"ours{rank}.pkl"))
+        torch.save({k: v.clone() for k, v in ref.state_dict().items()}, os.path.join(out_dir, f"ref{rank}.pt"))
+        dist.destroy_process_group()
+        return
     torch.manual_seed(3)
     ref = RefVTN(**VTN_HP)
     rs.disable_dropout(ref)
@@ -388,10 +418,11 @@ def _ddp_worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_reference_trainer_distributed_with_dropin_wrapper(trainers, tmp_path):
-    """Two ranks, rank-specific batches, ARVCTrainer with config["distributed"]: the reference model under torch DDP (apex is
-    not installed here) vs the drop-in under seq2seq_vc_b200.DistributedDataParallel land on the same parameters; the replicas
-    stay identical; the wrapper broadcast rank 0's initial parameters."""
+@pytest.mark.parametrize("family", ["vtn", "aasvc"])
+def test_reference_trainer_distributed_with_dropin_wrapper(trainers, tmp_path, family):
+    """Two ranks, rank-specific batches, ARVCTrainer / AASVCTrainer (gradient_accumulate_steps = 2) with config["distributed"]:
+    the reference model under torch DDP (apex is not installed here) vs the drop-in under seq2seq_vc_b200.DistributedDataParallel
+    land on the same parameters; the replicas stay identical; the wrapper broadcast rank 0's initial parameters."""
     import socket
 
     import torch.multiprocessing as mp
@@ -399,7 +430,7 @@ def test_reference_trainer_distributed_with_dropin_wrapper(trainers, tmp_path):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    mp.spawn(_ddp_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_ddp_worker, args=(2, port, str(tmp_path), family), nprocs=2, join=True)
     ours0 = torch.load(tmp_path / "ours0.pkl", map_location="cpu")["model"]
     ours1 = torch.load(tmp_path / "ours1.pkl", map_location="cpu")["model"]
     ref0 = torch.load(tmp_path / "ref0.pt")
