@@ -153,6 +153,27 @@ int s2s_attn_probs_bwd(const void* dctx, int64_t d_bs, int64_t d_ts, int64_t d_h
                        int64_t v_hs, const void* P, const void* dAtt, void* dS, int B, int H, int T1, int T2, int dk, int64_t ld,
                        float scale, void* stream);
 
+/* Flash-style fused multi-head attention on tcgen05 / TMEM (bf16; d_k a multiple of 16 in [16, 128]) -- replaces
+ * MultiHeadedAttention.forward_attention (modules/transformer/attention.py:76-111) and its autograd backward:
+ *   fwd: ctx[b,t,h,:] = sum_s P[b,h,t,s] v[b,s,h,:],  P = softmax_s(scale * q k^T) under the key-length / causal mask
+ *        (masked columns exactly 0; a row without a visible key gives P = 0, ctx = 0), S and P stay in tensor / shared
+ *        memory; lse (B, H, T1p) float32, T1p = T1 rounded up to 64, receives the log2-domain row statistic
+ *        max + log2(sum) (+inf for an empty row); when P != NULL the normalised probabilities are ALSO written as
+ *        (B, H, T1, ld) bf16 with columns >= the visible keys zeroed (source-attention maps are an output of
+ *        VTN.forward, models/vtn.py:280-287).
+ *   bwd: recomputes P from q, k and lse; dq = dS k, dk = dS^T q, dv = P^T dctx with dS = scale * P * (dctx v^T - D),
+ *        D = rowsum(dctx o ctx) (written to dvec (B, H, T1p) as a workspace).  Two launches (dQ; dK + dV), no atomics.
+ * q / ctx / dctx / dq are (B, T1, H, d_k) views, k / v / dk / dv (B, T2, H, d_k) views, each given by element strides
+ * (batch, time, head; d_k contiguous), 16-byte aligned with strides that are multiples of 8 elements. */
+int s2s_attn_fwd_tc(const void* q, int64_t q_bs, int64_t q_ts, int64_t q_hs, const void* k, const void* v, int64_t kv_bs,
+                    int64_t kv_ts, int64_t kv_hs, void* ctx, int64_t c_bs, int64_t c_ts, int64_t c_hs, float* lse, void* P,
+                    int64_t ld, const int32_t* klens, int B, int H, int T1, int T2, int dk, float scale, int causal, void* stream);
+int s2s_attn_bwd_tc(const void* q, int64_t q_bs, int64_t q_ts, int64_t q_hs, const void* k, const void* v, int64_t kv_bs,
+                    int64_t kv_ts, int64_t kv_hs, const void* ctx, const void* dctx, int64_t c_bs, int64_t c_ts, int64_t c_hs,
+                    const float* lse, float* dvec, void* dq, int64_t dq_bs, int64_t dq_ts, int64_t dq_hs, void* dk_out, void* dv_out,
+                    int64_t dkv_bs, int64_t dkv_ts, int64_t dkv_hs, const int32_t* klens, int B, int H, int T1, int T2, int dk,
+                    float scale, int causal, void* stream);
+
 /* -------------------------------------------------------------------------------------------
  * ScaledPositionalEncoding (layers/positional_encoding.py:73-106): y = dropout(x + alpha * pe[t])
  * pe is the float32 sinusoid table (>= T rows of d); alpha is a device scalar.

@@ -71,6 +71,11 @@ SIGNATURES = {
                                    c_int64, c_float, c_int, _P]),
     "s2s_attn_probs_bwd": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int64, c_int64, c_int64, _P, _P, _P, c_int, c_int, c_int, c_int,
                                    c_int, c_int64, c_float, _P]),
+    "s2s_attn_fwd_tc": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P, c_int64, c_int64, c_int64, _P, c_int64, c_int64, c_int64, _P, _P, c_int64,
+                                _P, c_int, c_int, c_int, c_int, c_int, c_float, c_int, _P]),
+    "s2s_attn_bwd_tc": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P, c_int64, c_int64, c_int64, _P, _P, c_int64, c_int64, c_int64, _P, _P,
+                                _P, c_int64, c_int64, c_int64, _P, _P, c_int64, c_int64, c_int64, _P, c_int, c_int, c_int, c_int, c_int,
+                                c_float, c_int, _P]),
     "s2s_scaled_pe_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _DP, c_int, _P]),
     "s2s_scaled_pe_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _DP, c_int, _P]),
     "s2s_embed_pe_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _DP, c_int, _P]),

@@ -246,15 +246,8 @@ class AASVCEngine(EngineBase):
         assert Tt >= 1, "source too short for the post-encoder reduction factor"
         tlens = [i // pr for i in ilens]
         assert all(t >= 1 for t in tlens) and all(o >= 1 for o in olens)
-        self._sig = (B, T, L, self.training)
-        host = self._lens_host.get(B)
-        if host is None:
-            host = torch.empty(3, B, dtype=_i32)
-            if self.device.type == "cuda":
-                host = host.pin_memory()
-            self._lens_host[B] = host
-        host.copy_(torch.tensor([ilens, tlens, olens], dtype=_i32))
-        self.buf("lens", (3, B), _i32).copy_(host, non_blocking=True)
+        self._use_sig((B, T, L, self.training))
+        self._ship_lens([ilens, tlens, olens])
         self.ilens_host, self.tlens_host, self.olens_host = ilens, tlens, olens
         # beta-binomial prior (B, L, Tt) in a shape-stable device buffer (a captured CUDA graph keeps reading it);
         # re-filled only when the length pattern changes.  -inf never enters: the kernel reads t < olen, k < tlen only
@@ -278,6 +271,10 @@ class AASVCEngine(EngineBase):
             self._prior_key[self._sig] = key
         self.prior = pbuf
         self._prepared = (B, T, L)
+
+    def _evict_sig(self, sig) -> None:
+        super()._evict_sig(sig)
+        self._prior_key.pop(sig, None)
 
     def _rel_table(self, T: int, d: int) -> torch.Tensor:
         t = self._relpe.get((T, d))

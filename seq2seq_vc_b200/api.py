@@ -233,6 +233,16 @@ class VTN(torch.nn.Module):
             if p.grad is None or p.grad.data_ptr() != g.data_ptr():
                 p.grad = g
 
+    def _publish_attn(self) -> None:
+        """`.attn` of the attention modules (attention.py:81-85).  The bf16 flash-attention path keeps only the maps the
+        engine's `attn_emit` policy asks for in HBM (default: the source-attention maps, the ones VTN.forward returns);
+        the others read None instead of a stale tensor.  `model.engine.attn_emit = "all"` restores every map."""
+        eng = self.engine
+        for name, mod in self.named_modules():
+            if isinstance(mod, MultiHeadedAttention):
+                P = eng.attn.get(name)
+                mod.attn = None if P is None else (P.float() if P.dtype != _f32 else P)
+
     def train(self, mode: bool = True):
         super().train(mode)
         if self.engine is not None:
@@ -271,9 +281,7 @@ class VTN(torch.nn.Module):
         ilens_ds_st = torch.tensor(eng.ilens_ds_st, dtype=torch.int64, device=xs.device)
         olens_in = torch.tensor(eng.olens_in_host, dtype=torch.int64, device=xs.device)
         att_ws = []
-        for name, P in eng.attn.items():
-            node = self.get_submodule(name)
-            node.attn = P.float() if P.dtype != _f32 else P
+        self._publish_attn()
         for l in reversed(range(self.hp["dlayers"])):           # vtn.py:280-287 (list, last layer first)
             att_ws.append(self.decoder.decoders[l].src_attn.attn)
         return after.float(), before.float(), logits.float(), ys_out, labels_out, olens_out, (att_ws, ilens_ds_st, olens_in)
@@ -375,8 +383,7 @@ class TransformerTTS(VTN):
             ops.fix_targets(labels, eng.olens_fix, labels_out, None, r)
         else:
             labels_out = labels
-        for name, P in eng.attn.items():
-            self.get_submodule(name).attn = P.float() if P.dtype != _f32 else P
+        self._publish_attn()
         ilens_out = torch.tensor(eng.ilens_ds_st, dtype=torch.int64, device=xs.device)      # ilens + 1 (transformer_tts.py:142)
         olens_in = torch.tensor(eng.olens_in_host, dtype=torch.int64, device=xs.device)
         return after.float(), before.float(), logits.float(), ys[:, :Lo], labels_out, olens_out, (att_ws, ilens_out, olens_in)
@@ -570,6 +577,12 @@ class _ReferenceCheckpoint:
     live in the engine's flat M / V buffers; the optimizer state is keyed by parameter ORDER, which the drop-in modules
     register exactly as the reference does.  Needs the drop-in module (not a bare engine) for that order."""
 
+    def _on_evict(self, sig) -> None:
+        """The engine dropped the activation buffers of batch shape `sig` (least recently used): graphs captured for that
+        shape address freed memory and go with them."""
+        for key in [k for k in self._graphs if tuple(k[:3]) == tuple(sig[:3])]:
+            del self._graphs[key]
+
     def _named_params(self):
         if self._model is None:
             raise S2SError("state_dict() / load_state_dict() need the drop-in module (VTN / TransformerTTS / AASVC), not a bare engine")
@@ -657,6 +670,12 @@ class VTNTrainStep(_ReferenceCheckpoint):
             self.world = torch.distributed.get_world_size(process_group)
         self._graphs: Dict[tuple, tuple] = {}
         self.replayed_launches = 0      # kernels of this library launched through graph replays
+        self.engine._evict_listeners.append(self._on_evict)
+        if guided_attn is not None:     # the guided-attention loss reads (and back-propagates into) these maps: keep them in HBM
+            nl = self.engine.hp["dlayers"]
+            self.engine.attn_emit_names = frozenset(
+                f"decoder.decoders.{l}.src_attn" for l in list(reversed(range(nl)))[:guided_attn.get("n_layers", 2)])
+        self.emit_attention = False     # True: the fused step also writes the source-attention maps (engine.attn) for monitoring
 
     def lr_at(self, step: int) -> float:
         """WarmupLR (schedulers/warmup_lr.py:54-61): lr * warmup^0.5 * min(step^-0.5, step * warmup^-1.5)."""
@@ -666,12 +685,18 @@ class VTNTrainStep(_ReferenceCheckpoint):
     # -- the two halves of a step (each is a fixed launch sequence for a given batch shape)
     def _fwd_bwd(self, xs, ys, labels):
         eng = self.engine
-        eng.forward(xs, ys)
-        eng.loss(ys, labels, self.pos_weight)
-        d_att = None
-        if self.guided_attn is not None:
-            self.ga_loss, d_att = eng.guided_attention(**self.guided_attn)
-        eng.backward(eng.d_after, eng.d_before, eng.d_logits, d_att=d_att)
+        saved = eng.attn_emit
+        if not self.emit_attention:
+            eng.attn_emit = "none"      # nothing in the fused step reads an attention map (guided layers: attn_emit_names)
+        try:
+            eng.forward(xs, ys)
+            eng.loss(ys, labels, self.pos_weight)
+            d_att = None
+            if self.guided_attn is not None:
+                self.ga_loss, d_att = eng.guided_attention(**self.guided_attn)
+            eng.backward(eng.d_after, eng.d_before, eng.d_logits, d_att=d_att)
+        finally:
+            eng.attn_emit = saved
 
     def _allreduce(self):
         if self.world > 1:
@@ -1034,6 +1059,7 @@ class AASVCTrainStep(_ReferenceCheckpoint):
             self.world = torch.distributed.get_world_size(process_group)
         self._graphs: Dict[tuple, tuple] = {}
         self.replayed_launches = 0
+        self.engine._evict_listeners.append(self._on_evict)
 
     lr_at = VTNTrainStep.lr_at
 

@@ -7,7 +7,8 @@ PyTorch only owns device memory here; all arithmetic happens in libs2svc_b200.so
 from __future__ import annotations
 
 import math
-from typing import Dict, List, Optional, Sequence, Tuple
+from collections import OrderedDict
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
 
@@ -58,8 +59,11 @@ class EngineBase:
         self.attn: Dict[str, torch.Tensor] = {}      # every attention map of the last forward
         self._sqn = torch.zeros(1, dtype=_f32, device=self.device)
         self.p16_dirty = True
-        self._lens_host: Dict[int, torch.Tensor] = {}
+        self._lens_ring: Dict[Tuple[int, int], dict] = {}
         self._prepared = None
+        self._retired: List[torch.Tensor] = []        # outgrown scratch / tables that captured CUDA graphs may still address
+        self._sig_lru: "OrderedDict[Tuple, bool]" = OrderedDict()
+        self._evict_listeners: List[Callable[[Tuple], None]] = []
 
     def named_drop(self, name: str, p: float) -> Drop:
         """Dropout site addressed by name (stable id per engine): forward and backward just ask for the same name."""
@@ -107,9 +111,60 @@ class EngineBase:
     def pe(self, d: int, length: int) -> torch.Tensor:
         t = self._pe.get(d)
         if t is None or t.shape[0] < length:
+            if t is not None:
+                self._retired.append(t)      # graphs captured for shorter batches keep reading the old table
             t = sinusoid_table(max(length, 2048), d, self.device)
             self._pe[d] = t
         return t
+
+    # ------------------------------------------------------------------ per-shape caches
+    # Activation buffers are cached per batch shape (B, T, L, training) and the fused steps capture one CUDA graph per
+    # shape; the reference collater pads to the batch maxima, so a long run sees many shapes.  At most
+    # `max_cached_shapes` training shapes stay resident (least recently used first out); evicting one drops its buffers
+    # and tells every listener (the train steps) to drop the graphs that address them.  Bucket T / L (e.g. to multiples
+    # of 64) in the collater to keep the set small -- see INTEGRATION.md.
+    max_cached_shapes = 8
+
+    def _use_sig(self, sig: Tuple) -> None:
+        self._sig = sig
+        lru = self._sig_lru
+        lru.pop(sig, None)
+        lru[sig] = True
+        while len(lru) > max(1, int(self.max_cached_shapes)):
+            old, _ = lru.popitem(last=False)
+            self._evict_sig(old)
+
+    def _evict_sig(self, sig: Tuple) -> None:
+        for cb in self._evict_listeners:
+            cb(sig)
+        for key in [k for k in self._bufs if k[0] == sig]:
+            del self._bufs[key]
+
+    def _ship_lens(self, rows: Sequence[Sequence[int]]) -> torch.Tensor:
+        """Per-utterance length vectors (host ints from the collater) -> the device `lens` buffer of the current shape in
+        ONE small non-blocking copy.  The pinned staging rows form a ring guarded by CUDA events: the step never
+        synchronises, so the host may run several steps ahead of the copy engine and must not overwrite a staging row
+        whose copy has not executed yet."""
+        n, B = len(rows), len(rows[0])
+        dst = self.buf("lens", (n, B), _i32)
+        vals = torch.tensor(rows, dtype=_i32)
+        if self.device.type != "cuda":
+            dst.copy_(vals)
+            return dst
+        ring = self._lens_ring.get((n, B))
+        if ring is None:
+            ring = {"slots": [[torch.empty(n, B, dtype=_i32).pin_memory(), None] for _ in range(4)], "next": 0}
+            self._lens_ring[(n, B)] = ring
+        slot = ring["slots"][ring["next"]]
+        ring["next"] = (ring["next"] + 1) % len(ring["slots"])
+        if slot[1] is not None:
+            slot[1].synchronize()          # returns at once unless the host is a full ring ahead of the device
+        slot[0].copy_(vals)
+        dst.copy_(slot[0], non_blocking=True)
+        if slot[1] is None:
+            slot[1] = torch.cuda.Event()
+        slot[1].record()
+        return dst
 
     def drop(self, p: float) -> Drop:
         """Next dropout site of the step (forward and backward enumerate sites in the same order)."""
@@ -154,11 +209,37 @@ class EngineBase:
         """bf16 path with a small head dimension: scores + softmax (and dP + softmax') run as one kernel each."""
         return self.mode == 1 and dk in ops.FUSED_ATTN_DK and getattr(self, "fused_attention", True)
 
+    # Which attention maps are written to HBM.  The reference keeps `self.attn` of every MultiHeadedAttention
+    # (attention.py:81-85) but only the decoder's source-attention maps leave VTN.forward (models/vtn.py:280-287), so:
+    #   "src"  (default) source-attention maps only      "all"  every map (as the reference module tree holds them)
+    #   "none" no map: the fused training steps, which consume none (maps named in `attn_emit_names` are still written,
+    #          e.g. the layers a guided-attention loss reads)
+    attn_emit = "src"
+    attn_emit_names: frozenset = frozenset()
+    flash_attention = True
+
+    def _flash_attn(self, dk: int) -> bool:
+        """bf16 path, d_k a multiple of 16 up to 128: one tcgen05 kernel per direction, S / P never leave the chip."""
+        return self.mode == 1 and dk % 16 == 0 and 16 <= dk <= 128 and self.flash_attention
+
+    def _want_P(self, store_name: str) -> bool:
+        if store_name in self.attn_emit_names or self.attn_emit == "all":
+            return True
+        return self.attn_emit == "src" and store_name.endswith("src_attn")
+
     def _attn_core_fwd(self, q, k, v, klens, causal, tag, store_name):
-        """q (B,T1,H,dk) / k, v (B,T2,H,dk) strided views -> ctx (B,T1,d); keeps P for backward."""
+        """q (B,T1,H,dk) / k, v (B,T2,H,dk) strided views -> ctx (B,T1,d); keeps P (or the row statistics) for backward."""
         B_, T1, H, dk = q.shape
         T2 = k.shape[1]
         ld = _r8(T2)
+        ctx = self.buf(tag + ".ctx", (B_, T1, H * dk))
+        if self._flash_attn(dk):
+            P = self.buf(tag + ".P", (B_, H, T1, ld)) if self._want_P(store_name) else None
+            lse = self.buf(tag + ".lse", ops.attn_lse_shape(B_, H, T1), _f32)
+            ops.attn_fwd_tc(q, k, v, ctx.view(B_, T1, H, dk), lse, klens, causal, 1.0 / math.sqrt(dk), P)
+            if P is not None:
+                self.attn[store_name] = P[..., :T2]
+            return ctx
         P = self.buf(tag + ".P", (B_, H, T1, ld))
         if self._fused_attn(dk, T2):
             ops.attn_probs_fwd(q, k, P, klens, causal, T2, 1.0 / math.sqrt(dk))
@@ -167,17 +248,24 @@ class EngineBase:
             ops.gemm(q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3), P[..., :T2], alpha=1.0 / math.sqrt(dk), mode=self.mode)
             ops.softmax_fwd(P, klens, causal, T2)
         self.attn[store_name] = P[..., :T2]
-        ctx = self.buf(tag + ".ctx", (B_, T1, H * dk))
         # ctx[b,t,h,:] = sum_s P[b,h,t,s] v[b,s,h,:]
         ops.gemm(P[..., :T2], v.permute(0, 2, 3, 1), ctx.view(B_, T1, H, dk).permute(0, 2, 1, 3), mode=self.mode)
         return ctx
 
-    def _attn_core_bwd(self, dctx, q, k, v, dq, dk_, dv, tag, d_att=None):
-        """Gradients of the attention core; dq/dk_/dv are (B,T,H,dk) strided views to be filled."""
+    def _attn_core_bwd(self, dctx, q, k, v, dq, dk_, dv, tag, d_att=None, klens=None, causal=False):
+        """Gradients of the attention core; dq/dk_/dv are (B,T,H,dk) strided views to be filled.  klens / causal: the
+        forward's mask (the flash backward recomputes P from them; the stored-P path does not need them)."""
         B_, T1, H, dk = q.shape
         T2 = k.shape[1]
         ld = _r8(T2)
-        P = self.buf(tag + ".P", (B_, H, T1, ld))
+        if self._flash_attn(dk) and d_att is None:
+            lse = self.buf(tag + ".lse", ops.attn_lse_shape(B_, H, T1), _f32)
+            dvec = self._scratch("attn.D", ops.attn_lse_shape(B_, H, T1), _f32)
+            ctx = self.buf(tag + ".ctx", (B_, T1, H * dk))
+            ops.attn_bwd_tc(q, k, v, ctx.view(B_, T1, H, dk), dctx.view(B_, T1, H, dk), lse, dvec, dq, dk_, dv, klens, causal,
+                            1.0 / math.sqrt(dk))
+            return
+        P = self.buf(tag + ".P", (B_, H, T1, ld))       # a d_att gradient needs the stored map: its site is in attn_emit_names
         dP = self._scratch("dP", (B_, H, T1, ld))
         dctx4 = dctx.view(B_, T1, H, dk).permute(0, 2, 1, 3)
         # dv[b,s,h,j] = sum_t P[b,h,t,s] dctx[b,t,h,j]
@@ -206,6 +294,10 @@ class EngineBase:
         key = ("scratch", name, dtype)
         t = self._bufs.get(key)
         if t is None or t.numel() < n:
+            if t is not None:
+                # CUDA graphs captured for smaller batch shapes have this pointer baked in: keep the old allocation
+                # alive (their replays keep using it) instead of handing it back to the caching allocator
+                self._retired.append(t)
             t = torch.empty(max(n, 1), dtype=dtype, device=self.device)
             self._bufs[key] = t
         return t[:n].view(shape)

@@ -189,6 +189,44 @@ def attn_probs_bwd(dctx, v, P, d_att, dS, T2: int, scale: float):
     return dS
 
 
+def _bthd(t):
+    assert t.dim() == 4 and t.stride(3) == 1 and t.dtype == torch.bfloat16, "(B,T,H,d_k) bf16 view with contiguous d_k"
+    return ptr(t), t.stride(0), t.stride(1), t.stride(2)
+
+
+def attn_lse_shape(B: int, H: int, T1: int):
+    """Shape of the row-statistics / D workspaces of attn_fwd_tc / attn_bwd_tc (row pitch = T1 rounded up to 64)."""
+    return (B, H, (T1 + 63) // 64 * 64)
+
+
+def attn_fwd_tc(q, k, v, ctx, lse, klens, causal: bool, scale: float, P=None):
+    """Fused attention forward on tcgen05: ctx (B,T1,H,dk) = softmax(scale q k^T, masked) v; lse (B,H,T1p) float32 row
+    statistics for the backward; P (B,H,T1,ld) bf16 receives the probabilities when given."""
+    B, T1, H, dk = q.shape
+    T2 = k.shape[1]
+    assert k.shape == v.shape and k.stride() == v.stride() and ctx.shape == q.shape
+    assert lse.dtype == torch.float32 and lse.is_contiguous() and tuple(lse.shape) == attn_lse_shape(B, H, T1)
+    ld = 0
+    if P is not None:
+        assert P.dtype == torch.bfloat16 and P.is_contiguous() and tuple(P.shape[:3]) == (B, H, T1)
+        ld = P.shape[3]
+    qp, kp, vp, cp = _bthd(q), _bthd(k), _bthd(v), _bthd(ctx)
+    check(_L().s2s_attn_fwd_tc(*qp, kp[0], vp[0], *kp[1:], *cp, ptr(lse), ptr(P), ld, ptr(klens), B, H, T1, T2, dk, float(scale),
+                               int(causal), stream()), "attn_fwd_tc")
+    return ctx
+
+
+def attn_bwd_tc(q, k, v, ctx, dctx, lse, dvec, dq, dk_, dv, klens, causal: bool, scale: float):
+    """Fused attention backward on tcgen05 (P recomputed from q, k, lse): fills dq (B,T1,H,dk), dk_ / dv (B,T2,H,dk)."""
+    B, T1, H, dk = q.shape
+    T2 = k.shape[1]
+    assert k.stride() == v.stride() and ctx.stride() == dctx.stride() and dk_.stride() == dv.stride()
+    assert lse.is_contiguous() and dvec.is_contiguous() and tuple(dvec.shape) == attn_lse_shape(B, H, T1) and dvec.dtype == torch.float32
+    qp, kp, vp, cp, gp, dqp, dkp, dvp = _bthd(q), _bthd(k), _bthd(v), _bthd(ctx), _bthd(dctx), _bthd(dq), _bthd(dk_), _bthd(dv)
+    check(_L().s2s_attn_bwd_tc(*qp, kp[0], vp[0], *kp[1:], cp[0], gp[0], *cp[1:], ptr(lse), ptr(dvec), *dqp, dkp[0], dvp[0], *dkp[1:],
+                               ptr(klens), B, H, T1, T2, dk, float(scale), int(causal), stream()), "attn_bwd_tc")
+
+
 def scaled_pe_fwd(x, pe, alpha, y, drop: Drop = NO_DROP):
     B, T, d = x.shape
     assert x.is_contiguous() and y.is_contiguous() and pe.shape[0] >= T and pe.shape[1] == d and pe.is_contiguous()

@@ -294,7 +294,7 @@ class VTNEngine(EngineBase):
         r = hp["decoder_reduction_factor"]
         embed = hp["encoder_input"] == "embed"
         T2 = T + 1 if embed else (((T - 1) // 2) - 1) // 2
-        self._sig = (B, T, L, self.training)
+        self._use_sig((B, T, L, self.training))
         ilens = [int(v) for v in ilens]
         olens = [int(v) for v in olens]
         assert len(ilens) == B and len(olens) == B
@@ -304,18 +304,11 @@ class VTNEngine(EngineBase):
             klens_enc = [min(T2, (i + 3) // 4) for i in ilens]       # mask[:, :, :-2:2][:, :, :-2:2] (subsampling.py:92-94)
         olens_in = [o // r for o in olens]
         olens_fix = [o - o % r for o in olens]
-        host = self._lens_host.get(B)
-        if host is None:
-            host = torch.empty(5, B, dtype=_i32)
-            if self.device.type == "cuda":
-                host = host.pin_memory()
-            self._lens_host[B] = host
         if embed:
             self.ilens_ds_st = klens_enc                                        # transformer_tts.py:222 returns ilens + 1
         else:
             self.ilens_ds_st = [((i - 2 + 1) // 2 - 2 + 1) // 2 for i in ilens]   # vtn.py:279
-        host.copy_(torch.tensor([klens_enc, olens_in, olens_fix, ilens, self.ilens_ds_st], dtype=_i32))
-        self.buf("lens", (5, B), _i32).copy_(host, non_blocking=True)
+        self._ship_lens([klens_enc, olens_in, olens_fix, ilens, self.ilens_ds_st])
         self.olens_in_host, self.olens_fix_host = olens_in, olens_fix
         self._prepared = (B, T, L)
 
@@ -689,7 +682,8 @@ class VTNEngine(EngineBase):
             kv = self.buf(p + ".kv", (B, T2, 2, H, dk))
             dq = self._scratch("g.q", (B, Lr, H, dk))
             dkv = self._scratch("g.kv", (B, T2, 2, H, dk))
-            self._attn_core_bwd(dctx, q, kv[:, :, 0], kv[:, :, 1], dq, dkv[:, :, 0], dkv[:, :, 1], p + ".ca", d_att.get(p + ".src_attn"))
+            self._attn_core_bwd(dctx, q, kv[:, :, 0], kv[:, :, 1], dq, dkv[:, :, 0], dkv[:, :, 1], p + ".ca", d_att.get(p + ".src_attn"),
+                                klens=self.klens_enc, causal=False)
             self._lin_bwd(dkv.view(B * T2, 2 * d), mem.view(B * T2, d), self.Wspan([p + ".src_attn.linear_k.weight"], (2 * d, d)),
                           st.span(st.G, [p + ".src_attn.linear_k.weight"], (2 * d, d)), st.span(st.G, [p + ".src_attn.linear_k.bias"], (2 * d,)),
                           dx=dmem.view(B * T2, d), dx_accumulate=True)
@@ -705,7 +699,7 @@ class VTNEngine(EngineBase):
             qkv = self.buf(p + ".qkv", (B, Lr, 3, H, dk))
             dqkv = self._scratch("g.qkv", (B, Lr, 3, H, dk))
             self._attn_core_bwd(dctx, qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2], p + ".sa",
-                                d_att.get(p + ".self_attn"))
+                                d_att.get(p + ".self_attn"), klens=self.olens_in, causal=True)
             self._lin_bwd(dqkv.view(B * Lr, 3 * d), xin.view(B * Lr, d), self.Wspan([p + ".self_attn.linear_q.weight"], (3 * d, d)),
                           st.span(st.G, [p + ".self_attn.linear_q.weight"], (3 * d, d)), st.span(st.G, [p + ".self_attn.linear_q.bias"], (3 * d,)),
                           dx=g.view(B * Lr, d), dx_residual=dt1.view(B * Lr, d))
@@ -760,7 +754,7 @@ class VTNEngine(EngineBase):
             qkv = self.buf(p + ".qkv", (B, T2, 3, H, dk))
             dqkv = self._scratch("g.eqkv", (B, T2, 3, H, dk))
             self._attn_core_bwd(dctx, qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2], p + ".sa",
-                                d_att.get(p + ".self_attn"))
+                                d_att.get(p + ".self_attn"), klens=self.klens_enc, causal=False)
             dn1 = gte
             self._lin_bwd(dqkv.view(B * T2, 3 * d), n1.view(B * T2, d), self.Wspan([p + ".self_attn.linear_q.weight"], (3 * d, d)),
                           st.span(st.G, [p + ".self_attn.linear_q.weight"], (3 * d, d)), st.span(st.G, [p + ".self_attn.linear_q.bias"], (3 * d,)),

@@ -157,6 +157,56 @@ def attn_probs_bwd(dctx, v, P, d_att, dS, T2, scale):
     return softmax_bwd(P, dS, T2, scale)
 
 
+def attn_lse_shape(B, H, T1):
+    return (B, H, (T1 + 63) // 64 * 64)
+
+
+def _attn_probs64(q, k, klens, causal, scale):
+    """float64 masked softmax probabilities (B,H,T1,T2) and log2-domain row statistics (attention.py:76-104)."""
+    B, T1, H, dk = q.shape
+    T2 = k.shape[1]
+    S = torch.einsum("bthj,bshj->bhts", q.double(), k.double()) * scale
+    vis = torch.arange(T2)[None, :] < klens.to(torch.int64).clamp(0, T2)[:, None]           # (B, T2)
+    vis = vis[:, None, None, :].expand(B, H, T1, T2)
+    if causal:
+        vis = vis & (torch.arange(T2)[None, :] <= torch.arange(T1)[:, None])[None, None]
+    Sm = S.masked_fill(~vis, float("-inf"))
+    m = Sm.max(-1, keepdim=True).values
+    e = torch.where(vis, torch.exp(Sm - torch.where(torch.isfinite(m), m, torch.zeros_like(m))), torch.zeros_like(S))
+    l = e.sum(-1, keepdim=True)
+    P = torch.where(l > 0, e / l.clamp_min(1e-300), torch.zeros_like(e))
+    lse2 = torch.where(l > 0, (m + torch.log(l.clamp_min(1e-300))) / math.log(2.0), torch.full_like(m, float("inf")))
+    return P, lse2.squeeze(-1)
+
+
+def attn_fwd_tc(q, k, v, ctx, lse, klens, causal, scale, P=None):
+    B, T1, H, dk = q.shape
+    T2 = k.shape[1]
+    Pd, lse2 = _attn_probs64(q, k, klens, causal, scale)
+    Pq = Pd.to(q.dtype).double()                                  # the second MMA consumes bf16 probabilities
+    ctx.copy_(torch.einsum("bhts,bshj->bthj", Pq, v.double()).to(ctx.dtype))
+    lse.zero_()
+    lse[..., :T1] = lse2.float()
+    if P is not None:
+        P.zero_()
+        P[..., :T2] = Pd.to(P.dtype)
+    return ctx
+
+
+def attn_bwd_tc(q, k, v, ctx, dctx, lse, dvec, dq, dk_, dv, klens, causal, scale):
+    B, T1, H, dk = q.shape
+    P, _ = _attn_probs64(q, k, klens, causal, scale)
+    dO = dctx.double()
+    dP = torch.einsum("bthj,bshj->bhts", dO, v.double())
+    D = (dO * ctx.double()).sum(-1).permute(0, 2, 1)              # (B,H,T1)
+    dS = P * (dP - D[..., None]) * scale
+    dvec.zero_()
+    dvec[..., :T1] = D.float()
+    dq.copy_(torch.einsum("bhts,bshj->bthj", dS, k.double()).to(dq.dtype))
+    dk_.copy_(torch.einsum("bhts,bthj->bshj", dS, q.double()).to(dk_.dtype))
+    dv.copy_(torch.einsum("bhts,bthj->bshj", P, dO).to(dv.dtype))
+
+
 def scaled_pe_fwd(x, pe, alpha, y, drop=NO_DROP):
     _nodrop(drop)
     T, d = x.shape[1], x.shape[2]

@@ -410,6 +410,56 @@ def test_fused_attention_probs_fwd_bwd(ops, causal, B, H, T1, T2, dk):
         close(gdS, ref, tol_abs, f"fused dS (d_att={with_att})")
 
 
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("emit", [False, True])
+@pytest.mark.parametrize("B,H,T1,T2,dk", [(2, 3, 70, 70, 48), (3, 2, 130, 50, 64), (2, 4, 64, 127, 48), (2, 2, 200, 600, 96), (1, 8, 512, 512, 48),
+                                           (3, 1, 17, 9, 16), (2, 2, 300, 300, 128), (2, 2, 129, 257, 32)])
+def test_flash_attention_tc_fwd_bwd(ops, causal, emit, B, H, T1, T2, dk):
+    """tcgen05 flash attention (S / P in tensor + shared memory) vs the float64 contract: context, row statistics, optional
+    probability output, and dq / dk / dv of the recomputing backward.  q/k/v are strided slices of one fused buffer."""
+    if causal and T1 != T2:
+        pytest.skip("causal masks are only used for self-attention")
+    dt = torch.bfloat16
+    ld = (T2 + 7) // 8 * 8
+    qkv = rnd(B, max(T1, T2), 3, H, dk, dt=dt, seed=1)
+    q, k, v = qkv[:, :T1, 0], qkv[:, :T2, 1], qkv[:, :T2, 2]
+    klens = torch.tensor([T2, max(1, T2 // 2 + 1), 0][:B], dtype=torch.int32)
+    scale = 1.0 / math.sqrt(dk)
+    shp = F.attn_lse_shape(B, H, T1)
+    ctx, lse = torch.empty(B, T1, H, dk, dtype=dt), torch.empty(shp)
+    P = torch.empty(B, H, T1, ld, dtype=dt) if emit else None
+    F.attn_fwd_tc(q, k, v, ctx, lse, klens, causal, scale, P)
+    dqkv = qkv.cuda()
+    gq, gk, gv = dqkv[:, :T1, 0], dqkv[:, :T2, 1], dqkv[:, :T2, 2]
+    gctx = torch.full((B, T1, H * dk), 7.0, dtype=dt, device="cuda").view(B, T1, H, dk)
+    glse = torch.full(shp, 3.0, device="cuda")
+    gP = torch.full((B, H, T1, ld), 3.0, dtype=dt, device="cuda") if emit else None
+    ops.attn_fwd_tc(gq, gk, gv, gctx, glse, klens.cuda(), causal, scale, gP)
+    torch.cuda.synchronize()
+    close(gctx, ctx, 2e-2, "flash ctx")
+    fin = torch.isfinite(lse[..., :T1])
+    assert torch.equal(torch.isfinite(glse[..., :T1]).cpu(), fin), "rows without a visible key carry lse = +inf"
+    assert (glse[..., :T1].cpu()[fin] - lse[..., :T1][fin]).abs().max().item() <= 2e-3
+    if emit:
+        close(gP, P, 1.5e-2, "flash probabilities")
+        assert (gP.float().sum(-1).cpu() - P.float().sum(-1)).abs().max().item() <= 3e-2
+    if B == 3:
+        assert (gctx[2] == 0).all(), "an utterance without visible keys gives a zero context"
+        if emit:
+            assert (gP[2] == 0).all()
+    # backward (recompute): contract fed with the DEVICE forward's ctx / lse, as the engine does
+    dctx = rnd(B, T1, H, dk, dt=dt, seed=2)
+    dq, dk_, dv = torch.empty(B, T1, H, dk, dtype=dt), torch.empty(B, T2, H, dk, dtype=dt), torch.empty(B, T2, H, dk, dtype=dt)
+    F.attn_bwd_tc(q, k, v, gctx.cpu(), dctx, lse, torch.empty(shp), dq, dk_, dv, klens, causal, scale)
+    gd = torch.full((B, max(T1, T2), 3, H, dk), 9.0, dtype=dt, device="cuda")
+    gdvec = torch.empty(shp, device="cuda")
+    ops.attn_bwd_tc(gq, gk, gv, gctx, dctx.cuda(), glse, gdvec, gd[:, :T1, 0], gd[:, :T2, 1], gd[:, :T2, 2], klens.cuda(), causal, scale)
+    torch.cuda.synchronize()
+    for name, got, ref in (("dq", gd[:, :T1, 0], dq), ("dk", gd[:, :T2, 1], dk_), ("dv", gd[:, :T2, 2], dv)):
+        close(got, ref, 3e-2 * max(1.0, ref.float().abs().max().item()), "flash " + name)
+    assert (gd[:, T1:, 0] == 9.0).all() and (gd[:, T2:, 1:] == 9.0).all(), "rows outside the views must stay untouched"
+
+
 @pytest.mark.parametrize("dt", DT)
 def test_decode_kernels(ops, dt):
     """Single-position decode kernels (KV cache) vs their contracts."""

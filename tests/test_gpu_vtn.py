@@ -274,3 +274,54 @@ def test_tts_inference_golden():
     assert tuple(outs.shape) == z["inf_outs"].shape and tuple(att.shape) == z["inf_att_ws"].shape
     assert np.abs(outs.cpu().numpy() - z["inf_outs"]).mean() <= 1e-4 and np.abs(probs.cpu().numpy() - z["inf_probs"]).max() <= 1e-4
     assert np.abs(att.cpu().numpy() - z["inf_att_ws"]).mean() <= 1e-3
+
+
+def test_graph_steps_alternating_shapes_match_eager():
+    """CUDA-graph replays of one batch shape must survive another (larger) shape growing the shared scratch buffers in
+    between: small / large / small / large steps through use_graph=True equal the same steps run eagerly (fp32, no dropout)."""
+    from seq2seq_vc_b200 import VTN, VTNTrainStep
+
+    hp = dict(idim=80, odim=80, adim=64, aheads=4, elayers=1, dlayers=1, eunits=96, dunits=96, dprenet_units=32, postnet_chans=32,
+              dprenet_dropout_rate=0.0, transformer_enc_dropout_rate=0.0)
+    steps = {}
+    for use_graph in (False, True):
+        model = VTN(**hp, compute_dtype="float32", device="cuda:0", seed=5)
+        for k in ("enc_positional_dropout_rate", "dec_dropout_rate", "dec_positional_dropout_rate", "postnet_dropout_rate"):
+            model.engine.hp[k] = 0.0
+        steps[use_graph] = VTNTrainStep(model, lr=1e-3, warmup_steps=1, use_graph=use_graph)
+    shapes = [(2, 40, 24), (3, 96, 60)]
+    g = torch.Generator().manual_seed(11)
+    batches = []
+    for (B, T, L) in shapes:
+        xs, ys = torch.randn(B, T, 80, generator=g).cuda(), torch.randn(B, L, 80, generator=g).cuda()
+        labels = torch.zeros(B, L)
+        labels[:, L - 1:] = 1
+        batches.append((xs, [T - 3 * b for b in range(B)], ys, labels.cuda(), [L - 2 * b for b in range(B)]))
+    for it in range(8):                                  # small, large, small, large, ...: replays start at it = 2
+        batch = batches[it % 2]
+        le = steps[False](*batch).clone()
+        lg = steps[True](*batch).clone()
+        assert (le - lg).abs().max().item() <= 1e-4 * max(1.0, le.abs().max().item()), (it, le.tolist(), lg.tolist())
+    pe, pg = steps[False].engine.store.P, steps[True].engine.store.P
+    assert (pe - pg).abs().max().item() <= 2e-4      # Adam turns the fp32 red.add ordering noise of the weight-gradient GEMMs into lr-sized steps
+
+
+def test_shape_cache_eviction_drops_graphs_and_buffers():
+    """More batch shapes than `max_cached_shapes`: the least recently used shape's buffers and graphs go, memory stays bounded,
+    and a shape that comes back is rebuilt and still trains."""
+    from seq2seq_vc_b200 import VTN, VTNTrainStep
+
+    model = VTN(idim=80, odim=80, adim=64, aheads=4, elayers=1, dlayers=1, eunits=96, dunits=96, dprenet_units=32, postnet_chans=32,
+                compute_dtype="bf16", device="cuda:0", seed=5)
+    model.engine.max_cached_shapes = 2
+    step = VTNTrainStep(model, lr=1e-3, warmup_steps=1, use_graph=True)
+    g = torch.Generator().manual_seed(3)
+    for it in range(12):
+        T, L = 40 + 8 * (it % 4), 24 + 4 * (it % 4)
+        xs, ys = torch.randn(2, T, 80, generator=g).cuda(), torch.randn(2, L, 80, generator=g).cuda()
+        labels = torch.zeros(2, L)
+        labels[:, L - 1:] = 1
+        losses = step(xs, [T, T - 5], ys, labels.cuda(), [L, L - 3])
+        assert torch.isfinite(losses).all()
+        sigs = {k[0] for k in model.engine._bufs if isinstance(k[0], tuple) and len(k[0]) == 4}
+        assert len(sigs) <= 2 and len(step._graphs) <= 2, (sigs, list(step._graphs))
