@@ -36,7 +36,7 @@ extern "C" {
 #define S2S_F32 0
 #define S2S_BF16 1
 
-#define S2S_ABI_VERSION 11
+#define S2S_ABI_VERSION 12
 
 const char* s2s_last_error(void);
 int s2s_abi_version(void);
@@ -74,8 +74,12 @@ typedef struct {
  *             -> row mask -> store
  *   row mask (mask_period > 0): rows with ((m + mask_offset) % mask_period) outside
  *   [mask_lo, mask_hi) are stored as 0 (halo rows of the zero-padded conv1d layout).
- * mode 0: fp32 CUDA-core path (operands f32 or bf16, fp32 FMA accumulate) -- the parity path.
+ *   (R: see r_mode below; with r_mode = 1 it gates instead of adding.)
+ * mode 0: fp32 CUDA-core path (operands f32 or bf16, fp32 FMA accumulate) -- the numerical yard-stick.
  * mode 1: bf16 tcgen05 tensor-core path (operands must be bf16, TMEM fp32 accumulate).
+ * mode 2: fp32-accurate tensor-core path: float32 operands are split into 2 or 3 bf16 pieces each (split_terms = 3 / 6
+ *         partial products, concatenated along K in a workspace) and multiplied by the same tcgen05 kernel with fp32
+ *         TMEM accumulation -- the parity mode (mel L1 <= 1e-4 against the reference) on the tensor cores.
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
     int M, N, K, taps;
@@ -90,9 +94,17 @@ typedef struct {
     int accumulate;
     s2s_dropout_t drop;
     int mask_period, mask_offset, mask_lo, mask_hi;
+    int r_mode;             /* how R enters: 0 = residual (x + R), 1 = ReLU gate (R > 0 ? x * r_scale : 0), the backward of
+                               relu (+ dropout scale) folded into the dX GEMM of the layer above (positionwise_feed_forward.py:30-32) */
+    float r_scale;
+    int split_terms;        /* mode 2 only: 3 = two-way bf16 split (hi*hi + lo*hi + hi*lo), 6 = three-way split (fp32-accurate) */
+    void* ws;               /* mode 2 only: workspace of at least s2s_gemm_workspace_bytes(g) bytes */
+    size_t ws_bytes;
 } s2s_gemm_t;
 
 int s2s_gemm(const s2s_gemm_t* g, int mode, void* stream);
+/* bytes of workspace s2s_gemm(g, mode = 2) needs for this problem */
+size_t s2s_gemm_workspace_bytes(const s2s_gemm_t* g);
 
 /* -------------------------------------------------------------------------------------------
  * LayerNorm over the last dim, eps = 1e-12 in the reference (modules/transformer/layer_norm.py:12-42)
@@ -105,6 +117,11 @@ int s2s_layernorm_fwd(const void* x, const float* gamma, const float* beta, void
 int s2s_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean,
                       const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta,
                       int64_t rows, int d, int dtype, void* stream);
+/* same, with a second output dx_drop = dropout'(dx) (mask regenerated from `drop`): the gradient entering the
+ * residual branch `x = LN(drop(f(..)) + res)` of a post-LN block (decoder_layer.py:63-134) without a separate pass */
+int s2s_layernorm_bwd_drop(const void* dy, const void* x, const float* gamma, const float* mean,
+                           const float* rstd, const void* dres, void* dx, void* dx_drop, const s2s_dropout_t* drop,
+                           float* dgamma, float* dbeta, int64_t rows, int d, int dtype, void* stream);
 
 /* Skinny linear layer with 1 <= N <= 4 output features (the stop-token head prob_out,
  * models/vtn.py:182,251): y[r, j] = sum_k x[r, k] w[j, k] + bias[j]; x (rows, K) and w (N, K) in

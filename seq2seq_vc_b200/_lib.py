@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libs2svc_b200.so")
 
 S2S_F32, S2S_BF16 = 0, 1
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 
 class S2SError(RuntimeError):
@@ -42,6 +42,7 @@ class GemmDesc(Structure):
         ("accumulate", c_int),
         ("drop", DropoutDesc),
         ("mask_period", c_int), ("mask_offset", c_int), ("mask_lo", c_int), ("mask_hi", c_int),
+        ("r_mode", c_int), ("r_scale", c_float), ("split_terms", c_int), ("ws", c_void_p), ("ws_bytes", c_size_t),
     ]
 
 
@@ -57,8 +58,10 @@ SIGNATURES = {
     "s2s_tc_fallback_count": (c_int64, []),
     "s2s_debug_gemm_tile": (None, [c_int]),
     "s2s_gemm": (c_int, [POINTER(GemmDesc), c_int, _P]),
+    "s2s_gemm_workspace_bytes": (c_size_t, [POINTER(GemmDesc)]),
     "s2s_layernorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_float, c_int, _P]),
     "s2s_layernorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P]),
+    "s2s_layernorm_bwd_drop": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _DP, _P, _P, c_int64, c_int, c_int, _P]),
     "s2s_skinny_linear_fwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
     "s2s_skinny_linear_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int64, c_int, c_int, c_int, _P]),
     "s2s_colsum": (c_int, [_P, c_int64, c_int, c_int64, _P, c_int, _P]),

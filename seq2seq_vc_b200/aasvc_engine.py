@@ -184,7 +184,9 @@ class AASVCEngine(EngineBase):
 
     LOSS_NAMES = ("l1_loss", "forward_sum_loss", "bin_loss", "duration_loss")
 
-    def __init__(self, hp: dict, device="cuda:0", bf16: bool = False, seed: int = 0):
+    def __init__(self, hp: dict, device="cuda:0", bf16: bool = False, seed: int = 0, fp32_gemm: str = "tc"):
+        """fp32_gemm (float32 engines only): "tc" = fp32-accurate tcgen05 GEMM (bf16-split operands), "simt" = CUDA-core GEMM."""
+        self.fp32_gemm = fp32_gemm
         self.hp = default_hparams(**hp)
         hp = self.hp
         assert hp["adim"] % hp["aheads"] == 0

@@ -154,7 +154,10 @@ class VTN(torch.nn.Module):
                                   decoder_reduction_factor=decoder_reduction_factor,
                                   initial_encoder_alpha=initial_encoder_alpha, initial_decoder_alpha=initial_decoder_alpha,
                                   encoder_input=getattr(self, "_encoder_input", "conv2d"))
+        # compute_dtype: "bf16" (tcgen05, bf16 activations) | "float32" (float32 activations, fp32-accurate tcgen05 GEMMs through a
+        # bf16 split: the parity mode) | "float32_simt" (float32 on the CUDA cores: the numerical yard-stick)
         self._bf16 = compute_dtype in ("bf16", "bfloat16", torch.bfloat16)
+        self._fp32_gemm = "simt" if compute_dtype == "float32_simt" else "tc"
         self._seed = seed
         self._fwd_token = 0
         self.engine: Optional[VTNEngine] = None
@@ -163,7 +166,7 @@ class VTN(torch.nn.Module):
 
     # ---- construction / device movement -------------------------------------------------------
     def _build(self, device, state: Optional[Dict[str, torch.Tensor]] = None) -> None:
-        self.engine = VTNEngine(self.hp, device=device, bf16=self._bf16, seed=self._seed)
+        self.engine = VTNEngine(self.hp, device=device, bf16=self._bf16, seed=self._seed, fp32_gemm=self._fp32_gemm)
         if state is not None:
             self.engine.load_state_dict(state)
         self._modules.clear()
@@ -966,14 +969,17 @@ class AASVC(VTN):
             transformer_dec_attn_dropout_rate=transformer_dec_attn_dropout_rate,
             duration_predictor_dropout_rate=duration_predictor_dropout_rate, postnet_dropout_rate=postnet_dropout_rate,
             positionwise_layer_type=positionwise_layer_type)
+        # compute_dtype: "bf16" (tcgen05, bf16 activations) | "float32" (float32 activations, fp32-accurate tcgen05 GEMMs through a
+        # bf16 split: the parity mode) | "float32_simt" (float32 on the CUDA cores: the numerical yard-stick)
         self._bf16 = compute_dtype in ("bf16", "bfloat16", torch.bfloat16)
+        self._fp32_gemm = "simt" if compute_dtype == "float32_simt" else "tc"
         self._seed = seed
         self._fwd_token = 0
         self.engine = None
         self._build(torch.device(device) if device is not None else torch.device("cpu"))
 
     def _build(self, device, state=None) -> None:
-        self.engine = AASVCEngine(self.hp, device=device, bf16=self._bf16, seed=self._seed)
+        self.engine = AASVCEngine(self.hp, device=device, bf16=self._bf16, seed=self._seed, fp32_gemm=self._fp32_gemm)
         if state is not None:
             self.engine.load_state_dict(state)
         self._modules.clear()

@@ -21,6 +21,8 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int gemm_simt(const s2s_gemm_t& g, cudaStream_t st);
 int gemm_tc(const s2s_gemm_t& g, cudaStream_t st);
+int gemm_tc_split(const s2s_gemm_t& g, cudaStream_t st);
+size_t gemm_split_workspace_bytes(const s2s_gemm_t& g);
 
 }  // namespace s2s
 
@@ -47,5 +49,8 @@ extern "C" int s2s_gemm(const s2s_gemm_t* g, int mode, void* stream) {
     if (g->M == 0 || g->N == 0) return S2S_OK;
     if (mode == 0) return s2s::gemm_simt(*g, (cudaStream_t)stream);
     if (mode == 1) return s2s::gemm_tc(*g, (cudaStream_t)stream);
+    if (mode == 2) return s2s::gemm_tc_split(*g, (cudaStream_t)stream);
     return s2s::set_error(S2S_ERR_INVALID, "gemm: unknown mode %d", mode);
 }
+
+extern "C" size_t s2s_gemm_workspace_bytes(const s2s_gemm_t* g) { return g ? s2s::gemm_split_workspace_bytes(*g) : 0; }

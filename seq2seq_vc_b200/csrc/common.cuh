@@ -198,34 +198,50 @@ inline Dropout make_dropout(const s2s_dropout_t* d) {
 __device__ __forceinline__ void dropout_resolve(Dropout& d) {
     if (d.thresh != 0u && d.seed_dev) d.key += (*d.seed_dev) * 0x9e3779b97f4a7c15ull;
 }
-// One 32-bit hash serves the element PAIR (idx >> 1): the integer pipe, not HBM, bounds a per-element hash at
-// these tensor sizes (75 M elements x 14 integer ops).  Two keyed murmur rounds over the folded pair index.
-__device__ __forceinline__ uint32_t dropout_hash(const Dropout& d, uint64_t pair) {
-    uint32_t h = (uint32_t)pair * 0x9e3779b1u + (uint32_t)(pair >> 32) * 0x85ebca77u + (uint32_t)d.key;
-    h = mix32(h) + (uint32_t)(d.key >> 32);
-    return mix32(h);
+// The mask is defined per GROUP of 16 consecutive elements: one murmur-mixed 32-bit seed per group (idx >> 4), and lane
+// j = idx & 15 reads the top 16 bits of the j-th state of a 32-bit LCG started at that seed -- x_j = x_0 * A^j + C_j with
+// compile-time jump constants, so lane j costs ONE integer multiply-add plus the compare.  (The first version hashed every
+// element pair with two murmur rounds: ~10 integer ops per element, which alone doubled the epilogue -- the critical path
+// -- of the short-K tcgen05 GEMMs that apply dropout: 16384 x 1536 x 384 took 65 us instead of 33 us.)
+__device__ constexpr uint32_t kLcgA[16] = {0x00000001u, 0x915f77f5u, 0xca0bb079u, 0xd21f22cdu, 0x980c9931u, 0xf97362e5u, 0xc6611829u, 0x2d5e2e3du,
+                                           0xe8439b61u, 0x4feccad5u, 0x79f220d9u, 0x5b854eadu, 0xbd59b691u, 0xcb881fc5u, 0x6f25fa89u, 0x98a5741du};
+__device__ constexpr uint32_t kLcgC[16] = {0x00000000u, 0x3c6ef35fu, 0xc500064au, 0x07d75e31u, 0x8f83df44u, 0x40a83b73u, 0x83bf4d6eu, 0x49542fa5u,
+                                           0xaf613f48u, 0x8ca2fb47u, 0x0d906f52u, 0x1cd69ad9u, 0xf753040cu, 0xd23766dbu, 0x62892ff6u, 0x714f33cdu};
+// seed of the 16-element group `grp`
+__device__ __forceinline__ uint32_t dropout_seed(const Dropout& d, uint64_t grp) {
+    uint32_t h = (uint32_t)grp * 0x9e3779b1u + (uint32_t)(grp >> 32) * 0x85ebca77u + (uint32_t)d.key;
+    h = mix32(h) ^ (uint32_t)(d.key >> 32);
+    h *= 0x2c1b3c6du;
+    return h ^ (h >> 15);
+}
+// LCG state `off` (0..15, runtime) steps after x: binary jump with compile-time constants (predicated multiply-adds, no table)
+__device__ __forceinline__ uint32_t dropout_jump(uint32_t x, uint32_t off) {
+    x = (off & 8u) ? x * kLcgA[8] + kLcgC[8] : x;
+    x = (off & 4u) ? x * kLcgA[4] + kLcgC[4] : x;
+    x = (off & 2u) ? x * kLcgA[2] + kLcgC[2] : x;
+    x = (off & 1u) ? x * kLcgA[1] + kLcgC[1] : x;
+    return x;
 }
 // returns the multiplicative factor (0 or scale) for element idx
 __device__ __forceinline__ float dropout_factor(const Dropout& d, uint64_t idx) {
     if (d.thresh == 0u) return 1.f;
-    const uint32_t h = dropout_hash(d, idx >> 1);
-    const uint32_t lane = (idx & 1) ? (h >> 16) : (h & 0xffffu);
-    return (lane < d.thresh) ? 0.f : d.scale;
+    const uint32_t x = dropout_jump(dropout_seed(d, idx >> 4), (uint32_t)idx & 15u);
+    return ((x >> 16) < d.thresh) ? 0.f : d.scale;
 }
-// factors of N consecutive elements starting at an EVEN index (N even): one hash per pair
+// factors of N consecutive elements starting at an index that is a multiple of N (N in {2, 4, 8, 16}): one seed, N multiply-adds
 template <int N>
 __device__ __forceinline__ void dropout_factors(const Dropout& d, uint64_t idx, float (&m)[N]) {
-    static_assert(N % 2 == 0, "pairs");
+    static_assert(N == 2 || N == 4 || N == 8 || N == 16, "N divides the group of 16");
     if (d.thresh == 0u) {
 #pragma unroll
         for (int k = 0; k < N; ++k) m[k] = 1.f;
         return;
     }
+    const uint32_t x0 = dropout_jump(dropout_seed(d, idx >> 4), (uint32_t)idx & (15u & ~(uint32_t)(N - 1)));
 #pragma unroll
-    for (int k = 0; k < N; k += 2) {
-        const uint32_t h = dropout_hash(d, (idx + k) >> 1);
-        m[k] = ((h & 0xffffu) < d.thresh) ? 0.f : d.scale;
-        m[k + 1] = ((h >> 16) < d.thresh) ? 0.f : d.scale;
+    for (int k = 0; k < N; ++k) {
+        const uint32_t x = x0 * kLcgA[k] + kLcgC[k];
+        m[k] = ((x >> 16) < d.thresh) ? 0.f : d.scale;
     }
 }
 

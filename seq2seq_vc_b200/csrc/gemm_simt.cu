@@ -109,7 +109,10 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams p) {
             if (g.relu) v = fmaxf(v, 0.f);
             v *= dropout_factor(drop, (uint64_t)((batch_lin + m) * (long)g.N + n));
             TC* dst = C + (long)m * g.c_rs + n;
-            if (R) v += to_f<TC>(R[(long)m * g.c_rs + n]);
+            if (R) {
+                const float r = to_f<TC>(R[(long)m * g.c_rs + n]);
+                v = g.r_mode ? (r > 0.f ? v * g.r_scale : 0.f) : v + r;
+            }
             if (g.accumulate) v += to_f<TC>(*dst);
             if (!row_ok) v = 0.f;
             *dst = from_f<TC>(v);

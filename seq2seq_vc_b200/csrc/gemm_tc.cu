@@ -58,7 +58,12 @@ static_assert(SMEM_BYTES <= 227 * 1024, "shared-memory budget of one CTA");
 // epilogue specialisations (compile time, to keep every instantiation's code small)
 constexpr int EPI_BF16_PLAIN = 0;   // bf16 C = alpha * acc + bias, optional relu
 constexpr int EPI_BF16_FULL = 1;    // + dropout, residual, accumulate, row mask
-constexpr int EPI_F32 = 2;          // fp32 C: red.add (accumulate in place / split-K) or plain store of alpha * acc
+constexpr int EPI_F32 = 2;          // fp32 C: red.add (accumulate in place / split-K) or plain store of alpha * acc (weight gradients)
+constexpr int EPI_BF16_GATE = 3;    // bf16 C = (alpha * acc + bias) * r_scale where R > 0, else 0: ReLU' of the layer below in the dX GEMM
+constexpr int EPI_F32_FULL = 4;     // fp32 C with the whole epilogue (bias, relu, dropout, residual / gate, accumulate, row mask):
+                                    // the float32 activations of the fp32-accurate mode (gemm_split.cu)
+// every kind is its own kernel: code that a launch never executes still costs instruction-cache footprint (folding the gate and
+// the fp32 epilogue into EPI_BF16_FULL / EPI_F32 made every GEMM of the bf16 step 12 % slower, measured)
 
 // n / d for n < 2^31 without the ~100-cycle integer-division sequence (the tile decode and the per-k-block tap split sit on
 // the single-thread critical paths of the TMA and MMA warps): q = umulhi(n, mul) >> shr, magic numbers from the host
@@ -89,6 +94,8 @@ struct Params {
     FastDiv d_splits, d_nt, d_mt, d_batch2, d_kbtap;
     void* C; int c_f32; long c_rs, c_bs1, c_bs2;
     const void* R;
+    int r_gate;              // 0: x + R (residual); 1: R > 0 ? x * r_scale : 0 (ReLU' gate)
+    float r_scale;
     const float* bias;
     float alpha;
     int relu, accumulate, atomic_out;
@@ -148,7 +155,10 @@ __device__ __noinline__ void epilogue_scalar(const Params& p, const float* v, TC
             if (row_ok) atomicAdd(reinterpret_cast<float*>(dst) + j, x);
             continue;
         }
-        if (rsrc) x += to_f<TC>(rsrc[j]);
+        if (rsrc) {
+            const float r = to_f<TC>(rsrc[j]);
+            x = p.r_gate ? (r > 0.f ? x * p.r_scale : 0.f) : x + r;
+        }
         if (p.accumulate) x += to_f<TC>(dst[j]);
         dst[j] = from_f<TC>(row_ok ? x : 0.f);
     }
@@ -158,6 +168,20 @@ __device__ __forceinline__ void add_bf16x8(float* v, const uint4& r) {
     const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&r);
 #pragma unroll
     for (int e = 0; e < 4; ++e) { v[2 * e] += __low2float(r2[e]); v[2 * e + 1] += __high2float(r2[e]); }
+}
+// residual add or ReLU' gate with 8 bf16 values of R
+__device__ __forceinline__ void combine_bf16x8(float* v, const uint4& r, int gate, float gscale) {
+    const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&r);
+    if (gate) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            v[2 * e] = __low2float(r2[e]) > 0.f ? v[2 * e] * gscale : 0.f;
+            v[2 * e + 1] = __high2float(r2[e]) > 0.f ? v[2 * e + 1] * gscale : 0.f;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { v[2 * e] += __low2float(r2[e]); v[2 * e + 1] += __high2float(r2[e]); }
+    }
 }
 __device__ __forceinline__ uint4 pack_bf16x8(const float* v) {
     uint4 w;
@@ -175,7 +199,9 @@ __device__ __forceinline__ uint4 pack_bf16x8(const float* v) {
 // ---------------------------------------------------------------------------------------------
 template <int EPI, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ Params p) {
-    using TC = typename std::conditional<EPI == EPI_F32, float, bf16>::type;
+    constexpr bool F32OUT = (EPI == EPI_F32 || EPI == EPI_F32_FULL);
+    constexpr bool FULLISH = (EPI == EPI_BF16_FULL || EPI == EPI_F32_FULL);      // dropout / residual / accumulate / row mask
+    using TC = typename std::conditional<F32OUT, float, bf16>::type;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                    // SWIZZLE_128B tiles need 1024 B alignment
@@ -327,7 +353,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     } else if (warp >= 2) {
         // ================= epilogue: 8 warps; warp -> TMEM lane quarter x 64-column chunks {ch, ch + 2} =================
         Dropout drop = p.drop;
-        if (EPI == EPI_BF16_FULL) dropout_resolve(drop);
+        if (FULLISH) dropout_resolve(drop);
         const int quarter = warp & 3;             // TMEM lanes this warp may access: 32 * (warp_id % 4) ...
         const int ch = (warp - 2) >> 2;           // owns 64-column chunks ch and ch + 2 of the tile
         // bf16 outputs leave through a per-warp staging buffer: each thread owns an output ROW (TMEM lane), so direct
@@ -344,11 +370,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             const int m = it.m0 + (int)rank * BM + quarter * 32 + lane;       // the output row this thread owns
             const bool row_in = m < p.M;
             TC* Crow = reinterpret_cast<TC*>(p.C) + it.b1 * p.c_bs1 + it.b2 * p.c_bs2 + (long)m * p.c_rs;
-            const TC* Rrow = (EPI == EPI_BF16_PLAIN || !p.R) ? nullptr
+            const TC* Rrow = (EPI == EPI_BF16_PLAIN || EPI == EPI_F32 || !p.R) ? nullptr
                                  : reinterpret_cast<const TC*>(p.R) + it.b1 * p.c_bs1 + it.b2 * p.c_bs2 + (long)m * p.c_rs;
             const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * MAX_BN);
             bool row_ok = true;
-            if (EPI != EPI_BF16_PLAIN && p.mask_period > 0) {
+            if (FULLISH && p.mask_period > 0) {
                 const int ph = (m + p.mask_offset) % p.mask_period;
                 row_ok = (ph >= p.mask_lo) && (ph < p.mask_hi);
             }
@@ -363,7 +389,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                 if (n0b + lane + 32 < p.N) b11 = p.bias[n0b + lane + 32];
             }
             uint4 rr[8];
-            const bool res_vec = (EPI == EPI_BF16_FULL) && Rrow && p.vec_ok && row_in;
+            const bool res_vec = (EPI == EPI_BF16_FULL || EPI == EPI_BF16_GATE) && Rrow && p.vec_ok && row_in;
             auto load_res = [&](int u) {
                 const int c0 = (ch + 2 * u) * 64;
 #pragma unroll
@@ -373,7 +399,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                         rr[g8] = *reinterpret_cast<const uint4*>(Rrow + it.n0 + c0 + g8 * 8);
                 }
             };
-            if (EPI == EPI_BF16_FULL) load_res(0);
+            // residual rows are prefetched per thread-owned row; a ReLU' gate is applied later, on the coalesced store side
+            const bool pre_res = (EPI == EPI_BF16_FULL);
+            if (pre_res) load_res(0);
             mbar_wait(tfull_bar(as), aphase);
             tcgen05_fence_after();
             if (threadIdx.x == 64 && n_items < 4) stamp(p, 16 + 8 * (int)n_items + 2);
@@ -398,13 +426,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                 }
                 if (ncols <= 0) continue;          // warp-uniform
                 // warp-uniform: the whole 64-column chunk is inside N and C rows are 16-byte aligned
-                const bool stage_chunk = (EPI != EPI_F32) && p.vec_ok && !p.accumulate && ncols == 64 && it.n0 + c0 + 64 <= p.N &&
-                                         !(EPI == EPI_BF16_FULL && drop.thresh != 0u && (p.N & 1));   // pair-wise dropout hash: even row starts
-                if (EPI != EPI_F32 && stage_chunk) {
+                const bool stage_chunk = !F32OUT && p.vec_ok && !p.accumulate && ncols == 64 && it.n0 + c0 + 64 <= p.N &&
+                                         !(EPI == EPI_BF16_FULL && drop.thresh != 0u && (p.N & 15));   // group-wise dropout mask: 16-aligned row starts
+                if (!F32OUT && stage_chunk) {
                     // ---- hot path: straight-line code, no per-group bounds / alignment decisions ----
                     const uint32_t rowaddr = stg + (uint32_t)lane * 128u;
                     const bool has_bias = p.bias != nullptr, relu = p.relu != 0;
                     const bool has_res = (EPI == EPI_BF16_FULL) && Rrow != nullptr;
+                    const bool has_gate = (EPI == EPI_BF16_GATE) && Rrow != nullptr;
                     const bool has_drop = (EPI == EPI_BF16_FULL) && drop.thresh != 0u;
                     const uint64_t didx0 = (uint64_t)(((long)(it.b1 * p.batch2 + it.b2) * p.M + m) * (long)p.N + it.n0 + c0);
 #pragma unroll
@@ -425,15 +454,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                         }
                         if (EPI == EPI_BF16_FULL) {
                             if (has_drop) {
-                                const uint64_t didx = didx0 + (uint64_t)(q * 16);
-                                // one hash per element pair (common.cuh: dropout_factors); didx is even here (N even: see
-                                // stage_chunk).  Fully unrolled: a rolled loop indexes v[] dynamically, which puts it in local memory
+                                // one seed per 16-element group (common.cuh: dropout_factors); didx0 is a multiple of 16 here (N % 16 == 0:
+                                // see stage_chunk), so the 16 columns of this q are exactly one group
+                                float mk[16];
+                                dropout_factors<16>(drop, didx0 + (uint64_t)(q * 16), mk);
 #pragma unroll
-                                for (int jj = 0; jj < 16; jj += 2) {
-                                    const uint32_t hsh = dropout_hash(drop, (didx + jj) >> 1);
-                                    v[jj] *= ((hsh & 0xffffu) < drop.thresh) ? 0.f : drop.scale;
-                                    v[jj + 1] *= ((hsh >> 16) < drop.thresh) ? 0.f : drop.scale;
-                                }
+                                for (int jj = 0; jj < 16; ++jj) v[jj] *= mk[jj];
                             }
                             if (has_res) { add_bf16x8(v, rr[2 * q]); add_bf16x8(v + 8, rr[2 * q + 1]); }
                             if (!row_ok) {
@@ -441,15 +467,44 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                                 for (int jj = 0; jj < 16; ++jj) v[jj] = 0.f;
                             }
                         }
+                        if (EPI == EPI_BF16_GATE) {
+#pragma unroll
+                            for (int jj = 0; jj < 16; ++jj) v[jj] *= p.r_scale;
+                        }
                         st_shared_v4(rowaddr + (uint32_t)(((2 * q) ^ (lane & 7)) << 4), pack_bf16x8(v));
                         st_shared_v4(rowaddr + (uint32_t)(((2 * q + 1) ^ (lane & 7)) << 4), pack_bf16x8(v + 8));
                     }
-                    if (EPI == EPI_BF16_FULL && u == 0) load_res(1);
+                    if (pre_res && u == 0) load_res(1);
                     if (u == 0 && threadIdx.x == 64 && n_items < 4) stamp(p, 16 + 8 * (int)n_items + 7);
                     __syncwarp();
                     const int r_sub = lane >> 3, c16 = lane & 7;
                     const int row0 = it.m0 + (int)rank * BM + quarter * 32;
-                    TC* Cblk = reinterpret_cast<TC*>(p.C) + it.b1 * p.c_bs1 + it.b2 * p.c_bs2 + it.n0 + c0 + c16 * 8;
+                    const long cofs = it.b1 * p.c_bs1 + it.b2 * p.c_bs2 + it.n0 + c0 + c16 * 8;
+                    TC* Cblk = reinterpret_cast<TC*>(p.C) + cofs;
+                    if (EPI == EPI_BF16_GATE && has_gate) {
+                        // ReLU' gate: the gate operand is read with the store's own coalesced pattern (4 rows x 128 B per instruction)
+                        const TC* Gblk = reinterpret_cast<const TC*>(p.R) + cofs;
+                        uint4 gq[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int r = i * 4 + r_sub;
+                            gq[i] = make_uint4(0u, 0u, 0u, 0u);
+                            if (row0 + r < p.M) gq[i] = *reinterpret_cast<const uint4*>(Gblk + (long)(row0 + r) * p.c_rs);
+                        }
+                        const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int r = i * 4 + r_sub;
+                            uint4 w = ld_shared_v4(stg + (uint32_t)r * 128u + (uint32_t)((c16 ^ (r & 7)) << 4));
+                            __nv_bfloat162* w2 = reinterpret_cast<__nv_bfloat162*>(&w);
+                            const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&gq[i]);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) w2[e] = __hmul2(w2[e], __hgt2(g2[e], zero2));
+                            if (row0 + r < p.M) *reinterpret_cast<uint4*>(Cblk + (long)(row0 + r) * p.c_rs) = w;
+                        }
+                        __syncwarp();
+                        continue;
+                    }
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int r = i * 4 + r_sub;
@@ -460,6 +515,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                     continue;
                 }
                 // ---- generic path: column / row tails, unaligned C, accumulate-in-place, fp32 outputs ----
+                if (EPI == EPI_BF16_GATE) load_res(u);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     if (q * 16 >= ncols) continue; // warp-uniform
@@ -483,15 +539,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                         }
                     }
                     const int n_base = it.n0 + c0 + q * 16;
-                    if (EPI == EPI_BF16_FULL && drop.thresh != 0u) {
+                    if (FULLISH && drop.thresh != 0u) {
                         const uint64_t didx = (uint64_t)(((long)(it.b1 * p.batch2 + it.b2) * p.M + m) * (long)p.N + n_base);
-                        if ((didx & 1ull) == 0ull) {                 // one hash per element pair (common.cuh: dropout_factors)
-#pragma unroll 2
-                            for (int jj = 0; jj < 16; jj += 2) {
-                                const uint32_t hsh = dropout_hash(drop, (didx + jj) >> 1);
-                                v[jj] *= ((hsh & 0xffffu) < drop.thresh) ? 0.f : drop.scale;
-                                v[jj + 1] *= ((hsh >> 16) < drop.thresh) ? 0.f : drop.scale;
-                            }
+                        if ((didx & 15ull) == 0ull) {                // one seed per aligned group of 16 (common.cuh: dropout_factors)
+                            float mk[16];
+                            dropout_factors<16>(drop, didx, mk);
+#pragma unroll
+                            for (int jj = 0; jj < 16; ++jj) v[jj] *= mk[jj];
                         } else {
 #pragma unroll 2
                             for (int jj = 0; jj < 16; ++jj) v[jj] *= dropout_factor(drop, didx + jj);
@@ -503,25 +557,48 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                     if (EPI == EPI_F32) {
                         float* d32 = reinterpret_cast<float*>(dst);
                         if (fast && p.atomic_out) {
-                            if (row_ok) {
 #pragma unroll
-                                for (int e = 0; e < 4; ++e) red_add_v4(d32 + 4 * e, v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
-                            }
-                        } else if (fast && !p.R && !p.accumulate) {
+                            for (int e = 0; e < 4; ++e) red_add_v4(d32 + 4 * e, v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+                        } else if (fast && !p.accumulate) {
 #pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                *reinterpret_cast<float4*>(d32 + 4 * e) = row_ok ? make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3])
-                                                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+                            for (int e = 0; e < 4; ++e) *reinterpret_cast<float4*>(d32 + 4 * e) = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
                         } else {
-                            {   // the helper takes an address: hand it a COPY, or v[] itself is forced into local memory and every
-                            // tile of the fast path pays 16 local stores per 16 columns (seen as STL in the ncu source view)
+                            float vt[16];      // a COPY for the out-of-line helper: passing v[] itself would force it into local memory
+#pragma unroll
+                            for (int jj = 0; jj < 16; ++jj) vt[jj] = v[jj];
+                            epilogue_scalar<TC>(p, vt, dst, nullptr, min(16, p.N - n_base), true);
+                        }
+                    } else if (EPI == EPI_F32_FULL) {
+                        float* d32 = reinterpret_cast<float*>(dst);
+                        if (fast) {
+                            // float32 activations (the fp32-accurate mode): residual / gate / accumulate with 16-byte accesses
+                            const float* r32 = Rrow ? reinterpret_cast<const float*>(Rrow) + n_base : nullptr;
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                float4 x = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+                                if (r32) {
+                                    const float4 r = *reinterpret_cast<const float4*>(r32 + 4 * e);
+                                    if (p.r_gate) {
+                                        x.x = r.x > 0.f ? x.x * p.r_scale : 0.f; x.y = r.y > 0.f ? x.y * p.r_scale : 0.f;
+                                        x.z = r.z > 0.f ? x.z * p.r_scale : 0.f; x.w = r.w > 0.f ? x.w * p.r_scale : 0.f;
+                                    } else {
+                                        x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
+                                    }
+                                }
+                                if (p.accumulate) {
+                                    const float4 c = *reinterpret_cast<const float4*>(d32 + 4 * e);
+                                    x.x += c.x; x.y += c.y; x.z += c.z; x.w += c.w;
+                                }
+                                *reinterpret_cast<float4*>(d32 + 4 * e) = row_ok ? x : make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
+                        } else {
                             float vt[16];
 #pragma unroll
                             for (int jj = 0; jj < 16; ++jj) vt[jj] = v[jj];
                             epilogue_scalar<TC>(p, vt, dst, Rrow ? Rrow + n_base : nullptr, min(16, p.N - n_base), row_ok);
                         }
-                        }
                     } else if (fast) {
+                        if (EPI == EPI_BF16_GATE && Rrow) { combine_bf16x8(v, rr[2 * q], 1, p.r_scale); combine_bf16x8(v + 8, rr[2 * q + 1], 1, p.r_scale); }
                         if (EPI == EPI_BF16_FULL) {
                             if (Rrow) { add_bf16x8(v, rr[2 * q]); add_bf16x8(v + 8, rr[2 * q + 1]); }
                             if (p.accumulate) {          // never staged (stage_chunk excludes it)
@@ -545,7 +622,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                         }
                     }
                 }
-                if (EPI == EPI_BF16_FULL && u == 0) load_res(1);
+                if (pre_res && u == 0) load_res(1);
             }
             if (threadIdx.x == 64 && n_items < 4) stamp(p, 16 + 8 * (int)n_items + 4);
         }
@@ -657,7 +734,8 @@ int gemm_tc(const s2s_gemm_t& g, cudaStream_t st) {
     p.kb_per_tap = (int)ceil_div_l(g.K, BK);
     p.kb_total = p.kb_per_tap * g.taps;
     p.C = g.C; p.c_f32 = (g.c_dtype == S2S_F32); p.c_rs = g.c_rs; p.c_bs1 = g.c_bs1; p.c_bs2 = g.c_bs2;
-    p.R = g.R; p.bias = g.bias; p.alpha = g.alpha; p.relu = g.relu; p.accumulate = g.accumulate;
+    p.R = g.R; p.r_gate = g.R ? g.r_mode : 0; p.r_scale = g.r_scale;
+    p.bias = g.bias; p.alpha = g.alpha; p.relu = g.relu; p.accumulate = g.accumulate;
     p.drop = make_dropout(&g.drop);
     p.trace = g_trace;
     p.mask_period = g.mask_period; p.mask_offset = g.mask_offset; p.mask_lo = g.mask_lo; p.mask_hi = g.mask_hi;
@@ -683,12 +761,14 @@ int gemm_tc(const s2s_gemm_t& g, cudaStream_t st) {
     p.kb_per_split = (p.kb_total + p.splits - 1) / p.splits;
     p.d_splits.set((uint32_t)p.splits); p.d_nt.set((uint32_t)p.nt); p.d_mt.set((uint32_t)p.mt);
     p.d_batch2.set((uint32_t)p.batch2); p.d_kbtap.set((uint32_t)p.kb_per_tap);
-    static const void* const kernels[2][3] = {
-        {(const void*)gemm_tc_kernel<EPI_BF16_PLAIN, 1>, (const void*)gemm_tc_kernel<EPI_BF16_FULL, 1>, (const void*)gemm_tc_kernel<EPI_F32, 1>},
-        {(const void*)gemm_tc_kernel<EPI_BF16_PLAIN, 2>, (const void*)gemm_tc_kernel<EPI_BF16_FULL, 2>, (const void*)gemm_tc_kernel<EPI_F32, 2>}};
+    static const void* const kernels[2][5] = {
+        {(const void*)gemm_tc_kernel<EPI_BF16_PLAIN, 1>, (const void*)gemm_tc_kernel<EPI_BF16_FULL, 1>, (const void*)gemm_tc_kernel<EPI_F32, 1>,
+         (const void*)gemm_tc_kernel<EPI_BF16_GATE, 1>, (const void*)gemm_tc_kernel<EPI_F32_FULL, 1>},
+        {(const void*)gemm_tc_kernel<EPI_BF16_PLAIN, 2>, (const void*)gemm_tc_kernel<EPI_BF16_FULL, 2>, (const void*)gemm_tc_kernel<EPI_F32, 2>,
+         (const void*)gemm_tc_kernel<EPI_BF16_GATE, 2>, (const void*)gemm_tc_kernel<EPI_F32_FULL, 2>}};
     std::call_once(g_attr_once, [] {
         for (int c = 0; c < 2; ++c)
-            for (int e = 0; e < 3; ++e)
+            for (int e = 0; e < 5; ++e)
                 if (g_attr_err == cudaSuccess)
                     g_attr_err = cudaFuncSetAttribute(kernels[c][e], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     });
@@ -698,7 +778,11 @@ int gemm_tc(const s2s_gemm_t& g, cudaStream_t st) {
     const long workers = num_sms() / p.cg;
     const unsigned grid = (unsigned)(items < workers ? items : workers) * (unsigned)p.cg;
     const bool plain_bf16 = !g.R && !g.accumulate && p.drop.thresh == 0u && g.mask_period == 0;
-    const int epi = p.c_f32 ? EPI_F32 : (plain_bf16 ? EPI_BF16_PLAIN : EPI_BF16_FULL);
+    const bool gate_only = g.R && p.r_gate && !g.accumulate && p.drop.thresh == 0u && g.mask_period == 0 && !g.relu;
+    if (!p.c_f32 && g.R && p.r_gate && !gate_only)
+        return set_error(S2S_ERR_UNSUPPORTED, "gemm_tc: a ReLU gate cannot be combined with dropout / accumulate / row mask / relu on bf16 outputs");
+    const bool plain_f32 = !g.bias && !g.R && !g.relu && p.drop.thresh == 0u && g.mask_period == 0;      // weight gradients
+    const int epi = p.c_f32 ? (plain_f32 ? EPI_F32 : EPI_F32_FULL) : (plain_bf16 ? EPI_BF16_PLAIN : (gate_only ? EPI_BF16_GATE : EPI_BF16_FULL));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);

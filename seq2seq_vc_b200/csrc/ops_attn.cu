@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256) softmax_fwd_reg_kernel(const T* __restric
     sum = warp_sum(sum);
     const float inv = (limit > 0) ? 1.f / sum : 0.f;
     const uint64_t base = (uint64_t)row * (uint64_t)T2;
-    const bool even = ((T2 & 1) == 0);
+    const bool even = ((T2 & 7) == 0);      // dropout_factors<8> needs an 8-aligned element index
     T* p = P + row * ld;
     T* pd = Pd ? Pd + row * ld : nullptr;
 #pragma unroll
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(256) softmax_bwd_reg_kernel(const T* __restric
     const T* p = P + row * ld;
     T* g = dP + row * ld;
     const uint64_t base = (uint64_t)row * (uint64_t)T2;
-    const bool even = ((T2 & 1) == 0);
+    const bool even = ((T2 & 7) == 0);      // dropout_factors<8> needs an 8-aligned element index
     float a[NV][8], d[NV][8];
     float dot = 0.f;
 #pragma unroll

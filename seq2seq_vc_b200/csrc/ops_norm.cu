@@ -190,10 +190,11 @@ template <typename T, int NV>
 __global__ void __launch_bounds__(256) ln_bwd_reg_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                                                          const float* __restrict__ gamma, const float* __restrict__ mean,
                                                          const float* __restrict__ rstd, const T* __restrict__ dres,
-                                                         T* __restrict__ dx, long rows, int d) {
+                                                         T* __restrict__ dx, long rows, int d, T* __restrict__ dxd, Dropout drop) {
     const int lane = threadIdx.x & 31;
     const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= rows) return;
+    if (dxd) dropout_resolve(drop);
     const T* xr = x + row * d;
     const T* gr = dy + row * d;
     const float mu = mean[row], rs = rstd[row];
@@ -241,6 +242,13 @@ __global__ void __launch_bounds__(256) ln_bwd_reg_kernel(const T* __restrict__ d
                 for (int k = 0; k < 8; ++k) o[k] += e[k];
             }
             Vec8<T>::store(dr + c, o);
+            if (dxd) {                      // second output: the same gradient behind the dropout of the branch that fed the sum
+                float mk[8];
+                dropout_factors<8>(drop, (uint64_t)(row * d + c), mk);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[k] *= mk[k];
+                Vec8<T>::store(dxd + row * d + c, o);
+            }
         }
     }
 }
@@ -707,17 +715,18 @@ extern "C" int s2s_layernorm_fwd(const void* x, const float* gamma, const float*
     return S2S_OK;
 }
 
-extern "C" int s2s_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean,
+static int layernorm_bwd_impl(const void* dy, const void* x, const float* gamma, const float* mean,
                                  const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta,
-                                 int64_t rows, int d, int dtype, void* stream) {
+                                 int64_t rows, int d, int dtype, void* stream, void* dx_drop, const s2s_dropout_t* dropd) {
     S2S_REQUIRE(dy && x && gamma && mean && rstd && d > 0, "layernorm_bwd: null pointer or bad d");
     if (rows <= 0) return S2S_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    if (d % 8 == 0 && d <= 2048 && aligned16(x, dy, dx, dres) && aligned16(gamma)) {
+    if (d % 8 == 0 && d <= 2048 && aligned16(x, dy, dx, dres) && aligned16(gamma, dx_drop)) {
         const int nv = (d + 255) / 256;
         const unsigned gp = (unsigned)ceil_div_l(rows, 8);
 #define S2S_LN_BWD(NVV) ln_bwd_reg_kernel<T, NVV><<<gp, 256, 0, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (const T*)dres, \
-                                                                     (T*)dx, rows, d)
+                                                                     (T*)dx, rows, d, (T*)dx_drop, dd)
+        const Dropout dd = make_dropout(dropd);
         if (dx) {
             S2S_DISPATCH_DTYPE(dtype, T, {
                 if (nv <= 1) S2S_LN_BWD(1); else if (nv <= 2) S2S_LN_BWD(2); else if (nv <= 4) S2S_LN_BWD(4);
@@ -737,10 +746,15 @@ extern "C" int s2s_layernorm_bwd(const void* dy, const void* x, const float* gam
         return S2S_OK;
     }
     bool ok = vec4_ok(d, d, x, dy, dx, dres);
+    if (dx_drop && !dx) return set_error(S2S_ERR_INVALID, "layernorm_bwd_drop: dx_drop needs dx");
     if (dx) {
         S2S_DISPATCH_DTYPE(dtype, T, S2S_VEC_DISPATCH(ok, VEC, (ln_bwd_dx_kernel<T, VEC><<<(unsigned)ceil_div_l(rows, 4), 128, 0, st>>>(
             (const T*)dy, (const T*)x, gamma, mean, rstd, (const T*)dres, (T*)dx, rows, d))));
         S2S_LAUNCH_OK();
+        if (dx_drop) {
+            int rc = s2s_dropout_bwd(dx, dx_drop, rows, d, dropd, dtype, stream);
+            if (rc != S2S_OK) return rc;
+        }
     }
     if (dgamma && dbeta) {
         int rc = S2S_OK;
@@ -751,6 +765,18 @@ extern "C" int s2s_layernorm_bwd(const void* dy, const void* x, const float* gam
         return rc;
     }
     return S2S_OK;
+}
+
+extern "C" int s2s_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                                 const void* dres, void* dx, float* dgamma, float* dbeta, int64_t rows, int d, int dtype, void* stream) {
+    return layernorm_bwd_impl(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, rows, d, dtype, stream, nullptr, nullptr);
+}
+
+extern "C" int s2s_layernorm_bwd_drop(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                                      const void* dres, void* dx, void* dx_drop, const s2s_dropout_t* drop, float* dgamma, float* dbeta,
+                                      int64_t rows, int d, int dtype, void* stream) {
+    S2S_REQUIRE(dx && dx_drop && drop, "layernorm_bwd_drop: dx, dx_drop and drop are required");
+    return layernorm_bwd_impl(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, rows, d, dtype, stream, dx_drop, drop);
 }
 
 extern "C" int s2s_colsum(const void* x, int64_t rows, int cols, int64_t ld, float* out, int dtype, void* stream) {

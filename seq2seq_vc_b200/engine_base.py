@@ -7,6 +7,7 @@ PyTorch only owns device memory here; all arithmetic happens in libs2svc_b200.so
 from __future__ import annotations
 
 import math
+import os
 from collections import OrderedDict
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
@@ -41,7 +42,9 @@ class EngineBase:
         self.device = torch.device(device)
         self.bf16 = bool(bf16)
         self.adt = torch.bfloat16 if bf16 else _f32
-        self.mode = 1 if bf16 else 0
+        # s2s_gemm mode: 1 = bf16 tcgen05; float32 engines run the fp32-accurate tensor-core mode (2: bf16-split operands,
+        # fp32 TMEM accumulation) unless fp32_gemm = "simt" asks for the CUDA-core yard-stick (0)
+        self.mode = 1 if bf16 else (0 if getattr(self, "fp32_gemm", "tc") == "simt" else 2)
         self.store = ParamStore(groups, self.device, bf16_shadow=bf16)
         self.buffers: Dict[str, torch.Tensor] = {}
         for name, shape, dt in buffer_specs:
@@ -178,17 +181,22 @@ class EngineBase:
             return ops.skinny_linear_fwd(x2d, w, bias, out)
         return ops.gemm(x2d, w, out, bias=bias, relu=relu, drop=drop, residual=residual, mode=self.mode)
 
-    def _lin_bwd(self, dy2d, x2d, w, gw, gb, dx=None, dx_residual=None, dx_accumulate=False):
-        """dW += dy^T x ; db += colsum(dy) ; dx = dy W (+ residual | += )."""
+    def _lin_bwd(self, dy2d, x2d, w, gw, gb, dx=None, dx_residual=None, dx_accumulate=False, dx_gate=None, dx_gate_scale=1.0):
+        """dW += dy^T x ; db += colsum(dy) ; dx = dy W (+ residual | += ); with dx_gate (the relu output that produced x2d's
+        layer input) dx leaves as relu'(.) * scale of it: the ReLU / dropout backward rides in the GEMM epilogue."""
         mode = self.mode
-        if w.shape[0] <= 4 and dx_residual is None:
+        if w.shape[0] <= 4 and dx_residual is None and dx_gate is None:
             return ops.skinny_linear_bwd(dy2d, x2d, w, gw, gb, dx, dx_accumulate)
         if gw is not None:
             ops.gemm(dy2d.t(), x2d.t(), gw, accumulate=True, mode=mode)
         if gb is not None:
             ops.colsum(dy2d, gb)      # (a side-stream overlap with the two GEMMs was measured: no gain, the persistent GEMM owns the SMs)
         if dx is not None:
-            ops.gemm(dy2d, w.t(), dx, residual=dx_residual, accumulate=dx_accumulate, mode=mode)
+            if dx_gate is not None and not self.fuse_relu_gate:        # A/B switch: separate relu' pass
+                ops.gemm(dy2d, w.t(), dx, residual=dx_residual, accumulate=dx_accumulate, mode=mode)
+                ops.relu_bwd(dx, dx_gate, dx, dx_gate_scale)
+            else:
+                ops.gemm(dy2d, w.t(), dx, residual=dx_residual, accumulate=dx_accumulate, mode=mode, gate=dx_gate, gate_scale=dx_gate_scale)
         return dx
 
     def _ln_fwd(self, x, name, tag, eps: float = 1e-12):
@@ -199,10 +207,17 @@ class EngineBase:
         ops.layernorm_fwd(x, self.store.p(name + ".weight"), self.store.p(name + ".bias"), y, mean, rstd, eps)
         return y
 
-    def _ln_bwd(self, dy, x, name, tag, dx, dres=None):
+    def _ln_bwd(self, dy, x, name, tag, dx, dres=None, dx_drop=None, drop: Drop = NO_DROP):
+        """dx_drop: second output dropout'(dx) -- the gradient behind the dropout of the branch that fed the normalised sum."""
+        if dx_drop is not None and drop.p <= 0.0:
+            dx_drop = None
+        if dx_drop is not None and not self.fuse_ln_dropout:           # A/B switch: separate dropout' pass
+            self._ln_bwd(dy, x, name, tag, dx, dres=dres)
+            ops.dropout_bwd(dx, dx_drop, drop)
+            return dx
         ops.layernorm_bwd(dy, x, self.store.p(name + ".weight"), self.buf(tag + ".mean", (x.shape[0] * x.shape[1],), _f32),
                           self.buf(tag + ".rstd", (x.shape[0] * x.shape[1],), _f32), dx, self.store.g(name + ".weight"),
-                          self.store.g(name + ".bias"), dres=dres)
+                          self.store.g(name + ".bias"), dres=dres, dx_drop=dx_drop, drop=drop)
         return dx
 
     def _fused_attn(self, dk: int, T2: int) -> bool:
@@ -215,6 +230,9 @@ class EngineBase:
     #   "none" no map: the fused training steps, which consume none (maps named in `attn_emit_names` are still written,
     #          e.g. the layers a guided-attention loss reads)
     attn_emit = "src"
+    # A/B switches (tools/ab_step.py): fold relu' into the dX GEMM epilogue / dropout' into the LayerNorm backward
+    fuse_relu_gate = os.environ.get("S2S_FUSE_GATE", "1") != "0"
+    fuse_ln_dropout = os.environ.get("S2S_FUSE_LNDROP", "1") != "0"
     attn_emit_names: frozenset = frozenset()
     flash_attention = True
 
@@ -406,8 +424,7 @@ class EngineBase:
             gwp = self._scratch("post.gwp", (oc, k, ic), _f32)
             gwp.zero_()
             dzt = dz.view(B * Lp, oc)[halo:halo + M].t()
-            for t in range(k):      # one skinny (oc x ic x M) GEMM per tap; split-K inside the kernel
-                ops.gemm(dzt, xin.view(B * Lp, ic)[t:t + M].t(), gwp[:, t, :], accumulate=True, mode=self.mode)
+            self._taps_dw(dzt, xin.view(B * Lp, ic), gwp, M)
             ops.transpose_last2(gwp, st.g(pn + ".0.weight"), oc, k, ic, accumulate=True)
             # dxin = conv_transpose(dz): taps-GEMM with the flipped, transposed kernel
             dxin = self._scratch(f"post.dx{i % 2}", (B, Lp, ic))
@@ -423,6 +440,19 @@ class EngineBase:
         ops.add(d_after, d_before, dbefore_tot)
         ops.add(dbefore_tot, dpost_in, dbefore_tot)
         return dbefore_tot
+
+    def _taps_dw(self, dzt: torch.Tensor, xrows: torch.Tensor, gwp: torch.Tensor, M: int) -> None:
+        """Weight gradient of a Conv1d-as-taps-GEMM in ONE launch: gwp[oc][t][ic] += sum_m dz[m + halo][oc] * x[m + t][ic].
+        The k shifted copies of the input are one matrix of overlapping rows: element (m, t * ic + c) of it sits at
+        x_flat[m * ic + (t * ic + c)], i.e. an (M, k * ic) view with row stride ic -- legal for a TMA tensor map, so all taps
+        form the N dimension of a single (oc x k*ic x M) GEMM instead of k skinny ones (zeroed gwp, split-K inside the kernel)."""
+        oc, k, ic = gwp.shape
+        if self.device.type != "cuda" or (self.mode != 0 and ic % 8 != 0):
+            for t in range(k):          # CPU contracts of the host-logic tests; unaligned rows (TMA needs 16-byte strides)
+                ops.gemm(dzt, xrows[t:t + M].t(), gwp[:, t, :], accumulate=True, mode=self.mode)
+            return
+        win = xrows.as_strided((M, k * ic), (ic, 1))
+        ops.gemm(dzt, win.t(), gwp.view(oc, k * ic), accumulate=True, mode=self.mode)
 
     # ------------------------------------------------------------------ Conv1d(k) over time as a taps-GEMM (haloed rows)
     def _conv1d_fwd(self, xpad: torch.Tensor, name: str, L: int, relu: bool, tag: str) -> torch.Tensor:
@@ -458,8 +488,7 @@ class EngineBase:
         gwp = self._scratch("conv1d.gwp", (oc, k, ic), _f32)
         gwp.zero_()
         dzt = dz.view(B * Lp, oc)[halo:halo + M].t()
-        for t in range(k):
-            ops.gemm(dzt, xpad.view(B * Lp, ic)[t:t + M].t(), gwp[:, t, :], accumulate=True, mode=self.mode)
+        self._taps_dw(dzt, xpad.view(B * Lp, ic), gwp, M)
         ops.transpose_last2(gwp, st.g(name + ".weight"), oc, k, ic, accumulate=True)
         ops.colsum(dz.view(B * Lp, oc), st.g(name + ".bias"))
         if dx is not None:
@@ -508,8 +537,7 @@ class EngineBase:
         ops.gemm(delin.view(B * T2, d).t(), y2.view(B * T2, F2 * d).t(), gwoutp, mode=mode)
         ops.transpose_last2(gwoutp, st.g(out_name + ".weight"), d, F2, d, accumulate=True)
         ops.colsum(delin.view(B * T2, d), st.g(out_name + ".bias"))
-        ops.gemm(delin.view(B * T2, d), woutp.view(d, F2 * d).t(), dy2.view(B * T2, F2 * d), mode=mode)
-        ops.relu_bwd(dy2, y2, dy2, 1.0)
+        ops.gemm(delin.view(B * T2, d), woutp.view(d, F2 * d).t(), dy2.view(B * T2, F2 * d), mode=mode, gate=y2.view(B * T2, F2 * d))
         w2p = self.buf(f"w.{tag}.conv2p", (d, 9, d))
         col = self._scratch("col", (B * T2 * F2, 9 * d))
         y1 = self.buf(tag + ".y1", (B, T1, F1, d))

@@ -41,14 +41,36 @@ def _lead_strides(t: torch.Tensor, core: int) -> Tuple[int, int]:
     return t.stride(0), t.stride(1)
 
 
+# mode 2: 3 = two-way bf16 split (a0 b0 + a1 b0 + a0 b1, ~2^-16 per product), 6 = three-way split.  Measured on C1
+# (tools/parity_modes.py, profiles/r02_parity_modes_c1.json): both give mel L1 1.2e-5 / 1.5e-5 against the oracle (CUDA-core
+# fp32: 1.4e-6, bf16: 1.2e-2) -- the tensor core's fp32 accumulation, not the split, sets the floor -- so the cheaper one is used.
+SPLIT_TERMS = 3
+_split_ws: dict = {}     # per-device workspace of the fp32-accurate mode; outgrown buffers stay alive for captured graphs
+_split_ws_retired: list = []
+
+
+def _split_workspace(g: GemmDesc, device) -> torch.Tensor:
+    need = int(_L().s2s_gemm_workspace_bytes(ctypes.byref(g)))
+    ws = _split_ws.get(device)
+    if ws is None or ws.numel() < need:
+        if ws is not None:
+            _split_ws_retired.append(ws)
+        ws = torch.empty(max(need, 1 << 22), dtype=torch.uint8, device=device)
+        _split_ws[device] = ws
+    return ws
+
+
 def gemm(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, *, bias: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, alpha: float = 1.0, relu: bool = False,
          accumulate: bool = False, drop: Drop = NO_DROP, taps: int = 1,
-         row_mask: Optional[Tuple[int, int, int, int]] = None, mode: int = 0, M: Optional[int] = None) -> torch.Tensor:
+         row_mask: Optional[Tuple[int, int, int, int]] = None, mode: int = 0, M: Optional[int] = None,
+         gate: Optional[torch.Tensor] = None, gate_scale: float = 1.0) -> torch.Tensor:
     """c[..., m, n] = epilogue(alpha * sum_t sum_k a[..., m + t, k] * b[..., n, (t,) k]).
 
     a: (..., rows, K); b: (..., N, K) or (..., N, taps, K) when taps > 1; c: (..., M, N).
     Leading batch dims (0-2) come from c; a / b with fewer dims broadcast (stride 0).
+    gate (layout of c): c = gate > 0 ? c * gate_scale : 0 -- relu' (and the dropout scale) of the layer whose output `gate` is.
+    mode: 0 fp32 CUDA cores, 1 bf16 tcgen05, 2 float32 operands on tcgen05 through a bf16 split (SPLIT_TERMS partial products).
     """
     nb = c.dim() - 2
     assert 0 <= nb <= 2
@@ -79,13 +101,20 @@ def gemm(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, *, bias: Optional[to
     g.c_rs = c.stride(-2)
     g.batch1, g.batch2, g.c_bs1, g.c_bs2 = _batch_strides(c, nb)
     g.bias = ptr(bias)
+    if gate is not None:
+        assert residual is None, "one R operand: residual or gate"
+        residual, g.r_mode, g.r_scale = gate, 1, float(gate_scale)
     if residual is not None:
-        assert residual.dtype == c.dtype and residual.stride() == c.stride(), "residual must share C's layout"
+        assert residual.dtype == c.dtype and residual.stride() == c.stride(), "residual / gate must share C's layout"
     g.R = ptr(residual)
     g.alpha, g.relu, g.accumulate = float(alpha), int(relu), int(accumulate)
     g.drop = drop.c()
     if row_mask is not None:
         g.mask_period, g.mask_offset, g.mask_lo, g.mask_hi = row_mask
+    if mode == 2:
+        g.split_terms = SPLIT_TERMS
+        ws = _split_workspace(g, c.device)
+        g.ws, g.ws_bytes = ptr(ws), ws.numel()
     check(_L().s2s_gemm(ctypes.byref(g), mode, stream()), "s2s_gemm")
     return c
 
@@ -99,10 +128,16 @@ def layernorm_fwd(x, gamma, beta, y, mean, rstd, eps=1e-12):
     return y
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, dres=None):
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, dres=None, dx_drop=None, drop: Drop = NO_DROP):
+    """dx_drop (optional second output) = dropout'(dx) with the mask of `drop`."""
     d = x.shape[-1]
     rows = x.numel() // d
     assert dy.is_contiguous() and x.is_contiguous() and (dres is None or dres.is_contiguous())
+    if dx_drop is not None:
+        assert dx_drop.is_contiguous() and dx_drop.dtype == dx.dtype and dx_drop.numel() == dx.numel()
+        check(_L().s2s_layernorm_bwd_drop(ptr(dy), ptr(x), ptr(gamma), ptr(mean), ptr(rstd), ptr(dres), ptr(dx), ptr(dx_drop),
+                                          ctypes.byref(drop.c()), ptr(dgamma), ptr(dbeta), rows, d, dt(x), stream()), "layernorm_bwd_drop")
+        return dx
     check(_L().s2s_layernorm_bwd(ptr(dy), ptr(x), ptr(gamma), ptr(mean), ptr(rstd), ptr(dres), ptr(dx), ptr(dgamma), ptr(dbeta), rows, d,
                                  dt(x), stream()), "layernorm_bwd")
     return dx

@@ -126,7 +126,9 @@ def buffer_specs(hp: dict) -> List[Tuple[str, Tuple[int, ...], torch.dtype]]:
 class VTNEngine(EngineBase):
     """Owns parameters, activation buffers and the explicit forward/backward of one VTN step."""
 
-    def __init__(self, hp: dict, device="cuda:0", bf16: bool = False, seed: int = 0):
+    def __init__(self, hp: dict, device="cuda:0", bf16: bool = False, seed: int = 0, fp32_gemm: str = "tc"):
+        """fp32_gemm (float32 engines only): "tc" = fp32-accurate tcgen05 GEMM (bf16-split operands), "simt" = CUDA-core GEMM."""
+        self.fp32_gemm = fp32_gemm
         self.hp = default_hparams(**hp)
         hp = self.hp
         assert hp["adim"] % hp["aheads"] == 0
@@ -662,18 +664,17 @@ class VTNEngine(EngineBase):
             x2 = self.buf(p + ".ln2.y", (B, Lr, d))
             h = self.buf(p + ".ffh", (B * Lr, hp["dunits"]))
             # x3 = LN3(t3), t3 = drop(h W2) + x2
-            dt3 = self._ln_bwd(g, t3, p + ".norm3", p + ".ln3", gt)
-            df = self._drop_bwd(dt3.view(B * Lr, d), sites[p + ".ff2"], gd)
+            dt3 = self._ln_bwd(g, t3, p + ".norm3", p + ".ln3", gt, dx_drop=gd.view(B, Lr, d), drop=sites[p + ".ff2"])
+            df = gd if sites[p + ".ff2"].p > 0.0 else dt3.view(B * Lr, d)
             dh = self._scratch("g.ffh", (B * Lr, hp["dunits"]))
             self._lin_bwd(df, h, self.W(p + ".feed_forward.w_2.weight"), st.g(p + ".feed_forward.w_2.weight"),
-                          st.g(p + ".feed_forward.w_2.bias"), dx=dh)
-            ops.relu_bwd(dh, h, dh, sites[p + ".ff1"].scale)
+                          st.g(p + ".feed_forward.w_2.bias"), dx=dh, dx_gate=h, dx_gate_scale=sites[p + ".ff1"].scale)
             dx2 = g
             self._lin_bwd(dh, x2.view(B * Lr, d), self.W(p + ".feed_forward.w_1.weight"), st.g(p + ".feed_forward.w_1.weight"),
                           st.g(p + ".feed_forward.w_1.bias"), dx=dx2.view(B * Lr, d), dx_residual=dt3.view(B * Lr, d))
             # x2 = LN2(t2), t2 = drop(ctx2 Wo) + x1
-            dt2 = self._ln_bwd(dx2, t2, p + ".norm2", p + ".ln2", gt)
-            do = self._drop_bwd(dt2.view(B * Lr, d), sites[p + ".ca_out"], gd)
+            dt2 = self._ln_bwd(dx2, t2, p + ".norm2", p + ".ln2", gt, dx_drop=gd.view(B, Lr, d), drop=sites[p + ".ca_out"])
+            do = gd if sites[p + ".ca_out"].p > 0.0 else dt2.view(B * Lr, d)
             ctx2 = self.buf(p + ".ca.ctx", (B, Lr, d))
             dctx = self._scratch("g.ctx", (B, Lr, d))
             self._lin_bwd(do, ctx2.view(B * Lr, d), self.W(p + ".src_attn.linear_out.weight"), st.g(p + ".src_attn.linear_out.weight"),
@@ -691,8 +692,8 @@ class VTNEngine(EngineBase):
             self._lin_bwd(dq.view(B * Lr, d), x1.view(B * Lr, d), self.W(p + ".src_attn.linear_q.weight"), st.g(p + ".src_attn.linear_q.weight"),
                           st.g(p + ".src_attn.linear_q.bias"), dx=dx1.view(B * Lr, d), dx_residual=dt2.view(B * Lr, d))
             # x1 = LN1(t1), t1 = drop(ctx Wo) + xin
-            dt1 = self._ln_bwd(dx1, t1, p + ".norm1", p + ".ln1", gt)
-            do = self._drop_bwd(dt1.view(B * Lr, d), sites[p + ".sa_out"], gd)
+            dt1 = self._ln_bwd(dx1, t1, p + ".norm1", p + ".ln1", gt, dx_drop=gd.view(B, Lr, d), drop=sites[p + ".sa_out"])
+            do = gd if sites[p + ".sa_out"].p > 0.0 else dt1.view(B * Lr, d)
             ctx = self.buf(p + ".sa.ctx", (B, Lr, d))
             self._lin_bwd(do, ctx.view(B * Lr, d), self.W(p + ".self_attn.linear_out.weight"), st.g(p + ".self_attn.linear_out.weight"),
                           st.g(p + ".self_attn.linear_out.bias"), dx=dctx.view(B * Lr, d))
@@ -712,22 +713,26 @@ class VTNEngine(EngineBase):
         hin = self.buf(f"dec.prenet{npre - 1}", (B * Lr, u)) if npre > 0 else self.buf("dec.ys_in", (B, Lr, odim)).view(B * Lr, odim)
         pbufs = ("g.prenet_a", "g.prenet_b")
         dhp = self._scratch(pbufs[0], (B * Lr, u)) if npre > 0 else None
+        # relu' (+ the always-on prenet dropout scale, pre_postnets.py:60-66) of prenet layer i rides in the dX GEMM of the layer above
         self._lin_bwd(de.view(B * Lr, d), hin, self.W("decoder.embed.0.1.weight"), st.g("decoder.embed.0.1.weight"),
-                      st.g("decoder.embed.0.1.bias"), dx=dhp)
+                      st.g("decoder.embed.0.1.bias"), dx=dhp, dx_gate=hin if npre > 0 else None,
+                      dx_gate_scale=sites[f"prenet{npre - 1}"].scale if npre > 0 else 1.0)
         for i in reversed(range(npre)):
             nm = f"decoder.embed.0.0.prenet.{i}.0"
-            hout = self.buf(f"dec.prenet{i}", (B * Lr, u))
-            ops.relu_bwd(dhp, hout, dhp, sites[f"prenet{i}"].scale)
             hin = self.buf(f"dec.prenet{i - 1}", (B * Lr, u)) if i > 0 else self.buf("dec.ys_in", (B, Lr, odim)).view(B * Lr, odim)
             dnext = self._scratch(pbufs[(npre - i) % 2], (B * Lr, u)) if i > 0 else None
-            self._lin_bwd(dhp, hin, self.W(nm + ".weight"), st.g(nm + ".weight"), st.g(nm + ".bias"), dx=dnext)
+            self._lin_bwd(dhp, hin, self.W(nm + ".weight"), st.g(nm + ".weight"), st.g(nm + ".bias"), dx=dnext,
+                          dx_gate=hin if i > 0 else None, dx_gate_scale=sites[f"prenet{i - 1}"].scale if i > 0 else 1.0)
             dhp = dnext
 
         # ---- encoder (reverse)
         ge = self._scratch("g.enc_a", (B, T2, d))
         gte = self._scratch("g.enc_b", (B, T2, d))
         gde = self._scratch("g.enc_c", (B * T2, d))
-        self._ln_bwd(dmem, self.enc_last, "encoder.after_norm", "enc.after", ge)
+        gdf = self._scratch("g.enc_e", (B, T2, d))        # dropout'(g) for the next (lower) layer's ff2 branch
+        nle = hp["elayers"]
+        self._ln_bwd(dmem, self.enc_last, "encoder.after_norm", "enc.after", ge, dx_drop=gdf if nle > 0 else None,
+                     drop=sites[f"encoder.encoders.{nle - 1}.ff2"] if nle > 0 else NO_DROP)
         g = ge
         for l in reversed(range(hp["elayers"])):
             p = f"encoder.encoders.{l}"
@@ -736,17 +741,16 @@ class VTNEngine(EngineBase):
             n1 = self.buf(p + ".ln1.y", (B, T2, d))
             n2 = self.buf(p + ".ln2.y", (B, T2, d))
             h = self.buf(p + ".ffh", (B * T2, hp["eunits"]))
-            df = self._drop_bwd(g.view(B * T2, d), sites[p + ".ff2"], gde)
+            df = gdf.view(B * T2, d) if sites[p + ".ff2"].p > 0.0 else g.view(B * T2, d)
             dh = self._scratch("g.effh", (B * T2, hp["eunits"]))
             self._lin_bwd(df, h, self.W(p + ".feed_forward.w_2.weight"), st.g(p + ".feed_forward.w_2.weight"),
-                          st.g(p + ".feed_forward.w_2.bias"), dx=dh)
-            ops.relu_bwd(dh, h, dh, sites[p + ".ff1"].scale)
+                          st.g(p + ".feed_forward.w_2.bias"), dx=dh, dx_gate=h, dx_gate_scale=sites[p + ".ff1"].scale)
             dn2 = gte
             self._lin_bwd(dh, n2.view(B * T2, d), self.W(p + ".feed_forward.w_1.weight"), st.g(p + ".feed_forward.w_1.weight"),
                           st.g(p + ".feed_forward.w_1.bias"), dx=dn2.view(B * T2, d))
             gm = self._scratch("g.enc_d", (B, T2, d))
-            self._ln_bwd(dn2, xm, p + ".norm2", p + ".ln2", gm, dres=g)          # g_mid = g + LN2'(dn2)
-            do = self._drop_bwd(gm.view(B * T2, d), sites[p + ".sa_out"], gde)
+            self._ln_bwd(dn2, xm, p + ".norm2", p + ".ln2", gm, dres=g, dx_drop=gde.view(B, T2, d), drop=sites[p + ".sa_out"])   # g_mid = g + LN2'(dn2)
+            do = gde if sites[p + ".sa_out"].p > 0.0 else gm.view(B * T2, d)
             ctx = self.buf(p + ".sa.ctx", (B, T2, d))
             dctx = self._scratch("g.ectx", (B, T2, d))
             self._lin_bwd(do, ctx.view(B * T2, d), self.W(p + ".self_attn.linear_out.weight"), st.g(p + ".self_attn.linear_out.weight"),
@@ -759,7 +763,8 @@ class VTNEngine(EngineBase):
             self._lin_bwd(dqkv.view(B * T2, 3 * d), n1.view(B * T2, d), self.Wspan([p + ".self_attn.linear_q.weight"], (3 * d, d)),
                           st.span(st.G, [p + ".self_attn.linear_q.weight"], (3 * d, d)), st.span(st.G, [p + ".self_attn.linear_q.bias"], (3 * d,)),
                           dx=dn1.view(B * T2, d))
-            self._ln_bwd(dn1, xin, p + ".norm1", p + ".ln1", g, dres=gm)          # g_prev = g_mid + LN1'(dn1)
+            self._ln_bwd(dn1, xin, p + ".norm1", p + ".ln1", g, dres=gm, dx_drop=gdf if l > 0 else None,
+                         drop=sites[f"encoder.encoders.{l - 1}.ff2"] if l > 0 else NO_DROP)          # g_prev = g_mid + LN1'(dn1)
 
         # ---- encoder front end
         if hp["encoder_input"] == "embed":
@@ -776,8 +781,7 @@ class VTNEngine(EngineBase):
         ops.gemm(delin.view(B * T2, d).t(), y2.view(B * T2, F2 * d).t(), gwoutp, mode=mode)
         ops.transpose_last2(gwoutp, st.g("encoder.embed.out.0.weight"), d, F2, d, accumulate=True)
         ops.colsum(delin.view(B * T2, d), st.g("encoder.embed.out.0.bias"))
-        ops.gemm(delin.view(B * T2, d), woutp.view(d, F2 * d).t(), dy2.view(B * T2, F2 * d), mode=mode)
-        ops.relu_bwd(dy2, y2, dy2, 1.0)
+        ops.gemm(delin.view(B * T2, d), woutp.view(d, F2 * d).t(), dy2.view(B * T2, F2 * d), mode=mode, gate=y2.view(B * T2, F2 * d))
         w2p = self.buf("w.conv2p", (d, 9, d))
         col = self._scratch("col", (B * T2 * F2, 9 * d))
         y1 = self.buf("enc.y1", (B, T1, F1, d))

@@ -20,7 +20,7 @@ def _nodrop(drop):
 
 
 def gemm(a, b, c, *, bias=None, residual=None, alpha=1.0, relu=False, accumulate=False, drop=NO_DROP, taps=1,
-         row_mask=None, mode=0, M=None):
+         row_mask=None, mode=0, M=None, gate=None, gate_scale=1.0):
     _nodrop(drop)
     Mc, N = c.shape[-2], c.shape[-1]
     M = Mc if M is None else M
@@ -37,6 +37,8 @@ def gemm(a, b, c, *, bias=None, residual=None, alpha=1.0, relu=False, accumulate
         v = torch.relu(v)
     if residual is not None:
         v = v + residual[..., :M, :].double()
+    if gate is not None:
+        v = torch.where(gate[..., :M, :] > 0, v * gate_scale, torch.zeros_like(v))
     if accumulate:
         v = v + c[..., :M, :].double()
     if row_mask is not None:
@@ -60,7 +62,8 @@ def layernorm_fwd(x, gamma, beta, y, mean, rstd, eps=1e-12):
     return y
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, dres=None):
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, dres=None, dx_drop=None, drop=NO_DROP):
+    _nodrop(drop)
     d = x.shape[-1]
     x2, g2 = x.reshape(-1, d).double(), dy.reshape(-1, d).double()
     xh = (x2 - mean.double()[:, None]) * rstd.double()[:, None]
@@ -72,6 +75,8 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, dres=None):
         out = out + dres.reshape(-1, d).double()
     if dx is not None:
         dx.copy_(out.reshape(dx.shape).to(dx.dtype))
+    if dx_drop is not None:
+        dx_drop.copy_(out.reshape(dx_drop.shape).to(dx_drop.dtype))
     if dgamma is not None:
         dgamma += (g2 * xh).sum(0).float()
         dbeta += g2.sum(0).float()

@@ -148,7 +148,8 @@ def check_tts(eng, z, tol_out=1e-5, tol_grad=2e-4):
     for name in eng.store.names():
         ref = z["grad." + name]
         got = eng.store.g(name).cpu().numpy()
-        assert np.abs(got - ref).max() <= tol_grad * (np.abs(ref).max() + 1e-5), name
+        assert np.abs(got - ref).max() <= tol_grad * (np.abs(ref).max() + 1e-5) + 1e-7, name     # 1e-7: gradients that are exactly 0 in
+        # exact arithmetic (key biases: softmax is shift-invariant) are pure rounding noise on either side
 
 
 def test_tts_forward_guided_attention_and_gradients(monkeypatch):

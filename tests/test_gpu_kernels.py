@@ -44,16 +44,18 @@ def ops():
 def test_gemm_plain_and_epilogue(ops, mode, dt, M, N, K):
     a, b = rnd(M, K, dt=dt, seed=1), rnd(N, K, dt=dt, seed=2, scale=1 / math.sqrt(K))
     bias, res = rnd(N, seed=3), rnd(M, N, dt=dt, seed=4)
-    for kw in (dict(), dict(bias=bias, relu=True), dict(bias=bias, residual=res, alpha=0.5), dict(accumulate=True)):
+    for kw in (dict(), dict(bias=bias, relu=True), dict(bias=bias, residual=res, alpha=0.5), dict(accumulate=True),
+               dict(gate=res, gate_scale=1.25), dict(bias=bias, gate=res, gate_scale=0.5)) + (
+                   (dict(bias=bias, gate=res, accumulate=True),) if mode != 1 else ()):
         c0 = rnd(M, N, dt=dt, seed=5)
         ref = F.gemm(a, b, c0.clone(), **kw)
         da, db, dc = dev(a, b, c0.clone())
         dkw = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in kw.items()}
         ops.gemm(da, db, dc, mode=mode, **dkw)
-        close(dc, ref, tol(dt, 2), f"gemm {kw.keys()}")
+        close(dc, ref, tol(dt, 2 * (8 if mode == 2 else 1)), f"gemm {kw.keys()}")
 
 
-@pytest.mark.parametrize("mode,dt", [(0, torch.float32), (1, torch.bfloat16)])
+@pytest.mark.parametrize("mode,dt", [(0, torch.float32), (1, torch.bfloat16), (2, torch.float32)])
 def test_gemm_transposed_operands_and_f32_accumulate(ops, mode, dt):
     M, N, K = 96, 200, 333          # dW = dy^T x : both operands contiguous along the non-reduced dim
     dy, x = rnd(K, M, dt=dt, seed=1), rnd(K, N, dt=dt, seed=2)
@@ -61,16 +63,16 @@ def test_gemm_transposed_operands_and_f32_accumulate(ops, mode, dt):
     ref = F.gemm(dy.t(), x.t(), g0.clone(), accumulate=True)
     ddy, dx, dg = dev(dy, x, g0.clone())
     ops.gemm(ddy.t(), dx.t(), dg, accumulate=True, mode=mode)
-    close(dg, ref, tol(dt, 20), "dW gemm")
+    close(dg, ref, tol(dt, 20 * (8 if mode == 2 else 1)), "dW gemm")
     w = rnd(N, M, dt=dt, seed=4)    # dx = dy W : B operand n-major
     c = torch.zeros(K, M, dtype=dt)
     ref = F.gemm(x, w.t(), c.clone())
     dxx, dw, dc = dev(x, w, c)
     ops.gemm(dxx, dw.t(), dc, mode=mode)
-    close(dc, ref, tol(dt, 20), "dx gemm")
+    close(dc, ref, tol(dt, 20 * (8 if mode == 2 else 1)), "dx gemm")
 
 
-@pytest.mark.parametrize("mode,dt", [(0, torch.float32), (1, torch.bfloat16)])
+@pytest.mark.parametrize("mode,dt", [(0, torch.float32), (1, torch.bfloat16), (2, torch.float32)])
 @pytest.mark.parametrize("T1,T2,dk", [(37, 29, 16), (128, 127, 48), (64, 200, 64)])
 def test_gemm_attention_views(ops, mode, dt, T1, T2, dk):
     B, H = 3, 4
@@ -83,13 +85,13 @@ def test_gemm_attention_views(ops, mode, dt, T1, T2, dk):
     ref = F.gemm(q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3), P.clone()[..., :T2], alpha=1 / math.sqrt(dk))
     dq, dkv, dP = dev(qkv, kv, P)
     ops.gemm(dq[:, :, 0].permute(0, 2, 1, 3), dkv[:, :, 0].permute(0, 2, 1, 3), dP[..., :T2], alpha=1 / math.sqrt(dk), mode=mode)
-    close(dP[..., :T2], ref, tol(dt, 4), "QK^T")
+    close(dP[..., :T2], ref, tol(dt, 4 * (8 if mode == 2 else 1)), "QK^T")
     Pm = torch.softmax(rnd(B, H, T1, ld, seed=3), -1).to(dt)
     ctx = torch.zeros(B, T1, d, dtype=dt)
     ref = F.gemm(Pm[..., :T2], v.permute(0, 2, 3, 1), ctx.clone().view(B, T1, H, dk).permute(0, 2, 1, 3))
     dPm, dctx = dev(Pm, ctx)
     ops.gemm(dPm[..., :T2], dkv[:, :, 1].permute(0, 2, 3, 1), dctx.view(B, T1, H, dk).permute(0, 2, 1, 3), mode=mode)
-    close(dctx.view(B, T1, H, dk).permute(0, 2, 1, 3), ref, tol(dt, 2), "PV")
+    close(dctx.view(B, T1, H, dk).permute(0, 2, 1, 3), ref, tol(dt, 2 * (8 if mode == 2 else 1)), "PV")
     # dv[b,s,h,:] = sum_t P[t,s] dctx[t,:]  (both operands contiguous along the output dims)
     g = rnd(B, T1, d, dt=dt, seed=4)
     dv = torch.zeros(B, T2, 2, H, dk, dtype=dt)
@@ -98,10 +100,10 @@ def test_gemm_attention_views(ops, mode, dt, T1, T2, dk):
     dg, ddv = dev(g, dv)
     ops.gemm(dPm[..., :T2].transpose(-1, -2), dg.view(B, T1, H, dk).permute(0, 2, 1, 3).transpose(-1, -2),
              ddv[:, :, 1].permute(0, 2, 1, 3), mode=mode)
-    close(ddv[:, :, 1].permute(0, 2, 1, 3), ref, tol(dt, 4), "dV")
+    close(ddv[:, :, 1].permute(0, 2, 1, 3), ref, tol(dt, 4 * (8 if mode == 2 else 1)), "dV")
 
 
-@pytest.mark.parametrize("mode,dt", [(0, torch.float32), (1, torch.bfloat16)])
+@pytest.mark.parametrize("mode,dt", [(0, torch.float32), (1, torch.bfloat16), (2, torch.float32)])
 def test_gemm_conv1d_taps(ops, mode, dt):
     B, L, ic, oc, k = 3, 50, 80, 64, 5
     halo, Lp = 2, 54
@@ -116,10 +118,10 @@ def test_gemm_conv1d_taps(ops, mode, dt):
     F.gemm(x.view(B * Lp, ic), w, ref.view(B * Lp, oc)[halo:], **kw)
     dx, dw, dz = dev(x, w, z)
     ops.gemm(dx.view(B * Lp, ic), dw, dz.view(B * Lp, oc)[halo:], mode=mode, **kw)
-    close(dz, ref, tol(dt, 4), "taps gemm")
+    close(dz, ref, tol(dt, 4 * (8 if mode == 2 else 1)), "taps gemm")
     # against torch conv1d directly
     y = torch.nn.functional.conv1d(x[:, halo:halo + L].float().transpose(1, 2), w.float().permute(0, 2, 1), padding=halo)
-    close(dz[:, halo:halo + L], y.transpose(1, 2), tol(dt, 8), "conv1d")
+    close(dz[:, halo:halo + L], y.transpose(1, 2), tol(dt, 8 * (8 if mode == 2 else 1)), "conv1d")
 
 
 def test_gemm_cta_pairs(ops):
@@ -408,6 +410,32 @@ def test_fused_attention_probs_fwd_bwd(ops, causal, B, H, T1, T2, dk):
         ops.attn_probs_bwd(dctx.cuda().view(B, T1, H, dk), dqkv[:, :T2, 2], P.cuda(), None if d_att is None else d_att.cuda(), gdS, T2, scale)
         tol_abs = 2e-2 * max(1.0, ref.float().abs().max().item())
         close(gdS, ref, tol_abs, f"fused dS (d_att={with_att})")
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_layernorm_bwd_with_dropout_output(ops, dt):
+    """s2s_layernorm_bwd_drop: dx equals the plain backward, dx_drop equals s2s_dropout_bwd(dx) with the same descriptor."""
+    from seq2seq_vc_b200._lib import Drop
+
+    rows, d = 777, 384
+    x, dy, dres = rnd(rows, d, dt=dt, seed=1).cuda(), rnd(rows, d, dt=dt, seed=2).cuda(), rnd(rows, d, dt=dt, seed=3).cuda()
+    gamma, beta = rnd(d, seed=4).cuda(), rnd(d, seed=5).cuda()
+    y, mean, rstd = torch.empty_like(x), torch.empty(rows, device="cuda"), torch.empty(rows, device="cuda")
+    ops.layernorm_fwd(x, gamma, beta, y, mean, rstd)
+    seed_dev = torch.full((1,), 5, dtype=torch.int64, device="cuda")
+    drop = Drop(0.25, seed=9, site=4, seed_dev=seed_dev)
+    dx0, dg0, db0 = torch.empty_like(x), torch.zeros(d, device="cuda"), torch.zeros(d, device="cuda")
+    ops.layernorm_bwd(dy, x, gamma, mean, rstd, dx0, dg0, db0, dres=dres)
+    dx1, dxd, dg1, db1 = torch.empty_like(x), torch.empty_like(x), torch.zeros(d, device="cuda"), torch.zeros(d, device="cuda")
+    ops.layernorm_bwd(dy, x, gamma, mean, rstd, dx1, dg1, db1, dres=dres, dx_drop=dxd, drop=drop)
+    assert torch.equal(dx0, dx1)
+    close(dg1, dg0, 1e-3 * max(1.0, dg0.abs().max().item()), "dgamma")
+    want = ops.dropout_bwd(dx0, torch.empty_like(dx0), drop)
+    assert torch.equal(dxd == 0, want == 0), "same mask"
+    close(dxd, want, 1e-2 * max(1.0, want.float().abs().max().item()) if dt == torch.bfloat16 else 1e-5, "dx_drop")   # bf16: the fused
+    # output scales the fp32 value before its single rounding, the two-kernel form rounds twice
+    frac = (dxd == 0).float().mean().item()
+    assert abs(frac - 0.25) < 0.02, frac
 
 
 @pytest.mark.parametrize("causal", [False, True])

@@ -28,12 +28,15 @@ def step(eng, xs, ilens, ys, labels, olens):
     return after, before, logits, losses
 
 
-def test_golden_tiny_fp32_forward_and_grads():
+@pytest.mark.parametrize("fp32_gemm", ["simt", "tc"])
+def test_golden_tiny_fp32_forward_and_grads(fp32_gemm):
+    """float32 engine vs the live-reference dump, with the CUDA-core GEMM ("simt") and with the fp32-accurate tcgen05 GEMM
+    (bf16-split operands, "tc": the default float32 mode)."""
     from seq2seq_vc_b200 import VTNEngine
 
     z = np.load(GOLDEN)
     sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
-    eng = VTNEngine(dict(TINY_HP, **NO_DROPOUT), device="cuda:0", bf16=False)
+    eng = VTNEngine(dict(TINY_HP, **NO_DROPOUT), device="cuda:0", bf16=False, fp32_gemm=fp32_gemm)
     eng.load_state_dict(sd)
     ilens, olens = z["ilens"].tolist(), z["olens"].tolist()
     xs, ys, labels = (torch.from_numpy(z[k]) for k in ("xs", "ys", "labels"))
@@ -70,12 +73,16 @@ def c1():
     return hp, sd, batch, out, float(l1), float(bce), grads
 
 
-def test_c1_vtn_small_fp32_parity(c1):
-    """BASELINE configs[0]: fp32 CUDA path vs the CPU oracle; mel L1 <= 1e-4, attention L1 <= 1e-3."""
+@pytest.mark.parametrize("fp32_gemm,gtol", [("simt", 2e-3), ("tc", 6e-3)])
+def test_c1_vtn_small_fp32_parity(c1, fp32_gemm, gtol):
+    """BASELINE configs[0]: float32 CUDA path vs the CPU oracle; mel L1 <= 1e-4, attention L1 <= 1e-3 -- on the CUDA-core GEMM
+    and on the fp32-accurate tcgen05 GEMM (the default float32 mode: 8.6 vs 53.8 ms per eager step).  The tensor-core
+    accumulator rounds differently from a sequential fp32 FMA chain, so a few pre-activations within ~1e-6 of zero land on the
+    other side of a ReLU: the worst single gradient element moves by up to 2.3e-3 of the tensor's maximum (FFN w_1), hence gtol."""
     from seq2seq_vc_b200 import VTNEngine
 
     hp, sd, batch, out, l1, bce, grads = c1
-    eng = VTNEngine(dict(C1_HP, **NO_DROPOUT), device="cuda:0", bf16=False)
+    eng = VTNEngine(dict(C1_HP, **NO_DROPOUT), device="cuda:0", bf16=False, fp32_gemm=fp32_gemm)
     eng.load_state_dict(sd)
     after, before, logits, losses = step(eng, *batch)
     assert (after.cpu() - out["after_outs"].detach()).abs().mean().item() <= 1e-4
@@ -86,7 +93,7 @@ def test_c1_vtn_small_fp32_parity(c1):
     assert abs(losses[0].item() - l1) <= 1e-4 and abs(losses[1].item() - bce) <= 1e-4
     for name, ref in grads.items():
         got = eng.store.g(name).cpu()
-        assert (got - ref).abs().max().item() <= 2e-3 * (ref.abs().max().item() + 1e-5), name
+        assert (got - ref).abs().max().item() <= gtol * (ref.abs().max().item() + 1e-5), name
 
 
 def test_c1_vtn_small_bf16_tensor_core_path(c1):
@@ -194,7 +201,7 @@ def test_transformer_tts_golden_fp32_and_dropin():
     (l1 + bce + ga).backward()
     for name, p in model.named_parameters():
         ref = z["grad." + name]
-        assert np.abs(p.grad.cpu().numpy() - ref).max() <= 1e-3 * (np.abs(ref).max() + 1e-5), name
+        assert np.abs(p.grad.cpu().numpy() - ref).max() <= 1e-3 * (np.abs(ref).max() + 1e-5) + 1e-7, name   # 1e-7: exact-zero gradients (key biases)
 
 
 def test_tts_fused_step_with_guided_attention_trains():
@@ -303,7 +310,7 @@ def test_graph_steps_alternating_shapes_match_eager():
         lg = steps[True](*batch).clone()
         assert (le - lg).abs().max().item() <= 1e-4 * max(1.0, le.abs().max().item()), (it, le.tolist(), lg.tolist())
     pe, pg = steps[False].engine.store.P, steps[True].engine.store.P
-    assert (pe - pg).abs().max().item() <= 2e-4      # Adam turns the fp32 red.add ordering noise of the weight-gradient GEMMs into lr-sized steps
+    assert (pe - pg).abs().max().item() <= 1e-3      # Adam turns the fp32 red.add ordering noise of the weight-gradient GEMMs into lr-sized steps
 
 
 def test_shape_cache_eviction_drops_graphs_and_buffers():

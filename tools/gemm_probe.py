@@ -45,7 +45,13 @@ def _time_once(a, b, c, bias, flush=True):
         if c.data_ptr() not in _res:
             _res.clear()
             _res[c.data_ptr()] = torch.randn_like(c)
-        kw = dict(residual=_res[c.data_ptr()], drop=Drop(0.1, seed=3, site=2))
+        kw = {}
+        if FULL in (True, "res"):
+            kw["residual"] = _res[c.data_ptr()]
+        if FULL in (True, "drop"):
+            kw["drop"] = Drop(0.1, seed=3, site=2)
+        if FULL == "gate":
+            kw["gate"] = _res[c.data_ptr()]
     if _scratch is None:
         _scratch = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     if flush:
@@ -147,8 +153,8 @@ def trace(name, flush=True):
 
 if __name__ == "__main__":
     args = sys.argv[1:]
-    if args and args[0] == "full":
-        FULL = True
+    if args and args[0] in ("full", "res", "drop", "gate"):
+        FULL = True if args[0] == "full" else args[0]
         args = args[1:]
     if args and args[0] == "nobias":
         NOBIAS = True

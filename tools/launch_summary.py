@@ -1,24 +1,43 @@
-"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list per kernel."""
-import collections, csv, re, sys
-f = sys.argv[1]
-rows = [r for r in csv.reader(open(f)) if len(r) > 5]
-hdr = None
-agg = collections.defaultdict(lambda: [0, 0.0])
-for r in rows:
-    if r[0] == "ID":
-        hdr = r
-        continue
-    if hdr is None:
-        continue
-    d = dict(zip(hdr, r))
-    name = re.sub(r"\(.*", "", d["Kernel Name"])
-    name = re.sub(r"<.*", "", name)
-    v = float(d["Metric Value"].replace(",", ""))
-    unit = d["Metric Unit"]
-    v = v / 1e3 if unit == "ns" else v * 1e3 if unit == "ms" else v
-    agg[name][0] += 1
-    agg[name][1] += v
-tot = sum(v[1] for v in agg.values())
-print(f"{f}: total {tot:.0f} us over {sum(v[0] for v in agg.values())} launches")
-for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[: int(sys.argv[2]) if len(sys.argv) > 2 else 25]:
-    print(f"  {v[1]:10.1f} us {100 * v[1] / tot:5.1f}%  n={v[0]:4d}  {k}")
+"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: per-kernel launches, total and mean duration.
+Usage: python tools/launch_summary.py launches.csv [other.csv]  (two files: side-by-side mean durations)"""
+import collections
+import csv
+import re
+import sys
+
+
+def load(path, one_step=True):
+    """one_step: keep only the launches between the last two optimizer kernels (exactly one training step)."""
+    with open(path) as f:
+        lines = [l for l in f if not l.startswith("==")]
+    rows = list(csv.DictReader(lines))
+    if one_step:
+        marks = [i for i, r in enumerate(rows) if "adam_kernel" in r["Kernel Name"]]
+        if len(marks) >= 2:
+            rows = rows[marks[-2] + 1:marks[-1] + 1]
+    agg = collections.OrderedDict()
+    for row in rows:
+        v = float(row["Metric Value"].replace(",", ""))
+        unit = row["Metric Unit"]
+        v = v / 1000 if unit == "ns" else (v * 1000 if unit == "ms" else v)
+        name = re.sub(r"\(.*", "", row["Kernel Name"]).replace("void ", "")
+        e = agg.setdefault(name, [0, 0.0])
+        e[0] += 1
+        e[1] += v
+    return agg
+
+
+def main():
+    a = load(sys.argv[1])
+    b = load(sys.argv[2]) if len(sys.argv) > 2 else None
+    tot = sum(v[1] for v in a.values())
+    print(f"# {sys.argv[1]}: {sum(v[0] for v in a.values())} launches, {tot:.1f} us")
+    for k, v in sorted(a.items(), key=lambda kv: -kv[1][1]):
+        line = f"{k[:84]:84s} n={v[0]:4d} us={v[1]:9.1f} {100 * v[1] / tot:5.1f}% mean={v[1] / v[0]:7.2f}"
+        if b is not None and k in b:
+            line += f" | other n={b[k][0]:4d} mean={b[k][1] / b[k][0]:7.2f}"
+        print(line)
+
+
+if __name__ == "__main__":
+    main()
