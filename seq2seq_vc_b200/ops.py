@@ -42,7 +42,7 @@ def _lead_strides(t: torch.Tensor, core: int) -> Tuple[int, int]:
 
 
 # mode 2: 3 = two-way bf16 split (a0 b0 + a1 b0 + a0 b1, ~2^-16 per product), 6 = three-way split.  Measured on C1
-# (tools/parity_modes.py, profiles/r02_parity_modes_c1.json): both give mel L1 1.2e-5 / 1.5e-5 against the oracle (CUDA-core
+# (tools/parity_modes.py, profiles/r02_parity_modes_c1.json): both give mel L1 1.2e-5 / 1.5e-5 against the CPU reference restatement (CUDA-core
 # fp32: 1.4e-6, bf16: 1.2e-2) -- the tensor core's fp32 accumulation, not the split, sets the floor -- so the cheaper one is used.
 SPLIT_TERMS = 3
 _split_ws: dict = {}     # per-device workspace of the fp32-accurate mode; outgrown buffers stay alive for captured graphs
