@@ -1,7 +1,11 @@
 #!/usr/bin/env python
 """Benchmark of the seq2seq-vc training hot path on B200 (contract: see the task statement / DESIGN.md).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c2b64]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|torch_gpu] [--workload c2|c1|c2b64|c3|c3b16|c4|c5]
+
+  --impl reference : the UNMODIFIED reference modules (baseline/_ref, installed by __graft_entry__.build()) on the host cores
+  --impl torch_gpu : the same reference modules on cuda (fp32 and bf16 autocast): the PyTorch-eager incumbent on this box
+  --workload c5    : STFT -> log-mel feature extraction (BASELINE.json configs[4]), HBM roofline
 
 One "step" = one full VTN training step (forward + Seq2SeqLoss + backward + gradient all-reduce +
 clip_grad_norm + Adam) over one synthetic padded mel batch.  Default workload = BASELINE.json
@@ -45,8 +49,12 @@ WORKLOADS = {
               16, 768, 768, True, "AAS-VC Conformer 4+4 (enc d384, dec d1536, h2, k15), B16 x (768->768, 80-mel), bf16 (the recipe's batch size)"),
     "c1": (dict(idim=80, odim=80, adim=256, aheads=4, elayers=2, dlayers=2, eunits=1024, dunits=1024, decoder_reduction_factor=2),
            4, 200, 400, False, "VTN-small 2+2 d256 h4 r2, B4 x (200->400, 80-mel), fp32"),
+    # STFT -> log-mel (BASELINE.json configs[4]): 256 clips x 10 s @ 48 kHz, n_fft 2048, hop 300, 80 mels
+    "c5": (dict(sr=48000, fft_size=2048, hop_size=300, num_mels=80), 256, 480000, 1601, False,
+           "STFT->log-mel, 256 x 10 s clips @ 48 kHz, n_fft 2048, hop 300, 80 mels, fp32"),
 }
 METRIC = "target mel-frames/sec, VTN-base enc-dec training step (80-mel, src512/tgt1024)"
+METRIC_C5 = "mel-frames/sec, STFT->log-mel feature extraction (48 kHz, n_fft 2048, hop 300, 80-mel)"
 METRIC_AAS = "target mel-frames/sec, AAS-VC Conformer non-AR training step (80-mel, 768 frames)"
 
 
@@ -206,10 +214,126 @@ def cpu_port_steps_aas(hp, B, T, L, steps, warmup):
     return sum(times) / len(times)
 
 
+def reference_modules():
+    """The unmodified reference package from baseline/_ref (pip-installed + completed by __graft_entry__.build()), imported
+    through oracle/ref_shim.py (lazy numba.jit, the missing diffsinger module).  None when it is not there."""
+    root = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(root, "seq2seq_vc", "modules")):
+        return None
+    os.environ["S2SVC_REFERENCE_ROOT"] = root
+    try:
+        from oracle import ref_shim
+
+        ref_shim.install()
+        import seq2seq_vc.losses as losses
+        import seq2seq_vc.models as models
+        from seq2seq_vc.schedulers.warmup_lr import WarmupLR
+    except Exception as e:          # noqa: BLE001 -- any import problem means "fall back to the port", reported in the line
+        sys.stderr.write(f"reference import failed: {e!r}\n")
+        return None
+    return models, losses, WarmupLR
+
+
+def reference_step_fn(mods, workload, B, device, autocast=False, seed=1234):
+    """ARVCTrainer._train_step / ARTTSTrainer._train_step (trainers/ar_vc.py:59-107) around the reference's own VTN /
+    TransformerTTS, Seq2SeqLoss, torch.optim.Adam, WarmupLR and clip_grad_norm_, on `device`.  Returns (step(), frames/step)."""
+    models, losses, WarmupLR = mods
+    hp, _, T, L, _, _ = WORKLOADS[workload]
+    tts = workload == "c4"
+    torch.manual_seed(0)
+    model = (models.TransformerTTS if tts else models.VTN)(**hp).to(device)
+    model.train()
+    crit = losses.Seq2SeqLoss().to(device)
+    opt = torch.optim.Adam(model.parameters(), lr=8e-5)
+    sched = WarmupLR(opt, warmup_steps=4000)
+    xs, ilens, ys, labels, olens = synthetic_batch(B, T, L, seed, tts)
+    xs, ys, labels = xs.to(device), ys.to(device), labels.to(device)
+    ilens_t, olens_t = torch.tensor(ilens, device=device), torch.tensor(olens, device=device)
+
+    def step():
+        with torch.autocast(device_type="cuda", dtype=torch.bfloat16, enabled=autocast):
+            after, before, logits, ys_, labels_, olens_, _ = model(xs, ilens_t, ys, labels, olens_t)
+            l1, bce = crit(after, before, logits, ys_, labels_, olens_)
+        loss = l1 + bce
+        opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        sched.step()
+        return loss
+
+    return step, B * L
+
+
+def cpu_reference_steps(mods, workload, B, steps, warmup):
+    torch.set_num_threads(os.cpu_count() or 1)
+    step, _ = reference_step_fn(mods, workload, B, torch.device("cpu"))
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        step()
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    return sum(times) / len(times)
+
+
+def logmel_cpu_frames_per_s(clips, n_samples, params):
+    """Oracle restatement of bin/preprocess.py:30-92 (librosa semantics) on `clips` clips, all host cores (joblib)."""
+    import numpy as np
+    from joblib import Parallel, delayed
+
+    from oracle import logmel_oracle
+
+    rng = np.random.default_rng(1234)
+    wavs = np.clip(0.1 * rng.standard_normal((clips, n_samples)), -1, 1).astype(np.float32)
+    cores = os.cpu_count() or 1
+    f = lambda w: logmel_oracle.logmelfilterbank(w, params["sr"], fft_size=params["fft_size"], hop_size=params["hop_size"],
+                                                 num_mels=params["num_mels"]).shape[0]
+    f(wavs[0])
+    t0 = time.perf_counter()
+    frames = sum(Parallel(n_jobs=cores)(delayed(f)(w) for w in wavs))
+    return frames / (time.perf_counter() - t0), cores
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
     hp, B, T, L, bf16, desc = WORKLOADS[args.workload]
+    if args.workload == "c5":
+        clips = max(2, min(2 * (os.cpu_count() or 1), 64))
+        val, cores = logmel_cpu_frames_per_s(clips, T, hp)
+        line = {"impl": "reference", "metric": METRIC_C5, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": clips * L / val * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": {"workload": desc, "sample": f"{clips} clips (of {B}) over {cores} processes"},
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                                 "sample": f"numpy/scipy restatement of preprocess.py:30-92 with librosa's conventions (librosa itself is not "
+                                           f"installable offline), {clips} x 10 s clips, joblib over {cores} cores"},
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+    mods = reference_modules() if not is_aas(args.workload) else None
+    if mods is not None:
+        # the reference's own modules; the full batch when a step stays within ~a minute, else a bounded sample (stated)
+        import psutil
+
+        roomy = psutil.virtual_memory().available >= (96 << 30) and (os.cpu_count() or 1) >= 16
+        Bs = B if (args.workload == "c1" or (roomy and B <= 32)) else min(B, 4)      # ~0.3 GB of fp32 activations per C2 utterance
+        timed = max(1, min(args.steps, 5 if Bs <= 4 else 2))
+        sec = cpu_reference_steps(mods, args.workload, Bs, timed, 1)
+        val = Bs * L / sec
+        cores = os.cpu_count() or 1
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": desc, "same_config": Bs == B,
+                           "sample": f"{Bs} utterances per step (of {B}); frames/s scales linearly in B", "timed_steps": timed},
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "reference",
+                                 "sample": f"unmodified reference modules (baseline/_ref: VTN/TransformerTTS + Seq2SeqLoss + Adam + WarmupLR + "
+                                           f"clip_grad_norm_, trainers/ar_vc.py:59-107), fp32, {Bs} x ({T}->{L}) per step, "
+                                           f"{torch.get_num_threads()} threads, {timed} steps after 1 warm-up"},
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
     aas = is_aas(args.workload)
     Bs = 1 if aas else min(B, 4)
     timed = max(1, min(args.steps, 2 if aas else 6))      # bounded sample: the CPU arm must end within minutes whatever K is
@@ -256,7 +380,20 @@ def gemm_roofline(stepper, batch, dev, table_path=None, run=None):
         rec.append((2.0 * nb * M * c.shape[-1] * a.shape[-1] * kw.get("taps", 1), e0, e1, key))
         return out
 
+    orig_grouped = ops.gemm_grouped
+
+    def timed_grouped(problems, mode=0):
+        if mode != 1 or len(problems) < 2:      # single problems go through ops.gemm (timed above)
+            return orig_grouped(problems, mode)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig_grouped(problems, mode)          # ops.gemm_grouped resolves the library itself: not re-entered through `timed`
+        e1.record()
+        fl = sum(2.0 * c.shape[-2] * c.shape[-1] * a.shape[-1] for a, b, c, kw in problems)
+        rec.append((fl, e0, e1, ("grouped dW", len(problems))))
+
     ops.gemm = timed
+    ops.gemm_grouped = timed_grouped
     try:
         eng = stepper.engine
         if run is None:
@@ -272,6 +409,7 @@ def gemm_roofline(stepper, batch, dev, table_path=None, run=None):
             torch.cuda.synchronize()
     finally:
         ops.gemm = orig
+        ops.gemm_grouped = orig_grouped
     flops = sum(r[0] for r in rec)
     ms = sum(r[1].elapsed_time(r[2]) for r in rec)
     if table_path:
@@ -288,9 +426,146 @@ def gemm_roofline(stepper, batch, dev, table_path=None, run=None):
     return flops, ms, len(rec)
 
 
+def incumbent_torch_gpu(workload, steps=5, warmup=3):
+    """PyTorch-eager incumbent on this box: the UNMODIFIED reference modules on cuda, same step
+    (trainers/ar_vc.py:59-107: forward, Seq2SeqLoss, backward, clip_grad_norm_, Adam, WarmupLR), fp32 and bf16 autocast."""
+    mods = reference_modules()
+    if mods is None:
+        return {"unavailable": "baseline/_ref not importable"}
+    hp, B, T, L, _, desc = WORKLOADS[workload]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    out = {"what": "unmodified reference modules on cuda (cuBLAS / cuDNN / ATen), same batch and step", "batch": B}
+    for name, ac in (("fp32", False), ("bf16_autocast", True)):
+        try:
+            torch.backends.cuda.matmul.allow_tf32 = False
+            torch.backends.cudnn.allow_tf32 = False
+            step, frames = reference_step_fn(mods, workload, B, dev, autocast=ac)
+            for _ in range(warmup):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                loss = step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {"ms_per_step": ms, "frames_per_s": frames / (ms * 1e-3), "loss": float(loss)}
+            del step
+            torch.cuda.empty_cache()
+        except Exception as e:      # noqa: BLE001
+            out[name] = {"error": repr(e)[:200]}
+    return out
+
+
+def run_torch_gpu(args, rank):
+    if rank != 0:
+        return
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+    hp, B, T, L, bf16, desc = WORKLOADS[args.workload]
+    res = incumbent_torch_gpu(args.workload, steps=max(1, min(args.steps, 10)), warmup=max(3, min(args.warmup, 5)))
+    best = max((v.get("frames_per_s", 0.0) for v in res.values() if isinstance(v, dict)), default=0.0)
+    print(json.dumps({"impl": "torch_gpu", "metric": METRIC, "value": best, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+                      "warmup": args.warmup, "higher_is_better": True, "data": "synthetic", "config": {"workload": desc}, "detail": res}), flush=True)
+
+
+def run_c5(args, rank, world):
+    """STFT -> log-mel (BASELINE.json configs[4]): every rank extracts its own 256 clips (the path shards by clip)."""
+    from seq2seq_vc_b200 import _lib, api
+
+    hp, B, ns, nf, _, desc = WORKLOADS["c5"]
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _lib.device_check()
+    g = torch.Generator().manual_seed(1234 + rank)
+    wav_h = (0.1 * torch.randn(B, ns, generator=g)).clamp_(-1, 1).pin_memory()
+    wav = wav_h.to(dev)
+    mel = torch.empty(B, nf, hp["num_mels"], device=dev)
+    mel_h = torch.empty(B, nf, hp["num_mels"]).pin_memory()
+    wav_stage = torch.empty_like(wav)
+    kw = dict(fft_size=hp["fft_size"], hop_size=hp["hop_size"], num_mels=hp["num_mels"])
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        api.logmel_batch(wav, hp["sr"], out=mel, **kw)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = _lib.launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for a, b in evs:
+        a.record()
+        api.logmel_batch(wav, hp["sr"], out=mel, **kw)
+        b.record()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    kernel_ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+    launches = _lib.launch_count() - l0
+    for _ in range(2):
+        wav_stage.copy_(wav_h, non_blocking=True)
+        api.logmel_batch(wav_stage, hp["sr"], out=mel, **kw)
+        mel_h.copy_(mel, non_blocking=True)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        wav_stage.copy_(wav_h, non_blocking=True)           # H2D of the step's clips from pinned host memory
+        api.logmel_batch(wav_stage, hp["sr"], out=mel, **kw)
+        mel_h.copy_(mel, non_blocking=True)                 # D2H of the features (the product of this path)
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+    clocks = sampler.stop()
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    if rank != 0:
+        return
+    assert torch.isfinite(mel_h).all()
+    frames = B * nf * world * args.steps
+    alg_bytes = wav.numel() * 4 + mel.numel() * 4
+    pk, pk_src = peaks()
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_logmel_traffic.json")))["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    ach = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    line = {"metric": METRIC_C5, "value": frames / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "clips_per_gpu": B, "parallelism": f"dp{world} (clips sharded, no collective)",
+                       "l2": "491 MB of input per step exceeds the 126 MB L2; no flush needed"},
+            "clocks": clocks,
+            "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": wav.numel() * 4,
+                    "d2h_bytes_per_step": mel.numel() * 4},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "logmel kernels (STFT + mel + log of one batch)", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": ach / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": kernel_ms * 1e3,
+                         "note": "SURVEY section 8(d): read 256 x 480000 x 4 B, write 256 x 1601 x 80 x 4 B = 622.7 MB per launch; the shape is fp32-FFT-"
+                                 "arithmetic bound (each sample is reused by 6.8 overlapping frames), see DESIGN.md"}}
+    if world == 1 and not args.no_cpu_baseline:
+        clips = max(2, min(os.cpu_count() or 1, 32))
+        val, cores = logmel_cpu_frames_per_s(clips, ns, hp)
+        line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"numpy/scipy restatement of preprocess.py:30-92 (librosa conventions), {clips} clips over {cores} processes"}
+    print(json.dumps(line), flush=True)
+
+
 def run_ours(args, rank, world):
     from seq2seq_vc_b200 import AASVC, AASVCTrainStep, VTN, TransformerTTS, VTNTrainStep, _lib
 
+    if args.workload == "c5":
+        return run_c5(args, rank, world)
     hp, B, T, L, bf16, desc = WORKLOADS[args.workload]
     tts = args.workload == "c4"
     aas = is_aas(args.workload)
@@ -409,10 +684,23 @@ def run_ours(args, rank, world):
                                 "avg_launch_us": gms * 1e3 / n, "gemm_share_of_step": gms / (ms / args.steps),
                                 "how": "CUDA events around every mode-1 s2s_gemm launch of one fwd+bwd queued behind a GPU spin (no host gaps), right after the timed region"}
         if not args.no_cpu_baseline:
-            Bs = 1 if aas else min(B, 4)
-            sec = cpu_port_steps_aas(hp, Bs, T, L, 1, 1) if aas else cpu_port_steps(hp, Bs, T, L, 2, 1, tts)
-            line["cpu_baseline"] = {"value": Bs * L / sec, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-                                    "sample": f"oracle port of the reference PyTorch-CPU path (fp32), {Bs} x ({T}->{L}) per step, 2 steps after 1 warm-up"}
+            mods = None if aas else reference_modules()
+            if mods is not None:
+                Bs = min(B, 4)
+                sec = cpu_reference_steps(mods, args.workload, Bs, 2, 1)
+                line["cpu_baseline"] = {"value": Bs * L / sec, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "reference",
+                                        "sample": f"unmodified reference modules (baseline/_ref), fp32, {Bs} x ({T}->{L}) per step (of {B}; frames/s "
+                                                  f"scales linearly in B), 2 steps after 1 warm-up, {torch.get_num_threads()} threads"}
+            else:
+                Bs = 1 if aas else min(B, 4)
+                sec = cpu_port_steps_aas(hp, Bs, T, L, 1, 1) if aas else cpu_port_steps(hp, Bs, T, L, 2, 1, tts)
+                line["cpu_baseline"] = {"value": Bs * L / sec, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                                        "sample": f"oracle port of the reference PyTorch-CPU path (fp32), {Bs} x ({T}->{L}) per step, 2 steps after 1 warm-up"}
+        if not aas and not args.no_incumbent:
+            # the practical incumbent on this box, timed after our own arm on the same GPU
+            del stepper, model
+            torch.cuda.empty_cache()
+            line["torch_gpu_incumbent"] = incumbent_torch_gpu(args.workload)
     print(json.dumps(line), flush=True)
 
 
@@ -421,16 +709,20 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_gpu"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-incumbent", action="store_true", help="skip the PyTorch-eager-on-this-GPU timing of the reference modules")
     ap.add_argument("--gemm-table", default=None, help="write a per-shape timing table of the tensor-core GEMM launches")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.impl == "torch_gpu":
+        run_torch_gpu(args, rank)
         return
     if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the single JSON line

@@ -103,6 +103,11 @@ typedef struct {
 } s2s_gemm_t;
 
 int s2s_gemm(const s2s_gemm_t* g, int mode, void* stream);
+/* n independent GEMMs issued together.  In mode 1, sets of up to 8 weight-gradient products (bf16 operands contiguous along
+ * M / N, float32 C accumulated in place, no epilogue extras, no batch / taps) share ONE persistent tcgen05 launch -- the
+ * dW = dy^T x products of a Transformer layer are too small to fill the machine one at a time; anything else is launched
+ * one by one, so the call is always equivalent to n s2s_gemm calls. */
+int s2s_gemm_grouped(const s2s_gemm_t* gs, int n, int mode, void* stream);
 /* bytes of workspace s2s_gemm(g, mode = 2) needs for this problem */
 size_t s2s_gemm_workspace_bytes(const s2s_gemm_t* g);
 
@@ -134,6 +139,15 @@ int s2s_skinny_linear_bwd(const void* dy, const void* x, const void* w, float* d
 
 /* out[c] += sum_r x[r, c]  (bias gradients); x row stride ld */
 int s2s_colsum(const void* x, int64_t rows, int cols, int64_t ld, float* out, int dtype, void* stream);
+/* n column sums in one launch (the bias gradients of one layer's backward, whose gradient tensors are all alive at its end) */
+typedef struct {
+    const void* x;
+    int64_t rows;
+    int cols;
+    int64_t ld;
+    float* out;             /* out[c] += sum_r x[r, c] */
+} s2s_colsum_t;
+int s2s_colsum_multi(const s2s_colsum_t* items, int n, int dtype, void* stream);
 /* dx = dy * (y > 0 ? scale : 0): backward of relu followed by dropout (scale = 1/(1-p)) */
 int s2s_relu_bwd(const void* dy, const void* y, void* dx, int64_t n, float scale, int dtype, void* stream);
 /* out = a + b (elementwise; out may alias a or b): residual joins that no GEMM epilogue absorbs

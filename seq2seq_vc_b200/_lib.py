@@ -46,6 +46,10 @@ class GemmDesc(Structure):
     ]
 
 
+class ColsumDesc(Structure):
+    _fields_ = [("x", c_void_p), ("rows", c_int64), ("cols", c_int), ("ld", c_int64), ("out", c_void_p)]
+
+
 # name -> (restype, argtypes).  Every symbol declared in include/s2svc_b200.h appears here; the CPU
 # test-suite checks that the library exports each of them.
 _P = c_void_p
@@ -59,6 +63,8 @@ SIGNATURES = {
     "s2s_debug_gemm_tile": (None, [c_int]),
     "s2s_gemm": (c_int, [POINTER(GemmDesc), c_int, _P]),
     "s2s_gemm_workspace_bytes": (c_size_t, [POINTER(GemmDesc)]),
+    "s2s_gemm_grouped": (c_int, [POINTER(GemmDesc), c_int, c_int, _P]),
+    "s2s_colsum_multi": (c_int, [POINTER(ColsumDesc), c_int, c_int, _P]),
     "s2s_layernorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_float, c_int, _P]),
     "s2s_layernorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P]),
     "s2s_layernorm_bwd_drop": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _DP, _P, _P, c_int64, c_int, c_int, _P]),

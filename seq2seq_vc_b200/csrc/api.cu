@@ -22,6 +22,7 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 int gemm_simt(const s2s_gemm_t& g, cudaStream_t st);
 int gemm_tc(const s2s_gemm_t& g, cudaStream_t st);
 int gemm_tc_split(const s2s_gemm_t& g, cudaStream_t st);
+int gemm_tc_grouped(const s2s_gemm_t* gs, int n, cudaStream_t st);
 size_t gemm_split_workspace_bytes(const s2s_gemm_t& g);
 
 }  // namespace s2s
@@ -54,3 +55,30 @@ extern "C" int s2s_gemm(const s2s_gemm_t* g, int mode, void* stream) {
 }
 
 extern "C" size_t s2s_gemm_workspace_bytes(const s2s_gemm_t* g) { return g ? s2s::gemm_split_workspace_bytes(*g) : 0; }
+
+extern "C" int s2s_gemm_grouped(const s2s_gemm_t* gs, int n, int mode, void* stream) {
+    S2S_REQUIRE(gs != nullptr && n >= 1, "gemm_grouped: bad arguments");
+    if (mode == 1 && n > 1) {
+        int done = 0;
+        bool all = true;
+        // full groups of up to 8 problems; anything the grouped kernel cannot take is launched on its own
+        while (done < n && all) {
+            const int m = n - done < 8 ? n - done : 8;
+            const int rc = s2s::gemm_tc_grouped(gs + done, m, (cudaStream_t)stream);
+            if (rc == S2S_OK) done += m;
+            else if (rc == S2S_ERR_UNSUPPORTED) all = false;
+            else return rc;
+        }
+        if (done == n) return S2S_OK;
+        for (int i = done; i < n; ++i) {
+            const int rc = s2s_gemm(gs + i, mode, stream);
+            if (rc != S2S_OK) return rc;
+        }
+        return S2S_OK;
+    }
+    for (int i = 0; i < n; ++i) {
+        const int rc = s2s_gemm(gs + i, mode, stream);
+        if (rc != S2S_OK) return rc;
+    }
+    return S2S_OK;
+}

@@ -103,6 +103,37 @@ struct Params {
     Dropout drop;
     int mask_period, mask_offset, mask_lo, mask_hi;
     long long* trace;        // optional (S2S_GEMM_TRACE builds): CTA 0 records clock64 stamps of pipeline milestones
+    static constexpr bool kGrouped = false;
+};
+
+// Grouped launch: up to MAX_GROUPS independent weight-gradient GEMMs (fp32 C accumulated in place with red.add, both operands
+// MN-major, no batch / taps) share ONE persistent launch -- the seven dW = dy^T x products of a decoder layer are 9-36 tiles
+// each, so alone every one of them needs a ~24-way split-K (14 MB of red.add traffic for a 590 KB result) and pays its own
+// launch + prologue; together they fill the machine with a 2-3-way split.  Items are numbered group by group.
+constexpr int MAX_GROUPS = 8;
+struct Group {
+    CUtensorMap tmA, tmB;
+    void* C;
+    long c_rs;
+    int M, N, K, nt, kb_total, splits, kb_per_split;
+    uint32_t item0, items;      // first item of the group and their number (= tiles x splits)
+    float alpha;
+    FastDiv d_splits, d_nt;
+};
+struct ParamsG : Params {
+    int ngroups;
+    Group grp[MAX_GROUPS];
+    static constexpr bool kGrouped = true;
+};
+static_assert(sizeof(ParamsG) <= 4096, "kernel parameter space");
+
+// the problem an item belongs to (the launch's only problem, or its group)
+struct Prob {
+    const CUtensorMap *tmA, *tmB;
+    void* C;
+    long c_rs;
+    int M, N, K, kb_per_tap;
+    float alpha;
 };
 
 #ifdef S2S_GEMM_TRACE
@@ -130,18 +161,39 @@ __device__ __forceinline__ void stamp(const Params&, int) {}
 struct Item {
     int b1, b2, m0, n0, kb0, kb1;
 };
-__device__ __noinline__ void decode_item(const Params& p, uint32_t item, Item& it) {
-    uint32_t tile, split, ntile, mtile, bz, b1, b2;
-    p.d_splits.divmod(item, tile, split);
-    p.d_nt.divmod(tile, tile, ntile);
-    p.d_mt.divmod(tile, bz, mtile);
-    p.d_batch2.divmod(bz, b1, b2);
-    it.b1 = (int)b1;
-    it.b2 = (int)b2;
-    it.m0 = (int)mtile * BM * p.cg;
-    it.n0 = (int)ntile * p.BN;
-    it.kb0 = (int)split * p.kb_per_split;
-    it.kb1 = min(p.kb_total, it.kb0 + p.kb_per_split);
+template <typename P>
+__device__ __noinline__ void decode_item(const P& p, uint32_t item, Item& it, Prob& pr) {
+    if constexpr (P::kGrouped) {
+        int g = 0;
+#pragma unroll 1
+        while (g + 1 < p.ngroups && item >= p.grp[g + 1].item0) ++g;
+        const Group& G = p.grp[g];
+        uint32_t tile, split, mtile, ntile;
+        G.d_splits.divmod(item - G.item0, tile, split);
+        G.d_nt.divmod(tile, mtile, ntile);
+        it.b1 = it.b2 = 0;
+        it.m0 = (int)mtile * BM;
+        it.n0 = (int)ntile * p.BN;
+        it.kb0 = (int)split * G.kb_per_split;
+        it.kb1 = min(G.kb_total, it.kb0 + G.kb_per_split);
+        pr.tmA = &G.tmA; pr.tmB = &G.tmB; pr.C = G.C; pr.c_rs = G.c_rs; pr.M = G.M; pr.N = G.N; pr.K = G.K;
+        pr.kb_per_tap = G.kb_total; pr.alpha = G.alpha;
+        return;
+    } else {
+        uint32_t tile, split, ntile, mtile, bz, b1, b2;
+        p.d_splits.divmod(item, tile, split);
+        p.d_nt.divmod(tile, tile, ntile);
+        p.d_mt.divmod(tile, bz, mtile);
+        p.d_batch2.divmod(bz, b1, b2);
+        it.b1 = (int)b1;
+        it.b2 = (int)b2;
+        it.m0 = (int)mtile * BM * p.cg;
+        it.n0 = (int)ntile * p.BN;
+        it.kb0 = (int)split * p.kb_per_split;
+        it.kb1 = min(p.kb_total, it.kb0 + p.kb_per_split);
+        pr.tmA = &p.tmA; pr.tmB = &p.tmB; pr.C = p.C; pr.c_rs = p.c_rs; pr.M = p.M; pr.N = p.N; pr.K = p.K;
+        pr.kb_per_tap = p.kb_per_tap; pr.alpha = p.alpha;
+    }
 }
 
 // rare epilogue paths (column tails, unaligned rows, fp32 C with residual): rolled and out of line
@@ -197,8 +249,11 @@ __device__ __forceinline__ uint4 pack_bf16x8(const float* v) {
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
-template <int EPI, int CG>
-__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ Params p) {
+__device__ __forceinline__ uint32_t total_items(const Params& p) { return (uint32_t)((long)p.batch1 * p.batch2 * p.mt * p.nt * p.splits); }
+__device__ __forceinline__ uint32_t total_items(const ParamsG& p) { return p.grp[p.ngroups - 1].item0 + p.grp[p.ngroups - 1].items; }
+
+template <int EPI, int CG, typename P = Params>
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ P p) {
     constexpr bool F32OUT = (EPI == EPI_F32 || EPI == EPI_F32_FULL);
     constexpr bool FULLISH = (EPI == EPI_BF16_FULL || EPI == EPI_F32_FULL);      // dropout / residual / accumulate / row mask
     using TC = typename std::conditional<F32OUT, float, bf16>::type;
@@ -245,7 +300,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (threadIdx.x == 0) stamp(p, 1);
 
-    const uint32_t total = (uint32_t)((long)p.batch1 * p.batch2 * p.mt * p.nt * p.splits);
+    const uint32_t total = total_items(p);
     const int BN = p.BN;
     const int BNH = BN / CG;                                  // B columns staged by this CTA
     const uint32_t worker = blockIdx.x / CG, n_workers = gridDim.x / CG;
@@ -259,15 +314,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             int stage = 0;
             uint32_t phase = 0;
             Item it;
+            Prob pr;
 #pragma unroll 1
             for (uint32_t item = worker; item < total; item += n_workers) {
-                decode_item(p, item, it);
+                decode_item(p, item, it, pr);
                 const int am0 = it.m0 + (int)rank * BM, bn0 = it.n0 + (int)rank * BNH;
-                int t = (int)p.d_kbtap.div((uint32_t)it.kb0);
-                int kk = (it.kb0 - t * p.kb_per_tap) * BK;
+                int t = P::kGrouped ? 0 : (int)p.d_kbtap.div((uint32_t)it.kb0);
+                int kk = (it.kb0 - t * pr.kb_per_tap) * BK;
 #pragma unroll 1
                 for (int kb = it.kb0; kb < it.kb1; ++kb, kk += BK) {
-                    if (kk >= p.kb_per_tap * BK) { kk = 0; ++t; }
+                    if (kk >= pr.kb_per_tap * BK) { kk = 0; ++t; }
                     TRACE_WAIT(10, mbar_wait(empty_bar(stage), phase ^ 1u));
                     const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_BYTES;
                     if (kb == it.kb0 && item == worker) stamp(p, 2);
@@ -278,16 +334,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                         else tma_load_4d(dst, map, fb, c0, c1, c2, c3);
                     };
                     if (p.a_mn) {
-                        load(sa, &p.tmA, am0, kk, it.b2, it.b1);
-                        load(sa + 8192, &p.tmA, am0 + 64, kk, it.b2, it.b1);
+                        load(sa, pr.tmA, am0, kk, it.b2, it.b1);
+                        load(sa + 8192, pr.tmA, am0 + 64, kk, it.b2, it.b1);
                     } else {
-                        load(sa, &p.tmA, kk, am0 + t, it.b2, it.b1);
+                        load(sa, pr.tmA, kk, am0 + t, it.b2, it.b1);
                     }
                     if (p.b_mn) {
 #pragma unroll 1
-                        for (int j = 0; j < b_boxes; ++j) load(sb + 8192 * j, &p.tmB, bn0 + 64 * j, kk, it.b2, it.b1);
+                        for (int j = 0; j < b_boxes; ++j) load(sb + 8192 * j, pr.tmB, bn0 + 64 * j, kk, it.b2, it.b1);
                     } else {
-                        load(sb, &p.tmB, kk, bn0, p.taps > 1 ? t : it.b2, it.b1);
+                        load(sb, pr.tmB, kk, bn0, p.taps > 1 ? t : it.b2, it.b1);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
@@ -304,19 +360,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         uint32_t phase = 0;
         uint32_t n_items = 0;
         Item it;
+        Prob pr;
 #pragma unroll 1
         for (uint32_t item = worker; item < total; item += n_workers, ++n_items) {
-            decode_item(p, item, it);
+            decode_item(p, item, it, pr);
             const int as = (int)(n_items & 1);
             const uint32_t aphase = (n_items >> 1) & 1u;
             TRACE_WAIT(9, mbar_wait(tempty_bar(as), aphase ^ 1u));
             tcgen05_fence_after();
             const uint32_t tmem_d = tmem_base + (uint32_t)(as * MAX_BN);
-            int kk = (it.kb0 - (int)p.d_kbtap.div((uint32_t)it.kb0) * p.kb_per_tap) * BK;
+            int kk = (it.kb0 - (P::kGrouped ? 0 : (int)p.d_kbtap.div((uint32_t)it.kb0)) * pr.kb_per_tap) * BK;
 #pragma unroll 1
             for (int kb = it.kb0; kb < it.kb1; ++kb, kk += BK) {
-                if (kk >= p.kb_per_tap * BK) kk = 0;
-                const int ksteps = (min(BK, p.K - kk) + UMMA_K - 1) / UMMA_K;
+                if (kk >= pr.kb_per_tap * BK) kk = 0;
+                const int ksteps = (min(BK, pr.K - kk) + UMMA_K - 1) / UMMA_K;
                 TRACE_WAIT(8, mbar_wait(full_bar(stage), phase));
                 TRACE_COUNT(11);
                 tcgen05_fence_after();
@@ -362,16 +419,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         const uint32_t stg = bars + 256u + (uint32_t)(warp - 2) * STG_WARP_BYTES;
         uint32_t n_items = 0;
         Item it;
+        Prob pr;
 #pragma unroll 1
         for (uint32_t item = worker; item < total; item += n_workers, ++n_items) {
-            decode_item(p, item, it);
+            decode_item(p, item, it, pr);
             const int as = (int)(n_items & 1);
             const uint32_t aphase = (n_items >> 1) & 1u;
             const int m = it.m0 + (int)rank * BM + quarter * 32 + lane;       // the output row this thread owns
-            const bool row_in = m < p.M;
-            TC* Crow = reinterpret_cast<TC*>(p.C) + it.b1 * p.c_bs1 + it.b2 * p.c_bs2 + (long)m * p.c_rs;
+            const bool row_in = m < pr.M;
+            TC* Crow = reinterpret_cast<TC*>(pr.C) + it.b1 * p.c_bs1 + it.b2 * p.c_bs2 + (long)m * pr.c_rs;
             const TC* Rrow = (EPI == EPI_BF16_PLAIN || EPI == EPI_F32 || !p.R) ? nullptr
-                                 : reinterpret_cast<const TC*>(p.R) + it.b1 * p.c_bs1 + it.b2 * p.c_bs2 + (long)m * p.c_rs;
+                                 : reinterpret_cast<const TC*>(p.R) + it.b1 * p.c_bs1 + it.b2 * p.c_bs2 + (long)m * pr.c_rs;
             const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * MAX_BN);
             bool row_ok = true;
             if (FULLISH && p.mask_period > 0) {
@@ -383,10 +441,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             float b00 = 0.f, b01 = 0.f, b10 = 0.f, b11 = 0.f;
             if (EPI != EPI_F32 && p.bias) {
                 const int n0a = it.n0 + ch * 64, n0b = it.n0 + (ch + 2) * 64;
-                if (n0a + lane < p.N) b00 = p.bias[n0a + lane];
-                if (n0a + lane + 32 < p.N) b01 = p.bias[n0a + lane + 32];
-                if (n0b + lane < p.N) b10 = p.bias[n0b + lane];
-                if (n0b + lane + 32 < p.N) b11 = p.bias[n0b + lane + 32];
+                if (n0a + lane < pr.N) b00 = p.bias[n0a + lane];
+                if (n0a + lane + 32 < pr.N) b01 = p.bias[n0a + lane + 32];
+                if (n0b + lane < pr.N) b10 = p.bias[n0b + lane];
+                if (n0b + lane + 32 < pr.N) b11 = p.bias[n0b + lane + 32];
             }
             uint4 rr[8];
             const bool res_vec = (EPI == EPI_BF16_FULL || EPI == EPI_BF16_GATE) && Rrow && p.vec_ok && row_in;
@@ -395,7 +453,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 #pragma unroll
                 for (int g8 = 0; g8 < 8; ++g8) {
                     rr[g8] = make_uint4(0u, 0u, 0u, 0u);
-                    if (res_vec && c0 + g8 * 8 < BN && it.n0 + c0 + g8 * 8 + 8 <= p.N)
+                    if (res_vec && c0 + g8 * 8 < BN && it.n0 + c0 + g8 * 8 + 8 <= pr.N)
                         rr[g8] = *reinterpret_cast<const uint4*>(Rrow + it.n0 + c0 + g8 * 8);
                 }
             };
@@ -426,8 +484,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                 }
                 if (ncols <= 0) continue;          // warp-uniform
                 // warp-uniform: the whole 64-column chunk is inside N and C rows are 16-byte aligned
-                const bool stage_chunk = !F32OUT && p.vec_ok && !p.accumulate && ncols == 64 && it.n0 + c0 + 64 <= p.N &&
-                                         !(EPI == EPI_BF16_FULL && drop.thresh != 0u && (p.N & 15));   // group-wise dropout mask: 16-aligned row starts
+                const bool stage_chunk = !F32OUT && p.vec_ok && !p.accumulate && ncols == 64 && it.n0 + c0 + 64 <= pr.N &&
+                                         !(EPI == EPI_BF16_FULL && drop.thresh != 0u && (pr.N & 15));   // group-wise dropout mask: 16-aligned row starts
                 if (!F32OUT && stage_chunk) {
                     // ---- hot path: straight-line code, no per-group bounds / alignment decisions ----
                     const uint32_t rowaddr = stg + (uint32_t)lane * 128u;
@@ -435,7 +493,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                     const bool has_res = (EPI == EPI_BF16_FULL) && Rrow != nullptr;
                     const bool has_gate = (EPI == EPI_BF16_GATE) && Rrow != nullptr;
                     const bool has_drop = (EPI == EPI_BF16_FULL) && drop.thresh != 0u;
-                    const uint64_t didx0 = (uint64_t)(((long)(it.b1 * p.batch2 + it.b2) * p.M + m) * (long)p.N + it.n0 + c0);
+                    const uint64_t didx0 = (uint64_t)(((long)(it.b1 * p.batch2 + it.b2) * pr.M + m) * (long)pr.N + it.n0 + c0);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         float v[16];
@@ -443,10 +501,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                             const float bsel = u ? ((q & 2) ? b11 : b10) : ((q & 2) ? b01 : b00);
 #pragma unroll
                             for (int jj = 0; jj < 16; ++jj)
-                                v[jj] = fmaf(__uint_as_float(acc[q][jj]), p.alpha, __shfl_sync(0xffffffffu, bsel, (q & 1) * 16 + jj));
+                                v[jj] = fmaf(__uint_as_float(acc[q][jj]), pr.alpha, __shfl_sync(0xffffffffu, bsel, (q & 1) * 16 + jj));
                         } else {
 #pragma unroll
-                            for (int jj = 0; jj < 16; ++jj) v[jj] = __uint_as_float(acc[q][jj]) * p.alpha;
+                            for (int jj = 0; jj < 16; ++jj) v[jj] = __uint_as_float(acc[q][jj]) * pr.alpha;
                         }
                         if (relu) {
 #pragma unroll
@@ -480,7 +538,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                     const int r_sub = lane >> 3, c16 = lane & 7;
                     const int row0 = it.m0 + (int)rank * BM + quarter * 32;
                     const long cofs = it.b1 * p.c_bs1 + it.b2 * p.c_bs2 + it.n0 + c0 + c16 * 8;
-                    TC* Cblk = reinterpret_cast<TC*>(p.C) + cofs;
+                    TC* Cblk = reinterpret_cast<TC*>(pr.C) + cofs;
                     if (EPI == EPI_BF16_GATE && has_gate) {
                         // ReLU' gate: the gate operand is read with the store's own coalesced pattern (4 rows x 128 B per instruction)
                         const TC* Gblk = reinterpret_cast<const TC*>(p.R) + cofs;
@@ -489,7 +547,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                         for (int i = 0; i < 8; ++i) {
                             const int r = i * 4 + r_sub;
                             gq[i] = make_uint4(0u, 0u, 0u, 0u);
-                            if (row0 + r < p.M) gq[i] = *reinterpret_cast<const uint4*>(Gblk + (long)(row0 + r) * p.c_rs);
+                            if (row0 + r < pr.M) gq[i] = *reinterpret_cast<const uint4*>(Gblk + (long)(row0 + r) * pr.c_rs);
                         }
                         const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
@@ -500,7 +558,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                             const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&gq[i]);
 #pragma unroll
                             for (int e = 0; e < 4; ++e) w2[e] = __hmul2(w2[e], __hgt2(g2[e], zero2));
-                            if (row0 + r < p.M) *reinterpret_cast<uint4*>(Cblk + (long)(row0 + r) * p.c_rs) = w;
+                            if (row0 + r < pr.M) *reinterpret_cast<uint4*>(Cblk + (long)(row0 + r) * pr.c_rs) = w;
                         }
                         __syncwarp();
                         continue;
@@ -509,7 +567,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                     for (int i = 0; i < 8; ++i) {
                         const int r = i * 4 + r_sub;
                         const uint4 w = ld_shared_v4(stg + (uint32_t)r * 128u + (uint32_t)((c16 ^ (r & 7)) << 4));
-                        if (row0 + r < p.M) *reinterpret_cast<uint4*>(Cblk + (long)(row0 + r) * p.c_rs) = w;
+                        if (row0 + r < pr.M) *reinterpret_cast<uint4*>(Cblk + (long)(row0 + r) * pr.c_rs) = w;
                     }
                     __syncwarp();
                     continue;
@@ -522,16 +580,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                     float v[16];
                     if (EPI == EPI_F32) {
 #pragma unroll
-                        for (int jj = 0; jj < 16; ++jj) v[jj] = __uint_as_float(acc[q][jj]) * p.alpha;
+                        for (int jj = 0; jj < 16; ++jj) v[jj] = __uint_as_float(acc[q][jj]) * pr.alpha;
                     } else {
                         if (p.bias) {                  // warp-uniform
                             const float bsel = u ? ((q & 2) ? b11 : b10) : ((q & 2) ? b01 : b00);
 #pragma unroll
                             for (int jj = 0; jj < 16; ++jj)
-                                v[jj] = fmaf(__uint_as_float(acc[q][jj]), p.alpha, __shfl_sync(0xffffffffu, bsel, (q & 1) * 16 + jj));
+                                v[jj] = fmaf(__uint_as_float(acc[q][jj]), pr.alpha, __shfl_sync(0xffffffffu, bsel, (q & 1) * 16 + jj));
                         } else {
 #pragma unroll
-                            for (int jj = 0; jj < 16; ++jj) v[jj] = __uint_as_float(acc[q][jj]) * p.alpha;
+                            for (int jj = 0; jj < 16; ++jj) v[jj] = __uint_as_float(acc[q][jj]) * pr.alpha;
                         }
                         if (p.relu) {
 #pragma unroll
@@ -540,7 +598,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                     }
                     const int n_base = it.n0 + c0 + q * 16;
                     if (FULLISH && drop.thresh != 0u) {
-                        const uint64_t didx = (uint64_t)(((long)(it.b1 * p.batch2 + it.b2) * p.M + m) * (long)p.N + n_base);
+                        const uint64_t didx = (uint64_t)(((long)(it.b1 * p.batch2 + it.b2) * pr.M + m) * (long)pr.N + n_base);
                         if ((didx & 15ull) == 0ull) {                // one seed per aligned group of 16 (common.cuh: dropout_factors)
                             float mk[16];
                             dropout_factors<16>(drop, didx, mk);
@@ -551,9 +609,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                             for (int jj = 0; jj < 16; ++jj) v[jj] *= dropout_factor(drop, didx + jj);
                         }
                     }
-                    if (!row_in || n_base >= p.N) continue;
+                    if (!row_in || n_base >= pr.N) continue;
                     TC* dst = Crow + n_base;
-                    const bool fast = p.vec_ok && n_base + 16 <= p.N;
+                    const bool fast = p.vec_ok && n_base + 16 <= pr.N;
                     if (EPI == EPI_F32) {
                         float* d32 = reinterpret_cast<float*>(dst);
                         if (fast && p.atomic_out) {
@@ -566,7 +624,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                             float vt[16];      // a COPY for the out-of-line helper: passing v[] itself would force it into local memory
 #pragma unroll
                             for (int jj = 0; jj < 16; ++jj) vt[jj] = v[jj];
-                            epilogue_scalar<TC>(p, vt, dst, nullptr, min(16, p.N - n_base), true);
+                            epilogue_scalar<TC>(p, vt, dst, nullptr, min(16, pr.N - n_base), true);
                         }
                     } else if (EPI == EPI_F32_FULL) {
                         float* d32 = reinterpret_cast<float*>(dst);
@@ -595,7 +653,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                             float vt[16];
 #pragma unroll
                             for (int jj = 0; jj < 16; ++jj) vt[jj] = v[jj];
-                            epilogue_scalar<TC>(p, vt, dst, Rrow ? Rrow + n_base : nullptr, min(16, p.N - n_base), row_ok);
+                            epilogue_scalar<TC>(p, vt, dst, Rrow ? Rrow + n_base : nullptr, min(16, pr.N - n_base), row_ok);
                         }
                     } else if (fast) {
                         if (EPI == EPI_BF16_GATE && Rrow) { combine_bf16x8(v, rr[2 * q], 1, p.r_scale); combine_bf16x8(v + 8, rr[2 * q + 1], 1, p.r_scale); }
@@ -618,7 +676,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                             float vt[16];
 #pragma unroll
                             for (int jj = 0; jj < 16; ++jj) vt[jj] = v[jj];
-                            epilogue_scalar<TC>(p, vt, dst, Rrow ? Rrow + n_base : nullptr, min(16, p.N - n_base), row_ok);
+                            epilogue_scalar<TC>(p, vt, dst, Rrow ? Rrow + n_base : nullptr, min(16, pr.N - n_base), row_ok);
                         }
                     }
                 }
@@ -804,7 +862,78 @@ int gemm_tc(const s2s_gemm_t& g, cudaStream_t st) {
     void* args[1] = {(void*)&p};
     const cudaError_t lerr = cudaLaunchKernelExC(&cfg, kernels[p.cg - 1][epi], args);
     if (lerr != cudaSuccess) return set_error(S2S_ERR_CUDA, "gemm_tc: launch failed: %s", cudaGetErrorString(lerr));
-    count_launch();
+    S2S_LAUNCH_OK();
+    return S2S_OK;
+}
+
+// Grouped weight-gradient launch (see ParamsG).  Returns S2S_ERR_UNSUPPORTED when the set does not fit the grouped form (the
+// caller then launches the GEMMs one by one).
+int gemm_tc_grouped(const s2s_gemm_t* gs, int n, cudaStream_t st) {
+    using namespace tc;
+    if (n < 1 || n > MAX_GROUPS) return S2S_ERR_UNSUPPORTED;
+    for (int i = 0; i < n; ++i) {
+        const s2s_gemm_t& g = gs[i];
+        const bool ok = g.a_dtype == S2S_BF16 && g.b_dtype == S2S_BF16 && g.c_dtype == S2S_F32 && g.accumulate && !g.bias && !g.R && !g.relu &&
+                        g.drop.p <= 0.f && g.mask_period == 0 && g.batch1 * g.batch2 == 1 && g.taps == 1 && g.a_cs != 1 && g.b_cs != 1 &&
+                        g.a_rs == 1 && g.b_rs == 1 && g.K > 1 && g.N >= 8 && g.M > 0 &&
+                        (reinterpret_cast<uintptr_t>(g.C) & 15) == 0 && g.c_rs % 4 == 0;
+        if (!ok) return S2S_ERR_UNSUPPORTED;
+    }
+    ParamsG p;
+    memset(&p, 0, sizeof(p));
+    // common N tile: the width that wastes the least padded work over the set
+    int best_bn = 256;
+    double best_waste = -1.0;
+    for (int bn : {256, 192, 128}) {
+        double w = 0.0;
+        for (int i = 0; i < n; ++i) w += (double)ceil_div_l(gs[i].M, BM) * BM * ceil_div_l(gs[i].N, bn) * bn * (double)gs[i].K;
+        if (best_waste < 0 || w < best_waste * 0.999) { best_waste = w; best_bn = bn; }
+    }
+    p.BN = best_bn; p.cg = 1; p.a_mn = 1; p.b_mn = 1; p.taps = 1; p.batch1 = p.batch2 = 1;
+    p.c_f32 = 1; p.accumulate = 1; p.atomic_out = 1; p.vec_ok = 1; p.alpha = 1.f; p.trace = nullptr;
+    p.ngroups = n;
+    double work = 0.0;
+    for (int i = 0; i < n; ++i) work += (double)ceil_div_l(gs[i].M, BM) * ceil_div_l(gs[i].N, p.BN) * ceil_div_l(gs[i].K, BK);
+    const double target = work / (2.0 * num_sms()) > 8.0 ? work / (2.0 * num_sms()) : 8.0;      // k-blocks per item
+    uint32_t item0 = 0;
+    for (int i = 0; i < n; ++i) {
+        const s2s_gemm_t& g = gs[i];
+        Group& G = p.grp[i];
+        long dimA[4] = {g.M, g.K, 1, 1}, strA[4] = {1, g.a_cs, 0, 0};
+        long dimB[4] = {g.N, g.K, 1, 1}, strB[4] = {1, g.b_cs, 0, 0};
+        if (!make_map(&G.tmA, g.A, dimA, strA, 64, BK) || !make_map(&G.tmB, g.B, dimB, strB, 64, BK)) return S2S_ERR_UNSUPPORTED;
+        G.C = g.C; G.c_rs = g.c_rs; G.M = g.M; G.N = g.N; G.K = g.K; G.alpha = g.alpha;
+        G.nt = (int)ceil_div_l(g.N, p.BN);
+        G.kb_total = (int)ceil_div_l(g.K, BK);
+        long sp = (long)(G.kb_total / target + 0.5);
+        const long max_s = G.kb_total / 4;
+        if (sp > max_s) sp = max_s;
+        if (sp < 1) sp = 1;
+        int per = (int)ceil_div_l(G.kb_total, sp);
+        G.splits = (int)ceil_div_l(G.kb_total, per);          // every split owns at least one k-block
+        G.kb_per_split = per;
+        G.item0 = item0;
+        G.items = (uint32_t)(ceil_div_l(g.M, BM) * G.nt * G.splits);
+        item0 += G.items;
+        G.d_splits.set((uint32_t)G.splits);
+        G.d_nt.set((uint32_t)G.nt);
+    }
+    const void* kern = (const void*)gemm_tc_kernel<EPI_F32, 1, ParamsG>;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [kern] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES); });
+    if (attr_err != cudaSuccess) return set_error(S2S_ERR_CUDA, "gemm_tc_grouped: cannot raise dynamic shared memory: %s", cudaGetErrorString(attr_err));
+    const long workers = num_sms();
+    const unsigned grid = (unsigned)(item0 < workers ? item0 : workers);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = st;
+    void* args[1] = {(void*)&p};
+    const cudaError_t lerr = cudaLaunchKernelExC(&cfg, kern, args);
+    if (lerr != cudaSuccess) return set_error(S2S_ERR_CUDA, "gemm_tc_grouped: launch failed: %s", cudaGetErrorString(lerr));
     S2S_LAUNCH_OK();
     return S2S_OK;
 }

@@ -798,6 +798,85 @@ extern "C" int s2s_colsum(const void* x, int64_t rows, int cols, int64_t ld, flo
     return rc;
 }
 
+// ---------------------------------------------------------------------------------------------
+// several column sums in one launch (the bias gradients of one Transformer layer's backward)
+// ---------------------------------------------------------------------------------------------
+namespace s2s {
+constexpr int COLSUM_MAX = 8;
+struct ColsumSet {
+    s2s_colsum_t it[COLSUM_MAX];
+};
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_multi_kernel(const __grid_constant__ ColsumSet set) {
+    __shared__ float red[8][256];
+    const s2s_colsum_t& d = set.it[blockIdx.z];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int c0 = (blockIdx.x * 32 + tx) * 8;
+    float acc[8];
+#pragma unroll
+    for (int v = 0; v < 8; ++v) acc[v] = 0.f;
+    const long per = (d.rows + gridDim.y - 1) / gridDim.y;
+    const long r0 = (long)blockIdx.y * per;
+    const long r1 = (r0 + per < d.rows) ? r0 + per : d.rows;
+    if (c0 < d.cols) {
+        const T* x = reinterpret_cast<const T*>(d.x);
+#pragma unroll 4
+        for (long r = r0 + ty; r < r1; r += 8) {
+            float v[8];
+            Vec8<T>::load(x + r * d.ld + c0, v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += v[i];
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < 8; ++v) red[ty][tx * 8 + v] = acc[v];
+    __syncthreads();
+    const int e = ty * 32 + tx;
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += red[w][e];
+    const int c = blockIdx.x * 256 + e;
+    if (c < d.cols && r0 < r1) atomicAdd(d.out + c, sum);
+}
+}  // namespace s2s
+
+extern "C" int s2s_colsum_multi(const s2s_colsum_t* items, int n, int dtype, void* stream) {
+    S2S_REQUIRE(items && n >= 1, "colsum_multi: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    int i = 0;
+    while (i < n) {
+        // pack runs of vectorisable items into one launch; anything else goes through s2s_colsum
+        ColsumSet set;
+        int m = 0, max_cols = 0;
+        long max_rows = 0;
+        while (i < n && m < COLSUM_MAX) {
+            const s2s_colsum_t& d = items[i];
+            S2S_REQUIRE(d.x && d.out && d.cols > 0 && d.ld >= d.cols, "colsum_multi: bad item %d", i);
+            if (!(d.cols % 8 == 0 && d.ld % 8 == 0 && aligned16(d.x))) break;
+            set.it[m++] = d;
+            max_cols = d.cols > max_cols ? d.cols : max_cols;
+            max_rows = d.rows > max_rows ? d.rows : max_rows;
+            ++i;
+        }
+        if (m > 0 && max_rows > 0) {
+            const unsigned gx = (unsigned)ceil_div_l(max_cols, 256);
+            long want = (long)num_sms() * 4 / ((long)gx * m);
+            const long maxy = ceil_div_l(max_rows, 64);
+            if (want > maxy) want = maxy;
+            if (want < 1) want = 1;
+            S2S_DISPATCH_DTYPE(dtype, T, (colsum_multi_kernel<T><<<dim3(gx, (unsigned)want, (unsigned)m), dim3(32, 8), 0, st>>>(set)));
+            S2S_LAUNCH_OK();
+        }
+        if (i < n && m < COLSUM_MAX) {          // the item that broke the run
+            const s2s_colsum_t& d = items[i];
+            const int rc = s2s_colsum(d.x, d.rows, d.cols, d.ld, d.out, dtype, stream);
+            if (rc != S2S_OK) return rc;
+            ++i;
+        }
+    }
+    return S2S_OK;
+}
+
 extern "C" int s2s_relu_bwd(const void* dy, const void* y, void* dx, int64_t n, float scale, int dtype, void* stream) {
     S2S_REQUIRE(dy && y && dx, "relu_bwd: null pointer");
     if (n <= 0) return S2S_OK;

@@ -188,9 +188,15 @@ class EngineBase:
         if w.shape[0] <= 4 and dx_residual is None and dx_gate is None:
             return ops.skinny_linear_bwd(dy2d, x2d, w, gw, gb, dx, dx_accumulate)
         if gw is not None:
-            ops.gemm(dy2d.t(), x2d.t(), gw, accumulate=True, mode=mode)
+            if self._defer is not None:
+                self._defer[0].append((dy2d.t(), x2d.t(), gw, dict(accumulate=True)))
+            else:
+                ops.gemm(dy2d.t(), x2d.t(), gw, accumulate=True, mode=mode)
         if gb is not None:
-            ops.colsum(dy2d, gb)      # (a side-stream overlap with the two GEMMs was measured: no gain, the persistent GEMM owns the SMs)
+            if self._defer is not None:
+                self._defer[1].append((dy2d, gb))
+            else:
+                ops.colsum(dy2d, gb)      # (a side-stream overlap with the two GEMMs was measured: no gain, the persistent GEMM owns the SMs)
         if dx is not None:
             if dx_gate is not None and not self.fuse_relu_gate:        # A/B switch: separate relu' pass
                 ops.gemm(dy2d, w.t(), dx, residual=dx_residual, accumulate=dx_accumulate, mode=mode)
@@ -198,6 +204,25 @@ class EngineBase:
             else:
                 ops.gemm(dy2d, w.t(), dx, residual=dx_residual, accumulate=dx_accumulate, mode=mode, gate=dx_gate, gate_scale=dx_gate_scale)
         return dx
+
+    # Deferred weight gradients: inside a layer's backward the dW = dy^T x products and the bias-gradient column sums are only
+    # recorded; _flush_defer() at the end of the layer issues them as ONE grouped tcgen05 launch and ONE multi-colsum launch
+    # (7 + 7 launches of a decoder layer become 2).  Every recorded dy / x must stay untouched until the flush: the engines
+    # give the per-layer gradient temporaries distinct buffers while deferring (see VTNEngine.backward).
+    _defer = None
+    group_dw = os.environ.get("S2S_GROUP_DW", "1") != "0"
+
+    def _begin_defer(self) -> bool:
+        if self.mode == 1 and self.group_dw and self.device.type == "cuda":
+            self._defer = ([], [])
+            return True
+        return False
+
+    def _flush_defer(self) -> None:
+        d, self._defer = self._defer, None
+        if d is not None:
+            ops.gemm_grouped(d[0], mode=self.mode)
+            ops.colsum_multi(d[1])
 
     def _ln_fwd(self, x, name, tag, eps: float = 1e-12):
         B_, T_, d = x.shape

@@ -12,7 +12,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import NO_DROP, Drop, GemmDesc, check, dt, ptr, stream
+from ._lib import NO_DROP, ColsumDesc, Drop, GemmDesc, check, dt, ptr, stream
 
 _i32 = torch.int32
 
@@ -60,11 +60,48 @@ def _split_workspace(g: GemmDesc, device) -> torch.Tensor:
     return ws
 
 
-def gemm(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, *, bias: Optional[torch.Tensor] = None,
-         residual: Optional[torch.Tensor] = None, alpha: float = 1.0, relu: bool = False,
-         accumulate: bool = False, drop: Drop = NO_DROP, taps: int = 1,
-         row_mask: Optional[Tuple[int, int, int, int]] = None, mode: int = 0, M: Optional[int] = None,
-         gate: Optional[torch.Tensor] = None, gate_scale: float = 1.0) -> torch.Tensor:
+def gemm(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, *, mode: int = 0, **kw) -> torch.Tensor:
+    """One s2s_gemm call: see _gemm_desc for the operand conventions and epilogue options."""
+    g = _gemm_desc(a, b, c, **kw)
+    if mode == 2:
+        g.split_terms = SPLIT_TERMS
+        ws = _split_workspace(g, c.device)
+        g.ws, g.ws_bytes = ptr(ws), ws.numel()
+    check(_L().s2s_gemm(ctypes.byref(g), mode, stream()), "s2s_gemm")
+    return c
+
+
+def gemm_grouped(problems, mode: int = 0) -> None:
+    """Several independent GEMMs [(a, b, c, kwargs), ...] issued together (s2s_gemm_grouped): in mode 1 the weight-gradient
+    products of one layer (bf16 operands contiguous along M / N, float32 c accumulated in place) share one persistent launch."""
+    if not problems:
+        return
+    if mode == 2 or len(problems) == 1:
+        for a, b, c, kw in problems:
+            gemm(a, b, c, mode=mode, **kw)
+        return
+    arr = (GemmDesc * len(problems))()
+    for i, (a, b, c, kw) in enumerate(problems):
+        arr[i] = _gemm_desc(a, b, c, **kw)
+    check(_L().s2s_gemm_grouped(arr, len(problems), mode, stream()), "s2s_gemm_grouped")
+
+
+def colsum_multi(items) -> None:
+    """[(x2d, out), ...]: out[c] += sum_r x2d[r, c] for every pair, in one launch (s2s_colsum_multi); one dtype per call."""
+    if not items:
+        return
+    arr = (ColsumDesc * len(items))()
+    for i, (x2d, out) in enumerate(items):
+        assert x2d.dim() == 2 and x2d.stride(1) == 1 and x2d.dtype == items[0][0].dtype
+        arr[i] = ColsumDesc(ptr(x2d), x2d.shape[0], x2d.shape[1], x2d.stride(0), ptr(out))
+    check(_L().s2s_colsum_multi(arr, len(items), dt(items[0][0]), stream()), "s2s_colsum_multi")
+
+
+def _gemm_desc(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, *, bias: Optional[torch.Tensor] = None,
+               residual: Optional[torch.Tensor] = None, alpha: float = 1.0, relu: bool = False,
+               accumulate: bool = False, drop: Drop = NO_DROP, taps: int = 1,
+               row_mask: Optional[Tuple[int, int, int, int]] = None, M: Optional[int] = None,
+               gate: Optional[torch.Tensor] = None, gate_scale: float = 1.0) -> GemmDesc:
     """c[..., m, n] = epilogue(alpha * sum_t sum_k a[..., m + t, k] * b[..., n, (t,) k]).
 
     a: (..., rows, K); b: (..., N, K) or (..., N, taps, K) when taps > 1; c: (..., M, N).
@@ -111,12 +148,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor, *, bias: Optional[to
     g.drop = drop.c()
     if row_mask is not None:
         g.mask_period, g.mask_offset, g.mask_lo, g.mask_hi = row_mask
-    if mode == 2:
-        g.split_terms = SPLIT_TERMS
-        ws = _split_workspace(g, c.device)
-        g.ws, g.ws_bytes = ptr(ws), ws.numel()
-    check(_L().s2s_gemm(ctypes.byref(g), mode, stream()), "s2s_gemm")
-    return c
+    return g
 
 
 def layernorm_fwd(x, gamma, beta, y, mean, rstd, eps=1e-12):

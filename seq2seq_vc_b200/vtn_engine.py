@@ -654,10 +654,14 @@ class VTNEngine(EngineBase):
         mem = self.buf("enc.after.y", (B, T2, d))
         dmem = self._scratch("g.mem", (B, T2, d))
         dmem.zero_()
-        gt = self._scratch("g.dec_b", (B, Lr, d))
-        gd = self._scratch("g.dec_c", (B * Lr, d))
         for l in reversed(range(hp["dlayers"])):
             p = f"decoder.decoders.{l}"
+            # weight / bias gradients of the layer are recorded and issued together at its end (EngineBase._flush_defer): the three
+            # LayerNorm-input gradients and their dropout' copies are dW operands, so they get a buffer each instead of sharing one
+            deferring = self._begin_defer()
+            gts = [self._scratch(f"g.dec_b{j if deferring else 0}", (B, Lr, d)) for j in range(3)]
+            gds = [self._scratch(f"g.dec_c{j if deferring else 0}", (B * Lr, d)) for j in range(3)]
+            gt, gd = gts[0], gds[0]
             xin = self.buf(f"decoder.decoders.{l - 1}.ln3.y", (B, Lr, d)) if l > 0 else self.buf("dec.x0", (B, Lr, d))
             t1, t2, t3 = (self.buf(p + f".t{i}", (B, Lr, d)) for i in (1, 2, 3))
             x1 = self.buf(p + ".ln1.y", (B, Lr, d))
@@ -673,6 +677,7 @@ class VTNEngine(EngineBase):
             self._lin_bwd(dh, x2.view(B * Lr, d), self.W(p + ".feed_forward.w_1.weight"), st.g(p + ".feed_forward.w_1.weight"),
                           st.g(p + ".feed_forward.w_1.bias"), dx=dx2.view(B * Lr, d), dx_residual=dt3.view(B * Lr, d))
             # x2 = LN2(t2), t2 = drop(ctx2 Wo) + x1
+            gt, gd = gts[1], gds[1]
             dt2 = self._ln_bwd(dx2, t2, p + ".norm2", p + ".ln2", gt, dx_drop=gd.view(B, Lr, d), drop=sites[p + ".ca_out"])
             do = gd if sites[p + ".ca_out"].p > 0.0 else dt2.view(B * Lr, d)
             ctx2 = self.buf(p + ".ca.ctx", (B, Lr, d))
@@ -692,6 +697,7 @@ class VTNEngine(EngineBase):
             self._lin_bwd(dq.view(B * Lr, d), x1.view(B * Lr, d), self.W(p + ".src_attn.linear_q.weight"), st.g(p + ".src_attn.linear_q.weight"),
                           st.g(p + ".src_attn.linear_q.bias"), dx=dx1.view(B * Lr, d), dx_residual=dt2.view(B * Lr, d))
             # x1 = LN1(t1), t1 = drop(ctx Wo) + xin
+            gt, gd = gts[2], gds[2]
             dt1 = self._ln_bwd(dx1, t1, p + ".norm1", p + ".ln1", gt, dx_drop=gd.view(B, Lr, d), drop=sites[p + ".sa_out"])
             do = gd if sites[p + ".sa_out"].p > 0.0 else dt1.view(B * Lr, d)
             ctx = self.buf(p + ".sa.ctx", (B, Lr, d))
@@ -704,9 +710,10 @@ class VTNEngine(EngineBase):
             self._lin_bwd(dqkv.view(B * Lr, 3 * d), xin.view(B * Lr, d), self.Wspan([p + ".self_attn.linear_q.weight"], (3 * d, d)),
                           st.span(st.G, [p + ".self_attn.linear_q.weight"], (3 * d, d)), st.span(st.G, [p + ".self_attn.linear_q.bias"], (3 * d,)),
                           dx=g.view(B * Lr, d), dx_residual=dt1.view(B * Lr, d))
+            self._flush_defer()
 
         # ---- decoder input layer
-        de = gt
+        de = self._scratch("g.dec_b0", (B, Lr, d))
         ops.scaled_pe_bwd(g, self.pe(d, Lr), de, st.g("decoder.embed.1.alpha"), sites["dec.pe"])
         u = hp["dprenet_units"]
         npre = hp["dprenet_layers"]
@@ -741,6 +748,7 @@ class VTNEngine(EngineBase):
             n1 = self.buf(p + ".ln1.y", (B, T2, d))
             n2 = self.buf(p + ".ln2.y", (B, T2, d))
             h = self.buf(p + ".ffh", (B * T2, hp["eunits"]))
+            self._begin_defer()
             df = gdf.view(B * T2, d) if sites[p + ".ff2"].p > 0.0 else g.view(B * T2, d)
             dh = self._scratch("g.effh", (B * T2, hp["eunits"]))
             self._lin_bwd(df, h, self.W(p + ".feed_forward.w_2.weight"), st.g(p + ".feed_forward.w_2.weight"),
@@ -763,6 +771,7 @@ class VTNEngine(EngineBase):
             self._lin_bwd(dqkv.view(B * T2, 3 * d), n1.view(B * T2, d), self.Wspan([p + ".self_attn.linear_q.weight"], (3 * d, d)),
                           st.span(st.G, [p + ".self_attn.linear_q.weight"], (3 * d, d)), st.span(st.G, [p + ".self_attn.linear_q.bias"], (3 * d,)),
                           dx=dn1.view(B * T2, d))
+            self._flush_defer()       # before g / gdf (operands of this layer's w_2 gradient) are overwritten
             self._ln_bwd(dn1, xin, p + ".norm1", p + ".ln1", g, dres=gm, dx_drop=gdf if l > 0 else None,
                          drop=sites[f"encoder.encoders.{l - 1}.ff2"] if l > 0 else NO_DROP)          # g_prev = g_mid + LN1'(dn1)
 

@@ -50,6 +50,16 @@ def gemm(a, b, c, *, bias=None, residual=None, alpha=1.0, relu=False, accumulate
     return c
 
 
+def gemm_grouped(problems, mode=0):
+    for a, b, c, kw in problems:
+        gemm(a, b, c, mode=mode, **kw)
+
+
+def colsum_multi(items):
+    for x2d, out in items:
+        colsum(x2d, out)
+
+
 def layernorm_fwd(x, gamma, beta, y, mean, rstd, eps=1e-12):
     d = x.shape[-1]
     x2 = x.reshape(-1, d).double()

@@ -124,6 +124,55 @@ def test_gemm_conv1d_taps(ops, mode, dt):
     close(dz[:, halo:halo + L], y.transpose(1, 2), tol(dt, 8 * (8 if mode == 2 else 1)), "conv1d")
 
 
+def test_gemm_grouped_weight_gradients_and_multi_colsum(ops):
+    """s2s_gemm_grouped: the dW = dy^T x products of one layer in ONE tcgen05 launch == the same products one by one (bit-level
+    differences only from the red.add order), incl. ragged M / N / K and a problem the grouped kernel must hand back
+    (K-major operand); s2s_colsum_multi == s2s_colsum per tensor."""
+    bf = torch.bfloat16
+    shapes = [(1152, 384, 16384), (384, 384, 16384), (768, 384, 4064), (1536, 384, 16384), (384, 1536, 16384), (80, 256, 3001), (160, 384, 777)]
+    probs, refs = [], []
+    for i, (M, N, K) in enumerate(shapes):
+        dy, x = rnd(K, M, dt=bf, seed=10 + i).cuda(), rnd(K, N, dt=bf, seed=20 + i).cuda()
+        g0 = rnd(M, N, seed=30 + i).cuda()
+        ref = g0.clone()
+        ops.gemm(dy.t(), x.t(), ref, accumulate=True, mode=1)
+        probs.append((dy.t(), x.t(), g0, dict(accumulate=True)))
+        refs.append(ref)
+    n0 = ops._lib.launch_count()
+    ops.gemm_grouped(probs, mode=1)
+    assert ops._lib.launch_count() - n0 == 1, "seven weight gradients, one launch"
+    for (M, N, K), (_, _, got, _), ref in zip(shapes, probs, refs):
+        close(got, ref, 2e-3 * math.sqrt(K), f"grouped dW {M}x{N}x{K}")
+        exact = (rnd(K, M, dt=bf, seed=0).float().t() @ rnd(K, N, dt=bf, seed=0).float()) if False else None
+    # against the float64 contract as well
+    M, N, K = shapes[0]
+    dy, x = rnd(K, M, dt=bf, seed=10), rnd(K, N, dt=bf, seed=20)
+    want = F.gemm(dy.t(), x.t(), rnd(M, N, seed=30), accumulate=True)
+    close(probs[0][2], want, tol(bf, 40), "grouped dW vs contract")
+    # a set with a member outside the grouped form: still every product is computed
+    a, b = rnd(300, 200, dt=bf, seed=1).cuda(), rnd(96, 200, dt=bf, seed=2).cuda()
+    c = torch.zeros(300, 96, dtype=bf, device="cuda")
+    g1 = torch.zeros(384, 384, device="cuda")
+    dy, x = rnd(5000, 384, dt=bf, seed=3).cuda(), rnd(5000, 384, dt=bf, seed=4).cuda()
+    ops.gemm_grouped([(a, b, c, {}), (dy.t(), x.t(), g1, dict(accumulate=True))], mode=1)
+    close(c, F.gemm(a.cpu(), b.cpu(), torch.zeros(300, 96, dtype=bf)), tol(bf, 4), "mixed set: plain member")
+    close(g1, F.gemm(dy.cpu().t(), x.cpu().t(), torch.zeros(384, 384), accumulate=True), tol(bf, 40), "mixed set: dW member")
+    # multi-colsum
+    items, want = [], []
+    for i, (rows, cols) in enumerate([(16384, 384), (4064, 768), (16384, 1536), (777, 80), (5, 8)]):
+        xx = rnd(rows, cols, dt=bf, seed=40 + i).cuda()
+        out = rnd(cols, seed=50 + i).cuda()
+        w = out.clone()
+        ops.colsum(xx, w)
+        items.append((xx, out))
+        want.append(w)
+    n0 = ops._lib.launch_count()
+    ops.colsum_multi(items)
+    assert ops._lib.launch_count() - n0 == 1
+    for (xx, out), w in zip(items, want):
+        close(out, w, 2e-3 * math.sqrt(xx.shape[0]), "multi colsum")
+
+
 def test_gemm_cta_pairs(ops):
     """The CTA-pair variant of the tcgen05 GEMM (cluster of 2, one 256 x BN cta_group::2 MMA per k-step, each CTA staging half
     of B), forced through the test hook, on every operand layout / epilogue the engines use; then the cost model's own
