@@ -64,6 +64,46 @@ def gen_vtn_tiny():
     print("vtn_tiny:", len(dump), "arrays")
 
 
+def gen_vtn_rfactor():
+    """decoder_reduction_factor 1 and 4 (the recipe's value, egs/arctic/vc1/conf/vtn.v1.yaml:43) with ragged target lengths that
+    are NOT multiples of r: the trimming / thinning / label fix-up paths of models/vtn.py:227-243,262-274."""
+    from seq2seq_vc.losses import Seq2SeqLoss
+    from seq2seq_vc.models import VTN
+
+    for r, olens in ((1, [37, 30, 21]), (4, [37, 30, 21]), (3, [35, 31, 22])):
+        torch.manual_seed(70 + r)
+        hp = dict(TINY_HP, decoder_reduction_factor=r)
+        model = VTN(dprenet_dropout_rate=0.0, **hp)
+        ref_shim.disable_dropout(model)
+        with torch.no_grad():
+            for n, p in model.named_parameters():
+                if n.endswith("alpha"):
+                    p.fill_(0.7 if "encoder" in n else 1.3)
+                elif p.dim() == 1 and ("norm" in n or ".1." in n):
+                    p.add_(0.1 * torch.randn_like(p))
+        model.train()
+        sd0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        ilens = [48, 41, 30]
+        xs, ilens, ys, labels, olens = vtn_oracle.synthetic_batch(3, 48, max(olens), ilens=ilens, olens=olens, seed=11 + r)
+        out = model(xs, torch.tensor(ilens), ys, labels, torch.tensor(olens))
+        l1, bce = Seq2SeqLoss()(*out[:6])
+        (l1 + bce).backward()
+        dump = {"sd." + k: v.numpy() for k, v in sd0.items()}
+        dump.update({"grad." + k: p.grad.numpy() for k, p in model.named_parameters()})
+        dump.update(xs=xs.numpy(), ilens=np.array(ilens), ys=ys.numpy(), labels=labels.numpy(), olens=np.array(olens), r=np.array(r),
+                    after_outs=out[0].detach().numpy(), before_outs=out[1].detach().numpy(), logits=out[2].detach().numpy(),
+                    ys_out=out[3].numpy(), labels_out=out[4].numpy(), olens_out=out[5].numpy(), ilens_ds_st=out[6][1].numpy(),
+                    olens_in=out[6][2].numpy(), l1_loss=l1.detach().numpy(), bce_loss=bce.detach().numpy())
+        for i, a in enumerate(out[6][0]):
+            dump[f"att_ws.{i}"] = a.detach().numpy()
+        with torch.no_grad():
+            model.eval()
+            io, ip, ia = model.inference(xs[0, :ilens[0]], dict(threshold=0.9999, minlenratio=0.0, maxlenratio=1.2))
+        dump.update(inf_outs=io.numpy(), inf_probs=ip.numpy(), inf_att_ws=ia.numpy())
+        np.savez_compressed(os.path.join(GOLDEN, f"vtn_r{r}_tiny.npz"), **dump)
+        print(f"vtn_r{r}_tiny:", len(dump), "arrays", "out len", out[0].shape[1], "olens_out", out[5].tolist())
+
+
 TTS_HP = dict(idim=40, odim=80, dprenet_layers=2, dprenet_units=16, adim=32, aheads=4, elayers=1, eunits=48,
               dlayers=2, dunits=48, postnet_layers=2, postnet_filts=5, postnet_chans=16, decoder_reduction_factor=2)
 
@@ -346,7 +386,7 @@ if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     import sys
 
-    gens = dict(vtn_tiny=gen_vtn_tiny, tts_tiny=gen_tts_tiny, aasvc_tiny=gen_aasvc_tiny, aasvc_conv1d_tiny=gen_aasvc_conv1d_tiny,
+    gens = dict(vtn_tiny=gen_vtn_tiny, vtn_rfactor=gen_vtn_rfactor, tts_tiny=gen_tts_tiny, aasvc_tiny=gen_aasvc_tiny, aasvc_conv1d_tiny=gen_aasvc_conv1d_tiny,
                 mas=gen_mas, kats=gen_kats, sdp_tiny=gen_sdp_tiny)
     for name in (sys.argv[1:] or list(gens)):      # e.g. `python oracle/gen_golden.py aasvc_conv1d_tiny` adds one fixture
         gens[name]()

@@ -37,9 +37,10 @@ def engine(monkeypatch):
 
 def run_step(eng, z):
     ilens, olens = z["ilens"].tolist(), z["olens"].tolist()
-    xs = torch.from_numpy(z["xs"])[:, :max(ilens)].contiguous()
-    ys = torch.from_numpy(z["ys"])[:, :max(olens)].contiguous()
-    labels = torch.from_numpy(z["labels"])[:, :max(olens)].contiguous()
+    dev = eng.device
+    xs = torch.from_numpy(z["xs"])[:, :max(ilens)].contiguous().to(dev)
+    ys = torch.from_numpy(z["ys"])[:, :max(olens)].contiguous().to(dev)
+    labels = torch.from_numpy(z["labels"])[:, :max(olens)].contiguous().to(dev)
     after, before, logits = eng.forward(xs, ys, ilens, olens)
     losses = eng.loss(ys, labels)
     eng.backward(eng.d_after, eng.d_before, eng.d_logits)
@@ -78,6 +79,36 @@ def test_gradients_match_reference(engine):
             worst = (name, err)
         assert err <= 2e-4, (name, err)
     print("worst relative grad error", worst)
+
+
+@pytest.mark.parametrize("r", [1, 3, 4])
+def test_reduction_factors_forward_and_gradients(monkeypatch, r):
+    """decoder_reduction_factor 1, 3 and 4 (recipe: egs/arctic/vc1/conf/vtn.v1.yaml:43), ragged olens not divisible by r."""
+    fake_ops.install(monkeypatch)
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", f"vtn_r{r}_tiny.npz"))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    eng = VTNEngine(dict(TINY_HP, **NO_DROPOUT, decoder_reduction_factor=r), device="cpu", bf16=False)
+    eng.load_state_dict(sd)
+    check_reduction_factor(eng, z, 1e-5, 2e-4)
+
+
+def check_reduction_factor(eng, z, tol_out, tol_grad):
+    after, before, logits, losses = run_step(eng, z)
+    assert after.shape == z["after_outs"].shape
+    assert np.abs(after.float().cpu().numpy() - z["after_outs"]).mean() <= tol_out
+    assert np.abs(before.float().cpu().numpy() - z["before_outs"]).mean() <= tol_out
+    assert np.abs(logits.float().cpu().numpy() - z["logits"]).mean() <= tol_out
+    assert abs(float(losses[0]) - float(z["l1_loss"])) <= 10 * tol_out and abs(float(losses[1]) - float(z["bce_loss"])) <= 10 * tol_out
+    np.testing.assert_array_equal(eng.labels_fix.cpu().numpy(), z["labels_out"])
+    assert eng.olens_fix_host == z["olens_out"].tolist() and eng.olens_in_host == z["olens_in"].tolist()
+    nl = eng.hp["dlayers"]
+    for i in range(nl):
+        got = eng.attn[f"decoder.decoders.{nl - 1 - i}.src_attn"].float().cpu().numpy()
+        assert np.abs(got - z[f"att_ws.{i}"]).mean() <= 1e-3
+    for name in eng.store.names():
+        ref = z["grad." + name]
+        got = eng.store.g(name).cpu().numpy()
+        assert np.abs(got - ref).max() <= tol_grad * (np.abs(ref).max() + 1e-5) + 1e-7, name
 
 
 def test_bn_running_stats(engine):

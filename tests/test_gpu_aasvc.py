@@ -389,6 +389,60 @@ def test_mid_size_fp32_vs_oracle_and_bf16_drift():
     assert cos >= 0.9
 
 
+def test_c3_widths_bf16_drift_vs_fp32_oracle():
+    """The widths bench.py times for AAS-VC (BASELINE configs[2]: encoder d384, x4 post-encoder reduction -> decoder d1536, 2 heads
+    of d_k 768, k15, 4+4 layers) at a length the CPU oracle finishes in seconds (B 2 x 192 -> 176 frames): bf16 path vs the float32
+    oracle on the same weights; drift printed, recorded and bounded; the float32 tensor-core mode held to 1e-4 / exact durations."""
+    import json
+
+    from oracle import aasvc_oracle as ao
+    from seq2seq_vc_b200.aasvc_engine import AASVCEngine
+
+    hp = dict(idim=80, odim=80, adim=384, aheads=2, elayers=4, eunits=1536, dlayers=4, dunits=1536, duration_predictor_input_dim=80,
+              duration_predictor_layers=2, duration_predictor_chans=256, duration_predictor_kernel_size=3, postnet_layers=5,
+              postnet_filts=5, postnet_chans=256, post_encoder_reduction_factor=4, conformer_enc_kernel_size=15,
+              conformer_dec_kernel_size=15)
+    sd = ao.init_state_dict(hp, seed=4)
+    ilens, olens = [192, 164], [176, 151]
+    xs, ilens, ys, olens, dpi = ao.synthetic_batch(2, 192, 176, ilens=ilens, olens=olens, seed=8)
+    out, parts, grads = ao.aasvc_loss_and_grads(sd, hp, xs, ilens, ys, olens, dpi)
+    rec = {}
+    for mode, kw in (("fp32_tc", dict(bf16=False)), ("bf16", dict(bf16=True))):
+        eng = AASVCEngine(dict(hp, **NO_DROPOUT), device="cuda:0", **kw)
+        eng.load_state_dict(sd)
+        after, before = eng.forward(xs.cuda(), ys.cuda(), dpi.cuda(), ilens, olens)
+        losses = eng.loss(ys.cuda())
+        eng.backward()
+        torch.cuda.synchronize()
+        cos = {}
+        gmax = max(float(g.abs().max()) for g in grads.values() if g is not None)
+        for name in eng.store.names():
+            ref = grads[name]
+            # gradients that are zero in exact arithmetic (a bias in front of BatchNorm) are rounding noise on both sides: skipped
+            if ref is not None and ref.numel() >= 256 and float(ref.abs().max()) >= 1e-5 * gmax:
+                cos[name] = torch.nn.functional.cosine_similarity(eng.store.g(name).cpu().flatten(), ref.flatten(), dim=0).item()
+        worst = min(cos, key=cos.get)
+        rec[mode] = dict(mel_L1=(after.float().cpu() - out["after_outs"].detach()).abs().mean().item(),
+                         durations_equal=(eng.ds.cpu() == out["ds"]).float().mean().item(),
+                         loss_rel_err={k: abs(losses[i].item() - float(parts[k])) / max(1.0, abs(float(parts[k]))) for i, k in enumerate(eng.LOSS_NAMES)},
+                         grad_cosine_min=cos[worst], grad_cosine_min_tensor=worst, grad_cosine_median=float(np.median(list(cos.values()))))
+        print(mode, rec[mode])
+        assert eng.ds.sum(1).cpu().tolist() == [float(o) for o in olens]
+        del eng
+        torch.cuda.empty_cache()
+    path = os.path.join(os.path.dirname(os.path.dirname(__file__)), "gpurun_out", "r02_bf16_drift.json")
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        data = json.load(open(path)) if os.path.exists(path) else {}
+        data["c3_widths_B2_192to176_aasvc"] = rec
+        json.dump(data, open(path, "w"), indent=1)
+    except OSError:
+        pass
+    assert rec["fp32_tc"]["mel_L1"] <= 1e-4 and rec["fp32_tc"]["durations_equal"] == 1.0 and rec["fp32_tc"]["grad_cosine_min"] >= 0.999
+    assert max(rec["fp32_tc"]["loss_rel_err"].values()) <= 1e-4
+    assert rec["bf16"]["mel_L1"] <= 0.15 and rec["bf16"]["grad_cosine_median"] >= 0.95
+
+
 def test_dropout_training_step_runs_and_is_reproducible():
     """Default dropout rates: two forwards with the same seed state are identical, and backward is finite."""
     from seq2seq_vc_b200.aasvc_engine import AASVCEngine

@@ -64,6 +64,46 @@ def test_golden_tiny_fp32_forward_and_grads(fp32_gemm):
     assert np.abs(after_e.cpu().numpy() - z["eval_after_outs"]).mean() <= 1e-4
 
 
+@pytest.mark.parametrize("fp32_gemm", ["simt", "tc"])
+@pytest.mark.parametrize("r", [1, 3, 4])
+def test_reduction_factors_golden_fp32(r, fp32_gemm):
+    """decoder_reduction_factor 1, 3 and 4 (the recipe's value) on the GPU vs the live-reference dumps: ragged target lengths that
+    are not multiples of r, trimmed outputs, fixed-up stop labels / lengths, every gradient; plus autoregressive inference."""
+    import test_engine_host_logic as H
+    from seq2seq_vc_b200 import VTNEngine
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", f"vtn_r{r}_tiny.npz"))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    eng = VTNEngine(dict(TINY_HP, **NO_DROPOUT, decoder_reduction_factor=r), device="cuda:0", bf16=False, fp32_gemm=fp32_gemm)
+    eng.load_state_dict(sd)
+    H.check_reduction_factor(eng, z, 1e-4, 1e-3 if fp32_gemm == "simt" else 5e-3)
+    il = int(z["ilens"][0])
+    outs, probs, att = eng.inference(torch.from_numpy(z["xs"])[0, :il].cuda(), threshold=0.9999, minlenratio=0.0, maxlenratio=1.2)
+    assert outs.shape == z["inf_outs"].shape
+    assert np.abs(outs.cpu().numpy() - z["inf_outs"]).mean() <= 1e-4
+    assert np.abs(probs.cpu().numpy() - z["inf_probs"]).mean() <= 1e-4
+    assert np.abs(att.cpu().numpy() - z["inf_att_ws"]).mean() <= 1e-3
+
+
+@pytest.mark.parametrize("r", [1, 4])
+def test_reduction_factors_bf16_fused_step_trains(r):
+    """bf16 fused step (flash attention, grouped weight gradients, CUDA graphs) with r = 1 / 4 and ragged lengths: finite, decreasing loss."""
+    from seq2seq_vc_b200 import VTN, VTNTrainStep
+
+    model = VTN(idim=80, odim=80, adim=64, aheads=4, elayers=1, dlayers=2, eunits=96, dunits=96, dprenet_units=32, postnet_chans=32,
+                decoder_reduction_factor=r, compute_dtype="bf16", device="cuda:0", seed=3)
+    step = VTNTrainStep(model, lr=1e-3, warmup_steps=1, use_graph=True)
+    g = torch.Generator().manual_seed(5)
+    B, T, L = 4, 72, 54
+    xs, ys = torch.randn(B, T, 80, generator=g).cuda(), torch.randn(B, L, 80, generator=g).cuda()
+    ilens, olens = [72, 60, 51, 33], [54, 47, 38, 21]
+    labels = torch.zeros(B, L)
+    for b in range(B):
+        labels[b, olens[b] - 1:] = 1
+    hist = [step(xs, ilens, ys, labels.cuda(), olens).sum().item() for _ in range(25)]
+    assert np.isfinite(hist).all() and np.mean(hist[-5:]) < np.mean(hist[:5]), hist
+
+
 @pytest.fixture(scope="module")
 def c1():
     hp = vtn_oracle.default_hparams(**C1_HP)
@@ -94,6 +134,59 @@ def test_c1_vtn_small_fp32_parity(c1, fp32_gemm, gtol):
     for name, ref in grads.items():
         got = eng.store.g(name).cpu()
         assert (got - ref).abs().max().item() <= gtol * (ref.abs().max().item() + 1e-5), name
+
+
+def _drift_report(name, rec):
+    """Append the measured drift of a bf16 run to gpurun_out/r02_bf16_drift.json (copied to profiles/ by hand)."""
+    import json
+
+    path = os.path.join(os.path.dirname(os.path.dirname(__file__)), "gpurun_out", "r02_bf16_drift.json")
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        data = json.load(open(path)) if os.path.exists(path) else {}
+        data[name] = rec
+        json.dump(data, open(path, "w"), indent=1)
+    except OSError:
+        pass
+
+
+def test_c2_shape_bf16_drift_vs_fp32_oracle():
+    """The configuration bench.py times -- VTN-base 6+6, d384, 8 heads, r2, 512 -> 1024 frames (BASELINE configs[1]) at B = 4 --
+    through the bf16 path (tcgen05 GEMMs, flash attention, grouped weight gradients) against the float32 CPU oracle on the same
+    weights and batch: mel / attention drift and the per-tensor gradient cosine are printed, recorded and bounded.  The float32
+    tensor-core mode is held to the north-star tolerances (mel L1 <= 1e-4, attention L1 <= 1e-3) at this shape too."""
+    from seq2seq_vc_b200 import VTNEngine
+
+    hp_model = dict(idim=80, odim=80, adim=384, aheads=8, elayers=6, dlayers=6, eunits=1536, dunits=1536, decoder_reduction_factor=2,
+                    dprenet_dropout_rate=0.0)
+    hp = vtn_oracle.default_hparams(**hp_model)
+    sd = vtn_oracle.init_state_dict(hp, seed=6)
+    ilens, olens = [512, 488, 401, 350], [1024, 990, 803, 611]
+    batch = vtn_oracle.synthetic_batch(4, 512, 1024, ilens=ilens, olens=olens, seed=77)
+    out, (l1, bce), grads = vtn_oracle.vtn_loss_and_grads(sd, hp, *batch)
+    rec = {}
+    for mode, kw in (("fp32_tc", dict(bf16=False)), ("bf16", dict(bf16=True))):
+        eng = VTNEngine(dict(hp_model, **NO_DROPOUT), device="cuda:0", **kw)
+        eng.load_state_dict(sd)
+        after, before, logits, losses = step(eng, *batch)
+        mel = (after.float().cpu() - out["after_outs"].detach()).abs().mean().item()
+        att = max((eng.attn[n].float().cpu() - ref.detach()).abs().mean().item() for n, ref in out["attn"].items() if n in eng.attn)
+        cos = {}
+        gmax = max(float(g.abs().max()) for g in grads.values())
+        for name, ref in grads.items():
+            # gradients that are zero in exact arithmetic (key biases: softmax is shift-invariant) are rounding noise: skipped
+            if ref.numel() >= 256 and float(ref.abs().max()) >= 1e-5 * gmax:
+                cos[name] = torch.nn.functional.cosine_similarity(eng.store.g(name).cpu().flatten(), ref.flatten(), dim=0).item()
+        worst = min(cos, key=cos.get)
+        rec[mode] = dict(mel_L1=mel, attention_L1=att, l1_loss_err=abs(losses[0].item() - float(l1)), bce_err=abs(losses[1].item() - float(bce)),
+                         grad_cosine_min=cos[worst], grad_cosine_min_tensor=worst, grad_cosine_median=float(np.median(list(cos.values()))))
+        print(mode, rec[mode])
+        del eng
+        torch.cuda.empty_cache()
+    _drift_report("c2_shape_B4_512to1024_vtn_base", rec)
+    assert rec["fp32_tc"]["mel_L1"] <= 1e-4 and rec["fp32_tc"]["attention_L1"] <= 1e-3 and rec["fp32_tc"]["grad_cosine_min"] >= 0.9999
+    assert rec["bf16"]["mel_L1"] <= 5e-2 and rec["bf16"]["attention_L1"] <= 1e-3
+    assert rec["bf16"]["grad_cosine_min"] >= 0.95 and rec["bf16"]["grad_cosine_median"] >= 0.99
 
 
 def test_c1_vtn_small_bf16_tensor_core_path(c1):
