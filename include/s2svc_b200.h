@@ -36,7 +36,7 @@ extern "C" {
 #define S2S_F32 0
 #define S2S_BF16 1
 
-#define S2S_ABI_VERSION 12
+#define S2S_ABI_VERSION 13
 
 const char* s2s_last_error(void);
 int s2s_abi_version(void);
@@ -468,6 +468,55 @@ int s2s_decode_pe(const void* x, const float* pe, const float* alpha, const int3
 /* end of a step: frames[pos] = feat (r * odim), logits[pos] = logit (r), next decoder input = last generated frame, ++*pos_dev */
 int s2s_decode_advance(const void* feat, const void* logit, void* next_in, float* frames, float* logits, int32_t* pos_dev, int odim,
                        int r, int dtype, void* stream);
+
+/* -------------------------------------------------------------------------------------------
+ * Stochastic duration predictor of AAS-VC (modules/duration_predictor.py:131-304, modules/vits/flow.py:19-310,
+ * modules/vits/transform.py:12-216) -- the shipped recipe's default (egs/arctic/vc2/conf/aas_vc.melmelmel.v1.yaml:57).
+ * Everything float32, channels-last (B, T, C) activations, flow state z as (B, 2, T); `tlens` (B) int32 is the text-length
+ * mask.  The 1x1 convolutions are s2s_gemm, the channel LayerNorms s2s_layernorm_* (eps 1e-5).  Scalar log-likelihood terms
+ * are ACCUMULATED into a per-utterance buffer nll (B) with a sign (atomicAdd; the caller threads one buffer through the chain).
+ * ------------------------------------------------------------------------------------------- */
+/* exact (erf) GELU: flow.py:165,178 */
+int s2s_gelu_fwd(const float* x, float* y, int64_t n, void* stream);
+int s2s_gelu_bwd(const float* dy, const float* x, float* dx, int64_t n, void* stream);
+/* dilated depthwise Conv1d over time on the MASKED input (flow.py:150-158,205): y[b,t,c] = bias[c] + sum_j w[c,j] *
+ * xm[b, t + (j - (K-1)/2) * dil, c]; bwd: dx (masked), dw (C, K) +=, db (C) +=   (K in {3, 5, 7} for bwd) */
+int s2s_dwconv_dilated_fwd(const float* x, const int32_t* tlens, const float* w, const float* bias, float* y, int B, int T, int C,
+                           int K, int dil, void* stream);
+int s2s_dwconv_dilated_bwd(const float* dy, const float* x, const int32_t* tlens, const float* w, float* dx, float* dw, float* db,
+                           int B, int T, int C, int K, int dil, void* stream);
+/* Piecewise rational-quadratic spline with linear tails, 10 bins on [-5, 5] (transform.py:44-209), one spline per position:
+ * h (B, T, 29) = [10 widths | 10 heights | 9 derivatives] as ConvFlow.proj emits them (widths / heights are divided by
+ * sqrt(hidden) inside, flow.py:296-300); x / y / gy / dx are rows of (B, 2, T) flow states given by a batch stride; padded
+ * positions give y = 0, lad = 0.  inverse != 0 evaluates the inverse (lad negated, as the reference).  bwd: gradient of
+ * sum(gy * y + glad * lad) w.r.t. x and h by forward-mode dual numbers (forward direction only; gy / glad may be NULL). */
+int s2s_rq_spline_fwd(const float* x, int64_t x_bs, const float* h, const int32_t* tlens, float* y, int64_t y_bs, float* lad, int B,
+                      int T, float hidden, int inverse, void* stream);
+int s2s_rq_spline_bwd(const float* x, int64_t x_bs, const float* h, const int32_t* tlens, const float* gy, int64_t gy_bs,
+                      const float* glad, float* dx, int64_t dx_bs, float* dh, int B, int T, float hidden, void* stream);
+/* ElementwiseAffineFlow (flow.py:96-112) on z (B, 2, T): y = (m + exp(logs) z) mask (inverse: (z - m) exp(-logs) mask);
+ * nll[b] += sign * sum_t mask (logs_0 + logs_1) when nll != NULL.  bwd (forward direction): dz, dm (2) +=, dlogs (2) +=. */
+int s2s_sdp_affine_fwd(const float* z, const float* m, const float* logs, const int32_t* tlens, float* y, float* nll, float sign,
+                       int B, int T, int inverse, void* stream);
+int s2s_sdp_affine_bwd(const float* z, const float* logs, const int32_t* tlens, const float* gy, const float* g_nll, float sign,
+                       float* dz, float* dm, float* dlogs, int B, int T, void* stream);
+/* Posterior head + LogFlow (duration_predictor.py:262-281, flow.py:62-65): from z_q = (z_u, z1) and durations w (B, T):
+ * u = sigmoid(z_u) mask, z0 = (w - u) mask, out = (log(max(z0, 1e-5)) mask, z1 mask),
+ * nll[b] += sum_t mask (out_0 - logsigmoid(z_u) - logsigmoid(-z_u)). */
+int s2s_sdp_head_fwd(const float* zq, const float* w, const int32_t* tlens, float* out, float* nll, int B, int T, void* stream);
+int s2s_sdp_head_bwd(const float* zq, const float* w, const int32_t* tlens, const float* gout, const float* g_nll, float* dzq, int B,
+                     int T, void* stream);
+/* nll[b] += sign * sum_{ch,t} mask 0.5 (log 2 pi + z^2)   (duration_predictor.py:270-273,284-287); bwd: dz (+)= sign g_nll[b] z mask */
+int s2s_sdp_gauss_fwd(const float* z, const int32_t* tlens, float* nll, float sign, int B, int T, void* stream);
+int s2s_sdp_gauss_bwd(const float* z, const int32_t* tlens, const float* g_nll, float sign, float* dz, int accumulate, int B, int T,
+                      void* stream);
+/* acc[b] += sign * sum_t x[b, t]  /  out[b, t] = sign * g[b]  (the spline log-determinants and their gradient) */
+int s2s_rowsum_acc(const float* x, float* acc, float sign, int B, int T, void* stream);
+int s2s_rowbcast(const float* g, float* out, float sign, int B, int T, void* stream);
+/* standard-normal draws (counter-based Box-Muller; *seed_dev is added to the seed so CUDA-graph replays differ) */
+int s2s_randn(float* out, int64_t n, uint64_t seed, const uint64_t* seed_dev, uint64_t stream_id, void* stream);
+/* dur[b, t] = min(ceil(exp(z[b, 0, t]) mask), clamp_max)   (duration_predictor.py:298-304, models/aas_vc.py:393) */
+int s2s_sdp_durations(const float* z, const int32_t* tlens, float* dur, float clamp_max, int B, int T, void* stream);
 
 #ifdef __cplusplus
 }

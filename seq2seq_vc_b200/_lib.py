@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libs2svc_b200.so")
 
 S2S_F32, S2S_BF16 = 0, 1
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 
 class S2SError(RuntimeError):
@@ -139,6 +139,22 @@ SIGNATURES = {
     "s2s_decode_advance": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "s2s_duration_infer": (c_int, [_P, _P, c_int, c_float, c_float, c_int, _P]),
     "s2s_duration_loss": (c_int, [_P, _P, _P, c_int, c_int, c_float, c_float, c_float, _P, _P, _P, _P, c_int, _P]),
+    "s2s_gelu_fwd": (c_int, [_P, _P, c_int64, _P]),
+    "s2s_gelu_bwd": (c_int, [_P, _P, _P, c_int64, _P]),
+    "s2s_dwconv_dilated_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "s2s_dwconv_dilated_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "s2s_rq_spline_fwd": (c_int, [_P, c_int64, _P, _P, _P, c_int64, _P, c_int, c_int, c_float, c_int, _P]),
+    "s2s_rq_spline_bwd": (c_int, [_P, c_int64, _P, _P, _P, c_int64, _P, _P, c_int64, _P, c_int, c_int, c_float, _P]),
+    "s2s_sdp_affine_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_float, c_int, c_int, c_int, _P]),
+    "s2s_sdp_affine_bwd": (c_int, [_P, _P, _P, _P, _P, c_float, _P, _P, _P, c_int, c_int, _P]),
+    "s2s_sdp_head_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, _P]),
+    "s2s_sdp_head_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, _P]),
+    "s2s_sdp_gauss_fwd": (c_int, [_P, _P, _P, c_float, c_int, c_int, _P]),
+    "s2s_sdp_gauss_bwd": (c_int, [_P, _P, _P, c_float, _P, c_int, c_int, c_int, _P]),
+    "s2s_rowsum_acc": (c_int, [_P, _P, c_float, c_int, c_int, _P]),
+    "s2s_rowbcast": (c_int, [_P, _P, c_float, c_int, c_int, _P]),
+    "s2s_randn": (c_int, [_P, c_int64, c_uint64, _P, c_uint64, _P]),
+    "s2s_sdp_durations": (c_int, [_P, _P, _P, c_float, c_int, c_int, _P]),
 }
 
 _lib = None

@@ -15,12 +15,14 @@ def ref():
     return True
 
 
-def test_vtn_c1_shape_against_live_reference(ref):
+@pytest.mark.parametrize("r", [2, 1, 4])
+def test_vtn_c1_shape_against_live_reference(ref, r):
+    """r = 2 (class default), 1 and 4 (the recipe's value, egs/arctic/vc1/conf/vtn.v1.yaml:43); olens 50 / 33 are not multiples of 4."""
     from seq2seq_vc.losses import Seq2SeqLoss
     from seq2seq_vc.models import VTN
 
     hp = vtn_oracle.default_hparams(adim=64, aheads=4, elayers=2, dlayers=2, eunits=128, dunits=128, dprenet_units=32,
-                                    postnet_chans=32)
+                                    postnet_chans=32, decoder_reduction_factor=r)
     torch.manual_seed(3)
     model = VTN(dprenet_dropout_rate=0.0, **hp)
     ref_shim.disable_dropout(model)
@@ -34,6 +36,7 @@ def test_vtn_c1_shape_against_live_reference(ref):
     assert (o["logits"] - out[2]).abs().max() <= 2e-5
     l1o, bceo = vtn_oracle.seq2seq_loss(o["after_outs"], o["before_outs"], o["logits"], o["ys"], o["labels"], o["olens"])
     assert abs(float(l1o) - float(l1)) <= 1e-6 and abs(float(bceo) - float(bce)) <= 1e-6
+    assert o["olens"] == out[5].tolist() and torch.equal(o["labels"], out[4]) and o["after_outs"].shape == out[0].shape
 
 
 def test_mas_fuzz_against_numba(ref):
