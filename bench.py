@@ -47,6 +47,12 @@ WORKLOADS = {
                    postnet_filts=5, postnet_chans=256, post_encoder_reduction_factor=4, conformer_enc_kernel_size=15,
                    conformer_dec_kernel_size=15),
               16, 768, 768, True, "AAS-VC Conformer 4+4 (enc d384, dec d1536, h2, k15), B16 x (768->768, 80-mel), bf16 (the recipe's batch size)"),
+    # the shipped yaml UNMODIFIED: stochastic duration predictor (VITS flows, egs/arctic/vc2/conf/aas_vc.melmelmel.v1.yaml:57)
+    "c3s": (dict(idim=80, odim=80, adim=384, aheads=2, elayers=4, eunits=1536, dlayers=4, dunits=1536, duration_predictor_input_dim=80,
+                 duration_predictor_layers=2, duration_predictor_chans=256, duration_predictor_kernel_size=3, postnet_layers=5,
+                 postnet_filts=5, postnet_chans=256, post_encoder_reduction_factor=4, conformer_enc_kernel_size=15,
+                 conformer_dec_kernel_size=15, duration_predictor_type="stochastic"),
+            64, 768, 768, True, "AAS-VC Conformer 4+4 (enc d384, dec d1536, h2, k15) with the stochastic duration predictor, B64 x (768->768, 80-mel), bf16"),
     "c1": (dict(idim=80, odim=80, adim=256, aheads=4, elayers=2, dlayers=2, eunits=1024, dunits=1024, decoder_reduction_factor=2),
            4, 200, 400, False, "VTN-small 2+2 d256 h4 r2, B4 x (200->400, 80-mel), fp32"),
     # STFT -> log-mel (BASELINE.json configs[4]): 256 clips x 10 s @ 48 kHz, n_fft 2048, hop 300, 80 mels
@@ -578,7 +584,8 @@ def run_ours(args, rank, world):
     pxs, pys, plabels = xs.pin_memory(), ys.pin_memory(), labels.pin_memory()
     if aas:
         yaml_fixed = dict(positionwise_layer_type="linear", duration_predictor_use_encoder_outputs=False, encoder_normalize_before=True,
-                          decoder_normalize_before=True, duration_predictor_type="deterministic", encoder_input_layer="linear",
+                          decoder_normalize_before=True, encoder_input_layer="linear",
+                          **({} if "duration_predictor_type" in hp else {"duration_predictor_type": "deterministic"}),
                           transformer_enc_dropout_rate=0.2, transformer_enc_positional_dropout_rate=0.2,
                           transformer_enc_attn_dropout_rate=0.2, transformer_dec_dropout_rate=0.2,
                           transformer_dec_positional_dropout_rate=0.2, transformer_dec_attn_dropout_rate=0.2)

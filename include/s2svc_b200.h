@@ -479,6 +479,10 @@ int s2s_decode_advance(const void* feat, const void* logit, void* next_in, float
 /* exact (erf) GELU: flow.py:165,178 */
 int s2s_gelu_fwd(const float* x, float* y, int64_t n, void* stream);
 int s2s_gelu_bwd(const float* dy, const float* x, float* dx, int64_t n, void* stream);
+/* Conv1d(1 -> C, kernel 1) (ConvFlow.input_conv flow.py:240, post_pre duration_predictor.py:184): y[n, c] = x[n] w[c] + b[c];
+ * bwd: dx[n] = sum_c dy[n, c] w[c] (dx may be NULL), dw (C) +=, db (C) += */
+int s2s_outer_fwd(const float* x, const float* w, const float* b, float* y, int64_t N, int C, void* stream);
+int s2s_outer_bwd(const float* dy, const float* x, const float* w, float* dx, float* dw, float* db, int64_t N, int C, void* stream);
 /* dilated depthwise Conv1d over time on the MASKED input (flow.py:150-158,205): y[b,t,c] = bias[c] + sum_j w[c,j] *
  * xm[b, t + (j - (K-1)/2) * dil, c]; bwd: dx (masked), dw (C, K) +=, db (C) +=   (K in {3, 5, 7} for bwd) */
 int s2s_dwconv_dilated_fwd(const float* x, const int32_t* tlens, const float* w, const float* bias, float* y, int B, int T, int C,

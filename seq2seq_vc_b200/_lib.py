@@ -141,6 +141,8 @@ SIGNATURES = {
     "s2s_duration_loss": (c_int, [_P, _P, _P, c_int, c_int, c_float, c_float, c_float, _P, _P, _P, _P, c_int, _P]),
     "s2s_gelu_fwd": (c_int, [_P, _P, c_int64, _P]),
     "s2s_gelu_bwd": (c_int, [_P, _P, _P, c_int64, _P]),
+    "s2s_outer_fwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P]),
+    "s2s_outer_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, _P]),
     "s2s_dwconv_dilated_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "s2s_dwconv_dilated_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "s2s_rq_spline_fwd": (c_int, [_P, c_int64, _P, _P, _P, c_int64, _P, c_int, c_int, c_float, c_int, _P]),

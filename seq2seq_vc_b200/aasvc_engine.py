@@ -49,11 +49,24 @@ def default_hparams(**over) -> dict:
               duration_predictor_dropout_rate=0.1, postnet_dropout_rate=0.5, lambda_align=2.0,
               # "linear": PositionwiseFeedForward + Swish (the shipped yaml); "conv1d": MultiLayeredConv1d, kernel size 1, ReLU
               # (the AASVC class default, models/aas_vc.py:52-53)
-              positionwise_layer_type="linear")
+              positionwise_layer_type="linear",
+              # "deterministic": DurationPredictor + DurationPredictorLoss; "stochastic": StochasticDurationPredictor (VITS flows),
+              # the shipped yaml's default (aas_vc.melmelmel.v1.yaml:57; constructor defaults models/aas_vc.py:105-110)
+              duration_predictor_type="deterministic", stochastic_duration_predictor_kernel_size=3,
+              stochastic_duration_predictor_dropout_rate=0.5, stochastic_duration_predictor_flows=4,
+              stochastic_duration_predictor_dds_conv_layers=3, stochastic_duration_predictor_noise_scale=0.8)
     hp.update(over)
+    if hp["duration_predictor_type"] not in ("deterministic", "stochastic"):
+        raise ValueError(f"Duration predictor type: {hp['duration_predictor_type']} is not supported.")
     if hp["positionwise_layer_type"] not in ("linear", "conv1d"):
         raise NotImplementedError(f"positionwise_layer_type {hp['positionwise_layer_type']!r}")
     return hp
+
+
+def sdp_hparams(hp: dict) -> dict:
+    """StochasticDurationPredictor(channels=adim, ...) as AASVC builds it (models/aas_vc.py:178-186)."""
+    return dict(channels=hp["adim"], kernel_size=hp["stochastic_duration_predictor_kernel_size"],
+                dds_conv_layers=hp["stochastic_duration_predictor_dds_conv_layers"], flows=hp["stochastic_duration_predictor_flows"])
 
 
 def rel_pos_table(T: int, d: int) -> torch.Tensor:
@@ -135,12 +148,17 @@ def param_groups(hp: dict) -> List[List[Tuple[str, Tuple[int, ...]]]]:
     lin("encoder.embed.0", d, idim)
     ln("encoder.embed.1", d)
     conformer("encoder", hp["elayers"], d, hp["eunits"], hp["conformer_enc_kernel_size"])
-    ch, k = hp["duration_predictor_chans"], hp["duration_predictor_kernel_size"]
-    for i in range(hp["duration_predictor_layers"]):
-        g.append([(f"duration_predictor.conv.{i}.0.weight", (ch, d if i == 0 else ch, k))])
-        g.append([(f"duration_predictor.conv.{i}.0.bias", (ch,))])
-        ln(f"duration_predictor.conv.{i}.2", ch)
-    lin("duration_predictor.linear", 1, ch)
+    if hp["duration_predictor_type"] == "stochastic":
+        from . import sdp
+        for name, shape in sdp.param_spec(sdp_hparams(hp), "duration_predictor"):
+            g.append([(name, shape)])
+    else:
+        ch, k = hp["duration_predictor_chans"], hp["duration_predictor_kernel_size"]
+        for i in range(hp["duration_predictor_layers"]):
+            g.append([(f"duration_predictor.conv.{i}.0.weight", (ch, d if i == 0 else ch, k))])
+            g.append([(f"duration_predictor.conv.{i}.0.bias", (ch,))])
+            ln(f"duration_predictor.conv.{i}.2", ch)
+        lin("duration_predictor.linear", 1, ch)
     f2 = ((hp["duration_predictor_input_dim"] - 1) // 2 - 1) // 2
     g.append([("duration_predictor_projection.conv.0.weight", (d, 1, 3, 3))])
     g.append([("duration_predictor_projection.conv.0.bias", (d,))])
@@ -207,6 +225,21 @@ class AASVCEngine(EngineBase):
         self._prior_tables: Dict[Tuple[int, int], torch.Tensor] = {}
         self._relpe: Dict[Tuple[int, int], torch.Tensor] = {}
         self._interp: Dict[Tuple[int, int], Tuple[torch.Tensor, ...]] = {}
+        self.stochastic = hp["duration_predictor_type"] == "stochastic"
+        self.sdp = None
+        if self.stochastic:
+            from . import sdp
+
+            # autograd leaves over the flat store: detached views whose .grad IS the matching slice of the flat gradient buffer
+            self._sdp_leaves: Dict[str, torch.Tensor] = {}
+            for name, _ in sdp.param_spec(sdp_hparams(hp), "duration_predictor"):
+                leaf = self.store.p(name).detach().requires_grad_(True)
+                leaf.grad = self.store.g(name)
+                self._sdp_leaves[name] = leaf
+            self.sdp = sdp.StochasticDurationPredictor(
+                sdp_hparams(hp), "duration_predictor", self._sdp_leaves.__getitem__, gemm_mode=0 if fp32_gemm == "simt" else 2,
+                dropout_rate=hp["stochastic_duration_predictor_dropout_rate"],
+                drop_of=lambda name, p: self.named_drop("sdp." + name, p))
         self.init_parameters(seed)
 
     # ------------------------------------------------------------------ parameters
@@ -214,10 +247,17 @@ class AASVCEngine(EngineBase):
         """torch-default Linear / Conv init distributions (uniform +-1/sqrt(fan_in)); LN/BN affine = 1/0; xavier-uniform
         pos_bias_u/v (attention.py:233-234)."""
         g = torch.Generator().manual_seed(seed)
+        sdp_init = {}
+        if self.hp["duration_predictor_type"] == "stochastic":
+            from . import sdp
+            sdp_init = sdp.init_params(sdp_hparams(self.hp), "duration_predictor", seed + 1)
         for name, (off, shape) in self.store.offsets.items():
             n = 1
             for s in shape:
                 n *= s
+            if name in sdp_init:
+                self.store.P[off:off + n].copy_(sdp_init[name].reshape(-1).to(self.device))
+                continue
             is_affine = (("norm" in name) or name.startswith("encoder.embed.1") or (name.startswith("postnet") and ".1." in name)
                          or (name.startswith("duration_predictor.conv") and name.split(".")[-2] == "2"))
             if is_affine:
@@ -573,6 +613,9 @@ class AASVCEngine(EngineBase):
         idx, ones, _, _ = self._interp_tables(Tp, Tt)
         dpi = self.buf("dp.in", (B, Tt, d))
         ops.gather_rows(proj.view(B, Tp, d), idx, ones, dpi)
+        self.dp_in = dpi
+        if self.stochastic:
+            return          # the stochastic predictor needs the MAS durations: it runs after the alignment search (_sdp_forward)
         # ---- duration predictor (duration_predictor.py:83-101)
         k = hp["duration_predictor_kernel_size"]
         halo = (k - 1) // 2
@@ -645,7 +688,32 @@ class AASVCEngine(EngineBase):
         hs = self.hs
 
         self._alignment_and_mas(ys)
+        if self.stochastic:
+            self._sdp_forward()
         return self._decoder_side(self.ds, L)
+
+    def _text_maskf(self, B: int, Tt: int) -> torch.Tensor:
+        """(B*Tt,) float 0/1 text mask on the device (index bookkeeping on a tiny tensor, no model arithmetic)."""
+        return (torch.arange(Tt, device=self.device)[None, :] < self.tlens_dev[:, None]).to(_f32).reshape(-1)
+
+    def _sdp_forward(self) -> None:
+        """dur_nll (B,) = StochasticDurationPredictor(dp_in^T, mask, w = ds) / sum(mask)  (models/aas_vc.py:412-419): the
+        predictor's graph (kernels of this library sequenced by torch's tape) is kept for backward()."""
+        from . import sdp
+
+        s = self.shapes
+        B, Tt = s["B"], s["Tt"]
+        x32 = self.dp_in if self.dp_in.dtype == _f32 else ops.cast(self.dp_in, self.buf("sdp.x32", self.dp_in.shape, _f32))
+        self._sdp_mask = self._text_maskf(B, Tt)
+        e_q = sdp.randn((B, 2, Tt), self.device, self.base_seed, self.seed_dev, 7001)
+        self._sdp_eq = e_q
+        self.sdp.dropout_rate = self.hp["stochastic_duration_predictor_dropout_rate"] if self.training else 0.0
+        with torch.enable_grad():
+            self.sdp_nll = self.sdp.nll(x32, self.tlens_dev, self._sdp_mask, self.ds, e_q)
+        self._sdp_norm = 1.0 / float(sum(self.tlens_host)) if getattr(self, "tlens_host", None) else None
+        self.dur_nll = self.buf("sdp.dur_nll", (B,), _f32)
+        self.dur_nll.zero_()
+        ops.axpy(self.sdp_nll.detach(), self.dur_nll, self._sdp_norm)
 
     def _alignment_and_mas(self, ys: torch.Tensor) -> None:
         """Alignment module + monotonic alignment search on self.hs (B, T_text, C) and ys (B, L, odim); needs self.shapes,
@@ -687,7 +755,7 @@ class AASVCEngine(EngineBase):
                      self._mas_ws(B, L, Tt))
 
     @torch.no_grad()
-    def inference(self, x: torch.Tensor, dp_input: torch.Tensor, y: Optional[torch.Tensor] = None):
+    def inference(self, x: torch.Tensor, dp_input: torch.Tensor, y: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None):
         """AASVC.inference (aas_vc.py:531-603, _forward(is_inference=True) :371-398) for one utterance:
         x (T, idim), dp_input (T_dp, dp_idim) float32 device tensors -> (outs (L, odim) float32, d_outs (T_text,) int64).
         Eval-mode BatchNorm, no dropout; durations = clamp(round(exp(d) - 1), 0, 10); T_feats = sum(durations) is read back
@@ -726,7 +794,16 @@ class AASVCEngine(EngineBase):
                 gt = (self.ds[0].clone(), self.log_p_attn[0].clone())
                 self._sig = (1, T, -1, False)
             ds = self.buf("inf.ds", (1, Tt), _f32)
-            ops.duration_infer(self.dp_pre, ds)
+            if self.stochastic:
+                # d_outs = clamp(sdp(dp_in^T, mask, inverse=True, noise_scale), max=10)   (models/aas_vc.py:385-393)
+                from . import sdp
+
+                x32 = self.dp_in if self.dp_in.dtype == _f32 else self.dp_in.float()
+                zn = sdp.randn((1, 2, Tt), self.device, self.base_seed, self.seed_dev, 7002) if noise is None else noise.to(self.device, _f32).reshape(1, 2, Tt)
+                self.sdp.dropout_rate = 0.0
+                ds.copy_(self.sdp.inverse(x32, self.tlens_dev, self._text_maskf(1, Tt), zn, hp["stochastic_duration_predictor_noise_scale"]))
+            else:
+                ops.duration_infer(self.dp_pre, ds)
             L = int(ds.sum().item())                          # the one host read-back of this path
             if L == 0:                                        # length_regulator.py:127-135 (all-zero prediction): every token gets one frame
                 ds.fill_(1.0)
@@ -767,6 +844,14 @@ class AASVCEngine(EngineBase):
         alpha_ws = self.buf("loss.alpha", (B, L, Tt), _f32)
         ops.forward_sum(self.log_p_attn, self.prior, self.tlens_dev, self.olens_dev, alpha_ws, self.losses[1:2], self.d_logp, lam)
         ops.axpy(self.d_logp_mas, self.d_logp, lam)
+        if self.stochastic:
+            # StochasticDurationPredictorLoss: duration_loss = sum(dur_nll) (trainers/aas_vc.py:125-127)
+            self.losses[3:4].zero_()
+            self._sdp_weight = 1.0 if duration_loss else 0.0
+            if duration_loss:
+                from . import _lib
+                _lib.check(_lib.load().s2s_rowsum_acc(_lib.ptr(self.dur_nll), _lib.ptr(self.losses[3:4]), 1.0, 1, B, _lib.stream()), "rowsum_acc")
+            return self.losses
         self.d_outs = self.buf("dp.d_outs", (B, Tt), _f32)
         self.d_dp_pre = self.buf("dp.d_pre", (B * Tt, 1))
         ops.duration_loss(self.dp_pre, self.ds, self.tlens_dev, self.d_outs, self.losses[3:4], self.d_dp_pre,
@@ -814,7 +899,8 @@ class AASVCEngine(EngineBase):
         d_after = self.d_after if d_after is None else d_after
         d_before = self.d_before if d_before is None else d_before
         d_logp = self.d_logp if d_logp is None else d_logp
-        d_dp_pre = self.d_dp_pre if d_dp_pre is None else d_dp_pre
+        if not self.stochastic:
+            d_dp_pre = self.d_dp_pre if d_dp_pre is None else d_dp_pre
         s = self.shapes
         B, T, L, Tt = s["B"], s["T"], s["L"], s["Tt"]
         d, H, pr, odim = hp["adim"], hp["aheads"], hp["post_encoder_reduction_factor"], hp["odim"]
@@ -842,6 +928,12 @@ class AASVCEngine(EngineBase):
         ops.gemm(Pg[..., :Tt].transpose(1, 2), gup.transpose(1, 2), dhs, mode=mode)
 
         # ---- duration predictor
+        if self.stochastic:
+            # the predictor sees a detached input (duration_predictor.py:236): its loss reaches its own parameters only, and the
+            # input projection receives no gradient at all.  d_dp_pre: None = the fused step (weight from loss()), or the
+            # (B,) gradient of dur_nll handed in by the drop-in module's autograd node
+            self.sdp_backward(d_dp_pre)
+            return self._backward_alignment_and_encoder(dhs, d_logp)
         ch = hp["duration_predictor_chans"]
         k = hp["duration_predictor_kernel_size"]
         halo = (k - 1) // 2
@@ -873,6 +965,36 @@ class AASVCEngine(EngineBase):
         ops.gather_rows(gdpi, first, cnt, gproj)
         self._conv2d_sub_bwd(gproj.view(B * Tp, d), self.dp_inputs, "duration_predictor_projection", "duration_predictor_projection.out", "dpp")
 
+        return self._backward_alignment_and_encoder(dhs, d_logp)
+
+    def sdp_backward(self, g_dur_nll: Optional[torch.Tensor] = None) -> None:
+        """Gradient of the stochastic predictor's loss into the flat gradient buffer (its leaves' .grad are views of it).
+        g_dur_nll (B,): d loss / d dur_nll from the drop-in module's tape; None: the fused step, sum(dur_nll) * weight of loss()."""
+        B = self.shapes["B"]
+        if g_dur_nll is None:
+            w = getattr(self, "_sdp_weight", 1.0)
+            if w == 0.0:
+                self.sdp_nll = None
+                return
+            g = torch.full((B,), w * self._sdp_norm, dtype=_f32, device=self.device)
+        else:
+            g = ops.axpy(g_dur_nll.to(_f32).contiguous(), torch.zeros(B, dtype=_f32, device=self.device), self._sdp_norm)
+        for name, leaf in self._sdp_leaves.items():
+            if leaf.grad is None or leaf.grad.data_ptr() != self.store.g(name).data_ptr():
+                leaf.grad = self.store.g(name)
+        self.sdp_nll.backward(gradient=g)
+        self.sdp_nll = None
+
+    def _backward_alignment_and_encoder(self, dhs: torch.Tensor, d_logp: torch.Tensor) -> None:
+        """Tail of backward(): alignment module (d log_p_attn -> d feats, d text), post-encoder reduction, conformer encoder and
+        input layer; dhs (B, Tt, C) is the gradient that reached the encoder output through the Gaussian upsampling."""
+        hp, st = self.hp, self.store
+        s = self.shapes
+        B, T, L, Tt = s["B"], s["T"], s["L"], s["Tt"]
+        d, H, pr, odim = hp["adim"], hp["aheads"], hp["post_encoder_reduction_factor"], hp["odim"]
+        C = d * pr
+        mode = self.mode
+        er, epr, ear = hp["transformer_enc_dropout_rate"], hp["transformer_enc_positional_dropout_rate"], hp["transformer_enc_attn_dropout_rate"]
         # ---- alignment module: d(log_p_attn) -> d(feats), d(text)
         ldw = _r8(Tt)
         Wm = self._scratch("g.alW", (B, L, ldw))

@@ -866,7 +866,7 @@ class _AASVCFunction(torch.autograd.Function):
     def forward(ctx, model, xs, ys, dp_inputs, ilens, olens, *params):
         eng = model.engine
         after, before = eng.forward(xs, ys, dp_inputs, ilens, olens)
-        d_outs = eng.forward_d_outs()
+        d_outs = eng.dur_nll if eng.stochastic else eng.forward_d_outs()      # (B,) dur_nll | (B, T_text) d_outs
         ctx.model, ctx.token = model, model._fwd_token
         ctx.set_materialize_grads(False)      # an output the loss does not use arrives as None (d_outs before dp_train_start_steps)
         ds = eng.ds.clone()
@@ -890,12 +890,19 @@ class _AASVCFunction(torch.autograd.Function):
             gb = torch.empty_like(eng.d_logp_mas)
             ops.rowscale(eng.d_logp_mas.view(1, -1), g_bin.to(_f32).reshape(1), gb.view(1, -1))
             ops.axpy(gb, d_logp, 1.0)
-        d_pre = torch.empty(B * Tt, 1, dtype=dt, device=eng.device)
-        ops.duration_loss(eng.dp_pre, eng.ds, eng.tlens_dev, None, None, d_pre, g_douts=z(g_douts, eng.d_outs, _f32))
+        if eng.stochastic:
+            eng._sdp_weight = 0.0          # no gradient arrived for dur_nll (before dp_train_start_steps): the predictor is skipped
+            d_pre = g_douts                # (B,) d loss / d dur_nll, or None
+        else:
+            d_pre = torch.empty(B * Tt, 1, dtype=dt, device=eng.device)
+            ops.duration_loss(eng.dp_pre, eng.ds, eng.tlens_dev, None, None, d_pre, g_douts=z(g_douts, eng.d_outs, _f32))
         eng.backward(d_after, d_before, d_logp, d_pre, zero_grad=fresh)
         model._sync_gradients()
         # trainers/aas_vc.py:119-133: without the duration loss the predictor's parameters are not in the graph
-        model._bind_grads(unused=("duration_predictor.", "duration_predictor_projection.") if g_douts is None else ())
+        # the stochastic predictor detaches its input (duration_predictor.py:236): its projection never sees a gradient
+        unused = ("duration_predictor.", "duration_predictor_projection.") if g_douts is None else (
+            ("duration_predictor_projection.",) if eng.stochastic else ())
+        model._bind_grads(unused=unused)
         return (None,) * (6 + len(model._param_names))
 
 
@@ -922,7 +929,10 @@ class AASVC(VTN):
                  transformer_dec_dropout_rate: float = 0.1, transformer_dec_positional_dropout_rate: float = 0.1,
                  transformer_dec_attn_dropout_rate: float = 0.1, duration_predictor_dropout_rate: float = 0.1,
                  postnet_dropout_rate: float = 0.5, init_type: str = "xavier_uniform", use_masking: bool = False,
-                 use_weighted_masking: bool = False, compute_dtype: str = "float32", device=None, seed: int = 0, **ignored):
+                 use_weighted_masking: bool = False, stochastic_duration_predictor_kernel_size: int = 3,
+                 stochastic_duration_predictor_dropout_rate: float = 0.5, stochastic_duration_predictor_flows: int = 4,
+                 stochastic_duration_predictor_dds_conv_layers: int = 3, stochastic_duration_predictor_noise_scale: float = 0.8,
+                 compute_dtype: str = "float32", device=None, seed: int = 0, **ignored):
         torch.nn.Module.__init__(self)
         unsupported = []
         if encoder_type != "conformer" or decoder_type != "conformer":
@@ -939,8 +949,8 @@ class AASVC(VTN):
             unsupported.append("non rel_pos / rel_selfattn attention")
         if not (use_macaron_style_in_conformer and use_cnn_in_conformer and use_batch_norm):
             unsupported.append("conformer blocks without macaron FFN / CNN module / BatchNorm")
-        if duration_predictor_type != "deterministic":
-            unsupported.append("stochastic duration predictor (SURVEY section 8f-2)")
+        if duration_predictor_type not in ("deterministic", "stochastic"):
+            raise ValueError(f"Duration predictor type: {duration_predictor_type} is not supported.")      # models/aas_vc.py:187-190
         if duration_predictor_use_encoder_outputs or duration_predictor_input_dim is None:
             unsupported.append("duration_predictor_use_encoder_outputs=True")
         if encoder_reduction_factor != 1 or decoder_reduction_factor != 1:
@@ -968,7 +978,13 @@ class AASVC(VTN):
             transformer_dec_positional_dropout_rate=transformer_dec_positional_dropout_rate,
             transformer_dec_attn_dropout_rate=transformer_dec_attn_dropout_rate,
             duration_predictor_dropout_rate=duration_predictor_dropout_rate, postnet_dropout_rate=postnet_dropout_rate,
-            positionwise_layer_type=positionwise_layer_type)
+            positionwise_layer_type=positionwise_layer_type, duration_predictor_type=duration_predictor_type,
+            stochastic_duration_predictor_kernel_size=stochastic_duration_predictor_kernel_size,
+            stochastic_duration_predictor_dropout_rate=stochastic_duration_predictor_dropout_rate,
+            stochastic_duration_predictor_flows=stochastic_duration_predictor_flows,
+            stochastic_duration_predictor_dds_conv_layers=stochastic_duration_predictor_dds_conv_layers,
+            stochastic_duration_predictor_noise_scale=stochastic_duration_predictor_noise_scale)
+        self.stochastic_duration_predictor_noise_scale = stochastic_duration_predictor_noise_scale
         # compute_dtype: "bf16" (tcgen05, bf16 activations) | "float32" (float32 activations, fp32-accurate tcgen05 GEMMs through a
         # bf16 split: the parity mode) | "float32_simt" (float32 on the CUDA cores: the numerical yard-stick)
         self._bf16 = compute_dtype in ("bf16", "bfloat16", torch.bfloat16)
@@ -1010,8 +1026,10 @@ class AASVC(VTN):
         dev = xs.device
         ilens_out = torch.tensor(eng.tlens_host, dtype=torch.int64, device=dev)
         olens_out = torch.tensor(ol, dtype=torch.int64, device=dev)
-        return dict(d_outs=d_outs, before_outs=before.float(), after_outs=after.float(), ds=ds, ilens=ilens_out, bin_loss=bin_loss,
-                    log_p_attn=logp, olens_reduced=olens_out, olens=olens_out, ys=ys)
+        ret = dict(before_outs=before.float(), after_outs=after.float(), ds=ds, ilens=ilens_out, bin_loss=bin_loss,
+                   log_p_attn=logp, olens_reduced=olens_out, olens=olens_out, ys=ys)
+        ret["dur_nll" if eng.stochastic else "d_outs"] = d_outs          # models/aas_vc.py:408-419
+        return ret
 
 
 def _aasvc_inference(self, src_speech, tgt_speech=None, spembs=None, dp_input=None, use_teacher_forcing=False):

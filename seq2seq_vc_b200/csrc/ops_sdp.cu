@@ -147,91 +147,149 @@ __global__ void __launch_bounds__(128) spline_fwd_kernel(const float* __restrict
     if (lad) lad[n] = ll;
 }
 
-// gradient of sum(gy * y + glad * lad) w.r.t. x and the 29 spline parameters: one dual evaluation per input direction
+// gradient of sum(gy * y + glad * lad) w.r.t. x and the 29 spline parameters: one dual evaluation per input direction --
+// one WARP per element, lane j evaluates direction j (lanes 0..28: the parameters, lane 29: the abscissa)
 __global__ void __launch_bounds__(128) spline_bwd_kernel(const float* __restrict__ x, long x_bs, const float* __restrict__ h,
                                                          const int32_t* __restrict__ tlens, const float* __restrict__ gy, long gy_bs,
                                                          const float* __restrict__ glad, float* __restrict__ dx, long dx_bs,
                                                          float* __restrict__ dh, int B, int T, float inv_den) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int j = threadIdx.x & 31;
     if (n >= B * T) return;
     const int b = n / T, t = n - b * T;
     float* dhp = dh + (long)n * NPAR;
     if (t >= tlens[b]) {
-        dx[b * dx_bs + t] = 0.f;
-        for (int j = 0; j < NPAR; ++j) dhp[j] = 0.f;
+        if (j < NPAR) dhp[j] = 0.f;
+        if (j == NPAR) dx[b * dx_bs + t] = 0.f;
         return;
     }
+    if (j > NPAR) return;
     const float* hp = h + (long)n * NPAR;
     const float g_y = gy ? gy[b * gy_bs + t] : 0.f, g_l = glad ? glad[n] : 0.f;
     const float xv = x[b * x_bs + t];
-#pragma unroll 1
-    for (int j = 0; j <= NPAR; ++j) {              // j == NPAR: the abscissa itself
-        Dual uw[BINS], uh[BINS], ud[BINS - 1];
+    Dual uw[BINS], uh[BINS], ud[BINS - 1];
 #pragma unroll
-        for (int i = 0; i < BINS; ++i) {
-            uw[i] = Dual{hp[i] * inv_den, j == i ? inv_den : 0.f};
-            uh[i] = Dual{hp[BINS + i] * inv_den, j == BINS + i ? inv_den : 0.f};
-        }
-#pragma unroll
-        for (int i = 0; i < BINS - 1; ++i) ud[i] = Dual{hp[2 * BINS + i], j == 2 * BINS + i ? 1.f : 0.f};
-        Dual yy, ll;
-        rq_spline<Dual>(Dual{xv, j == NPAR ? 1.f : 0.f}, uw, uh, ud, false, yy, ll);
-        const float g = g_y * yy.d + g_l * ll.d;
-        if (j == NPAR) dx[b * dx_bs + t] = g; else dhp[j] = g;
+    for (int i = 0; i < BINS; ++i) {
+        uw[i] = Dual{hp[i] * inv_den, j == i ? inv_den : 0.f};
+        uh[i] = Dual{hp[BINS + i] * inv_den, j == BINS + i ? inv_den : 0.f};
     }
+#pragma unroll
+    for (int i = 0; i < BINS - 1; ++i) ud[i] = Dual{hp[2 * BINS + i], j == 2 * BINS + i ? 1.f : 0.f};
+    Dual yy, ll;
+    rq_spline<Dual>(Dual{xv, j == NPAR ? 1.f : 0.f}, uw, uh, ud, false, yy, ll);
+    const float g = g_y * yy.d + g_l * ll.d;
+    if (j == NPAR) dx[b * dx_bs + t] = g; else dhp[j] = g;
 }
 
 // ---- exact GELU ----------------------------------------------------------------------------------
+__device__ __forceinline__ float gelu1(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752f)); }
+__device__ __forceinline__ float dgelu1(float v) {
+    return 0.5f * (1.f + erff(v * 0.70710678118654752f)) + v * 0.39894228040143268f * expf(-0.5f * v * v);
+}
 __global__ void gelu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long n) {
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-        const float v = x[i];
-        y[i] = 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+    const long n4 = n >> 2;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(x)[i];
+        reinterpret_cast<float4*>(y)[i] = make_float4(gelu1(v.x), gelu1(v.y), gelu1(v.z), gelu1(v.w));
     }
+    for (long i = (n4 << 2) + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) y[i] = gelu1(x[i]);
 }
 __global__ void gelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dx, long n) {
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-        const float v = x[i];
-        const float cdf = 0.5f * (1.f + erff(v * 0.70710678118654752f));
-        const float pdf = 0.39894228040143268f * expf(-0.5f * v * v);
-        dx[i] = dy[i] * (cdf + v * pdf);
+    const long n4 = n >> 2;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(x)[i], g = reinterpret_cast<const float4*>(dy)[i];
+        reinterpret_cast<float4*>(dx)[i] = make_float4(g.x * dgelu1(v.x), g.y * dgelu1(v.y), g.z * dgelu1(v.z), g.w * dgelu1(v.w));
     }
+    for (long i = (n4 << 2) + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) dx[i] = dy[i] * dgelu1(x[i]);
+}
+
+// ---- Conv1d(1 -> C, k = 1): y[n, c] = x[n] w[c] + b[c]  (ConvFlow.input_conv, post_pre) -------------------------------------
+__global__ void __launch_bounds__(128) outer_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                                                        float* __restrict__ y, long N, int C) {
+    for (long n = blockIdx.x; n < N; n += gridDim.x) {
+        const float xv = x[n];
+        for (int c = threadIdx.x; c < C; c += blockDim.x) y[n * C + c] = fmaf(xv, w[c], b[c]);
+    }
+}
+// dx[n] = sum_c dy[n, c] w[c]
+__global__ void __launch_bounds__(128) outer_bwd_dx_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx, long N, int C) {
+    __shared__ float red[32];
+    for (long n = blockIdx.x; n < N; n += gridDim.x) {
+        float s = 0.f;
+        for (int c = threadIdx.x; c < C; c += blockDim.x) s = fmaf(dy[n * C + c], w[c], s);
+        s = block_sum(s, red);
+        if (threadIdx.x == 0) dx[n] = s;
+        __syncthreads();
+    }
+}
+// dw[c] += sum_n dy[n, c] x[n] ; db[c] += sum_n dy[n, c].  blockDim = 128 channels, gridDim.y row chunks
+__global__ void __launch_bounds__(128) outer_bwd_dw_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dw,
+                                                           float* __restrict__ db, long N, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const long per = (N + gridDim.y - 1) / gridDim.y;
+    const long r0 = blockIdx.y * per, r1 = (r0 + per < N) ? r0 + per : N;
+    float aw = 0.f, ab = 0.f;
+    for (long r = r0; r < r1; ++r) {
+        const float g = dy[r * C + c];
+        aw = fmaf(g, x[r], aw);
+        ab += g;
+    }
+    atomicAdd(dw + c, aw);
+    atomicAdd(db + c, ab);
 }
 
 // ---- dilated depthwise Conv1d over time on the masked input (flow.py:192-204), channels-last ---------
-__global__ void dwdil_fwd_kernel(const float* __restrict__ x, const int32_t* __restrict__ tlens, const float* __restrict__ w,
-                                 const float* __restrict__ bias, float* __restrict__ y, int B, int T, int C, int K, int dil) {
-    const long total = (long)B * T * C;
+// one block per (b, t) row, each thread owns VEC consecutive channels (16-byte loads when C % 4 == 0): no per-element division
+template <int VEC>
+__global__ void __launch_bounds__(128) dwdil_fwd_kernel(const float* __restrict__ x, const int32_t* __restrict__ tlens, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, float* __restrict__ y, int B, int T, int C, int K, int dil) {
     const int half = (K - 1) / 2;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C);
-        const long bt = i / C;
-        const int t = (int)(bt % T), b = (int)(bt / T);
-        const int tl = tlens[b];
-        float acc = bias[c];
-        for (int j = 0; j < K; ++j) {
-            const int s = t + (j - half) * dil;
-            if (s >= 0 && s < T && s < tl) acc = fmaf(w[c * K + j], x[((long)b * T + s) * C + c], acc);
+    for (long r = blockIdx.x; r < (long)B * T; r += gridDim.x) {
+        const int b = (int)(r / T), t = (int)(r - (long)b * T);
+        const int tl = min(tlens[b], T);
+        for (int c = threadIdx.x * VEC; c < C; c += blockDim.x * VEC) {
+            float acc[VEC];
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc[e] = bias[c + e];
+            for (int j = 0; j < K; ++j) {
+                const int s = t + (j - half) * dil;
+                if (s >= 0 && s < tl) {
+                    float v[VEC];
+                    if (VEC == 4) Vec4<float>::load(x + ((long)b * T + s) * C + c, reinterpret_cast<float(&)[4]>(v)); else v[0] = x[((long)b * T + s) * C + c];
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) acc[e] = fmaf(w[(c + e) * K + j], v[e], acc[e]);
+                }
+            }
+            if (VEC == 4) Vec4<float>::store(y + r * C + c, reinterpret_cast<float(&)[4]>(acc)); else y[r * C + c] = acc[0];
         }
-        y[i] = acc;
     }
 }
 // dx[b,s,c] = mask(s) * sum_j w[c,j] dy[b, s - (j - half) dil, c]
-__global__ void dwdil_bwd_dx_kernel(const float* __restrict__ dy, const int32_t* __restrict__ tlens, const float* __restrict__ w,
-                                    float* __restrict__ dx, int B, int T, int C, int K, int dil) {
-    const long total = (long)B * T * C;
+template <int VEC>
+__global__ void __launch_bounds__(128) dwdil_bwd_dx_kernel(const float* __restrict__ dy, const int32_t* __restrict__ tlens, const float* __restrict__ w,
+                                                           float* __restrict__ dx, int B, int T, int C, int K, int dil) {
     const int half = (K - 1) / 2;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C);
-        const long bt = i / C;
-        const int s = (int)(bt % T), b = (int)(bt / T);
-        float acc = 0.f;
-        if (s < tlens[b]) {
-            for (int j = 0; j < K; ++j) {
-                const int t = s - (j - half) * dil;
-                if (t >= 0 && t < T) acc = fmaf(w[c * K + j], dy[((long)b * T + t) * C + c], acc);
+    for (long r = blockIdx.x; r < (long)B * T; r += gridDim.x) {
+        const int b = (int)(r / T), s = (int)(r - (long)b * T);
+        const bool on = s < tlens[b];
+        for (int c = threadIdx.x * VEC; c < C; c += blockDim.x * VEC) {
+            float acc[VEC];
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
+            if (on) {
+                for (int j = 0; j < K; ++j) {
+                    const int t = s - (j - half) * dil;
+                    if (t >= 0 && t < T) {
+                        float v[VEC];
+                        if (VEC == 4) Vec4<float>::load(dy + ((long)b * T + t) * C + c, reinterpret_cast<float(&)[4]>(v)); else v[0] = dy[((long)b * T + t) * C + c];
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) acc[e] = fmaf(w[(c + e) * K + j], v[e], acc[e]);
+                    }
+                }
             }
+            if (VEC == 4) Vec4<float>::store(dx + r * C + c, reinterpret_cast<float(&)[4]>(acc)); else dx[r * C + c] = acc[0];
         }
-        dx[i] = acc;
     }
 }
 // dw[c,j] += sum_{b,t} dy[b,t,c] xm[b, t + (j - half) dil, c] ; db[c] += sum dy.  blockDim = 128 channels, gridDim.y row chunks
@@ -445,10 +503,33 @@ extern "C" int s2s_gelu_bwd(const float* dy, const float* x, float* dx, int64_t 
     S2S_LAUNCH_OK();
     return S2S_OK;
 }
+extern "C" int s2s_outer_fwd(const float* x, const float* w, const float* b, float* y, int64_t N, int C, void* stream) {
+    S2S_REQUIRE(x && w && b && y && N > 0 && C > 0, "outer_fwd: bad arguments");
+    outer_fwd_kernel<<<ew_grid(N, 1), 128, 0, (cudaStream_t)stream>>>(x, w, b, y, N, C);
+    S2S_LAUNCH_OK();
+    return S2S_OK;
+}
+extern "C" int s2s_outer_bwd(const float* dy, const float* x, const float* w, float* dx, float* dw, float* db, int64_t N, int C, void* stream) {
+    S2S_REQUIRE(dy && x && w && N > 0 && C > 0, "outer_bwd: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dx) {
+        outer_bwd_dx_kernel<<<ew_grid(N, 1), 128, 0, st>>>(dy, w, dx, N, C);
+        S2S_LAUNCH_OK();
+    }
+    if (dw && db) {
+        long chunks = ceil_div_l(N, 64);
+        const long cap = (long)num_sms() * 4 / ceil_div_l(C, 128);
+        if (chunks > cap) chunks = cap < 1 ? 1 : cap;
+        outer_bwd_dw_kernel<<<dim3((unsigned)ceil_div_l(C, 128), (unsigned)chunks), 128, 0, st>>>(dy, x, dw, db, N, C);
+        S2S_LAUNCH_OK();
+    }
+    return S2S_OK;
+}
 extern "C" int s2s_dwconv_dilated_fwd(const float* x, const int32_t* tlens, const float* w, const float* bias, float* y, int B, int T, int C,
                                       int K, int dil, void* stream) {
     S2S_REQUIRE(x && tlens && w && bias && y && B > 0 && T > 0 && C > 0 && K >= 1 && (K & 1) && dil >= 1, "dwconv_dilated_fwd: bad arguments");
-    dwdil_fwd_kernel<<<ew_grid((long)B * T * C, 256), 256, 0, (cudaStream_t)stream>>>(x, tlens, w, bias, y, B, T, C, K, dil);
+    if (C % 4 == 0 && aligned16(x, y)) dwdil_fwd_kernel<4><<<ew_grid((long)B * T, 1), 128, 0, (cudaStream_t)stream>>>(x, tlens, w, bias, y, B, T, C, K, dil);
+    else dwdil_fwd_kernel<1><<<ew_grid((long)B * T, 1), 128, 0, (cudaStream_t)stream>>>(x, tlens, w, bias, y, B, T, C, K, dil);
     S2S_LAUNCH_OK();
     return S2S_OK;
 }
@@ -457,7 +538,8 @@ extern "C" int s2s_dwconv_dilated_bwd(const float* dy, const float* x, const int
     S2S_REQUIRE(dy && x && tlens && w && B > 0 && T > 0 && C > 0 && (K == 3 || K == 5 || K == 7) && dil >= 1, "dwconv_dilated_bwd: bad arguments (K in 3, 5, 7)");
     cudaStream_t st = (cudaStream_t)stream;
     if (dx) {
-        dwdil_bwd_dx_kernel<<<ew_grid((long)B * T * C, 256), 256, 0, st>>>(dy, tlens, w, dx, B, T, C, K, dil);
+        if (C % 4 == 0 && aligned16(dy, dx)) dwdil_bwd_dx_kernel<4><<<ew_grid((long)B * T, 1), 128, 0, st>>>(dy, tlens, w, dx, B, T, C, K, dil);
+        else dwdil_bwd_dx_kernel<1><<<ew_grid((long)B * T, 1), 128, 0, st>>>(dy, tlens, w, dx, B, T, C, K, dil);
         S2S_LAUNCH_OK();
     }
     if (dw && db) {
@@ -482,8 +564,8 @@ extern "C" int s2s_rq_spline_fwd(const float* x, int64_t x_bs, const float* h, c
 extern "C" int s2s_rq_spline_bwd(const float* x, int64_t x_bs, const float* h, const int32_t* tlens, const float* gy, int64_t gy_bs,
                                  const float* glad, float* dx, int64_t dx_bs, float* dh, int B, int T, float hidden, void* stream) {
     S2S_REQUIRE(x && h && tlens && dx && dh && B > 0 && T > 0 && hidden > 0.f, "rq_spline_bwd: bad arguments");
-    spline_bwd_kernel<<<nblk((long)B * T, 128), 128, 0, (cudaStream_t)stream>>>(x, x_bs, h, tlens, gy, gy_bs, glad, dx, dx_bs, dh, B, T,
-                                                                                 1.f / sqrtf(hidden));
+    spline_bwd_kernel<<<nblk((long)B * T * 32, 128), 128, 0, (cudaStream_t)stream>>>(x, x_bs, h, tlens, gy, gy_bs, glad, dx, dx_bs, dh, B, T,
+                                                                                      1.f / sqrtf(hidden));
     S2S_LAUNCH_OK();
     return S2S_OK;
 }

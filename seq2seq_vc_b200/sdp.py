@@ -113,7 +113,7 @@ class _Linear(torch.autograd.Function):
         x = x.contiguous()
         w2 = w.reshape(w.shape[0], -1)
         y = torch.empty(x.shape[0], w2.shape[0], dtype=_f32, device=x.device)
-        m = mode if (w2.shape[1] % 8 == 0 and w2.shape[0] % 8 == 0) else 0        # 1 -> C and C -> 29 products: CUDA-core GEMM
+        m = mode if (mode != 2 or w2.shape[0] >= 8) else 0        # the split-operand tcgen05 GEMM pads K itself; N >= 8 for TMA
         ops.gemm(x, w2, y, bias=b, mode=m)
         ctx.save_for_backward(x, w2)
         ctx.mode, ctx.wshape = m, w.shape
@@ -132,6 +132,31 @@ class _Linear(torch.autograd.Function):
         db = torch.zeros(w2.shape[0], dtype=_f32, device=x.device)
         ops.colsum(dy, db)
         return dx, dw.reshape(ctx.wshape), db, None
+
+
+class _Outer(torch.autograd.Function):
+    """Conv1d(1 -> C, k = 1): y (N, C) = x (N) w^T + b   (s2s_outer_fwd / bwd)"""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        x = x.contiguous().view(-1)
+        C = w.shape[0]
+        w1 = w.reshape(C).contiguous()
+        y = torch.empty(x.numel(), C, dtype=_f32, device=x.device)
+        check(_L().s2s_outer_fwd(ptr(x), ptr(w1), ptr(b), ptr(y), x.numel(), C, stream()), "outer_fwd")
+        ctx.save_for_backward(x, w1)
+        ctx.wshape = w.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w1 = ctx.saved_tensors
+        dy = dy.contiguous()
+        C = w1.numel()
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dw, db = torch.zeros_like(w1), torch.zeros_like(w1)
+        check(_L().s2s_outer_bwd(ptr(dy), ptr(x), ptr(w1), ptr(dx), ptr(dw), ptr(db), x.numel(), C, stream()), "outer_bwd")
+        return dx, dw.reshape(ctx.wshape), db
 
 
 class _DWConv(torch.autograd.Function):
@@ -369,7 +394,7 @@ class StochasticDurationPredictor:
     def _conv_flow(self, name, z, g, tlens, maskf, nll, sign):
         B, _, T = z.shape
         C = self.hp["channels"]
-        h = self._lin(name + ".input_conv", z[:, 0].reshape(B * T, 1)).view(B, T, C)
+        h = _Outer.apply(z[:, 0].reshape(B * T), self.P(name + ".input_conv.weight"), self.P(name + ".input_conv.bias")).view(B, T, C)
         h = self._dds(name + ".dds_conv", h, tlens, maskf, g=g)
         h = self._lin(name + ".proj", h.view(B * T, C)).view(B, T, NPAR)
         return _Coupling.apply(z, h, tlens, nll, sign, float(C))
@@ -388,7 +413,7 @@ class StochasticDurationPredictor:
         B, T, C = x.shape
         p = self.prefix
         xc = self._condition(x, tlens, maskf)
-        hw = self._lin(p + ".post_pre", w.reshape(B * T, 1)).view(B, T, C)
+        hw = _Outer.apply(w.reshape(B * T), self.P(p + ".post_pre.weight"), self.P(p + ".post_pre.bias")).view(B, T, C)
         hw = self._dds(p + ".post_dds", hw, tlens, maskf, dropout=self.dropout_rate)
         hw = _RowMask.apply(self._lin(p + ".post_proj", hw.view(B * T, C)).view(B, T, C), maskf)
         nll = torch.zeros(B, dtype=_f32, device=x.device)
@@ -410,7 +435,7 @@ class StochasticDurationPredictor:
         for i in reversed(range(1, n)):
             name = f"{p}.flows.{1 + 2 * i}"
             # Flip first: (a, b) -> (b, a); then the coupling inverts its second row from its first
-            h = self._lin(name + ".input_conv", z[:, 1].reshape(B * T, 1)).view(B, T, C)
+            h = _Outer.apply(z[:, 1].reshape(B * T), self.P(name + ".input_conv.weight"), self.P(name + ".input_conv.bias")).view(B, T, C)
             h = self._dds(name + ".dds_conv", h, tlens, maskf, g=xc)
             h = self._lin(name + ".proj", h.view(B * T, C)).view(B, T, NPAR).contiguous()
             out = torch.empty_like(z)

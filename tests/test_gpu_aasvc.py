@@ -671,3 +671,77 @@ def test_edge_cases_alignment_block(ops):
     ref = F.gauss_weights(ds0, torch.tensor([3, 3]), torch.tensor([4, 2]), torch.empty(2, 3, 8))
     close(P, ref, 1e-6, "gaussian weights with zero durations")
     assert torch.isfinite(P).all()
+
+
+STOCH_HP = dict(AAS_HP, duration_predictor_type="stochastic")
+
+
+def test_stochastic_duration_predictor_in_the_engine_matches_the_oracle():
+    """AAS-VC with the shipped recipe's stochastic duration predictor (aas_vc.melmelmel.v1.yaml:57): dur_nll (models/aas_vc.py:412-419)
+    and every gradient of sum(dur_nll) equal the CPU oracle fed with the engine's own predictor input, MAS durations and noise draw;
+    the input projection receives no gradient (the predictor detaches its input, duration_predictor.py:236)."""
+    from oracle import sdp_oracle
+    from seq2seq_vc_b200.aasvc_engine import AASVCEngine, sdp_hparams
+
+    eng = AASVCEngine(dict(STOCH_HP, **NO_DROPOUT, stochastic_duration_predictor_dropout_rate=0.0), device="cuda:0", bf16=False, seed=3)
+    g = torch.Generator().manual_seed(9)
+    for name in eng.store.names():          # ConvFlow.proj starts at zero (identity splines): perturb so every branch is exercised
+        if name.startswith("duration_predictor.") and ((".proj." in name and "flows" in name) or name.endswith((".m", ".logs"))):
+            eng.store.p(name).add_((0.2 * torch.randn(eng.store.p(name).shape, generator=g)).cuda())
+    z, _ = _golden()
+    ilens, olens = z["ilens"].tolist(), z["olens"].tolist()
+    xs, ys, dpi = (torch.from_numpy(z[k]).cuda() for k in ("xs", "ys", "dp_inputs"))
+    eng.forward(xs, ys, dpi, ilens, olens)
+    losses = eng.loss(ys)
+    eng.backward()
+    torch.cuda.synchronize()
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in eng.state_dict().items() if k.startswith("duration_predictor.")}
+    ref = sdp_oracle.aasvc_dur_nll(sd, "duration_predictor", sdp_hparams(eng.hp), eng.dp_in.float().cpu(), eng.tlens_host, eng.ds.cpu(), eng._sdp_eq.cpu())
+    assert (eng.dur_nll.cpu() - ref.detach()).abs().max().item() <= 1e-4 * ref.detach().abs().max().item()
+    assert abs(losses[3].item() - float(ref.sum())) <= 1e-4 * abs(float(ref.sum()))
+    ref.sum().backward()
+    gmax = max(float(p.grad.abs().max()) for p in sd.values())
+    for k, p in sd.items():
+        got = eng.store.g(k).cpu()
+        assert (got - p.grad).abs().max().item() <= 6e-3 * float(p.grad.abs().max()) + 2e-5 * gmax, k
+    for name in eng.store.names():
+        if name.startswith("duration_predictor_projection."):
+            assert (eng.store.g(name) == 0).all(), name
+
+
+def test_stochastic_recipe_fused_step_and_dropin_and_inference():
+    """The stochastic recipe end to end: fused AASVCTrainStep under CUDA graphs (bf16) trains with finite, decreasing loss; the
+    drop-in module returns `dur_nll` and back-propagates sum(dur_nll) into the predictor only; inference draws durations."""
+    from seq2seq_vc_b200 import AASVC, AASVCTrainStep, ForwardSumLoss, L1Loss
+
+    z, _ = _golden()
+    ilens, olens = z["ilens"].tolist(), z["olens"].tolist()
+    xs, ys, dpi = (torch.from_numpy(z[k]).cuda() for k in ("xs", "ys", "dp_inputs"))
+    kw = dict(positionwise_layer_type="linear", duration_predictor_use_encoder_outputs=False, encoder_normalize_before=True,
+              decoder_normalize_before=True, encoder_input_layer="linear", duration_predictor_type="stochastic")
+    model = AASVC(**AAS_HP, **kw, compute_dtype="bf16", device="cuda:0", seed=4)
+    step = AASVCTrainStep(model, lr=2e-3, warmup_steps=1, use_graph=True)
+    hist = []
+    for it in range(30):
+        losses = step(xs, ilens, ys, olens, dpi)
+        hist.append(losses.clone())
+    hist = torch.stack(hist).cpu()
+    assert torch.isfinite(hist).all()
+    assert hist[-5:, 0].mean() < hist[:5, 0].mean() and hist[-5:, 3].mean() < hist[1:6, 3].mean(), hist[:, [0, 3]]
+    # drop-in module through torch autograd with the reference-style loss assembly (trainers/aas_vc.py:73-134)
+    m2 = AASVC(**AAS_HP, **kw, compute_dtype="float32", device="cuda:0", seed=4)
+    ret = m2(xs, torch.tensor(ilens), ys, torch.tensor(olens), dpi, dp_lengths=torch.tensor(ilens))
+    assert "dur_nll" in ret and "d_outs" not in ret and ret["dur_nll"].shape == (xs.shape[0],)
+    l1 = L1Loss()(ret["after_outs"], ret["before_outs"], ret["ys"], ret["olens"])
+    fs = ForwardSumLoss()(ret["log_p_attn"], ret["ilens"], ret["olens_reduced"])
+    total = l1 + 2.0 * (fs + ret["bin_loss"]) + torch.sum(ret["dur_nll"].float())
+    total.backward()
+    got = {n: p.grad for n, p in m2.named_parameters()}
+    assert all(got[n] is not None and torch.isfinite(got[n]).all() for n in got if n.startswith("duration_predictor."))
+    assert any(got[n].abs().max() > 0 for n in got if n.startswith("duration_predictor."))
+    assert all(got[n] is None for n in got if n.startswith("duration_predictor_projection."))
+    assert got["encoder.embed.0.weight"] is not None
+    # inference: stochastic durations, clamped to <= 10 (models/aas_vc.py:385-393)
+    m2.eval()
+    outs, d = m2.inference(xs[0, :ilens[0]], dp_input=dpi[0])
+    assert d.dtype == torch.int64 and int(d.max()) <= 10 and outs.shape[0] == int(d.sum()) and torch.isfinite(outs).all()

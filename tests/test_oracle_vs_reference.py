@@ -126,3 +126,25 @@ def test_sdp_oracle_against_live_reference(ref, channels, k, layers, flows, B, T
         torch.manual_seed(9)
         z = torch.randn(B, 2, T)
         assert torch.equal(sdp_oracle.sdp_inverse(sd, "dp", hp, x, mask, z, scale), d)
+
+
+def test_shipped_aas_vc_yaml_constructs_with_the_reference_state_dict(ref):
+    """`AASVC(**model_params)` of the shipped recipe (egs/arctic/vc2/conf/aas_vc.melmelmel.v1.yaml: stochastic duration predictor)
+    builds unmodified, with the reference's state-dict keys / shapes and parameter registration order."""
+    import os
+
+    import yaml
+
+    from seq2seq_vc.models import AASVC as Ref
+    from seq2seq_vc_b200 import AASVC
+
+    cfg = yaml.safe_load(open(os.path.join(ref_shim.REFERENCE_ROOT, "egs/arctic/vc2/conf/aas_vc.melmelmel.v1.yaml")))
+    mp = dict(cfg["model_params"])
+    assert mp["duration_predictor_type"] == "stochastic"
+    mp.setdefault("idim", 80)
+    mp.setdefault("odim", 80)
+    ours, theirs = AASVC(**mp), Ref(**mp)
+    so, st = ours.state_dict(), theirs.state_dict()
+    assert set(so) == set(st) and all(tuple(so[k].shape) == tuple(st[k].shape) for k in st)
+    assert [n for n, _ in ours.named_parameters()] == [n for n, _ in theirs.named_parameters()]
+    ours.load_state_dict(st)
