@@ -625,8 +625,10 @@ class VTNEngine(EngineBase):
 
     # ------------------------------------------------------------------ backward
     def backward(self, d_after: torch.Tensor, d_before: torch.Tensor, d_logits: torch.Tensor,
-                 d_att: Optional[Dict[str, torch.Tensor]] = None, zero_grad: bool = True) -> None:
-        """Accumulates parameter gradients into ParamStore.G (d_* are overwritten as scratch)."""
+                 d_att: Optional[Dict[str, torch.Tensor]] = None, zero_grad: bool = True, on_decoder_done=None) -> None:
+        """Accumulates parameter gradients into ParamStore.G (d_* are overwritten as scratch).
+        on_decoder_done(): called once every gradient of the postnet, the output heads and the decoder is final and only the
+        encoder's backward remains -- the data-parallel step starts all-reducing that part of the flat buffer there."""
         hp, st = self.hp, self.store
         s = self.shapes
         B, T, L, T1, F1, T2, F2, Lr = s["B"], s["T"], s["L"], s["T1"], s["F1"], s["T2"], s["F2"], s["Lr"]
@@ -732,6 +734,9 @@ class VTNEngine(EngineBase):
                           dx_gate=hin if i > 0 else None, dx_gate_scale=sites[f"prenet{i - 1}"].scale if i > 0 else 1.0)
             dhp = dnext
 
+        if on_decoder_done is not None:
+            on_decoder_done()
+
         # ---- encoder (reverse)
         ge = self._scratch("g.enc_a", (B, T2, d))
         gte = self._scratch("g.enc_b", (B, T2, d))
@@ -806,6 +811,13 @@ class VTNEngine(EngineBase):
         ops.relu_bwd(dy1, y1, dy1, 1.0)
         ops.conv1_bwd(self.xs, dy1, st.g("encoder.embed.conv.0.weight"), st.g("encoder.embed.conv.0.bias"))
 
+
+    def encoder_span(self) -> int:
+        """Number of leading elements of the flat parameter / gradient buffers that belong to the encoder (its parameters are
+        registered first): [0, n) is final only at the very end of backward(), [n, numel) already at on_decoder_done."""
+        names = self.store.names()
+        first_dec = next(i for i, n in enumerate(names) if not n.startswith("encoder."))
+        return self.store.offsets[names[first_dec]][0]
 
     def _site_table(self) -> Dict[str, Drop]:
         """Re-enumerate the forward's dropout sites (same order as forward())."""
