@@ -464,6 +464,50 @@ def incumbent_torch_gpu(workload, steps=5, warmup=3):
     return out
 
 
+def dropin_boundary(workload, steps=10, warmup=4):
+    """The reference trainer's step (trainers/ar_vc.py:59-107) around the DROP-IN module -- seq2seq_vc_b200.VTN -> Seq2SeqLoss ->
+    backward -> clip_grad_norm_ -> torch.optim.Adam (+ WarmupLR) -- on the same batch as the fused step: what a user who only
+    swaps the model / criterion classes gets, timed with CUDA events incl. the host-side glue."""
+    from seq2seq_vc_b200 import VTN, Seq2SeqLoss, TransformerTTS
+
+    hp, B, T, L, bf16, desc = WORKLOADS[workload]
+    tts = workload == "c4"
+    dev = torch.device("cuda", torch.cuda.current_device())
+    model = (TransformerTTS if tts else VTN)(**hp, compute_dtype="bf16" if bf16 else "float32", device=dev, seed=0)
+    model.train()
+    crit = Seq2SeqLoss()
+    opt = torch.optim.Adam(model.parameters(), lr=8e-5)
+    xs, ilens, ys, labels, olens = synthetic_batch(B, T, L, 1234, tts)
+    xs, ys, labels = xs.to(dev), ys.to(dev), labels.to(dev)
+    ilens_t, olens_t = torch.tensor(ilens), torch.tensor(olens)          # the collater hands CPU int64 length tensors
+
+    def step():
+        after, before, logits, ys_, labels_, olens_, _ = model(xs, ilens_t, ys, labels, olens_t)
+        l1, bce = crit(after, before, logits, ys_, labels_, olens_)
+        loss = l1 + bce
+        opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        return loss
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    out = {"ms_per_step": ms, "frames_per_s": B * L / (ms * 1e-3), "loss": float(loss),
+           "what": "reference-style step around the drop-in module (model -> Seq2SeqLoss -> backward -> clip_grad_norm_ -> torch.optim.Adam), eager"}
+    del model, opt
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_torch_gpu(args, rank):
     if rank != 0:
         return
@@ -707,6 +751,7 @@ def run_ours(args, rank, world):
             # the practical incumbent on this box, timed after our own arm on the same GPU
             del stepper, model
             torch.cuda.empty_cache()
+            line["dropin_boundary"] = dropin_boundary(args.workload)
             line["torch_gpu_incumbent"] = incumbent_torch_gpu(args.workload)
     print(json.dumps(line), flush=True)
 
