@@ -1,15 +1,16 @@
 // STFT -> log-mel front end (bin/preprocess.py:30-92 of the reference, librosa semantics).
 //
-// Fast path (n_fft = 2048): ONE WARP PER FRAME, no block-level synchronisation.
+// Fast path (n_fft = 2048): persistent CTA of 16 warps, one frame per warp and 16 frames per round.
 //   The real 2048-point FFT is a 1024-point complex FFT of z[m] = x[2m] + i x[2m+1], computed as
 //   32 x 32 Cooley-Tukey: every lane runs a 32-point FFT in registers over the stride-32 samples it
-//   loaded straight from HBM (reflect padding and the window folded into the load), applies the
-//   inter-stage twiddle by recurrence, the warp transposes through its private 8 KB of shared
-//   memory (__syncwarp only), every lane runs a second 32-point FFT, and the spectrum is unpacked
-//   to |X[k]|, k = 0..1024.  The mel projection walks each band's non-zero bins (triangular
-//   filters are sparse: ~2 x 1025 non-zeros for 80 bands) and the 80 log values are written coalesced.
-//   Arithmetic: ~64 kFLOP per frame in fp32; each sample is re-used by n_fft / hop ~ 6.8 frames, so
-//   the kernel is bound by fp32 FFT arithmetic, not by its 1.52 kB / frame of HBM traffic.
+//   loaded straight from HBM (reflect padding and the window folded into the load), multiplies by the
+//   inter-stage twiddles (a conflict-free 8 KB table), the warp transposes through its private 8 KB of
+//   shared memory (__syncwarp only), every lane runs a second 32-point FFT, and the spectrum is unpacked
+//   in conjugate pairs (one complex multiply per two bins) to |X[k]|, k = 0..1024.  The mel projection of the
+//   CTA's 16 magnitude rows runs on warp-level tensor-core MMAs over the non-zero blocks of the banded
+//   filterbank with bf16 high + low splits of both operands (fp32 accuracy), and 16 x n_mels logs leave as one
+//   contiguous store.  Arithmetic: ~45 kFLOP per frame in fp32; each sample is re-used by n_fft / hop ~ 6.8
+//   frames, so the kernel is bound by instruction issue / fp32 FFT arithmetic, not by its 1.52 kB / frame of HBM traffic.
 // Generic path (other power-of-two n_fft): one CTA per frame, radix-2 in shared memory.
 #include "common.cuh"
 
@@ -48,151 +49,297 @@ __device__ __forceinline__ void fft32_dif(float2 (&v)[32]) {
     }
 }
 
-constexpr int LM_WARPS = 12;
-constexpr int LM_ZLD = 33;                        // padded row length of the per-warp transpose / spectrum buffer
+// ---------------------------------------------------------------------------------------------
+// n_fft = 2048 fast path: persistent CTA of 16 warps, 16 frames per round (one frame per warp)
+// ---------------------------------------------------------------------------------------------
+constexpr int LM_WARPS = 16;
+constexpr int LM_ZLD = 33;                        // padded row length (float2) of the per-warp transpose / spectrum buffer
+constexpr int LM_FS = 2120;                       // floats per warp region: >= 2 * 32 * 33, = 8 (mod 32) so the A-fragment LDS.64 are conflict-free
+constexpr int LM_MAX_ITEMS = 96;                  // (8-band tile, 16-bin block) pairs of the mel projection
+constexpr int LM_MAX_NT = 16;                     // 8-band tiles: n_mels <= 128 on the tensor-core mel path
+constexpr int LM_MAX_PAIRS = LM_MAX_NT + LM_WARPS;
 
-struct LogmelShared {
-    // offsets (in floats) inside dynamic shared memory for the fast path
-    int tw1024, tw2048, win, wpk, rng, per_warp, warp_stride;
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// (x0, x1) -> bf16x2 high part (x0 in the low half) and bf16x2 of the remainders: x = hi + lo to ~2^-17 relative
+__device__ __forceinline__ void split_bf16x2(float x0, float x1, unsigned& hi, unsigned& lo) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+    const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - h1), "f"(x0 - h0));
+}
+
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+struct LogmelMeta {                               // built once per CTA from the filterbank matrix
+    int n_items, use_tc;
+    int item_nt[LM_MAX_ITEMS], item_k0[LM_MAX_ITEMS];
+    int nt_lo[LM_MAX_NT], nt_cnt[LM_MAX_NT], nt_wfirst[LM_MAX_NT], nt_wlast[LM_MAX_NT];
+    int chunk[LM_WARPS + 1], warp_ft[LM_WARPS], warp_pbase[LM_WARPS];
 };
 
-__global__ void __launch_bounds__(LM_WARPS * 32) logmel2048_kernel(const float* __restrict__ wav, const float* __restrict__ window,
-                                                                  const float* __restrict__ basis, float* __restrict__ mel, int B,
-                                                                  int ns, int hop, int n_frames, int n_mels, float eps,
-                                                                  float log_scale, int wpk_cap, const float* __restrict__ nmean,
-                                                                  const float* __restrict__ nscale) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int NFFT = 2048, H = 1024, NB = 1025;
-    float2* tw1024 = reinterpret_cast<float2*>(smem_raw);           // e^{-2 pi i j / 1024}, j < 32 only needed as base; keep 32
-    float2* tw2048 = tw1024 + 32;                                   // e^{-2 pi i k / 2048}, k <= 1024
-    float* swin = reinterpret_cast<float*>(tw2048 + NB + 1);        // [2048]
-    float* wpk = swin + NFFT;                                       // packed non-zero filter weights [wpk_cap]
-    int* rng = reinterpret_cast<int*>(wpk + wpk_cap);               // [n_mels][3] = start, end, packed offset
-    float* warp_base = reinterpret_cast<float*>(rng + ((3 * n_mels + 4) & ~3));   // keep 16-byte alignment
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // per-warp scratch: zbuf float2[32 * 33] (transpose, then spectrum), mag float[1025 + pad]
-    float2* zbuf = reinterpret_cast<float2*>(warp_base + (size_t)warp * (2 * 32 * LM_ZLD + NB + 7));
-    float* mag = reinterpret_cast<float*>(zbuf + 32 * LM_ZLD);
+// Layout of dynamic shared memory (bytes): tw32 float2[1024] | tw2048 float2[520] | swin float[2048] (x 0.5) | btab uint4[96 * 32] |
+// partial float[LM_MAX_PAIRS * 128] | meta | regions float[16 * LM_FS]
+constexpr size_t LM_OFF_TW2048 = 1024 * 8;
+constexpr size_t LM_OFF_WIN = LM_OFF_TW2048 + 520 * 8;
+constexpr size_t LM_OFF_BTAB = LM_OFF_WIN + 2048 * 4;
+constexpr size_t LM_OFF_PART = LM_OFF_BTAB + (size_t)LM_MAX_ITEMS * 32 * 16;
+constexpr size_t LM_OFF_META = LM_OFF_PART + (size_t)LM_MAX_PAIRS * 128 * 4;
+constexpr size_t LM_OFF_REG = (LM_OFF_META + sizeof(LogmelMeta) + 15) & ~(size_t)15;
+constexpr size_t LM_SMEM = LM_OFF_REG + (size_t)LM_WARPS * LM_FS * 4;
+static_assert(LM_SMEM <= 227 * 1024, "logmel2048: shared memory budget");
 
-    // ---- CTA-wide tables (built once per persistent CTA)
-    if (tid < 32) {
+// Per round: every warp turns one frame into |X[0..1024]| (load + window -> 32x32 Cooley-Tukey in registers with one transpose
+// through its own shared-memory region -> real-FFT unpack in conjugate pairs), the CTA then projects its 16 magnitude rows onto
+// the mel bands with warp-level tensor-core MMAs (M = 16 frames, N = 8 bands, K = 16 bins; the filterbank is banded, so only
+// the (band tile, bin block) pairs that hold non-zeros are visited; magnitudes and weights are split into bf16 high + low parts
+// and three products are accumulated in fp32, which keeps the projection at fp32 accuracy), and 16 x n_mels logs are stored
+// as one contiguous run.
+__global__ void __launch_bounds__(LM_WARPS * 32, 1) logmel2048_kernel(const float* __restrict__ wav, const float* __restrict__ window,
+                                                                     const float* __restrict__ basis, float* __restrict__ mel, int B,
+                                                                     int ns, int hop, int n_frames, int n_mels, float eps,
+                                                                     float log_scale, const float* __restrict__ nmean,
+                                                                     const float* __restrict__ nscale) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int H = 1024, NB = 1025;
+    float2* tw32 = reinterpret_cast<float2*>(smem_raw);                       // [k1 * 32 + n2] = e^{-2 pi i k1 n2 / 1024}
+    float2* tw2048 = reinterpret_cast<float2*>(smem_raw + LM_OFF_TW2048);     // e^{-2 pi i k / 2048}, k <= 512
+    float* swin = reinterpret_cast<float*>(smem_raw + LM_OFF_WIN);            // 0.5 * window: the 1/2 of the real-FFT unpack
+    uint4* btab = reinterpret_cast<uint4*>(smem_raw + LM_OFF_BTAB);           // B fragments {b0 hi, b1 hi, b0 lo, b1 lo} per (item, lane)
+    float* part = reinterpret_cast<float*>(smem_raw + LM_OFF_PART);           // per (warp, band tile) partial 16 x 8 tiles
+    LogmelMeta& meta = *reinterpret_cast<LogmelMeta*>(smem_raw + LM_OFF_META);
+    float* regions = reinterpret_cast<float*>(smem_raw + LM_OFF_REG);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gid = lane >> 2, tig = lane & 3;
+    float2* zb = reinterpret_cast<float2*>(regions + (size_t)warp * LM_FS);
+    float* mg = regions + (size_t)warp * LM_FS;
+
+    // ---- CTA-wide tables
+    for (int e = tid; e < 1024; e += blockDim.x) {
         float s, c;
-        sincospif(-2.0f * (float)tid / 1024.f, &s, &c);
-        tw1024[tid] = make_float2(c, s);
+        sincospif(-2.0f * (float)(((e >> 5) * (e & 31)) & 1023) / 1024.f, &s, &c);
+        tw32[e] = make_float2(c, s);
     }
-    for (int k = tid; k <= H; k += blockDim.x) {
+    for (int k = tid; k <= 512; k += blockDim.x) {
         float s, c;
         sincospif(-2.0f * (float)k / 2048.f, &s, &c);
         tw2048[k] = make_float2(c, s);
     }
-    for (int k = tid; k < NFFT; k += blockDim.x) swin[k] = window[k];
-    for (int m = warp; m < n_mels; m += LM_WARPS) {
-        int lo = NB, hi = -1;
-        for (int k = lane; k < NB; k += 32)
-            if (basis[(size_t)m * NB + k] != 0.f) { lo = min(lo, k); hi = max(hi, k); }
+    for (int k = tid; k < 2048; k += blockDim.x) swin[k] = 0.5f * window[k];
+    const int NT = (n_mels + 7) >> 3;
+    if (NT <= LM_MAX_NT) {
+        // non-zero bin range of every 8-band tile: one warp per tile
+        if (warp < NT) {
+            int lo = NB, hi = -1;
+            for (int r = 0; r < 8; ++r) {
+                const int m = warp * 8 + r;
+                if (m >= n_mels) break;
+                for (int k = lane; k < NB; k += 32)
+                    if (basis[(size_t)m * NB + k] != 0.f) { lo = min(lo, k); hi = max(hi, k); }
+            }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            for (int o = 16; o > 0; o >>= 1) {
+                lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+                hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            }
+            if (lane == 0) {
+                lo &= ~1;
+                meta.nt_lo[warp] = lo;
+                meta.nt_cnt[warp] = hi < 0 ? 0 : (hi + 1 - lo + 15) >> 4;
+            }
         }
-        if (lane == 0) { rng[3 * m] = lo; rng[3 * m + 1] = hi + 1; }
     }
     __syncthreads();
     if (tid == 0) {
-        int off = 0;
-        for (int m = 0; m < n_mels; ++m) {
-            int len = max(rng[3 * m + 1] - rng[3 * m], 0);
-            if (off + len > wpk_cap) { len = 0; rng[3 * m + 1] = rng[3 * m]; }
-            rng[3 * m + 2] = off;
-            off += len;
+        int n = 0;
+        bool ok = NT <= LM_MAX_NT;
+        for (int j = 0; ok && j < NT; ++j) {
+            if (n + meta.nt_cnt[j] > LM_MAX_ITEMS) { ok = false; break; }
+            for (int c = 0; c < meta.nt_cnt[j]; ++c) { meta.item_nt[n] = j; meta.item_k0[n] = meta.nt_lo[j] + 16 * c; ++n; }
+        }
+        meta.use_tc = ok ? 1 : 0;
+        meta.n_items = ok ? n : 0;
+        if (ok) {
+            for (int j = 0; j < NT; ++j) { meta.nt_wfirst[j] = LM_WARPS; meta.nt_wlast[j] = -1; }
+            int pb = 0;
+            for (int w = 0; w <= LM_WARPS; ++w) meta.chunk[w] = (w * n) / LM_WARPS;
+            for (int w = 0; w < LM_WARPS; ++w) {
+                const int i0 = meta.chunk[w], i1 = meta.chunk[w + 1];
+                meta.warp_pbase[w] = pb;
+                meta.warp_ft[w] = i0 < i1 ? meta.item_nt[i0] : 0;
+                for (int i = i0; i < i1; ++i) {
+                    const int j = meta.item_nt[i];
+                    meta.nt_wfirst[j] = min(meta.nt_wfirst[j], w);
+                    meta.nt_wlast[j] = max(meta.nt_wlast[j], w);
+                }
+                if (i0 < i1) pb += meta.item_nt[i1 - 1] - meta.item_nt[i0] + 1;   // <= NT + 16 in total
+            }
         }
     }
     __syncthreads();
-    for (int m = warp; m < n_mels; m += LM_WARPS) {
-        const int lo = rng[3 * m], hi = rng[3 * m + 1], off = rng[3 * m + 2];
-        for (int k = lo + lane; k < hi; k += 32) wpk[off + k - lo] = basis[(size_t)m * NB + k];
+    const bool use_tc = meta.use_tc != 0;
+    for (int e = tid; e < meta.n_items * 32; e += blockDim.x) {
+        const int it = e >> 5, ln = e & 31;
+        const int m = meta.item_nt[it] * 8 + (ln >> 2), k = meta.item_k0[it] + 2 * (ln & 3);
+        float w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int kk = k + (q & 1) + 8 * (q >> 1);
+            w[q] = (m < n_mels && kk < NB) ? basis[(size_t)m * NB + kk] : 0.f;
+        }
+        uint4 f;
+        split_bf16x2(w[0], w[1], f.x, f.z);
+        split_bf16x2(w[2], w[3], f.y, f.w);
+        btab[e] = f;
     }
     __syncthreads();
 
     const long total = (long)B * n_frames;
-    const long wstride = (long)gridDim.x * LM_WARPS;
-    for (long fr = (long)blockIdx.x * LM_WARPS + warp; fr < total; fr += wstride) {
-        const int b = (int)(fr / n_frames), f = (int)(fr % n_frames);
-        const float* x = wav + (size_t)b * ns;
-        const long start = (long)f * hop - H;                       // center = True: frame f covers [f*hop - n_fft/2, ...)
-        // ---- step 1: lane n2 loads z[32 n1 + n2] = (x[2m], x[2m+1]) * window, n1 = 0..31 (coalesced 256 B per n1)
-        float2 v[32];
-        const bool interior = (start >= 0) && (start + NFFT <= ns);
-        const bool even = (((size_t)b * ns + start) & 1) == 0 && ((reinterpret_cast<uintptr_t>(wav) & 7) == 0);
+    const long n_groups = (total + LM_WARPS - 1) / LM_WARPS;
+    for (long g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        const long fr = g * LM_WARPS + warp;
+        if (fr < total) {
+            const int b = (int)(fr / n_frames), f = (int)(fr - (long)b * n_frames);
+            const float* x = wav + (size_t)b * ns;
+            const int start = f * hop - H;                              // center = True: frame f covers [f*hop - n_fft/2, ...)
+            // ---- lane n2 loads z[32 n1 + n2] = (x[2m], x[2m+1]) * window, n1 = 0..31 (256 contiguous bytes per n1)
+            float2 v[32];
+            const float2* sw2 = reinterpret_cast<const float2*>(swin) + lane;
+            if (start >= 0 && start + 2 * H <= ns && (reinterpret_cast<uintptr_t>(x + start) & 7) == 0) {
+                const float2* p = reinterpret_cast<const float2*>(x + start) + lane;
 #pragma unroll
-        for (int n1 = 0; n1 < 32; ++n1) {
-            const int mi = 32 * n1 + lane;
-            long s0 = start + 2 * mi, s1 = s0 + 1;
-            if (!interior) {
-                if (s0 < 0) s0 = -s0; else if (s0 >= ns) s0 = 2L * (ns - 1) - s0;
-                if (s1 < 0) s1 = -s1; else if (s1 >= ns) s1 = 2L * (ns - 1) - s1;
-            }
-            const float2 w = *reinterpret_cast<const float2*>(swin + 2 * mi);
-            if (interior && even) {
-                const float2 xv = *reinterpret_cast<const float2*>(x + s0);
-                v[n1] = make_float2(xv.x * w.x, xv.y * w.y);
+                for (int n1 = 0; n1 < 32; ++n1) v[n1] = __ldg(p + 32 * n1);
+#pragma unroll
+                for (int n1 = 0; n1 < 32; ++n1) {
+                    const float2 w = sw2[32 * n1];
+                    v[n1] = make_float2(v[n1].x * w.x, v[n1].y * w.y);
+                }
             } else {
-                v[n1] = make_float2(x[s0] * w.x, x[s1] * w.y);
+#pragma unroll
+                for (int n1 = 0; n1 < 32; ++n1) {
+                    int s0 = start + 2 * (32 * n1 + lane), s1 = s0 + 1;  // reflect padding (n_samples > n_fft / 2: one bounce)
+                    s0 = s0 < 0 ? -s0 : (s0 >= ns ? 2 * (ns - 1) - s0 : s0);
+                    s1 = s1 < 0 ? -s1 : (s1 >= ns ? 2 * (ns - 1) - s1 : s1);
+                    const float2 w = sw2[32 * n1];
+                    v[n1] = make_float2(__ldg(x + s0) * w.x, __ldg(x + s1) * w.y);
+                }
+            }
+            // ---- 1024-point complex FFT as 32 x 32: in-register 32-point DFTs around one transpose
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                fft32_dif(v);                                           // v[brev5(k)] = sum_n v[n] W_32^(n k)
+                if (pass == 0) {
+#pragma unroll
+                    for (int k1 = 0; k1 < 32; ++k1) zb[k1 * LM_ZLD + lane] = cmul(v[brev5(k1)], tw32[k1 * 32 + lane]);
+                    __syncwarp();
+#pragma unroll
+                    for (int n2 = 0; n2 < 32; ++n2) v[n2] = zb[lane * LM_ZLD + n2];    // lane = k1 now
+                    __syncwarp();
+                } else {
+#pragma unroll
+                    for (int k2 = 0; k2 < 32; ++k2) zb[k2 * LM_ZLD + lane] = v[brev5(k2)];   // Z[k] at [(k >> 5) * 33 + (k & 31)]
+                    __syncwarp();
+                }
+            }
+            // ---- real-FFT unpack in conjugate pairs (k, 1024 - k): with e = Z[k] + conj Z[H-k], t = W_2048^k (Z[k] - conj Z[H-k]),
+            //      X[k] = e - i t and X[H-k] = conj(e + i t); lane handles k = lane + 32 j, j < 16; k = 512 pairs with itself (lane 0)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int kb = (H - lane - 32 * j) & (H - 1);
+                v[2 * j] = zb[j * LM_ZLD + lane];
+                v[2 * j + 1] = zb[(kb >> 5) * LM_ZLD + (kb & 31)];
+            }
+            float m512 = 0.f;
+            if (lane == 0) {
+                const float2 z = zb[16 * LM_ZLD];
+                m512 = 2.f * sqrt_approx(z.x * z.x + z.y * z.y);
+            }
+            __syncwarp();                                               // the region now becomes the magnitude row
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int k = lane + 32 * j;
+                const float2 zk = v[2 * j], zc = v[2 * j + 1];
+                const float2 e = make_float2(zk.x + zc.x, zk.y - zc.y);
+                const float2 t = cmul(make_float2(zk.x - zc.x, zk.y + zc.y), tw2048[k]);
+                const float ar = e.x + t.y, ai = e.y - t.x, br = e.x - t.y, bi = e.y + t.x;
+                mg[k] = sqrt_approx(ar * ar + ai * ai);
+                mg[H - k] = sqrt_approx(br * br + bi * bi);
+            }
+            if (lane == 0) mg[512] = m512;
+            else mg[H + lane] = 0.f;                                    // bins 1025 .. 1055 are read (times zero weights) by the last bin blocks
+            if (!use_tc) {
+                // dense fallback for filterbanks the banded table cannot hold: one warp per frame, every band over every bin
+                __syncwarp();
+                float* out = mel + (size_t)fr * n_mels;
+                for (int m = 0; m < n_mels; ++m) {
+                    float acc = 0.f;
+                    for (int k = lane; k < NB; k += 32) acc = fmaf(mg[k], basis[(size_t)m * NB + k], acc);
+                    acc = warp_sum(acc);
+                    if (lane == 0) {
+                        float o = log2f(fmaxf(eps, acc)) * log_scale;
+                        if (nmean) o = (o - nmean[m]) / nscale[m];
+                        out[m] = o;
+                    }
+                }
+                __syncwarp();
             }
         }
-        fft32_dif(v);                                               // v[brev5(k1)] = sum_n1 z[32 n1 + lane] W_32^(n1 k1)
-        // ---- step 2: twiddle W_1024^(lane * k1) by recurrence, step 3: transpose through shared memory
+        if (!use_tc) continue;
+        __syncthreads();
+        // ---- mel projection of the 16 magnitude rows: this warp's share of the (band tile, bin block) list
         {
-            const float2 wl = tw1024[lane];
-            float2 w = make_float2(1.f, 0.f);
-#pragma unroll
-            for (int k1 = 0; k1 < 32; ++k1) {
-                const float2 y = cmul(v[brev5(k1)], w);
-                zbuf[k1 * LM_ZLD + lane] = y;                       // row k1, column n2 = lane
-                w = cmul(w, wl);
+            const int i0 = meta.chunk[warp], i1 = meta.chunk[warp + 1];
+            float d[4] = {0.f, 0.f, 0.f, 0.f};
+            float* ps = part + (size_t)meta.warp_pbase[warp] * 128;
+            const float* r0 = regions + (size_t)gid * LM_FS + 2 * tig;
+            const float* r1 = r0 + 8 * LM_FS;
+            int prev = i0 < i1 ? meta.item_nt[i0] : 0;
+            for (int i = i0; i < i1; ++i) {
+                const int nt = meta.item_nt[i], k0 = meta.item_k0[i];
+                if (nt != prev) {
+                    *reinterpret_cast<float2*>(ps + gid * 8 + 2 * tig) = make_float2(d[0], d[1]);
+                    *reinterpret_cast<float2*>(ps + (gid + 8) * 8 + 2 * tig) = make_float2(d[2], d[3]);
+                    ps += (size_t)(nt - prev) * 128;
+                    d[0] = d[1] = d[2] = d[3] = 0.f;
+                    prev = nt;
+                }
+                const float2 x0 = *reinterpret_cast<const float2*>(r0 + k0), x1 = *reinterpret_cast<const float2*>(r1 + k0);
+                const float2 x2 = *reinterpret_cast<const float2*>(r0 + k0 + 8), x3 = *reinterpret_cast<const float2*>(r1 + k0 + 8);
+                unsigned ah[4], al[4];
+                split_bf16x2(x0.x, x0.y, ah[0], al[0]);
+                split_bf16x2(x1.x, x1.y, ah[1], al[1]);
+                split_bf16x2(x2.x, x2.y, ah[2], al[2]);
+                split_bf16x2(x3.x, x3.y, ah[3], al[3]);
+                const uint4 bw = btab[i * 32 + lane];
+                mma_bf16_16816(d, ah, bw.x, bw.y);
+                mma_bf16_16816(d, al, bw.x, bw.y);
+                mma_bf16_16816(d, ah, bw.z, bw.w);
+            }
+            if (i0 < i1) {
+                *reinterpret_cast<float2*>(ps + gid * 8 + 2 * tig) = make_float2(d[0], d[1]);
+                *reinterpret_cast<float2*>(ps + (gid + 8) * 8 + 2 * tig) = make_float2(d[2], d[3]);
             }
         }
-        __syncwarp();
-#pragma unroll
-        for (int n2 = 0; n2 < 32; ++n2) v[n2] = zbuf[lane * LM_ZLD + n2];    // lane = k1 now
-        __syncwarp();
-        fft32_dif(v);                                               // v[brev5(k2)] = Z[k1 + 32 k2]
-#pragma unroll
-        for (int k2 = 0; k2 < 32; ++k2) zbuf[k2 * LM_ZLD + lane] = v[brev5(k2)];   // Z[k] at [(k >> 5) * 33 + (k & 31)]
-        __syncwarp();
-        // ---- real-FFT unpack: X[k] = (Z[k] + conj Z[H-k]) / 2 - i/2 * W_2048^k (Z[k] - conj Z[H-k]), k = 0..1024
-        for (int k = lane; k <= H; k += 32) {
-            const int ka = k & (H - 1), kb = (H - k) & (H - 1);
-            const float2 zk = zbuf[(ka >> 5) * LM_ZLD + (ka & 31)];
-            float2 zc = zbuf[(kb >> 5) * LM_ZLD + (kb & 31)];
-            zc.y = -zc.y;
-            const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
-            const float2 o = make_float2(0.5f * (zk.x - zc.x), 0.5f * (zk.y - zc.y));
-            const float2 ow = cmul(o, tw2048[k]);                   // then multiply by -i: (a + ib)(-i) = b - ia
-            const float re = e.x + ow.y, im = e.y - ow.x;
-            mag[k] = sqrtf(re * re + im * im);
-        }
-        __syncwarp();
-        // ---- mel bands: 8-lane groups, 4 bands per pass (triangular filters are narrow at low frequencies), + log
-        float* out = mel + (size_t)fr * n_mels;
-        const int grp = lane >> 3, gl = lane & 7;
-        for (int m0 = 0; m0 < n_mels; m0 += 4) {
-            const int m = m0 + grp;
+        __syncthreads();
+        // ---- band sums in a fixed order over the contributing warps, log, (normalise,) one contiguous store per group
+        for (int o = tid; o < LM_WARPS * n_mels; o += blockDim.x) {
+            const int f = o / n_mels, m = o - f * n_mels;
+            if (g * LM_WARPS + f >= total) break;
+            const int nt = m >> 3;
             float acc = 0.f;
-            if (m < n_mels) {
-                const int lo = rng[3 * m], hi = rng[3 * m + 1], off = rng[3 * m + 2];
-                for (int k = lo + gl; k < hi; k += 8) acc = fmaf(mag[k], wpk[off + k - lo], acc);
-            }
-            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-            if (gl == 0 && m < n_mels) {
-                float v = log2f(fmaxf(eps, acc)) * log_scale;
-                if (nmean) v = (v - nmean[m]) / nscale[m];          // StandardScaler.transform (bin/normalize.py:193) fused
-                out[m] = v;
-            }
+            for (int w = meta.nt_wfirst[nt]; w <= meta.nt_wlast[nt]; ++w)
+                acc += part[(size_t)(meta.warp_pbase[w] + nt - meta.warp_ft[w]) * 128 + f * 8 + (m & 7)];
+            float val = log2f(fmaxf(eps, acc)) * log_scale;
+            if (nmean) val = (val - nmean[m]) / nscale[m];          // StandardScaler.transform (bin/normalize.py:193) fused
+            mel[(size_t)(g * LM_WARPS) * n_mels + o] = val;
         }
-        __syncwarp();
     }
 }
 
@@ -344,31 +491,21 @@ static int logmel_impl(const float* wav, const float* window, const float* mel_b
     S2S_REQUIRE(lb > 1.0, "logmel: bad log base");
     float log_scale = (float)(1.0 / log2(lb));
     long total = (long)B * n_frames;
-    if (n_fft == 2048 && n_mels <= 256) {
-        // warp-per-frame fast path
-        const int wpk_cap = (4 * nbins + 3) & ~3;
-        size_t smem = (size_t)(32 + nbins + 1) * 8 + (size_t)n_fft * 4 + (size_t)wpk_cap * 4 + (size_t)((3 * n_mels + 4) & ~3) * 4 +
-                      (size_t)LM_WARPS * (2 * 32 * LM_ZLD + nbins + 7) * 4;
-        static bool attr2 = false;
-        if (!attr2) {
-            S2S_CUDA_OK(cudaFuncSetAttribute(logmel2048_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr2 = true;
-        }
-        S2S_REQUIRE(smem <= 200 * 1024, "logmel: shared memory request too large");
+    if (n_fft == 2048) {
+        // 16 frames per round per persistent CTA; filterbanks the banded table cannot hold take the kernel's dense fallback
+        S2S_REQUIRE((long)n_samples + n_fft < (1L << 30), "logmel: clip too long for 32-bit sample indices");
+        S2S_CUDA_OK(cudaFuncSetAttribute(logmel2048_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LM_SMEM));
         long grid = (long)num_sms();
         long need = ceil_div_l(total, LM_WARPS);
         if (grid > need) grid = need;
-        logmel2048_kernel<<<(unsigned)grid, LM_WARPS * 32, smem, (cudaStream_t)stream>>>(wav, window, mel_basis, mel, B, n_samples, hop,
-                                                                                         n_frames, n_mels, eps, log_scale, wpk_cap, nmean, nscale);
+        logmel2048_kernel<<<(unsigned)grid, LM_WARPS * 32, LM_SMEM, (cudaStream_t)stream>>>(wav, window, mel_basis, mel, B, n_samples, hop,
+                                                                                            n_frames, n_mels, eps, log_scale, nmean, nscale);
         S2S_LAUNCH_OK();
         return S2S_OK;
     }
     size_t smem = (size_t)half * 8 * 2 + (size_t)(nbins + 3) * 4 + (size_t)4 * nbins * 4 + (size_t)3 * n_mels * 4 + (size_t)n_fft * 4;
-    static bool attr_set = false;
-    if (smem > 48 * 1024 && !attr_set) {
+    if (smem > 48 * 1024)      // the attribute is per device: set it on every call that needs it (cheap)
         S2S_CUDA_OK(cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        attr_set = true;
-    }
     S2S_REQUIRE(smem <= 160 * 1024, "logmel: shared memory request too large");
     long grid = (long)num_sms() * 4;
     if (grid > total) grid = total;

@@ -85,6 +85,37 @@ def test_logmel_vs_oracle(sr, n_fft, hop, ns, win):
     assert np.abs(got - ref).max() <= 5e-2
 
 
+@pytest.mark.parametrize("num_mels,fmin,fmax", [(80, 80, 7600), (128, 0, None), (160, 0, None), (40, 1000, 20000)])
+def test_logmel_2048_filterbank_shapes(num_mels, fmin, fmax):
+    """n_fft = 2048 fast path: narrow / full-band / sparse-low banks on the banded tensor-core projection, and a bank with more
+    than 128 bands on the kernel's dense projection; two clips whose frame groups straddle the clip boundary, odd sample count."""
+    from seq2seq_vc_b200 import api
+
+    rng = np.random.default_rng(num_mels)
+    wav = np.clip(0.2 * rng.standard_normal((2, 30001)), -1, 1).astype(np.float32)
+    wav[1, 5000:9000] = 0.0
+    got = api.logmel_batch(torch.from_numpy(wav).cuda(), 48000, fft_size=2048, hop_size=300, num_mels=num_mels, fmin=fmin,
+                           fmax=fmax).cpu().numpy()
+    for b in range(2):
+        ref = logmel_oracle.logmelfilterbank(wav[b], 48000, fft_size=2048, hop_size=300, num_mels=num_mels, fmin=fmin, fmax=fmax)
+        assert got[b].shape == ref.shape
+        live = ref > -9.0
+        assert np.abs(got[b] - ref)[live].max() <= 1e-4, np.abs(got[b] - ref)[live].max()
+        assert np.abs(got[b] - ref).max() <= 5e-2
+
+
+def test_logmel_2048_unaligned_view():
+    """A clip that starts on an odd float offset takes the scalar load path and gives the same frames."""
+    from seq2seq_vc_b200 import api
+
+    rng = np.random.default_rng(5)
+    buf = torch.from_numpy((0.1 * rng.standard_normal(2 * 20001 + 1)).astype(np.float32)).cuda()
+    a = buf[1:].view(2, 20001)
+    got = api.logmel_batch(a, 48000, fft_size=2048, hop_size=300, num_mels=80)
+    want = api.logmel_batch(a.clone(), 48000, fft_size=2048, hop_size=300, num_mels=80)
+    assert torch.equal(got, want)
+
+
 def test_logmel_batched_and_silence():
     from seq2seq_vc_b200 import api
 
