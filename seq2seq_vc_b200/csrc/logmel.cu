@@ -28,6 +28,36 @@ __host__ __device__ constexpr int brev5(int x) {
     return ((x & 1) << 4) | ((x & 2) << 2) | (x & 4) | ((x & 8) >> 2) | ((x & 16) >> 4);
 }
 
+// Packed fp32 pairs (sm_100 FADD2 / FMUL2 / FFMA2): a complex value is one 64-bit register pair, a complex add is one
+// instruction and a multiply by a constant twiddle is two (ptxas folds the component swap / sign into operand modifiers).
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float x, float y) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(x), "f"(y)); return r; }
+__device__ __forceinline__ float2 upk2(u64 r) { float2 d; asm("mov.b64 {%0,%1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(r)); return d; }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    u64 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a.x, a.y)), "l"(pk2(b.x, b.y)));
+    return upk2(r);
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+    u64 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a.x, a.y)), "l"(pk2(b.x, b.y)));
+    return upk2(r);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    u64 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a.x, a.y)), "l"(pk2(b.x, b.y)));
+    return upk2(r);
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    u64 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk2(a.x, a.y)), "l"(pk2(b.x, b.y)), "l"(pk2(c.x, c.y)));
+    return upk2(r);
+}
+// d * (c + i s) = (d.x c - d.y s, d.y c + d.x s)
+__device__ __forceinline__ float2 cmul2(float2 d, float c, float s) {
+    return fma2(make_float2(d.y, d.x), make_float2(-s, s), mul2(d, make_float2(c, c)));
+}
+
 // in-place 32-point forward DFT, decimation in frequency, fully unrolled; output v[brev5(k)] = X[k]
 __device__ __forceinline__ void fft32_dif(float2 (&v)[32]) {
 #pragma unroll
@@ -38,12 +68,12 @@ __device__ __forceinline__ void fft32_dif(float2 (&v)[32]) {
 #pragma unroll
             for (int j = 0; j < half; ++j) {
                 const float2 a = v[g + j], b = v[g + j + half];
-                v[g + j] = make_float2(a.x + b.x, a.y + b.y);
-                const float2 d = make_float2(a.x - b.x, a.y - b.y);
+                v[g + j] = add2(a, b);
+                const float2 d = sub2(a, b);
                 const int tw = j << s;         // W_32^(j * 2^s)
                 if (tw == 0) v[g + j + half] = d;
                 else if (tw == 8) v[g + j + half] = make_float2(d.y, -d.x);   // * (-i)
-                else v[g + j + half] = make_float2(d.x * kCos32[tw] - d.y * kSin32[tw], d.x * kSin32[tw] + d.y * kCos32[tw]);
+                else v[g + j + half] = cmul2(d, kCos32[tw], kSin32[tw]);
             }
         }
     }
@@ -81,8 +111,9 @@ __device__ __forceinline__ float sqrt_approx(float x) {
 struct LogmelMeta {                               // built once per CTA from the filterbank matrix
     int n_items, use_tc;
     int item_nt[LM_MAX_ITEMS], item_k0[LM_MAX_ITEMS];
-    int nt_lo[LM_MAX_NT], nt_cnt[LM_MAX_NT], nt_wfirst[LM_MAX_NT], nt_wlast[LM_MAX_NT];
-    int chunk[LM_WARPS + 1], warp_ft[LM_WARPS], warp_pbase[LM_WARPS];
+    int nt_lo[LM_MAX_NT], nt_cnt[LM_MAX_NT];
+    int nt_np[LM_MAX_NT], nt_pair[LM_MAX_NT][LM_WARPS];     // partial tiles (offsets in floats) that make up a band tile, in warp order
+    int chunk[LM_WARPS + 1], warp_pbase[LM_WARPS];
 };
 
 // Layout of dynamic shared memory (bytes): tw32 float2[1024] | tw2048 float2[520] | swin float[2048] (x 0.5) | btab uint4[96 * 32] |
@@ -134,26 +165,25 @@ __global__ void __launch_bounds__(LM_WARPS * 32, 1) logmel2048_kernel(const floa
     }
     for (int k = tid; k < 2048; k += blockDim.x) swin[k] = 0.5f * window[k];
     const int NT = (n_mels + 7) >> 3;
+    if (tid < LM_MAX_NT) { meta.nt_lo[tid] = NB; meta.nt_cnt[tid] = -1; }      // nt_cnt holds the last non-zero bin until the list is built
+    __syncthreads();
     if (NT <= LM_MAX_NT) {
-        // non-zero bin range of every 8-band tile: one warp per tile
-        if (warp < NT) {
+        // non-zero bin range of every 8-band tile: one warp per band row, all loads of a row in flight at once
+        for (int m = warp; m < n_mels; m += LM_WARPS) {
+            const float* row = basis + (size_t)m * NB;
+            float w[33];
+#pragma unroll
+            for (int i = 0; i < 33; ++i) w[i] = (lane + 32 * i < NB) ? __ldg(row + lane + 32 * i) : 0.f;
             int lo = NB, hi = -1;
-            for (int r = 0; r < 8; ++r) {
-                const int m = warp * 8 + r;
-                if (m >= n_mels) break;
-                for (int k = lane; k < NB; k += 32)
-                    if (basis[(size_t)m * NB + k] != 0.f) { lo = min(lo, k); hi = max(hi, k); }
-            }
+#pragma unroll
+            for (int i = 0; i < 33; ++i)
+                if (w[i] != 0.f) { lo = min(lo, lane + 32 * i); hi = max(hi, lane + 32 * i); }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
                 hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
             }
-            if (lane == 0) {
-                lo &= ~1;
-                meta.nt_lo[warp] = lo;
-                meta.nt_cnt[warp] = hi < 0 ? 0 : (hi + 1 - lo + 15) >> 4;
-            }
+            if (lane == 0) { atomicMin(&meta.nt_lo[m >> 3], lo); atomicMax(&meta.nt_cnt[m >> 3], hi); }
         }
     }
     __syncthreads();
@@ -161,23 +191,24 @@ __global__ void __launch_bounds__(LM_WARPS * 32, 1) logmel2048_kernel(const floa
         int n = 0;
         bool ok = NT <= LM_MAX_NT;
         for (int j = 0; ok && j < NT; ++j) {
+            const int lo = meta.nt_lo[j] & ~1, hi = meta.nt_cnt[j];
+            meta.nt_lo[j] = lo;
+            meta.nt_cnt[j] = hi < 0 ? 0 : (hi + 1 - lo + 15) >> 4;
             if (n + meta.nt_cnt[j] > LM_MAX_ITEMS) { ok = false; break; }
             for (int c = 0; c < meta.nt_cnt[j]; ++c) { meta.item_nt[n] = j; meta.item_k0[n] = meta.nt_lo[j] + 16 * c; ++n; }
         }
         meta.use_tc = ok ? 1 : 0;
         meta.n_items = ok ? n : 0;
         if (ok) {
-            for (int j = 0; j < NT; ++j) { meta.nt_wfirst[j] = LM_WARPS; meta.nt_wlast[j] = -1; }
+            for (int j = 0; j < NT; ++j) meta.nt_np[j] = 0;
             int pb = 0;
             for (int w = 0; w <= LM_WARPS; ++w) meta.chunk[w] = (w * n) / LM_WARPS;
             for (int w = 0; w < LM_WARPS; ++w) {
                 const int i0 = meta.chunk[w], i1 = meta.chunk[w + 1];
                 meta.warp_pbase[w] = pb;
-                meta.warp_ft[w] = i0 < i1 ? meta.item_nt[i0] : 0;
                 for (int i = i0; i < i1; ++i) {
                     const int j = meta.item_nt[i];
-                    meta.nt_wfirst[j] = min(meta.nt_wfirst[j], w);
-                    meta.nt_wlast[j] = max(meta.nt_wlast[j], w);
+                    if (i == i0 || j != meta.item_nt[i - 1]) meta.nt_pair[j][meta.nt_np[j]++] = (pb + j - meta.item_nt[i0]) * 128;
                 }
                 if (i0 < i1) pb += meta.item_nt[i1 - 1] - meta.item_nt[i0] + 1;   // <= NT + 16 in total
             }
@@ -203,32 +234,39 @@ __global__ void __launch_bounds__(LM_WARPS * 32, 1) logmel2048_kernel(const floa
 
     const long total = (long)B * n_frames;
     const long n_groups = (total + LM_WARPS - 1) / LM_WARPS;
+    // lane n2 holds z[32 n1 + n2] = (x[2m], x[2m+1]), n1 = 0..31 (256 contiguous bytes per n1); frame f covers
+    // [f * hop - n_fft / 2, ...) (center = True) with reflect padding (n_samples > n_fft / 2: one bounce)
+    float2 v[32];
+    auto fetch = [&](long frame) {
+        if (frame >= total) return;
+        const int b = (int)(frame / n_frames), f = (int)(frame - (long)b * n_frames);
+        const float* x = wav + (size_t)b * ns;
+        const int start = f * hop - H;
+        if (start >= 0 && start + 2 * H <= ns && (reinterpret_cast<uintptr_t>(x + start) & 7) == 0) {
+            const float2* p = reinterpret_cast<const float2*>(x + start) + lane;
+#pragma unroll
+            for (int n1 = 0; n1 < 32; ++n1) v[n1] = __ldg(p + 32 * n1);
+        } else {
+#pragma unroll
+            for (int n1 = 0; n1 < 32; ++n1) {
+                int s0 = start + 2 * (32 * n1 + lane), s1 = s0 + 1;
+                s0 = s0 < 0 ? -s0 : (s0 >= ns ? 2 * (ns - 1) - s0 : s0);
+                s1 = s1 < 0 ? -s1 : (s1 >= ns ? 2 * (ns - 1) - s1 : s1);
+                v[n1] = make_float2(__ldg(x + s0), __ldg(x + s1));
+            }
+        }
+    };
+    fetch((long)blockIdx.x * LM_WARPS + warp);
     for (long g = blockIdx.x; g < n_groups; g += gridDim.x) {
         const long fr = g * LM_WARPS + warp;
         if (fr < total) {
-            const int b = (int)(fr / n_frames), f = (int)(fr - (long)b * n_frames);
-            const float* x = wav + (size_t)b * ns;
-            const int start = f * hop - H;                              // center = True: frame f covers [f*hop - n_fft/2, ...)
-            // ---- lane n2 loads z[32 n1 + n2] = (x[2m], x[2m+1]) * window, n1 = 0..31 (256 contiguous bytes per n1)
-            float2 v[32];
-            const float2* sw2 = reinterpret_cast<const float2*>(swin) + lane;
-            if (start >= 0 && start + 2 * H <= ns && (reinterpret_cast<uintptr_t>(x + start) & 7) == 0) {
-                const float2* p = reinterpret_cast<const float2*>(x + start) + lane;
-#pragma unroll
-                for (int n1 = 0; n1 < 32; ++n1) v[n1] = __ldg(p + 32 * n1);
+            // ---- window (the raw samples were fetched during the previous round's projection / store stages)
+            {
+                const float2* sw2 = reinterpret_cast<const float2*>(swin) + lane;
 #pragma unroll
                 for (int n1 = 0; n1 < 32; ++n1) {
                     const float2 w = sw2[32 * n1];
                     v[n1] = make_float2(v[n1].x * w.x, v[n1].y * w.y);
-                }
-            } else {
-#pragma unroll
-                for (int n1 = 0; n1 < 32; ++n1) {
-                    int s0 = start + 2 * (32 * n1 + lane), s1 = s0 + 1;  // reflect padding (n_samples > n_fft / 2: one bounce)
-                    s0 = s0 < 0 ? -s0 : (s0 >= ns ? 2 * (ns - 1) - s0 : s0);
-                    s1 = s1 < 0 ? -s1 : (s1 >= ns ? 2 * (ns - 1) - s1 : s1);
-                    const float2 w = sw2[32 * n1];
-                    v[n1] = make_float2(__ldg(x + s0) * w.x, __ldg(x + s1) * w.y);
                 }
             }
             // ---- 1024-point complex FFT as 32 x 32: in-register 32-point DFTs around one transpose
@@ -266,14 +304,17 @@ __global__ void __launch_bounds__(LM_WARPS * 32, 1) logmel2048_kernel(const floa
             for (int j = 0; j < 16; ++j) {
                 const int k = lane + 32 * j;
                 const float2 zk = v[2 * j], zc = v[2 * j + 1];
-                const float2 e = make_float2(zk.x + zc.x, zk.y - zc.y);
-                const float2 t = cmul(make_float2(zk.x - zc.x, zk.y + zc.y), tw2048[k]);
-                const float ar = e.x + t.y, ai = e.y - t.x, br = e.x - t.y, bi = e.y + t.x;
+                const float2 zcc = make_float2(zc.x, -zc.y);                // conj Z[H-k]
+                const float2 e = add2(zk, zcc);
+                const float2 t = cmul(sub2(zk, zcc), tw2048[k]);
+                const float2 xa = add2(e, make_float2(t.y, -t.x)), xb = sub2(e, make_float2(t.y, -t.x));
+                const float ar = xa.x, ai = xa.y, br = xb.x, bi = xb.y;
                 mg[k] = sqrt_approx(ar * ar + ai * ai);
                 mg[H - k] = sqrt_approx(br * br + bi * bi);
             }
             if (lane == 0) mg[512] = m512;
             else mg[H + lane] = 0.f;                                    // bins 1025 .. 1055 are read (times zero weights) by the last bin blocks
+            fetch(fr + (long)gridDim.x * LM_WARPS);                     // next round's samples: in flight across the projection and the store
             if (!use_tc) {
                 // dense fallback for filterbanks the banded table cannot hold: one warp per frame, every band over every bin
                 __syncwarp();
@@ -328,17 +369,32 @@ __global__ void __launch_bounds__(LM_WARPS * 32, 1) logmel2048_kernel(const floa
             }
         }
         __syncthreads();
-        // ---- band sums in a fixed order over the contributing warps, log, (normalise,) one contiguous store per group
-        for (int o = tid; o < LM_WARPS * n_mels; o += blockDim.x) {
-            const int f = o / n_mels, m = o - f * n_mels;
-            if (g * LM_WARPS + f >= total) break;
-            const int nt = m >> 3;
-            float acc = 0.f;
-            for (int w = meta.nt_wfirst[nt]; w <= meta.nt_wlast[nt]; ++w)
-                acc += part[(size_t)(meta.warp_pbase[w] + nt - meta.warp_ft[w]) * 128 + f * 8 + (m & 7)];
-            float val = log2f(fmaxf(eps, acc)) * log_scale;
-            if (nmean) val = (val - nmean[m]) / nscale[m];          // StandardScaler.transform (bin/normalize.py:193) fused
-            mel[(size_t)(g * LM_WARPS) * n_mels + o] = val;
+        // ---- band sums in a fixed order over the contributing warps, log, (normalise,): warp w stores frame w's row, the 16 rows of
+        //      a group are one contiguous run
+        if (fr < total) {
+            float* out = mel + (size_t)fr * n_mels;
+            for (int m0 = lane; m0 < n_mels; m0 += 96) {
+                float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const int m = m0 + 32 * q;
+                    if (m < n_mels) {
+                        const int nt = m >> 3, np = meta.nt_np[nt];
+                        const float* pp = part + warp * 8 + (m & 7);
+#pragma unroll 1
+                        for (int c = 0; c < np; ++c) acc[q] += pp[meta.nt_pair[nt][c]];
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const int m = m0 + 32 * q;
+                    if (m < n_mels) {
+                        float val = __log2f(fmaxf(eps, acc[q])) * log_scale;
+                        if (nmean) val = (val - nmean[m]) / nscale[m];      // StandardScaler.transform (bin/normalize.py:193) fused
+                        out[m] = val;
+                    }
+                }
+            }
         }
     }
 }
