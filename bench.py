@@ -601,8 +601,10 @@ def run_c5(args, rank, world):
             "roofline": {"bound": "hbm", "kernel": "logmel kernels (STFT + mel + log of one batch)", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                          "frac": ach / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": kernel_ms * 1e3,
-                         "note": "SURVEY section 8(d): read 256 x 480000 x 4 B, write 256 x 1601 x 80 x 4 B = 622.7 MB per launch; the shape is fp32-FFT-"
-                                 "arithmetic bound (each sample is reused by 6.8 overlapping frames), see DESIGN.md"}}
+                         "note": "SURVEY section 8(d): read 256 x 480000 x 4 B, write 256 x 1601 x 80 x 4 B = 622.7 MB per launch; DRAM traffic equals "
+                                 "it (ncu: 609 MB), but every sample is used by 6.8 overlapping 2048-point FFTs, so the kernel is bound by instruction "
+                                 "issue / shared-memory bandwidth of the FFT (1.83 k warp instructions and 465 shared-memory wavefronts per frame), "
+                                 "not by HBM: see DESIGN.md section 4"}}
     if world == 1 and not args.no_cpu_baseline:
         clips = max(2, min(os.cpu_count() or 1, 32))
         val, cores = logmel_cpu_frames_per_s(clips, ns, hp)

@@ -88,6 +88,7 @@ constexpr int LM_FS = 2120;                       // floats per warp region: >= 
 constexpr int LM_MAX_ITEMS = 96;                  // (8-band tile, 16-bin block) pairs of the mel projection
 constexpr int LM_MAX_NT = 16;                     // 8-band tiles: n_mels <= 128 on the tensor-core mel path
 constexpr int LM_MAX_PAIRS = LM_MAX_NT + LM_WARPS;
+constexpr int LM_ITEMS_PER_WARP = LM_MAX_ITEMS / LM_WARPS;
 
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
@@ -256,6 +257,48 @@ __global__ void __launch_bounds__(LM_WARPS * 32, 1) logmel2048_kernel(const floa
             }
         }
     };
+    // band sums in a fixed order over the contributing warps, log, (normalise,): warp w stores frame w's row of group gq, the 16
+    // rows of a group are one contiguous run.  Half of the warps store right after the projection, the other half after their
+    // next frame's FFT (any time before the next projection overwrites the partial tiles): the two halves then run half a phase
+    // apart, so the arithmetic-bound and the shared-memory-bound stretches of different warps overlap.
+    auto store_rows = [&](long gq) {
+        const long fq = gq * LM_WARPS + warp;
+        if (fq >= total) return;
+        float* out = mel + (size_t)fq * n_mels;
+        for (int m0 = lane; m0 < n_mels; m0 += 96) {
+            float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const int m = m0 + 32 * q;
+                if (m < n_mels) {
+                    const int nt = m >> 3, np = meta.nt_np[nt];
+                    const float* pp = part + warp * 8 + (m & 7);
+#pragma unroll 1
+                    for (int c = 0; c < np; ++c) acc[q] += pp[meta.nt_pair[nt][c]];
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const int m = m0 + 32 * q;
+                if (m < n_mels) {
+                    float val = __log2f(fmaxf(eps, acc[q])) * log_scale;
+                    if (nmean) val = (val - nmean[m]) / nscale[m];      // StandardScaler.transform (bin/normalize.py:193) fused
+                    out[m] = val;
+                }
+            }
+        }
+    };
+    // this warp's share of the (band tile, bin block) list is the same in every round
+    const int i0 = meta.chunk[warp], n_it = meta.chunk[warp + 1] - i0;
+    int it_k0[LM_ITEMS_PER_WARP], it_nt[LM_ITEMS_PER_WARP];
+#pragma unroll
+    for (int c = 0; c < LM_ITEMS_PER_WARP; ++c) {
+        it_k0[c] = c < n_it ? meta.item_k0[i0 + c] : 0;
+        it_nt[c] = c < n_it ? meta.item_nt[i0 + c] : 0;
+    }
+    float* part_w = part + (size_t)meta.warp_pbase[warp] * 128;
+    const bool defer = ((warp >> 2) & 1) != 0;
+    long pend = -1;
     fetch((long)blockIdx.x * LM_WARPS + warp);
     for (long g = blockIdx.x; g < n_groups; g += gridDim.x) {
         const long fr = g * LM_WARPS + warp;
@@ -280,38 +323,29 @@ __global__ void __launch_bounds__(LM_WARPS * 32, 1) logmel2048_kernel(const floa
 #pragma unroll
                     for (int n2 = 0; n2 < 32; ++n2) v[n2] = zb[lane * LM_ZLD + n2];    // lane = k1 now
                     __syncwarp();
-                } else {
-#pragma unroll
-                    for (int k2 = 0; k2 < 32; ++k2) zb[k2 * LM_ZLD + lane] = v[brev5(k2)];   // Z[k] at [(k >> 5) * 33 + (k & 31)]
-                    __syncwarp();
                 }
             }
-            // ---- real-FFT unpack in conjugate pairs (k, 1024 - k): with e = Z[k] + conj Z[H-k], t = W_2048^k (Z[k] - conj Z[H-k]),
-            //      X[k] = e - i t and X[H-k] = conj(e + i t); lane handles k = lane + 32 j, j < 16; k = 512 pairs with itself (lane 0)
+            // ---- lane k1 now holds Z[k1 + 32 k2] in v[brev5(k2)].  Real-FFT unpack in conjugate pairs (k, 1024 - k): with
+            //      e = Z[k] + conj Z[H-k], t = W_2048^k (Z[k] - conj Z[H-k]): X[k] = e - i t and X[H-k] = conj(e + i t).  Lane k1 takes
+            //      k = k1 + 32 k2, k2 < 16; the partner Z[H-k] is lane (32 - k1)'s value k2' = 31 - k2 (one shuffle), for k1 = 0 the
+            //      lane's own k2' = (32 - k2) & 31; k = 512 pairs with itself (lane 0).  The warp's region becomes the magnitude row.
+            {
+                const int src = (32 - lane) & 31;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int kb = (H - lane - 32 * j) & (H - 1);
-                v[2 * j] = zb[j * LM_ZLD + lane];
-                v[2 * j + 1] = zb[(kb >> 5) * LM_ZLD + (kb & 31)];
+                for (int k2 = 0; k2 < 16; ++k2) {
+                    const int k = lane + 32 * k2;
+                    const float2 zk = v[brev5(k2)], up = v[brev5(31 - k2)], own = v[brev5((32 - k2) & 31)];
+                    float2 zcc = make_float2(__shfl_sync(0xffffffffu, up.x, src), -__shfl_sync(0xffffffffu, up.y, src));
+                    if (lane == 0) zcc = make_float2(own.x, -own.y);            // conj Z[H-k]
+                    const float2 e = add2(zk, zcc);
+                    const float2 t = cmul(sub2(zk, zcc), tw2048[k]);
+                    const float2 xa = add2(e, make_float2(t.y, -t.x)), xb = sub2(e, make_float2(t.y, -t.x));
+                    mg[k] = sqrt_approx(xa.x * xa.x + xa.y * xa.y);
+                    mg[H - k] = sqrt_approx(xb.x * xb.x + xb.y * xb.y);
+                }
             }
-            float m512 = 0.f;
-            if (lane == 0) {
-                const float2 z = zb[16 * LM_ZLD];
-                m512 = 2.f * sqrt_approx(z.x * z.x + z.y * z.y);
-            }
-            __syncwarp();                                               // the region now becomes the magnitude row
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int k = lane + 32 * j;
-                const float2 zk = v[2 * j], zc = v[2 * j + 1];
-                const float2 zcc = make_float2(zc.x, -zc.y);                // conj Z[H-k]
-                const float2 e = add2(zk, zcc);
-                const float2 t = cmul(sub2(zk, zcc), tw2048[k]);
-                const float2 xa = add2(e, make_float2(t.y, -t.x)), xb = sub2(e, make_float2(t.y, -t.x));
-                const float ar = xa.x, ai = xa.y, br = xb.x, bi = xb.y;
-                mg[k] = sqrt_approx(ar * ar + ai * ai);
-                mg[H - k] = sqrt_approx(br * br + bi * bi);
-            }
+            const float2 z512 = v[brev5(16)];
+            const float m512 = 2.f * sqrt_approx(z512.x * z512.x + z512.y * z512.y);
             if (lane == 0) mg[512] = m512;
             else mg[H + lane] = 0.f;                                    // bins 1025 .. 1055 are read (times zero weights) by the last bin blocks
             fetch(fr + (long)gridDim.x * LM_WARPS);                     // next round's samples: in flight across the projection and the store
@@ -333,70 +367,49 @@ __global__ void __launch_bounds__(LM_WARPS * 32, 1) logmel2048_kernel(const floa
             }
         }
         if (!use_tc) continue;
+        if (pend >= 0) { store_rows(pend); pend = -1; }
         __syncthreads();
         // ---- mel projection of the 16 magnitude rows: this warp's share of the (band tile, bin block) list
         {
-            const int i0 = meta.chunk[warp], i1 = meta.chunk[warp + 1];
-            float d[4] = {0.f, 0.f, 0.f, 0.f};
-            float* ps = part + (size_t)meta.warp_pbase[warp] * 128;
+            float d[4] = {0.f, 0.f, 0.f, 0.f}, dx[4] = {0.f, 0.f, 0.f, 0.f};     // hi x hi and the two cross products: independent chains
+            float* ps = part_w;
             const float* r0 = regions + (size_t)gid * LM_FS + 2 * tig;
             const float* r1 = r0 + 8 * LM_FS;
-            int prev = i0 < i1 ? meta.item_nt[i0] : 0;
-            for (int i = i0; i < i1; ++i) {
-                const int nt = meta.item_nt[i], k0 = meta.item_k0[i];
-                if (nt != prev) {
-                    *reinterpret_cast<float2*>(ps + gid * 8 + 2 * tig) = make_float2(d[0], d[1]);
-                    *reinterpret_cast<float2*>(ps + (gid + 8) * 8 + 2 * tig) = make_float2(d[2], d[3]);
-                    ps += (size_t)(nt - prev) * 128;
-                    d[0] = d[1] = d[2] = d[3] = 0.f;
-                    prev = nt;
+            int prev = it_nt[0];
+#pragma unroll
+            for (int c = 0; c < LM_ITEMS_PER_WARP; ++c) {
+                if (c < n_it) {
+                    const int nt = it_nt[c], k0 = it_k0[c];
+                    if (nt != prev) {
+                        *reinterpret_cast<float2*>(ps + gid * 8 + 2 * tig) = make_float2(d[0] + dx[0], d[1] + dx[1]);
+                        *reinterpret_cast<float2*>(ps + (gid + 8) * 8 + 2 * tig) = make_float2(d[2] + dx[2], d[3] + dx[3]);
+                        ps += (size_t)(nt - prev) * 128;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) d[q] = dx[q] = 0.f;
+                        prev = nt;
+                    }
+                    const float2 x0 = *reinterpret_cast<const float2*>(r0 + k0), x1 = *reinterpret_cast<const float2*>(r1 + k0);
+                    const float2 x2 = *reinterpret_cast<const float2*>(r0 + k0 + 8), x3 = *reinterpret_cast<const float2*>(r1 + k0 + 8);
+                    unsigned ah[4], al[4];
+                    split_bf16x2(x0.x, x0.y, ah[0], al[0]);
+                    split_bf16x2(x1.x, x1.y, ah[1], al[1]);
+                    split_bf16x2(x2.x, x2.y, ah[2], al[2]);
+                    split_bf16x2(x3.x, x3.y, ah[3], al[3]);
+                    const uint4 bw = btab[(i0 + c) * 32 + lane];
+                    mma_bf16_16816(d, ah, bw.x, bw.y);
+                    mma_bf16_16816(dx, al, bw.x, bw.y);
+                    mma_bf16_16816(dx, ah, bw.z, bw.w);
                 }
-                const float2 x0 = *reinterpret_cast<const float2*>(r0 + k0), x1 = *reinterpret_cast<const float2*>(r1 + k0);
-                const float2 x2 = *reinterpret_cast<const float2*>(r0 + k0 + 8), x3 = *reinterpret_cast<const float2*>(r1 + k0 + 8);
-                unsigned ah[4], al[4];
-                split_bf16x2(x0.x, x0.y, ah[0], al[0]);
-                split_bf16x2(x1.x, x1.y, ah[1], al[1]);
-                split_bf16x2(x2.x, x2.y, ah[2], al[2]);
-                split_bf16x2(x3.x, x3.y, ah[3], al[3]);
-                const uint4 bw = btab[i * 32 + lane];
-                mma_bf16_16816(d, ah, bw.x, bw.y);
-                mma_bf16_16816(d, al, bw.x, bw.y);
-                mma_bf16_16816(d, ah, bw.z, bw.w);
             }
-            if (i0 < i1) {
-                *reinterpret_cast<float2*>(ps + gid * 8 + 2 * tig) = make_float2(d[0], d[1]);
-                *reinterpret_cast<float2*>(ps + (gid + 8) * 8 + 2 * tig) = make_float2(d[2], d[3]);
+            if (n_it > 0) {
+                *reinterpret_cast<float2*>(ps + gid * 8 + 2 * tig) = make_float2(d[0] + dx[0], d[1] + dx[1]);
+                *reinterpret_cast<float2*>(ps + (gid + 8) * 8 + 2 * tig) = make_float2(d[2] + dx[2], d[3] + dx[3]);
             }
         }
         __syncthreads();
-        // ---- band sums in a fixed order over the contributing warps, log, (normalise,): warp w stores frame w's row, the 16 rows of
-        //      a group are one contiguous run
-        if (fr < total) {
-            float* out = mel + (size_t)fr * n_mels;
-            for (int m0 = lane; m0 < n_mels; m0 += 96) {
-                float acc[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    const int m = m0 + 32 * q;
-                    if (m < n_mels) {
-                        const int nt = m >> 3, np = meta.nt_np[nt];
-                        const float* pp = part + warp * 8 + (m & 7);
-#pragma unroll 1
-                        for (int c = 0; c < np; ++c) acc[q] += pp[meta.nt_pair[nt][c]];
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    const int m = m0 + 32 * q;
-                    if (m < n_mels) {
-                        float val = __log2f(fmaxf(eps, acc[q])) * log_scale;
-                        if (nmean) val = (val - nmean[m]) / nscale[m];      // StandardScaler.transform (bin/normalize.py:193) fused
-                        out[m] = val;
-                    }
-                }
-            }
-        }
+        if (defer) pend = g; else store_rows(g);
     }
+    if (pend >= 0) store_rows(pend);
 }
 
 // ---------------------------------------------------------------------------------------------
