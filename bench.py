@@ -464,7 +464,7 @@ def incumbent_torch_gpu(workload, steps=5, warmup=3):
     return out
 
 
-def dropin_boundary(workload, steps=10, warmup=4):
+def dropin_boundary(workload, steps=10, warmup=4, use_graph=False):
     """The reference trainer's step (trainers/ar_vc.py:59-107) around the DROP-IN module -- seq2seq_vc_b200.VTN -> Seq2SeqLoss ->
     backward -> clip_grad_norm_ -> torch.optim.Adam (+ WarmupLR) -- on the same batch as the fused step: what a user who only
     swaps the model / criterion classes gets, timed with CUDA events incl. the host-side glue."""
@@ -473,7 +473,7 @@ def dropin_boundary(workload, steps=10, warmup=4):
     hp, B, T, L, bf16, desc = WORKLOADS[workload]
     tts = workload == "c4"
     dev = torch.device("cuda", torch.cuda.current_device())
-    model = (TransformerTTS if tts else VTN)(**hp, compute_dtype="bf16" if bf16 else "float32", device=dev, seed=0)
+    model = (TransformerTTS if tts else VTN)(**hp, compute_dtype="bf16" if bf16 else "float32", device=dev, seed=0, use_graph=use_graph)
     model.train()
     crit = Seq2SeqLoss()
     opt = torch.optim.Adam(model.parameters(), lr=8e-5)
@@ -502,7 +502,8 @@ def dropin_boundary(workload, steps=10, warmup=4):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     out = {"ms_per_step": ms, "frames_per_s": B * L / (ms * 1e-3), "loss": float(loss),
-           "what": "reference-style step around the drop-in module (model -> Seq2SeqLoss -> backward -> clip_grad_norm_ -> torch.optim.Adam), eager"}
+           "what": "reference-style step around the drop-in module (model -> Seq2SeqLoss -> backward -> clip_grad_norm_ -> torch.optim.Adam), "
+                   + ("forward / backward of the module replayed from CUDA graphs (use_graph=True)" if use_graph else "eager")}
     del model, opt
     torch.cuda.empty_cache()
     return out
@@ -754,6 +755,7 @@ def run_ours(args, rank, world):
             del stepper, model
             torch.cuda.empty_cache()
             line["dropin_boundary"] = dropin_boundary(args.workload)
+            line["dropin_boundary_graph"] = dropin_boundary(args.workload, use_graph=True)
             line["torch_gpu_incumbent"] = incumbent_torch_gpu(args.workload)
     print(json.dumps(line), flush=True)
 

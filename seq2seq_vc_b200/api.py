@@ -65,6 +65,59 @@ class MultiHeadedAttention(_Node):
     attn = None
 
 
+def _dropin_graph_forward(model, xs, ys, ilens, olens):
+    """Opt-in CUDA-graph mode of the drop-in modules (`model.use_graph = True`, training only): the reference trainer's eager
+    step around the drop-in is bound by the host cost of ~450 kernel launches, so from the second batch of a (B, T, L) shape on
+    the engine's forward is replayed from a captured graph (the first batch runs eagerly and allocates every buffer outside
+    the graph's pool; `_dropin_graph_backward` does the same for the backward).  Returns None while the shape is still new.
+    Everything forward() assigns on the engine (shapes, output / attention views, dropout-site counter) is snapshotted at
+    capture time and restored on replay, so backward() and the attribute seams read the state of THIS shape."""
+    eng = model.engine
+    B, T, L = xs.shape[0], xs.shape[1], ys.shape[1]
+    eng.prepare(B, T, L, ilens, olens)
+    graphs = eng._dropin_graphs
+    key = (B, T, L)
+    e = graphs.get(key)
+    if e is None:
+        graphs[key] = {"seen_fwd": True}
+        return None
+    if "gF" not in e:
+        if not e.get("seen_bwd"):
+            return None                     # no eager backward of this shape yet: its buffers are not all allocated
+        sx, sy = torch.empty_like(xs), torch.empty_like(ys)
+        torch.cuda.synchronize()
+        before = dict(eng.__dict__)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            eng.p16_dirty = True            # an external optimizer owns the parameters: the bf16 shadow is refreshed inside the graph
+            outs = eng.forward(sx, sy)
+        e.update(gF=g, sx=sx, sy=sy, outs=outs,
+                 pystate={k: v for k, v in eng.__dict__.items() if k not in before or before[k] is not v})
+    e["sx"].copy_(xs, non_blocking=True)
+    e["sy"].copy_(ys, non_blocking=True)
+    e["gF"].replay()
+    eng.__dict__.update(e["pystate"])
+    return e
+
+
+def _dropin_graph_backward(eng, e, grads, fresh: bool) -> None:
+    if "d" not in e:
+        e["d"] = tuple(torch.zeros_like(t) for t in e["outs"])
+    for dst, g in zip(e["d"], grads):
+        if g is None:
+            dst.zero_()
+        else:
+            dst.copy_(g, non_blocking=True)         # engine.backward() uses its upstream gradients as scratch: always re-fill
+    name = "gB0" if fresh else "gB1"                # zero the flat gradient buffer first / accumulate (gradient accumulation)
+    if name not in e:
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            eng.backward(*e["d"], zero_grad=fresh)
+        e[name] = g
+    e[name].replay()
+
+
 class _VTNFunction(torch.autograd.Function):
     """Whole-model autograd node: forward = engine.forward, backward = the engine's hand-written backward.
     When `n_att` > 0 the concatenated source-attention maps (last layers x first heads) are a differentiable
@@ -73,7 +126,14 @@ class _VTNFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, xs, ys, ilens, olens, n_att_layers, n_att_heads, *params):
         eng = model.engine
-        after, before, logits = eng.forward(xs, ys, ilens, olens)
+        entry = None
+        if model.use_graph and eng.training and n_att_layers == 0:
+            entry = _dropin_graph_forward(model, xs, ys, ilens, olens)
+        if entry is None:
+            after, before, logits = eng.forward(xs, ys, ilens, olens)
+        else:
+            after, before, logits = entry["outs"]
+        ctx.entry = entry
         ctx.model = model
         ctx.token = model._fwd_token
         ctx.att = (n_att_layers, n_att_heads)
@@ -106,7 +166,13 @@ class _VTNFunction(torch.autograd.Function):
         def z(g, like):
             return torch.zeros_like(like, dtype=dt) if g is None else g.to(dt).contiguous()
 
-        eng.backward(z(d_after, eng.after), z(d_before, eng.before), z(d_logits, eng.logits), d_att=d_att, zero_grad=fresh)
+        if ctx.entry is not None:
+            _dropin_graph_backward(eng, ctx.entry, (d_after, d_before, d_logits), fresh)
+        else:
+            eng.backward(z(d_after, eng.after), z(d_before, eng.before), z(d_logits, eng.logits), d_att=d_att, zero_grad=fresh)
+            seen = eng._dropin_graphs.get((eng.shapes["B"], eng.shapes["T"], eng.shapes["L"]))
+            if seen is not None:
+                seen["seen_bwd"] = True
         model._sync_gradients()
         model._bind_grads()
         return (None,) * (7 + len(model._param_names))
@@ -127,8 +193,10 @@ class VTN(torch.nn.Module):
                  conformer_rel_pos_type: str = "legacy", conformer_pos_enc_layer_type: str = "rel_pos",
                  conformer_self_attn_layer_type: str = "rel_selfattn", use_macaron_style_in_conformer: bool = True,
                  use_cnn_in_conformer: bool = True, zero_triu: bool = False, conformer_enc_kernel_size: int = 7,
-                 conformer_dec_kernel_size: int = 31, compute_dtype: str = "float32", device=None, seed: int = 0):
+                 conformer_dec_kernel_size: int = 31, compute_dtype: str = "float32", device=None, seed: int = 0,
+                 use_graph: bool = False):
         super().__init__()
+        self.use_graph = bool(use_graph)     # replay captured CUDA graphs of forward / backward per batch shape (training mode)
         unsupported = []
         if encoder_type != "transformer" or decoder_type != "transformer":
             unsupported.append("encoder_type/decoder_type != 'transformer'")
@@ -170,6 +238,7 @@ class VTN(torch.nn.Module):
         self.engine = VTNEngine(self.hp, device=device, bf16=self._bf16, seed=self._seed, fp32_gemm=self._fp32_gemm)
         if state is not None:
             self.engine.load_state_dict(state)
+        self._attach_graph_cache()
         self._modules.clear()
         self._param_names: List[str] = []
         st = self.engine.store
@@ -180,6 +249,17 @@ class VTN(torch.nn.Module):
         for name, buf in self.engine.buffers.items():
             node, leaf = self._node_for(name)
             node.register_buffer(leaf, buf)
+
+    use_graph = False
+
+    def _attach_graph_cache(self) -> None:
+        eng = self.engine
+        eng._dropin_graphs = {}
+
+        def on_evict(sig, graphs=eng._dropin_graphs):       # the engine dropped this shape's buffers: its graphs go with them
+            graphs.pop(tuple(sig[:3]), None)
+
+        eng._evict_listeners.append(on_evict)
 
     def _node_for(self, dotted: str):
         parts = dotted.split(".")
@@ -272,6 +352,8 @@ class VTN(torch.nn.Module):
         if r > 1:
             assert all(o >= r for o in ol), "Output length must be greater than or equal to reduction factor."
         self._fwd_token += 1
+        if eng.training:
+            ops.step_advance(None, eng.seed_dev)     # fresh dropout masks per forward (the fused steps advance it in their optimizer tail)
         after, before, logits = _VTNFunction.apply(self, xs, ys, il, ol, 0, 0, *self.parameters())
         Lo = after.shape[1]
         # target fix-ups (vtn.py:262-274)
@@ -347,7 +429,7 @@ class TransformerTTS(VTN):
                  decoder_concat_after=False, decoder_reduction_factor=2, spk_embed_dim=None, spk_embed_integration_type="add",
                  initial_encoder_alpha=1.0, initial_decoder_alpha=1.0, use_guided_attn_loss=False,
                  num_heads_applied_guided_attn=2, num_layers_applied_guided_attn=2, compute_dtype: str = "float32", device=None,
-                 seed: int = 0):
+                 seed: int = 0, use_graph: bool = False):
         self._encoder_input = "embed"
         super().__init__(idim, odim, dprenet_layers=dprenet_layers, dprenet_units=dprenet_units, adim=adim, aheads=aheads,
                          elayers=elayers, eunits=eunits, dlayers=dlayers, dunits=dunits, postnet_layers=postnet_layers,
@@ -359,7 +441,7 @@ class TransformerTTS(VTN):
                          initial_encoder_alpha=initial_encoder_alpha, initial_decoder_alpha=initial_decoder_alpha,
                          use_guided_attn_loss=use_guided_attn_loss, num_heads_applied_guided_attn=num_heads_applied_guided_attn,
                          num_layers_applied_guided_attn=num_layers_applied_guided_attn, compute_dtype=compute_dtype,
-                         device=device, seed=seed)
+                         device=device, seed=seed, use_graph=use_graph)
         self.eos = idim - 1
         self.padding_idx = 0
 
@@ -377,6 +459,8 @@ class TransformerTTS(VTN):
         self._fwd_token += 1
         nl = self.num_layers_applied_guided_attn if self.use_guided_attn_loss else 0
         nh = self.num_heads_applied_guided_attn if self.use_guided_attn_loss else 0
+        if eng.training:
+            ops.step_advance(None, eng.seed_dev)     # fresh dropout masks per forward
         outs = _VTNFunction.apply(self, xs, ys, il, ol, nl, nh, *self.parameters())
         after, before, logits = outs[:3]
         att_ws = outs[3] if nl > 0 else []
@@ -1059,6 +1143,8 @@ class AASVC(VTN):
         ys = tgt_speech[:, :max(ol)].to(_f32).contiguous()
         dpi = dp_inputs.to(_f32).contiguous()
         self._fwd_token += 1
+        if eng.training:
+            ops.step_advance(None, eng.seed_dev)     # fresh dropout masks (and duration-predictor noise) per forward
         after, before, logp, d_outs, bin_loss, ds = _AASVCFunction.apply(self, xs, ys, dpi, il, ol, *self.parameters())
         for name, P in eng.attn.items():
             self.get_submodule(name).attn = P.float() if P.dtype != _f32 else P

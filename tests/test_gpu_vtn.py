@@ -425,3 +425,47 @@ def test_shape_cache_eviction_drops_graphs_and_buffers():
         assert torch.isfinite(losses).all()
         sigs = {k[0] for k in model.engine._bufs if isinstance(k[0], tuple) and len(k[0]) == 4}
         assert len(sigs) <= 2 and len(step._graphs) <= 2, (sigs, list(step._graphs))
+
+
+@pytest.mark.gpu
+def test_dropin_graph_mode_matches_eager_across_shapes():
+    """Drop-in VTN with use_graph=True (forward / backward replayed from CUDA graphs per batch shape) == the eager drop-in:
+    two alternating batch shapes, the reference-style step (Seq2SeqLoss, clip_grad_norm_, torch Adam), dropout off so the
+    two runs are comparable; outputs, gradients and parameters after 6 steps agree, incl. a gradient-accumulation pair."""
+    from oracle import vtn_oracle
+    from seq2seq_vc_b200 import VTN, Seq2SeqLoss
+
+    hp = dict(idim=80, odim=80, dprenet_layers=2, dprenet_units=32, adim=64, aheads=4, elayers=2, eunits=96, dlayers=2, dunits=96,
+              postnet_layers=2, postnet_filts=5, postnet_chans=32, decoder_reduction_factor=2, dprenet_dropout_rate=0.0,
+              transformer_enc_dropout_rate=0.0)
+    batches = [vtn_oracle.synthetic_batch(2, 64, 40, ilens=[64, 50], olens=[40, 31], seed=3),
+               vtn_oracle.synthetic_batch(3, 48, 56, ilens=[48, 40, 33], olens=[56, 50, 21], seed=4)]
+    results = []
+    for use_graph in (False, True):
+        model = VTN(**hp, compute_dtype="float32", device="cuda:0", seed=1, use_graph=use_graph)
+        model.engine.hp.update({k: 0.0 for k in model.engine.hp if "dropout" in k})
+        model.train()
+        crit = Seq2SeqLoss()
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+        trace = []
+        for step in range(8):
+            xs, ilens, ys, labels, olens = batches[step % 2] if step < 6 else batches[0]
+            after, before, logits, ys_, labels_, olens_, _ = model(xs.cuda(), torch.tensor(ilens), ys.cuda(), labels.cuda(), torch.tensor(olens))
+            l1, bce = crit(after, before, logits, ys_, labels_, olens_)
+            if step != 7:
+                opt.zero_grad()                 # step 7 accumulates on top of step 6's gradients (accumulate graph)
+            (l1 + bce).backward()
+            trace.append((after.detach().clone(), float(l1), float(bce)))
+            if step != 6:
+                torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+                opt.step()
+        results.append((trace, {k: v.detach().clone() for k, v in model.state_dict().items()}))
+    (t0, p0), (t1, p1) = results
+    assert "gB1" in model.engine._dropin_graphs[(2, 64, 40)] and "gB0" in model.engine._dropin_graphs[(3, 48, 56)]
+    # weight gradients are summed with floating-point atomics (split-K), so two runs differ in the last bits and Adam turns a
+    # sign flip of a near-zero gradient into +-lr: bound the drift by the number of steps x lr, outputs a little looser
+    for i, ((a0, l0, b0), (a1, l1, b1)) in enumerate(zip(t0, t1)):
+        assert torch.allclose(a0, a1, atol=2e-5 if i == 0 else 5e-3, rtol=1e-3), i
+        assert abs(l0 - l1) <= 2e-3 * max(1, abs(l0)) and abs(b0 - b1) <= 2e-3 * max(1, abs(b0)), i
+    for k in p0:
+        assert torch.allclose(p0[k].float(), p1[k].float(), atol=1e-3, rtol=1e-3), k
