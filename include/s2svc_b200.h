@@ -36,7 +36,7 @@ extern "C" {
 #define S2S_F32 0
 #define S2S_BF16 1
 
-#define S2S_ABI_VERSION 13
+#define S2S_ABI_VERSION 14
 
 const char* s2s_last_error(void);
 int s2s_abi_version(void);
@@ -406,6 +406,14 @@ int s2s_rowscale(const void* x, const float* s, void* out, int64_t rows, int C, 
  * (models/aas_vc.py:339-351; count = 1) and its adjoint (runs of destination rows per source row). */
 int s2s_gather_rows(const void* x, const int32_t* start, const int32_t* count, void* y, int B, int Tin, int Tout, int C,
                     int dtype, void* stream);
+/* LengthRegulator (modules/length_regulator.py:46-97): y[b] = pad(repeat_interleave(x[b], ds[b])) as a gather over per-utterance
+ * prefix sums.  s2s_lr_cumsum: cum (B, T+1) int32 = exclusive prefix sums of round(ds * alpha) (ds int64 as the reference's
+ * LongTensor; alpha == 1: ds itself; all_ones != 0: every duration 1, the reference's rescue when ALL predicted durations are 0),
+ * cum[b, T] = the utterance's output length.  s2s_lr_fwd: y (B, Lmax, D), frames past cum[b, T] = pad_value.  s2s_lr_bwd: the
+ * adjoint, dx[b, i] = sum of dy over row i's run of frames. */
+int s2s_lr_cumsum(const int64_t* ds, int32_t* cum, int B, int T, float alpha, int all_ones, void* stream);
+int s2s_lr_fwd(const void* x, const int32_t* cum, void* y, int B, int T, int Lmax, int D, float pad_value, int dtype, void* stream);
+int s2s_lr_bwd(const void* dy, const int32_t* cum, void* dx, int B, int T, int Lmax, int D, int dtype, void* stream);
 
 /* ===========================================================================================
  * AAS-VC alignment block

@@ -101,6 +101,8 @@ def ffn_swish(sd, prefix, x):
     if w1.dim() == 3:
         k = w1.shape[2]
         h = F.relu(F.conv1d(x.transpose(1, 2), w1, sd[prefix + ".w_1.bias"], padding=(k - 1) // 2))
+        if sd[prefix + ".w_2.weight"].dim() == 2:       # "conv1d-linear": Conv1dLinear (multi_layer_conv.py:66-108), w_2 is a Linear
+            return linear(h.transpose(1, 2), sd, prefix + ".w_2")
         return F.conv1d(h, sd[prefix + ".w_2.weight"], sd[prefix + ".w_2.bias"], padding=(k - 1) // 2).transpose(1, 2)
     return linear(swish(linear(x, sd, prefix + ".w_1")), sd, prefix + ".w_2")
 
@@ -404,10 +406,11 @@ def state_dict_spec(hp) -> List:
                 lin(f"{p}.self_attn.{s}", dm, dm)
             lin(p + ".self_attn.linear_pos", dm, dm, bias=False)
             for ff in ("feed_forward", "feed_forward_macaron"):
-                if hp.get("positionwise_layer_type", "linear") == "conv1d":
+                if hp.get("positionwise_layer_type", "linear") in ("conv1d", "conv1d-linear"):
                     pk_ = hp.get("positionwise_conv_kernel_size", 1)
+                    w2 = (dm, units, pk_) if hp["positionwise_layer_type"] == "conv1d" else (dm, units)
                     spec.extend([(f"{p}.{ff}.w_1.weight", (units, dm, pk_)), (f"{p}.{ff}.w_1.bias", (units,)),
-                                 (f"{p}.{ff}.w_2.weight", (dm, units, pk_)), (f"{p}.{ff}.w_2.bias", (dm,))])
+                                 (f"{p}.{ff}.w_2.weight", w2), (f"{p}.{ff}.w_2.bias", (dm,))])
                 else:
                     lin(f"{p}.{ff}.w_1", units, dm)
                     lin(f"{p}.{ff}.w_2", dm, units)

@@ -219,14 +219,15 @@ def gen_aasvc_tiny():
     print("aasvc_tiny:", len(dump), "arrays")
 
 
-def gen_aasvc_conv1d_tiny():
+def gen_aasvc_conv1d_tiny(name="aasvc_conv1d_tiny", layer="conv1d", k=1, seed=29):
     """Same step as gen_aasvc_tiny with the position-wise layer the AASVC class defaults to (models/aas_vc.py:52-53):
-    MultiLayeredConv1d, kernel size 1, ReLU (modules/transformer/multi_layer_conv.py) instead of Linear + Swish."""
+    MultiLayeredConv1d, kernel size 1, ReLU (modules/transformer/multi_layer_conv.py) instead of Linear + Swish.  Also the
+    generator of the kernel-size-3 MultiLayeredConv1d and Conv1dLinear fixtures (multi_layer_conv.py:12-108)."""
     from seq2seq_vc.losses import DurationPredictorLoss, ForwardSumLoss, L1Loss
     from seq2seq_vc.models import AASVC
 
-    torch.manual_seed(29)
-    model = AASVC(**AAS_HP, **dict(AAS_FIXED, positionwise_layer_type="conv1d", positionwise_conv_kernel_size=1))
+    torch.manual_seed(seed)
+    model = AASVC(**AAS_HP, **dict(AAS_FIXED, positionwise_layer_type=layer, positionwise_conv_kernel_size=k))
     ref_shim.disable_dropout(model)
     with torch.no_grad():
         for n, p in model.named_parameters():
@@ -263,8 +264,16 @@ def gen_aasvc_conv1d_tiny():
         for k, v in model.state_dict().items():
             if "running_" in k:
                 dump["inf_bn." + k] = v.numpy().copy()
-    np.savez_compressed(os.path.join(GOLDEN, "aasvc_conv1d_tiny.npz"), **dump)
-    print("aasvc_conv1d_tiny:", len(dump), "arrays")
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **dump)
+    print(name + ":", len(dump), "arrays")
+
+
+def gen_aasvc_conv1d_k3_tiny():
+    gen_aasvc_conv1d_tiny("aasvc_conv1d_k3_tiny", "conv1d", 3, 37)
+
+
+def gen_aasvc_conv1d_linear_k3_tiny():
+    gen_aasvc_conv1d_tiny("aasvc_conv1d_linear_k3_tiny", "conv1d-linear", 3, 41)
 
 
 SDP_HP = dict(channels=16, kernel_size=3, dds_conv_layers=3, flows=4)
@@ -386,7 +395,8 @@ if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     import sys
 
-    gens = dict(vtn_tiny=gen_vtn_tiny, vtn_rfactor=gen_vtn_rfactor, tts_tiny=gen_tts_tiny, aasvc_tiny=gen_aasvc_tiny, aasvc_conv1d_tiny=gen_aasvc_conv1d_tiny,
+    gens = dict(vtn_tiny=gen_vtn_tiny, vtn_rfactor=gen_vtn_rfactor, tts_tiny=gen_tts_tiny, aasvc_tiny=gen_aasvc_tiny, aasvc_conv1d_tiny=gen_aasvc_conv1d_tiny, aasvc_conv1d_k3_tiny=gen_aasvc_conv1d_k3_tiny,
+                aasvc_conv1d_linear_k3_tiny=gen_aasvc_conv1d_linear_k3_tiny,
                 mas=gen_mas, kats=gen_kats, sdp_tiny=gen_sdp_tiny)
     for name in (sys.argv[1:] or list(gens)):      # e.g. `python oracle/gen_golden.py aasvc_conv1d_tiny` adds one fixture
         gens[name]()

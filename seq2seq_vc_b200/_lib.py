@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libs2svc_b200.so")
 
 S2S_F32, S2S_BF16 = 0, 1
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 
 class S2SError(RuntimeError):
@@ -129,6 +129,9 @@ SIGNATURES = {
     "s2s_axpy": (c_int, [_P, _P, c_int64, c_float, c_int, _P]),
     "s2s_rowscale": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P]),
     "s2s_gather_rows": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "s2s_lr_cumsum": (c_int, [_P, _P, c_int, c_int, c_float, c_int, _P]),
+    "s2s_lr_fwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_int, _P]),
+    "s2s_lr_bwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "s2s_align_logp_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "s2s_align_logp_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int64, c_int, _P]),
     "s2s_forward_sum": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_float, _P, _P, _P, c_float, _P]),

@@ -47,9 +47,10 @@ def default_hparams(**over) -> dict:
               transformer_enc_attn_dropout_rate=0.2, transformer_dec_dropout_rate=0.2,
               transformer_dec_positional_dropout_rate=0.2, transformer_dec_attn_dropout_rate=0.2,
               duration_predictor_dropout_rate=0.1, postnet_dropout_rate=0.5, lambda_align=2.0,
-              # "linear": PositionwiseFeedForward + Swish (the shipped yaml); "conv1d": MultiLayeredConv1d, kernel size 1, ReLU
-              # (the AASVC class default, models/aas_vc.py:52-53)
-              positionwise_layer_type="linear",
+              # "linear": PositionwiseFeedForward + Swish (the shipped yaml); "conv1d": MultiLayeredConv1d + ReLU (kernel size 1 is
+              # the AASVC class default, models/aas_vc.py:52-53; odd kernel sizes > 1 run as taps-GEMMs over haloed rows);
+              # "conv1d-linear": Conv1dLinear (multi_layer_conv.py:66-108)
+              positionwise_layer_type="linear", positionwise_conv_kernel_size=1,
               # "deterministic": DurationPredictor + DurationPredictorLoss; "stochastic": StochasticDurationPredictor (VITS flows),
               # the shipped yaml's default (aas_vc.melmelmel.v1.yaml:57; constructor defaults models/aas_vc.py:105-110)
               duration_predictor_type="deterministic", stochastic_duration_predictor_kernel_size=3,
@@ -58,8 +59,10 @@ def default_hparams(**over) -> dict:
     hp.update(over)
     if hp["duration_predictor_type"] not in ("deterministic", "stochastic"):
         raise ValueError(f"Duration predictor type: {hp['duration_predictor_type']} is not supported.")
-    if hp["positionwise_layer_type"] not in ("linear", "conv1d"):
-        raise NotImplementedError(f"positionwise_layer_type {hp['positionwise_layer_type']!r}")
+    if hp["positionwise_layer_type"] not in ("linear", "conv1d", "conv1d-linear"):
+        raise NotImplementedError("Support only linear or conv1d.")          # conformer/encoder.py:205
+    if hp["positionwise_layer_type"] != "linear" and hp["positionwise_conv_kernel_size"] % 2 != 1:
+        raise NotImplementedError("even positionwise_conv_kernel_size (the reference's padding (k - 1) // 2 then shortens the sequence)")
     return hp
 
 
@@ -126,10 +129,11 @@ def param_groups(hp: dict) -> List[List[Tuple[str, Tuple[int, ...]]]]:
             lin(p + ".self_attn.linear_out", dm, dm)
             lin(p + ".self_attn.linear_pos", dm, dm, bias=False)
             for ff in ("feed_forward", "feed_forward_macaron"):
-                if hp.get("positionwise_layer_type", "linear") == "conv1d":     # Conv1d(k = 1) weights keep their (out, in, 1) shape
-                    g.append([(f"{p}.{ff}.w_1.weight", (units, dm, 1))])
+                if hp.get("positionwise_layer_type", "linear") != "linear":     # Conv1d weights keep their (out, in, k) shape
+                    pk = hp.get("positionwise_conv_kernel_size", 1)
+                    g.append([(f"{p}.{ff}.w_1.weight", (units, dm, pk))])
                     g.append([(f"{p}.{ff}.w_1.bias", (units,))])
-                    g.append([(f"{p}.{ff}.w_2.weight", (dm, units, 1))])
+                    g.append([(f"{p}.{ff}.w_2.weight", (dm, units, pk) if hp["positionwise_layer_type"] == "conv1d" else (dm, units))])
                     g.append([(f"{p}.{ff}.w_2.bias", (dm,))])
                 else:
                     lin(f"{p}.{ff}.w_1", units, dm)
@@ -349,6 +353,8 @@ class AASVCEngine(EngineBase):
         B, T, dm = x.shape
         norm = "norm_ff_macaron" if ff == "feed_forward_macaron" else "norm_ff"
         n = self._ln_fwd(x, f"{p}.{norm}", f"{tag}.ln")
+        if self._ffn_is_conv():
+            return self._ffn_conv_fwd(x, n, p, ff, tag, U, rate, out)
         h = self.buf(tag + ".h", (B * T, U))
         w1, w2 = self.W(f"{p}.{ff}.w_1.weight").view(U, dm), self.W(f"{p}.{ff}.w_2.weight").view(dm, U)
         if self.hp["positionwise_layer_type"] == "conv1d":
@@ -369,6 +375,8 @@ class AASVCEngine(EngineBase):
         B, T, dm = x.shape
         norm = "norm_ff_macaron" if ff == "feed_forward_macaron" else "norm_ff"
         n = self.buf(f"{tag}.ln.y", (B, T, dm))
+        if self._ffn_is_conv():
+            return self._ffn_conv_bwd(g, x, n, p, ff, tag, U, rate, gout)
         h = self.buf(tag + ".h", (B * T, U))
         dy = self._scratch("cf.dy", (B * T, dm))
         ops.scale_dropout(g.view(B * T, dm), dy, 0.5, self.named_drop(tag + ".d2", rate))
@@ -382,6 +390,67 @@ class AASVCEngine(EngineBase):
         dn = self._scratch("cf.dn", (B, T, dm))
         self._lin_bwd(dh, n.view(B * T, dm), w1, st.g(f"{p}.{ff}.w_1.weight").view(U, dm), st.g(f"{p}.{ff}.w_1.bias"),
                       dx=dn.view(B * T, dm))
+        self._ln_bwd(dn, x, f"{p}.{norm}", f"{tag}.ln", gout, dres=g)
+        return gout
+
+    # ---- MultiLayeredConv1d (kernel size > 1) / Conv1dLinear position-wise layers (multi_layer_conv.py:12-108)
+    def _ffn_is_conv(self) -> bool:
+        t = self.hp["positionwise_layer_type"]
+        return t == "conv1d-linear" or (t == "conv1d" and self.hp.get("positionwise_conv_kernel_size", 1) > 1)
+
+    def _ffn_conv_fwd(self, x, n, p, ff, tag, U, rate, out):
+        """out = x + 0.5 * dropout(w_2(dropout(relu(w_1 n)))) with w_1 a Conv1d(k) over time (zero padding (k-1)/2 per utterance
+        row, padded frames take part like any other frame: the reference does not mask inside the block) and w_2 a Conv1d(k)
+        ("conv1d") or a Linear ("conv1d-linear").  The convolutions are taps-GEMMs over zero-haloed channels-last rows."""
+        st = self.store
+        B, T, dm = x.shape
+        halo = (self.hp["positionwise_conv_kernel_size"] - 1) // 2
+        Lp = T + 2 * halo
+        npad = self.buf(tag + ".npad", (B, Lp, dm))
+        ops.pad_rows(n, npad, halo)
+        h = self._conv1d_fwd(npad, f"{p}.{ff}.w_1", T, True, tag + ".c1")             # (B, Lp, U), zero halos
+        d1 = self.named_drop(tag + ".d1", rate)
+        if d1.p > 0.0:
+            h = ops.scale_dropout(h, self.buf(tag + ".hd", (B, Lp, U)), 1.0, d1)
+        y = self._scratch("cf.y", (B, T, dm))
+        if self.hp["positionwise_layer_type"] == "conv1d":
+            z2 = self._conv1d_fwd(h, f"{p}.{ff}.w_2", T, False, tag + ".c2")
+            ops.unpad_rows(z2, y, halo)
+        else:
+            hu = self.buf(tag + ".hu", (B, T, U))
+            ops.unpad_rows(h, hu, halo)
+            self._lin_fwd(hu.view(B * T, U), self.W(f"{p}.{ff}.w_2.weight"), st.p(f"{p}.{ff}.w_2.bias"), y.view(B * T, dm))
+        ops.scale_dropout(y, y, 0.5, self.named_drop(tag + ".d2", rate))
+        ops.add(x, y, out)
+        return out
+
+    def _ffn_conv_bwd(self, g, x, n, p, ff, tag, U, rate, gout):
+        st = self.store
+        B, T, dm = x.shape
+        halo = (self.hp["positionwise_conv_kernel_size"] - 1) // 2
+        Lp = T + 2 * halo
+        d1 = self.named_drop(tag + ".d1", rate)
+        h = self.buf(tag + (".hd" if d1.p > 0.0 else ".c1.z"), (B, Lp, U))            # dropout(relu(.)): zero where cut or dropped
+        dy = self._scratch("cf.dy", (B, T, dm))
+        ops.scale_dropout(g, dy, 0.5, self.named_drop(tag + ".d2", rate))
+        dh = self._scratch("cf.dhp", (B, Lp, U))
+        if self.hp["positionwise_layer_type"] == "conv1d":
+            dz2 = self._scratch("cf.dz2", (B, Lp, dm))
+            ops.pad_rows(dy, dz2, halo)
+            self._conv1d_bwd(dz2, h, f"{p}.{ff}.w_2", T, tag + ".c2", dh)
+        else:
+            hu = self.buf(tag + ".hu", (B, T, U))
+            dhu = self._scratch("cf.dhu", (B, T, U))
+            self._lin_bwd(dy.view(B * T, dm), hu.view(B * T, U), self.W(f"{p}.{ff}.w_2.weight"), st.g(f"{p}.{ff}.w_2.weight"),
+                          st.g(f"{p}.{ff}.w_2.bias"), dx=dhu.view(B * T, U))
+            ops.pad_rows(dhu, dh, halo)
+        ops.relu_bwd(dh, h, dh, d1.scale)
+        npad = self.buf(tag + ".npad", (B, Lp, dm))
+        dnp = self._scratch("cf.dnp", (B, Lp, dm))
+        self._conv1d_bwd(dh, npad, f"{p}.{ff}.w_1", T, tag + ".c1", dnp)
+        dn = self._scratch("cf.dn", (B, T, dm))
+        ops.unpad_rows(dnp, dn, halo)
+        norm = "norm_ff_macaron" if ff == "feed_forward_macaron" else "norm_ff"
         self._ln_bwd(dn, x, f"{p}.{norm}", f"{tag}.ln", gout, dres=g)
         return gout
 

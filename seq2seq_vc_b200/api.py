@@ -12,6 +12,7 @@ library or a CPU tensor raises (there is no fallback).
 """
 from __future__ import annotations
 
+import logging
 import math
 import os
 from typing import Dict, List, Optional, Sequence
@@ -981,6 +982,52 @@ class DurationPredictorLoss(torch.nn.Module):
         return _DurationLossFn.apply(d_outs.to(_f32).contiguous(), ds.to(_f32).contiguous(), tl, self.offset)
 
 
+class _LengthRegulatorFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xs, cum, Lmax, pad_value):
+        y = torch.empty(xs.shape[0], Lmax, xs.shape[2], dtype=xs.dtype, device=xs.device)
+        ops.lr_fwd(xs, cum, y, pad_value)
+        ctx.save_for_backward(cum)
+        ctx.shape = xs.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (cum,) = ctx.saved_tensors
+        dx = torch.empty(ctx.shape, dtype=g.dtype, device=g.device)
+        ops.lr_bwd(g.contiguous(), cum, dx)
+        return dx, None, None, None
+
+
+class LengthRegulator(torch.nn.Module):
+    """modules/length_regulator.py:46-97: repeat every row of xs (B, Tmax, D) ds[b, i] times and pad the ragged result with
+    `pad_value` -> (B, max_b sum_i ds[b, i], D).  Same call (`forward(xs, ds, alpha=1.0)`, ds a LongTensor), same rounding of
+    `ds * alpha` (torch.round), same rescue when every predicted duration is 0 (all durations become 1).  One host read of the
+    output lengths sizes the result, as the reference's pad_list does; the repeat itself is a device gather and its adjoint."""
+
+    def __init__(self, pad_value=0.0):
+        super().__init__()
+        self.pad_value = pad_value
+
+    def forward(self, xs, ds, alpha=1.0):
+        _require_cuda(xs, "LengthRegulator")
+        if alpha != 1.0:
+            assert alpha > 0
+        B, T, _ = xs.shape
+        ds = ds.to(torch.int64).contiguous()
+        cum = torch.empty(B, T + 1, dtype=torch.int32, device=xs.device)
+        ops.lr_cumsum(ds, cum, alpha)
+        lens = cum[:, T].tolist()
+        if sum(lens) == 0:
+            logging.warning("predicted durations includes all 0 sequences. fill the first element with 1.")
+            ops.lr_cumsum(ds, cum, alpha, all_ones=True)
+            lens = [T] * B
+        x = xs.contiguous()
+        if x.dtype not in (_f32, torch.bfloat16):
+            x = x.to(_f32)
+        return _LengthRegulatorFn.apply(x, cum, max(lens), float(self.pad_value))
+
+
 class _AASVCFunction(torch.autograd.Function):
     """Whole-model autograd node over AASVCEngine: differentiable outputs are after / before / log_p_attn / d_outs /
     bin_loss; ds (the integer MAS durations) is not."""
@@ -1060,10 +1107,8 @@ class AASVC(VTN):
         unsupported = []
         if encoder_type != "conformer" or decoder_type != "conformer":
             unsupported.append("encoder_type/decoder_type != 'conformer'")
-        if positionwise_layer_type not in ("linear", "conv1d"):
-            unsupported.append("positionwise_layer_type not in ('linear', 'conv1d')")
-        if positionwise_layer_type == "conv1d" and positionwise_conv_kernel_size != 1:
-            unsupported.append("positionwise_conv_kernel_size != 1")
+        if positionwise_layer_type not in ("linear", "conv1d", "conv1d-linear"):
+            unsupported.append("positionwise_layer_type not in ('linear', 'conv1d', 'conv1d-linear')")
         if encoder_input_layer != "linear":
             unsupported.append("encoder_input_layer != 'linear'")
         if not (encoder_normalize_before and decoder_normalize_before):
@@ -1101,7 +1146,8 @@ class AASVC(VTN):
             transformer_dec_positional_dropout_rate=transformer_dec_positional_dropout_rate,
             transformer_dec_attn_dropout_rate=transformer_dec_attn_dropout_rate,
             duration_predictor_dropout_rate=duration_predictor_dropout_rate, postnet_dropout_rate=postnet_dropout_rate,
-            positionwise_layer_type=positionwise_layer_type, duration_predictor_type=duration_predictor_type,
+            positionwise_layer_type=positionwise_layer_type, positionwise_conv_kernel_size=positionwise_conv_kernel_size,
+            duration_predictor_type=duration_predictor_type,
             stochastic_duration_predictor_kernel_size=stochastic_duration_predictor_kernel_size,
             stochastic_duration_predictor_dropout_rate=stochastic_duration_predictor_dropout_rate,
             stochastic_duration_predictor_flows=stochastic_duration_predictor_flows,

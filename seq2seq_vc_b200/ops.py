@@ -620,6 +620,28 @@ def gather_rows(x, start, count, y):
     return y
 
 
+def lr_cumsum(ds, cum, alpha=1.0, all_ones=False):
+    """cum (B, T+1) int32 = exclusive prefix sums of round(ds * alpha); cum[:, T] = output lengths (length_regulator.py:81-96)."""
+    B, T = ds.shape
+    assert ds.dtype == torch.int64 and ds.is_contiguous() and cum.dtype == _i32 and cum.shape == (B, T + 1)
+    check(_L().s2s_lr_cumsum(ptr(ds), ptr(cum), B, T, float(alpha), int(bool(all_ones)), stream()), "lr_cumsum")
+    return cum
+
+
+def lr_fwd(x, cum, y, pad_value=0.0):
+    B, T, D = x.shape
+    assert x.is_contiguous() and y.is_contiguous() and y.shape[0] == B and y.shape[2] == D and x.dtype == y.dtype
+    check(_L().s2s_lr_fwd(ptr(x), ptr(cum), ptr(y), B, T, y.shape[1], D, float(pad_value), dt(x), stream()), "lr_fwd")
+    return y
+
+
+def lr_bwd(dy, cum, dx):
+    B, T, D = dx.shape
+    assert dy.is_contiguous() and dx.is_contiguous() and dy.dtype == dx.dtype
+    check(_L().s2s_lr_bwd(ptr(dy), ptr(cum), ptr(dx), B, T, dy.shape[1], D, dt(dx), stream()), "lr_bwd")
+    return dx
+
+
 # ----------------------------------------------------------------------------------------------
 # AAS-VC alignment block
 # ----------------------------------------------------------------------------------------------

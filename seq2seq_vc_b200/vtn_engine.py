@@ -197,6 +197,7 @@ class VTNEngine(EngineBase):
             ops.conv1_fwd(xs, st.p("encoder.embed.conv.0.weight"), st.p("encoder.embed.conv.0.bias"), y1)
             col = self._scratch("col", (B * T2 * F2, 9 * d))
             ops.im2col_s2(y1, col)
+            self._col_of = self._sig                       # the patch matrix stays valid until backward() turns it into dcol
             y2 = self.buf("enc.y2", (B * T2 * F2, d))
             ops.gemm(col, w2p.view(d, 9 * d), y2, bias=st.p("encoder.embed.conv.2.bias"), relu=True, mode=self.mode)
             elin = self.buf("enc.elin", (B * T2, d))
@@ -799,7 +800,9 @@ class VTNEngine(EngineBase):
         w2p = self.buf("w.conv2p", (d, 9, d))
         col = self._scratch("col", (B * T2 * F2, 9 * d))
         y1 = self.buf("enc.y1", (B, T1, F1, d))
-        ops.im2col_s2(y1, col)                      # recompute the patch matrix instead of keeping ~1 GB alive
+        if getattr(self, "_col_of", None) != self._sig:
+            ops.im2col_s2(y1, col)                  # normally still there from this step's forward (0.5 GB at C2 is cheap on 180 GB)
+        self._col_of = None
         gw2p = self._scratch("g.w2p", (d, 9 * d), _f32)
         ops.gemm(dy2.t(), col.t(), gw2p, mode=mode)
         ops.transpose_last2(gw2p, st.g("encoder.embed.conv.2.weight"), d, 9, d, accumulate=True)

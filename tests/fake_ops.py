@@ -432,6 +432,29 @@ def unpad_rows(x, y, halo):
     return y
 
 
+def lr_cumsum(ds, cum, alpha=1.0, all_ones=False):
+    d = torch.ones_like(ds) if all_ones else (ds if alpha == 1.0 else torch.round(ds.float() * alpha).long())
+    cum[:, 0] = 0
+    cum[:, 1:] = torch.cumsum(d.clamp(min=0), 1).to(cum.dtype)
+    return cum
+
+
+def lr_fwd(x, cum, y, pad_value=0.0):
+    y.fill_(pad_value)
+    for b in range(x.shape[0]):
+        d = (cum[b, 1:] - cum[b, :-1]).long()
+        r = torch.repeat_interleave(x[b], d, dim=0)
+        y[b, :r.shape[0]] = r
+    return y
+
+
+def lr_bwd(dy, cum, dx):
+    for b in range(dx.shape[0]):
+        for i in range(dx.shape[1]):
+            dx[b, i] = dy[b, int(cum[b, i]):int(cum[b, i + 1])].sum(0)
+    return dx
+
+
 def seq2seq_loss(after, before, logits, ys, labels, olens, pos_weight, losses, d_after, d_before, d_logits, ws):
     B, L, odim = after.shape
     m = (torch.arange(L)[None, :] < olens.long()[:, None])

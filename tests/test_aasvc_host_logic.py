@@ -25,7 +25,14 @@ NO_DROPOUT = dict(transformer_enc_dropout_rate=0.0, transformer_enc_positional_d
 
 
 # the shipped yaml's Linear + Swish position-wise layers, and the AASVC class default (MultiLayeredConv1d k = 1 + ReLU)
-FIXTURES = {"linear": "aasvc_tiny.npz", "conv1d": "aasvc_conv1d_tiny.npz"}
+# plus MultiLayeredConv1d / Conv1dLinear with kernel size 3 (multi_layer_conv.py:12-108)
+FIXTURES = {"linear": "aasvc_tiny.npz", "conv1d": "aasvc_conv1d_tiny.npz", "conv1d:3": "aasvc_conv1d_k3_tiny.npz",
+            "conv1d-linear:3": "aasvc_conv1d_linear_k3_tiny.npz"}
+
+
+def _pw(key):
+    t, _, k = key.partition(":")
+    return dict(positionwise_layer_type=t, positionwise_conv_kernel_size=int(k or 1))
 
 
 @pytest.fixture(params=sorted(FIXTURES))
@@ -33,7 +40,7 @@ def engine(monkeypatch, request):
     fake_ops.install(monkeypatch)
     z = np.load(os.path.join(os.path.dirname(GOLDEN), FIXTURES[request.param]))
     sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
-    eng = AASVCEngine(dict(AAS_HP, positionwise_layer_type=request.param, **NO_DROPOUT), device="cpu", bf16=False)
+    eng = AASVCEngine(dict(AAS_HP, **_pw(request.param), **NO_DROPOUT), device="cpu", bf16=False)
     assert set(eng.state_dict()) == set(sd)
     eng.load_state_dict(sd)
     return eng, z
@@ -140,5 +147,34 @@ def test_dropin_class_default_positionwise_layer():
     assert tuple(msd["decoder.encoders.0.feed_forward_macaron.w_2.weight"].shape) == (128, 48, 1)
     m.load_state_dict(sd)
     assert torch.equal(m.state_dict()["encoder.encoders.0.feed_forward.w_1.weight"], sd["encoder.encoders.0.feed_forward.w_1.weight"])
+    m3 = AASVC(**AAS_HP, **fixed, positionwise_conv_kernel_size=3)          # kernel size 3: same keys and shapes as the reference's
+    z3 = np.load(os.path.join(os.path.dirname(GOLDEN), FIXTURES["conv1d:3"]))
+    assert {k: tuple(v.shape) for k, v in m3.state_dict().items()} == {k[3:]: z3[k].shape for k in z3.files if k.startswith("sd.")}
     with pytest.raises(NotImplementedError):
-        AASVC(**AAS_HP, **fixed, positionwise_conv_kernel_size=3)
+        AASVC(**AAS_HP, **fixed, positionwise_conv_kernel_size=4)          # even kernels shorten the sequence in the reference
+
+
+def test_length_regulator_host_logic(monkeypatch):
+    """LengthRegulator drop-in (length_regulator.py:46-97) with the kernels replaced by their CPU contracts vs the reference module."""
+    from oracle import ref_shim
+
+    if not ref_shim.available():
+        pytest.skip("reference tree not present")
+    fake_ops.install(monkeypatch)
+    ref_shim.install()
+    from seq2seq_vc.modules.length_regulator import LengthRegulator as RefLR
+    from seq2seq_vc_b200 import LengthRegulator
+
+    g = torch.Generator().manual_seed(3)
+    xs = torch.randn(3, 9, 8, generator=g)
+    ds = torch.randint(0, 4, (3, 9), generator=g)
+    for alpha, pad in ((1.0, 0.0), (1.7, 2.0)):
+        a = xs.clone().requires_grad_(True)
+        b = xs.clone().requires_grad_(True)
+        got, want = LengthRegulator(pad)(a, ds, alpha), RefLR(pad)(b, ds.clone(), alpha)
+        assert torch.equal(got, want)
+        w = torch.randn(want.shape, generator=g)
+        (got * w).sum().backward()
+        (want * w).sum().backward()
+        assert torch.allclose(a.grad, b.grad, atol=1e-6)
+    assert torch.equal(LengthRegulator()(xs, torch.zeros(3, 9, dtype=torch.long)), RefLR()(xs, torch.zeros(3, 9, dtype=torch.long)))

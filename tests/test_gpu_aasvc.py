@@ -297,7 +297,8 @@ def _step(eng, z):
 
 
 @pytest.mark.parametrize("fp32_gemm", ["simt", "tc"])
-@pytest.mark.parametrize("pw,fixture", [("linear", "aasvc_tiny.npz"), ("conv1d", "aasvc_conv1d_tiny.npz")])
+@pytest.mark.parametrize("pw,fixture", [("linear", "aasvc_tiny.npz"), ("conv1d", "aasvc_conv1d_tiny.npz"),
+                                        ("conv1d:3", "aasvc_conv1d_k3_tiny.npz"), ("conv1d-linear:3", "aasvc_conv1d_linear_k3_tiny.npz")])
 def test_golden_tiny_fp32_forward_losses_grads(pw, fixture, fp32_gemm):
     """Live-reference dumps of one training step: the shipped yaml's Linear + Swish position-wise layers and the AASVC class
     default (MultiLayeredConv1d k = 1 + ReLU, models/aas_vc.py:52-53); float32 engine on the CUDA-core GEMM ("simt") and on
@@ -305,7 +306,9 @@ def test_golden_tiny_fp32_forward_losses_grads(pw, fixture, fp32_gemm):
     from seq2seq_vc_b200.aasvc_engine import AASVCEngine
 
     z, sd = _golden(fixture)
-    eng = AASVCEngine(dict(AAS_HP, positionwise_layer_type=pw, **NO_DROPOUT), device="cuda:0", bf16=False, fp32_gemm=fp32_gemm)
+    pw, _, pk = pw.partition(":")      # also MultiLayeredConv1d / Conv1dLinear with kernel size 3 (multi_layer_conv.py:12-108)
+    eng = AASVCEngine(dict(AAS_HP, positionwise_layer_type=pw, positionwise_conv_kernel_size=int(pk or 1), **NO_DROPOUT), device="cuda:0",
+                      bf16=False, fp32_gemm=fp32_gemm)
     eng.load_state_dict(sd)
     after, before, losses = _step(eng, z)
     assert np.abs(after.cpu().numpy() - z["after_outs"]).mean() <= 1e-4
@@ -745,3 +748,44 @@ def test_stochastic_recipe_fused_step_and_dropin_and_inference():
     m2.eval()
     outs, d = m2.inference(xs[0, :ilens[0]], dp_input=dpi[0])
     assert d.dtype == torch.int64 and int(d.max()) <= 10 and outs.shape[0] == int(d.sum()) and torch.isfinite(outs).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_length_regulator_matches_reference_semantics(dtype):
+    """seq2seq_vc_b200.LengthRegulator vs the reference's forward (length_regulator.py:69-97: repeat_interleave + pad_list):
+    ragged durations with zeros, alpha scaling (torch.round), the all-zero rescue, pad_value, and the gradient (run sums)."""
+    from seq2seq_vc_b200 import LengthRegulator
+
+    g = torch.Generator().manual_seed(7)
+    B, T, D = 3, 11, 40
+    xs = torch.randn(B, T, D, generator=g).to(dtype)
+    ds = torch.randint(0, 5, (B, T), generator=g)
+    ds[1, 6:] = 0
+
+    def ref(xs, ds, alpha, pad):
+        if alpha != 1.0:
+            ds = torch.round(ds.float() * alpha).long()
+        if ds.sum() == 0:
+            ds = ds.clone()
+            ds[ds.sum(dim=1).eq(0)] = 1
+        rep = [torch.repeat_interleave(x, d, dim=0) for x, d in zip(xs, ds)]
+        out = xs.new_full((len(rep), max(r.shape[0] for r in rep), xs.shape[2]), pad)
+        for i, r in enumerate(rep):
+            out[i, :r.shape[0]] = r
+        return out
+
+    for alpha, pad in ((1.0, 0.0), (1.3, -1.5), (0.5, 0.0)):
+        x_dev = xs.cuda().requires_grad_(True)
+        got = LengthRegulator(pad_value=pad)(x_dev, ds.cuda(), alpha)
+        x_ref = xs.clone().float().requires_grad_(True)
+        want = ref(x_ref, ds, alpha, pad)
+        assert got.shape == want.shape
+        assert torch.equal(got.detach().cpu().float(), want.detach().to(dtype).float())
+        w = torch.randn(want.shape, generator=g)
+        (got.float() * w.cuda()).sum().backward()
+        (want * w).sum().backward()
+        tol = 1e-5 if dtype == torch.float32 else 5e-2
+        assert torch.allclose(x_dev.grad.cpu().float(), x_ref.grad, atol=tol, rtol=tol)
+    z = LengthRegulator()(xs.cuda(), torch.zeros(B, T, dtype=torch.long).cuda())
+    assert torch.equal(z.cpu(), xs)                                   # all durations 0 -> every duration becomes 1

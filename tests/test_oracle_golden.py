@@ -99,10 +99,11 @@ AAS_HP = dict(idim=80, odim=80, adim=32, aheads=2, elayers=1, eunits=48, dlayers
               post_encoder_reduction_factor=4, conformer_enc_kernel_size=7, conformer_dec_kernel_size=7)
 
 
-@pytest.mark.parametrize("fixture", ["aasvc_tiny.npz", "aasvc_conv1d_tiny.npz"])
+@pytest.mark.parametrize("fixture", ["aasvc_tiny.npz", "aasvc_conv1d_tiny.npz", "aasvc_conv1d_k3_tiny.npz", "aasvc_conv1d_linear_k3_tiny.npz"])
 def test_aasvc_oracle_forward_loss_grads(fixture):
     """AASVC forward, the four losses of AASVCTrainer._train_step and every gradient vs the live-reference dump
-    (Linear + Swish position-wise layers of the shipped yaml; MultiLayeredConv1d k = 1 + ReLU of the class default)."""
+    (Linear + Swish position-wise layers of the shipped yaml; MultiLayeredConv1d k = 1 + ReLU of the class default;
+    MultiLayeredConv1d and Conv1dLinear with kernel size 3, multi_layer_conv.py:12-108)."""
     from oracle import aasvc_oracle
 
     z = np.load(os.path.join(GOLD, fixture))
