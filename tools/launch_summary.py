@@ -13,8 +13,13 @@ def load(path, one_step=True):
     rows = list(csv.DictReader(lines))
     if one_step:
         marks = [i for i, r in enumerate(rows) if "adam_kernel" in r["Kernel Name"]]
-        if len(marks) >= 2:
-            rows = rows[marks[-2] + 1:marks[-1] + 1]
+        # the AAS-VC step ends with several Adam launches (the duration predictor keeps its own clock): a step boundary is the
+        # LAST launch of a run of Adam kernels
+        ends = [m for j, m in enumerate(marks) if j + 1 == len(marks) or not all(
+            "adam_kernel" in rows[q]["Kernel Name"] or "sqnorm" in rows[q]["Kernel Name"] or "step_advance" in rows[q]["Kernel Name"]
+            for q in range(m + 1, marks[j + 1]))]
+        if len(ends) >= 2:
+            rows = rows[ends[-2] + 1:ends[-1] + 1]
     agg = collections.OrderedDict()
     for row in rows:
         v = float(row["Metric Value"].replace(",", ""))
