@@ -209,6 +209,10 @@ class VTN(torch.nn.Module):
             unsupported.append("concat_after / speaker embeddings")
         if unsupported:
             raise NotImplementedError("B200 VTN hot path does not cover: " + ", ".join(unsupported))
+        if use_guided_attn_loss and getattr(self, "_encoder_input", "conv2d") != "embed":
+            # the reference's VTN stores the flag and never uses it (models/vtn.py:73; ARVCTrainer has no guided-attention
+            # criterion); the maps VTN.forward returns are detached here, so a loss on them would train nothing
+            raise NotImplementedError("use_guided_attn_loss on VTN: only TransformerTTS returns differentiable attention maps")
         self.idim, self.odim = idim, odim
         self.spk_embed_dim = None
         self.decoder_reduction_factor = decoder_reduction_factor

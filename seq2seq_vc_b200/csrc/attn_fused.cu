@@ -349,11 +349,8 @@ extern "C" int s2s_attn_probs_bwd(const void* dctx, int64_t d_bs, int64_t d_ts, 
     const size_t dyn = cache ? cache_bytes : 0;
 #define S2S_AT_BWD(D)                                                                                                          \
     do {                                                                                                                       \
-        static bool attr_done = false;                                                                                         \
-        if (!attr_done) {                                                                                                      \
+        if (dyn > 0) /* static + dynamic shared memory can pass 48 KB; per-device attribute, set on every such call */          \
             S2S_CUDA_OK(cudaFuncSetAttribute(attn_probs_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024)); \
-            attr_done = true;                                                                                                  \
-        }                                                                                                                      \
         attn_probs_bwd_kernel<D><<<grid, 128, dyn, st>>>(dv, vv, (const bf16*)P, (const bf16*)dAtt, (bf16*)dS, H, T1, T2, ld, scale, cache); \
     } while (0)
     if (dk == 16) S2S_AT_BWD(16); else if (dk == 32) S2S_AT_BWD(32); else if (dk == 48) S2S_AT_BWD(48); else if (dk == 64) S2S_AT_BWD(64);

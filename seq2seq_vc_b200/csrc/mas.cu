@@ -130,11 +130,8 @@ extern "C" int s2s_mas(const float* log_p, const int32_t* text_lens, const int32
     int block = mas_block(T_text), nw = block / 32;
     size_t smem = (size_t)2 * nw * sizeof(double) + (size_t)T_feats * sizeof(int);
     S2S_REQUIRE(smem <= 200 * 1024, "mas: T_feats %d too long for shared-memory path buffer", T_feats);
-    static bool attr_set = false;
-    if (smem > 48 * 1024 && !attr_set) {
+    if (smem > 48 * 1024)      // per-device attribute: set on every call that needs it (cheap, thread-safe)
         S2S_CUDA_OK(cudaFuncSetAttribute(mas_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
     if (bin_loss) S2S_CUDA_OK(cudaMemsetAsync(bin_loss, 0, sizeof(float), st));
     mas_kernel<<<B, block, smem, st>>>(log_p, text_lens, feats_lens, B, T_feats, T_text, paths, ds, bin_loss, d_log_p,
                                        (uint32_t*)workspace, T_feats * nw);

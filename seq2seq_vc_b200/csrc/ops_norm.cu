@@ -559,6 +559,112 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restric
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// BatchNorm apply / backward-apply without halos (the Conformer convolution module): flat 16-byte grid-stride kernels with the
+// per-channel constants staged once per CTA in shared memory and the channel index advanced incrementally (no division, no
+// per-element parameter loads from global memory), few registers so that many CTAs keep enough bytes in flight.
+// ---------------------------------------------------------------------------------------------
+template <int ACT> __device__ __forceinline__ float bn_act(float t) {
+    if (ACT == 1) return tanhf(t);
+    if (ACT == 2) return __fdividef(t, 1.f + __expf(-t));          // Swish (conformer/convolution.py:75)
+    return t;
+}
+template <int ACT> __device__ __forceinline__ float bn_act_grad(float z) {
+    if (ACT == 1) { const float a = tanhf(z); return 1.f - a * a; }
+    if (ACT == 2) { const float sg = __fdividef(1.f, 1.f + __expf(-z)); return sg * (1.f + z * (1.f - sg)); }
+    return 1.f;
+}
+
+template <typename T, int ACT>
+__global__ void __launch_bounds__(256) bn_apply_flat_kernel(const T* __restrict__ x, const float* __restrict__ mean,
+                                                            const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, T* __restrict__ y, long nvec, int C,
+                                                            Dropout drop) {
+    extern __shared__ float bnp[];                     // a[C] = invstd * gamma, sh[C] = beta - mean * a
+    dropout_resolve(drop);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float a = invstd[c] * gamma[c];
+        bnp[c] = a;
+        bnp[C + c] = beta[c] - mean[c] * a;
+    }
+    __syncthreads();
+    const int cv = C >> 3;
+    const long step = (long)gridDim.x * blockDim.x;
+    const int cstep = (int)(step % cv);
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    int ci = (int)(i % cv);
+    for (; i < nvec; i += step) {
+        float v[8], o[8], mk[8];
+        Vec8<T>::load(x + i * 8, v);
+        const float4 a0 = *reinterpret_cast<const float4*>(bnp + ci * 8), a1 = *reinterpret_cast<const float4*>(bnp + ci * 8 + 4);
+        const float4 s0 = *reinterpret_cast<const float4*>(bnp + C + ci * 8), s1 = *reinterpret_cast<const float4*>(bnp + C + ci * 8 + 4);
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, sh[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        dropout_factors<8>(drop, (uint64_t)i * 8, mk);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = bn_act<ACT>(fmaf(v[k], a[k], sh[k])) * mk[k];
+        Vec8<T>::store(y + i * 8, o);
+        ci += cstep;
+        if (ci >= cv) ci -= cv;
+    }
+}
+
+template <typename T, int ACT>
+__global__ void __launch_bounds__(256) bn_bwd_apply_flat_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                                const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                const float* __restrict__ sums, T* __restrict__ dx, long nvec, int C,
+                                                                float inv_n, Dropout drop) {
+    extern __shared__ float bnp[];                     // mean | invstd | gamma | beta | sums0 / n | sums1 / n
+    dropout_resolve(drop);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        bnp[c] = mean[c]; bnp[C + c] = invstd[c]; bnp[2 * C + c] = gamma[c]; bnp[3 * C + c] = beta[c];
+        bnp[4 * C + c] = sums ? sums[c] * inv_n : 0.f;
+        bnp[5 * C + c] = sums ? sums[C + c] * inv_n : 0.f;
+    }
+    __syncthreads();
+    const int cv = C >> 3;
+    const long step = (long)gridDim.x * blockDim.x;
+    const int cstep = (int)(step % cv);
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    int ci = (int)(i % cv);
+    for (; i < nvec; i += step) {
+        float gy[8], xv[8], o[8], mk[8];
+        Vec8<T>::load(dy + i * 8, gy);
+        Vec8<T>::load(x + i * 8, xv);
+        dropout_factors<8>(drop, (uint64_t)i * 8, mk);
+        float pr[6][8];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            const float4 lo = *reinterpret_cast<const float4*>(bnp + a * C + ci * 8), hi = *reinterpret_cast<const float4*>(bnp + a * C + ci * 8 + 4);
+            pr[a][0] = lo.x; pr[a][1] = lo.y; pr[a][2] = lo.z; pr[a][3] = lo.w; pr[a][4] = hi.x; pr[a][5] = hi.y; pr[a][6] = hi.z; pr[a][7] = hi.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float is = pr[1][k], ga = pr[2][k];
+            const float xh = (xv[k] - pr[0][k]) * is;
+            const float dz = gy[k] * mk[k] * bn_act_grad<ACT>(fmaf(xh, ga, pr[3][k]));
+            o[k] = (dz - pr[4][k] - xh * pr[5][k]) * ga * is;
+        }
+        Vec8<T>::store(dx + i * 8, o);
+        ci += cstep;
+        if (ci >= cv) ci -= cv;
+    }
+}
+
+static inline unsigned bn_flat_grid(long nvec) {          // every CTA stages the per-channel constants: keep the grid near-persistent
+    long b = ceil_div_l(nvec, 256 * 4);
+    const long cap = (long)num_sms() * 6;
+    if (b > cap) b = cap;
+    return (unsigned)(b < 1 ? 1 : b);
+}
+
+#define S2S_BN_ACT_DISPATCH(act, ACT, ...)                 \
+    do {                                                    \
+        if ((act) == 1) { constexpr int ACT = 1; __VA_ARGS__; }      \
+        else if ((act) == 2) { constexpr int ACT = 2; __VA_ARGS__; } \
+        else { constexpr int ACT = 0; __VA_ARGS__; }                 \
+    } while (0)
+
 __global__ void bn_param_grad_kernel(const float* __restrict__ sums, float* dgamma, float* dbeta, int C) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
@@ -943,6 +1049,13 @@ extern "C" int s2s_bn_apply(const void* x, const float* mean, const float* invst
     cudaStream_t st = (cudaStream_t)stream;
     BNGeom g{L, L + 2 * halo, halo, C};
     Dropout d = make_dropout(drop);
+    if (halo == 0 && C % 8 == 0 && C <= 4096 && aligned16(x, y)) {
+        const long nvec = (long)B * L * (C / 8);
+        S2S_DISPATCH_DTYPE(dtype, T, S2S_BN_ACT_DISPATCH(use_tanh, ACT, (bn_apply_flat_kernel<T, ACT><<<bn_flat_grid(nvec), 256,
+            (size_t)2 * C * sizeof(float), st>>>((const T*)x, mean, invstd, gamma, beta, (T*)y, nvec, C, d))));
+        S2S_LAUNCH_OK();
+        return S2S_OK;
+    }
     bool ok = vec4_ok(C, C, x, y);
     long total = (long)B * g.Lp * C;
     S2S_DISPATCH_DTYPE(dtype, T, S2S_VEC_DISPATCH(ok, VEC, (bn_apply_kernel<T, VEC><<<ew_grid(total / VEC, 256), 256, 0, st>>>(
@@ -976,10 +1089,17 @@ extern "C" int s2s_bn_bwd_apply(const void* dy, const void* y, const void* x, co
     cudaStream_t st = (cudaStream_t)stream;
     BNGeom g{L, L + 2 * halo, halo, C};
     Dropout d = make_dropout(drop);
-    bool ok = vec4_ok(C, C, x, dy, dx);
-    long total = (long)B * g.Lp * C;
-    S2S_DISPATCH_DTYPE(dtype, T, S2S_VEC_DISPATCH(ok, VEC, (bn_bwd_apply_kernel<T, VEC><<<ew_grid(total / VEC, 256), 256, 0, st>>>(
-        (const T*)dy, (const T*)y, (const T*)x, mean, invstd, gamma, beta, sums, (T*)dx, B, g, use_tanh, d))));
+    if (halo == 0 && C % 8 == 0 && C <= 1536 && aligned16(x, dy, dx)) {
+        const long nvec = (long)B * L * (C / 8);
+        S2S_DISPATCH_DTYPE(dtype, T, S2S_BN_ACT_DISPATCH(use_tanh, ACT, (bn_bwd_apply_flat_kernel<T, ACT><<<bn_flat_grid(nvec), 256,
+            (size_t)6 * C * sizeof(float), st>>>((const T*)dy, (const T*)x, mean, invstd, gamma, beta, sums, (T*)dx, nvec, C,
+                                                  1.f / (float)((long)B * L), d))));
+    } else {
+        bool ok = vec4_ok(C, C, x, dy, dx);
+        long total = (long)B * g.Lp * C;
+        S2S_DISPATCH_DTYPE(dtype, T, S2S_VEC_DISPATCH(ok, VEC, (bn_bwd_apply_kernel<T, VEC><<<ew_grid(total / VEC, 256), 256, 0, st>>>(
+            (const T*)dy, (const T*)y, (const T*)x, mean, invstd, gamma, beta, sums, (T*)dx, B, g, use_tanh, d))));
+    }
     S2S_LAUNCH_OK();
     if (sums && (dgamma || dbeta)) {
         bn_param_grad_kernel<<<(unsigned)ceil_div_l(C, 128), 128, 0, st>>>(sums, dgamma, dbeta, C);
