@@ -299,6 +299,8 @@ static int launch_colreduce(F f, long rows, int cols, cudaStream_t st) {
     if (want < 1) want = 1;
     long maxy = ceil_div_l(rows, 64);
     if (want > maxy) want = maxy;
+    if (rows <= 512) want = 1;      // small problems: one row chunk per column tile, so no floating-point atomics meet and the
+                                    // sums (BatchNorm statistics feed the forward pass) are bit-reproducible run to run
     if (want < 1) want = 1;
     colreduce_kernel<NOUT, VEC, F><<<dim3(gx, (unsigned)want), dim3(32, 8), 0, st>>>(f, rows, cols);
     S2S_LAUNCH_OK();
@@ -575,13 +577,42 @@ template <int ACT> __device__ __forceinline__ float bn_act_grad(float z) {
     return 1.f;
 }
 
-template <typename T, int ACT>
+// position of a thread's current 8-channel vector inside a (B, Lp = L + 2 * halo, C) buffer, advanced by the grid stride with
+// carries instead of divisions
+template <bool HALO> struct BNCursor;
+template <> struct BNCursor<true> {
+    int ci, lp, b;
+    int dci, dlp, db;            // the grid stride split into (channel vectors, rows inside an utterance, utterances)
+    __device__ __forceinline__ void init(long i, long step, int cv, int Lp) {
+        long row = i / cv; ci = (int)(i - row * cv); b = (int)(row / Lp); lp = (int)(row - (long)b * Lp);
+        long srow = step / cv; dci = (int)(step - srow * cv); db = (int)(srow / Lp); dlp = (int)(srow - (long)db * Lp);
+    }
+    __device__ __forceinline__ void next(int cv, int Lp) {
+        ci += dci; lp += dlp; b += db;
+        if (ci >= cv) { ci -= cv; ++lp; }
+        if (lp >= Lp) { lp -= Lp; ++b; }
+    }
+    __device__ __forceinline__ bool frame(const BNGeom& g, long, uint64_t& idx) const {   // element index of the frame (dropout counter)
+        const int l = lp - g.halo;
+        idx = (uint64_t)(((long)b * g.L + l) * (long)g.C + ci * 8);
+        return l >= 0 && l < g.L;
+    }
+};
+template <> struct BNCursor<false> {                       // no halos: physical rows are frames, only the channel vector is tracked
+    int ci, dci;
+    __device__ __forceinline__ void init(long i, long step, int cv, int) { ci = (int)(i % cv); dci = (int)(step % cv); }
+    __device__ __forceinline__ void next(int cv, int) { ci += dci; if (ci >= cv) ci -= cv; }
+    __device__ __forceinline__ bool frame(const BNGeom&, long i, uint64_t& idx) const { idx = (uint64_t)i * 8; return true; }
+};
+
+template <typename T, int ACT, bool HALO>
 __global__ void __launch_bounds__(256) bn_apply_flat_kernel(const T* __restrict__ x, const float* __restrict__ mean,
                                                             const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                                            const float* __restrict__ beta, T* __restrict__ y, long nvec, int C,
+                                                            const float* __restrict__ beta, T* __restrict__ y, long nvec, BNGeom g,
                                                             Dropout drop) {
     extern __shared__ float bnp[];                     // a[C] = invstd * gamma, sh[C] = beta - mean * a
     dropout_resolve(drop);
+    const int C = g.C;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const float a = invstd[c] * gamma[c];
         bnp[c] = a;
@@ -590,32 +621,57 @@ __global__ void __launch_bounds__(256) bn_apply_flat_kernel(const T* __restrict_
     __syncthreads();
     const int cv = C >> 3;
     const long step = (long)gridDim.x * blockDim.x;
-    const int cstep = (int)(step % cv);
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    int ci = (int)(i % cv);
-    for (; i < nvec; i += step) {
-        float v[8], o[8], mk[8];
-        Vec8<T>::load(x + i * 8, v);
-        const float4 a0 = *reinterpret_cast<const float4*>(bnp + ci * 8), a1 = *reinterpret_cast<const float4*>(bnp + ci * 8 + 4);
-        const float4 s0 = *reinterpret_cast<const float4*>(bnp + C + ci * 8), s1 = *reinterpret_cast<const float4*>(bnp + C + ci * 8 + 4);
-        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, sh[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-        dropout_factors<8>(drop, (uint64_t)i * 8, mk);
+    BNCursor<HALO> cur;
+    cur.init(i, step, cv, g.Lp);
+    for (; i < nvec; i += step, cur.next(cv, g.Lp)) {
+        float o[8];
+        uint64_t idx;
+        if (cur.frame(g, i, idx)) {
+            float v[8], mk[8];
+            Vec8<T>::load(x + i * 8, v);
+            const float* pa = bnp + cur.ci * 8;
+            const float4 a0 = *reinterpret_cast<const float4*>(pa), a1 = *reinterpret_cast<const float4*>(pa + 4);
+            const float4 s0 = *reinterpret_cast<const float4*>(pa + C), s1 = *reinterpret_cast<const float4*>(pa + C + 4);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, sh[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            dropout_factors<8>(drop, idx, mk);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] = bn_act<ACT>(fmaf(v[k], a[k], sh[k])) * mk[k];
+            for (int k = 0; k < 8; ++k) o[k] = bn_act<ACT>(fmaf(v[k], a[k], sh[k])) * mk[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = 0.f;         // halo rows of the output stay zero
+        }
         Vec8<T>::store(y + i * 8, o);
-        ci += cstep;
-        if (ci >= cv) ci -= cv;
     }
 }
 
-template <typename T, int ACT>
+// dz = dy * dropmask * act'(xhat * gamma + beta) and xhat for one 8-channel vector; pc -> {mean, invstd, gamma, beta, ...}[C]
+template <int ACT>
+__device__ __forceinline__ void bn_dz_flat(const float (&gy)[8], const float (&xv)[8], const float* pc, int C, const Dropout& drop,
+                                           uint64_t idx, float (&pr)[4][8], float (&dz)[8], float (&xh)[8]) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const float4 lo = *reinterpret_cast<const float4*>(pc + a * C), hi = *reinterpret_cast<const float4*>(pc + a * C + 4);
+        pr[a][0] = lo.x; pr[a][1] = lo.y; pr[a][2] = lo.z; pr[a][3] = lo.w; pr[a][4] = hi.x; pr[a][5] = hi.y; pr[a][6] = hi.z; pr[a][7] = hi.w;
+    }
+    float mk[8];
+    dropout_factors<8>(drop, idx, mk);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        xh[k] = (xv[k] - pr[0][k]) * pr[1][k];
+        dz[k] = gy[k] * mk[k] * bn_act_grad<ACT>(fmaf(xh[k], pr[2][k], pr[3][k]));
+    }
+}
+
+template <typename T, int ACT, bool HALO>
 __global__ void __launch_bounds__(256) bn_bwd_apply_flat_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                                                                 const float* __restrict__ mean, const float* __restrict__ invstd,
                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                const float* __restrict__ sums, T* __restrict__ dx, long nvec, int C,
+                                                                const float* __restrict__ sums, T* __restrict__ dx, long nvec, BNGeom g,
                                                                 float inv_n, Dropout drop) {
     extern __shared__ float bnp[];                     // mean | invstd | gamma | beta | sums0 / n | sums1 / n
     dropout_resolve(drop);
+    const int C = g.C;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         bnp[c] = mean[c]; bnp[C + c] = invstd[c]; bnp[2 * C + c] = gamma[c]; bnp[3 * C + c] = beta[c];
         bnp[4 * C + c] = sums ? sums[c] * inv_n : 0.f;
@@ -624,30 +680,28 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_flat_kernel(const T* __restr
     __syncthreads();
     const int cv = C >> 3;
     const long step = (long)gridDim.x * blockDim.x;
-    const int cstep = (int)(step % cv);
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    int ci = (int)(i % cv);
-    for (; i < nvec; i += step) {
-        float gy[8], xv[8], o[8], mk[8];
-        Vec8<T>::load(dy + i * 8, gy);
-        Vec8<T>::load(x + i * 8, xv);
-        dropout_factors<8>(drop, (uint64_t)i * 8, mk);
-        float pr[6][8];
+    BNCursor<HALO> cur;
+    cur.init(i, step, cv, g.Lp);
+    for (; i < nvec; i += step, cur.next(cv, g.Lp)) {
+        float o[8];
+        uint64_t idx;
+        if (cur.frame(g, i, idx)) {
+            float gy[8], xv[8], pr[4][8], dz[8], xh[8];
+            Vec8<T>::load(dy + i * 8, gy);
+            Vec8<T>::load(x + i * 8, xv);
+            const float* pc = bnp + cur.ci * 8;
+            bn_dz_flat<ACT>(gy, xv, pc, C, drop, idx, pr, dz, xh);
+            const float4 p0 = *reinterpret_cast<const float4*>(pc + 4 * C), p1 = *reinterpret_cast<const float4*>(pc + 4 * C + 4);
+            const float4 q0 = *reinterpret_cast<const float4*>(pc + 5 * C), q1 = *reinterpret_cast<const float4*>(pc + 5 * C + 4);
+            const float s0[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w}, s1[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
 #pragma unroll
-        for (int a = 0; a < 6; ++a) {
-            const float4 lo = *reinterpret_cast<const float4*>(bnp + a * C + ci * 8), hi = *reinterpret_cast<const float4*>(bnp + a * C + ci * 8 + 4);
-            pr[a][0] = lo.x; pr[a][1] = lo.y; pr[a][2] = lo.z; pr[a][3] = lo.w; pr[a][4] = hi.x; pr[a][5] = hi.y; pr[a][6] = hi.z; pr[a][7] = hi.w;
-        }
+            for (int k = 0; k < 8; ++k) o[k] = (dz[k] - s0[k] - xh[k] * s1[k]) * pr[2][k] * pr[1][k];
+        } else {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float is = pr[1][k], ga = pr[2][k];
-            const float xh = (xv[k] - pr[0][k]) * is;
-            const float dz = gy[k] * mk[k] * bn_act_grad<ACT>(fmaf(xh, ga, pr[3][k]));
-            o[k] = (dz - pr[4][k] - xh * pr[5][k]) * ga * is;
+            for (int k = 0; k < 8; ++k) o[k] = 0.f;
         }
         Vec8<T>::store(dx + i * 8, o);
-        ci += cstep;
-        if (ci >= cv) ci -= cv;
     }
 }
 
@@ -658,11 +712,16 @@ static inline unsigned bn_flat_grid(long nvec) {          // every CTA stages th
     return (unsigned)(b < 1 ? 1 : b);
 }
 
-#define S2S_BN_ACT_DISPATCH(act, ACT, ...)                 \
+#define S2S_BN_ACT_DISPATCH2(act, ACT, ...)                \
     do {                                                    \
         if ((act) == 1) { constexpr int ACT = 1; __VA_ARGS__; }      \
         else if ((act) == 2) { constexpr int ACT = 2; __VA_ARGS__; } \
         else { constexpr int ACT = 0; __VA_ARGS__; }                 \
+    } while (0)
+#define S2S_BN_ACT_DISPATCH(act, ACT, ...)                 \
+    do {                                                    \
+        if (halo > 0) { constexpr bool HALO = true; S2S_BN_ACT_DISPATCH2(act, ACT, __VA_ARGS__); }  \
+        else { constexpr bool HALO = false; S2S_BN_ACT_DISPATCH2(act, ACT, __VA_ARGS__); }          \
     } while (0)
 
 __global__ void bn_param_grad_kernel(const float* __restrict__ sums, float* dgamma, float* dbeta, int C) {
@@ -1049,10 +1108,10 @@ extern "C" int s2s_bn_apply(const void* x, const float* mean, const float* invst
     cudaStream_t st = (cudaStream_t)stream;
     BNGeom g{L, L + 2 * halo, halo, C};
     Dropout d = make_dropout(drop);
-    if (halo == 0 && C % 8 == 0 && C <= 4096 && aligned16(x, y)) {
-        const long nvec = (long)B * L * (C / 8);
-        S2S_DISPATCH_DTYPE(dtype, T, S2S_BN_ACT_DISPATCH(use_tanh, ACT, (bn_apply_flat_kernel<T, ACT><<<bn_flat_grid(nvec), 256,
-            (size_t)2 * C * sizeof(float), st>>>((const T*)x, mean, invstd, gamma, beta, (T*)y, nvec, C, d))));
+    if (C % 8 == 0 && C <= 4096 && aligned16(x, y)) {
+        const long nvec = (long)B * g.Lp * (C / 8);
+        S2S_DISPATCH_DTYPE(dtype, T, S2S_BN_ACT_DISPATCH(use_tanh, ACT, (bn_apply_flat_kernel<T, ACT, HALO><<<bn_flat_grid(nvec), 256,
+            (size_t)2 * C * sizeof(float), st>>>((const T*)x, mean, invstd, gamma, beta, (T*)y, nvec, g, d))));
         S2S_LAUNCH_OK();
         return S2S_OK;
     }
@@ -1072,6 +1131,9 @@ extern "C" int s2s_bn_bwd_reduce(const void* dy, const void* y, const void* x, c
     cudaStream_t st = (cudaStream_t)stream;
     BNGeom g{L, L + 2 * halo, halo, C};
     Dropout d = make_dropout(drop);
+    // (a flat column-owned form of this reduction measured 127-139 us vs 166 us at the C3 decoder
+    // shape, but its different summation order made the multi-step graph-vs-eager comparisons of the test suite flaky at their
+    // 1e-4 bound; the row-chunked reduction below stays)
     bool ok = vec4_ok(C, C, x, dy);
     int rc = S2S_OK;
     S2S_DISPATCH_DTYPE(dtype, T, S2S_VEC_DISPATCH(ok, VEC, {
@@ -1089,10 +1151,10 @@ extern "C" int s2s_bn_bwd_apply(const void* dy, const void* y, const void* x, co
     cudaStream_t st = (cudaStream_t)stream;
     BNGeom g{L, L + 2 * halo, halo, C};
     Dropout d = make_dropout(drop);
-    if (halo == 0 && C % 8 == 0 && C <= 1536 && aligned16(x, dy, dx)) {
-        const long nvec = (long)B * L * (C / 8);
-        S2S_DISPATCH_DTYPE(dtype, T, S2S_BN_ACT_DISPATCH(use_tanh, ACT, (bn_bwd_apply_flat_kernel<T, ACT><<<bn_flat_grid(nvec), 256,
-            (size_t)6 * C * sizeof(float), st>>>((const T*)dy, (const T*)x, mean, invstd, gamma, beta, sums, (T*)dx, nvec, C,
+    if (C % 8 == 0 && C <= 1536 && aligned16(x, dy, dx)) {
+        const long nvec = (long)B * g.Lp * (C / 8);
+        S2S_DISPATCH_DTYPE(dtype, T, S2S_BN_ACT_DISPATCH(use_tanh, ACT, (bn_bwd_apply_flat_kernel<T, ACT, HALO><<<bn_flat_grid(nvec), 256,
+            (size_t)6 * C * sizeof(float), st>>>((const T*)dy, (const T*)x, mean, invstd, gamma, beta, sums, (T*)dx, nvec, g,
                                                   1.f / (float)((long)B * L), d))));
     } else {
         bool ok = vec4_ok(C, C, x, dy, dx);
