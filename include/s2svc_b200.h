@@ -36,7 +36,7 @@ extern "C" {
 #define S2S_F32 0
 #define S2S_BF16 1
 
-#define S2S_ABI_VERSION 14
+#define S2S_ABI_VERSION 15
 
 const char* s2s_last_error(void);
 int s2s_abi_version(void);
@@ -379,6 +379,12 @@ int s2s_add_strided(const void* a, const void* b, void* out, int64_t ldo, int64_
 int s2s_relshift_add(void* S, const void* BD, int B, int H, int T, int64_t ldS, int64_t ldB, int dtype, void* stream);
 /* adjoint of the gather: dBD[h,b,i,k] = dS[b,h,i,k-(T-1-i)] inside the band, 0 elsewhere (every column written) */
 int s2s_relshift_bwd(const void* dS, void* dBD, int B, int H, int T, int64_t ldS, int64_t ldB, int dtype, void* stream);
+/* LegacyRelPositionMultiHeadedAttention.rel_shift (modules/transformer/attention.py:138-157, the default of
+ * VTN(encoder_type="conformer"), models/vtn.py:83-99): S (B,H,T,ldS) += shift(BD) with BD (H,B,T,ldB >= T) the T x T product
+ * (q + pos_bias_v) p^T; the shift pads a zero column, re-views (T, T+1) as (T+1, T) and drops the first row, so rows wrap
+ * around.  s2s_relshift_legacy_bwd is its adjoint (dBD from dS, dropped / padding elements zero). */
+int s2s_relshift_legacy_add(void* S, const void* BD, int B, int H, int T, int64_t ldS, int64_t ldB, int dtype, void* stream);
+int s2s_relshift_legacy_bwd(const void* dS, void* dBD, int B, int H, int T, int64_t ldS, int64_t ldB, int dtype, void* stream);
 /* GLU over channels (convolution.py:69): x (rows, 2C) -> y (rows, C) = x[:, :C] * sigmoid(x[:, C:]); dx (rows, 2C) */
 int s2s_glu_fwd(const void* x, void* y, int64_t rows, int C, int dtype, void* stream);
 int s2s_glu_bwd(const void* dy, const void* x, void* dx, int64_t rows, int C, int dtype, void* stream);

@@ -100,8 +100,88 @@ def conv2d_subsample(sd, prefix, xs, x_mask):
     return x, x_mask[:, :, :-2:2][:, :, :-2:2]
 
 
-def encoder(sd, hp, xs, x_mask, attn_store=None):
-    """Transformer Encoder (pre-LN), modules/transformer/encoder.py:283-329 + encoder_layer.py:61-119."""
+LEGACY_PE_MAX_LEN = 5000
+
+
+def legacy_rel_pos_table(T: int, d: int) -> torch.Tensor:
+    """pos_emb of LegacyRelPositionalEncoding.forward (layers/positional_encoding.py:192-235): the table is built ONCE at
+    construction, reversed, for max_len = 5000 (positional_encoding.py:44,52-60) and then only sliced, so row k holds the
+    sinusoid of position 4999 - k whatever the utterance length."""
+    pos = torch.arange(LEGACY_PE_MAX_LEN - 1, LEGACY_PE_MAX_LEN - 1 - T, -1, dtype=torch.float32).unsqueeze(1)
+    div = torch.exp(torch.arange(0, d, 2, dtype=torch.float32) * -(math.log(10000.0) / d))
+    pe = torch.zeros(T, d)
+    pe[:, 0::2] = torch.sin(pos * div)
+    pe[:, 1::2] = torch.cos(pos * div)
+    return pe
+
+
+def legacy_rel_shift(bd: torch.Tensor) -> torch.Tensor:
+    """LegacyRelPositionMultiHeadedAttention.rel_shift (attention.py:138-157) restated as an index map: with one zero column
+    padded on the left, out[i, j] is flat element T + i T + j of the (T, T + 1) block, i.e. zero when that index is a multiple
+    of T + 1 and bd[f // (T + 1), f % (T + 1) - 1] otherwise (rows wrap around)."""
+    T = bd.shape[-1]
+    f = T + torch.arange(T)[:, None] * T + torch.arange(T)[None, :]
+    r, c = f // (T + 1), f % (T + 1)
+    src = (r * T + (c - 1).clamp(min=0)).reshape(-1)
+    out = bd.reshape(*bd.shape[:-2], T * T)[..., src].reshape(bd.shape)
+    return out * (c > 0).to(bd.dtype)
+
+
+def legacy_rel_attention(sd, prefix, x, pos_emb, mask, n_head, store=None):
+    """LegacyRelPositionMultiHeadedAttention.forward (attention.py:159-207)."""
+    B, T, d = x.shape
+    dk = d // n_head
+    q = linear(x, sd, prefix + ".linear_q").view(B, T, n_head, dk)
+    k = linear(x, sd, prefix + ".linear_k").view(B, T, n_head, dk).transpose(1, 2)
+    v = linear(x, sd, prefix + ".linear_v").view(B, T, n_head, dk).transpose(1, 2)
+    p = F.linear(pos_emb, sd[prefix + ".linear_pos.weight"]).view(T, n_head, dk).transpose(0, 1)      # (H, T, dk)
+    qu = (q + sd[prefix + ".pos_bias_u"]).transpose(1, 2)
+    qv = (q + sd[prefix + ".pos_bias_v"]).transpose(1, 2)
+    ac = torch.matmul(qu, k.transpose(-2, -1))
+    bd = legacy_rel_shift(torch.matmul(qv, p.transpose(-2, -1).unsqueeze(0)))
+    scores = (ac + bd) / math.sqrt(dk)
+    dead = ~mask.unsqueeze(1)
+    scores = scores.masked_fill(dead, torch.finfo(scores.dtype).min)
+    pr = torch.softmax(scores, dim=-1).masked_fill(dead, 0.0)
+    if store is not None:
+        store[prefix] = pr
+    ctx = torch.matmul(pr, v).transpose(1, 2).reshape(B, T, d)
+    return linear(ctx, sd, prefix + ".linear_out")
+
+
+def conformer_encoder(sd, hp, xs, x_mask, training=True, bn_stats=None, attn_store=None):
+    """ConformerEncoder as VTN builds it (models/vtn.py:122-143): Conv2dSubsampling whose positional layer is the (legacy) rel-pos
+    encoding (x * sqrt(d), pos_emb on the side), macaron conformer blocks with the convolution module, after_norm
+    (conformer/encoder.py:249-293, encoder_layer.py:79-179)."""
+    from oracle import aasvc_oracle as ao           # conformer block pieces shared with AAS-VC (imported lazily: it imports this module)
+
+    prefix = "encoder.embed"
+    x = xs.unsqueeze(1)
+    x = torch.relu(F.conv2d(x, sd[prefix + ".conv.0.weight"], sd[prefix + ".conv.0.bias"], stride=2))
+    x = torch.relu(F.conv2d(x, sd[prefix + ".conv.2.weight"], sd[prefix + ".conv.2.bias"], stride=2))
+    b, c, t, f = x.shape
+    x = linear(x.transpose(1, 2).reshape(b, t, c * f), sd, prefix + ".out.0")
+    mask = x_mask[:, :, :-2:2][:, :, :-2:2]
+    d = x.shape[-1]
+    legacy = hp.get("conformer_rel_pos_type", "legacy") == "legacy"
+    x = x * math.sqrt(d)
+    pos_emb = legacy_rel_pos_table(t, d) if legacy else ao.rel_pos_table(t, d)
+    att = legacy_rel_attention if legacy else ao.rel_attention
+    for l in range(hp["elayers"]):
+        p = f"encoder.encoders.{l}"
+        x = x + 0.5 * ao.ffn_swish(sd, p + ".feed_forward_macaron", ao.layer_norm(x, sd, p + ".norm_ff_macaron"))
+        x = x + att(sd, p + ".self_attn", ao.layer_norm(x, sd, p + ".norm_mha"), pos_emb, mask, hp["aheads"], attn_store)
+        x = x + ao.conv_module(sd, p + ".conv_module", ao.layer_norm(x, sd, p + ".norm_conv"), training, bn_stats)
+        x = x + 0.5 * ao.ffn_swish(sd, p + ".feed_forward", ao.layer_norm(x, sd, p + ".norm_ff"))
+        x = ao.layer_norm(x, sd, p + ".norm_final")
+    return ao.layer_norm(x, sd, "encoder.after_norm"), mask
+
+
+def encoder(sd, hp, xs, x_mask, attn_store=None, training=True, bn_stats=None):
+    """Transformer Encoder (pre-LN), modules/transformer/encoder.py:283-329 + encoder_layer.py:61-119; the conformer encoder of
+    VTN(encoder_type="conformer") when the hyper-parameters say so."""
+    if hp.get("encoder_type", "transformer") == "conformer":
+        return conformer_encoder(sd, hp, xs, x_mask, training, bn_stats, attn_store)
     x, mask = conv2d_subsample(sd, "encoder.embed", xs, x_mask)
     for l in range(hp["elayers"]):
         p = f"encoder.encoders.{l}"
@@ -243,7 +323,7 @@ def vtn_forward(sd, hp, xs, ilens, ys, labels, olens, training: bool = True, bn_
     attn: Dict[str, torch.Tensor] = {}
 
     x_mask = non_pad_mask(ilens, xs.shape[1]).unsqueeze(-2)                        # vtn.py:217,553-572
-    hs, h_mask = encoder(sd, hp, xs, x_mask, attn)
+    hs, h_mask = encoder(sd, hp, xs, x_mask, attn, training, bn_stats)
 
     ys_in = ys[:, r - 1 :: r] if r > 1 else ys                                   # vtn.py:227-240
     olens_in = [o // r for o in olens]

@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libs2svc_b200.so")
 
 S2S_F32, S2S_BF16 = 0, 1
-ABI_VERSION = 14
+ABI_VERSION = 15
 
 
 class S2SError(RuntimeError):
@@ -119,6 +119,8 @@ SIGNATURES = {
     "s2s_add_strided": (c_int, [_P, _P, _P, c_int64, c_int64, c_int, c_int, _P]),
     "s2s_relshift_add": (c_int, [_P, _P, c_int, c_int, c_int, c_int64, c_int64, c_int, _P]),
     "s2s_relshift_bwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int64, c_int64, c_int, _P]),
+    "s2s_relshift_legacy_add": (c_int, [_P, _P, c_int, c_int, c_int, c_int64, c_int64, c_int, _P]),
+    "s2s_relshift_legacy_bwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int64, c_int64, c_int, _P]),
     "s2s_glu_fwd": (c_int, [_P, _P, c_int64, c_int, c_int, _P]),
     "s2s_glu_bwd": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P]),
     "s2s_dwconv_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),

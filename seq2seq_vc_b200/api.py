@@ -199,10 +199,35 @@ class VTN(torch.nn.Module):
         super().__init__()
         self.use_graph = bool(use_graph)     # replay captured CUDA graphs of forward / backward per batch shape (training mode)
         unsupported = []
-        if encoder_type != "transformer" or decoder_type != "transformer":
-            unsupported.append("encoder_type/decoder_type != 'transformer'")
-        if positionwise_layer_type != "linear":
-            unsupported.append("positionwise_layer_type != 'linear'")
+        if encoder_type not in ("transformer", "conformer") or decoder_type != "transformer":
+            unsupported.append("encoder_type not in ('transformer', 'conformer') / decoder_type != 'transformer'")
+        conformer = encoder_type == "conformer"
+        if conformer:
+            # relative positional encoding compatibility (models/vtn.py:83-104): "legacy" turns the default rel_pos / rel_selfattn
+            # into their legacy forms, "latest" keeps the new ones
+            if conformer_rel_pos_type == "legacy":
+                if conformer_pos_enc_layer_type == "rel_pos":
+                    conformer_pos_enc_layer_type = "legacy_rel_pos"
+                    logging.warning("Fallback to conformer_pos_enc_layer_type = 'legacy_rel_pos' due to the compatibility. "
+                                    "If you want to use the new one, please use conformer_pos_enc_layer_type = 'latest'.")
+                if conformer_self_attn_layer_type == "rel_selfattn":
+                    conformer_self_attn_layer_type = "legacy_rel_selfattn"
+                    logging.warning("Fallback to conformer_self_attn_layer_type = 'legacy_rel_selfattn' due to the compatibility. "
+                                    "If you want to use the new one, please use conformer_pos_enc_layer_type = 'latest'.")
+            elif conformer_rel_pos_type == "latest":
+                assert conformer_pos_enc_layer_type != "legacy_rel_pos"
+                assert conformer_self_attn_layer_type != "legacy_rel_selfattn"
+            else:
+                raise ValueError(f"Unknown rel_pos_type: {conformer_rel_pos_type}")
+            pair = (conformer_pos_enc_layer_type, conformer_self_attn_layer_type)
+            if pair not in (("legacy_rel_pos", "legacy_rel_selfattn"), ("rel_pos", "rel_selfattn")):
+                unsupported.append(f"conformer positional / attention pair {pair} (rel_pos + rel_selfattn and their legacy forms are covered)")
+            if not use_macaron_style_in_conformer or not use_cnn_in_conformer or zero_triu:
+                unsupported.append("conformer without macaron / CNN module, zero_triu")
+            if positionwise_layer_type not in ("linear", "conv1d", "conv1d-linear"):
+                unsupported.append("positionwise_layer_type not in ('linear', 'conv1d', 'conv1d-linear')")
+        elif positionwise_layer_type != "linear":
+            unsupported.append("positionwise_layer_type != 'linear' with the transformer encoder")
         if not use_batch_norm or not encoder_normalize_before or decoder_normalize_before:
             unsupported.append("non-default normalisation wiring")
         if encoder_concat_after or decoder_concat_after or spk_embed_dim is not None:
@@ -228,6 +253,13 @@ class VTN(torch.nn.Module):
                                   decoder_reduction_factor=decoder_reduction_factor,
                                   initial_encoder_alpha=initial_encoder_alpha, initial_decoder_alpha=initial_decoder_alpha,
                                   encoder_input=getattr(self, "_encoder_input", "conv2d"))
+        if conformer:       # models/vtn.py:122-143: the conformer encoder takes the positional / attention dropout rates of the constructor
+            self.hp.update(encoder_type="conformer", conformer_enc_kernel_size=conformer_enc_kernel_size,
+                           conformer_rel_pos_type="legacy" if conformer_self_attn_layer_type == "legacy_rel_selfattn" else "latest",
+                           enc_positional_dropout_rate=transformer_enc_positional_dropout_rate,
+                           enc_attn_dropout_rate=transformer_enc_attn_dropout_rate, positionwise_layer_type=positionwise_layer_type,
+                           positionwise_conv_kernel_size=positionwise_conv_kernel_size)
+            default_hparams(**self.hp)      # validates the combination
         # compute_dtype: "bf16" (tcgen05, bf16 activations) | "float32" (float32 activations, fp32-accurate tcgen05 GEMMs through a
         # bf16 split: the parity mode) | "float32_simt" (float32 on the CUDA cores: the numerical yard-stick)
         self._bf16 = compute_dtype in ("bf16", "bfloat16", torch.bfloat16)

@@ -108,6 +108,55 @@ __global__ void __launch_bounds__(256) relshift_bwd_kernel(const T* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
+// Legacy rel_shift (LegacyRelPositionMultiHeadedAttention.rel_shift, attention.py:138-157): pad one zero column on the left
+// of bd (T, T), re-view the (T, T+1) block as (T+1, T), drop its first row.  In flat terms out[i][j] is element
+// f = T + i T + j of the padded block: zero when f % (T+1) == 0, else bd[f / (T+1)][f % (T+1) - 1] -- rows wrap around, which is
+// the behaviour checkpoints trained with it depend on.  S (B,H,T,ldS) += that; BD is (H,B,T,ldB).  One warp per (b,h,i) row.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) relshift_legacy_add_kernel(T* __restrict__ S, const T* __restrict__ BD, int B, int H, int Tn,
+                                                                  long ldS, long ldB) {
+    const int lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const long rows = (long)B * H * Tn;
+    if (row >= rows) return;
+    const int i = (int)(row % Tn);
+    const int h = (int)((row / Tn) % H);
+    const long b = row / ((long)Tn * H);
+    T* s = S + row * ldS;
+    const T* bd = BD + ((long)h * B + b) * Tn * ldB;
+    for (int j = lane; j < Tn; j += 32) {
+        const int f = Tn + i * Tn + j, r = f / (Tn + 1), c = f - r * (Tn + 1);
+        if (c > 0) s[j] = from_f<T>(to_f<T>(s[j]) + to_f<T>(bd[(long)r * ldB + c - 1]));
+    }
+}
+
+// adjoint: dBD[r][c] = dS[i][j] with r (T+1) + c + 1 = T + i T + j, zero for the T - 1 elements of bd's first row that the
+// shift drops; columns >= T of the padded leading dimension are zeroed too (they are GEMM operands)
+template <typename T>
+__global__ void __launch_bounds__(256) relshift_legacy_bwd_kernel(const T* __restrict__ dS, T* __restrict__ dBD, int B, int H, int Tn,
+                                                                  long ldS, long ldB) {
+    const int lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const long rows = (long)B * H * Tn;
+    if (row >= rows) return;
+    const int r = (int)(row % Tn);
+    const int h = (int)((row / Tn) % H);
+    const long b = row / ((long)Tn * H);
+    const T* ds = dS + ((b * H + h) * (long)Tn) * ldS;
+    T* bd = dBD + (((long)h * B + b) * Tn + r) * ldB;
+    for (int c = lane; c < (int)ldB; c += 32) {
+        float v = 0.f;
+        const int q = r * (Tn + 1) + c + 1 - Tn;
+        if (c < Tn && q >= 0) {
+            const int i = q / Tn, j = q - i * Tn;
+            v = to_f<T>(ds[(long)i * ldS + j]);
+        }
+        bd[c] = from_f<T>(v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // GLU over the channel dim of (rows, 2C): y = x[:, :C] * sigmoid(x[:, C:])
 // ---------------------------------------------------------------------------------------------
 template <typename T, int VEC>
@@ -566,6 +615,28 @@ extern "C" int s2s_relshift_bwd(const void* dS, void* dBD, int B, int H, int T, 
     cudaStream_t st = (cudaStream_t)stream;
     long rows = (long)B * H * T;
     S2S_DISPATCH_DTYPE(dtype, TT, (relshift_bwd_kernel<TT><<<(unsigned)ceil_div_l(rows, 8), 256, 0, st>>>(
+        (const TT*)dS, (TT*)dBD, B, H, T, ldS, ldB)));
+    S2S_LAUNCH_OK();
+    return S2S_OK;
+}
+
+extern "C" int s2s_relshift_legacy_add(void* S, const void* BD, int B, int H, int T, int64_t ldS, int64_t ldB, int dtype,
+                                       void* stream) {
+    S2S_REQUIRE(S && BD && B > 0 && H > 0 && T > 0 && ldS >= T && ldB >= T && T < 46000, "relshift_legacy_add: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    long rows = (long)B * H * T;
+    S2S_DISPATCH_DTYPE(dtype, TT, (relshift_legacy_add_kernel<TT><<<(unsigned)ceil_div_l(rows, 8), 256, 0, st>>>(
+        (TT*)S, (const TT*)BD, B, H, T, ldS, ldB)));
+    S2S_LAUNCH_OK();
+    return S2S_OK;
+}
+
+extern "C" int s2s_relshift_legacy_bwd(const void* dS, void* dBD, int B, int H, int T, int64_t ldS, int64_t ldB, int dtype,
+                                       void* stream) {
+    S2S_REQUIRE(dS && dBD && B > 0 && H > 0 && T > 0 && ldS >= T && ldB >= T && T < 46000, "relshift_legacy_bwd: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    long rows = (long)B * H * T;
+    S2S_DISPATCH_DTYPE(dtype, TT, (relshift_legacy_bwd_kernel<TT><<<(unsigned)ceil_div_l(rows, 8), 256, 0, st>>>(
         (const TT*)dS, (TT*)dBD, B, H, T, ldS, ldB)));
     S2S_LAUNCH_OK();
     return S2S_OK;

@@ -551,6 +551,21 @@ def relshift_bwd(dS, dBD, T):
     return dBD
 
 
+def relshift_legacy_add(S, BD, T):
+    """S (B,H,T,ldS) += legacy rel_shift(BD) (attention.py:138-157) with BD (H,B,T,ldB >= T) the T x T bd term."""
+    B, H, T1, ldS = S.shape
+    assert S.is_contiguous() and BD.is_contiguous() and BD.shape[:3] == (H, B, T1) and T1 == T
+    check(_L().s2s_relshift_legacy_add(ptr(S), ptr(BD), B, H, T, ldS, BD.shape[3], dt(S), stream()), "relshift_legacy_add")
+    return S
+
+
+def relshift_legacy_bwd(dS, dBD, T):
+    B, H, T1, ldS = dS.shape
+    assert dS.is_contiguous() and dBD.is_contiguous() and dBD.shape[:3] == (H, B, T1) and T1 == T
+    check(_L().s2s_relshift_legacy_bwd(ptr(dS), ptr(dBD), B, H, T, ldS, dBD.shape[3], dt(dS), stream()), "relshift_legacy_bwd")
+    return dBD
+
+
 def glu_fwd(x, y):
     C = y.shape[-1]
     assert x.is_contiguous() and y.is_contiguous() and x.shape[-1] == 2 * C

@@ -26,6 +26,7 @@ import torch
 from . import ops
 from ._lib import NO_DROP, Drop
 from .engine_base import EngineBase, _r8, sinusoid_table
+from .conformer_blocks import ConformerBlocks, conformer_buffer_specs, conformer_param_groups
 from .params import ParamStore
 
 _f32 = torch.float32
@@ -42,8 +43,17 @@ def default_hparams(**over) -> dict:
               postnet_dropout_rate=0.5, decoder_reduction_factor=2,
               initial_encoder_alpha=1.0, initial_decoder_alpha=1.0,
               # "conv2d": VTN (Conv2dSubsampling + ScaledPE); "embed": TransformerTTS (token embedding + <eos> + ScaledPE)
-              encoder_input="conv2d")
+              encoder_input="conv2d",
+              # "transformer" | "conformer" (models/vtn.py:83-140: Conv2dSubsampling + rel-pos encoding, macaron conformer blocks with
+              # the convolution module; the decoder stays a Transformer decoder).  conformer_rel_pos_type "legacy" is the class default
+              # (LegacyRelPositionalEncoding + LegacyRelPositionMultiHeadedAttention), "latest" the 2T-1 form AAS-VC uses
+              encoder_type="transformer", conformer_rel_pos_type="legacy", conformer_enc_kernel_size=7,
+              enc_attn_dropout_rate=0.1, positionwise_layer_type="linear", positionwise_conv_kernel_size=1)
     hp.update(over)
+    if hp["encoder_type"] not in ("transformer", "conformer"):
+        raise NotImplementedError(f"encoder_type {hp['encoder_type']!r}")
+    if hp["encoder_type"] == "conformer" and hp["encoder_input"] != "conv2d":
+        raise NotImplementedError("the conformer encoder takes the Conv2dSubsampling input layer (models/vtn.py:129)")
     return hp
 
 
@@ -77,15 +87,19 @@ def param_groups(hp: dict) -> List[List[Tuple[str, Tuple[int, ...]]]]:
         g.append([("encoder.embed.conv.2.weight", (d, d, 3, 3))])
         g.append([("encoder.embed.conv.2.bias", (d,))])
         lin("encoder.embed.out.0", d, d * f2)
-        g.append([("encoder.embed.out.1.alpha", ())])
-    for l in range(hp["elayers"]):
-        p = f"encoder.encoders.{l}"
-        mha(p + ".self_attn", ("linear_q", "linear_k", "linear_v"))
-        lin(p + ".feed_forward.w_1", hp["eunits"], d)
-        lin(p + ".feed_forward.w_2", d, hp["eunits"])
-        ln(p + ".norm1", d)
-        ln(p + ".norm2", d)
-    ln("encoder.after_norm", d)
+        if hp.get("encoder_type", "transformer") != "conformer":      # the conformer's rel-pos encoding has no alpha
+            g.append([("encoder.embed.out.1.alpha", ())])
+    if hp.get("encoder_type", "transformer") == "conformer":
+        conformer_param_groups(g, hp, "encoder", hp["elayers"], d, hp["eunits"], hp["conformer_enc_kernel_size"], hp["aheads"])
+    else:
+        for l in range(hp["elayers"]):
+            p = f"encoder.encoders.{l}"
+            mha(p + ".self_attn", ("linear_q", "linear_k", "linear_v"))
+            lin(p + ".feed_forward.w_1", hp["eunits"], d)
+            lin(p + ".feed_forward.w_2", d, hp["eunits"])
+            ln(p + ".norm1", d)
+            ln(p + ".norm2", d)
+        ln("encoder.after_norm", d)
     u = hp["dprenet_units"]
     for i in range(hp["dprenet_layers"]):
         lin(f"decoder.embed.0.0.prenet.{i}.0", u, odim if i == 0 else u)
@@ -114,6 +128,8 @@ def param_groups(hp: dict) -> List[List[Tuple[str, Tuple[int, ...]]]]:
 def buffer_specs(hp: dict) -> List[Tuple[str, Tuple[int, ...], torch.dtype]]:
     """Non-trainable state-dict entries (BatchNorm running statistics)."""
     out = []
+    if hp.get("encoder_type", "transformer") == "conformer":
+        out += conformer_buffer_specs("encoder", hp["elayers"], hp["adim"])
     ch, odim = hp["postnet_chans"], hp["odim"]
     for i in range(hp["postnet_layers"]):
         oc = odim if i == hp["postnet_layers"] - 1 else ch
@@ -123,7 +139,7 @@ def buffer_specs(hp: dict) -> List[Tuple[str, Tuple[int, ...], torch.dtype]]:
     return out
 
 
-class VTNEngine(EngineBase):
+class VTNEngine(ConformerBlocks, EngineBase):
     """Owns parameters, activation buffers and the explicit forward/backward of one VTN step."""
 
     def __init__(self, hp: dict, device="cuda:0", bf16: bool = False, seed: int = 0, fp32_gemm: str = "tc"):
@@ -202,6 +218,12 @@ class VTNEngine(EngineBase):
             ops.gemm(col, w2p.view(d, 9 * d), y2, bias=st.p("encoder.embed.conv.2.bias"), relu=True, mode=self.mode)
             elin = self.buf("enc.elin", (B * T2, d))
             ops.gemm(y2.view(B * T2, F2 * d), woutp.view(d, F2 * d), elin, bias=st.p("encoder.embed.out.0.bias"), mode=self.mode)
+            if hp["encoder_type"] == "conformer":
+                # rel-pos encoding of the input layer: x * sqrt(d) then the positional dropout (positional_encoding.py:192-235 /
+                # :263-309); conformer blocks + after_norm (conformer/encoder.py:249-293)
+                ops.scale_dropout(elin.view(B, T2, d), x, math.sqrt(d), NO_DROP, self.named_drop("enc.posx", hp["enc_positional_dropout_rate"]))
+                return self._conformer_fwd(x, "encoder", hp["elayers"], H, hp["eunits"], hp["conformer_enc_kernel_size"], self.klens_enc,
+                                           hp["transformer_enc_dropout_rate"], hp["enc_positional_dropout_rate"], hp["enc_attn_dropout_rate"])
             ops.scaled_pe_fwd(elin.view(B, T2, d), self.pe(d, T2), st.p("encoder.embed.out.1.alpha"), x,
                               self.drop(hp["enc_positional_dropout_rate"]))
 
@@ -654,7 +676,7 @@ class VTNEngine(EngineBase):
                       st.g("prob_out.bias"), dx=g.view(B * Lr, d), dx_accumulate=True)
 
         # ---- decoder layers (reverse)
-        mem = self.buf("enc.after.y", (B, T2, d))
+        mem = self.buf("encoder.after.y" if hp["encoder_type"] == "conformer" else "enc.after.y", (B, T2, d))
         dmem = self._scratch("g.mem", (B, T2, d))
         dmem.zero_()
         for l in reversed(range(hp["dlayers"])):
@@ -744,10 +766,17 @@ class VTNEngine(EngineBase):
         gde = self._scratch("g.enc_c", (B * T2, d))
         gdf = self._scratch("g.enc_e", (B, T2, d))        # dropout'(g) for the next (lower) layer's ff2 branch
         nle = hp["elayers"]
-        self._ln_bwd(dmem, self.enc_last, "encoder.after_norm", "enc.after", ge, dx_drop=gdf if nle > 0 else None,
-                     drop=sites[f"encoder.encoders.{nle - 1}.ff2"] if nle > 0 else NO_DROP)
+        conformer = hp["encoder_type"] == "conformer"
+        if conformer:
+            gx0 = self._conformer_bwd(dmem, self.buf("enc.x0", (B, T2, d)), "encoder", nle, H, hp["eunits"], hp["conformer_enc_kernel_size"],
+                                      hp["transformer_enc_dropout_rate"], hp["enc_positional_dropout_rate"], hp["enc_attn_dropout_rate"])
+            ops.scale_dropout(gx0, gte, math.sqrt(d), NO_DROP, self.named_drop("enc.posx", hp["enc_positional_dropout_rate"]))
+            nle = 0
+        else:
+            self._ln_bwd(dmem, self.enc_last, "encoder.after_norm", "enc.after", ge, dx_drop=gdf if nle > 0 else None,
+                         drop=sites[f"encoder.encoders.{nle - 1}.ff2"] if nle > 0 else NO_DROP)
         g = ge
-        for l in reversed(range(hp["elayers"])):
+        for l in reversed(range(nle)):
             p = f"encoder.encoders.{l}"
             xin = self.buf(f"encoder.encoders.{l - 1}.xout", (B, T2, d)) if l > 0 else self.buf("enc.x0", (B, T2, d))
             xm = self.buf(p + ".xmid", (B, T2, d))
@@ -787,7 +816,8 @@ class VTNEngine(EngineBase):
                              hp["idim"] - 1, 0, sites["enc.pe"])
             return
         delin = gte
-        ops.scaled_pe_bwd(g, self.pe(d, T2), delin, st.g("encoder.embed.out.1.alpha"), sites["enc.pe"])
+        if not conformer:
+            ops.scaled_pe_bwd(g, self.pe(d, T2), delin, st.g("encoder.embed.out.1.alpha"), sites["enc.pe"])
         y2 = self.buf("enc.y2", (B * T2 * F2, d))
         woutp = self.buf("w.outp", (d, F2, d))
         gwoutp = self._scratch("g.woutp", (d, F2 * d), _f32)
@@ -828,12 +858,13 @@ class VTNEngine(EngineBase):
         saved = self._site
         self._site = 0
         t: Dict[str, Drop] = {}
-        t["enc.pe"] = self.drop(hp["enc_positional_dropout_rate"])
-        for l in range(hp["elayers"]):
-            p = f"encoder.encoders.{l}"
-            t[p + ".sa_out"] = self.drop(hp["transformer_enc_dropout_rate"])
-            t[p + ".ff1"] = self.drop(hp["transformer_enc_dropout_rate"])
-            t[p + ".ff2"] = self.drop(hp["transformer_enc_dropout_rate"])
+        if hp["encoder_type"] != "conformer":           # the conformer blocks use name-keyed dropout sites (named_drop)
+            t["enc.pe"] = self.drop(hp["enc_positional_dropout_rate"])
+            for l in range(hp["elayers"]):
+                p = f"encoder.encoders.{l}"
+                t[p + ".sa_out"] = self.drop(hp["transformer_enc_dropout_rate"])
+                t[p + ".ff1"] = self.drop(hp["transformer_enc_dropout_rate"])
+                t[p + ".ff2"] = self.drop(hp["transformer_enc_dropout_rate"])
         for i in range(hp["dprenet_layers"]):
             self._site += 1
             pd = hp["dprenet_dropout_rate"]

@@ -559,6 +559,31 @@ def relshift_bwd(dS, dBD, T):
     return dBD
 
 
+def _legacy_shift(x):
+    """attention.py:138-157 on the last two dims of x (..., T, T)."""
+    zero_pad = torch.zeros((*x.shape[:-1], 1), dtype=x.dtype)
+    xp = torch.cat([zero_pad, x], dim=-1)
+    xp = xp.view(*x.shape[:-2], x.shape[-1] + 1, x.shape[-2])
+    return xp[..., 1:, :].reshape(x.shape)
+
+
+def relshift_legacy_add(S, BD, T):
+    bd = BD.permute(1, 0, 2, 3)[..., :T].contiguous()
+    S[..., :T] += _legacy_shift(bd).to(S.dtype)
+    return S
+
+
+def relshift_legacy_bwd(dS, dBD, T):
+    # adjoint of the (linear) shift through autograd on the same construction
+    B, H = dS.shape[0], dS.shape[1]
+    x = torch.zeros(B, H, T, T, dtype=torch.float64, requires_grad=True)
+    (_legacy_shift(x) * dS[..., :T].double()).sum().backward()
+    out = torch.zeros(B, H, T, dBD.shape[-1], dtype=dBD.dtype)
+    out[..., :T] = x.grad.to(dBD.dtype)
+    dBD.copy_(out.permute(1, 0, 2, 3))
+    return dBD
+
+
 def glu_fwd(x, y):
     C = y.shape[-1]
     xd = x.double().reshape(-1, 2 * C)

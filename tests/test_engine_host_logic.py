@@ -92,6 +92,35 @@ def test_reduction_factors_forward_and_gradients(monkeypatch, r):
     check_reduction_factor(eng, z, 1e-5, 2e-4)
 
 
+@pytest.mark.parametrize("rel", ["legacy", "latest"])
+def test_conformer_encoder_forward_and_gradients(monkeypatch, rel):
+    """VTN(encoder_type="conformer") (models/vtn.py:83-143) with the class-default legacy rel-pos attention and with
+    conformer_rel_pos_type="latest": outputs, losses, encoder attention maps, BatchNorm running statistics and every gradient vs
+    the live-reference dump; eval mode on the updated statistics."""
+    fake_ops.install(monkeypatch)
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", f"vtn_conformer_{rel}_tiny.npz"))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    eng = VTNEngine(dict(TINY_HP, **NO_DROPOUT, elayers=2, encoder_type="conformer", conformer_rel_pos_type=rel, enc_attn_dropout_rate=0.0),
+                    device="cpu", bf16=False)
+    assert set(eng.state_dict()) == set(sd)
+    eng.load_state_dict(sd)
+    check_conformer(eng, z, 1e-5, 2e-4)
+
+
+def check_conformer(eng, z, tol_out, tol_grad):
+    check_reduction_factor(eng, z, tol_out, tol_grad)
+    for k in [k for k in z.files if k.startswith("attn.encoder.")]:
+        assert np.abs(eng.attn[k[5:]].float().cpu().numpy() - z[k]).mean() <= 1e-3 if tol_out > 1e-5 else 1e-6, k
+    for k in [k for k in z.files if k.startswith("bn_after.")]:
+        np.testing.assert_allclose(eng.buffers[k[9:]].float().cpu().numpy(), z[k], rtol=1e-4, atol=1e-5)
+    eng.training = False
+    ilens, olens = z["ilens"].tolist(), z["olens"].tolist()
+    dev = eng.device
+    after_e, _, _ = eng.forward(torch.from_numpy(z["xs"])[:, :max(ilens)].contiguous().to(dev),
+                                torch.from_numpy(z["ys"])[:, :max(olens)].contiguous().to(dev), ilens, olens)
+    assert np.abs(after_e.float().cpu().numpy() - z["eval_after_outs"]).mean() <= tol_out
+
+
 def check_reduction_factor(eng, z, tol_out, tol_grad):
     after, before, logits, losses = run_step(eng, z)
     assert after.shape == z["after_outs"].shape
@@ -226,3 +255,39 @@ def test_tts_inference_matches_reference(monkeypatch):
         assert outs.shape == z["inf_outs"].shape and att.shape == z["inf_att_ws"].shape
         assert np.abs(outs.numpy() - z["inf_outs"]).mean() <= 1e-5 and np.abs(probs.numpy() - z["inf_probs"]).max() <= 1e-5
         assert np.abs(att.numpy() - z["inf_att_ws"]).max() <= 1e-5
+
+
+def test_conformer_dropin_matches_reference_registration(monkeypatch):
+    """seq2seq_vc_b200.VTN(encoder_type="conformer") registers the reference's parameters in the reference's ORDER (optimizer
+    state dicts are keyed by order) with its state-dict keys and shapes, loads the reference's state dict and reproduces its
+    forward through the drop-in path (CPU contracts)."""
+    from oracle import ref_shim
+
+    if not ref_shim.available():
+        pytest.skip("reference tree not present")
+    fake_ops.install(monkeypatch)
+    ref_shim.install()
+    from seq2seq_vc.models import VTN as RefVTN
+    from seq2seq_vc_b200 import VTN
+
+    kw = dict(TINY_HP, elayers=2, encoder_type="conformer", conformer_enc_kernel_size=7, dprenet_dropout_rate=0.0)
+    torch.manual_seed(3)
+    ref = RefVTN(**kw)
+    ref_shim.disable_dropout(ref)
+    ours = VTN(**kw, transformer_enc_dropout_rate=0.0, transformer_enc_positional_dropout_rate=0.0, transformer_enc_attn_dropout_rate=0.0)
+    assert [n for n, _ in ours.named_parameters()] == [n for n, _ in ref.named_parameters()]
+    assert {k: tuple(v.shape) for k, v in ours.state_dict().items()} == {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+    ours.load_state_dict(ref.state_dict())
+    ours.engine.hp.update({k: 0.0 for k in ours.engine.hp if "dropout" in k})
+    from oracle import vtn_oracle
+
+    xs, ilens, ys, labels, olens = vtn_oracle.synthetic_batch(2, 44, 30, ilens=[44, 37], olens=[30, 23], seed=5)
+    ref.train()
+    ours.train()
+    a = ref(xs, torch.tensor(ilens), ys, labels, torch.tensor(olens))
+    b = ours(xs, torch.tensor(ilens), ys, labels, torch.tensor(olens))
+    for i in range(3):
+        assert (a[i] - b[i]).abs().max().item() <= 2e-5
+    assert torch.equal(a[4], b[4]) and torch.equal(a[5], b[5])
+    with pytest.raises(NotImplementedError):
+        VTN(**dict(kw, conformer_self_attn_layer_type="selfattn"))

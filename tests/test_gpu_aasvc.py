@@ -86,6 +86,29 @@ def test_relshift_add_and_bwd(ops, dt, B, H, T):
     assert abs(float(lhs - rhs)) <= 1e-6 * max(1.0, abs(float(lhs)))
 
 
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,H,T", [(2, 2, 11), (1, 3, 64), (3, 2, 37)])
+def test_relshift_legacy_add_and_bwd(ops, dt, B, H, T):
+    """Legacy rel_shift (attention.py:138-157: pad, re-view, drop the first row -- rows wrap around) and its adjoint vs the
+    reference's construction itself (tests/fake_ops._legacy_shift) and vs each other (<shift(x), y> == <x, shift^T(y)>)."""
+    g = torch.Generator().manual_seed(T)
+    ld, ldb = (T + 7) // 8 * 8, (T + 7) // 8 * 8
+    S = torch.randn(B, H, T, ld, generator=g).to(dt)
+    BD = torch.randn(H, B, T, ldb, generator=g).to(dt)
+    ref = F.relshift_legacy_add(S.clone().float(), BD.float(), T)
+    got = ops.relshift_legacy_add(S.cuda(), BD.cuda(), T)
+    close(got[..., :T], ref[..., :T], tol(dt, 2), "relshift_legacy_add")
+    dS = torch.randn(B, H, T, ld, generator=g).to(dt)
+    dref = F.relshift_legacy_bwd(dS, torch.empty(H, B, T, ldb, dtype=dt), T)
+    dg = ops.relshift_legacy_bwd(dS.cuda(), torch.full((H, B, T, ldb), 7.0, dtype=dt, device="cuda"), T)
+    close(dg, dref, 0.0, "relshift_legacy_bwd")
+    sh = F.relshift_legacy_add(torch.zeros(B, H, T, ld, dtype=torch.float64), BD.double(), T)
+    lhs = (sh[..., :T] * dS[..., :T].double()).sum()
+    rhs = (BD.double()[..., :T] * dg.cpu().double()[..., :T]).sum()
+    assert abs(lhs - rhs) <= 1e-6 * max(1.0, abs(lhs))
+
+
+
 @pytest.mark.parametrize("dt", DT)
 @pytest.mark.parametrize("rows,C", [(50, 12), (333, 384)])
 def test_glu_swish_scale(ops, dt, rows, C):

@@ -85,6 +85,49 @@ def test_reduction_factors_golden_fp32(r, fp32_gemm):
     assert np.abs(att.cpu().numpy() - z["inf_att_ws"]).mean() <= 1e-3
 
 
+@pytest.mark.parametrize("fp32_gemm", ["simt", "tc"])
+@pytest.mark.parametrize("rel", ["legacy", "latest"])
+def test_conformer_encoder_golden_fp32(rel, fp32_gemm):
+    """VTN(encoder_type="conformer") (models/vtn.py:83-143) on the GPU vs the live-reference dumps: the class-default legacy
+    rel-pos attention (reversed 5000-row table, wrap-around rel_shift) and conformer_rel_pos_type="latest"; outputs, losses,
+    encoder attention maps, BatchNorm running statistics, every gradient, eval mode."""
+    import test_engine_host_logic as H
+    from seq2seq_vc_b200 import VTNEngine
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", f"vtn_conformer_{rel}_tiny.npz"))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    eng = VTNEngine(dict(TINY_HP, **NO_DROPOUT, elayers=2, encoder_type="conformer", conformer_rel_pos_type=rel, enc_attn_dropout_rate=0.0),
+                    device="cuda:0", bf16=False, fp32_gemm=fp32_gemm)
+    eng.load_state_dict(sd)
+    H.check_conformer(eng, z, 1e-4, 1e-3 if fp32_gemm == "simt" else 5e-3)
+
+
+def test_conformer_encoder_bf16_fused_step_trains_and_dropin():
+    """bf16 fused step (CUDA graphs) of the conformer-encoder VTN with dropout on: finite, decreasing loss; the drop-in module
+    trains through torch autograd and exposes the encoder's attention maps."""
+    from seq2seq_vc_b200 import VTN, VTNTrainStep
+
+    kw = dict(idim=80, odim=80, adim=64, aheads=4, elayers=2, dlayers=2, eunits=96, dunits=96, dprenet_units=32, postnet_chans=32,
+              encoder_type="conformer", conformer_enc_kernel_size=7, compute_dtype="bf16", device="cuda:0", seed=3)
+    model = VTN(**kw)
+    step = VTNTrainStep(model, lr=1e-3, warmup_steps=1, use_graph=True)
+    g = torch.Generator().manual_seed(5)
+    B, T, L = 4, 72, 54
+    xs, ys = torch.randn(B, T, 80, generator=g).cuda(), torch.randn(B, L, 80, generator=g).cuda()
+    ilens, olens = [72, 60, 51, 33], [54, 47, 38, 21]
+    labels = torch.zeros(B, L)
+    for b in range(B):
+        labels[b, olens[b] - 1:] = 1
+    hist = [step(xs, ilens, ys, labels.cuda(), olens).sum().item() for _ in range(25)]
+    assert np.isfinite(hist).all() and np.mean(hist[-5:]) < np.mean(hist[:5]), hist
+    m2 = VTN(**kw)
+    out = m2(xs, torch.tensor(ilens), ys, labels.cuda(), torch.tensor(olens))
+    (out[0].abs().mean() + out[2].abs().mean()).backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m2.parameters())
+    att = m2.encoder.encoders[1].self_attn.attn
+    assert att.shape == (B, 4, 17, 17) and torch.allclose(att[0].sum(-1), torch.ones(4, 17, device="cuda"), atol=2e-2)
+
+
 @pytest.mark.parametrize("r", [1, 4])
 def test_reduction_factors_bf16_fused_step_trains(r):
     """bf16 fused step (flash attention, grouped weight gradients, CUDA graphs) with r = 1 / 4 and ragged lengths: finite, decreasing loss."""

@@ -34,6 +34,34 @@ def test_vtn_oracle_forward_loss_grads(fixture, r):
         assert np.abs(g.numpy() - ref).max() <= 2e-4 * (np.abs(ref).max() + 1e-5) + 1e-7, k      # 1e-7: scalar sums (alpha) in another order
 
 
+@pytest.mark.parametrize("rel", ["legacy", "latest"])
+def test_vtn_conformer_oracle_forward_loss_grads(rel):
+    """VTN(encoder_type="conformer") (models/vtn.py:83-143): the class-default legacy rel-pos attention (reversed 5000-row table,
+    wrap-around rel_shift, attention.py:114-207) and conformer_rel_pos_type="latest", against the live-reference dumps."""
+    z = np.load(os.path.join(GOLD, f"vtn_conformer_{rel}_tiny.npz"))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    hp = dict(TINY_HP, elayers=2, encoder_type="conformer", conformer_rel_pos_type=rel)
+    args = (torch.from_numpy(z["xs"]), z["ilens"].tolist(), torch.from_numpy(z["ys"]), torch.from_numpy(z["labels"]), z["olens"].tolist())
+    bn = {}
+    out = vtn_oracle.vtn_forward(sd, hp, *args, training=True, bn_stats=bn)
+    for k in ("after_outs", "before_outs", "logits"):
+        assert np.abs(out[k].detach().numpy() - z[k]).max() <= 2e-5, k
+    for k in [k for k in z.files if k.startswith("attn.encoder.")]:
+        assert np.abs(out["attn"]["encoder." + k[len("attn.encoder."):]].detach().numpy() - z[k]).max() <= 1e-6, k
+    for i, a in enumerate(out["att_ws"]):
+        assert np.abs(a.detach().numpy() - z[f"att_ws.{i}"]).max() <= 1e-6
+    for k, v in bn.items():
+        assert np.abs(v.numpy() - z["bn_after." + k]).max() <= 1e-5, k
+    _, (l1, bce), grads = vtn_oracle.vtn_loss_and_grads(sd, hp, *args)
+    assert abs(float(l1) - float(z["l1_loss"])) <= 1e-6 and abs(float(bce) - float(z["bce_loss"])) <= 1e-6
+    gmax = max(np.abs(z[k]).max() for k in z.files if k.startswith("grad."))
+    for k, g in grads.items():
+        ref = z["grad." + k]
+        assert np.abs(g.numpy() - ref).max() <= 2e-4 * np.abs(ref).max() + 2e-6 * gmax, k
+    oute = vtn_oracle.vtn_forward({**sd, **{k[9:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("bn_after.")}}, hp, *args, training=False)
+    assert np.abs(oute["after_outs"].detach().numpy() - z["eval_after_outs"]).max() <= 2e-5
+
+
 def test_mas_oracle_matches_reference_numba():
     z = np.load(os.path.join(GOLD, "mas.npz"))
     keys = [k for k in z.files if k.startswith("lp.")]
