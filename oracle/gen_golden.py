@@ -104,6 +104,40 @@ def gen_vtn_rfactor():
         print(f"vtn_r{r}_tiny:", len(dump), "arrays", "out len", out[0].shape[1], "olens_out", out[5].tolist())
 
 
+def gen_vtn_convffn_tiny():
+    """VTN with the Transformer encoder's position-wise layer replaced by MultiLayeredConv1d / Conv1dLinear, kernel size 3
+    (models/vtn.py:116-117, modules/transformer/encoder.py:143-175, multi_layer_conv.py:12-108)."""
+    from seq2seq_vc.losses import Seq2SeqLoss
+    from seq2seq_vc.models import VTN
+
+    for tag, layer, seed in (("conv1d", "conv1d", 101), ("conv1d_linear", "conv1d-linear", 103)):
+        torch.manual_seed(seed)
+        model = VTN(dprenet_dropout_rate=0.0, positionwise_layer_type=layer, positionwise_conv_kernel_size=3, **dict(TINY_HP, elayers=2))
+        ref_shim.disable_dropout(model)
+        with torch.no_grad():
+            for n, p in model.named_parameters():
+                if n.endswith("alpha"):
+                    p.fill_(0.7 if "encoder" in n else 1.3)
+                elif p.dim() == 1 and ("norm" in n or ".1." in n):
+                    p.add_(0.1 * torch.randn_like(p))
+        model.train()
+        sd0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        xs, ilens, ys, labels, olens = vtn_oracle.synthetic_batch(3, 52, 37, ilens=[52, 45, 31], olens=[37, 30, 21], seed=seed)
+        out = model(xs, torch.tensor(ilens), ys, labels, torch.tensor(olens))
+        l1, bce = Seq2SeqLoss()(*out[:6])
+        (l1 + bce).backward()
+        dump = {"sd." + k: v.numpy() for k, v in sd0.items()}
+        dump.update({"grad." + k: p.grad.numpy() for k, p in model.named_parameters()})
+        dump.update(xs=xs.numpy(), ilens=np.array(ilens), ys=ys.numpy(), labels=labels.numpy(), olens=np.array(olens),
+                    after_outs=out[0].detach().numpy(), before_outs=out[1].detach().numpy(), logits=out[2].detach().numpy(),
+                    ys_out=out[3].numpy(), labels_out=out[4].numpy(), olens_out=out[5].numpy(), ilens_ds_st=out[6][1].numpy(),
+                    olens_in=out[6][2].numpy(), l1_loss=l1.detach().numpy(), bce_loss=bce.detach().numpy())
+        for i, a in enumerate(out[6][0]):
+            dump[f"att_ws.{i}"] = a.detach().numpy()
+        np.savez_compressed(os.path.join(GOLDEN, f"vtn_{tag}_k3_tiny.npz"), **dump)
+        print(f"vtn_{tag}_k3_tiny:", len(dump), "arrays")
+
+
 def gen_vtn_conformer_tiny():
     """VTN(encoder_type="conformer") (models/vtn.py:83-143): Conv2dSubsampling + LegacyRelPositionalEncoding, macaron conformer
     blocks with LegacyRelPositionMultiHeadedAttention and the convolution module (the class defaults), Transformer decoder;
@@ -143,6 +177,9 @@ def gen_vtn_conformer_tiny():
         with torch.no_grad():
             oute = model(xs, torch.tensor(ilens), ys, labels, torch.tensor(olens))
         dump["eval_after_outs"] = oute[0].numpy()
+        with torch.no_grad():               # autoregressive inference on the updated running statistics (models/vtn.py:302-394)
+            io, ip, ia = model.inference(xs[0, :ilens[0]], dict(threshold=0.9999, minlenratio=0.0, maxlenratio=1.3))
+        dump.update(inf_outs=io.numpy(), inf_probs=ip.numpy(), inf_att_ws=ia.numpy())
         np.savez_compressed(os.path.join(GOLDEN, f"vtn_conformer_{tag}_tiny.npz"), **dump)
         print(f"vtn_conformer_{tag}_tiny:", len(dump), "arrays")
 
@@ -438,7 +475,7 @@ if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     import sys
 
-    gens = dict(vtn_tiny=gen_vtn_tiny, vtn_rfactor=gen_vtn_rfactor, vtn_conformer_tiny=gen_vtn_conformer_tiny, tts_tiny=gen_tts_tiny, aasvc_tiny=gen_aasvc_tiny, aasvc_conv1d_tiny=gen_aasvc_conv1d_tiny, aasvc_conv1d_k3_tiny=gen_aasvc_conv1d_k3_tiny,
+    gens = dict(vtn_tiny=gen_vtn_tiny, vtn_rfactor=gen_vtn_rfactor, vtn_conformer_tiny=gen_vtn_conformer_tiny, vtn_convffn_tiny=gen_vtn_convffn_tiny, tts_tiny=gen_tts_tiny, aasvc_tiny=gen_aasvc_tiny, aasvc_conv1d_tiny=gen_aasvc_conv1d_tiny, aasvc_conv1d_k3_tiny=gen_aasvc_conv1d_k3_tiny,
                 aasvc_conv1d_linear_k3_tiny=gen_aasvc_conv1d_linear_k3_tiny,
                 mas=gen_mas, kats=gen_kats, sdp_tiny=gen_sdp_tiny)
     for name in (sys.argv[1:] or list(gens)):      # e.g. `python oracle/gen_golden.py aasvc_conv1d_tiny` adds one fixture

@@ -85,7 +85,16 @@ def attention(sd, prefix, q_in, kv_in, mask, n_head, store: Dict[str, torch.Tens
 
 
 def feed_forward(sd, prefix, x):
-    """PositionwiseFeedForward (ReLU), modules/transformer/positionwise_feed_forward.py:12-32."""
+    """PositionwiseFeedForward (ReLU), modules/transformer/positionwise_feed_forward.py:12-32; told apart by the weight rank:
+    MultiLayeredConv1d (Conv1d(k) -> ReLU -> Conv1d(k)) and Conv1dLinear (Conv1d(k) -> ReLU -> Linear) over time with zero padding
+    (k-1)//2 (modules/transformer/multi_layer_conv.py:12-108)."""
+    w1 = sd[prefix + ".w_1.weight"]
+    if w1.dim() == 3:
+        k = w1.shape[2]
+        h = torch.relu(F.conv1d(x.transpose(1, 2), w1, sd[prefix + ".w_1.bias"], padding=(k - 1) // 2))
+        if sd[prefix + ".w_2.weight"].dim() == 2:
+            return linear(h.transpose(1, 2), sd, prefix + ".w_2")
+        return F.conv1d(h, sd[prefix + ".w_2.weight"], sd[prefix + ".w_2.bias"], padding=(k - 1) // 2).transpose(1, 2)
     return linear(torch.relu(linear(x, sd, prefix + ".w_1")), sd, prefix + ".w_2")
 
 
@@ -470,7 +479,7 @@ def vtn_inference(sd, hp, x, threshold=0.5, minlenratio=0.0, maxlenratio=10.0, t
     else:
         xs = x.unsqueeze(0)
         T = xs.shape[1]
-        hs, _ = encoder(sd, hp, xs, torch.ones(1, 1, T, dtype=torch.bool))
+        hs, _ = encoder(sd, hp, xs, torch.ones(1, 1, T, dtype=torch.bool), training=False)      # model.eval(): running BatchNorm statistics
     T2 = hs.shape[1]
     mem_mask = torch.ones(1, 1, T2, dtype=torch.bool)
     maxlen, minlen = int(T2 * maxlenratio / r), int(T2 * minlenratio / r)

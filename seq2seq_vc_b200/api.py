@@ -226,8 +226,8 @@ class VTN(torch.nn.Module):
                 unsupported.append("conformer without macaron / CNN module, zero_triu")
             if positionwise_layer_type not in ("linear", "conv1d", "conv1d-linear"):
                 unsupported.append("positionwise_layer_type not in ('linear', 'conv1d', 'conv1d-linear')")
-        elif positionwise_layer_type != "linear":
-            unsupported.append("positionwise_layer_type != 'linear' with the transformer encoder")
+        elif positionwise_layer_type not in ("linear", "conv1d", "conv1d-linear") or getattr(self, "_encoder_input", "conv2d") == "embed":
+            unsupported.append("positionwise_layer_type not in ('linear', 'conv1d', 'conv1d-linear')")
         if not use_batch_norm or not encoder_normalize_before or decoder_normalize_before:
             unsupported.append("non-default normalisation wiring")
         if encoder_concat_after or decoder_concat_after or spk_embed_dim is not None:
@@ -253,6 +253,9 @@ class VTN(torch.nn.Module):
                                   decoder_reduction_factor=decoder_reduction_factor,
                                   initial_encoder_alpha=initial_encoder_alpha, initial_decoder_alpha=initial_decoder_alpha,
                                   encoder_input=getattr(self, "_encoder_input", "conv2d"))
+        if not conformer and positionwise_layer_type != "linear":     # the Transformer ENCODER only (the decoder is built without it)
+            self.hp.update(positionwise_layer_type=positionwise_layer_type, positionwise_conv_kernel_size=positionwise_conv_kernel_size)
+            default_hparams(**self.hp)
         if conformer:       # models/vtn.py:122-143: the conformer encoder takes the positional / attention dropout rates of the constructor
             self.hp.update(encoder_type="conformer", conformer_enc_kernel_size=conformer_enc_kernel_size,
                            conformer_rel_pos_type="legacy" if conformer_self_attn_layer_type == "legacy_rel_selfattn" else "latest",

@@ -166,8 +166,8 @@ class ConformerBlocks:
         t = self.hp["positionwise_layer_type"]
         return t == "conv1d-linear" or (t == "conv1d" and self.hp.get("positionwise_conv_kernel_size", 1) > 1)
 
-    def _ffn_conv_fwd(self, x, n, p, ff, tag, U, rate, out):
-        """out = x + 0.5 * dropout(w_2(dropout(relu(w_1 n)))) with w_1 a Conv1d(k) over time (zero padding (k-1)/2 per utterance
+    def _ffn_conv_fwd(self, x, n, p, ff, tag, U, rate, out, scale: float = 0.5):
+        """out = x + scale * dropout(w_2(dropout(relu(w_1 n)))) (scale 0.5: conformer block, 1: Transformer encoder layer) with w_1 a Conv1d(k) over time (zero padding (k-1)/2 per utterance
         row, padded frames take part like any other frame: the reference does not mask inside the block) and w_2 a Conv1d(k)
         ("conv1d") or a Linear ("conv1d-linear").  The convolutions are taps-GEMMs over zero-haloed channels-last rows."""
         st = self.store
@@ -188,19 +188,26 @@ class ConformerBlocks:
             hu = self.buf(tag + ".hu", (B, T, U))
             ops.unpad_rows(h, hu, halo)
             self._lin_fwd(hu.view(B * T, U), self.W(f"{p}.{ff}.w_2.weight"), st.p(f"{p}.{ff}.w_2.bias"), y.view(B * T, dm))
-        ops.scale_dropout(y, y, 0.5, self.named_drop(tag + ".d2", rate))
+        ops.scale_dropout(y, y, scale, self.named_drop(tag + ".d2", rate))
         ops.add(x, y, out)
         return out
 
     def _ffn_conv_bwd(self, g, x, n, p, ff, tag, U, rate, gout):
+        dn = self._ffn_conv_bwd_core(g, n, p, ff, tag, U, rate)
+        norm = "norm_ff_macaron" if ff == "feed_forward_macaron" else "norm_ff"
+        self._ln_bwd(dn, x, f"{p}.{norm}", f"{tag}.ln", gout, dres=g)
+        return gout
+
+    def _ffn_conv_bwd_core(self, g, n, p, ff, tag, U, rate, scale: float = 0.5, dn=None):
+        """g = d(out) -> d(n) (gradient at the LayerNorm output that feeds w_1); accumulates the parameter gradients."""
         st = self.store
-        B, T, dm = x.shape
+        B, T, dm = n.shape
         halo = (self.hp["positionwise_conv_kernel_size"] - 1) // 2
         Lp = T + 2 * halo
         d1 = self.named_drop(tag + ".d1", rate)
         h = self.buf(tag + (".hd" if d1.p > 0.0 else ".c1.z"), (B, Lp, U))            # dropout(relu(.)): zero where cut or dropped
         dy = self._scratch("cf.dy", (B, T, dm))
-        ops.scale_dropout(g, dy, 0.5, self.named_drop(tag + ".d2", rate))
+        ops.scale_dropout(g, dy, scale, self.named_drop(tag + ".d2", rate))
         dh = self._scratch("cf.dhp", (B, Lp, U))
         if self.hp["positionwise_layer_type"] == "conv1d":
             dz2 = self._scratch("cf.dz2", (B, Lp, dm))
@@ -216,11 +223,10 @@ class ConformerBlocks:
         npad = self.buf(tag + ".npad", (B, Lp, dm))
         dnp = self._scratch("cf.dnp", (B, Lp, dm))
         self._conv1d_bwd(dh, npad, f"{p}.{ff}.w_1", T, tag + ".c1", dnp)
-        dn = self._scratch("cf.dn", (B, T, dm))
+        if dn is None:
+            dn = self._scratch("cf.dn", (B, T, dm))
         ops.unpad_rows(dnp, dn, halo)
-        norm = "norm_ff_macaron" if ff == "feed_forward_macaron" else "norm_ff"
-        self._ln_bwd(dn, x, f"{p}.{norm}", f"{tag}.ln", gout, dres=g)
-        return gout
+        return dn
 
     def _relattn_fwd(self, x, p, tag, H, klens, pos_emb, rate, attn_rate, out):
         """out = x + dropout(RelPositionMultiHeadedAttention(LN(x)))   (encoder_layer.py:125-150, attention.py:262-305)."""

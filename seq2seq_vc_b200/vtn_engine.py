@@ -54,6 +54,10 @@ def default_hparams(**over) -> dict:
         raise NotImplementedError(f"encoder_type {hp['encoder_type']!r}")
     if hp["encoder_type"] == "conformer" and hp["encoder_input"] != "conv2d":
         raise NotImplementedError("the conformer encoder takes the Conv2dSubsampling input layer (models/vtn.py:129)")
+    if hp["positionwise_layer_type"] not in ("linear", "conv1d", "conv1d-linear"):
+        raise NotImplementedError("Support only linear or conv1d.")
+    if hp["positionwise_layer_type"] != "linear" and (hp["positionwise_conv_kernel_size"] % 2 != 1 or hp["encoder_input"] == "embed"):
+        raise NotImplementedError("conv position-wise layers: odd kernel sizes, VTN encoders only (TransformerTTS builds none)")
     return hp
 
 
@@ -95,8 +99,15 @@ def param_groups(hp: dict) -> List[List[Tuple[str, Tuple[int, ...]]]]:
         for l in range(hp["elayers"]):
             p = f"encoder.encoders.{l}"
             mha(p + ".self_attn", ("linear_q", "linear_k", "linear_v"))
-            lin(p + ".feed_forward.w_1", hp["eunits"], d)
-            lin(p + ".feed_forward.w_2", d, hp["eunits"])
+            if hp.get("positionwise_layer_type", "linear") != "linear":     # MultiLayeredConv1d / Conv1dLinear (multi_layer_conv.py:12-108)
+                pk = hp.get("positionwise_conv_kernel_size", 1)
+                g.append([(p + ".feed_forward.w_1.weight", (hp["eunits"], d, pk))])
+                g.append([(p + ".feed_forward.w_1.bias", (hp["eunits"],))])
+                g.append([(p + ".feed_forward.w_2.weight", (d, hp["eunits"], pk) if hp["positionwise_layer_type"] == "conv1d" else (d, hp["eunits"]))])
+                g.append([(p + ".feed_forward.w_2.bias", (d,))])
+            else:
+                lin(p + ".feed_forward.w_1", hp["eunits"], d)
+                lin(p + ".feed_forward.w_2", d, hp["eunits"])
             ln(p + ".norm1", d)
             ln(p + ".norm2", d)
         ln("encoder.after_norm", d)
@@ -240,12 +251,15 @@ class VTNEngine(ConformerBlocks, EngineBase):
             self._lin_fwd(ctx.view(B * T2, d), self.W(p + ".self_attn.linear_out.weight"), st.p(p + ".self_attn.linear_out.bias"),
                           xm.view(B * T2, d), drop=self.drop(pe_), residual=x.view(B * T2, d))
             n2 = self._ln_fwd(xm, p + ".norm2", p + ".ln2")
-            h = self.buf(p + ".ffh", (B * T2, hp["eunits"]))
-            self._lin_fwd(n2.view(B * T2, d), self.W(p + ".feed_forward.w_1.weight"), st.p(p + ".feed_forward.w_1.bias"), h,
-                          relu=True, drop=self.drop(pe_))
             xn = self.buf(p + ".xout", (B, T2, d))
-            self._lin_fwd(h, self.W(p + ".feed_forward.w_2.weight"), st.p(p + ".feed_forward.w_2.bias"), xn.view(B * T2, d),
-                          drop=self.drop(pe_), residual=xm.view(B * T2, d))
+            if hp["positionwise_layer_type"] != "linear":       # MultiLayeredConv1d / Conv1dLinear: name-keyed dropout sites
+                self._ffn_conv_fwd(xm, n2, p, "feed_forward", p + ".ffc", hp["eunits"], pe_, xn, scale=1.0)
+            else:
+                h = self.buf(p + ".ffh", (B * T2, hp["eunits"]))
+                self._lin_fwd(n2.view(B * T2, d), self.W(p + ".feed_forward.w_1.weight"), st.p(p + ".feed_forward.w_1.bias"), h,
+                              relu=True, drop=self.drop(pe_))
+                self._lin_fwd(h, self.W(p + ".feed_forward.w_2.weight"), st.p(p + ".feed_forward.w_2.bias"), xn.view(B * T2, d),
+                              drop=self.drop(pe_), residual=xm.view(B * T2, d))
             x = xn
         self.enc_last = x
         mem = self._ln_fwd(x, "encoder.after_norm", "enc.after")
@@ -782,15 +796,18 @@ class VTNEngine(ConformerBlocks, EngineBase):
             xm = self.buf(p + ".xmid", (B, T2, d))
             n1 = self.buf(p + ".ln1.y", (B, T2, d))
             n2 = self.buf(p + ".ln2.y", (B, T2, d))
-            h = self.buf(p + ".ffh", (B * T2, hp["eunits"]))
             self._begin_defer()
-            df = gdf.view(B * T2, d) if sites[p + ".ff2"].p > 0.0 else g.view(B * T2, d)
-            dh = self._scratch("g.effh", (B * T2, hp["eunits"]))
-            self._lin_bwd(df, h, self.W(p + ".feed_forward.w_2.weight"), st.g(p + ".feed_forward.w_2.weight"),
-                          st.g(p + ".feed_forward.w_2.bias"), dx=dh, dx_gate=h, dx_gate_scale=sites[p + ".ff1"].scale)
             dn2 = gte
-            self._lin_bwd(dh, n2.view(B * T2, d), self.W(p + ".feed_forward.w_1.weight"), st.g(p + ".feed_forward.w_1.weight"),
-                          st.g(p + ".feed_forward.w_1.bias"), dx=dn2.view(B * T2, d))
+            if hp["positionwise_layer_type"] != "linear":
+                self._ffn_conv_bwd_core(g, n2, p, "feed_forward", p + ".ffc", hp["eunits"], hp["transformer_enc_dropout_rate"], scale=1.0, dn=dn2)
+            else:
+                h = self.buf(p + ".ffh", (B * T2, hp["eunits"]))
+                df = gdf.view(B * T2, d) if sites[p + ".ff2"].p > 0.0 else g.view(B * T2, d)
+                dh = self._scratch("g.effh", (B * T2, hp["eunits"]))
+                self._lin_bwd(df, h, self.W(p + ".feed_forward.w_2.weight"), st.g(p + ".feed_forward.w_2.weight"),
+                              st.g(p + ".feed_forward.w_2.bias"), dx=dh, dx_gate=h, dx_gate_scale=sites[p + ".ff1"].scale)
+                self._lin_bwd(dh, n2.view(B * T2, d), self.W(p + ".feed_forward.w_1.weight"), st.g(p + ".feed_forward.w_1.weight"),
+                              st.g(p + ".feed_forward.w_1.bias"), dx=dn2.view(B * T2, d))
             gm = self._scratch("g.enc_d", (B, T2, d))
             self._ln_bwd(dn2, xm, p + ".norm2", p + ".ln2", gm, dres=g, dx_drop=gde.view(B, T2, d), drop=sites[p + ".sa_out"])   # g_mid = g + LN2'(dn2)
             do = gde if sites[p + ".sa_out"].p > 0.0 else gm.view(B * T2, d)
@@ -863,8 +880,9 @@ class VTNEngine(ConformerBlocks, EngineBase):
             for l in range(hp["elayers"]):
                 p = f"encoder.encoders.{l}"
                 t[p + ".sa_out"] = self.drop(hp["transformer_enc_dropout_rate"])
-                t[p + ".ff1"] = self.drop(hp["transformer_enc_dropout_rate"])
-                t[p + ".ff2"] = self.drop(hp["transformer_enc_dropout_rate"])
+                conv_ffn = hp["positionwise_layer_type"] != "linear"          # conv position-wise layers use name-keyed sites
+                t[p + ".ff1"] = NO_DROP if conv_ffn else self.drop(hp["transformer_enc_dropout_rate"])
+                t[p + ".ff2"] = NO_DROP if conv_ffn else self.drop(hp["transformer_enc_dropout_rate"])
         for i in range(hp["dprenet_layers"]):
             self._site += 1
             pd = hp["dprenet_dropout_rate"]

@@ -92,6 +92,18 @@ def test_reduction_factors_forward_and_gradients(monkeypatch, r):
     check_reduction_factor(eng, z, 1e-5, 2e-4)
 
 
+@pytest.mark.parametrize("layer", ["conv1d", "conv1d-linear"])
+def test_conv_positionwise_encoder_forward_and_gradients(monkeypatch, layer):
+    """Transformer-encoder VTN with MultiLayeredConv1d / Conv1dLinear (kernel size 3) position-wise layers vs the live-reference dump."""
+    fake_ops.install(monkeypatch)
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", f"vtn_{layer.replace('-', '_')}_k3_tiny.npz"))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    eng = VTNEngine(dict(TINY_HP, **NO_DROPOUT, elayers=2, positionwise_layer_type=layer, positionwise_conv_kernel_size=3), device="cpu", bf16=False)
+    assert set(eng.state_dict()) == set(sd)
+    eng.load_state_dict(sd)
+    check_reduction_factor(eng, z, 1e-5, 2e-4)
+
+
 @pytest.mark.parametrize("rel", ["legacy", "latest"])
 def test_conformer_encoder_forward_and_gradients(monkeypatch, rel):
     """VTN(encoder_type="conformer") (models/vtn.py:83-143) with the class-default legacy rel-pos attention and with
@@ -291,3 +303,33 @@ def test_conformer_dropin_matches_reference_registration(monkeypatch):
     assert torch.equal(a[4], b[4]) and torch.equal(a[5], b[5])
     with pytest.raises(NotImplementedError):
         VTN(**dict(kw, conformer_self_attn_layer_type="selfattn"))
+
+
+@pytest.mark.parametrize("rel", ["legacy", "latest"])
+def test_conformer_encoder_inference_matches_oracle(monkeypatch, rel):
+    """Autoregressive inference (models/vtn.py:302-394) with the conformer encoder: the oracle vs the live-reference dump, then the
+    KV-cache decode and the prefix-recomputing cross-check vs the oracle."""
+    from oracle import vtn_oracle
+
+    fake_ops.install(monkeypatch)
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", f"vtn_conformer_{rel}_tiny.npz"))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    hp = dict(TINY_HP, elayers=2, encoder_type="conformer", conformer_rel_pos_type=rel)
+    eng = VTNEngine(dict(hp, **NO_DROPOUT, enc_attn_dropout_rate=0.0), device="cpu", bf16=False)
+    eng.load_state_dict(sd)
+    il = int(z["ilens"][0])
+    x = torch.from_numpy(z["xs"])[0, :il]
+    sd_eval = {**sd, **{k[9:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("bn_after.")}}     # the dump ran after a training step
+    eng.load_state_dict(sd_eval)
+    for k in z.files:
+        if k.startswith("bn_after."):
+            eng.buffers[k[9:]].copy_(torch.from_numpy(z[k]))
+    ref_o, ref_p, ref_a = vtn_oracle.vtn_inference(sd_eval, vtn_oracle.default_hparams(**hp), x, threshold=0.9999, minlenratio=0.0, maxlenratio=1.3)
+    assert ref_o.shape == z["inf_outs"].shape                                 # oracle == live reference
+    assert np.abs(ref_o.numpy() - z["inf_outs"]).mean() <= 1e-5 and np.abs(ref_p.numpy() - z["inf_probs"]).mean() <= 1e-5
+    assert np.abs(ref_a.numpy() - z["inf_att_ws"]).mean() <= 1e-6
+    for fn in (eng.inference, eng.inference_recompute):
+        outs, probs, att = fn(x, threshold=0.9999, minlenratio=0.0, maxlenratio=1.3)
+        assert outs.shape == ref_o.shape
+        assert (outs - ref_o).abs().mean().item() <= 1e-5 and (probs - ref_p).abs().mean().item() <= 1e-5
+        assert (att - ref_a).abs().mean().item() <= 1e-6

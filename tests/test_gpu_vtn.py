@@ -85,6 +85,29 @@ def test_reduction_factors_golden_fp32(r, fp32_gemm):
     assert np.abs(att.cpu().numpy() - z["inf_att_ws"]).mean() <= 1e-3
 
 
+@pytest.mark.parametrize("layer", ["conv1d", "conv1d-linear"])
+def test_conv_positionwise_encoder_golden_fp32_and_bf16_trains(layer):
+    """Transformer-encoder VTN with MultiLayeredConv1d / Conv1dLinear (kernel size 3) position-wise layers on the GPU vs the
+    live-reference dump (fp32-accurate tcgen05 mode); the bf16 fused step with dropout on trains."""
+    import test_engine_host_logic as H
+    from seq2seq_vc_b200 import VTN, VTNEngine, VTNTrainStep
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", f"vtn_{layer.replace('-', '_')}_k3_tiny.npz"))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    eng = VTNEngine(dict(TINY_HP, **NO_DROPOUT, elayers=2, positionwise_layer_type=layer, positionwise_conv_kernel_size=3), device="cuda:0", bf16=False)
+    eng.load_state_dict(sd)
+    H.check_reduction_factor(eng, z, 1e-4, 5e-3)
+    model = VTN(idim=80, odim=80, adim=64, aheads=4, elayers=2, dlayers=1, eunits=96, dunits=96, dprenet_units=32, postnet_chans=32,
+                positionwise_layer_type=layer, positionwise_conv_kernel_size=3, compute_dtype="bf16", device="cuda:0", seed=3)
+    step = VTNTrainStep(model, lr=1e-3, warmup_steps=1, use_graph=True)
+    g = torch.Generator().manual_seed(5)
+    xs, ys = torch.randn(3, 72, 80, generator=g).cuda(), torch.randn(3, 54, 80, generator=g).cuda()
+    labels = torch.zeros(3, 54)
+    labels[:, 53:] = 1
+    hist = [step(xs, [72, 60, 51], ys, labels.cuda(), [54, 47, 38]).sum().item() for _ in range(25)]
+    assert np.isfinite(hist).all() and np.mean(hist[-5:]) < np.mean(hist[:5]), hist
+
+
 @pytest.mark.parametrize("fp32_gemm", ["simt", "tc"])
 @pytest.mark.parametrize("rel", ["legacy", "latest"])
 def test_conformer_encoder_golden_fp32(rel, fp32_gemm):
@@ -100,6 +123,11 @@ def test_conformer_encoder_golden_fp32(rel, fp32_gemm):
                     device="cuda:0", bf16=False, fp32_gemm=fp32_gemm)
     eng.load_state_dict(sd)
     H.check_conformer(eng, z, 1e-4, 1e-3 if fp32_gemm == "simt" else 5e-3)
+    il = int(z["ilens"][0])            # autoregressive inference on the running statistics the training step above left behind
+    outs, probs, att = eng.inference(torch.from_numpy(z["xs"])[0, :il].cuda(), threshold=0.9999, minlenratio=0.0, maxlenratio=1.3)
+    assert outs.shape == z["inf_outs"].shape
+    assert np.abs(outs.cpu().numpy() - z["inf_outs"]).mean() <= 1e-4 and np.abs(probs.cpu().numpy() - z["inf_probs"]).mean() <= 1e-4
+    assert np.abs(att.cpu().numpy() - z["inf_att_ws"]).mean() <= 1e-3
 
 
 def test_conformer_encoder_bf16_fused_step_trains_and_dropin():

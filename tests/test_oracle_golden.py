@@ -34,6 +34,22 @@ def test_vtn_oracle_forward_loss_grads(fixture, r):
         assert np.abs(g.numpy() - ref).max() <= 2e-4 * (np.abs(ref).max() + 1e-5) + 1e-7, k      # 1e-7: scalar sums (alpha) in another order
 
 
+@pytest.mark.parametrize("layer", ["conv1d", "conv1d_linear"])
+def test_vtn_conv_positionwise_oracle_forward_loss_grads(layer):
+    """VTN whose Transformer encoder uses MultiLayeredConv1d / Conv1dLinear (kernel size 3) position-wise layers
+    (modules/transformer/encoder.py:143-175, multi_layer_conv.py:12-108) against the live-reference dumps."""
+    z = np.load(os.path.join(GOLD, f"vtn_{layer}_k3_tiny.npz"))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    out, (l1, bce), grads = vtn_oracle.vtn_loss_and_grads(sd, dict(TINY_HP, elayers=2), torch.from_numpy(z["xs"]), z["ilens"].tolist(),
+                                                          torch.from_numpy(z["ys"]), torch.from_numpy(z["labels"]), z["olens"].tolist())
+    for k in ("after_outs", "before_outs", "logits"):
+        assert np.abs(out[k].detach().numpy() - z[k]).max() <= 2e-5, k
+    assert abs(float(l1) - float(z["l1_loss"])) <= 1e-6 and abs(float(bce) - float(z["bce_loss"])) <= 1e-6
+    for k, g in grads.items():
+        ref = z["grad." + k]
+        assert np.abs(g.numpy() - ref).max() <= 2e-4 * (np.abs(ref).max() + 1e-5) + 1e-7, k
+
+
 @pytest.mark.parametrize("rel", ["legacy", "latest"])
 def test_vtn_conformer_oracle_forward_loss_grads(rel):
     """VTN(encoder_type="conformer") (models/vtn.py:83-143): the class-default legacy rel-pos attention (reversed 5000-row table,
