@@ -226,7 +226,7 @@ class VTN(torch.nn.Module):
                 unsupported.append("conformer without macaron / CNN module, zero_triu")
             if positionwise_layer_type not in ("linear", "conv1d", "conv1d-linear"):
                 unsupported.append("positionwise_layer_type not in ('linear', 'conv1d', 'conv1d-linear')")
-        elif positionwise_layer_type not in ("linear", "conv1d", "conv1d-linear") or getattr(self, "_encoder_input", "conv2d") == "embed":
+        elif positionwise_layer_type not in ("linear", "conv1d", "conv1d-linear"):
             unsupported.append("positionwise_layer_type not in ('linear', 'conv1d', 'conv1d-linear')")
         if not use_batch_norm or not encoder_normalize_before or decoder_normalize_before:
             unsupported.append("non-default normalisation wiring")
