@@ -28,31 +28,6 @@ __host__ __device__ constexpr int brev5(int x) {
     return ((x & 1) << 4) | ((x & 2) << 2) | (x & 4) | ((x & 8) >> 2) | ((x & 16) >> 4);
 }
 
-// Packed fp32 pairs (sm_100 FADD2 / FMUL2 / FFMA2): a complex value is one 64-bit register pair, a complex add is one
-// instruction and a multiply by a constant twiddle is two (ptxas folds the component swap / sign into operand modifiers).
-typedef unsigned long long u64;
-__device__ __forceinline__ u64 pk2(float x, float y) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(x), "f"(y)); return r; }
-__device__ __forceinline__ float2 upk2(u64 r) { float2 d; asm("mov.b64 {%0,%1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(r)); return d; }
-__device__ __forceinline__ float2 add2(float2 a, float2 b) {
-    u64 r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a.x, a.y)), "l"(pk2(b.x, b.y)));
-    return upk2(r);
-}
-__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
-    u64 r;
-    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a.x, a.y)), "l"(pk2(b.x, b.y)));
-    return upk2(r);
-}
-__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
-    u64 r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a.x, a.y)), "l"(pk2(b.x, b.y)));
-    return upk2(r);
-}
-__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
-    u64 r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk2(a.x, a.y)), "l"(pk2(b.x, b.y)), "l"(pk2(c.x, c.y)));
-    return upk2(r);
-}
 // d * (c + i s) = (d.x c - d.y s, d.y c + d.x s)
 __device__ __forceinline__ float2 cmul2(float2 d, float c, float s) {
     return fma2(make_float2(d.y, d.x), make_float2(-s, s), mul2(d, make_float2(c, c)));

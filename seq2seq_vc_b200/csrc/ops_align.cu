@@ -28,6 +28,10 @@ __global__ void __launch_bounds__(256) pairdist_kernel(const T* __restrict__ f, 
     const int tx = tid & 15, ty = tid >> 4;
     const T* fb = f + (long)b * Tf * C;
     const T* xb = x + (long)b * Tt * C;
+    // thread (tx, ty) owns the 4 x 4 block of frames ty * 4 + i and tokens tx * 4 + j.  Measured and rejected (C3 shape, 1.42 ms
+    // for this form): an interleaved mapping (frames ty + 16 i, tokens tx + 16 j) that removes the 2-way bank conflict on the
+    // token tile -- 1.51 ms; the same with packed FADD2 / FFMA2 accumulators -- 1.58 ms (124 registers, and the packed ops do not
+    // raise the fp32 pipe's throughput).
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -253,6 +257,95 @@ __global__ void __launch_bounds__(1024) forward_sum_kernel(const float* __restri
     }
 }
 
+// Same recursions with the alpha and the beta sweep running CONCURRENTLY in one CTA (threads [0, SH) walk frames 0 .. T-1,
+// threads [SH, 2 SH) walk frames T-1 .. 0, one __syncthreads per frame serves both), each sweep fetching its next frame's
+// emissions one step ahead: the serial chain is T steps instead of 2 T.  Beta is parked in the gradient block and a final
+// fully parallel pass turns (alpha, beta) into torch's ctc_loss gradient in place.  Used when 2 SH <= 1024 and a gradient is wanted.
+__global__ void __launch_bounds__(1024) forward_sum_par_kernel(const float* __restrict__ logp, const float* __restrict__ prior,
+                                                               const int32_t* __restrict__ text_lens,
+                                                               const int32_t* __restrict__ feats_lens, int B, int Tf, int Tt, int SH,
+                                                               float blank_logp, float* __restrict__ alpha_ws, float* __restrict__ loss,
+                                                               float* __restrict__ dlogp, float gscale) {
+    extern __shared__ float sm[];                 // 4 x (Smax + 4): alpha cur / next, beta cur / next, two -inf guards in front of each
+    __shared__ float s_ll;
+    const int b = blockIdx.x;
+    const bool beta_half = (int)threadIdx.x >= SH;
+    const int s = beta_half ? (int)threadIdx.x - SH : (int)threadIdx.x;
+    int N = text_lens[b], T = feats_lens[b];
+    N = N < 0 ? 0 : (N > Tt ? Tt : N);
+    T = T < 0 ? 0 : (T > Tf ? Tf : T);
+    const int S = 2 * N + 1;
+    const int Smax = 2 * Tt + 1;
+    const int stride = Smax + 4;
+    float* cur = sm + (beta_half ? 2 * stride : 0) + 2;
+    float* nxt = cur + stride;
+    const float* lp_b = logp + (long)b * Tf * Tt;
+    const float* pr_b = prior + (long)b * Tf * Tt;
+    float* al_b = alpha_ws + (long)b * Tf * Tt;
+    float* g_b = dlogp + (long)b * Tf * Tt;
+    const bool is_label = (s & 1) && s < S;
+    const int k = s >> 1;
+    const bool active = s < S;
+    const long total = (long)Tf * Tt;
+    if (N == 0 || T == 0) {
+        for (long i = threadIdx.x; i < total; i += blockDim.x) g_b[i] = 0.f;
+        return;
+    }
+    if (s < 2) { cur[-1 - s] = -INFINITY; nxt[-1 - s] = -INFINITY; }
+    // ---- first frame of each sweep
+    const int t0 = beta_half ? T - 1 : 0;
+    float e = is_label ? lp_b[(long)t0 * Tt + k] + pr_b[(long)t0 * Tt + k] : blank_logp;
+    float a;
+    if (!beta_half) a = (s < 2 && active) ? e : -INFINITY;
+    else a = (active && s >= S - 2) ? e : -INFINITY;
+    if (s <= Smax + 1) cur[s] = active ? a : -INFINITY;
+    if (is_label) (beta_half ? g_b : al_b)[(long)t0 * Tt + k] = a;
+    __syncthreads();
+    int tn = beta_half ? T - 2 : 1;               // frame of the next step, its emission is fetched one step ahead
+    e = (is_label && T > 1) ? lp_b[(long)tn * Tt + k] + pr_b[(long)tn * Tt + k] : blank_logp;
+    for (int j = 1; j < T; ++j) {
+        const int t = tn;
+        const float e_t = e;
+        tn = beta_half ? t - 1 : t + 1;
+        if (is_label && j + 1 < T) e = lp_b[(long)tn * Tt + k] + pr_b[(long)tn * Tt + k];
+        if (active) {
+            float x0, x1, x2;
+            if (!beta_half) {
+                x0 = cur[s]; x1 = cur[s - 1];
+                x2 = (is_label && s >= 3) ? cur[s - 2] : -INFINITY;
+            } else {
+                x0 = cur[s];
+                x1 = (s + 1 < S) ? cur[s + 1] : -INFINITY;
+                x2 = (is_label && s + 2 < S) ? cur[s + 2] : -INFINITY;
+            }
+            a = lse3f(x0, x1, x2) + e_t;
+            nxt[s] = a;
+            if (is_label) (beta_half ? g_b : al_b)[(long)t * Tt + k] = a;
+        }
+        __syncthreads();
+        float* tmp = cur; cur = nxt; nxt = tmp;
+    }
+    if (threadIdx.x == 0) {                        // alpha half, after the last frame
+        const float x = cur[S - 1], y = (S >= 2) ? cur[S - 2] : -INFINITY;
+        s_ll = lse3f(x, y, -INFINITY);
+    }
+    __syncthreads();                               // also orders the parked alpha / beta values before the pass below
+    const float ll = s_ll;
+    const bool feasible = ll > -INFINITY && ll < INFINITY;
+    if (threadIdx.x == 0 && feasible) atomicAdd(loss, -ll / ((float)N * (float)B));
+    const float sc = gscale / ((float)N * (float)B);
+    const float nll = -ll;
+    for (long i = threadIdx.x; i < total; i += blockDim.x) {
+        const int tt = (int)(i / Tt), kk = (int)(i - (long)tt * Tt);
+        float g = 0.f;
+        if (feasible && tt < T && kk < N) {
+            const float ee = lp_b[i] + pr_b[i];
+            g = sc * (expf(ee) - expf(al_b[i] + g_b[i] - ee + nll));
+        }
+        g_b[i] = g;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Gaussian upsampling weights: P[b,t,s] = softmax_s( -delta * (t_eff - c_s)^2 ), c = cumsum(ds) - ds/2,
 // t_eff = t for t < feats_len[b] else 0 (reference quirk), text padding masked.   P: (B,Tf,ldP)
@@ -382,6 +475,13 @@ extern "C" int s2s_forward_sum(const float* logp, const float* prior, const int3
     if (threads > 1024) threads = 1024;
     size_t smem = 2 * (size_t)(2 * T_text + 1 + 4) * sizeof(float);
     S2S_CUDA_OK(cudaMemsetAsync(loss, 0, sizeof(float), st));
+    const int SH = ((2 * T_text + 1 + 2) + 31) / 32 * 32;
+    if (dlogp && 2 * SH <= 1024) {                 // alpha and beta sweeps side by side in one CTA
+        forward_sum_par_kernel<<<B, 2 * SH, 4 * (size_t)(2 * T_text + 1 + 4) * sizeof(float), st>>>(
+            logp, prior, text_lens, feats_lens, B, T_feats, T_text, SH, blank_logp, alpha_ws, loss, dlogp, grad_scale);
+        S2S_LAUNCH_OK();
+        return S2S_OK;
+    }
     forward_sum_kernel<<<B, threads, smem, st>>>(logp, prior, text_lens, feats_lens, B, T_feats, T_text, blank_logp, alpha_ws, loss,
                                                  dlogp, grad_scale);
     S2S_LAUNCH_OK();
