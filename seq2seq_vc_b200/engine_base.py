@@ -542,6 +542,7 @@ class EngineBase:
         ops.conv1_fwd(xs, st.p(prefix + ".conv.0.weight"), st.p(prefix + ".conv.0.bias"), y1)
         col = self._scratch("col", (B * T2 * F2, 9 * d))
         ops.im2col_s2(y1, col)
+        self._col_of = (self._sig, tag)         # the patch matrix stays valid until a backward turns it into dcol (or another forward reuses it)
         y2 = self.buf(tag + ".y2", (B * T2 * F2, d))
         ops.gemm(col, w2p.view(d, 9 * d), y2, bias=st.p(prefix + ".conv.2.bias"), relu=True, mode=self.mode)
         elin = self.buf(tag + ".elin", (B * T2, d))
@@ -566,7 +567,9 @@ class EngineBase:
         w2p = self.buf(f"w.{tag}.conv2p", (d, 9, d))
         col = self._scratch("col", (B * T2 * F2, 9 * d))
         y1 = self.buf(tag + ".y1", (B, T1, F1, d))
-        ops.im2col_s2(y1, col)
+        if getattr(self, "_col_of", None) != (self._sig, tag):
+            ops.im2col_s2(y1, col)              # normally still there from this step's forward
+        self._col_of = None
         gw2p = self._scratch("g.w2p", (d, 9 * d), _f32)
         ops.gemm(dy2.t(), col.t(), gw2p, mode=mode)
         ops.transpose_last2(gw2p, st.g(prefix + ".conv.2.weight"), d, 9, d, accumulate=True)
