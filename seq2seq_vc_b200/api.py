@@ -705,6 +705,55 @@ class _ReferenceCheckpoint:
     live in the engine's flat M / V buffers; the optimizer state is keyed by parameter ORDER, which the drop-in modules
     register exactly as the reference does.  Needs the drop-in module (not a bare engine) for that order."""
 
+    # ---- input staging: the next batch's host -> device copy overlapped with the running step ------------------------------
+    _stage = None
+
+    def prefetch(self, *host_tensors) -> None:
+        """Start copying the NEXT batch's pinned host tensors (the same objects, in the order the step takes them: xs, ys, labels
+        for VTNTrainStep; xs, ys, dp_inputs for AASVCTrainStep) to the device on a side stream.  The next __call__ that is handed
+        these tensors moves the staged copies into place device-to-device instead of waiting for PCIe, so with CUDA graphs the
+        copy of batch n + 1 runs under the kernels of batch n (what a pin_memory DataLoader worker gives the reference trainer).
+        Optional: without it __call__ copies on the compute stream as before."""
+        if any(t.is_cuda for t in host_tensors):
+            return
+        st = self._stage
+        if st is None:
+            st = self._stage = {"stream": torch.cuda.Stream(), "ready": torch.cuda.Event(), "consumed": None, "bufs": {}, "key": None}
+        shape_key = tuple((tuple(t.shape), t.dtype) for t in host_tensors)
+        bufs = st["bufs"].get(shape_key)
+        if bufs is None:
+            bufs = st["bufs"][shape_key] = [torch.empty(t.shape, dtype=t.dtype, device=self.engine.device) for t in host_tensors]
+            if len(st["bufs"]) > 8:
+                st["bufs"].pop(next(iter(st["bufs"])))
+        side = st["stream"]
+        if st["consumed"] is not None:
+            side.wait_event(st["consumed"])            # the previous staged batch has been moved out of these buffers
+        with torch.cuda.stream(side):
+            for b, t in zip(bufs, host_tensors):
+                b.copy_(t, non_blocking=True)
+            st["ready"].record(side)
+        st["key"] = tuple(t.data_ptr() for t in host_tensors) + (shape_key,)
+        st["cur"] = bufs
+
+    def _take_staged(self, *tensors):
+        """The device copies `prefetch` staged for exactly these host tensors (the compute stream then waits for the copy), or None."""
+        st = self._stage
+        if st is None or st["key"] is None:
+            return None
+        key = tuple(t.data_ptr() for t in tensors) + (tuple((tuple(t.shape), t.dtype) for t in tensors),)
+        if key != st["key"]:
+            return None
+        st["key"] = None
+        torch.cuda.current_stream().wait_event(st["ready"])
+        return st["cur"]
+
+    def _staged_consumed(self) -> None:
+        st = self._stage
+        if st is not None:
+            ev = torch.cuda.Event()
+            ev.record()
+            st["consumed"] = ev
+
     def _on_evict(self, sig) -> None:
         """The engine dropped the activation buffers of batch shape `sig` (least recently used): graphs captured for that
         shape address freed memory and go with them."""
@@ -850,12 +899,17 @@ class VTNTrainStep(_ReferenceCheckpoint):
         B, T, L = xs.shape[0], xs.shape[1], ys.shape[1]
         eng.training = True
         eng.prepare(B, T, L, ilens, olens)
+        staged = self._take_staged(xs, ys, labels)
+        if staged is not None:
+            xs, ys, labels = staged
         if not self.use_graph:
             if not xs.is_cuda:
                 xs, ys, labels = (t.to(eng.device, non_blocking=True) for t in (xs, ys, labels))
             self._fwd_bwd(xs, ys, labels)
             self._allreduce()
             self._update()
+            if staged is not None:
+                self._staged_consumed()
             return eng.losses
         key = (B, T, L)
         entry = self._graphs.get(key)
@@ -865,6 +919,8 @@ class VTNTrainStep(_ReferenceCheckpoint):
             sl = torch.empty(labels.shape, dtype=_f32, device=eng.device)
             for dst, src in ((sx, xs), (sy, ys), (sl, labels)):
                 dst.copy_(src, non_blocking=True)
+            if staged is not None:
+                self._staged_consumed()
             # one eager step first: allocates every activation buffer outside the graph's private pool
             self._fwd_bwd(sx, sy, sl)
             self._allreduce()
@@ -903,6 +959,8 @@ class VTNTrainStep(_ReferenceCheckpoint):
         for dst, src in ((sx, xs), (sy, ys), (sl, labels)):
             if src.data_ptr() != dst.data_ptr():
                 dst.copy_(src, non_blocking=True)
+        if staged is not None:
+            self._staged_consumed()         # the staging buffers are free again: the next prefetch may run under this step's kernels
         g1.replay()
         if g1b is None:
             self._allreduce()
@@ -1331,6 +1389,9 @@ class AASVCTrainStep(_ReferenceCheckpoint):
         B, T, L = xs.shape[0], xs.shape[1], ys.shape[1]
         eng.training = True
         eng.prepare(B, T, L, ilens, olens)
+        staged = self._take_staged(xs, ys, dp_inputs)
+        if staged is not None:
+            xs, ys, dp_inputs = staged
         if not self.use_graph:
             if not xs.is_cuda:
                 xs, ys, dp_inputs = (t.to(eng.device, non_blocking=True) for t in (xs, ys, dp_inputs))
@@ -1338,6 +1399,8 @@ class AASVCTrainStep(_ReferenceCheckpoint):
             if boundary:
                 self._allreduce()
                 self._update(with_dur)
+            if staged is not None:
+                self._staged_consumed()
             return eng.losses
         key = (B, T, L, dp_inputs.shape[1], with_dur, fresh, boundary)
         entry = self._graphs.get(key)
@@ -1345,6 +1408,8 @@ class AASVCTrainStep(_ReferenceCheckpoint):
             statics = [torch.empty(t.shape, dtype=_f32, device=eng.device) for t in (xs, ys, dp_inputs)]
             for dst, src in zip(statics, (xs, ys, dp_inputs)):
                 dst.copy_(src, non_blocking=True)
+            if staged is not None:
+                self._staged_consumed()
             self._fwd_bwd(*statics, with_dur, fresh, boundary)   # eager step: allocates every buffer outside the graph pool
             if boundary:
                 self._allreduce()
@@ -1366,6 +1431,8 @@ class AASVCTrainStep(_ReferenceCheckpoint):
         for dst, src in zip(statics, (xs, ys, dp_inputs)):
             if src.data_ptr() != dst.data_ptr():
                 dst.copy_(src, non_blocking=True)
+        if staged is not None:
+            self._staged_consumed()
         g1.replay()
         if boundary:
             self._allreduce()

@@ -540,3 +540,38 @@ def test_dropin_graph_mode_matches_eager_across_shapes():
         assert abs(l0 - l1) <= 2e-3 * max(1, abs(l0)) and abs(b0 - b1) <= 2e-3 * max(1, abs(b0)), i
     for k in p0:
         assert torch.allclose(p0[k].float(), p1[k].float(), atol=1e-3, rtol=1e-3), k
+
+
+@pytest.mark.gpu
+def test_prefetch_staging_matches_direct_copies():
+    """VTNTrainStep.prefetch (next batch's H2D copy on a side stream, staged copies moved in device-to-device) gives the same
+    steps as handing the pinned tensors to __call__ directly; batches alternate so a stale staging buffer would be noticed."""
+    from seq2seq_vc_b200 import VTN, VTNTrainStep
+
+    hp = dict(idim=80, odim=80, adim=64, aheads=4, elayers=1, dlayers=1, eunits=96, dunits=96, dprenet_units=32, postnet_chans=32,
+              dprenet_dropout_rate=0.0, transformer_enc_dropout_rate=0.0)
+    g = torch.Generator().manual_seed(9)
+    batches = []
+    for _ in range(3):
+        xs, ys = torch.randn(2, 48, 80, generator=g).pin_memory(), torch.randn(2, 32, 80, generator=g).pin_memory()
+        labels = torch.zeros(2, 32)
+        labels[:, 31:] = 1
+        batches.append((xs, [48, 40], ys, labels.pin_memory(), [32, 27]))
+    runs = []
+    for pf in (False, True):
+        model = VTN(**hp, compute_dtype="float32", device="cuda:0", seed=2)
+        model.engine.hp.update({k: 0.0 for k in model.engine.hp if "dropout" in k})
+        step = VTNTrainStep(model, lr=1e-4, warmup_steps=1, use_graph=True)
+        out = []
+        if pf:
+            step.prefetch(batches[0][0], batches[0][2], batches[0][3])
+        for it in range(6):
+            xs, il, ys, lab, ol = batches[it % 3]
+            losses = step(xs, il, ys, lab, ol)
+            if pf:
+                nxt = batches[(it + 1) % 3]
+                step.prefetch(nxt[0], nxt[2], nxt[3])
+            out.append(losses.cpu().clone())
+        runs.append(out)
+    for a, b in zip(*runs):
+        assert torch.allclose(a, b, rtol=2e-4, atol=1e-5), (a, b)
