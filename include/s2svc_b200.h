@@ -36,7 +36,7 @@ extern "C" {
 #define S2S_F32 0
 #define S2S_BF16 1
 
-#define S2S_ABI_VERSION 15
+#define S2S_ABI_VERSION 16
 
 const char* s2s_last_error(void);
 int s2s_abi_version(void);
@@ -244,6 +244,8 @@ int s2s_conv1_bwd(const float* x, const void* dy1, float* dw, float* dbias, int 
                   int dtype, void* stream);
 int s2s_im2col_s2(const void* y1, void* col, int B, int T1, int F1, int C, int dtype, void* stream);
 int s2s_col2im_s2(const void* dcol, void* dy1, int B, int T1, int F1, int C, int dtype, void* stream);
+/* the same scatter-add with the ReLU' of conv.0's output y1 (subsampling.py:60-61) applied at the store: dy1 = col2im(dcol) * (y1 > 0) */
+int s2s_col2im_s2_relu(const void* dcol, const void* y1, void* dy1, int B, int T1, int F1, int C, int dtype, void* stream);
 
 /* Decoder input glue (models/vtn.py:227-243,523-527): out[b, 0] = 0, out[b, l] = ys[b, l*r - 1]
  * for l >= 1;  ys (B, L, odim) float32 -> out (B, Lr, odim) dtype. */

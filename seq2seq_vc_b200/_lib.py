@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libs2svc_b200.so")
 
 S2S_F32, S2S_BF16 = 0, 1
-ABI_VERSION = 15
+ABI_VERSION = 16
 
 
 class S2SError(RuntimeError):
@@ -93,6 +93,7 @@ SIGNATURES = {
     "s2s_conv1_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "s2s_im2col_s2": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "s2s_col2im_s2": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "s2s_col2im_s2_relu": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "s2s_shift_thin": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "s2s_fix_targets": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "s2s_bn_stats": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P]),

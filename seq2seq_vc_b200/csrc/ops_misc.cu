@@ -182,24 +182,34 @@ __global__ void __launch_bounds__(256) conv1_fwd_reg_kernel(const float* __restr
         for (int tap = 0; tap < 9; ++tap) wr[tap][k] = w[(c + k) * 9 + tap];
     }
     const unsigned P = (unsigned)B * (unsigned)T1 * (unsigned)F1;
-    for (unsigned pos = blockIdx.x * blockDim.y + threadIdx.y; pos < P; pos += gridDim.x * blockDim.y) {
+    const unsigned stride = gridDim.x * blockDim.y;
+    // two output positions per iteration: 18 independent broadcast loads in flight and two FMA chains per channel
+    for (unsigned pos = blockIdx.x * blockDim.y + threadIdx.y; pos < P; pos += 2 * stride) {
+        const unsigned pos2 = pos + stride;
+        const bool two = pos2 < P;
         const unsigned r = pos / (unsigned)F1, b = r / (unsigned)T1;
         const int f1 = (int)(pos - r * (unsigned)F1), t1 = (int)(r - b * (unsigned)T1);
+        const unsigned pq = two ? pos2 : pos;
+        const unsigned r2 = pq / (unsigned)F1, b2 = r2 / (unsigned)T1;
+        const int f12 = (int)(pq - r2 * (unsigned)F1), t12 = (int)(r2 - b2 * (unsigned)T1);
         const float* xp = x + ((long)b * Tn + 2 * t1) * F + 2 * f1;
-        float acc[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = bs[k];
+        const float* xq = x + ((long)b2 * Tn + 2 * t12) * F + 2 * f12;
+        float xa[9], xb[9];
 #pragma unroll
         for (int kt = 0; kt < 3; ++kt)
 #pragma unroll
-            for (int kf = 0; kf < 3; ++kf) {
-                const float xv = xp[kt * F + kf];
+            for (int kf = 0; kf < 3; ++kf) { xa[kt * 3 + kf] = xp[kt * F + kf]; xb[kt * 3 + kf] = xq[kt * F + kf]; }
+        float acc[8], acc2[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) acc[k] = fmaf(xv, wr[kt * 3 + kf][k], acc[k]);
-            }
+        for (int k = 0; k < 8; ++k) acc[k] = acc2[k] = bs[k];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = fmaxf(acc[k], 0.f);
+        for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { acc[k] = fmaf(xa[tap], wr[tap][k], acc[k]); acc2[k] = fmaf(xb[tap], wr[tap][k], acc2[k]); }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { acc[k] = fmaxf(acc[k], 0.f); acc2[k] = fmaxf(acc2[k], 0.f); }
         Vec8<T>::store(y + (long)pos * C + c, acc);
+        if (two) Vec8<T>::store(y + (long)pos2 * C + c, acc2);
     }
 }
 
@@ -358,7 +368,7 @@ __global__ void im2col_s2_kernel(const T* __restrict__ y1, T* __restrict__ col, 
 
 template <typename T, int VEC>
 __global__ void col2im_s2_kernel(const T* __restrict__ dcol, T* __restrict__ dy1, int B, int T1, int F1, int C,
-                                 int T2, int F2) {
+                                 int T2, int F2, const T* __restrict__ gate) {
     const int cv = C / VEC;
     const long total = (long)B * T1 * F1 * cv;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -409,6 +419,12 @@ __global__ void col2im_s2_kernel(const T* __restrict__ dcol, T* __restrict__ dy1
                     acc[0] += to_f<T>(*src);
                 }
             }
+        }
+        if (gate) {                                   // ReLU' of the conv1 output fused into the scatter-add: dy1 *= (y1 > 0)
+            const T* gp = gate + q * C + c;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k)
+                if (!(to_f<T>(gp[k]) > 0.f)) acc[k] = 0.f;
         }
         T* dst = dy1 + q * C + c;
         if (VEC == 8) {
@@ -777,18 +793,25 @@ extern "C" int s2s_im2col_s2(const void* y1, void* col, int B, int T1, int F1, i
     S2S_LAUNCH_OK();
     return S2S_OK;
 }
-extern "C" int s2s_col2im_s2(const void* dcol, void* dy1, int B, int T1, int F1, int C, int dtype, void* stream) {
+static int col2im_s2_impl(const void* dcol, const void* y1, void* dy1, int B, int T1, int F1, int C, int dtype, void* stream) {
     S2S_REQUIRE(dcol && dy1 && B > 0 && T1 >= 3 && F1 >= 3 && C > 0, "col2im_s2: bad arguments");
     int T2 = (T1 - 1) / 2, F2 = (F1 - 1) / 2;
     long total = (long)B * T1 * F1 * C;
     bool ok = (C % 4 == 0) && ((uintptr_t)dy1 % 16 == 0) && ((uintptr_t)dcol % 16 == 0);
     S2S_DISPATCH_DTYPE(dtype, TT, {
-        if (ok && C % 8 == 0) col2im_s2_kernel<TT, 8><<<ew_grid(total / 8, 256), 256, 0, (cudaStream_t)stream>>>((const TT*)dcol, (TT*)dy1, B, T1, F1, C, T2, F2);
-        else if (ok) col2im_s2_kernel<TT, 4><<<ew_grid(total / 4, 256), 256, 0, (cudaStream_t)stream>>>((const TT*)dcol, (TT*)dy1, B, T1, F1, C, T2, F2);
-        else col2im_s2_kernel<TT, 1><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const TT*)dcol, (TT*)dy1, B, T1, F1, C, T2, F2);
+        if (ok && C % 8 == 0) col2im_s2_kernel<TT, 8><<<ew_grid(total / 8, 256), 256, 0, (cudaStream_t)stream>>>((const TT*)dcol, (TT*)dy1, B, T1, F1, C, T2, F2, (const TT*)y1);
+        else if (ok) col2im_s2_kernel<TT, 4><<<ew_grid(total / 4, 256), 256, 0, (cudaStream_t)stream>>>((const TT*)dcol, (TT*)dy1, B, T1, F1, C, T2, F2, (const TT*)y1);
+        else col2im_s2_kernel<TT, 1><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const TT*)dcol, (TT*)dy1, B, T1, F1, C, T2, F2, (const TT*)y1);
     });
     S2S_LAUNCH_OK();
     return S2S_OK;
+}
+extern "C" int s2s_col2im_s2(const void* dcol, void* dy1, int B, int T1, int F1, int C, int dtype, void* stream) {
+    return col2im_s2_impl(dcol, nullptr, dy1, B, T1, F1, C, dtype, stream);
+}
+extern "C" int s2s_col2im_s2_relu(const void* dcol, const void* y1, void* dy1, int B, int T1, int F1, int C, int dtype, void* stream) {
+    S2S_REQUIRE(y1, "col2im_s2_relu: null y1");
+    return col2im_s2_impl(dcol, y1, dy1, B, T1, F1, C, dtype, stream);
 }
 
 extern "C" int s2s_shift_thin(const float* ys, void* out, int B, int L, int Lr, int odim, int r, int dtype,

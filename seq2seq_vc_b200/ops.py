@@ -352,6 +352,14 @@ def col2im_s2(dcol, dy1):
     return dy1
 
 
+def col2im_s2_relu(dcol, y1, dy1):
+    """dy1 = col2im(dcol) * (y1 > 0): the scatter-add with conv.0's ReLU' fused into its store."""
+    B, T1, F1, C = dy1.shape
+    assert y1.shape == dy1.shape and y1.dtype == dy1.dtype and y1.is_contiguous()
+    check(_L().s2s_col2im_s2_relu(ptr(dcol), ptr(y1), ptr(dy1), B, T1, F1, C, dt(dy1), stream()), "col2im_s2_relu")
+    return dy1
+
+
 def shift_thin(ys, out, r):
     B, L, odim = ys.shape
     Lr = out.shape[1]

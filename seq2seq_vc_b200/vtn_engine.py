@@ -857,8 +857,7 @@ class VTNEngine(ConformerBlocks, EngineBase):
         dcol = col
         ops.gemm(dy2, w2p.view(d, 9 * d).t(), dcol, mode=mode)
         dy1 = self._scratch("g.y1", (B, T1, F1, d))
-        ops.col2im_s2(dcol, dy1)
-        ops.relu_bwd(dy1, y1, dy1, 1.0)
+        ops.col2im_s2_relu(dcol, y1, dy1)          # scatter-add + conv.0's ReLU' in one pass
         ops.conv1_bwd(self.xs, dy1, st.g("encoder.embed.conv.0.weight"), st.g("encoder.embed.conv.0.bias"))
 
 

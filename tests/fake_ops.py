@@ -310,6 +310,12 @@ def col2im_s2(dcol, dy1):
     return dy1
 
 
+def col2im_s2_relu(dcol, y1, dy1):
+    col2im_s2(dcol, dy1)
+    dy1.copy_(torch.where(y1 > 0, dy1, torch.zeros_like(dy1)))
+    return dy1
+
+
 def shift_thin(ys, out, r):
     B, L, odim = ys.shape
     Lr = out.shape[1]

@@ -306,6 +306,9 @@ def test_conv2d_subsampling_pieces(ops, dt):
     dy1 = F.col2im_s2(dcol, torch.empty(B, T1, F1, C, dtype=dt))
     cdy1 = ops.col2im_s2(dcol.cuda(), torch.empty(B, T1, F1, C, dtype=dt, device="cuda"))
     close(cdy1, dy1, tol(dt, 4), "col2im")
+    y1g = torch.randn(B, T1, F1, C).to(dt)
+    close(ops.col2im_s2_relu(dcol.cuda(), y1g.cuda(), torch.empty(B, T1, F1, C, dtype=dt, device="cuda")),
+          F.col2im_s2_relu(dcol, y1g, torch.empty(B, T1, F1, C, dtype=dt)), tol(dt, 4), "col2im_relu")
     dw, db = torch.zeros(C, 1, 3, 3), torch.zeros(C)
     F.conv1_bwd(x, dy1, dw, db)
     cdw, cdb = torch.zeros(C, 1, 3, 3, device="cuda"), torch.zeros(C, device="cuda")
