@@ -36,7 +36,7 @@ extern "C" {
 #define S2S_F32 0
 #define S2S_BF16 1
 
-#define S2S_ABI_VERSION 16
+#define S2S_ABI_VERSION 17
 
 const char* s2s_last_error(void);
 int s2s_abi_version(void);
@@ -364,6 +364,19 @@ int s2s_logmel(const float* wav, const float* window, const float* mel_basis, fl
  * the store: mel[b,t,m] = (logmel - mean[m]) / scale[m]; mean / scale are (n_mels) float32 (bin/compute_statistics.py). */
 int s2s_logmel_norm(const float* wav, const float* window, const float* mel_basis, const float* mean, const float* scale, float* mel,
                     int B, int n_samples, int n_fft, int hop, int n_mels, float eps, float log_base, void* stream);
+
+/* Griffin-Lim phase reconstruction (vocoder/griffin_lim.py:52-106 -> librosa.griffinlim / stft / istft, center = True), fp32,
+ * one utterance, n_fft a power of two in [64, 4096].  Spectra are (T, n_fft/2 + 1) row-major, complex values interleaved (re, im).
+ *  s2s_gl_istft:  y (hop * (T - 1)) = istft(mag * angles): inverse rFFT of every frame (imaginary parts of the DC / Nyquist bins
+ *                 ignored), synthesis window, overlap-add divided by the sum of squared windows, n_fft/2 trimmed on both sides;
+ *                 frames (T, n_fft) is workspace.
+ *  s2s_gl_stft:   spec = stft(y) of the T centred frames, padding n_fft/2 with zeros (pad_reflect = 0) or by reflection (1).
+ *  s2s_gl_update: angles = rebuilt - c * tprev; angles /= |angles| + tiny; tprev = rebuilt   (n complex elements; c = momentum / (1 + momentum)). */
+int s2s_gl_istft(const float* mag, const float* angles, const float* window, float* frames, float* y, int T, int n_fft, int hop,
+                 void* stream);
+int s2s_gl_stft(const float* y, const float* window, float* spec, int T, int64_t n_samples, int n_fft, int hop, int pad_reflect,
+                void* stream);
+int s2s_gl_update(const float* rebuilt, float* tprev, float* angles, int64_t n, float c, void* stream);
 
 /* ===========================================================================================
  * Conformer block (AAS-VC encoder / decoder): modules/conformer/encoder_layer.py:79-179,

@@ -696,6 +696,99 @@ def logmelfilterbank(audio, sampling_rate, fft_size=1024, hop_size=256, win_leng
 
 
 # =================================================================================================
+# Griffin-Lim vocoder path (vocoder/griffin_lim.py:20-222): the inverse of the log-mel front end, same mel basis and window
+# =================================================================================================
+GL_EPS = 1e-10
+
+
+def logmel2linear(lmspc, fs, n_fft, n_mels, fmin=None, fmax=None) -> np.ndarray:
+    """griffin_lim.py:20-50: log-mel (T, n_mels) -> linear magnitudes (T, n_fft // 2 + 1) = max(EPS, pinv(mel_basis) @ 10 ** lmspc).
+    The pseudo-inverse of the (n_mels x bins) basis is a one-off host computation (numpy, as in the reference); the product of
+    every frame with it runs through s2s_gemm."""
+    lmspc = np.asarray(lmspc)
+    assert lmspc.shape[1] == n_mels
+    fmin = 0 if fmin is None else fmin
+    fmax = fs / 2 if fmax is None else fmax
+    key = ("pinv", fs, n_fft, n_mels, fmin, fmax)
+    inv = _DEV_CACHE.get(key)
+    if inv is None:
+        inv = torch.from_numpy(np.linalg.pinv(mel_filterbank(fs, n_fft, n_mels, fmin, fmax)).astype(np.float32)).cuda().contiguous()
+        _DEV_CACHE[key] = inv                                         # (bins, n_mels)
+    mspc = torch.from_numpy(np.power(10.0, lmspc).astype(np.float32)).cuda().contiguous()
+    out = torch.empty(mspc.shape[0], inv.shape[0], dtype=_f32, device=mspc.device)
+    ops.gemm(mspc, inv, out, mode=0)                                  # (T, n_mels) x (bins, n_mels)^T, fp32 on the CUDA cores
+    return np.maximum(GL_EPS, out.cpu().numpy())
+
+
+def griffin_lim(spc, n_fft, n_shift, win_length=None, window="hann", n_iter=32, init_angles=None, momentum=0.99,
+                pad_mode="constant", seed=None) -> np.ndarray:
+    """griffin_lim.py:52-106 (-> librosa.griffinlim, center = True): linear magnitudes (T, n_fft // 2 + 1) -> waveform
+    (n_shift * (T - 1),).  The whole iteration runs on the device (s2s_gl_istft / s2s_gl_stft / s2s_gl_update).  librosa draws the
+    initial phases from numpy's global generator; here they come from `init_angles` (T, bins) complex, or from
+    numpy.random.default_rng(seed)."""
+    if window != "hann":
+        raise NotImplementedError("only the hann window (every shipped recipe) is implemented")
+    if pad_mode not in ("constant", "reflect"):
+        raise ValueError(f"pad_mode {pad_mode!r}")
+    S = np.abs(np.asarray(spc, dtype=np.float32))
+    T, bins = S.shape
+    assert bins == n_fft // 2 + 1 and T >= 2
+    if init_angles is None:
+        init_angles = np.exp(2j * np.pi * np.random.default_rng(seed).random(S.shape))
+    ang = np.asarray(init_angles, dtype=np.complex64)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    mag = torch.from_numpy(S).to(dev).contiguous()
+    angles = torch.view_as_real(torch.from_numpy(ang).to(dev)).contiguous()
+    win = torch.from_numpy(hann_window(n_fft, win_length)).to(dev)
+    frames = torch.empty(T, n_fft, dtype=_f32, device=dev)
+    y = torch.empty(n_shift * (T - 1), dtype=_f32, device=dev)
+    rebuilt = torch.empty(T, bins, 2, dtype=_f32, device=dev)
+    tprev = torch.zeros(T, bins, 2, dtype=_f32, device=dev)
+    c = momentum / (1.0 + momentum)
+    for _ in range(n_iter):
+        ops.gl_istft(mag, angles, win, frames, y, n_fft, n_shift)
+        ops.gl_stft(y, win, rebuilt, n_fft, n_shift, pad_mode == "reflect")
+        ops.gl_update(rebuilt, tprev, angles, c)
+    ops.gl_istft(mag, angles, win, frames, y, n_fft, n_shift)
+    return y.cpu().numpy()
+
+
+class Spectrogram2Waveform:
+    """vocoder/griffin_lim.py:110-222: log-mel (or linear) spectrogram -> waveform by (pseudo-inverse mel basis +) Griffin-Lim;
+    same constructor arguments, `decode(spc)` takes and returns torch tensors."""
+
+    def __init__(self, n_fft, n_shift, stats=None, fs=None, n_mels=None, win_length=None, window="hann", fmin=None, fmax=None,
+                 griffin_lim_iters=8, take_norm_feat=True):
+        self.take_norm_feat = take_norm_feat
+        self.stats = stats
+        if self.take_norm_feat:
+            assert self.stats is not None, "must specify stats if take_norm_feat=True."
+        self.fs = fs
+        self.n_mels = n_mels
+        self.params = dict(n_fft=n_fft, n_shift=n_shift, win_length=win_length, window=window, n_iter=griffin_lim_iters)
+        self.mel_params = dict(fs=fs, n_fft=n_fft, n_mels=n_mels, fmin=fmin, fmax=fmax)
+        if n_mels is not None:
+            self.params.update(fs=fs, n_mels=n_mels, fmin=fmin, fmax=fmax)
+
+    def __repr__(self):
+        return f"{self.__class__.__name__}(" + "".join(f"{k}={v}, " for k, v in self.params.items()) + ")"
+
+    def decode(self, spc: torch.Tensor, init_angles=None, seed=None) -> torch.Tensor:
+        device, dtype = spc.device, spc.dtype
+        spc = spc.detach().cpu().numpy()
+        if self.take_norm_feat:
+            spc = spc * self.stats["scale"] + self.stats["mean"]
+        if self.n_mels is not None:
+            spc = logmel2linear(spc, **self.mel_params)
+        gl = {k: self.params[k] for k in ("n_fft", "n_shift", "win_length", "window", "n_iter")}
+        wav = griffin_lim(spc, init_angles=init_angles, seed=seed, **gl)
+        return torch.tensor(wav).to(device=device, dtype=dtype)
+
+    def __call__(self, spc):
+        return self.decode(spc)
+
+
+# =================================================================================================
 # fused training step (trainers/ar_vc.py:59-112 without the host round trips)
 # =================================================================================================
 class _ReferenceCheckpoint:

@@ -3,7 +3,7 @@
 set -e
 cd "$(dirname "$0")"
 OUT=../libs2svc_b200.so
-SRCS="api.cu gemm_simt.cu gemm_tc.cu gemm_split.cu ops_norm.cu ops_attn.cu attn_fused.cu attn_tc.cu ops_misc.cu ops_conformer.cu ops_align.cu decode.cu mas.cu logmel.cu ops_sdp.cu ops_lr.cu"
+SRCS="api.cu gemm_simt.cu gemm_tc.cu gemm_split.cu ops_norm.cu ops_attn.cu attn_fused.cu attn_tc.cu ops_misc.cu ops_conformer.cu ops_align.cu decode.cu mas.cu logmel.cu ops_sdp.cu ops_lr.cu griffinlim.cu"
 mkdir -p _obj
 pids=()
 for s in $SRCS; do

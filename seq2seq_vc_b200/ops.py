@@ -521,6 +521,26 @@ def logmel(wav, window, basis, mel, n_fft, hop, eps, log_base, mean=None, scale=
 # ----------------------------------------------------------------------------------------------
 # Conformer block
 # ----------------------------------------------------------------------------------------------
+def gl_istft(mag, angles, window, frames, y, n_fft, hop):
+    """y = istft(mag * angles): mag (T, bins) float32, angles (T, bins, 2) float32 (re, im); frames (T, n_fft) workspace."""
+    T = mag.shape[0]
+    assert mag.dtype == angles.dtype == torch.float32 and mag.is_contiguous() and angles.is_contiguous() and y.numel() == hop * (T - 1)
+    check(_L().s2s_gl_istft(ptr(mag), ptr(angles), ptr(window), ptr(frames), ptr(y), T, n_fft, hop, stream()), "gl_istft")
+    return y
+
+
+def gl_stft(y, window, spec, n_fft, hop, pad_reflect=False):
+    T = spec.shape[0]
+    assert y.dtype == spec.dtype == torch.float32 and y.is_contiguous() and spec.is_contiguous()
+    check(_L().s2s_gl_stft(ptr(y), ptr(window), ptr(spec), T, y.numel(), n_fft, hop, int(bool(pad_reflect)), stream()), "gl_stft")
+    return spec
+
+
+def gl_update(rebuilt, tprev, angles, c):
+    check(_L().s2s_gl_update(ptr(rebuilt), ptr(tprev), ptr(angles), rebuilt.numel() // 2, float(c), stream()), "gl_update")
+    return angles
+
+
 def bias_add2(q, u, v, qu, qv):
     """qu = q + u, qv = q + v for a (rows, d) view q with arbitrary row stride (slice of the fused QKV buffer)."""
     d = q.shape[-1]
