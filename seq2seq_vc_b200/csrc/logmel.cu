@@ -33,19 +33,28 @@ __device__ __forceinline__ float2 cmul2(float2 d, float c, float s) {
     return fma2(make_float2(d.y, d.x), make_float2(-s, s), mul2(d, make_float2(c, c)));
 }
 
-// in-place 32-point forward DFT, decimation in frequency, fully unrolled; output v[brev5(k)] = X[k]
-__device__ __forceinline__ void fft32_dif(float2 (&v)[32]) {
+// in-place N-point forward DFT (N = 8, 16, 32), decimation in frequency, fully unrolled; output v[brev(k)] = X[k] with brev the
+// log2(N)-bit reversal
+template <int N> __host__ __device__ constexpr int brevn(int x) {
+    int r = 0;
+    for (int b = 1, t = N >> 1; b < N; b <<= 1, t >>= 1)
+        if (x & b) r |= t;
+    return r;
+}
+template <int N>
+__device__ __forceinline__ void fft_dif(float2 (&v)[32]) {
+    constexpr int LOG = N == 32 ? 5 : (N == 16 ? 4 : 3);
 #pragma unroll
-    for (int s = 0; s < 5; ++s) {
-        const int half = 16 >> s;              // butterfly span
+    for (int s = 0; s < LOG; ++s) {
+        const int half = (N / 2) >> s;         // butterfly span
 #pragma unroll
-        for (int g = 0; g < 32; g += 2 * half) {
+        for (int g = 0; g < N; g += 2 * half) {
 #pragma unroll
             for (int j = 0; j < half; ++j) {
                 const float2 a = v[g + j], b = v[g + j + half];
                 v[g + j] = add2(a, b);
                 const float2 d = sub2(a, b);
-                const int tw = j << s;         // W_32^(j * 2^s)
+                const int tw = (j << s) * (32 / N);          // W_N^(j * 2^s) = W_32^tw
                 if (tw == 0) v[g + j + half] = d;
                 else if (tw == 8) v[g + j + half] = make_float2(d.y, -d.x);   // * (-i)
                 else v[g + j + half] = cmul2(d, kCos32[tw], kSin32[tw]);
@@ -53,6 +62,7 @@ __device__ __forceinline__ void fft32_dif(float2 (&v)[32]) {
         }
     }
 }
+__device__ __forceinline__ void fft32_dif(float2 (&v)[32]) { fft_dif<32>(v); }
 
 // ---------------------------------------------------------------------------------------------
 // n_fft = 2048 fast path: persistent CTA of 16 warps, 16 frames per round (one frame per warp)
@@ -109,15 +119,16 @@ static_assert(LM_SMEM <= 227 * 1024, "logmel2048: shared memory budget");
 // the (band tile, bin block) pairs that hold non-zeros are visited; magnitudes and weights are split into bf16 high + low parts
 // and three products are accumulated in fp32, which keeps the projection at fp32 accuracy), and 16 x n_mels logs are stored
 // as one contiguous run.
+template <int N1>      // n_fft = 64 * N1: 32 (2048), 16 (1024) or 8 (512); the complex FFT of H = 32 * N1 points is N1 x 32
 __global__ void __launch_bounds__(LM_WARPS * 32, 1) logmel2048_kernel(const float* __restrict__ wav, const float* __restrict__ window,
                                                                      const float* __restrict__ basis, float* __restrict__ mel, int B,
                                                                      int ns, int hop, int n_frames, int n_mels, float eps,
                                                                      float log_scale, const float* __restrict__ nmean,
                                                                      const float* __restrict__ nscale) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int H = 1024, NB = 1025;
-    float2* tw32 = reinterpret_cast<float2*>(smem_raw);                       // [k1 * 32 + n2] = e^{-2 pi i k1 n2 / 1024}
-    float2* tw2048 = reinterpret_cast<float2*>(smem_raw + LM_OFF_TW2048);     // e^{-2 pi i k / 2048}, k <= 512
+    constexpr int H = 32 * N1, NB = H + 1;
+    float2* tw32 = reinterpret_cast<float2*>(smem_raw);                       // [k1 * 32 + n2] = e^{-2 pi i k1 n2 / H}, k1 < N1
+    float2* tw2048 = reinterpret_cast<float2*>(smem_raw + LM_OFF_TW2048);     // e^{-2 pi i k / (2 H)}, k <= H / 2
     float* swin = reinterpret_cast<float*>(smem_raw + LM_OFF_WIN);            // 0.5 * window: the 1/2 of the real-FFT unpack
     uint4* btab = reinterpret_cast<uint4*>(smem_raw + LM_OFF_BTAB);           // B fragments {b0 hi, b1 hi, b0 lo, b1 lo} per (item, lane)
     float* part = reinterpret_cast<float*>(smem_raw + LM_OFF_PART);           // per (warp, band tile) partial 16 x 8 tiles
@@ -129,17 +140,17 @@ __global__ void __launch_bounds__(LM_WARPS * 32, 1) logmel2048_kernel(const floa
     float* mg = regions + (size_t)warp * LM_FS;
 
     // ---- CTA-wide tables
-    for (int e = tid; e < 1024; e += blockDim.x) {
+    for (int e = tid; e < 32 * N1; e += blockDim.x) {
         float s, c;
-        sincospif(-2.0f * (float)(((e >> 5) * (e & 31)) & 1023) / 1024.f, &s, &c);
+        sincospif(-2.0f * (float)((e >> 5) * (e & 31)) / (float)H, &s, &c);
         tw32[e] = make_float2(c, s);
     }
-    for (int k = tid; k <= 512; k += blockDim.x) {
+    for (int k = tid; k <= H / 2; k += blockDim.x) {
         float s, c;
-        sincospif(-2.0f * (float)k / 2048.f, &s, &c);
+        sincospif(-2.0f * (float)k / (float)(2 * H), &s, &c);
         tw2048[k] = make_float2(c, s);
     }
-    for (int k = tid; k < 2048; k += blockDim.x) swin[k] = 0.5f * window[k];
+    for (int k = tid; k < 2 * H; k += blockDim.x) swin[k] = 0.5f * window[k];
     const int NT = (n_mels + 7) >> 3;
     if (tid < LM_MAX_NT) { meta.nt_lo[tid] = NB; meta.nt_cnt[tid] = -1; }      // nt_cnt holds the last non-zero bin until the list is built
     __syncthreads();
@@ -221,10 +232,10 @@ __global__ void __launch_bounds__(LM_WARPS * 32, 1) logmel2048_kernel(const floa
         if (start >= 0 && start + 2 * H <= ns && (reinterpret_cast<uintptr_t>(x + start) & 7) == 0) {
             const float2* p = reinterpret_cast<const float2*>(x + start) + lane;
 #pragma unroll
-            for (int n1 = 0; n1 < 32; ++n1) v[n1] = __ldg(p + 32 * n1);
+            for (int n1 = 0; n1 < N1; ++n1) v[n1] = __ldg(p + 32 * n1);
         } else {
 #pragma unroll
-            for (int n1 = 0; n1 < 32; ++n1) {
+            for (int n1 = 0; n1 < N1; ++n1) {
                 int s0 = start + 2 * (32 * n1 + lane), s1 = s0 + 1;
                 s0 = s0 < 0 ? -s0 : (s0 >= ns ? 2 * (ns - 1) - s0 : s0);
                 s1 = s1 < 0 ? -s1 : (s1 >= ns ? 2 * (ns - 1) - s1 : s1);
@@ -282,47 +293,62 @@ __global__ void __launch_bounds__(LM_WARPS * 32, 1) logmel2048_kernel(const floa
             {
                 const float2* sw2 = reinterpret_cast<const float2*>(swin) + lane;
 #pragma unroll
-                for (int n1 = 0; n1 < 32; ++n1) {
+                for (int n1 = 0; n1 < N1; ++n1) {
                     const float2 w = sw2[32 * n1];
                     v[n1] = make_float2(v[n1].x * w.x, v[n1].y * w.y);
                 }
             }
-            // ---- 1024-point complex FFT as 32 x 32: in-register 32-point DFTs around one transpose
+            // ---- H-point complex FFT as N1 x 32: in-register DFTs around one transpose
+            if constexpr (N1 == 32) {
 #pragma unroll 1
-            for (int pass = 0; pass < 2; ++pass) {
-                fft32_dif(v);                                           // v[brev5(k)] = sum_n v[n] W_32^(n k)
-                if (pass == 0) {
+                for (int pass = 0; pass < 2; ++pass) {                  // one copy of the 32-point code for both passes
+                    fft32_dif(v);                                       // v[brev5(k)] = sum_n v[n] W_32^(n k)
+                    if (pass == 0) {
 #pragma unroll
-                    for (int k1 = 0; k1 < 32; ++k1) zb[k1 * LM_ZLD + lane] = cmul(v[brev5(k1)], tw32[k1 * 32 + lane]);
-                    __syncwarp();
+                        for (int k1 = 0; k1 < 32; ++k1) zb[k1 * LM_ZLD + lane] = cmul(v[brev5(k1)], tw32[k1 * 32 + lane]);
+                        __syncwarp();
 #pragma unroll
-                    for (int n2 = 0; n2 < 32; ++n2) v[n2] = zb[lane * LM_ZLD + n2];    // lane = k1 now
-                    __syncwarp();
+                        for (int n2 = 0; n2 < 32; ++n2) v[n2] = zb[lane * LM_ZLD + n2];    // lane = k1 now
+                        __syncwarp();
+                    }
                 }
+            } else {
+                // N1 < 32: the first pass is an N1-point DFT per lane, the second a 32-point DFT on lanes k1 < N1 (the other
+                // lanes idle through it: a 1024-point frame costs ~60 % of a 2048-point one)
+                fft_dif<N1>(v);
+#pragma unroll
+                for (int k1 = 0; k1 < N1; ++k1) zb[k1 * LM_ZLD + lane] = cmul(v[brevn<N1>(k1)], tw32[k1 * 32 + lane]);
+                __syncwarp();
+#pragma unroll
+                for (int n2 = 0; n2 < 32; ++n2) v[n2] = lane < N1 ? zb[lane * LM_ZLD + n2] : make_float2(0.f, 0.f);
+                __syncwarp();
+                fft32_dif(v);
             }
             // ---- lane k1 now holds Z[k1 + 32 k2] in v[brev5(k2)].  Real-FFT unpack in conjugate pairs (k, 1024 - k): with
             //      e = Z[k] + conj Z[H-k], t = W_2048^k (Z[k] - conj Z[H-k]): X[k] = e - i t and X[H-k] = conj(e + i t).  Lane k1 takes
             //      k = k1 + 32 k2, k2 < 16; the partner Z[H-k] is lane (32 - k1)'s value k2' = 31 - k2 (one shuffle), for k1 = 0 the
             //      lane's own k2' = (32 - k2) & 31; k = 512 pairs with itself (lane 0).  The warp's region becomes the magnitude row.
             {
-                const int src = (32 - lane) & 31;
+                const int src = (N1 - (lane & (N1 - 1))) & (N1 - 1);
 #pragma unroll
                 for (int k2 = 0; k2 < 16; ++k2) {
-                    const int k = lane + 32 * k2;
+                    const int k = (lane & (N1 - 1)) + N1 * k2;
                     const float2 zk = v[brev5(k2)], up = v[brev5(31 - k2)], own = v[brev5((32 - k2) & 31)];
                     float2 zcc = make_float2(__shfl_sync(0xffffffffu, up.x, src), -__shfl_sync(0xffffffffu, up.y, src));
                     if (lane == 0) zcc = make_float2(own.x, -own.y);            // conj Z[H-k]
                     const float2 e = add2(zk, zcc);
                     const float2 t = cmul(sub2(zk, zcc), tw2048[k]);
                     const float2 xa = add2(e, make_float2(t.y, -t.x)), xb = sub2(e, make_float2(t.y, -t.x));
-                    mg[k] = sqrt_approx(xa.x * xa.x + xa.y * xa.y);
-                    mg[H - k] = sqrt_approx(xb.x * xb.x + xb.y * xb.y);
+                    if (N1 == 32 || lane < N1) {
+                        mg[k] = sqrt_approx(xa.x * xa.x + xa.y * xa.y);
+                        mg[H - k] = sqrt_approx(xb.x * xb.x + xb.y * xb.y);
+                    }
                 }
             }
             const float2 z512 = v[brev5(16)];
             const float m512 = 2.f * sqrt_approx(z512.x * z512.x + z512.y * z512.y);
-            if (lane == 0) mg[512] = m512;
-            else mg[H + lane] = 0.f;                                    // bins 1025 .. 1055 are read (times zero weights) by the last bin blocks
+            if (lane == 0) mg[H / 2] = m512;
+            else mg[H + lane] = 0.f;                                    // bins H + 1 .. H + 31 are read (times zero weights) by the last bin blocks
             fetch(fr + (long)gridDim.x * LM_WARPS);                     // next round's samples: in flight across the projection and the store
             if (!use_tc) {
                 // dense fallback for filterbanks the banded table cannot hold: one warp per frame, every band over every bin
@@ -535,15 +561,22 @@ static int logmel_impl(const float* wav, const float* window, const float* mel_b
     S2S_REQUIRE(lb > 1.0, "logmel: bad log base");
     float log_scale = (float)(1.0 / log2(lb));
     long total = (long)B * n_frames;
-    if (n_fft == 2048) {
+    if (n_fft == 2048 || n_fft == 1024 || n_fft == 512) {
         // 16 frames per round per persistent CTA; filterbanks the banded table cannot hold take the kernel's dense fallback
         S2S_REQUIRE((long)n_samples + n_fft < (1L << 30), "logmel: clip too long for 32-bit sample indices");
-        S2S_CUDA_OK(cudaFuncSetAttribute(logmel2048_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LM_SMEM));
         long grid = (long)num_sms();
         long need = ceil_div_l(total, LM_WARPS);
         if (grid > need) grid = need;
-        logmel2048_kernel<<<(unsigned)grid, LM_WARPS * 32, LM_SMEM, (cudaStream_t)stream>>>(wav, window, mel_basis, mel, B, n_samples, hop,
-                                                                                            n_frames, n_mels, eps, log_scale, nmean, nscale);
+#define S2S_LM_LAUNCH(N1)                                                                                                      \
+        do {                                                                                                                   \
+            S2S_CUDA_OK(cudaFuncSetAttribute(logmel2048_kernel<N1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LM_SMEM)); \
+            logmel2048_kernel<N1><<<(unsigned)grid, LM_WARPS * 32, LM_SMEM, (cudaStream_t)stream>>>(                           \
+                wav, window, mel_basis, mel, B, n_samples, hop, n_frames, n_mels, eps, log_scale, nmean, nscale);             \
+        } while (0)
+        if (n_fft == 2048) S2S_LM_LAUNCH(32);
+        else if (n_fft == 1024) S2S_LM_LAUNCH(16);
+        else S2S_LM_LAUNCH(8);
+#undef S2S_LM_LAUNCH
         S2S_LAUNCH_OK();
         return S2S_OK;
     }

@@ -70,7 +70,8 @@ def test_mas_bin_loss_gradient():
 
 
 @pytest.mark.parametrize("sr,n_fft,hop,ns,win", [(24000, 1024, 256, 12000, None), (48000, 2048, 300, 48000, None),
-                                                 (16000, 1024, 256, 5000, 800), (48000, 2048, 300, 4801, 1200)])
+                                                 (16000, 1024, 256, 5000, 800), (48000, 2048, 300, 4801, 1200),
+                                                 (16000, 512, 128, 7001, None), (16000, 1024, 256, 16001, None), (8000, 256, 64, 3000, None)])
 def test_logmel_vs_oracle(sr, n_fft, hop, ns, win):
     from seq2seq_vc_b200 import api
 
