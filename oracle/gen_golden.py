@@ -356,6 +356,68 @@ def gen_aasvc_conv1d_linear_k3_tiny():
     gen_aasvc_conv1d_tiny("aasvc_conv1d_linear_k3_tiny", "conv1d-linear", 3, 41)
 
 
+FS_HP = dict(idim=80, odim=80, adim=32, aheads=2, elayers=2, eunits=48, dlayers=2, dunits=48, duration_predictor_input_dim=80,
+             duration_predictor_layers=2, duration_predictor_chans=16, duration_predictor_kernel_size=3, postnet_layers=2, postnet_filts=5,
+             postnet_chans=16, conformer_enc_kernel_size=7, conformer_dec_kernel_size=7)
+FS_FIXED = dict(positionwise_layer_type="linear", positionwise_conv_kernel_size=1, duration_predictor_use_encoder_outputs=False,
+                encoder_normalize_before=True, decoder_normalize_before=True, encoder_reduction_factor=1, decoder_reduction_factor=1,
+                encoder_type="conformer", decoder_type="conformer", encoder_input_layer="conv2d", conformer_pos_enc_layer_type="rel_pos",
+                conformer_self_attn_layer_type="rel_selfattn", use_macaron_style_in_conformer=True, use_cnn_in_conformer=True,
+                teacher_model_decoder_reduction_factor=1)
+
+
+def gen_fsvc_tiny():
+    """FastSpeechVC in the configuration of egs/arctic/vc2/conf/fs2_vc.melmelmel.v1.yaml (conformer encoder / decoder, conv2d input
+    layer, teacher durations) + L1Loss + DurationPredictorLoss as NARVCTrainer._train_step assembles them (trainers/nar_vc.py:53-99)."""
+    from seq2seq_vc.losses import DurationPredictorLoss, L1Loss
+    from seq2seq_vc.models import FastSpeechVC
+
+    torch.manual_seed(51)
+    model = FastSpeechVC(**FS_HP, **FS_FIXED)
+    ref_shim.disable_dropout(model)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if p.dim() == 1 and ("norm" in n or ".2." in n or ".1." in n):
+                p.add_(0.1 * torch.randn_like(p))
+    model.train()
+    sd0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(53)
+    B, T = 3, 70
+    ilens = [70, 61, 47]
+    xs = torch.randn(B, T, 80, generator=g)
+    tl = [((i - 2 + 1) // 2 - 2 + 1) // 2 for i in ilens]
+    Tt = max(tl)
+    ds = torch.randint(0, 5, (B, Tt), generator=g)
+    for b in range(B):
+        ds[b, tl[b]:] = 0
+        ds[b, 0] = max(int(ds[b, 0]), 1)
+    olens = ds.sum(1).tolist()
+    ys = torch.randn(B, max(olens), 80, generator=g)
+    for b in range(B):
+        xs[b, ilens[b]:] = 0
+        ys[b, olens[b]:] = 0
+    out = model(xs, torch.tensor(ilens), ys, torch.tensor(olens), ds, torch.tensor(tl), xs, dp_lengths=torch.tensor(ilens))
+    before, after, d_outs, ilens_o, olens_o, ys_o = out
+    l1 = L1Loss()(after, before, ys_o, olens_o)
+    dur = DurationPredictorLoss()(d_outs, ds, ilens_o)
+    (l1 + dur).backward()
+    dump = {"sd." + k: v.numpy() for k, v in sd0.items()}
+    dump.update({"grad." + k: p.grad.numpy() for k, p in model.named_parameters() if p.grad is not None})
+    dump.update({"bn_after." + k: v.numpy() for k, v in model.state_dict().items() if "running_" in k})
+    dump.update(xs=xs.numpy(), ilens=np.array(ilens), ys=ys.numpy(), olens=np.array(olens), ds=ds.numpy(), dp_inputs=xs.numpy(),
+                after_outs=after.detach().numpy(), before_outs=before.detach().numpy(), d_outs=d_outs.detach().numpy(),
+                ilens_out=ilens_o.numpy(), olens_out=olens_o.numpy(), l1_loss=l1.detach().numpy(), duration_loss=dur.detach().numpy())
+    for n, m in model.named_modules():
+        if hasattr(m, "attn") and isinstance(getattr(m, "attn"), torch.Tensor):
+            dump["attn." + n] = m.attn.detach().numpy()
+    model.eval()
+    with torch.no_grad():
+        oe = model(xs, torch.tensor(ilens), ys, torch.tensor(olens), ds, torch.tensor(tl), xs, dp_lengths=torch.tensor(ilens))
+    dump["eval_after_outs"] = oe[1].numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "fsvc_tiny.npz"), **dump)
+    print("fsvc_tiny:", len(dump), "arrays", "olens", olens)
+
+
 SDP_HP = dict(channels=16, kernel_size=3, dds_conv_layers=3, flows=4)
 
 
@@ -475,7 +537,7 @@ if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     import sys
 
-    gens = dict(vtn_tiny=gen_vtn_tiny, vtn_rfactor=gen_vtn_rfactor, vtn_conformer_tiny=gen_vtn_conformer_tiny, vtn_convffn_tiny=gen_vtn_convffn_tiny, tts_tiny=gen_tts_tiny, aasvc_tiny=gen_aasvc_tiny, aasvc_conv1d_tiny=gen_aasvc_conv1d_tiny, aasvc_conv1d_k3_tiny=gen_aasvc_conv1d_k3_tiny,
+    gens = dict(vtn_tiny=gen_vtn_tiny, vtn_rfactor=gen_vtn_rfactor, vtn_conformer_tiny=gen_vtn_conformer_tiny, vtn_convffn_tiny=gen_vtn_convffn_tiny, fsvc_tiny=gen_fsvc_tiny, tts_tiny=gen_tts_tiny, aasvc_tiny=gen_aasvc_tiny, aasvc_conv1d_tiny=gen_aasvc_conv1d_tiny, aasvc_conv1d_k3_tiny=gen_aasvc_conv1d_k3_tiny,
                 aasvc_conv1d_linear_k3_tiny=gen_aasvc_conv1d_linear_k3_tiny,
                 mas=gen_mas, kats=gen_kats, sdp_tiny=gen_sdp_tiny)
     for name in (sys.argv[1:] or list(gens)):      # e.g. `python oracle/gen_golden.py aasvc_conv1d_tiny` adds one fixture

@@ -176,6 +176,41 @@ def test_aasvc_oracle_forward_loss_grads(fixture):
         assert np.abs(g.numpy() - ref).max() <= 2e-4 * np.abs(ref).max() + 2e-6 * gmax, k
 
 
+FS_HP = dict(idim=80, odim=80, adim=32, aheads=2, elayers=2, eunits=48, dlayers=2, dunits=48, duration_predictor_input_dim=80,
+             duration_predictor_layers=2, duration_predictor_chans=16, duration_predictor_kernel_size=3, postnet_layers=2, postnet_filts=5,
+             postnet_chans=16, conformer_enc_kernel_size=7, conformer_dec_kernel_size=7)
+
+
+def test_fastspeech_vc_oracle_forward_loss_grads():
+    """FastSpeechVC (conformer encoder / decoder, conv2d input layer, LengthRegulator with teacher durations: the configuration of
+    egs/arctic/vc2/conf/fs2_vc.melmelmel.v1.yaml) + the two losses of NARVCTrainer._train_step vs the live-reference dump."""
+    from oracle import fsvc_oracle
+
+    z = np.load(os.path.join(GOLD, "fsvc_tiny.npz"))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    args = (torch.from_numpy(z["xs"]), z["ilens"].tolist(), torch.from_numpy(z["ys"]), z["olens"].tolist(), torch.from_numpy(z["ds"]),
+            torch.from_numpy(z["dp_inputs"]))
+    bn = {}
+    out = fsvc_oracle.fsvc_forward(sd, FS_HP, *args, training=True, bn_stats=bn)
+    for k in ("after_outs", "before_outs", "d_outs"):
+        assert np.abs(out[k].detach().numpy() - z[k]).max() <= 2e-5, k
+    assert out["ilens"] == z["ilens_out"].tolist() and out["olens"] == z["olens_out"].tolist()
+    for k, v in bn.items():
+        assert np.abs(v.numpy() - z["bn_after." + k]).max() <= 1e-5, k
+    for k in [k for k in z.files if k.startswith("attn.")]:
+        assert np.abs(out["attn"][k[5:]].detach().numpy() - z[k]).max() <= 1e-6, k
+    _, parts, grads = fsvc_oracle.fsvc_loss_and_grads(sd, FS_HP, *args)
+    for k in ("l1_loss", "duration_loss"):
+        assert abs(float(parts[k]) - float(z[k])) <= 2e-6 * max(1.0, abs(float(z[k]))), k
+    gmax = max(np.abs(z[k]).max() for k in z.files if k.startswith("grad."))
+    for k, g in grads.items():
+        ref = z["grad." + k]
+        assert np.abs(g.numpy() - ref).max() <= 2e-4 * np.abs(ref).max() + 2e-6 * gmax, k
+    sd_e = {**sd, **{k[9:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("bn_after.")}}
+    oe = fsvc_oracle.fsvc_forward(sd_e, FS_HP, *args, training=False)
+    assert np.abs(oe["after_outs"].detach().numpy() - z["eval_after_outs"]).max() <= 2e-5
+
+
 def test_forward_sum_oracle_matches_reference_ctc():
     """Hand-rolled alpha recursion vs the reference's F.ctc_loss path incl. an infeasible utterance (zero_infinity)."""
     from oracle import aasvc_oracle
