@@ -195,8 +195,9 @@ def gaussian_upsampling(hs, ds, feats_lens, text_lens, T_feats):
     return torch.matmul(torch.softmax(energy, dim=2), hs)
 
 
-def duration_predictor(sd, prefix, hp, xs, text_lens):
-    """DurationPredictor.forward (duration_predictor.py:83-114) + clamp(max=10) (aas_vc.py:408-410)."""
+def duration_predictor(sd, prefix, hp, xs, text_lens, clamp: bool = True):
+    """DurationPredictor.forward (duration_predictor.py:83-114) + clamp(max=10) (aas_vc.py:408-410; AAS-VC only: FastSpeechVC uses
+    the predictor's output as it is, fastspeech_vc.py:270-275)."""
     k = hp["duration_predictor_kernel_size"]
     x = xs.transpose(1, 2)
     for i in range(hp["duration_predictor_layers"]):
@@ -205,7 +206,7 @@ def duration_predictor(sd, prefix, hp, xs, text_lens):
         x = layer_norm(x.transpose(1, 2), sd, p + ".2").transpose(1, 2)
     out = linear(x.transpose(1, 2), sd, prefix + ".linear").squeeze(-1)
     out = out * non_pad_mask(text_lens, xs.shape[1])
-    return torch.clamp(out, max=MAX_DP_OUTPUT)
+    return torch.clamp(out, max=MAX_DP_OUTPUT) if clamp else out
 
 
 def beta_binomial_prior(N: int, T: int) -> np.ndarray:

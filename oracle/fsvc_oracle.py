@@ -61,7 +61,7 @@ def fsvc_forward(sd, hp, xs, ilens, ys, olens, ds, dp_inputs, training: bool = T
     tlens = [((i - 2 + 1) // 2 - 2 + 1) // 2 for i in ilens]                   # fastspeech_vc.py:236-238
     # duration predictor on the projected side input (fastspeech_vc.py:244-275)
     dpi = ao.dp_projection(sd, "duration_predictor_projection", dp_inputs, hs.shape[1])
-    d_outs = ao.duration_predictor(sd, "duration_predictor", hp, dpi, tlens)
+    d_outs = ao.duration_predictor(sd, "duration_predictor", hp, dpi, tlens, clamp=False)
     # length regulator with the teacher's durations (:276-279), conformer decoder on the result (:281-305)
     up = length_regulate(hs, ds * hp["teacher_model_decoder_reduction_factor"])
     L = up.shape[1]

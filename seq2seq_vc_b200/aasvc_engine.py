@@ -335,17 +335,29 @@ class AASVCEngine(ConformerBlocks, EngineBase):
             hs = self.buf("hs.red", (B, Tt, C))
             hs.view(B, Tt * pr, d).copy_(henc[:, :Tt * pr])
         self.hs = hs
-        # ---- duration-predictor input: Conv2dSubsampling projection + nearest interpolation (aas_vc.py:335-351)
-        Tdp = dp_inputs.shape[1]
+        self._dp_input_fwd(dp_inputs, Tt)
+        if self.stochastic:
+            return          # the stochastic predictor needs the MAS durations: it runs after the alignment search (_sdp_forward)
+        self._dp_forward(Tt)
+
+    def _dp_input_fwd(self, dp_inputs: torch.Tensor, Tt: int) -> torch.Tensor:
+        """Duration-predictor input: Conv2dSubsampling projection + nearest interpolation to the encoder length (aas_vc.py:335-351,
+        fastspeech_vc.py:247-260) -> self.dp_in (B, Tt, d)."""
+        d = self.hp["adim"]
+        B, Tdp = dp_inputs.shape[0], dp_inputs.shape[1]
         Tp = (((Tdp - 1) // 2) - 1) // 2
         proj = self._conv2d_sub_fwd(dp_inputs, "duration_predictor_projection", "duration_predictor_projection.out", "dpp")
         idx, ones, _, _ = self._interp_tables(Tp, Tt)
         dpi = self.buf("dp.in", (B, Tt, d))
         ops.gather_rows(proj.view(B, Tp, d), idx, ones, dpi)
         self.dp_in = dpi
-        if self.stochastic:
-            return          # the stochastic predictor needs the MAS durations: it runs after the alignment search (_sdp_forward)
-        # ---- duration predictor (duration_predictor.py:83-101)
+        return dpi
+
+    def _dp_forward(self, Tt: int) -> None:
+        """DurationPredictor (duration_predictor.py:83-101) on self.dp_in -> self.dp_pre (B*Tt, 1) (log-domain pre-activation), self.dp_last."""
+        hp, st = self.hp, self.store
+        dpi = self.dp_in
+        B = dpi.shape[0]
         k = hp["duration_predictor_kernel_size"]
         halo = (k - 1) // 2
         ch = hp["duration_predictor_chans"]
@@ -663,13 +675,21 @@ class AASVCEngine(ConformerBlocks, EngineBase):
             # (B,) gradient of dur_nll handed in by the drop-in module's autograd node
             self.sdp_backward(d_dp_pre)
             return self._backward_alignment_and_encoder(dhs, d_logp)
+        self._dp_backward(d_dp_pre, Tt)
+
+        return self._backward_alignment_and_encoder(dhs, d_logp)
+
+    def _dp_backward(self, d_dp_pre: torch.Tensor, Tt: int) -> None:
+        """Backward of the duration predictor and of its input projection (the side input itself needs no gradient)."""
+        hp, st = self.hp, self.store
+        s = self.shapes
+        B, d = s["B"], hp["adim"]
         ch = hp["duration_predictor_chans"]
         k = hp["duration_predictor_kernel_size"]
         halo = (k - 1) // 2
         gcur = self._scratch("g.dp_a", (B, Tt, ch))
         self._lin_bwd(d_dp_pre, self.dp_last.view(B * Tt, ch), self.W("duration_predictor.linear.weight"),
                       st.g("duration_predictor.linear.weight"), st.g("duration_predictor.linear.bias"), dx=gcur.view(B * Tt, ch))
-        gdpi = None
         for i in reversed(range(hp["duration_predictor_layers"])):
             ic = d if i == 0 else ch
             drop = self.named_drop(f"dp.drop{i}", hp["duration_predictor_dropout_rate"])
@@ -693,8 +713,6 @@ class AASVCEngine(ConformerBlocks, EngineBase):
         gproj = self._scratch("g.dpproj", (B, Tp, d))
         ops.gather_rows(gdpi, first, cnt, gproj)
         self._conv2d_sub_bwd(gproj.view(B * Tp, d), self.dp_inputs, "duration_predictor_projection", "duration_predictor_projection.out", "dpp")
-
-        return self._backward_alignment_and_encoder(dhs, d_logp)
 
     def sdp_backward(self, g_dur_nll: Optional[torch.Tensor] = None) -> None:
         """Gradient of the stochastic predictor's loss into the flat gradient buffer (its leaves' .grad are views of it).

@@ -1413,6 +1413,174 @@ def _aasvc_inference(self, src_speech, tgt_speech=None, spembs=None, dp_input=No
 AASVC.inference = _aasvc_inference
 
 
+# =================================================================================================
+# FastSpeechVC (models/fastspeech_vc.py, trainers/nar_vc.py): drop-in model over FastSpeechVCEngine
+# =================================================================================================
+from .fsvc_engine import FastSpeechVCEngine  # noqa: E402
+from .fsvc_engine import default_hparams as fsvc_default_hparams  # noqa: E402
+
+
+class _FastSpeechVCFunction(torch.autograd.Function):
+    """Whole-model autograd node over FastSpeechVCEngine: differentiable outputs are before / after / d_outs."""
+
+    @staticmethod
+    def forward(ctx, model, xs, ys, ds, dp_inputs, ilens, olens, *params):
+        eng = model.engine
+        after, before = eng.forward(xs, ys, ds, dp_inputs, ilens, olens)
+        ctx.model, ctx.token = model, model._fwd_token
+        ctx.set_materialize_grads(False)
+        return before.clone(), after.clone(), eng.forward_d_outs()
+
+    @staticmethod
+    def backward(ctx, g_before, g_after, g_douts):
+        model = ctx.model
+        if ctx.token != model._fwd_token:
+            raise S2SError("backward() after a newer forward(): the engine keeps one set of activations")
+        eng = model.engine
+        fresh = all(p.grad is None for p in model.parameters())
+        dt = eng.adt
+        B, Tt = eng.shapes["B"], eng.shapes["Tt"]
+        z = lambda g, like, d: torch.zeros_like(like, dtype=d) if g is None else g.to(d).contiguous()
+        d_pre = torch.zeros(B * Tt, 1, dtype=dt, device=eng.device)
+        if g_douts is not None:          # d_outs = pre * mask: the gradient of the predictor's pre-activation is the masked incoming one
+            m = (torch.arange(Tt, device=eng.device)[None, :] < eng.tlens_dev[:, None])
+            d_pre.copy_((g_douts.to(_f32) * m).reshape(B * Tt, 1))
+        eng.backward(z(g_after, eng.after, dt), z(g_before, eng.before, dt), d_pre, zero_grad=fresh)
+        model._sync_gradients()
+        model._bind_grads(unused=("duration_predictor.", "duration_predictor_projection.") if g_douts is None else ())
+        return (None,) * (7 + len(model._param_names))
+
+
+class FastSpeechVC(AASVC):
+    """Drop-in for seq2seq_vc.models.FastSpeechVC (models/fastspeech_vc.py:21-513) in the configuration family of
+    egs/arctic/vc2/conf/fs2_vc.melmelmel.v1.yaml: conformer encoder / decoder (rel_pos / rel_selfattn, macaron, CNN module), `conv2d`
+    encoder input layer, duration predictor on a projected side input, LengthRegulator with the teacher's durations.  Same
+    constructor kwargs, `forward(src_speech, src_speech_lengths, tgt_speech, tgt_speech_lengths, durations, durations_lengths,
+    dp_inputs, dp_lengths)` -> `(before_outs, after_outs, d_outs, ilens, olens, ys)`, `inference(...)`, state-dict keys and
+    parameter registration order."""
+
+    def __init__(self, idim, odim, adim: int = 384, aheads: int = 4, elayers: int = 6, eunits: int = 1536, dlayers: int = 6,
+                 dunits: int = 1536, postnet_layers: int = 5, postnet_chans: int = 512, postnet_filts: int = 5,
+                 postnet_dropout_rate: float = 0.5, positionwise_layer_type: str = "conv1d", positionwise_conv_kernel_size: int = 1,
+                 use_scaled_pos_enc: bool = True, use_batch_norm: bool = True, encoder_input_layer: str = "linear", encoder_input_conv_kernel_size: int = 3,
+                 encoder_normalize_before: bool = False, decoder_normalize_before: bool = False, encoder_concat_after: bool = False,
+                 decoder_concat_after: bool = False, duration_predictor_use_encoder_outputs: bool = True,
+                 duration_predictor_input_dim: Optional[int] = None, duration_predictor_layers: int = 2,
+                 duration_predictor_chans: int = 384, duration_predictor_kernel_size: int = 3, duration_predictor_dropout_rate: float = 0.1,
+                 encoder_reduction_factor: int = 1, decoder_reduction_factor: int = 1, teacher_model_decoder_reduction_factor: int = 4,
+                 encoder_type: str = "transformer", decoder_type: str = "transformer", transformer_enc_dropout_rate: float = 0.1,
+                 transformer_enc_positional_dropout_rate: float = 0.1, transformer_enc_attn_dropout_rate: float = 0.1,
+                 transformer_dec_dropout_rate: float = 0.1, transformer_dec_positional_dropout_rate: float = 0.1,
+                 transformer_dec_attn_dropout_rate: float = 0.1, conformer_pos_enc_layer_type: str = "rel_pos",
+                 conformer_self_attn_layer_type: str = "rel_selfattn", use_macaron_style_in_conformer: bool = True,
+                 use_cnn_in_conformer: bool = True, conformer_enc_kernel_size: int = 7, conformer_dec_kernel_size: int = 31,
+                 spk_embed_dim: Optional[int] = None, spk_embed_integration_type: str = "add",
+                 compute_dtype: str = "float32", device=None, seed: int = 0, **ignored):
+        torch.nn.Module.__init__(self)
+        unsupported = []
+        if encoder_type != "conformer" or decoder_type != "conformer":
+            unsupported.append("encoder_type / decoder_type != 'conformer' (the reference's transformer decoder branch does not construct: fastspeech_vc.py:183)")
+        if encoder_input_layer != "conv2d":
+            unsupported.append("encoder_input_layer != 'conv2d'")
+        if conformer_pos_enc_layer_type != "rel_pos" or conformer_self_attn_layer_type != "rel_selfattn":
+            unsupported.append("conformer layers other than rel_pos / rel_selfattn")
+        if not use_macaron_style_in_conformer or not use_cnn_in_conformer:
+            unsupported.append("conformer without macaron / CNN module")
+        if duration_predictor_use_encoder_outputs or duration_predictor_input_dim is None:
+            unsupported.append("duration_predictor_use_encoder_outputs=True")
+        if encoder_reduction_factor != 1 or decoder_reduction_factor != 1:
+            unsupported.append("encoder / decoder reduction factors != 1")
+        if not encoder_normalize_before or not decoder_normalize_before or encoder_concat_after or decoder_concat_after or not use_batch_norm:
+            unsupported.append("non-default normalisation wiring")
+        if spk_embed_dim is not None:
+            unsupported.append("speaker embeddings")
+        if positionwise_layer_type not in ("linear", "conv1d", "conv1d-linear"):
+            unsupported.append("positionwise_layer_type not in ('linear', 'conv1d', 'conv1d-linear')")
+        if unsupported:
+            raise NotImplementedError("B200 FastSpeechVC hot path does not cover: " + ", ".join(unsupported))
+        self.idim, self.odim = idim, odim
+        self.spk_embed_dim = None
+        self.encoder_reduction_factor, self.decoder_reduction_factor = 1, 1
+        self.teacher_model_decoder_reduction_factor = teacher_model_decoder_reduction_factor
+        self.encoder_type, self.decoder_type, self.encoder_input_layer = encoder_type, decoder_type, encoder_input_layer
+        self.duration_predictor_use_encoder_outputs = False
+        self.hp = fsvc_default_hparams(
+            idim=idim, odim=odim, adim=adim, aheads=aheads, elayers=elayers, eunits=eunits, dlayers=dlayers, dunits=dunits,
+            duration_predictor_input_dim=duration_predictor_input_dim, duration_predictor_layers=duration_predictor_layers,
+            duration_predictor_chans=duration_predictor_chans, duration_predictor_kernel_size=duration_predictor_kernel_size,
+            postnet_layers=postnet_layers, postnet_filts=postnet_filts, postnet_chans=postnet_chans,
+            conformer_enc_kernel_size=conformer_enc_kernel_size, conformer_dec_kernel_size=conformer_dec_kernel_size,
+            transformer_enc_dropout_rate=transformer_enc_dropout_rate,
+            transformer_enc_positional_dropout_rate=transformer_enc_positional_dropout_rate,
+            transformer_enc_attn_dropout_rate=transformer_enc_attn_dropout_rate, transformer_dec_dropout_rate=transformer_dec_dropout_rate,
+            transformer_dec_positional_dropout_rate=transformer_dec_positional_dropout_rate,
+            transformer_dec_attn_dropout_rate=transformer_dec_attn_dropout_rate,
+            duration_predictor_dropout_rate=duration_predictor_dropout_rate, postnet_dropout_rate=postnet_dropout_rate,
+            positionwise_layer_type=positionwise_layer_type, positionwise_conv_kernel_size=positionwise_conv_kernel_size,
+            teacher_model_decoder_reduction_factor=teacher_model_decoder_reduction_factor)
+        self._bf16 = compute_dtype in ("bf16", "bfloat16", torch.bfloat16)
+        self._fp32_gemm = "simt" if compute_dtype == "float32_simt" else "tc"
+        self._seed = seed
+        self._fwd_token = 0
+        self.engine = None
+        self._build(torch.device(device) if device is not None else torch.device("cpu"))
+
+    def _build(self, device, state=None) -> None:
+        self.engine = FastSpeechVCEngine(self.hp, device=device, bf16=self._bf16, seed=self._seed, fp32_gemm=self._fp32_gemm)
+        if state is not None:
+            self.engine.load_state_dict(state)
+        self._modules.clear()
+        self._param_names = []
+        st = self.engine.store
+        for name in st.names():
+            node, leaf = self._node_for(name)
+            node.register_parameter(leaf, torch.nn.Parameter(st.p(name), requires_grad=True))
+            self._param_names.append(name)
+        for name, buf in self.engine.buffers.items():
+            node, leaf = self._node_for(name)
+            node.register_buffer(leaf, buf)
+
+    def forward(self, src_speech, src_speech_lengths, tgt_speech, tgt_speech_lengths, durations, durations_lengths, dp_inputs=None,
+                dp_lengths=None, spembs=None):
+        _require_cuda(src_speech, "FastSpeechVC")
+        if dp_inputs is None:
+            raise S2SError("dp_inputs is required (duration_predictor_use_encoder_outputs=False)")
+        eng = self.engine
+        eng.p16_dirty = True
+        il, ol = _host_lens(src_speech_lengths), _host_lens(tgt_speech_lengths)
+        dl = _host_lens(durations_lengths)
+        xs = src_speech[:, :max(il)].to(_f32).contiguous()                     # fastspeech_vc.py:413-415
+        ys = tgt_speech[:, :max(ol)].to(_f32).contiguous()
+        T2 = (((xs.shape[1] - 1) // 2) - 1) // 2
+        ds = durations[:, :max(dl)].to(device=xs.device, dtype=torch.int64)
+        if ds.shape[1] != T2:
+            raise S2SError(f"durations cover {ds.shape[1]} encoder frames, the conv2d input layer yields {T2}")
+        ds = ds.contiguous()
+        # the regulated length is data: the reference's LengthRegulator reads it on the host too (repeat_interleave + pad_list)
+        L = int(ds.sum(1).max().item()) * self.teacher_model_decoder_reduction_factor
+        if L != ys.shape[1]:
+            raise S2SError(f"sum of durations ({L}) != target length ({ys.shape[1]}): the L1 loss needs them equal (trainers/nar_vc.py:74)")
+        dpi = dp_inputs.to(_f32).contiguous()
+        self._fwd_token += 1
+        if eng.training:
+            ops.step_advance(None, eng.seed_dev)
+        before, after, d_outs = _FastSpeechVCFunction.apply(self, xs, ys, ds, dpi, il, ol, *self.parameters())
+        for name, P in eng.attn.items():
+            self.get_submodule(name).attn = P.float() if P.dtype != _f32 else P
+        ilens_out = torch.tensor(eng.tlens_host, dtype=torch.int64, device=xs.device)
+        olens_out = torch.as_tensor(tgt_speech_lengths).to(xs.device)
+        return before.float(), after.float(), d_outs, ilens_out, olens_out, ys
+
+    def inference(self, src_speech, tgt_speech=None, spembs=None, dp_input=None, alpha: float = 1.0, use_teacher_forcing: bool = False):
+        """fastspeech_vc.py:427-470 without teacher forcing: (outs (L, odim), d_outs (T',))."""
+        if use_teacher_forcing:
+            raise NotImplementedError("inference(use_teacher_forcing=True)")
+        _require_cuda(src_speech, "FastSpeechVC")
+        outs, d_outs = self.engine.inference(src_speech, dp_input, alpha)
+        return outs, d_outs
+
+
+
 class AASVCTrainStep(_ReferenceCheckpoint):
     """forward + L1 / forward-sum / bin / duration losses + backward (+ gradient all-reduce) + clip + Adam + WarmupLR,
     device-resident: mirrors AASVCTrainer._train_step (trainers/aas_vc.py:56-159).
