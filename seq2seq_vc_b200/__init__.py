@@ -9,7 +9,7 @@ from ._lib import S2SError  # noqa: F401
 from .vtn_engine import VTNEngine, default_hparams  # noqa: F401
 from .aasvc_engine import AASVCEngine  # noqa: F401
 from .api import VTN, TransformerTTS, Seq2SeqLoss, GuidedMultiHeadAttentionLoss, VTNTrainStep, viterbi_decode, logmelfilterbank  # noqa: F401
-from .api import AASVC, AASVCTrainStep, FastSpeechVC, L1Loss, ForwardSumLoss, DurationPredictorLoss  # noqa: F401
+from .api import AASVC, AASVCTrainStep, FastSpeechVC, NARVCTrainStep, L1Loss, ForwardSumLoss, DurationPredictorLoss  # noqa: F401
 from .api import DistributedDataParallel, LengthRegulator  # noqa: F401
 from .api import Spectrogram2Waveform, griffin_lim, logmel2linear  # noqa: F401
 

@@ -1699,3 +1699,97 @@ class AASVCTrainStep(_ReferenceCheckpoint):
             self._allreduce()
             g2.replay()
         return eng.losses
+
+
+class NARVCTrainStep(AASVCTrainStep):
+    """forward + L1 / duration losses + backward (+ gradient all-reduce) + clip + Adam + WarmupLR, device-resident: mirrors
+    NARVCTrainer._train_step (trainers/nar_vc.py:52-103) for the FastSpeechVC drop-in.  Same options as AASVCTrainStep (CUDA graphs
+    per batch shape, ``prefetch`` of the next batch, gradient accumulation, process group); the teacher's durations are a fourth
+    input tensor (int64) and there is no duration-predictor warm-up."""
+
+    def __init__(self, model, lr: float = 8e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, grad_norm: float = 1.0,
+                 warmup_steps: int = 4000, use_graph: bool = False, process_group=None, gradient_accumulate_steps: int = 1):
+        super().__init__(model, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, grad_norm=grad_norm, warmup_steps=warmup_steps,
+                         dp_train_start_steps=0, use_graph=use_graph, process_group=process_group,
+                         gradient_accumulate_steps=gradient_accumulate_steps)
+
+    def _clock_of(self, name: str) -> torch.Tensor:
+        return self.engine.step_dev
+
+    def _fwd_bwd(self, xs, ys, ds, dpi, fresh=True, boundary=True):
+        eng = self.engine
+        eng.forward(xs, ys, ds, dpi)
+        eng.loss(ys)
+        eng.backward(zero_grad=fresh)
+        if not boundary:
+            ops.step_advance(None, eng.seed_dev)
+
+    def _update(self, with_duration=True):
+        self.engine.optimizer_step(self.grad_norm, self.betas, self.eps, self.wd, grad_scale=1.0 / (self.world * self.accum))
+
+    def __call__(self, xs, ilens, ys, olens, durations, dp_inputs):
+        """xs (B,T,idim), ys (B,L,odim), dp_inputs (B,T_dp,dp_idim) float32 and durations (B,T') int64 with
+        T' = ((T - 1) // 2 - 1) // 2 and max_b sum(durations[b]) * teacher factor == L: CUDA-resident or pinned host memory.
+        Returns the device tensor (l1, duration) of this step without synchronising."""
+        eng = self.engine
+        fresh = self.backward_steps % self.accum == 0
+        self.backward_steps += 1
+        boundary = self.backward_steps % self.accum == 0
+        if boundary:
+            self.steps += 1
+            eng.lr_dev.fill_(self.lr_at(self.steps))
+        B, T, L = xs.shape[0], xs.shape[1], ys.shape[1]
+        if durations.dtype != torch.int64 or tuple(durations.shape) != (B, ((T - 1) // 2 - 1) // 2):
+            raise S2SError(f"durations must be int64 of shape (B, ((T - 1) // 2 - 1) // 2), got {durations.dtype} {tuple(durations.shape)}")
+        eng.training = True
+        eng.prepare(B, T, L, ilens, olens)
+        ins = (xs, ys, durations, dp_inputs)
+        staged = self._take_staged(*ins)
+        if staged is not None:
+            ins = tuple(staged)
+        if not self.use_graph:
+            if not ins[0].is_cuda:
+                ins = tuple(t.to(eng.device, non_blocking=True) for t in ins)
+            self._fwd_bwd(*ins, fresh, boundary)
+            if boundary:
+                self._allreduce()
+                self._update()
+            if staged is not None:
+                self._staged_consumed()
+            return eng.losses
+        key = (B, T, L, dp_inputs.shape[1], True, fresh, boundary)
+        entry = self._graphs.get(key)
+        if entry is None:
+            statics = [torch.empty(t.shape, dtype=t.dtype, device=eng.device) for t in ins]
+            for dst, src in zip(statics, ins):
+                dst.copy_(src, non_blocking=True)
+            if staged is not None:
+                self._staged_consumed()
+            self._fwd_bwd(*statics, fresh, boundary)            # eager step: allocates every buffer outside the graph pool
+            if boundary:
+                self._allreduce()
+                self._update()
+            torch.cuda.synchronize()
+            g1, g2 = torch.cuda.CUDAGraph(), (torch.cuda.CUDAGraph() if boundary else None)
+            n0 = _lib.launch_count()
+            with torch.cuda.graph(g1):
+                self._fwd_bwd(*statics, fresh, boundary)
+            if boundary:
+                with torch.cuda.graph(g2):
+                    self._update()
+            self._graphs[key] = (g1, g2, statics, _lib.launch_count() - n0)
+            return eng.losses
+        g1, g2, statics, n_kernels = entry
+        if eng.p16_dirty:
+            eng.sync_shadow()
+        self.replayed_launches += n_kernels
+        for dst, src in zip(statics, ins):
+            if src.data_ptr() != dst.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        if staged is not None:
+            self._staged_consumed()
+        g1.replay()
+        if boundary:
+            self._allreduce()
+            g2.replay()
+        return eng.losses

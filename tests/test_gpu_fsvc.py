@@ -228,3 +228,30 @@ def test_inference_matches_oracle_pipeline():
     assert tuple(outs.shape) == (L, 80) and (outs.cpu() - ref["after_outs"][0]).abs().mean().item() <= 1e-4
     outs2, _ = model.inference(x.cuda(), dp_input=x.cuda(), alpha=1.5)
     assert outs2.shape[0] == int(torch.round(ds[0].float() * 1.5).long().sum())
+
+
+def test_fused_train_step_graph_matches_eager_and_prefetch():
+    """NARVCTrainStep: CUDA-graph replay == eager launches (same seeds, dropout on) from pinned host batches staged with prefetch();
+    losses finite, parameters move."""
+    from seq2seq_vc_b200 import FastSpeechVC, NARVCTrainStep
+
+    z, sd = _golden()
+    ilens, olens = z["ilens"].tolist(), z["olens"].tolist()
+    host = [torch.from_numpy(z[k]).pin_memory() for k in ("xs", "ys", "ds", "dp_inputs")]
+    outs = []
+    for use_graph in (False, True):
+        model = FastSpeechVC(**FS_HP, **FIXED, seed=11).to("cuda:0")
+        model.load_state_dict(sd)
+        st = NARVCTrainStep(model, lr=1e-3, warmup_steps=10, use_graph=use_graph)
+        ls = []
+        for i in range(4):
+            if i % 2 == 1:
+                st.prefetch(*host)
+            ls.append(st(host[0], ilens, host[1], olens, host[2], host[3]).clone())
+        torch.cuda.synchronize()
+        outs.append((torch.stack(ls).cpu(), model.engine.store.P.clone().cpu()))
+        assert st.steps == 4 and (not use_graph or st.replayed_launches > 0)
+    assert torch.isfinite(outs[0][0]).all() and torch.isfinite(outs[1][0]).all()
+    assert (outs[0][0] - outs[1][0]).abs().max().item() <= 5e-3 * outs[0][0].abs().max().item()
+    assert (outs[0][1] - outs[1][1]).abs().max().item() <= 1e-4
+    assert (model.engine.state_dict()["feat_out.weight"].cpu() - sd["feat_out.weight"]).abs().max().item() > 0

@@ -728,3 +728,100 @@ def test_reference_aasvc_trainer_eval_hook_with_dropin_inference(trainers, monke
         assert a.shape == b.shape
         m = np.isfinite(a)
         assert np.array_equal(m, np.isfinite(b)) and np.abs(a[m] - b[m]).max() <= 2e-4
+
+
+# ------------------------------------------------------------------ FastSpeechVC (trainers/nar_vc.py)
+FS_HP = dict(idim=80, odim=80, adim=32, aheads=2, elayers=2, eunits=48, dlayers=2, dunits=48, duration_predictor_input_dim=80,
+             duration_predictor_layers=2, duration_predictor_chans=16, duration_predictor_kernel_size=3, postnet_layers=2, postnet_filts=5,
+             postnet_chans=16, conformer_enc_kernel_size=7, conformer_dec_kernel_size=7)
+FS_FIXED = dict(encoder_type="conformer", decoder_type="conformer", encoder_input_layer="conv2d", positionwise_layer_type="linear",
+                duration_predictor_use_encoder_outputs=False, encoder_normalize_before=True, decoder_normalize_before=True,
+                teacher_model_decoder_reduction_factor=1)
+
+
+def _fs_batch():
+    """Out of the reference's own collater (collaters/nar_vc.py:49-91, the branch with teacher durations)."""
+    from seq2seq_vc.collaters.nar_vc import NARVCCollater
+
+    rng = np.random.default_rng(31)
+    items = []
+    for t in (62, 51):
+        tl = ((t - 1) // 2 - 1) // 2
+        d = rng.integers(0, 4, tl).astype(np.int64)
+        d[0] = max(d[0], 1)
+        src = rng.standard_normal((t, 80)).astype(np.float32)
+        items.append(dict(src_feat=src, trg_feat=rng.standard_normal((int(d.sum()), 80)).astype(np.float32), dp_input=src.copy(), duration=d))
+    return NARVCCollater()(items)
+
+
+def _nar_trainer(monkeypatch):
+    import seq2seq_vc.trainers.nar_vc as t_nar
+
+    return t_nar.NARVCTrainer
+
+
+FS_CONFIG = dict(grad_norm=1.0, train_max_steps=10 ** 9, distributed=False, save_interval_steps=10 ** 9, eval_interval_steps=10 ** 9,
+                 log_interval_steps=10 ** 9)
+
+
+@pytest.mark.parametrize("criterions", ["reference", "dropin"])
+def test_reference_narvc_trainer_drives_dropin_fastspeech_vc(trainers, monkeypatch, criterions):
+    """NARVCTrainer._train_step (trainers/nar_vc.py:52-103) with the reference's batch dict, L1Loss / DurationPredictorLoss,
+    torch.optim.Adam, WarmupLR and clip_grad_norm_ around seq2seq_vc_b200.FastSpeechVC vs around the reference model."""
+    _, _, outdir = trainers
+    import seq2seq_vc_b200
+    from seq2seq_vc.losses import DurationPredictorLoss, L1Loss
+    from seq2seq_vc.models import FastSpeechVC as RefFS
+
+    NARVCTrainer = _nar_trainer(monkeypatch)
+    torch.manual_seed(37)
+    ref = RefFS(**FS_HP, **FS_FIXED)
+    ref_shim.disable_dropout(ref)
+    ref.train()
+    ours = seq2seq_vc_b200.FastSpeechVC(**FS_HP, **FS_FIXED, **AAS_NO_DROPOUT)
+    ours.load_state_dict(ref.state_dict())
+    ours.train()
+    _same_parameter_order(ref, ours)
+    batch = _fs_batch()
+    config = dict(FS_CONFIG, outdir=outdir)
+    crit = lambda: {"L1Loss": L1Loss(), "DurationPredictorLoss": DurationPredictorLoss()}
+    t_ref = _run(NARVCTrainer, ref, crit(), config, batch, 3)
+    our_crit = crit() if criterions == "reference" else {"L1Loss": seq2seq_vc_b200.L1Loss(),
+                                                         "DurationPredictorLoss": seq2seq_vc_b200.DurationPredictorLoss()}
+    t_our = _run(NARVCTrainer, ours, our_crit, config, batch, 3)
+    assert t_ref.steps == t_our.steps == 3
+    for k in ("train/l1_loss", "train/duration_loss", "train/loss"):
+        assert abs(t_ref.total_train_loss[k] - t_our.total_train_loss[k]) <= 1e-4 * max(1.0, abs(t_ref.total_train_loss[k])), k
+    _compare_grads(t_ref, t_our)
+    sd_ref, sd_our = ref.state_dict(), ours.state_dict()
+    assert set(sd_ref) == set(sd_our)
+    _close(sd_ref, sd_our)
+
+
+def test_fused_narvc_train_step_matches_reference_trainer(trainers, monkeypatch):
+    """seq2seq_vc_b200.NARVCTrainStep (own clip + Adam + WarmupLR on flat buffers) == NARVCTrainer._train_step around the reference
+    FastSpeechVC: same logged losses, same parameters after 3 steps."""
+    _, _, outdir = trainers
+    import seq2seq_vc_b200
+    from seq2seq_vc.losses import DurationPredictorLoss, L1Loss
+    from seq2seq_vc.models import FastSpeechVC as RefFS
+
+    NARVCTrainer = _nar_trainer(monkeypatch)
+    torch.manual_seed(41)
+    ref = RefFS(**FS_HP, **FS_FIXED)
+    ref_shim.disable_dropout(ref)
+    ref.train()
+    ours = seq2seq_vc_b200.FastSpeechVC(**FS_HP, **FS_FIXED, **AAS_NO_DROPOUT)
+    ours.load_state_dict(ref.state_dict())
+    batch = _fs_batch()
+    t_ref = _run(NARVCTrainer, ref, {"L1Loss": L1Loss(), "DurationPredictorLoss": DurationPredictorLoss()}, dict(FS_CONFIG, outdir=outdir), batch, 3)
+    step = seq2seq_vc_b200.NARVCTrainStep(ours, lr=1e-3, warmup_steps=3, grad_norm=1.0)
+    tot = torch.zeros(2)
+    for _ in range(3):
+        tot += step(batch["xs"], batch["ilens"].tolist(), batch["ys"], batch["olens"].tolist(), batch["durations"], batch["dp_inputs"]).float().cpu()
+    assert step.steps == t_ref.steps == 3
+    for i, k in enumerate(("train/l1_loss", "train/duration_loss")):
+        assert abs(float(tot[i]) - t_ref.total_train_loss[k]) <= 2e-4 * max(1.0, abs(t_ref.total_train_loss[k])), k
+    _close(ref.state_dict(), ours.engine.state_dict())
+    ck = step.state_dict()                           # reference checkpoint layout (trainers/base.py:86-104)
+    assert ck["steps"] == 3 and set(ck["model"]) == set(ref.state_dict())
