@@ -7,7 +7,9 @@ fallback").  PyTorch tensors are used purely as device-memory handles; every cal
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
+import gc
 import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 
@@ -192,7 +194,49 @@ def load(path: str | None = None) -> ctypes.CDLL:
     return lib
 
 
+@contextlib.contextmanager
+def no_gc():
+    """Collect cyclic garbage now and keep the collector off inside the block.  Every stream capture of this package runs under it:
+    torch.cuda.graph() no longer calls gc.collect() itself (torch.compiler.config.force_cudagraph_gc), so a dead reference cycle that
+    still owns CUDA graphs or device memory (an engine and its train step from an earlier batch of work) could be finalised by a
+    collection that happens to trigger *inside* the capture -- its cudaFree / graph destruction invalidates a global-mode capture
+    ("operation failed due to a previous error during capture", seen as an order-dependent test failure)."""
+    gc.collect()
+    was = gc.isenabled()
+    gc.disable()
+    try:
+        yield
+    finally:
+        if was:
+            gc.enable()
+
+
+@contextlib.contextmanager
+def graph_capture(graph, **kw):
+    """`with torch.cuda.graph(graph, **kw)` under no_gc()."""
+    with no_gc():
+        with torch.cuda.graph(graph, **kw):
+            yield
+
+
+_DEBUG_CAPTURE = os.environ.get("S2S_DEBUG_CAPTURE", "0") == "1"
+_last_ok = ""
+
+
+def _capture_invalidated() -> bool:
+    """Debug aid (S2S_DEBUG_CAPTURE=1): has the stream capture under way on torch's current stream been invalidated?"""
+    from cuda.bindings import runtime as cudart
+
+    err, status = cudart.cudaStreamIsCapturing(torch.cuda.current_stream().cuda_stream)
+    return err != cudart.cudaError_t.cudaSuccess or status == cudart.cudaStreamCaptureStatus.cudaStreamCaptureStatusInvalidated
+
+
 def check(rc: int, what: str = "") -> None:
+    if _DEBUG_CAPTURE:
+        global _last_ok
+        if _capture_invalidated():
+            raise S2SError(f"stream capture invalidated at or before {what} (rc={rc}); last call seen with a live capture: {_last_ok}")
+        _last_ok = what
     if rc != 0:
         msg = load().s2s_last_error()
         raise S2SError(f"{what} failed (rc={rc}): {msg.decode() if msg else '?'}")

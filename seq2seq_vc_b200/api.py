@@ -15,6 +15,7 @@ from __future__ import annotations
 import logging
 import math
 import os
+import weakref
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
@@ -89,7 +90,7 @@ def _dropin_graph_forward(model, xs, ys, ilens, olens):
         torch.cuda.synchronize()
         before = dict(eng.__dict__)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with _lib.graph_capture(g):
             eng.p16_dirty = True            # an external optimizer owns the parameters: the bf16 shadow is refreshed inside the graph
             outs = eng.forward(sx, sy)
         e.update(gF=g, sx=sx, sy=sy, outs=outs,
@@ -113,7 +114,7 @@ def _dropin_graph_backward(eng, e, grads, fresh: bool) -> None:
     if name not in e:
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with _lib.graph_capture(g):
             eng.backward(*e["d"], zero_grad=fresh)
         e[name] = g
     e[name].replay()
@@ -940,7 +941,7 @@ class VTNTrainStep(_ReferenceCheckpoint):
             self.world = torch.distributed.get_world_size(process_group)
         self._graphs: Dict[tuple, tuple] = {}
         self.replayed_launches = 0      # kernels of this library launched through graph replays
-        self.engine._evict_listeners.append(self._on_evict)
+        self.engine._evict_listeners.append(weakref.WeakMethod(self._on_evict))
         if guided_attn is not None:     # the guided-attention loss reads (and back-propagates into) these maps: keep them in HBM
             nl = self.engine.hp["dlayers"]
             self.engine.attn_emit_names = frozenset(
@@ -1028,7 +1029,7 @@ class VTNTrainStep(_ReferenceCheckpoint):
                 g1b = torch.cuda.CUDAGraph()
                 cap = torch.cuda.Stream()
                 cap.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(cap):
+                with _lib.no_gc(), torch.cuda.stream(cap):
                     g1.capture_begin()
 
                     def cut():
@@ -1039,9 +1040,9 @@ class VTNTrainStep(_ReferenceCheckpoint):
                     g1b.capture_end()
                 torch.cuda.current_stream().wait_stream(cap)
             else:
-                with torch.cuda.graph(g1):
+                with _lib.graph_capture(g1):
                     self._fwd_bwd(sx, sy, sl)
-            with torch.cuda.graph(g2):
+            with _lib.graph_capture(g2):
                 self._update()
             self._graphs[key] = (g1, g2, sx, sy, sl, _lib.launch_count() - n0, g1b)
             return eng.losses
@@ -1612,7 +1613,7 @@ class AASVCTrainStep(_ReferenceCheckpoint):
             self.world = torch.distributed.get_world_size(process_group)
         self._graphs: Dict[tuple, tuple] = {}
         self.replayed_launches = 0
-        self.engine._evict_listeners.append(self._on_evict)
+        self.engine._evict_listeners.append(weakref.WeakMethod(self._on_evict))
 
     lr_at = VTNTrainStep.lr_at
 
@@ -1678,10 +1679,10 @@ class AASVCTrainStep(_ReferenceCheckpoint):
             torch.cuda.synchronize()
             g1, g2 = torch.cuda.CUDAGraph(), (torch.cuda.CUDAGraph() if boundary else None)
             n0 = _lib.launch_count()
-            with torch.cuda.graph(g1):
+            with _lib.graph_capture(g1):
                 self._fwd_bwd(*statics, with_dur, fresh, boundary)
             if boundary:
-                with torch.cuda.graph(g2):
+                with _lib.graph_capture(g2):
                     self._update(with_dur)
             self._graphs[key] = (g1, g2, statics, _lib.launch_count() - n0)
             return eng.losses
@@ -1772,10 +1773,10 @@ class NARVCTrainStep(AASVCTrainStep):
             torch.cuda.synchronize()
             g1, g2 = torch.cuda.CUDAGraph(), (torch.cuda.CUDAGraph() if boundary else None)
             n0 = _lib.launch_count()
-            with torch.cuda.graph(g1):
+            with _lib.graph_capture(g1):
                 self._fwd_bwd(*statics, fresh, boundary)
             if boundary:
-                with torch.cuda.graph(g2):
+                with _lib.graph_capture(g2):
                     self._update()
             self._graphs[key] = (g1, g2, statics, _lib.launch_count() - n0)
             return eng.losses

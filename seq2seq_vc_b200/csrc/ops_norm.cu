@@ -253,6 +253,106 @@ __global__ void __launch_bounds__(256) ln_bwd_reg_kernel(const T* __restrict__ d
     }
 }
 
+// Same dX, plus the parameter gradients in the same pass: every warp walks rows blockIdx.x * 8 + warp, + gridDim.x * 8, ... and keeps
+// its columns' sums of dy * xhat / dy in registers; the CTA folds its 8 warps through shared-memory atomics and issues ONE global
+// float atomicAdd per (column, CTA).  Replaces ln_bwd_reg + a colreduce launch that re-read dy and x (rows > 512 only: below that the
+// two-kernel route's single row chunk keeps the sums bit-reproducible, see launch_colreduce).
+template <typename T, int NV>
+__global__ void __launch_bounds__(256, NV <= 2 ? 3 : 1) ln_bwd_grad_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                          const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                          const float* __restrict__ rstd, const T* __restrict__ dres,
+                                                          T* __restrict__ dx, long rows, int d, T* __restrict__ dxd, Dropout drop,
+                                                          float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    __shared__ float sacc[2][NV * 256];
+    const int lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 2 * NV * 256; i += 256) (&sacc[0][0])[i] = 0.f;
+    __syncthreads();
+    if (dxd) dropout_resolve(drop);
+    float ag[NV][8], ab[NV][8];
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { ag[j][k] = 0.f; ab[j][k] = 0.f; }
+    for (long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5); row < rows; row += (long)gridDim.x * 8) {
+        const T* xr = x + row * d;
+        const T* gr = dy + row * d;
+        const float mu = mean[row], rs = rstd[row];
+        Raw8<T> rx[NV], rg[NV];
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int c = (j * 32 + lane) * 8;
+            if (c < d) { rx[j].load(xr + c); rg[j].load(gr + c); }
+        }
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int c = (j * 32 + lane) * 8;
+            if (c < d) {
+                float xv[8], gv[8], gm[8];
+                rx[j].get(xv);
+                rg[j].get(gv);
+                Vec8<float>::load(gamma + c, gm);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float xh = (xv[k] - mu) * rs, gg = gv[k] * gm[k];
+                    a += gg;
+                    b += gg * xh;
+                    ag[j][k] += gv[k] * xh;
+                    ab[j][k] += gv[k];
+                }
+            }
+        }
+        a = warp_sum(a) / (float)d;
+        b = warp_sum(b) / (float)d;
+        T* dr = dx + row * d;
+        const T* rr = dres ? dres + row * d : nullptr;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int c = (j * 32 + lane) * 8;
+            if (c < d) {
+                float xv[8], gv[8], gm[8], o[8];
+                rx[j].get(xv);
+                rg[j].get(gv);
+                Vec8<float>::load(gamma + c, gm);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[k] = rs * (gv[k] * gm[k] - a - (xv[k] - mu) * rs * b);
+                if (rr) {
+                    float e[8];
+                    Vec8<T>::load(rr + c, e);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) o[k] += e[k];
+                }
+                Vec8<T>::store(dr + c, o);
+                if (dxd) {
+                    float mk[8];
+                    dropout_factors<8>(drop, (uint64_t)(row * d + c), mk);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) o[k] *= mk[k];
+                    Vec8<T>::store(dxd + row * d + c, o);
+                }
+            }
+        }
+    }
+    // shared layout [k][column group] so that a warp's 32 lanes hit 32 different banks
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int g = j * 32 + lane;
+        if (g * 8 < d) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                atomicAdd(&sacc[0][k * (NV * 32) + g], ag[j][k]);
+                atomicAdd(&sacc[1][k * (NV * 32) + g], ab[j][k]);
+            }
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < d; c += 256) {
+        const int i = (c & 7) * (NV * 32) + (c >> 3);
+        atomicAdd(dgamma + c, sacc[0][i]);
+        atomicAdd(dbeta + c, sacc[1][i]);
+    }
+}
+
 // =============================================================================================
 // Generic column reduction: out_k[c] += sum_r f_k(r, c).  blockDim = (32, 8); each thread owns
 // VEC consecutive columns; grid = (col tiles, row chunks); cross-warp reduce in shared memory and
@@ -880,6 +980,9 @@ extern "C" int s2s_layernorm_fwd(const void* x, const float* gamma, const float*
     return S2S_OK;
 }
 
+// S2S_LN_FUSED=0 restores the two-kernel route (A/B measurements)
+static int g_ln_fused = [] { const char* e = getenv("S2S_LN_FUSED"); return e ? atoi(e) : 1; }();
+
 static int layernorm_bwd_impl(const void* dy, const void* x, const float* gamma, const float* mean,
                                  const float* rstd, const void* dres, void* dx, float* dgamma, float* dbeta,
                                  int64_t rows, int d, int dtype, void* stream, void* dx_drop, const s2s_dropout_t* dropd) {
@@ -892,6 +995,20 @@ static int layernorm_bwd_impl(const void* dy, const void* x, const float* gamma,
 #define S2S_LN_BWD(NVV) ln_bwd_reg_kernel<T, NVV><<<gp, 256, 0, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (const T*)dres, \
                                                                      (T*)dx, rows, d, (T*)dx_drop, dd)
         const Dropout dd = make_dropout(dropd);
+        if (dx && dgamma && dbeta && rows > 512 && nv <= 2 && g_ln_fused) {
+            // one pass: dX and the gamma / beta gradients (3 resident CTAs per SM, every CTA loops over its share of the rows)
+            const long groups = ceil_div_l(rows, 8);
+            const long cap = (long)num_sms() * 3;
+            const unsigned gf = (unsigned)(groups < cap ? groups : cap);
+#define S2S_LN_BWDG(NVV) ln_bwd_grad_kernel<T, NVV><<<gf, 256, 0, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (const T*)dres, \
+                                                                      (T*)dx, rows, d, (T*)dx_drop, dd, dgamma, dbeta)
+            S2S_DISPATCH_DTYPE(dtype, T, {
+                if (nv <= 1) S2S_LN_BWDG(1); else S2S_LN_BWDG(2);
+            });
+#undef S2S_LN_BWDG
+            S2S_LAUNCH_OK();
+            return S2S_OK;
+        }
         if (dx) {
             S2S_DISPATCH_DTYPE(dtype, T, {
                 if (nv <= 1) S2S_LN_BWD(1); else if (nv <= 2) S2S_LN_BWD(2); else if (nv <= 4) S2S_LN_BWD(4);

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import math
 import os
+import weakref
 from collections import OrderedDict
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
@@ -138,7 +139,13 @@ class EngineBase:
             self._evict_sig(old)
 
     def _evict_sig(self, sig: Tuple) -> None:
-        for cb in self._evict_listeners:
+        for cb in list(self._evict_listeners):
+            if isinstance(cb, weakref.WeakMethod):      # train steps register weakly: engine -> step -> engine must not be a cycle
+                fn = cb()
+                if fn is None:
+                    self._evict_listeners.remove(cb)
+                    continue
+                cb = fn
             cb(sig)
         for key in [k for k in self._bufs if k[0] == sig]:
             del self._bufs[key]

@@ -23,7 +23,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 
-from . import ops
+from . import _lib, ops
 from ._lib import NO_DROP, Drop
 from .engine_base import EngineBase, _r8, sinusoid_table
 from .conformer_blocks import ConformerBlocks, conformer_buffer_specs, conformer_param_groups
@@ -507,7 +507,7 @@ class VTNEngine(ConformerBlocks, EngineBase):
                     if idx == 1 and self.device.type == "cuda":
                         torch.cuda.synchronize()
                         graph = torch.cuda.CUDAGraph()
-                        with torch.cuda.graph(graph):
+                        with _lib.graph_capture(graph):
                             step()
                 else:
                     graph.replay()
@@ -590,7 +590,7 @@ class VTNEngine(ConformerBlocks, EngineBase):
                     if use_graph:
                         torch.cuda.synchronize()
                         g = torch.cuda.CUDAGraph()
-                        with torch.cuda.graph(g):
+                        with _lib.graph_capture(g):
                             step_body(Lq)
                         graphs[Lq] = g
                 elif graphs[Lq] is not None:

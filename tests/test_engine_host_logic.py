@@ -333,3 +333,42 @@ def test_conformer_encoder_inference_matches_oracle(monkeypatch, rel):
         assert outs.shape == ref_o.shape
         assert (outs - ref_o).abs().mean().item() <= 1e-5 and (probs - ref_p).abs().mean().item() <= 1e-5
         assert (att - ref_a).abs().mean().item() <= 1e-6
+
+
+def test_train_step_and_engine_form_no_reference_cycle(monkeypatch):
+    """A train step registers its shape-eviction callback weakly, so dropping the step and its engine frees both by reference
+    counting alone: a dead engine <-> step cycle would keep CUDA graphs and device memory alive until some later cyclic collection,
+    and a collection that triggers inside another stream capture invalidates it.  Captures themselves run with the collector off
+    (_lib.no_gc) -- torch.cuda.graph() does not collect any more."""
+    import gc
+    import weakref
+
+    from seq2seq_vc_b200 import VTNTrainStep, _lib
+
+    fake_ops.install(monkeypatch)
+    gc.collect()
+    was = gc.isenabled()
+    gc.disable()
+    try:
+        eng = VTNEngine(dict(TINY_HP), device="cpu", bf16=False)
+        step = VTNTrainStep(eng, lr=1e-3, warmup_steps=1)
+        seen = []
+        eng._evict_listeners.append(lambda sig: seen.append(sig))
+        eng._evict_sig((1, 2, 3, True))                 # weak listeners are resolved and called
+        assert seen == [(1, 2, 3, True)]
+        w_eng, w_step = weakref.ref(eng), weakref.ref(step)
+        del step
+        assert w_step() is None                         # the engine does not keep the step alive
+        eng._evict_sig((1, 2, 3, True))                 # ... and drops the dead listener
+        assert not any(isinstance(cb, weakref.WeakMethod) for cb in eng._evict_listeners)
+        del eng
+        assert w_eng() is None
+        with _lib.no_gc():
+            assert not gc.isenabled()
+        assert not gc.isenabled()                       # restored to what it was (off, here)
+    finally:
+        if was:
+            gc.enable()
+    with _lib.no_gc():
+        assert not gc.isenabled()
+    assert gc.isenabled() == was

@@ -219,7 +219,8 @@ def test_gemm_cta_pairs(ops):
 
 
 @pytest.mark.parametrize("dt", DT)
-@pytest.mark.parametrize("rows,d", [(7, 32), (1000, 384), (33, 50), (3001, 1536), (130, 256), (65, 1032), (40, 2048), (9, 2056)])
+@pytest.mark.parametrize("rows,d", [(7, 32), (1000, 384), (33, 50), (3001, 1536), (130, 256), (65, 1032), (40, 2048), (9, 2056), (5000, 80), (20011, 384),
+                                     (4064, 512)])
 def test_layernorm(ops, dt, rows, d):
     x, dy, res = rnd(rows, 1, d, dt=dt, seed=1), rnd(rows, 1, d, dt=dt, seed=2), rnd(rows, 1, d, dt=dt, seed=3)
     gam, bet = 1 + 0.1 * rnd(d, seed=4), 0.1 * rnd(d, seed=5)

@@ -472,7 +472,10 @@ def test_graph_steps_alternating_shapes_match_eager():
         batch = batches[it % 2]
         le = steps[False](*batch).clone()
         lg = steps[True](*batch).clone()
-        assert (le - lg).abs().max().item() <= 1e-4 * max(1.0, le.abs().max().item()), (it, le.tolist(), lg.tolist())
+        # the two runs differ by the ordering of float atomics (split-K red.add, column reductions); Adam's first steps turn that
+        # round-off into lr-sized moves of near-zero-gradient parameters, so the losses drift apart by ~1e-4 relative over 8 steps
+        # (seen: 1.5e-4 at it = 6).  A replay reading a stale or relocated buffer is off by orders of magnitude more.
+        assert (le - lg).abs().max().item() <= 1e-3 * max(1.0, le.abs().max().item()), (it, le.tolist(), lg.tolist())
     pe, pg = steps[False].engine.store.P, steps[True].engine.store.P
     assert (pe - pg).abs().max().item() <= 1e-3      # Adam turns the fp32 red.add ordering noise of the weight-gradient GEMMs into lr-sized steps
 
