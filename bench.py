@@ -53,6 +53,13 @@ WORKLOADS = {
                  postnet_filts=5, postnet_chans=256, post_encoder_reduction_factor=4, conformer_enc_kernel_size=15,
                  conformer_dec_kernel_size=15, duration_predictor_type="stochastic"),
             64, 768, 768, True, "AAS-VC Conformer 4+4 (enc d384, dec d1536, h2, k15) with the stochastic duration predictor, B64 x (768->768, 80-mel), bf16"),
+    # FastSpeechVC (egs/arctic/vc2/conf/fs2_vc.melmelmel.v1.yaml): conformer 4+4 behind the conv2d input layer, teacher durations;
+    # a widening workload, not a BASELINE.json config
+    "c6": (dict(idim=80, odim=80, adim=384, aheads=2, elayers=4, eunits=1536, dlayers=4, dunits=1536, duration_predictor_input_dim=80,
+                duration_predictor_layers=2, duration_predictor_chans=256, duration_predictor_kernel_size=3, postnet_layers=5,
+                postnet_filts=5, postnet_chans=256, conformer_enc_kernel_size=15, conformer_dec_kernel_size=15,
+                teacher_model_decoder_reduction_factor=1),
+           64, 768, 768, True, "FastSpeechVC Conformer 4+4 (d384, h2, k15, conv2d input layer, teacher durations), B64 x (768->768, 80-mel), bf16"),
     "c1": (dict(idim=80, odim=80, adim=256, aheads=4, elayers=2, dlayers=2, eunits=1024, dunits=1024, decoder_reduction_factor=2),
            4, 200, 400, False, "VTN-small 2+2 d256 h4 r2, B4 x (200->400, 80-mel), fp32"),
     # STFT -> log-mel (BASELINE.json configs[4]): 256 clips x 10 s @ 48 kHz, n_fft 2048, hop 300, 80 mels
@@ -61,6 +68,7 @@ WORKLOADS = {
 }
 METRIC = "target mel-frames/sec, VTN-base enc-dec training step (80-mel, src512/tgt1024)"
 METRIC_C5 = "mel-frames/sec, STFT->log-mel feature extraction (48 kHz, n_fft 2048, hop 300, 80-mel)"
+METRIC_FS = "target mel-frames/sec, FastSpeechVC Conformer non-AR training step (80-mel, 768 frames)"
 METRIC_AAS = "target mel-frames/sec, AAS-VC Conformer non-AR training step (80-mel, 768 frames)"
 
 
@@ -220,6 +228,53 @@ def cpu_port_steps_aas(hp, B, T, L, steps, warmup):
     return sum(times) / len(times)
 
 
+def fs_batch(B, T, L, seed):
+    """Synthetic FastSpeechVC batch: mels + ragged teacher durations, every utterance summing to L (the data loader trims the target
+    to the duration sum, fs2_vc.melmelmel.v1.yaml: teacher_duration_reduction_factor)."""
+    g = torch.Generator().manual_seed(seed)
+    xs, ys = torch.randn(B, T, 80, generator=g), torch.randn(B, L, 80, generator=g)
+    Tt = ((T - 1) // 2 - 1) // 2
+    ds = torch.zeros(B, Tt, dtype=torch.int64)
+    for b in range(B):
+        cuts = torch.sort(torch.randint(0, L + 1, (Tt - 1,), generator=g)).values
+        ds[b] = torch.diff(torch.cat([torch.zeros(1, dtype=torch.int64), cuts, torch.full((1,), L, dtype=torch.int64)]))
+    assert int(ds.sum(1).min()) == L == int(ds.sum(1).max())
+    return xs, ys, ds
+
+
+def cpu_port_steps_fs(hp, B, T, L, steps, warmup):
+    """fwd + L1 / duration losses + bwd + clip + Adam of the FastSpeechVC oracle (plain torch fp32 CPU) on B utterances."""
+    from oracle import fsvc_oracle as fo
+    from seq2seq_vc_b200.fsvc_engine import param_groups, buffer_specs, default_hparams
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(0)
+    full_hp = default_hparams(**hp)
+    sd = {}
+    for grp in param_groups(full_hp):
+        for name, shape in grp:
+            sd[name] = (torch.randn(*shape, generator=g) * (0.05 if len(shape) > 1 else 0.0) + (1.0 if name.endswith(("norm.weight", "norm1.weight", "norm2.weight")) else 0.0))
+    for name, shape, dtype in buffer_specs(full_hp):
+        sd[name] = torch.ones(shape, dtype=dtype) if name.endswith("running_var") else torch.zeros(shape, dtype=dtype)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.dtype.is_floating_point and "running_" not in k}
+    full = dict(sd)
+    full.update(params)
+    opt = torch.optim.Adam(list(params.values()), lr=8e-5)
+    xs, ys, ds = fs_batch(B, T, L, 1234)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = fo.fsvc_forward(full, hp, xs, [T] * B, ys, [L] * B, ds, xs, training=True)
+        total, _ = fo.fsvc_losses(out, ds)
+        opt.zero_grad()
+        total.backward()
+        torch.nn.utils.clip_grad_norm_(list(params.values()), 1.0)
+        opt.step()
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    return sum(times) / len(times)
+
+
 def reference_modules():
     """The unmodified reference package from baseline/_ref (pip-installed + completed by __graft_entry__.build()), imported
     through oracle/ref_shim.py (lazy numba.jit, the missing diffsinger module).  None when it is not there."""
@@ -317,7 +372,7 @@ def run_reference(args, rank):
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)
         return
-    mods = reference_modules() if not is_aas(args.workload) else None
+    mods = reference_modules() if not (is_aas(args.workload) or args.workload == "c6") else None
     if mods is not None:
         # the reference's own modules; the full batch when a step stays within ~a minute, else a bounded sample (stated)
         import psutil
@@ -340,16 +395,18 @@ def run_reference(args, rank):
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)
         return
-    aas = is_aas(args.workload)
+    aas = is_aas(args.workload) or args.workload == "c6"
     Bs = 1 if aas else min(B, 4)
     timed = max(1, min(args.steps, 2 if aas else 6))      # bounded sample: the CPU arm must end within minutes whatever K is
-    if aas:
+    if args.workload == "c6":
+        sec = cpu_port_steps_fs(hp, Bs, T, L, timed, 1)
+    elif aas:
         sec = cpu_port_steps_aas(hp, Bs, T, L, timed, 1)
     else:
         sec = cpu_port_steps(hp, Bs, T, L, timed, max(1, min(args.warmup, 1)), args.workload == "c4")
     val = Bs * L / sec
     cores = os.cpu_count() or 1
-    line = {"impl": "reference", "metric": METRIC_AAS if aas else METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+    line = {"impl": "reference", "metric": (METRIC_FS if args.workload == "c6" else METRIC_AAS) if aas else METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "sample": f"{Bs} utterances per step (of {B}); frames/s scales linearly in B",
@@ -520,6 +577,99 @@ def run_torch_gpu(args, rank):
                       "warmup": args.warmup, "higher_is_better": True, "data": "synthetic", "config": {"workload": desc}, "detail": res}), flush=True)
 
 
+def run_c6(args, rank, world):
+    """FastSpeechVC training step (NARVCTrainer._train_step, trainers/nar_vc.py:52-103) through NARVCTrainStep; shards by utterance
+    batch like the other models (gradient all-reduce only)."""
+    from seq2seq_vc_b200 import FastSpeechVC, NARVCTrainStep, _lib
+
+    hp, B, T, L, bf16, desc = WORKLOADS["c6"]
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _lib.device_check()
+    xs, ys, ds = fs_batch(B, T, L, 1234 + rank)
+    ilens, olens = [T] * B, [L] * B
+    yaml_fixed = dict(positionwise_layer_type="linear", duration_predictor_use_encoder_outputs=False, encoder_normalize_before=True,
+                      decoder_normalize_before=True, encoder_type="conformer", decoder_type="conformer", encoder_input_layer="conv2d",
+                      transformer_enc_dropout_rate=0.2, transformer_enc_positional_dropout_rate=0.2, transformer_enc_attn_dropout_rate=0.2,
+                      transformer_dec_dropout_rate=0.2, transformer_dec_positional_dropout_rate=0.2, transformer_dec_attn_dropout_rate=0.2)
+    model = FastSpeechVC(**hp, **yaml_fixed, compute_dtype="bf16", device=dev, seed=0)
+    step = NARVCTrainStep(model, lr=8e-5, warmup_steps=4000, use_graph=not args.no_graph)
+    dev_in = [t.to(dev) for t in (xs, ys, ds)]
+    pin_in = [t.pin_memory() for t in (xs, ys, ds)]
+    call = lambda x, y, d: step(x, ilens, y, olens, d, x)          # duration_predictor_feat: mel -> dp_inputs are the source mels
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        call(*dev_in)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = _lib.launch_count() + step.replayed_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        call(*dev_in)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() + step.replayed_launches - l0
+    for _ in range(2):
+        call(*pin_in).cpu()
+    barrier()
+    step.prefetch(pin_in[0], pin_in[1], pin_in[2], pin_in[0])
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        out = call(*pin_in)
+        step.prefetch(pin_in[0], pin_in[1], pin_in[2], pin_in[0])
+        host_losses = out.cpu()
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+    clocks = sampler.stop()
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    if rank != 0:
+        return
+    assert all(v == v for v in host_losses.tolist()), "NaN loss"
+    frames = B * L * world * args.steps
+    pk, pk_src = peaks()
+    line = {"metric": METRIC_FS, "value": frames / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": desc, "global_batch": B * world, "per_gpu_batch": B, "parallelism": f"dp{world}", "cuda_graph": not args.no_graph,
+                       "l2": "per-step working set exceeds the 126 MB L2; no flush needed", "losses_last_step": host_losses.tolist(),
+                       "tc_fallbacks": int(_lib.load().s2s_tc_fallback_count())},
+            "clocks": clocks,
+            "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": 2 * xs.numel() * 4 + ys.numel() * 4 + ds.numel() * 8 + 3 * B * 4, "d2h_bytes_per_step": 8,
+                    "h2d_overlap": "next step's inputs prefetched on a side stream (step.prefetch)"},
+            "gpu_launches": int(launches)}
+    if world == 1:
+        step.engine.prepare(B, T, L, ilens, olens)
+        run = lambda: step._fwd_bwd(dev_in[0], dev_in[1], dev_in[2], dev_in[0])
+        gf, gms, n = gemm_roofline(step, None, dev, args.gemm_table, run)
+        peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
+        ach = gf / (gms * 1e-3) / 1e12
+        line["roofline"] = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05.mma bf16, all shapes of one step)", "achieved": ach, "peak": peak,
+                            "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": pk_src + " (sustained)", "launches_per_step": n,
+                            "algorithmic_gflop_per_launch_avg": gf / n / 1e9, "avg_launch_us": gms * 1e3 / n,
+                            "gemm_share_of_step": gms / (ms / args.steps),
+                            "how": "CUDA events around every mode-1 s2s_gemm launch of one fwd+bwd queued behind a GPU spin, right after the timed region"}
+        if not args.no_cpu_baseline:
+            sec = cpu_port_steps_fs(hp, 1, T, L, 1, 1)
+            line["cpu_baseline"] = {"value": L / sec, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                                    "sample": f"oracle port of the reference PyTorch-CPU path (fp32), 1 x ({T}->{L}) per step (of {B}), 1 step after "
+                                              f"1 warm-up, {torch.get_num_threads()} threads"}
+    print(json.dumps(line), flush=True)
+
+
 def run_c5(args, rank, world):
     """STFT -> log-mel (BASELINE.json configs[4]): every rank extracts its own 256 clips (the path shards by clip)."""
     from seq2seq_vc_b200 import _lib, api
@@ -619,6 +769,8 @@ def run_ours(args, rank, world):
 
     if args.workload == "c5":
         return run_c5(args, rank, world)
+    if args.workload == "c6":
+        return run_c6(args, rank, world)
     hp, B, T, L, bf16, desc = WORKLOADS[args.workload]
     tts = args.workload == "c4"
     aas = is_aas(args.workload)

@@ -36,7 +36,7 @@ extern "C" {
 #define S2S_F32 0
 #define S2S_BF16 1
 
-#define S2S_ABI_VERSION 17
+#define S2S_ABI_VERSION 18
 
 const char* s2s_last_error(void);
 int s2s_abi_version(void);
@@ -364,6 +364,12 @@ int s2s_logmel(const float* wav, const float* window, const float* mel_basis, fl
  * the store: mel[b,t,m] = (logmel - mean[m]) / scale[m]; mean / scale are (n_mels) float32 (bin/compute_statistics.py). */
 int s2s_logmel_norm(const float* wav, const float* window, const float* mel_basis, const float* mean, const float* scale, float* mel,
                     int B, int n_samples, int n_fft, int hop, int n_mels, float eps, float log_base, void* stream);
+
+/* Dataset statistics for the global mean-variance normalisation (bin/compute_statistics.py:128-132: sklearn
+ * StandardScaler.partial_fit over every utterance): feats (B, T, D) float32 zero-padded, lens (B) int32 valid frames per utterance
+ * (NULL = all T), acc (2 * D + 1) float64 accumulated IN PLACE: acc[c] += sum_r x[r, c], acc[D + c] += sum_r x[r, c]^2,
+ * acc[2 * D] += number of valid rows.  The host turns them into mean_ / var_ / scale_ (float64, as sklearn does). */
+int s2s_feat_stats(const float* feats, const int* lens, double* acc, int B, int T, int D, void* stream);
 
 /* Griffin-Lim phase reconstruction (vocoder/griffin_lim.py:52-106 -> librosa.griffinlim / stft / istft, center = True), fp32,
  * one utterance, n_fft a power of two in [64, 4096].  Spectra are (T, n_fft/2 + 1) row-major, complex values interleaved (re, im).

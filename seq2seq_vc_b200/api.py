@@ -696,6 +696,74 @@ def logmelfilterbank(audio, sampling_rate, fft_size=1024, hop_size=256, win_leng
     return mel[0].cpu().numpy()
 
 
+class FeatureStatistics:
+    """Global mean / scale of a feature set, accumulated on the device: what bin/compute_statistics.py:128-152 obtains from
+    sklearn's ``StandardScaler().partial_fit(mel)`` over every utterance -- same attribute names (``mean_``, ``var_``, ``scale_``,
+    ``n_samples_seen_``), float64, population variance, zero variance -> scale 1 -- so that ``stats()`` is the (2, D) float32
+    array the reference saves as ``stats.npy`` and ``logmel_batch(..., mean=, scale=)`` / bin/normalize.py consume.
+    ``partial_fit`` takes one utterance (T, D) like the reference loop, or a zero-padded batch (B, T, D) with ``lens``
+    (e.g. the output of ``logmel_batch`` with its per-clip frame counts), numpy or CUDA tensors."""
+
+    def __init__(self, device="cuda:0"):
+        self.device = torch.device(device)
+        self._acc = None
+
+    def partial_fit(self, feats, lens=None):
+        x = torch.as_tensor(np.ascontiguousarray(feats, dtype=np.float32) if isinstance(feats, np.ndarray) else feats)
+        x = x.to(device=self.device, dtype=_f32)
+        if x.dim() == 2:
+            x = x.unsqueeze(0)
+        if x.dim() != 3:
+            raise ValueError("feats must be (T, D) or (B, T, D)")
+        x = x.contiguous()
+        D = x.shape[2]
+        if self._acc is None:
+            self._acc = torch.zeros(2 * D + 1, dtype=torch.float64, device=self.device)
+        elif self._acc.numel() != 2 * D + 1:
+            raise ValueError(f"feature dimension changed: {(self._acc.numel() - 1) // 2} -> {D}")
+        if lens is not None:
+            lens = torch.as_tensor(lens).to(device=self.device, dtype=torch.int32).contiguous()
+            if lens.numel() != x.shape[0]:
+                raise ValueError("lens must hold one length per utterance")
+        ops.feat_stats(x, lens, self._acc)
+        return self
+
+    def _host(self):
+        if self._acc is None:
+            raise S2SError("FeatureStatistics: partial_fit() has not been called")
+        a = self._acc.cpu().numpy()
+        D = (a.size - 1) // 2
+        return a[:D], a[D:2 * D], a[2 * D]
+
+    @property
+    def n_samples_seen_(self) -> int:
+        return int(self._host()[2])
+
+    @property
+    def mean_(self) -> np.ndarray:
+        s1, _, n = self._host()
+        return s1 / n
+
+    @property
+    def var_(self) -> np.ndarray:
+        s1, s2, n = self._host()
+        return np.maximum(s2 / n - (s1 / n) ** 2, 0.0)
+
+    @property
+    def scale_(self) -> np.ndarray:
+        s1, _, n = self._host()
+        v, m = self.var_, s1 / n
+        eps = np.finfo(np.float64).eps
+        sc = np.sqrt(v)
+        # sklearn (_is_constant_feature + _handle_zeros_in_scale): features whose variance is at round-off level are left unscaled
+        sc[(v <= n * eps * v + (n * m * eps) ** 2) | (sc == 0.0)] = 1.0
+        return sc
+
+    def stats(self) -> np.ndarray:
+        """(2, D) float32 [mean_, scale_]: the array compute_statistics.py writes to stats.npy."""
+        return np.stack([self.mean_, self.scale_], axis=0).astype(np.float32)
+
+
 # =================================================================================================
 # Griffin-Lim vocoder path (vocoder/griffin_lim.py:20-222): the inverse of the log-mel front end, same mel basis and window
 # =================================================================================================
@@ -1708,7 +1776,7 @@ class NARVCTrainStep(AASVCTrainStep):
     per batch shape, ``prefetch`` of the next batch, gradient accumulation, process group); the teacher's durations are a fourth
     input tensor (int64) and there is no duration-predictor warm-up."""
 
-    def __init__(self, model, lr: float = 8e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, grad_norm: float = 1.0,
+    def __init__(self, model, lr: float = 8e-5, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, grad_norm: float = 1.0,
                  warmup_steps: int = 4000, use_graph: bool = False, process_group=None, gradient_accumulate_steps: int = 1):
         super().__init__(model, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, grad_norm=grad_norm, warmup_steps=warmup_steps,
                          dp_train_start_steps=0, use_graph=use_graph, process_group=process_group,

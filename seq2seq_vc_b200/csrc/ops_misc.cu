@@ -961,3 +961,84 @@ extern "C" int s2s_embed_pe_bwd(const void* dy, const int64_t* tokens, const int
     S2S_LAUNCH_OK();
     return S2S_OK;
 }
+
+
+// =============================================================================================
+// Dataset statistics (bin/compute_statistics.py:128-132): per-feature sum, sum of squares and row count over the valid frames of
+// a zero-padded batch, accumulated in float64.  A CTA owns a contiguous slab of rows; thread t < RPI * D always works on column
+// t % D (RPI = 256 / D rows per iteration), so the loads of one iteration are contiguous and the accumulators stay in registers.
+// HBM-bound: 4 * D bytes per valid frame, read once.
+// =============================================================================================
+namespace s2s {
+// V = 4: D % 4 == 0 and 16-byte aligned rows, every thread owns four consecutive columns (one float4 per row); V = 1: any D.
+template <int V>
+__global__ void __launch_bounds__(256) feat_stats_kernel(const float* __restrict__ x, const int* __restrict__ lens, double* __restrict__ acc,
+                                                         long rows, int T, int D, int rows_per_cta) {
+    __shared__ double ssum[256 * V], ssq[256 * V];
+    __shared__ unsigned long long scount;
+    const int G = D / V;                                  // column groups of the whole row
+    const int g0 = blockIdx.y * 256;                      // column-group tile (G > 256)
+    const int Gt = min(256, G - g0);
+    const int rpi = 256 / Gt;
+    const int cg = threadIdx.x % Gt, rl = threadIdx.x / Gt;
+    const bool active = rl < rpi;
+    if (threadIdx.x == 0) scount = 0ull;
+    __syncthreads();
+    double s1[V], s2[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) { s1[k] = 0.0; s2[k] = 0.0; }
+    unsigned long long cnt = 0;
+    const long r0 = (long)blockIdx.x * rows_per_cta;
+    const long r1 = min(rows, r0 + rows_per_cta);
+    if (active) {
+        // (utterance, frame) of the row advance incrementally: one division per thread, not one per row
+        long r = r0 + rl;
+        int b = (int)(r / T), t = (int)(r - (long)b * T), cur_b = -1, len = T;
+        for (; r < r1; r += rpi, t += rpi) {
+            while (t >= T) { t -= T; ++b; }
+            if (lens && b != cur_b) { len = lens[b]; cur_b = b; }
+            if (t >= len) continue;
+            float v[V];
+            if constexpr (V == 4) {
+                const float4 q = *reinterpret_cast<const float4*>(x + r * D + (long)(g0 + cg) * 4);
+                v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+            } else {
+                v[0] = x[r * D + g0 + cg];
+            }
+#pragma unroll
+            for (int k = 0; k < V; ++k) { s1[k] += (double)v[k]; s2[k] += (double)v[k] * (double)v[k]; }
+            ++cnt;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < V; ++k) { ssum[k * 256 + threadIdx.x] = s1[k]; ssq[k * 256 + threadIdx.x] = s2[k]; }
+    if (active && cg == 0 && blockIdx.y == 0 && cnt) atomicAdd(&scount, cnt);
+    __syncthreads();
+    for (int i = threadIdx.x; i < Gt * V; i += 256) {
+        const int g = i / V, k = i % V;
+        double a = 0.0, b = 0.0;
+        for (int j = 0; j < rpi; ++j) { a += ssum[k * 256 + j * Gt + g]; b += ssq[k * 256 + j * Gt + g]; }
+        const int c = (g0 + g) * V + k;
+        atomicAdd(acc + c, a);
+        atomicAdd(acc + D + c, b);
+    }
+    if (threadIdx.x == 0 && blockIdx.y == 0 && scount) atomicAdd(acc + 2 * D, (double)scount);
+}
+}  // namespace s2s
+
+extern "C" int s2s_feat_stats(const float* feats, const int* lens, double* acc, int B, int T, int D, void* stream) {
+    using namespace s2s;
+    S2S_REQUIRE(feats && acc && B >= 0 && T >= 0 && D > 0, "feat_stats: bad arguments");
+    const long rows = (long)B * T;
+    if (rows == 0) return S2S_OK;
+    const long want = (long)num_sms() * 8;
+    long per = ceil_div_l(rows, want);
+    if (per < 64) per = 64;
+    const unsigned gx = (unsigned)ceil_div_l(rows, per);
+    if (D % 4 == 0 && (reinterpret_cast<uintptr_t>(feats) & 15) == 0)
+        feat_stats_kernel<4><<<dim3(gx, (unsigned)ceil_div_l(D / 4, 256)), 256, 0, (cudaStream_t)stream>>>(feats, lens, acc, rows, T, D, (int)per);
+    else
+        feat_stats_kernel<1><<<dim3(gx, (unsigned)ceil_div_l(D, 256)), 256, 0, (cudaStream_t)stream>>>(feats, lens, acc, rows, T, D, (int)per);
+    S2S_LAUNCH_OK();
+    return S2S_OK;
+}

@@ -765,3 +765,13 @@ def decode_advance(feat, logit, next_in, frames, logits, pos_dev, odim, r):
     assert frames.dtype == torch.float32 and logits.dtype == torch.float32 and pos_dev.dtype == _i32
     check(_L().s2s_decode_advance(ptr(feat), ptr(logit), ptr(next_in), ptr(frames), ptr(logits), ptr(pos_dev), odim, r, dt(feat), stream()),
           "decode_advance")
+
+
+def feat_stats(feats, lens, acc):
+    """acc (2 D + 1) float64 += per-feature sum, sum of squares and the number of valid frames of feats (B, T, D) float32
+    (bin/compute_statistics.py:128-132: what StandardScaler.partial_fit accumulates)."""
+    B, T, D = feats.shape
+    assert feats.dtype == torch.float32 and feats.is_contiguous() and acc.dtype == torch.float64 and acc.numel() == 2 * D + 1
+    assert lens is None or (lens.dtype == _i32 and lens.numel() == B)
+    check(_L().s2s_feat_stats(ptr(feats), ptr(lens) if lens is not None else None, ptr(acc), B, T, D, stream()), "feat_stats")
+    return acc

@@ -822,6 +822,17 @@ def mas_into(log_p, text_lens, feats_lens, paths, ds, bin_loss, d_log_p, ws):
     if d_log_p is not None:
         d_log_p.copy_(d_)
 
+def feat_stats(feats, lens, acc):
+    B, T, D = feats.shape
+    x = feats.double()
+    m = torch.ones(B, T, dtype=torch.bool) if lens is None else (torch.arange(T)[None, :] < lens[:, None].long())
+    xm = x * m[..., None]
+    acc[:D] += xm.sum((0, 1))
+    acc[D:2 * D] += (xm * xm).sum((0, 1))
+    acc[2 * D] += float(m.sum())
+    return acc
+
+
 ALL = [n for n, f in list(globals().items()) if callable(f) and not n.startswith("_") and n not in ("NO_DROP",)]
 
 
@@ -836,3 +847,4 @@ def install(monkeypatch):
     import seq2seq_vc_b200.api as api
 
     monkeypatch.setattr(api, "_require_cuda", lambda t, who: None)
+

@@ -149,3 +149,45 @@ def test_logmel_with_fused_normalisation(n_fft, hop):
         ref = scaler.transform(refs[b])
         assert np.abs(got[b] - ref).max() <= 1e-4 / scaler.scale_.min() + 1e-5
     assert abs(got.mean()) <= 1e-2 and abs(got.std() - 1.0) <= 5e-2
+
+
+@pytest.mark.parametrize("B,T,D", [(1, 37, 80), (6, 301, 80), (3, 50, 7), (2, 40, 300), (64, 1601, 80), (2, 33, 1032), (2, 33, 258)])
+def test_feature_statistics_matches_sklearn(B, T, D):
+    """s2s_feat_stats / FeatureStatistics vs sklearn StandardScaler.partial_fit per utterance (bin/compute_statistics.py:128-132):
+    float64 sums on the device; mean_ / scale_ agree to 1e-9 relative, the frame count exactly; then log-mel normalised with these
+    statistics (the fused store of s2s_logmel_norm) has zero mean and unit variance per bin."""
+    from sklearn.preprocessing import StandardScaler
+
+    from seq2seq_vc_b200 import FeatureStatistics
+
+    rng = np.random.default_rng(B * 1000 + T + D)
+    lens = rng.integers(1, T + 1, B)
+    lens[0] = T
+    x = (rng.standard_normal((B, T, D)) * rng.uniform(0.1, 3.0, D) + rng.uniform(-4, 4, D)).astype(np.float32)
+    sk = StandardScaler()
+    for b in range(B):
+        x[b, lens[b]:] = 0
+        sk.partial_fit(x[b, : lens[b]])
+    ours = FeatureStatistics().partial_fit(torch.from_numpy(x).cuda(), lens=lens)
+    assert ours.n_samples_seen_ == int(sk.n_samples_seen_)
+    np.testing.assert_allclose(ours.mean_, sk.mean_, rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(ours.scale_, sk.scale_, rtol=1e-9, atol=1e-10)
+    one = FeatureStatistics()
+    for b in range(B):                                             # the reference's loop: one utterance at a time
+        one.partial_fit(x[b, : lens[b]])
+    np.testing.assert_allclose(one.mean_, sk.mean_, rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(one.stats(), np.stack([sk.mean_, sk.scale_]).astype(np.float32), rtol=1e-6, atol=1e-7)
+
+
+def test_statistics_then_fused_normalisation_roundtrip():
+    from seq2seq_vc_b200 import FeatureStatistics
+    from seq2seq_vc_b200.api import logmel_batch
+
+    g = torch.Generator().manual_seed(3)
+    wav = (0.1 * torch.randn(8, 24000, generator=g)).cuda()
+    mel = logmel_batch(wav, 24000, 2048, 300, 1200, 80, 80, 7600)
+    st = FeatureStatistics().partial_fit(mel)
+    stats = st.stats()
+    norm = logmel_batch(wav, 24000, 2048, 300, 1200, 80, 80, 7600, mean=torch.from_numpy(stats[0]).cuda(), scale=torch.from_numpy(stats[1]).cuda())
+    flat = norm.reshape(-1, 80).double()
+    assert flat.mean(0).abs().max().item() <= 1e-4 and (flat.std(0, unbiased=False) - 1).abs().max().item() <= 1e-4

@@ -54,3 +54,36 @@ def test_logmel2linear_inverts_the_mel_projection_in_the_least_squares_sense():
     # projecting the reconstruction again reproduces the mel spectrum wherever the clamp at EPS did not bite
     free = np.dot(np.linalg.pinv(basis), (10.0 ** lmspc).T).T
     assert np.abs((free @ basis.T) - 10.0 ** lmspc).max() <= 1e-6 * (10.0 ** lmspc).max()
+
+
+def test_feature_statistics_host_logic_matches_sklearn(monkeypatch):
+    """seq2seq_vc_b200.FeatureStatistics (the device accumulator replaced by its CPU contract) == sklearn StandardScaler.partial_fit
+    over the same utterances (bin/compute_statistics.py:128-132), incl. a constant feature (scale 1) and the ragged-batch form."""
+    import fake_ops
+    import torch
+    from sklearn.preprocessing import StandardScaler
+
+    from seq2seq_vc_b200 import FeatureStatistics
+
+    fake_ops.install(monkeypatch)
+    rng = np.random.default_rng(5)
+    utts = [(rng.standard_normal((t, 12)) * rng.uniform(0.1, 3.0, 12) + rng.uniform(-4, 4, 12)).astype(np.float32) for t in (31, 7, 120, 64)]
+    for u in utts:
+        u[:, 3] = 1.25                                    # constant feature
+    sk = StandardScaler()
+    ours = FeatureStatistics(device="cpu")
+    for u in utts:
+        sk.partial_fit(u)
+        ours.partial_fit(u)
+    assert ours.n_samples_seen_ == int(sk.n_samples_seen_)
+    np.testing.assert_allclose(ours.mean_, sk.mean_, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(ours.var_, sk.var_, rtol=1e-8, atol=1e-12)
+    np.testing.assert_allclose(ours.scale_, sk.scale_, rtol=1e-8, atol=1e-12)
+    assert ours.scale_[3] == 1.0
+    assert ours.stats().dtype == np.float32 and ours.stats().shape == (2, 12)
+    batch = np.zeros((4, 120, 12), np.float32)
+    for b, u in enumerate(utts):
+        batch[b, : len(u)] = u
+    both = FeatureStatistics(device="cpu").partial_fit(torch.from_numpy(batch), lens=[len(u) for u in utts])
+    np.testing.assert_allclose(both.mean_, sk.mean_, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(both.scale_, sk.scale_, rtol=1e-8, atol=1e-12)
