@@ -36,7 +36,7 @@ extern "C" {
 #define S2S_F32 0
 #define S2S_BF16 1
 
-#define S2S_ABI_VERSION 18
+#define S2S_ABI_VERSION 19
 
 const char* s2s_last_error(void);
 int s2s_abi_version(void);
@@ -364,6 +364,13 @@ int s2s_logmel(const float* wav, const float* window, const float* mel_basis, fl
  * the store: mel[b,t,m] = (logmel - mean[m]) / scale[m]; mean / scale are (n_mels) float32 (bin/compute_statistics.py). */
 int s2s_logmel_norm(const float* wav, const float* window, const float* mel_basis, const float* mean, const float* scale, float* mel,
                     int B, int n_samples, int n_fft, int hop, int n_mels, float eps, float log_base, void* stream);
+
+/* Generic square-kernel / stride patch gather and its adjoint over channels-last maps (the later convolutions of
+ * Conv2dSubsampling2 / 6 / 8, modules/transformer/subsampling.py:108-279: (k, s) = (3, 1), (5, 3), (3, 2)):
+ *  s2s_im2col2d: col ((B T2 F2), k*k, C) with col[(b,t2,f2), kt*k+kf, c] = y[b, s t2 + kt, s f2 + kf, c]; T2 = (T1-k)/s + 1, F2 likewise.
+ *  s2s_col2im2d: dy (B, T1, F1, C) = scatter-add of dcol; with gate != NULL (the map itself) times ReLU'(gate). */
+int s2s_im2col2d(const void* y, void* col, int B, int T1, int F1, int C, int k, int s, int dtype, void* stream);
+int s2s_col2im2d(const void* dcol, const void* gate, void* dy, int B, int T1, int F1, int C, int k, int s, int dtype, void* stream);
 
 /* Dataset statistics for the global mean-variance normalisation (bin/compute_statistics.py:128-132: sklearn
  * StandardScaler.partial_fit over every utterance): feats (B, T, D) float32 zero-padded, lens (B) int32 valid frames per utterance

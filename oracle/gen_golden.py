@@ -532,6 +532,33 @@ def gen_kats():
     print("kats:", len(dump), "arrays")
 
 
+
+def gen_subsampling_tiny():
+    """Conv2dSubsampling2 / 6 / 8 (modules/transformer/subsampling.py:108-279) with their default PositionalEncoding, dropout 0:
+    output, sliced mask and every parameter gradient of sum(y * r) for a fixed random r."""
+    from seq2seq_vc.modules.transformer.subsampling import Conv2dSubsampling2, Conv2dSubsampling6, Conv2dSubsampling8
+
+    out = {}
+    g = torch.Generator().manual_seed(71)
+    for n, cls in ((2, Conv2dSubsampling2), (6, Conv2dSubsampling6), (8, Conv2dSubsampling8)):
+        torch.manual_seed(70 + n)
+        m = cls(40, 16, 0.0)
+        m.train()
+        B, T = 2, 61
+        x = torch.randn(B, T, 40, generator=g)
+        mask = torch.ones(B, 1, T, dtype=torch.bool)
+        mask[1, :, 50:] = False
+        y, ym = m(x, mask)
+        r = torch.randn(y.shape, generator=g)
+        (y * r).sum().backward()
+        out[f"s{n}.x"], out[f"s{n}.y"], out[f"s{n}.r"] = x.numpy(), y.detach().numpy(), r.numpy()
+        out[f"s{n}.mask_in"], out[f"s{n}.mask_out"] = mask.numpy(), ym.numpy()
+        for k, v in m.state_dict().items():
+            out[f"s{n}.sd.{k}"] = v.numpy()
+        for k, p in m.named_parameters():
+            out[f"s{n}.grad.{k}"] = p.grad.numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "subsampling_tiny.npz"), **out)
+
 if __name__ == "__main__":
     ref_shim.install()
     os.makedirs(GOLDEN, exist_ok=True)
@@ -539,6 +566,6 @@ if __name__ == "__main__":
 
     gens = dict(vtn_tiny=gen_vtn_tiny, vtn_rfactor=gen_vtn_rfactor, vtn_conformer_tiny=gen_vtn_conformer_tiny, vtn_convffn_tiny=gen_vtn_convffn_tiny, fsvc_tiny=gen_fsvc_tiny, tts_tiny=gen_tts_tiny, aasvc_tiny=gen_aasvc_tiny, aasvc_conv1d_tiny=gen_aasvc_conv1d_tiny, aasvc_conv1d_k3_tiny=gen_aasvc_conv1d_k3_tiny,
                 aasvc_conv1d_linear_k3_tiny=gen_aasvc_conv1d_linear_k3_tiny,
-                mas=gen_mas, kats=gen_kats, sdp_tiny=gen_sdp_tiny)
+                mas=gen_mas, kats=gen_kats, sdp_tiny=gen_sdp_tiny, subsampling_tiny=gen_subsampling_tiny)
     for name in (sys.argv[1:] or list(gens)):      # e.g. `python oracle/gen_golden.py aasvc_conv1d_tiny` adds one fixture
         gens[name]()

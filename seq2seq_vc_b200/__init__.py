@@ -11,7 +11,7 @@ from .aasvc_engine import AASVCEngine  # noqa: F401
 from .api import VTN, TransformerTTS, Seq2SeqLoss, GuidedMultiHeadAttentionLoss, VTNTrainStep, viterbi_decode, logmelfilterbank  # noqa: F401
 from .api import AASVC, AASVCTrainStep, FastSpeechVC, NARVCTrainStep, L1Loss, ForwardSumLoss, DurationPredictorLoss  # noqa: F401
 from .api import DistributedDataParallel, LengthRegulator  # noqa: F401
-from .api import FeatureStatistics, Spectrogram2Waveform, griffin_lim, logmel2linear  # noqa: F401
+from .api import Conv2dSubsampling2, Conv2dSubsampling6, Conv2dSubsampling8, FeatureStatistics, Spectrogram2Waveform, griffin_lim, logmel2linear  # noqa: F401
 
 AR_VC_MODELS = [VTN]
 NAR_VC_MODELS = [FastSpeechVC, AASVC]

@@ -696,6 +696,203 @@ def logmelfilterbank(audio, sampling_rate, fft_size=1024, hop_size=256, win_leng
     return mel[0].cpu().numpy()
 
 
+# =================================================================================================
+# Conv2dSubsampling2 / 6 / 8 (modules/transformer/subsampling.py:108-279): stand-alone drop-in operators
+# =================================================================================================
+class _Holder(torch.nn.Module):
+    """Parameter container that reproduces the reference's `conv.N.*` / `out.0.*` state-dict keys."""
+
+
+class _PositionalEncoding(torch.nn.Module):
+    """Default `out.1` (layers/positional_encoding.py:14-70 PositionalEncoding): dropout(x * sqrt(d) + pe[:T]) through s2s_scaled_pe_fwd / _bwd."""
+
+    def __init__(self, d_model, dropout_rate, max_len=5000):
+        super().__init__()
+        from .engine_base import sinusoid_table
+
+        self.d_model, self.rate, self.max_len = d_model, float(dropout_rate), max_len
+        self.xscale = math.sqrt(d_model)
+        self._table = sinusoid_table(max_len, d_model, torch.device("cpu"))
+        self._seed = 0
+
+    def forward(self, x):
+        return _PosEncFn.apply(self, x)
+
+
+class _PosEncFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mod, x):
+        B, T, d = x.shape
+        if T > mod.max_len:
+            raise S2SError(f"sequence of {T} frames exceeds the positional table ({mod.max_len})")
+        pe = mod._table.to(x.device)
+        if pe is not mod._table:
+            mod._table = pe
+        mod._seed += 1
+        drop = _lib.Drop(mod.rate, seed=mod._seed, site=0) if (mod.training and mod.rate > 0) else _lib.NO_DROP
+        xs = torch.empty_like(x)
+        ops.scale_dropout(x.contiguous(), xs, mod.xscale)
+        one = torch.ones(1, dtype=_f32, device=x.device)
+        y = torch.empty_like(x)
+        ops.scaled_pe_fwd(xs, pe, one, y, drop)
+        ctx.mod, ctx.drop, ctx.pe = mod, drop, pe
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        dx = torch.empty_like(g)
+        dalpha = torch.zeros(1, dtype=_f32, device=g.device)
+        ops.scaled_pe_bwd(g.contiguous(), ctx.pe, dx, dalpha, ctx.drop)
+        out = torch.empty_like(dx)
+        ops.scale_dropout(dx, out, ctx.mod.xscale)
+        return None, out
+
+
+class _Conv2dSubFn(torch.autograd.Function):
+    """Conv2d(1 -> C, 3, 2) + ReLU, then Conv2d(C -> C, k, s) + ReLU per entry of `mod.LATER`, then Linear(C * F -> odim): the first
+    convolution by the direct kernel, the later ones as patch matrix x weights on the GEMM path (ReLU in the epilogue), every
+    parameter gradient by the hand-written backward (the input gets none: it is a feature tensor, as in the training path)."""
+
+    @staticmethod
+    def forward(ctx, mod, x, *params):
+        adt, mode = mod._adt, mod._mode
+        B, T, idim = x.shape
+        C = params[0].shape[0]
+        x = x.to(_f32).contiguous()
+        dev = x.device
+        T1, F1 = (T - 1) // 2, (idim - 1) // 2
+        if T1 < 1 or F1 < 1:
+            raise S2SError("input too short for the first convolution")
+        maps = [torch.empty(B, T1, F1, C, dtype=adt, device=dev)]
+        ops.conv1_fwd(x, params[0].contiguous(), params[1], maps[0])
+        wps = []
+        for i, (k, s) in enumerate(mod.LATER):
+            w, b = params[2 + 2 * i], params[3 + 2 * i]
+            Tp, Fp = maps[-1].shape[1], maps[-1].shape[2]
+            if Tp < k or Fp < k:
+                raise S2SError("input too short for this subsampling module")
+            Tn, Fn = (Tp - k) // s + 1, (Fp - k) // s + 1
+            wp = torch.empty(C, k * k, C, dtype=adt, device=dev)
+            ops.transpose_last2(w.detach().contiguous(), wp, C, C, k * k)          # fp32 parameter -> compute dtype
+            col = torch.empty(B * Tn * Fn, k * k * C, dtype=adt, device=dev)
+            ops.im2col2d(maps[-1], col, k, s)
+            y = torch.empty(B * Tn * Fn, C, dtype=adt, device=dev)
+            ops.gemm(col, wp.view(C, k * k * C), y, bias=b, relu=True, mode=mode)
+            maps.append(y.view(B, Tn, Fn, C))
+            wps.append(wp)
+        Tn, Fn = maps[-1].shape[1], maps[-1].shape[2]
+        wo, bo = params[-2], params[-1]
+        odim = wo.shape[0]
+        wop = torch.empty(odim, Fn, C, dtype=adt, device=dev)
+        ops.transpose_last2(wo.detach().contiguous(), wop, odim, C, Fn)
+        lin = torch.empty(B * Tn, odim, dtype=adt, device=dev)
+        ops.gemm(maps[-1].view(B * Tn, Fn * C), wop.view(odim, Fn * C), lin, bias=bo, mode=mode)
+        ctx.mod, ctx.x, ctx.maps, ctx.wps, ctx.wop = mod, x, maps, wps, wop
+        ctx.shapes = [tuple(p.shape) for p in params]
+        return lin.view(B, Tn, odim).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        mod, x, maps, wps, wop = ctx.mod, ctx.x, ctx.maps, ctx.wps, ctx.wop
+        adt, mode = mod._adt, mod._mode
+        dev = x.device
+        B = x.shape[0]
+        C = maps[0].shape[3]
+        Tn, Fn = maps[-1].shape[1], maps[-1].shape[2]
+        odim = wop.shape[0]
+        grads = [torch.zeros(s, dtype=_f32, device=dev) for s in ctx.shapes]
+        dlin = g.reshape(B * Tn, odim).to(adt).contiguous()
+        ylast = maps[-1].view(B * Tn, Fn * C)
+        gwop = torch.empty(odim, Fn * C, dtype=_f32, device=dev)
+        ops.gemm(dlin.t(), ylast.t(), gwop, mode=mode)
+        ops.transpose_last2(gwop, grads[-2].view(odim, C, Fn), odim, Fn, C)
+        ops.colsum(dlin, grads[-1])
+        dy = torch.empty(B * Tn, Fn * C, dtype=adt, device=dev)
+        ops.gemm(dlin, wop.view(odim, Fn * C).t(), dy, mode=mode, gate=ylast)            # ReLU' of the last convolution
+        dy = dy.view(B * Tn * Fn, C)
+        for i in reversed(range(len(mod.LATER))):
+            k, s = mod.LATER[i]
+            prev = maps[i]
+            col = torch.empty(dy.shape[0], k * k * C, dtype=adt, device=dev)
+            ops.im2col2d(prev, col, k, s)
+            gwp = torch.empty(C, k * k * C, dtype=_f32, device=dev)
+            ops.gemm(dy.t(), col.t(), gwp, mode=mode)
+            ops.transpose_last2(gwp, grads[2 + 2 * i].view(C, C, k * k), C, k * k, C)
+            ops.colsum(dy, grads[3 + 2 * i])
+            ops.gemm(dy, wps[i].view(C, k * k * C).t(), col, mode=mode)                   # d(patches), in place of the patches
+            dprev = torch.empty_like(prev)
+            ops.col2im2d(col, prev, dprev, k, s)                                            # scatter-add + ReLU' of the map below
+            dy = dprev.view(-1, C)
+        ops.conv1_bwd(x, dy.view(maps[0].shape), grads[0], grads[1])
+        return (None, None) + tuple(grads)
+
+
+class _Conv2dSubsamplingN(torch.nn.Module):
+    LATER: tuple = ()
+    MASKS: tuple = ()
+
+    def __init__(self, idim, odim, dropout_rate, pos_enc=None, compute_dtype: str = "float32"):
+        super().__init__()
+        self._adt = torch.bfloat16 if compute_dtype in ("bf16", "bfloat16", torch.bfloat16) else _f32
+        self._mode = 1 if self._adt == torch.bfloat16 else (0 if compute_dtype == "float32_simt" else 2)
+        f = (idim - 1) // 2
+        self.conv = _Holder()
+        convs = [torch.nn.Conv2d(1, odim, 3, 2)] + [torch.nn.Conv2d(odim, odim, k, s) for k, s in self.LATER]   # reference initialisation
+        for i, c in enumerate(convs):
+            h = _Holder()
+            h.weight, h.bias = c.weight, c.bias
+            self.conv.add_module(str(2 * i), h)
+        for k, s in self.LATER:
+            f = (f - k) // s + 1
+        lin = torch.nn.Linear(odim * f, odim)
+        h = _Holder()
+        h.weight, h.bias = lin.weight, lin.bias
+        self.out = _Holder()
+        self.out.add_module("0", h)
+        self.out.add_module("1", pos_enc if pos_enc is not None else _PositionalEncoding(odim, dropout_rate))
+
+    def _params(self):
+        ps = []
+        for i in range(1 + len(self.LATER)):
+            h = getattr(self.conv, str(2 * i))
+            ps += [h.weight, h.bias]
+        h = getattr(self.out, "0")
+        return ps + [h.weight, h.bias]
+
+    def forward(self, x, x_mask):
+        _require_cuda(x, type(self).__name__)
+        y = _Conv2dSubFn.apply(self, x, *self._params())
+        y = getattr(self.out, "1")(y)
+        if x_mask is None:
+            return y, None
+        for sl in self.MASKS:
+            x_mask = x_mask[:, :, sl]
+        return y, x_mask
+
+    def __getitem__(self, key):
+        if key != -1:
+            raise NotImplementedError("Support only `-1` (for `reset_parameters`).")
+        return getattr(self.out, "1")
+
+
+class Conv2dSubsampling2(_Conv2dSubsamplingN):
+    """Drop-in for subsampling.py:108-165 (time / 2): Conv2d(1, C, 3, 2) + ReLU + Conv2d(C, C, 3, 1) + ReLU + Linear + pos_enc."""
+    LATER = ((3, 1),)
+    MASKS = (slice(None, -2, 2), slice(None, -2, 1))
+
+
+class Conv2dSubsampling6(_Conv2dSubsamplingN):
+    """Drop-in for subsampling.py:167-213 (time / 6): Conv2d(1, C, 3, 2) + ReLU + Conv2d(C, C, 5, 3) + ReLU + Linear + pos_enc."""
+    LATER = ((5, 3),)
+    MASKS = (slice(None, -2, 2), slice(None, -4, 3))
+
+
+class Conv2dSubsampling8(_Conv2dSubsamplingN):
+    """Drop-in for subsampling.py:215-279 (time / 8): three Conv2d(., C, 3, 2) + ReLU, Linear, pos_enc."""
+    LATER = ((3, 2), (3, 2))
+    MASKS = (slice(None, -2, 2), slice(None, -2, 2), slice(None, -2, 2))
+
+
 class FeatureStatistics:
     """Global mean / scale of a feature set, accumulated on the device: what bin/compute_statistics.py:128-152 obtains from
     sklearn's ``StandardScaler().partial_fit(mel)`` over every utterance -- same attribute names (``mean_``, ``var_``, ``scale_``,

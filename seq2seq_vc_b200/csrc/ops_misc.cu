@@ -1042,3 +1042,117 @@ extern "C" int s2s_feat_stats(const float* feats, const int* lens, double* acc, 
     S2S_LAUNCH_OK();
     return S2S_OK;
 }
+
+
+// =============================================================================================
+// Generic square-kernel / stride im2col and col2im over channels-last maps (the second and third convolutions of
+// Conv2dSubsampling2 / 6 / 8, subsampling.py:108-279: (k, s) = (3, 1), (5, 3), (3, 2)); the (3, 2) hot path of Conv2dSubsampling
+// keeps its specialised kernels above.  col[(b, t2, f2), tap, c] = y[b, s t2 + kt, s f2 + kf, c], T2 = (T1 - k) / s + 1.
+// =============================================================================================
+namespace s2s {
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) im2col2d_kernel(const T* __restrict__ y, T* __restrict__ col, int B, int T1, int F1, int C, int T2, int F2,
+                                                       int k, int s) {
+    const int cv = C / VEC, kk = k * k;
+    const long total = (long)B * T2 * F2 * kk * cv;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % cv) * VEC;
+        const long q = i / cv;
+        const int tap = (int)(q % kk);
+        const long m = q / kk;
+        const int f2 = (int)(m % F2);
+        const long r = m / F2;
+        const int t2 = (int)(r % T2);
+        const long b = r / T2;
+        const int kt = tap / k, kf = tap - kt * k;
+        const T* src = y + (((b * T1 + (long)s * t2 + kt) * F1) + (long)s * f2 + kf) * C + c;
+        T* dst = col + (m * kk + tap) * C + c;
+        if constexpr (VEC == 8) {
+            float v[8];
+            Vec8<T>::load(src, v);
+            Vec8<T>::store(dst, v);
+        } else {
+            *dst = *src;
+        }
+    }
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) col2im2d_kernel(const T* __restrict__ dcol, T* __restrict__ dy, int B, int T1, int F1, int C, int T2, int F2,
+                                                       int k, int s, const T* __restrict__ gate) {
+    const int cv = C / VEC, kk = k * k;
+    const long total = (long)B * T1 * F1 * cv;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % cv) * VEC;
+        const long q = i / cv;
+        const int f1 = (int)(q % F1);
+        const long r = q / F1;
+        const int t1 = (int)(r % T1);
+        const long b = r / T1;
+        float acc[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+        for (int kt = 0; kt < k; ++kt) {
+            const int tt = t1 - kt;
+            if (tt < 0 || tt % s) continue;
+            const int t2 = tt / s;
+            if (t2 >= T2) continue;
+            for (int kf = 0; kf < k; ++kf) {
+                const int ff = f1 - kf;
+                if (ff < 0 || ff % s) continue;
+                const int f2 = ff / s;
+                if (f2 >= F2) continue;
+                const long m = (b * T2 + t2) * F2 + f2;
+                const T* src = dcol + (m * kk + kt * k + kf) * C + c;
+                if constexpr (VEC == 8) {
+                    float v[8];
+                    Vec8<T>::load(src, v);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] += v[j];
+                } else {
+                    acc[0] += to_f<T>(*src);
+                }
+            }
+        }
+        T* dst = dy + q * C + c;
+        if (gate) {                                   // ReLU' of the layer that produced the map
+            if constexpr (VEC == 8) {
+                float g[8];
+                Vec8<T>::load(gate + q * C + c, g);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = g[j] > 0.f ? acc[j] : 0.f;
+            } else {
+                if (!(to_f<T>(gate[q * C + c]) > 0.f)) acc[0] = 0.f;
+            }
+        }
+        if constexpr (VEC == 8) Vec8<T>::store(dst, acc);
+        else *dst = from_f<T>(acc[0]);
+    }
+}
+}  // namespace s2s
+
+extern "C" int s2s_im2col2d(const void* y, void* col, int B, int T1, int F1, int C, int k, int s, int dtype, void* stream) {
+    S2S_REQUIRE(y && col && B > 0 && k >= 1 && s >= 1 && T1 >= k && F1 >= k && C > 0, "im2col2d: bad arguments");
+    const int T2 = (T1 - k) / s + 1, F2 = (F1 - k) / s + 1;
+    const long total = (long)B * T2 * F2 * k * k * C;
+    const bool ok = (C % 8 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)col % 16 == 0);
+    S2S_DISPATCH_DTYPE(dtype, TT, {
+        if (ok) im2col2d_kernel<TT, 8><<<ew_grid(total / 8, 256), 256, 0, (cudaStream_t)stream>>>((const TT*)y, (TT*)col, B, T1, F1, C, T2, F2, k, s);
+        else im2col2d_kernel<TT, 1><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const TT*)y, (TT*)col, B, T1, F1, C, T2, F2, k, s);
+    });
+    S2S_LAUNCH_OK();
+    return S2S_OK;
+}
+
+extern "C" int s2s_col2im2d(const void* dcol, const void* gate, void* dy, int B, int T1, int F1, int C, int k, int s, int dtype, void* stream) {
+    S2S_REQUIRE(dcol && dy && B > 0 && k >= 1 && s >= 1 && T1 >= k && F1 >= k && C > 0, "col2im2d: bad arguments");
+    const int T2 = (T1 - k) / s + 1, F2 = (F1 - k) / s + 1;
+    const long total = (long)B * T1 * F1 * C;
+    const bool ok = (C % 8 == 0) && ((uintptr_t)dy % 16 == 0) && ((uintptr_t)dcol % 16 == 0) && ((uintptr_t)gate % 16 == 0);
+    S2S_DISPATCH_DTYPE(dtype, TT, {
+        if (ok) col2im2d_kernel<TT, 8><<<ew_grid(total / 8, 256), 256, 0, (cudaStream_t)stream>>>((const TT*)dcol, (TT*)dy, B, T1, F1, C, T2, F2, k, s, (const TT*)gate);
+        else col2im2d_kernel<TT, 1><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const TT*)dcol, (TT*)dy, B, T1, F1, C, T2, F2, k, s, (const TT*)gate);
+    });
+    S2S_LAUNCH_OK();
+    return S2S_OK;
+}

@@ -775,3 +775,20 @@ def feat_stats(feats, lens, acc):
     assert lens is None or (lens.dtype == _i32 and lens.numel() == B)
     check(_L().s2s_feat_stats(ptr(feats), ptr(lens) if lens is not None else None, ptr(acc), B, T, D, stream()), "feat_stats")
     return acc
+
+
+def im2col2d(y, col, k, s):
+    """col ((B T2 F2), k*k*C) patches of the channels-last map y (B, T1, F1, C) for a k x k convolution of stride s."""
+    B, T1, F1, C = y.shape
+    T2, F2 = (T1 - k) // s + 1, (F1 - k) // s + 1
+    assert y.is_contiguous() and col.is_contiguous() and col.numel() == B * T2 * F2 * k * k * C and col.dtype == y.dtype
+    check(_L().s2s_im2col2d(ptr(y), ptr(col), B, T1, F1, C, k, s, dt(y), stream()), "im2col2d")
+    return col
+
+
+def col2im2d(dcol, gate, dy, k, s):
+    """dy (B, T1, F1, C) = adjoint of im2col2d applied to dcol, times ReLU'(gate) when gate (the forward map) is given."""
+    B, T1, F1, C = dy.shape
+    assert dcol.is_contiguous() and dy.is_contiguous() and dcol.dtype == dy.dtype and (gate is None or (gate.shape == dy.shape and gate.is_contiguous()))
+    check(_L().s2s_col2im2d(ptr(dcol), ptr(gate) if gate is not None else None, ptr(dy), B, T1, F1, C, k, s, dt(dy), stream()), "col2im2d")
+    return dy

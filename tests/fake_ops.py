@@ -833,6 +833,30 @@ def feat_stats(feats, lens, acc):
     return acc
 
 
+def im2col2d(y, col, k, s):
+    B, T1, F1, C = y.shape
+    T2, F2 = (T1 - k) // s + 1, (F1 - k) // s + 1
+    out = col.view(B, T2, F2, k * k, C)
+    for kt in range(k):
+        for kf in range(k):
+            out[:, :, :, kt * k + kf, :] = y[:, kt:kt + s * (T2 - 1) + 1:s, kf:kf + s * (F2 - 1) + 1:s, :]
+    return col
+
+
+def col2im2d(dcol, gate, dy, k, s):
+    B, T1, F1, C = dy.shape
+    T2, F2 = (T1 - k) // s + 1, (F1 - k) // s + 1
+    src = dcol.view(B, T2, F2, k * k, C).double()
+    acc = torch.zeros(B, T1, F1, C, dtype=torch.float64)
+    for kt in range(k):
+        for kf in range(k):
+            acc[:, kt:kt + s * (T2 - 1) + 1:s, kf:kf + s * (F2 - 1) + 1:s, :] += src[:, :, :, kt * k + kf, :]
+    if gate is not None:
+        acc = acc * (gate > 0)
+    dy.copy_(acc.to(dy.dtype))
+    return dy
+
+
 ALL = [n for n, f in list(globals().items()) if callable(f) and not n.startswith("_") and n not in ("NO_DROP",)]
 
 
