@@ -36,7 +36,7 @@ extern "C" {
 #define S2S_F32 0
 #define S2S_BF16 1
 
-#define S2S_ABI_VERSION 19
+#define S2S_ABI_VERSION 20
 
 const char* s2s_last_error(void);
 int s2s_abi_version(void);
@@ -461,6 +461,12 @@ int s2s_align_logp_fwd(const void* feats, const void* text, const int32_t* text_
                        int T_feats, int T_text, int C, int dtype, void* stream);
 /* backward: W[b,t,s] = (d loss / d dist) / dist (B,T_feats,ldW) in `dtype`, rowsum (B,T_feats), colsum (B,T_text) so
  * that d_feats = rowsum * feats - W text and d_text = colsum * text - W^T feats (two s2s_gemm + s2s_rowscale). */
+/* The same log-probabilities through the tensor-core product (bf16 engine): s2s_row_sqnorm gives |row|^2 (fp32) of feats / text,
+ * s2s_gemm writes f . x into logp (B, T_feats, T_text) fp32, s2s_align_logp_from_dot turns it in place into
+ * log_softmax_s(-sqrt(max(|f|^2 + |x|^2 - 2 f.x, 0))) with the same masking / lse output as s2s_align_logp_fwd. */
+int s2s_row_sqnorm(const void* x, float* out, int64_t rows, int C, int dtype, void* stream);
+int s2s_align_logp_from_dot(float* logp, const float* feats_sqnorm, const float* text_sqnorm, const int32_t* text_lens, float* lse,
+                            int B, int T_feats, int T_text, void* stream);
 int s2s_align_logp_bwd(const float* dlogp, const float* logp, const float* lse, const int32_t* text_lens, void* W,
                        float* rowsum, float* colsum, int B, int T_feats, int T_text, int64_t ldW, int dtype,
                        void* stream);

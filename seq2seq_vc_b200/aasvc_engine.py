@@ -23,6 +23,7 @@ Data layout in HBM
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -167,6 +168,8 @@ def buffer_specs(hp: dict) -> List[Tuple[str, Tuple[int, ...], torch.dtype]]:
 
 class AASVCEngine(ConformerBlocks, EngineBase):
     """Owns parameters, activation buffers and the explicit forward / loss / backward of one AAS-VC step."""
+
+    align_dot = os.environ.get("S2S_ALIGN_DOT", "1") != "0"      # A/B switch: tensor-core pairwise distances in the bf16 engine
 
     LOSS_NAMES = ("l1_loss", "forward_sum_loss", "bin_loss", "duration_loss")
 
@@ -484,7 +487,15 @@ class AASVCEngine(ConformerBlocks, EngineBase):
                       feats.view(B * L, C))
         logp = self.buf("al.logp", (B, L, Tt), _f32)
         lse = self.buf("al.lse", (B, L), _f32)
-        ops.align_logp_fwd(feats, text, self.tlens_dev, logp, lse)
+        if self.mode == 1 and self.align_dot:
+            # bf16 engine: the pairwise distances through the tensor cores, ||f - x||^2 = |f|^2 + |x|^2 - 2 f.x  (the direct-difference
+            # kernel took 1.42 ms of the C3 step on the CUDA cores; this form ~0.1 ms).  The float32 parity path keeps the direct kernel.
+            nf = ops.row_sqnorm(feats.view(B * L, C), self.buf("al.nf", (B * L,), _f32))
+            nt = ops.row_sqnorm(text.view(B * Tt, C), self.buf("al.nt", (B * Tt,), _f32))
+            ops.gemm(feats, text, logp, mode=1)
+            ops.align_logp_from_dot(logp, nf, nt, self.tlens_dev, lse)
+        else:
+            ops.align_logp_fwd(feats, text, self.tlens_dev, logp, lse)
         self.log_p_attn = logp
 
         # ---- monotonic alignment search (alignments.py:281-310): durations + bin loss (+ its gradient), on the device

@@ -93,6 +93,59 @@ __global__ void __launch_bounds__(256) neg_logsoftmax_kernel(float* __restrict__
     if (lane == 0) lse[row] = l;
 }
 
+// out[r] = sum_c x[r,c]^2 (fp32), warp per row
+template <typename T>
+__global__ void __launch_bounds__(256) row_sqnorm_kernel(const T* __restrict__ x, float* __restrict__ out, long rows, int C) {
+    const int lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const T* p = x + row * C;
+    float acc = 0.f;
+    if ((C & 7) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        for (int c = lane * 8; c < C; c += 256) {
+            float v[8];
+            Vec8<T>::load(p + c, v);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc = fmaf(v[k], v[k], acc);
+        }
+    } else {
+        for (int c = lane; c < C; c += 32) { const float v = to_f<T>(p[c]); acc = fmaf(v, v, acc); }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[row] = acc;
+}
+
+// The same log-probabilities from the tensor-core product: logp holds f . x (B,Tf,Tt) on entry; dist = sqrt(max(|f|^2 + |x|^2 - 2 f.x, 0)),
+// then the masked log-softmax of -dist in place.  Used by the bf16 engine only: its operands are bf16 values, so the products are
+// exact in the fp32 accumulator and the expansion's cancellation error (~1e-7 |f|^2 in dist^2) is far below the operands' rounding; the
+// float32 parity path keeps the direct-difference kernel above.  warp per row
+__global__ void __launch_bounds__(256) dot_to_logp_kernel(float* __restrict__ logp, const float* __restrict__ nf, const float* __restrict__ nx,
+                                                          float* __restrict__ lse, const int32_t* __restrict__ text_lens, long rows, int Tf,
+                                                          int Tt) {
+    const int lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int b = (int)(row / Tf);
+    int n = text_lens[b];
+    n = n < 0 ? 0 : (n > Tt ? Tt : n);
+    float* p = logp + row * Tt;
+    const float* nxb = nx + (long)b * Tt;
+    const float a = nf[row];
+    float mx = -INFINITY;
+    for (int s = lane; s < n; s += 32) {
+        const float d = sqrtf(fmaxf(a + nxb[s] - 2.f * p[s], 0.f));
+        p[s] = d;
+        mx = fmaxf(mx, -d);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int s = lane; s < n; s += 32) sum += expf(-p[s] - mx);
+    sum = warp_sum(sum);
+    const float l = (n > 0) ? mx + logf(sum) : 0.f;
+    for (int s = lane; s < Tt; s += 32) p[s] = (s < n) ? -p[s] - l : -INFINITY;
+    if (lane == 0) lse[row] = l;
+}
+
 // backward of (-dist -> log_softmax): W[b,t,s] = d_dist / dist with d_dist = -(dlogp - exp(logp) * sum_s dlogp);
 // rowsum[b,t] = sum_s W.  W: (B,Tf,ldW) activation dtype, columns >= text_len are zero.  warp per row
 template <typename T>
@@ -444,6 +497,23 @@ extern "C" int s2s_align_logp_fwd(const void* feats, const void* text, const int
     S2S_LAUNCH_OK();
     long rows = (long)B * T_feats;
     neg_logsoftmax_kernel<<<(unsigned)ceil_div_l(rows, 8), 256, 0, st>>>(logp, lse, text_lens, rows, T_feats, T_text);
+    S2S_LAUNCH_OK();
+    return S2S_OK;
+}
+
+extern "C" int s2s_row_sqnorm(const void* x, float* out, int64_t rows, int C, int dtype, void* stream) {
+    S2S_REQUIRE(x && out && rows > 0 && C > 0, "row_sqnorm: bad arguments");
+    S2S_DISPATCH_DTYPE(dtype, T, (row_sqnorm_kernel<T><<<(unsigned)ceil_div_l(rows, 8), 256, 0, (cudaStream_t)stream>>>((const T*)x, out, rows, C)));
+    S2S_LAUNCH_OK();
+    return S2S_OK;
+}
+
+extern "C" int s2s_align_logp_from_dot(float* logp, const float* feats_sqnorm, const float* text_sqnorm, const int32_t* text_lens, float* lse,
+                                       int B, int T_feats, int T_text, void* stream) {
+    S2S_REQUIRE(logp && feats_sqnorm && text_sqnorm && text_lens && lse && B > 0 && T_feats > 0 && T_text > 0, "align_logp_from_dot: bad arguments");
+    const long rows = (long)B * T_feats;
+    dot_to_logp_kernel<<<(unsigned)ceil_div_l(rows, 8), 256, 0, (cudaStream_t)stream>>>(logp, feats_sqnorm, text_sqnorm, lse, text_lens, rows,
+                                                                                      T_feats, T_text);
     S2S_LAUNCH_OK();
     return S2S_OK;
 }

@@ -792,3 +792,19 @@ def col2im2d(dcol, gate, dy, k, s):
     assert dcol.is_contiguous() and dy.is_contiguous() and dcol.dtype == dy.dtype and (gate is None or (gate.shape == dy.shape and gate.is_contiguous()))
     check(_L().s2s_col2im2d(ptr(dcol), ptr(gate) if gate is not None else None, ptr(dy), B, T1, F1, C, k, s, dt(dy), stream()), "col2im2d")
     return dy
+
+
+def row_sqnorm(x2d, out):
+    """out[r] = sum_c x2d[r, c]^2 (float32)."""
+    rows, C = x2d.shape
+    assert x2d.is_contiguous() and out.dtype == torch.float32 and out.numel() == rows
+    check(_L().s2s_row_sqnorm(ptr(x2d), ptr(out), rows, C, dt(x2d), stream()), "row_sqnorm")
+    return out
+
+
+def align_logp_from_dot(logp, nf, nt, text_lens, lse):
+    """logp (B, TF, TT) float32 holds feats . text on entry and log_softmax(-||feats - text||) on return (align_logp_fwd's result)."""
+    B, TF, TT = logp.shape
+    assert logp.is_contiguous() and logp.dtype == torch.float32 and nf.numel() == B * TF and nt.numel() == B * TT
+    check(_L().s2s_align_logp_from_dot(ptr(logp), ptr(nf), ptr(nt), ptr(text_lens), ptr(lse), B, TF, TT, stream()), "align_logp_from_dot")
+    return logp

@@ -857,6 +857,24 @@ def col2im2d(dcol, gate, dy, k, s):
     return dy
 
 
+def row_sqnorm(x2d, out):
+    out.copy_((x2d.double() ** 2).sum(1).float())
+    return out
+
+
+def align_logp_from_dot(logp, nf, nt, text_lens, lse):
+    B, TF, TT = logp.shape
+    d2 = nf.view(B, TF, 1).double() + nt.view(B, 1, TT).double() - 2.0 * logp.double()
+    score = -torch.sqrt(d2.clamp_min(0.0))
+    mask = torch.arange(TT)[None, None, :] < text_lens.view(B, 1, 1).long()
+    score = score.masked_fill(~mask, float("-inf"))
+    l = torch.logsumexp(score, dim=2)
+    l = torch.where(text_lens.view(B, 1) > 0, l, torch.zeros_like(l))
+    logp.copy_((score - l[..., None]).float())
+    lse.copy_(l.float().view(lse.shape))
+    return logp
+
+
 ALL = [n for n, f in list(globals().items()) if callable(f) and not n.startswith("_") and n not in ("NO_DROP",)]
 
 

@@ -246,6 +246,31 @@ def test_align_logp_fwd_bwd(ops, dt, B, TF, TT, C):
     close(gcs, cs, tol(dt, 4) * scale * math.sqrt(TF), "colsum")
 
 
+@pytest.mark.parametrize("B,TF,TT,C", [(2, 13, 5, 24), (3, 70, 33, 128), (2, 130, 65, 40), (4, 768, 192, 384)])
+def test_align_logp_through_tensor_core_product(ops, B, TF, TT, C):
+    """The bf16 engine's form of the same block: |f|^2 + |x|^2 - 2 f.x with the product on the tcgen05 GEMM (bf16 operands, fp32
+    accumulation) == the direct-difference kernel on the same bf16 inputs, up to the expansion's fp32 cancellation."""
+    bf = torch.bfloat16
+    feats, text = rnd(B, TF, C, dt=bf, seed=1).cuda(), rnd(B, TT, C, dt=bf, seed=2).cuda()
+    tl = torch.tensor([TT, max(1, TT // 2), max(1, TT - 3), TT][:B], dtype=torch.int32).cuda()
+    ref, rlse = torch.empty(B, TF, TT, device="cuda"), torch.empty(B, TF, device="cuda")
+    ops.align_logp_fwd(feats, text, tl, ref, rlse)
+    nf = ops.row_sqnorm(feats.view(B * TF, C), torch.empty(B * TF, device="cuda"))
+    nt = ops.row_sqnorm(text.view(B * TT, C), torch.empty(B * TT, device="cuda"))
+    close(nf, (feats.float() ** 2).sum(-1).view(-1), 1e-4 * C, "row_sqnorm")
+    got, glse = torch.full((B, TF, TT), 9.0, device="cuda"), torch.empty(B, TF, device="cuda")
+    ops.gemm(feats, text, got, mode=1)
+    ops.align_logp_from_dot(got, nf, nt, tl, glse)
+    fin = torch.isfinite(ref)
+    assert torch.equal(torch.isfinite(got), fin)
+    close(got[fin], ref[fin], 2e-4, "log_p_attn via f.x")
+    close(glse, rlse, 2e-4, "lse")
+    cpu, clse = torch.empty(B, TF, TT), torch.empty(B, TF)
+    dot = torch.einsum("btc,bsc->bts", feats.float().cpu(), text.float().cpu())
+    F.align_logp_from_dot(cpu.copy_(dot), nf.cpu(), nt.cpu(), tl.cpu(), clse)
+    close(got.cpu()[fin.cpu()], cpu[fin.cpu()], 2e-4, "contract")
+
+
 def test_forward_sum_matches_reference_ctc_golden(ops):
     """Loss and gradient of the reference's ForwardSumLoss (F.ctc_loss path, incl. an infeasible utterance)."""
     from seq2seq_vc_b200.aasvc_engine import beta_binomial_log_prior
