@@ -771,8 +771,8 @@ class AASVCEngine(ConformerBlocks, EngineBase):
         f2u = self.buf("al.f2u", (B, L, C))
         gf2u = self._scratch("g.al_a", (B, L, C))
         self._lin_bwd(dfeats.view(B * L, C), f2u.view(B * L, C), self.W("alignment_module.f_conv3.weight").view(C, C),
-                      st.g("alignment_module.f_conv3.weight").view(C, C), st.g("alignment_module.f_conv3.bias"), dx=gf2u.view(B * L, C))
-        ops.relu_bwd(gf2u, f2u, gf2u, 1.0)
+                      st.g("alignment_module.f_conv3.weight").view(C, C), st.g("alignment_module.f_conv3.bias"), dx=gf2u.view(B * L, C),
+                      dx_gate=f2u.view(B * L, C))                    # ReLU' of f_conv2 rides in the GEMM epilogue
         gf2p = ops.pad_rows(gf2u, self._scratch("g.al_p", (B, L + 2, C)), 1)
         f1 = self.buf("al.f1.z", (B, L + 2, C))
         gf1 = self._scratch("g.al_p2", (B, L + 2, C))
@@ -783,8 +783,8 @@ class AASVCEngine(ConformerBlocks, EngineBase):
         t1u = self.buf("al.t1u", (B, Tt, C))
         gt1u = self._scratch("g.al_a", (B, Tt, C))
         self._lin_bwd(dtext.view(B * Tt, C), t1u.view(B * Tt, C), self.W("alignment_module.t_conv2.weight").view(C, C),
-                      st.g("alignment_module.t_conv2.weight").view(C, C), st.g("alignment_module.t_conv2.bias"), dx=gt1u.view(B * Tt, C))
-        ops.relu_bwd(gt1u, t1u, gt1u, 1.0)
+                      st.g("alignment_module.t_conv2.weight").view(C, C), st.g("alignment_module.t_conv2.bias"), dx=gt1u.view(B * Tt, C),
+                      dx_gate=t1u.view(B * Tt, C))
         gt1p = ops.pad_rows(gt1u, self._scratch("g.al_p", (B, Tt + 2, C)), 1)
         ghp = self._scratch("g.al_p2", (B, Tt + 2, C))
         self._conv1d_bwd(gt1p, self.buf("al.tpad", (B, Tt + 2, C)), "alignment_module.t_conv1", Tt, "al.t1", ghp)

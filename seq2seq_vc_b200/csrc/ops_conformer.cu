@@ -15,6 +15,17 @@ template <typename T> __device__ __forceinline__ void ld8(const T* p, float (&v)
 template <typename T> __device__ __forceinline__ void st8(T* p, const float (&v)[8]) { Vec8<T>::store(p, v); }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+// bf16 activations: one MUFU (tanh.approx, |err| ~ 2^-11, far below bf16's 2^-8 rounding) instead of ex2 + rcp -- the Swish / GLU
+// passes over (B T, 1536) are issue-bound on the special-function unit once dropout is on
+template <typename T> __device__ __forceinline__ float sigmoid_act(float x) {
+    if constexpr (sizeof(T) == 2) {
+        float t;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+        return fmaf(0.5f, t, 0.5f);
+    } else {
+        return sigmoidf_(x);
+    }
+}
 
 // ---------------------------------------------------------------------------------------------
 // q (rows, d) with row stride ldq  ->  qu = q + u, qv = q + v   (contiguous (rows, d))
@@ -174,7 +185,7 @@ __global__ void __launch_bounds__(256) glu_fwd_kernel(const T* __restrict__ x, T
             ld8<T>(x + r * 2 * C + C + c, reinterpret_cast<float(&)[8]>(g));
         } else { a[0] = to_f<T>(x[r * 2 * C + c]); g[0] = to_f<T>(x[r * 2 * C + C + c]); }
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) a[k] *= sigmoidf_(g[k]);
+        for (int k = 0; k < VEC; ++k) a[k] *= sigmoid_act<T>(g[k]);
         if constexpr (VEC == 8) st8<T>(y + r * C + c, reinterpret_cast<float(&)[8]>(a));
         else y[r * C + c] = from_f<T>(a[0]);
     }
@@ -198,7 +209,7 @@ __global__ void __launch_bounds__(256) glu_bwd_kernel(const T* __restrict__ dy, 
         } else { a[0] = to_f<T>(x[r * 2 * C + c]); g[0] = to_f<T>(x[r * 2 * C + C + c]); d[0] = to_f<T>(dy[r * C + c]); }
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
-            float s = sigmoidf_(g[k]);
+            float s = sigmoid_act<T>(g[k]);
             da[k] = d[k] * s;
             dg[k] = d[k] * a[k] * s * (1.f - s);
         }
@@ -465,7 +476,7 @@ __global__ void __launch_bounds__(256) swish_kernel(const T* __restrict__ g, con
         else mk[0] = dropout_factor(drop, (uint64_t)i);
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
-            const float s = sigmoidf_(a[k]);
+            const float s = sigmoid_act<T>(a[k]);
             const float m = mk[k];
             a[k] = BWD ? d[k] * m * (s + a[k] * s * (1.f - s)) : a[k] * s * m;
         }
