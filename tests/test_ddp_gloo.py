@@ -225,3 +225,82 @@ def test_aasvc_gradient_accumulation_rejects_zero():
 
     with pytest.raises(ValueError):
         AASVCTrainStep(object(), gradient_accumulate_steps=0)
+
+
+# ------------------------------------------------------------- FastSpeechVC (NARVCTrainStep), world size 2
+FS_HP = dict(idim=80, odim=80, adim=32, aheads=2, elayers=1, eunits=48, dlayers=1, dunits=48, duration_predictor_input_dim=80,
+             duration_predictor_layers=2, duration_predictor_chans=16, duration_predictor_kernel_size=3, postnet_layers=2, postnet_filts=5,
+             postnet_chans=16, conformer_enc_kernel_size=7, conformer_dec_kernel_size=7, transformer_enc_dropout_rate=0.0,
+             transformer_enc_positional_dropout_rate=0.0, transformer_enc_attn_dropout_rate=0.0, transformer_dec_dropout_rate=0.0,
+             transformer_dec_positional_dropout_rate=0.0, transformer_dec_attn_dropout_rate=0.0, duration_predictor_dropout_rate=0.0,
+             postnet_dropout_rate=0.0)
+
+
+def _fs_batch(rank):
+    g = torch.Generator().manual_seed(400 + rank)
+    B, T = 2, 46
+    ilens = [46, 39 - rank]
+    tl = [((i - 2 + 1) // 2 - 2 + 1) // 2 for i in ilens]
+    xs = torch.randn(B, T, 80, generator=g)
+    ds = torch.randint(0, 4, (B, max(tl)), generator=g)
+    for b in range(B):
+        xs[b, ilens[b]:] = 0
+        ds[b, tl[b]:] = 0
+        ds[b, 0] = max(int(ds[b, 0]), 1)
+    olens = ds.sum(1).tolist()
+    ys = torch.randn(B, max(olens), 80, generator=g)
+    for b in range(B):
+        ys[b, olens[b]:] = 0
+    return xs, ilens, ys, olens, ds
+
+
+def _fs_worker(rank, world, port, out_dir):
+    _install_fakes_all()
+    import torch.distributed as dist
+
+    from seq2seq_vc_b200 import NARVCTrainStep
+    from seq2seq_vc_b200.fsvc_engine import FastSpeechVCEngine
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    eng = FastSpeechVCEngine(FS_HP, device="cpu", bf16=False, seed=5)
+    step = NARVCTrainStep(eng, lr=1e-3, warmup_steps=1, use_graph=False)
+    xs, ilens, ys, olens, ds = _fs_batch(rank)
+    for _ in range(2):
+        step(xs, ilens, ys, olens, ds, xs)
+    torch.save(eng.store.P.clone(), os.path.join(out_dir, f"f{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_fastspeech_vc_two_rank_step_matches_mean_gradient_step(tmp_path, monkeypatch):
+    """NARVCTrainStep under a world-size-2 gloo group (rank-specific ragged batches and durations): the replicas stay identical and
+    equal one process stepping on the mean of the two gradients -- the path shards by utterance batch, one all-reduce per step."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_fs_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    p0, p1 = torch.load(tmp_path / "f0.pt"), torch.load(tmp_path / "f1.pt")
+    assert torch.equal(p0, p1), "replicas diverged"
+
+    import fake_ops
+    from seq2seq_vc_b200 import NARVCTrainStep
+    from seq2seq_vc_b200.fsvc_engine import FastSpeechVCEngine
+
+    fake_ops.install(monkeypatch)
+    engs = [FastSpeechVCEngine(FS_HP, device="cpu", bf16=False, seed=5) for _ in range(2)]
+    ref = FastSpeechVCEngine(FS_HP, device="cpu", bf16=False, seed=5)
+    stepper = NARVCTrainStep(ref, lr=1e-3, warmup_steps=1)
+    for it in range(2):
+        g = torch.zeros_like(ref.store.G)
+        for r, e in enumerate(engs):
+            e.store.P.copy_(ref.store.P)
+            e.seed_dev.copy_(ref.seed_dev)
+            xs, ilens, ys, olens, ds = _fs_batch(r)
+            e.forward(xs, ys, ds, xs, ilens, olens)
+            e.loss(ys)
+            e.backward()
+            g += e.store.G
+        ref.store.G.copy_(g / 2)
+        stepper.steps += 1
+        ref.lr_dev.fill_(stepper.lr_at(stepper.steps))
+        ref.optimizer_step(1.0)
+    assert (ref.store.P - p0).abs().max().item() <= 1e-6

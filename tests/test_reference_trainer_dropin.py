@@ -825,3 +825,43 @@ def test_fused_narvc_train_step_matches_reference_trainer(trainers, monkeypatch)
     _close(ref.state_dict(), ours.engine.state_dict())
     ck = step.state_dict()                           # reference checkpoint layout (trainers/base.py:86-104)
     assert ck["steps"] == 3 and set(ck["model"]) == set(ref.state_dict())
+
+
+def test_reference_narvc_trainer_eval_hook_with_dropin_inference(trainers, monkeypatch, tmp_path):
+    """NARVCTrainer._genearete_and_save_intermediate_result (trainers/nar_vc.py:103-203) calls
+    model.inference(x, spembs=None, dp_input=dp_input) on every (padded) row of the batch and unpacks (outs, d_outs): the drop-in's
+    predicted durations are exact and everything drawn matches the reference model's."""
+    _, _, outdir = trainers
+    import seq2seq_vc.trainers.nar_vc as t_nar
+    import seq2seq_vc_b200
+    from seq2seq_vc.losses import L1Loss
+    from seq2seq_vc.models import FastSpeechVC as RefFS
+
+    torch.manual_seed(67)
+    ref = RefFS(**FS_HP, **FS_FIXED)
+    with torch.no_grad():
+        ref.duration_predictor.linear.bias.add_(1.0)          # so that the predicted durations are not all zero
+    ours = seq2seq_vc_b200.FastSpeechVC(**FS_HP, **FS_FIXED, **AAS_NO_DROPOUT)
+    ours.load_state_dict(ref.state_dict())
+    ref.eval()
+    ours.eval()
+    batch = _fs_batch()
+    r = ref.inference(batch["xs"][0], spembs=None, dp_input=batch["dp_inputs"][0])
+    o = ours.inference(batch["xs"][0], spembs=None, dp_input=batch["dp_inputs"][0])
+    assert len(r) == len(o) == 2
+    assert torch.equal(r[1].long(), o[1].long()) and r[0].shape == o[0].shape and (r[0] - o[0]).abs().max().item() <= 2e-4
+    r2 = ref.inference(batch["xs"][1], spembs=None, dp_input=batch["dp_inputs"][1], alpha=1.3)
+    o2 = ours.inference(batch["xs"][1], spembs=None, dp_input=batch["dp_inputs"][1], alpha=1.3)
+    assert r2[0].shape == o2[0].shape and (r2[0] - o2[0]).abs().max().item() <= 2e-4
+    drawn = []
+    for i, model in enumerate((ref, ours)):
+        config = dict(FS_CONFIG, outdir=str(tmp_path / f"run{i}"), num_save_intermediate_results=4)
+        plt = _RecordingPlt()
+        monkeypatch.setattr(t_nar, "plt", plt)
+        tr = _run(t_nar.NARVCTrainer, model, {"L1Loss": L1Loss()}, config, batch, 0)
+        tr.vocoder = None
+        tr._genearete_and_save_intermediate_result(batch)
+        drawn.append(plt.arrays)
+    assert len(drawn[0]) == len(drawn[1]) > 0
+    for a, b in zip(*drawn):
+        assert a.shape == b.shape and np.abs(a - b).max() <= 2e-4
