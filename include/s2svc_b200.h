@@ -36,7 +36,7 @@ extern "C" {
 #define S2S_F32 0
 #define S2S_BF16 1
 
-#define S2S_ABI_VERSION 20
+#define S2S_ABI_VERSION 21
 
 const char* s2s_last_error(void);
 int s2s_abi_version(void);
@@ -364,6 +364,13 @@ int s2s_logmel(const float* wav, const float* window, const float* mel_basis, fl
  * the store: mel[b,t,m] = (logmel - mean[m]) / scale[m]; mean / scale are (n_mels) float32 (bin/compute_statistics.py). */
 int s2s_logmel_norm(const float* wav, const float* window, const float* mel_basis, const float* mean, const float* scale, float* mel,
                     int B, int n_samples, int n_fft, int hop, int n_mels, float eps, float log_base, void* stream);
+
+/* Weight gradient of Conv2dSubsampling's first convolution through the GEMM path (bf16 engine): s2s_conv1_xcol builds the
+ * (B T1 F1, 16) patch matrix of the INPUT x (B, T, F) float32 -- nine taps of Conv2d(1, C, 3, 2), a column of ones, six zero columns --
+ * in `dtype`; s2s_gemm forms dy1^T x it into a (C, 16) float32 block; s2s_conv1_dw_scatter adds columns 0..8 into dw (C, 9) and
+ * column 9 into dbias (C) (subsampling.py:58-63). */
+int s2s_conv1_xcol(const float* x, void* xcol, int B, int T, int F, int dtype, void* stream);
+int s2s_conv1_dw_scatter(const float* g16, float* dw, float* dbias, int C, void* stream);
 
 /* Generic square-kernel / stride patch gather and its adjoint over channels-last maps (the later convolutions of
  * Conv2dSubsampling2 / 6 / 8, modules/transformer/subsampling.py:108-279: (k, s) = (3, 1), (5, 3), (3, 2)):

@@ -19,7 +19,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libs2svc_b200.so")
 
 S2S_F32, S2S_BF16 = 0, 1
-ABI_VERSION = 20
+ABI_VERSION = 21
 
 
 class S2SError(RuntimeError):
@@ -122,6 +122,8 @@ SIGNATURES = {
     "s2s_gl_update": (c_int, [_P, _P, _P, c_int64, c_float, _P]),
     "s2s_row_sqnorm": (c_int, [_P, _P, c_int64, c_int, c_int, _P]),
     "s2s_align_logp_from_dot": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "s2s_conv1_xcol": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
+    "s2s_conv1_dw_scatter": (c_int, [_P, _P, _P, c_int, _P]),
     "s2s_im2col2d": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "s2s_col2im2d": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "s2s_feat_stats": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),

@@ -272,6 +272,26 @@ __device__ __forceinline__ void dropout_factors(const Dropout& d, uint64_t idx, 
     }
 }
 
+// 8 consecutive elements kept as loaded (bf16: one 16-byte register quad) until they are needed as floats
+template <typename T> struct Raw8;
+template <> struct Raw8<bf16> {
+    uint4 r;
+    __device__ __forceinline__ void load(const bf16* p) { r = *reinterpret_cast<const uint4*>(p); }
+    __device__ __forceinline__ void get(float (&v)[8]) const {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
+    }
+};
+template <> struct Raw8<float> {
+    float4 a, b;
+    __device__ __forceinline__ void load(const float* p) { a = reinterpret_cast<const float4*>(p)[0]; b = reinterpret_cast<const float4*>(p)[1]; }
+    __device__ __forceinline__ void get(float (&v)[8]) const {
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+};
+
+
 // grid size for grid-stride elementwise kernels: enough CTAs to fill the chip a few times over
 inline unsigned ew_grid(long n_items, int per_block) {
     long b = ceil_div_l(n_items, per_block);

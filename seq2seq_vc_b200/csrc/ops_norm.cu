@@ -117,24 +117,6 @@ __global__ void __launch_bounds__(128) ln_bwd_dx_kernel(const T* __restrict__ dy
 // (a register-accumulating fused variant was measured slower: 255 registers -> 8 warps per SM).
 // ---------------------------------------------------------------------------------------------
 // raw 16-byte row chunks: 8 bf16 in 4 registers (decoded on every use) or 8 floats in 8 registers
-template <typename T> struct Raw8;
-template <> struct Raw8<bf16> {
-    uint4 r;
-    __device__ __forceinline__ void load(const bf16* p) { r = *reinterpret_cast<const uint4*>(p); }
-    __device__ __forceinline__ void get(float (&v)[8]) const {
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
-    }
-};
-template <> struct Raw8<float> {
-    float4 a, b;
-    __device__ __forceinline__ void load(const float* p) { a = reinterpret_cast<const float4*>(p)[0]; b = reinterpret_cast<const float4*>(p)[1]; }
-    __device__ __forceinline__ void get(float (&v)[8]) const {
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-    }
-};
-
 template <typename T, int NV>
 __global__ void __launch_bounds__(256) ln_fwd_reg_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, T* __restrict__ y, float* __restrict__ mean,

@@ -218,6 +218,7 @@ class EngineBase:
     # give the per-layer gradient temporaries distinct buffers while deferring (see VTNEngine.backward).
     _defer = None
     group_dw = os.environ.get("S2S_GROUP_DW", "1") != "0"
+    conv1_dw_tc = os.environ.get("S2S_CONV1_DW_TC", "1") != "0"      # A/B switch: first-convolution weight gradient on the GEMM path
 
     def _begin_defer(self) -> bool:
         if self.mode == 1 and self.group_dw and self.device.type == "cuda":
@@ -585,4 +586,10 @@ class EngineBase:
         ops.gemm(dy2, w2p.view(d, 9 * d).t(), dcol, mode=mode)
         dy1 = self._scratch("g.y1", (B, T1, F1, d))
         ops.col2im_s2_relu(dcol, y1, dy1)          # scatter-add + conv.0's ReLU' in one pass
-        ops.conv1_bwd(xs, dy1, st.g(prefix + ".conv.0.weight"), st.g(prefix + ".conv.0.bias"))
+        if self.mode == 1 and self.conv1_dw_tc:
+            # bf16 engine: conv.0's weight / bias gradient as dy1^T x (16-column patch matrix of the input) on the tcgen05 GEMM
+            xcol = self._scratch("conv1.xcol", (B * T1 * F1, 16))
+            g16 = self._scratch("conv1.g16", (d, 16), _f32)
+            ops.conv1_bwd_tc(xs, dy1, st.g(prefix + ".conv.0.weight"), st.g(prefix + ".conv.0.bias"), xcol, g16, mode=1)
+        else:
+            ops.conv1_bwd(xs, dy1, st.g(prefix + ".conv.0.weight"), st.g(prefix + ".conv.0.bias"))

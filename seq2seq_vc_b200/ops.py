@@ -808,3 +808,17 @@ def align_logp_from_dot(logp, nf, nt, text_lens, lse):
     assert logp.is_contiguous() and logp.dtype == torch.float32 and nf.numel() == B * TF and nt.numel() == B * TT
     check(_L().s2s_align_logp_from_dot(ptr(logp), ptr(nf), ptr(nt), ptr(text_lens), ptr(lse), B, TF, TT, stream()), "align_logp_from_dot")
     return logp
+
+
+def conv1_bwd_tc(x, dy1, dw, dbias, xcol, g16, mode=1):
+    """conv1_bwd through the tensor cores: dw (C,1,3,3) += dy1^T patches(x), dbias += colsum(dy1).  xcol (B T1 F1, 16) in dy1's dtype
+    and g16 (C, 16) float32 are caller-provided scratch."""
+    B, T, F = x.shape
+    C = dy1.shape[-1]
+    P = dy1.numel() // C
+    assert x.dtype == torch.float32 and x.is_contiguous() and dy1.is_contiguous() and xcol.shape == (P, 16) and xcol.dtype == dy1.dtype
+    assert g16.shape == (C, 16) and g16.dtype == torch.float32 and dw.is_contiguous() and dw.numel() == C * 9
+    check(_L().s2s_conv1_xcol(ptr(x), ptr(xcol), B, T, F, dt(xcol), stream()), "conv1_xcol")
+    g16.zero_()
+    gemm(dy1.view(P, C).t(), xcol.t(), g16, accumulate=True, mode=mode)      # accumulate-in-place float32 output: split-K over the positions
+    check(_L().s2s_conv1_dw_scatter(ptr(g16), ptr(dw), ptr(dbias), C, stream()), "conv1_dw_scatter")

@@ -588,3 +588,28 @@ def test_decode_kernels(ops, dt):
     ops.decode_advance(feat.cuda(), logit.cuda(), nxt, frames, logits, p2, odim, r)
     assert p2.item() == 12 and torch.equal(nxt.cpu(), feat[odim:]) and torch.equal(frames[11].cpu(), feat.float())
     assert torch.equal(logits[11].cpu(), logit.float()) and frames[12].abs().sum().item() == 0
+
+
+@pytest.mark.parametrize("B,T,Fq,C", [(2, 23, 80, 16), (3, 64, 80, 384), (32, 512, 80, 384)])
+def test_conv1_weight_gradient_through_gemm(ops, B, T, Fq, C):
+    """conv.0's weight / bias gradient as dy1^T x (16-column patch matrix of the input) on the tcgen05 GEMM (bf16 engine) vs the
+    CUDA-core kernel on the same bf16 dy1: the only difference is the bf16 rounding of the input patches (2^-9 relative per term)."""
+    bf = torch.bfloat16
+    T1, F1 = (T - 1) // 2, (Fq - 1) // 2
+    g = torch.Generator().manual_seed(B + T)
+    x = torch.randn(B, T, Fq, generator=g).cuda()
+    dy1 = (torch.randn(B, T1, F1, C, generator=g) * 0.1).to(bf).cuda()
+    dw0, db0 = torch.zeros(C, 1, 3, 3, device="cuda"), torch.zeros(C, device="cuda")
+    ops.conv1_bwd(x, dy1, dw0, db0)
+    dw1, db1 = torch.ones(C, 1, 3, 3, device="cuda"), torch.ones(C, device="cuda")          # accumulates into what is there
+    xcol = torch.empty(B * T1 * F1, 16, dtype=bf, device="cuda")
+    g16 = torch.empty(C, 16, device="cuda")
+    ops.conv1_bwd_tc(x, dy1, dw1, db1, xcol, g16)
+    assert (xcol[:, 9] == 1).all() and (xcol[:, 10:] == 0).all()
+    ref_col = torch.nn.functional.unfold(x.unsqueeze(1), 3, stride=2).transpose(1, 2).reshape(-1, 9)      # (B T1 F1, 9), taps kt*3+kf
+    assert torch.equal(xcol[:, :9].float(), ref_col.to(bf).float())
+    scale = dw0.abs().max().item()
+    assert ((dw1 - 1) - dw0).abs().max().item() <= 1e-2 * scale + 1e-3
+    assert ((db1 - 1) - db0).abs().max().item() <= 2e-3 * db0.abs().max().item() + 1e-3
+    cos = torch.nn.functional.cosine_similarity((dw1 - 1).flatten(), dw0.flatten(), dim=0).item()
+    assert cos >= 0.9999, cos
