@@ -36,7 +36,7 @@ extern "C" {
 #define S2S_F32 0
 #define S2S_BF16 1
 
-#define S2S_ABI_VERSION 21
+#define S2S_ABI_VERSION 22
 
 const char* s2s_last_error(void);
 int s2s_abi_version(void);
@@ -371,6 +371,9 @@ int s2s_logmel_norm(const float* wav, const float* window, const float* mel_basi
  * column 9 into dbias (C) (subsampling.py:58-63). */
 int s2s_conv1_xcol(const float* x, void* xcol, int B, int T, int F, int dtype, void* stream);
 int s2s_conv1_dw_scatter(const float* g16, float* dw, float* dbias, int C, void* stream);
+/* forward of the same convolution on the GEMM path: w16 (C, 16) = [w (C, 9) | bias | 0 x 6] in `dtype`; y1 = relu(patches x w16^T) through
+ * s2s_gemm (the ones column of the patch matrix carries the bias). */
+int s2s_conv1_pack_w(const float* w, const float* bias, void* w16, int C, int dtype, void* stream);
 
 /* Generic square-kernel / stride patch gather and its adjoint over channels-last maps (the later convolutions of
  * Conv2dSubsampling2 / 6 / 8, modules/transformer/subsampling.py:108-279: (k, s) = (3, 1), (5, 3), (3, 2)):

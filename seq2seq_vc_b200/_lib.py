@@ -19,7 +19,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libs2svc_b200.so")
 
 S2S_F32, S2S_BF16 = 0, 1
-ABI_VERSION = 21
+ABI_VERSION = 22
 
 
 class S2SError(RuntimeError):
@@ -124,6 +124,7 @@ SIGNATURES = {
     "s2s_align_logp_from_dot": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "s2s_conv1_xcol": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
     "s2s_conv1_dw_scatter": (c_int, [_P, _P, _P, c_int, _P]),
+    "s2s_conv1_pack_w": (c_int, [_P, _P, _P, c_int, c_int, _P]),
     "s2s_im2col2d": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "s2s_col2im2d": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "s2s_feat_stats": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),

@@ -1202,6 +1202,15 @@ __global__ void __launch_bounds__(256) conv1_xcol_kernel(const float* __restrict
         Vec8<T>::store(dst + 8, reinterpret_cast<float(&)[8]>(v[8]));
     }
 }
+// w16[c] = [w[c, 0..8] | bias[c] | 0 x 6]: the first convolution's weights as the (C, 16) operand of patches x w16^T (+ bias through the
+// ones column of the patch matrix)
+template <typename T>
+__global__ void conv1_pack_w_kernel(const float* __restrict__ w, const float* __restrict__ bias, T* __restrict__ w16, int C) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C * 16) return;
+    const int c = i >> 4, k = i & 15;
+    w16[i] = from_f<T>(k < 9 ? w[c * 9 + k] : (k == 9 ? bias[c] : 0.f));
+}
 __global__ void conv1_dw_scatter_kernel(const float* __restrict__ g16, float* __restrict__ dw, float* __restrict__ dbias, int C) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= C * 10) return;
@@ -1217,6 +1226,13 @@ extern "C" int s2s_conv1_xcol(const float* x, void* xcol, int B, int T, int F, i
     const int T1 = (T - 1) / 2, F1 = (F - 1) / 2;
     const long P = (long)B * T1 * F1;
     S2S_DISPATCH_DTYPE(dtype, TT, (conv1_xcol_kernel<TT><<<ew_grid(P, 256), 256, 0, (cudaStream_t)stream>>>(x, (TT*)xcol, P, T, F, T1, F1)));
+    S2S_LAUNCH_OK();
+    return S2S_OK;
+}
+
+extern "C" int s2s_conv1_pack_w(const float* w, const float* bias, void* w16, int C, int dtype, void* stream) {
+    S2S_REQUIRE(w && bias && w16 && C > 0, "conv1_pack_w: bad arguments");
+    S2S_DISPATCH_DTYPE(dtype, TT, (conv1_pack_w_kernel<TT><<<(unsigned)ceil_div_l((long)C * 16, 256), 256, 0, (cudaStream_t)stream>>>(w, bias, (TT*)w16, C)));
     S2S_LAUNCH_OK();
     return S2S_OK;
 }

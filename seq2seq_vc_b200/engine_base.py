@@ -68,6 +68,7 @@ class EngineBase:
         self._retired: List[torch.Tensor] = []        # outgrown scratch / tables that captured CUDA graphs may still address
         self._sig_lru: "OrderedDict[Tuple, bool]" = OrderedDict()
         self._evict_listeners: List[Callable[[Tuple], None]] = []
+        self._xcol_ready = set()
 
     def named_drop(self, name: str, p: float) -> Drop:
         """Dropout site addressed by name (stable id per engine): forward and backward just ask for the same name."""
@@ -533,6 +534,36 @@ class EngineBase:
                      mode=self.mode, M=M)
         return dx
 
+    # ------------------------------------------------------------------ first convolution of Conv2dSubsampling
+    conv1_fwd_tc = os.environ.get("S2S_CONV1_FWD_TC", "1") != "0"      # A/B switch: forward on the GEMM path (bf16 engines)
+    _xcol_ready: set = set()
+
+    def _conv1_fwd(self, xs, prefix: str, y1, tag: str):
+        """y1 (B, T1, F1, d) = relu(Conv2d(1 -> d, 3, 2)(xs)).  bf16 engines: a 16-column patch matrix of the input (kept for the
+        weight gradient) times the packed weights on the tcgen05 GEMM; float32 engines: the direct kernel."""
+        st = self.store
+        w, b = st.p(prefix + ".conv.0.weight"), st.p(prefix + ".conv.0.bias")
+        if self.mode == 1 and self.conv1_fwd_tc and self.device.type == "cuda":
+            B, T1, F1, d = y1.shape
+            xcol = self.buf(tag + ".xcol", (B * T1 * F1, 16))
+            ops.conv1_fwd_tc(xs, w, b, y1, xcol, self.buf(f"w.{tag}.conv1p", (d, 16)), mode=1)
+            self._xcol_ready.add((self._sig, tag))
+        else:
+            ops.conv1_fwd(xs, w, b, y1)
+        return y1
+
+    def _conv1_bwd(self, xs, dy1, prefix: str, tag: str) -> None:
+        st = self.store
+        gw, gb = st.g(prefix + ".conv.0.weight"), st.g(prefix + ".conv.0.bias")
+        if self.mode == 1 and self.conv1_dw_tc and self.device.type == "cuda":
+            # conv.0's weight / bias gradient as dy1^T x (16-column patch matrix of the input) on the tcgen05 GEMM
+            B, T1, F1, d = dy1.shape
+            ready = (self._sig, tag) in self._xcol_ready          # the forward of this batch shape left the patch matrix in its buffer
+            xcol = self.buf(tag + ".xcol", (B * T1 * F1, 16))
+            ops.conv1_bwd_tc(xs, dy1, gw, gb, xcol, self._scratch("conv1.g16", (d, 16), _f32), mode=1, xcol_ready=ready)
+        else:
+            ops.conv1_bwd(xs, dy1, gw, gb)
+
     # ------------------------------------------------------------------ Conv2dSubsampling without positional encoding
     def _conv2d_sub_fwd(self, xs: torch.Tensor, prefix: str, out_name: str, tag: str) -> torch.Tensor:
         """(B, T, idim) float32 -> (B*T2, d): Conv2d(1->d,3,s2)+ReLU, Conv2d(d->d,3,s2)+ReLU, Linear(d*F2 -> d)
@@ -547,7 +578,7 @@ class EngineBase:
         woutp = self.buf(f"w.{tag}.outp", (d, F2, d))
         ops.transpose_last2(st.p(out_name + ".weight"), woutp, d, d, F2)
         y1 = self.buf(tag + ".y1", (B, T1, F1, d))
-        ops.conv1_fwd(xs, st.p(prefix + ".conv.0.weight"), st.p(prefix + ".conv.0.bias"), y1)
+        self._conv1_fwd(xs, prefix, y1, tag)
         col = self._scratch("col", (B * T2 * F2, 9 * d))
         ops.im2col_s2(y1, col)
         self._col_of = (self._sig, tag)         # the patch matrix stays valid until a backward turns it into dcol (or another forward reuses it)
@@ -586,10 +617,4 @@ class EngineBase:
         ops.gemm(dy2, w2p.view(d, 9 * d).t(), dcol, mode=mode)
         dy1 = self._scratch("g.y1", (B, T1, F1, d))
         ops.col2im_s2_relu(dcol, y1, dy1)          # scatter-add + conv.0's ReLU' in one pass
-        if self.mode == 1 and self.conv1_dw_tc:
-            # bf16 engine: conv.0's weight / bias gradient as dy1^T x (16-column patch matrix of the input) on the tcgen05 GEMM
-            xcol = self._scratch("conv1.xcol", (B * T1 * F1, 16))
-            g16 = self._scratch("conv1.g16", (d, 16), _f32)
-            ops.conv1_bwd_tc(xs, dy1, st.g(prefix + ".conv.0.weight"), st.g(prefix + ".conv.0.bias"), xcol, g16, mode=1)
-        else:
-            ops.conv1_bwd(xs, dy1, st.g(prefix + ".conv.0.weight"), st.g(prefix + ".conv.0.bias"))
+        self._conv1_bwd(xs, dy1, prefix, tag)

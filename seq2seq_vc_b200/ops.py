@@ -810,15 +810,34 @@ def align_logp_from_dot(logp, nf, nt, text_lens, lse):
     return logp
 
 
-def conv1_bwd_tc(x, dy1, dw, dbias, xcol, g16, mode=1):
-    """conv1_bwd through the tensor cores: dw (C,1,3,3) += dy1^T patches(x), dbias += colsum(dy1).  xcol (B T1 F1, 16) in dy1's dtype
-    and g16 (C, 16) float32 are caller-provided scratch."""
+def conv1_xcol(x, xcol):
+    """xcol (B T1 F1, 16): the nine taps of Conv2d(1, C, 3, 2) around every output position of x (B, T, F) float32, a column of
+    ones, six zero columns."""
     B, T, F = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous() and xcol.is_contiguous() and xcol.shape == (B * ((T - 1) // 2) * ((F - 1) // 2), 16)
+    check(_L().s2s_conv1_xcol(ptr(x), ptr(xcol), B, T, F, dt(xcol), stream()), "conv1_xcol")
+    return xcol
+
+
+def conv1_fwd_tc(x, w, bias, y1, xcol, w16, mode=1):
+    """conv1_fwd through the tensor cores: y1 (B, T1, F1, C) = relu(patches(x) w16^T), w16 = [w | bias | 0]; leaves xcol for backward."""
+    C = w.shape[0]
+    conv1_xcol(x, xcol)
+    assert w16.shape == (C, 16) and w16.dtype == xcol.dtype == y1.dtype and y1.is_contiguous()
+    check(_L().s2s_conv1_pack_w(ptr(w), ptr(bias), ptr(w16), C, dt(w16), stream()), "conv1_pack_w")
+    gemm(xcol, w16, y1.view(-1, C), relu=True, mode=mode)
+    return y1
+
+
+def conv1_bwd_tc(x, dy1, dw, dbias, xcol, g16, mode=1, xcol_ready=False):
+    """conv1_bwd through the tensor cores: dw (C,1,3,3) += dy1^T patches(x), dbias += colsum(dy1).  xcol (B T1 F1, 16) in dy1's dtype
+    (rebuilt here unless the forward left it: xcol_ready) and g16 (C, 16) float32 are caller-provided scratch."""
     C = dy1.shape[-1]
     P = dy1.numel() // C
-    assert x.dtype == torch.float32 and x.is_contiguous() and dy1.is_contiguous() and xcol.shape == (P, 16) and xcol.dtype == dy1.dtype
+    assert dy1.is_contiguous() and xcol.shape == (P, 16) and xcol.dtype == dy1.dtype
     assert g16.shape == (C, 16) and g16.dtype == torch.float32 and dw.is_contiguous() and dw.numel() == C * 9
-    check(_L().s2s_conv1_xcol(ptr(x), ptr(xcol), B, T, F, dt(xcol), stream()), "conv1_xcol")
+    if not xcol_ready:
+        conv1_xcol(x, xcol)
     g16.zero_()
     gemm(dy1.view(P, C).t(), xcol.t(), g16, accumulate=True, mode=mode)      # accumulate-in-place float32 output: split-K over the positions
     check(_L().s2s_conv1_dw_scatter(ptr(g16), ptr(dw), ptr(dbias), C, stream()), "conv1_dw_scatter")

@@ -221,7 +221,7 @@ class VTNEngine(ConformerBlocks, EngineBase):
             ops.transpose_last2(st.p("encoder.embed.out.0.weight"), woutp, d, d, F2)
             # ---- encoder front end (subsampling.py:74-94)
             y1 = self.buf("enc.y1", (B, T1, F1, d))
-            ops.conv1_fwd(xs, st.p("encoder.embed.conv.0.weight"), st.p("encoder.embed.conv.0.bias"), y1)
+            self._conv1_fwd(xs, "encoder.embed", y1, "enc")
             col = self._scratch("col", (B * T2 * F2, 9 * d))
             ops.im2col_s2(y1, col)
             self._col_of = self._sig                       # the patch matrix stays valid until backward() turns it into dcol
@@ -858,12 +858,7 @@ class VTNEngine(ConformerBlocks, EngineBase):
         ops.gemm(dy2, w2p.view(d, 9 * d).t(), dcol, mode=mode)
         dy1 = self._scratch("g.y1", (B, T1, F1, d))
         ops.col2im_s2_relu(dcol, y1, dy1)          # scatter-add + conv.0's ReLU' in one pass
-        if mode == 1 and self.conv1_dw_tc:
-            # bf16 engine: conv.0's weight / bias gradient as dy1^T x (16-column patch matrix of the input) on the tcgen05 GEMM
-            ops.conv1_bwd_tc(self.xs, dy1, st.g("encoder.embed.conv.0.weight"), st.g("encoder.embed.conv.0.bias"),
-                             self._scratch("conv1.xcol", (B * T1 * F1, 16)), self._scratch("conv1.g16", (d, 16), _f32), mode=1)
-        else:
-            ops.conv1_bwd(self.xs, dy1, st.g("encoder.embed.conv.0.weight"), st.g("encoder.embed.conv.0.bias"))
+        self._conv1_bwd(self.xs, dy1, "encoder.embed", "enc")
 
 
     def encoder_span(self) -> int:

@@ -613,3 +613,13 @@ def test_conv1_weight_gradient_through_gemm(ops, B, T, Fq, C):
     assert ((db1 - 1) - db0).abs().max().item() <= 2e-3 * db0.abs().max().item() + 1e-3
     cos = torch.nn.functional.cosine_similarity((dw1 - 1).flatten(), dw0.flatten(), dim=0).item()
     assert cos >= 0.9999, cos
+    # forward on the same path: relu(patches x [w | bias | 0]^T) vs the direct kernel (fp32 input and weights, bf16 output)
+    w, bias = (torch.randn(C, 1, 3, 3, generator=g) * 0.3).cuda(), (torch.randn(C, generator=g) * 0.1).cuda()
+    y_ref = ops.conv1_fwd(x, w, bias, torch.empty(B, T1, F1, C, dtype=bf, device="cuda"))
+    y_tc = ops.conv1_fwd_tc(x, w, bias, torch.empty(B, T1, F1, C, dtype=bf, device="cuda"), xcol, torch.empty(C, 16, dtype=bf, device="cuda"))
+    err = (y_tc.float() - y_ref.float()).abs()
+    assert err.max().item() <= 3e-2 * max(1.0, y_ref.float().abs().max().item()) and err.mean().item() <= 3e-3
+    assert torch.equal(y_tc == 0, y_ref == 0) or ((y_tc == 0) != (y_ref == 0)).float().mean().item() < 2e-3      # ReLU cut at the same places
+    dw2, db2 = torch.zeros(C, 1, 3, 3, device="cuda"), torch.zeros(C, device="cuda")
+    ops.conv1_bwd_tc(x, dy1, dw2, db2, xcol, g16, xcol_ready=True)                                               # the forward left xcol
+    assert (dw2 - (dw1 - 1)).abs().max().item() <= 1e-3 * scale + 1e-5
