@@ -890,7 +890,7 @@ def run_ours(args, rank, world):
             peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
             ach = gf / (gms * 1e-3) / 1e12
             traffic = None
-            for fn in ("r01_gemm_tc_traffic.json", "r01_gemm_tc_traffic_c3.json"):     # ncu dram bytes per launch, per workload
+            for fn in ("r01_gemm_tc_traffic.json", "r01_gemm_tc_traffic_c3.json", "r02_gemm_tc_traffic.json", "r02_gemm_tc_traffic_c3.json"):   # later files win     # ncu dram bytes per launch, per workload
                 try:
                     tj = json.load(open(os.path.join(ROOT, "profiles", fn)))
                     if tj.get("workload") == args.workload:
