@@ -184,3 +184,46 @@ def test_dropin_teacher_reduction_factor(monkeypatch):
         assert a[i].shape == b[i].shape and (a[i] - b[i]).abs().max().item() <= 3e-5, i
     with pytest.raises(Exception):
         ours(xs, ilens, ys[:, :-1], olens - 1, ds, dlens, dpi, dp_lengths=ilens)          # sum of durations != target length
+
+
+@pytest.mark.parametrize("pw,k", [("conv1d", 1), ("conv1d", 3), ("conv1d-linear", 3)])
+def test_dropin_positionwise_variants_match_live_reference(monkeypatch, pw, k):
+    """FastSpeechVC with the MultiLayeredConv1d / Conv1dLinear position-wise layers (multi_layer_conv.py:12-108) in both conformer
+    stacks: same registration order, outputs and every parameter gradient as the live reference (CPU contracts)."""
+    from oracle import ref_shim
+
+    if not ref_shim.available():
+        pytest.skip("reference tree not present")
+    fake_ops.install(monkeypatch)
+    ref_shim.install()
+    from seq2seq_vc.models.fastspeech_vc import FastSpeechVC as RefFS
+    from seq2seq_vc_b200 import FastSpeechVC
+
+    kw = dict(FS_HP, encoder_type="conformer", decoder_type="conformer", encoder_input_layer="conv2d", positionwise_layer_type=pw,
+              positionwise_conv_kernel_size=k, duration_predictor_use_encoder_outputs=False, encoder_normalize_before=True,
+              decoder_normalize_before=True, teacher_model_decoder_reduction_factor=1)
+    torch.manual_seed(21 + k)
+    ref = RefFS(**kw)
+    ref_shim.disable_dropout(ref)
+    ours = FastSpeechVC(**kw, **NO_DROPOUT)
+    assert [n for n, _ in ours.named_parameters()] == [n for n, _ in ref.named_parameters()]
+    ours.load_state_dict(ref.state_dict())
+    z, _ = load()
+    ilens, olens = torch.from_numpy(z["ilens"]), torch.from_numpy(z["olens"])
+    xs, ys, dpi, ds = (torch.from_numpy(z[k_]) for k_ in ("xs", "ys", "dp_inputs", "ds"))
+    dlens = torch.from_numpy(z["ilens_out"])
+    ref.train()
+    ours.train()
+    a = ref(xs, ilens, ys, olens, ds, dlens, dpi, dp_lengths=ilens)
+    b = ours(xs, ilens, ys, olens, ds, dlens, dpi, dp_lengths=ilens)
+    for i in range(3):
+        assert (a[i] - b[i]).abs().max().item() <= 5e-5, i
+    r = torch.randn(a[1].shape, generator=torch.Generator().manual_seed(2))
+    ((a[1] * r).sum() + a[2].sum()).backward()
+    ((b[1] * r).sum() + b[2].sum()).backward()
+    gref = dict(ref.named_parameters())
+    gmax = max(p.grad.abs().max().item() for p in gref.values() if p.grad is not None)
+    for n, p in ours.named_parameters():
+        rg = gref[n].grad
+        assert rg is not None and p.grad is not None, n
+        assert (p.grad - rg).abs().max().item() <= 2e-3 * rg.abs().max().item() + 1e-5 * gmax, n
