@@ -255,3 +255,27 @@ def test_fused_train_step_graph_matches_eager_and_prefetch():
     assert (outs[0][0] - outs[1][0]).abs().max().item() <= 5e-3 * outs[0][0].abs().max().item()
     assert (outs[0][1] - outs[1][1]).abs().max().item() <= 1e-4
     assert (model.engine.state_dict()["feat_out.weight"].cpu() - sd["feat_out.weight"]).abs().max().item() > 0
+
+
+@pytest.mark.parametrize("pw,k", [("conv1d", 1), ("conv1d", 3), ("conv1d-linear", 3)])
+def test_positionwise_variants_fp32_vs_oracle(pw, k):
+    """MultiLayeredConv1d / Conv1dLinear position-wise layers in both conformer stacks of FastSpeechVC: float32 engine vs the CPU
+    oracle (forward, losses, every gradient) on the golden batch with freshly initialised parameters."""
+    from oracle import fsvc_oracle as fo
+    from seq2seq_vc_b200.fsvc_engine import FastSpeechVCEngine
+
+    z, _ = _golden()
+    hp = dict(FS_HP, positionwise_layer_type=pw, positionwise_conv_kernel_size=k, **NO_DROPOUT)
+    eng = FastSpeechVCEngine(hp, device="cuda:0", bf16=False, seed=9)
+    sd = {n: v.detach().cpu().clone() for n, v in eng.state_dict().items()}
+    ilens, olens = z["ilens"].tolist(), z["olens"].tolist()
+    xs, ys, dpi, ds = (torch.from_numpy(z[n]) for n in ("xs", "ys", "dp_inputs", "ds"))
+    out, parts, grads = fo.fsvc_loss_and_grads(sd, hp, xs, ilens, ys, olens, ds, dpi)
+    after, before, losses = _step(eng, z)
+    assert (after.cpu() - out["after_outs"].detach()).abs().mean().item() <= 1e-4
+    for i, n in enumerate(("l1_loss", "duration_loss")):
+        assert abs(losses[i].item() - parts[n].item()) <= 1e-4 * max(1.0, abs(parts[n].item())), n
+    gmax = max(g.abs().max().item() for g in grads.values())
+    for n in eng.store.names():
+        r, got = grads[n], eng.store.g(n).cpu()
+        assert (got - r).abs().mean().item() <= 2e-3 * r.abs().mean().item() + 1e-6 * gmax, n
