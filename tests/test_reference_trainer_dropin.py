@@ -865,3 +865,31 @@ def test_reference_narvc_trainer_eval_hook_with_dropin_inference(trainers, monke
     assert len(drawn[0]) == len(drawn[1]) > 0
     for a, b in zip(*drawn):
         assert a.shape == b.shape and np.abs(a - b).max() <= 2e-4
+
+
+@pytest.mark.parametrize("recipe,cls", [("egs/arctic/vc2/conf/fs2_vc.melmelmel.v1.yaml", "FastSpeechVC"),
+                                        ("egs/arctic/vc2/conf/aas_vc.melmelmel.v1.yaml", "AASVC"),
+                                        ("egs/arctic/vc1/conf/vtn.v1.yaml", "VTN")])
+def test_shipped_yaml_constructs_the_dropin_with_the_reference_state_dict(recipe, cls):
+    """`getattr(seq2seq_vc_b200, config["model_type"])(**config["model_params"])` on the recipes as shipped (bin/vc_train.py:348):
+    the drop-in builds, and its parameters / buffers carry the reference model's names, shapes and registration order."""
+    import os
+
+    import yaml
+
+    ref_shim.install()
+    import seq2seq_vc.models as ref_models
+    import seq2seq_vc_b200
+
+    path = os.path.join("/root/reference", recipe)
+    with open(path) as f:
+        config = yaml.load(f, Loader=yaml.Loader)
+    assert config["model_type"] == cls
+    params = dict(config["model_params"])
+    if cls == "VTN":
+        params.update(idim=config["num_mels"], odim=config["num_mels"])          # bin/vc_train.py:339-346 fills these in from the data
+    torch.manual_seed(0)
+    ref = getattr(ref_models, cls)(**params)
+    ours = getattr(seq2seq_vc_b200, cls)(**params)
+    assert [(n, tuple(p.shape)) for n, p in ours.named_parameters()] == [(n, tuple(p.shape)) for n, p in ref.named_parameters()]
+    assert {k: tuple(v.shape) for k, v in ours.state_dict().items()} == {k: tuple(v.shape) for k, v in ref.state_dict().items()}
