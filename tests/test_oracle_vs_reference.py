@@ -148,3 +148,44 @@ def test_shipped_aas_vc_yaml_constructs_with_the_reference_state_dict(ref):
     assert set(so) == set(st) and all(tuple(so[k].shape) == tuple(st[k].shape) for k in st)
     assert [n for n, _ in ours.named_parameters()] == [n for n, _ in theirs.named_parameters()]
     ours.load_state_dict(st)
+
+
+@pytest.mark.parametrize("factor", [1, 2])
+def test_fastspeech_vc_oracle_against_live_reference(ref, factor):
+    """oracle/fsvc_oracle.py == the live FastSpeechVC (conformer stacks, conv2d input layer, teacher durations x the teacher model's
+    reduction factor) + L1Loss + DurationPredictorLoss: outputs, lengths, both losses, every parameter gradient."""
+    from oracle import fsvc_oracle as fo
+    from seq2seq_vc.losses import DurationPredictorLoss, L1Loss
+    from seq2seq_vc.models import FastSpeechVC
+
+    hp = dict(idim=80, odim=80, adim=32, aheads=2, elayers=2, eunits=48, dlayers=1, dunits=48, duration_predictor_input_dim=80,
+              duration_predictor_layers=2, duration_predictor_chans=16, duration_predictor_kernel_size=3, postnet_layers=2, postnet_filts=5,
+              postnet_chans=16, conformer_enc_kernel_size=7, conformer_dec_kernel_size=7, teacher_model_decoder_reduction_factor=factor)
+    torch.manual_seed(13)
+    model = FastSpeechVC(**hp, positionwise_layer_type="linear", duration_predictor_use_encoder_outputs=False, encoder_normalize_before=True,
+                         decoder_normalize_before=True, encoder_type="conformer", decoder_type="conformer", encoder_input_layer="conv2d")
+    ref_shim.disable_dropout(model)
+    model.train()
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(17)
+    B, T, ilens = 2, 58, [58, 45]
+    tl = [((i - 2 + 1) // 2 - 2 + 1) // 2 for i in ilens]
+    xs = torch.randn(B, T, 80, generator=g)
+    ds = torch.randint(0, 4, (B, max(tl)), generator=g)
+    for b in range(B):
+        xs[b, ilens[b]:] = 0
+        ds[b, tl[b]:] = 0
+        ds[b, 0] = max(int(ds[b, 0]), 1)
+    olens = (factor * ds.sum(1)).tolist()
+    ys = torch.randn(B, max(olens), 80, generator=g)
+    out = model(xs, torch.tensor(ilens), ys, torch.tensor(olens), ds, torch.tensor(tl), xs, dp_lengths=torch.tensor(ilens))
+    l1 = L1Loss()(out[1], out[0], out[5], out[4])
+    dur = DurationPredictorLoss()(out[2], ds, out[3])
+    (l1 + dur).backward()
+    o, parts, grads = fo.fsvc_loss_and_grads(sd, hp, xs, ilens, ys, olens, ds, xs)
+    assert (o["after_outs"] - out[1]).abs().max() <= 2e-5 and (o["before_outs"] - out[0]).abs().max() <= 2e-5
+    assert (o["d_outs"] - out[2]).abs().max() <= 2e-5 and list(o["ilens"]) == out[3].tolist()
+    assert abs(float(parts["l1_loss"]) - float(l1)) <= 1e-6 and abs(float(parts["duration_loss"]) - float(dur)) <= 1e-6
+    gmax = max(p.grad.abs().max().item() for p in model.parameters())
+    for n, p in model.named_parameters():
+        assert (grads[n] - p.grad).abs().max().item() <= 1e-4 * p.grad.abs().max().item() + 1e-6 * gmax, n
